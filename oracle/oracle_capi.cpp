@@ -1,0 +1,411 @@
+// oracle_capi.cpp -- C ABI over thea_oracle.hpp for ctypes (tests/, bench.py cpu_baseline / --impl reference).
+//
+// TEST INFRASTRUCTURE ONLY (see the header of thea_oracle.hpp).  PARITY UNPINNED.
+#include "thea_oracle.hpp"
+
+#include <chrono>
+#include <functional>
+#include <thread>
+
+using namespace oracle;
+
+namespace {
+
+struct Handle { KdTree tree; };
+
+void parallel_for(int64_t n, int nthreads, std::function<void(int64_t, int64_t)> const & fn)
+{
+  if (nthreads <= 1 || n < 2 * nthreads) { fn(0, n); return; }
+  std::vector<std::thread> th;
+  int64_t chunk = (n + nthreads - 1) / nthreads;
+  for (int t = 0; t < nthreads; ++t)
+  {
+    int64_t b = t * chunk, e = std::min(n, b + chunk);
+    if (b >= e) break;
+    th.emplace_back([=, &fn] { fn(b, e); });
+  }
+  for (auto & t : th) t.join();
+}
+
+inline V3 ld3(float const * p, int64_t i) { return mk(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
+inline void st3(float * p, int64_t i, V3 v) { p[3 * i] = v.x; p[3 * i + 1] = v.y; p[3 * i + 2] = v.z; }
+
+// Deterministic generator of SURVEY.md 8(d): counter-based splitmix64, u01 = (x >> 40) * 2^-24.
+inline uint64_t splitmix64_at(uint64_t seed, uint64_t i)
+{
+  uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+inline float u01_at(uint64_t seed, uint64_t i) { return (float)(splitmix64_at(seed, i) >> 40) * (1.0f / 16777216.0f); }
+
+// 3x3 polar rotation R = U V^T of M via one-sided Jacobi in double (stand-in for Eigen::JacobiSVD, Icp3.hpp:369-370).
+void polar_rotation(double const M[9], double R[9])
+{
+  double A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int i = 0; i < 9; ++i) A[i] = M[i];   // row-major; columns are rotated
+  for (int sweep = 0; sweep < 60; ++sweep)
+  {
+    double off = 0;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q)
+      {
+        double a = 0, b = 0, c = 0;
+        for (int r = 0; r < 3; ++r) { a += A[3 * r + p] * A[3 * r + p]; b += A[3 * r + q] * A[3 * r + q]; c += A[3 * r + p] * A[3 * r + q]; }
+        off = std::max(off, std::fabs(c) / std::sqrt(std::max(a * b, 1e-300)));
+        if (std::fabs(c) <= 1e-300) continue;
+        double zeta = (b - a) / (2.0 * c);
+        double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+        double cs = 1.0 / std::sqrt(1.0 + t * t), sn = cs * t;
+        for (int r = 0; r < 3; ++r)
+        {
+          double ap = A[3 * r + p], aq = A[3 * r + q];
+          A[3 * r + p] = cs * ap - sn * aq; A[3 * r + q] = sn * ap + cs * aq;
+          double vp = V[3 * r + p], vq = V[3 * r + q];
+          V[3 * r + p] = cs * vp - sn * vq; V[3 * r + q] = sn * vp + cs * vq;
+        }
+      }
+    if (off < 1e-15) break;
+  }
+  // A = U * diag(s); normalise columns (rank-deficient columns completed by cross product).
+  double U[9]; double s[3];
+  for (int c = 0; c < 3; ++c)
+  {
+    s[c] = std::sqrt(A[c] * A[c] + A[3 + c] * A[3 + c] + A[6 + c] * A[6 + c]);
+    for (int r = 0; r < 3; ++r) U[3 * r + c] = s[c] > 0 ? A[3 * r + c] / s[c] : 0.0;
+  }
+  int mn = 0; for (int c = 1; c < 3; ++c) if (s[c] < s[mn]) mn = c;
+  if (s[mn] <= 1e-14 * std::max(s[0], std::max(s[1], s[2])))
+  {
+    int a = (mn + 1) % 3, b = (mn + 2) % 3;
+    U[mn] = U[3 + a] * U[6 + b] - U[6 + a] * U[3 + b];
+    U[3 + mn] = U[6 + a] * U[b] - U[a] * U[6 + b];
+    U[6 + mn] = U[a] * U[3 + b] - U[3 + a] * U[b];
+  }
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+    { double acc = 0; for (int k = 0; k < 3; ++k) acc += U[3 * r + k] * V[3 * c + k]; R[3 * r + c] = acc; }
+}
+
+struct Affine { float L[9]; V3 t; };   // row-major linear part
+
+inline V3 apply_linear(float const L[9], V3 v)
+{ return mk(sum3(L[0] * v.x, L[1] * v.y, L[2] * v.z), sum3(L[3] * v.x, L[4] * v.y, L[5] * v.z), sum3(L[6] * v.x, L[7] * v.y, L[8] * v.z)); }
+inline V3 apply(Affine const & a, V3 v) { return apply_linear(a.L, v) + a.t; }            // AffineTransformN.hpp:160
+inline Affine compose(Affine const & a, Affine const & b)                                     // AffineTransformN.hpp:154-157
+{
+  Affine r;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r.L[3 * i + j] = sum3(a.L[3 * i] * b.L[j], a.L[3 * i + 1] * b.L[3 + j], a.L[3 * i + 2] * b.L[6 + j]);
+  r.t = apply_linear(a.L, b.t) + a.t;
+  return r;
+}
+inline Affine identity_tr() { Affine a; for (int i = 0; i < 9; ++i) a.L[i] = (i % 4 == 0) ? 1.0f : 0.0f; a.t = mk(0, 0, 0); return a; }
+
+// Icp3.hpp:410-464 measureError(tr, n, from, nullptr, to) with ScalarT = float.
+float icp_error(Affine const & tr, int64_t n, V3 const * from, V3 const * to)
+{
+  V3 pm = mk(0, 0, 0), qm = mk(0, 0, 0); float sw = 0;
+  for (int64_t i = 0; i < n; ++i) { pm = pm + from[i]; qm = qm + to[i]; sw += 1; }
+  pm = pm / sw; qm = qm / sw;
+  float err = sqnorm(apply(tr, pm) - qm);
+  for (int64_t i = 0; i < n; ++i)
+  { V3 dp = from[i] - pm, dq = to[i] - qm; err += sqnorm(apply_linear(tr.L, dp) - dq); }
+  return err;
+}
+
+// Icp3.hpp:298-384 alignOneStep with known correspondences (no weights, no symmetry, no up vector).
+Affine icp_step(int64_t n, V3 const * from, V3 const * to)
+{
+  V3 pm = mk(0, 0, 0), qm = mk(0, 0, 0); float sw = 0;
+  for (int64_t i = 0; i < n; ++i) { pm = pm + from[i]; qm = qm + to[i]; sw += 1; }
+  pm = pm / sw; qm = qm / sw;
+  float cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int64_t i = 0; i < n; ++i)
+  {
+    V3 dp = from[i] - pm, dq = to[i] - qm;
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) cov[3 * r + c] += dp[r] * dq[c];
+  }
+  // rot = U V^T of cov = sum dp dq^T (Icp3.hpp:369-370); note that this maps q-space to p-space exactly as the
+  // reference writes it.
+  double M[9], R[9]; for (int i = 0; i < 9; ++i) M[i] = cov[i];
+  polar_rotation(M, R);
+  Affine a; for (int i = 0; i < 9; ++i) a.L[i] = (float)R[i];
+  a.t = qm - apply_linear(a.L, pm);
+  return a;
+}
+
+}  // namespace
+
+extern "C" {
+
+void * orc_create_tris(float const * v9, int64_t T)
+{
+  Handle * h = new Handle;
+  h->tree.is_points = false;
+  h->tree.tris.resize((size_t)T);
+  for (int64_t i = 0; i < T; ++i) h->tree.tris[(size_t)i] = make_tri(ld3(v9, 3 * i), ld3(v9, 3 * i + 1), ld3(v9, 3 * i + 2));
+  h->tree.build();
+  return h;
+}
+
+void * orc_create_points(float const * p3, int64_t P, float const * n3)
+{
+  Handle * h = new Handle;
+  h->tree.is_points = true;
+  h->tree.pts.resize((size_t)P);
+  for (int64_t i = 0; i < P; ++i) h->tree.pts[(size_t)i] = ld3(p3, i);
+  if (n3) { h->tree.nrm.resize((size_t)P); for (int64_t i = 0; i < P; ++i) h->tree.nrm[(size_t)i] = ld3(n3, i); }
+  h->tree.build();
+  return h;
+}
+
+void orc_destroy(void * h) { delete (Handle *)h; }
+int64_t orc_num_nodes(void * h) { return (int64_t)((Handle *)h)->tree.nodes.size(); }
+int64_t orc_max_depth(void * h) { return ((Handle *)h)->tree.max_depth; }
+
+void orc_tri_cache(void * h, float * n3, float * d, int32_t * axis, float * area)
+{
+  KdTree & T = ((Handle *)h)->tree;
+  for (size_t i = 0; i < T.tris.size(); ++i)
+  { st3(n3, (int64_t)i, T.tris[i].n); d[i] = T.tris[i].d; axis[i] = T.tris[i].axis; if (area) area[i] = T.tris[i].area; }
+}
+
+// mode 0: reference order (kd-tree DFS, first found wins); 1: canonical via kd-tree; 2: canonical brute force.
+// exclude_self: query i ignores element i (PointSet3::FilterSelf).
+void orc_closest(void * h, float const * q3, int64_t Q, double dist_bound, int mode, int exclude_self, int nthreads,
+                 int64_t * idx, float * d2, float * cp3)
+{
+  KdTree const & T = ((Handle *)h)->tree;
+  parallel_for(Q, nthreads, [&](int64_t b, int64_t e) {
+    for (int64_t i = b; i < e; ++i)
+    {
+      V3 q = ld3(q3, i); int64_t skip = exclude_self ? i : -1;
+      Closest r = mode == 0 ? T.closest<false>(q, dist_bound, skip)
+                : mode == 1 ? T.closest<true>(q, dist_bound, skip) : brute_closest(T, q, dist_bound, skip);
+      idx[i] = r.idx; if (d2) d2[i] = r.d2; if (cp3) st3(cp3, i, r.cp);
+    }
+  });
+}
+
+void orc_ray_first(void * h, float const * o3, float const * d3, float const * tmax, int64_t R, int mode, int nthreads,
+                   int64_t * idx, float * t)
+{
+  KdTree const & T = ((Handle *)h)->tree;
+  parallel_for(R, nthreads, [&](int64_t b, int64_t e) {
+    for (int64_t i = b; i < e; ++i)
+    {
+      V3 o = ld3(o3, i), d = ld3(d3, i); float mt = tmax ? tmax[i] : -1.0f;
+      RayHit r = mode == 0 ? T.ray_first_ref(o, d, mt) : mode == 1 ? T.ray_first_canon(o, d, mt) : brute_ray_first(T, o, d, mt);
+      idx[i] = r.idx; t[i] = r.t;
+    }
+  });
+}
+
+void orc_knn(void * h, float const * q3, int64_t Q, int k, double dist_bound, int exclude_self, int mode, int nthreads,
+             int64_t * idx, float * d2)
+{
+  KdTree const & T = ((Handle *)h)->tree;
+  double bound2 = dist_bound >= 0 ? dist_bound * dist_bound : -1;
+  parallel_for(Q, nthreads, [&](int64_t b, int64_t e) {
+    for (int64_t i = b; i < e; ++i)
+    {
+      V3 q = ld3(q3, i); int64_t skip = exclude_self ? i : -1;
+      int64_t * oi = idx + (int64_t)k * i; float * od = d2 + (int64_t)k * i;
+      if (mode == 2) { brute_knn(T, q, k, dist_bound, skip, oi, od); continue; }
+      if (mode == 0)
+      {
+        KdTree::KnnSet s; s.k = k;
+        if (!T.nodes.empty()) T.knn_rec(0, q, bound2, skip, s);
+        for (int j = 0; j < k; ++j) { oi[j] = j < (int)s.d.size() ? s.id[(size_t)j] : -1; od[j] = j < (int)s.d.size() ? (float)s.d[(size_t)j] : -1.0f; }
+      }
+      else
+      {
+        std::vector<std::pair<float, int64_t>> s;
+        if (!T.nodes.empty()) T.knn_canon_rec(0, q, bound2, skip, k, s);
+        for (int j = 0; j < k; ++j) { oi[j] = j < (int)s.size() ? s[(size_t)j].second : -1; od[j] = j < (int)s.size() ? s[(size_t)j].first : -1.0f; }
+      }
+    }
+  });
+}
+
+// PointSet3.hpp:363-376: RMS nearest-neighbour separation over fixed seed samples (float accumulation).
+float orc_avg_separation(void * h, int64_t const * seeds, int n)
+{
+  KdTree const & T = ((Handle *)h)->tree;
+  float acc = 0;
+  for (int i = 0; i < n; ++i)
+  {
+    int64_t s = seeds[i];
+    Closest r = T.closest<true>(T.pts[(size_t)s], -1, s);
+    acc += sqnorm(T.pts[(size_t)r.idx] - T.pts[(size_t)s]);
+  }
+  return std::sqrt(acc / (float)n);
+}
+
+// mode 0: kd-tree processRange (reference traversal); 2: brute force over all points.
+void orc_ball_graph(void * h, int max_degree, float init_radius, int mode, int nthreads, int64_t * idx, float * sep,
+                    int32_t * count)
+{
+  KdTree const & T = ((Handle *)h)->tree;
+  int64_t P = T.size();
+  parallel_for(P, nthreads, [&](int64_t b, int64_t e) {
+    for (int64_t i = b; i < e; ++i)
+    {
+      auto range = [&](V3 c, float r2, std::function<void(int64_t)> emit) {
+        if (mode == 2) { for (int64_t j = 0; j < P; ++j) if (sqnorm(T.pts[(size_t)j] - c) <= r2) emit(j); }
+        else kd_ball_range(T, 0, c, r2, emit);
+      };
+      int c = ball_graph_one(T, i, max_degree, init_radius, range, idx + (int64_t)max_degree * i, sep + (int64_t)max_degree * i);
+      if (count) count[i] = c;
+    }
+  });
+}
+
+// ShapeDiameter::compute(p, n, only_hit_interior) for S samples: emits the 30 rays, their first hits and the SDF.
+void orc_sdf(void * h, float const * p3, float const * n3, int64_t S, float scale, int only_interior, int mode, int nthreads,
+             float * ray_o3, float * ray_d3, int64_t * hit_idx, float * hit_t, double * sdf)
+{
+  KdTree const & T = ((Handle *)h)->tree;
+  parallel_for(S, nthreads, [&](int64_t b, int64_t e) {
+    for (int64_t s = b; s < e; ++s)
+    {
+      V3 org, dirs[30]; sdf_rays(ld3(p3, s), ld3(n3, s), scale, org, dirs);
+      float t[30]; bool valid[30];
+      for (int i = 0; i < 30; ++i)
+      {
+        RayHit r = mode == 0 ? T.ray_first_ref(org, dirs[i], -1) : mode == 1 ? T.ray_first_canon(org, dirs[i], -1)
+                                                                              : brute_ray_first(T, org, dirs[i], -1);
+        t[i] = r.t;
+        valid[i] = r.idx >= 0 && (!only_interior || dot(T.tris[(size_t)r.idx].n, dirs[i]) >= 0);
+        if (ray_o3) st3(ray_o3, 30 * s + i, org);
+        if (ray_d3) st3(ray_d3, 30 * s + i, dirs[i]);
+        if (hit_idx) hit_idx[30 * s + i] = r.idx;
+        if (hit_t) hit_t[30 * s + i] = r.t;
+      }
+      sdf[s] = sdf_stats(t, valid, scale);
+    }
+  });
+}
+
+// Statistics only (for checking a GPU epilogue given identical per-ray hits).
+double orc_sdf_stats(float const * t30, uint8_t const * valid30, float scale)
+{
+  bool v[30]; for (int i = 0; i < 30; ++i) v[i] = valid30[i] != 0;
+  return sdf_stats(t30, v, scale);
+}
+
+// Icp3<float>::align (Icp3.hpp:193-275) against a triangle structure; records the per-batch correspondences.
+// out_idx: (iters_done + 1) x n ; out_tr: 12 floats row-major [L | t]; returns the number of query batches run.
+int orc_icp(void * h, float const * from3, int64_t n, int min_iters, int max_iters, double frac_thresh, int mode, int nthreads,
+            int64_t * out_idx, float * out_tr, float * out_err)
+{
+  KdTree const & T = ((Handle *)h)->tree;
+  std::vector<V3> orig((size_t)n), from((size_t)n), to((size_t)n);
+  for (int64_t i = 0; i < n; ++i) orig[(size_t)i] = from[(size_t)i] = ld3(from3, i);
+  int batches = 0;
+  auto correspond = [&]() {
+    int64_t * oi = out_idx ? out_idx + (int64_t)batches * n : nullptr;
+    parallel_for(n, nthreads, [&](int64_t b, int64_t e) {
+      for (int64_t i = b; i < e; ++i)
+      {
+        Closest r = mode == 0 ? T.closest<false>(from[(size_t)i], -1) : mode == 1 ? T.closest<true>(from[(size_t)i], -1)
+                                                                                  : brute_closest(T, from[(size_t)i], -1);
+        to[(size_t)i] = r.cp; if (oi) oi[i] = r.idx;
+      }
+    });
+    batches++;
+  };
+  auto emit = [&](Affine const & a, float err) {
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) out_tr[4 * r + c] = a.L[3 * r + c]; out_tr[4 * r + 3] = a.t[r]; }
+    if (out_err) *out_err = err;
+  };
+  Affine old_tr = identity_tr();
+  correspond();
+  float old_err = icp_error(old_tr, n, from.data(), to.data());
+  if (old_err <= std::numeric_limits<float>::min()) { emit(old_tr, old_err); return batches; }
+  float new_err = old_err; Affine new_tr = old_tr;
+  for (int it = 0; it < max_iters; ++it)
+  {
+    Affine inc = icp_step(n, from.data(), to.data());
+    new_tr = compose(inc, old_tr);
+    // (error is always requested by this entry point, so the last iteration measures too: Icp3.hpp:236-237)
+    correspond();
+    new_err = icp_error(inc, n, from.data(), to.data());
+    if (it < max_iters - 1)
+    {
+      float frac = (old_err - new_err) / old_err;
+      if (it >= min_iters && frac < frac_thresh)
+      {
+        if (frac > 0) { emit(new_tr, new_err); return batches; }
+        else { emit(old_tr, old_err); return batches; }
+      }
+      for (int64_t j = 0; j < n; ++j) from[(size_t)j] = apply(new_tr, orig[(size_t)j]);
+    }
+    old_err = new_err; old_tr = new_tr;
+  }
+  emit(new_tr, new_err);
+  return batches;
+}
+
+// MeshSampler::sampleEvenlyByArea EXACT mode (MeshSampler.hpp:147-185, Triangle3.hpp:179-195) driven by the
+// counter-based generator: sample i consumes draws 3i, 3i+1, 3i+2.
+void orc_area_sample(void * h, int64_t S, uint64_t seed, float * p3, float * n3, int64_t * tri)
+{
+  KdTree const & T = ((Handle *)h)->tree;
+  size_t n = T.tris.size();
+  if (n == 0) return;
+  double total = 0; for (size_t i = 0; i < n; ++i) total += T.tris[i].area;
+  std::vector<double> cum(n);
+  cum[0] = T.tris[0].area; for (size_t i = 1; i < n; ++i) cum[i] = cum[i - 1] + T.tris[i].area;
+  for (int64_t i = 0; i < S; ++i)
+  {
+    double t = u01_at(seed, 3 * (uint64_t)i) * total;
+    int64_t ti = std::min((int64_t)(std::lower_bound(cum.begin(), cum.end(), t) - cum.begin()), (int64_t)n - 1);
+    Tri const & tr = T.tris[(size_t)ti];
+    float s = u01_at(seed, 3 * (uint64_t)i + 1), u = u01_at(seed, 3 * (uint64_t)i + 2);
+    if (s + u > 1) { u = 1 - u; s = 1 - s; }
+    st3(p3, i, (s * tr.e01 + u * tr.e02) + tr.v0);
+    if (n3) st3(n3, i, tr.n);
+    if (tri) tri[i] = ti;
+  }
+}
+
+// Single-primitive entry points for known-answer tests.
+float orc_tri_point(float const * v9, float const * p, float * cp)
+{
+  Tri t = make_tri(ld3(v9, 0), ld3(v9, 1), ld3(v9, 2)); V3 c; float d2 = tri_point_sqdist(t, ld3(p, 0), c);
+  if (cp) st3(cp, 0, c); return d2;
+}
+float orc_ray_tri(float const * v9, float const * o, float const * d)
+{ Tri t = make_tri(ld3(v9, 0), ld3(v9, 1), ld3(v9, 2)); return ray_tri_time(ld3(o, 0), ld3(d, 0), t.v0, t.e01, t.e02); }
+float orc_fast_sqrt(float x) { return fast_sqrt(x); }
+float orc_box_ray_time(float const * lo, float const * hi, float const * o, float const * d, float max_time)
+{ Box b; b.merge(ld3(lo, 0), ld3(hi, 0)); return b.ray_time(ld3(o, 0), ld3(d, 0), max_time); }
+void orc_polar_rotation(double const * M, double * R) { polar_rotation(M, R); }
+
+// Thea::Random (Random.cpp:48-125): MT19937 whose regeneration skips state[227]; uniform01 (Random.hpp:126-130).
+void orc_thea_random_uniform01(uint32_t seed, int64_t n, float * out)
+{
+  enum { N = 624, M = 397 };
+  uint32_t st[N]; st[0] = seed;
+  for (int i = 1; i < N; ++i) st[i] = 1812433253UL * (st[i - 1] ^ (st[i - 1] >> 30)) + (uint32_t)i;
+  int index = N;
+  uint32_t const LOWER = (1u << 31) - 1, UPPER = 0xFFFFFFFFu << 31; uint32_t const mag[2] = {0u, 0x9908B0DFu};
+  for (int64_t k = 0; k < n; ++k)
+  {
+    if (index >= N)
+    {
+      for (int i = 0; i < N - M; ++i) { uint32_t x = (st[i] & UPPER) | (st[i + 1] & LOWER); st[i] = st[i + M] ^ (x >> 1) ^ mag[x & 1]; }
+      for (int i = N - M + 1; i < N - 1; ++i) { uint32_t x = (st[i] & UPPER) | (st[i + 1] & LOWER); st[i] = st[i + (M - N)] ^ (x >> 1) ^ mag[x & 1]; }
+      uint32_t y = (st[N - 1] & UPPER) | (st[0] & LOWER); st[N - 1] = st[M - 1] ^ (y >> 1) ^ mag[y & 1];
+      index = 0;
+    }
+    uint32_t r = st[index++];
+    r ^= r >> 11; r ^= (r << 7) & 0x9D2C5680u; r ^= (r << 15) & 0xEFC60000u; r ^= r >> 18;
+    out[k] = (float)r * (1.0f / (float)0xFFFFFFFFu);
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,222 @@
+"""ctypes binding of the CPU oracle (oracle/liborc.so).
+
+TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  The product package (thea_b200) never imports this module.  PARITY UNPINNED
+(see oracle/thea_oracle.hpp).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+MODE_REFERENCE = 0   # kd-tree of BvhN.hpp:1450-1525, DFS order, first-found wins (the reference's exact behaviour)
+MODE_CANON = 1       # canonical tie rule (lowest element index) through the kd-tree
+MODE_BRUTE = 2       # canonical rule by exhaustive scan (the definition)
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liborc.so")
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "thea_oracle.hpp")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        L = _LIB
+        L.orc_create_tris.restype = C.c_void_p
+        L.orc_create_tris.argtypes = [C.c_void_p, C.c_int64]
+        L.orc_create_points.restype = C.c_void_p
+        L.orc_create_points.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_num_nodes.restype = C.c_int64
+        L.orc_num_nodes.argtypes = [C.c_void_p]
+        L.orc_max_depth.restype = C.c_int64
+        L.orc_max_depth.argtypes = [C.c_void_p]
+        L.orc_tri_cache.argtypes = [C.c_void_p] * 5
+        L.orc_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_ray_first.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_void_p]
+        L.orc_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
+                              C.c_void_p, C.c_void_p]
+        L.orc_avg_separation.restype = C.c_float
+        L.orc_avg_separation.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_ball_graph.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_sdf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_int, C.c_int, C.c_int,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_sdf_stats.restype = C.c_double
+        L.orc_sdf_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
+        L.orc_icp.restype = C.c_int
+        L.orc_icp.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                              C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_area_sample.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_tri_point.restype = C.c_float
+        L.orc_tri_point.argtypes = [C.c_void_p] * 3
+        L.orc_ray_tri.restype = C.c_float
+        L.orc_ray_tri.argtypes = [C.c_void_p] * 3
+        L.orc_fast_sqrt.restype = C.c_float
+        L.orc_fast_sqrt.argtypes = [C.c_float]
+        L.orc_box_ray_time.restype = C.c_float
+        L.orc_box_ray_time.argtypes = [C.c_void_p] * 4 + [C.c_float]
+        L.orc_polar_rotation.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_thea_random_uniform01.argtypes = [C.c_uint32, C.c_int64, C.c_void_p]
+    return _LIB
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def ncores() -> int:
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+class Oracle:
+    """CPU BvhN restatement over triangles (T,9) or points (P,3) [+ normals]."""
+
+    def __init__(self, tris9=None, points=None, normals=None):
+        L = lib()
+        self._keep = []
+        if tris9 is not None:
+            t = _f32(tris9).reshape(-1, 9)
+            self.n = t.shape[0]
+            self.is_points = False
+            self.h = L.orc_create_tris(_p(t), self.n)
+        else:
+            p = _f32(points).reshape(-1, 3)
+            nn = None if normals is None else _f32(normals).reshape(-1, 3)
+            self.n = p.shape[0]
+            self.is_points = True
+            self.h = L.orc_create_points(_p(p), self.n, _p(nn))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().orc_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def tri_cache(self):
+        n = np.empty((self.n, 3), np.float32)
+        d = np.empty(self.n, np.float32)
+        ax = np.empty(self.n, np.int32)
+        ar = np.empty(self.n, np.float32)
+        lib().orc_tri_cache(self.h, _p(n), _p(d), _p(ax), _p(ar))
+        return n, d, ax, ar
+
+    def closest(self, q, dist_bound=-1.0, mode=MODE_CANON, exclude_self=False, threads=None):
+        q = _f32(q).reshape(-1, 3)
+        Q = q.shape[0]
+        idx = np.empty(Q, np.int64)
+        d2 = np.empty(Q, np.float32)
+        cp = np.empty((Q, 3), np.float32)
+        lib().orc_closest(self.h, _p(q), Q, float(dist_bound), mode, int(exclude_self), threads or ncores(),
+                          _p(idx), _p(d2), _p(cp))
+        return idx, d2, cp
+
+    def ray_first(self, o, d, tmax=None, mode=MODE_CANON, threads=None):
+        o = _f32(o).reshape(-1, 3)
+        d = _f32(d).reshape(-1, 3)
+        tm = None if tmax is None else _f32(tmax)
+        R = o.shape[0]
+        idx = np.empty(R, np.int64)
+        t = np.empty(R, np.float32)
+        lib().orc_ray_first(self.h, _p(o), _p(d), _p(tm), R, mode, threads or ncores(), _p(idx), _p(t))
+        return idx, t
+
+    def knn(self, q, k, dist_bound=-1.0, exclude_self=False, mode=MODE_CANON, threads=None):
+        q = _f32(q).reshape(-1, 3)
+        Q = q.shape[0]
+        idx = np.empty((Q, k), np.int64)
+        d2 = np.empty((Q, k), np.float32)
+        lib().orc_knn(self.h, _p(q), Q, k, float(dist_bound), int(exclude_self), mode, threads or ncores(), _p(idx), _p(d2))
+        return idx, d2
+
+    def avg_separation(self, seeds):
+        s = np.ascontiguousarray(seeds, np.int64)
+        return float(lib().orc_avg_separation(self.h, _p(s), len(s)))
+
+    def ball_graph(self, max_degree, init_radius, mode=MODE_REFERENCE, threads=None):
+        idx = np.empty((self.n, max_degree), np.int64)
+        sep = np.empty((self.n, max_degree), np.float32)
+        cnt = np.empty(self.n, np.int32)
+        lib().orc_ball_graph(self.h, max_degree, float(init_radius), mode, threads or ncores(), _p(idx), _p(sep), _p(cnt))
+        return idx, sep, cnt
+
+    def sdf(self, p, n, scale, only_interior=True, mode=MODE_CANON, threads=None):
+        p = _f32(p).reshape(-1, 3)
+        n = _f32(n).reshape(-1, 3)
+        S = p.shape[0]
+        ro = np.empty((S * 30, 3), np.float32)
+        rd = np.empty((S * 30, 3), np.float32)
+        hi = np.empty(S * 30, np.int64)
+        ht = np.empty(S * 30, np.float32)
+        out = np.empty(S, np.float64)
+        lib().orc_sdf(self.h, _p(p), _p(n), S, float(scale), int(only_interior), mode, threads or ncores(),
+                      _p(ro), _p(rd), _p(hi), _p(ht), _p(out))
+        return out, ro, rd, hi, ht
+
+    def icp(self, src, min_iters=3, max_iters=10, frac_thresh=1e-4, mode=MODE_CANON, threads=None):
+        s = _f32(src).reshape(-1, 3)
+        n = s.shape[0]
+        idx = np.full((max_iters + 1, n), -1, np.int64)
+        tr = np.zeros((3, 4), np.float32)
+        err = np.zeros(1, np.float32)
+        b = lib().orc_icp(self.h, _p(s), n, min_iters, max_iters, float(frac_thresh), mode, threads or ncores(),
+                          _p(idx), _p(tr), _p(err))
+        return tr, float(err[0]), idx[:b]
+
+    def area_sample(self, count, seed):
+        p = np.empty((count, 3), np.float32)
+        n = np.empty((count, 3), np.float32)
+        t = np.empty(count, np.int64)
+        lib().orc_area_sample(self.h, count, seed, _p(p), _p(n), _p(t))
+        return p, n, t
+
+
+def tri_point(v9, p):
+    v = _f32(v9).reshape(9)
+    q = _f32(p).reshape(3)
+    cp = np.empty(3, np.float32)
+    d2 = lib().orc_tri_point(_p(v), _p(q), _p(cp))
+    return float(d2), cp
+
+
+def ray_tri(v9, o, d):
+    return float(lib().orc_ray_tri(_p(_f32(v9).reshape(9)), _p(_f32(o).reshape(3)), _p(_f32(d).reshape(3))))
+
+
+def fast_sqrt(x):
+    return float(lib().orc_fast_sqrt(float(x)))
+
+
+def box_ray_time(lo, hi, o, d, max_time=-1.0):
+    return float(lib().orc_box_ray_time(_p(_f32(lo)), _p(_f32(hi)), _p(_f32(o)), _p(_f32(d)), float(max_time)))
+
+
+def polar_rotation(M):
+    m = np.ascontiguousarray(M, np.float64).reshape(9)
+    r = np.empty(9, np.float64)
+    lib().orc_polar_rotation(_p(m), _p(r))
+    return r.reshape(3, 3)
+
+
+def thea_random_uniform01(seed, n):
+    out = np.empty(n, np.float32)
+    lib().orc_thea_random_uniform01(seed, n, _p(out))
+    return out
