@@ -1,0 +1,179 @@
+/* thea_gpu_query.h -- C ABI of the B200 batched spatial-query engine (libtgq.so).
+ *
+ * Drop-in boundary for the query path of Thea's Algorithms::BvhN / MeshBvh.  The reference API is a
+ * compile-time C++ concept that answers ONE query per call (Algorithms/ProximityQueryStructureN.hpp:29-35,
+ * Algorithms/RayQueryStructureN.hpp:55-60); each entry point below answers a whole batch of the query it cites, and the
+ * header-only adaptor include/thea_gpu/GpuBvh.hpp re-exposes them under the reference's member-function names.
+ * File:line citations are relative to /root/reference/Code/Source/.
+ *
+ * Conventions
+ *   - Every function returns 0 on success, a TGQ_E* code otherwise; tgq_last_error() gives the message.  Nothing throws.
+ *   - All array arguments may be HOST or DEVICE pointers (detected with cudaPointerGetAttributes); device pointers must
+ *     belong to the handle's device.  Host arrays are staged through pinned buffers in chunks, copies overlapped with
+ *     the kernels.  The caller owns every buffer; the library owns its device copies (BvhN copies its elements too,
+ *     Algorithms/BvhN.hpp:722-724).
+ *   - Element indices are int32 positions in the caller's build array, -1 = not found (the reference returns intx -1,
+ *     BvhN.hpp:1086-1087); "not found" is never an error.  At most 2^27 elements per structure.
+ *   - Results are the canonical answer: optimum over all elements of the reference's per-element fp32 arithmetic, ties
+ *     broken by the lowest element index (BASELINE.json north_star).  There is no CPU fallback: without a CUDA device
+ *     tgq_create fails.
+ *   - A handle is externally synchronised: one call at a time per handle.  Work is issued on the handle's stream
+ *     (tgq_set_stream) and every query call returns after its results are complete, unless TGQ_OPT_ASYNC is set and all
+ *     arguments are device pointers.
+ */
+#ifndef THEA_GPU_QUERY_H
+#define THEA_GPU_QUERY_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tgq_handle tgq_handle;
+
+enum
+{
+  TGQ_OK = 0,
+  TGQ_EINVAL = 1,     /* bad argument (null pointer, negative count, k out of range, wrong structure kind) */
+  TGQ_ECUDA = 2,      /* CUDA runtime error, message in tgq_last_error */
+  TGQ_ENODEVICE = 3,  /* no usable CUDA device: the engine has no CPU path */
+  TGQ_ESTATE = 4,     /* structure not built / refit with a different element count */
+  TGQ_ELIMIT = 5      /* more than 2^27 elements, k > TGQ_MAX_K */
+};
+
+enum
+{
+  TGQ_KIND_NONE = 0,
+  TGQ_KIND_TRIANGLES = 1,
+  TGQ_KIND_POINTS = 2
+};
+
+enum
+{
+  TGQ_OPT_SORT_QUERIES = 1,   /* 0 = never, 1 = always, 2 = auto (default: batches >= 4096 are Morton-ordered first) */
+  TGQ_OPT_LEAF_SIZE = 2,      /* max elements per leaf, 1..15 (default 4); takes effect at the next build */
+  TGQ_OPT_ASYNC = 3,          /* 1: device-pointer calls return without synchronising the stream (default 0) */
+  TGQ_OPT_CHUNK = 4           /* queries per staged chunk for host-pointer calls (default 4194304) */
+};
+
+#define TGQ_MAX_K 64
+
+/* ---- lifetime --------------------------------------------------------------------------------------------------- */
+
+/* Creates an engine bound to CUDA device `device` (>= 0).  Replaces the BvhN constructor (BvhN.hpp:664-676). */
+int tgq_create(int device, tgq_handle ** out);
+/* Releases all device memory.  Replaces BvhN::clear + destructor (BvhN.hpp:796-813). */
+int tgq_destroy(tgq_handle * h);
+/* Message of the last failure on this handle (or of the last failed tgq_create when h is null). */
+const char * tgq_last_error(tgq_handle * h);
+/* Issue all work on this cudaStream_t (passed as void*); null = the handle's own stream. */
+int tgq_set_stream(tgq_handle * h, void * cuda_stream);
+int tgq_set_option(tgq_handle * h, int option, int64_t value);
+
+/* ---- build ------------------------------------------------------------------------------------------------------ */
+
+/* Builds the structure over T triangles given as T x 9 floats (v0 v1 v2), element index = position.
+ * Replaces MeshBvh::add + init -> BvhN::init -> createKdTree (Algorithms/MeshBvh.hpp:55-111, BvhN.hpp:704-794,
+ * 1365-1525) with a Morton-code LBVH (radix sort + Karras hierarchy + bottom-up refit) built on the device, and the
+ * per-triangle cache of Triangle3.hpp:143-155 (unit normal, plane offset, primary axis, area). */
+int tgq_build_triangles(tgq_handle * h, const float * v9, int64_t T);
+/* Same, from V x 3 vertices and T x 3 int32 vertex indices (MeshTriangles::addTriangles ordering,
+ * Algorithms/MeshTriangles.hpp:173-339). */
+int tgq_build_triangles_indexed(tgq_handle * h, const float * verts3, int64_t V, const int32_t * tri3, int64_t T);
+/* Builds the structure over P points (P x 3 floats) with optional unit normals (P x 3, may be null).
+ * Replaces BvhN<Sample*,3>::init of PointSet3 (Algorithms/PointSet3.hpp:329-358,709-723). */
+int tgq_build_points(tgq_handle * h, const float * p3, int64_t P, const float * n3);
+/* New vertex positions for the same T triangles, same order: recomputes the triangle cache and refits all boxes
+ * bottom-up without re-sorting.  Replaces MeshBvh::updateElements + BvhN::updateNodeBounds
+ * (MeshBvh.hpp:123-134, BvhN.hpp:816-834,1694-1730). */
+int tgq_refit_triangles(tgq_handle * h, const float * v9, int64_t T);
+
+/* BvhN::numElements / getBounds (BvhN.hpp:952-995): kind, element count, unpadded bounds (lo[3], hi[3]; may be null). */
+int tgq_info(tgq_handle * h, int32_t * kind, int64_t * num_elements, float * lo3, float * hi3);
+/* Per-triangle cache in element order (any pointer may be null): unit normals T x 3 (what
+ * getElements()[i].getNormal() returns, ShapeDiameter.hpp:152-153), plane offsets, primary axes, areas. */
+int tgq_triangle_cache(tgq_handle * h, float * n3, float * d, int32_t * axis, float * area);
+
+/* ---- queries ---------------------------------------------------------------------------------------------------- */
+
+/* Q closest-element queries.  Replaces Q calls of
+ *   BvhN::closestElement<MetricL2>(q, dist_bound, UniversalCompatibility(), &dist, &closest_point)   (BvhN.hpp:1049-1063)
+ * dist_bound < 0: unbounded; otherwise only elements with squared distance < dist_bound^2 (strict, in double) count
+ * (BvhN.hpp:448,462).  exclude_self != 0: query i ignores element i (PointSet3::FilterSelf, PointSet3.hpp:576-583).
+ * Outputs (each may be null): idx[Q]; d2[Q] = fp32 squared distance (the reference's monotone approximation; its
+ * *dist is sqrt((double)d2), BvhN.hpp:1058), untouched slots get -1; cp3[Q x 3] = closest point on the element. */
+int tgq_closest(tgq_handle * h, const float * q3, int64_t Q, double dist_bound, int32_t exclude_self,
+                int32_t * idx, float * d2, float * cp3);
+
+/* Q k-nearest-neighbour queries on a point structure.  Replaces BvhN::kClosestPairs<MetricL2> into an empty
+ * BoundedSortedArray of capacity k (BvhN.hpp:1137-1146,474-500).  idx[Q x k], d2[Q x k] ascending by (d2, idx),
+ * unused slots -1. */
+int tgq_knn(tgq_handle * h, const float * q3, int64_t Q, int32_t k, double dist_bound, int32_t exclude_self,
+            int32_t * idx, float * d2);
+
+/* Proximity graph over the P points of a point structure.  Replaces the loop of PointSet3::updateGraph over
+ * findSampleNeighbors (PointSet3.hpp:380-381,586-681): for every sample, a ball range query of radius init_radius
+ * (doubled for up to `rounds` rounds while fewer than min_degree neighbours were found), candidates filtered by
+ * self, n.n' >= min_dot (when the structure has normals), kept as the max_degree smallest by (Math::fastSqrt(d2), idx).
+ * idx[P x max_degree], sep[P x max_degree] ascending, unused slots -1; count[P] may be null.
+ * Reference defaults: rounds 3, min_dot -0.5, min_degree clamp(int(0.25 * max_degree), 4, max_degree). */
+int tgq_ball_graph(tgq_handle * h, int32_t max_degree, float init_radius, int32_t rounds, float min_dot, int32_t min_degree,
+                   int32_t * idx, float * sep, int32_t * count);
+
+/* RMS nearest-neighbour separation over n seed samples (PointSet3.hpp:363-376; the reference draws the seeds from
+ * Random::common(), here the caller fixes them): sqrt(sum_f32 |x_nn(s) - x_s|^2 / n). */
+int tgq_avg_separation(tgq_handle * h, const int32_t * seeds, int32_t n, float * out);
+
+/* R ray first-hit queries on a triangle structure.  Replaces BvhN::rayStructureIntersection<RayIntersectionTester>
+ * (ray, max_time) (BvhN.hpp:1291-1316,2240-2291) and rayIntersectionTime (BvhN.hpp:1271-1289).
+ * tmax may be null (unbounded) else tmax[R], negative = unbounded; hits need 0 <= t and t < tmax (strict, BvhN.hpp:2257).
+ * Outputs (each may be null): t[R] (-1 = miss), idx[R] (-1 = miss), normal3[R x 3] = unit normal of the hit triangle
+ * (RayStructureIntersectionN::getNormal, Algorithms/RayQueryStructureN.hpp:28-53). */
+int tgq_ray_first(tgq_handle * h, const float * o3, const float * d3, const float * tmax, int64_t R,
+                  float * t, int32_t * idx, float * normal3);
+/* BvhN::rayIntersects (BvhN.hpp:1266-1269) with early exit: hit[R] = 1/0. */
+int tgq_ray_any(tgq_handle * h, const float * o3, const float * d3, const float * tmax, int64_t R, uint8_t * hit);
+
+/* Shape diameter function for S samples with outward normals.  Replaces the loop of
+ * ShapeDiameter::compute(position, normal, only_hit_interior_surfaces) (Algorithms/SurfaceFeatures/Local/
+ * ShapeDiameter.hpp:168-258): 30 cone rays per sample, first hits, hit-normal sign test, median +- sigma outlier
+ * rejection, cos-weighted mean, divided by `scale` and clamped to [0,1]; -1 when no ray counts.
+ * Outputs (may be null): sdf[S] (double), ray_t[S x 30], ray_idx[S x 30]. */
+int tgq_sdf(tgq_handle * h, const float * p3, const float * n3, int64_t S, float scale, int32_t only_hit_interior,
+            double * sdf, float * ray_t, int32_t * ray_idx);
+
+/* ICP sums for n correspondences (from3[i] -> to3[i]) in fixed-order double precision (deterministic for any GPU
+ * count): out[0..2] = mean p, out[3..5] = mean q, out[6..14] = sum (p - pm)(q - qm)^T row-major, and with tr12
+ * (row-major 3x4 [L|t], may be null = identity) out[15] = |tr pm - qm|^2 + sum |L (p - pm) - (q - qm)|^2.
+ * Replaces the accumulation loops of Icp3::alignOneStep / measureError (Algorithms/Icp3.hpp:298-367,410-464). */
+int tgq_icp_sums(tgq_handle * h, const float * from3, const float * to3, int64_t n, const float * tr12, double * out16);
+/* out3[i] = L in3[i] + t with the reference's fp32 operation order (AffineTransformN.hpp:160). */
+int tgq_transform_points(tgq_handle * h, const float * in3, int64_t n, const float * tr12, float * out3);
+
+/* Area-weighted surface samples of a triangle structure: MeshSampler::sampleEvenlyByArea in EXACT mode
+ * (Algorithms/MeshSampler.hpp:147-185, Triangle3.hpp:179-195) driven by the counter-based generator of
+ * thea_b200/gen.py (sample i uses draws 3i..3i+2 of splitmix64 stream `seed`).  Outputs may be null. */
+int tgq_area_sample(tgq_handle * h, int64_t S, uint64_t seed, float * p3, float * n3, int32_t * tri);
+
+/* ---- introspection ------------------------------------------------------------------------------------------------ */
+
+typedef struct tgq_stats
+{
+  int64_t num_elements;
+  int64_t num_nodes;        /* inner nodes of the device LBVH */
+  int64_t node_bytes;       /* HBM bytes of the node array */
+  int64_t element_bytes;    /* HBM bytes of the element records */
+  double last_build_ms;     /* device time of the last build / refit */
+  double last_query_ms;     /* device time of the kernels of the last query call (sort + traversal), CUDA events */
+  double last_sort_ms;      /* share of last_query_ms spent ordering the batch */
+  int64_t last_launches;    /* kernels launched by the last query call */
+  int64_t total_launches;   /* kernels launched since tgq_create */
+} tgq_stats;
+
+int tgq_get_stats(tgq_handle * h, tgq_stats * out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,218 @@
+// emu.cpp -- TEST-ONLY host build of the engine's __host__ __device__ headers (thea_b200/csrc/tgq_*.cuh).
+//
+// There is no GPU in the development container, so the traversal / hierarchy / selection code is written as
+// host+device inline functions and this file drives the *same* functions from plain C++ loops, letting the CPU test
+// suite (-m "not gpu") check the pruning logic, tie rules and the libstdc++ nth_element restatement against the oracle
+// before any GPU time is spent.  It is NOT a fallback: nothing under thea_b200/ links or loads it, and libtgq.so has
+// no code path that reaches it.
+#include "../../thea_b200/csrc/tgq_traverse.cuh"
+#include "../../thea_b200/csrc/tgq_select.cuh"
+
+#include <algorithm>
+#include <cstdint>
+#include <numeric>
+#include <vector>
+
+using namespace tgq;
+
+namespace {
+
+struct Emu
+{
+  bool tri = false, has_n = false;
+  int n = 0, leaf = 4;
+  std::vector<TriRec> tris; std::vector<f4> pts, nrm;
+  std::vector<NodeRec> nodes;
+  BvhView view() const
+  {
+    BvhView v; v.nodes = nodes.data(); v.tris = tri ? tris.data() : nullptr; v.pts = tri ? nullptr : pts.data();
+    v.nrm = has_n ? nrm.data() : nullptr; v.n_nodes = (int)nodes.size(); v.n_prims = n; return v;
+  }
+};
+
+v3 ld(float const * p, int64_t i) { return mk3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
+
+void build(Emu & E, float const * src, float const * n3)
+{
+  int n = E.n;
+  E.nodes.clear();
+  if (n == 0) return;
+  // scene bounds (k_scene_bounds) and pad (scene_decode)
+  v3 lo = mk3(FLT_MAX, FLT_MAX, FLT_MAX), hi = mk3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+  int64_t np = E.tri ? 3 * (int64_t)n : n;
+  for (int64_t i = 0; i < np; ++i) { v3 p = ld(src, i); lo = min3(lo, p); hi = max3(hi, p); }
+  v3 e = sub3(hi, lo);
+  v3 inv = mk3(e.x > 0 ? 1.0f / e.x : 0.0f, e.y > 0 ? 1.0f / e.y : 0.0f, e.z > 0 ? 1.0f / e.z : 0.0f);
+  float m = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))), fmaxf(fabsf(lo.z), fabsf(hi.z)));
+  float pad = m * 1.9073486328125e-06f + FLT_MIN;
+  // keys + stable sort (k_morton_*, radix sort)
+  std::vector<uint64_t> keys((size_t)n); std::vector<uint32_t> perm((size_t)n);
+  for (int i = 0; i < n; ++i)
+  {
+    v3 c = E.tri ? tri_centroid(ld(src, 3 * (int64_t)i), ld(src, 3 * (int64_t)i + 1), ld(src, 3 * (int64_t)i + 2)) : ld(src, i);
+    keys[(size_t)i] = morton63(c, lo, inv);
+  }
+  std::iota(perm.begin(), perm.end(), 0u);
+  std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+  std::vector<uint64_t> skeys((size_t)n);
+  for (int s = 0; s < n; ++s) skeys[(size_t)s] = keys[perm[(size_t)s]];
+  // records + element boxes (k_gather_*)
+  std::vector<v3> plo((size_t)n), phi((size_t)n);
+  if (E.tri) E.tris.resize((size_t)n); else { E.pts.resize((size_t)n); if (E.has_n) E.nrm.resize((size_t)n); }
+  for (int s = 0; s < n; ++s)
+  {
+    int64_t i = perm[(size_t)s];
+    if (E.tri)
+    {
+      v3 v0 = ld(src, 3 * i), v1 = ld(src, 3 * i + 1), v2 = ld(src, 3 * i + 2);
+      TriPlane pl = tri_plane(v0, v1, v2);
+      TriRec r;
+      r.q0 = f4{v0.x, v0.y, v0.z, i2f((int)i)}; r.q1 = f4{v1.x, v1.y, v1.z, i2f(pl.axis)};
+      r.q2 = f4{v2.x, v2.y, v2.z, pl.d}; r.q3 = f4{pl.n.x, pl.n.y, pl.n.z, tri_area(pl.n, v0, v1, v2)};
+      E.tris[(size_t)s] = r;
+      plo[(size_t)s] = min3(v0, min3(v1, v2)); phi[(size_t)s] = max3(v0, max3(v1, v2));
+    }
+    else
+    {
+      v3 p = ld(src, i);
+      E.pts[(size_t)s] = f4{p.x, p.y, p.z, i2f((int)i)};
+      if (E.has_n) { v3 q = ld(n3, i); E.nrm[(size_t)s] = f4{q.x, q.y, q.z, 0.0f}; }
+      plo[(size_t)s] = phi[(size_t)s] = p;
+    }
+  }
+  if (n == 1)
+  {
+    E.nodes.push_back(make_node(mk3(plo[0].x - pad, plo[0].y - pad, plo[0].z - pad), mk3(phi[0].x + pad, phi[0].y + pad, phi[0].z + pad),
+                                mk3(FLT_MAX, FLT_MAX, FLT_MAX), mk3(-FLT_MAX, -FLT_MAX, -FLT_MAX), ~((0 << TGQ_LEAF_BITS) | 1), ~0, 0, 0));
+    return;
+  }
+  // hierarchy (k_hierarchy), refit (k_refit, here by processing nodes in decreasing range order), live + scan, emit
+  int ni = n - 1;
+  std::vector<int> first((size_t)ni), last((size_t)ni), split((size_t)ni);
+  for (int i = 0; i < ni; ++i) lbvh_range(skeys.data(), n, i, first[(size_t)i], last[(size_t)i], split[(size_t)i]);
+  std::vector<int> order((size_t)ni); std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return (last[(size_t)a] - first[(size_t)a]) < (last[(size_t)b] - first[(size_t)b]); });
+  std::vector<v3> nlo((size_t)ni), nhi((size_t)ni);
+  for (int i : order)
+  {
+    int f = first[(size_t)i], l = last[(size_t)i], sp = split[(size_t)i];
+    v3 alo = f == sp ? plo[(size_t)sp] : nlo[(size_t)sp], ahi = f == sp ? phi[(size_t)sp] : nhi[(size_t)sp];
+    v3 blo = sp + 1 == l ? plo[(size_t)l] : nlo[(size_t)sp + 1], bhi = sp + 1 == l ? phi[(size_t)l] : nhi[(size_t)sp + 1];
+    nlo[(size_t)i] = min3(alo, blo); nhi[(size_t)i] = max3(ahi, bhi);
+  }
+  std::vector<int> live((size_t)ni), newidx((size_t)ni);
+  int cnt = 0;
+  for (int i = 0; i < ni; ++i) { live[(size_t)i] = (i == 0 || (last[(size_t)i] - first[(size_t)i] + 1) > E.leaf) ? 1 : 0; newidx[(size_t)i] = cnt; cnt += live[(size_t)i]; }
+  E.nodes.resize((size_t)cnt);
+  for (int i = 0; i < ni; ++i)
+  {
+    if (!live[(size_t)i]) continue;
+    int f = first[(size_t)i], l = last[(size_t)i], sp = split[(size_t)i];
+    int child[2]; v3 clo[2], chi[2];
+    for (int c = 0; c < 2; ++c)
+    {
+      int cf = c == 0 ? f : sp + 1, cl = c == 0 ? sp : l, k = cl - cf + 1, inner = c == 0 ? sp : sp + 1;
+      v3 blo = k == 1 ? plo[(size_t)cf] : nlo[(size_t)inner], bhi = k == 1 ? phi[(size_t)cf] : nhi[(size_t)inner];
+      child[c] = (k <= E.leaf) ? ~((cf << TGQ_LEAF_BITS) | k) : newidx[(size_t)inner];
+      clo[c] = mk3(blo.x - pad, blo.y - pad, blo.z - pad); chi[c] = mk3(bhi.x + pad, bhi.y + pad, bhi.z + pad);
+    }
+    E.nodes[(size_t)newidx[(size_t)i]] = make_node(clo[0], chi[0], clo[1], chi[1], child[0], child[1], 0, 0);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+void * emu_build(float const * src, int64_t n, int is_tri, float const * n3, int leaf)
+{
+  Emu * E = new Emu; E->tri = is_tri != 0; E->has_n = (!is_tri && n3); E->n = (int)n; E->leaf = leaf;
+  build(*E, src, n3);
+  return E;
+}
+void emu_destroy(void * h) { delete (Emu *)h; }
+int64_t emu_num_nodes(void * h) { return (int64_t)((Emu *)h)->nodes.size(); }
+
+void emu_closest(void * h, float const * q3, int64_t Q, float bound_ub, int exclude_self, int32_t * idx, float * d2, float * cp3)
+{
+  Emu & E = *(Emu *)h; BvhView v = E.view();
+  for (int64_t i = 0; i < Q; ++i)
+  {
+    float best = bound_ub; int bi = -1; v3 cp = mk3(0, 0, 0);
+    if (E.tri) closest_query<true>(v, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp);
+    else closest_query<false>(v, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp);
+    idx[i] = bi; d2[i] = bi >= 0 ? best : -1.0f; cp3[3 * i] = cp.x; cp3[3 * i + 1] = cp.y; cp3[3 * i + 2] = cp.z;
+  }
+}
+
+void emu_knn(void * h, float const * q3, int64_t Q, int k, float bound_ub, int exclude_self, int32_t * idx, float * d2)
+{
+  Emu & E = *(Emu *)h; BvhView v = E.view();
+  std::vector<float> keys((size_t)k); std::vector<int> ids((size_t)k);
+  for (int64_t i = 0; i < Q; ++i)
+  {
+    SortedSet set; set.init(keys.data(), ids.data(), 1, k);
+    knn_query(v, ld(q3, i), exclude_self ? (int)i : -1, bound_ub, set);
+    for (int j = 0; j < k; ++j) { idx[i * k + j] = j < set.n ? ids[(size_t)j] : -1; d2[i * k + j] = j < set.n ? keys[(size_t)j] : -1.0f; }
+  }
+}
+
+void emu_ball_graph(void * h, int k, float init_radius, int rounds, float min_dot, int min_degree, int32_t * idx, float * sep, int32_t * count)
+{
+  Emu & E = *(Emu *)h; BvhView v = E.view();
+  std::vector<float> keys((size_t)k); std::vector<int> ids((size_t)k);
+  for (int s = 0; s < E.n; ++s)
+  {
+    f4 e = E.pts[(size_t)s]; int64_t i = f2i(e.w);
+    v3 nc = mk3(0, 0, 0); if (E.has_n) nc = mk3(E.nrm[(size_t)s].x, E.nrm[(size_t)s].y, E.nrm[(size_t)s].z);
+    SortedSet set; set.init(keys.data(), ids.data(), 1, k);
+    ball_graph_query(v, mk3(e.x, e.y, e.z), nc, E.has_n, min_dot, (int)i, init_radius, rounds, min_degree, set);
+    for (int j = 0; j < k; ++j) { idx[i * k + j] = j < set.n ? ids[(size_t)j] : -1; sep[i * k + j] = j < set.n ? keys[(size_t)j] : -1.0f; }
+    if (count) count[i] = set.n;
+  }
+}
+
+void emu_ray(void * h, float const * o3, float const * d3, float const * tmax, int64_t R, int any, float * t, int32_t * idx)
+{
+  Emu & E = *(Emu *)h; BvhView v = E.view();
+  for (int64_t i = 0; i < R; ++i)
+  {
+    float best = tmax ? tmax[i] : -1.0f; int bi = -1, bk = -1;
+    if (any) ray_query<true>(v, ld(o3, i), ld(d3, i), best, bi, bk); else ray_query<false>(v, ld(o3, i), ld(d3, i), best, bi, bk);
+    t[i] = bi >= 0 ? best : -1.0f; idx[i] = bi;
+  }
+}
+
+// libstdc++'s own std::nth_element next to the restatement, for permutation-exact comparison.
+void emu_select(double * a, int n, int nth) { sdf_select(a, n, nth); }
+void emu_std_nth_element(double * a, int n, int nth) { std::nth_element(a, a + nth, a + n); }
+double emu_sdf_statistics(double * values, double const * weights, int nv, float scale) { return sdf_statistics(values, weights, nv, scale); }
+
+void emu_sdf_rays(float const * p3, float const * n3, int64_t S, float scale, float * o3, float * d3)
+{
+  static float const cone[30][3] = {
+    { 0.407497f,  0.134086f,  0.903309f}, { 0.128722f, -0.822715f,  0.553688f}, { 0.359298f,  0.686129f,  0.632560f},
+    { 0.813318f, -0.153956f,  0.561081f}, {-0.707169f,  0.296987f,  0.641647f}, {-0.478783f, -0.543441f,  0.689520f},
+    { 0.561083f,  0.523634f,  0.641087f}, {-0.380898f, -0.655789f,  0.651811f}, { 0.722588f,  0.472155f,  0.504912f},
+    {-0.535205f,  0.421235f,  0.732200f}, { 0.577593f, -0.477896f,  0.661817f}, { 0.393652f, -0.144484f,  0.907834f},
+    { 0.141508f, -0.660777f,  0.737122f}, {-0.274967f, -0.141703f,  0.950954f}, {-0.304935f,  0.474085f,  0.825989f},
+    { 0.711150f,  0.301383f,  0.635164f}, {-0.696119f, -0.112341f,  0.709082f}, {-0.248327f,  0.381035f,  0.890588f},
+    {-0.0772394f, 0.0462501f, 0.995939f}, { 0.438024f,  0.656463f,  0.614159f}, {-0.483384f, -0.542477f,  0.687065f},
+    { 0.498569f, -0.697466f,  0.514752f}, {-0.128902f, -0.0173429f, 0.991506f}, { 0.338759f, -0.318772f,  0.885227f},
+    {-0.574364f, -0.463887f,  0.674474f}, {-0.459207f,  0.260125f,  0.849390f}, {-0.628057f, -0.528928f,  0.570771f},
+    { 0.232916f, -0.328273f,  0.915416f}, { 0.231667f, -0.796882f,  0.557951f}, {-0.270612f, -0.809654f,  0.520797f},
+  };
+  for (int64_t s = 0; s < S; ++s)
+  {
+    SdfFrame f = sdf_frame(ld(p3, s), ld(n3, s), scale);
+    for (int k = 0; k < 30; ++k)
+    {
+      v3 d = sdf_dir(f, mk3(cone[k][0], cone[k][1], cone[k][2]));
+      int64_t r = 30 * s + k;
+      o3[3 * r] = f.origin.x; o3[3 * r + 1] = f.origin.y; o3[3 * r + 2] = f.origin.z;
+      d3[3 * r] = d.x; d3[3 * r + 1] = d.y; d3[3 * r + 2] = d.z;
+    }
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,124 @@
+"""ctypes binding of tests/emu/libtgq_emu.so -- the TEST-ONLY host build of the engine headers (see emu.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        subprocess.check_call(["make", "-C", os.path.join(_HERE, "emu"), "-s"])
+        L = C.CDLL(os.path.join(_HERE, "emu", "libtgq_emu.so"))
+        vp = C.c_void_p
+        L.emu_build.restype = vp
+        L.emu_build.argtypes = [vp, C.c_int64, C.c_int, vp, C.c_int]
+        L.emu_destroy.argtypes = [vp]
+        L.emu_num_nodes.restype = C.c_int64
+        L.emu_num_nodes.argtypes = [vp]
+        L.emu_closest.argtypes = [vp, vp, C.c_int64, C.c_float, C.c_int, vp, vp, vp]
+        L.emu_knn.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_float, C.c_int, vp, vp]
+        L.emu_ball_graph.argtypes = [vp, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, vp, vp, vp]
+        L.emu_ray.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, vp, vp]
+        L.emu_select.argtypes = [vp, C.c_int, C.c_int]
+        L.emu_std_nth_element.argtypes = [vp, C.c_int, C.c_int]
+        L.emu_sdf_statistics.restype = C.c_double
+        L.emu_sdf_statistics.argtypes = [vp, vp, C.c_int, C.c_float]
+        L.emu_sdf_rays.argtypes = [vp, vp, C.c_int64, C.c_float, vp, vp]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Emu:
+    def __init__(self, tris9=None, points=None, normals=None, leaf=4):
+        L = lib()
+        if tris9 is not None:
+            self.src = np.ascontiguousarray(tris9, np.float32).reshape(-1, 9)
+            self.n = len(self.src)
+            self.h = L.emu_build(_p(self.src), self.n, 1, None, leaf)
+        else:
+            self.src = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+            self.nrm = None if normals is None else np.ascontiguousarray(normals, np.float32)
+            self.n = len(self.src)
+            self.h = L.emu_build(_p(self.src), self.n, 0, _p(self.nrm), leaf)
+
+    def __del__(self):
+        try:
+            lib().emu_destroy(self.h)
+        except Exception:
+            pass
+
+    def num_nodes(self):
+        return lib().emu_num_nodes(self.h)
+
+    def closest(self, q, bound_ub=np.inf, exclude_self=False):
+        q = np.ascontiguousarray(q, np.float32)
+        Q = len(q)
+        idx = np.empty(Q, np.int32)
+        d2 = np.empty(Q, np.float32)
+        cp = np.empty((Q, 3), np.float32)
+        lib().emu_closest(self.h, _p(q), Q, float(bound_ub), int(exclude_self), _p(idx), _p(d2), _p(cp))
+        return idx, d2, cp
+
+    def knn(self, q, k, bound_ub=np.inf, exclude_self=False):
+        q = np.ascontiguousarray(q, np.float32)
+        Q = len(q)
+        idx = np.empty((Q, k), np.int32)
+        d2 = np.empty((Q, k), np.float32)
+        lib().emu_knn(self.h, _p(q), Q, k, float(bound_ub), int(exclude_self), _p(idx), _p(d2))
+        return idx, d2
+
+    def ball_graph(self, k, r0, rounds=3, min_dot=-0.5, min_degree=None):
+        if min_degree is None:
+            min_degree = min(max(int(0.25 * k), 4), k)
+        idx = np.empty((self.n, k), np.int32)
+        sep = np.empty((self.n, k), np.float32)
+        cnt = np.empty(self.n, np.int32)
+        lib().emu_ball_graph(self.h, k, float(r0), rounds, float(min_dot), min_degree, _p(idx), _p(sep), _p(cnt))
+        return idx, sep, cnt
+
+    def ray(self, o, d, tmax=None, any_hit=False):
+        o = np.ascontiguousarray(o, np.float32)
+        d = np.ascontiguousarray(d, np.float32)
+        tm = None if tmax is None else np.ascontiguousarray(tmax, np.float32)
+        R = len(o)
+        t = np.empty(R, np.float32)
+        idx = np.empty(R, np.int32)
+        lib().emu_ray(self.h, _p(o), _p(d), _p(tm), R, int(any_hit), _p(t), _p(idx))
+        return t, idx
+
+
+def select(a, nth):
+    b = np.array(a, np.float64)
+    lib().emu_select(_p(b), len(b), nth)
+    return b
+
+
+def std_nth_element(a, nth):
+    b = np.array(a, np.float64)
+    lib().emu_std_nth_element(_p(b), len(b), nth)
+    return b
+
+
+def sdf_statistics(values, weights, scale):
+    v = np.array(values, np.float64)
+    w = np.array(weights, np.float64)
+    return float(lib().emu_sdf_statistics(_p(v), _p(w), len(v), float(scale)))
+
+
+def sdf_rays(p, n, scale):
+    p = np.ascontiguousarray(p, np.float32)
+    n = np.ascontiguousarray(n, np.float32)
+    S = len(p)
+    o = np.empty((S * 30, 3), np.float32)
+    d = np.empty((S * 30, 3), np.float32)
+    lib().emu_sdf_rays(_p(p), _p(n), S, float(scale), _p(o), _p(d))
+    return o, d

@@ -1,0 +1,198 @@
+"""Engine logic on the CPU: the host+device headers of thea_b200/csrc compiled for the host (tests/emu, TEST-ONLY)
+against the oracle.  Covers what does not need a GPU to be wrong: Morton/Karras hierarchy, leaf collapsing, conservative
+pruning, tie rules, the bounded sorted set, the slab test and the libstdc++ nth_element restatement.
+"""
+import numpy as np
+import pytest
+
+import emu_lib
+from oracle import orc
+from thea_b200 import gen
+
+
+@pytest.fixture(scope="module")
+def mesh_case():
+    mesh = gen.torus_mesh(56)          # 6,272 triangles
+    return mesh, emu_lib.Emu(tris9=mesh), orc.Oracle(tris9=mesh)
+
+
+@pytest.mark.parametrize("leaf", [1, 2, 4, 8, 15])
+def test_closest_all_leaf_sizes(leaf):
+    mesh = gen.torus_mesh(24)
+    e = emu_lib.Emu(tris9=mesh, leaf=leaf)
+    ora = orc.Oracle(tris9=mesh)
+    q = gen.closest_queries(3000, gen.mesh_bounds(mesh))
+    idx, d2, cp = e.closest(q)
+    oi, od, oc = ora.closest(q, mode=orc.MODE_BRUTE)
+    assert np.array_equal(idx, oi.astype(np.int32)) and np.array_equal(d2, od) and np.array_equal(cp, oc)
+
+
+def test_closest_and_rays_on_mesh(mesh_case):
+    mesh, e, ora = mesh_case
+    b = gen.mesh_bounds(mesh)
+    q = gen.closest_queries(20000, b)
+    idx, d2, cp = e.closest(q)
+    oi, od, oc = ora.closest(q, mode=orc.MODE_CANON)
+    assert np.array_equal(idx, oi.astype(np.int32)) and np.array_equal(d2, od) and np.array_equal(cp, oc)
+    o, d = gen.random_rays(20000, b)
+    t, ridx = e.ray(o, d)
+    ri, rt = ora.ray_first(o, d, mode=orc.MODE_CANON)
+    assert np.array_equal(ridx, ri.astype(np.int32)) and np.array_equal(t, rt)
+    ta, ia = e.ray(o, d, any_hit=True)
+    assert np.array_equal(ia >= 0, ri >= 0)
+
+
+def test_queries_on_the_surface_and_on_vertices(mesh_case):
+    # d2 == 0 ties across the triangles sharing a vertex: the lowest index must win
+    mesh, e, ora = mesh_case
+    verts = mesh.reshape(-1, 3)[::7][:3000]
+    idx, d2, _ = e.closest(verts)
+    oi, od, _ = ora.closest(verts, mode=orc.MODE_BRUTE)
+    assert np.array_equal(idx, oi.astype(np.int32)) and np.array_equal(d2, od)
+    assert (d2 == 0).mean() > 0.9
+    p, _, _ = gen.area_samples(mesh, 3000)
+    idx, d2, _ = e.closest(p)
+    oi, od, _ = ora.closest(p, mode=orc.MODE_BRUTE)
+    assert np.array_equal(idx, oi.astype(np.int32)) and np.array_equal(d2, od)
+
+
+def test_axis_aligned_flat_mesh_degenerate_boxes():
+    # a planar grid: every box has zero extent in z, so pruning relies on the absolute pad, not on relative slack
+    n = 24
+    xs = np.arange(n + 1, dtype=np.float32) / n
+    X, Y = np.meshgrid(xs, xs, indexing="ij")
+    V = np.stack([X, Y, np.full_like(X, 0.3)], -1)
+    tris = []
+    for i in range(n):
+        for j in range(n):
+            tris.append(np.concatenate([V[i, j], V[i + 1, j], V[i + 1, j + 1]]))
+            tris.append(np.concatenate([V[i, j], V[i + 1, j + 1], V[i, j + 1]]))
+    mesh = np.array(tris, np.float32)
+    e = emu_lib.Emu(tris9=mesh)
+    ora = orc.Oracle(tris9=mesh)
+    rng = np.random.default_rng(0)
+    q = (rng.random((5000, 3)) * [1.4, 1.4, 1.0] - [0.2, 0.2, 0.2]).astype(np.float32)
+    q[::5, 2] = 0.7                                          # many queries at the same height: equal distances abound
+    idx, d2, cp = e.closest(q)
+    oi, od, oc = ora.closest(q, mode=orc.MODE_BRUTE)
+    assert np.array_equal(idx, oi.astype(np.int32)) and np.array_equal(d2, od) and np.array_equal(cp, oc)
+    o = q.copy()
+    d = rng.standard_normal((5000, 3)).astype(np.float32)
+    d[::3] = [0, 0, -1]                                      # axis-parallel rays: zero direction components in the slab test
+    d[1::3, 2] = 0                                           # rays parallel to the plane
+    t, ridx = e.ray(o, d)
+    ri, rt = ora.ray_first(o, d, mode=orc.MODE_BRUTE)
+    assert np.array_equal(ridx, ri.astype(np.int32)) and np.array_equal(t, rt)
+
+
+def test_point_queries_knn_and_graph():
+    mesh = gen.torus_mesh(40)
+    p, n, _ = gen.area_samples(mesh, 4000)
+    e = emu_lib.Emu(points=p, normals=n)
+    ora = orc.Oracle(points=p, normals=n)
+    for k in (1, 5, 16):
+        ki, kd = e.knn(p, k, exclude_self=True)
+        oi, od = ora.knn(p, k, exclude_self=True, mode=orc.MODE_BRUTE)
+        assert np.array_equal(ki, oi.astype(np.int32)) and np.array_equal(kd, od)
+    seeds = (gen.splitmix64(7, 100) % np.uint64(len(p))).astype(np.int64)
+    avg = np.float32(ora.avg_separation(seeds))
+    for scale in (4.0, 0.4):
+        gi, gs, gc = e.ball_graph(16, np.float32(scale) * avg)
+        oi, os_, oc = ora.ball_graph(16, np.float32(scale) * avg, mode=orc.MODE_BRUTE)
+        assert np.array_equal(gi, oi.astype(np.int32)) and np.array_equal(gs, os_) and np.array_equal(gc, oc)
+
+
+def test_duplicates_and_tiny_structures():
+    rng = np.random.default_rng(2)
+    pts = np.repeat(rng.random((30, 3)).astype(np.float32), 6, axis=0)
+    e = emu_lib.Emu(points=pts)
+    ora = orc.Oracle(points=pts)
+    ki, kd = e.knn(pts, 9, exclude_self=True)
+    oi, od = ora.knn(pts, 9, exclude_self=True, mode=orc.MODE_BRUTE)
+    assert np.array_equal(ki, oi.astype(np.int32)) and np.array_equal(kd, od)
+    for T in (1, 2, 3, 5, 6, 17):
+        tris = rng.random((T, 9)).astype(np.float32)
+        e = emu_lib.Emu(tris9=tris)
+        ora = orc.Oracle(tris9=tris)
+        q = (rng.random((300, 3)) * 2 - 0.5).astype(np.float32)
+        idx, d2, cp = e.closest(q)
+        oi, od, oc = ora.closest(q, mode=orc.MODE_BRUTE)
+        assert np.array_equal(idx, oi.astype(np.int32)) and np.array_equal(d2, od) and np.array_equal(cp, oc)
+
+
+def test_select_is_libstdcxx_nth_element():
+    rng = np.random.default_rng(9)
+    for trial in range(4000):
+        n = int(rng.integers(1, 31))
+        kind = trial % 5
+        if kind == 0:
+            a = rng.random(n)
+        elif kind == 1:
+            a = rng.integers(0, 4, n).astype(np.float64)          # many duplicates
+        elif kind == 2:
+            a = np.sort(rng.random(n))
+        elif kind == 3:
+            a = np.sort(rng.random(n))[::-1].copy()
+        else:
+            a = np.concatenate([np.sort(rng.random(n // 2)), np.sort(rng.random(n - n // 2))[::-1]])   # organ pipe
+        nth = n // 2
+        assert np.array_equal(emu_lib.select(a, nth), emu_lib.std_nth_element(a, nth)), (n, a)
+
+
+def _median_of_3_killer(n):
+    # Musser's adversary for median-of-3 quickselect: drives introselect into its heap-select fallback
+    k = n // 2
+    a = np.zeros(n)
+    for i in range(1, k + 1):
+        if i % 2 == 1:
+            a[i - 1] = i
+            a[i] = k + i
+        a[k + i - 1] = 2 * i
+    return a
+
+
+def test_select_heap_fallback_path():
+    for n in range(8, 31):
+        a = _median_of_3_killer(n)
+        for nth in (n // 2, 0, n - 1):
+            assert np.array_equal(emu_lib.select(a, nth), emu_lib.std_nth_element(a, nth)), (n, nth)
+    # brute-force small permutations: every ordering of 7 distinct keys
+    import itertools
+    for perm in itertools.permutations(range(7)):
+        a = np.array(perm, np.float64)
+        assert np.array_equal(emu_lib.select(a, 3), emu_lib.std_nth_element(a, 3))
+
+
+def test_sdf_rays_and_statistics_match_oracle():
+    mesh = gen.torus_mesh(40)
+    ora = orc.Oracle(tris9=mesh)
+    lo, hi = gen.mesh_bounds(mesh)
+    scale = float(np.linalg.norm(hi - lo))
+    p, n, _ = gen.area_samples(mesh, 300)
+    sdf, ro, rd, hi_, ht = ora.sdf(p, n, scale, mode=orc.MODE_CANON)
+    eo, ed = emu_lib.sdf_rays(p, n, scale)
+    assert np.array_equal(eo, ro) and np.array_equal(ed, rd)
+    e = emu_lib.Emu(tris9=mesh)
+    t, idx = e.ray(eo, ed)
+    assert np.array_equal(idx, hi_.astype(np.int32)) and np.array_equal(t, ht)
+    tn = ora.tri_cache()[0]
+    cone_z = np.array([0.903309, 0.553688, 0.632560, 0.561081, 0.641647, 0.689520, 0.641087, 0.651811, 0.504912, 0.732200,
+                       0.661817, 0.907834, 0.737122, 0.950954, 0.825989, 0.635164, 0.709082, 0.890588, 0.995939, 0.614159,
+                       0.687065, 0.514752, 0.991506, 0.885227, 0.674474, 0.849390, 0.570771, 0.915416, 0.557951, 0.520797],
+                      np.float32)
+    hits = 0
+    for s in range(300):
+        vals, wts = [], []
+        for k in range(30):
+            r = 30 * s + k
+            if idx[r] >= 0:
+                nn, dd = tn[idx[r]], ed[r]
+                dot = np.float32(nn[0] * dd[0]) + (np.float32(nn[1] * dd[1]) + np.float32(nn[2] * dd[2]))
+                if dot >= 0:
+                    vals.append(float(t[r]))
+                    wts.append(float(cone_z[k]))
+        got = emu_lib.sdf_statistics(vals, wts, scale) if vals else -1.0
+        assert got == sdf[s]
+        hits += len(vals)
+    assert hits > 300 * 20
+    assert (sdf > 0).mean() > 0.95 and (sdf <= 1).all()

@@ -1,0 +1,176 @@
+"""GPU parity: the CUDA engine through its C ABI (ctypes) against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): element indices and hit flags bit-exact (ties -> lowest index); distances and hit
+times within 1e-5 relative -- the parity build (-fmad=false) actually reproduces them bit for bit, and that is what is
+asserted here.
+"""
+import numpy as np
+import pytest
+
+from oracle import orc
+from thea_b200 import gen
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng_mesh(built):
+    from thea_b200 import Engine
+    mesh = gen.torus_mesh(64)          # 8,192 triangles
+    e = Engine(0)
+    e.build_triangles(mesh)
+    return e, mesh, orc.Oracle(tris9=mesh)
+
+
+def test_triangle_cache_bit_exact(eng_mesh):
+    e, mesh, ora = eng_mesh
+    n, d, ax, ar = e.triangle_cache()
+    on, od, oax, oar = ora.tri_cache()
+    assert np.array_equal(n, on) and np.array_equal(d, od) and np.array_equal(ax, oax) and np.array_equal(ar, oar)
+
+
+@pytest.mark.parametrize("sort", [0, 1])
+def test_closest_vs_brute_force(eng_mesh, sort):
+    e, mesh, ora = eng_mesh
+    e.set_option(1, sort)
+    q = gen.closest_queries(30000, gen.mesh_bounds(mesh))
+    idx, d2, cp = e.closest(q)
+    oi, od, oc = ora.closest(q, mode=orc.MODE_BRUTE)
+    e.set_option(1, 2)
+    assert np.array_equal(idx, oi.astype(np.int32))
+    assert np.array_equal(d2, od)
+    assert np.array_equal(cp, oc)
+
+
+def test_closest_dist_bound_is_strict(eng_mesh):
+    e, mesh, ora = eng_mesh
+    q = gen.closest_queries(5000, gen.mesh_bounds(mesh), seed=77)
+    _, d2, _ = e.closest(q)
+    # bound exactly at the true distance of each query must reject it (BvhN.hpp:448,462), a hair above must accept
+    for i in range(0, 5000, 250):
+        d = float(np.sqrt(np.float64(d2[i])))
+        bi, _, _ = e.closest(q[i:i + 1], dist_bound=d)
+        oi, _, _ = ora.closest(q[i:i + 1], dist_bound=d, mode=orc.MODE_BRUTE)
+        assert bi[0] == oi[0]
+        bi2, _, _ = e.closest(q[i:i + 1], dist_bound=d * (1 + 1e-6) + 1e-12)
+        oi2, _, _ = ora.closest(q[i:i + 1], dist_bound=d * (1 + 1e-6) + 1e-12, mode=orc.MODE_BRUTE)
+        assert bi2[0] == oi2[0] and bi2[0] >= 0
+    idx, d2b, _ = e.closest(q, dist_bound=0.05)
+    oi, od, _ = ora.closest(q, dist_bound=0.05, mode=orc.MODE_BRUTE)
+    assert np.array_equal(idx, oi.astype(np.int32)) and np.array_equal(d2b, od)
+    assert (idx < 0).any() and (idx >= 0).any()
+
+
+def test_ray_first_vs_brute_force(eng_mesh):
+    e, mesh, ora = eng_mesh
+    o, d = gen.random_rays(30000, gen.mesh_bounds(mesh))
+    t, idx, nrm = e.ray_first(o, d, want_normal=True)
+    oi, ot = ora.ray_first(o, d, mode=orc.MODE_BRUTE)
+    assert np.array_equal(idx, oi.astype(np.int32))
+    assert np.array_equal(t, ot)
+    on = ora.tri_cache()[0]
+    hit = idx >= 0
+    assert hit.any() and (~hit).any()
+    assert np.array_equal(nrm[hit], on[idx[hit]])
+    assert np.array_equal(e.ray_any(o, d), hit.astype(np.uint8))
+
+
+def test_ray_max_time_is_strict(eng_mesh):
+    e, mesh, ora = eng_mesh
+    o, d = gen.random_rays(8000, gen.mesh_bounds(mesh), seed=5)
+    t, idx, _ = e.ray_first(o, d)
+    tm = np.where(idx >= 0, t, np.float32(1.0)).astype(np.float32)   # bound exactly at the first hit: must be rejected
+    tm[::2] = -1.0
+    t2, idx2, _ = e.ray_first(o, d, tmax=tm)
+    oi, ot = ora.ray_first(o, d, tmax=tm, mode=orc.MODE_BRUTE)
+    assert np.array_equal(idx2, oi.astype(np.int32)) and np.array_equal(t2, ot)
+
+
+def test_points_knn_closest_graph(built):
+    from thea_b200 import Engine
+    mesh = gen.torus_mesh(48)
+    p, n, _ = gen.area_samples(mesh, 6000)
+    e = Engine(0)
+    e.build_points(p, n)
+    ora = orc.Oracle(points=p, normals=n)
+    for k in (1, 3, 16, 33):
+        ki, kd = e.knn(p, k, exclude_self=True)
+        oi, od = ora.knn(p, k, exclude_self=True, mode=orc.MODE_BRUTE)
+        assert np.array_equal(ki, oi.astype(np.int32)) and np.array_equal(kd, od)
+    q = gen.closest_queries(4000, gen.mesh_bounds(mesh))
+    ki, kd = e.knn(q, 8, dist_bound=0.2)
+    oi, od = ora.knn(q, 8, dist_bound=0.2, mode=orc.MODE_BRUTE)
+    assert np.array_equal(ki, oi.astype(np.int32)) and np.array_equal(kd, od)
+    ci, cd, cc = e.closest(q)
+    oci, ocd, occ = ora.closest(q, mode=orc.MODE_BRUTE)
+    assert np.array_equal(ci, oci.astype(np.int32)) and np.array_equal(cd, ocd) and np.array_equal(cc, occ)
+    seeds = (gen.splitmix64(7, 100) % np.uint64(len(p))).astype(np.int64)
+    avg = e.avg_separation(seeds)
+    assert avg == ora.avg_separation(seeds)
+    gi, gs, gc = e.ball_graph(16, np.float32(4.0) * np.float32(avg))
+    oi, os_, oc = ora.ball_graph(16, np.float32(4.0) * np.float32(avg), mode=orc.MODE_BRUTE)
+    assert np.array_equal(gi, oi.astype(np.int32)) and np.array_equal(gs, os_) and np.array_equal(gc, oc)
+    # a tiny radius forces the doubling rounds
+    gi, gs, gc = e.ball_graph(16, np.float32(0.3) * np.float32(avg))
+    oi, os_, oc = ora.ball_graph(16, np.float32(0.3) * np.float32(avg), mode=orc.MODE_BRUTE)
+    assert np.array_equal(gi, oi.astype(np.int32)) and np.array_equal(gs, os_) and np.array_equal(gc, oc)
+
+
+def test_edge_cases(built):
+    from thea_b200 import Engine, TgqError
+    e = Engine(0)
+    with pytest.raises(TgqError):
+        e.closest(np.zeros((1, 3), np.float32))          # nothing built
+    e.build_triangles(np.zeros((0, 9), np.float32))      # empty structure: -1, never an error (BvhN.hpp:1086-1087)
+    idx, d2, _ = e.closest(np.zeros((5, 3), np.float32))
+    assert (idx == -1).all() and (d2 == -1).all()
+    t, ridx, _ = e.ray_first(np.zeros((5, 3), np.float32), np.ones((5, 3), np.float32))
+    assert (ridx == -1).all() and (t == -1).all()
+    one = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32)
+    e.build_triangles(one)
+    idx, d2, cp = e.closest(np.array([[0.25, 0.25, 2.0], [5, 5, 0]], np.float32))
+    assert idx.tolist() == [0, 0] and d2[0] == 4.0
+    assert np.allclose(cp[0], [0.25, 0.25, 0.0])
+    idx, _, _ = e.closest(np.zeros((0, 3), np.float32))
+    assert idx.shape == (0,)
+    # ragged sizes around the leaf size and block size
+    rng = np.random.default_rng(3)
+    for T in (2, 3, 4, 5, 7, 129):
+        tris = rng.random((T, 9)).astype(np.float32)
+        e.build_triangles(tris)
+        ora = orc.Oracle(tris9=tris)
+        q = rng.random((257, 3)).astype(np.float32) * 2 - 0.5
+        idx, d2, cp = e.closest(q)
+        oi, od, oc = ora.closest(q, mode=orc.MODE_BRUTE)
+        assert np.array_equal(idx, oi.astype(np.int32)) and np.array_equal(d2, od) and np.array_equal(cp, oc)
+        o = rng.random((257, 3)).astype(np.float32) * 2 - 0.5
+        d = rng.standard_normal((257, 3)).astype(np.float32)
+        t, ridx, _ = e.ray_first(o, d)
+        ri, rt = ora.ray_first(o, d, mode=orc.MODE_BRUTE)
+        assert np.array_equal(ridx, ri.astype(np.int32)) and np.array_equal(t, rt)
+
+
+def test_duplicate_elements_tie_to_lowest_index(built):
+    from thea_b200 import Engine
+    rng = np.random.default_rng(11)
+    base = rng.random((50, 9)).astype(np.float32)
+    tris = np.concatenate([base, base, base])[rng.permutation(150)]
+    e = Engine(0)
+    e.build_triangles(tris)
+    ora = orc.Oracle(tris9=tris)
+    q = rng.random((2000, 3)).astype(np.float32)
+    idx, d2, _ = e.closest(q)
+    oi, od, _ = ora.closest(q, mode=orc.MODE_BRUTE)
+    assert np.array_equal(idx, oi.astype(np.int32)) and np.array_equal(d2, od)
+    o = rng.random((2000, 3)).astype(np.float32)
+    d = rng.standard_normal((2000, 3)).astype(np.float32)
+    t, ridx, _ = e.ray_first(o, d)
+    ri, rt = ora.ray_first(o, d, mode=orc.MODE_BRUTE)
+    assert np.array_equal(ridx, ri.astype(np.int32)) and np.array_equal(t, rt)
+    pts = np.repeat(rng.random((40, 3)).astype(np.float32), 5, axis=0)
+    pe = Engine(0)
+    pe.build_points(pts)
+    po = orc.Oracle(points=pts)
+    ki, kd = pe.knn(pts, 7, exclude_self=True)
+    oki, okd = po.knn(pts, 7, exclude_self=True, mode=orc.MODE_BRUTE)
+    assert np.array_equal(ki, oki.astype(np.int32)) and np.array_equal(kd, okd)

@@ -1,0 +1,808 @@
+// tgq.cu -- host side of libtgq.so: the handle, device memory, launch sequences and the C ABI declared in
+// include/thea_gpu_query.h.  No CPU query path exists here: every query entry point ends in kernels from
+// tgq_kernels.cuh, and tgq_create fails when there is no CUDA device.
+#include "../../include/thea_gpu_query.h"
+#include "tgq_kernels.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace tgq;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf
+{
+  void * p = nullptr; size_t cap = 0;
+  cudaError_t reserve(size_t bytes)
+  {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 16 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T * as() const { return (T *)p; }
+};
+
+#define TGQ_MAX_ARGS 8
+
+// Scratch of one pipeline slot.  Host-pointer calls alternate two slots, each with its own stream, so that the copies of
+// one chunk overlap the kernels of the other.
+struct Slot
+{
+  cudaStream_t stream = nullptr;
+  DevBuf in[TGQ_MAX_ARGS], out[TGQ_MAX_ARGS], keys[2], vals[2], cubtmp;
+};
+
+}  // namespace
+
+struct tgq_handle
+{
+  int device = 0;
+  std::string err;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+
+  int opt_sort = 2, opt_leaf = 4, opt_async = 0; int64_t opt_chunk = 4194304;
+
+  int kind = TGQ_KIND_NONE; int n = 0; int n_nodes = 0; bool has_normals = false; int leaf_built = 4;
+  DevBuf nodes, elems, nrm, scene;                                  // NodeRec[], TriRec[] | f4[], f4[], SceneBox
+  DevBuf perm, pos_of_elem, first, last, split, parent, live, newidx;   // kept for refit
+  DevBuf pbox_lo, pbox_hi, nbox_lo, nbox_hi, arrive, keys_a, keys_b, vals_a, cubtmp, src, src2, misc;
+  DevBuf area_by_elem, cum;
+  bool cum_valid = false;
+  float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+
+  Slot slot[2];
+  std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+  tgq_stats st = {};
+};
+
+namespace {
+
+#define CK(call)                                                                                                      \
+  do {                                                                                                                \
+    cudaError_t e__ = (call);                                                                                         \
+    if (e__ != cudaSuccess) {                                                                                         \
+      char buf__[512];                                                                                                \
+      snprintf(buf__, sizeof buf__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);     \
+      h->err = buf__;                                                                                                 \
+      return TGQ_ECUDA;                                                                                               \
+    }                                                                                                                 \
+  } while (0)
+
+#define CKRC(call) do { int rc__ = (call); if (rc__ != TGQ_OK) return rc__; } while (0)
+
+int fail(tgq_handle * h, int code, char const * msg) { if (h) h->err = msg; return code; }
+
+inline int grid_for(int64_t n, int block = TGQ_BLOCK) { return (int)((n + block - 1) / block); }
+
+bool is_device_ptr(void const * p)
+{
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+BvhView view_of(tgq_handle * h)
+{
+  BvhView v;
+  v.nodes = h->nodes.as<NodeRec>();
+  v.tris = h->kind == TGQ_KIND_TRIANGLES ? h->elems.as<TriRec>() : nullptr;
+  v.pts = h->kind == TGQ_KIND_POINTS ? h->elems.as<f4>() : nullptr;
+  v.nrm = (h->kind == TGQ_KIND_POINTS && h->has_normals) ? h->nrm.as<f4>() : nullptr;
+  v.n_nodes = h->n_nodes; v.n_prims = h->n;
+  return v;
+}
+
+cudaEvent_t get_event(tgq_handle * h)
+{
+  if (h->ev_used == h->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); h->ev_pool.push_back(e); }
+  return h->ev_pool[h->ev_used++];
+}
+
+// Exclusive squared-distance bound as a float: d2 < ub  <=>  (double)d2 < bound^2 (BvhN.hpp:448,462).
+float bound_to_ub(double dist_bound)
+{
+  if (!(dist_bound >= 0)) return INFINITY;
+  double b2 = dist_bound * dist_bound;
+  if (b2 > (double)FLT_MAX) return INFINITY;
+  float f = (float)b2;
+  if ((double)f < b2) f = std::nextafterf(f, INFINITY);
+  return f;   // smallest float >= bound^2
+}
+
+// Returns a device pointer holding `bytes` of p (copying when p is a host pointer).
+int to_device(tgq_handle * h, void const * p, size_t bytes, DevBuf & buf, cudaStream_t s, void const ** out)
+{
+  if (is_device_ptr(p)) { *out = p; return TGQ_OK; }
+  CK(buf.reserve(bytes));
+  CK(cudaMemcpyAsync(buf.p, p, bytes, cudaMemcpyHostToDevice, s));
+  *out = buf.p;
+  return TGQ_OK;
+}
+
+int from_device(tgq_handle * h, void * dst, void const * src_dev, size_t bytes, cudaStream_t s)
+{
+  CK(cudaMemcpyAsync(dst, src_dev, bytes, is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+  return TGQ_OK;
+}
+
+// ---- build --------------------------------------------------------------------------------------------------------------
+
+int refit_and_emit(tgq_handle * h, cudaStream_t s)
+{
+  int n = h->n;
+  if (n >= 2)
+  {
+    CK(cudaMemsetAsync(h->arrive.p, 0, sizeof(unsigned) * (size_t)(n - 1), s));
+    k_refit<<<grid_for(n), TGQ_BLOCK, 0, s>>>(n, h->first.as<int>(), h->last.as<int>(), h->split.as<int>(), h->parent.as<int>(),
+                                              h->pbox_lo.as<f4>(), h->pbox_hi.as<f4>(), h->nbox_lo.as<f4>(), h->nbox_hi.as<f4>(),
+                                              h->arrive.as<unsigned>());
+    k_emit<<<grid_for(n - 1), TGQ_BLOCK, 0, s>>>(n, h->leaf_built, h->first.as<int>(), h->last.as<int>(), h->split.as<int>(),
+                                                 h->live.as<int>(), h->newidx.as<int>(), h->pbox_lo.as<f4>(), h->pbox_hi.as<f4>(),
+                                                 h->nbox_lo.as<f4>(), h->nbox_hi.as<f4>(), h->scene.as<SceneBox>(), h->nodes.as<NodeRec>());
+    h->st.total_launches += 2;
+  }
+  else if (n == 1)
+  {
+    k_emit_single<<<1, 1, 0, s>>>(h->pbox_lo.as<f4>(), h->pbox_hi.as<f4>(), h->scene.as<SceneBox>(), h->nodes.as<NodeRec>());
+    h->st.total_launches += 1;
+  }
+  CK(cudaGetLastError());
+  return TGQ_OK;
+}
+
+int scene_bounds(tgq_handle * h, float const * d_pts, int64_t npts, cudaStream_t s)
+{
+  CK(h->scene.reserve(sizeof(SceneBox)));
+  k_scene_init<<<1, 1, 0, s>>>(h->scene.as<SceneBox>());
+  if (npts > 0)
+  {
+    int grid = (int)std::min<int64_t>((npts + 255) / 256, (int64_t)h->st.num_elements * 0 + 148 * 8);
+    k_scene_bounds<<<grid, 256, 0, s>>>(d_pts, npts, h->scene.as<SceneBox>());
+  }
+  h->st.total_launches += 2;
+  CK(cudaGetLastError());
+  return TGQ_OK;
+}
+
+int fetch_scene(tgq_handle * h, cudaStream_t s)
+{
+  SceneBox sb;
+  CK(cudaMemcpyAsync(&sb, h->scene.p, sizeof sb, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  for (int a = 0; a < 3; ++a)
+  {
+    int l = sb.lo[a], u = sb.hi[a];
+    l = l >= 0 ? l : l ^ 0x7fffffff; u = u >= 0 ? u : u ^ 0x7fffffff;
+    memcpy(&h->lo[a], &l, 4); memcpy(&h->hi[a], &u, 4);
+  }
+  return TGQ_OK;
+}
+
+// d_src: device pointer to T x 9 floats (triangles) or P x 3 floats (points); d_n3: device normals or null.
+int build_common(tgq_handle * h, int kind, float const * d_src, float const * d_n3, int64_t n64)
+{
+  cudaStream_t s = h->stream;
+  if (n64 < 0) return fail(h, TGQ_EINVAL, "negative element count");
+  if (n64 >= ((int64_t)1 << (31 - TGQ_LEAF_BITS))) return fail(h, TGQ_ELIMIT, "more than 2^27 - 1 elements in one structure");
+  int n = (int)n64;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  h->ev_used = 0; e0 = get_event(h); e1 = get_event(h);
+  CK(cudaEventRecord(e0, s));
+
+  h->kind = kind; h->n = n; h->n_nodes = 0; h->has_normals = (kind == TGQ_KIND_POINTS && d_n3 != nullptr);
+  h->leaf_built = h->opt_leaf; h->cum_valid = false;
+  h->st.num_elements = n;
+  for (int a = 0; a < 3; ++a) { h->lo[a] = 0; h->hi[a] = 0; }
+  if (n == 0) { h->st.num_nodes = 0; h->st.node_bytes = 0; h->st.element_bytes = 0; h->st.last_build_ms = 0; return TGQ_OK; }
+
+  CKRC(scene_bounds(h, d_src, kind == TGQ_KIND_TRIANGLES ? 3 * n64 : n64, s));
+
+  size_t nn = (size_t)n;
+  CK(h->keys_a.reserve(8 * nn)); CK(h->keys_b.reserve(8 * nn)); CK(h->vals_a.reserve(4 * nn)); CK(h->perm.reserve(4 * nn));
+  CK(h->pos_of_elem.reserve(4 * nn));
+  CK(h->pbox_lo.reserve(16 * nn)); CK(h->pbox_hi.reserve(16 * nn));
+  size_t rec = kind == TGQ_KIND_TRIANGLES ? sizeof(TriRec) : sizeof(f4);
+  CK(h->elems.reserve(rec * nn));
+  if (h->has_normals) CK(h->nrm.reserve(16 * nn));
+
+  if (kind == TGQ_KIND_TRIANGLES) k_morton_tris<<<grid_for(n), TGQ_BLOCK, 0, s>>>(d_src, n, h->scene.as<SceneBox>(), h->keys_a.as<uint64_t>(), h->vals_a.as<uint32_t>());
+  else k_morton_points<<<grid_for(n), TGQ_BLOCK, 0, s>>>(d_src, n, h->scene.as<SceneBox>(), h->keys_a.as<uint64_t>(), h->vals_a.as<uint32_t>());
+  CK(cudaGetLastError());
+
+  // K2: stable LSD radix sort of (morton63, element index)
+  size_t tmp_bytes = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->keys_a.as<uint64_t>(), h->keys_b.as<uint64_t>(), h->vals_a.as<uint32_t>(),
+                                     h->perm.as<uint32_t>(), n, 0, 63, s));
+  CK(h->cubtmp.reserve(tmp_bytes));
+  CK(cub::DeviceRadixSort::SortPairs(h->cubtmp.p, tmp_bytes, h->keys_a.as<uint64_t>(), h->keys_b.as<uint64_t>(), h->vals_a.as<uint32_t>(),
+                                     h->perm.as<uint32_t>(), n, 0, 63, s));
+
+  if (kind == TGQ_KIND_TRIANGLES)
+    k_gather_tris<<<grid_for(n), TGQ_BLOCK, 0, s>>>(d_src, h->perm.as<uint32_t>(), n, h->elems.as<TriRec>(), h->pbox_lo.as<f4>(),
+                                                    h->pbox_hi.as<f4>(), h->pos_of_elem.as<int>());
+  else
+    k_gather_points<<<grid_for(n), TGQ_BLOCK, 0, s>>>(d_src, d_n3, h->perm.as<uint32_t>(), n, h->elems.as<f4>(), h->nrm.as<f4>(),
+                                                      h->pbox_lo.as<f4>(), h->pbox_hi.as<f4>(), h->pos_of_elem.as<int>());
+  CK(cudaGetLastError());
+  h->st.total_launches += 8;
+
+  if (n >= 2)
+  {
+    size_t ni = nn - 1;
+    CK(h->first.reserve(4 * ni)); CK(h->last.reserve(4 * ni)); CK(h->split.reserve(4 * ni)); CK(h->parent.reserve(4 * (2 * nn)));
+    CK(h->live.reserve(4 * ni)); CK(h->newidx.reserve(4 * ni)); CK(h->arrive.reserve(4 * ni));
+    CK(h->nbox_lo.reserve(16 * ni)); CK(h->nbox_hi.reserve(16 * ni));
+    k_hierarchy<<<grid_for(n - 1), TGQ_BLOCK, 0, s>>>(h->keys_b.as<uint64_t>(), n, h->first.as<int>(), h->last.as<int>(), h->split.as<int>(),
+                                                      h->parent.as<int>());
+    k_live<<<grid_for(n - 1), TGQ_BLOCK, 0, s>>>(n, h->leaf_built, h->first.as<int>(), h->last.as<int>(), h->live.as<int>());
+    CK(cudaGetLastError());
+    size_t scan_bytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, h->live.as<int>(), h->newidx.as<int>(), n - 1, s));
+    CK(h->cubtmp.reserve(scan_bytes));
+    CK(cub::DeviceScan::ExclusiveSum(h->cubtmp.p, scan_bytes, h->live.as<int>(), h->newidx.as<int>(), n - 1, s));
+    int tail[2];
+    CK(cudaMemcpyAsync(&tail[0], h->newidx.as<int>() + (n - 2), 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&tail[1], h->live.as<int>() + (n - 2), 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    h->n_nodes = tail[0] + tail[1];
+    h->st.total_launches += 4;
+  }
+  else h->n_nodes = 1;
+
+  CK(h->nodes.reserve(sizeof(NodeRec) * (size_t)h->n_nodes));
+  CKRC(refit_and_emit(h, s));
+  CK(cudaEventRecord(e1, s));
+  CKRC(fetch_scene(h, s));
+  float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+  h->st.last_build_ms = ms;
+  h->st.num_nodes = h->n_nodes; h->st.node_bytes = (int64_t)sizeof(NodeRec) * h->n_nodes; h->st.element_bytes = (int64_t)(rec * nn);
+  return TGQ_OK;
+}
+
+// ---- batched query driver ---------------------------------------------------------------------------------------------------
+
+struct Arg { void const * in; void * out; size_t stride; };   // one of in/out non-null; stride = bytes per query
+
+struct ChunkCtx
+{
+  Slot * slot; cudaStream_t stream; int64_t offset; int n;
+  void const * din[TGQ_MAX_ARGS]; void * dout[TGQ_MAX_ARGS];
+  uint32_t const * perm;   // Morton order of the chunk, or null
+};
+
+// Orders the chunk's queries by the Morton code of their first input (positions / ray origins).
+int sort_chunk(tgq_handle * h, ChunkCtx & c)
+{
+  bool want = h->opt_sort == 1 || (h->opt_sort == 2 && c.n >= 4096);
+  c.perm = nullptr;
+  if (!want || h->n == 0) return TGQ_OK;
+  Slot & sl = *c.slot; size_t nn = (size_t)c.n;
+  for (int i = 0; i < 2; ++i) { CK(sl.keys[i].reserve(4 * nn)); CK(sl.vals[i].reserve(4 * nn)); }
+  k_query_codes<<<grid_for(c.n), TGQ_BLOCK, 0, c.stream>>>((float const *)c.din[0], c.n, h->scene.as<SceneBox>(), sl.keys[0].as<uint32_t>(),
+                                                           sl.vals[0].as<uint32_t>());
+  CK(cudaGetLastError());
+  size_t tmp = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, sl.keys[0].as<uint32_t>(), sl.keys[1].as<uint32_t>(), sl.vals[0].as<uint32_t>(),
+                                     sl.vals[1].as<uint32_t>(), c.n, 0, 30, c.stream));
+  CK(sl.cubtmp.reserve(tmp));
+  CK(cub::DeviceRadixSort::SortPairs(sl.cubtmp.p, tmp, sl.keys[0].as<uint32_t>(), sl.keys[1].as<uint32_t>(), sl.vals[0].as<uint32_t>(),
+                                     sl.vals[1].as<uint32_t>(), c.n, 0, 30, c.stream));
+  c.perm = sl.vals[1].as<uint32_t>();
+  h->st.last_launches += 4; h->st.total_launches += 4;
+  return TGQ_OK;
+}
+
+template <typename Launch>
+int run_batched(tgq_handle * h, int64_t Q, Arg * args, int nargs, bool sortable, Launch launch)
+{
+  h->st.last_query_ms = 0; h->st.last_sort_ms = 0; h->st.last_launches = 0; h->ev_used = 0;
+  if (Q == 0) return TGQ_OK;
+  bool all_dev = true;
+  for (int a = 0; a < nargs; ++a)
+  {
+    void const * p = args[a].in ? args[a].in : args[a].out;
+    if (p && !is_device_ptr(p)) all_dev = false;
+  }
+  int64_t chunk = all_dev ? ((int64_t)1 << 26) : std::max<int64_t>(1024, h->opt_chunk);
+  int nslots = all_dev ? 1 : 2;
+  if (!all_dev) CK(cudaStreamSynchronize(h->stream));     // the structure must be complete before other streams read it
+  std::vector<cudaEvent_t> evs;
+  int ci = 0;
+  for (int64_t off = 0; off < Q; off += chunk, ++ci)
+  {
+    ChunkCtx c; c.slot = &h->slot[ci % nslots]; c.stream = all_dev ? h->stream : c.slot->stream; c.offset = off;
+    c.n = (int)std::min<int64_t>(chunk, Q - off); c.perm = nullptr;
+    for (int a = 0; a < nargs; ++a)
+    {
+      c.din[a] = nullptr; c.dout[a] = nullptr;
+      size_t bytes = args[a].stride * (size_t)c.n, skip = args[a].stride * (size_t)off;
+      if (args[a].in)
+      {
+        char const * p = (char const *)args[a].in + skip;
+        if (is_device_ptr(args[a].in)) c.din[a] = p;
+        else { CK(c.slot->in[a].reserve(bytes)); CK(cudaMemcpyAsync(c.slot->in[a].p, p, bytes, cudaMemcpyHostToDevice, c.stream)); c.din[a] = c.slot->in[a].p; }
+      }
+      else if (args[a].out)
+      {
+        if (is_device_ptr(args[a].out)) c.dout[a] = (char *)args[a].out + skip;
+        else { CK(c.slot->out[a].reserve(bytes)); c.dout[a] = c.slot->out[a].p; }
+      }
+    }
+    cudaEvent_t e0 = get_event(h), e1 = get_event(h), e2 = get_event(h);
+    CK(cudaEventRecord(e0, c.stream));
+    if (sortable) CKRC(sort_chunk(h, c));
+    CK(cudaEventRecord(e1, c.stream));
+    CKRC(launch(c));
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e2, c.stream));
+    evs.push_back(e0); evs.push_back(e1); evs.push_back(e2);
+    for (int a = 0; a < nargs; ++a)
+      if (args[a].out && !is_device_ptr(args[a].out))
+        CK(cudaMemcpyAsync((char *)args[a].out + args[a].stride * (size_t)off, c.dout[a], args[a].stride * (size_t)c.n, cudaMemcpyDeviceToHost, c.stream));
+  }
+  if (all_dev && h->opt_async) return TGQ_OK;
+  if (all_dev) CK(cudaStreamSynchronize(h->stream));
+  else for (int s = 0; s < 2; ++s) CK(cudaStreamSynchronize(h->slot[s].stream));
+  for (size_t i = 0; i + 2 < evs.size() + 0 && i < evs.size(); i += 3)
+  {
+    float a = 0, b = 0;
+    CK(cudaEventElapsedTime(&a, evs[i], evs[i + 1])); CK(cudaEventElapsedTime(&b, evs[i], evs[i + 2]));
+    h->st.last_sort_ms += a; h->st.last_query_ms += b;
+  }
+  return TGQ_OK;
+}
+
+int need_built(tgq_handle * h, int kind_mask)
+{
+  if (!h) return TGQ_EINVAL;
+  if (h->kind == TGQ_KIND_NONE) return fail(h, TGQ_ESTATE, "no structure built on this handle");
+  if (!((1 << h->kind) & kind_mask)) return fail(h, TGQ_EINVAL, "query not supported by this structure kind");
+  return TGQ_OK;
+}
+
+struct Guard
+{
+  int prev = -1; bool ok = true;
+  explicit Guard(tgq_handle * h) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (prev != h->device) ok = cudaSetDevice(h->device) == cudaSuccess; }
+  ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+// =================================================================================================================================
+// C ABI
+// =================================================================================================================================
+extern "C" {
+
+int tgq_create(int device, tgq_handle ** out)
+{
+  if (!out) { g_create_error = "tgq_create: null output pointer"; return TGQ_EINVAL; }
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+  {
+    g_create_error = std::string("tgq_create: no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                     "); the engine has no CPU path";
+    cudaGetLastError();
+    return TGQ_ENODEVICE;
+  }
+  if (device < 0 || device >= count) { g_create_error = "tgq_create: device index out of range"; return TGQ_EINVAL; }
+  tgq_handle * h = new tgq_handle;
+  h->device = device;
+  int prev = -1; cudaGetDevice(&prev);
+  auto bail = [&](char const * what, cudaError_t err) {
+    g_create_error = std::string("tgq_create: ") + what + ": " + cudaGetErrorString(err);
+    if (prev >= 0) cudaSetDevice(prev);
+    delete h; return TGQ_ECUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  h->stream = h->own_stream;
+  for (int s = 0; s < 2; ++s)
+    if ((e = cudaStreamCreateWithFlags(&h->slot[s].stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  int const smem = 2 * TGQ_MAX_K * TGQ_BLOCK * 4;
+  if ((e = cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute(k_knn)", e);
+  if ((e = cudaFuncSetAttribute(k_ball_graph, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute(k_ball_graph)", e);
+  if (prev >= 0) cudaSetDevice(prev);
+  *out = h;
+  return TGQ_OK;
+}
+
+int tgq_destroy(tgq_handle * h)
+{
+  if (!h) return TGQ_OK;
+  Guard g(h);
+  cudaDeviceSynchronize();
+  DevBuf * bufs[] = {&h->nodes, &h->elems, &h->nrm, &h->scene, &h->perm, &h->pos_of_elem, &h->first, &h->last, &h->split, &h->parent, &h->live,
+                     &h->newidx, &h->pbox_lo, &h->pbox_hi, &h->nbox_lo, &h->nbox_hi, &h->arrive, &h->keys_a, &h->keys_b, &h->vals_a,
+                     &h->cubtmp, &h->src, &h->src2, &h->misc, &h->area_by_elem, &h->cum};
+  for (DevBuf * b : bufs) b->release();
+  for (int s = 0; s < 2; ++s)
+  {
+    Slot & sl = h->slot[s];
+    for (int a = 0; a < TGQ_MAX_ARGS; ++a) { sl.in[a].release(); sl.out[a].release(); }
+    sl.keys[0].release(); sl.keys[1].release(); sl.vals[0].release(); sl.vals[1].release(); sl.cubtmp.release();
+    if (sl.stream) cudaStreamDestroy(sl.stream);
+  }
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return TGQ_OK;
+}
+
+const char * tgq_last_error(tgq_handle * h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int tgq_set_stream(tgq_handle * h, void * cuda_stream)
+{
+  if (!h) return TGQ_EINVAL;
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return TGQ_OK;
+}
+
+int tgq_set_option(tgq_handle * h, int option, int64_t value)
+{
+  if (!h) return TGQ_EINVAL;
+  switch (option)
+  {
+    case TGQ_OPT_SORT_QUERIES: if (value < 0 || value > 2) return fail(h, TGQ_EINVAL, "TGQ_OPT_SORT_QUERIES takes 0, 1 or 2"); h->opt_sort = (int)value; return TGQ_OK;
+    case TGQ_OPT_LEAF_SIZE: if (value < 1 || value > TGQ_LEAF_MASK) return fail(h, TGQ_EINVAL, "TGQ_OPT_LEAF_SIZE takes 1..15"); h->opt_leaf = (int)value; return TGQ_OK;
+    case TGQ_OPT_ASYNC: h->opt_async = value ? 1 : 0; return TGQ_OK;
+    case TGQ_OPT_CHUNK: if (value < 1024) return fail(h, TGQ_EINVAL, "TGQ_OPT_CHUNK must be >= 1024"); h->opt_chunk = value; return TGQ_OK;
+    default: return fail(h, TGQ_EINVAL, "unknown option");
+  }
+}
+
+int tgq_build_triangles(tgq_handle * h, const float * v9, int64_t T)
+{
+  if (!h) return TGQ_EINVAL;
+  if (T < 0 || (T > 0 && !v9)) return fail(h, TGQ_EINVAL, "tgq_build_triangles: bad arguments");
+  Guard g(h);
+  void const * d = nullptr;
+  if (T > 0) CKRC(to_device(h, v9, sizeof(float) * 9 * (size_t)T, h->src, h->stream, &d));
+  return build_common(h, TGQ_KIND_TRIANGLES, (float const *)d, nullptr, T);
+}
+
+int tgq_build_triangles_indexed(tgq_handle * h, const float * verts3, int64_t V, const int32_t * tri3, int64_t T)
+{
+  if (!h) return TGQ_EINVAL;
+  if (T < 0 || V < 0 || (T > 0 && (!verts3 || !tri3))) return fail(h, TGQ_EINVAL, "tgq_build_triangles_indexed: bad arguments");
+  Guard g(h);
+  if (T == 0) return build_common(h, TGQ_KIND_TRIANGLES, nullptr, nullptr, 0);
+  void const * dv = nullptr; void const * di = nullptr;
+  CKRC(to_device(h, verts3, sizeof(float) * 3 * (size_t)V, h->src2, h->stream, &dv));
+  CKRC(to_device(h, tri3, sizeof(int32_t) * 3 * (size_t)T, h->misc, h->stream, &di));
+  CK(h->src.reserve(sizeof(float) * 9 * (size_t)T));
+  k_expand_indexed<<<grid_for(3 * T), TGQ_BLOCK, 0, h->stream>>>((float const *)dv, (int const *)di, 3 * T, V, h->src.as<float>());
+  CK(cudaGetLastError());
+  h->st.total_launches += 1;
+  return build_common(h, TGQ_KIND_TRIANGLES, h->src.as<float>(), nullptr, T);
+}
+
+int tgq_build_points(tgq_handle * h, const float * p3, int64_t P, const float * n3)
+{
+  if (!h) return TGQ_EINVAL;
+  if (P < 0 || (P > 0 && !p3)) return fail(h, TGQ_EINVAL, "tgq_build_points: bad arguments");
+  Guard g(h);
+  void const * d = nullptr; void const * dn = nullptr;
+  if (P > 0) CKRC(to_device(h, p3, sizeof(float) * 3 * (size_t)P, h->src, h->stream, &d));
+  if (P > 0 && n3) CKRC(to_device(h, n3, sizeof(float) * 3 * (size_t)P, h->src2, h->stream, &dn));
+  return build_common(h, TGQ_KIND_POINTS, (float const *)d, (float const *)dn, P);
+}
+
+int tgq_refit_triangles(tgq_handle * h, const float * v9, int64_t T)
+{
+  CKRC(need_built(h, 1 << TGQ_KIND_TRIANGLES));
+  if (T != h->n) return fail(h, TGQ_ESTATE, "tgq_refit_triangles: element count differs from the built structure");
+  if (T == 0) return TGQ_OK;
+  if (!v9) return fail(h, TGQ_EINVAL, "tgq_refit_triangles: null vertices");
+  Guard g(h);
+  cudaStream_t s = h->stream;
+  h->ev_used = 0; cudaEvent_t e0 = get_event(h), e1 = get_event(h);
+  CK(cudaEventRecord(e0, s));
+  void const * d = nullptr;
+  CKRC(to_device(h, v9, sizeof(float) * 9 * (size_t)T, h->src, s, &d));
+  CKRC(scene_bounds(h, (float const *)d, 3 * T, s));
+  k_gather_tris<<<grid_for(h->n), TGQ_BLOCK, 0, s>>>((float const *)d, h->perm.as<uint32_t>(), h->n, h->elems.as<TriRec>(), h->pbox_lo.as<f4>(),
+                                                     h->pbox_hi.as<f4>(), h->pos_of_elem.as<int>());
+  CK(cudaGetLastError());
+  h->st.total_launches += 1; h->cum_valid = false;
+  CKRC(refit_and_emit(h, s));
+  CK(cudaEventRecord(e1, s));
+  CKRC(fetch_scene(h, s));
+  float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1)); h->st.last_build_ms = ms;
+  return TGQ_OK;
+}
+
+int tgq_info(tgq_handle * h, int32_t * kind, int64_t * num_elements, float * lo3, float * hi3)
+{
+  if (!h) return TGQ_EINVAL;
+  if (kind) *kind = h->kind;
+  if (num_elements) *num_elements = h->n;
+  for (int a = 0; a < 3; ++a) { if (lo3) lo3[a] = h->lo[a]; if (hi3) hi3[a] = h->hi[a]; }
+  return TGQ_OK;
+}
+
+int tgq_triangle_cache(tgq_handle * h, float * n3, float * d, int32_t * axis, float * area)
+{
+  CKRC(need_built(h, 1 << TGQ_KIND_TRIANGLES));
+  if (h->n == 0) return TGQ_OK;
+  Guard g(h);
+  cudaStream_t s = h->stream; size_t nn = (size_t)h->n;
+  // device staging for host outputs: [n3 | d | axis | area]
+  CK(h->misc.reserve(4 * nn * 6));
+  float * dn = h->misc.as<float>(); float * dd = dn + 3 * nn; int * da = (int *)(dd + nn); float * dar = (float *)(da + nn);
+  float * on = n3 ? (is_device_ptr(n3) ? n3 : dn) : nullptr; float * od = d ? (is_device_ptr(d) ? d : dd) : nullptr;
+  int * oa = axis ? (is_device_ptr(axis) ? axis : da) : nullptr; float * oar = area ? (is_device_ptr(area) ? area : dar) : nullptr;
+  k_scatter_cache<<<grid_for(h->n), TGQ_BLOCK, 0, s>>>(h->elems.as<TriRec>(), h->n, on, od, oa, oar);
+  CK(cudaGetLastError());
+  h->st.total_launches += 1;
+  if (n3 && on == dn) CKRC(from_device(h, n3, dn, 12 * nn, s));
+  if (d && od == dd) CKRC(from_device(h, d, dd, 4 * nn, s));
+  if (axis && oa == da) CKRC(from_device(h, axis, da, 4 * nn, s));
+  if (area && oar == dar) CKRC(from_device(h, area, dar, 4 * nn, s));
+  CK(cudaStreamSynchronize(s));
+  return TGQ_OK;
+}
+
+int tgq_closest(tgq_handle * h, const float * q3, int64_t Q, double dist_bound, int32_t exclude_self, int32_t * idx, float * d2, float * cp3)
+{
+  CKRC(need_built(h, (1 << TGQ_KIND_TRIANGLES) | (1 << TGQ_KIND_POINTS)));
+  if (Q < 0 || (Q > 0 && !q3)) return fail(h, TGQ_EINVAL, "tgq_closest: bad arguments");
+  Guard g(h);
+  float ub = bound_to_ub(dist_bound);
+  Arg args[4] = {{q3, nullptr, 12}, {nullptr, idx, 4}, {nullptr, d2, 4}, {nullptr, cp3, 12}};
+  BvhView v = view_of(h); bool tri = h->kind == TGQ_KIND_TRIANGLES;
+  return run_batched(h, Q, args, 4, true, [&](ChunkCtx & c) {
+    if (tri) k_closest<true><<<grid_for(c.n), TGQ_BLOCK, 0, c.stream>>>(v, (float const *)c.din[0], c.perm, c.n, ub, exclude_self, c.offset,
+                                                                        (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3]);
+    else k_closest<false><<<grid_for(c.n), TGQ_BLOCK, 0, c.stream>>>(v, (float const *)c.din[0], c.perm, c.n, ub, exclude_self, c.offset,
+                                                                     (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3]);
+    h->st.last_launches += 1; h->st.total_launches += 1;
+    return TGQ_OK;
+  });
+}
+
+int tgq_knn(tgq_handle * h, const float * q3, int64_t Q, int32_t k, double dist_bound, int32_t exclude_self, int32_t * idx, float * d2)
+{
+  CKRC(need_built(h, 1 << TGQ_KIND_POINTS));
+  if (Q < 0 || (Q > 0 && !q3) || k < 1) return fail(h, TGQ_EINVAL, "tgq_knn: bad arguments");
+  if (k > TGQ_MAX_K) return fail(h, TGQ_ELIMIT, "tgq_knn: k exceeds TGQ_MAX_K");
+  Guard g(h);
+  float ub = bound_to_ub(dist_bound);
+  Arg args[3] = {{q3, nullptr, 12}, {nullptr, idx, 4 * (size_t)k}, {nullptr, d2, 4 * (size_t)k}};
+  BvhView v = view_of(h);
+  size_t smem = 2 * (size_t)k * TGQ_BLOCK * 4;
+  return run_batched(h, Q, args, 3, true, [&](ChunkCtx & c) {
+    k_knn<<<grid_for(c.n), TGQ_BLOCK, smem, c.stream>>>(v, (float const *)c.din[0], c.perm, c.n, k, ub, exclude_self, c.offset, (int *)c.dout[1],
+                                                        (float *)c.dout[2]);
+    h->st.last_launches += 1; h->st.total_launches += 1;
+    return TGQ_OK;
+  });
+}
+
+int tgq_ball_graph(tgq_handle * h, int32_t max_degree, float init_radius, int32_t rounds, float min_dot, int32_t min_degree, int32_t * idx,
+                   float * sep, int32_t * count)
+{
+  CKRC(need_built(h, 1 << TGQ_KIND_POINTS));
+  if (max_degree < 1 || rounds < 1) return fail(h, TGQ_EINVAL, "tgq_ball_graph: bad arguments");
+  if (max_degree > TGQ_MAX_K) return fail(h, TGQ_ELIMIT, "tgq_ball_graph: max_degree exceeds TGQ_MAX_K");
+  Guard g(h);
+  h->st.last_query_ms = 0; h->st.last_sort_ms = 0; h->st.last_launches = 0; h->ev_used = 0;
+  if (h->n == 0) return TGQ_OK;
+  cudaStream_t s = h->stream; size_t nn = (size_t)h->n, k = (size_t)max_degree;
+  CK(h->slot[0].out[0].reserve(4 * nn * k)); CK(h->slot[0].out[1].reserve(4 * nn * k)); CK(h->slot[0].out[2].reserve(4 * nn));
+  int * di = idx ? (is_device_ptr(idx) ? idx : h->slot[0].out[0].as<int>()) : nullptr;
+  float * ds = sep ? (is_device_ptr(sep) ? sep : h->slot[0].out[1].as<float>()) : nullptr;
+  int * dc = count ? (is_device_ptr(count) ? count : h->slot[0].out[2].as<int>()) : nullptr;
+  cudaEvent_t e0 = get_event(h), e1 = get_event(h);
+  CK(cudaEventRecord(e0, s));
+  k_ball_graph<<<grid_for(h->n), TGQ_BLOCK, 2 * k * TGQ_BLOCK * 4, s>>>(view_of(h), h->n, max_degree, init_radius, rounds, min_dot, min_degree, di, ds, dc);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(e1, s));
+  h->st.last_launches += 1; h->st.total_launches += 1;
+  if (idx && !is_device_ptr(idx)) CKRC(from_device(h, idx, di, 4 * nn * k, s));
+  if (sep && !is_device_ptr(sep)) CKRC(from_device(h, sep, ds, 4 * nn * k, s));
+  if (count && !is_device_ptr(count)) CKRC(from_device(h, count, dc, 4 * nn, s));
+  CK(cudaStreamSynchronize(s));
+  float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1)); h->st.last_query_ms = ms;
+  return TGQ_OK;
+}
+
+int tgq_avg_separation(tgq_handle * h, const int32_t * seeds, int32_t n, float * out)
+{
+  CKRC(need_built(h, 1 << TGQ_KIND_POINTS));
+  if (n < 1 || !seeds || !out) return fail(h, TGQ_EINVAL, "tgq_avg_separation: bad arguments");
+  if (h->n < 2) return fail(h, TGQ_ESTATE, "tgq_avg_separation: needs at least two points");
+  Guard g(h);
+  cudaStream_t s = h->stream;
+  std::vector<int32_t> hs(seeds, seeds + n);
+  if (is_device_ptr(seeds)) { CK(cudaMemcpyAsync(hs.data(), seeds, 4 * (size_t)n, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s)); }
+  for (int i = 0; i < n; ++i) if (hs[(size_t)i] < 0 || hs[(size_t)i] >= h->n) return fail(h, TGQ_EINVAL, "tgq_avg_separation: seed index out of range");
+  CK(h->misc.reserve(8 * (size_t)n));
+  int * ds = h->misc.as<int>(); float * dd = (float *)(ds + n);
+  CK(cudaMemcpyAsync(ds, hs.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+  k_self_nn<<<grid_for(n), TGQ_BLOCK, 0, s>>>(view_of(h), h->pos_of_elem.as<int>(), ds, n, dd);
+  CK(cudaGetLastError());
+  h->st.total_launches += 1;
+  std::vector<float> d2((size_t)n);
+  CK(cudaMemcpyAsync(d2.data(), dd, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  float acc = 0;                                    // PointSet3.hpp:363-376: float accumulation in trial order
+  for (int i = 0; i < n; ++i) acc += d2[(size_t)i];
+  *out = std::sqrt(acc / (float)n);
+  return TGQ_OK;
+}
+
+static int ray_common(tgq_handle * h, const float * o3, const float * d3, const float * tmax, int64_t R, float * t, int32_t * idx,
+                      float * normal3, uint8_t * hit, bool any)
+{
+  CKRC(need_built(h, 1 << TGQ_KIND_TRIANGLES));
+  if (R < 0 || (R > 0 && (!o3 || !d3))) return fail(h, TGQ_EINVAL, "ray query: bad arguments");
+  Guard g(h);
+  BvhView v = view_of(h);
+  Arg args[7] = {{o3, nullptr, 12}, {d3, nullptr, 12}, {tmax, nullptr, 4}, {nullptr, t, 4}, {nullptr, idx, 4}, {nullptr, normal3, 12}, {nullptr, hit, 1}};
+  return run_batched(h, R, args, 7, true, [&](ChunkCtx & c) {
+    if (any) k_ray<true><<<grid_for(c.n), TGQ_BLOCK, 0, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], (float const *)c.din[2], c.perm,
+                                                                   c.n, (float *)c.dout[3], (int *)c.dout[4], (float *)c.dout[5], (uint8_t *)c.dout[6]);
+    else k_ray<false><<<grid_for(c.n), TGQ_BLOCK, 0, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], (float const *)c.din[2], c.perm,
+                                                                c.n, (float *)c.dout[3], (int *)c.dout[4], (float *)c.dout[5], (uint8_t *)c.dout[6]);
+    h->st.last_launches += 1; h->st.total_launches += 1;
+    return TGQ_OK;
+  });
+}
+
+int tgq_ray_first(tgq_handle * h, const float * o3, const float * d3, const float * tmax, int64_t R, float * t, int32_t * idx, float * normal3)
+{ return ray_common(h, o3, d3, tmax, R, t, idx, normal3, nullptr, false); }
+
+int tgq_ray_any(tgq_handle * h, const float * o3, const float * d3, const float * tmax, int64_t R, uint8_t * hit)
+{ return ray_common(h, o3, d3, tmax, R, nullptr, nullptr, nullptr, hit, true); }
+
+int tgq_sdf(tgq_handle * h, const float * p3, const float * n3, int64_t S, float scale, int32_t only_hit_interior, double * sdf, float * ray_t,
+            int32_t * ray_idx)
+{
+  CKRC(need_built(h, 1 << TGQ_KIND_TRIANGLES));
+  if (S < 0 || (S > 0 && (!p3 || !n3))) return fail(h, TGQ_EINVAL, "tgq_sdf: bad arguments");
+  Guard g(h);
+  BvhView v = view_of(h);
+  // per-sample arrays; the 30 rays of a sample stay together so the epilogue is one thread per sample
+  Arg args[5] = {{p3, nullptr, 12}, {n3, nullptr, 12}, {nullptr, sdf, 8}, {nullptr, ray_t, 120}, {nullptr, ray_idx, 120}};
+  return run_batched(h, S, args, 5, false, [&](ChunkCtx & c) {
+    Slot & sl = *c.slot; size_t nr = 30 * (size_t)c.n;
+    CK(sl.keys[0].reserve(4 * nr)); CK(sl.keys[1].reserve(nr));
+    float * dt = c.dout[3] ? (float *)c.dout[3] : sl.keys[0].as<float>();
+    uint8_t * dv = sl.keys[1].as<uint8_t>();
+    k_sdf_rays<<<grid_for((int64_t)nr), TGQ_BLOCK, 0, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], (int64_t)nr, scale,
+                                                                 only_hit_interior, dt, (int *)c.dout[4], dv);
+    if (c.dout[2]) k_sdf_stats<<<grid_for(c.n), TGQ_BLOCK, 0, c.stream>>>(dt, dv, c.n, scale, (double *)c.dout[2]);
+    h->st.last_launches += c.dout[2] ? 2 : 1; h->st.total_launches += c.dout[2] ? 2 : 1;
+    return TGQ_OK;
+  });
+}
+
+int tgq_icp_sums(tgq_handle * h, const float * from3, const float * to3, int64_t n, const float * tr12, double * out16)
+{
+  if (!h) return TGQ_EINVAL;
+  if (n < 1 || !from3 || !to3 || !out16) return fail(h, TGQ_EINVAL, "tgq_icp_sums: bad arguments");
+  Guard g(h);
+  cudaStream_t s = h->stream;
+  void const * df = nullptr; void const * dt = nullptr;
+  CKRC(to_device(h, from3, 12 * (size_t)n, h->slot[0].in[0], s, &df));
+  CKRC(to_device(h, to3, 12 * (size_t)n, h->slot[0].in[1], s, &dt));
+  CK(h->misc.reserve(16 * 8 + 12 * 4 + 64));
+  long long * acc = h->misc.as<long long>(); float * dtr = (float *)(acc + 16); int * dexp = (int *)(dtr + 12);
+  CK(cudaMemsetAsync(acc, 0, 16 * 8, s));
+  if (tr12) CK(cudaMemcpyAsync(dtr, tr12, 48, is_device_ptr(tr12) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  // fixed-point units from the data range: 2^-34 of the largest coordinate magnitude (2^-34 of its square for products)
+  CK(cudaMemsetAsync(dexp, 0, 4, s));
+  k_max_abs<<<148 * 4, 256, 0, s>>>((float const *)df, (float const *)dt, 3 * n, dexp);
+  int mbits = 0;
+  CK(cudaMemcpyAsync(&mbits, dexp, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  float maxabs; memcpy(&maxabs, &mbits, 4);
+  int e = 0; std::frexp(maxabs > 0 ? maxabs : 1.0f, &e);          // maxabs < 2^e
+  double unit_pos = std::ldexp(1.0, e - 34), unit_prod = std::ldexp(1.0, 2 * e + 2 - 34);
+  int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  k_icp_sums<<<grid, 256, 0, s>>>((float const *)df, (float const *)dt, n, tr12 ? dtr : nullptr, 1.0 / unit_pos, 1.0 / unit_prod, acc);
+  CK(cudaGetLastError());
+  h->st.total_launches += 2;
+  long long ha[16];
+  CK(cudaMemcpyAsync(ha, acc, 16 * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  double N = (double)n, sp[3], sq[3], spq[9];
+  for (int i = 0; i < 3; ++i) { sp[i] = (double)ha[i] * unit_pos; sq[i] = (double)ha[3 + i] * unit_pos; }
+  for (int i = 0; i < 9; ++i) spq[i] = (double)ha[6 + i] * unit_prod;
+  double res[16];
+  for (int i = 0; i < 3; ++i) { res[i] = sp[i] / N; res[3 + i] = sq[i] / N; }
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) res[6 + 3 * r + c] = spq[3 * r + c] - N * res[r] * res[3 + c];
+  // sum |L p + t - q|^2 = sum |(L(p-pm) - (q-qm)) + (L pm + t - qm)|^2 = centred sum + N |L pm + t - qm|^2
+  double L[12]; for (int i = 0; i < 12; ++i) L[i] = tr12 ? 0.0 : ((i % 5 == 0) ? 1.0 : 0.0);
+  if (tr12)
+  {
+    float ht[12];
+    CK(cudaMemcpyAsync(ht, dtr, 48, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+    for (int i = 0; i < 12; ++i) L[i] = ht[i];
+  }
+  double rbar2 = 0;
+  for (int r = 0; r < 3; ++r) { double vv = L[4 * r] * res[0] + L[4 * r + 1] * res[1] + L[4 * r + 2] * res[2] + L[4 * r + 3] - res[3 + r]; rbar2 += vv * vv; }
+  double total = (double)ha[15] * unit_prod;
+  res[15] = rbar2 + (total - N * rbar2);     // Icp3.hpp:441-461: |tr pm - qm|^2 + sum |L dp - dq|^2
+  if (is_device_ptr(out16)) { CK(cudaMemcpyAsync(out16, res, 128, cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s)); }
+  else memcpy(out16, res, 128);
+  return TGQ_OK;
+}
+
+int tgq_transform_points(tgq_handle * h, const float * in3, int64_t n, const float * tr12, float * out3)
+{
+  if (!h) return TGQ_EINVAL;
+  if (n < 0 || (n > 0 && (!in3 || !out3)) || !tr12) return fail(h, TGQ_EINVAL, "tgq_transform_points: bad arguments");
+  if (n == 0) return TGQ_OK;
+  Guard g(h);
+  cudaStream_t s = h->stream;
+  void const * di = nullptr;
+  CKRC(to_device(h, in3, 12 * (size_t)n, h->slot[0].in[0], s, &di));
+  CK(h->misc.reserve(64));
+  CK(cudaMemcpyAsync(h->misc.p, tr12, 48, is_device_ptr(tr12) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  float * dout = out3;
+  if (!is_device_ptr(out3)) { CK(h->slot[0].out[0].reserve(12 * (size_t)n)); dout = h->slot[0].out[0].as<float>(); }
+  k_transform<<<grid_for(n), TGQ_BLOCK, 0, s>>>((float const *)di, n, h->misc.as<float>(), dout);
+  CK(cudaGetLastError());
+  h->st.total_launches += 1;
+  if (dout != out3) CKRC(from_device(h, out3, dout, 12 * (size_t)n, s));
+  CK(cudaStreamSynchronize(s));
+  return TGQ_OK;
+}
+
+int tgq_area_sample(tgq_handle * h, int64_t S, uint64_t seed, float * p3, float * n3, int32_t * tri)
+{
+  CKRC(need_built(h, 1 << TGQ_KIND_TRIANGLES));
+  if (S < 0) return fail(h, TGQ_EINVAL, "tgq_area_sample: bad arguments");
+  if (S == 0 || h->n == 0) return TGQ_OK;
+  Guard g(h);
+  cudaStream_t s = h->stream; size_t nn = (size_t)h->n;
+  if (!h->cum_valid)
+  {
+    CK(h->area_by_elem.reserve(8 * nn)); CK(h->cum.reserve(8 * nn));
+    k_elem_areas<<<grid_for(h->n), TGQ_BLOCK, 0, s>>>(h->elems.as<TriRec>(), h->n, h->area_by_elem.as<double>());
+    k_seq_scan<<<1, 32, 0, s>>>(h->area_by_elem.as<double>(), h->n, h->cum.as<double>());
+    CK(cudaGetLastError());
+    h->st.total_launches += 2; h->cum_valid = true;
+  }
+  size_t ns = (size_t)S;
+  CK(h->slot[0].out[0].reserve(12 * ns)); CK(h->slot[0].out[1].reserve(12 * ns)); CK(h->slot[0].out[2].reserve(4 * ns));
+  float * dp = p3 ? (is_device_ptr(p3) ? p3 : h->slot[0].out[0].as<float>()) : nullptr;
+  float * dn = n3 ? (is_device_ptr(n3) ? n3 : h->slot[0].out[1].as<float>()) : nullptr;
+  int * dt = tri ? (is_device_ptr(tri) ? tri : h->slot[0].out[2].as<int>()) : nullptr;
+  k_area_sample<<<grid_for(S), TGQ_BLOCK, 0, s>>>(h->elems.as<TriRec>(), h->pos_of_elem.as<int>(), h->cum.as<double>(), h->n, S, seed, dp, dn, dt);
+  CK(cudaGetLastError());
+  h->st.total_launches += 1;
+  if (p3 && dp != p3) CKRC(from_device(h, p3, dp, 12 * ns, s));
+  if (n3 && dn != n3) CKRC(from_device(h, n3, dn, 12 * ns, s));
+  if (tri && dt != tri) CKRC(from_device(h, tri, dt, 4 * ns, s));
+  CK(cudaStreamSynchronize(s));
+  return TGQ_OK;
+}
+
+int tgq_get_stats(tgq_handle * h, tgq_stats * out)
+{
+  if (!h || !out) return TGQ_EINVAL;
+  *out = h->st;
+  return TGQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,191 @@
+// tgq_math.cuh -- per-pair fp32 arithmetic of the Thea BvhN query path, in the reference's exact operation order.
+//
+// Every function here must produce bit-identical fp32 results to the reference CPU build (x86-64 SSE2 scalar, no FMA
+// contraction, Code/Build/Common/BuildSetup.cmake:95-111), so this translation unit family is compiled with
+// -fmad=false and IEEE division / square root (nvcc defaults -prec-div=true -prec-sqrt=true).  Three-term sums use
+// Eigen's fixed-size-3 reduction order t0 + (t1 + t2).  Citations are relative to /root/reference/Code/Source/.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <float.h>
+#include <string.h>
+
+#ifdef __CUDACC__
+#define TGQ_HD __host__ __device__ __forceinline__
+#else
+#define TGQ_HD inline
+#endif
+
+namespace tgq {
+
+#ifdef __CUDACC__
+typedef float4 f4;
+#else
+struct alignas(16) f4 { float x, y, z, w; };
+#endif
+
+struct v3 { float x, y, z; };
+
+TGQ_HD v3 mk3(float x, float y, float z) { v3 r; r.x = x; r.y = y; r.z = z; return r; }
+TGQ_HD v3 add3(v3 a, v3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+TGQ_HD v3 sub3(v3 a, v3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+TGQ_HD v3 neg3(v3 a) { return mk3(-a.x, -a.y, -a.z); }
+TGQ_HD v3 mul3(v3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+TGQ_HD v3 div3(v3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+TGQ_HD v3 min3(v3 a, v3 b) { return mk3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
+TGQ_HD v3 max3(v3 a, v3 b) { return mk3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
+TGQ_HD float sum3(float a, float b, float c) { return a + (b + c); }
+TGQ_HD float dot3(v3 a, v3 b) { return sum3(a.x * b.x, a.y * b.y, a.z * b.z); }
+TGQ_HD float sqn3(v3 a) { return dot3(a, a); }
+TGQ_HD v3 cross3(v3 l, v3 r) { return mk3(l.y * r.z - l.z * r.y, l.z * r.x - l.x * r.z, l.x * r.y - l.y * r.x); }
+TGQ_HD v3 normalized3(v3 a) { float z = sqn3(a); return z > 0.0f ? div3(a, sqrtf(z)) : a; }
+TGQ_HD float comp3(v3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+// MatrixUtil.hpp:108-115 maxAbsAxis: first maximum of |v_i|.
+TGQ_HD int max_abs_axis3(v3 v)
+{
+  float ax = fabsf(v.x), ay = fabsf(v.y), az = fabsf(v.z);
+  int m = 0; float mv = ax;
+  if (ay > mv) { m = 1; mv = ay; }
+  if (az > mv) { m = 2; }
+  return m;
+}
+
+TGQ_HD int f2i(float f)
+{
+#ifdef __CUDA_ARCH__
+  return __float_as_int(f);
+#else
+  int i; memcpy(&i, &f, 4); return i;
+#endif
+}
+TGQ_HD float i2f(int i)
+{
+#ifdef __CUDA_ARCH__
+  return __int_as_float(i);
+#else
+  float f; memcpy(&f, &i, 4); return f;
+#endif
+}
+
+// ---- Triangle cache (Triangle3.hpp:143-155, Hyperplane3.hpp:34-41) ------------------------------------------------
+struct TriPlane { v3 n; float d; int axis; };
+
+TGQ_HD TriPlane tri_plane(v3 v0, v3 v1, v3 v2)
+{
+  TriPlane p;
+  p.n = normalized3(cross3(sub3(v1, v0), sub3(v2, v0)));
+  p.d = dot3(p.n, v0);
+  p.axis = max_abs_axis3(p.n);
+  return p;
+}
+TGQ_HD v3 tri_centroid(v3 v0, v3 v1, v3 v2) { return div3(add3(add3(v0, v1), v2), 3.0f); }
+TGQ_HD float tri_area(v3 n, v3 v0, v3 v1, v3 v2) { return 0.5f * fabsf(dot3(n, cross3(sub3(v1, v0), sub3(v2, v0)))); }
+
+// ---- Point -> triangle (MetricL2.hpp:210-215, Triangle3.hpp:294-304,1310-1462, HyperplaneN.hpp:145-160) -----------
+TGQ_HD float tri_area2(v3 d, v3 e, v3 f, int i, int j)
+{ return (comp3(e, i) - comp3(d, i)) * (comp3(f, j) - comp3(d, j)) - (comp3(f, i) - comp3(d, i)) * (comp3(e, j) - comp3(d, j)); }
+
+TGQ_HD bool point_inside_tri(v3 v0, v3 v1, v3 v2, int axis, v3 p)
+{
+  int i, j;
+  if (axis == 1) { i = 2; j = 0; } else if (axis == 2) { i = 0; j = 1; } else { i = 1; j = 2; }
+  float area = tri_area2(v0, v1, v2, i, j);
+  if (area == 0.0f) return v0.x == p.x && v0.y == p.y && v0.z == p.z;
+  float inv = 1.0f / area;
+  float b0 = tri_area2(p, v1, v2, i, j) * inv;
+  if (b0 < 0.0f || b0 > 1.0f) return false;
+  float b1 = tri_area2(v0, p, v2, i, j) * inv;
+  if (b1 < 0.0f || b1 > 1.0f) return false;
+  float b2 = 1.0f - b0 - b1;
+  return b2 >= 0.0f && b2 <= 1.0f;
+}
+
+TGQ_HD v3 closest_on_edge(v3 a, v3 b, v3 p, float & d2)
+{
+  v3 e = sub3(b, a);
+  float len = sqrtf(sqn3(e));
+  v3 dir = div3(e, len);
+  v3 c = sub3(p, a);
+  float t = dot3(dir, c);
+  v3 r;
+  if (t <= 0.0f) r = a;
+  else if (t >= len) r = b;
+  else r = add3(a, mul3(dir, t));
+  d2 = sqn3(sub3(r, p));
+  return r;
+}
+
+TGQ_HD float tri_point_sqdist(v3 v0, v3 v1, v3 v2, v3 n, float d, int axis, v3 p, v3 & cp)
+{
+  float sd = dot3(p, n) - d;
+  v3 proj = sub3(p, mul3(n, sd));          // sd * n, commutative per component
+  if (point_inside_tri(v0, v1, v2, axis, proj)) cp = proj;
+  else
+  {
+    float d0, d1, d2;
+    v3 r0 = closest_on_edge(v0, v1, p, d0);
+    v3 r1 = closest_on_edge(v1, v2, p, d1);
+    v3 r2 = closest_on_edge(v2, v0, p, d2);
+    if (d0 < d1) cp = (d0 < d2) ? r0 : r2;
+    else         cp = (d1 < d2) ? r1 : r2;
+  }
+  return sqn3(sub3(cp, p));
+}
+
+// ---- Ray -> triangle (Triangle3.hpp:1464-1524); returns -1 for a miss ---------------------------------------------
+TGQ_HD float ray_tri_time(v3 o, v3 D, v3 v0, v3 e01, v3 e02)
+{
+  v3 diff = sub3(o, v0);
+  v3 N = cross3(e01, e02);
+  float DdN = dot3(D, N);
+  float s;
+  if (DdN > FLT_EPSILON) s = 1.0f;
+  else if (DdN < -FLT_EPSILON) { s = -1.0f; DdN = -DdN; }
+  else return -1.0f;
+  float a = s * dot3(D, cross3(diff, e02));
+  if (!(a >= 0.0f)) return -1.0f;
+  float b = s * dot3(D, cross3(e01, diff));
+  if (!(b >= 0.0f)) return -1.0f;
+  if (!(a + b <= DdN)) return -1.0f;
+  float q = (-s) * dot3(diff, N);
+  if (!(q >= 0.0f)) return -1.0f;
+  return q / DdN;
+}
+
+// ---- Math::fastSqrt (Math.hpp:194-223) -------------------------------------------------------------------------
+TGQ_HD float fast_sqrt(float x)
+{
+  float x2 = x * 0.5f;
+  int i = f2i(x);
+  i = 0x5f3759df - (i >> 1);
+  float y = i2f(i);
+  y = y * (1.5f - (x2 * y * y));
+  return 1.0f / y;
+}
+
+// ---- Box lower bound (AxisAlignedBoxN.hpp:429-456).  Used for ordering and pruning only. ---------------------------
+TGQ_HD float box_point_sqdist(v3 lo, v3 hi, v3 p)
+{
+  v3 g = max3(sub3(max3(lo, p), min3(hi, p)), mk3(0.0f, 0.0f, 0.0f));
+  return sqn3(g);
+}
+
+// ---- ShapeDiameter cone rays (ShapeDiameter.hpp:168-214, MatrixUtil.hpp:225-249) ------------------------------------
+struct SdfFrame { v3 origin, u, v, w; };
+TGQ_HD SdfFrame sdf_frame(v3 position, v3 normal, float scale)
+{
+  SdfFrame f;
+  v3 in = neg3(normalized3(normal));
+  f.w = normalized3(in);
+  f.u = (max_abs_axis3(in) == 0) ? normalized3(mk3(in.y, -in.x, 0.0f)) : normalized3(mk3(0.0f, in.z, -in.y));
+  f.v = cross3(f.w, f.u);
+  f.origin = add3(position, mul3(in, 0.001f * scale));
+  return f;
+}
+TGQ_HD v3 sdf_dir(SdfFrame const & f, v3 c)
+{
+  return mk3(sum3(f.u.x * c.x, f.v.x * c.y, f.w.x * c.z), sum3(f.u.y * c.x, f.v.y * c.y, f.w.y * c.z),
+             sum3(f.u.z * c.x, f.v.z * c.y, f.w.z * c.z));
+}
+
+}  // namespace tgq

@@ -1,0 +1,311 @@
+"""ctypes binding of libtgq.so (include/thea_gpu_query.h).
+
+Arrays may be numpy arrays (host memory, staged by the library) or torch CUDA tensors (device pointers, zero copy).
+Nothing here computes: every method forwards to one C-ABI entry point.  There is no fallback -- a missing library or a
+missing GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+KIND_NONE, KIND_TRIANGLES, KIND_POINTS = 0, 1, 2
+OPT_SORT_QUERIES, OPT_LEAF_SIZE, OPT_ASYNC, OPT_CHUNK = 1, 2, 3, 4
+MAX_K = 64
+
+SYMBOLS = [
+    "tgq_create", "tgq_destroy", "tgq_last_error", "tgq_set_stream", "tgq_set_option",
+    "tgq_build_triangles", "tgq_build_triangles_indexed", "tgq_build_points", "tgq_refit_triangles",
+    "tgq_info", "tgq_triangle_cache", "tgq_closest", "tgq_knn", "tgq_ball_graph", "tgq_avg_separation",
+    "tgq_ray_first", "tgq_ray_any", "tgq_sdf", "tgq_icp_sums", "tgq_transform_points", "tgq_area_sample",
+    "tgq_get_stats",
+]
+
+
+class TgqError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"tgq error {code}: {msg}")
+        self.code = code
+
+
+class Stats(C.Structure):
+    _fields_ = [("num_elements", C.c_int64), ("num_nodes", C.c_int64), ("node_bytes", C.c_int64),
+                ("element_bytes", C.c_int64), ("last_build_ms", C.c_double), ("last_query_ms", C.c_double),
+                ("last_sort_ms", C.c_double), ("last_launches", C.c_int64), ("total_launches", C.c_int64)]
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libtgq.so")
+
+
+def load_library():
+    """Loads libtgq.so; raises if it has not been built (run ``python -c 'import __graft_entry__ as g; g.build()'``)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `make -C thea_b200/csrc` (there is no CPU fallback)")
+    L = C.CDLL(path)
+    vp, i32, i64, f32, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
+    L.tgq_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.tgq_destroy.argtypes = [vp]
+    L.tgq_last_error.restype = C.c_char_p
+    L.tgq_last_error.argtypes = [vp]
+    L.tgq_set_stream.argtypes = [vp, vp]
+    L.tgq_set_option.argtypes = [vp, C.c_int, i64]
+    L.tgq_build_triangles.argtypes = [vp, vp, i64]
+    L.tgq_build_triangles_indexed.argtypes = [vp, vp, i64, vp, i64]
+    L.tgq_build_points.argtypes = [vp, vp, i64, vp]
+    L.tgq_refit_triangles.argtypes = [vp, vp, i64]
+    L.tgq_info.argtypes = [vp, vp, vp, vp, vp]
+    L.tgq_triangle_cache.argtypes = [vp, vp, vp, vp, vp]
+    L.tgq_closest.argtypes = [vp, vp, i64, f64, i32, vp, vp, vp]
+    L.tgq_knn.argtypes = [vp, vp, i64, i32, f64, i32, vp, vp]
+    L.tgq_ball_graph.argtypes = [vp, i32, f32, i32, f32, i32, vp, vp, vp]
+    L.tgq_avg_separation.argtypes = [vp, vp, i32, vp]
+    L.tgq_ray_first.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp]
+    L.tgq_ray_any.argtypes = [vp, vp, vp, vp, i64, vp]
+    L.tgq_sdf.argtypes = [vp, vp, vp, i64, f32, i32, vp, vp, vp]
+    L.tgq_icp_sums.argtypes = [vp, vp, vp, i64, vp, vp]
+    L.tgq_transform_points.argtypes = [vp, vp, i64, vp, vp]
+    L.tgq_area_sample.argtypes = [vp, i64, C.c_uint64, vp, vp, vp]
+    L.tgq_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    for name in SYMBOLS:
+        if name not in ("tgq_last_error",):
+            getattr(L, name).restype = C.c_int
+    _LIB = L
+    return L
+
+
+def _ptr(a):
+    """Raw pointer of a numpy array or torch tensor (None passes through)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(f"unsupported array type {type(a)}")
+
+
+def _is_torch(a):
+    return a is not None and not isinstance(a, np.ndarray) and hasattr(a, "data_ptr")
+
+
+def _as_in(a, dtype=np.float32):
+    """Contiguous input of the right dtype: numpy arrays are converted, torch tensors must already match."""
+    if a is None:
+        return None
+    if _is_torch(a):
+        if not a.is_contiguous():
+            raise ValueError("torch inputs must be contiguous")
+        return a
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Engine:
+    """One BvhN-like structure on one GPU.  Method names follow the C ABI; see include/thea_gpu_query.h."""
+
+    def __init__(self, device: int = 0):
+        self._L = load_library()
+        h = C.c_void_p()
+        rc = self._L.tgq_create(device, C.byref(h))
+        if rc != 0:
+            raise TgqError(rc, self._L.tgq_last_error(None).decode())
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.tgq_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise TgqError(rc, self._L.tgq_last_error(self._h).decode())
+
+    # ---- configuration ----
+    def set_option(self, opt, value):
+        self._ck(self._L.tgq_set_option(self._h, opt, int(value)))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self._L.tgq_set_stream(self._h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    # ---- build ----
+    def build_triangles(self, v9):
+        v9 = _as_in(v9)
+        T = int((v9.size if isinstance(v9, np.ndarray) else v9.numel()) // 9)
+        self._ck(self._L.tgq_build_triangles(self._h, _ptr(v9), T))
+        return T
+
+    def build_triangles_indexed(self, verts, tris):
+        verts = _as_in(verts)
+        tris = _as_in(tris, np.int32)
+        self._ck(self._L.tgq_build_triangles_indexed(self._h, _ptr(verts), int(verts.shape[0]), _ptr(tris), int(tris.shape[0])))
+        return int(tris.shape[0])
+
+    def build_points(self, p3, n3=None):
+        p3 = _as_in(p3)
+        n3 = _as_in(n3)
+        self._ck(self._L.tgq_build_points(self._h, _ptr(p3), int(p3.shape[0]), _ptr(n3)))
+        return int(p3.shape[0])
+
+    def refit_triangles(self, v9):
+        v9 = _as_in(v9)
+        self._ck(self._L.tgq_refit_triangles(self._h, _ptr(v9), int(v9.shape[0])))
+
+    def info(self):
+        kind = C.c_int32()
+        n = C.c_int64()
+        lo = (C.c_float * 3)()
+        hi = (C.c_float * 3)()
+        self._ck(self._L.tgq_info(self._h, C.byref(kind), C.byref(n), lo, hi))
+        return kind.value, n.value, np.array(lo[:], np.float32), np.array(hi[:], np.float32)
+
+    def triangle_cache(self):
+        _, n, _, _ = self.info()
+        nn = np.empty((n, 3), np.float32)
+        d = np.empty(n, np.float32)
+        ax = np.empty(n, np.int32)
+        ar = np.empty(n, np.float32)
+        self._ck(self._L.tgq_triangle_cache(self._h, _ptr(nn), _ptr(d), _ptr(ax), _ptr(ar)))
+        return nn, d, ax, ar
+
+    # ---- queries (numpy in -> numpy out; torch in -> caller supplies torch outputs) ----
+    def closest(self, q3, dist_bound=-1.0, exclude_self=False, out=None, want_cp=True):
+        q3 = _as_in(q3)
+        Q = int(q3.shape[0])
+        if out is None:
+            if _is_torch(q3):
+                import torch
+                idx = torch.empty(Q, dtype=torch.int32, device=q3.device)
+                d2 = torch.empty(Q, dtype=torch.float32, device=q3.device)
+                cp = torch.empty((Q, 3), dtype=torch.float32, device=q3.device) if want_cp else None
+            else:
+                idx = np.empty(Q, np.int32)
+                d2 = np.empty(Q, np.float32)
+                cp = np.empty((Q, 3), np.float32) if want_cp else None
+        else:
+            idx, d2, cp = out
+        self._ck(self._L.tgq_closest(self._h, _ptr(q3), Q, float(dist_bound), int(exclude_self), _ptr(idx), _ptr(d2), _ptr(cp)))
+        return idx, d2, cp
+
+    def knn(self, q3, k, dist_bound=-1.0, exclude_self=False, out=None):
+        q3 = _as_in(q3)
+        Q = int(q3.shape[0])
+        if out is None:
+            if _is_torch(q3):
+                import torch
+                idx = torch.empty((Q, k), dtype=torch.int32, device=q3.device)
+                d2 = torch.empty((Q, k), dtype=torch.float32, device=q3.device)
+            else:
+                idx = np.empty((Q, k), np.int32)
+                d2 = np.empty((Q, k), np.float32)
+        else:
+            idx, d2 = out
+        self._ck(self._L.tgq_knn(self._h, _ptr(q3), Q, int(k), float(dist_bound), int(exclude_self), _ptr(idx), _ptr(d2)))
+        return idx, d2
+
+    def ball_graph(self, max_degree, init_radius, rounds=3, min_dot=-0.5, min_degree=None, out=None):
+        _, n, _, _ = self.info()
+        if min_degree is None:
+            min_degree = min(max(int(0.25 * max_degree), 4), max_degree)   # PointSet3.hpp:665
+        if out is None:
+            idx = np.empty((n, max_degree), np.int32)
+            sep = np.empty((n, max_degree), np.float32)
+            cnt = np.empty(n, np.int32)
+        else:
+            idx, sep, cnt = out
+        self._ck(self._L.tgq_ball_graph(self._h, int(max_degree), float(init_radius), int(rounds), float(min_dot), int(min_degree),
+                                        _ptr(idx), _ptr(sep), _ptr(cnt)))
+        return idx, sep, cnt
+
+    def avg_separation(self, seeds):
+        s = np.ascontiguousarray(seeds, np.int32)
+        out = C.c_float()
+        self._ck(self._L.tgq_avg_separation(self._h, _ptr(s), len(s), C.byref(out)))
+        return float(out.value)
+
+    def ray_first(self, o3, d3, tmax=None, out=None, want_normal=False):
+        o3 = _as_in(o3)
+        d3 = _as_in(d3)
+        tmax = _as_in(tmax)
+        R = int(o3.shape[0])
+        if out is None:
+            if _is_torch(o3):
+                import torch
+                t = torch.empty(R, dtype=torch.float32, device=o3.device)
+                idx = torch.empty(R, dtype=torch.int32, device=o3.device)
+                nrm = torch.empty((R, 3), dtype=torch.float32, device=o3.device) if want_normal else None
+            else:
+                t = np.empty(R, np.float32)
+                idx = np.empty(R, np.int32)
+                nrm = np.empty((R, 3), np.float32) if want_normal else None
+        else:
+            t, idx, nrm = out
+        self._ck(self._L.tgq_ray_first(self._h, _ptr(o3), _ptr(d3), _ptr(tmax), R, _ptr(t), _ptr(idx), _ptr(nrm)))
+        return t, idx, nrm
+
+    def ray_any(self, o3, d3, tmax=None):
+        o3 = _as_in(o3)
+        d3 = _as_in(d3)
+        tmax = _as_in(tmax)
+        R = int(o3.shape[0])
+        hit = np.empty(R, np.uint8)
+        self._ck(self._L.tgq_ray_any(self._h, _ptr(o3), _ptr(d3), _ptr(tmax), R, _ptr(hit)))
+        return hit
+
+    def sdf(self, p3, n3, scale, only_hit_interior=True, want_rays=True):
+        p3 = _as_in(p3)
+        n3 = _as_in(n3)
+        S = int(p3.shape[0])
+        sdf = np.empty(S, np.float64)
+        rt = np.empty((S, 30), np.float32) if want_rays else None
+        ri = np.empty((S, 30), np.int32) if want_rays else None
+        self._ck(self._L.tgq_sdf(self._h, _ptr(p3), _ptr(n3), S, float(scale), int(only_hit_interior), _ptr(sdf), _ptr(rt), _ptr(ri)))
+        return sdf, rt, ri
+
+    def icp_sums(self, from3, to3, tr12=None):
+        from3 = _as_in(from3)
+        to3 = _as_in(to3)
+        tr = None if tr12 is None else np.ascontiguousarray(tr12, np.float32).reshape(12)
+        out = np.empty(16, np.float64)
+        self._ck(self._L.tgq_icp_sums(self._h, _ptr(from3), _ptr(to3), int(from3.shape[0]), _ptr(tr), _ptr(out)))
+        return out
+
+    def transform_points(self, in3, tr12, out=None):
+        in3 = _as_in(in3)
+        tr = np.ascontiguousarray(tr12, np.float32).reshape(12)
+        n = int(in3.shape[0])
+        if out is None:
+            if _is_torch(in3):
+                import torch
+                out = torch.empty((n, 3), dtype=torch.float32, device=in3.device)
+            else:
+                out = np.empty((n, 3), np.float32)
+        self._ck(self._L.tgq_transform_points(self._h, _ptr(in3), n, _ptr(tr), _ptr(out)))
+        return out
+
+    def area_sample(self, count, seed):
+        p = np.empty((count, 3), np.float32)
+        n = np.empty((count, 3), np.float32)
+        t = np.empty(count, np.int32)
+        self._ck(self._L.tgq_area_sample(self._h, int(count), int(seed), _ptr(p), _ptr(n), _ptr(t)))
+        return p, n, t
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._ck(self._L.tgq_get_stats(self._h, C.byref(s)))
+        return {f[0]: getattr(s, f[0]) for f in Stats._fields_}
