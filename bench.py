@@ -1,0 +1,434 @@
+#!/usr/bin/env python
+"""bench.py -- BVH queries/sec on the BASELINE.json configs, with the HBM roofline and the CPU reference beside it.
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload cfg5|cfg1] [--scale F]
+
+Workload (default cfg5, BASELINE.json configs[4]): 10M-triangle bumpy torus (9,999,392 triangles), 100M mixed queries
+= 50M closest-point (BvhN::closestElement with closest point) + 50M ray first-hit (BvhN::rayStructureIntersection),
+issued in alternating blocks of 1M, sharded contiguously over the ranks; the BVH is replicated (each rank builds it).
+One step = one pass over all queries of the rank.  `value` is device-resident throughput (inputs already in HBM);
+`e2e` goes through the same C-ABI calls with pinned HOST buffers, H2D/D2H inside the timed region.
+
+The CPU oracle (oracle/, the restatement of the reference's BvhN in reference traversal order) is used here ONLY for
+the `cpu_baseline` object and for `--impl reference`; it is never on the measured GPU path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from thea_b200 import gen  # noqa: E402
+
+BLOCK = 1_000_000
+WORKLOADS = {
+    # name: (torus grid, closest queries, rays, description)
+    "cfg5": (gen.TORUS_10M, 50_000_000, 50_000_000, "cfg5: 9,999,392-tri torus, 50M closest-point + 50M ray first-hit, blocks of 1M"),
+    "cfg1": (gen.TORUS_70K, 1_000_000, 0, "cfg1: 70,688-tri torus, 1M closest-point queries"),
+    "cfg4r": (gen.TORUS_1M, 0, 3_000_000, "cfg4-like: 1,002,528-tri torus, 3M random first-hit rays"),
+    "cfg1m": (gen.TORUS_1M, 5_000_000, 5_000_000, "1,002,528-tri torus, 5M closest-point + 5M ray first-hit"),
+}
+
+
+def algorithmic_bytes(T: int, kind: str) -> int:
+    """in + out + D*2*24 + 5*elem with D = ceil(log2(T/5)) (one root-to-leaf path, leaf 5)."""
+    D = int(np.ceil(np.log2(T / 5.0)))
+    if kind == "closest":
+        return 12 + 20 + D * 48 + 5 * 36
+    return 28 + 8 + D * 48 + 5 * 36
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, name in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def torch_u01(seed: int, n: int, offset: int, device):
+    """thea_b200.gen.u01 on a torch device (int64 two's-complement arithmetic == uint64 wraparound)."""
+    import torch
+
+    def c(x):  # uint64 constant as int64
+        return x - (1 << 64) if x >= (1 << 63) else x
+
+    def lsr(z, s):
+        return (z >> s) & ((1 << (64 - s)) - 1)
+
+    i = torch.arange(offset + 1, offset + n + 1, dtype=torch.int64, device=device)
+    z = i * c(0x9E3779B97F4A7C15) + c(seed)
+    z = (z ^ lsr(z, 30)) * c(0xBF58476D1CE4E5B9)
+    z = (z ^ lsr(z, 27)) * c(0x94D049BB133111EB)
+    z = z ^ lsr(z, 31)
+    return lsr(z, 40).to(torch.float32) * (2.0 ** -24)
+
+
+def torch_closest_queries(count, bounds, seed, offset, device):
+    import torch
+    lo, hi = gen.box_scaled(*bounds, 1.5)
+    u = torch_u01(seed, 3 * count, 3 * offset, device).reshape(count, 3)
+    lo_t = torch.from_numpy(lo).to(device)
+    hi_t = torch.from_numpy(hi).to(device)
+    return (lo_t + u * (hi_t - lo_t)).contiguous()
+
+
+def torch_random_rays(count, bounds, seed, offset, device):
+    import torch
+    lo, hi = gen.box_scaled(*bounds, 1.5)
+    u = torch_u01(seed, 9 * count, 9 * offset, device).reshape(count, 9)
+    lo_t = torch.from_numpy(lo).to(device)
+    hi_t = torch.from_numpy(hi).to(device)
+    o = (lo_t + u[:, 0:3] * (hi_t - lo_t)).contiguous()
+    u1 = torch.clamp(u[:, 3:6].double(), min=2.0 ** -25)
+    u2 = u[:, 6:9].double()
+    g = torch.sqrt(-2.0 * torch.log(u1)) * torch.cos(2.0 * np.pi * u2)
+    nrm = torch.sqrt((g * g).sum(dim=1, keepdim=True))
+    nrm[nrm == 0] = 1.0
+    return o, (g / nrm).float().contiguous()
+
+
+def shard(total: int, rank: int, world: int):
+    b = total * rank // world
+    e = total * (rank + 1) // world
+    return b, e - b
+
+
+def blocks(n: int):
+    return [(b, min(BLOCK, n - b)) for b in range(0, n, BLOCK)]
+
+
+def run_reference(args, world, rank):
+    """--impl reference: the CPU restatement of the reference's BvhN (kd-tree, DFS order) on all host cores."""
+    if rank != 0:
+        return
+    from oracle import orc
+    grid, nq, nr, desc = WORKLOADS[args.workload]
+    mesh = gen.torus_mesh(max(8, int(grid * args.scale)))
+    T = len(mesh)
+    bounds = gen.mesh_bounds(mesh)
+    cores = orc.ncores()
+    t0 = time.time()
+    ora = orc.Oracle(tris9=mesh)
+    build_s = time.time() - t0
+    # bounded sample per step, sized from a pilot so that steps+warmup stay within a few minutes
+    sq = 2000 if nq else 0
+    sr = 20000 if nr else 0
+    t0 = time.time()
+    if sq:
+        ora.closest(gen.closest_queries(sq, bounds), mode=orc.MODE_REFERENCE, threads=cores)
+    tq = time.time() - t0
+    t0 = time.time()
+    if sr:
+        o, d = gen.random_rays(sr, bounds)
+        ora.ray_first(o, d, mode=orc.MODE_REFERENCE, threads=cores)
+    tr = time.time() - t0
+    budget = 60.0 / max(1, args.steps + args.warmup)          # seconds per step
+    mix_q = nq / max(1, nq + nr)
+    per_pair = (tq / sq if sq else 0) * mix_q + (tr / sr if sr else 0) * (1 - mix_q)
+    n_total = int(max(2000, min(2_000_000, budget / max(per_pair, 1e-9))))
+    n_q = int(n_total * mix_q)
+    n_r = n_total - n_q
+    q = gen.closest_queries(n_q, bounds) if n_q else None
+    if n_r:
+        o, d = gen.random_rays(n_r, bounds)
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        if n_q:
+            ora.closest(q, mode=orc.MODE_REFERENCE, threads=cores)
+        if n_r:
+            ora.ray_first(o, d, mode=orc.MODE_REFERENCE, threads=cores)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = (n_q + n_r) * len(times) / total
+    sample = f"{n_q} closest + {n_r} rays per step (prefix of the same streams), kd-tree build {build_s:.1f}s excluded"
+    line = {"impl": "reference", "metric": "bvh_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "triangles": T, "scale": args.scale},
+            "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="development aid: scales the torus grid and query counts")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg")
+    args = ap.parse_args()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, world, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from thea_b200 import Engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    grid, nq_total, nr_total, desc = WORKLOADS[args.workload]
+    grid = max(8, int(grid * args.scale))
+    nq_total = int(nq_total * args.scale)
+    nr_total = int(nr_total * args.scale)
+    mesh = gen.torus_mesh(grid)
+    T = len(mesh)
+    bounds = gen.mesh_bounds(mesh)
+
+    eng = Engine(local_rank)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    d_mesh = torch.from_numpy(mesh).to(dev)
+    eng.build_triangles(d_mesh)
+    build_ms = eng.stats()["last_build_ms"]
+    del d_mesh
+
+    # this rank's contiguous shard of both query streams, generated on the device from the counter-based streams
+    q_off, nq = shard(nq_total, rank, world)
+    r_off, nr = shard(nr_total, rank, world)
+    dq = torch.empty((nq, 3), dtype=torch.float32, device=dev)
+    for b, n in blocks(nq):
+        dq[b:b + n] = torch_closest_queries(n, bounds, gen.SEED_CLOSEST, q_off + b, dev)
+    dro = torch.empty((nr, 3), dtype=torch.float32, device=dev)
+    drd = torch.empty((nr, 3), dtype=torch.float32, device=dev)
+    for b, n in blocks(nr):
+        o, d = torch_random_rays(n, bounds, gen.SEED_RAYS, r_off + b, dev)
+        dro[b:b + n] = o
+        drd[b:b + n] = d
+    c_idx = torch.empty(nq, dtype=torch.int32, device=dev)
+    c_d2 = torch.empty(nq, dtype=torch.float32, device=dev)
+    c_cp = torch.empty((nq, 3), dtype=torch.float32, device=dev)
+    r_t = torch.empty(nr, dtype=torch.float32, device=dev)
+    r_idx = torch.empty(nr, dtype=torch.int32, device=dev)
+
+    kern = {"closest_ms": 0.0, "closest_q": 0, "ray_ms": 0.0, "ray_q": 0, "sort_ms": 0.0, "launches": 0}
+
+    def step_device(record: bool):
+        qb, rb = blocks(nq), blocks(nr)
+        for i in range(max(len(qb), len(rb))):
+            if i < len(qb):
+                b, n = qb[i]
+                eng.closest(dq[b:b + n], out=(c_idx[b:b + n], c_d2[b:b + n], c_cp[b:b + n]))
+                if record:
+                    s = eng.stats()
+                    kern["closest_ms"] += s["last_query_ms"] - s["last_sort_ms"]
+                    kern["sort_ms"] += s["last_sort_ms"]
+                    kern["closest_q"] += n
+                    kern["launches"] += s["last_launches"]
+            if i < len(rb):
+                b, n = rb[i]
+                eng.ray_first(dro[b:b + n], drd[b:b + n], out=(r_t[b:b + n], r_idx[b:b + n], None))
+                if record:
+                    s = eng.stats()
+                    kern["ray_ms"] += s["last_query_ms"] - s["last_sort_ms"]
+                    kern["sort_ms"] += s["last_sort_ms"]
+                    kern["ray_q"] += n
+                    kern["launches"] += s["last_launches"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device(False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device(True)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    dev_ms = float(ms.item())
+    total_queries = nq_total + nr_total
+    value = total_queries * args.steps / (dev_ms / 1e3)
+
+    # checksum of the results (device resident) so that the timed work cannot be optimised away and runs can be compared
+    checksum = int((c_idx.long().sum() + r_idx.long().sum()).item())
+
+    # ---- e2e: same calls, pinned host buffers, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        hq = dq.cpu().pin_memory().numpy()
+        hro, hrd = dro.cpu().pin_memory().numpy(), drd.cpu().pin_memory().numpy()
+        h_idx = torch.empty(nq, dtype=torch.int32).pin_memory().numpy()
+        h_d2 = torch.empty(nq, dtype=torch.float32).pin_memory().numpy()
+        h_cp = torch.empty((nq, 3), dtype=torch.float32).pin_memory().numpy()
+        h_t = torch.empty(nr, dtype=torch.float32).pin_memory().numpy()
+        h_ri = torch.empty(nr, dtype=torch.int32).pin_memory().numpy()
+
+        def step_host():
+            if nq:
+                eng.closest(hq, out=(h_idx, h_d2, h_cp))
+            if nr:
+                eng.ray_first(hro, hrd, out=(h_t, h_ri, None))
+
+        step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+        barrier()
+        wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        e2e_s = float(wall.item())
+        h2d = nq * 12 + nr * 24
+        d2h = nq * 20 + nr * 8
+        hsum = int(h_idx.astype(np.int64).sum() + h_ri.astype(np.int64).sum())
+        e2e = {"value": total_queries * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "matches_device_checksum": bool(hsum == checksum)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----
+    peak, peak_kind = measured_peak()
+    dominant = "k_closest<true>" if kern["closest_ms"] >= kern["ray_ms"] else "k_ray<false>"
+    if dominant.startswith("k_closest"):
+        bytes_per_q, k_ms, k_q = algorithmic_bytes(T, "closest"), kern["closest_ms"], kern["closest_q"]
+    else:
+        bytes_per_q, k_ms, k_q = algorithmic_bytes(T, "ray"), kern["ray_ms"], kern["ray_q"]
+    achieved = (bytes_per_q * k_q / 1e9) / (k_ms / 1e3) if k_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(f"{args.workload}:{dominant}")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": dominant, "peak_source": peak_kind, "algorithmic_bytes_per_query": bytes_per_q,
+                "queries_per_launch": BLOCK if k_q >= BLOCK else k_q, "avg_launch_ms": k_ms / max(1, (k_q + BLOCK - 1) // BLOCK)}
+
+    # ---- CPU baseline on rank 0: oracle in reference traversal order, all host cores, bounded sample ----
+    cpu = None
+    if not args.no_cpu:
+        from oracle import orc
+        cores = orc.ncores()
+        ora = orc.Oracle(tris9=mesh)
+        sq, sr = (2000 if nq_total else 0), (200000 if nr_total else 0)
+        t0 = time.perf_counter()
+        if sq:
+            qs = gen.closest_queries(sq, bounds)
+            oi, od, _ = ora.closest(qs, mode=orc.MODE_REFERENCE, threads=cores)
+        tq = time.perf_counter() - t0
+        # scale the closest sample to ~10 s of CPU work
+        if sq and tq < 8.0:
+            sq = int(min(2_000_000, sq * 10.0 / max(tq, 1e-3)))
+            qs = gen.closest_queries(sq, bounds)
+            t0 = time.perf_counter()
+            oi, od, _ = ora.closest(qs, mode=orc.MODE_REFERENCE, threads=cores)
+            tq = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        if sr:
+            o, d = gen.random_rays(sr, bounds)
+            ora.ray_first(o, d, mode=orc.MODE_REFERENCE, threads=cores)
+        tr = time.perf_counter() - t0
+        # per-query costs combined in the workload's mix
+        per_q = (tq / sq if sq else 0.0) * nq_total + (tr / sr if sr else 0.0) * nr_total
+        cpu = {"value": total_queries / per_q if per_q > 0 else None, "unit": "queries/s", "cores": cores, "kind": "port",
+               "sample": f"{sq} closest-point ({tq:.2f}s) + {sr} rays ({tr:.2f}s) of the same streams, combined in the workload's "
+                         f"{nq_total}:{nr_total} mix; oracle = reference kd-tree (leaf 5, x1.05 boxes) in DFS order"}
+        # the same prefix through the GPU path must agree with the canonical oracle distances (sanity, not timing)
+        if sq:
+            gi, gd, _ = eng.closest(qs[:2000])
+            assert np.array_equal(gd, od[:2000]), "GPU closest-point distances differ from the CPU reference on the bench sample"
+
+    line = {
+        "metric": "bvh_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": desc, "triangles": T, "closest_queries": nq_total, "ray_queries": nr_total, "sharding": f"queries/{world}, BVH replicated",
+                   "l2_policy": "inputs_exceed_l2" if (nq_total * 32 + nr_total * 32) / world > 126e6 else "structure+inputs may be L2 resident",
+                   "scale": args.scale, "build_ms": build_ms},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": kern["launches"], "clocks": clocks,
+        "breakdown": {"closest_Mqps_kernel": kern["closest_q"] / kern["closest_ms"] / 1e3 if kern["closest_ms"] else None,
+                      "ray_Mqps_kernel": kern["ray_q"] / kern["ray_ms"] / 1e3 if kern["ray_ms"] else None,
+                      "sort_ms_per_step": kern["sort_ms"] / args.steps, "checksum": checksum},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

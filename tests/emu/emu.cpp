@@ -5,6 +5,9 @@
 // suite (-m "not gpu") check the pruning logic, tie rules and the libstdc++ nth_element restatement against the oracle
 // before any GPU time is spent.  It is NOT a fallback: nothing under thea_b200/ links or loads it, and libtgq.so has
 // no code path that reaches it.
+static thread_local long long g_cnt_node = 0, g_cnt_prim = 0;
+#define TGQ_COUNT_NODE() (++g_cnt_node)
+#define TGQ_COUNT_PRIM() (++g_cnt_prim)
 #include "../../thea_b200/csrc/tgq_traverse.cuh"
 #include "../../thea_b200/csrc/tgq_select.cuh"
 
@@ -23,6 +26,7 @@ struct Emu
   int n = 0, leaf = 4;
   std::vector<TriRec> tris; std::vector<f4> pts, nrm;
   std::vector<NodeRec> nodes;
+  std::vector<SlabRec> slabs;
   BvhView view() const
   {
     BvhView v; v.nodes = nodes.data(); v.tris = tri ? tris.data() : nullptr; v.pts = tri ? nullptr : pts.data();
@@ -104,6 +108,7 @@ void build(Emu & E, float const * src, float const * n3)
   int cnt = 0;
   for (int i = 0; i < ni; ++i) { live[(size_t)i] = (i == 0 || (last[(size_t)i] - first[(size_t)i] + 1) > E.leaf) ? 1 : 0; newidx[(size_t)i] = cnt; cnt += live[(size_t)i]; }
   E.nodes.resize((size_t)cnt);
+  if (E.tri) E.slabs.resize((size_t)cnt);
   for (int i = 0; i < ni; ++i)
   {
     if (!live[(size_t)i]) continue;
@@ -117,6 +122,38 @@ void build(Emu & E, float const * src, float const * n3)
       clo[c] = mk3(blo.x - pad, blo.y - pad, blo.z - pad); chi[c] = mk3(bhi.x + pad, bhi.y + pad, bhi.z + pad);
     }
     E.nodes[(size_t)newidx[(size_t)i]] = make_node(clo[0], chi[0], clo[1], chi[1], child[0], child[1], 0, 0);
+    if (E.tri)
+    {
+      // prototype of the pancake bounds, brute force over each child's element range
+      float dirs[2][3], smin[2], smax[2], rad[2];
+      for (int c = 0; c < 2; ++c)
+      {
+        int cf = c == 0 ? f : sp + 1, cl = c == 0 ? sp : l;
+        double sx = 0, sy = 0, sz = 0;
+        for (int k = cf; k <= cl; ++k)
+        {
+          TriRec const & r = E.tris[(size_t)k];
+          v3 v0 = mk3(r.q0.x, r.q0.y, r.q0.z), n = cross3(sub3(mk3(r.q1.x, r.q1.y, r.q1.z), v0), sub3(mk3(r.q2.x, r.q2.y, r.q2.z), v0));
+          sx += n.x; sy += n.y; sz += n.z;
+        }
+        double len = std::sqrt(sx * sx + sy * sy + sz * sz);
+        v3 dir = len > 0 ? normalized3(mk3((float)(sx / len), (float)(sy / len), (float)(sz / len))) : mk3(0, 0, 0);
+        v3 cc = mul3(add3(clo[c], chi[c]), 0.5f);
+        float mn = FLT_MAX, mx = -FLT_MAX, R = 0;
+        for (int k = cf; k <= cl; ++k)
+        {
+          TriRec const & r = E.tris[(size_t)k];
+          v3 vs[3] = {mk3(r.q0.x, r.q0.y, r.q0.z), mk3(r.q1.x, r.q1.y, r.q1.z), mk3(r.q2.x, r.q2.y, r.q2.z)};
+          for (int j = 0; j < 3; ++j) { float s = dot3(dir, vs[j]); mn = fminf(mn, s); mx = fmaxf(mx, s); R = fmaxf(R, sqrtf(sqn3(sub3(vs[j], cc)))); }
+        }
+        dirs[c][0] = dir.x; dirs[c][1] = dir.y; dirs[c][2] = dir.z;
+        smin[c] = mn - 2 * pad; smax[c] = mx + 2 * pad; rad[c] = R * 1.000001f + 2 * pad;
+      }
+      SlabRec sr;
+      sr.a = f4{dirs[0][0], dirs[0][1], dirs[0][2], smin[0]}; sr.b = f4{smax[0], dirs[1][0], dirs[1][1], dirs[1][2]};
+      sr.c = f4{smin[1], smax[1], rad[0], rad[1]};
+      E.slabs[(size_t)newidx[(size_t)i]] = sr;
+    }
   }
 }
 
@@ -141,6 +178,17 @@ void emu_closest(void * h, float const * q3, int64_t Q, float bound_ub, int excl
     float best = bound_ub; int bi = -1; v3 cp = mk3(0, 0, 0);
     if (E.tri) closest_query<true>(v, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp);
     else closest_query<false>(v, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp);
+    idx[i] = bi; d2[i] = bi >= 0 ? best : -1.0f; cp3[3 * i] = cp.x; cp3[3 * i + 1] = cp.y; cp3[3 * i + 2] = cp.z;
+  }
+}
+
+void emu_closest_slab(void * h, float const * q3, int64_t Q, float bound_ub, int32_t * idx, float * d2, float * cp3)
+{
+  Emu & E = *(Emu *)h; BvhView v = E.view();
+  for (int64_t i = 0; i < Q; ++i)
+  {
+    float best = bound_ub; int bi = -1; v3 cp = mk3(0, 0, 0);
+    closest_query_slab<true>(v, E.slabs.data(), ld(q3, i), -1, best, bi, cp);
     idx[i] = bi; d2[i] = bi >= 0 ? best : -1.0f; cp3[3 * i] = cp.x; cp3[3 * i + 1] = cp.y; cp3[3 * i + 2] = cp.z;
   }
 }
@@ -182,6 +230,9 @@ void emu_ray(void * h, float const * o3, float const * d3, float const * tmax, i
     t[i] = bi >= 0 ? best : -1.0f; idx[i] = bi;
   }
 }
+
+void emu_counters(long long * nodes, long long * prims, int reset)
+{ *nodes = g_cnt_node; *prims = g_cnt_prim; if (reset) { g_cnt_node = 0; g_cnt_prim = 0; } }
 
 // libstdc++'s own std::nth_element next to the restatement, for permutation-exact comparison.
 void emu_select(double * a, int n, int nth) { sdf_select(a, n, nth); }

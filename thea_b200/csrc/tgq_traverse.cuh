@@ -17,6 +17,12 @@ namespace tgq {
 #define TGQ_LEAF_MASK 15
 #define TGQ_LB_DEFLATE 0.99999905f   // 1 - 2^-20: lower bounds are shrunk so fp32 rounding can never over-prune
 
+// Visit counters: compiled out everywhere except the test-only host build, which uses them to study pruning quality.
+#ifndef TGQ_COUNT_NODE
+#define TGQ_COUNT_NODE()
+#define TGQ_COUNT_PRIM()
+#endif
+
 struct BvhView
 {
   NodeRec const * nodes;   // n_nodes inner nodes, root = 0
@@ -52,6 +58,7 @@ TGQ_HD void closest_leaf(BvhView const & b, int first, int count, v3 p, int skip
   for (int k = first; k < first + count; ++k)
   {
     int idx; v3 cp; float d2;
+    TGQ_COUNT_PRIM();
     if (TRI)
     {
       f4 const * t = (f4 const *)(b.tris + k);
@@ -82,11 +89,93 @@ TGQ_HD void closest_query(BvhView const & b, v3 p, int skip, float & best_d2, in
     while (cur >= 0)
     {
       NodeRec nd = load_node(b, cur);
+      TGQ_COUNT_NODE();
       v3 lo0, hi0, lo1, hi1; node_boxes(nd, lo0, hi0, lo1, hi1);
       float lb0 = box_point_sqdist(lo0, hi0, p) * TGQ_LB_DEFLATE;
       float lb1 = box_point_sqdist(lo1, hi1, p) * TGQ_LB_DEFLATE;
       int c0 = f2i(nd.q3.x), c1 = f2i(nd.q3.y);
       bool go0 = lb0 <= best_d2, go1 = lb1 <= best_d2;
+      if (go0 && go1)
+      {
+        bool swap = lb1 < lb0;
+        int nearc = swap ? c1 : c0, farc = swap ? c0 : c1;
+        stk_node[sp] = farc; stk_lb[sp] = swap ? lb0 : lb1; ++sp;
+        cur = nearc;
+      }
+      else if (go0) cur = c0;
+      else if (go1) cur = c1;
+      else goto pop;
+    }
+    {
+      int code = ~cur;
+      closest_leaf<TRI>(b, code >> TGQ_LEAF_BITS, code & TGQ_LEAF_MASK, p, skip, best_d2, best_idx, best_cp);
+    }
+  pop:
+    for (;;)
+    {
+      if (sp == 0) return;
+      --sp;
+      if (stk_lb[sp] <= best_d2) { cur = stk_node[sp]; break; }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Closest element with "pancake" bounds.  AABBs of a smooth surface that is oblique to the axes stick out towards an
+// off-surface query by about their own size, so a far query must open every box in a wide disc around its foot point
+// (hundreds of leaves on a 1M-triangle mesh).  Each child therefore also carries a slab {x : smin <= dir.x <= smax}
+// around the mean normal of its triangles and the radius R of its elements about the box centre c.  For any x in the
+// child, |p - x|^2 = (dir.(p - x))^2 + |(p - x)_perp|^2 >= slab_dist^2 + max(0, |(p - c)_perp| - R)^2, a bound that
+// keeps the lateral offset the box bound loses.  Both bounds are valid, the traversal prunes on their maximum.
+//   SlabRec (48 B): a = (dir0.xyz, smin0)  b = (smax0, dir1.xyz)  c = (smin1, smax1, R0, R1)
+// ---------------------------------------------------------------------------------------------------------------------
+struct SlabRec { f4 a, b, c; };
+
+TGQ_HD float pancake_sqdist(v3 lo, v3 hi, v3 dir, float smin, float smax, float R, v3 p)
+{
+  float s = dot3(dir, p);
+  float sd = fmaxf(fmaxf(s - smax, smin - s), 0.0f);
+  v3 c = mul3(add3(lo, hi), 0.5f);
+  v3 pc = sub3(p, c);
+  float sc = dot3(dir, pc);
+  float perp2 = fmaxf(sqn3(pc) - sc * sc, 0.0f);
+  float lat = fmaxf(sqrtf(perp2) * 0.999999f - R, 0.0f);
+  return sd * sd + lat * lat;
+}
+
+template <bool TRI>
+TGQ_HD void closest_query_slab(BvhView const & b, SlabRec const * slabs, v3 p, int skip, float & best_d2, int & best_idx, v3 & best_cp)
+{
+  if (b.n_nodes <= 0) return;
+  int stk_node[TGQ_STACK]; float stk_lb[TGQ_STACK];
+  int sp = 0;
+  int cur = 0;
+  for (;;)
+  {
+    while (cur >= 0)
+    {
+      NodeRec nd = load_node(b, cur);
+      TGQ_COUNT_NODE();
+      v3 lo0, hi0, lo1, hi1; node_boxes(nd, lo0, hi0, lo1, hi1);
+      float lb0 = box_point_sqdist(lo0, hi0, p) * TGQ_LB_DEFLATE;
+      float lb1 = box_point_sqdist(lo1, hi1, p) * TGQ_LB_DEFLATE;
+      int c0 = f2i(nd.q3.x), c1 = f2i(nd.q3.y);
+      bool go0 = lb0 <= best_d2, go1 = lb1 <= best_d2;
+      if (go0 || go1)
+      {
+        f4 const * sq = (f4 const *)(slabs + cur);
+        f4 sa = ldq(sq), sb = ldq(sq + 1), sc = ldq(sq + 2);
+        if (go0)
+        {
+          lb0 = fmaxf(lb0, pancake_sqdist(lo0, hi0, mk3(sa.x, sa.y, sa.z), sa.w, sb.x, sc.z, p) * TGQ_LB_DEFLATE);
+          go0 = lb0 <= best_d2;
+        }
+        if (go1)
+        {
+          lb1 = fmaxf(lb1, pancake_sqdist(lo1, hi1, mk3(sb.y, sb.z, sb.w), sc.x, sc.y, sc.w, p) * TGQ_LB_DEFLATE);
+          go1 = lb1 <= best_d2;
+        }
+      }
       if (go0 && go1)
       {
         bool swap = lb1 < lb0;
