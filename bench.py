@@ -5,7 +5,7 @@
 
 Workload (default cfg5, BASELINE.json configs[4]): 10M-triangle bumpy torus (9,999,392 triangles), 100M mixed queries
 = 50M closest-point (BvhN::closestElement with closest point) + 50M ray first-hit (BvhN::rayStructureIntersection),
-issued in alternating blocks of 1M, sharded contiguously over the ranks; the BVH is replicated (each rank builds it).
+sharded contiguously over the ranks (one C-ABI call per query kind per step); the BVH is replicated (each rank builds it).
 One step = one pass over all queries of the rank.  `value` is device-resident throughput (inputs already in HBM);
 `e2e` goes through the same C-ABI calls with pinned HOST buffers, H2D/D2H inside the timed region.
 
@@ -32,7 +32,7 @@ from thea_b200 import gen  # noqa: E402
 BLOCK = 1_000_000
 WORKLOADS = {
     # name: (torus grid, closest queries, rays, description)
-    "cfg5": (gen.TORUS_10M, 50_000_000, 50_000_000, "cfg5: 9,999,392-tri torus, 50M closest-point + 50M ray first-hit, blocks of 1M"),
+    "cfg5": (gen.TORUS_10M, 50_000_000, 50_000_000, "cfg5: 9,999,392-tri torus, 50M closest-point + 50M ray first-hit"),
     "cfg1": (gen.TORUS_70K, 1_000_000, 0, "cfg1: 70,688-tri torus, 1M closest-point queries"),
     "cfg4r": (gen.TORUS_1M, 0, 3_000_000, "cfg4-like: 1,002,528-tri torus, 3M random first-hit rays"),
     "cfg1m": (gen.TORUS_1M, 5_000_000, 5_000_000, "1,002,528-tri torus, 5M closest-point + 5M ray first-hit"),
@@ -276,26 +276,25 @@ def main():
     kern = {"closest_ms": 0.0, "closest_q": 0, "ray_ms": 0.0, "ray_q": 0, "sort_ms": 0.0, "launches": 0}
 
     def step_device(record: bool):
-        qb, rb = blocks(nq), blocks(nr)
-        for i in range(max(len(qb), len(rb))):
-            if i < len(qb):
-                b, n = qb[i]
-                eng.closest(dq[b:b + n], out=(c_idx[b:b + n], c_d2[b:b + n], c_cp[b:b + n]))
-                if record:
-                    s = eng.stats()
-                    kern["closest_ms"] += s["last_query_ms"] - s["last_sort_ms"]
-                    kern["sort_ms"] += s["last_sort_ms"]
-                    kern["closest_q"] += n
-                    kern["launches"] += s["last_launches"]
-            if i < len(rb):
-                b, n = rb[i]
-                eng.ray_first(dro[b:b + n], drd[b:b + n], out=(r_t[b:b + n], r_idx[b:b + n], None))
-                if record:
-                    s = eng.stats()
-                    kern["ray_ms"] += s["last_query_ms"] - s["last_sort_ms"]
-                    kern["sort_ms"] += s["last_sort_ms"]
-                    kern["ray_q"] += n
-                    kern["launches"] += s["last_launches"]
+        # one C-ABI call per query kind over the whole shard (the library splits batches above 2^26 queries)
+        if nq:
+            eng.closest(dq, out=(c_idx, c_d2, c_cp))
+            if record:
+                s = eng.stats()
+                kern["closest_ms"] += s["last_query_ms"] - s["last_sort_ms"]
+                kern["sort_ms"] += s["last_sort_ms"]
+                kern["closest_q"] += nq
+                kern["closest_launches"] = kern.get("closest_launches", 0) + 1
+                kern["launches"] += s["last_launches"]
+        if nr:
+            eng.ray_first(dro, drd, out=(r_t, r_idx, None))
+            if record:
+                s = eng.stats()
+                kern["ray_ms"] += s["last_query_ms"] - s["last_sort_ms"]
+                kern["sort_ms"] += s["last_sort_ms"]
+                kern["ray_q"] += nr
+                kern["ray_launches"] = kern.get("ray_launches", 0) + 1
+                kern["launches"] += s["last_launches"]
 
     def barrier():
         if world > 1:
@@ -367,9 +366,9 @@ def main():
     peak, peak_kind = measured_peak()
     dominant = "k_closest<true>" if kern["closest_ms"] >= kern["ray_ms"] else "k_ray<false>"
     if dominant.startswith("k_closest"):
-        bytes_per_q, k_ms, k_q = algorithmic_bytes(T, "closest"), kern["closest_ms"], kern["closest_q"]
+        bytes_per_q, k_ms, k_q, k_n = algorithmic_bytes(T, "closest"), kern["closest_ms"], kern["closest_q"], kern.get("closest_launches", 1)
     else:
-        bytes_per_q, k_ms, k_q = algorithmic_bytes(T, "ray"), kern["ray_ms"], kern["ray_q"]
+        bytes_per_q, k_ms, k_q, k_n = algorithmic_bytes(T, "ray"), kern["ray_ms"], kern["ray_q"], kern.get("ray_launches", 1)
     achieved = (bytes_per_q * k_q / 1e9) / (k_ms / 1e3) if k_ms > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -377,7 +376,7 @@ def main():
         traffic = json.load(open(tp)).get(f"{args.workload}:{dominant}")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": dominant, "peak_source": peak_kind, "algorithmic_bytes_per_query": bytes_per_q,
-                "queries_per_launch": BLOCK if k_q >= BLOCK else k_q, "avg_launch_ms": k_ms / max(1, (k_q + BLOCK - 1) // BLOCK)}
+                "queries_per_launch": k_q // max(1, k_n), "avg_launch_ms": k_ms / max(1, k_n)}
 
     # ---- CPU baseline on rank 0: oracle in reference traversal order, all host cores, bounded sample ----
     cpu = None

@@ -23,7 +23,7 @@ namespace {
 struct Emu
 {
   bool tri = false, has_n = false;
-  int n = 0, leaf = 4;
+  int n = 0, leaf = 4; float pad = 0;
   std::vector<TriRec> tris; std::vector<f4> pts, nrm;
   std::vector<NodeRec> nodes;
   std::vector<SlabRec> slabs;
@@ -49,6 +49,7 @@ void build(Emu & E, float const * src, float const * n3)
   v3 inv = mk3(e.x > 0 ? 1.0f / e.x : 0.0f, e.y > 0 ? 1.0f / e.y : 0.0f, e.z > 0 ? 1.0f / e.z : 0.0f);
   float m = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))), fmaxf(fabsf(lo.z), fabsf(hi.z)));
   float pad = m * 1.9073486328125e-06f + FLT_MIN;
+  E.pad = pad;
   // keys + stable sort (k_morton_*, radix sort)
   std::vector<uint64_t> keys((size_t)n); std::vector<uint32_t> perm((size_t)n);
   for (int i = 0; i < n; ++i)
@@ -72,7 +73,7 @@ void build(Emu & E, float const * src, float const * n3)
       TriPlane pl = tri_plane(v0, v1, v2);
       TriRec r;
       r.q0 = f4{v0.x, v0.y, v0.z, i2f((int)i)}; r.q1 = f4{v1.x, v1.y, v1.z, i2f(pl.axis)};
-      r.q2 = f4{v2.x, v2.y, v2.z, pl.d}; r.q3 = f4{pl.n.x, pl.n.y, pl.n.z, tri_area(pl.n, v0, v1, v2)};
+      r.q2 = f4{v2.x, v2.y, v2.z, pl.d}; r.q3 = f4{pl.n.x, pl.n.y, pl.n.z, tri_screen_radius(v0, v1, v2, pad)};
       E.tris[(size_t)s] = r;
       plo[(size_t)s] = min3(v0, min3(v1, v2)); phi[(size_t)s] = max3(v0, max3(v1, v2));
     }
@@ -86,6 +87,7 @@ void build(Emu & E, float const * src, float const * n3)
   }
   if (n == 1)
   {
+    if (E.tri) { SlabRec r; r.a = f4{0, 0, 0, -FLT_MAX}; r.b = f4{FLT_MAX, 0, 0, 0}; r.c = f4{-FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX}; E.slabs.assign(1, r); }
     E.nodes.push_back(make_node(mk3(plo[0].x - pad, plo[0].y - pad, plo[0].z - pad), mk3(phi[0].x + pad, phi[0].y + pad, phi[0].z + pad),
                                 mk3(FLT_MAX, FLT_MAX, FLT_MAX), mk3(-FLT_MAX, -FLT_MAX, -FLT_MAX), ~((0 << TGQ_LEAF_BITS) | 1), ~0, 0, 0));
     return;
@@ -124,30 +126,29 @@ void build(Emu & E, float const * src, float const * n3)
     E.nodes[(size_t)newidx[(size_t)i]] = make_node(clo[0], chi[0], clo[1], chi[1], child[0], child[1], 0, 0);
     if (E.tri)
     {
-      // prototype of the pancake bounds, brute force over each child's element range
+      // pancake bounds through the same helpers as k_slab_small / k_slab_big / k_emit (direction from a plain sum here)
       float dirs[2][3], smin[2], smax[2], rad[2];
       for (int c = 0; c < 2; ++c)
       {
         int cf = c == 0 ? f : sp + 1, cl = c == 0 ? sp : l;
-        double sx = 0, sy = 0, sz = 0;
+        v3 sum = mk3(0, 0, 0);
         for (int k = cf; k <= cl; ++k)
         {
           TriRec const & r = E.tris[(size_t)k];
-          v3 v0 = mk3(r.q0.x, r.q0.y, r.q0.z), n = cross3(sub3(mk3(r.q1.x, r.q1.y, r.q1.z), v0), sub3(mk3(r.q2.x, r.q2.y, r.q2.z), v0));
-          sx += n.x; sy += n.y; sz += n.z;
+          v3 v0 = mk3(r.q0.x, r.q0.y, r.q0.z);
+          sum = add3(sum, cross3(sub3(mk3(r.q1.x, r.q1.y, r.q1.z), v0), sub3(mk3(r.q2.x, r.q2.y, r.q2.z), v0)));
         }
-        double len = std::sqrt(sx * sx + sy * sy + sz * sz);
-        v3 dir = len > 0 ? normalized3(mk3((float)(sx / len), (float)(sy / len), (float)(sz / len))) : mk3(0, 0, 0);
-        v3 cc = mul3(add3(clo[c], chi[c]), 0.5f);
-        float mn = FLT_MAX, mx = -FLT_MAX, R = 0;
+        v3 dir = normalized3(sum);
+        if (!(sqn3(dir) > 0.5f)) dir = mk3(0, 0, 0);
+        v3 cc = box_centre(clo[c], chi[c]);
+        float mn = FLT_MAX, mx = -FLT_MAX, r2 = 0;
         for (int k = cf; k <= cl; ++k)
         {
           TriRec const & r = E.tris[(size_t)k];
-          v3 vs[3] = {mk3(r.q0.x, r.q0.y, r.q0.z), mk3(r.q1.x, r.q1.y, r.q1.z), mk3(r.q2.x, r.q2.y, r.q2.z)};
-          for (int j = 0; j < 3; ++j) { float s = dot3(dir, vs[j]); mn = fminf(mn, s); mx = fmaxf(mx, s); R = fmaxf(R, sqrtf(sqn3(sub3(vs[j], cc)))); }
+          slab_accumulate(dir, cc, mk3(r.q0.x, r.q0.y, r.q0.z), mk3(r.q1.x, r.q1.y, r.q1.z), mk3(r.q2.x, r.q2.y, r.q2.z), mn, mx, r2);
         }
         dirs[c][0] = dir.x; dirs[c][1] = dir.y; dirs[c][2] = dir.z;
-        smin[c] = mn - 2 * pad; smax[c] = mx + 2 * pad; rad[c] = R * 1.000001f + 2 * pad;
+        smin[c] = mn - 2 * pad; smax[c] = mx + 2 * pad; rad[c] = slab_radius(r2, pad);
       }
       SlabRec sr;
       sr.a = f4{dirs[0][0], dirs[0][1], dirs[0][2], smin[0]}; sr.b = f4{smax[0], dirs[1][0], dirs[1][1], dirs[1][2]};
@@ -170,25 +171,17 @@ void * emu_build(float const * src, int64_t n, int is_tri, float const * n3, int
 void emu_destroy(void * h) { delete (Emu *)h; }
 int64_t emu_num_nodes(void * h) { return (int64_t)((Emu *)h)->nodes.size(); }
 
+static int use_slabs = 1;
+void emu_use_slabs(int on) { use_slabs = on; }
 void emu_closest(void * h, float const * q3, int64_t Q, float bound_ub, int exclude_self, int32_t * idx, float * d2, float * cp3)
 {
   Emu & E = *(Emu *)h; BvhView v = E.view();
   for (int64_t i = 0; i < Q; ++i)
   {
     float best = bound_ub; int bi = -1; v3 cp = mk3(0, 0, 0);
-    if (E.tri) closest_query<true>(v, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp);
-    else closest_query<false>(v, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp);
-    idx[i] = bi; d2[i] = bi >= 0 ? best : -1.0f; cp3[3 * i] = cp.x; cp3[3 * i + 1] = cp.y; cp3[3 * i + 2] = cp.z;
-  }
-}
-
-void emu_closest_slab(void * h, float const * q3, int64_t Q, float bound_ub, int32_t * idx, float * d2, float * cp3)
-{
-  Emu & E = *(Emu *)h; BvhView v = E.view();
-  for (int64_t i = 0; i < Q; ++i)
-  {
-    float best = bound_ub; int bi = -1; v3 cp = mk3(0, 0, 0);
-    closest_query_slab<true>(v, E.slabs.data(), ld(q3, i), -1, best, bi, cp);
+    if (E.tri && use_slabs) closest_query<true, true>(v, E.slabs.data(), E.pad, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp);
+    else if (E.tri) closest_query<true, false>(v, nullptr, 0.0f, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp);
+    else closest_query<false, false>(v, nullptr, 0.0f, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp);
     idx[i] = bi; d2[i] = bi >= 0 ? best : -1.0f; cp3[3 * i] = cp.x; cp3[3 * i + 1] = cp.y; cp3[3 * i + 2] = cp.z;
   }
 }

@@ -60,9 +60,10 @@ struct tgq_handle
   DevBuf nodes, elems, nrm, scene;                                  // NodeRec[], TriRec[] | f4[], f4[], SceneBox
   DevBuf perm, pos_of_elem, first, last, split, parent, live, newidx;   // kept for refit
   DevBuf pbox_lo, pbox_hi, nbox_lo, nbox_hi, arrive, keys_a, keys_b, vals_a, cubtmp, src, src2, misc;
-  DevBuf area_by_elem, cum;
+  DevBuf area_by_elem, cum;                                           // float[n] in element order; double[n] cumulative
+  DevBuf slabs, pnrm, nsum, sinfo, big, big_count;                    // pancake bounds (triangle structures)
   bool cum_valid = false;
-  float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}; float pad = 0;
 
   Slot slot[2];
   std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
@@ -148,17 +149,32 @@ int refit_and_emit(tgq_handle * h, cudaStream_t s)
   if (n >= 2)
   {
     CK(cudaMemsetAsync(h->arrive.p, 0, sizeof(unsigned) * (size_t)(n - 1), s));
+    bool tri = h->kind == TGQ_KIND_TRIANGLES;
     k_refit<<<grid_for(n), TGQ_BLOCK, 0, s>>>(n, h->first.as<int>(), h->last.as<int>(), h->split.as<int>(), h->parent.as<int>(),
                                               h->pbox_lo.as<f4>(), h->pbox_hi.as<f4>(), h->nbox_lo.as<f4>(), h->nbox_hi.as<f4>(),
-                                              h->arrive.as<unsigned>());
+                                              h->arrive.as<unsigned>(), tri ? h->pnrm.as<f4>() : nullptr, h->nsum.as<f4>());
+    if (tri)
+    {
+      CK(cudaMemsetAsync(h->big_count.p, 0, 4, s));
+      k_slab_small<<<grid_for(n - 1), TGQ_BLOCK, 0, s>>>(n, h->leaf_built, h->first.as<int>(), h->last.as<int>(), h->parent.as<int>(),
+                                                         h->nbox_lo.as<f4>(), h->nbox_hi.as<f4>(), h->nsum.as<f4>(), h->elems.as<TriRec>(),
+                                                         h->scene.as<SceneBox>(), h->sinfo.as<f4>(), h->big.as<int>(), h->big_count.as<int>());
+      int big_grid = std::max(1, std::min(n / TGQ_SLAB_SMALL + 1, 148 * 64));
+      k_slab_big<<<big_grid, 128, 0, s>>>(h->big.as<int>(), h->big_count.as<int>(), h->first.as<int>(), h->last.as<int>(), h->nbox_lo.as<f4>(),
+                                          h->nbox_hi.as<f4>(), h->nsum.as<f4>(), h->elems.as<TriRec>(), h->scene.as<SceneBox>(), h->sinfo.as<f4>());
+      h->st.total_launches += 2;
+    }
     k_emit<<<grid_for(n - 1), TGQ_BLOCK, 0, s>>>(n, h->leaf_built, h->first.as<int>(), h->last.as<int>(), h->split.as<int>(),
                                                  h->live.as<int>(), h->newidx.as<int>(), h->pbox_lo.as<f4>(), h->pbox_hi.as<f4>(),
-                                                 h->nbox_lo.as<f4>(), h->nbox_hi.as<f4>(), h->scene.as<SceneBox>(), h->nodes.as<NodeRec>());
+                                                 h->nbox_lo.as<f4>(), h->nbox_hi.as<f4>(), h->scene.as<SceneBox>(), h->nodes.as<NodeRec>(),
+                                                 tri ? h->elems.as<TriRec>() : nullptr, tri ? h->sinfo.as<f4>() : nullptr,
+                                                 tri ? h->slabs.as<SlabRec>() : nullptr);
     h->st.total_launches += 2;
   }
   else if (n == 1)
   {
-    k_emit_single<<<1, 1, 0, s>>>(h->pbox_lo.as<f4>(), h->pbox_hi.as<f4>(), h->scene.as<SceneBox>(), h->nodes.as<NodeRec>());
+    k_emit_single<<<1, 1, 0, s>>>(h->pbox_lo.as<f4>(), h->pbox_hi.as<f4>(), h->scene.as<SceneBox>(), h->nodes.as<NodeRec>(),
+                                  h->kind == TGQ_KIND_TRIANGLES ? h->slabs.as<SlabRec>() : nullptr);
     h->st.total_launches += 1;
   }
   CK(cudaGetLastError());
@@ -190,6 +206,9 @@ int fetch_scene(tgq_handle * h, cudaStream_t s)
     l = l >= 0 ? l : l ^ 0x7fffffff; u = u >= 0 ? u : u ^ 0x7fffffff;
     memcpy(&h->lo[a], &l, 4); memcpy(&h->hi[a], &u, 4);
   }
+  float m = 0;
+  for (int a = 0; a < 3; ++a) m = std::max(m, std::max(std::fabs(h->lo[a]), std::fabs(h->hi[a])));
+  h->pad = m * 1.9073486328125e-06f + FLT_MIN;      // same expression as scene_decode() on the device
   return TGQ_OK;
 }
 
@@ -219,6 +238,7 @@ int build_common(tgq_handle * h, int kind, float const * d_src, float const * d_
   size_t rec = kind == TGQ_KIND_TRIANGLES ? sizeof(TriRec) : sizeof(f4);
   CK(h->elems.reserve(rec * nn));
   if (h->has_normals) CK(h->nrm.reserve(16 * nn));
+  if (kind == TGQ_KIND_TRIANGLES) { CK(h->pnrm.reserve(16 * nn)); CK(h->area_by_elem.reserve(4 * nn)); }
 
   if (kind == TGQ_KIND_TRIANGLES) k_morton_tris<<<grid_for(n), TGQ_BLOCK, 0, s>>>(d_src, n, h->scene.as<SceneBox>(), h->keys_a.as<uint64_t>(), h->vals_a.as<uint32_t>());
   else k_morton_points<<<grid_for(n), TGQ_BLOCK, 0, s>>>(d_src, n, h->scene.as<SceneBox>(), h->keys_a.as<uint64_t>(), h->vals_a.as<uint32_t>());
@@ -233,8 +253,9 @@ int build_common(tgq_handle * h, int kind, float const * d_src, float const * d_
                                      h->perm.as<uint32_t>(), n, 0, 63, s));
 
   if (kind == TGQ_KIND_TRIANGLES)
-    k_gather_tris<<<grid_for(n), TGQ_BLOCK, 0, s>>>(d_src, h->perm.as<uint32_t>(), n, h->elems.as<TriRec>(), h->pbox_lo.as<f4>(),
-                                                    h->pbox_hi.as<f4>(), h->pos_of_elem.as<int>());
+    k_gather_tris<<<grid_for(n), TGQ_BLOCK, 0, s>>>(d_src, h->perm.as<uint32_t>(), n, h->scene.as<SceneBox>(), h->elems.as<TriRec>(),
+                                                    h->pbox_lo.as<f4>(), h->pbox_hi.as<f4>(), h->pos_of_elem.as<int>(), h->pnrm.as<f4>(),
+                                                    h->area_by_elem.as<float>());
   else
     k_gather_points<<<grid_for(n), TGQ_BLOCK, 0, s>>>(d_src, d_n3, h->perm.as<uint32_t>(), n, h->elems.as<f4>(), h->nrm.as<f4>(),
                                                       h->pbox_lo.as<f4>(), h->pbox_hi.as<f4>(), h->pos_of_elem.as<int>());
@@ -246,7 +267,8 @@ int build_common(tgq_handle * h, int kind, float const * d_src, float const * d_
     size_t ni = nn - 1;
     CK(h->first.reserve(4 * ni)); CK(h->last.reserve(4 * ni)); CK(h->split.reserve(4 * ni)); CK(h->parent.reserve(4 * (2 * nn)));
     CK(h->live.reserve(4 * ni)); CK(h->newidx.reserve(4 * ni)); CK(h->arrive.reserve(4 * ni));
-    CK(h->nbox_lo.reserve(16 * ni)); CK(h->nbox_hi.reserve(16 * ni));
+    CK(h->nbox_lo.reserve(16 * ni)); CK(h->nbox_hi.reserve(16 * ni)); CK(h->nsum.reserve(16 * ni));
+    if (kind == TGQ_KIND_TRIANGLES) { CK(h->sinfo.reserve(32 * ni)); CK(h->big.reserve(4 * ni)); CK(h->big_count.reserve(4)); }
     k_hierarchy<<<grid_for(n - 1), TGQ_BLOCK, 0, s>>>(h->keys_b.as<uint64_t>(), n, h->first.as<int>(), h->last.as<int>(), h->split.as<int>(),
                                                       h->parent.as<int>());
     k_live<<<grid_for(n - 1), TGQ_BLOCK, 0, s>>>(n, h->leaf_built, h->first.as<int>(), h->last.as<int>(), h->live.as<int>());
@@ -265,12 +287,14 @@ int build_common(tgq_handle * h, int kind, float const * d_src, float const * d_
   else h->n_nodes = 1;
 
   CK(h->nodes.reserve(sizeof(NodeRec) * (size_t)h->n_nodes));
+  if (kind == TGQ_KIND_TRIANGLES) CK(h->slabs.reserve(sizeof(SlabRec) * (size_t)h->n_nodes));
   CKRC(refit_and_emit(h, s));
   CK(cudaEventRecord(e1, s));
   CKRC(fetch_scene(h, s));
   float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
   h->st.last_build_ms = ms;
-  h->st.num_nodes = h->n_nodes; h->st.node_bytes = (int64_t)sizeof(NodeRec) * h->n_nodes; h->st.element_bytes = (int64_t)(rec * nn);
+  h->st.num_nodes = h->n_nodes;
+  h->st.node_bytes = (int64_t)(sizeof(NodeRec) + (kind == TGQ_KIND_TRIANGLES ? sizeof(SlabRec) : 0)) * h->n_nodes; h->st.element_bytes = (int64_t)(rec * nn);
   return TGQ_OK;
 }
 
@@ -431,7 +455,7 @@ int tgq_destroy(tgq_handle * h)
   cudaDeviceSynchronize();
   DevBuf * bufs[] = {&h->nodes, &h->elems, &h->nrm, &h->scene, &h->perm, &h->pos_of_elem, &h->first, &h->last, &h->split, &h->parent, &h->live,
                      &h->newidx, &h->pbox_lo, &h->pbox_hi, &h->nbox_lo, &h->nbox_hi, &h->arrive, &h->keys_a, &h->keys_b, &h->vals_a,
-                     &h->cubtmp, &h->src, &h->src2, &h->misc, &h->area_by_elem, &h->cum};
+                     &h->cubtmp, &h->src, &h->src2, &h->misc, &h->area_by_elem, &h->cum, &h->slabs, &h->pnrm, &h->nsum, &h->sinfo, &h->big, &h->big_count};
   for (DevBuf * b : bufs) b->release();
   for (int s = 0; s < 2; ++s)
   {
@@ -518,8 +542,9 @@ int tgq_refit_triangles(tgq_handle * h, const float * v9, int64_t T)
   void const * d = nullptr;
   CKRC(to_device(h, v9, sizeof(float) * 9 * (size_t)T, h->src, s, &d));
   CKRC(scene_bounds(h, (float const *)d, 3 * T, s));
-  k_gather_tris<<<grid_for(h->n), TGQ_BLOCK, 0, s>>>((float const *)d, h->perm.as<uint32_t>(), h->n, h->elems.as<TriRec>(), h->pbox_lo.as<f4>(),
-                                                     h->pbox_hi.as<f4>(), h->pos_of_elem.as<int>());
+  k_gather_tris<<<grid_for(h->n), TGQ_BLOCK, 0, s>>>((float const *)d, h->perm.as<uint32_t>(), h->n, h->scene.as<SceneBox>(), h->elems.as<TriRec>(),
+                                                     h->pbox_lo.as<f4>(), h->pbox_hi.as<f4>(), h->pos_of_elem.as<int>(), h->pnrm.as<f4>(),
+                                                     h->area_by_elem.as<float>());
   CK(cudaGetLastError());
   h->st.total_launches += 1; h->cum_valid = false;
   CKRC(refit_and_emit(h, s));
@@ -549,7 +574,7 @@ int tgq_triangle_cache(tgq_handle * h, float * n3, float * d, int32_t * axis, fl
   float * dn = h->misc.as<float>(); float * dd = dn + 3 * nn; int * da = (int *)(dd + nn); float * dar = (float *)(da + nn);
   float * on = n3 ? (is_device_ptr(n3) ? n3 : dn) : nullptr; float * od = d ? (is_device_ptr(d) ? d : dd) : nullptr;
   int * oa = axis ? (is_device_ptr(axis) ? axis : da) : nullptr; float * oar = area ? (is_device_ptr(area) ? area : dar) : nullptr;
-  k_scatter_cache<<<grid_for(h->n), TGQ_BLOCK, 0, s>>>(h->elems.as<TriRec>(), h->n, on, od, oa, oar);
+  k_scatter_cache<<<grid_for(h->n), TGQ_BLOCK, 0, s>>>(h->elems.as<TriRec>(), h->area_by_elem.as<float>(), h->n, on, od, oa, oar);
   CK(cudaGetLastError());
   h->st.total_launches += 1;
   if (n3 && on == dn) CKRC(from_device(h, n3, dn, 12 * nn, s));
@@ -569,10 +594,10 @@ int tgq_closest(tgq_handle * h, const float * q3, int64_t Q, double dist_bound, 
   Arg args[4] = {{q3, nullptr, 12}, {nullptr, idx, 4}, {nullptr, d2, 4}, {nullptr, cp3, 12}};
   BvhView v = view_of(h); bool tri = h->kind == TGQ_KIND_TRIANGLES;
   return run_batched(h, Q, args, 4, true, [&](ChunkCtx & c) {
-    if (tri) k_closest<true><<<grid_for(c.n), TGQ_BLOCK, 0, c.stream>>>(v, (float const *)c.din[0], c.perm, c.n, ub, exclude_self, c.offset,
-                                                                        (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3]);
-    else k_closest<false><<<grid_for(c.n), TGQ_BLOCK, 0, c.stream>>>(v, (float const *)c.din[0], c.perm, c.n, ub, exclude_self, c.offset,
-                                                                     (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3]);
+    if (tri) k_closest<true, true><<<grid_for(c.n), TGQ_BLOCK, 0, c.stream>>>(v, h->slabs.as<SlabRec>(), h->pad, (float const *)c.din[0], c.perm, c.n, ub,
+                                                                              exclude_self, c.offset, (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3]);
+    else k_closest<false, false><<<grid_for(c.n), TGQ_BLOCK, 0, c.stream>>>(v, nullptr, 0.0f, (float const *)c.din[0], c.perm, c.n, ub, exclude_self,
+                                                                            c.offset, (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3]);
     h->st.last_launches += 1; h->st.total_launches += 1;
     return TGQ_OK;
   });
@@ -777,11 +802,10 @@ int tgq_area_sample(tgq_handle * h, int64_t S, uint64_t seed, float * p3, float 
   cudaStream_t s = h->stream; size_t nn = (size_t)h->n;
   if (!h->cum_valid)
   {
-    CK(h->area_by_elem.reserve(8 * nn)); CK(h->cum.reserve(8 * nn));
-    k_elem_areas<<<grid_for(h->n), TGQ_BLOCK, 0, s>>>(h->elems.as<TriRec>(), h->n, h->area_by_elem.as<double>());
-    k_seq_scan<<<1, 32, 0, s>>>(h->area_by_elem.as<double>(), h->n, h->cum.as<double>());
+    CK(h->cum.reserve(8 * nn));
+    k_seq_scan<<<1, 32, 0, s>>>(h->area_by_elem.as<float>(), h->n, h->cum.as<double>());
     CK(cudaGetLastError());
-    h->st.total_launches += 2; h->cum_valid = true;
+    h->st.total_launches += 1; h->cum_valid = true;
   }
   size_t ns = (size_t)S;
   CK(h->slot[0].out[0].reserve(12 * ns)); CK(h->slot[0].out[1].reserve(12 * ns)); CK(h->slot[0].out[2].reserve(4 * ns));

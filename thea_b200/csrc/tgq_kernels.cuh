@@ -67,20 +67,23 @@ __global__ void k_morton_points(float const * __restrict__ p3, int n, SceneBox c
 }
 
 // Element records in Morton order + element boxes.
-__global__ void k_gather_tris(float const * __restrict__ v9, uint32_t const * __restrict__ perm, int n, TriRec * tris,
-                              f4 * pbox_lo, f4 * pbox_hi, int * pos_of_elem)
+__global__ void k_gather_tris(float const * __restrict__ v9, uint32_t const * __restrict__ perm, int n, SceneBox const * sb, TriRec * tris,
+                              f4 * pbox_lo, f4 * pbox_hi, int * pos_of_elem, f4 * pnrm, float * area_by_elem)
 {
   int s = blockIdx.x * blockDim.x + threadIdx.x; if (s >= n) return;
   int64_t i = perm[s];
   pos_of_elem[i] = s;
+  float pad = scene_decode(sb).pad;
   v3 v0 = ld3(v9, 3 * i), v1 = ld3(v9, 3 * i + 1), v2 = ld3(v9, 3 * i + 2);
   TriPlane pl = tri_plane(v0, v1, v2);
-  float area = tri_area(pl.n, v0, v1, v2);
+  area_by_elem[i] = tri_area(pl.n, v0, v1, v2);
+  v3 cr = cross3(sub3(v1, v0), sub3(v2, v0));       // area-weighted normal, summed up the tree for the slab directions
+  pnrm[s] = make_float4(cr.x, cr.y, cr.z, 0.0f);
   TriRec r;
   r.q0 = make_float4(v0.x, v0.y, v0.z, __int_as_float((int)i));
   r.q1 = make_float4(v1.x, v1.y, v1.z, __int_as_float(pl.axis));
   r.q2 = make_float4(v2.x, v2.y, v2.z, pl.d);
-  r.q3 = make_float4(pl.n.x, pl.n.y, pl.n.z, area);
+  r.q3 = make_float4(pl.n.x, pl.n.y, pl.n.z, tri_screen_radius(v0, v1, v2, pad));
   tris[s] = r;
   v3 lo = min3(v0, min3(v1, v2)), hi = max3(v0, max3(v1, v2));      // Triangle3.hpp:215-219
   pbox_lo[s] = make_float4(lo.x, lo.y, lo.z, 0.0f); pbox_hi[s] = make_float4(hi.x, hi.y, hi.z, 0.0f);
@@ -113,7 +116,7 @@ __global__ void k_hierarchy(uint64_t const * __restrict__ keys, int n, int * fir
 // owns it.  nbox = unpadded box of every inner node of the binary radix tree.
 __global__ void k_refit(int n, int const * __restrict__ first, int const * __restrict__ last, int const * __restrict__ split,
                         int const * __restrict__ parent, f4 const * pbox_lo, f4 const * pbox_hi, f4 * nbox_lo, f4 * nbox_hi,
-                        unsigned int * arrive)
+                        unsigned int * arrive, f4 const * pnrm, f4 * nsum)
 {
   int s = blockIdx.x * blockDim.x + threadIdx.x; if (s >= n) return;
   int cur = parent[n - 1 + s];
@@ -123,13 +126,23 @@ __global__ void k_refit(int n, int const * __restrict__ first, int const * __res
     if (atomicAdd(&arrive[cur], 1u) == 0u) return;
     int f = first[cur], l = last[cur], sp = split[cur];
     volatile f4 const * vlo = nbox_lo; volatile f4 const * vhi = nbox_hi;
-    f4 alo, ahi, blo, bhi;
-    if (f == sp) { alo = pbox_lo[sp]; ahi = pbox_hi[sp]; }
-    else { alo.x = vlo[sp].x; alo.y = vlo[sp].y; alo.z = vlo[sp].z; ahi.x = vhi[sp].x; ahi.y = vhi[sp].y; ahi.z = vhi[sp].z; }
-    if (sp + 1 == l) { blo = pbox_lo[l]; bhi = pbox_hi[l]; }
-    else { blo.x = vlo[sp + 1].x; blo.y = vlo[sp + 1].y; blo.z = vlo[sp + 1].z; bhi.x = vhi[sp + 1].x; bhi.y = vhi[sp + 1].y; bhi.z = vhi[sp + 1].z; }
+    volatile f4 const * vns = nsum;
+    f4 alo, ahi, blo, bhi, an, bn;
+    if (f == sp) { alo = pbox_lo[sp]; ahi = pbox_hi[sp]; if (pnrm) an = pnrm[sp]; }
+    else
+    {
+      alo.x = vlo[sp].x; alo.y = vlo[sp].y; alo.z = vlo[sp].z; ahi.x = vhi[sp].x; ahi.y = vhi[sp].y; ahi.z = vhi[sp].z;
+      if (pnrm) { an.x = vns[sp].x; an.y = vns[sp].y; an.z = vns[sp].z; }
+    }
+    if (sp + 1 == l) { blo = pbox_lo[l]; bhi = pbox_hi[l]; if (pnrm) bn = pnrm[l]; }
+    else
+    {
+      blo.x = vlo[sp + 1].x; blo.y = vlo[sp + 1].y; blo.z = vlo[sp + 1].z; bhi.x = vhi[sp + 1].x; bhi.y = vhi[sp + 1].y; bhi.z = vhi[sp + 1].z;
+      if (pnrm) { bn.x = vns[sp + 1].x; bn.y = vns[sp + 1].y; bn.z = vns[sp + 1].z; }
+    }
     nbox_lo[cur] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.0f);
     nbox_hi[cur] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.0f);
+    if (pnrm) nsum[cur] = make_float4(an.x + bn.x, an.y + bn.y, an.z + bn.z, 0.0f);   // left + right: order fixed by the tree
     cur = parent[cur];
   }
 }
@@ -141,11 +154,85 @@ __global__ void k_live(int n, int leaf, int const * __restrict__ first, int cons
   live[i] = (i == 0 || (last[i] - first[i] + 1) > leaf) ? 1 : 0;
 }
 
-// Emits the 64-byte traversal node of every surviving inner node at its compacted index.
+// ---- pancake statistics of every radix-tree node that a surviving node references as a child -------------------------------
+// sinfo[2x] = (dir.xyz, smin), sinfo[2x+1] = (smax, R, 0, 0) for inner node x, about the centre of x's padded box.
+struct SlabAcc { v3 dir, c; float mn, mx, r2; };
+
+__device__ __forceinline__ SlabAcc slab_begin(f4 ns, f4 blo, f4 bhi, float pad)
+{
+  SlabAcc a;
+  a.dir = normalized3(mk3(ns.x, ns.y, ns.z));
+  if (!(sqn3(a.dir) > 0.5f)) a.dir = mk3(0.0f, 0.0f, 0.0f);          // cancelled normals (closed surface): no usable slab
+  a.c = box_centre(mk3(blo.x - pad, blo.y - pad, blo.z - pad), mk3(bhi.x + pad, bhi.y + pad, bhi.z + pad));
+  a.mn = FLT_MAX; a.mx = -FLT_MAX; a.r2 = 0.0f;
+  return a;
+}
+__device__ __forceinline__ void slab_add_tri(SlabAcc & a, TriRec const * tris, int k)
+{
+  f4 const * t = (f4 const *)(tris + k);
+  f4 q0 = __ldg(t), q1 = __ldg(t + 1), q2 = __ldg(t + 2);
+  slab_accumulate(a.dir, a.c, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), mk3(q2.x, q2.y, q2.z), a.mn, a.mx, a.r2);
+}
+__device__ __forceinline__ void slab_store(SlabAcc const & a, float pad, f4 * sinfo, int x)
+{
+  sinfo[2 * x] = make_float4(a.dir.x, a.dir.y, a.dir.z, a.mn - 2.0f * pad);
+  sinfo[2 * x + 1] = make_float4(a.mx + 2.0f * pad, slab_radius(a.r2, pad), 0.0f, 0.0f);
+}
+
+#define TGQ_SLAB_SMALL 32
+// Nodes of up to TGQ_SLAB_SMALL elements: one thread scans the node's element range; larger nodes are appended to `big`.
+__global__ void k_slab_small(int n, int leaf, int const * __restrict__ first, int const * __restrict__ last, int const * __restrict__ parent,
+                             f4 const * __restrict__ nbox_lo, f4 const * __restrict__ nbox_hi, f4 const * __restrict__ nsum,
+                             TriRec const * __restrict__ tris, SceneBox const * sb, f4 * sinfo, int * big, int * big_count)
+{
+  int x = blockIdx.x * blockDim.x + threadIdx.x; if (x >= n - 1 || x == 0) return;
+  int pa = parent[x];
+  bool parent_live = pa == 0 || (last[pa] - first[pa] + 1) > leaf;
+  if (!parent_live) return;                     // strictly inside a collapsed leaf: never referenced
+  int f = first[x], l = last[x];
+  if (l - f + 1 > TGQ_SLAB_SMALL) { big[atomicAdd(big_count, 1)] = x; return; }
+  float pad = scene_decode(sb).pad;
+  SlabAcc a = slab_begin(nsum[x], nbox_lo[x], nbox_hi[x], pad);
+  for (int k = f; k <= l; ++k) slab_add_tri(a, tris, k);
+  slab_store(a, pad, sinfo, x);
+}
+
+// Larger nodes: one thread block per node, block-wide min / max reduction (exact, order independent).
+__global__ void __launch_bounds__(128)
+k_slab_big(int const * __restrict__ big, int const * __restrict__ big_count, int const * __restrict__ first, int const * __restrict__ last,
+           f4 const * __restrict__ nbox_lo, f4 const * __restrict__ nbox_hi, f4 const * __restrict__ nsum, TriRec const * __restrict__ tris,
+           SceneBox const * sb, f4 * sinfo)
+{
+  __shared__ float s_mn[4], s_mx[4], s_r2[4];
+  for (int w = blockIdx.x; w < *big_count; w += gridDim.x)
+  {
+    int x = big[w];
+    float pad = scene_decode(sb).pad;
+    SlabAcc a = slab_begin(nsum[x], nbox_lo[x], nbox_hi[x], pad);
+    for (int k = first[x] + threadIdx.x; k <= last[x]; k += blockDim.x) slab_add_tri(a, tris, k);
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      a.mn = fminf(a.mn, __shfl_xor_sync(0xffffffffu, a.mn, o)); a.mx = fmaxf(a.mx, __shfl_xor_sync(0xffffffffu, a.mx, o));
+      a.r2 = fmaxf(a.r2, __shfl_xor_sync(0xffffffffu, a.r2, o));
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = a.mn; s_mx[threadIdx.x >> 5] = a.mx; s_r2[threadIdx.x >> 5] = a.r2; }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      for (int j = 1; j < 4; ++j) { s_mn[0] = fminf(s_mn[0], s_mn[j]); s_mx[0] = fmaxf(s_mx[0], s_mx[j]); s_r2[0] = fmaxf(s_r2[0], s_r2[j]); }
+      a.mn = s_mn[0]; a.mx = s_mx[0]; a.r2 = s_r2[0];
+      slab_store(a, pad, sinfo, x);
+    }
+  }
+}
+
+// Emits the 64-byte traversal node (and, for triangle structures, the 48-byte slab record) of every surviving inner node
+// at its compacted index.
 __global__ void k_emit(int n, int leaf, int const * __restrict__ first, int const * __restrict__ last, int const * __restrict__ split,
                        int const * __restrict__ live, int const * __restrict__ newidx, f4 const * __restrict__ pbox_lo,
                        f4 const * __restrict__ pbox_hi, f4 const * __restrict__ nbox_lo, f4 const * __restrict__ nbox_hi,
-                       SceneBox const * sb, NodeRec * nodes)
+                       SceneBox const * sb, NodeRec * nodes, TriRec const * __restrict__ tris, f4 const * __restrict__ sinfo, SlabRec * slabs)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n - 1 || !live[i]) return;
   float pad = scene_decode(sb).pad;
@@ -162,26 +249,56 @@ __global__ void k_emit(int n, int leaf, int const * __restrict__ first, int cons
     lo[c] = mk3(blo.x - pad, blo.y - pad, blo.z - pad); hi[c] = mk3(bhi.x + pad, bhi.y + pad, bhi.z + pad);
   }
   nodes[newidx[i]] = make_node(lo[0], hi[0], lo[1], hi[1], child[0], child[1], 0, 0);
+  if (slabs)
+  {
+    f4 sa[2], sb2[2];
+    for (int c = 0; c < 2; ++c)
+    {
+      int cf = c == 0 ? f : sp + 1, cl = c == 0 ? sp : l;
+      int inner = c == 0 ? sp : sp + 1;
+      if (cl == cf)
+      {
+        // single triangle: its own plane and its radius about the box centre
+        f4 const * t = (f4 const *)(tris + cf);
+        f4 q0 = __ldg(t), q1 = __ldg(t + 1), q2 = __ldg(t + 2);
+        v3 v0 = mk3(q0.x, q0.y, q0.z), v1 = mk3(q1.x, q1.y, q1.z), v2 = mk3(q2.x, q2.y, q2.z);
+        v3 cr = cross3(sub3(v1, v0), sub3(v2, v0));
+        SlabAcc a = slab_begin(make_float4(cr.x, cr.y, cr.z, 0.0f), pbox_lo[cf], pbox_hi[cf], pad);
+        slab_accumulate(a.dir, a.c, v0, v1, v2, a.mn, a.mx, a.r2);
+        sa[c] = make_float4(a.dir.x, a.dir.y, a.dir.z, a.mn - 2.0f * pad);
+        sb2[c] = make_float4(a.mx + 2.0f * pad, slab_radius(a.r2, pad), 0.0f, 0.0f);
+      }
+      else { sa[c] = sinfo[2 * inner]; sb2[c] = sinfo[2 * inner + 1]; }
+    }
+    SlabRec r;
+    r.a = make_float4(sa[0].x, sa[0].y, sa[0].z, sa[0].w);
+    r.b = make_float4(sb2[0].x, sa[1].x, sa[1].y, sa[1].z);
+    r.c = make_float4(sa[1].w, sb2[1].x, sb2[0].y, sb2[1].y);
+    slabs[newidx[i]] = r;
+  }
 }
 
 // Structure with a single element: one node whose second child is an empty leaf behind an inverted box.
-__global__ void k_emit_single(f4 const * pbox_lo, f4 const * pbox_hi, SceneBox const * sb, NodeRec * nodes)
+__global__ void k_emit_single(f4 const * pbox_lo, f4 const * pbox_hi, SceneBox const * sb, NodeRec * nodes, SlabRec * slabs)
 {
   float pad = scene_decode(sb).pad;
+  if (slabs)   // no usable direction: zero dir, unbounded slab, unbounded radius => the pancake bound is 0
+  { SlabRec r; r.a = make_float4(0, 0, 0, -FLT_MAX); r.b = make_float4(FLT_MAX, 0, 0, 0); r.c = make_float4(-FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX); slabs[0] = r; }
   f4 blo = pbox_lo[0], bhi = pbox_hi[0];
   nodes[0] = make_node(mk3(blo.x - pad, blo.y - pad, blo.z - pad), mk3(bhi.x + pad, bhi.y + pad, bhi.z + pad),
                        mk3(FLT_MAX, FLT_MAX, FLT_MAX), mk3(-FLT_MAX, -FLT_MAX, -FLT_MAX), ~((0 << TGQ_LEAF_BITS) | 1), ~0, 0, 0);
 }
 
 // Element-order copy of the triangle cache (for tgq_triangle_cache and hit normals).
-__global__ void k_scatter_cache(TriRec const * __restrict__ tris, int n, float * n3, float * d, int * axis, float * area)
+__global__ void k_scatter_cache(TriRec const * __restrict__ tris, float const * __restrict__ area_by_elem, int n, float * n3, float * d,
+                                int * axis, float * area)
 {
   int s = blockIdx.x * blockDim.x + threadIdx.x; if (s >= n) return;
   TriRec r = tris[s]; int64_t i = __float_as_int(r.q0.w);
   if (n3) st3(n3, i, mk3(r.q3.x, r.q3.y, r.q3.z));
   if (d) d[i] = r.q2.w;
   if (axis) axis[i] = __float_as_int(r.q1.w);
-  if (area) area[i] = r.q3.w;
+  if (area) area[i] = area_by_elem[i];
 }
 
 // ---- query ordering ---------------------------------------------------------------------------------------------------
@@ -197,16 +314,16 @@ __global__ void k_query_codes(float const * __restrict__ q3, int n, SceneBox con
 }
 
 // ---- K5 closest element -------------------------------------------------------------------------------------------------
-template <bool TRI>
+template <bool TRI, bool SLAB>
 __global__ void __launch_bounds__(TGQ_BLOCK)
-k_closest(BvhView b, float const * __restrict__ q3, uint32_t const * __restrict__ perm, int n, float bound_ub, int exclude_self,
-          int64_t self_offset, int * idx, float * d2, float * cp3)
+k_closest(BvhView b, SlabRec const * __restrict__ slabs, float scene_pad, float const * __restrict__ q3, uint32_t const * __restrict__ perm,
+          int n, float bound_ub, int exclude_self, int64_t self_offset, int * idx, float * d2, float * cp3)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= n) return;
   int64_t i = perm ? perm[t] : t;
   v3 p = ld3(q3, i);
   float best = bound_ub; int bi = -1; v3 cp = mk3(0.0f, 0.0f, 0.0f);
-  closest_query<TRI>(b, p, exclude_self ? (int)(self_offset + i) : -1, best, bi, cp);
+  closest_query<TRI, SLAB>(b, slabs, scene_pad, p, exclude_self ? (int)(self_offset + i) : -1, best, bi, cp);
   if (idx) idx[i] = bi;
   if (d2) d2[i] = bi >= 0 ? best : -1.0f;
   if (cp3) st3(cp3, i, cp);
@@ -370,21 +487,14 @@ __global__ void k_area_sample(TriRec const * __restrict__ tris, int const * __re
   if (tri) tri[i] = ti;
 }
 
-__global__ void k_elem_areas(TriRec const * __restrict__ tris, int n, double * area_by_elem)
-{
-  int s = blockIdx.x * blockDim.x + threadIdx.x; if (s >= n) return;
-  TriRec r = tris[s]; int i = __float_as_int(r.q0.w);
-  area_by_elem[i] = (double)r.q3.w;
-}
-
 // Sequential inclusive scan in double: cum[i] = cum[i-1] + a[i], the exact accumulation order of MeshSampler.hpp:166-168
 // (a parallel scan would round differently and could move a lower_bound boundary).  One thread walks the chain; this is
 // a one-off set-up step per structure (about T x 20 ns), not part of any query path.
-__global__ void k_seq_scan(double const * __restrict__ a, int n, double * cum)
+__global__ void k_seq_scan(float const * __restrict__ a, int n, double * cum)
 {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   double acc = 0.0;
-  for (int i = 0; i < n; ++i) { acc = (i == 0) ? a[0] : acc + a[i]; cum[i] = acc; }
+  for (int i = 0; i < n; ++i) { acc = (i == 0) ? (double)a[0] : acc + (double)a[i]; cum[i] = acc; }
 }
 
 // Indexed mesh -> triangle soup: out[3 * (3t + c) ..] = verts[tri[3t + c]] (MeshTriangles::addTriangles order).
@@ -402,7 +512,7 @@ __global__ void k_self_nn(BvhView b, int const * __restrict__ pos_of_elem, int c
   int i = seeds[j];
   f4 e = b.pts[pos_of_elem[i]];
   float best = INFINITY; int bi = -1; v3 cp = mk3(0.0f, 0.0f, 0.0f);
-  closest_query<false>(b, mk3(e.x, e.y, e.z), i, best, bi, cp);
+  closest_query<false, false>(b, nullptr, 0.0f, mk3(e.x, e.y, e.z), i, best, bi, cp);
   d2_out[j] = bi >= 0 ? best : 0.0f;
 }
 

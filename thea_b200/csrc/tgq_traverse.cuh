@@ -50,24 +50,84 @@ TGQ_HD NodeRec load_node(BvhView const & b, int i)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Closest element.  best_d2 enters as the (exclusive) squared bound or +inf, best_idx as -1.
+// "Pancake" bounds.  AABBs of a smooth surface that is oblique to the axes stick out towards an off-surface query by
+// about their own size, so a far query would have to open every box in a wide disc around its foot point (hundreds of
+// leaves on a 1M-triangle mesh).  Each child of a triangle-structure node therefore also carries a slab
+// {x : smin <= dir.x <= smax} around the mean normal of its triangles and the radius R of its vertices about the centre
+// c of its box.  For any x in the child
+//     |p - x|^2 = (dir.(p - x))^2 + |(p - x)_perp|^2 >= slab_dist(p)^2 + max(0, |(p - c)_perp| - R)^2,
+// which keeps the lateral offset that the box bound loses.  Box and pancake bounds are both valid; the traversal prunes
+// on their maximum.  The same bound with the triangle's own plane and the radius about its centroid screens single
+// triangles before the exact (and expensive) reference arithmetic is run.
+//   SlabRec (48 B): a = (dir0.xyz, smin0)  b = (smax0, dir1.xyz)  c = (smin1, smax1, R0, R1)
+// All stored quantities are padded outwards at build time (scene pad); `mq` absorbs the rounding of the query-side dot
+// products (it grows with the magnitude of the query coordinates), and the result is deflated like the box bound.
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool TRI>
-TGQ_HD void closest_leaf(BvhView const & b, int first, int count, v3 p, int skip, float & best_d2, int & best_idx, v3 & best_cp)
+struct SlabRec { f4 a, b, c; };
+
+TGQ_HD float query_margin(v3 p, float scene_pad) { return scene_pad + 1e-6f * (fabsf(p.x) + fabsf(p.y) + fabsf(p.z)); }
+
+TGQ_HD float pancake_sqdist(v3 c, v3 dir, float smin, float smax, float R, v3 p, float mq)
+{
+  float s = dot3(dir, p);
+  float sd = fmaxf(fmaxf(s - smax, smin - s) - mq, 0.0f);
+  v3 pc = sub3(p, c);
+  float sc = dot3(dir, pc);
+  v3 perp = sub3(pc, mul3(dir, sc));
+  float lat = fmaxf(sqrtf(sqn3(perp)) - R - mq, 0.0f);
+  return (sd * sd + lat * lat) * TGQ_LB_DEFLATE;
+}
+
+// Accumulates one triangle into the slab statistics of a node: extent along dir and radius about c.
+TGQ_HD void slab_accumulate(v3 dir, v3 c, v3 v0, v3 v1, v3 v2, float & mn, float & mx, float & r2)
+{
+  float s0 = dot3(dir, v0), s1 = dot3(dir, v1), s2 = dot3(dir, v2);
+  mn = fminf(mn, fminf(s0, fminf(s1, s2))); mx = fmaxf(mx, fmaxf(s0, fmaxf(s1, s2)));
+  r2 = fmaxf(r2, fmaxf(sqn3(sub3(v0, c)), fmaxf(sqn3(sub3(v1, c)), sqn3(sub3(v2, c)))));
+}
+TGQ_HD float slab_radius(float r2, float pad) { return sqrtf(r2) * 1.000001f + 2.0f * pad; }
+TGQ_HD v3 box_centre(v3 lo, v3 hi) { return mul3(add3(lo, hi), 0.5f); }
+// Screening radius of one triangle about its centroid (stored in TriRec.q3.w).
+TGQ_HD float tri_screen_radius(v3 v0, v3 v1, v3 v2, float pad)
+{
+  v3 c = mul3(add3(add3(v0, v1), v2), 0.33333334f);
+  float r2 = fmaxf(sqn3(sub3(v0, c)), fmaxf(sqn3(sub3(v1, c)), sqn3(sub3(v2, c))));
+  return slab_radius(r2, pad);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Closest element.  best_d2 enters as the (exclusive) squared bound or +inf, best_idx as -1.
+// SLAB: triangle structure with pancake bounds (slabs != null) and per-triangle screening.
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool TRI, bool SLAB>
+TGQ_HD void closest_leaf(BvhView const & b, int first, int count, v3 p, int skip, float mq, float & best_d2, int & best_idx, v3 & best_cp)
 {
   for (int k = first; k < first + count; ++k)
   {
     int idx; v3 cp; float d2;
-    TGQ_COUNT_PRIM();
     if (TRI)
     {
       f4 const * t = (f4 const *)(b.tris + k);
       f4 a = ldq(t), bq = ldq(t + 1), c = ldq(t + 2), d = ldq(t + 3);
+      v3 v0 = mk3(a.x, a.y, a.z), v1 = mk3(bq.x, bq.y, bq.z), v2 = mk3(c.x, c.y, c.z), n = mk3(d.x, d.y, d.z);
+      if (SLAB)
+      {
+        // screen: plane distance and lateral distance to the triangle's bounding circle
+        v3 cen = mul3(add3(add3(v0, v1), v2), 0.33333334f);
+        float sdp = dot3(p, n) - c.w;
+        float sd = fmaxf(fabsf(sdp) - mq, 0.0f);
+        v3 pc = sub3(p, cen);
+        v3 perp = sub3(pc, mul3(n, dot3(n, pc)));
+        float lat = fmaxf(sqrtf(sqn3(perp)) - d.w - mq, 0.0f);
+        if ((sd * sd + lat * lat) * TGQ_LB_DEFLATE > best_d2) continue;
+      }
+      TGQ_COUNT_PRIM();
       idx = f2i(a.w);
-      d2 = tri_point_sqdist(mk3(a.x, a.y, a.z), mk3(bq.x, bq.y, bq.z), mk3(c.x, c.y, c.z), mk3(d.x, d.y, d.z), c.w, f2i(bq.w), p, cp);
+      d2 = tri_point_sqdist(v0, v1, v2, n, c.w, f2i(bq.w), p, cp);
     }
     else
     {
+      TGQ_COUNT_PRIM();
       f4 e = ldq(b.pts + k);
       idx = f2i(e.w); cp = mk3(e.x, e.y, e.z);
       d2 = sqn3(sub3(cp, p));
@@ -77,110 +137,65 @@ TGQ_HD void closest_leaf(BvhView const & b, int first, int count, v3 p, int skip
   }
 }
 
-template <bool TRI>
-TGQ_HD void closest_query(BvhView const & b, v3 p, int skip, float & best_d2, int & best_idx, v3 & best_cp)
+// Resumable traversal state: the persistent kernels advance every lane by a bounded burst of steps, retire finished
+// queries and hand fresh ones to the idle lanes, so a warp stays full even though query costs are heavy tailed.
+template <bool TRI, bool SLAB>
+struct ClosestState
 {
-  if (b.n_nodes <= 0) return;
+  v3 p; float mq; int skip;
+  float best_d2; int best_idx; v3 best_cp;
+  int cur, sp;
   int stk_node[TGQ_STACK]; float stk_lb[TGQ_STACK];
-  int sp = 0;
-  int cur = 0;
+};
+
+template <bool TRI, bool SLAB>
+TGQ_HD void closest_begin(ClosestState<TRI, SLAB> & s, BvhView const & b, float scene_pad, v3 p, int skip, float bound_ub)
+{
+  s.p = p; s.skip = skip; s.mq = SLAB ? query_margin(p, scene_pad) : 0.0f;
+  s.best_d2 = bound_ub; s.best_idx = -1; s.best_cp = mk3(0.0f, 0.0f, 0.0f);
+  s.sp = 0; s.cur = b.n_nodes > 0 ? 0 : -1;
+  if (b.n_nodes <= 0) s.sp = -1;          // empty structure: nothing to do
+}
+
+// Advances by at most `budget` node steps; returns true when the query is finished.
+template <bool TRI, bool SLAB>
+TGQ_HD bool closest_run(ClosestState<TRI, SLAB> & s, BvhView const & b, SlabRec const * slabs, int budget)
+{
+  if (s.sp < 0) return true;
+  v3 p = s.p; float mq = s.mq;
+  int cur = s.cur, sp = s.sp;
   for (;;)
   {
     while (cur >= 0)
     {
+      if (--budget < 0) { s.cur = cur; s.sp = sp; return false; }
       NodeRec nd = load_node(b, cur);
       TGQ_COUNT_NODE();
       v3 lo0, hi0, lo1, hi1; node_boxes(nd, lo0, hi0, lo1, hi1);
       float lb0 = box_point_sqdist(lo0, hi0, p) * TGQ_LB_DEFLATE;
       float lb1 = box_point_sqdist(lo1, hi1, p) * TGQ_LB_DEFLATE;
       int c0 = f2i(nd.q3.x), c1 = f2i(nd.q3.y);
-      bool go0 = lb0 <= best_d2, go1 = lb1 <= best_d2;
-      if (go0 && go1)
-      {
-        bool swap = lb1 < lb0;
-        int nearc = swap ? c1 : c0, farc = swap ? c0 : c1;
-        stk_node[sp] = farc; stk_lb[sp] = swap ? lb0 : lb1; ++sp;
-        cur = nearc;
-      }
-      else if (go0) cur = c0;
-      else if (go1) cur = c1;
-      else goto pop;
-    }
-    {
-      int code = ~cur;
-      closest_leaf<TRI>(b, code >> TGQ_LEAF_BITS, code & TGQ_LEAF_MASK, p, skip, best_d2, best_idx, best_cp);
-    }
-  pop:
-    for (;;)
-    {
-      if (sp == 0) return;
-      --sp;
-      if (stk_lb[sp] <= best_d2) { cur = stk_node[sp]; break; }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Closest element with "pancake" bounds.  AABBs of a smooth surface that is oblique to the axes stick out towards an
-// off-surface query by about their own size, so a far query must open every box in a wide disc around its foot point
-// (hundreds of leaves on a 1M-triangle mesh).  Each child therefore also carries a slab {x : smin <= dir.x <= smax}
-// around the mean normal of its triangles and the radius R of its elements about the box centre c.  For any x in the
-// child, |p - x|^2 = (dir.(p - x))^2 + |(p - x)_perp|^2 >= slab_dist^2 + max(0, |(p - c)_perp| - R)^2, a bound that
-// keeps the lateral offset the box bound loses.  Both bounds are valid, the traversal prunes on their maximum.
-//   SlabRec (48 B): a = (dir0.xyz, smin0)  b = (smax0, dir1.xyz)  c = (smin1, smax1, R0, R1)
-// ---------------------------------------------------------------------------------------------------------------------
-struct SlabRec { f4 a, b, c; };
-
-TGQ_HD float pancake_sqdist(v3 lo, v3 hi, v3 dir, float smin, float smax, float R, v3 p)
-{
-  float s = dot3(dir, p);
-  float sd = fmaxf(fmaxf(s - smax, smin - s), 0.0f);
-  v3 c = mul3(add3(lo, hi), 0.5f);
-  v3 pc = sub3(p, c);
-  float sc = dot3(dir, pc);
-  float perp2 = fmaxf(sqn3(pc) - sc * sc, 0.0f);
-  float lat = fmaxf(sqrtf(perp2) * 0.999999f - R, 0.0f);
-  return sd * sd + lat * lat;
-}
-
-template <bool TRI>
-TGQ_HD void closest_query_slab(BvhView const & b, SlabRec const * slabs, v3 p, int skip, float & best_d2, int & best_idx, v3 & best_cp)
-{
-  if (b.n_nodes <= 0) return;
-  int stk_node[TGQ_STACK]; float stk_lb[TGQ_STACK];
-  int sp = 0;
-  int cur = 0;
-  for (;;)
-  {
-    while (cur >= 0)
-    {
-      NodeRec nd = load_node(b, cur);
-      TGQ_COUNT_NODE();
-      v3 lo0, hi0, lo1, hi1; node_boxes(nd, lo0, hi0, lo1, hi1);
-      float lb0 = box_point_sqdist(lo0, hi0, p) * TGQ_LB_DEFLATE;
-      float lb1 = box_point_sqdist(lo1, hi1, p) * TGQ_LB_DEFLATE;
-      int c0 = f2i(nd.q3.x), c1 = f2i(nd.q3.y);
-      bool go0 = lb0 <= best_d2, go1 = lb1 <= best_d2;
-      if (go0 || go1)
+      bool go0 = lb0 <= s.best_d2, go1 = lb1 <= s.best_d2;
+      if (SLAB && (go0 || go1))
       {
         f4 const * sq = (f4 const *)(slabs + cur);
         f4 sa = ldq(sq), sb = ldq(sq + 1), sc = ldq(sq + 2);
         if (go0)
         {
-          lb0 = fmaxf(lb0, pancake_sqdist(lo0, hi0, mk3(sa.x, sa.y, sa.z), sa.w, sb.x, sc.z, p) * TGQ_LB_DEFLATE);
-          go0 = lb0 <= best_d2;
+          lb0 = fmaxf(lb0, pancake_sqdist(box_centre(lo0, hi0), mk3(sa.x, sa.y, sa.z), sa.w, sb.x, sc.z, p, mq));
+          go0 = lb0 <= s.best_d2;
         }
         if (go1)
         {
-          lb1 = fmaxf(lb1, pancake_sqdist(lo1, hi1, mk3(sb.y, sb.z, sb.w), sc.x, sc.y, sc.w, p) * TGQ_LB_DEFLATE);
-          go1 = lb1 <= best_d2;
+          lb1 = fmaxf(lb1, pancake_sqdist(box_centre(lo1, hi1), mk3(sb.y, sb.z, sb.w), sc.x, sc.y, sc.w, p, mq));
+          go1 = lb1 <= s.best_d2;
         }
       }
       if (go0 && go1)
       {
         bool swap = lb1 < lb0;
         int nearc = swap ? c1 : c0, farc = swap ? c0 : c1;
-        stk_node[sp] = farc; stk_lb[sp] = swap ? lb0 : lb1; ++sp;
+        s.stk_node[sp] = farc; s.stk_lb[sp] = swap ? lb0 : lb1; ++sp;
         cur = nearc;
       }
       else if (go0) cur = c0;
@@ -189,16 +204,26 @@ TGQ_HD void closest_query_slab(BvhView const & b, SlabRec const * slabs, v3 p, i
     }
     {
       int code = ~cur;
-      closest_leaf<TRI>(b, code >> TGQ_LEAF_BITS, code & TGQ_LEAF_MASK, p, skip, best_d2, best_idx, best_cp);
+      closest_leaf<TRI, SLAB>(b, code >> TGQ_LEAF_BITS, code & TGQ_LEAF_MASK, p, s.skip, mq, s.best_d2, s.best_idx, s.best_cp);
     }
   pop:
     for (;;)
     {
-      if (sp == 0) return;
+      if (sp == 0) { s.sp = -1; return true; }
       --sp;
-      if (stk_lb[sp] <= best_d2) { cur = stk_node[sp]; break; }
+      if (s.stk_lb[sp] <= s.best_d2) { cur = s.stk_node[sp]; break; }
     }
   }
+}
+
+template <bool TRI, bool SLAB>
+TGQ_HD void closest_query(BvhView const & b, SlabRec const * slabs, float scene_pad, v3 p, int skip, float & best_d2, int & best_idx,
+                          v3 & best_cp)
+{
+  ClosestState<TRI, SLAB> s;
+  closest_begin(s, b, scene_pad, p, skip, best_d2);
+  closest_run(s, b, slabs, 0x7fffffff);
+  best_d2 = s.best_d2; best_idx = s.best_idx; best_cp = s.best_cp;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -367,27 +392,42 @@ TGQ_HD float slab_entry(RaySlab const & r, v3 lo, v3 hi)
 }
 
 template <bool ANY>
-TGQ_HD void ray_query(BvhView const & b, v3 o, v3 d, float & best_t, int & best_idx, int & best_k)
+struct RayState
 {
-  if (b.n_nodes <= 0) return;
-  RaySlab r; r.o = o; r.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+  v3 o, d; RaySlab r;
+  float best_t; int best_idx, best_k;
+  int cur, sp;
   int stk_node[TGQ_STACK]; float stk_t[TGQ_STACK];
-  int sp = 0;
-  int cur = 0;
+};
+
+template <bool ANY>
+TGQ_HD void ray_begin(RayState<ANY> & s, BvhView const & b, v3 o, v3 d, float max_time)
+{
+  s.o = o; s.d = d; s.r.o = o; s.r.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+  s.best_t = max_time; s.best_idx = -1; s.best_k = -1;
+  s.sp = b.n_nodes > 0 ? 0 : -1; s.cur = 0;
+}
+
+template <bool ANY>
+TGQ_HD bool ray_run(RayState<ANY> & s, BvhView const & b, int budget)
+{
+  if (s.sp < 0) return true;
+  int cur = s.cur, sp = s.sp;
   for (;;)
   {
     while (cur >= 0)
     {
+      if (--budget < 0) { s.cur = cur; s.sp = sp; return false; }
       NodeRec nd = load_node(b, cur);
       v3 lo0, hi0, lo1, hi1; node_boxes(nd, lo0, hi0, lo1, hi1);
-      float t0 = slab_entry(r, lo0, hi0), t1 = slab_entry(r, lo1, hi1);
+      float t0 = slab_entry(s.r, lo0, hi0), t1 = slab_entry(s.r, lo1, hi1);
       int c0 = f2i(nd.q3.x), c1 = f2i(nd.q3.y);
-      bool go0 = t0 >= 0.0f && (best_t < 0.0f || t0 <= best_t);
-      bool go1 = t1 >= 0.0f && (best_t < 0.0f || t1 <= best_t);
+      bool go0 = t0 >= 0.0f && (s.best_t < 0.0f || t0 <= s.best_t);
+      bool go1 = t1 >= 0.0f && (s.best_t < 0.0f || t1 <= s.best_t);
       if (go0 && go1)
       {
         bool swap = t1 < t0;
-        stk_node[sp] = swap ? c0 : c1; stk_t[sp] = swap ? t0 : t1; ++sp;
+        s.stk_node[sp] = swap ? c0 : c1; s.stk_t[sp] = swap ? t0 : t1; ++sp;
         cur = swap ? c1 : c0;
       }
       else if (go0) cur = c0;
@@ -401,20 +441,29 @@ TGQ_HD void ray_query(BvhView const & b, v3 o, v3 d, float & best_t, int & best_
         f4 const * t = (f4 const *)(b.tris + k);
         f4 a = ldq(t), bq = ldq(t + 1), c = ldq(t + 2);
         v3 v0 = mk3(a.x, a.y, a.z);
-        float tm = ray_tri_time(o, d, v0, sub3(mk3(bq.x, bq.y, bq.z), v0), sub3(mk3(c.x, c.y, c.z), v0));
+        float tm = ray_tri_time(s.o, s.d, v0, sub3(mk3(bq.x, bq.y, bq.z), v0), sub3(mk3(c.x, c.y, c.z), v0));
         int idx = f2i(a.w);
-        if (tm >= 0.0f && (best_idx < 0 ? (best_t < 0.0f || tm < best_t) : (tm < best_t || (tm == best_t && idx < best_idx))))
-        { best_t = tm; best_idx = idx; best_k = k; if (ANY) return; }
+        if (tm >= 0.0f && (s.best_idx < 0 ? (s.best_t < 0.0f || tm < s.best_t) : (tm < s.best_t || (tm == s.best_t && idx < s.best_idx))))
+        { s.best_t = tm; s.best_idx = idx; s.best_k = k; if (ANY) { s.sp = -1; return true; } }
       }
     }
   pop:
     for (;;)
     {
-      if (sp == 0) return;
+      if (sp == 0) { s.sp = -1; return true; }
       --sp;
-      if (best_t < 0.0f || stk_t[sp] <= best_t) { cur = stk_node[sp]; break; }
+      if (s.best_t < 0.0f || s.stk_t[sp] <= s.best_t) { cur = s.stk_node[sp]; break; }
     }
   }
+}
+
+template <bool ANY>
+TGQ_HD void ray_query(BvhView const & b, v3 o, v3 d, float & best_t, int & best_idx, int & best_k)
+{
+  RayState<ANY> s;
+  ray_begin(s, b, o, d, best_t);
+  ray_run(s, b, 0x7fffffff);
+  best_t = s.best_t; best_idx = s.best_idx; best_k = s.best_k;
 }
 
 }  // namespace tgq
