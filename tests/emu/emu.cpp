@@ -26,10 +26,10 @@ struct Emu
   int n = 0, leaf = 4; float pad = 0;
   std::vector<TriRec> tris; std::vector<f4> pts, nrm;
   std::vector<NodeRec> nodes;
-  std::vector<SlabRec> slabs;
+  std::vector<ObbNode> obbs;
   BvhView view() const
   {
-    BvhView v; v.nodes = nodes.data(); v.tris = tri ? tris.data() : nullptr; v.pts = tri ? nullptr : pts.data();
+    BvhView v; v.nodes = nodes.data(); v.obbs = tri ? obbs.data() : nullptr; v.tris = tri ? tris.data() : nullptr; v.pts = tri ? nullptr : pts.data();
     v.nrm = has_n ? nrm.data() : nullptr; v.n_nodes = (int)nodes.size(); v.n_prims = n; return v;
   }
 };
@@ -87,7 +87,15 @@ void build(Emu & E, float const * src, float const * n3)
   }
   if (n == 1)
   {
-    if (E.tri) { SlabRec r; r.a = f4{0, 0, 0, -FLT_MAX}; r.b = f4{FLT_MAX, 0, 0, 0}; r.c = f4{-FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX}; E.slabs.assign(1, r); }
+    if (E.tri)
+    {
+      ObbNode r; TriRec const & t = E.tris[0];
+      v3 v0 = mk3(t.q0.x, t.q0.y, t.q0.z), v1 = mk3(t.q1.x, t.q1.y, t.q1.z), v2 = mk3(t.q2.x, t.q2.y, t.q2.z);
+      ObbAcc a; obb_acc_begin(a, cross3(sub3(v1, v0), sub3(v2, v0)));
+      obb_acc_point(a, v0); obb_acc_point(a, v1); obb_acc_point(a, v2);
+      obb_acc_store(a, pad, ~((0 << TGQ_LEAF_BITS) | 1), r.q); obb_store_empty(~0, r.q + 4);
+      E.obbs.assign(1, r);
+    }
     E.nodes.push_back(make_node(mk3(plo[0].x - pad, plo[0].y - pad, plo[0].z - pad), mk3(phi[0].x + pad, phi[0].y + pad, phi[0].z + pad),
                                 mk3(FLT_MAX, FLT_MAX, FLT_MAX), mk3(-FLT_MAX, -FLT_MAX, -FLT_MAX), ~((0 << TGQ_LEAF_BITS) | 1), ~0, 0, 0));
     return;
@@ -110,7 +118,7 @@ void build(Emu & E, float const * src, float const * n3)
   int cnt = 0;
   for (int i = 0; i < ni; ++i) { live[(size_t)i] = (i == 0 || (last[(size_t)i] - first[(size_t)i] + 1) > E.leaf) ? 1 : 0; newidx[(size_t)i] = cnt; cnt += live[(size_t)i]; }
   E.nodes.resize((size_t)cnt);
-  if (E.tri) E.slabs.resize((size_t)cnt);
+  if (E.tri) E.obbs.resize((size_t)cnt);
   for (int i = 0; i < ni; ++i)
   {
     if (!live[(size_t)i]) continue;
@@ -126,34 +134,27 @@ void build(Emu & E, float const * src, float const * n3)
     E.nodes[(size_t)newidx[(size_t)i]] = make_node(clo[0], chi[0], clo[1], chi[1], child[0], child[1], 0, 0);
     if (E.tri)
     {
-      // pancake bounds through the same helpers as k_slab_small / k_slab_big / k_emit (direction from a plain sum here)
-      float dirs[2][3], smin[2], smax[2], rad[2];
+      // oriented boxes through the same helpers as k_obb_small / k_obb_big / k_emit (normal sum taken in plain order here)
+      ObbNode r;
       for (int c = 0; c < 2; ++c)
       {
         int cf = c == 0 ? f : sp + 1, cl = c == 0 ? sp : l;
         v3 sum = mk3(0, 0, 0);
         for (int k = cf; k <= cl; ++k)
         {
-          TriRec const & r = E.tris[(size_t)k];
-          v3 v0 = mk3(r.q0.x, r.q0.y, r.q0.z);
-          sum = add3(sum, cross3(sub3(mk3(r.q1.x, r.q1.y, r.q1.z), v0), sub3(mk3(r.q2.x, r.q2.y, r.q2.z), v0)));
+          TriRec const & t = E.tris[(size_t)k];
+          v3 v0 = mk3(t.q0.x, t.q0.y, t.q0.z);
+          sum = add3(sum, cross3(sub3(mk3(t.q1.x, t.q1.y, t.q1.z), v0), sub3(mk3(t.q2.x, t.q2.y, t.q2.z), v0)));
         }
-        v3 dir = normalized3(sum);
-        if (!(sqn3(dir) > 0.5f)) dir = mk3(0, 0, 0);
-        v3 cc = box_centre(clo[c], chi[c]);
-        float mn = FLT_MAX, mx = -FLT_MAX, r2 = 0;
+        ObbAcc a; obb_acc_begin(a, sum);
         for (int k = cf; k <= cl; ++k)
         {
-          TriRec const & r = E.tris[(size_t)k];
-          slab_accumulate(dir, cc, mk3(r.q0.x, r.q0.y, r.q0.z), mk3(r.q1.x, r.q1.y, r.q1.z), mk3(r.q2.x, r.q2.y, r.q2.z), mn, mx, r2);
+          TriRec const & t = E.tris[(size_t)k];
+          obb_acc_point(a, mk3(t.q0.x, t.q0.y, t.q0.z)); obb_acc_point(a, mk3(t.q1.x, t.q1.y, t.q1.z)); obb_acc_point(a, mk3(t.q2.x, t.q2.y, t.q2.z));
         }
-        dirs[c][0] = dir.x; dirs[c][1] = dir.y; dirs[c][2] = dir.z;
-        smin[c] = mn - 2 * pad; smax[c] = mx + 2 * pad; rad[c] = slab_radius(r2, pad);
+        obb_acc_store(a, pad, child[c], r.q + 4 * c);
       }
-      SlabRec sr;
-      sr.a = f4{dirs[0][0], dirs[0][1], dirs[0][2], smin[0]}; sr.b = f4{smax[0], dirs[1][0], dirs[1][1], dirs[1][2]};
-      sr.c = f4{smin[1], smax[1], rad[0], rad[1]};
-      E.slabs[(size_t)newidx[(size_t)i]] = sr;
+      E.obbs[(size_t)newidx[(size_t)i]] = r;
     }
   }
 }
@@ -171,18 +172,29 @@ void * emu_build(float const * src, int64_t n, int is_tri, float const * n3, int
 void emu_destroy(void * h) { delete (Emu *)h; }
 int64_t emu_num_nodes(void * h) { return (int64_t)((Emu *)h)->nodes.size(); }
 
-static int use_slabs = 1;
-void emu_use_slabs(int on) { use_slabs = on; }
 void emu_closest(void * h, float const * q3, int64_t Q, float bound_ub, int exclude_self, int32_t * idx, float * d2, float * cp3)
 {
   Emu & E = *(Emu *)h; BvhView v = E.view();
   for (int64_t i = 0; i < Q; ++i)
   {
     float best = bound_ub; int bi = -1; v3 cp = mk3(0, 0, 0);
-    if (E.tri && use_slabs) closest_query<true, true>(v, E.slabs.data(), E.pad, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp);
-    else if (E.tri) closest_query<true, false>(v, nullptr, 0.0f, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp);
-    else closest_query<false, false>(v, nullptr, 0.0f, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp);
+    if (E.tri) closest_query<true>(v, E.pad, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp);
+    else closest_query<false>(v, 0.0f, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp);
     idx[i] = bi; d2[i] = bi >= 0 ? best : -1.0f; cp3[3 * i] = cp.x; cp3[3 * i + 1] = cp.y; cp3[3 * i + 2] = cp.z;
+  }
+}
+
+// Per-query visit counts (development aid for studying pruning quality).
+void emu_closest_counts(void * h, float const * q3, int64_t Q, float const * ub, int32_t * nodes, int32_t * prims)
+{
+  Emu & E = *(Emu *)h; BvhView v = E.view();
+  for (int64_t i = 0; i < Q; ++i)
+  {
+    long long n0 = g_cnt_node, p0 = g_cnt_prim;
+    float best = ub ? ub[i] : INFINITY; int bi = -1; v3 cp = mk3(0, 0, 0);
+    if (E.tri) closest_query<true>(v, E.pad, ld(q3, i), -1, best, bi, cp);
+    else closest_query<false>(v, 0.0f, ld(q3, i), -1, best, bi, cp);
+    nodes[i] = (int32_t)(g_cnt_node - n0); prims[i] = (int32_t)(g_cnt_prim - p0);
   }
 }
 

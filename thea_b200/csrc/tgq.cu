@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -43,7 +44,7 @@ struct DevBuf
 struct Slot
 {
   cudaStream_t stream = nullptr;
-  DevBuf in[TGQ_MAX_ARGS], out[TGQ_MAX_ARGS], keys[2], vals[2], cubtmp;
+  DevBuf in[TGQ_MAX_ARGS], out[TGQ_MAX_ARGS], keys[2], vals[2], cubtmp, counter;
 };
 
 }  // namespace
@@ -61,7 +62,8 @@ struct tgq_handle
   DevBuf perm, pos_of_elem, first, last, split, parent, live, newidx;   // kept for refit
   DevBuf pbox_lo, pbox_hi, nbox_lo, nbox_hi, arrive, keys_a, keys_b, vals_a, cubtmp, src, src2, misc;
   DevBuf area_by_elem, cum;                                           // float[n] in element order; double[n] cumulative
-  DevBuf slabs, pnrm, nsum, sinfo, big, big_count;                    // pancake bounds (triangle structures)
+  DevBuf obbs, pnrm, nsum, obbinfo, big, big_count;                   // oriented boxes (triangle structures)
+  int sm_count = 148; std::map<std::pair<void const *, size_t>, int> occupancy;   // resident blocks per SM of the persistent kernels
   bool cum_valid = false;
   float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}; float pad = 0;
 
@@ -101,6 +103,7 @@ BvhView view_of(tgq_handle * h)
 {
   BvhView v;
   v.nodes = h->nodes.as<NodeRec>();
+  v.obbs = h->kind == TGQ_KIND_TRIANGLES ? h->obbs.as<ObbNode>() : nullptr;
   v.tris = h->kind == TGQ_KIND_TRIANGLES ? h->elems.as<TriRec>() : nullptr;
   v.pts = h->kind == TGQ_KIND_POINTS ? h->elems.as<f4>() : nullptr;
   v.nrm = (h->kind == TGQ_KIND_POINTS && h->has_normals) ? h->nrm.as<f4>() : nullptr;
@@ -156,25 +159,26 @@ int refit_and_emit(tgq_handle * h, cudaStream_t s)
     if (tri)
     {
       CK(cudaMemsetAsync(h->big_count.p, 0, 4, s));
-      k_slab_small<<<grid_for(n - 1), TGQ_BLOCK, 0, s>>>(n, h->leaf_built, h->first.as<int>(), h->last.as<int>(), h->parent.as<int>(),
-                                                         h->nbox_lo.as<f4>(), h->nbox_hi.as<f4>(), h->nsum.as<f4>(), h->elems.as<TriRec>(),
-                                                         h->scene.as<SceneBox>(), h->sinfo.as<f4>(), h->big.as<int>(), h->big_count.as<int>());
+      k_obb_small<<<grid_for(n - 1), TGQ_BLOCK, 0, s>>>(n, h->leaf_built, h->first.as<int>(), h->last.as<int>(), h->parent.as<int>(),
+                                                        h->nsum.as<f4>(), h->elems.as<TriRec>(), h->scene.as<SceneBox>(), h->obbinfo.as<f4>(),
+                                                        h->big.as<int>(), h->big_count.as<int>());
       int big_grid = std::max(1, std::min(n / TGQ_SLAB_SMALL + 1, 148 * 64));
-      k_slab_big<<<big_grid, 128, 0, s>>>(h->big.as<int>(), h->big_count.as<int>(), h->first.as<int>(), h->last.as<int>(), h->nbox_lo.as<f4>(),
-                                          h->nbox_hi.as<f4>(), h->nsum.as<f4>(), h->elems.as<TriRec>(), h->scene.as<SceneBox>(), h->sinfo.as<f4>());
+      k_obb_big<<<big_grid, 128, 0, s>>>(h->big.as<int>(), h->big_count.as<int>(), h->first.as<int>(), h->last.as<int>(), h->nsum.as<f4>(),
+                                         h->elems.as<TriRec>(), h->scene.as<SceneBox>(), h->obbinfo.as<f4>());
       h->st.total_launches += 2;
     }
     k_emit<<<grid_for(n - 1), TGQ_BLOCK, 0, s>>>(n, h->leaf_built, h->first.as<int>(), h->last.as<int>(), h->split.as<int>(),
                                                  h->live.as<int>(), h->newidx.as<int>(), h->pbox_lo.as<f4>(), h->pbox_hi.as<f4>(),
                                                  h->nbox_lo.as<f4>(), h->nbox_hi.as<f4>(), h->scene.as<SceneBox>(), h->nodes.as<NodeRec>(),
-                                                 tri ? h->elems.as<TriRec>() : nullptr, tri ? h->sinfo.as<f4>() : nullptr,
-                                                 tri ? h->slabs.as<SlabRec>() : nullptr);
+                                                 tri ? h->elems.as<TriRec>() : nullptr, tri ? h->obbinfo.as<f4>() : nullptr,
+                                                 tri ? h->obbs.as<ObbNode>() : nullptr);
     h->st.total_launches += 2;
   }
   else if (n == 1)
   {
+    bool tri = h->kind == TGQ_KIND_TRIANGLES;
     k_emit_single<<<1, 1, 0, s>>>(h->pbox_lo.as<f4>(), h->pbox_hi.as<f4>(), h->scene.as<SceneBox>(), h->nodes.as<NodeRec>(),
-                                  h->kind == TGQ_KIND_TRIANGLES ? h->slabs.as<SlabRec>() : nullptr);
+                                  tri ? h->elems.as<TriRec>() : nullptr, tri ? h->obbs.as<ObbNode>() : nullptr);
     h->st.total_launches += 1;
   }
   CK(cudaGetLastError());
@@ -268,7 +272,7 @@ int build_common(tgq_handle * h, int kind, float const * d_src, float const * d_
     CK(h->first.reserve(4 * ni)); CK(h->last.reserve(4 * ni)); CK(h->split.reserve(4 * ni)); CK(h->parent.reserve(4 * (2 * nn)));
     CK(h->live.reserve(4 * ni)); CK(h->newidx.reserve(4 * ni)); CK(h->arrive.reserve(4 * ni));
     CK(h->nbox_lo.reserve(16 * ni)); CK(h->nbox_hi.reserve(16 * ni)); CK(h->nsum.reserve(16 * ni));
-    if (kind == TGQ_KIND_TRIANGLES) { CK(h->sinfo.reserve(32 * ni)); CK(h->big.reserve(4 * ni)); CK(h->big_count.reserve(4)); }
+    if (kind == TGQ_KIND_TRIANGLES) { CK(h->obbinfo.reserve(64 * ni)); CK(h->big.reserve(4 * ni)); CK(h->big_count.reserve(4)); }
     k_hierarchy<<<grid_for(n - 1), TGQ_BLOCK, 0, s>>>(h->keys_b.as<uint64_t>(), n, h->first.as<int>(), h->last.as<int>(), h->split.as<int>(),
                                                       h->parent.as<int>());
     k_live<<<grid_for(n - 1), TGQ_BLOCK, 0, s>>>(n, h->leaf_built, h->first.as<int>(), h->last.as<int>(), h->live.as<int>());
@@ -287,14 +291,14 @@ int build_common(tgq_handle * h, int kind, float const * d_src, float const * d_
   else h->n_nodes = 1;
 
   CK(h->nodes.reserve(sizeof(NodeRec) * (size_t)h->n_nodes));
-  if (kind == TGQ_KIND_TRIANGLES) CK(h->slabs.reserve(sizeof(SlabRec) * (size_t)h->n_nodes));
+  if (kind == TGQ_KIND_TRIANGLES) CK(h->obbs.reserve(sizeof(ObbNode) * (size_t)h->n_nodes));
   CKRC(refit_and_emit(h, s));
   CK(cudaEventRecord(e1, s));
   CKRC(fetch_scene(h, s));
   float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
   h->st.last_build_ms = ms;
   h->st.num_nodes = h->n_nodes;
-  h->st.node_bytes = (int64_t)(sizeof(NodeRec) + (kind == TGQ_KIND_TRIANGLES ? sizeof(SlabRec) : 0)) * h->n_nodes; h->st.element_bytes = (int64_t)(rec * nn);
+  h->st.node_bytes = (int64_t)(sizeof(NodeRec) + (kind == TGQ_KIND_TRIANGLES ? sizeof(ObbNode) : 0)) * h->n_nodes; h->st.element_bytes = (int64_t)(rec * nn);
   return TGQ_OK;
 }
 
@@ -391,6 +395,25 @@ int run_batched(tgq_handle * h, int64_t Q, Arg * args, int nargs, bool sortable,
   return TGQ_OK;
 }
 
+// Grid of a persistent kernel: enough blocks to fill the device (resident blocks per SM x SMs), fewer for small batches.
+// Also zeroes the chunk counter the kernel's warps draw work from.
+template <typename K>
+int persistent_grid(tgq_handle * h, K kernel, size_t smem, int64_t n, int * counter, cudaStream_t s, int * grid_out)
+{
+  auto key = std::make_pair((void const *)kernel, smem);
+  auto it = h->occupancy.find(key);
+  if (it == h->occupancy.end())
+  {
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TGQ_BLOCK, smem));
+    it = h->occupancy.insert(std::make_pair(key, std::max(1, per_sm))).first;
+  }
+  int64_t want = (n + (int64_t)TGQ_CHUNK * (TGQ_BLOCK / 32) - 1) / ((int64_t)TGQ_CHUNK * (TGQ_BLOCK / 32));
+  *grid_out = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)it->second * h->sm_count));
+  CK(cudaMemsetAsync(counter, 0, sizeof(int), s));
+  return TGQ_OK;
+}
+
 int need_built(tgq_handle * h, int kind_mask)
 {
   if (!h) return TGQ_EINVAL;
@@ -439,7 +462,11 @@ int tgq_create(int device, tgq_handle ** out)
   if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
   h->stream = h->own_stream;
   for (int s = 0; s < 2; ++s)
+  {
     if ((e = cudaStreamCreateWithFlags(&h->slot[s].stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = h->slot[s].counter.reserve(sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+  }
+  if ((e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return bail("cudaDeviceGetAttribute", e);
   int const smem = 2 * TGQ_MAX_K * TGQ_BLOCK * 4;
   if ((e = cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute(k_knn)", e);
   if ((e = cudaFuncSetAttribute(k_ball_graph, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute(k_ball_graph)", e);
@@ -455,13 +482,13 @@ int tgq_destroy(tgq_handle * h)
   cudaDeviceSynchronize();
   DevBuf * bufs[] = {&h->nodes, &h->elems, &h->nrm, &h->scene, &h->perm, &h->pos_of_elem, &h->first, &h->last, &h->split, &h->parent, &h->live,
                      &h->newidx, &h->pbox_lo, &h->pbox_hi, &h->nbox_lo, &h->nbox_hi, &h->arrive, &h->keys_a, &h->keys_b, &h->vals_a,
-                     &h->cubtmp, &h->src, &h->src2, &h->misc, &h->area_by_elem, &h->cum, &h->slabs, &h->pnrm, &h->nsum, &h->sinfo, &h->big, &h->big_count};
+                     &h->cubtmp, &h->src, &h->src2, &h->misc, &h->area_by_elem, &h->cum, &h->obbs, &h->pnrm, &h->nsum, &h->obbinfo, &h->big, &h->big_count};
   for (DevBuf * b : bufs) b->release();
   for (int s = 0; s < 2; ++s)
   {
     Slot & sl = h->slot[s];
     for (int a = 0; a < TGQ_MAX_ARGS; ++a) { sl.in[a].release(); sl.out[a].release(); }
-    sl.keys[0].release(); sl.keys[1].release(); sl.vals[0].release(); sl.vals[1].release(); sl.cubtmp.release();
+    sl.keys[0].release(); sl.keys[1].release(); sl.vals[0].release(); sl.vals[1].release(); sl.cubtmp.release(); sl.counter.release();
     if (sl.stream) cudaStreamDestroy(sl.stream);
   }
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -593,11 +620,20 @@ int tgq_closest(tgq_handle * h, const float * q3, int64_t Q, double dist_bound, 
   float ub = bound_to_ub(dist_bound);
   Arg args[4] = {{q3, nullptr, 12}, {nullptr, idx, 4}, {nullptr, d2, 4}, {nullptr, cp3, 12}};
   BvhView v = view_of(h); bool tri = h->kind == TGQ_KIND_TRIANGLES;
-  return run_batched(h, Q, args, 4, true, [&](ChunkCtx & c) {
-    if (tri) k_closest<true, true><<<grid_for(c.n), TGQ_BLOCK, 0, c.stream>>>(v, h->slabs.as<SlabRec>(), h->pad, (float const *)c.din[0], c.perm, c.n, ub,
-                                                                              exclude_self, c.offset, (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3]);
-    else k_closest<false, false><<<grid_for(c.n), TGQ_BLOCK, 0, c.stream>>>(v, nullptr, 0.0f, (float const *)c.din[0], c.perm, c.n, ub, exclude_self,
-                                                                            c.offset, (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3]);
+  return run_batched(h, Q, args, 4, true, [&](ChunkCtx & c) -> int {
+    int grid = 0; int * cnt = c.slot->counter.as<int>();
+    if (tri)
+    {
+      CKRC(persistent_grid(h, k_closest<true>, 0, c.n, cnt, c.stream, &grid));
+      k_closest<true><<<grid, TGQ_BLOCK, 0, c.stream>>>(v, h->pad, (float const *)c.din[0], c.perm, c.n, ub, exclude_self, c.offset, cnt,
+                                                      (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3]);
+    }
+    else
+    {
+      CKRC(persistent_grid(h, k_closest<false>, 0, c.n, cnt, c.stream, &grid));
+      k_closest<false><<<grid, TGQ_BLOCK, 0, c.stream>>>(v, 0.0f, (float const *)c.din[0], c.perm, c.n, ub, exclude_self, c.offset, cnt,
+                                                       (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3]);
+    }
     h->st.last_launches += 1; h->st.total_launches += 1;
     return TGQ_OK;
   });
@@ -613,9 +649,11 @@ int tgq_knn(tgq_handle * h, const float * q3, int64_t Q, int32_t k, double dist_
   Arg args[3] = {{q3, nullptr, 12}, {nullptr, idx, 4 * (size_t)k}, {nullptr, d2, 4 * (size_t)k}};
   BvhView v = view_of(h);
   size_t smem = 2 * (size_t)k * TGQ_BLOCK * 4;
-  return run_batched(h, Q, args, 3, true, [&](ChunkCtx & c) {
-    k_knn<<<grid_for(c.n), TGQ_BLOCK, smem, c.stream>>>(v, (float const *)c.din[0], c.perm, c.n, k, ub, exclude_self, c.offset, (int *)c.dout[1],
-                                                        (float *)c.dout[2]);
+  return run_batched(h, Q, args, 3, true, [&](ChunkCtx & c) -> int {
+    int grid = 0; int * cnt = c.slot->counter.as<int>();
+    CKRC(persistent_grid(h, k_knn, smem, c.n, cnt, c.stream, &grid));
+    k_knn<<<grid, TGQ_BLOCK, smem, c.stream>>>(v, (float const *)c.din[0], c.perm, c.n, k, ub, exclude_self, c.offset, cnt, (int *)c.dout[1],
+                                               (float *)c.dout[2]);
     h->st.last_launches += 1; h->st.total_launches += 1;
     return TGQ_OK;
   });
@@ -637,7 +675,9 @@ int tgq_ball_graph(tgq_handle * h, int32_t max_degree, float init_radius, int32_
   int * dc = count ? (is_device_ptr(count) ? count : h->slot[0].out[2].as<int>()) : nullptr;
   cudaEvent_t e0 = get_event(h), e1 = get_event(h);
   CK(cudaEventRecord(e0, s));
-  k_ball_graph<<<grid_for(h->n), TGQ_BLOCK, 2 * k * TGQ_BLOCK * 4, s>>>(view_of(h), h->n, max_degree, init_radius, rounds, min_dot, min_degree, di, ds, dc);
+  int grid = 0; int * cnt = h->slot[0].counter.as<int>();
+  CKRC(persistent_grid(h, k_ball_graph, 2 * k * TGQ_BLOCK * 4, h->n, cnt, s, &grid));
+  k_ball_graph<<<grid, TGQ_BLOCK, 2 * k * TGQ_BLOCK * 4, s>>>(view_of(h), h->n, max_degree, init_radius, rounds, min_dot, min_degree, cnt, di, ds, dc);
   CK(cudaGetLastError());
   CK(cudaEventRecord(e1, s));
   h->st.last_launches += 1; h->st.total_launches += 1;
@@ -682,11 +722,20 @@ static int ray_common(tgq_handle * h, const float * o3, const float * d3, const 
   Guard g(h);
   BvhView v = view_of(h);
   Arg args[7] = {{o3, nullptr, 12}, {d3, nullptr, 12}, {tmax, nullptr, 4}, {nullptr, t, 4}, {nullptr, idx, 4}, {nullptr, normal3, 12}, {nullptr, hit, 1}};
-  return run_batched(h, R, args, 7, true, [&](ChunkCtx & c) {
-    if (any) k_ray<true><<<grid_for(c.n), TGQ_BLOCK, 0, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], (float const *)c.din[2], c.perm,
-                                                                   c.n, (float *)c.dout[3], (int *)c.dout[4], (float *)c.dout[5], (uint8_t *)c.dout[6]);
-    else k_ray<false><<<grid_for(c.n), TGQ_BLOCK, 0, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], (float const *)c.din[2], c.perm,
-                                                                c.n, (float *)c.dout[3], (int *)c.dout[4], (float *)c.dout[5], (uint8_t *)c.dout[6]);
+  return run_batched(h, R, args, 7, true, [&](ChunkCtx & c) -> int {
+    int grid = 0; int * cnt = c.slot->counter.as<int>();
+    if (any)
+    {
+      CKRC(persistent_grid(h, k_ray<true>, 0, c.n, cnt, c.stream, &grid));
+      k_ray<true><<<grid, TGQ_BLOCK, 0, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], (float const *)c.din[2], c.perm, c.n, cnt,
+                                                    (float *)c.dout[3], (int *)c.dout[4], (float *)c.dout[5], (uint8_t *)c.dout[6]);
+    }
+    else
+    {
+      CKRC(persistent_grid(h, k_ray<false>, 0, c.n, cnt, c.stream, &grid));
+      k_ray<false><<<grid, TGQ_BLOCK, 0, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], (float const *)c.din[2], c.perm, c.n, cnt,
+                                                     (float *)c.dout[3], (int *)c.dout[4], (float *)c.dout[5], (uint8_t *)c.dout[6]);
+    }
     h->st.last_launches += 1; h->st.total_launches += 1;
     return TGQ_OK;
   });
@@ -707,13 +756,15 @@ int tgq_sdf(tgq_handle * h, const float * p3, const float * n3, int64_t S, float
   BvhView v = view_of(h);
   // per-sample arrays; the 30 rays of a sample stay together so the epilogue is one thread per sample
   Arg args[5] = {{p3, nullptr, 12}, {n3, nullptr, 12}, {nullptr, sdf, 8}, {nullptr, ray_t, 120}, {nullptr, ray_idx, 120}};
-  return run_batched(h, S, args, 5, false, [&](ChunkCtx & c) {
+  return run_batched(h, S, args, 5, false, [&](ChunkCtx & c) -> int {
     Slot & sl = *c.slot; size_t nr = 30 * (size_t)c.n;
     CK(sl.keys[0].reserve(4 * nr)); CK(sl.keys[1].reserve(nr));
     float * dt = c.dout[3] ? (float *)c.dout[3] : sl.keys[0].as<float>();
     uint8_t * dv = sl.keys[1].as<uint8_t>();
-    k_sdf_rays<<<grid_for((int64_t)nr), TGQ_BLOCK, 0, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], (int64_t)nr, scale,
-                                                                 only_hit_interior, dt, (int *)c.dout[4], dv);
+    int grid = 0; int * cnt = sl.counter.as<int>();
+    CKRC(persistent_grid(h, k_sdf_rays, 0, (int64_t)nr, cnt, c.stream, &grid));
+    k_sdf_rays<<<grid, TGQ_BLOCK, 0, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], (int)nr, scale, only_hit_interior, cnt, dt,
+                                                 (int *)c.dout[4], dv);
     if (c.dout[2]) k_sdf_stats<<<grid_for(c.n), TGQ_BLOCK, 0, c.stream>>>(dt, dv, c.n, scale, (double *)c.dout[2]);
     h->st.last_launches += c.dout[2] ? 2 : 1; h->st.total_launches += c.dout[2] ? 2 : 1;
     return TGQ_OK;

@@ -9,7 +9,9 @@
 //        q2 = (c1.lo.z, c1.hi.x, c1.hi.y, c1.hi.z)   q3 = (child0, child1, count0, count1) as int bits
 //        child >= 0: index of an inner node; child < 0: leaf holding elements [~child, ~child + count) of the
 //        Morton-ordered element array.
-//   Tri   (64 B)  : q0 = (v0, orig_index)  q1 = (v1, axis)  q2 = (v2, plane d)  q3 = (unit normal, area)
+//   Obb   (128 B) : triangle structures only, same index as Node: per child (centre, h0) (axis0, h1) (axis1, h2)
+//        (axis2, child link); read by closest-point queries INSTEAD of Node (rays, k-NN and ball queries read Node).
+//   Tri   (64 B)  : q0 = (v0, orig_index)  q1 = (v1, axis)  q2 = (v2, plane d)  q3 = (unit normal, screening radius about the centroid)
 //        (ray queries read q0..q2 = 48 B, closest-point queries all 64 B)
 //   Point (16 B)  : (x, y, z, orig_index); optional normals (16 B) in a parallel array.
 #pragma once
@@ -20,6 +22,7 @@ namespace tgq {
 
 struct NodeRec { f4 q0, q1, q2, q3; };
 struct TriRec  { f4 q0, q1, q2, q3; };
+struct ObbNode { f4 q[8]; };     // oriented boxes of both children, see tgq_traverse.cuh
 
 // ---- Morton codes: 21 bits per axis, 63-bit keys --------------------------------------------------------------------
 TGQ_HD uint64_t expand21(uint64_t v)

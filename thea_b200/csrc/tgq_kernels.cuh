@@ -154,36 +154,21 @@ __global__ void k_live(int n, int leaf, int const * __restrict__ first, int cons
   live[i] = (i == 0 || (last[i] - first[i] + 1) > leaf) ? 1 : 0;
 }
 
-// ---- pancake statistics of every radix-tree node that a surviving node references as a child -------------------------------
-// sinfo[2x] = (dir.xyz, smin), sinfo[2x+1] = (smax, R, 0, 0) for inner node x, about the centre of x's padded box.
-struct SlabAcc { v3 dir, c; float mn, mx, r2; };
-
-__device__ __forceinline__ SlabAcc slab_begin(f4 ns, f4 blo, f4 bhi, float pad)
-{
-  SlabAcc a;
-  a.dir = normalized3(mk3(ns.x, ns.y, ns.z));
-  if (!(sqn3(a.dir) > 0.5f)) a.dir = mk3(0.0f, 0.0f, 0.0f);          // cancelled normals (closed surface): no usable slab
-  a.c = box_centre(mk3(blo.x - pad, blo.y - pad, blo.z - pad), mk3(bhi.x + pad, bhi.y + pad, bhi.z + pad));
-  a.mn = FLT_MAX; a.mx = -FLT_MAX; a.r2 = 0.0f;
-  return a;
-}
-__device__ __forceinline__ void slab_add_tri(SlabAcc & a, TriRec const * tris, int k)
+// ---- oriented boxes of every radix-tree node that a surviving node references as a child --------------------------------
+// obbinfo[4x .. 4x+3] = child half of an ObbNode (without the link) for inner radix node x, extents taken over all vertices of
+// the node's triangles along the frame derived from the node's normal sum (obb_frame).
+__device__ __forceinline__ void obb_add_tri(ObbAcc & a, TriRec const * tris, int k)
 {
   f4 const * t = (f4 const *)(tris + k);
   f4 q0 = __ldg(t), q1 = __ldg(t + 1), q2 = __ldg(t + 2);
-  slab_accumulate(a.dir, a.c, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), mk3(q2.x, q2.y, q2.z), a.mn, a.mx, a.r2);
-}
-__device__ __forceinline__ void slab_store(SlabAcc const & a, float pad, f4 * sinfo, int x)
-{
-  sinfo[2 * x] = make_float4(a.dir.x, a.dir.y, a.dir.z, a.mn - 2.0f * pad);
-  sinfo[2 * x + 1] = make_float4(a.mx + 2.0f * pad, slab_radius(a.r2, pad), 0.0f, 0.0f);
+  obb_acc_point(a, mk3(q0.x, q0.y, q0.z)); obb_acc_point(a, mk3(q1.x, q1.y, q1.z)); obb_acc_point(a, mk3(q2.x, q2.y, q2.z));
 }
 
 #define TGQ_SLAB_SMALL 32
 // Nodes of up to TGQ_SLAB_SMALL elements: one thread scans the node's element range; larger nodes are appended to `big`.
-__global__ void k_slab_small(int n, int leaf, int const * __restrict__ first, int const * __restrict__ last, int const * __restrict__ parent,
-                             f4 const * __restrict__ nbox_lo, f4 const * __restrict__ nbox_hi, f4 const * __restrict__ nsum,
-                             TriRec const * __restrict__ tris, SceneBox const * sb, f4 * sinfo, int * big, int * big_count)
+__global__ void k_obb_small(int n, int leaf, int const * __restrict__ first, int const * __restrict__ last, int const * __restrict__ parent,
+                            f4 const * __restrict__ nsum, TriRec const * __restrict__ tris, SceneBox const * sb, f4 * obbinfo, int * big,
+                            int * big_count)
 {
   int x = blockIdx.x * blockDim.x + threadIdx.x; if (x >= n - 1 || x == 0) return;
   int pa = parent[x];
@@ -192,47 +177,49 @@ __global__ void k_slab_small(int n, int leaf, int const * __restrict__ first, in
   int f = first[x], l = last[x];
   if (l - f + 1 > TGQ_SLAB_SMALL) { big[atomicAdd(big_count, 1)] = x; return; }
   float pad = scene_decode(sb).pad;
-  SlabAcc a = slab_begin(nsum[x], nbox_lo[x], nbox_hi[x], pad);
-  for (int k = f; k <= l; ++k) slab_add_tri(a, tris, k);
-  slab_store(a, pad, sinfo, x);
+  f4 ns = nsum[x];
+  ObbAcc a; obb_acc_begin(a, mk3(ns.x, ns.y, ns.z));
+  for (int k = f; k <= l; ++k) obb_add_tri(a, tris, k);
+  obb_acc_store(a, pad, 0, obbinfo + 4 * (size_t)x);
 }
 
 // Larger nodes: one thread block per node, block-wide min / max reduction (exact, order independent).
 __global__ void __launch_bounds__(128)
-k_slab_big(int const * __restrict__ big, int const * __restrict__ big_count, int const * __restrict__ first, int const * __restrict__ last,
-           f4 const * __restrict__ nbox_lo, f4 const * __restrict__ nbox_hi, f4 const * __restrict__ nsum, TriRec const * __restrict__ tris,
-           SceneBox const * sb, f4 * sinfo)
+k_obb_big(int const * __restrict__ big, int const * __restrict__ big_count, int const * __restrict__ first, int const * __restrict__ last,
+          f4 const * __restrict__ nsum, TriRec const * __restrict__ tris, SceneBox const * sb, f4 * obbinfo)
 {
-  __shared__ float s_mn[4], s_mx[4], s_r2[4];
+  __shared__ float s_mn[4][3], s_mx[4][3];
   for (int w = blockIdx.x; w < *big_count; w += gridDim.x)
   {
     int x = big[w];
     float pad = scene_decode(sb).pad;
-    SlabAcc a = slab_begin(nsum[x], nbox_lo[x], nbox_hi[x], pad);
-    for (int k = first[x] + threadIdx.x; k <= last[x]; k += blockDim.x) slab_add_tri(a, tris, k);
-    for (int o = 16; o > 0; o >>= 1)
-    {
-      a.mn = fminf(a.mn, __shfl_xor_sync(0xffffffffu, a.mn, o)); a.mx = fmaxf(a.mx, __shfl_xor_sync(0xffffffffu, a.mx, o));
-      a.r2 = fmaxf(a.r2, __shfl_xor_sync(0xffffffffu, a.r2, o));
-    }
+    f4 ns = nsum[x];
+    ObbAcc a; obb_acc_begin(a, mk3(ns.x, ns.y, ns.z));
+    for (int k = first[x] + threadIdx.x; k <= last[x]; k += blockDim.x) obb_add_tri(a, tris, k);
+    for (int j = 0; j < 3; ++j)
+      for (int o = 16; o > 0; o >>= 1)
+      { a.mn[j] = fminf(a.mn[j], __shfl_xor_sync(0xffffffffu, a.mn[j], o)); a.mx[j] = fmaxf(a.mx[j], __shfl_xor_sync(0xffffffffu, a.mx[j], o)); }
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = a.mn; s_mx[threadIdx.x >> 5] = a.mx; s_r2[threadIdx.x >> 5] = a.r2; }
+    if ((threadIdx.x & 31) == 0) for (int j = 0; j < 3; ++j) { s_mn[threadIdx.x >> 5][j] = a.mn[j]; s_mx[threadIdx.x >> 5][j] = a.mx[j]; }
     __syncthreads();
     if (threadIdx.x == 0)
     {
-      for (int j = 1; j < 4; ++j) { s_mn[0] = fminf(s_mn[0], s_mn[j]); s_mx[0] = fmaxf(s_mx[0], s_mx[j]); s_r2[0] = fmaxf(s_r2[0], s_r2[j]); }
-      a.mn = s_mn[0]; a.mx = s_mx[0]; a.r2 = s_r2[0];
-      slab_store(a, pad, sinfo, x);
+      for (int j = 0; j < 3; ++j)
+      {
+        a.mn[j] = fminf(fminf(s_mn[0][j], s_mn[1][j]), fminf(s_mn[2][j], s_mn[3][j]));
+        a.mx[j] = fmaxf(fmaxf(s_mx[0][j], s_mx[1][j]), fmaxf(s_mx[2][j], s_mx[3][j]));
+      }
+      obb_acc_store(a, pad, 0, obbinfo + 4 * (size_t)x);
     }
   }
 }
 
-// Emits the 64-byte traversal node (and, for triangle structures, the 48-byte slab record) of every surviving inner node
-// at its compacted index.
+// Emits the 64-byte traversal node (and, for triangle structures, the 128-byte oriented-box node) of every surviving inner
+// node at its compacted index.
 __global__ void k_emit(int n, int leaf, int const * __restrict__ first, int const * __restrict__ last, int const * __restrict__ split,
                        int const * __restrict__ live, int const * __restrict__ newidx, f4 const * __restrict__ pbox_lo,
                        f4 const * __restrict__ pbox_hi, f4 const * __restrict__ nbox_lo, f4 const * __restrict__ nbox_hi,
-                       SceneBox const * sb, NodeRec * nodes, TriRec const * __restrict__ tris, f4 const * __restrict__ sinfo, SlabRec * slabs)
+                       SceneBox const * sb, NodeRec * nodes, TriRec const * __restrict__ tris, f4 const * __restrict__ obbinfo, ObbNode * obbs)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n - 1 || !live[i]) return;
   float pad = scene_decode(sb).pad;
@@ -249,44 +236,53 @@ __global__ void k_emit(int n, int leaf, int const * __restrict__ first, int cons
     lo[c] = mk3(blo.x - pad, blo.y - pad, blo.z - pad); hi[c] = mk3(bhi.x + pad, bhi.y + pad, bhi.z + pad);
   }
   nodes[newidx[i]] = make_node(lo[0], hi[0], lo[1], hi[1], child[0], child[1], 0, 0);
-  if (slabs)
+  if (obbs)
   {
-    f4 sa[2], sb2[2];
+    ObbNode r;
     for (int c = 0; c < 2; ++c)
     {
       int cf = c == 0 ? f : sp + 1, cl = c == 0 ? sp : l;
       int inner = c == 0 ? sp : sp + 1;
       if (cl == cf)
       {
-        // single triangle: its own plane and its radius about the box centre
+        // single triangle: box along its own normal
         f4 const * t = (f4 const *)(tris + cf);
         f4 q0 = __ldg(t), q1 = __ldg(t + 1), q2 = __ldg(t + 2);
         v3 v0 = mk3(q0.x, q0.y, q0.z), v1 = mk3(q1.x, q1.y, q1.z), v2 = mk3(q2.x, q2.y, q2.z);
-        v3 cr = cross3(sub3(v1, v0), sub3(v2, v0));
-        SlabAcc a = slab_begin(make_float4(cr.x, cr.y, cr.z, 0.0f), pbox_lo[cf], pbox_hi[cf], pad);
-        slab_accumulate(a.dir, a.c, v0, v1, v2, a.mn, a.mx, a.r2);
-        sa[c] = make_float4(a.dir.x, a.dir.y, a.dir.z, a.mn - 2.0f * pad);
-        sb2[c] = make_float4(a.mx + 2.0f * pad, slab_radius(a.r2, pad), 0.0f, 0.0f);
+        ObbAcc a; obb_acc_begin(a, cross3(sub3(v1, v0), sub3(v2, v0)));
+        obb_acc_point(a, v0); obb_acc_point(a, v1); obb_acc_point(a, v2);
+        obb_acc_store(a, pad, child[c], r.q + 4 * c);
       }
-      else { sa[c] = sinfo[2 * inner]; sb2[c] = sinfo[2 * inner + 1]; }
+      else
+      {
+        for (int j = 0; j < 4; ++j) r.q[4 * c + j] = obbinfo[4 * (size_t)inner + j];
+        r.q[4 * c + 3].w = __int_as_float(child[c]);
+      }
     }
-    SlabRec r;
-    r.a = make_float4(sa[0].x, sa[0].y, sa[0].z, sa[0].w);
-    r.b = make_float4(sb2[0].x, sa[1].x, sa[1].y, sa[1].z);
-    r.c = make_float4(sa[1].w, sb2[1].x, sb2[0].y, sb2[1].y);
-    slabs[newidx[i]] = r;
+    obbs[newidx[i]] = r;
   }
 }
 
-// Structure with a single element: one node whose second child is an empty leaf behind an inverted box.
-__global__ void k_emit_single(f4 const * pbox_lo, f4 const * pbox_hi, SceneBox const * sb, NodeRec * nodes, SlabRec * slabs)
+// Structure with a single element: one node whose second child is an empty leaf behind an unreachable box.
+__global__ void k_emit_single(f4 const * pbox_lo, f4 const * pbox_hi, SceneBox const * sb, NodeRec * nodes, TriRec const * tris, ObbNode * obbs)
 {
   float pad = scene_decode(sb).pad;
-  if (slabs)   // no usable direction: zero dir, unbounded slab, unbounded radius => the pancake bound is 0
-  { SlabRec r; r.a = make_float4(0, 0, 0, -FLT_MAX); r.b = make_float4(FLT_MAX, 0, 0, 0); r.c = make_float4(-FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX); slabs[0] = r; }
+  int leaf0 = ~((0 << TGQ_LEAF_BITS) | 1);
+  if (obbs)
+  {
+    ObbNode r;
+    f4 const * t = (f4 const *)tris;
+    f4 q0 = t[0], q1 = t[1], q2 = t[2];
+    v3 v0 = mk3(q0.x, q0.y, q0.z), v1 = mk3(q1.x, q1.y, q1.z), v2 = mk3(q2.x, q2.y, q2.z);
+    ObbAcc a; obb_acc_begin(a, cross3(sub3(v1, v0), sub3(v2, v0)));
+    obb_acc_point(a, v0); obb_acc_point(a, v1); obb_acc_point(a, v2);
+    obb_acc_store(a, pad, leaf0, r.q);
+    obb_store_empty(~0, r.q + 4);
+    obbs[0] = r;
+  }
   f4 blo = pbox_lo[0], bhi = pbox_hi[0];
   nodes[0] = make_node(mk3(blo.x - pad, blo.y - pad, blo.z - pad), mk3(bhi.x + pad, bhi.y + pad, bhi.z + pad),
-                       mk3(FLT_MAX, FLT_MAX, FLT_MAX), mk3(-FLT_MAX, -FLT_MAX, -FLT_MAX), ~((0 << TGQ_LEAF_BITS) | 1), ~0, 0, 0);
+                       mk3(FLT_MAX, FLT_MAX, FLT_MAX), mk3(-FLT_MAX, -FLT_MAX, -FLT_MAX), leaf0, ~0, 0, 0);
 }
 
 // Element-order copy of the triangle cache (for tgq_triangle_cache and hit normals).
@@ -313,82 +309,209 @@ __global__ void k_query_codes(float const * __restrict__ q3, int n, SceneBox con
   keys[i] = morton30(ld3(q3, i), lo, inv); vals[i] = (uint32_t)i;
 }
 
-// ---- K5 closest element -------------------------------------------------------------------------------------------------
-template <bool TRI, bool SLAB>
-__global__ void __launch_bounds__(TGQ_BLOCK)
-k_closest(BvhView b, SlabRec const * __restrict__ slabs, float scene_pad, float const * __restrict__ q3, uint32_t const * __restrict__ perm,
-          int n, float bound_ub, int exclude_self, int64_t self_offset, int * idx, float * d2, float * cp3)
+// ---- persistent warp scheduler -------------------------------------------------------------------------------------------
+// Query costs are heavy tailed and lanes follow different paths, so a thread-per-query kernel leaves most lanes of a warp
+// idle (ncu: 1.2 - 10 active threads per instruction on the bench workload).  Instead every warp drives 32 resumable
+// state machines (tgq_traverse.cuh) from a warp-uniform loop: in each iteration the lanes that have an inner node pending
+// take one node step and / or the lanes that have leaf elements pending take one leaf step (whichever group is larger, or
+// both when both are large), so the lanes reconverge after every step; lanes whose query finished write their result and
+// are refilled from the warp's current chunk of the (Morton-ordered) batch.  Chunks are handed out through one atomic
+// counter, which also balances the load across SMs.
+//   W: int state() ; void begin(int t) ; void node_step() ; void leaf_step() ; void finish()  [finish leaves the lane
+//   in TGQ_ST_IDLE, or restarts it]
+#define TGQ_CHUNK 64
+#define TGQ_BOTH 12      // a group of at least this many lanes is stepped even when it is the smaller one
+
+template <typename W>
+__device__ __forceinline__ void warp_run(W & w, int n, int * counter)
 {
-  int t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= n) return;
-  int64_t i = perm ? perm[t] : t;
-  v3 p = ld3(q3, i);
-  float best = bound_ub; int bi = -1; v3 cp = mk3(0.0f, 0.0f, 0.0f);
-  closest_query<TRI, SLAB>(b, slabs, scene_pad, p, exclude_self ? (int)(self_offset + i) : -1, best, bi, cp);
-  if (idx) idx[i] = bi;
-  if (d2) d2[i] = bi >= 0 ? best : -1.0f;
-  if (cp3) st3(cp3, i, cp);
+  unsigned const FULL = 0xffffffffu;
+  int lane = threadIdx.x & 31;
+  int chunk_next = 0, chunk_end = 0; bool exhausted = false;
+  for (;;)
+  {
+    if (w.state() == TGQ_ST_DONE) w.finish();
+    unsigned idle = __ballot_sync(FULL, w.state() == TGQ_ST_IDLE);
+    if (idle != 0u && !exhausted)
+    {
+      if (chunk_next >= chunk_end)
+      {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(counter, TGQ_CHUNK);
+        base = __shfl_sync(FULL, base, 0);
+        chunk_next = base; chunk_end = min(base + TGQ_CHUNK, n);
+        if (base >= n) exhausted = true;
+      }
+      if (!exhausted)
+      {
+        int t = chunk_next + __popc(idle & ((1u << lane) - 1u));
+        if (w.state() == TGQ_ST_IDLE && t < chunk_end) w.begin(t);
+        chunk_next = min(chunk_next + __popc(idle), chunk_end);
+      }
+    }
+    int st = w.state();
+    unsigned mi = __ballot_sync(FULL, st >= 0), ml = __ballot_sync(FULL, st == TGQ_ST_LEAF);
+    if ((mi | ml) == 0u)
+    {
+      if (exhausted && __all_sync(FULL, w.state() != TGQ_ST_DONE)) break;
+      continue;
+    }
+    int ni = __popc(mi), nl = __popc(ml);
+    if ((ni >= nl || ni >= TGQ_BOTH) && st >= 0) w.node_step();
+    if ((nl > ni || nl >= TGQ_BOTH) && st == TGQ_ST_LEAF) w.leaf_step();
+  }
+}
+
+// ---- K5 closest element -------------------------------------------------------------------------------------------------
+template <bool TRI>
+struct ClosestW
+{
+  ClosestState<TRI> s; BvhView b; float scene_pad; float const * q3; uint32_t const * perm; float ub; int exclude_self; int64_t self_offset;
+  int * idx; float * d2; float * cp3; int64_t qi;
+  __device__ __forceinline__ int state() const { return s.t.cur; }
+  __device__ __forceinline__ void begin(int t)
+  {
+    qi = perm ? perm[t] : t;
+    closest_begin(s, b, scene_pad, ld3(q3, qi), exclude_self ? (int)(self_offset + qi) : -1, ub);
+  }
+  __device__ __forceinline__ void node_step() { closest_node_step(s, b); }
+  __device__ __forceinline__ void leaf_step() { closest_leaf_step(s, b); }
+  __device__ __forceinline__ void finish()
+  {
+    if (idx) idx[qi] = s.best_idx;
+    if (d2) d2[qi] = s.best_idx >= 0 ? s.best_d2 : -1.0f;
+    if (cp3) st3(cp3, qi, s.best_cp);
+    s.t.cur = TGQ_ST_IDLE;
+  }
+};
+
+template <bool TRI>
+__global__ void __launch_bounds__(TGQ_BLOCK)
+k_closest(BvhView b, float scene_pad, float const * __restrict__ q3, uint32_t const * __restrict__ perm, int n, float bound_ub, int exclude_self,
+          int64_t self_offset, int * counter, int * idx, float * d2, float * cp3)
+{
+  ClosestW<TRI> w;
+  w.b = b; w.scene_pad = scene_pad; w.q3 = q3; w.perm = perm; w.ub = bound_ub; w.exclude_self = exclude_self; w.self_offset = self_offset;
+  w.idx = idx; w.d2 = d2; w.cp3 = cp3; w.qi = 0; w.s.t.cur = TGQ_ST_IDLE; TravStack st; trav_bind(w.s.t, st);
+  warp_run(w, n, counter);
 }
 
 // ---- K6 k nearest neighbours: one bounded sorted set per thread in shared memory -------------------------------------
+struct KnnW
+{
+  KnnState s; BvhView b; float const * q3; uint32_t const * perm; int k; float ub; int exclude_self; int64_t self_offset;
+  int * idx; float * d2; int64_t qi;
+  __device__ __forceinline__ int state() const { return s.t.cur; }
+  __device__ __forceinline__ void begin(int t)
+  {
+    qi = perm ? perm[t] : t;
+    knn_begin(s, b, ld3(q3, qi), exclude_self ? (int)(self_offset + qi) : -1, ub);
+  }
+  __device__ __forceinline__ void node_step() { knn_node_step(s, b); }
+  __device__ __forceinline__ void leaf_step() { knn_leaf_step(s, b); }
+  __device__ __forceinline__ void finish()
+  {
+    for (int j = 0; j < k; ++j)
+    {
+      bool v = j < s.set.n;
+      if (idx) idx[qi * k + j] = v ? s.set.idx[j * s.set.stride] : -1;
+      if (d2) d2[qi * k + j] = v ? s.set.key[j * s.set.stride] : -1.0f;
+    }
+    s.t.cur = TGQ_ST_IDLE;
+  }
+};
+
 __global__ void __launch_bounds__(TGQ_BLOCK)
 k_knn(BvhView b, float const * __restrict__ q3, uint32_t const * __restrict__ perm, int n, int k, float bound_ub, int exclude_self,
-      int64_t self_offset, int * idx, float * d2)
+      int64_t self_offset, int * counter, int * idx, float * d2)
 {
   extern __shared__ float smem[];
-  float * keys = smem + threadIdx.x; int * ids = (int *)(smem + (size_t)k * blockDim.x) + threadIdx.x;
-  int t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= n) return;
-  int64_t i = perm ? perm[t] : t;
-  SortedSet set; set.init(keys, ids, blockDim.x, k);
-  knn_query(b, ld3(q3, i), exclude_self ? (int)(self_offset + i) : -1, bound_ub, set);
-  for (int j = 0; j < k; ++j)
-  {
-    bool v = j < set.n;
-    if (idx) idx[i * k + j] = v ? ids[j * blockDim.x] : -1;
-    if (d2) d2[i * k + j] = v ? keys[j * blockDim.x] : -1.0f;
-  }
+  KnnW w;
+  w.b = b; w.q3 = q3; w.perm = perm; w.k = k; w.ub = bound_ub; w.exclude_self = exclude_self; w.self_offset = self_offset;
+  w.idx = idx; w.d2 = d2; w.qi = 0; w.s.t.cur = TGQ_ST_IDLE; TravStack st; trav_bind(w.s.t, st);
+  w.s.set.init(smem + threadIdx.x, (int *)(smem + (size_t)k * blockDim.x) + threadIdx.x, blockDim.x, k);
+  warp_run(w, n, counter);
 }
 
-// ---- K7 ball graph over the structure's own points (thread t handles the point at Morton position t) ------------------
+// ---- K7 ball graph over the structure's own points (query t is the point at Morton position t) ---------------------------
+struct BallW
+{
+  BallState s; BvhView b; int k; float init_radius; int rounds; float min_dot; int min_degree;
+  int * idx; float * sep; int * count; int64_t qi;
+  __device__ __forceinline__ int state() const { return s.t.cur; }
+  __device__ __forceinline__ void begin(int t)
+  {
+    f4 e = b.pts[t]; qi = __float_as_int(e.w);
+    bool has_n = b.nrm != nullptr;
+    v3 nc = mk3(0.0f, 0.0f, 0.0f);
+    if (has_n) { f4 q = b.nrm[t]; nc = mk3(q.x, q.y, q.z); }
+    ball_begin(s, b, mk3(e.x, e.y, e.z), nc, has_n, min_dot, (int)qi, init_radius, rounds, min_degree);
+  }
+  __device__ __forceinline__ void node_step() { ball_node_step(s, b); }
+  __device__ __forceinline__ void leaf_step() { ball_leaf_step(s, b); }
+  __device__ __forceinline__ void finish()
+  {
+    if (!ball_round_done(s, b)) return;          // next round started
+    for (int j = 0; j < k; ++j)
+    {
+      bool v = j < s.set.n;
+      if (idx) idx[qi * k + j] = v ? s.set.idx[j * s.set.stride] : -1;
+      if (sep) sep[qi * k + j] = v ? s.set.key[j * s.set.stride] : -1.0f;
+    }
+    if (count) count[qi] = s.set.n;
+    s.t.cur = TGQ_ST_IDLE;
+  }
+};
+
 __global__ void __launch_bounds__(TGQ_BLOCK)
-k_ball_graph(BvhView b, int n, int k, float init_radius, int rounds, float min_dot, int min_degree, int * idx, float * sep, int * count)
+k_ball_graph(BvhView b, int n, int k, float init_radius, int rounds, float min_dot, int min_degree, int * counter, int * idx, float * sep, int * count)
 {
   extern __shared__ float smem[];
-  float * keys = smem + threadIdx.x; int * ids = (int *)(smem + (size_t)k * blockDim.x) + threadIdx.x;
-  int s = blockIdx.x * blockDim.x + threadIdx.x; if (s >= n) return;
-  f4 e = b.pts[s]; int64_t i = __float_as_int(e.w);
-  bool has_n = b.nrm != nullptr;
-  v3 nc = mk3(0.0f, 0.0f, 0.0f);
-  if (has_n) { f4 q = b.nrm[s]; nc = mk3(q.x, q.y, q.z); }
-  SortedSet set; set.init(keys, ids, blockDim.x, k);
-  ball_graph_query(b, mk3(e.x, e.y, e.z), nc, has_n, min_dot, (int)i, init_radius, rounds, min_degree, set);
-  for (int j = 0; j < k; ++j)
-  {
-    bool v = j < set.n;
-    if (idx) idx[i * k + j] = v ? ids[j * blockDim.x] : -1;
-    if (sep) sep[i * k + j] = v ? keys[j * blockDim.x] : -1.0f;
-  }
-  if (count) count[i] = set.n;
+  BallW w;
+  w.b = b; w.k = k; w.init_radius = init_radius; w.rounds = rounds; w.min_dot = min_dot; w.min_degree = min_degree;
+  w.idx = idx; w.sep = sep; w.count = count; w.qi = 0; w.s.t.cur = TGQ_ST_IDLE; TravStack st; trav_bind(w.s.t, st);
+  w.s.set.init(smem + threadIdx.x, (int *)(smem + (size_t)k * blockDim.x) + threadIdx.x, blockDim.x, k);
+  warp_run(w, n, counter);
 }
 
 // ---- K8 ray first hit / any hit ------------------------------------------------------------------------------------------
 template <bool ANY>
+struct RayW
+{
+  RayState<ANY> s; BvhView b; float const * o3; float const * d3; float const * tmax; uint32_t const * perm;
+  float * t_out; int * idx; float * normal3; uint8_t * hit; int64_t qi;
+  __device__ __forceinline__ int state() const { return s.t.cur; }
+  __device__ __forceinline__ void begin(int t)
+  {
+    qi = perm ? perm[t] : t;
+    ray_begin(s, b, ld3(o3, qi), ld3(d3, qi), tmax ? tmax[qi] : -1.0f);
+  }
+  __device__ __forceinline__ void node_step() { ray_node_step(s, b); }
+  __device__ __forceinline__ void leaf_step() { ray_leaf_step(s, b); }
+  __device__ __forceinline__ void finish()
+  {
+    if (t_out) t_out[qi] = s.best_idx >= 0 ? s.best_t : -1.0f;
+    if (idx) idx[qi] = s.best_idx;
+    if (hit) hit[qi] = s.best_idx >= 0 ? 1 : 0;
+    if (normal3)
+    {
+      v3 nn = mk3(0.0f, 0.0f, 0.0f);
+      if (s.best_k >= 0) { f4 q = ((f4 const *)(b.tris + s.best_k))[3]; nn = mk3(q.x, q.y, q.z); }
+      st3(normal3, qi, nn);
+    }
+    s.t.cur = TGQ_ST_IDLE;
+  }
+};
+
+template <bool ANY>
 __global__ void __launch_bounds__(TGQ_BLOCK)
 k_ray(BvhView b, float const * __restrict__ o3, float const * __restrict__ d3, float const * __restrict__ tmax,
-      uint32_t const * __restrict__ perm, int n, float * t_out, int * idx, float * normal3, uint8_t * hit)
+      uint32_t const * __restrict__ perm, int n, int * counter, float * t_out, int * idx, float * normal3, uint8_t * hit)
 {
-  int t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= n) return;
-  int64_t i = perm ? perm[t] : t;
-  float best = tmax ? tmax[i] : -1.0f; int bi = -1, bk = -1;
-  ray_query<ANY>(b, ld3(o3, i), ld3(d3, i), best, bi, bk);
-  if (t_out) t_out[i] = bi >= 0 ? best : -1.0f;
-  if (idx) idx[i] = bi;
-  if (hit) hit[i] = bi >= 0 ? 1 : 0;
-  if (normal3)
-  {
-    v3 nn = mk3(0.0f, 0.0f, 0.0f);
-    if (bk >= 0) { f4 q = ((f4 const *)(b.tris + bk))[3]; nn = mk3(q.x, q.y, q.z); }
-    st3(normal3, i, nn);
-  }
+  RayW<ANY> w;
+  w.b = b; w.o3 = o3; w.d3 = d3; w.tmax = tmax; w.perm = perm; w.t_out = t_out; w.idx = idx; w.normal3 = normal3; w.hit = hit; w.qi = 0;
+  w.s.t.cur = TGQ_ST_IDLE; TravStack st; trav_bind(w.s.t, st);
+  warp_run(w, n, counter);
 }
 
 // SDF cone rays (ShapeDiameter.hpp:168-220): thread = (sample, ray).  valid = hit && (!interior || n_hit . dir >= 0).
@@ -405,21 +528,39 @@ __constant__ float c_cone_dirs[30][3] = {
   { 0.232916f, -0.328273f,  0.915416f}, { 0.231667f, -0.796882f,  0.557951f}, {-0.270612f, -0.809654f,  0.520797f},
 };
 
+struct SdfW
+{
+  RayState<false> s; BvhView b; float const * p3; float const * n3; float scale; int interior;
+  float * t_out; int * idx; uint8_t * valid; int64_t r;
+  __device__ __forceinline__ int state() const { return s.t.cur; }
+  __device__ __forceinline__ void begin(int t)
+  {
+    r = t;
+    int64_t sm = r / 30; int k = (int)(r - sm * 30);
+    SdfFrame f = sdf_frame(ld3(p3, sm), ld3(n3, sm), scale);
+    ray_begin(s, b, f.origin, sdf_dir(f, mk3(c_cone_dirs[k][0], c_cone_dirs[k][1], c_cone_dirs[k][2])), -1.0f);
+  }
+  __device__ __forceinline__ void node_step() { ray_node_step(s, b); }
+  __device__ __forceinline__ void leaf_step() { ray_leaf_step(s, b); }
+  __device__ __forceinline__ void finish()
+  {
+    bool ok = s.best_idx >= 0;
+    if (ok && interior) { f4 q = ((f4 const *)(b.tris + s.best_k))[3]; ok = dot3(mk3(q.x, q.y, q.z), s.d) >= 0.0f; }
+    if (t_out) t_out[r] = s.best_idx >= 0 ? s.best_t : -1.0f;
+    if (idx) idx[r] = s.best_idx;
+    valid[r] = ok ? 1 : 0;
+    s.t.cur = TGQ_ST_IDLE;
+  }
+};
+
 __global__ void __launch_bounds__(TGQ_BLOCK)
-k_sdf_rays(BvhView b, float const * __restrict__ p3, float const * __restrict__ n3, int64_t nrays, float scale, int interior,
+k_sdf_rays(BvhView b, float const * __restrict__ p3, float const * __restrict__ n3, int nrays, float scale, int interior, int * counter,
            float * t_out, int * idx, uint8_t * valid)
 {
-  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; if (r >= nrays) return;
-  int64_t s = r / 30; int k = (int)(r - s * 30);
-  SdfFrame f = sdf_frame(ld3(p3, s), ld3(n3, s), scale);
-  v3 dir = sdf_dir(f, mk3(c_cone_dirs[k][0], c_cone_dirs[k][1], c_cone_dirs[k][2]));
-  float best = -1.0f; int bi = -1, bk = -1;
-  ray_query<false>(b, f.origin, dir, best, bi, bk);
-  bool ok = bi >= 0;
-  if (ok && interior) { f4 q = ((f4 const *)(b.tris + bk))[3]; ok = dot3(mk3(q.x, q.y, q.z), dir) >= 0.0f; }
-  if (t_out) t_out[r] = bi >= 0 ? best : -1.0f;
-  if (idx) idx[r] = bi;
-  valid[r] = ok ? 1 : 0;
+  SdfW w;
+  w.b = b; w.p3 = p3; w.n3 = n3; w.scale = scale; w.interior = interior; w.t_out = t_out; w.idx = idx; w.valid = valid; w.r = 0;
+  w.s.t.cur = TGQ_ST_IDLE; TravStack st; trav_bind(w.s.t, st);
+  warp_run(w, nrays, counter);
 }
 
 // ---- K9 ICP sums: order-independent fixed-point accumulation (bit-identical for any launch shape / GPU count) ---------
@@ -512,7 +653,7 @@ __global__ void k_self_nn(BvhView b, int const * __restrict__ pos_of_elem, int c
   int i = seeds[j];
   f4 e = b.pts[pos_of_elem[i]];
   float best = INFINITY; int bi = -1; v3 cp = mk3(0.0f, 0.0f, 0.0f);
-  closest_query<false, false>(b, nullptr, 0.0f, mk3(e.x, e.y, e.z), i, best, bi, cp);
+  closest_query<false>(b, 0.0f, mk3(e.x, e.y, e.z), i, best, bi, cp);
   d2_out[j] = bi >= 0 ? best : 0.0f;
 }
 

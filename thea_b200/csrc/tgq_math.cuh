@@ -37,6 +37,17 @@ TGQ_HD v3 max3(v3 a, v3 b) { return mk3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(
 TGQ_HD float sum3(float a, float b, float c) { return a + (b + c); }
 TGQ_HD float dot3(v3 a, v3 b) { return sum3(a.x * b.x, a.y * b.y, a.z * b.z); }
 TGQ_HD float sqn3(v3 a) { return dot3(a, a); }
+// Bounds-only helpers: fused multiply-add where the hardware has it.  NEVER used in reference arithmetic (the library is
+// compiled with -fmad=false so that plain a * b + c is never contracted; these opt in explicitly).
+TGQ_HD float ffma(float a, float b, float c)
+{
+#ifdef __CUDA_ARCH__
+  return __fmaf_rn(a, b, c);
+#else
+  return a * b + c;
+#endif
+}
+TGQ_HD float fdot3(v3 a, v3 b) { return ffma(a.x, b.x, ffma(a.y, b.y, a.z * b.z)); }
 TGQ_HD v3 cross3(v3 l, v3 r) { return mk3(l.y * r.z - l.z * r.y, l.z * r.x - l.x * r.z, l.x * r.y - l.y * r.x); }
 TGQ_HD v3 normalized3(v3 a) { float z = sqn3(a); return z > 0.0f ? div3(a, sqrtf(z)) : a; }
 TGQ_HD float comp3(v3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
@@ -167,7 +178,7 @@ TGQ_HD float fast_sqrt(float x)
 TGQ_HD float box_point_sqdist(v3 lo, v3 hi, v3 p)
 {
   v3 g = max3(sub3(max3(lo, p), min3(hi, p)), mk3(0.0f, 0.0f, 0.0f));
-  return sqn3(g);
+  return fdot3(g, g);
 }
 
 // ---- ShapeDiameter cone rays (ShapeDiameter.hpp:168-214, MatrixUtil.hpp:225-249) ------------------------------------

@@ -1,12 +1,18 @@
-// tgq_traverse.cuh -- single-query traversals of the device LBVH (one query per thread).
+// tgq_traverse.cuh -- resumable single-query traversals of the device LBVH.
 //
-// Each routine computes the *canonical* answer of the corresponding BvhN query (SURVEY.md findings 4-5): the optimum
+// Each traversal computes the *canonical* answer of the corresponding BvhN query (SURVEY.md findings 4-5): the optimum
 // over ALL elements of the reference's per-element fp32 function, ties broken by the lowest element index.  The tree
 // only prunes: a subtree is skipped when a conservative bound proves that none of its elements can win or tie.
-//   closest_query  <- BvhN::closestElement / closestPair        (Algorithms/BvhN.hpp:1049-1114,1866-1893,2036-2089)
-//   knn_query      <- BvhN::kClosestPairs                       (BvhN.hpp:1137-1146, functor :474-500)
-//   ball_graph_query <- processRange<Ball3> + NeighborFunctor   (BvhN.hpp:2118-2171, PointSet3.hpp:586-681)
-//   ray_query      <- BvhN::rayStructureIntersection / rayIntersectionTime / rayIntersects (BvhN.hpp:1266-1316,2188-2291)
+//   Closest*   <- BvhN::closestElement / closestPair        (Algorithms/BvhN.hpp:1049-1114,1866-1893,2036-2089)
+//   Knn*       <- BvhN::kClosestPairs                       (BvhN.hpp:1137-1146, functor :474-500)
+//   Ball*      <- processRange<Ball3> + NeighborFunctor     (BvhN.hpp:2118-2171, PointSet3.hpp:586-681)
+//   Ray*       <- BvhN::rayStructureIntersection / rayIntersectionTime / rayIntersects (BvhN.hpp:1266-1316,2188-2291)
+//
+// Every traversal is a small state machine: `cur` >= 0 means "an inner node is pending", TGQ_ST_LEAF "elements
+// [k, kend) of a leaf are pending", TGQ_ST_DONE "finished".  One call of *_node_step / *_leaf_step advances the query
+// by one unit of work.  The kernels (tgq_kernels.cuh) drive 32 such machines per warp from a warp-uniform loop, so the
+// lanes reconverge after every step and finished lanes are refilled with fresh queries; the host emulation
+// of the test suite drives the same step functions from a plain loop.
 #pragma once
 #include "tgq_bvh.cuh"
 
@@ -17,6 +23,10 @@ namespace tgq {
 #define TGQ_LEAF_MASK 15
 #define TGQ_LB_DEFLATE 0.99999905f   // 1 - 2^-20: lower bounds are shrunk so fp32 rounding can never over-prune
 
+#define TGQ_ST_DONE (-1)
+#define TGQ_ST_LEAF (-2)
+#define TGQ_ST_IDLE (-3)
+
 // Visit counters: compiled out everywhere except the test-only host build, which uses them to study pruning quality.
 #ifndef TGQ_COUNT_NODE
 #define TGQ_COUNT_NODE()
@@ -25,7 +35,8 @@ namespace tgq {
 
 struct BvhView
 {
-  NodeRec const * nodes;   // n_nodes inner nodes, root = 0
+  NodeRec const * nodes;   // n_nodes inner nodes with the AABBs of both children, root = 0
+  ObbNode const * obbs;    // same nodes with oriented boxes of both children (triangle structures), or null
   TriRec const * tris;     // Morton-ordered triangle records (triangle structures)
   f4 const * pts;          // Morton-ordered points (point structures)
   f4 const * nrm;          // Morton-ordered normals or null
@@ -49,42 +60,61 @@ TGQ_HD NodeRec load_node(BvhView const & b, int i)
   return r;
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// "Pancake" bounds.  AABBs of a smooth surface that is oblique to the axes stick out towards an off-surface query by
-// about their own size, so a far query would have to open every box in a wide disc around its foot point (hundreds of
-// leaves on a 1M-triangle mesh).  Each child of a triangle-structure node therefore also carries a slab
-// {x : smin <= dir.x <= smax} around the mean normal of its triangles and the radius R of its vertices about the centre
-// c of its box.  For any x in the child
-//     |p - x|^2 = (dir.(p - x))^2 + |(p - x)_perp|^2 >= slab_dist(p)^2 + max(0, |(p - c)_perp| - R)^2,
-// which keeps the lateral offset that the box bound loses.  Box and pancake bounds are both valid; the traversal prunes
-// on their maximum.  The same bound with the triangle's own plane and the radius about its centroid screens single
-// triangles before the exact (and expensive) reference arithmetic is run.
-//   SlabRec (48 B): a = (dir0.xyz, smin0)  b = (smax0, dir1.xyz)  c = (smin1, smax1, R0, R1)
-// All stored quantities are padded outwards at build time (scene pad); `mq` absorbs the rounding of the query-side dot
-// products (it grows with the magnitude of the query coordinates), and the result is deflated like the box bound.
-// ---------------------------------------------------------------------------------------------------------------------
-struct SlabRec { f4 a, b, c; };
+// Traversal bookkeeping shared by all query kinds: pending node / leaf range and the stack of deferred siblings.
+// The stack arrays live outside the struct (TravStack, declared by the caller) so that the scalar state stays in registers.
+struct TravStack { int node[TGQ_STACK]; float key[TGQ_STACK]; };
+struct Trav
+{
+  int cur, k, kend, sp;
+  int * stk_node; float * stk_key;
+};
+TGQ_HD void trav_bind(Trav & t, TravStack & st) { t.stk_node = st.node; t.stk_key = st.key; }
 
+TGQ_HD void trav_enter(Trav & t, int code)
+{
+  if (code >= 0) t.cur = code;
+  else { int c = ~code; t.k = c >> TGQ_LEAF_BITS; t.kend = t.k + (c & TGQ_LEAF_MASK); t.cur = (t.kend > t.k) ? TGQ_ST_LEAF : TGQ_ST_DONE; }
+}
+TGQ_HD void trav_begin(Trav & t, int n_nodes) { t.sp = 0; t.k = t.kend = 0; t.cur = n_nodes > 0 ? 0 : TGQ_ST_DONE; }
+TGQ_HD void trav_push(Trav & t, int code, float key) { t.stk_node[t.sp] = code; t.stk_key[t.sp] = key; ++t.sp; }
+// Pops deferred siblings until one whose key is still <= limit (keys are lower bounds / entry times), else finishes.
+TGQ_HD void trav_pop(Trav & t, float limit)
+{
+  t.cur = TGQ_ST_DONE;
+  while (t.sp > 0)
+  {
+    --t.sp;
+    if (t.stk_key[t.sp] <= limit) { trav_enter(t, t.stk_node[t.sp]); if (t.cur != TGQ_ST_DONE) return; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Oriented bounds for closest-point queries on triangle structures.  AABBs of a smooth surface that is oblique to the
+// axes stick out towards an off-surface query by about their own size, so a far query would have to open every box in
+// a wide disc around its foot point (hundreds of leaves on a 1M-triangle mesh).  Each child of a triangle-structure
+// node therefore carries a box oriented along the mean normal of its triangles (axis a0) and two tangent directions:
+//     |p - x|^2 >= sum_i max(|a_i . (p - c)| - h_i, 0)^2   for every x in the child,
+// which is thin across the surface and keeps the lateral offset.  ObbNode (128 B), per child four float4:
+//     (c.xyz, h0) (a0.xyz, h1) (a1.xyz, h2) (a2.xyz, child link)
+// Half extents are padded outwards at build time (scene pad); `mq` absorbs the rounding of the query-side products (it
+// grows with the magnitude of the query coordinates), and the result is deflated.  Children are visited in the order
+// of their centre distance (a better predictor of where the foot point lies than the lower bound for far queries:
+// 1.5x fewer node visits on the bench workload), and pruned on the lower bound.
+// The same idea with the triangle's own plane and the radius about its centroid screens single triangles before the
+// exact (and expensive) reference arithmetic is run.
+// ---------------------------------------------------------------------------------------------------------------------
 TGQ_HD float query_margin(v3 p, float scene_pad) { return scene_pad + 1e-6f * (fabsf(p.x) + fabsf(p.y) + fabsf(p.z)); }
 
-TGQ_HD float pancake_sqdist(v3 c, v3 dir, float smin, float smax, float R, v3 p, float mq)
+TGQ_HD void obb_bounds(f4 q0, f4 q1, f4 q2, f4 q3, v3 p, float mq, float & lb, float & key)
 {
-  float s = dot3(dir, p);
-  float sd = fmaxf(fmaxf(s - smax, smin - s) - mq, 0.0f);
-  v3 pc = sub3(p, c);
-  float sc = dot3(dir, pc);
-  v3 perp = sub3(pc, mul3(dir, sc));
-  float lat = fmaxf(sqrtf(sqn3(perp)) - R - mq, 0.0f);
-  return (sd * sd + lat * lat) * TGQ_LB_DEFLATE;
+  v3 pc = sub3(p, mk3(q0.x, q0.y, q0.z));
+  float x = fmaxf(fabsf(fdot3(mk3(q1.x, q1.y, q1.z), pc)) - (q0.w + mq), 0.0f);
+  float y = fmaxf(fabsf(fdot3(mk3(q2.x, q2.y, q2.z), pc)) - (q1.w + mq), 0.0f);
+  float z = fmaxf(fabsf(fdot3(mk3(q3.x, q3.y, q3.z), pc)) - (q2.w + mq), 0.0f);
+  lb = fdot3(mk3(x, y, z), mk3(x, y, z)) * TGQ_LB_DEFLATE;
+  key = fdot3(pc, pc);
 }
 
-// Accumulates one triangle into the slab statistics of a node: extent along dir and radius about c.
-TGQ_HD void slab_accumulate(v3 dir, v3 c, v3 v0, v3 v1, v3 v2, float & mn, float & mx, float & r2)
-{
-  float s0 = dot3(dir, v0), s1 = dot3(dir, v1), s2 = dot3(dir, v2);
-  mn = fminf(mn, fminf(s0, fminf(s1, s2))); mx = fmaxf(mx, fmaxf(s0, fmaxf(s1, s2)));
-  r2 = fmaxf(r2, fmaxf(sqn3(sub3(v0, c)), fmaxf(sqn3(sub3(v1, c)), sqn3(sub3(v2, c)))));
-}
 TGQ_HD float slab_radius(float r2, float pad) { return sqrtf(r2) * 1.000001f + 2.0f * pad; }
 TGQ_HD v3 box_centre(v3 lo, v3 hi) { return mul3(add3(lo, hi), 0.5f); }
 // Screening radius of one triangle about its centroid (stored in TriRec.q3.w).
@@ -95,134 +125,158 @@ TGQ_HD float tri_screen_radius(v3 v0, v3 v1, v3 v2, float pad)
   return slab_radius(r2, pad);
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Closest element.  best_d2 enters as the (exclusive) squared bound or +inf, best_idx as -1.
-// SLAB: triangle structure with pancake bounds (slabs != null) and per-triangle screening.
-// ---------------------------------------------------------------------------------------------------------------------
-template <bool TRI, bool SLAB>
-TGQ_HD void closest_leaf(BvhView const & b, int first, int count, v3 p, int skip, float mq, float & best_d2, int & best_idx, v3 & best_cp)
+// Frame of an oriented box from the (unnormalised) normal sum of its triangles: a0 = mean normal (or +z when the
+// normals cancel, e.g. a closed surface), a1 = the world axis least aligned with a0 made orthogonal to it, a2 = a0 x a1.
+struct ObbFrame { v3 a0, a1, a2; };
+TGQ_HD ObbFrame obb_frame(v3 nsum)
 {
-  for (int k = first; k < first + count; ++k)
-  {
-    int idx; v3 cp; float d2;
-    if (TRI)
-    {
-      f4 const * t = (f4 const *)(b.tris + k);
-      f4 a = ldq(t), bq = ldq(t + 1), c = ldq(t + 2), d = ldq(t + 3);
-      v3 v0 = mk3(a.x, a.y, a.z), v1 = mk3(bq.x, bq.y, bq.z), v2 = mk3(c.x, c.y, c.z), n = mk3(d.x, d.y, d.z);
-      if (SLAB)
-      {
-        // screen: plane distance and lateral distance to the triangle's bounding circle
-        v3 cen = mul3(add3(add3(v0, v1), v2), 0.33333334f);
-        float sdp = dot3(p, n) - c.w;
-        float sd = fmaxf(fabsf(sdp) - mq, 0.0f);
-        v3 pc = sub3(p, cen);
-        v3 perp = sub3(pc, mul3(n, dot3(n, pc)));
-        float lat = fmaxf(sqrtf(sqn3(perp)) - d.w - mq, 0.0f);
-        if ((sd * sd + lat * lat) * TGQ_LB_DEFLATE > best_d2) continue;
-      }
-      TGQ_COUNT_PRIM();
-      idx = f2i(a.w);
-      d2 = tri_point_sqdist(v0, v1, v2, n, c.w, f2i(bq.w), p, cp);
-    }
-    else
-    {
-      TGQ_COUNT_PRIM();
-      f4 e = ldq(b.pts + k);
-      idx = f2i(e.w); cp = mk3(e.x, e.y, e.z);
-      d2 = sqn3(sub3(cp, p));
-    }
-    if (idx == skip) continue;
-    if (d2 < best_d2 || (d2 == best_d2 && idx < best_idx)) { best_d2 = d2; best_idx = idx; best_cp = cp; }
-  }
+  ObbFrame f;
+  f.a0 = normalized3(nsum);
+  if (!(sqn3(f.a0) > 0.5f)) f.a0 = mk3(0.0f, 0.0f, 1.0f);
+  float ax = fabsf(f.a0.x), ay = fabsf(f.a0.y), az = fabsf(f.a0.z);
+  v3 e = (ax <= ay && ax <= az) ? mk3(1.0f, 0.0f, 0.0f) : (ay <= az ? mk3(0.0f, 1.0f, 0.0f) : mk3(0.0f, 0.0f, 1.0f));
+  f.a1 = normalized3(sub3(e, mul3(f.a0, dot3(f.a0, e))));
+  f.a2 = cross3(f.a0, f.a1);
+  return f;
+}
+// Extent accumulator of one oriented box.
+struct ObbAcc { ObbFrame f; float mn[3], mx[3]; };
+TGQ_HD void obb_acc_begin(ObbAcc & a, v3 nsum)
+{
+  a.f = obb_frame(nsum);
+  for (int j = 0; j < 3; ++j) { a.mn[j] = FLT_MAX; a.mx[j] = -FLT_MAX; }
+}
+TGQ_HD void obb_acc_point(ObbAcc & a, v3 v)
+{
+  float s0 = dot3(a.f.a0, v), s1 = dot3(a.f.a1, v), s2 = dot3(a.f.a2, v);
+  a.mn[0] = fminf(a.mn[0], s0); a.mx[0] = fmaxf(a.mx[0], s0);
+  a.mn[1] = fminf(a.mn[1], s1); a.mx[1] = fmaxf(a.mx[1], s1);
+  a.mn[2] = fminf(a.mn[2], s2); a.mx[2] = fmaxf(a.mx[2], s2);
+}
+// Packs the child half of an ObbNode.  `pad` covers the rounding of the build-side projections and of the centre.
+TGQ_HD void obb_acc_store(ObbAcc const & a, float pad, int child, f4 * out4)
+{
+  float c0 = 0.5f * (a.mn[0] + a.mx[0]), c1 = 0.5f * (a.mn[1] + a.mx[1]), c2 = 0.5f * (a.mn[2] + a.mx[2]);
+  v3 c = add3(add3(mul3(a.f.a0, c0), mul3(a.f.a1, c1)), mul3(a.f.a2, c2));
+  float h0 = 0.5f * (a.mx[0] - a.mn[0]) + 4.0f * pad, h1 = 0.5f * (a.mx[1] - a.mn[1]) + 4.0f * pad, h2 = 0.5f * (a.mx[2] - a.mn[2]) + 4.0f * pad;
+  out4[0].x = c.x; out4[0].y = c.y; out4[0].z = c.z; out4[0].w = h0;
+  out4[1].x = a.f.a0.x; out4[1].y = a.f.a0.y; out4[1].z = a.f.a0.z; out4[1].w = h1;
+  out4[2].x = a.f.a1.x; out4[2].y = a.f.a1.y; out4[2].z = a.f.a1.z; out4[2].w = h2;
+  out4[3].x = a.f.a2.x; out4[3].y = a.f.a2.y; out4[3].z = a.f.a2.z; out4[3].w = i2f(child);
+}
+// An oriented box that no query can reach (the missing second child of a one-element structure).
+TGQ_HD void obb_store_empty(int child, f4 * out4)
+{
+  out4[0].x = 0.0f; out4[0].y = 0.0f; out4[0].z = 0.0f; out4[0].w = -1e30f;
+  out4[1].x = 1.0f; out4[1].y = 0.0f; out4[1].z = 0.0f; out4[1].w = -1e30f;
+  out4[2].x = 0.0f; out4[2].y = 1.0f; out4[2].z = 0.0f; out4[2].w = -1e30f;
+  out4[3].x = 0.0f; out4[3].y = 0.0f; out4[3].z = 1.0f; out4[3].w = i2f(child);
 }
 
-// Resumable traversal state: the persistent kernels advance every lane by a bounded burst of steps, retire finished
-// queries and hand fresh ones to the idle lanes, so a warp stays full even though query costs are heavy tailed.
-template <bool TRI, bool SLAB>
+// ---------------------------------------------------------------------------------------------------------------------
+// Closest element.  best_d2 starts as the (exclusive) squared bound or +inf, best_idx as -1.
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool TRI>
 struct ClosestState
 {
   v3 p; float mq; int skip;
   float best_d2; int best_idx; v3 best_cp;
-  int cur, sp;
-  int stk_node[TGQ_STACK]; float stk_lb[TGQ_STACK];
+  Trav t;
 };
 
-template <bool TRI, bool SLAB>
-TGQ_HD void closest_begin(ClosestState<TRI, SLAB> & s, BvhView const & b, float scene_pad, v3 p, int skip, float bound_ub)
+template <bool TRI>
+TGQ_HD void closest_begin(ClosestState<TRI> & s, BvhView const & b, float scene_pad, v3 p, int skip, float bound_ub)
 {
-  s.p = p; s.skip = skip; s.mq = SLAB ? query_margin(p, scene_pad) : 0.0f;
+  s.p = p; s.skip = skip; s.mq = TRI ? query_margin(p, scene_pad) : 0.0f;
   s.best_d2 = bound_ub; s.best_idx = -1; s.best_cp = mk3(0.0f, 0.0f, 0.0f);
-  s.sp = 0; s.cur = b.n_nodes > 0 ? 0 : -1;
-  if (b.n_nodes <= 0) s.sp = -1;          // empty structure: nothing to do
+  trav_begin(s.t, b.n_nodes);
 }
 
-// Advances by at most `budget` node steps; returns true when the query is finished.
-template <bool TRI, bool SLAB>
-TGQ_HD bool closest_run(ClosestState<TRI, SLAB> & s, BvhView const & b, SlabRec const * slabs, int budget)
+template <bool TRI>
+TGQ_HD void closest_node_step(ClosestState<TRI> & s, BvhView const & b)
 {
-  if (s.sp < 0) return true;
-  v3 p = s.p; float mq = s.mq;
-  int cur = s.cur, sp = s.sp;
-  for (;;)
+  TGQ_COUNT_NODE();
+  float lb0, lb1, key0, key1; int c0, c1;
+  if (TRI)
   {
-    while (cur >= 0)
+    f4 const * q = (f4 const *)(b.obbs + s.t.cur);
+    f4 a0 = ldq(q), a1 = ldq(q + 1), a2 = ldq(q + 2), a3 = ldq(q + 3), b0 = ldq(q + 4), b1 = ldq(q + 5), b2 = ldq(q + 6), b3 = ldq(q + 7);
+    obb_bounds(a0, a1, a2, a3, s.p, s.mq, lb0, key0);
+    obb_bounds(b0, b1, b2, b3, s.p, s.mq, lb1, key1);
+    c0 = f2i(a3.w); c1 = f2i(b3.w);
+  }
+  else
+  {
+    NodeRec nd = load_node(b, s.t.cur);
+    v3 lo0, hi0, lo1, hi1; node_boxes(nd, lo0, hi0, lo1, hi1);
+    lb0 = box_point_sqdist(lo0, hi0, s.p) * TGQ_LB_DEFLATE; lb1 = box_point_sqdist(lo1, hi1, s.p) * TGQ_LB_DEFLATE;
+    key0 = lb0; key1 = lb1;
+    c0 = f2i(nd.q3.x); c1 = f2i(nd.q3.y);
+  }
+  bool go0 = lb0 <= s.best_d2, go1 = lb1 <= s.best_d2;
+  if (go0 && go1)
+  {
+    bool swap = key1 < key0;
+    trav_push(s.t, swap ? c0 : c1, swap ? lb0 : lb1);
+    trav_enter(s.t, swap ? c1 : c0);
+    if (s.t.cur == TGQ_ST_DONE) trav_pop(s.t, s.best_d2);
+  }
+  else if (go0 || go1)
+  {
+    trav_enter(s.t, go0 ? c0 : c1);
+    if (s.t.cur == TGQ_ST_DONE) trav_pop(s.t, s.best_d2);
+  }
+  else trav_pop(s.t, s.best_d2);
+}
+
+// One pending element (triangles) or the whole pending leaf (points).
+template <bool TRI>
+TGQ_HD void closest_leaf_step(ClosestState<TRI> & s, BvhView const & b)
+{
+  if (TRI)
+  {
+    int k = s.t.k++;
+    f4 const * t = (f4 const *)(b.tris + k);
+    f4 a = ldq(t), bq = ldq(t + 1), c = ldq(t + 2), d = ldq(t + 3);
+    v3 v0 = mk3(a.x, a.y, a.z), v1 = mk3(bq.x, bq.y, bq.z), v2 = mk3(c.x, c.y, c.z), n = mk3(d.x, d.y, d.z);
+    // screen: plane distance and lateral distance to the triangle's bounding circle
+    v3 cen = mul3(add3(add3(v0, v1), v2), 0.33333334f);
+    float sd = fmaxf(fabsf(fdot3(s.p, n) - c.w) - s.mq, 0.0f);
+    v3 pc = sub3(s.p, cen);
+    v3 perp = sub3(pc, mul3(n, fdot3(n, pc)));
+    float lat = fmaxf(sqrtf(fdot3(perp, perp)) - d.w - s.mq, 0.0f);
+    int idx = f2i(a.w);
+    if ((sd * sd + lat * lat) * TGQ_LB_DEFLATE <= s.best_d2 && idx != s.skip)
     {
-      if (--budget < 0) { s.cur = cur; s.sp = sp; return false; }
-      NodeRec nd = load_node(b, cur);
-      TGQ_COUNT_NODE();
-      v3 lo0, hi0, lo1, hi1; node_boxes(nd, lo0, hi0, lo1, hi1);
-      float lb0 = box_point_sqdist(lo0, hi0, p) * TGQ_LB_DEFLATE;
-      float lb1 = box_point_sqdist(lo1, hi1, p) * TGQ_LB_DEFLATE;
-      int c0 = f2i(nd.q3.x), c1 = f2i(nd.q3.y);
-      bool go0 = lb0 <= s.best_d2, go1 = lb1 <= s.best_d2;
-      if (SLAB && (go0 || go1))
-      {
-        f4 const * sq = (f4 const *)(slabs + cur);
-        f4 sa = ldq(sq), sb = ldq(sq + 1), sc = ldq(sq + 2);
-        if (go0)
-        {
-          lb0 = fmaxf(lb0, pancake_sqdist(box_centre(lo0, hi0), mk3(sa.x, sa.y, sa.z), sa.w, sb.x, sc.z, p, mq));
-          go0 = lb0 <= s.best_d2;
-        }
-        if (go1)
-        {
-          lb1 = fmaxf(lb1, pancake_sqdist(box_centre(lo1, hi1), mk3(sb.y, sb.z, sb.w), sc.x, sc.y, sc.w, p, mq));
-          go1 = lb1 <= s.best_d2;
-        }
-      }
-      if (go0 && go1)
-      {
-        bool swap = lb1 < lb0;
-        int nearc = swap ? c1 : c0, farc = swap ? c0 : c1;
-        s.stk_node[sp] = farc; s.stk_lb[sp] = swap ? lb0 : lb1; ++sp;
-        cur = nearc;
-      }
-      else if (go0) cur = c0;
-      else if (go1) cur = c1;
-      else goto pop;
-    }
-    {
-      int code = ~cur;
-      closest_leaf<TRI, SLAB>(b, code >> TGQ_LEAF_BITS, code & TGQ_LEAF_MASK, p, s.skip, mq, s.best_d2, s.best_idx, s.best_cp);
-    }
-  pop:
-    for (;;)
-    {
-      if (sp == 0) { s.sp = -1; return true; }
-      --sp;
-      if (s.stk_lb[sp] <= s.best_d2) { cur = s.stk_node[sp]; break; }
+      TGQ_COUNT_PRIM();
+      v3 cp;
+      float d2 = tri_point_sqdist(v0, v1, v2, n, c.w, f2i(bq.w), s.p, cp);
+      if (d2 < s.best_d2 || (d2 == s.best_d2 && idx < s.best_idx)) { s.best_d2 = d2; s.best_idx = idx; s.best_cp = cp; }
     }
   }
+  else
+  {
+    for (int k = s.t.k; k < s.t.kend; ++k)
+    {
+      TGQ_COUNT_PRIM();
+      f4 e = ldq(b.pts + k);
+      int idx = f2i(e.w); v3 cp = mk3(e.x, e.y, e.z);
+      float d2 = sqn3(sub3(cp, s.p));
+      if (idx == s.skip) continue;
+      if (d2 < s.best_d2 || (d2 == s.best_d2 && idx < s.best_idx)) { s.best_d2 = d2; s.best_idx = idx; s.best_cp = cp; }
+    }
+    s.t.k = s.t.kend;
+  }
+  if (s.t.k >= s.t.kend) trav_pop(s.t, s.best_d2);
 }
 
-template <bool TRI, bool SLAB>
-TGQ_HD void closest_query(BvhView const & b, SlabRec const * slabs, float scene_pad, v3 p, int skip, float & best_d2, int & best_idx,
-                          v3 & best_cp)
+// Whole query in one go (host emulation; single-lane device uses).
+template <bool TRI>
+TGQ_HD void closest_query(BvhView const & b, float scene_pad, v3 p, int skip, float & best_d2, int & best_idx, v3 & best_cp)
 {
-  ClosestState<TRI, SLAB> s;
+  ClosestState<TRI> s; TravStack st; trav_bind(s.t, st);
   closest_begin(s, b, scene_pad, p, skip, best_d2);
-  closest_run(s, b, slabs, 0x7fffffff);
+  while (s.t.cur != TGQ_ST_DONE) { if (s.t.cur >= 0) closest_node_step(s, b); else closest_leaf_step(s, b); }
   best_d2 = s.best_d2; best_idx = s.best_idx; best_cp = s.best_cp;
 }
 
@@ -256,124 +310,154 @@ struct SortedSet
 };
 
 // k nearest points to p: k smallest (d2, idx); d2 < bound_ub (exclusive) when bounded.
-TGQ_HD void knn_query(BvhView const & b, v3 p, int skip, float bound_ub, SortedSet & set)
+struct KnnState
 {
-  if (b.n_nodes <= 0 || set.cap <= 0) return;
-  int stk_node[TGQ_STACK]; float stk_lb[TGQ_STACK];
-  int sp = 0;
-  int cur = 0;
-  float worst = bound_ub;     // prune radius: k-th best once the set is full, else the bound (or +inf)
-  for (;;)
-  {
-    while (cur >= 0)
-    {
-      NodeRec nd = load_node(b, cur);
-      v3 lo0, hi0, lo1, hi1; node_boxes(nd, lo0, hi0, lo1, hi1);
-      float lb0 = box_point_sqdist(lo0, hi0, p) * TGQ_LB_DEFLATE;
-      float lb1 = box_point_sqdist(lo1, hi1, p) * TGQ_LB_DEFLATE;
-      int c0 = f2i(nd.q3.x), c1 = f2i(nd.q3.y);
-      bool go0 = lb0 <= worst, go1 = lb1 <= worst;
-      if (go0 && go1)
-      {
-        bool swap = lb1 < lb0;
-        stk_node[sp] = swap ? c0 : c1; stk_lb[sp] = swap ? lb0 : lb1; ++sp;
-        cur = swap ? c1 : c0;
-      }
-      else if (go0) cur = c0;
-      else if (go1) cur = c1;
-      else goto pop;
-    }
-    {
-      int code = ~cur; int first = code >> TGQ_LEAF_BITS, count = code & TGQ_LEAF_MASK;
-      for (int k = first; k < first + count; ++k)
-      {
-        f4 e = ldq(b.pts + k);
-        int idx = f2i(e.w);
-        float d2 = sqn3(sub3(mk3(e.x, e.y, e.z), p));
-        if (idx == skip || !(d2 < bound_ub)) continue;
-        if (set.accepts(d2, idx))
-        {
-          set.insert(d2, idx);
-          if (set.full()) worst = set.worst_key();
-        }
-      }
-    }
-  pop:
-    for (;;)
-    {
-      if (sp == 0) return;
-      --sp;
-      if (stk_lb[sp] <= worst) { cur = stk_node[sp]; break; }
-    }
-  }
+  v3 p; int skip; float bound_ub;
+  float worst;     // prune radius: k-th best once the set is full, else the bound (or +inf)
+  SortedSet set;
+  Trav t;
+};
+
+TGQ_HD void knn_begin(KnnState & s, BvhView const & b, v3 p, int skip, float bound_ub)
+{
+  s.p = p; s.skip = skip; s.bound_ub = bound_ub; s.worst = bound_ub; s.set.n = 0;
+  trav_begin(s.t, s.set.cap > 0 ? b.n_nodes : 0);
 }
 
-// One round of PointSet3::findSampleNeighbors for sample `self` (position c, normal nc): every point j != self with
-// sq(x_j - c) <= r2 and (no normals or n_c . n_j >= min_dot) is offered with key fastSqrt(d2); the set keeps the
-// max_degree smallest (key, idx).  The ball/box test uses the reference arithmetic on padded boxes (a superset).
-TGQ_HD void ball_round(BvhView const & b, v3 c, v3 nc, bool has_n, float min_dot, int self, float r2, SortedSet & set)
+TGQ_HD void knn_node_step(KnnState & s, BvhView const & b)
 {
-  set.n = 0;
-  if (b.n_nodes <= 0) return;
-  int stk_node[TGQ_STACK];
-  int sp = 0;
-  int cur = 0;
-  for (;;)
+  TGQ_COUNT_NODE();
+  NodeRec nd = load_node(b, s.t.cur);
+  v3 lo0, hi0, lo1, hi1; node_boxes(nd, lo0, hi0, lo1, hi1);
+  float lb0 = box_point_sqdist(lo0, hi0, s.p) * TGQ_LB_DEFLATE;
+  float lb1 = box_point_sqdist(lo1, hi1, s.p) * TGQ_LB_DEFLATE;
+  int c0 = f2i(nd.q3.x), c1 = f2i(nd.q3.y);
+  bool go0 = lb0 <= s.worst, go1 = lb1 <= s.worst;
+  if (go0 && go1)
   {
-    while (cur >= 0)
-    {
-      NodeRec nd = load_node(b, cur);
-      v3 lo0, hi0, lo1, hi1; node_boxes(nd, lo0, hi0, lo1, hi1);
-      bool go0 = box_point_sqdist(lo0, hi0, c) * TGQ_LB_DEFLATE <= r2;
-      bool go1 = box_point_sqdist(lo1, hi1, c) * TGQ_LB_DEFLATE <= r2;
-      int c0 = f2i(nd.q3.x), c1 = f2i(nd.q3.y);
-      if (go0 && go1) { stk_node[sp++] = c1; cur = c0; }
-      else if (go0) cur = c0;
-      else if (go1) cur = c1;
-      else goto pop;
-    }
-    {
-      int code = ~cur; int first = code >> TGQ_LEAF_BITS, count = code & TGQ_LEAF_MASK;
-      for (int k = first; k < first + count; ++k)
-      {
-        f4 e = ldq(b.pts + k);
-        int idx = f2i(e.w);
-        if (idx == self) continue;
-        v3 diff = sub3(mk3(e.x, e.y, e.z), c);
-        float d2 = sqn3(diff);
-        if (!(d2 <= r2)) continue;
-        if (has_n)
-        {
-          f4 nj = ldq(b.nrm + k);
-          if (dot3(nc, mk3(nj.x, nj.y, nj.z)) < min_dot) continue;
-        }
-        float sep = fast_sqrt(d2);
-        if (set.accepts(sep, idx)) set.insert(sep, idx);
-      }
-    }
-  pop:
-    if (sp == 0) return;
-    cur = stk_node[--sp];
+    bool swap = lb1 < lb0;
+    trav_push(s.t, swap ? c0 : c1, swap ? lb0 : lb1);
+    trav_enter(s.t, swap ? c1 : c0);
+    if (s.t.cur == TGQ_ST_DONE) trav_pop(s.t, s.worst);
   }
+  else if (go0 || go1)
+  {
+    trav_enter(s.t, go0 ? c0 : c1);
+    if (s.t.cur == TGQ_ST_DONE) trav_pop(s.t, s.worst);
+  }
+  else trav_pop(s.t, s.worst);
+}
+
+TGQ_HD void knn_leaf_step(KnnState & s, BvhView const & b)
+{
+  for (int k = s.t.k; k < s.t.kend; ++k)
+  {
+    TGQ_COUNT_PRIM();
+    f4 e = ldq(b.pts + k);
+    int idx = f2i(e.w);
+    float d2 = sqn3(sub3(mk3(e.x, e.y, e.z), s.p));
+    if (idx == s.skip || !(d2 < s.bound_ub)) continue;
+    if (s.set.accepts(d2, idx))
+    {
+      s.set.insert(d2, idx);
+      if (s.set.full()) s.worst = s.set.worst_key();
+    }
+  }
+  s.t.k = s.t.kend;
+  trav_pop(s.t, s.worst);
+}
+
+TGQ_HD void knn_query(BvhView const & b, v3 p, int skip, float bound_ub, SortedSet & set)
+{
+  KnnState s; TravStack st; trav_bind(s.t, st); s.set = set;
+  knn_begin(s, b, p, skip, bound_ub);
+  while (s.t.cur != TGQ_ST_DONE) { if (s.t.cur >= 0) knn_node_step(s, b); else knn_leaf_step(s, b); }
+  set.n = s.set.n;
+}
+
+// PointSet3::findSampleNeighbors for sample `self` (position c, normal nc): in each round every point j != self with
+// sq(x_j - c) <= r2 and (no normals or n_c . n_j >= min_dot) is offered with key fastSqrt(d2); the set keeps the
+// max_degree smallest (key, idx); the radius doubles for up to `rounds` rounds while fewer than min_degree neighbours were
+// found (PointSet3.hpp:660-681).  The ball/box test uses the reference arithmetic on padded boxes (a superset).
+struct BallState
+{
+  v3 c, nc; bool has_n; float min_dot; int self; float radius, r2; int round, rounds, min_degree;
+  SortedSet set;
+  Trav t;
+};
+
+TGQ_HD void ball_begin(BallState & s, BvhView const & b, v3 c, v3 nc, bool has_n, float min_dot, int self, float init_radius, int rounds,
+                       int min_degree)
+{
+  s.c = c; s.nc = nc; s.has_n = has_n; s.min_dot = min_dot; s.self = self; s.radius = init_radius; s.r2 = init_radius * init_radius;
+  s.round = 0; s.rounds = rounds; s.min_degree = min_degree; s.set.n = 0;
+  trav_begin(s.t, b.n_nodes);
+}
+
+TGQ_HD void ball_node_step(BallState & s, BvhView const & b)
+{
+  TGQ_COUNT_NODE();
+  NodeRec nd = load_node(b, s.t.cur);
+  v3 lo0, hi0, lo1, hi1; node_boxes(nd, lo0, hi0, lo1, hi1);
+  bool go0 = box_point_sqdist(lo0, hi0, s.c) * TGQ_LB_DEFLATE <= s.r2;
+  bool go1 = box_point_sqdist(lo1, hi1, s.c) * TGQ_LB_DEFLATE <= s.r2;
+  int c0 = f2i(nd.q3.x), c1 = f2i(nd.q3.y);
+  if (go0 && go1) { trav_push(s.t, c1, 0.0f); trav_enter(s.t, c0); if (s.t.cur == TGQ_ST_DONE) trav_pop(s.t, 0.0f); }
+  else if (go0 || go1) { trav_enter(s.t, go0 ? c0 : c1); if (s.t.cur == TGQ_ST_DONE) trav_pop(s.t, 0.0f); }
+  else trav_pop(s.t, 0.0f);
+}
+
+TGQ_HD void ball_leaf_step(BallState & s, BvhView const & b)
+{
+  for (int k = s.t.k; k < s.t.kend; ++k)
+  {
+    TGQ_COUNT_PRIM();
+    f4 e = ldq(b.pts + k);
+    int idx = f2i(e.w);
+    if (idx == s.self) continue;
+    v3 diff = sub3(mk3(e.x, e.y, e.z), s.c);
+    float d2 = sqn3(diff);
+    if (!(d2 <= s.r2)) continue;
+    if (s.has_n)
+    {
+      f4 nj = ldq(b.nrm + k);
+      if (dot3(s.nc, mk3(nj.x, nj.y, nj.z)) < s.min_dot) continue;
+    }
+    float sep = fast_sqrt(d2);
+    if (s.set.accepts(sep, idx)) s.set.insert(sep, idx);
+  }
+  s.t.k = s.t.kend;
+  trav_pop(s.t, 0.0f);
+}
+
+// Called when a round's traversal is done: returns true when the query is complete, else starts the next round.
+TGQ_HD bool ball_round_done(BallState & s, BvhView const & b)
+{
+  ++s.round;
+  if (s.set.n >= s.min_degree || s.round >= s.rounds) return true;
+  s.radius *= 2.0f; s.r2 = s.radius * s.radius; s.set.n = 0;
+  trav_begin(s.t, b.n_nodes);
+  return s.t.cur == TGQ_ST_DONE;
 }
 
 TGQ_HD void ball_graph_query(BvhView const & b, v3 c, v3 nc, bool has_n, float min_dot, int self, float init_radius,
                              int rounds, int min_degree, SortedSet & set)
 {
-  float radius = init_radius;
-  for (int it = 0; it < rounds; ++it)
+  BallState s; TravStack st; trav_bind(s.t, st); s.set = set;
+  ball_begin(s, b, c, nc, has_n, min_dot, self, init_radius, rounds, min_degree);
+  for (;;)
   {
-    ball_round(b, c, nc, has_n, min_dot, self, radius * radius, set);
-    if (set.n >= min_degree) break;
-    radius *= 2.0f;
+    while (s.t.cur != TGQ_ST_DONE) { if (s.t.cur >= 0) ball_node_step(s, b); else ball_leaf_step(s, b); }
+    if (ball_round_done(s, b)) break;
   }
+  set.n = s.set.n;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Ray first hit.  best_t enters as max_time (negative = unbounded), best_idx as -1; best_k returns the Morton position
-// of the hit triangle (for its cached normal).  A hit is accepted iff t >= 0 and
-// (unbounded or t < best_t) or it ties the current best with a lower index.  ANY == true stops at the first hit found
-// (BvhN::rayIntersects returns the same boolean as a full first-hit search, BvhN.hpp:1266-1269).
+// Ray first hit.  best_t starts as max_time (negative = unbounded), best_idx as -1; best_k is the Morton position of
+// the hit triangle (for its cached normal).  A hit is accepted iff t >= 0 and (unbounded or t < best_t) or it ties the
+// current best with a lower index.  ANY == true stops at the first hit found (BvhN::rayIntersects returns the same
+// boolean as a full first-hit search, BvhN.hpp:1266-1269).
 // ---------------------------------------------------------------------------------------------------------------------
 struct RaySlab { v3 o, inv; };
 
@@ -396,73 +480,70 @@ struct RayState
 {
   v3 o, d; RaySlab r;
   float best_t; int best_idx, best_k;
-  int cur, sp;
-  int stk_node[TGQ_STACK]; float stk_t[TGQ_STACK];
+  Trav t;
 };
+
+template <bool ANY>
+TGQ_HD float ray_limit(RayState<ANY> const & s) { return s.best_t < 0.0f ? FLT_MAX : s.best_t; }
 
 template <bool ANY>
 TGQ_HD void ray_begin(RayState<ANY> & s, BvhView const & b, v3 o, v3 d, float max_time)
 {
   s.o = o; s.d = d; s.r.o = o; s.r.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
   s.best_t = max_time; s.best_idx = -1; s.best_k = -1;
-  s.sp = b.n_nodes > 0 ? 0 : -1; s.cur = 0;
+  trav_begin(s.t, b.n_nodes);
 }
 
 template <bool ANY>
-TGQ_HD bool ray_run(RayState<ANY> & s, BvhView const & b, int budget)
+TGQ_HD void ray_node_step(RayState<ANY> & s, BvhView const & b)
 {
-  if (s.sp < 0) return true;
-  int cur = s.cur, sp = s.sp;
-  for (;;)
+  TGQ_COUNT_NODE();
+  NodeRec nd = load_node(b, s.t.cur);
+  v3 lo0, hi0, lo1, hi1; node_boxes(nd, lo0, hi0, lo1, hi1);
+  float t0 = slab_entry(s.r, lo0, hi0), t1 = slab_entry(s.r, lo1, hi1);
+  int c0 = f2i(nd.q3.x), c1 = f2i(nd.q3.y);
+  float lim = ray_limit(s);
+  bool go0 = t0 >= 0.0f && t0 <= lim, go1 = t1 >= 0.0f && t1 <= lim;
+  if (go0 && go1)
   {
-    while (cur >= 0)
-    {
-      if (--budget < 0) { s.cur = cur; s.sp = sp; return false; }
-      NodeRec nd = load_node(b, cur);
-      v3 lo0, hi0, lo1, hi1; node_boxes(nd, lo0, hi0, lo1, hi1);
-      float t0 = slab_entry(s.r, lo0, hi0), t1 = slab_entry(s.r, lo1, hi1);
-      int c0 = f2i(nd.q3.x), c1 = f2i(nd.q3.y);
-      bool go0 = t0 >= 0.0f && (s.best_t < 0.0f || t0 <= s.best_t);
-      bool go1 = t1 >= 0.0f && (s.best_t < 0.0f || t1 <= s.best_t);
-      if (go0 && go1)
-      {
-        bool swap = t1 < t0;
-        s.stk_node[sp] = swap ? c0 : c1; s.stk_t[sp] = swap ? t0 : t1; ++sp;
-        cur = swap ? c1 : c0;
-      }
-      else if (go0) cur = c0;
-      else if (go1) cur = c1;
-      else goto pop;
-    }
-    {
-      int code = ~cur; int first = code >> TGQ_LEAF_BITS, count = code & TGQ_LEAF_MASK;
-      for (int k = first; k < first + count; ++k)
-      {
-        f4 const * t = (f4 const *)(b.tris + k);
-        f4 a = ldq(t), bq = ldq(t + 1), c = ldq(t + 2);
-        v3 v0 = mk3(a.x, a.y, a.z);
-        float tm = ray_tri_time(s.o, s.d, v0, sub3(mk3(bq.x, bq.y, bq.z), v0), sub3(mk3(c.x, c.y, c.z), v0));
-        int idx = f2i(a.w);
-        if (tm >= 0.0f && (s.best_idx < 0 ? (s.best_t < 0.0f || tm < s.best_t) : (tm < s.best_t || (tm == s.best_t && idx < s.best_idx))))
-        { s.best_t = tm; s.best_idx = idx; s.best_k = k; if (ANY) { s.sp = -1; return true; } }
-      }
-    }
-  pop:
-    for (;;)
-    {
-      if (sp == 0) { s.sp = -1; return true; }
-      --sp;
-      if (s.best_t < 0.0f || s.stk_t[sp] <= s.best_t) { cur = s.stk_node[sp]; break; }
-    }
+    bool swap = t1 < t0;
+    trav_push(s.t, swap ? c0 : c1, swap ? t0 : t1);
+    trav_enter(s.t, swap ? c1 : c0);
+    if (s.t.cur == TGQ_ST_DONE) trav_pop(s.t, lim);
   }
+  else if (go0 || go1)
+  {
+    trav_enter(s.t, go0 ? c0 : c1);
+    if (s.t.cur == TGQ_ST_DONE) trav_pop(s.t, lim);
+  }
+  else trav_pop(s.t, lim);
+}
+
+// One pending triangle.
+template <bool ANY>
+TGQ_HD void ray_leaf_step(RayState<ANY> & s, BvhView const & b)
+{
+  int k = s.t.k++;
+  TGQ_COUNT_PRIM();
+  f4 const * t = (f4 const *)(b.tris + k);
+  f4 a = ldq(t), bq = ldq(t + 1), c = ldq(t + 2);
+  v3 v0 = mk3(a.x, a.y, a.z);
+  float tm = ray_tri_time(s.o, s.d, v0, sub3(mk3(bq.x, bq.y, bq.z), v0), sub3(mk3(c.x, c.y, c.z), v0));
+  int idx = f2i(a.w);
+  if (tm >= 0.0f && (s.best_idx < 0 ? (s.best_t < 0.0f || tm < s.best_t) : (tm < s.best_t || (tm == s.best_t && idx < s.best_idx))))
+  {
+    s.best_t = tm; s.best_idx = idx; s.best_k = k;
+    if (ANY) { s.t.cur = TGQ_ST_DONE; s.t.sp = 0; return; }
+  }
+  if (s.t.k >= s.t.kend) trav_pop(s.t, ray_limit(s));
 }
 
 template <bool ANY>
 TGQ_HD void ray_query(BvhView const & b, v3 o, v3 d, float & best_t, int & best_idx, int & best_k)
 {
-  RayState<ANY> s;
+  RayState<ANY> s; TravStack st; trav_bind(s.t, st);
   ray_begin(s, b, o, d, best_t);
-  ray_run(s, b, 0x7fffffff);
+  while (s.t.cur != TGQ_ST_DONE) { if (s.t.cur >= 0) ray_node_step(s, b); else ray_leaf_step(s, b); }
   best_t = s.best_t; best_idx = s.best_idx; best_k = s.best_k;
 }
 
