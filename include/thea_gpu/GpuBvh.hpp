@@ -1,0 +1,465 @@
+// GpuBvh.hpp -- header-only C++ adaptor that re-exposes libtgq.so (include/thea_gpu_query.h) under the member-function
+// names of Thea's Algorithms::BvhN / MeshBvh query concept, so that code written against
+//   ProximityQueryStructureN   (Algorithms/ProximityQueryStructureN.hpp:29-35,150-276)
+//   RayQueryStructureN         (Algorithms/RayQueryStructureN.hpp:55-88)
+//   BvhN                       (Algorithms/BvhN.hpp:254-266,704-794,952-995,1036-1146,1266-1316)
+//   MeshBvh                    (Algorithms/MeshBvh.hpp:55-141)
+// can take a TheaGpu::GpuMeshBvh / GpuPointBvh as its structure template argument.  The reference interface is a
+// compile-time concept ("None of the functions are virtual, this just defines a concept"), so being a drop-in means
+// having the same member templates, argument meaning, return conventions (-1 index / negative time = not found) and
+// error behaviour (Thea::Error == std::runtime_error, Error.hpp:27).  File:line citations are relative to
+// /root/reference/Code/Source/.
+//
+// The header depends on nothing but the C ABI and the standard library.  It is templated on the 3-vector type, which
+// only needs `operator[](int)` returning a float-convertible lvalue and a default constructor: Thea's own
+// Vector3 (Eigen::Matrix<Real,3,1,DontAlign>, MatVec.hpp:56) qualifies, as does the bundled TheaGpu::Vec3.
+//
+// Scalar calls (one query per call, the reference's shape) are routed to a batch of one.  The `*Batch` members are the
+// new surface: one C-ABI call for the whole loop that the reference's callers run serially.
+//
+// What is NOT supported, and fails loudly instead of falling back to a CPU path:
+//   - pushFilter / compatibility functors other than UniversalCompatibility (arbitrary host callables cannot run on the
+//     device): pushFilter throws; the built-in device predicates are `exclude_self` and the ball-graph normal test.
+//   - metrics other than L2, BVH-to-BVH queries, setTransform.
+#ifndef THEA_GPU_GPUBVH_HPP
+#define THEA_GPU_GPUBVH_HPP
+
+#include "../thea_gpu_query.h"
+
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace TheaGpu {
+
+typedef std::ptrdiff_t intx;   // Platform.hpp:161
+typedef float Real;            // NumericType.hpp:40
+
+/** Thea::Error (Error.hpp:27). */
+typedef std::runtime_error Error;
+
+/** Minimal 3-vector for callers that do not bring Thea's Vector3. */
+struct Vec3
+{
+  float v[3];
+  Vec3() { v[0] = v[1] = v[2] = 0; }
+  Vec3(float x, float y, float z) { v[0] = x; v[1] = y; v[2] = z; }
+  float & operator[](int i) { return v[i]; }
+  float const & operator[](int i) const { return v[i]; }
+};
+
+/** Tag with the one member of Algorithms::MetricL2 the structure itself uses (MetricL2.hpp:97). */
+struct MetricL2
+{
+  static double invertMonotoneApprox(double d2) { return std::sqrt(d2); }
+};
+/** Tags standing in for Algorithms::RayIntersectionTester / IntersectionTester / UniversalCompatibility. */
+struct RayIntersectionTester {};
+struct IntersectionTester {};
+struct UniversalCompatibility { template <typename U, typename V> bool operator()(U const &, V const &) const { return true; } };
+
+/** ProximityQueryStructureN::NeighborPair (ProximityQueryStructureN.hpp:48-144), including its operator< quirk. */
+template <typename VectorT>
+class NeighborPairT
+{
+  public:
+    NeighborPairT(intx q = -1, intx t = -1, double mad = -1) : query_index(q), target_index(t), mon_approx_dist(mad) {}
+    NeighborPairT(intx q, intx t, double mad, VectorT const & qp, VectorT const & tp)
+    : query_index(q), target_index(t), mon_approx_dist(mad), query_point(qp), target_point(tp) {}
+    bool isValid() const { return query_index >= 0 && target_index >= 0; }
+    intx getQueryIndex() const { return query_index; }
+    void setQueryIndex(intx i) { query_index = i; }
+    intx getTargetIndex() const { return target_index; }
+    void setTargetIndex(intx i) { target_index = i; }
+    double getMonotoneApproxDistance() const { return mon_approx_dist; }
+    void setMonotoneApproxDistance(double d) { mon_approx_dist = d; }
+    template <typename MetricT> double getDistance() const { return MetricT::invertMonotoneApprox(mon_approx_dist); }
+    VectorT const & getQueryPoint() const { return query_point; }
+    VectorT const & getTargetPoint() const { return target_point; }
+    void setQueryPoint(VectorT const & p) { query_point = p; }
+    void setTargetPoint(VectorT const & p) { target_point = p; }
+    bool operator<(NeighborPairT const & o) const
+    {
+      return mon_approx_dist < o.mon_approx_dist
+          || (mon_approx_dist == o.mon_approx_dist
+           && (query_index < o.query_index || (query_index == o.query_index && target_index == o.target_index)));
+    }
+    bool operator==(NeighborPairT const & o) const { return query_index == o.query_index && target_index == o.target_index; }
+
+  private:
+    intx query_index, target_index;
+    double mon_approx_dist;
+    VectorT query_point, target_point;
+};
+
+/** RayStructureIntersectionN<3> (RayQueryStructureN.hpp:28-53; base RayIntersectionN, RayIntersectableN.hpp:27-65). */
+template <typename VectorT>
+class RayStructureIntersectionT
+{
+  public:
+    RayStructureIntersectionT(Real time_ = -1, VectorT const * normal_ = nullptr, intx element_index_ = -1)
+    : time(time_), has_normal(normal_ != nullptr), element_index(element_index_)
+    { if (normal_) normal = *normal_; }
+    bool isValid() const { return time >= 0; }
+    Real getTime() const { return time; }
+    void setTime(Real t) { time = t; }
+    bool hasNormal() const { return has_normal; }
+    VectorT const & getNormal() const { return normal; }
+    intx getElementIndex() const { return element_index; }
+    void setElementIndex(intx i) { element_index = i; }
+
+  private:
+    Real time; bool has_normal; VectorT normal; intx element_index;
+};
+
+/** RayN<3> (RayN.hpp:27-139): origin + direction, direction NOT normalised by the structure. */
+template <typename VectorT>
+struct RayT
+{
+  VectorT origin, direction;
+  RayT() {}
+  RayT(VectorT const & o, VectorT const & d) : origin(o), direction(d) {}
+  VectorT const & getOrigin() const { return origin; }
+  VectorT const & getDirection() const { return direction; }
+};
+
+/** BoundedSortedArray<T> (BoundedSortedArray.hpp:28-308): the subset kClosestPairs and its callers use. */
+template <typename T>
+class BoundedSortedArray
+{
+  public:
+    explicit BoundedSortedArray(size_t capacity_ = 0) : capacity(capacity_) { values.reserve(capacity_); }
+    size_t getCapacity() const { return capacity; }
+    size_t size() const { return values.size(); }
+    bool empty() const { return values.empty(); }
+    T const & operator[](size_t i) const { return values[i]; }
+    T const & first() const { return values.front(); }
+    T const & last() const { return values.back(); }
+    void clear() { values.clear(); }
+    bool isInsertable(T const & t) const { return capacity > 0 && (values.size() < capacity || t < values.back()); }
+    /** Insert keeping ascending order, after any equal elements (upper bound, BoundedSortedArray.hpp:243-265). */
+    size_t insert(T const & t)
+    {
+      if (!isInsertable(t)) return capacity;
+      size_t lo = 0, hi = values.size();
+      while (lo < hi) { size_t mid = (lo + hi) / 2; if (t < values[mid]) hi = mid; else lo = mid + 1; }
+      if (values.size() == capacity) values.pop_back();
+      values.insert(values.begin() + (std::ptrdiff_t)lo, t);
+      return lo;
+    }
+
+  private:
+    size_t capacity;
+    std::vector<T> values;
+};
+
+namespace detail {
+
+inline void check(tgq_handle * h, int rc, char const * what)
+{
+  if (rc != TGQ_OK)
+    throw Error(std::string("TheaGpu: ") + what + " failed (" + std::to_string(rc) + "): " + tgq_last_error(h));
+}
+
+template <typename VectorT> inline void put3(float * dst, VectorT const & v) { dst[0] = (float)v[0]; dst[1] = (float)v[1]; dst[2] = (float)v[2]; }
+template <typename VectorT> inline VectorT get3(float const * src) { VectorT v; v[0] = src[0]; v[1] = src[1]; v[2] = src[2]; return v; }
+
+}  // namespace detail
+
+/**
+ * Common part of the two structures: owns the engine handle.  Mirrors the non-query members of BvhN
+ * (numElements / isEmpty / getBounds / clear, BvhN.hpp:796-813,952-995; enable/disableNearestNeighborAcceleration,
+ * :853-883; pushFilter / popFilter, :1005-1032).
+ */
+template <typename VectorT>
+class GpuBvhBase
+{
+  public:
+    typedef NeighborPairT<VectorT> NeighborPair;
+    typedef RayStructureIntersectionT<VectorT> RayStructureIntersection3;
+    typedef RayT<VectorT> Ray3;
+
+    explicit GpuBvhBase(int device = 0) : h(nullptr)
+    {
+      int rc = tgq_create(device, &h);
+      if (rc != TGQ_OK) throw Error(std::string("TheaGpu: no engine (") + std::to_string(rc) + "): " + tgq_last_error(nullptr));
+    }
+    ~GpuBvhBase() { if (h) tgq_destroy(h); }
+    GpuBvhBase(GpuBvhBase const &) = delete;
+    GpuBvhBase & operator=(GpuBvhBase const &) = delete;
+
+    tgq_handle * handle() const { return h; }
+    void setStream(void * cuda_stream) { detail::check(h, tgq_set_stream(h, cuda_stream), "tgq_set_stream"); }
+    void setOption(int option, int64_t value) { detail::check(h, tgq_set_option(h, option, value), "tgq_set_option"); }
+
+    intx numElements() const { int64_t n = 0; detail::check(h, tgq_info(h, nullptr, &n, nullptr, nullptr), "tgq_info"); return (intx)n; }
+    bool isEmpty() const { return numElements() <= 0; }
+    bool empty() const { return isEmpty(); }
+    /** Unpadded bounds of all elements (BvhN::getBounds, BvhN.hpp:981-995). */
+    void getBounds(VectorT & lo, VectorT & hi) const
+    {
+      float l[3], u[3]; detail::check(h, tgq_info(h, nullptr, nullptr, l, u), "tgq_info");
+      lo = detail::get3<VectorT>(l); hi = detail::get3<VectorT>(u);
+    }
+
+    /** Result-neutral in the reference (it only seeds the pruning bound, BvhN.hpp:2365-2377): accepted and ignored. */
+    void enableNearestNeighborAcceleration(intx = -1) {}
+    void disableNearestNeighborAcceleration(bool = true) {}
+    bool hasNearestNeighborAcceleration() const { return false; }
+
+    /** Host-side filters cannot run on the device and there is no CPU fallback. */
+    template <typename FilterT> void pushFilter(FilterT *) { throw Error("TheaGpu: element filters are not supported by the GPU structure"); }
+    void popFilter() {}
+
+  protected:
+    tgq_handle * h;
+};
+
+/**
+ * Triangle structure: Algorithms::MeshBvh (MeshBvh.hpp:36-141) restricted to the query surface.  Element index = position
+ * of the triangle in the order it was added (MeshTriangles::addTriangles push order, MeshTriangles.hpp:411-418).
+ */
+template <typename VectorT = Vec3>
+class GpuMeshBvhT : public GpuBvhBase<VectorT>
+{
+    typedef GpuBvhBase<VectorT> Base;
+    using Base::h;
+
+  public:
+    typedef typename Base::NeighborPair NeighborPair;
+    typedef typename Base::RayStructureIntersection3 RayStructureIntersection3;
+    typedef typename Base::Ray3 Ray3;
+
+    explicit GpuMeshBvhT(int device = 0) : Base(device), built(false) {}
+
+    /** MeshBvh::addTriangles analogue: appends one triangle to the pending soup (MeshTriangles.hpp:361-370). */
+    void addTriangle(VectorT const & v0, VectorT const & v1, VectorT const & v2)
+    {
+      size_t o = soup.size(); soup.resize(o + 9);
+      detail::put3(&soup[o], v0); detail::put3(&soup[o + 3], v1); detail::put3(&soup[o + 6], v2);
+    }
+    /** Appends T triangles given as T x 9 floats. */
+    void addTriangles(float const * v9, intx T) { soup.insert(soup.end(), v9, v9 + 9 * T); }
+    /** Appends an indexed mesh; faces must be triangles (quads / n-gons are triangulated by the caller as
+     *  MeshTriangles.hpp:173-339 does). */
+    void addMesh(float const * verts3, intx V, int32_t const * tri3, intx T)
+    {
+      for (intx t = 0; t < T; ++t)
+        for (int c = 0; c < 3; ++c)
+        {
+          int32_t v = tri3[3 * t + c];
+          if (v < 0 || v >= V) throw Error("TheaGpu: vertex index out of range");
+          soup.insert(soup.end(), verts3 + 3 * v, verts3 + 3 * v + 3);
+        }
+    }
+
+    /** MeshBvh::init (MeshBvh.hpp:104-111): builds over the pending triangles and, like the reference, clears the
+     *  triangle cache.  The BvhN tuning arguments (method, max_depth, max_elems_per_leaf, save_memory) are accepted for
+     *  source compatibility; only max_elems_per_leaf is meaningful to the LBVH. */
+    void init(int /* method */ = 0, intx /* max_depth */ = -1, intx max_elems_per_leaf = -1, bool /* save_memory */ = false)
+    {
+      if (max_elems_per_leaf > 0) this->setOption(TGQ_OPT_LEAF_SIZE, max_elems_per_leaf > 15 ? 15 : max_elems_per_leaf);
+      detail::check(h, tgq_build_triangles(h, soup.data(), (int64_t)(soup.size() / 9)), "tgq_build_triangles");
+      std::vector<float>().swap(soup); built = true;
+    }
+    /** Build straight from caller-owned (host or device) memory. */
+    void init(float const * v9, intx T) { detail::check(h, tgq_build_triangles(h, v9, T), "tgq_build_triangles"); built = true; }
+
+    void clear() { soup.clear(); detail::check(h, tgq_build_triangles(h, nullptr, 0), "tgq_build_triangles"); built = false; }
+
+    /** MeshBvh::updateElements + BvhN::updateNodeBounds (MeshBvh.hpp:123-134, BvhN.hpp:816-834): same triangles, moved
+     *  vertices. */
+    void updateElements(float const * v9, intx T) { detail::check(h, tgq_refit_triangles(h, v9, T), "tgq_refit_triangles"); }
+
+    /** getElements()[i].getNormal() for all i (used by ShapeDiameter.hpp:152-153). */
+    void getElementNormals(std::vector<float> & n3) const
+    {
+      n3.resize(3 * (size_t)this->numElements());
+      detail::check(h, tgq_triangle_cache(h, n3.data(), nullptr, nullptr, nullptr), "tgq_triangle_cache");
+    }
+
+    // ---- ProximityQueryStructureN ---------------------------------------------------------------------------------------
+
+    /** BvhN::closestElement (BvhN.hpp:1049-1063). */
+    template <typename MetricT, typename CompatibilityFunctorT = UniversalCompatibility>
+    intx closestElement(VectorT const & query, double dist_bound = -1, CompatibilityFunctorT = CompatibilityFunctorT(),
+                        double * dist = nullptr, VectorT * closest_point = nullptr) const
+    {
+      float q[3], d2 = -1, cp[3]; int32_t idx = -1;
+      detail::put3(q, query);
+      detail::check(h, tgq_closest(h, q, 1, dist_bound, 0, &idx, &d2, closest_point ? cp : nullptr), "tgq_closest");
+      if (idx >= 0)
+      {
+        if (dist) *dist = MetricT::invertMonotoneApprox((double)d2);
+        if (closest_point) *closest_point = detail::get3<VectorT>(cp);
+      }
+      return idx;
+    }
+
+    /** BvhN::distance (BvhN.hpp:1036-1047). */
+    template <typename MetricT, typename CompatibilityFunctorT = UniversalCompatibility>
+    double distance(VectorT const & query, double dist_bound = -1, CompatibilityFunctorT c = CompatibilityFunctorT()) const
+    {
+      double result = -1;
+      return closestElement<MetricT>(query, dist_bound, c, &result) >= 0 ? result : -1;
+    }
+
+    /** BvhN::closestPair (BvhN.hpp:1081-1114) for a point query: query index 0, as the reference sets it for
+     *  non-structure queries. */
+    template <typename MetricT, typename CompatibilityFunctorT = UniversalCompatibility>
+    NeighborPair closestPair(VectorT const & query, double dist_bound = -1, CompatibilityFunctorT = CompatibilityFunctorT(),
+                             bool get_closest_points = false) const
+    {
+      float q[3], d2 = -1, cp[3] = {0, 0, 0}; int32_t idx = -1;
+      detail::put3(q, query);
+      detail::check(h, tgq_closest(h, q, 1, dist_bound, 0, &idx, &d2, get_closest_points ? cp : nullptr), "tgq_closest");
+      if (idx < 0) return NeighborPair();
+      return NeighborPair(0, idx, (double)d2, query, detail::get3<VectorT>(cp));
+    }
+
+    /** Q calls of closestElement in one launch.  q3: Q x 3 floats; outputs may be null; host or device pointers. */
+    void closestElementBatch(float const * q3, intx Q, int32_t * idx, float * d2, float * cp3, double dist_bound = -1) const
+    { detail::check(h, tgq_closest(h, q3, Q, dist_bound, 0, idx, d2, cp3), "tgq_closest"); }
+
+    // ---- RayQueryStructureN ---------------------------------------------------------------------------------------------
+
+    /** BvhN::rayIntersects (BvhN.hpp:1266-1269). */
+    template <typename RayIntersectionTesterT>
+    bool rayIntersects(Ray3 const & ray, Real max_time = -1) const
+    {
+      float o[3], d[3]; uint8_t hit = 0; detail::put3(o, ray.getOrigin()); detail::put3(d, ray.getDirection());
+      detail::check(h, tgq_ray_any(h, o, d, &max_time, 1, &hit), "tgq_ray_any");
+      return hit != 0;
+    }
+    /** BvhN::rayIntersectionTime (BvhN.hpp:1271-1289). */
+    template <typename RayIntersectionTesterT>
+    Real rayIntersectionTime(Ray3 const & ray, Real max_time = -1) const
+    {
+      float o[3], d[3], t = -1; detail::put3(o, ray.getOrigin()); detail::put3(d, ray.getDirection());
+      detail::check(h, tgq_ray_first(h, o, d, &max_time, 1, &t, nullptr, nullptr), "tgq_ray_first");
+      return t;
+    }
+    /** BvhN::rayStructureIntersection (BvhN.hpp:1291-1316). */
+    template <typename RayIntersectionTesterT>
+    RayStructureIntersection3 rayStructureIntersection(Ray3 const & ray, Real max_time = -1) const
+    {
+      float o[3], d[3], t = -1, n[3]; int32_t idx = -1; detail::put3(o, ray.getOrigin()); detail::put3(d, ray.getDirection());
+      detail::check(h, tgq_ray_first(h, o, d, &max_time, 1, &t, &idx, n), "tgq_ray_first");
+      if (idx < 0) return RayStructureIntersection3();
+      VectorT nv = detail::get3<VectorT>(n);
+      return RayStructureIntersection3(t, &nv, idx);
+    }
+    /** R first-hit queries in one launch (tmax may be null = unbounded). */
+    void rayStructureIntersectionBatch(float const * o3, float const * d3, float const * tmax, intx R, float * t, int32_t * idx,
+                                       float * normal3 = nullptr) const
+    { detail::check(h, tgq_ray_first(h, o3, d3, tmax, R, t, idx, normal3), "tgq_ray_first"); }
+    void rayIntersectsBatch(float const * o3, float const * d3, float const * tmax, intx R, uint8_t * hit) const
+    { detail::check(h, tgq_ray_any(h, o3, d3, tmax, R, hit), "tgq_ray_any"); }
+
+    // ---- callers' building blocks ---------------------------------------------------------------------------------------
+
+    /** The loop of ShapeDiameter::compute over S samples (ShapeDiameter.hpp:168-258). */
+    void shapeDiameterBatch(float const * p3, float const * n3, intx S, float scale, bool only_hit_interior_surfaces, double * sdf,
+                            float * ray_t = nullptr, int32_t * ray_idx = nullptr) const
+    { detail::check(h, tgq_sdf(h, p3, n3, S, scale, only_hit_interior_surfaces ? 1 : 0, sdf, ray_t, ray_idx), "tgq_sdf"); }
+
+    /** MeshSampler::sampleEvenlyByArea, EXACT mode (MeshSampler.hpp:147-185), with the engine's counter-based generator. */
+    void sampleEvenlyByArea(intx S, uint64_t seed, float * p3, float * n3 = nullptr, int32_t * tri = nullptr) const
+    { detail::check(h, tgq_area_sample(h, S, seed, p3, n3, tri), "tgq_area_sample"); }
+
+  private:
+    std::vector<float> soup;
+    bool built;
+};
+
+/**
+ * Point structure: BvhN<Sample*, 3> of PointSet3 (PointSet3.hpp:329-358,709-723) and BvhN<Vector3, 3> of the k-NN
+ * callers (Tools/Register/Register.cpp:222).  Element index = position in the build array.
+ */
+template <typename VectorT = Vec3>
+class GpuPointBvhT : public GpuBvhBase<VectorT>
+{
+    typedef GpuBvhBase<VectorT> Base;
+    using Base::h;
+
+  public:
+    typedef typename Base::NeighborPair NeighborPair;
+
+    explicit GpuPointBvhT(int device = 0) : Base(device) {}
+
+    /** BvhN::init over P points with optional unit normals (P x 3 each; host or device pointers). */
+    void init(float const * p3, intx P, float const * n3 = nullptr) { detail::check(h, tgq_build_points(h, p3, P, n3), "tgq_build_points"); }
+    void clear() { detail::check(h, tgq_build_points(h, nullptr, 0, nullptr), "tgq_build_points"); }
+
+    template <typename MetricT, typename CompatibilityFunctorT = UniversalCompatibility>
+    intx closestElement(VectorT const & query, double dist_bound = -1, CompatibilityFunctorT = CompatibilityFunctorT(),
+                        double * dist = nullptr, VectorT * closest_point = nullptr) const
+    {
+      float q[3], d2 = -1, cp[3]; int32_t idx = -1;
+      detail::put3(q, query);
+      detail::check(h, tgq_closest(h, q, 1, dist_bound, 0, &idx, &d2, closest_point ? cp : nullptr), "tgq_closest");
+      if (idx >= 0)
+      {
+        if (dist) *dist = MetricT::invertMonotoneApprox((double)d2);
+        if (closest_point) *closest_point = detail::get3<VectorT>(cp);
+      }
+      return idx;
+    }
+    template <typename MetricT, typename CompatibilityFunctorT = UniversalCompatibility>
+    double distance(VectorT const & query, double dist_bound = -1, CompatibilityFunctorT c = CompatibilityFunctorT()) const
+    {
+      double result = -1;
+      return closestElement<MetricT>(query, dist_bound, c, &result) >= 0 ? result : -1;
+    }
+    void closestElementBatch(float const * q3, intx Q, int32_t * idx, float * d2, float * cp3, double dist_bound = -1,
+                             bool exclude_self = false) const
+    { detail::check(h, tgq_closest(h, q3, Q, dist_bound, exclude_self ? 1 : 0, idx, d2, cp3), "tgq_closest"); }
+
+    /** BvhN::kClosestPairs (BvhN.hpp:1137-1146).  Like the reference the set is NOT cleared first: the k nearest are
+     *  offered to it in ascending order through its own isInsertable / insert. */
+    template <typename MetricT, typename BoundedNeighborPairSetT, typename CompatibilityFunctorT = UniversalCompatibility>
+    intx kClosestPairs(VectorT const & query, BoundedNeighborPairSetT & k_closest_pairs, double dist_bound = -1,
+                       CompatibilityFunctorT = CompatibilityFunctorT(), bool get_closest_points = false) const
+    {
+      int32_t k = (int32_t)k_closest_pairs.getCapacity();
+      if (k > TGQ_MAX_K) throw Error("TheaGpu: kClosestPairs supports at most TGQ_MAX_K neighbours");
+      if (k > 0)
+      {
+        float q[3]; detail::put3(q, query);
+        std::vector<int32_t> idx((size_t)k); std::vector<float> d2((size_t)k);
+        detail::check(h, tgq_knn(h, q, 1, k, dist_bound, 0, idx.data(), d2.data()), "tgq_knn");
+        for (int32_t j = 0; j < k && idx[(size_t)j] >= 0; ++j)
+        {
+          NeighborPair pair(0, idx[(size_t)j], (double)d2[(size_t)j]);
+          if (get_closest_points) pair.setQueryPoint(query);
+          if (k_closest_pairs.isInsertable(pair)) k_closest_pairs.insert(pair);
+        }
+      }
+      return (intx)k_closest_pairs.size();
+    }
+    /** Q k-NN queries in one launch: idx / d2 are Q x k, ascending by (d2, idx), unused slots -1. */
+    void kClosestPairsBatch(float const * q3, intx Q, int32_t k, int32_t * idx, float * d2, double dist_bound = -1,
+                            bool exclude_self = false) const
+    { detail::check(h, tgq_knn(h, q3, Q, k, dist_bound, exclude_self ? 1 : 0, idx, d2), "tgq_knn"); }
+
+    /** PointSet3::updateGraph's neighbour search for every sample (PointSet3.hpp:324-391,586-681). */
+    void sampleGraphBatch(int32_t max_degree, float init_radius, int32_t * idx, float * sep, int32_t * count = nullptr, int32_t rounds = 3,
+                          float min_dot = -0.5f, int32_t min_degree = -1) const
+    {
+      if (min_degree < 0) { min_degree = (int32_t)(0.25 * max_degree); if (min_degree < 4) min_degree = 4; if (min_degree > max_degree) min_degree = max_degree; }
+      detail::check(h, tgq_ball_graph(h, max_degree, init_radius, rounds, min_dot, min_degree, idx, sep, count), "tgq_ball_graph");
+    }
+    /** PointSet3.hpp:363-376 with caller-fixed seed samples. */
+    float averageSeparation(int32_t const * seeds, int32_t n) const
+    { float out = 0; detail::check(h, tgq_avg_separation(h, seeds, n, &out), "tgq_avg_separation"); return out; }
+};
+
+typedef GpuMeshBvhT<Vec3> GpuMeshBvh;
+typedef GpuPointBvhT<Vec3> GpuPointBvh;
+
+}  // namespace TheaGpu
+
+#endif

@@ -1,0 +1,126 @@
+// adaptor_driver.cpp -- TEST-ONLY program: exercises include/thea_gpu/GpuBvh.hpp and Callers.hpp the way a Thea caller
+// would (member templates with MetricL2 / RayIntersectionTester tags, scalar and batch forms) and dumps the results for
+// tests/test_adaptor.py to compare with the oracle.  Usage: adaptor_driver <in.bin> <out.bin>
+#include "../../include/thea_gpu/Callers.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+using namespace TheaGpu;
+
+template <typename T> static std::vector<T> rd(FILE * f, size_t n) { std::vector<T> v(n); if (n && fread(v.data(), sizeof(T), n, f) != n) { fprintf(stderr, "short read\n"); exit(2); } return v; }
+template <typename T> static void wr(FILE * f, std::vector<T> const & v) { if (!v.empty()) fwrite(v.data(), sizeof(T), v.size(), f); }
+
+int main(int argc, char ** argv)
+{
+  if (argc < 3) { fprintf(stderr, "usage: %s in.bin out.bin\n", argv[0]); return 2; }
+  try
+  {
+    FILE * fi = fopen(argv[1], "rb"); if (!fi) return 2;
+    std::vector<int64_t> hdr = rd<int64_t>(fi, 5);
+    int64_t T = hdr[0], Q = hdr[1], R = hdr[2], S = hdr[3], NS = hdr[4];
+    std::vector<float> v9 = rd<float>(fi, 9 * T), q3 = rd<float>(fi, 3 * Q), o3 = rd<float>(fi, 3 * R), d3 = rd<float>(fi, 3 * R),
+                       src = rd<float>(fi, 3 * S), sp = rd<float>(fi, 3 * NS), sn = rd<float>(fi, 3 * NS);
+    fclose(fi);
+    FILE * fo = fopen(argv[2], "wb"); if (!fo) return 2;
+
+    // ---- MeshBvh-style build: add triangles one by one, init() ----
+    GpuMeshBvh bvh;
+    for (int64_t t = 0; t < T; ++t)
+      bvh.addTriangle(Vec3(v9[9 * t], v9[9 * t + 1], v9[9 * t + 2]), Vec3(v9[9 * t + 3], v9[9 * t + 4], v9[9 * t + 5]),
+                      Vec3(v9[9 * t + 6], v9[9 * t + 7], v9[9 * t + 8]));
+    bvh.init();
+    bvh.enableNearestNeighborAcceleration();
+    if (bvh.numElements() != T || bvh.isEmpty()) { fprintf(stderr, "numElements mismatch\n"); return 3; }
+
+    // ---- closestElement: batch, then the reference's scalar form for the first few ----
+    std::vector<int32_t> ci(Q); std::vector<float> cd(Q), cc(3 * Q);
+    bvh.closestElementBatch(q3.data(), Q, ci.data(), cd.data(), cc.data());
+    wr(fo, ci); wr(fo, cd); wr(fo, cc);
+    int64_t ns = Q < 16 ? Q : 16;
+    std::vector<int64_t> si(ns); std::vector<double> sd(ns), sdist(ns); std::vector<float> sc(3 * ns);
+    for (int64_t i = 0; i < ns; ++i)
+    {
+      Vec3 q(q3[3 * i], q3[3 * i + 1], q3[3 * i + 2]), cp; double dist = -1;
+      si[i] = bvh.closestElement<MetricL2>(q, -1, UniversalCompatibility(), &dist, &cp);
+      sd[i] = dist; sc[3 * i] = cp[0]; sc[3 * i + 1] = cp[1]; sc[3 * i + 2] = cp[2];
+      sdist[i] = bvh.distance<MetricL2>(q);
+      GpuMeshBvh::NeighborPair pair = bvh.closestPair<MetricL2>(q, -1, UniversalCompatibility(), true);
+      if (pair.getTargetIndex() != si[i] || pair.getDistance<MetricL2>() != dist) { fprintf(stderr, "closestPair disagrees\n"); return 3; }
+    }
+    wr(fo, si); wr(fo, sd); wr(fo, sdist); wr(fo, sc);
+    // dist_bound smaller than the true distance: not found, in band (-1), no exception
+    if (ns > 0)
+    {
+      Vec3 q(q3[0], q3[1], q3[2]);
+      if (bvh.closestElement<MetricL2>(q, sd[0] * 0.5) != -1 || bvh.distance<MetricL2>(q, sd[0] * 0.5) != -1) { fprintf(stderr, "dist_bound not honoured\n"); return 3; }
+    }
+
+    // ---- rays ----
+    std::vector<float> rt(R), rn(3 * R); std::vector<int32_t> ri(R); std::vector<uint8_t> rh(R);
+    bvh.rayStructureIntersectionBatch(o3.data(), d3.data(), nullptr, R, rt.data(), ri.data(), rn.data());
+    bvh.rayIntersectsBatch(o3.data(), d3.data(), nullptr, R, rh.data());
+    wr(fo, rt); wr(fo, ri); wr(fo, rn); wr(fo, rh);
+    int64_t nr = R < 16 ? R : 16;
+    std::vector<float> st(nr), stime(nr), snrm(3 * nr); std::vector<int64_t> sidx(nr); std::vector<uint8_t> shit(nr);
+    for (int64_t i = 0; i < nr; ++i)
+    {
+      GpuMeshBvh::Ray3 ray(Vec3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), Vec3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]));
+      GpuMeshBvh::RayStructureIntersection3 isec = bvh.rayStructureIntersection<RayIntersectionTester>(ray);
+      st[i] = isec.getTime(); sidx[i] = isec.getElementIndex();
+      for (int c = 0; c < 3; ++c) snrm[3 * i + c] = isec.getNormal()[c];
+      stime[i] = bvh.rayIntersectionTime<RayIntersectionTester>(ray);
+      shit[i] = bvh.rayIntersects<RayIntersectionTester>(ray) ? 1 : 0;
+    }
+    wr(fo, st); wr(fo, sidx); wr(fo, snrm); wr(fo, stime); wr(fo, shit);
+
+    // ---- ICP (Icp3 defaults: 3..10 iterations, 1e-4) ----
+    Icp3Gpu icp;
+    float err = -1; intx batches = 0; std::vector<int32_t> corr;
+    Affine3 tr = icp.align(S, src.data(), bvh, &err, &batches, &corr);
+    std::vector<float> trv(tr.m, tr.m + 12); trv.push_back(err);
+    std::vector<int64_t> nb(1, batches);
+    wr(fo, trv); wr(fo, nb); wr(fo, corr);
+
+    // ---- SDF with the retry pass ----
+    float lo[3], hi[3]; { Vec3 l, u; bvh.getBounds(l, u); for (int c = 0; c < 3; ++c) { lo[c] = l[c]; hi[c] = u[c]; } }
+    float diag = std::sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + ((hi[1] - lo[1]) * (hi[1] - lo[1]) + (hi[2] - lo[2]) * (hi[2] - lo[2])));
+    std::vector<double> sdf(NS);
+    shapeDiameter(bvh, sp.data(), sn.data(), NS, diag, sdf.data());
+    std::vector<float> dg(1, diag); wr(fo, dg); wr(fo, sdf);
+
+    // ---- point structure: k-NN batch + kClosestPairs into a BoundedSortedArray, sample graph ----
+    GpuPointBvh pts;
+    pts.init(sp.data(), NS, sn.data());
+    int const K = 8;
+    std::vector<int32_t> ki(NS * K); std::vector<float> kd(NS * K);
+    pts.kClosestPairsBatch(sp.data(), NS, K, ki.data(), kd.data(), -1, true);
+    wr(fo, ki); wr(fo, kd);
+    int64_t nk = NS < 4 ? NS : 4;
+    std::vector<int64_t> ski(nk * 3, -1); std::vector<double> skd(nk * 3, -1);
+    for (int64_t i = 0; i < nk; ++i)
+    {
+      BoundedSortedArray<GpuPointBvh::NeighborPair> set(3);
+      intx found = pts.kClosestPairs<MetricL2>(Vec3(sp[3 * i], sp[3 * i + 1], sp[3 * i + 2]), set);
+      for (intx j = 0; j < found; ++j) { ski[3 * i + j] = set[(size_t)j].getTargetIndex(); skd[3 * i + j] = set[(size_t)j].getMonotoneApproxDistance(); }
+    }
+    wr(fo, ski); wr(fo, skd);
+    std::vector<int32_t> seeds; for (int j = 0; j < 100 && j < NS; ++j) seeds.push_back((int32_t)((j * 7919) % NS));
+    std::vector<int32_t> gi(NS * 6), gc(NS); std::vector<float> gs(NS * 6);
+    float avg = sampleGraph(pts, 6, seeds.data(), (int32_t)seeds.size(), gi.data(), gs.data(), gc.data());
+    std::vector<float> av(1, avg); wr(fo, av); wr(fo, gi); wr(fo, gs); wr(fo, gc);
+
+    // ---- error behaviour: filters are refused loudly, wrong structure kind raises ----
+    bool threw = false;
+    try { int dummy = 0; bvh.pushFilter(&dummy); } catch (Error const &) { threw = true; }
+    if (!threw) { fprintf(stderr, "pushFilter did not throw\n"); return 3; }
+    threw = false;
+    try { BoundedSortedArray<GpuPointBvh::NeighborPair> s2(2); GpuPointBvh empty; empty.kClosestPairs<MetricL2>(Vec3(0, 0, 0), s2); } catch (Error const &) { threw = true; }
+    if (!threw) { fprintf(stderr, "query on an unbuilt structure did not throw\n"); return 3; }
+    fclose(fo);
+    printf("adaptor driver ok\n");
+    return 0;
+  }
+  catch (std::exception const & e) { fprintf(stderr, "exception: %s\n", e.what()); return 4; }
+}

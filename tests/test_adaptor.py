@@ -1,0 +1,130 @@
+"""The header-only C++ adaptor (include/thea_gpu/GpuBvh.hpp, Callers.hpp): compiles against the C ABI on any box; on
+the GPU box a C++ driver written like a Thea caller must reproduce the oracle."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from thea_b200 import gen
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRIVER = os.path.join(ROOT, "tests", "cpp", "adaptor_driver")
+
+
+def _build():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "-s"])
+
+
+def test_adaptor_compiles_and_links(built):
+    _build()
+    assert os.path.exists(DRIVER)
+
+
+def test_adaptor_headers_are_self_contained(built, tmp_path):
+    src = tmp_path / "t.cpp"
+    src.write_text('#include "thea_gpu/Callers.hpp"\nint main() { return sizeof(TheaGpu::GpuMeshBvh) > 0 ? 0 : 1; }\n')
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src)])
+
+
+def test_driver_fails_loudly_without_a_gpu(built, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    _build()
+    inp = tmp_path / "in.bin"
+    inp.write_bytes(struct.pack("<5q", 0, 0, 0, 0, 0))
+    r = subprocess.run([DRIVER, str(inp), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert r.returncode != 0 and "no engine" in r.stderr
+
+
+@pytest.mark.gpu
+def test_adaptor_driver_matches_oracle(built, tmp_path):
+    from oracle import orc
+    _build()
+    mesh = gen.torus_mesh(48)
+    T = len(mesh)
+    b = gen.mesh_bounds(mesh)
+    Q, R, S, NS = 5000, 5000, 1500, 600
+    q = gen.closest_queries(Q, b)
+    o, d = gen.random_rays(R, b)
+    p, n, _ = gen.area_samples(mesh, S)
+    Rm, t = gen.rigid_pose()
+    src = gen.apply_pose(p, Rm, t)
+    sp, sn, _ = gen.area_samples(mesh, NS, seed=99)
+    inp, out = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(inp, "wb") as f:
+        f.write(struct.pack("<5q", T, Q, R, S, NS))
+        for a in (mesh, q, o, d, src, sp, sn):
+            f.write(np.ascontiguousarray(a, np.float32).tobytes())
+    r = subprocess.run([DRIVER, str(inp), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    buf = open(out, "rb").read()
+    pos = [0]
+
+    def take(dtype, count):
+        a = np.frombuffer(buf, dtype=dtype, count=count, offset=pos[0])
+        pos[0] += a.nbytes
+        return a
+
+    ora = orc.Oracle(tris9=mesh)
+    oi, od, oc = ora.closest(q, mode=orc.MODE_BRUTE)
+    assert np.array_equal(take(np.int32, Q), oi.astype(np.int32))
+    assert np.array_equal(take(np.float32, Q), od)
+    assert np.array_equal(take(np.float32, 3 * Q).reshape(-1, 3), oc)
+    ns = 16
+    assert np.array_equal(take(np.int64, ns), oi[:ns])
+    dist = take(np.float64, ns)
+    assert np.array_equal(dist, np.sqrt(od[:ns].astype(np.float64)))        # BvhN.hpp:1058
+    assert np.array_equal(take(np.float64, ns), dist)
+    assert np.array_equal(take(np.float32, 3 * ns).reshape(-1, 3), oc[:ns])
+
+    ori, ort = ora.ray_first(o, d, mode=orc.MODE_BRUTE)
+    rt, ri = take(np.float32, R), take(np.int32, R)
+    rn, rh = take(np.float32, 3 * R).reshape(-1, 3), take(np.uint8, R)
+    assert np.array_equal(rt, ort) and np.array_equal(ri, ori.astype(np.int32))
+    on = ora.tri_cache()[0]
+    hit = ori >= 0
+    assert np.array_equal(rh, hit.astype(np.uint8))
+    assert np.array_equal(rn[hit], on[ori[hit]]) and not rn[~hit].any()
+    assert np.array_equal(take(np.float32, ns), ort[:ns])
+    assert np.array_equal(take(np.int64, ns), ori[:ns])
+    assert np.array_equal(take(np.float32, 3 * ns).reshape(-1, 3), rn[:ns])
+    assert np.array_equal(take(np.float32, ns), ort[:ns])
+    assert np.array_equal(take(np.uint8, ns), hit[:ns].astype(np.uint8))
+
+    trv = take(np.float32, 13)
+    batches = int(take(np.int64, 1)[0])
+    corr = take(np.int32, batches * S).reshape(batches, S)
+    otr, oerr, ocorr = ora.icp(src, mode=orc.MODE_BRUTE)
+    assert batches == ocorr.shape[0]
+    assert np.array_equal(corr[0], ocorr[0].astype(np.int32))
+    assert np.allclose(trv[:12].reshape(3, 4), otr, rtol=1e-5, atol=1e-5)
+    assert abs(trv[12] - oerr) <= 1e-4 * abs(oerr) + 1e-9
+
+    diag = float(take(np.float32, 1)[0])
+    sdf = take(np.float64, NS)
+    osdf = ora.sdf(sp, sn, diag, True, mode=orc.MODE_BRUTE)[0]
+    bad = osdf < 0
+    if bad.any():
+        osdf = osdf.copy()
+        osdf[bad] = ora.sdf(sp[bad], sn[bad], diag, False, mode=orc.MODE_BRUTE)[0]
+    assert np.array_equal(sdf, osdf)
+
+    po = orc.Oracle(points=sp, normals=sn)
+    K = 8
+    oki, okd = po.knn(sp, K, exclude_self=True, mode=orc.MODE_BRUTE)
+    assert np.array_equal(take(np.int32, NS * K).reshape(NS, K), oki.astype(np.int32))
+    assert np.array_equal(take(np.float32, NS * K).reshape(NS, K), okd)
+    ski, skd = take(np.int64, 12).reshape(4, 3), take(np.float64, 12).reshape(4, 3)
+    o3i, o3d = po.knn(sp[:4], 3, mode=orc.MODE_BRUTE)
+    assert np.array_equal(ski, o3i) and np.array_equal(skd, o3d.astype(np.float64))
+    seeds = np.array([(j * 7919) % NS for j in range(100)], np.int64)
+    avg = float(take(np.float32, 1)[0])
+    assert avg == po.avg_separation(seeds)
+    ogi, ogs, ogc = po.ball_graph(6, float(np.float32(np.sqrt(np.float32(6))) * np.float32(avg)), mode=orc.MODE_BRUTE)
+    assert np.array_equal(take(np.int32, NS * 6).reshape(NS, 6), ogi.astype(np.int32))
+    assert np.array_equal(take(np.float32, NS * 6).reshape(NS, 6), ogs)
+    assert np.array_equal(take(np.int32, NS), ogc)
+    assert pos[0] == len(buf)

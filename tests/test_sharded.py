@@ -1,0 +1,114 @@
+"""Multi-rank host logic on CPU (gloo, world_size 2): sharding, result gather and the pooled ICP sums.  The per-rank
+"engine" here is the CPU oracle standing in for thea_b200.Engine (same method shapes), so what is tested is the N>1
+plumbing: 1-rank and 2-rank results must be byte-identical (SURVEY.md 8e determinism requirement)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_ranges_tile_the_batch():
+    from thea_b200.sharded import shard_range
+    for total in (0, 1, 7, 100, 50_000_001):
+        for world in (1, 2, 3, 4, 8):
+            pos = 0
+            for r in range(world):
+                b, c = shard_range(total, r, world)
+                assert b == pos and c >= 0
+                pos += c
+            assert pos == total
+            sizes = [shard_range(total, r, world)[1] for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_combine_icp_sums_matches_pooled_statistics():
+    from thea_b200.sharded import combine_icp_sums
+    rng = np.random.default_rng(0)
+    p, q = rng.normal(size=(1000, 3)), rng.normal(size=(1000, 3))
+    L = np.hstack([np.linalg.qr(rng.normal(size=(3, 3)))[0], rng.normal(size=(3, 1))])
+
+    def sums(p, q):
+        pm, qm = p.mean(0), q.mean(0)
+        cov = (p - pm).T @ (q - qm)
+        r = (L[:, :3] @ pm + L[:, 3] - qm)
+        e = r @ r + (((p - pm) @ L[:, :3].T - (q - qm)) ** 2).sum()
+        return np.concatenate([pm, qm, cov.reshape(9), [e]])
+
+    whole = sums(p, q)
+    parts = [(300, sums(p[:300], q[:300])), (0, np.zeros(16)), (700, sums(p[300:], q[300:]))]
+    assert np.allclose(combine_icp_sums(parts, L), whole, rtol=1e-10, atol=1e-10)
+
+
+class _OracleEngine:
+    """Oracle behind the Engine method shapes (tests only)."""
+
+    def __init__(self, mesh):
+        from oracle import orc
+        self.orc = orc
+        self.o = orc.Oracle(tris9=mesh)
+
+    def closest(self, q):
+        i, d, c = self.o.closest(q, mode=self.orc.MODE_CANON, threads=2)
+        return i.astype(np.int32), d, c
+
+    def ray_first(self, o, d):
+        i, t = self.o.ray_first(o, d, mode=self.orc.MODE_CANON, threads=2)
+        return t, i.astype(np.int32), None
+
+    def icp_sums(self, p, q, tr=None):
+        p, q = np.asarray(p, np.float64), np.asarray(q, np.float64)
+        L = np.eye(3, 4) if tr is None else np.asarray(tr, np.float64).reshape(3, 4)
+        pm, qm = p.mean(0), q.mean(0)
+        r = L[:, :3] @ pm + L[:, 3] - qm
+        e = r @ r + (((p - pm) @ L[:, :3].T - (q - qm)) ** 2).sum()
+        return np.concatenate([pm, qm, ((p - pm).T @ (q - qm)).reshape(9), [e]])
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from thea_b200 import gen
+    from thea_b200.sharded import ShardedEngine, shard_range
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mesh = gen.torus_mesh(24)
+    eng = ShardedEngine(_OracleEngine(mesh))
+    b = gen.mesh_bounds(mesh)
+    q = gen.closest_queries(3001, b)              # odd size: uneven shards
+    o, d = gen.random_rays(2000, b)
+    idx, d2, cp = eng.closest(q)
+    t, ri = eng.ray_first(o, d)
+    s0, c0 = shard_range(len(q), rank, world)
+    sums = eng.icp_sums(q[s0:s0 + c0], cp[s0:s0 + c0])
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), idx=idx, d2=d2, cp=cp, t=t, ri=ri, sums=sums)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_is_byte_identical_to_one_rank(built, tmp_path):
+    import torch.multiprocessing as mp
+    from thea_b200 import gen
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.start_processes(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True, start_method="spawn")
+    mesh = gen.torus_mesh(24)
+    one = _OracleEngine(mesh)
+    b = gen.mesh_bounds(mesh)
+    q = gen.closest_queries(3001, b)
+    o, d = gen.random_rays(2000, b)
+    idx, d2, cp = one.closest(q)
+    t, ri, _ = one.ray_first(o, d)
+    whole = one.icp_sums(q, cp)
+    for r in range(2):
+        z = np.load(tmp_path / f"r{r}.npz")
+        assert z["idx"].tobytes() == idx.tobytes() and z["d2"].tobytes() == d2.tobytes() and z["cp"].tobytes() == cp.tobytes()
+        assert z["t"].tobytes() == t.tobytes() and z["ri"].tobytes() == ri.tobytes()
+        assert np.allclose(z["sums"], whole, rtol=1e-9, atol=1e-12)
+    assert np.load(tmp_path / "r0.npz")["sums"].tobytes() == np.load(tmp_path / "r1.npz")["sums"].tobytes()

@@ -405,6 +405,8 @@ int persistent_grid(tgq_handle * h, K kernel, size_t smem, int64_t n, int * coun
   if (it == h->occupancy.end())
   {
     int per_sm = 0;
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TGQ_BLOCK, smem));
     it = h->occupancy.insert(std::make_pair(key, std::max(1, per_sm))).first;
   }
@@ -620,18 +622,19 @@ int tgq_closest(tgq_handle * h, const float * q3, int64_t Q, double dist_bound, 
   float ub = bound_to_ub(dist_bound);
   Arg args[4] = {{q3, nullptr, 12}, {nullptr, idx, 4}, {nullptr, d2, 4}, {nullptr, cp3, 12}};
   BvhView v = view_of(h); bool tri = h->kind == TGQ_KIND_TRIANGLES;
+  size_t smem = trav_smem_bytes(1);
   return run_batched(h, Q, args, 4, true, [&](ChunkCtx & c) -> int {
     int grid = 0; int * cnt = c.slot->counter.as<int>();
     if (tri)
     {
-      CKRC(persistent_grid(h, k_closest<true>, 0, c.n, cnt, c.stream, &grid));
-      k_closest<true><<<grid, TGQ_BLOCK, 0, c.stream>>>(v, h->pad, (float const *)c.din[0], c.perm, c.n, ub, exclude_self, c.offset, cnt,
+      CKRC(persistent_grid(h, k_closest<true>, smem, c.n, cnt, c.stream, &grid));
+      k_closest<true><<<grid, TGQ_BLOCK, smem, c.stream>>>(v, h->pad, (float const *)c.din[0], c.perm, c.n, ub, exclude_self, c.offset, cnt,
                                                       (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3]);
     }
     else
     {
-      CKRC(persistent_grid(h, k_closest<false>, 0, c.n, cnt, c.stream, &grid));
-      k_closest<false><<<grid, TGQ_BLOCK, 0, c.stream>>>(v, 0.0f, (float const *)c.din[0], c.perm, c.n, ub, exclude_self, c.offset, cnt,
+      CKRC(persistent_grid(h, k_closest<false>, smem, c.n, cnt, c.stream, &grid));
+      k_closest<false><<<grid, TGQ_BLOCK, smem, c.stream>>>(v, 0.0f, (float const *)c.din[0], c.perm, c.n, ub, exclude_self, c.offset, cnt,
                                                        (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3]);
     }
     h->st.last_launches += 1; h->st.total_launches += 1;
@@ -648,7 +651,7 @@ int tgq_knn(tgq_handle * h, const float * q3, int64_t Q, int32_t k, double dist_
   float ub = bound_to_ub(dist_bound);
   Arg args[3] = {{q3, nullptr, 12}, {nullptr, idx, 4 * (size_t)k}, {nullptr, d2, 4 * (size_t)k}};
   BvhView v = view_of(h);
-  size_t smem = 2 * (size_t)k * TGQ_BLOCK * 4;
+  size_t smem = trav_smem_bytes(KnnW::STAGE) + 2 * (size_t)k * TGQ_BLOCK * 4;
   return run_batched(h, Q, args, 3, true, [&](ChunkCtx & c) -> int {
     int grid = 0; int * cnt = c.slot->counter.as<int>();
     CKRC(persistent_grid(h, k_knn, smem, c.n, cnt, c.stream, &grid));
@@ -676,8 +679,9 @@ int tgq_ball_graph(tgq_handle * h, int32_t max_degree, float init_radius, int32_
   cudaEvent_t e0 = get_event(h), e1 = get_event(h);
   CK(cudaEventRecord(e0, s));
   int grid = 0; int * cnt = h->slot[0].counter.as<int>();
-  CKRC(persistent_grid(h, k_ball_graph, 2 * k * TGQ_BLOCK * 4, h->n, cnt, s, &grid));
-  k_ball_graph<<<grid, TGQ_BLOCK, 2 * k * TGQ_BLOCK * 4, s>>>(view_of(h), h->n, max_degree, init_radius, rounds, min_dot, min_degree, cnt, di, ds, dc);
+  size_t smem = trav_smem_bytes(BallW::STAGE) + 2 * k * TGQ_BLOCK * 4;
+  CKRC(persistent_grid(h, k_ball_graph, smem, h->n, cnt, s, &grid));
+  k_ball_graph<<<grid, TGQ_BLOCK, smem, s>>>(view_of(h), h->n, max_degree, init_radius, rounds, min_dot, min_degree, cnt, di, ds, dc);
   CK(cudaGetLastError());
   CK(cudaEventRecord(e1, s));
   h->st.last_launches += 1; h->st.total_launches += 1;
@@ -721,19 +725,20 @@ static int ray_common(tgq_handle * h, const float * o3, const float * d3, const 
   if (R < 0 || (R > 0 && (!o3 || !d3))) return fail(h, TGQ_EINVAL, "ray query: bad arguments");
   Guard g(h);
   BvhView v = view_of(h);
+  size_t smem = trav_smem_bytes(2);
   Arg args[7] = {{o3, nullptr, 12}, {d3, nullptr, 12}, {tmax, nullptr, 4}, {nullptr, t, 4}, {nullptr, idx, 4}, {nullptr, normal3, 12}, {nullptr, hit, 1}};
   return run_batched(h, R, args, 7, true, [&](ChunkCtx & c) -> int {
     int grid = 0; int * cnt = c.slot->counter.as<int>();
     if (any)
     {
-      CKRC(persistent_grid(h, k_ray<true>, 0, c.n, cnt, c.stream, &grid));
-      k_ray<true><<<grid, TGQ_BLOCK, 0, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], (float const *)c.din[2], c.perm, c.n, cnt,
+      CKRC(persistent_grid(h, k_ray<true>, smem, c.n, cnt, c.stream, &grid));
+      k_ray<true><<<grid, TGQ_BLOCK, smem, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], (float const *)c.din[2], c.perm, c.n, cnt,
                                                     (float *)c.dout[3], (int *)c.dout[4], (float *)c.dout[5], (uint8_t *)c.dout[6]);
     }
     else
     {
-      CKRC(persistent_grid(h, k_ray<false>, 0, c.n, cnt, c.stream, &grid));
-      k_ray<false><<<grid, TGQ_BLOCK, 0, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], (float const *)c.din[2], c.perm, c.n, cnt,
+      CKRC(persistent_grid(h, k_ray<false>, smem, c.n, cnt, c.stream, &grid));
+      k_ray<false><<<grid, TGQ_BLOCK, smem, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], (float const *)c.din[2], c.perm, c.n, cnt,
                                                      (float *)c.dout[3], (int *)c.dout[4], (float *)c.dout[5], (uint8_t *)c.dout[6]);
     }
     h->st.last_launches += 1; h->st.total_launches += 1;
@@ -755,6 +760,7 @@ int tgq_sdf(tgq_handle * h, const float * p3, const float * n3, int64_t S, float
   Guard g(h);
   BvhView v = view_of(h);
   // per-sample arrays; the 30 rays of a sample stay together so the epilogue is one thread per sample
+  size_t smem = trav_smem_bytes(SdfW::STAGE);
   Arg args[5] = {{p3, nullptr, 12}, {n3, nullptr, 12}, {nullptr, sdf, 8}, {nullptr, ray_t, 120}, {nullptr, ray_idx, 120}};
   return run_batched(h, S, args, 5, false, [&](ChunkCtx & c) -> int {
     Slot & sl = *c.slot; size_t nr = 30 * (size_t)c.n;
@@ -762,8 +768,8 @@ int tgq_sdf(tgq_handle * h, const float * p3, const float * n3, int64_t S, float
     float * dt = c.dout[3] ? (float *)c.dout[3] : sl.keys[0].as<float>();
     uint8_t * dv = sl.keys[1].as<uint8_t>();
     int grid = 0; int * cnt = sl.counter.as<int>();
-    CKRC(persistent_grid(h, k_sdf_rays, 0, (int64_t)nr, cnt, c.stream, &grid));
-    k_sdf_rays<<<grid, TGQ_BLOCK, 0, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], (int)nr, scale, only_hit_interior, cnt, dt,
+    CKRC(persistent_grid(h, k_sdf_rays, smem, (int64_t)nr, cnt, c.stream, &grid));
+    k_sdf_rays<<<grid, TGQ_BLOCK, smem, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], (int)nr, scale, only_hit_interior, cnt, dt,
                                                  (int *)c.dout[4], dv);
     if (c.dout[2]) k_sdf_stats<<<grid_for(c.n), TGQ_BLOCK, 0, c.stream>>>(dt, dv, c.n, scale, (double *)c.dout[2]);
     h->st.last_launches += c.dout[2] ? 2 : 1; h->st.total_launches += c.dout[2] ? 2 : 1;

@@ -321,13 +321,19 @@ __global__ void k_query_codes(float const * __restrict__ q3, int n, SceneBox con
 //   in TGQ_ST_IDLE, or restarts it]
 #define TGQ_CHUNK 64
 #define TGQ_BOTH 12      // a group of at least this many lanes is stepped even when it is the smaller one
+#define TGQ_SSTACK 20    // stack entries per thread kept in shared memory (deeper ones spill to local memory)
+#define TGQ_WARPS (TGQ_BLOCK / 32)
+
+// Shared memory of one block of a traversal kernel: the short stacks, then one staging buffer of TGQ_CHUNK query records
+// per warp (STAGE float4 per record), then whatever the kernel itself needs (k-NN sets).
+__host__ __device__ constexpr size_t trav_smem_bytes(int stage_f4) { return (size_t)TGQ_SSTACK * TGQ_BLOCK * sizeof(StackEntry) + (size_t)TGQ_WARPS * TGQ_CHUNK * stage_f4 * sizeof(f4); }
 
 template <typename W>
-__device__ __forceinline__ void warp_run(W & w, int n, int * counter)
+__device__ __forceinline__ void warp_run(W & w, int n, int * counter, f4 * stage)
 {
   unsigned const FULL = 0xffffffffu;
   int lane = threadIdx.x & 31;
-  int chunk_next = 0, chunk_end = 0; bool exhausted = false;
+  int chunk_base = 0, chunk_next = 0, chunk_end = 0; bool exhausted = false;
   for (;;)
   {
     if (w.state() == TGQ_ST_DONE) w.finish();
@@ -339,13 +345,20 @@ __device__ __forceinline__ void warp_run(W & w, int n, int * counter)
         int base = 0;
         if (lane == 0) base = atomicAdd(counter, TGQ_CHUNK);
         base = __shfl_sync(FULL, base, 0);
-        chunk_next = base; chunk_end = min(base + TGQ_CHUNK, n);
+        chunk_base = chunk_next = base; chunk_end = min(base + TGQ_CHUNK, n);
         if (base >= n) exhausted = true;
+        else
+        {
+          // all lanes fetch the chunk's query records (coalesced, one latency per TGQ_CHUNK queries instead of one per refill)
+          __syncwarp();
+          for (int j = lane; j < chunk_end - chunk_base; j += 32) w.stage(chunk_base + j, stage + (size_t)j * W::STAGE);
+          __syncwarp();
+        }
       }
       if (!exhausted)
       {
         int t = chunk_next + __popc(idle & ((1u << lane) - 1u));
-        if (w.state() == TGQ_ST_IDLE && t < chunk_end) w.begin(t);
+        if (w.state() == TGQ_ST_IDLE && t < chunk_end) w.begin(t, stage + (size_t)(t - chunk_base) * W::STAGE);
         chunk_next = min(chunk_next + __popc(idle), chunk_end);
       }
     }
@@ -362,17 +375,33 @@ __device__ __forceinline__ void warp_run(W & w, int n, int * counter)
   }
 }
 
+// Binds the calling thread's short stack and returns its warp's staging buffer; `extra` = first byte after both.
+__device__ __forceinline__ f4 * trav_setup(Trav & t, TravStack & st, unsigned char * smem, int stage_f4, unsigned char ** extra)
+{
+  trav_bind(t, st);
+  trav_bind_fast(t, (StackEntry *)smem + threadIdx.x, TGQ_BLOCK, TGQ_SSTACK);
+  f4 * stage_all = (f4 *)(smem + (size_t)TGQ_SSTACK * TGQ_BLOCK * sizeof(StackEntry));
+  if (extra) *extra = (unsigned char *)(stage_all + (size_t)TGQ_WARPS * TGQ_CHUNK * stage_f4);
+  return stage_all + (size_t)(threadIdx.x >> 5) * TGQ_CHUNK * stage_f4;
+}
+
 // ---- K5 closest element -------------------------------------------------------------------------------------------------
 template <bool TRI>
 struct ClosestW
 {
+  static constexpr int STAGE = 1;       // (x, y, z, query index)
   ClosestState<TRI> s; BvhView b; float scene_pad; float const * q3; uint32_t const * perm; float ub; int exclude_self; int64_t self_offset;
-  int * idx; float * d2; float * cp3; int64_t qi;
+  int * idx; float * d2; float * cp3; int qi;
   __device__ __forceinline__ int state() const { return s.t.cur; }
-  __device__ __forceinline__ void begin(int t)
+  __device__ __forceinline__ void stage(int t, f4 * dst) const
   {
-    qi = perm ? perm[t] : t;
-    closest_begin(s, b, scene_pad, ld3(q3, qi), exclude_self ? (int)(self_offset + qi) : -1, ub);
+    int i = perm ? (int)perm[t] : t; v3 p = ld3(q3, i);
+    *dst = make_float4(p.x, p.y, p.z, __int_as_float(i));
+  }
+  __device__ __forceinline__ void begin(int, f4 const * src)
+  {
+    f4 r = *src; qi = __float_as_int(r.w);
+    closest_begin(s, b, scene_pad, mk3(r.x, r.y, r.z), exclude_self ? (int)(self_offset + qi) : -1, ub);
   }
   __device__ __forceinline__ void node_step() { closest_node_step(s, b); }
   __device__ __forceinline__ void leaf_step() { closest_leaf_step(s, b); }
@@ -390,22 +419,30 @@ __global__ void __launch_bounds__(TGQ_BLOCK)
 k_closest(BvhView b, float scene_pad, float const * __restrict__ q3, uint32_t const * __restrict__ perm, int n, float bound_ub, int exclude_self,
           int64_t self_offset, int * counter, int * idx, float * d2, float * cp3)
 {
+  extern __shared__ __align__(16) unsigned char smem[];
   ClosestW<TRI> w;
   w.b = b; w.scene_pad = scene_pad; w.q3 = q3; w.perm = perm; w.ub = bound_ub; w.exclude_self = exclude_self; w.self_offset = self_offset;
-  w.idx = idx; w.d2 = d2; w.cp3 = cp3; w.qi = 0; w.s.t.cur = TGQ_ST_IDLE; TravStack st; trav_bind(w.s.t, st);
-  warp_run(w, n, counter);
+  w.idx = idx; w.d2 = d2; w.cp3 = cp3; w.qi = 0; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
+  f4 * stage = trav_setup(w.s.t, st, smem, ClosestW<TRI>::STAGE, nullptr);
+  warp_run(w, n, counter, stage);
 }
 
 // ---- K6 k nearest neighbours: one bounded sorted set per thread in shared memory -------------------------------------
 struct KnnW
 {
+  static constexpr int STAGE = 1;
   KnnState s; BvhView b; float const * q3; uint32_t const * perm; int k; float ub; int exclude_self; int64_t self_offset;
   int * idx; float * d2; int64_t qi;
   __device__ __forceinline__ int state() const { return s.t.cur; }
-  __device__ __forceinline__ void begin(int t)
+  __device__ __forceinline__ void stage(int t, f4 * dst) const
   {
-    qi = perm ? perm[t] : t;
-    knn_begin(s, b, ld3(q3, qi), exclude_self ? (int)(self_offset + qi) : -1, ub);
+    int i = perm ? (int)perm[t] : t; v3 p = ld3(q3, i);
+    *dst = make_float4(p.x, p.y, p.z, __int_as_float(i));
+  }
+  __device__ __forceinline__ void begin(int, f4 const * src)
+  {
+    f4 r = *src; qi = __float_as_int(r.w);
+    knn_begin(s, b, mk3(r.x, r.y, r.z), exclude_self ? (int)(self_offset + qi) : -1, ub);
   }
   __device__ __forceinline__ void node_step() { knn_node_step(s, b); }
   __device__ __forceinline__ void leaf_step() { knn_leaf_step(s, b); }
@@ -425,27 +462,32 @@ __global__ void __launch_bounds__(TGQ_BLOCK)
 k_knn(BvhView b, float const * __restrict__ q3, uint32_t const * __restrict__ perm, int n, int k, float bound_ub, int exclude_self,
       int64_t self_offset, int * counter, int * idx, float * d2)
 {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) unsigned char smem[];
   KnnW w;
   w.b = b; w.q3 = q3; w.perm = perm; w.k = k; w.ub = bound_ub; w.exclude_self = exclude_self; w.self_offset = self_offset;
-  w.idx = idx; w.d2 = d2; w.qi = 0; w.s.t.cur = TGQ_ST_IDLE; TravStack st; trav_bind(w.s.t, st);
-  w.s.set.init(smem + threadIdx.x, (int *)(smem + (size_t)k * blockDim.x) + threadIdx.x, blockDim.x, k);
-  warp_run(w, n, counter);
+  w.idx = idx; w.d2 = d2; w.qi = 0; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
+  unsigned char * extra; f4 * stage = trav_setup(w.s.t, st, smem, KnnW::STAGE, &extra);
+  float * sets = (float *)extra;
+  w.s.set.init(sets + threadIdx.x, (int *)(sets + (size_t)k * blockDim.x) + threadIdx.x, blockDim.x, k);
+  warp_run(w, n, counter, stage);
 }
 
 // ---- K7 ball graph over the structure's own points (query t is the point at Morton position t) ---------------------------
 struct BallW
 {
+  static constexpr int STAGE = 2;       // (x, y, z, element index) (normal, -)
   BallState s; BvhView b; int k; float init_radius; int rounds; float min_dot; int min_degree;
   int * idx; float * sep; int * count; int64_t qi;
   __device__ __forceinline__ int state() const { return s.t.cur; }
-  __device__ __forceinline__ void begin(int t)
+  __device__ __forceinline__ void stage(int t, f4 * dst) const
   {
-    f4 e = b.pts[t]; qi = __float_as_int(e.w);
-    bool has_n = b.nrm != nullptr;
-    v3 nc = mk3(0.0f, 0.0f, 0.0f);
-    if (has_n) { f4 q = b.nrm[t]; nc = mk3(q.x, q.y, q.z); }
-    ball_begin(s, b, mk3(e.x, e.y, e.z), nc, has_n, min_dot, (int)qi, init_radius, rounds, min_degree);
+    dst[0] = b.pts[t];
+    dst[1] = b.nrm ? b.nrm[t] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  }
+  __device__ __forceinline__ void begin(int, f4 const * src)
+  {
+    f4 e = src[0], q = src[1]; qi = __float_as_int(e.w);
+    ball_begin(s, b, mk3(e.x, e.y, e.z), mk3(q.x, q.y, q.z), b.nrm != nullptr, min_dot, (int)qi, init_radius, rounds, min_degree);
   }
   __device__ __forceinline__ void node_step() { ball_node_step(s, b); }
   __device__ __forceinline__ void leaf_step() { ball_leaf_step(s, b); }
@@ -466,25 +508,34 @@ struct BallW
 __global__ void __launch_bounds__(TGQ_BLOCK)
 k_ball_graph(BvhView b, int n, int k, float init_radius, int rounds, float min_dot, int min_degree, int * counter, int * idx, float * sep, int * count)
 {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) unsigned char smem[];
   BallW w;
   w.b = b; w.k = k; w.init_radius = init_radius; w.rounds = rounds; w.min_dot = min_dot; w.min_degree = min_degree;
-  w.idx = idx; w.sep = sep; w.count = count; w.qi = 0; w.s.t.cur = TGQ_ST_IDLE; TravStack st; trav_bind(w.s.t, st);
-  w.s.set.init(smem + threadIdx.x, (int *)(smem + (size_t)k * blockDim.x) + threadIdx.x, blockDim.x, k);
-  warp_run(w, n, counter);
+  w.idx = idx; w.sep = sep; w.count = count; w.qi = 0; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
+  unsigned char * extra; f4 * stage = trav_setup(w.s.t, st, smem, BallW::STAGE, &extra);
+  float * sets = (float *)extra;
+  w.s.set.init(sets + threadIdx.x, (int *)(sets + (size_t)k * blockDim.x) + threadIdx.x, blockDim.x, k);
+  warp_run(w, n, counter, stage);
 }
 
 // ---- K8 ray first hit / any hit ------------------------------------------------------------------------------------------
 template <bool ANY>
 struct RayW
 {
+  static constexpr int STAGE = 2;       // (origin, query index) (direction, max time)
   RayState<ANY> s; BvhView b; float const * o3; float const * d3; float const * tmax; uint32_t const * perm;
-  float * t_out; int * idx; float * normal3; uint8_t * hit; int64_t qi;
+  float * t_out; int * idx; float * normal3; uint8_t * hit; int qi;
   __device__ __forceinline__ int state() const { return s.t.cur; }
-  __device__ __forceinline__ void begin(int t)
+  __device__ __forceinline__ void stage(int t, f4 * dst) const
   {
-    qi = perm ? perm[t] : t;
-    ray_begin(s, b, ld3(o3, qi), ld3(d3, qi), tmax ? tmax[qi] : -1.0f);
+    int i = perm ? (int)perm[t] : t; v3 o = ld3(o3, i), d = ld3(d3, i);
+    dst[0] = make_float4(o.x, o.y, o.z, __int_as_float(i));
+    dst[1] = make_float4(d.x, d.y, d.z, tmax ? tmax[i] : -1.0f);
+  }
+  __device__ __forceinline__ void begin(int, f4 const * src)
+  {
+    f4 o = src[0], d = src[1]; qi = __float_as_int(o.w);
+    ray_begin(s, b, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), d.w);
   }
   __device__ __forceinline__ void node_step() { ray_node_step(s, b); }
   __device__ __forceinline__ void leaf_step() { ray_leaf_step(s, b); }
@@ -508,10 +559,12 @@ __global__ void __launch_bounds__(TGQ_BLOCK)
 k_ray(BvhView b, float const * __restrict__ o3, float const * __restrict__ d3, float const * __restrict__ tmax,
       uint32_t const * __restrict__ perm, int n, int * counter, float * t_out, int * idx, float * normal3, uint8_t * hit)
 {
+  extern __shared__ __align__(16) unsigned char smem[];
   RayW<ANY> w;
   w.b = b; w.o3 = o3; w.d3 = d3; w.tmax = tmax; w.perm = perm; w.t_out = t_out; w.idx = idx; w.normal3 = normal3; w.hit = hit; w.qi = 0;
-  w.s.t.cur = TGQ_ST_IDLE; TravStack st; trav_bind(w.s.t, st);
-  warp_run(w, n, counter);
+  w.s.t.cur = TGQ_ST_IDLE; TravStack st;
+  f4 * stage = trav_setup(w.s.t, st, smem, RayW<ANY>::STAGE, nullptr);
+  warp_run(w, n, counter, stage);
 }
 
 // SDF cone rays (ShapeDiameter.hpp:168-220): thread = (sample, ray).  valid = hit && (!interior || n_hit . dir >= 0).
@@ -530,15 +583,22 @@ __constant__ float c_cone_dirs[30][3] = {
 
 struct SdfW
 {
+  static constexpr int STAGE = 2;       // (origin, ray number) (direction, -)
   RayState<false> s; BvhView b; float const * p3; float const * n3; float scale; int interior;
   float * t_out; int * idx; uint8_t * valid; int64_t r;
   __device__ __forceinline__ int state() const { return s.t.cur; }
-  __device__ __forceinline__ void begin(int t)
+  __device__ __forceinline__ void stage(int t, f4 * dst) const
   {
-    r = t;
-    int64_t sm = r / 30; int k = (int)(r - sm * 30);
+    int sm = t / 30, k = t - sm * 30;
     SdfFrame f = sdf_frame(ld3(p3, sm), ld3(n3, sm), scale);
-    ray_begin(s, b, f.origin, sdf_dir(f, mk3(c_cone_dirs[k][0], c_cone_dirs[k][1], c_cone_dirs[k][2])), -1.0f);
+    v3 d = sdf_dir(f, mk3(c_cone_dirs[k][0], c_cone_dirs[k][1], c_cone_dirs[k][2]));
+    dst[0] = make_float4(f.origin.x, f.origin.y, f.origin.z, __int_as_float(t));
+    dst[1] = make_float4(d.x, d.y, d.z, 0.0f);
+  }
+  __device__ __forceinline__ void begin(int, f4 const * src)
+  {
+    f4 o = src[0], d = src[1]; r = __float_as_int(o.w);
+    ray_begin(s, b, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), -1.0f);
   }
   __device__ __forceinline__ void node_step() { ray_node_step(s, b); }
   __device__ __forceinline__ void leaf_step() { ray_leaf_step(s, b); }
@@ -557,10 +617,12 @@ __global__ void __launch_bounds__(TGQ_BLOCK)
 k_sdf_rays(BvhView b, float const * __restrict__ p3, float const * __restrict__ n3, int nrays, float scale, int interior, int * counter,
            float * t_out, int * idx, uint8_t * valid)
 {
+  extern __shared__ __align__(16) unsigned char smem[];
   SdfW w;
   w.b = b; w.p3 = p3; w.n3 = n3; w.scale = scale; w.interior = interior; w.t_out = t_out; w.idx = idx; w.valid = valid; w.r = 0;
-  w.s.t.cur = TGQ_ST_IDLE; TravStack st; trav_bind(w.s.t, st);
-  warp_run(w, nrays, counter);
+  w.s.t.cur = TGQ_ST_IDLE; TravStack st;
+  f4 * stage = trav_setup(w.s.t, st, smem, SdfW::STAGE, nullptr);
+  warp_run(w, nrays, counter, stage);
 }
 
 // ---- K9 ICP sums: order-independent fixed-point accumulation (bit-identical for any launch shape / GPU count) ---------

@@ -61,14 +61,20 @@ TGQ_HD NodeRec load_node(BvhView const & b, int i)
 }
 
 // Traversal bookkeeping shared by all query kinds: pending node / leaf range and the stack of deferred siblings.
-// The stack arrays live outside the struct (TravStack, declared by the caller) so that the scalar state stays in registers.
+// The first `fast_cap` stack entries live in a caller-provided strided array (shared memory on the device: entry j of a
+// thread at fast[j * fast_stride], conflict free for any mix of depths because the stride is a multiple of the bank
+// count), deeper entries in TravStack (thread-local memory; ordered DFS rarely gets that deep).  ncu on the
+// local-memory-only version showed 30 % of all stall samples on the pop loop's dependent local loads.
+struct alignas(8) StackEntry { int node; float key; };
 struct TravStack { int node[TGQ_STACK]; float key[TGQ_STACK]; };
 struct Trav
 {
   int cur, k, kend, sp;
+  StackEntry * fast; int fast_stride, fast_cap;
   int * stk_node; float * stk_key;
 };
-TGQ_HD void trav_bind(Trav & t, TravStack & st) { t.stk_node = st.node; t.stk_key = st.key; }
+TGQ_HD void trav_bind(Trav & t, TravStack & st) { t.stk_node = st.node; t.stk_key = st.key; t.fast = nullptr; t.fast_stride = 0; t.fast_cap = 0; }
+TGQ_HD void trav_bind_fast(Trav & t, StackEntry * fast, int stride, int cap) { t.fast = fast; t.fast_stride = stride; t.fast_cap = cap; }
 
 TGQ_HD void trav_enter(Trav & t, int code)
 {
@@ -76,7 +82,12 @@ TGQ_HD void trav_enter(Trav & t, int code)
   else { int c = ~code; t.k = c >> TGQ_LEAF_BITS; t.kend = t.k + (c & TGQ_LEAF_MASK); t.cur = (t.kend > t.k) ? TGQ_ST_LEAF : TGQ_ST_DONE; }
 }
 TGQ_HD void trav_begin(Trav & t, int n_nodes) { t.sp = 0; t.k = t.kend = 0; t.cur = n_nodes > 0 ? 0 : TGQ_ST_DONE; }
-TGQ_HD void trav_push(Trav & t, int code, float key) { t.stk_node[t.sp] = code; t.stk_key[t.sp] = key; ++t.sp; }
+TGQ_HD void trav_push(Trav & t, int code, float key)
+{
+  if (t.sp < t.fast_cap) { StackEntry e; e.node = code; e.key = key; t.fast[t.sp * t.fast_stride] = e; }
+  else { t.stk_node[t.sp - t.fast_cap] = code; t.stk_key[t.sp - t.fast_cap] = key; }
+  ++t.sp;
+}
 // Pops deferred siblings until one whose key is still <= limit (keys are lower bounds / entry times), else finishes.
 TGQ_HD void trav_pop(Trav & t, float limit)
 {
@@ -84,7 +95,10 @@ TGQ_HD void trav_pop(Trav & t, float limit)
   while (t.sp > 0)
   {
     --t.sp;
-    if (t.stk_key[t.sp] <= limit) { trav_enter(t, t.stk_node[t.sp]); if (t.cur != TGQ_ST_DONE) return; }
+    int code; float key;
+    if (t.sp < t.fast_cap) { StackEntry e = t.fast[t.sp * t.fast_stride]; code = e.node; key = e.key; }
+    else { code = t.stk_node[t.sp - t.fast_cap]; key = t.stk_key[t.sp - t.fast_cap]; }
+    if (key <= limit) { trav_enter(t, code); if (t.cur != TGQ_ST_DONE) return; }
   }
 }
 

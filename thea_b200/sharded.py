@@ -1,0 +1,154 @@
+"""Multi-GPU driver: the BVH is replicated (every rank builds the same structure), the query batch is sharded
+contiguously over the ranks, and the per-shard results are gathered once at the end.
+
+One process per GPU, ``torch.distributed`` for the plumbing: NCCL over NVLink/NVSwitch when the result tensors live on
+the GPU, gloo when they are host tensors (the CPU tests).  The queries themselves never cross GPUs: each one reads the
+immutable structure and writes its own result slot, so there is no data-path collective; the only exchanges are the
+final gather of the result arrays and, for ICP, 17 doubles per iteration.
+
+Nothing here computes queries: `engine` is a thea_b200.Engine (or anything with the same methods).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(total: int, rank: int, world: int):
+    """Contiguous shard [begin, begin + count) of `total` items for `rank` of `world` (sizes differ by at most one)."""
+    b = total * rank // world
+    e = total * (rank + 1) // world
+    return b, e - b
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def world_info(group=None):
+    dist = _dist()
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def gather_shards(local, total: int, group=None):
+    """All-gathers the per-rank shards (first dimension sharded by shard_range) into the full array on every rank.
+
+    `local` is a torch tensor (CUDA -> NCCL, CPU -> gloo) or a numpy array (gathered through a CPU tensor).  Shards are
+    padded to the largest shard so that one all_gather_into_tensor moves everything; the result is byte-identical to
+    what a single rank would have produced for the whole batch.
+    """
+    import torch
+    dist = _dist()
+    rank, world = world_info(group)
+    is_np = isinstance(local, np.ndarray)
+    t = torch.from_numpy(np.ascontiguousarray(local)) if is_np else local.contiguous()
+    if world == 1:
+        return local
+    counts = [shard_range(total, r, world)[1] for r in range(world)]
+    assert t.shape[0] == counts[rank], f"rank {rank}: shard has {t.shape[0]} rows, expected {counts[rank]}"
+    mx = max(counts)
+    tail = tuple(t.shape[1:])
+    if t.shape[0] < mx:
+        pad = torch.zeros((mx - t.shape[0],) + tail, dtype=t.dtype, device=t.device)
+        t = torch.cat([t, pad], dim=0)
+    out = torch.empty((world * mx,) + tail, dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    if all(c == mx for c in counts):
+        full = out
+    else:
+        full = torch.cat([out[r * mx:r * mx + counts[r]] for r in range(world)], dim=0)
+    return full.numpy() if is_np else full
+
+
+def combine_icp_sums(parts, tr12=None):
+    """Combines per-shard tgq_icp_sums outputs [(n_s, out16_s), ...] (in rank order) into the sums of the whole set.
+
+    out16 = (mean p, mean q, centred cross-covariance, error) as documented in include/thea_gpu_query.h; the pooled
+    statistics follow from the raw sums, accumulated in float64 in rank order (deterministic for a given world size).
+    """
+    L = np.eye(3, 4) if tr12 is None else np.asarray(tr12, np.float64).reshape(3, 4)
+    N = 0.0
+    sp = np.zeros(3)
+    sq = np.zeros(3)
+    spq = np.zeros((3, 3))
+    tot = 0.0
+    for n_s, o in parts:
+        o = np.asarray(o, np.float64)
+        n_s = float(n_s)
+        if n_s <= 0:
+            continue
+        pm, qm, cov, err = o[0:3], o[3:6], o[6:15].reshape(3, 3), o[15]
+        rbar = L[:, :3] @ pm + L[:, 3] - qm
+        N += n_s
+        sp += n_s * pm
+        sq += n_s * qm
+        spq += cov + n_s * np.outer(pm, qm)
+        tot += (err - rbar @ rbar) + n_s * (rbar @ rbar)       # raw sum |L p + t - q|^2 of the shard
+    out = np.zeros(16)
+    if N == 0:
+        return out
+    pm, qm = sp / N, sq / N
+    out[0:3], out[3:6] = pm, qm
+    out[6:15] = (spq - N * np.outer(pm, qm)).reshape(9)
+    rbar = L[:, :3] @ pm + L[:, 3] - qm
+    out[15] = rbar @ rbar + (tot - N * (rbar @ rbar))
+    return out
+
+
+class ShardedEngine:
+    """Query front end for one rank of a replicated-BVH / sharded-queries job.
+
+    Every rank calls the same method with the same GLOBAL query arrays (or with `local=True` and only its own shard);
+    each returns the gathered global results.
+    """
+
+    def __init__(self, engine, group=None):
+        self.engine = engine
+        self.group = group
+        self.rank, self.world = world_info(group)
+
+    def _slice(self, a, total, local):
+        if local:
+            return a
+        b, c = shard_range(total, self.rank, self.world)
+        return a[b:b + c]
+
+    def closest(self, q3, total=None, local=False, **kw):
+        total = int(q3.shape[0]) if total is None else total
+        idx, d2, cp = self.engine.closest(self._slice(q3, total, local), **kw)
+        return tuple(gather_shards(x, total, self.group) for x in (idx, d2, cp))
+
+    def ray_first(self, o3, d3, total=None, local=False, **kw):
+        total = int(o3.shape[0]) if total is None else total
+        t, idx, _ = self.engine.ray_first(self._slice(o3, total, local), self._slice(d3, total, local), **kw)
+        return gather_shards(t, total, self.group), gather_shards(idx, total, self.group)
+
+    def knn(self, q3, k, total=None, local=False, **kw):
+        total = int(q3.shape[0]) if total is None else total
+        b, _ = shard_range(total, self.rank, self.world)
+        q = self._slice(q3, total, local)
+        if kw.get("exclude_self"):
+            # "self" is the element with the query's GLOBAL position: shift the shard's indices
+            raise ValueError("exclude_self needs global query positions: query the shard through Engine.knn on a slice of the build array")
+        idx, d2 = self.engine.knn(q, k, **kw)
+        return gather_shards(idx, total, self.group), gather_shards(d2, total, self.group)
+
+    def icp_sums(self, from3, to3, tr12=None):
+        """from3 / to3: this rank's shard of the correspondences; returns the pooled 16 sums on every rank."""
+        import torch
+        dist = _dist()
+        n = int(from3.shape[0])
+        local = np.zeros(17)
+        if n > 0:
+            local[0] = n
+            local[1:] = self.engine.icp_sums(from3, to3, tr12)
+        if self.world == 1:
+            return combine_icp_sums([(local[0], local[1:])], tr12)
+        dev = "cuda" if (torch.cuda.is_available() and dist.get_backend(self.group) == "nccl") else "cpu"
+        t = torch.from_numpy(local).to(dev)
+        out = torch.empty(self.world * 17, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(out, t, group=self.group)
+        parts = out.cpu().numpy().reshape(self.world, 17)
+        return combine_icp_sums([(p[0], p[1:]) for p in parts], tr12)

@@ -11,7 +11,7 @@ def run(n_grid, Q, leaf=4, sort=2, what=("closest", "ray")):
     e.set_option(2, leaf); e.set_option(1, sort)
     e.build_triangles(torch.from_numpy(mesh).cuda())
     st = e.stats()
-    out = {"tris": len(mesh), "leaf": leaf, "sort": sort, "nodes": st["num_nodes"], "build_ms": round(st["last_build_ms"], 3)}
+    out = {"tris": len(mesh), "Q": Q, "leaf": leaf, "sort": sort, "nodes": st["num_nodes"], "build_ms": round(st["last_build_ms"], 3)}
     if "closest" in what:
         q = torch.from_numpy(gen.closest_queries(Q, b)).cuda()
         for _ in range(3):
@@ -31,10 +31,12 @@ def run(n_grid, Q, leaf=4, sort=2, what=("closest", "ray")):
     e.close()
 
 if __name__ == "__main__":
-    run(188, 1_000_000)
-    run(188, 1_000_000, sort=0)
-    run(708, 1_000_000)
-    run(708, 4_000_000)
-    for leaf in (2, 8):
-        run(708, 1_000_000, leaf=leaf)
-    run(2236, 4_000_000)
+    if len(sys.argv) > 1 and sys.argv[1] == "short":
+        run(708, 4_000_000)
+        run(2236, 8_000_000)
+    else:
+        run(188, 1_000_000)
+        run(708, 4_000_000)
+        for leaf in (2, 8):
+            run(708, 1_000_000, leaf=leaf)
+        run(2236, 8_000_000)
