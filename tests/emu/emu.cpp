@@ -63,7 +63,7 @@ void build(Emu & E, float const * src, float const * n3)
   for (int s = 0; s < n; ++s) skeys[(size_t)s] = keys[perm[(size_t)s]];
   // records + element boxes (k_gather_*)
   std::vector<v3> plo((size_t)n), phi((size_t)n);
-  if (E.tri) E.tris.resize((size_t)n); else { E.pts.resize((size_t)n); if (E.has_n) E.nrm.resize((size_t)n); }
+  if (E.tri) E.tris.resize((size_t)n); else { E.pts.resize((size_t)n + 4); if (E.has_n) E.nrm.resize((size_t)n + 4); }   // + one fetch of slack (a leaf fetch always reads 4 points)
   for (int s = 0; s < n; ++s)
   {
     int64_t i = perm[(size_t)s];
@@ -74,6 +74,7 @@ void build(Emu & E, float const * src, float const * n3)
       TriRec r;
       r.q0 = f4{v0.x, v0.y, v0.z, i2f((int)i)}; r.q1 = f4{v1.x, v1.y, v1.z, i2f(pl.axis)};
       r.q2 = f4{v2.x, v2.y, v2.z, pl.d}; r.q3 = f4{pl.n.x, pl.n.y, pl.n.z, tri_screen_radius(v0, v1, v2, pad)};
+      r.e0 = tri_edge_frame(v0, v1); r.e1 = tri_edge_frame(v1, v2); r.e2 = tri_edge_frame(v2, v0); r.x = tri_area_frame(v0, v1, v2, pl.axis);
       E.tris[(size_t)s] = r;
       plo[(size_t)s] = min3(v0, min3(v1, v2)); phi[(size_t)s] = max3(v0, max3(v1, v2));
     }

@@ -11,8 +11,10 @@
 //        Morton-ordered element array.
 //   Obb   (128 B) : triangle structures only, same index as Node: per child (centre, h0) (axis0, h1) (axis1, h2)
 //        (axis2, child link); read by closest-point queries INSTEAD of Node (rays, k-NN and ball queries read Node).
-//   Tri   (64 B)  : q0 = (v0, orig_index)  q1 = (v1, axis)  q2 = (v2, plane d)  q3 = (unit normal, screening radius about the centroid)
-//        (ray queries read q0..q2 = 48 B, closest-point queries all 64 B)
+//   Tri   (128 B) : q0 = (v0, orig_index)  q1 = (v1, axis)  q2 = (v2, plane d)  q3 = (unit normal, screening radius about the centroid)
+//        e0 e1 e2 = (unit direction, length) of the edges v0->v1, v1->v2, v2->v0   x = (1 / area2, area2, -, -)
+//        (ray queries read q0..q2 = 48 B; a closest-point step reads the whole 128-byte line, the same fetch shape as an
+//        oriented-box node, so that one load phase serves the lanes that are at a node and the lanes that are at a triangle)
 //   Point (16 B)  : (x, y, z, orig_index); optional normals (16 B) in a parallel array.
 #pragma once
 #include "tgq_math.cuh"
@@ -21,7 +23,7 @@
 namespace tgq {
 
 struct NodeRec { f4 q0, q1, q2, q3; };
-struct TriRec  { f4 q0, q1, q2, q3; };
+struct TriRec  { f4 q0, q1, q2, q3, e0, e1, e2, x; };
 struct ObbNode { f4 q[8]; };     // oriented boxes of both children, see tgq_traverse.cuh
 
 // ---- Morton codes: 21 bits per axis, 63-bit keys --------------------------------------------------------------------

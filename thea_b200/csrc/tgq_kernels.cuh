@@ -84,6 +84,8 @@ __global__ void k_gather_tris(float const * __restrict__ v9, uint32_t const * __
   r.q1 = make_float4(v1.x, v1.y, v1.z, __int_as_float(pl.axis));
   r.q2 = make_float4(v2.x, v2.y, v2.z, pl.d);
   r.q3 = make_float4(pl.n.x, pl.n.y, pl.n.z, tri_screen_radius(v0, v1, v2, pad));
+  r.e0 = tri_edge_frame(v0, v1); r.e1 = tri_edge_frame(v1, v2); r.e2 = tri_edge_frame(v2, v0);
+  r.x = tri_area_frame(v0, v1, v2, pl.axis);
   tris[s] = r;
   v3 lo = min3(v0, min3(v1, v2)), hi = max3(v0, max3(v1, v2));      // Triangle3.hpp:215-219
   pbox_lo[s] = make_float4(lo.x, lo.y, lo.z, 0.0f); pbox_hi[s] = make_float4(hi.x, hi.y, hi.z, 0.0f);
@@ -312,15 +314,15 @@ __global__ void k_query_codes(float const * __restrict__ q3, int n, SceneBox con
 // ---- persistent warp scheduler -------------------------------------------------------------------------------------------
 // Query costs are heavy tailed and lanes follow different paths, so a thread-per-query kernel leaves most lanes of a warp
 // idle (ncu: 1.2 - 10 active threads per instruction on the bench workload).  Instead every warp drives 32 resumable
-// state machines (tgq_traverse.cuh) from a warp-uniform loop: in each iteration the lanes that have an inner node pending
-// take one node step and / or the lanes that have leaf elements pending take one leaf step (whichever group is larger, or
-// both when both are large), so the lanes reconverge after every step; lanes whose query finished write their result and
-// are refilled from the warp's current chunk of the (Morton-ordered) batch.  Chunks are handed out through one atomic
-// counter, which also balances the load across SMs.
-//   W: int state() ; void begin(int t) ; void node_step() ; void leaf_step() ; void finish()  [finish leaves the lane
-//   in TGQ_ST_IDLE, or restarts it]
+// state machines (tgq_traverse.cuh) from a warp-uniform loop: in each iteration every lane with work pending fetches ONE
+// record (an inner node or a leaf element: same fetch shape, one load phase for the warp), then the lanes at a node do
+// the node arithmetic and the lanes at a leaf the element arithmetic, so the lanes reconverge after every step; lanes
+// whose query finished write their result and are refilled from the warp's current chunk of the (Morton-ordered) batch,
+// which the warp stages in shared memory with coalesced loads.  Chunks are handed out through one atomic counter, which
+// also balances the load across SMs.
+//   W: FETCH, STAGE ; int state() ; void stage(t, dst) ; void begin(t, src) ; void fetch(r) ; void node_compute(r) ;
+//      void leaf_compute(r) ; void finish()  [finish leaves the lane in TGQ_ST_IDLE, or restarts it]
 #define TGQ_CHUNK 64
-#define TGQ_BOTH 12      // a group of at least this many lanes is stepped even when it is the smaller one
 #define TGQ_SSTACK 20    // stack entries per thread kept in shared memory (deeper ones spill to local memory)
 #define TGQ_WARPS (TGQ_BLOCK / 32)
 
@@ -363,15 +365,17 @@ __device__ __forceinline__ void warp_run(W & w, int n, int * counter, f4 * stage
       }
     }
     int st = w.state();
-    unsigned mi = __ballot_sync(FULL, st >= 0), ml = __ballot_sync(FULL, st == TGQ_ST_LEAF);
-    if ((mi | ml) == 0u)
+    bool at_node = st >= 0, at_leaf = st == TGQ_ST_LEAF;
+    if (!__any_sync(FULL, at_node || at_leaf))
     {
       if (exhausted && __all_sync(FULL, w.state() != TGQ_ST_DONE)) break;
       continue;
     }
-    int ni = __popc(mi), nl = __popc(ml);
-    if ((ni >= nl || ni >= TGQ_BOTH) && st >= 0) w.node_step();
-    if ((nl > ni || nl >= TGQ_BOTH) && st == TGQ_ST_LEAF) w.leaf_step();
+    // one load phase for the whole warp (nodes and leaf records have the same fetch shape), then the arithmetic
+    f4 r[W::FETCH];
+    if (at_node || at_leaf) w.fetch(r);
+    if (at_node) w.node_compute(r);
+    else if (at_leaf) w.leaf_compute(r);
   }
 }
 
@@ -403,8 +407,10 @@ struct ClosestW
     f4 r = *src; qi = __float_as_int(r.w);
     closest_begin(s, b, scene_pad, mk3(r.x, r.y, r.z), exclude_self ? (int)(self_offset + qi) : -1, ub);
   }
-  __device__ __forceinline__ void node_step() { closest_node_step(s, b); }
-  __device__ __forceinline__ void leaf_step() { closest_leaf_step(s, b); }
+  static constexpr int FETCH = ClosestFetch<TRI>::N;
+  __device__ __forceinline__ void fetch(f4 * r) const { closest_fetch(s, b, r); }
+  __device__ __forceinline__ void node_compute(f4 const * r) { closest_node_compute(s, b, r); }
+  __device__ __forceinline__ void leaf_compute(f4 const * r) { closest_leaf_compute(s, b, r); }
   __device__ __forceinline__ void finish()
   {
     if (idx) idx[qi] = s.best_idx;
@@ -444,8 +450,10 @@ struct KnnW
     f4 r = *src; qi = __float_as_int(r.w);
     knn_begin(s, b, mk3(r.x, r.y, r.z), exclude_self ? (int)(self_offset + qi) : -1, ub);
   }
-  __device__ __forceinline__ void node_step() { knn_node_step(s, b); }
-  __device__ __forceinline__ void leaf_step() { knn_leaf_step(s, b); }
+  static constexpr int FETCH = TGQ_FETCH_BOX;
+  __device__ __forceinline__ void fetch(f4 * r) const { knn_fetch(s, b, r); }
+  __device__ __forceinline__ void node_compute(f4 const * r) { knn_node_compute(s, b, r); }
+  __device__ __forceinline__ void leaf_compute(f4 const * r) { knn_leaf_compute(s, b, r); }
   __device__ __forceinline__ void finish()
   {
     for (int j = 0; j < k; ++j)
@@ -489,8 +497,10 @@ struct BallW
     f4 e = src[0], q = src[1]; qi = __float_as_int(e.w);
     ball_begin(s, b, mk3(e.x, e.y, e.z), mk3(q.x, q.y, q.z), b.nrm != nullptr, min_dot, (int)qi, init_radius, rounds, min_degree);
   }
-  __device__ __forceinline__ void node_step() { ball_node_step(s, b); }
-  __device__ __forceinline__ void leaf_step() { ball_leaf_step(s, b); }
+  static constexpr int FETCH = TGQ_FETCH_BOX;
+  __device__ __forceinline__ void fetch(f4 * r) const { ball_fetch(s, b, r); }
+  __device__ __forceinline__ void node_compute(f4 const * r) { ball_node_compute(s, b, r); }
+  __device__ __forceinline__ void leaf_compute(f4 const * r) { ball_leaf_compute(s, b, r); }
   __device__ __forceinline__ void finish()
   {
     if (!ball_round_done(s, b)) return;          // next round started
@@ -537,8 +547,10 @@ struct RayW
     f4 o = src[0], d = src[1]; qi = __float_as_int(o.w);
     ray_begin(s, b, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), d.w);
   }
-  __device__ __forceinline__ void node_step() { ray_node_step(s, b); }
-  __device__ __forceinline__ void leaf_step() { ray_leaf_step(s, b); }
+  static constexpr int FETCH = TGQ_FETCH_BOX;
+  __device__ __forceinline__ void fetch(f4 * r) const { ray_fetch(s, b, r); }
+  __device__ __forceinline__ void node_compute(f4 const * r) { ray_node_compute(s, b, r); }
+  __device__ __forceinline__ void leaf_compute(f4 const * r) { ray_leaf_compute(s, b, r); }
   __device__ __forceinline__ void finish()
   {
     if (t_out) t_out[qi] = s.best_idx >= 0 ? s.best_t : -1.0f;
@@ -600,8 +612,10 @@ struct SdfW
     f4 o = src[0], d = src[1]; r = __float_as_int(o.w);
     ray_begin(s, b, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), -1.0f);
   }
-  __device__ __forceinline__ void node_step() { ray_node_step(s, b); }
-  __device__ __forceinline__ void leaf_step() { ray_leaf_step(s, b); }
+  static constexpr int FETCH = TGQ_FETCH_BOX;
+  __device__ __forceinline__ void fetch(f4 * r) const { ray_fetch(s, b, r); }
+  __device__ __forceinline__ void node_compute(f4 const * r) { ray_node_compute(s, b, r); }
+  __device__ __forceinline__ void leaf_compute(f4 const * r) { ray_leaf_compute(s, b, r); }
   __device__ __forceinline__ void finish()
   {
     bool ok = s.best_idx >= 0;

@@ -143,6 +143,77 @@ TGQ_HD float tri_point_sqdist(v3 v0, v3 v1, v3 v2, v3 n, float d, int axis, v3 p
   return sqn3(sub3(cp, p));
 }
 
+// ---- The same function with the query-independent sub-expressions taken from the triangle record --------------------
+// The reference recomputes, for every (triangle, query) pair, three edge lengths (3 sqrt), three unit edge directions
+// (9 divisions) and the reciprocal of the projected area (1 division) -- values that depend on the triangle alone
+// (Triangle3.hpp:1319-1336,1401-1407,1435-1445).  They are computed ONCE per triangle at build time by exactly the
+// operations above (same order, same rounding), so tri_point_sqdist_pre returns the bit pattern tri_point_sqdist does.
+//   e0 = (dir(v0->v1), len)  e1 = (dir(v1->v2), len)  e2 = (dir(v2->v0), len)   ax = (1 / area2, area2)
+TGQ_HD void tri_axes(int axis, int & i, int & j) { if (axis == 1) { i = 2; j = 0; } else if (axis == 2) { i = 0; j = 1; } else { i = 1; j = 2; } }
+
+TGQ_HD f4 mkf4(float x, float y, float z, float w) { f4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+
+TGQ_HD f4 tri_edge_frame(v3 a, v3 b)
+{
+  v3 e = sub3(b, a); float len = sqrtf(sqn3(e)); v3 d = div3(e, len);
+  return mkf4(d.x, d.y, d.z, len);
+}
+TGQ_HD f4 tri_area_frame(v3 v0, v3 v1, v3 v2, int axis)
+{
+  int i, j; tri_axes(axis, i, j);
+  float area = tri_area2(v0, v1, v2, i, j);
+  return mkf4(1.0f / area, area, 0.0f, 0.0f);
+}
+
+TGQ_HD v3 closest_on_edge_pre(v3 a, v3 b, f4 e, v3 p, float & d2)
+{
+  v3 dir = mk3(e.x, e.y, e.z);
+  v3 c = sub3(p, a);
+  float t = dot3(dir, c);
+  v3 r;
+  if (t <= 0.0f) r = a;
+  else if (t >= e.w) r = b;
+  else r = add3(a, mul3(dir, t));
+  d2 = sqn3(sub3(r, p));
+  return r;
+}
+
+TGQ_HD float tri_point_sqdist_pre(v3 v0, v3 v1, v3 v2, v3 n, float d, int axis, f4 e0, f4 e1, f4 e2, f4 ax, v3 p, v3 & cp)
+{
+  float sd = dot3(p, n) - d;
+  v3 proj = sub3(p, mul3(n, sd));
+  bool inside;
+  float area = ax.y;
+  if (area == 0.0f) inside = v0.x == proj.x && v0.y == proj.y && v0.z == proj.z;
+  else
+  {
+    int i, j; tri_axes(axis, i, j);
+    float inv = ax.x;
+    inside = false;
+    float b0 = tri_area2(proj, v1, v2, i, j) * inv;
+    if (!(b0 < 0.0f || b0 > 1.0f))
+    {
+      float b1 = tri_area2(v0, proj, v2, i, j) * inv;
+      if (!(b1 < 0.0f || b1 > 1.0f))
+      {
+        float b2 = 1.0f - b0 - b1;
+        inside = b2 >= 0.0f && b2 <= 1.0f;
+      }
+    }
+  }
+  if (inside) cp = proj;
+  else
+  {
+    float d0, d1, d2;
+    v3 r0 = closest_on_edge_pre(v0, v1, e0, p, d0);
+    v3 r1 = closest_on_edge_pre(v1, v2, e1, p, d1);
+    v3 r2 = closest_on_edge_pre(v2, v0, e2, p, d2);
+    if (d0 < d1) cp = (d0 < d2) ? r0 : r2;
+    else         cp = (d1 < d2) ? r1 : r2;
+  }
+  return sqn3(sub3(cp, p));
+}
+
 // ---- Ray -> triangle (Triangle3.hpp:1464-1524); returns -1 for a miss ---------------------------------------------
 TGQ_HD float ray_tri_time(v3 o, v3 D, v3 v0, v3 e01, v3 e02)
 {

@@ -9,7 +9,7 @@
 //   Ray*       <- BvhN::rayStructureIntersection / rayIntersectionTime / rayIntersects (BvhN.hpp:1266-1316,2188-2291)
 //
 // Every traversal is a small state machine: `cur` >= 0 means "an inner node is pending", TGQ_ST_LEAF "elements
-// [k, kend) of a leaf are pending", TGQ_ST_DONE "finished".  One call of *_node_step / *_leaf_step advances the query
+// [k, kend) of a leaf are pending", TGQ_ST_DONE "finished".  One fetch + *_node_compute / *_leaf_compute advances the query
 // by one unit of work.  The kernels (tgq_kernels.cuh) drive 32 such machines per warp from a warp-uniform loop, so the
 // lanes reconverge after every step and finished lanes are refilled with fresh queries; the host emulation
 // of the test suite drives the same step functions from a plain loop.
@@ -50,6 +50,20 @@ TGQ_HD f4 ldq(f4 const * p)
   return __ldg(p);
 #else
   return *p;
+#endif
+}
+
+// Two consecutive float4 (32-byte aligned) in ONE 256-bit load (sm_100: LDG.E.256).  The traversal kernels are bound by
+// the number of L1 wavefronts -- every lane reads a different line, so each load instruction costs one wavefront per lane
+// (ncu: l1tex data-pipe wavefronts at 75 % of peak with 128-bit loads) -- and a 256-bit load halves the instruction count
+// per record.
+TGQ_HD void ldq2(f4 const * p, f4 & a, f4 & b)
+{
+#ifdef __CUDA_ARCH__
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+#else
+  a = p[0]; b = p[1];
 #endif
 }
 
@@ -188,6 +202,18 @@ TGQ_HD void obb_store_empty(int child, f4 * out4)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Step protocol.  Every traversal advances in steps of ONE record fetch followed by arithmetic on the fetched registers:
+//   *_fetch(s, b, r)      loads the record the state is waiting for -- an inner node (cur >= 0) or the pending leaf
+//                         element(s) (TGQ_ST_LEAF) -- into r[]; both kinds have the same fetch shape (FETCH float4), so a
+//                         warp issues ONE load phase per iteration for all its lanes, whatever they are waiting for;
+//   *_node_compute(s, b, r) / *_leaf_compute(s, b, r)   consume r[] and move the state on.
+// ncu on the previous layout (node step and leaf step each with their own dependent load) showed the kernels latency and
+// issue bound at once: 54 % issue utilisation with ~300 dependent fetches per closest-point query.
+// ---------------------------------------------------------------------------------------------------------------------
+#define TGQ_FETCH_TRI 8        // closest point on triangle structures: 128-byte ObbNode / 128-byte TriRec
+#define TGQ_FETCH_BOX 4        // everything else: 64-byte NodeRec / up to 4 points / the 48 used bytes of a TriRec
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Closest element.  best_d2 starts as the (exclusive) squared bound or +inf, best_idx as -1.
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool TRI>
@@ -197,6 +223,7 @@ struct ClosestState
   float best_d2; int best_idx; v3 best_cp;
   Trav t;
 };
+template <bool TRI> struct ClosestFetch { static constexpr int N = TRI ? TGQ_FETCH_TRI : TGQ_FETCH_BOX; };
 
 template <bool TRI>
 TGQ_HD void closest_begin(ClosestState<TRI> & s, BvhView const & b, float scene_pad, v3 p, int skip, float bound_ub)
@@ -207,51 +234,64 @@ TGQ_HD void closest_begin(ClosestState<TRI> & s, BvhView const & b, float scene_
 }
 
 template <bool TRI>
-TGQ_HD void closest_node_step(ClosestState<TRI> & s, BvhView const & b)
+TGQ_HD void closest_fetch(ClosestState<TRI> const & s, BvhView const & b, f4 * r)
+{
+  f4 const * q;
+  if (TRI) q = s.t.cur >= 0 ? (f4 const *)(b.obbs + s.t.cur) : (f4 const *)(b.tris + s.t.k);
+  else q = s.t.cur >= 0 ? (f4 const *)(b.nodes + s.t.cur) : b.pts + s.t.k;
+  if (TRI) { for (int i = 0; i < ClosestFetch<TRI>::N; i += 2) ldq2(q + i, r[i], r[i + 1]); }       // records are 128-byte aligned
+  else { for (int i = 0; i < ClosestFetch<TRI>::N; ++i) r[i] = ldq(q + i); }                        // point leaves start anywhere
+}
+
+// Descends into / defers the two children given their lower bounds, ordering keys and links.
+TGQ_HD void trav_descend(Trav & t, float lb0, float lb1, float key0, float key1, int c0, int c1, float limit)
+{
+  bool go0 = lb0 <= limit, go1 = lb1 <= limit;
+  if (go0 && go1)
+  {
+    bool swap = key1 < key0;
+    trav_push(t, swap ? c0 : c1, swap ? lb0 : lb1);
+    trav_enter(t, swap ? c1 : c0);
+    if (t.cur == TGQ_ST_DONE) trav_pop(t, limit);
+  }
+  else if (go0 || go1)
+  {
+    trav_enter(t, go0 ? c0 : c1);
+    if (t.cur == TGQ_ST_DONE) trav_pop(t, limit);
+  }
+  else trav_pop(t, limit);
+}
+
+template <bool TRI>
+TGQ_HD void closest_node_compute(ClosestState<TRI> & s, BvhView const & b, f4 const * r)
 {
   TGQ_COUNT_NODE();
   float lb0, lb1, key0, key1; int c0, c1;
   if (TRI)
   {
-    f4 const * q = (f4 const *)(b.obbs + s.t.cur);
-    f4 a0 = ldq(q), a1 = ldq(q + 1), a2 = ldq(q + 2), a3 = ldq(q + 3), b0 = ldq(q + 4), b1 = ldq(q + 5), b2 = ldq(q + 6), b3 = ldq(q + 7);
-    obb_bounds(a0, a1, a2, a3, s.p, s.mq, lb0, key0);
-    obb_bounds(b0, b1, b2, b3, s.p, s.mq, lb1, key1);
-    c0 = f2i(a3.w); c1 = f2i(b3.w);
+    obb_bounds(r[0], r[1], r[2], r[3], s.p, s.mq, lb0, key0);
+    obb_bounds(r[4], r[5], r[6], r[7], s.p, s.mq, lb1, key1);
+    c0 = f2i(r[3].w); c1 = f2i(r[7].w);
   }
   else
   {
-    NodeRec nd = load_node(b, s.t.cur);
+    NodeRec nd; nd.q0 = r[0]; nd.q1 = r[1]; nd.q2 = r[2]; nd.q3 = r[3];
     v3 lo0, hi0, lo1, hi1; node_boxes(nd, lo0, hi0, lo1, hi1);
     lb0 = box_point_sqdist(lo0, hi0, s.p) * TGQ_LB_DEFLATE; lb1 = box_point_sqdist(lo1, hi1, s.p) * TGQ_LB_DEFLATE;
     key0 = lb0; key1 = lb1;
     c0 = f2i(nd.q3.x); c1 = f2i(nd.q3.y);
   }
-  bool go0 = lb0 <= s.best_d2, go1 = lb1 <= s.best_d2;
-  if (go0 && go1)
-  {
-    bool swap = key1 < key0;
-    trav_push(s.t, swap ? c0 : c1, swap ? lb0 : lb1);
-    trav_enter(s.t, swap ? c1 : c0);
-    if (s.t.cur == TGQ_ST_DONE) trav_pop(s.t, s.best_d2);
-  }
-  else if (go0 || go1)
-  {
-    trav_enter(s.t, go0 ? c0 : c1);
-    if (s.t.cur == TGQ_ST_DONE) trav_pop(s.t, s.best_d2);
-  }
-  else trav_pop(s.t, s.best_d2);
+  trav_descend(s.t, lb0, lb1, key0, key1, c0, c1, s.best_d2);
 }
 
-// One pending element (triangles) or the whole pending leaf (points).
+// One pending triangle (triangle structures) or up to four pending points of the leaf (point structures).
 template <bool TRI>
-TGQ_HD void closest_leaf_step(ClosestState<TRI> & s, BvhView const & b)
+TGQ_HD void closest_leaf_compute(ClosestState<TRI> & s, BvhView const & b, f4 const * r)
 {
   if (TRI)
   {
-    int k = s.t.k++;
-    f4 const * t = (f4 const *)(b.tris + k);
-    f4 a = ldq(t), bq = ldq(t + 1), c = ldq(t + 2), d = ldq(t + 3);
+    ++s.t.k;
+    f4 a = r[0], bq = r[1], c = r[2], d = r[3];
     v3 v0 = mk3(a.x, a.y, a.z), v1 = mk3(bq.x, bq.y, bq.z), v2 = mk3(c.x, c.y, c.z), n = mk3(d.x, d.y, d.z);
     // screen: plane distance and lateral distance to the triangle's bounding circle
     v3 cen = mul3(add3(add3(v0, v1), v2), 0.33333334f);
@@ -264,22 +304,24 @@ TGQ_HD void closest_leaf_step(ClosestState<TRI> & s, BvhView const & b)
     {
       TGQ_COUNT_PRIM();
       v3 cp;
-      float d2 = tri_point_sqdist(v0, v1, v2, n, c.w, f2i(bq.w), s.p, cp);
+      float d2 = tri_point_sqdist_pre(v0, v1, v2, n, c.w, f2i(bq.w), r[4], r[5], r[6], r[7], s.p, cp);
       if (d2 < s.best_d2 || (d2 == s.best_d2 && idx < s.best_idx)) { s.best_d2 = d2; s.best_idx = idx; s.best_cp = cp; }
     }
   }
   else
   {
-    for (int k = s.t.k; k < s.t.kend; ++k)
+    int cnt = s.t.kend - s.t.k; if (cnt > TGQ_FETCH_BOX) cnt = TGQ_FETCH_BOX;
+    for (int j = 0; j < TGQ_FETCH_BOX; ++j)
     {
+      if (j >= cnt) break;
       TGQ_COUNT_PRIM();
-      f4 e = ldq(b.pts + k);
+      f4 e = r[j];
       int idx = f2i(e.w); v3 cp = mk3(e.x, e.y, e.z);
       float d2 = sqn3(sub3(cp, s.p));
       if (idx == s.skip) continue;
       if (d2 < s.best_d2 || (d2 == s.best_d2 && idx < s.best_idx)) { s.best_d2 = d2; s.best_idx = idx; s.best_cp = cp; }
     }
-    s.t.k = s.t.kend;
+    s.t.k += cnt;
   }
   if (s.t.k >= s.t.kend) trav_pop(s.t, s.best_d2);
 }
@@ -290,7 +332,12 @@ TGQ_HD void closest_query(BvhView const & b, float scene_pad, v3 p, int skip, fl
 {
   ClosestState<TRI> s; TravStack st; trav_bind(s.t, st);
   closest_begin(s, b, scene_pad, p, skip, best_d2);
-  while (s.t.cur != TGQ_ST_DONE) { if (s.t.cur >= 0) closest_node_step(s, b); else closest_leaf_step(s, b); }
+  f4 r[ClosestFetch<TRI>::N];
+  while (s.t.cur != TGQ_ST_DONE)
+  {
+    closest_fetch(s, b, r);
+    if (s.t.cur >= 0) closest_node_compute(s, b, r); else closest_leaf_compute(s, b, r);
+  }
   best_d2 = s.best_d2; best_idx = s.best_idx; best_cp = s.best_cp;
 }
 
@@ -323,6 +370,20 @@ struct SortedSet
   }
 };
 
+// Fetch of the AABB tree over points: a 64-byte node or the next (up to) four 16-byte points of the pending leaf.
+TGQ_HD void box_fetch(Trav const & t, BvhView const & b, f4 * r)
+{
+  f4 const * q = t.cur >= 0 ? (f4 const *)(b.nodes + t.cur) : b.pts + t.k;
+  for (int i = 0; i < TGQ_FETCH_BOX; ++i) r[i] = ldq(q + i);
+}
+TGQ_HD void box_node_bounds(f4 const * r, v3 p, float & lb0, float & lb1, int & c0, int & c1)
+{
+  NodeRec nd; nd.q0 = r[0]; nd.q1 = r[1]; nd.q2 = r[2]; nd.q3 = r[3];
+  v3 lo0, hi0, lo1, hi1; node_boxes(nd, lo0, hi0, lo1, hi1);
+  lb0 = box_point_sqdist(lo0, hi0, p) * TGQ_LB_DEFLATE; lb1 = box_point_sqdist(lo1, hi1, p) * TGQ_LB_DEFLATE;
+  c0 = f2i(nd.q3.x); c1 = f2i(nd.q3.y);
+}
+
 // k nearest points to p: k smallest (d2, idx); d2 < bound_ub (exclusive) when bounded.
 struct KnnState
 {
@@ -337,37 +398,23 @@ TGQ_HD void knn_begin(KnnState & s, BvhView const & b, v3 p, int skip, float bou
   s.p = p; s.skip = skip; s.bound_ub = bound_ub; s.worst = bound_ub; s.set.n = 0;
   trav_begin(s.t, s.set.cap > 0 ? b.n_nodes : 0);
 }
+TGQ_HD void knn_fetch(KnnState const & s, BvhView const & b, f4 * r) { box_fetch(s.t, b, r); }
 
-TGQ_HD void knn_node_step(KnnState & s, BvhView const & b)
+TGQ_HD void knn_node_compute(KnnState & s, BvhView const & b, f4 const * r)
 {
   TGQ_COUNT_NODE();
-  NodeRec nd = load_node(b, s.t.cur);
-  v3 lo0, hi0, lo1, hi1; node_boxes(nd, lo0, hi0, lo1, hi1);
-  float lb0 = box_point_sqdist(lo0, hi0, s.p) * TGQ_LB_DEFLATE;
-  float lb1 = box_point_sqdist(lo1, hi1, s.p) * TGQ_LB_DEFLATE;
-  int c0 = f2i(nd.q3.x), c1 = f2i(nd.q3.y);
-  bool go0 = lb0 <= s.worst, go1 = lb1 <= s.worst;
-  if (go0 && go1)
-  {
-    bool swap = lb1 < lb0;
-    trav_push(s.t, swap ? c0 : c1, swap ? lb0 : lb1);
-    trav_enter(s.t, swap ? c1 : c0);
-    if (s.t.cur == TGQ_ST_DONE) trav_pop(s.t, s.worst);
-  }
-  else if (go0 || go1)
-  {
-    trav_enter(s.t, go0 ? c0 : c1);
-    if (s.t.cur == TGQ_ST_DONE) trav_pop(s.t, s.worst);
-  }
-  else trav_pop(s.t, s.worst);
+  float lb0, lb1; int c0, c1; box_node_bounds(r, s.p, lb0, lb1, c0, c1);
+  trav_descend(s.t, lb0, lb1, lb0, lb1, c0, c1, s.worst);
 }
 
-TGQ_HD void knn_leaf_step(KnnState & s, BvhView const & b)
+TGQ_HD void knn_leaf_compute(KnnState & s, BvhView const & b, f4 const * r)
 {
-  for (int k = s.t.k; k < s.t.kend; ++k)
+  int cnt = s.t.kend - s.t.k; if (cnt > TGQ_FETCH_BOX) cnt = TGQ_FETCH_BOX;
+  for (int j = 0; j < TGQ_FETCH_BOX; ++j)
   {
+    if (j >= cnt) break;
     TGQ_COUNT_PRIM();
-    f4 e = ldq(b.pts + k);
+    f4 e = r[j];
     int idx = f2i(e.w);
     float d2 = sqn3(sub3(mk3(e.x, e.y, e.z), s.p));
     if (idx == s.skip || !(d2 < s.bound_ub)) continue;
@@ -377,15 +424,20 @@ TGQ_HD void knn_leaf_step(KnnState & s, BvhView const & b)
       if (s.set.full()) s.worst = s.set.worst_key();
     }
   }
-  s.t.k = s.t.kend;
-  trav_pop(s.t, s.worst);
+  s.t.k += cnt;
+  if (s.t.k >= s.t.kend) trav_pop(s.t, s.worst);
 }
 
 TGQ_HD void knn_query(BvhView const & b, v3 p, int skip, float bound_ub, SortedSet & set)
 {
   KnnState s; TravStack st; trav_bind(s.t, st); s.set = set;
   knn_begin(s, b, p, skip, bound_ub);
-  while (s.t.cur != TGQ_ST_DONE) { if (s.t.cur >= 0) knn_node_step(s, b); else knn_leaf_step(s, b); }
+  f4 r[TGQ_FETCH_BOX];
+  while (s.t.cur != TGQ_ST_DONE)
+  {
+    knn_fetch(s, b, r);
+    if (s.t.cur >= 0) knn_node_compute(s, b, r); else knn_leaf_compute(s, b, r);
+  }
   set.n = s.set.n;
 }
 
@@ -407,26 +459,24 @@ TGQ_HD void ball_begin(BallState & s, BvhView const & b, v3 c, v3 nc, bool has_n
   s.round = 0; s.rounds = rounds; s.min_degree = min_degree; s.set.n = 0;
   trav_begin(s.t, b.n_nodes);
 }
+TGQ_HD void ball_fetch(BallState const & s, BvhView const & b, f4 * r) { box_fetch(s.t, b, r); }
 
-TGQ_HD void ball_node_step(BallState & s, BvhView const & b)
+TGQ_HD void ball_node_compute(BallState & s, BvhView const & b, f4 const * r)
 {
   TGQ_COUNT_NODE();
-  NodeRec nd = load_node(b, s.t.cur);
-  v3 lo0, hi0, lo1, hi1; node_boxes(nd, lo0, hi0, lo1, hi1);
-  bool go0 = box_point_sqdist(lo0, hi0, s.c) * TGQ_LB_DEFLATE <= s.r2;
-  bool go1 = box_point_sqdist(lo1, hi1, s.c) * TGQ_LB_DEFLATE <= s.r2;
-  int c0 = f2i(nd.q3.x), c1 = f2i(nd.q3.y);
-  if (go0 && go1) { trav_push(s.t, c1, 0.0f); trav_enter(s.t, c0); if (s.t.cur == TGQ_ST_DONE) trav_pop(s.t, 0.0f); }
-  else if (go0 || go1) { trav_enter(s.t, go0 ? c0 : c1); if (s.t.cur == TGQ_ST_DONE) trav_pop(s.t, 0.0f); }
-  else trav_pop(s.t, 0.0f);
+  float lb0, lb1; int c0, c1; box_node_bounds(r, s.c, lb0, lb1, c0, c1);
+  // keys 0: every deferred child that intersected the ball stays wanted (the radius does not shrink within a round)
+  trav_descend(s.t, lb0, lb1, 0.0f, 0.0f, c0, c1, s.r2);
 }
 
-TGQ_HD void ball_leaf_step(BallState & s, BvhView const & b)
+TGQ_HD void ball_leaf_compute(BallState & s, BvhView const & b, f4 const * r)
 {
-  for (int k = s.t.k; k < s.t.kend; ++k)
+  int cnt = s.t.kend - s.t.k; if (cnt > TGQ_FETCH_BOX) cnt = TGQ_FETCH_BOX;
+  for (int j = 0; j < TGQ_FETCH_BOX; ++j)
   {
+    if (j >= cnt) break;
     TGQ_COUNT_PRIM();
-    f4 e = ldq(b.pts + k);
+    f4 e = r[j];
     int idx = f2i(e.w);
     if (idx == s.self) continue;
     v3 diff = sub3(mk3(e.x, e.y, e.z), s.c);
@@ -434,14 +484,14 @@ TGQ_HD void ball_leaf_step(BallState & s, BvhView const & b)
     if (!(d2 <= s.r2)) continue;
     if (s.has_n)
     {
-      f4 nj = ldq(b.nrm + k);
+      f4 nj = ldq(b.nrm + s.t.k + j);
       if (dot3(s.nc, mk3(nj.x, nj.y, nj.z)) < s.min_dot) continue;
     }
     float sep = fast_sqrt(d2);
     if (s.set.accepts(sep, idx)) s.set.insert(sep, idx);
   }
-  s.t.k = s.t.kend;
-  trav_pop(s.t, 0.0f);
+  s.t.k += cnt;
+  if (s.t.k >= s.t.kend) trav_pop(s.t, s.r2);
 }
 
 // Called when a round's traversal is done: returns true when the query is complete, else starts the next round.
@@ -459,9 +509,14 @@ TGQ_HD void ball_graph_query(BvhView const & b, v3 c, v3 nc, bool has_n, float m
 {
   BallState s; TravStack st; trav_bind(s.t, st); s.set = set;
   ball_begin(s, b, c, nc, has_n, min_dot, self, init_radius, rounds, min_degree);
+  f4 r[TGQ_FETCH_BOX];
   for (;;)
   {
-    while (s.t.cur != TGQ_ST_DONE) { if (s.t.cur >= 0) ball_node_step(s, b); else ball_leaf_step(s, b); }
+    while (s.t.cur != TGQ_ST_DONE)
+    {
+      ball_fetch(s, b, r);
+      if (s.t.cur >= 0) ball_node_compute(s, b, r); else ball_leaf_compute(s, b, r);
+    }
     if (ball_round_done(s, b)) break;
   }
   set.n = s.set.n;
@@ -509,38 +564,32 @@ TGQ_HD void ray_begin(RayState<ANY> & s, BvhView const & b, v3 o, v3 d, float ma
 }
 
 template <bool ANY>
-TGQ_HD void ray_node_step(RayState<ANY> & s, BvhView const & b)
+TGQ_HD void ray_fetch(RayState<ANY> const & s, BvhView const & b, f4 * r)
+{
+  f4 const * q = s.t.cur >= 0 ? (f4 const *)(b.nodes + s.t.cur) : (f4 const *)(b.tris + s.t.k);
+  ldq2(q, r[0], r[1]); ldq2(q + 2, r[2], r[3]);
+}
+
+template <bool ANY>
+TGQ_HD void ray_node_compute(RayState<ANY> & s, BvhView const & b, f4 const * r)
 {
   TGQ_COUNT_NODE();
-  NodeRec nd = load_node(b, s.t.cur);
+  NodeRec nd; nd.q0 = r[0]; nd.q1 = r[1]; nd.q2 = r[2]; nd.q3 = r[3];
   v3 lo0, hi0, lo1, hi1; node_boxes(nd, lo0, hi0, lo1, hi1);
   float t0 = slab_entry(s.r, lo0, hi0), t1 = slab_entry(s.r, lo1, hi1);
   int c0 = f2i(nd.q3.x), c1 = f2i(nd.q3.y);
   float lim = ray_limit(s);
-  bool go0 = t0 >= 0.0f && t0 <= lim, go1 = t1 >= 0.0f && t1 <= lim;
-  if (go0 && go1)
-  {
-    bool swap = t1 < t0;
-    trav_push(s.t, swap ? c0 : c1, swap ? t0 : t1);
-    trav_enter(s.t, swap ? c1 : c0);
-    if (s.t.cur == TGQ_ST_DONE) trav_pop(s.t, lim);
-  }
-  else if (go0 || go1)
-  {
-    trav_enter(s.t, go0 ? c0 : c1);
-    if (s.t.cur == TGQ_ST_DONE) trav_pop(s.t, lim);
-  }
-  else trav_pop(s.t, lim);
+  // a miss (-1) is mapped above every limit (lim is at most FLT_MAX)
+  trav_descend(s.t, t0 >= 0.0f ? t0 : INFINITY, t1 >= 0.0f ? t1 : INFINITY, t0, t1, c0, c1, lim);
 }
 
 // One pending triangle.
 template <bool ANY>
-TGQ_HD void ray_leaf_step(RayState<ANY> & s, BvhView const & b)
+TGQ_HD void ray_leaf_compute(RayState<ANY> & s, BvhView const & b, f4 const * r)
 {
   int k = s.t.k++;
   TGQ_COUNT_PRIM();
-  f4 const * t = (f4 const *)(b.tris + k);
-  f4 a = ldq(t), bq = ldq(t + 1), c = ldq(t + 2);
+  f4 a = r[0], bq = r[1], c = r[2];
   v3 v0 = mk3(a.x, a.y, a.z);
   float tm = ray_tri_time(s.o, s.d, v0, sub3(mk3(bq.x, bq.y, bq.z), v0), sub3(mk3(c.x, c.y, c.z), v0));
   int idx = f2i(a.w);
@@ -557,7 +606,12 @@ TGQ_HD void ray_query(BvhView const & b, v3 o, v3 d, float & best_t, int & best_
 {
   RayState<ANY> s; TravStack st; trav_bind(s.t, st);
   ray_begin(s, b, o, d, best_t);
-  while (s.t.cur != TGQ_ST_DONE) { if (s.t.cur >= 0) ray_node_step(s, b); else ray_leaf_step(s, b); }
+  f4 r[TGQ_FETCH_BOX];
+  while (s.t.cur != TGQ_ST_DONE)
+  {
+    ray_fetch(s, b, r);
+    if (s.t.cur >= 0) ray_node_compute(s, b, r); else ray_leaf_compute(s, b, r);
+  }
   best_t = s.best_t; best_idx = s.best_idx; best_k = s.best_k;
 }
 

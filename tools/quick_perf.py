@@ -34,6 +34,10 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "short":
         run(708, 4_000_000)
         run(2236, 8_000_000)
+    elif len(sys.argv) > 1 and sys.argv[1] == "leaf":
+        for leaf in (1, 2, 4):
+            run(708, 4_000_000, leaf=leaf)
+            run(2236, 8_000_000, leaf=leaf)
     else:
         run(188, 1_000_000)
         run(708, 4_000_000)
