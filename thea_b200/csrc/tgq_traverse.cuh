@@ -21,7 +21,10 @@ namespace tgq {
 #define TGQ_STACK 128            // > 63 Morton bits + 32 tie-break bits: ordered DFS never holds more than depth entries
 #define TGQ_LEAF_BITS 4
 #define TGQ_LEAF_MASK 15
-#define TGQ_LB_DEFLATE 0.99999905f   // 1 - 2^-20: lower bounds are shrunk so fp32 rounding can never over-prune
+#define TGQ_LB_DEFLATE 0.99999714f   // 1 - 3 * 2^-20 (48 u): relative part of the error budget below
+#ifndef TGQ_MARGIN_SCALE
+#define TGQ_MARGIN_SCALE 1.0f        // test builds widen every absolute margin (libtgq_wide.so) for differential checks
+#endif
 
 #define TGQ_ST_DONE (-1)
 #define TGQ_ST_LEAF (-2)
@@ -131,7 +134,27 @@ TGQ_HD void trav_pop(Trav & t, float limit)
 // The same idea with the triangle's own plane and the radius about its centroid screens single triangles before the
 // exact (and expensive) reference arithmetic is run.
 // ---------------------------------------------------------------------------------------------------------------------
-TGQ_HD float query_margin(v3 p, float scene_pad) { return scene_pad + 1e-6f * (fabsf(p.x) + fabsf(p.y) + fabsf(p.z)); }
+// Error budget of the closest-point bounds (u = 2^-24, M = largest |coordinate| of the scene, pad = 32 u M = scene pad,
+// D = distance from the query p to the element).  A bound may prune an element only if it is provably below the value
+// f = fl(|cp - p|^2) that the REFERENCE arithmetic returns for it, where cp is the reference's computed closest point.
+//   (1) cp versus the true triangle.  cp is a vertex (exact), a + dir * t on an edge (off the edge by
+//       <= u (sqrt3 |a|_inf + 4 len)), or the projection p - sd n accepted by the inside test.  For the projection:
+//       |d(sd)| <= 3u|p| + u D (three products, two sums, the subtraction), the subtraction p - sd n adds u(|p| + 2D), the
+//       stored normal is unit to 4u (another 4u D), the plane offset d = fl(n . v0) is off by <= 3u|v0|: cp lies within
+//       4u|p| + 7u D + 3 sqrt3 u M of the triangle (the barycentric test can accept a projection outside the triangle only
+//       by ~4u * extent * aspect, negligible next to this for triangles of aspect < 1e3).
+//   (2) f versus |cp - p|^2: three subtractions, three squares, two sums: relative 4u.
+//   (3) query side of a box bound: pc = fl(p - c) (u|pc|), fused dot with a unit axis (3u|pc|): 4u(|p| + sqrt3 M); the frame
+//       is orthonormal to 4u per pair, so sum_j (a_j . w)^2 <= (1 + 12u)|w|^2.
+//   (4) build side of a box: vertex projections 3u sqrt3 M, centre reconstruction c = sum_j a_j c_j 4u sqrt3 M, centre
+//       versus frame 4u sqrt3 M: 19u M.
+// Absolute terms: (1) + (3) <= 8u|p|_2 + 12.2u M  ->  query margin mq = 10u|p|_1 + 16u M;  (4) -> box half extents grow by
+// pad = 32u M;  centroid rounding of the triangle screen (3 sqrt3 u M) -> radius grows by 16u M.  Relative terms: 14u (the
+// 7u D of (1), squared) + 4u (2) + 12u (3) = 30u -> TGQ_LB_DEFLATE = 1 - 48u.
+// tests/test_gpu_scale.py checks, at the full bench size, that a build with every absolute margin x4 returns the same
+// bits, and the CPU suite checks the same code (host emulation) against brute force.
+TGQ_HD float query_margin(v3 p, float scene_pad)
+{ return TGQ_MARGIN_SCALE * (0.5f * scene_pad + 5.9604645e-7f * (fabsf(p.x) + fabsf(p.y) + fabsf(p.z))); }
 
 TGQ_HD void obb_bounds(f4 q0, f4 q1, f4 q2, f4 q3, v3 p, float mq, float & lb, float & key)
 {
@@ -143,7 +166,7 @@ TGQ_HD void obb_bounds(f4 q0, f4 q1, f4 q2, f4 q3, v3 p, float mq, float & lb, f
   key = fdot3(pc, pc);
 }
 
-TGQ_HD float slab_radius(float r2, float pad) { return sqrtf(r2) * 1.000001f + 2.0f * pad; }
+TGQ_HD float slab_radius(float r2, float pad) { return sqrtf(r2) * 1.000001f + TGQ_MARGIN_SCALE * 0.5f * pad; }
 TGQ_HD v3 box_centre(v3 lo, v3 hi) { return mul3(add3(lo, hi), 0.5f); }
 // Screening radius of one triangle about its centroid (stored in TriRec.q3.w).
 TGQ_HD float tri_screen_radius(v3 v0, v3 v1, v3 v2, float pad)
@@ -186,7 +209,8 @@ TGQ_HD void obb_acc_store(ObbAcc const & a, float pad, int child, f4 * out4)
 {
   float c0 = 0.5f * (a.mn[0] + a.mx[0]), c1 = 0.5f * (a.mn[1] + a.mx[1]), c2 = 0.5f * (a.mn[2] + a.mx[2]);
   v3 c = add3(add3(mul3(a.f.a0, c0), mul3(a.f.a1, c1)), mul3(a.f.a2, c2));
-  float h0 = 0.5f * (a.mx[0] - a.mn[0]) + 4.0f * pad, h1 = 0.5f * (a.mx[1] - a.mn[1]) + 4.0f * pad, h2 = 0.5f * (a.mx[2] - a.mn[2]) + 4.0f * pad;
+  float hp = TGQ_MARGIN_SCALE * pad;
+  float h0 = 0.5f * (a.mx[0] - a.mn[0]) * 1.000001f + hp, h1 = 0.5f * (a.mx[1] - a.mn[1]) * 1.000001f + hp, h2 = 0.5f * (a.mx[2] - a.mn[2]) * 1.000001f + hp;
   out4[0].x = c.x; out4[0].y = c.y; out4[0].z = c.z; out4[0].w = h0;
   out4[1].x = a.f.a0.x; out4[1].y = a.f.a0.y; out4[1].z = a.f.a0.z; out4[1].w = h1;
   out4[2].x = a.f.a1.x; out4[2].y = a.f.a1.y; out4[2].z = a.f.a1.z; out4[2].w = h2;

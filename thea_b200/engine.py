@@ -43,12 +43,19 @@ def lib_path() -> str:
     return os.path.join(_HERE, "libtgq.so")
 
 
-def load_library():
-    """Loads libtgq.so; raises if it has not been built (run ``python -c 'import __graft_entry__ as g; g.build()'``)."""
+_LIBS = {}
+
+
+def load_library(path=None):
+    """Loads libtgq.so; raises if it has not been built (run ``python -c 'import __graft_entry__ as g; g.build()'``).
+    `path` selects another build of the same ABI (the tests load libtgq_wide.so, the wide-margin variant)."""
     global _LIB
-    if _LIB is not None:
+    if path is None and _LIB is not None:
         return _LIB
-    path = lib_path()
+    if path is not None and path in _LIBS:
+        return _LIBS[path]
+    default = path is None
+    path = lib_path() if path is None else path
     if not os.path.exists(path):
         raise ImportError(f"{path} is missing: build it with `make -C thea_b200/csrc` (there is no CPU fallback)")
     L = C.CDLL(path)
@@ -79,7 +86,10 @@ def load_library():
     for name in SYMBOLS:
         if name not in ("tgq_last_error",):
             getattr(L, name).restype = C.c_int
-    _LIB = L
+    if default:
+        _LIB = L
+    else:
+        _LIBS[path] = L
     return L
 
 
@@ -112,8 +122,8 @@ def _as_in(a, dtype=np.float32):
 class Engine:
     """One BvhN-like structure on one GPU.  Method names follow the C ABI; see include/thea_gpu_query.h."""
 
-    def __init__(self, device: int = 0):
-        self._L = load_library()
+    def __init__(self, device: int = 0, lib: str | None = None):
+        self._L = load_library(lib)
         h = C.c_void_p()
         rc = self._L.tgq_create(device, C.byref(h))
         if rc != 0:
