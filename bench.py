@@ -275,6 +275,22 @@ def main():
 
     kern = {"closest_ms": 0.0, "closest_q": 0, "ray_ms": 0.0, "ray_q": 0, "sort_ms": 0.0, "launches": 0}
 
+    # N > 1: the one real exchange of the path -- every rank ends a step holding the results of the WHOLE batch
+    # (all-gather of the per-shard result arrays over NCCL / NVLink).  Equal shard sizes by construction.
+    gathered = None
+    if world > 1:
+        assert nq_total % world == 0 and nr_total % world == 0, "bench workloads shard evenly over 1/2/4/8 ranks"
+        gathered = {"c_idx": torch.empty(nq_total, dtype=torch.int32, device=dev), "c_d2": torch.empty(nq_total, dtype=torch.float32, device=dev),
+                    "c_cp": torch.empty((nq_total, 3), dtype=torch.float32, device=dev), "r_t": torch.empty(nr_total, dtype=torch.float32, device=dev),
+                    "r_idx": torch.empty(nr_total, dtype=torch.int32, device=dev)}
+
+    def gather_results():
+        if world == 1:
+            return
+        for name, t in (("c_idx", c_idx), ("c_d2", c_d2), ("c_cp", c_cp), ("r_t", r_t), ("r_idx", r_idx)):
+            if t.numel():
+                dist.all_gather_into_tensor(gathered[name], t)
+
     def step_device(record: bool):
         # one C-ABI call per query kind over the whole shard (the library splits batches above 2^26 queries)
         if nq:
@@ -295,6 +311,7 @@ def main():
                 kern["ray_q"] += nr
                 kern["ray_launches"] = kern.get("ray_launches", 0) + 1
                 kern["launches"] += s["last_launches"]
+        gather_results()
 
     def barrier():
         if world > 1:
@@ -322,7 +339,10 @@ def main():
     value = total_queries * args.steps / (dev_ms / 1e3)
 
     # checksum of the results (device resident) so that the timed work cannot be optimised away and runs can be compared
-    checksum = int((c_idx.long().sum() + r_idx.long().sum()).item())
+    if world > 1:
+        checksum = int((gathered["c_idx"].long().sum() + gathered["r_idx"].long().sum()).item())
+    else:
+        checksum = int((c_idx.long().sum() + r_idx.long().sum()).item())
 
     # ---- e2e: same calls, pinned host buffers, copies inside the timed region ----
     e2e = None
@@ -353,9 +373,11 @@ def main():
         e2e_s = float(wall.item())
         h2d = nq * 12 + nr * 24
         d2h = nq * 20 + nr * 8
-        hsum = int(h_idx.astype(np.int64).sum() + h_ri.astype(np.int64).sum())
-        e2e = {"value": total_queries * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "matches_device_checksum": bool(hsum == checksum)}
+        hs = torch.tensor([int(h_idx.astype(np.int64).sum() + h_ri.astype(np.int64).sum())], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(hs)
+        e2e = {"value": total_queries * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
+               "matches_device_checksum": bool(int(hs.item()) == checksum)}
 
     if rank != 0:
         if world > 1:
@@ -416,7 +438,7 @@ def main():
         "metric": "bvh_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": desc, "triangles": T, "closest_queries": nq_total, "ray_queries": nr_total, "sharding": f"queries/{world}, BVH replicated",
+        "config": {"workload": desc, "triangles": T, "closest_queries": nq_total, "ray_queries": nr_total, "sharding": f"queries/{world}, BVH replicated" + (", results all-gathered per step (NCCL)" if world > 1 else ""),
                    "l2_policy": "inputs_exceed_l2" if (nq_total * 32 + nr_total * 32) / world > 126e6 else "structure+inputs may be L2 resident",
                    "scale": args.scale, "build_ms": build_ms},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": kern["launches"], "clocks": clocks,
