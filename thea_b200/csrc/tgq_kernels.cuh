@@ -395,7 +395,7 @@ struct ClosestW
 {
   static constexpr int STAGE = 1;       // (x, y, z, query index)
   ClosestState<TRI> s; BvhView b; float scene_pad; float const * q3; uint32_t const * perm; float ub; int exclude_self; int64_t self_offset;
-  int * idx; float * d2; float * cp3; int qi;
+  int * idx; float * d2; float * cp3; int qi; int seed;
   __device__ __forceinline__ int state() const { return s.t.cur; }
   __device__ __forceinline__ void stage(int t, f4 * dst) const
   {
@@ -405,7 +405,7 @@ struct ClosestW
   __device__ __forceinline__ void begin(int, f4 const * src)
   {
     f4 r = *src; qi = __float_as_int(r.w);
-    closest_begin(s, b, scene_pad, mk3(r.x, r.y, r.z), exclude_self ? (int)(self_offset + qi) : -1, ub);
+    closest_begin(s, b, scene_pad, mk3(r.x, r.y, r.z), exclude_self ? (int)(self_offset + qi) : -1, ub, seed);
   }
   static constexpr int FETCH = ClosestFetch<TRI>::N;
   __device__ __forceinline__ void fetch(f4 * r) const { closest_fetch(s, b, r); }
@@ -416,6 +416,7 @@ struct ClosestW
     if (idx) idx[qi] = s.best_idx;
     if (d2) d2[qi] = s.best_idx >= 0 ? s.best_d2 : -1.0f;
     if (cp3) st3(cp3, qi, s.best_cp);
+    seed = perm ? s.best_k : -1;            // only Morton-ordered batches have neighbouring queries next to each other
     s.t.cur = TGQ_ST_IDLE;
   }
 };
@@ -428,7 +429,7 @@ k_closest(BvhView b, float scene_pad, float const * __restrict__ q3, uint32_t co
   extern __shared__ __align__(16) unsigned char smem[];
   ClosestW<TRI> w;
   w.b = b; w.scene_pad = scene_pad; w.q3 = q3; w.perm = perm; w.ub = bound_ub; w.exclude_self = exclude_self; w.self_offset = self_offset;
-  w.idx = idx; w.d2 = d2; w.cp3 = cp3; w.qi = 0; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
+  w.idx = idx; w.d2 = d2; w.cp3 = cp3; w.qi = 0; w.seed = -1; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
   f4 * stage = trav_setup(w.s.t, st, smem, ClosestW<TRI>::STAGE, nullptr);
   warp_run(w, n, counter, stage);
 }
