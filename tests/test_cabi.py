@@ -26,12 +26,13 @@ def test_library_exports_every_declared_symbol(built):
 
 
 def test_product_never_imports_the_oracle():
-    for base, _, files in os.walk(os.path.join(ROOT, "thea_b200")):
+    import itertools
+    for base, _, files in itertools.chain(os.walk(os.path.join(ROOT, "thea_b200")), os.walk(os.path.join(ROOT, "include"))):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
                 src = open(os.path.join(base, f), errors="ignore").read()
                 for needle in ("import oracle", "from oracle", "liborc", "orc_", "thea_oracle", "libtgq_emu", "tests/emu"):
-                    assert needle not in src, f"thea_b200/{f} references test infrastructure ({needle})"
+                    assert needle not in src, f"{base}/{f} references test infrastructure ({needle})"
 
 
 def test_no_gpu_means_loud_failure(built):
