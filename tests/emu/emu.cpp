@@ -176,11 +176,14 @@ int64_t emu_num_nodes(void * h) { return (int64_t)((Emu *)h)->nodes.size(); }
 void emu_closest(void * h, float const * q3, int64_t Q, float bound_ub, int exclude_self, int32_t * idx, float * d2, float * cp3)
 {
   Emu & E = *(Emu *)h; BvhView v = E.view();
+  // every query is seeded with the Morton position of the previous query's answer, as a lane of the kernel does
+  // (exclude_self < 0: unseeded)
+  int seed = -1; bool seeded = exclude_self >= 0; if (!seeded) exclude_self = -exclude_self - 1;
   for (int64_t i = 0; i < Q; ++i)
   {
     float best = bound_ub; int bi = -1; v3 cp = mk3(0, 0, 0);
-    if (E.tri) closest_query<true>(v, E.pad, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp);
-    else closest_query<false>(v, 0.0f, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp);
+    if (E.tri) closest_query<true>(v, E.pad, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp, seeded ? &seed : nullptr);
+    else closest_query<false>(v, 0.0f, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp, seeded ? &seed : nullptr);
     idx[i] = bi; d2[i] = bi >= 0 ? best : -1.0f; cp3[3 * i] = cp.x; cp3[3 * i + 1] = cp.y; cp3[3 * i + 2] = cp.z;
   }
 }

@@ -59,13 +59,15 @@ class Emu:
     def num_nodes(self):
         return lib().emu_num_nodes(self.h)
 
-    def closest(self, q, bound_ub=np.inf, exclude_self=False):
+    def closest(self, q, bound_ub=np.inf, exclude_self=False, seeded=True):
+        """seeded: every query starts from the previous query's answer (what a kernel lane does on ordered batches)."""
         q = np.ascontiguousarray(q, np.float32)
         Q = len(q)
         idx = np.empty(Q, np.int32)
         d2 = np.empty(Q, np.float32)
         cp = np.empty((Q, 3), np.float32)
-        lib().emu_closest(self.h, _p(q), Q, float(bound_ub), int(exclude_self), _p(idx), _p(d2), _p(cp))
+        flag = int(exclude_self) if seeded else -int(exclude_self) - 1
+        lib().emu_closest(self.h, _p(q), Q, float(bound_ub), flag, _p(idx), _p(d2), _p(cp))
         return idx, d2, cp
 
     def knn(self, q, k, bound_ub=np.inf, exclude_self=False):

@@ -196,3 +196,20 @@ def test_sdf_rays_and_statistics_match_oracle():
         hits += len(vals)
     assert hits > 300 * 20
     assert (sdf > 0).mean() > 0.95 and (sdf <= 1).all()
+
+
+def test_seeding_a_query_with_any_element_never_changes_the_answer():
+    mesh = gen.torus_mesh(32)
+    E = emu_lib.Emu(tris9=mesh)
+    rng = np.random.default_rng(5)
+    q = gen.closest_queries(4000, gen.mesh_bounds(mesh), seed=321)
+    q = q[rng.permutation(len(q))]                       # unordered: seeds are far-away elements most of the time
+    a = E.closest(q, seeded=True)
+    b = E.closest(q, seeded=False)
+    oi, od, oc = orc.Oracle(tris9=mesh).closest(q, mode=orc.MODE_BRUTE)
+    for r in (a, b):
+        assert np.array_equal(r[0], oi.astype(np.int32)) and np.array_equal(r[1], od) and np.array_equal(r[2], oc)
+    # with a bound: the seed must not leak an element at or beyond the bound
+    a = E.closest(q, bound_ub=0.01, seeded=True)
+    oi, od, _ = orc.Oracle(tris9=mesh).closest(q, dist_bound=0.1, mode=orc.MODE_BRUTE)
+    assert np.array_equal(a[0], oi.astype(np.int32))

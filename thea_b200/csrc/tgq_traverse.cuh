@@ -361,10 +361,10 @@ TGQ_HD void closest_leaf_compute(ClosestState<TRI> & s, BvhView const & b, f4 co
 
 // Whole query in one go (host emulation; single-lane device uses).
 template <bool TRI>
-TGQ_HD void closest_query(BvhView const & b, float scene_pad, v3 p, int skip, float & best_d2, int & best_idx, v3 & best_cp)
+TGQ_HD void closest_query(BvhView const & b, float scene_pad, v3 p, int skip, float & best_d2, int & best_idx, v3 & best_cp, int * seed_k = nullptr)
 {
   ClosestState<TRI> s; TravStack st; trav_bind(s.t, st);
-  closest_begin(s, b, scene_pad, p, skip, best_d2);
+  closest_begin(s, b, scene_pad, p, skip, best_d2, seed_k ? *seed_k : -1);
   f4 r[ClosestFetch<TRI>::N];
   while (s.t.cur != TGQ_ST_DONE)
   {
@@ -372,6 +372,7 @@ TGQ_HD void closest_query(BvhView const & b, float scene_pad, v3 p, int skip, fl
     if (s.t.cur >= 0) closest_node_compute(s, b, r); else closest_leaf_compute(s, b, r);
   }
   best_d2 = s.best_d2; best_idx = s.best_idx; best_cp = s.best_cp;
+  if (seed_k) *seed_k = s.best_k;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
