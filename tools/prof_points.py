@@ -1,0 +1,26 @@
+"""Development aid: cfg2-shaped point-structure queries (k-NN k=16, PointSet3 ball graph) for ncu captures."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from thea_b200 import Engine, gen, callers
+
+def main(grid=708, P=1_000_000):
+    mesh = gen.torus_mesh(grid)
+    e = Engine(0); e.build_triangles(torch.from_numpy(mesh).cuda())
+    p, n, _ = e.area_sample(P, gen.SEED_SAMPLES)
+    pe = Engine(0); pe.build_points(p, n)
+    dp = torch.from_numpy(p).cuda()
+    for _ in range(2):
+        pe.knn(dp, 16, exclude_self=True)
+    s1 = pe.stats()
+    seeds = (gen.splitmix64(0x5EED, 100) % np.uint64(P)).astype(np.int64)
+    avg = pe.avg_separation(seeds)
+    di = torch.empty((P, 16), dtype=torch.int32, device="cuda"); ds = torch.empty((P, 16), dtype=torch.float32, device="cuda"); dc = torch.empty(P, dtype=torch.int32, device="cuda")
+    for _ in range(2):
+        pe.ball_graph(16, float(np.float32(4.0) * np.float32(avg)), out=(di, ds, dc))
+    s2 = pe.stats()
+    print(json.dumps({"P": P, "knn_ms": s1["last_query_ms"], "knn_Mqps": P / s1["last_query_ms"] / 1e3, "graph_ms": s2["last_query_ms"],
+                      "graph_Mqps": P / s2["last_query_ms"] / 1e3, "mean_degree": float(dc.float().mean().item())}))
+
+if __name__ == "__main__":
+    main()
