@@ -218,6 +218,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="development aid: scales the torus grid and query counts")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg")
+    ap.add_argument("--chunk", type=int, default=0, help="queries per staged chunk of the host-buffer leg (0: library default)")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -369,6 +370,9 @@ def main():
         h_cp = torch.empty((nq, 3), dtype=torch.float32).pin_memory().numpy()
         h_t = torch.empty(nr, dtype=torch.float32).pin_memory().numpy()
         h_ri = torch.empty(nr, dtype=torch.int32).pin_memory().numpy()
+
+        if args.chunk:
+            eng.set_option(4, args.chunk)
 
         def step_host():
             if nq:

@@ -54,7 +54,7 @@ enum
   TGQ_OPT_SORT_QUERIES = 1,   /* 0 = never, 1 = always, 2 = auto (default: batches >= 4096 are Morton-ordered first) */
   TGQ_OPT_LEAF_SIZE = 2,      /* max elements per leaf, 1..15 (default 4); takes effect at the next build */
   TGQ_OPT_ASYNC = 3,          /* 1: device-pointer calls return without synchronising the stream (default 0) */
-  TGQ_OPT_CHUNK = 4           /* queries per staged chunk for host-pointer calls (default 4194304) */
+  TGQ_OPT_CHUNK = 4           /* queries per staged chunk for host-pointer calls (default 8388608) */
 };
 
 #define TGQ_MAX_K 64

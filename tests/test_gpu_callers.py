@@ -143,7 +143,7 @@ def test_device_pointers_and_host_pointers_agree(setup):
     q = gen.closest_queries(300000, gen.mesh_bounds(mesh), seed=5)
     e.set_option(4, 65536)                      # several staged chunks on the host path
     hi, hd, hc = e.closest(q)
-    e.set_option(4, 4194304)
+    e.set_option(4, 8388608)
     dq = torch.from_numpy(q).cuda()
     di, dd, dc = e.closest(dq)
     assert np.array_equal(hi, di.cpu().numpy()) and np.array_equal(hd, dd.cpu().numpy()) and np.array_equal(hc, dc.cpu().numpy())

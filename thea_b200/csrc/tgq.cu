@@ -55,7 +55,7 @@ struct tgq_handle
   std::string err;
   cudaStream_t own_stream = nullptr, stream = nullptr;
 
-  int opt_sort = 2, opt_leaf = 4, opt_async = 0; int64_t opt_chunk = 4194304;
+  int opt_sort = 2, opt_leaf = 4, opt_async = 0; int64_t opt_chunk = 8388608;
 
   int kind = TGQ_KIND_NONE; int n = 0; int n_nodes = 0; bool has_normals = false; int leaf_built = 4;
   DevBuf nodes, elems, nrm, scene;                                  // NodeRec[], TriRec[] | f4[], f4[], SceneBox
