@@ -417,7 +417,10 @@ def main():
         rec = json.load(open(tp)).get(f"{args.workload}:{dominant}")
         if rec:   # ncu dram bytes of the bench's own launch, scaled to this run's queries per launch
             traffic = rec["dram_bytes_per_launch"] / rec["queries_per_launch"] * (k_q // max(1, k_n))
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+    limiter = None
+    if os.path.exists(tp):
+        limiter = (json.load(open(tp)).get(f"{args.workload}:{dominant}") or {}).get("limiter")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "limiter": limiter,
                 "kernel": dominant, "peak_source": peak_kind, "algorithmic_bytes_per_query": bytes_per_q,
                 "queries_per_launch": k_q // max(1, k_n), "avg_launch_ms": k_ms / max(1, k_n)}
 

@@ -213,3 +213,31 @@ def test_seeding_a_query_with_any_element_never_changes_the_answer():
     a = E.closest(q, bound_ub=0.01, seeded=True)
     oi, od, _ = orc.Oracle(tris9=mesh).closest(q, dist_bound=0.1, mode=orc.MODE_BRUTE)
     assert np.array_equal(a[0], oi.astype(np.int32))
+
+
+def test_degenerate_triangles_behave_like_the_reference():
+    """Quirk Q7: zero-area triangles (a repeated vertex, three collinear vertices, a single point) give
+    NaN candidates in the reference arithmetic and are only ever returned when the query coincides with v0; the precomputed
+    edge frames (1/0, 0/0) must reproduce that, and the bounds must stay conservative around them."""
+    mesh = gen.torus_mesh(16).copy()
+    rng = np.random.default_rng(9)
+    pick = rng.choice(len(mesh), 60, replace=False)
+    for j, t in enumerate(pick):
+        v = mesh[t].reshape(3, 3)
+        if j % 3 == 0:
+            v[1] = v[0]                                  # repeated vertex
+        elif j % 3 == 1:
+            v[2] = v[0] + np.float32(0.5) * (v[1] - v[0])   # collinear
+        else:
+            v[1] = v[0]; v[2] = v[0]                     # a point
+    E = emu_lib.Emu(tris9=mesh)
+    ora = orc.Oracle(tris9=mesh)
+    q = gen.closest_queries(3000, gen.mesh_bounds(mesh), seed=77)
+    q[:60] = mesh[pick].reshape(-1, 3, 3)[:, 0]          # queries exactly on v0 of the degenerate triangles
+    gi, gd, gc = E.closest(q)
+    oi, od, oc = ora.closest(q, mode=orc.MODE_BRUTE)
+    assert np.array_equal(gi, oi.astype(np.int32)) and np.array_equal(gd, od) and np.array_equal(gc, oc)
+    o, d = gen.random_rays(3000, gen.mesh_bounds(mesh), seed=78)
+    t, ri = E.ray(o, d)
+    ori, ort = ora.ray_first(o, d, mode=orc.MODE_BRUTE)
+    assert np.array_equal(ri, ori.astype(np.int32)) and np.array_equal(t, ort)

@@ -174,3 +174,31 @@ def test_duplicate_elements_tie_to_lowest_index(built):
     ki, kd = pe.knn(pts, 7, exclude_self=True)
     oki, okd = po.knn(pts, 7, exclude_self=True, mode=orc.MODE_BRUTE)
     assert np.array_equal(ki, oki.astype(np.int32)) and np.array_equal(kd, okd)
+
+
+def test_degenerate_triangles_match_the_reference_quirk(built):
+    """Zero-area triangles: same answers as the oracle, including queries that sit exactly on them."""
+    from thea_b200 import Engine
+    mesh = gen.torus_mesh(16).copy()
+    rng = np.random.default_rng(9)
+    pick = rng.choice(len(mesh), 60, replace=False)
+    for j, t in enumerate(pick):
+        v = mesh[t].reshape(3, 3)
+        if j % 3 == 0:
+            v[1] = v[0]
+        elif j % 3 == 1:
+            v[2] = v[0] + np.float32(0.5) * (v[1] - v[0])
+        else:
+            v[1] = v[0]; v[2] = v[0]
+    e = Engine(0)
+    e.build_triangles(mesh)
+    ora = orc.Oracle(tris9=mesh)
+    q = gen.closest_queries(20000, gen.mesh_bounds(mesh), seed=77)
+    q[:60] = mesh[pick].reshape(-1, 3, 3)[:, 0]
+    gi, gd, gc = e.closest(q)
+    oi, od, oc = ora.closest(q, mode=orc.MODE_BRUTE)
+    assert np.array_equal(gi, oi.astype(np.int32)) and np.array_equal(gd, od) and np.array_equal(gc, oc)
+    o, d = gen.random_rays(20000, gen.mesh_bounds(mesh), seed=78)
+    t, ri, _ = e.ray_first(o, d)
+    ori, ort = ora.ray_first(o, d, mode=orc.MODE_BRUTE)
+    assert np.array_equal(ri, ori.astype(np.int32)) and np.array_equal(t, ort)
