@@ -18,8 +18,9 @@
 // new surface: one C-ABI call for the whole loop that the reference's callers run serially.
 //
 // What is NOT supported, and fails loudly instead of falling back to a CPU path:
-//   - pushFilter / compatibility functors other than UniversalCompatibility (arbitrary host callables cannot run on the
-//     device): pushFilter throws; the built-in device predicates are `exclude_self` and the ball-graph normal test.
+//   - pushFilter with arbitrary host callables and compatibility functors other than UniversalCompatibility (they cannot
+//     run on the device): pushFilter throws, except for the built-in NNFilter (same label, compatible normal) on point
+//     structures; the other device predicates are `exclude_self` and the ball-graph normal test.
 //   - metrics other than L2, BVH-to-BVH queries, setTransform.
 #ifndef THEA_GPU_GPUBVH_HPP
 #define THEA_GPU_GPUBVH_HPP
@@ -168,6 +169,19 @@ template <typename VectorT> inline void put3(float * dst, VectorT const & v) { d
 template <typename VectorT> inline VectorT get3(float const * src) { VectorT v; v[0] = src[0]; v[1] = src[1]; v[2] = src[2]; return v; }
 
 }  // namespace detail
+
+/**
+ * The one element filter the device evaluates: same label and compatible normal, the NNFilter of
+ * Tools/Register/Register.cpp:92-101 (`sample->label == label && n.dot(sample->n) >= 0`).  Push it around a query on a
+ * GpuPointBvh exactly as Register pushes its filter on a BvhN (Register.cpp:218-223,274-277).
+ */
+template <typename VectorT>
+struct NNFilterT
+{
+  VectorT n; int32_t label; bool use_normals, use_labels; float min_dot;
+  NNFilterT(VectorT const & n_, int32_t label_, bool use_normals_ = true, bool use_labels_ = true, float min_dot_ = 0.0f)
+  : n(n_), label(label_), use_normals(use_normals_), use_labels(use_labels_), min_dot(min_dot_) {}
+};
 
 /**
  * Common part of the two structures: owns the engine handle.  Mirrors the non-query members of BvhN
@@ -388,7 +402,18 @@ class GpuPointBvhT : public GpuBvhBase<VectorT>
   public:
     typedef typename Base::NeighborPair NeighborPair;
 
-    explicit GpuPointBvhT(int device = 0) : Base(device) {}
+    typedef NNFilterT<VectorT> NNFilter;
+
+    explicit GpuPointBvhT(int device = 0) : Base(device), filter(nullptr) {}
+
+    /** Per-element labels (P int32, element order; null clears): the `label` member of Register's samples. */
+    void setLabels(int32_t const * labels) { detail::check(h, tgq_set_point_labels(h, labels), "tgq_set_point_labels"); }
+    /** BvhN::pushFilter / popFilter (BvhN.hpp:1005-1032) for the device-evaluated NNFilter; one level deep, like every use
+     *  in the reference.  Any other filter type falls to the base template and throws. */
+    using Base::pushFilter;
+    void pushFilter(NNFilter const * f) { if (filter) throw Error("TheaGpu: only one NNFilter can be active"); filter = f; }
+    void pushFilter(NNFilter * f) { pushFilter(static_cast<NNFilter const *>(f)); }   // (a non-const pointer would pick the throwing template)
+    void popFilter() { filter = nullptr; }
 
     /** BvhN::init over P points with optional unit normals (P x 3 each; host or device pointers). */
     void init(float const * p3, intx P, float const * n3 = nullptr) { detail::check(h, tgq_build_points(h, p3, P, n3), "tgq_build_points"); }
@@ -400,7 +425,13 @@ class GpuPointBvhT : public GpuBvhBase<VectorT>
     {
       float q[3], d2 = -1, cp[3]; int32_t idx = -1;
       detail::put3(q, query);
-      detail::check(h, tgq_closest(h, q, 1, dist_bound, 0, &idx, &d2, closest_point ? cp : nullptr), "tgq_closest");
+      if (filter)
+      {
+        float fn[3]; detail::put3(fn, filter->n);
+        detail::check(h, tgq_closest_filtered(h, q, filter->use_normals ? fn : nullptr, filter->use_labels ? &filter->label : nullptr, 1,
+                                              filter->min_dot, dist_bound, &idx, &d2, closest_point ? cp : nullptr), "tgq_closest_filtered");
+      }
+      else detail::check(h, tgq_closest(h, q, 1, dist_bound, 0, &idx, &d2, closest_point ? cp : nullptr), "tgq_closest");
       if (idx >= 0)
       {
         if (dist) *dist = MetricT::invertMonotoneApprox((double)d2);
@@ -414,6 +445,14 @@ class GpuPointBvhT : public GpuBvhBase<VectorT>
       double result = -1;
       return closestElement<MetricT>(query, dist_bound, c, &result) >= 0 ? result : -1;
     }
+    /** Q filtered closestElement calls (Register.cpp:262-287 updateOffsets): qn3 / qlabel per query, either may be null. */
+    void closestElementFilteredBatch(float const * q3, float const * qn3, int32_t const * qlabel, intx Q, int32_t * idx, float * d2, float * cp3,
+                                     float min_dot = 0.0f, double dist_bound = -1) const
+    { detail::check(h, tgq_closest_filtered(h, q3, qn3, qlabel, Q, min_dot, dist_bound, idx, d2, cp3), "tgq_closest_filtered"); }
+    /** Q filtered kClosestPairs calls (Register.cpp:210-236 findNeighbors). */
+    void kClosestPairsFilteredBatch(float const * q3, float const * qn3, int32_t const * qlabel, intx Q, int32_t k, int32_t * idx, float * d2,
+                                    float min_dot = 0.0f, double dist_bound = -1) const
+    { detail::check(h, tgq_knn_filtered(h, q3, qn3, qlabel, Q, k, min_dot, dist_bound, idx, d2), "tgq_knn_filtered"); }
     void closestElementBatch(float const * q3, intx Q, int32_t * idx, float * d2, float * cp3, double dist_bound = -1,
                              bool exclude_self = false) const
     { detail::check(h, tgq_closest(h, q3, Q, dist_bound, exclude_self ? 1 : 0, idx, d2, cp3), "tgq_closest"); }
@@ -430,7 +469,13 @@ class GpuPointBvhT : public GpuBvhBase<VectorT>
       {
         float q[3]; detail::put3(q, query);
         std::vector<int32_t> idx((size_t)k); std::vector<float> d2((size_t)k);
-        detail::check(h, tgq_knn(h, q, 1, k, dist_bound, 0, idx.data(), d2.data()), "tgq_knn");
+        if (filter)
+        {
+          float fn[3]; detail::put3(fn, filter->n);
+          detail::check(h, tgq_knn_filtered(h, q, filter->use_normals ? fn : nullptr, filter->use_labels ? &filter->label : nullptr, 1, k,
+                                            filter->min_dot, dist_bound, idx.data(), d2.data()), "tgq_knn_filtered");
+        }
+        else detail::check(h, tgq_knn(h, q, 1, k, dist_bound, 0, idx.data(), d2.data()), "tgq_knn");
         for (int32_t j = 0; j < k && idx[(size_t)j] >= 0; ++j)
         {
           NeighborPair pair(0, idx[(size_t)j], (double)d2[(size_t)j]);
@@ -455,6 +500,9 @@ class GpuPointBvhT : public GpuBvhBase<VectorT>
     /** PointSet3.hpp:363-376 with caller-fixed seed samples. */
     float averageSeparation(int32_t const * seeds, int32_t n) const
     { float out = 0; detail::check(h, tgq_avg_separation(h, seeds, n, &out), "tgq_avg_separation"); return out; }
+
+  private:
+    NNFilter const * filter;
 };
 
 typedef GpuMeshBvhT<Vec3> GpuMeshBvh;

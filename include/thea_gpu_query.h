@@ -112,6 +112,22 @@ int tgq_closest(tgq_handle * h, const float * q3, int64_t Q, double dist_bound, 
 int tgq_knn(tgq_handle * h, const float * q3, int64_t Q, int32_t k, double dist_bound, int32_t exclude_self,
             int32_t * idx, float * d2);
 
+/* ---- filtered nearest neighbours on point structures ----------------------------------------- */
+
+/* Per-element labels of a point structure (P int32 in element order; null clears them).  The reference's elements carry
+ * their label as a member (Tools/Register/Register.cpp:60-75); here it is a parallel array. */
+int tgq_set_point_labels(tgq_handle * h, const int32_t * labels);
+/* closestElement / kClosestPairs with an element filter pushed around every query.  Replaces
+ *   NNFilter filter(n_i, label_i); bvh.pushFilter(&filter); bvh.closestElement<MetricL2>(p_i) | kClosestPairs<MetricL2>(p_i, set);
+ *   bvh.popFilter();                      (Tools/Register/Register.cpp:92-101,218-223,274-277; BvhN.hpp:1005-1032,1674-1683)
+ * Query i admits element e iff (qlabel == null or label[e] == qlabel[i]) and (qn3 == null or qn3[i] . n[e] >= min_dot);
+ * Register's NNFilter is min_dot = 0.  Filtered-out elements are skipped before any distance is taken, as in the reference.
+ * qn3 needs a structure built with normals, qlabel one with labels (else TGQ_ESTATE). */
+int tgq_closest_filtered(tgq_handle * h, const float * q3, const float * qn3, const int32_t * qlabel, int64_t Q, float min_dot,
+                         double dist_bound, int32_t * idx, float * d2, float * cp3);
+int tgq_knn_filtered(tgq_handle * h, const float * q3, const float * qn3, const int32_t * qlabel, int64_t Q, int32_t k, float min_dot,
+                     double dist_bound, int32_t * idx, float * d2);
+
 /* Proximity graph over the P points of a point structure.  Replaces the loop of PointSet3::updateGraph over
  * findSampleNeighbors (PointSet3.hpp:380-381,586-681): for every sample, a ball range query of radius init_radius
  * (doubled for up to `rounds` rounds while fewer than min_degree neighbours were found), candidates filtered by

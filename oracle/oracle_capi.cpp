@@ -189,6 +189,64 @@ void orc_closest(void * h, float const * q3, int64_t Q, double dist_bound, int m
   });
 }
 
+// Labels of a point structure (element order) and the per-query filter of filtered queries: query i admits element e iff
+// (qlabel == null or label[e] == qlabel[i]) and (qn3 == null or qn[i] . n[e] >= min_dot)   (Register.cpp:92-101 NNFilter).
+void orc_set_labels(void * h, int32_t const * labels)
+{
+  KdTree & T = ((Handle *)h)->tree;
+  T.labels.clear();
+  if (labels) T.labels.assign(labels, labels + T.size());
+}
+
+void orc_closest_filtered(void * h, float const * q3, float const * qn3, int32_t const * qlabel, int64_t Q, float min_dot, double dist_bound,
+                          int mode, int nthreads, int64_t * idx, float * d2, float * cp3)
+{
+  KdTree const & T = ((Handle *)h)->tree;
+  parallel_for(Q, nthreads, [&](int64_t b, int64_t e) {
+    for (int64_t i = b; i < e; ++i)
+    {
+      ElemFilter f; f.use_normal = qn3 != nullptr; f.n = qn3 ? ld3(qn3, i) : mk(0, 0, 0); f.min_dot = min_dot;
+      f.use_label = qlabel != nullptr; f.label = qlabel ? qlabel[i] : 0;
+      g_filter = &f;                                              // pushFilter
+      V3 q = ld3(q3, i);
+      Closest r = mode == 0 ? T.closest<false>(q, dist_bound, -1) : mode == 1 ? T.closest<true>(q, dist_bound, -1) : brute_closest(T, q, dist_bound, -1);
+      g_filter = nullptr;                                         // popFilter
+      idx[i] = r.idx; if (d2) d2[i] = r.d2; if (cp3) st3(cp3, i, r.cp);
+    }
+  });
+}
+
+void orc_knn_filtered(void * h, float const * q3, float const * qn3, int32_t const * qlabel, int64_t Q, int k, float min_dot, double dist_bound,
+                      int mode, int nthreads, int64_t * idx, float * d2)
+{
+  KdTree const & T = ((Handle *)h)->tree;
+  double bound2 = dist_bound >= 0 ? dist_bound * dist_bound : -1;
+  parallel_for(Q, nthreads, [&](int64_t b, int64_t e) {
+    for (int64_t i = b; i < e; ++i)
+    {
+      ElemFilter f; f.use_normal = qn3 != nullptr; f.n = qn3 ? ld3(qn3, i) : mk(0, 0, 0); f.min_dot = min_dot;
+      f.use_label = qlabel != nullptr; f.label = qlabel ? qlabel[i] : 0;
+      g_filter = &f;
+      V3 q = ld3(q3, i);
+      int64_t * oi = idx + (int64_t)k * i; float * od = d2 + (int64_t)k * i;
+      if (mode == 2) brute_knn(T, q, k, dist_bound, -1, oi, od);
+      else if (mode == 0)
+      {
+        KdTree::KnnSet s; s.k = k;
+        if (!T.nodes.empty()) T.knn_rec(0, q, bound2, -1, s);
+        for (int j = 0; j < k; ++j) { oi[j] = j < (int)s.d.size() ? s.id[(size_t)j] : -1; od[j] = j < (int)s.d.size() ? (float)s.d[(size_t)j] : -1.0f; }
+      }
+      else
+      {
+        std::vector<std::pair<float, int64_t>> s;
+        if (!T.nodes.empty()) T.knn_canon_rec(0, q, bound2, -1, k, s);
+        for (int j = 0; j < k; ++j) { oi[j] = j < (int)s.size() ? s[(size_t)j].second : -1; od[j] = j < (int)s.size() ? s[(size_t)j].first : -1.0f; }
+      }
+      g_filter = nullptr;
+    }
+  });
+}
+
 void orc_ray_first(void * h, float const * o3, float const * d3, float const * tmax, int64_t R, int mode, int nthreads,
                    int64_t * idx, float * t)
 {

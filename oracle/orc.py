@@ -49,6 +49,11 @@ def lib():
                                     C.c_void_p, C.c_void_p]
         L.orc_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
                               C.c_void_p, C.c_void_p]
+        L.orc_set_labels.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_closest_filtered.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_double, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_knn_filtered.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_double, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_void_p]
         L.orc_avg_separation.restype = C.c_float
         L.orc_avg_separation.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_ball_graph.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -145,6 +150,32 @@ class Oracle:
         idx = np.empty((Q, k), np.int64)
         d2 = np.empty((Q, k), np.float32)
         lib().orc_knn(self.h, _p(q), Q, k, float(dist_bound), int(exclude_self), mode, threads or ncores(), _p(idx), _p(d2))
+        return idx, d2
+
+    def set_labels(self, labels):
+        """Per-element labels of a point structure (for filtered queries)."""
+        self._labels = None if labels is None else np.ascontiguousarray(labels, np.int32)
+        lib().orc_set_labels(self.h, _p(self._labels))
+
+    def closest_filtered(self, q, qn=None, qlabel=None, min_dot=0.0, dist_bound=-1.0, mode=MODE_CANON, threads=None):
+        q = _f32(q).reshape(-1, 3)
+        qn = None if qn is None else _f32(qn).reshape(-1, 3)
+        ql = None if qlabel is None else np.ascontiguousarray(qlabel, np.int32)
+        Q = q.shape[0]
+        idx = np.empty(Q, np.int64)
+        d2 = np.empty(Q, np.float32)
+        cp = np.empty((Q, 3), np.float32)
+        lib().orc_closest_filtered(self.h, _p(q), _p(qn), _p(ql), Q, float(min_dot), float(dist_bound), mode, threads or ncores(), _p(idx), _p(d2), _p(cp))
+        return idx, d2, cp
+
+    def knn_filtered(self, q, k, qn=None, qlabel=None, min_dot=0.0, dist_bound=-1.0, mode=MODE_CANON, threads=None):
+        q = _f32(q).reshape(-1, 3)
+        qn = None if qn is None else _f32(qn).reshape(-1, 3)
+        ql = None if qlabel is None else np.ascontiguousarray(qlabel, np.int32)
+        Q = q.shape[0]
+        idx = np.empty((Q, k), np.int64)
+        d2 = np.empty((Q, k), np.float32)
+        lib().orc_knn_filtered(self.h, _p(q), _p(qn), _p(ql), Q, int(k), float(min_dot), float(dist_bound), mode, threads or ncores(), _p(idx), _p(d2))
         return idx, d2
 
     def avg_separation(self, seeds):

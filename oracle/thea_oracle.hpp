@@ -288,6 +288,12 @@ inline bool better_canon(float d2, int64_t idx, float best, int64_t best_idx)
 // Kd-tree of BvhN (Method::KDTREE, the default): BvhN.hpp:1365-1440 (initTree), 1450-1525 (createKdTree),
 // 1320-1335 (ObjectLess), Math.cpp:22-36 (treeDepth).  Elements are triangles (elem_kind 0) or points (1).
 // ------------------------------------------------------------------------------------------------
+// Element filter of the reference's filtered queries: BvhN::pushFilter / elementPassesFilters (BvhN.hpp:1005-1032,1674-1683)
+// with the NNFilter of Tools/Register/Register.cpp:92-101 -- same label and n . n_e >= min_dot (Register uses 0).  Installed
+// per worker thread around a query, exactly like the reference pushes a filter around each closestElement / kClosestPairs call.
+struct ElemFilter { bool use_normal; V3 n; float min_dot; bool use_label; int32_t label; };
+inline thread_local ElemFilter const * g_filter = nullptr;
+
 struct KdNode
 {
   Box bounds;             // stored padded x1.05 (BvhN.hpp:1437,1514,2458)
@@ -301,6 +307,7 @@ struct KdTree
   std::vector<Tri> tris;          // triangle elements (copied, BvhN.hpp:722-724)
   std::vector<V3> pts;            // point elements
   std::vector<V3> nrm;            // optional per-point normals (SamplePoint3)
+  std::vector<int32_t> labels;    // optional per-point labels (the `label` member of Register's samples)
   bool is_points = false;
   std::vector<int64_t> order;     // element indices; node ranges index into this
   std::vector<KdNode> nodes;      // nodes[0] = root
@@ -308,6 +315,16 @@ struct KdTree
   int max_leaf = 5;
 
   int64_t size() const { return is_points ? (int64_t)pts.size() : (int64_t)tris.size(); }
+  // elementPassesFilters (BvhN.hpp:1674-1683): self exclusion (PointSet3::FilterSelf) and the thread's installed filter.
+  bool rejects(int64_t e, int64_t skip) const
+  {
+    if (e == skip) return true;
+    ElemFilter const * f = g_filter;
+    if (!f) return false;
+    if (f->use_label && !labels.empty() && labels[(size_t)e] != f->label) return true;
+    if (f->use_normal && !nrm.empty() && dot(f->n, nrm[(size_t)e]) < f->min_dot) return true;
+    return false;
+  }
   V3 elem_center(int64_t i) const { return is_points ? pts[i] : tris[i].centroid; }
   void elem_bounds(int64_t i, V3 & l, V3 & h) const
   { if (is_points) { l = h = pts[i]; } else { l = tris[i].lo; h = tris[i].hi; } }
@@ -380,7 +397,7 @@ struct KdTree
       for (int64_t k = nd.begin; k < nd.begin + nd.count; ++k)
       {
         int64_t e = order[(size_t)k];
-        if (e == s.skip) continue;                      // FilterSelf (PointSet3.hpp:576-583)
+        if (rejects(e, s.skip)) continue;               // FilterSelf (PointSet3.hpp:576-583) / pushed filters
         V3 cp; double mad = (double)elem_sqdist(e, q, cp);
         bool take = Canon ? (s.best < 0 ? (mad == mad) : (mad < s.best || (mad == s.best && s.idx >= 0 && e < s.idx)))
                           : (s.best < 0 || mad < s.best);
@@ -501,7 +518,7 @@ struct KdTree
       for (int64_t kk = nd.begin; kk < nd.begin + nd.count; ++kk)
       {
         int64_t e = order[(size_t)kk];
-        if (e == skip) continue;
+        if (rejects(e, skip)) continue;
         V3 cp; float d2 = elem_sqdist(e, q, cp);
         if (!(d2 == d2)) continue;
         if (bound2 >= 0 && !((double)d2 < bound2)) continue;
@@ -532,7 +549,7 @@ struct KdTree
       for (int64_t k = nd.begin; k < nd.begin + nd.count; ++k)
       {
         int64_t e = order[(size_t)k];
-        if (e == skip) continue;
+        if (rejects(e, skip)) continue;
         V3 cp; double mad = (double)elem_sqdist(e, q, cp);
         if ((bound2 < 0 || mad < bound2) && insertable(mad))
         {
@@ -563,7 +580,7 @@ inline Closest brute_closest(KdTree const & T, V3 q, double dist_bound, int64_t 
   int64_t n = T.size();
   for (int64_t e = 0; e < n; ++e)
   {
-    if (e == skip) continue;
+    if (T.rejects(e, skip)) continue;
     V3 cp; float d2 = T.elem_sqdist(e, q, cp);
     if (!(d2 == d2)) continue;
     if (bound2 >= 0 && !((double)d2 < bound2)) continue;     // strict (BvhN.hpp:448,462)
@@ -595,7 +612,7 @@ inline int brute_knn(KdTree const & T, V3 q, int k, double dist_bound, int64_t s
   int64_t n = T.size();
   for (int64_t e = 0; e < n; ++e)
   {
-    if (e == skip) continue;
+    if (T.rejects(e, skip)) continue;
     V3 cp; float d2 = T.elem_sqdist(e, q, cp);
     if (!(d2 == d2)) continue;
     if (bound2 >= 0 && !((double)d2 < bound2)) continue;

@@ -111,6 +111,26 @@ int main(int argc, char ** argv)
     float avg = sampleGraph(pts, 6, seeds.data(), (int32_t)seeds.size(), gi.data(), gs.data(), gc.data());
     std::vector<float> av(1, avg); wr(fo, av); wr(fo, gi); wr(fo, gs); wr(fo, gc);
 
+    // ---- filtered nearest neighbours the way Tools/Register/Register.cpp:210-236,262-287 writes them ----
+    std::vector<int32_t> labels(NS); for (int64_t i = 0; i < NS; ++i) labels[i] = (int32_t)(i % 3);
+    pts.setLabels(labels.data());
+    std::vector<int32_t> fci(NS), fki(NS * 4); std::vector<float> fd(NS), fkd(NS * 4);
+    pts.closestElementFilteredBatch(sp.data(), sn.data(), labels.data(), NS, fci.data(), fd.data(), nullptr);
+    pts.kClosestPairsFilteredBatch(sp.data(), sn.data(), labels.data(), NS, 4, fki.data(), fkd.data());
+    wr(fo, fci); wr(fo, fd); wr(fo, fki); wr(fo, fkd);
+    for (int64_t i = 0; i < nk; ++i)
+    {
+      GpuPointBvh::NNFilter filter(Vec3(sn[3 * i], sn[3 * i + 1], sn[3 * i + 2]), labels[i]);
+      pts.pushFilter(&filter);
+        intx nn = pts.closestElement<MetricL2>(Vec3(sp[3 * i], sp[3 * i + 1], sp[3 * i + 2]));
+        BoundedSortedArray<GpuPointBvh::NeighborPair> set(4);
+        pts.kClosestPairs<MetricL2>(Vec3(sp[3 * i], sp[3 * i + 1], sp[3 * i + 2]), set);
+      pts.popFilter();
+      if (nn != fci[i]) { fprintf(stderr, "scalar filtered closestElement disagrees with the batch\n"); return 3; }
+      for (size_t j = 0; j < set.size(); ++j)
+        if (set[j].getTargetIndex() != fki[4 * i + (int64_t)j]) { fprintf(stderr, "scalar filtered kClosestPairs disagrees with the batch\n"); return 3; }
+    }
+
     // ---- error behaviour: filters are refused loudly, wrong structure kind raises ----
     bool threw = false;
     try { int dummy = 0; bvh.pushFilter(&dummy); } catch (Error const &) { threw = true; }

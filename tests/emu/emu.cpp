@@ -24,12 +24,12 @@ struct Emu
 {
   bool tri = false, has_n = false;
   int n = 0, leaf = 4; float pad = 0;
-  std::vector<TriRec> tris; std::vector<f4> pts, nrm;
+  std::vector<TriRec> tris; std::vector<f4> pts, nrm; std::vector<int> lab; std::vector<uint32_t> perm_keep;
   std::vector<NodeRec> nodes;
   std::vector<ObbNode> obbs;
   BvhView view() const
   {
-    BvhView v; v.nodes = nodes.data(); v.obbs = tri ? obbs.data() : nullptr; v.tris = tri ? tris.data() : nullptr; v.pts = tri ? nullptr : pts.data();
+    BvhView v; v.nodes = nodes.data(); v.obbs = tri ? obbs.data() : nullptr; v.tris = tri ? tris.data() : nullptr; v.pts = tri ? nullptr : pts.data(); v.lab = lab.empty() ? nullptr : lab.data();
     v.nrm = has_n ? nrm.data() : nullptr; v.n_nodes = (int)nodes.size(); v.n_prims = n; return v;
   }
 };
@@ -61,6 +61,7 @@ void build(Emu & E, float const * src, float const * n3)
   std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
   std::vector<uint64_t> skeys((size_t)n);
   for (int s = 0; s < n; ++s) skeys[(size_t)s] = keys[perm[(size_t)s]];
+  E.perm_keep = perm;
   // records + element boxes (k_gather_*)
   std::vector<v3> plo((size_t)n), phi((size_t)n);
   if (E.tri) E.tris.resize((size_t)n); else { E.pts.resize((size_t)n + 4); if (E.has_n) E.nrm.resize((size_t)n + 4); }   // + one fetch of slack (a leaf fetch always reads 4 points)
@@ -210,6 +211,50 @@ void emu_knn(void * h, float const * q3, int64_t Q, int k, float bound_ub, int e
   {
     SortedSet set; set.init(keys.data(), ids.data(), 1, k);
     knn_query(v, ld(q3, i), exclude_self ? (int)i : -1, bound_ub, set);
+    for (int j = 0; j < k; ++j) { idx[i * k + j] = j < set.n ? ids[(size_t)j] : -1; d2[i * k + j] = j < set.n ? keys[(size_t)j] : -1.0f; }
+  }
+}
+
+// Filtered queries on point structures (tgq_set_point_labels / tgq_closest_filtered / tgq_knn_filtered).
+void emu_set_labels(void * h, int32_t const * labels)
+{
+  Emu & E = *(Emu *)h; E.lab.clear();
+  if (!labels) return;
+  E.lab.resize((size_t)E.n + 4);
+  for (int s = 0; s < E.n; ++s) E.lab[(size_t)s] = labels[E.perm_keep[(size_t)s]];
+}
+
+static ElemFilterD make_filter(float const * qn3, int32_t const * qlabel, int64_t i, float min_dot)
+{
+  ElemFilterD f = no_filter(); f.mode = (qn3 ? 1 : 0) | (qlabel ? 2 : 0); f.min_dot = min_dot;
+  if (qn3) f.n = ld(qn3, i);
+  if (qlabel) f.label = qlabel[i];
+  return f;
+}
+
+void emu_closest_filtered(void * h, float const * q3, float const * qn3, int32_t const * qlabel, int64_t Q, float min_dot, float bound_ub,
+                          int32_t * idx, float * d2, float * cp3)
+{
+  Emu & E = *(Emu *)h; BvhView v = E.view(); int seed = -1;
+  for (int64_t i = 0; i < Q; ++i)
+  {
+    float best = bound_ub; int bi = -1; v3 cp = mk3(0, 0, 0);
+    ElemFilterD f = make_filter(qn3, qlabel, i, min_dot);
+    closest_query<false>(v, 0.0f, ld(q3, i), -1, best, bi, cp, &seed, &f);
+    idx[i] = bi; d2[i] = bi >= 0 ? best : -1.0f; cp3[3 * i] = cp.x; cp3[3 * i + 1] = cp.y; cp3[3 * i + 2] = cp.z;
+  }
+}
+
+void emu_knn_filtered(void * h, float const * q3, float const * qn3, int32_t const * qlabel, int64_t Q, int k, float min_dot, float bound_ub,
+                      int32_t * idx, float * d2)
+{
+  Emu & E = *(Emu *)h; BvhView v = E.view();
+  std::vector<float> keys((size_t)k); std::vector<int> ids((size_t)k);
+  for (int64_t i = 0; i < Q; ++i)
+  {
+    SortedSet set; set.init(keys.data(), ids.data(), 1, k);
+    ElemFilterD f = make_filter(qn3, qlabel, i, min_dot);
+    knn_query(v, ld(q3, i), -1, bound_ub, set, &f);
     for (int j = 0; j < k; ++j) { idx[i * k + j] = j < set.n ? ids[(size_t)j] : -1; d2[i * k + j] = j < set.n ? keys[(size_t)j] : -1.0f; }
   }
 }

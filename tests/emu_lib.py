@@ -23,6 +23,9 @@ def lib():
         L.emu_closest.argtypes = [vp, vp, C.c_int64, C.c_float, C.c_int, vp, vp, vp]
         L.emu_knn.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_float, C.c_int, vp, vp]
         L.emu_ball_graph.argtypes = [vp, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, vp, vp, vp]
+        L.emu_set_labels.argtypes = [vp, vp]
+        L.emu_closest_filtered.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, vp, vp, vp]
+        L.emu_knn_filtered.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, C.c_float, C.c_float, vp, vp]
         L.emu_ray.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, vp, vp]
         L.emu_select.argtypes = [vp, C.c_int, C.c_int]
         L.emu_std_nth_element.argtypes = [vp, C.c_int, C.c_int]
@@ -69,6 +72,31 @@ class Emu:
         flag = int(exclude_self) if seeded else -int(exclude_self) - 1
         lib().emu_closest(self.h, _p(q), Q, float(bound_ub), flag, _p(idx), _p(d2), _p(cp))
         return idx, d2, cp
+
+    def set_labels(self, labels):
+        self._lab = None if labels is None else np.ascontiguousarray(labels, np.int32)
+        lib().emu_set_labels(self.h, _p(self._lab))
+
+    def closest_filtered(self, q, qn=None, qlabel=None, min_dot=0.0, bound_ub=np.inf):
+        q = np.ascontiguousarray(q, np.float32)
+        qn = None if qn is None else np.ascontiguousarray(qn, np.float32)
+        ql = None if qlabel is None else np.ascontiguousarray(qlabel, np.int32)
+        Q = len(q)
+        idx = np.empty(Q, np.int32)
+        d2 = np.empty(Q, np.float32)
+        cp = np.empty((Q, 3), np.float32)
+        lib().emu_closest_filtered(self.h, _p(q), _p(qn), _p(ql), Q, float(min_dot), float(bound_ub), _p(idx), _p(d2), _p(cp))
+        return idx, d2, cp
+
+    def knn_filtered(self, q, k, qn=None, qlabel=None, min_dot=0.0, bound_ub=np.inf):
+        q = np.ascontiguousarray(q, np.float32)
+        qn = None if qn is None else np.ascontiguousarray(qn, np.float32)
+        ql = None if qlabel is None else np.ascontiguousarray(qlabel, np.int32)
+        Q = len(q)
+        idx = np.empty((Q, k), np.int32)
+        d2 = np.empty((Q, k), np.float32)
+        lib().emu_knn_filtered(self.h, _p(q), _p(qn), _p(ql), Q, int(k), float(min_dot), float(bound_ub), _p(idx), _p(d2))
+        return idx, d2
 
     def knn(self, q, k, bound_ub=np.inf, exclude_self=False):
         q = np.ascontiguousarray(q, np.float32)

@@ -127,4 +127,11 @@ def test_adaptor_driver_matches_oracle(built, tmp_path):
     assert np.array_equal(take(np.int32, NS * 6).reshape(NS, 6), ogi.astype(np.int32))
     assert np.array_equal(take(np.float32, NS * 6).reshape(NS, 6), ogs)
     assert np.array_equal(take(np.int32, NS), ogc)
+    labels = (np.arange(NS) % 3).astype(np.int32)
+    po.set_labels(labels)
+    ofi, ofd, _ = po.closest_filtered(sp, sn, labels, mode=orc.MODE_BRUTE)
+    assert np.array_equal(take(np.int32, NS), ofi.astype(np.int32)) and np.array_equal(take(np.float32, NS), ofd)
+    oki, okd = po.knn_filtered(sp, 4, sn, labels, mode=orc.MODE_BRUTE)
+    assert np.array_equal(take(np.int32, NS * 4).reshape(NS, 4), oki.astype(np.int32))
+    assert np.array_equal(take(np.float32, NS * 4).reshape(NS, 4), okd)
     assert pos[0] == len(buf)

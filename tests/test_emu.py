@@ -241,3 +241,35 @@ def test_degenerate_triangles_behave_like_the_reference():
     t, ri = E.ray(o, d)
     ori, ort = ora.ray_first(o, d, mode=orc.MODE_BRUTE)
     assert np.array_equal(ri, ori.astype(np.int32)) and np.array_equal(t, ort)
+
+
+def test_filtered_nearest_neighbours_register_semantics():
+    """NNFilter of Tools/Register/Register.cpp:92-101 (same label, n . n_e >= 0) pushed around
+    closestElement / kClosestPairs; all three oracle modes and the engine's traversal agree."""
+    mesh = gen.torus_mesh(24)
+    p, n, _ = gen.area_samples(mesh, 4000)
+    lab = (gen.splitmix64(5, 4000) % np.uint64(3)).astype(np.int32)
+    E = emu_lib.Emu(points=p, normals=n)
+    E.set_labels(lab)
+    ora = orc.Oracle(points=p, normals=n)
+    ora.set_labels(lab)
+    rng = np.random.default_rng(2)
+    q = (p[:1500] + rng.normal(scale=0.03, size=(1500, 3))).astype(np.float32)
+    qn, ql = n[:1500], lab[:1500]
+    for kw in ({"qn": qn, "qlabel": ql}, {"qn": qn}, {"qlabel": ql}, {"qn": qn, "qlabel": ql, "min_dot": 0.7}):
+        gi, gd, gc = E.closest_filtered(q, **kw)
+        ki, kd = E.knn_filtered(q, 24, **kw)                       # 3 * MAX_NBRS of Register.cpp:30,215
+        for mode in (orc.MODE_REFERENCE, orc.MODE_CANON, orc.MODE_BRUTE):
+            oi, od, oc = ora.closest_filtered(q, mode=mode, **kw)
+            assert np.array_equal(gi, oi.astype(np.int32)) and np.array_equal(gd, od) and np.array_equal(gc, oc)
+        oki, okd = ora.knn_filtered(q, 24, mode=orc.MODE_BRUTE, **kw)
+        assert np.array_equal(ki, oki.astype(np.int32)) and np.array_equal(kd, okd)
+        ok = gi >= 0
+        if "qlabel" in kw:
+            assert (lab[gi[ok]] == ql[ok]).all()
+        if "qn" in kw:
+            assert ((n[gi[ok]] * qn[ok]).sum(axis=1) >= kw.get("min_dot", 0.0) - 1e-6).all()
+    # the filter really bites: unfiltered answers differ for a visible share of the queries
+    ui, _, _ = E.closest(q)
+    fi, _, _ = E.closest_filtered(q, qn=qn, qlabel=ql)
+    assert 0.2 < (ui != fi).mean() < 0.95

@@ -147,3 +147,35 @@ def test_device_pointers_and_host_pointers_agree(setup):
     dq = torch.from_numpy(q).cuda()
     di, dd, dc = e.closest(dq)
     assert np.array_equal(hi, di.cpu().numpy()) and np.array_equal(hd, dd.cpu().numpy()) and np.array_equal(hc, dc.cpu().numpy())
+
+
+def test_filtered_nearest_neighbours_register_shape(built):
+    """SURVEY 8f rank 1 (Register.cpp findNeighbors / updateOffsets): label- and normal-filtered NN and 3*MAX_NBRS k-NN."""
+    from thea_b200 import Engine
+    mesh = gen.torus_mesh(64)
+    p, n, _ = gen.area_samples(mesh, 30000)
+    lab = (gen.splitmix64(5, len(p)) % np.uint64(4)).astype(np.int32)
+    e = Engine(0)
+    e.build_points(p, n)
+    e.set_point_labels(lab)
+    ora = orc.Oracle(points=p, normals=n)
+    ora.set_labels(lab)
+    rng = np.random.default_rng(2)
+    q = (p[:8000] + rng.normal(scale=0.02, size=(8000, 3))).astype(np.float32)
+    qn, ql = n[:8000], lab[:8000]
+    for kw in ({"qn3": qn, "qlabel": ql}, {"qn3": qn}, {"qlabel": ql}, {"qn3": qn, "qlabel": ql, "min_dot": 0.5}):
+        okw = {("qn" if k == "qn3" else k): v for k, v in kw.items()}
+        gi, gd, gc = e.closest_filtered(q, **kw)
+        oi, od, oc = ora.closest_filtered(q, mode=orc.MODE_CANON, **okw)
+        assert np.array_equal(gi, oi.astype(np.int32)) and np.array_equal(gd, od) and np.array_equal(gc, oc)
+        ki, kd = e.knn_filtered(q[:3000], 24, **{k: (v[:3000] if hasattr(v, "__len__") else v) for k, v in kw.items()})
+        oki, okd = ora.knn_filtered(q[:3000], 24, mode=orc.MODE_CANON, **{k: (v[:3000] if hasattr(v, "__len__") else v) for k, v in okw.items()})
+        assert np.array_equal(ki, oki.astype(np.int32)) and np.array_equal(kd, okd)
+    # misuse is an error, not a silent unfiltered answer
+    from thea_b200 import TgqError
+    bare = Engine(0)
+    bare.build_points(p)
+    with pytest.raises(TgqError):
+        bare.closest_filtered(q[:10], qn3=qn[:10])
+    with pytest.raises(TgqError):
+        bare.closest_filtered(q[:10], qlabel=ql[:10])

@@ -57,8 +57,8 @@ struct tgq_handle
 
   int opt_sort = 2, opt_leaf = 4, opt_async = 0; int64_t opt_chunk = 8388608;
 
-  int kind = TGQ_KIND_NONE; int n = 0; int n_nodes = 0; bool has_normals = false; int leaf_built = 4;
-  DevBuf nodes, elems, nrm, scene;                                  // NodeRec[], TriRec[] | f4[], f4[], SceneBox
+  int kind = TGQ_KIND_NONE; int n = 0; int n_nodes = 0; bool has_normals = false, has_labels = false; int leaf_built = 4;
+  DevBuf nodes, elems, nrm, lab, scene;                                // NodeRec[], TriRec[] | f4[], f4[], SceneBox
   DevBuf perm, pos_of_elem, first, last, split, parent, live, newidx;   // kept for refit
   DevBuf pbox_lo, pbox_hi, nbox_lo, nbox_hi, arrive, keys_a, keys_b, vals_a, cubtmp, src, src2, misc;
   DevBuf area_by_elem, cum;                                           // float[n] in element order; double[n] cumulative
@@ -107,6 +107,7 @@ BvhView view_of(tgq_handle * h)
   v.tris = h->kind == TGQ_KIND_TRIANGLES ? h->elems.as<TriRec>() : nullptr;
   v.pts = h->kind == TGQ_KIND_POINTS ? h->elems.as<f4>() : nullptr;
   v.nrm = (h->kind == TGQ_KIND_POINTS && h->has_normals) ? h->nrm.as<f4>() : nullptr;
+  v.lab = (h->kind == TGQ_KIND_POINTS && h->has_labels) ? h->lab.as<int>() : nullptr;
   v.n_nodes = h->n_nodes; v.n_prims = h->n;
   return v;
 }
@@ -228,7 +229,7 @@ int build_common(tgq_handle * h, int kind, float const * d_src, float const * d_
   CK(cudaEventRecord(e0, s));
 
   h->kind = kind; h->n = n; h->n_nodes = 0; h->has_normals = (kind == TGQ_KIND_POINTS && d_n3 != nullptr);
-  h->leaf_built = h->opt_leaf; h->cum_valid = false;
+  h->leaf_built = h->opt_leaf; h->cum_valid = false; h->has_labels = false;
   h->st.num_elements = n;
   for (int a = 0; a < 3; ++a) { h->lo[a] = 0; h->hi[a] = 0; }
   if (n == 0) { h->st.num_nodes = 0; h->st.node_bytes = 0; h->st.element_bytes = 0; h->st.last_build_ms = 0; return TGQ_OK; }
@@ -482,7 +483,7 @@ int tgq_destroy(tgq_handle * h)
   if (!h) return TGQ_OK;
   Guard g(h);
   cudaDeviceSynchronize();
-  DevBuf * bufs[] = {&h->nodes, &h->elems, &h->nrm, &h->scene, &h->perm, &h->pos_of_elem, &h->first, &h->last, &h->split, &h->parent, &h->live,
+  DevBuf * bufs[] = {&h->nodes, &h->elems, &h->nrm, &h->lab, &h->scene, &h->perm, &h->pos_of_elem, &h->first, &h->last, &h->split, &h->parent, &h->live,
                      &h->newidx, &h->pbox_lo, &h->pbox_hi, &h->nbox_lo, &h->nbox_hi, &h->arrive, &h->keys_a, &h->keys_b, &h->vals_a,
                      &h->cubtmp, &h->src, &h->src2, &h->misc, &h->area_by_elem, &h->cum, &h->obbs, &h->pnrm, &h->nsum, &h->obbinfo, &h->big, &h->big_count};
   for (DevBuf * b : bufs) b->release();
@@ -614,52 +615,103 @@ int tgq_triangle_cache(tgq_handle * h, float * n3, float * d, int32_t * axis, fl
   return TGQ_OK;
 }
 
-int tgq_closest(tgq_handle * h, const float * q3, int64_t Q, double dist_bound, int32_t exclude_self, int32_t * idx, float * d2, float * cp3)
+static int closest_common(tgq_handle * h, const float * q3, const float * qn3, const int32_t * qlabel, float min_dot, int64_t Q, double dist_bound,
+                          int32_t exclude_self, int32_t * idx, float * d2, float * cp3)
 {
   CKRC(need_built(h, (1 << TGQ_KIND_TRIANGLES) | (1 << TGQ_KIND_POINTS)));
   if (Q < 0 || (Q > 0 && !q3)) return fail(h, TGQ_EINVAL, "tgq_closest: bad arguments");
   Guard g(h);
   float ub = bound_to_ub(dist_bound);
-  Arg args[4] = {{q3, nullptr, 12}, {nullptr, idx, 4}, {nullptr, d2, 4}, {nullptr, cp3, 12}};
+  Arg args[6] = {{q3, nullptr, 12}, {nullptr, idx, 4}, {nullptr, d2, 4}, {nullptr, cp3, 12}, {qn3, nullptr, 12}, {qlabel, nullptr, 4}};
   BvhView v = view_of(h); bool tri = h->kind == TGQ_KIND_TRIANGLES;
   size_t smem = trav_smem_bytes(1);
-  return run_batched(h, Q, args, 4, true, [&](ChunkCtx & c) -> int {
+  return run_batched(h, Q, args, 6, true, [&](ChunkCtx & c) -> int {
     int grid = 0; int * cnt = c.slot->counter.as<int>();
     if (tri)
     {
       CKRC(persistent_grid(h, k_closest<true>, smem, c.n, cnt, c.stream, &grid));
       k_closest<true><<<grid, TGQ_BLOCK, smem, c.stream>>>(v, h->pad, (float const *)c.din[0], c.perm, c.n, ub, exclude_self, c.offset, cnt,
-                                                      (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3]);
+                                                         (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3], nullptr, nullptr, 0.0f);
     }
     else
     {
       CKRC(persistent_grid(h, k_closest<false>, smem, c.n, cnt, c.stream, &grid));
       k_closest<false><<<grid, TGQ_BLOCK, smem, c.stream>>>(v, 0.0f, (float const *)c.din[0], c.perm, c.n, ub, exclude_self, c.offset, cnt,
-                                                       (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3]);
+                                                          (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3], (float const *)c.din[4],
+                                                          (int const *)c.din[5], min_dot);
     }
     h->st.last_launches += 1; h->st.total_launches += 1;
     return TGQ_OK;
   });
 }
 
-int tgq_knn(tgq_handle * h, const float * q3, int64_t Q, int32_t k, double dist_bound, int32_t exclude_self, int32_t * idx, float * d2)
+int tgq_closest(tgq_handle * h, const float * q3, int64_t Q, double dist_bound, int32_t exclude_self, int32_t * idx, float * d2, float * cp3)
+{ return closest_common(h, q3, nullptr, nullptr, 0.0f, Q, dist_bound, exclude_self, idx, d2, cp3); }
+
+// Validates the filter arguments of the *_filtered entry points against the structure.
+static int check_filter(tgq_handle * h, const float * qn3, const int32_t * qlabel)
+{
+  CKRC(need_built(h, 1 << TGQ_KIND_POINTS));
+  if (qn3 && !h->has_normals) return fail(h, TGQ_ESTATE, "filtered query with normals on a structure built without normals");
+  if (qlabel && !h->has_labels) return fail(h, TGQ_ESTATE, "filtered query with labels on a structure without labels (tgq_set_point_labels)");
+  return TGQ_OK;
+}
+
+int tgq_closest_filtered(tgq_handle * h, const float * q3, const float * qn3, const int32_t * qlabel, int64_t Q, float min_dot, double dist_bound,
+                         int32_t * idx, float * d2, float * cp3)
+{
+  if (!h) return TGQ_EINVAL;
+  CKRC(check_filter(h, qn3, qlabel));
+  return closest_common(h, q3, qn3, qlabel, min_dot, Q, dist_bound, 0, idx, d2, cp3);
+}
+
+int tgq_set_point_labels(tgq_handle * h, const int32_t * labels)
+{
+  CKRC(need_built(h, 1 << TGQ_KIND_POINTS));
+  Guard g(h);
+  if (!labels || h->n == 0) { h->has_labels = false; return TGQ_OK; }
+  cudaStream_t s = h->stream;
+  void const * dl = nullptr;
+  CKRC(to_device(h, labels, 4 * (size_t)h->n, h->src2, s, &dl));
+  CK(h->lab.reserve(4 * (size_t)h->n));
+  k_gather_labels<<<grid_for(h->n), TGQ_BLOCK, 0, s>>>((int const *)dl, h->perm.as<uint32_t>(), h->n, h->lab.as<int>());
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(s));
+  h->st.total_launches += 1;
+  h->has_labels = true;
+  return TGQ_OK;
+}
+
+static int knn_common(tgq_handle * h, const float * q3, const float * qn3, const int32_t * qlabel, float min_dot, int64_t Q, int32_t k,
+                      double dist_bound, int32_t exclude_self, int32_t * idx, float * d2)
 {
   CKRC(need_built(h, 1 << TGQ_KIND_POINTS));
   if (Q < 0 || (Q > 0 && !q3) || k < 1) return fail(h, TGQ_EINVAL, "tgq_knn: bad arguments");
   if (k > TGQ_MAX_K) return fail(h, TGQ_ELIMIT, "tgq_knn: k exceeds TGQ_MAX_K");
   Guard g(h);
   float ub = bound_to_ub(dist_bound);
-  Arg args[3] = {{q3, nullptr, 12}, {nullptr, idx, 4 * (size_t)k}, {nullptr, d2, 4 * (size_t)k}};
+  Arg args[5] = {{q3, nullptr, 12}, {nullptr, idx, 4 * (size_t)k}, {nullptr, d2, 4 * (size_t)k}, {qn3, nullptr, 12}, {qlabel, nullptr, 4}};
   BvhView v = view_of(h);
   size_t smem = trav_smem_bytes(KnnW::STAGE) + 2 * (size_t)k * TGQ_BLOCK * 4;
-  return run_batched(h, Q, args, 3, true, [&](ChunkCtx & c) -> int {
+  return run_batched(h, Q, args, 5, true, [&](ChunkCtx & c) -> int {
     int grid = 0; int * cnt = c.slot->counter.as<int>();
     CKRC(persistent_grid(h, k_knn, smem, c.n, cnt, c.stream, &grid));
     k_knn<<<grid, TGQ_BLOCK, smem, c.stream>>>(v, (float const *)c.din[0], c.perm, c.n, k, ub, exclude_self, c.offset, cnt, (int *)c.dout[1],
-                                               (float *)c.dout[2]);
+                                               (float *)c.dout[2], (float const *)c.din[3], (int const *)c.din[4], min_dot);
     h->st.last_launches += 1; h->st.total_launches += 1;
     return TGQ_OK;
   });
+}
+
+int tgq_knn(tgq_handle * h, const float * q3, int64_t Q, int32_t k, double dist_bound, int32_t exclude_self, int32_t * idx, float * d2)
+{ return knn_common(h, q3, nullptr, nullptr, 0.0f, Q, k, dist_bound, exclude_self, idx, d2); }
+
+int tgq_knn_filtered(tgq_handle * h, const float * q3, const float * qn3, const int32_t * qlabel, int64_t Q, int32_t k, float min_dot,
+                     double dist_bound, int32_t * idx, float * d2)
+{
+  if (!h) return TGQ_EINVAL;
+  CKRC(check_filter(h, qn3, qlabel));
+  return knn_common(h, q3, qn3, qlabel, min_dot, Q, k, dist_bound, 0, idx, d2);
 }
 
 int tgq_ball_graph(tgq_handle * h, int32_t max_degree, float init_radius, int32_t rounds, float min_dot, int32_t min_degree, int32_t * idx,

@@ -102,6 +102,13 @@ __global__ void k_gather_points(float const * __restrict__ p3, float const * __r
   pbox_lo[s] = make_float4(p.x, p.y, p.z, 0.0f); pbox_hi[s] = pbox_lo[s];
 }
 
+// Labels of a point structure in Morton order (filtered queries).
+__global__ void k_gather_labels(int const * __restrict__ labels, uint32_t const * __restrict__ perm, int n, int * out)
+{
+  int s = blockIdx.x * blockDim.x + threadIdx.x; if (s >= n) return;
+  out[s] = labels[perm[s]];
+}
+
 // K3: binary radix tree over the sorted keys.  Inner node i: range [first,last], split; parents of inner nodes at
 // parent[i], of leaves (sorted position s) at parent[n - 1 + s].
 __global__ void k_hierarchy(uint64_t const * __restrict__ keys, int n, int * first, int * last, int * split, int * parent)
@@ -396,6 +403,7 @@ struct ClosestW
   static constexpr int STAGE = 1;       // (x, y, z, query index)
   ClosestState<TRI> s; BvhView b; float scene_pad; float const * q3; uint32_t const * perm; float ub; int exclude_self; int64_t self_offset;
   int * idx; float * d2; float * cp3; int qi; int seed;
+  float const * qn3; int const * qlabel; float min_dot;      // per-query element filter (point structures), null = none
   __device__ __forceinline__ int state() const { return s.t.cur; }
   __device__ __forceinline__ void stage(int t, f4 * dst) const
   {
@@ -406,6 +414,12 @@ struct ClosestW
   {
     f4 r = *src; qi = __float_as_int(r.w);
     closest_begin(s, b, scene_pad, mk3(r.x, r.y, r.z), exclude_self ? (int)(self_offset + qi) : -1, ub, seed);
+    if (!TRI && (qn3 || qlabel))
+    {
+      s.f.mode = (qn3 ? 1 : 0) | (qlabel ? 2 : 0); s.f.min_dot = min_dot;
+      if (qn3) s.f.n = ld3(qn3, qi);
+      if (qlabel) s.f.label = qlabel[qi];
+    }
   }
   static constexpr int FETCH = ClosestFetch<TRI>::N;
   __device__ __forceinline__ void fetch(f4 * r) const { closest_fetch(s, b, r); }
@@ -424,12 +438,13 @@ struct ClosestW
 template <bool TRI>
 __global__ void __launch_bounds__(TGQ_BLOCK)
 k_closest(BvhView b, float scene_pad, float const * __restrict__ q3, uint32_t const * __restrict__ perm, int n, float bound_ub, int exclude_self,
-          int64_t self_offset, int * counter, int * idx, float * d2, float * cp3)
+          int64_t self_offset, int * counter, int * idx, float * d2, float * cp3, float const * __restrict__ qn3, int const * __restrict__ qlabel,
+          float min_dot)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   ClosestW<TRI> w;
   w.b = b; w.scene_pad = scene_pad; w.q3 = q3; w.perm = perm; w.ub = bound_ub; w.exclude_self = exclude_self; w.self_offset = self_offset;
-  w.idx = idx; w.d2 = d2; w.cp3 = cp3; w.qi = 0; w.seed = -1; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
+  w.idx = idx; w.d2 = d2; w.cp3 = cp3; w.qi = 0; w.seed = -1; w.qn3 = qn3; w.qlabel = qlabel; w.min_dot = min_dot; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
   f4 * stage = trav_setup(w.s.t, st, smem, ClosestW<TRI>::STAGE, nullptr);
   warp_run(w, n, counter, stage);
 }
@@ -440,6 +455,7 @@ struct KnnW
   static constexpr int STAGE = 1;
   KnnState s; BvhView b; float const * q3; uint32_t const * perm; int k; float ub; int exclude_self; int64_t self_offset;
   int * idx; float * d2; int64_t qi;
+  float const * qn3; int const * qlabel; float min_dot;      // per-query element filter, null = none
   __device__ __forceinline__ int state() const { return s.t.cur; }
   __device__ __forceinline__ void stage(int t, f4 * dst) const
   {
@@ -450,6 +466,12 @@ struct KnnW
   {
     f4 r = *src; qi = __float_as_int(r.w);
     knn_begin(s, b, mk3(r.x, r.y, r.z), exclude_self ? (int)(self_offset + qi) : -1, ub);
+    if (qn3 || qlabel)
+    {
+      s.f.mode = (qn3 ? 1 : 0) | (qlabel ? 2 : 0); s.f.min_dot = min_dot;
+      if (qn3) s.f.n = ld3(qn3, qi);
+      if (qlabel) s.f.label = qlabel[qi];
+    }
   }
   static constexpr int FETCH = TGQ_FETCH_BOX;
   __device__ __forceinline__ void fetch(f4 * r) const { knn_fetch(s, b, r); }
@@ -469,12 +491,12 @@ struct KnnW
 
 __global__ void __launch_bounds__(TGQ_BLOCK)
 k_knn(BvhView b, float const * __restrict__ q3, uint32_t const * __restrict__ perm, int n, int k, float bound_ub, int exclude_self,
-      int64_t self_offset, int * counter, int * idx, float * d2)
+      int64_t self_offset, int * counter, int * idx, float * d2, float const * __restrict__ qn3, int const * __restrict__ qlabel, float min_dot)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   KnnW w;
   w.b = b; w.q3 = q3; w.perm = perm; w.k = k; w.ub = bound_ub; w.exclude_self = exclude_self; w.self_offset = self_offset;
-  w.idx = idx; w.d2 = d2; w.qi = 0; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
+  w.idx = idx; w.d2 = d2; w.qi = 0; w.qn3 = qn3; w.qlabel = qlabel; w.min_dot = min_dot; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
   unsigned char * extra; f4 * stage = trav_setup(w.s.t, st, smem, KnnW::STAGE, &extra);
   float * sets = (float *)extra;
   w.s.set.init(sets + threadIdx.x, (int *)(sets + (size_t)k * blockDim.x) + threadIdx.x, blockDim.x, k);

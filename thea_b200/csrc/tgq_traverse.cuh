@@ -43,6 +43,7 @@ struct BvhView
   TriRec const * tris;     // Morton-ordered triangle records (triangle structures)
   f4 const * pts;          // Morton-ordered points (point structures)
   f4 const * nrm;          // Morton-ordered normals or null
+  int const * lab;         // Morton-ordered element labels or null (filtered queries on point structures)
   int n_nodes;
   int n_prims;
 };
@@ -240,12 +241,35 @@ TGQ_HD void obb_store_empty(int child, f4 * out4)
 // ---------------------------------------------------------------------------------------------------------------------
 // Closest element.  best_d2 starts as the (exclusive) squared bound or +inf, best_idx as -1.
 // ---------------------------------------------------------------------------------------------------------------------
+// Element filter of the reference's filtered nearest-neighbour queries on point structures: BvhN::pushFilter +
+// elementPassesFilters (BvhN.hpp:1005-1032,1674-1683) with the NNFilter of Tools/Register/Register.cpp:92-101: an element e is
+// admissible iff (labels unused or label[e] == label) and (normals unused or n . n_e >= min_dot; Register uses 0).  The dot
+// product is the reference's (Eigen order); filtered-out elements are skipped before any distance is computed, as there.
+struct ElemFilterD { v3 n; float min_dot; int label; int mode; };      // mode bit 0: normals, bit 1: labels
+TGQ_HD ElemFilterD no_filter() { ElemFilterD f; f.n = mk3(0.0f, 0.0f, 0.0f); f.min_dot = 0.0f; f.label = 0; f.mode = 0; return f; }
+TGQ_HD bool filtered_out(BvhView const & b, int k, ElemFilterD const & f)
+{
+  if (f.mode == 0) return false;
+  if (f.mode & 2)
+  {
+#ifdef __CUDA_ARCH__
+    int l = __ldg(b.lab + k);
+#else
+    int l = b.lab[k];
+#endif
+    if (l != f.label) return true;
+  }
+  if (f.mode & 1) { f4 nj = ldq(b.nrm + k); if (dot3(f.n, mk3(nj.x, nj.y, nj.z)) < f.min_dot) return true; }
+  return false;
+}
+
 template <bool TRI>
 struct ClosestState
 {
   v3 p; float mq; int skip;
   float best_d2; int best_idx; v3 best_cp;
   int best_k;              // Morton position of the best element (seed for the lane's next query)
+  ElemFilterD f;           // point structures only
   Trav t;
 };
 template <bool TRI> struct ClosestFetch { static constexpr int N = TRI ? TGQ_FETCH_TRI : TGQ_FETCH_BOX; };
@@ -257,7 +281,7 @@ template <bool TRI>
 TGQ_HD void closest_begin(ClosestState<TRI> & s, BvhView const & b, float scene_pad, v3 p, int skip, float bound_ub, int seed_k = -1)
 {
   s.p = p; s.skip = skip; s.mq = TRI ? query_margin(p, scene_pad) : 0.0f;
-  s.best_d2 = bound_ub; s.best_idx = -1; s.best_cp = mk3(0.0f, 0.0f, 0.0f); s.best_k = -1;
+  s.best_d2 = bound_ub; s.best_idx = -1; s.best_cp = mk3(0.0f, 0.0f, 0.0f); s.best_k = -1; s.f = no_filter();
   trav_begin(s.t, b.n_nodes);
   if (seed_k >= 0 && seed_k < b.n_prims && s.t.cur == 0)
   {
@@ -351,7 +375,7 @@ TGQ_HD void closest_leaf_compute(ClosestState<TRI> & s, BvhView const & b, f4 co
       f4 e = r[j];
       int idx = f2i(e.w); v3 cp = mk3(e.x, e.y, e.z);
       float d2 = sqn3(sub3(cp, s.p));
-      if (idx == s.skip) continue;
+      if (idx == s.skip || filtered_out(b, s.t.k + j, s.f)) continue;
       if (d2 < s.best_d2 || (d2 == s.best_d2 && idx < s.best_idx)) { s.best_d2 = d2; s.best_idx = idx; s.best_cp = cp; s.best_k = s.t.k + j; }
     }
     s.t.k += cnt;
@@ -361,10 +385,12 @@ TGQ_HD void closest_leaf_compute(ClosestState<TRI> & s, BvhView const & b, f4 co
 
 // Whole query in one go (host emulation; single-lane device uses).
 template <bool TRI>
-TGQ_HD void closest_query(BvhView const & b, float scene_pad, v3 p, int skip, float & best_d2, int & best_idx, v3 & best_cp, int * seed_k = nullptr)
+TGQ_HD void closest_query(BvhView const & b, float scene_pad, v3 p, int skip, float & best_d2, int & best_idx, v3 & best_cp, int * seed_k = nullptr,
+                          ElemFilterD const * filter = nullptr)
 {
   ClosestState<TRI> s; TravStack st; trav_bind(s.t, st);
   closest_begin(s, b, scene_pad, p, skip, best_d2, seed_k ? *seed_k : -1);
+  if (filter) s.f = *filter;
   f4 r[ClosestFetch<TRI>::N];
   while (s.t.cur != TGQ_ST_DONE)
   {
@@ -423,13 +449,14 @@ struct KnnState
 {
   v3 p; int skip; float bound_ub;
   float worst;     // prune radius: k-th best once the set is full, else the bound (or +inf)
+  ElemFilterD f;
   SortedSet set;
   Trav t;
 };
 
 TGQ_HD void knn_begin(KnnState & s, BvhView const & b, v3 p, int skip, float bound_ub)
 {
-  s.p = p; s.skip = skip; s.bound_ub = bound_ub; s.worst = bound_ub; s.set.n = 0;
+  s.p = p; s.skip = skip; s.bound_ub = bound_ub; s.worst = bound_ub; s.set.n = 0; s.f = no_filter();
   trav_begin(s.t, s.set.cap > 0 ? b.n_nodes : 0);
 }
 TGQ_HD void knn_fetch(KnnState const & s, BvhView const & b, f4 * r) { box_fetch(s.t, b, r); }
@@ -451,7 +478,7 @@ TGQ_HD void knn_leaf_compute(KnnState & s, BvhView const & b, f4 const * r)
     f4 e = r[j];
     int idx = f2i(e.w);
     float d2 = sqn3(sub3(mk3(e.x, e.y, e.z), s.p));
-    if (idx == s.skip || !(d2 < s.bound_ub)) continue;
+    if (idx == s.skip || !(d2 < s.bound_ub) || filtered_out(b, s.t.k + j, s.f)) continue;
     if (s.set.accepts(d2, idx))
     {
       s.set.insert(d2, idx);
@@ -462,10 +489,11 @@ TGQ_HD void knn_leaf_compute(KnnState & s, BvhView const & b, f4 const * r)
   if (s.t.k >= s.t.kend) trav_pop(s.t, s.worst);
 }
 
-TGQ_HD void knn_query(BvhView const & b, v3 p, int skip, float bound_ub, SortedSet & set)
+TGQ_HD void knn_query(BvhView const & b, v3 p, int skip, float bound_ub, SortedSet & set, ElemFilterD const * filter = nullptr)
 {
   KnnState s; TravStack st; trav_bind(s.t, st); s.set = set;
   knn_begin(s, b, p, skip, bound_ub);
+  if (filter) s.f = *filter;
   f4 r[TGQ_FETCH_BOX];
   while (s.t.cur != TGQ_ST_DONE)
   {

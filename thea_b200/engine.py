@@ -23,7 +23,7 @@ SYMBOLS = [
     "tgq_build_triangles", "tgq_build_triangles_indexed", "tgq_build_points", "tgq_refit_triangles",
     "tgq_info", "tgq_triangle_cache", "tgq_closest", "tgq_knn", "tgq_ball_graph", "tgq_avg_separation",
     "tgq_ray_first", "tgq_ray_any", "tgq_sdf", "tgq_icp_sums", "tgq_transform_points", "tgq_area_sample",
-    "tgq_get_stats",
+    "tgq_get_stats", "tgq_set_point_labels", "tgq_closest_filtered", "tgq_knn_filtered",
 ]
 
 
@@ -83,6 +83,9 @@ def load_library(path=None):
     L.tgq_transform_points.argtypes = [vp, vp, i64, vp, vp]
     L.tgq_area_sample.argtypes = [vp, i64, C.c_uint64, vp, vp, vp]
     L.tgq_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.tgq_set_point_labels.argtypes = [vp, vp]
+    L.tgq_closest_filtered.argtypes = [vp, vp, vp, vp, i64, f32, f64, vp, vp, vp]
+    L.tgq_knn_filtered.argtypes = [vp, vp, vp, vp, i64, i32, f32, f64, vp, vp]
     for name in SYMBOLS:
         if name not in ("tgq_last_error",):
             getattr(L, name).restype = C.c_int
@@ -226,6 +229,32 @@ class Engine:
         else:
             idx, d2 = out
         self._ck(self._L.tgq_knn(self._h, _ptr(q3), Q, int(k), float(dist_bound), int(exclude_self), _ptr(idx), _ptr(d2)))
+        return idx, d2
+
+    # ---- filtered nearest neighbours (point structures; Register.cpp NNFilter semantics) ----
+    def set_point_labels(self, labels):
+        lab = None if labels is None else _as_in(labels, np.int32)
+        self._ck(self._L.tgq_set_point_labels(self._h, _ptr(lab)))
+
+    def closest_filtered(self, q3, qn3=None, qlabel=None, min_dot=0.0, dist_bound=-1.0):
+        q3 = _as_in(q3)
+        qn3 = _as_in(qn3)
+        qlabel = _as_in(qlabel, np.int32)
+        Q = int(q3.shape[0])
+        idx = np.empty(Q, np.int32)
+        d2 = np.empty(Q, np.float32)
+        cp = np.empty((Q, 3), np.float32)
+        self._ck(self._L.tgq_closest_filtered(self._h, _ptr(q3), _ptr(qn3), _ptr(qlabel), Q, float(min_dot), float(dist_bound), _ptr(idx), _ptr(d2), _ptr(cp)))
+        return idx, d2, cp
+
+    def knn_filtered(self, q3, k, qn3=None, qlabel=None, min_dot=0.0, dist_bound=-1.0):
+        q3 = _as_in(q3)
+        qn3 = _as_in(qn3)
+        qlabel = _as_in(qlabel, np.int32)
+        Q = int(q3.shape[0])
+        idx = np.empty((Q, k), np.int32)
+        d2 = np.empty((Q, k), np.float32)
+        self._ck(self._L.tgq_knn_filtered(self._h, _ptr(q3), _ptr(qn3), _ptr(qlabel), Q, int(k), float(min_dot), float(dist_bound), _ptr(idx), _ptr(d2)))
         return idx, d2
 
     def ball_graph(self, max_degree, init_radius, rounds=3, min_dot=-0.5, min_degree=None, out=None):

@@ -46,6 +46,15 @@ def main():
     res["cfg2"] = {"samples": len(p), "k": 16, "knn_Mqps_device": len(p) / dt_knn / 1e6, "ball_graph_Mqps_e2e": len(p) / dt_graph / 1e6,
                    "area_sampling_s": t_sample, "avg_separation": avg, "mean_degree": float(gc.mean()), "point_build_ms": pe.stats()["last_build_ms"],
                    "knn_sample_matches_oracle": bool(np.array_equal(ki.cpu().numpy()[sub][:, :15], oki[:, 1:].astype(np.int32)))}
+    # Register-style filtered neighbours (same label, n . n' >= 0): NN and 3 * MAX_NBRS = 24 k-NN
+    lab = (gen.splitmix64(5, len(p)) % np.uint64(4)).astype(np.int32)
+    pe.set_point_labels(lab)
+    t0 = time.perf_counter(); fi, fd, _ = pe.closest_filtered(p, n, lab); dt_fnn = time.perf_counter() - t0
+    t0 = time.perf_counter(); fki, fkd = pe.knn_filtered(p, 24, n, lab); dt_fknn = time.perf_counter() - t0
+    po.set_labels(lab)
+    ofi, ofd, _ = po.closest_filtered(p[sub], n[sub], lab[sub], mode=orc.MODE_CANON)
+    res["next1_filtered"] = {"samples": len(p), "filtered_nn_Mqps_e2e": len(p) / dt_fnn / 1e6, "filtered_knn24_Mqps_e2e": len(p) / dt_fknn / 1e6,
+                             "sample_matches_oracle": bool(np.array_equal(fi[sub], ofi.astype(np.int32)) and np.array_equal(fd[sub], ofd))}
     # cfg3: ICP, 100k-point source vs the 1M-triangle target, 50 iterations (51 correspondence batches)
     src_p, _, _ = e.area_sample(100_000, gen.SEED_SAMPLES + 1)
     R, t = gen.rigid_pose(); src = gen.apply_pose(src_p, R, t)
