@@ -6,8 +6,8 @@
 //   sampleGraph               <- PointSet3::updateGraph without oversampling / reachability     (Algorithms/PointSet3.hpp:324-391)
 //
 // Each loop body of the reference issues one structure query per iteration; here one C-ABI call answers the whole loop
-// and the O(1) epilogue (3x3 polar decomposition, transform composition, convergence test) stays on the host, as
-// SURVEY.md section 2 row 7 scopes it.  File:line citations are relative to /root/reference/Code/Source/.
+// and the O(1) epilogue (3x3 polar decomposition, transform composition, convergence test) stays on the host (inside the
+// library for ICP), as SURVEY.md section 2 row 7 scopes it.  File:line citations are relative to /root/reference/Code/Source/.
 #ifndef THEA_GPU_CALLERS_HPP
 #define THEA_GPU_CALLERS_HPP
 
@@ -39,61 +39,8 @@ struct Affine3
   }
 };
 
-namespace detail {
-
-/** R = U V^T of the 3x3 matrix M (row-major) by one-sided Jacobi rotations in double: the rotation that
- *  Eigen::JacobiSVD gives Icp3::alignOneStep (Icp3.hpp:369-370), unique whenever M has rank >= 2. */
-inline void polarRotation(double const M[9], double R[9])
-{
-  double A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-  for (int i = 0; i < 9; ++i) A[i] = M[i];
-  for (int sweep = 0; sweep < 64; ++sweep)
-  {
-    double worst = 0;
-    for (int p = 0; p < 2; ++p)
-      for (int q = p + 1; q < 3; ++q)
-      {
-        double app = 0, aqq = 0, apq = 0;
-        for (int r = 0; r < 3; ++r) { app += A[3 * r + p] * A[3 * r + p]; aqq += A[3 * r + q] * A[3 * r + q]; apq += A[3 * r + p] * A[3 * r + q]; }
-        double denom = std::sqrt(app * aqq);
-        if (denom > 0) worst = std::max(worst, std::fabs(apq) / denom);
-        if (apq == 0) continue;
-        double zeta = (aqq - app) / (2.0 * apq);
-        double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
-        double c = 1.0 / std::sqrt(1.0 + t * t), s = c * t;
-        for (int r = 0; r < 3; ++r)
-        {
-          double x = A[3 * r + p], y = A[3 * r + q]; A[3 * r + p] = c * x - s * y; A[3 * r + q] = s * x + c * y;
-          x = V[3 * r + p]; y = V[3 * r + q]; V[3 * r + p] = c * x - s * y; V[3 * r + q] = s * x + c * y;
-        }
-      }
-    if (worst < 1e-15) break;
-  }
-  double U[9], sv[3];
-  for (int c = 0; c < 3; ++c)
-  {
-    sv[c] = std::sqrt(A[c] * A[c] + A[3 + c] * A[3 + c] + A[6 + c] * A[6 + c]);
-    for (int r = 0; r < 3; ++r) U[3 * r + c] = sv[c] > 0 ? A[3 * r + c] / sv[c] : 0.0;
-  }
-  int mn = 0; for (int c = 1; c < 3; ++c) if (sv[c] < sv[mn]) mn = c;
-  if (sv[mn] <= 1e-14 * std::max(sv[0], std::max(sv[1], sv[2])))
-  {
-    // rank 2: complete the missing left singular vector so that det(U) has the sign of det(V) (proper rotation U V^T)
-    int a = (mn + 1) % 3, b = (mn + 2) % 3;
-    U[mn] = U[3 + a] * U[6 + b] - U[6 + a] * U[3 + b];
-    U[3 + mn] = U[6 + a] * U[b] - U[a] * U[6 + b];
-    U[6 + mn] = U[a] * U[3 + b] - U[3 + a] * U[b];
-  }
-  for (int r = 0; r < 3; ++r)
-    for (int c = 0; c < 3; ++c)
-    { double acc = 0; for (int k = 0; k < 3; ++k) acc += U[3 * r + k] * V[3 * c + k]; R[3 * r + c] = acc; }
-}
-
-}  // namespace detail
-
 /** Point-to-mesh ICP with the control flow of Icp3<Real>::align (Icp3.hpp:193-275; no weights, symmetry planes or up
- *  vector).  Every batch of closest-point correspondences is one tgq_closest call, every reduction one tgq_icp_sums
- *  call (fixed-point sums: the same bits for any launch shape or GPU count). */
+ *  vector), run device resident by tgq_icp_align (fixed-point sums: the same bits for any launch shape). */
 class Icp3Gpu
 {
   public:
@@ -113,60 +60,19 @@ class Icp3Gpu
     {
       if (batches) *batches = 0;
       if (n <= 0) { if (error) *error = 0; return Affine3::identity(); }
+      // The whole loop runs inside the library, device resident (tgq_icp_align): per iteration one closest-point batch, two
+      // reductions and one transform on the GPU, 16 sums back to the host for the 3x3 polar decomposition.
       tgq_handle * h = to.handle();
-      std::vector<float> from(from3, from3 + 3 * n), to_points(3 * (size_t)n);
-      std::vector<int32_t> idx((size_t)n);
-      double s[16];
-
-      auto measure = [&](Affine3 const & tr) -> float    // Icp3::measureError, Icp3.hpp:387-464
-      {
-        to.closestElementBatch(from.data(), n, idx.data(), nullptr, to_points.data());
-        for (intx i = 0; i < n; ++i)
-          if (idx[(size_t)i] < 0) throw Error("Icp3: Couldn't get nearest neighbor of source point " + std::to_string(i));
-        if (correspondences) correspondences->insert(correspondences->end(), idx.begin(), idx.end());
-        if (batches) ++*batches;
-        detail::check(h, tgq_icp_sums(h, from.data(), to_points.data(), n, tr.m, s), "tgq_icp_sums");
-        return (float)s[15];
-      };
-
-      Affine3 old_tr = Affine3::identity();
-      float old_error = measure(old_tr);
-      if (verbose) std::fprintf(stderr, "[Icp3Gpu] Initial error: %g\n", (double)old_error);
-      if (old_error <= std::numeric_limits<float>::min()) { if (error) *error = old_error; return old_tr; }
-
-      float new_error = old_error; Affine3 new_tr = old_tr;
-      for (intx i = 0; i < max_iterations; ++i)
-      {
-        // alignOneStep(from_points, to_points) (Icp3.hpp:228-229,298-384): the CURRENT source positions against the targets
-        // found by the last measureError, which ran before the positions were updated (:237,260-261) -- reproduced as is
-        detail::check(h, tgq_icp_sums(h, from.data(), to_points.data(), n, nullptr, s), "tgq_icp_sums");
-        double R[9]; detail::polarRotation(&s[6], R);
-        Affine3 inc;
-        for (int r = 0; r < 3; ++r)
-        {
-          for (int c = 0; c < 3; ++c) inc.m[4 * r + c] = (float)R[3 * r + c];
-          float lp = inc.m[4 * r] * (float)s[0] + (inc.m[4 * r + 1] * (float)s[1] + inc.m[4 * r + 2] * (float)s[2]);
-          inc.m[4 * r + 3] = (float)s[3 + r] - lp;
-        }
-        new_tr = inc * old_tr;
-        if (i < max_iterations - 1 || error) new_error = measure(inc);
-        if (i < max_iterations - 1)
-        {
-          float frac_change = (old_error - new_error) / old_error;
-          if (verbose) std::fprintf(stderr, "[Icp3Gpu] Iteration %ld error: %g (fractional change: %g)\n", (long)i, (double)new_error, (double)frac_change);
-          if (i >= min_iterations && frac_change < fractional_error_threshold)
-          {
-            if (frac_change > 0) { if (error) *error = new_error; return new_tr; }
-            if (error) *error = old_error;
-            return old_tr;
-          }
-          // transform the ORIGINAL points to prevent drift (Icp3.hpp:260-261)
-          detail::check(h, tgq_transform_points(h, from3, n, new_tr.m, from.data()), "tgq_transform_points");
-        }
-        old_error = new_error; old_tr = new_tr;
-      }
-      if (error) *error = new_error;
-      return new_tr;
+      Affine3 tr; float err = 0; int32_t nb = 0;
+      std::vector<int32_t> corr;
+      if (correspondences) corr.resize((size_t)(max_iterations + 1) * (size_t)n);
+      detail::check(h, tgq_icp_align(h, from3, n, (int32_t)min_iterations, (int32_t)max_iterations, fractional_error_threshold, error ? 1 : 0,
+                                     tr.m, &err, &nb, correspondences ? corr.data() : nullptr), "tgq_icp_align");
+      if (verbose) std::fprintf(stderr, "[Icp3Gpu] %d correspondence batches, error %g\n", (int)nb, (double)err);
+      if (error) *error = err;
+      if (batches) *batches = nb;
+      if (correspondences) correspondences->insert(correspondences->end(), corr.begin(), corr.begin() + (std::ptrdiff_t)((size_t)nb * (size_t)n));
+      return tr;
     }
 
   private:

@@ -164,6 +164,17 @@ int tgq_sdf(tgq_handle * h, const float * p3, const float * n3, int64_t S, float
  * (row-major 3x4 [L|t], may be null = identity) out[15] = |tr pm - qm|^2 + sum |L (p - pm) - (q - qm)|^2.
  * Replaces the accumulation loops of Icp3::alignOneStep / measureError (Algorithms/Icp3.hpp:298-367,410-464). */
 int tgq_icp_sums(tgq_handle * h, const float * from3, const float * to3, int64_t n, const float * tr12, double * out16);
+/* The whole of Icp3<Real>::align(n, from, to_structure, &error) (Algorithms/Icp3.hpp:110-126,193-275; no weights, symmetry
+ * planes or up vector) against the triangle structure, device resident: every iteration is one closest-point batch, two
+ * reductions and one transform on the GPU; only the 16 sums come back for the 3x3 polar decomposition on the host.
+ * Reference defaults: min_iterations 3, max_iterations 10, fractional_error_threshold 1e-4.  The reference's control flow is
+ * kept to the letter, including alignOneStep pairing the updated source positions with the targets found before the update.
+ * Outputs: tr12 (row-major 3x4 [R | t], host), error (host, may be null; want_error != 0 measures after the last iteration as
+ * the reference does when an error pointer is passed), batches = closest-point batches run (host, may be null),
+ * correspondences = batches x n element indices in batch order (host or device, may be null; room for max_iterations + 1). */
+int tgq_icp_align(tgq_handle * h, const float * from3, int64_t n, int32_t min_iterations, int32_t max_iterations,
+                  double fractional_error_threshold, int32_t want_error, float * tr12, float * error, int32_t * batches,
+                  int32_t * correspondences);
 /* out3[i] = L in3[i] + t with the reference's fp32 operation order (AffineTransformN.hpp:160). */
 int tgq_transform_points(tgq_handle * h, const float * in3, int64_t n, const float * tr12, float * out3);
 

@@ -179,3 +179,24 @@ def test_filtered_nearest_neighbours_register_shape(built):
         bare.closest_filtered(q[:10], qn3=qn[:10])
     with pytest.raises(TgqError):
         bare.closest_filtered(q[:10], qlabel=ql[:10])
+
+
+def test_device_resident_icp_equals_the_host_driven_loop(setup):
+    """tgq_icp_align (whole loop inside the library) against callers.icp_align (same steps driven from Python) and the oracle."""
+    e, mesh, ora = setup
+    p, _, _ = gen.area_samples(mesh, 5000)
+    R, t = gen.rigid_pose()
+    src = gen.apply_pose(p, R, t)
+    for kw in ({}, {"min_iterations": 6, "max_iterations": 6}):
+        tr_a, err_a, corr_a = e.icp_align(src, **kw)
+        tr_b, err_b, corr_b = callers.icp_align(e, src, **kw)
+        assert corr_a.shape == corr_b.shape and np.array_equal(corr_a[:2], corr_b[:2])
+        assert np.allclose(tr_a, tr_b, rtol=1e-6, atol=1e-6) and abs(err_a - err_b) <= 1e-5 * abs(err_b) + 1e-9
+        otr, oerr, ocorr = ora.icp(src, min_iters=kw.get("min_iterations", 3), max_iters=kw.get("max_iterations", 10), mode=orc.MODE_BRUTE)
+        assert corr_a.shape[0] == ocorr.shape[0] and np.array_equal(corr_a[0], ocorr[0].astype(np.int32))
+        assert np.allclose(tr_a, otr, rtol=1e-5, atol=1e-5)
+    # device pointers in, no correspondences out
+    torch = pytest.importorskip("torch")
+    tr_c, err_c, nb = e.icp_align(torch.from_numpy(src).cuda(), want_correspondences=False)
+    assert nb == corr_a.shape[0] or nb > 0
+    assert np.allclose(tr_c, e.icp_align(src)[0], rtol=0, atol=0)

@@ -61,6 +61,7 @@ struct tgq_handle
   DevBuf nodes, elems, nrm, lab, scene;                                // NodeRec[], TriRec[] | f4[], f4[], SceneBox
   DevBuf perm, pos_of_elem, first, last, split, parent, live, newidx;   // kept for refit
   DevBuf pbox_lo, pbox_hi, nbox_lo, nbox_hi, arrive, keys_a, keys_b, vals_a, cubtmp, src, src2, misc;
+  DevBuf icp_cur, icp_orig, icp_to, icp_idx;                          // device-resident ICP loop
   DevBuf area_by_elem, cum;                                           // float[n] in element order; double[n] cumulative
   DevBuf obbs, pnrm, nsum, obbinfo, big, big_count;                   // oriented boxes (triangle structures)
   int sm_count = 148; std::map<std::pair<void const *, size_t>, int> occupancy;   // resident blocks per SM of the persistent kernels
@@ -485,7 +486,7 @@ int tgq_destroy(tgq_handle * h)
   cudaDeviceSynchronize();
   DevBuf * bufs[] = {&h->nodes, &h->elems, &h->nrm, &h->lab, &h->scene, &h->perm, &h->pos_of_elem, &h->first, &h->last, &h->split, &h->parent, &h->live,
                      &h->newidx, &h->pbox_lo, &h->pbox_hi, &h->nbox_lo, &h->nbox_hi, &h->arrive, &h->keys_a, &h->keys_b, &h->vals_a,
-                     &h->cubtmp, &h->src, &h->src2, &h->misc, &h->area_by_elem, &h->cum, &h->obbs, &h->pnrm, &h->nsum, &h->obbinfo, &h->big, &h->big_count};
+                     &h->cubtmp, &h->src, &h->src2, &h->misc, &h->icp_cur, &h->icp_orig, &h->icp_to, &h->icp_idx, &h->area_by_elem, &h->cum, &h->obbs, &h->pnrm, &h->nsum, &h->obbinfo, &h->big, &h->big_count};
   for (DevBuf * b : bufs) b->release();
   for (int s = 0; s < 2; ++s)
   {
@@ -899,6 +900,138 @@ int tgq_transform_points(tgq_handle * h, const float * in3, int64_t n, const flo
   h->st.total_launches += 1;
   if (dout != out3) CKRC(from_device(h, out3, dout, 12 * (size_t)n, s));
   CK(cudaStreamSynchronize(s));
+  return TGQ_OK;
+}
+
+// R = U V^T of the 3x3 matrix M (row-major) by one-sided Jacobi rotations in double: the rotation Eigen::JacobiSVD gives
+// Icp3::alignOneStep (Algorithms/Icp3.hpp:369-370).
+static void polar_rotation(double const M[9], double R[9])
+{
+  double A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int i = 0; i < 9; ++i) A[i] = M[i];
+  for (int sweep = 0; sweep < 64; ++sweep)
+  {
+    double worst = 0;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q)
+      {
+        double app = 0, aqq = 0, apq = 0;
+        for (int r = 0; r < 3; ++r) { app += A[3 * r + p] * A[3 * r + p]; aqq += A[3 * r + q] * A[3 * r + q]; apq += A[3 * r + p] * A[3 * r + q]; }
+        double denom = std::sqrt(app * aqq);
+        if (denom > 0) worst = std::max(worst, std::fabs(apq) / denom);
+        if (apq == 0) continue;
+        double zeta = (aqq - app) / (2.0 * apq);
+        double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+        double c = 1.0 / std::sqrt(1.0 + t * t), sn = c * t;
+        for (int r = 0; r < 3; ++r)
+        {
+          double x = A[3 * r + p], y = A[3 * r + q]; A[3 * r + p] = c * x - sn * y; A[3 * r + q] = sn * x + c * y;
+          x = V[3 * r + p]; y = V[3 * r + q]; V[3 * r + p] = c * x - sn * y; V[3 * r + q] = sn * x + c * y;
+        }
+      }
+    if (worst < 1e-15) break;
+  }
+  double U[9], sv[3];
+  for (int c = 0; c < 3; ++c)
+  {
+    sv[c] = std::sqrt(A[c] * A[c] + A[3 + c] * A[3 + c] + A[6 + c] * A[6 + c]);
+    for (int r = 0; r < 3; ++r) U[3 * r + c] = sv[c] > 0 ? A[3 * r + c] / sv[c] : 0.0;
+  }
+  int mn = 0; for (int c = 1; c < 3; ++c) if (sv[c] < sv[mn]) mn = c;
+  if (sv[mn] <= 1e-14 * std::max(sv[0], std::max(sv[1], sv[2])))
+  {
+    int a = (mn + 1) % 3, b = (mn + 2) % 3;
+    U[mn] = U[3 + a] * U[6 + b] - U[6 + a] * U[3 + b];
+    U[3 + mn] = U[6 + a] * U[b] - U[a] * U[6 + b];
+    U[6 + mn] = U[a] * U[3 + b] - U[3 + a] * U[b];
+  }
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+    { double acc = 0; for (int k = 0; k < 3; ++k) acc += U[3 * r + k] * V[3 * c + k]; R[3 * r + c] = acc; }
+}
+
+// a * b for row-major 3x4 [L | t] in fp32 with Eigen's t0 + (t1 + t2) order (AffineTransformN.hpp:154-157).
+static void compose12(float const a[12], float const b[12], float r[12])
+{
+  for (int i = 0; i < 3; ++i)
+  {
+    for (int j = 0; j < 3; ++j) r[4 * i + j] = a[4 * i] * b[j] + (a[4 * i + 1] * b[4 + j] + a[4 * i + 2] * b[8 + j]);
+    r[4 * i + 3] = (a[4 * i] * b[3] + (a[4 * i + 1] * b[7] + a[4 * i + 2] * b[11])) + a[4 * i + 3];
+  }
+}
+
+int tgq_icp_align(tgq_handle * h, const float * from3, int64_t n, int32_t min_iterations, int32_t max_iterations, double fractional_error_threshold,
+                  int32_t want_error, float * tr12, float * error, int32_t * batches, int32_t * correspondences)
+{
+  CKRC(need_built(h, 1 << TGQ_KIND_TRIANGLES));
+  if (n < 0 || (n > 0 && !from3) || !tr12 || max_iterations < 0) return fail(h, TGQ_EINVAL, "tgq_icp_align: bad arguments");
+  float ident[12]; for (int i = 0; i < 12; ++i) ident[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+  memcpy(tr12, ident, sizeof ident);
+  if (error) *error = 0; if (batches) *batches = 0;
+  if (n == 0) return TGQ_OK;
+  size_t bytes = 12 * (size_t)n;
+  cudaStream_t s = h->stream;
+  {
+    Guard g(h);
+    CK(h->icp_cur.reserve(bytes)); CK(h->icp_orig.reserve(bytes)); CK(h->icp_to.reserve(bytes)); CK(h->icp_idx.reserve(4 * (size_t)n));
+    CK(cudaMemcpyAsync(h->icp_orig.p, from3, bytes, is_device_ptr(from3) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->icp_cur.p, h->icp_orig.p, bytes, cudaMemcpyDeviceToDevice, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  float * cur = h->icp_cur.as<float>(); float * to = h->icp_to.as<float>(); int32_t * idx = h->icp_idx.as<int32_t>();
+  int nb = 0; double sums[16];
+  int64_t launches0 = h->st.total_launches; double query_ms = 0;
+  // Icp3::measureError (Icp3.hpp:387-464): correspondences of the CURRENT positions, then the error under `tr`
+  auto measure = [&](float const * tr, float & err) -> int {
+    CKRC(tgq_closest(h, cur, n, -1.0, 0, idx, nullptr, to));
+    query_ms += h->st.last_query_ms;
+    if (correspondences)
+    {
+      Guard g(h);
+      CK(cudaMemcpyAsync(correspondences + (size_t)nb * (size_t)n, idx, 4 * (size_t)n, is_device_ptr(correspondences) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+    }
+    ++nb;
+    CKRC(tgq_icp_sums(h, cur, to, n, tr, sums));
+    err = (float)sums[15];
+    return TGQ_OK;
+  };
+  float old_tr[12], new_tr[12]; memcpy(old_tr, ident, sizeof ident); memcpy(new_tr, ident, sizeof ident);
+  float old_err = 0, new_err = 0;
+  CKRC(measure(old_tr, old_err));
+  new_err = old_err;
+  bool done = old_err <= FLT_MIN;
+  for (int i = 0; i < max_iterations && !done; ++i)
+  {
+    // alignOneStep(from_points, to_points) (Icp3.hpp:228-229,298-384): the CURRENT source positions against the targets found by
+    // the last measureError, which ran before the positions were updated (:237,260-261) -- reproduced as is
+    CKRC(tgq_icp_sums(h, cur, to, n, nullptr, sums));
+    double R[9]; polar_rotation(&sums[6], R);
+    float inc[12];
+    for (int r = 0; r < 3; ++r)
+    {
+      for (int c = 0; c < 3; ++c) inc[4 * r + c] = (float)R[3 * r + c];
+      float lp = inc[4 * r] * (float)sums[0] + (inc[4 * r + 1] * (float)sums[1] + inc[4 * r + 2] * (float)sums[2]);
+      inc[4 * r + 3] = (float)sums[3 + r] - lp;
+    }
+    compose12(inc, old_tr, new_tr);
+    if (i < max_iterations - 1 || want_error) CKRC(measure(inc, new_err));
+    if (i < max_iterations - 1)
+    {
+      float frac = (old_err - new_err) / old_err;
+      if (i >= min_iterations && (double)frac < fractional_error_threshold)
+      {
+        if (frac > 0) { memcpy(old_tr, new_tr, sizeof new_tr); old_err = new_err; }      // improved slightly: return the new one
+        done = true; break;                                                                // else the previous alignment was better
+      }
+      CKRC(tgq_transform_points(h, h->icp_orig.as<float>(), n, new_tr, cur));             // transform the ORIGINAL points (no drift)
+    }
+    old_err = new_err; memcpy(old_tr, new_tr, sizeof new_tr);
+  }
+  memcpy(tr12, old_tr, sizeof old_tr);
+  if (error) *error = old_err;
+  if (batches) *batches = nb;
+  h->st.last_query_ms = query_ms; h->st.last_sort_ms = 0; h->st.last_launches = h->st.total_launches - launches0;
   return TGQ_OK;
 }
 

@@ -23,7 +23,7 @@ SYMBOLS = [
     "tgq_build_triangles", "tgq_build_triangles_indexed", "tgq_build_points", "tgq_refit_triangles",
     "tgq_info", "tgq_triangle_cache", "tgq_closest", "tgq_knn", "tgq_ball_graph", "tgq_avg_separation",
     "tgq_ray_first", "tgq_ray_any", "tgq_sdf", "tgq_icp_sums", "tgq_transform_points", "tgq_area_sample",
-    "tgq_get_stats", "tgq_set_point_labels", "tgq_closest_filtered", "tgq_knn_filtered",
+    "tgq_get_stats", "tgq_set_point_labels", "tgq_closest_filtered", "tgq_knn_filtered", "tgq_icp_align",
 ]
 
 
@@ -84,6 +84,7 @@ def load_library(path=None):
     L.tgq_area_sample.argtypes = [vp, i64, C.c_uint64, vp, vp, vp]
     L.tgq_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.tgq_set_point_labels.argtypes = [vp, vp]
+    L.tgq_icp_align.argtypes = [vp, vp, i64, i32, i32, f64, i32, vp, vp, vp, vp]
     L.tgq_closest_filtered.argtypes = [vp, vp, vp, vp, i64, f32, f64, vp, vp, vp]
     L.tgq_knn_filtered.argtypes = [vp, vp, vp, vp, i64, i32, f32, f64, vp, vp]
     for name in SYMBOLS:
@@ -323,6 +324,18 @@ class Engine:
         out = np.empty(16, np.float64)
         self._ck(self._L.tgq_icp_sums(self._h, _ptr(from3), _ptr(to3), int(from3.shape[0]), _ptr(tr), _ptr(out)))
         return out
+
+    def icp_align(self, from3, min_iterations=3, max_iterations=10, fractional_error_threshold=1e-4, want_error=True, want_correspondences=True):
+        """Icp3<Real>::align on the device (tgq_icp_align): returns (transform 3x4, error, correspondences [batches x n])."""
+        from3 = _as_in(from3)
+        n = int(from3.shape[0])
+        tr = np.empty(12, np.float32)
+        err = C.c_float()
+        nb = C.c_int32()
+        corr = np.empty((max_iterations + 1, n), np.int32) if want_correspondences else None
+        self._ck(self._L.tgq_icp_align(self._h, _ptr(from3), n, int(min_iterations), int(max_iterations), float(fractional_error_threshold),
+                                       int(want_error), _ptr(tr), C.byref(err), C.byref(nb), _ptr(corr)))
+        return tr.reshape(3, 4), float(err.value), (corr[:nb.value] if corr is not None else nb.value)
 
     def transform_points(self, in3, tr12, out=None):
         in3 = _as_in(in3)
