@@ -330,6 +330,9 @@ __global__ void k_query_codes(float const * __restrict__ q3, int n, SceneBox con
 //   W: FETCH, STAGE ; int state() ; void stage(t, dst) ; void begin(t, src) ; void fetch(r) ; void node_compute(r) ;
 //      void leaf_compute(r) ; void finish()  [finish leaves the lane in TGQ_ST_IDLE, or restarts it]
 #define TGQ_CHUNK 64
+#ifndef TGQ_POPS
+#define TGQ_POPS 2
+#endif
 #define TGQ_SSTACK 20    // stack entries per thread kept in shared memory (deeper ones spill to local memory)
 #define TGQ_WARPS (TGQ_BLOCK / 32)
 
@@ -373,7 +376,7 @@ __device__ __forceinline__ void warp_run(W & w, int n, int * counter, f4 * stage
     }
     int st = w.state();
     bool at_node = st >= 0, at_leaf = st == TGQ_ST_LEAF;
-    if (!__any_sync(FULL, at_node || at_leaf))
+    if (!__any_sync(FULL, at_node || at_leaf || st == TGQ_ST_POP))
     {
       if (exhausted && __all_sync(FULL, w.state() != TGQ_ST_DONE)) break;
       continue;
@@ -383,6 +386,9 @@ __device__ __forceinline__ void warp_run(W & w, int n, int * counter, f4 * stage
     if (at_node || at_leaf) w.fetch(r);
     if (at_node) w.node_compute(r);
     else if (at_leaf) w.leaf_compute(r);
+    // pop phase: every lane that needs a deferred sibling takes (up to) TGQ_POPS off its stack, all such lanes together
+#pragma unroll
+    for (int j = 0; j < TGQ_POPS; ++j) if (w.state() == TGQ_ST_POP) w.pop_step();
   }
 }
 
@@ -422,6 +428,7 @@ struct ClosestW
     }
   }
   static constexpr int FETCH = ClosestFetch<TRI>::N;
+  __device__ __forceinline__ void pop_step() { trav_pop_step(s.t, s.best_d2); }
   __device__ __forceinline__ void fetch(f4 * r) const { closest_fetch(s, b, r); }
   __device__ __forceinline__ void node_compute(f4 const * r) { closest_node_compute(s, b, r); }
   __device__ __forceinline__ void leaf_compute(f4 const * r) { closest_leaf_compute(s, b, r); }
@@ -474,6 +481,7 @@ struct KnnW
     }
   }
   static constexpr int FETCH = TGQ_FETCH_BOX;
+  __device__ __forceinline__ void pop_step() { trav_pop_step(s.t, s.worst); }
   __device__ __forceinline__ void fetch(f4 * r) const { knn_fetch(s, b, r); }
   __device__ __forceinline__ void node_compute(f4 const * r) { knn_node_compute(s, b, r); }
   __device__ __forceinline__ void leaf_compute(f4 const * r) { knn_leaf_compute(s, b, r); }
@@ -521,6 +529,7 @@ struct BallW
     ball_begin(s, b, mk3(e.x, e.y, e.z), mk3(q.x, q.y, q.z), b.nrm != nullptr, min_dot, (int)qi, init_radius, rounds, min_degree);
   }
   static constexpr int FETCH = TGQ_FETCH_BOX;
+  __device__ __forceinline__ void pop_step() { trav_pop_step(s.t, s.r2); }
   __device__ __forceinline__ void fetch(f4 * r) const { ball_fetch(s, b, r); }
   __device__ __forceinline__ void node_compute(f4 const * r) { ball_node_compute(s, b, r); }
   __device__ __forceinline__ void leaf_compute(f4 const * r) { ball_leaf_compute(s, b, r); }
@@ -571,6 +580,7 @@ struct RayW
     ray_begin(s, b, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), d.w);
   }
   static constexpr int FETCH = TGQ_FETCH_BOX;
+  __device__ __forceinline__ void pop_step() { trav_pop_step(s.t, ray_limit(s)); }
   __device__ __forceinline__ void fetch(f4 * r) const { ray_fetch(s, b, r); }
   __device__ __forceinline__ void node_compute(f4 const * r) { ray_node_compute(s, b, r); }
   __device__ __forceinline__ void leaf_compute(f4 const * r) { ray_leaf_compute(s, b, r); }
@@ -636,6 +646,7 @@ struct SdfW
     ray_begin(s, b, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), -1.0f);
   }
   static constexpr int FETCH = TGQ_FETCH_BOX;
+  __device__ __forceinline__ void pop_step() { trav_pop_step(s.t, ray_limit(s)); }
   __device__ __forceinline__ void fetch(f4 * r) const { ray_fetch(s, b, r); }
   __device__ __forceinline__ void node_compute(f4 const * r) { ray_node_compute(s, b, r); }
   __device__ __forceinline__ void leaf_compute(f4 const * r) { ray_leaf_compute(s, b, r); }

@@ -29,6 +29,7 @@ namespace tgq {
 #define TGQ_ST_DONE (-1)
 #define TGQ_ST_LEAF (-2)
 #define TGQ_ST_IDLE (-3)
+#define TGQ_ST_POP (-4)            // wants the next deferred sibling from its stack
 
 // Visit counters: compiled out everywhere except the test-only host build, which uses them to study pruning quality.
 #ifndef TGQ_COUNT_NODE
@@ -97,7 +98,7 @@ TGQ_HD void trav_bind_fast(Trav & t, StackEntry * fast, int stride, int cap) { t
 TGQ_HD void trav_enter(Trav & t, int code)
 {
   if (code >= 0) t.cur = code;
-  else { int c = ~code; t.k = c >> TGQ_LEAF_BITS; t.kend = t.k + (c & TGQ_LEAF_MASK); t.cur = (t.kend > t.k) ? TGQ_ST_LEAF : TGQ_ST_DONE; }
+  else { int c = ~code; t.k = c >> TGQ_LEAF_BITS; t.kend = t.k + (c & TGQ_LEAF_MASK); t.cur = (t.kend > t.k) ? TGQ_ST_LEAF : TGQ_ST_POP; }
 }
 TGQ_HD void trav_begin(Trav & t, int n_nodes) { t.sp = 0; t.k = t.kend = 0; t.cur = n_nodes > 0 ? 0 : TGQ_ST_DONE; }
 TGQ_HD void trav_push(Trav & t, int code, float key)
@@ -106,19 +107,20 @@ TGQ_HD void trav_push(Trav & t, int code, float key)
   else { t.stk_node[t.sp - t.fast_cap] = code; t.stk_key[t.sp - t.fast_cap] = key; }
   ++t.sp;
 }
-// Pops deferred siblings until one whose key is still <= limit (keys are lower bounds / entry times), else finishes.
-TGQ_HD void trav_pop(Trav & t, float limit)
+// Popping is a state of its own (TGQ_ST_POP), not a loop inside the node / leaf arithmetic: ncu showed the pop loop running
+// with 2.6 of 32 lanes active (a quarter of all stall samples) when every lane looped on its own stack inside divergent code.
+// One call takes ONE deferred sibling: entered if its key (lower bound / entry time) is still <= limit, else dropped and the
+// lane stays in TGQ_ST_POP; an empty stack finishes the query.
+TGQ_HD void trav_pop_step(Trav & t, float limit)
 {
-  t.cur = TGQ_ST_DONE;
-  while (t.sp > 0)
-  {
-    --t.sp;
-    int code; float key;
-    if (t.sp < t.fast_cap) { StackEntry e = t.fast[t.sp * t.fast_stride]; code = e.node; key = e.key; }
-    else { code = t.stk_node[t.sp - t.fast_cap]; key = t.stk_key[t.sp - t.fast_cap]; }
-    if (key <= limit) { trav_enter(t, code); if (t.cur != TGQ_ST_DONE) return; }
-  }
+  if (t.sp <= 0) { t.cur = TGQ_ST_DONE; return; }
+  --t.sp;
+  int code; float key;
+  if (t.sp < t.fast_cap) { StackEntry e = t.fast[t.sp * t.fast_stride]; code = e.node; key = e.key; }
+  else { code = t.stk_node[t.sp - t.fast_cap]; key = t.stk_key[t.sp - t.fast_cap]; }
+  if (key <= limit) trav_enter(t, code);
 }
+TGQ_HD void trav_pop(Trav & t) { t.cur = TGQ_ST_POP; }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Oriented bounds for closest-point queries on triangle structures.  AABBs of a smooth surface that is oblique to the
@@ -309,14 +311,9 @@ TGQ_HD void trav_descend(Trav & t, float lb0, float lb1, float key0, float key1,
     bool swap = key1 < key0;
     trav_push(t, swap ? c0 : c1, swap ? lb0 : lb1);
     trav_enter(t, swap ? c1 : c0);
-    if (t.cur == TGQ_ST_DONE) trav_pop(t, limit);
   }
-  else if (go0 || go1)
-  {
-    trav_enter(t, go0 ? c0 : c1);
-    if (t.cur == TGQ_ST_DONE) trav_pop(t, limit);
-  }
-  else trav_pop(t, limit);
+  else if (go0 || go1) trav_enter(t, go0 ? c0 : c1);
+  else trav_pop(t);
 }
 
 template <bool TRI>
@@ -380,7 +377,7 @@ TGQ_HD void closest_leaf_compute(ClosestState<TRI> & s, BvhView const & b, f4 co
     }
     s.t.k += cnt;
   }
-  if (s.t.k >= s.t.kend) trav_pop(s.t, s.best_d2);
+  if (s.t.k >= s.t.kend) trav_pop(s.t);
 }
 
 // Whole query in one go (host emulation; single-lane device uses).
@@ -394,6 +391,7 @@ TGQ_HD void closest_query(BvhView const & b, float scene_pad, v3 p, int skip, fl
   f4 r[ClosestFetch<TRI>::N];
   while (s.t.cur != TGQ_ST_DONE)
   {
+    if (s.t.cur == TGQ_ST_POP) { trav_pop_step(s.t, s.best_d2); continue; }
     closest_fetch(s, b, r);
     if (s.t.cur >= 0) closest_node_compute(s, b, r); else closest_leaf_compute(s, b, r);
   }
@@ -486,7 +484,7 @@ TGQ_HD void knn_leaf_compute(KnnState & s, BvhView const & b, f4 const * r)
     }
   }
   s.t.k += cnt;
-  if (s.t.k >= s.t.kend) trav_pop(s.t, s.worst);
+  if (s.t.k >= s.t.kend) trav_pop(s.t);
 }
 
 TGQ_HD void knn_query(BvhView const & b, v3 p, int skip, float bound_ub, SortedSet & set, ElemFilterD const * filter = nullptr)
@@ -497,6 +495,7 @@ TGQ_HD void knn_query(BvhView const & b, v3 p, int skip, float bound_ub, SortedS
   f4 r[TGQ_FETCH_BOX];
   while (s.t.cur != TGQ_ST_DONE)
   {
+    if (s.t.cur == TGQ_ST_POP) { trav_pop_step(s.t, s.worst); continue; }
     knn_fetch(s, b, r);
     if (s.t.cur >= 0) knn_node_compute(s, b, r); else knn_leaf_compute(s, b, r);
   }
@@ -553,7 +552,7 @@ TGQ_HD void ball_leaf_compute(BallState & s, BvhView const & b, f4 const * r)
     if (s.set.accepts(sep, idx)) s.set.insert(sep, idx);
   }
   s.t.k += cnt;
-  if (s.t.k >= s.t.kend) trav_pop(s.t, s.r2);
+  if (s.t.k >= s.t.kend) trav_pop(s.t);
 }
 
 // Called when a round's traversal is done: returns true when the query is complete, else starts the next round.
@@ -576,6 +575,7 @@ TGQ_HD void ball_graph_query(BvhView const & b, v3 c, v3 nc, bool has_n, float m
   {
     while (s.t.cur != TGQ_ST_DONE)
     {
+      if (s.t.cur == TGQ_ST_POP) { trav_pop_step(s.t, s.r2); continue; }
       ball_fetch(s, b, r);
       if (s.t.cur >= 0) ball_node_compute(s, b, r); else ball_leaf_compute(s, b, r);
     }
@@ -660,7 +660,7 @@ TGQ_HD void ray_leaf_compute(RayState<ANY> & s, BvhView const & b, f4 const * r)
     s.best_t = tm; s.best_idx = idx; s.best_k = k;
     if (ANY) { s.t.cur = TGQ_ST_DONE; s.t.sp = 0; return; }
   }
-  if (s.t.k >= s.t.kend) trav_pop(s.t, ray_limit(s));
+  if (s.t.k >= s.t.kend) trav_pop(s.t);
 }
 
 template <bool ANY>
@@ -671,6 +671,7 @@ TGQ_HD void ray_query(BvhView const & b, v3 o, v3 d, float & best_t, int & best_
   f4 r[TGQ_FETCH_BOX];
   while (s.t.cur != TGQ_ST_DONE)
   {
+    if (s.t.cur == TGQ_ST_POP) { trav_pop_step(s.t, ray_limit(s)); continue; }
     ray_fetch(s, b, r);
     if (s.t.cur >= 0) ray_node_compute(s, b, r); else ray_leaf_compute(s, b, r);
   }
