@@ -95,7 +95,7 @@ void build(Emu & E, float const * src, float const * n3)
       v3 v0 = mk3(t.q0.x, t.q0.y, t.q0.z), v1 = mk3(t.q1.x, t.q1.y, t.q1.z), v2 = mk3(t.q2.x, t.q2.y, t.q2.z);
       ObbAcc a; obb_acc_begin(a, cross3(sub3(v1, v0), sub3(v2, v0)));
       obb_acc_point(a, v0); obb_acc_point(a, v1); obb_acc_point(a, v2);
-      obb_acc_store(a, pad, ~((0 << TGQ_LEAF_BITS) | 1), r.q); obb_store_empty(~0, r.q + 4);
+      obb_acc_store(a, pad, ~((0 << TGQ_LEAF_BITS) | 1), r.q); obb_store_empty(~0, r.q + TGQ_OBB_F4);
       E.obbs.assign(1, r);
     }
     E.nodes.push_back(make_node(mk3(plo[0].x - pad, plo[0].y - pad, plo[0].z - pad), mk3(phi[0].x + pad, phi[0].y + pad, phi[0].z + pad),
@@ -154,7 +154,7 @@ void build(Emu & E, float const * src, float const * n3)
           TriRec const & t = E.tris[(size_t)k];
           obb_acc_point(a, mk3(t.q0.x, t.q0.y, t.q0.z)); obb_acc_point(a, mk3(t.q1.x, t.q1.y, t.q1.z)); obb_acc_point(a, mk3(t.q2.x, t.q2.y, t.q2.z));
         }
-        obb_acc_store(a, pad, child[c], r.q + 4 * c);
+        obb_acc_store(a, pad, child[c], r.q + TGQ_OBB_F4 * c);
       }
       E.obbs[(size_t)newidx[(size_t)i]] = r;
     }

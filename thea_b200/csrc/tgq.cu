@@ -274,7 +274,7 @@ int build_common(tgq_handle * h, int kind, float const * d_src, float const * d_
     CK(h->first.reserve(4 * ni)); CK(h->last.reserve(4 * ni)); CK(h->split.reserve(4 * ni)); CK(h->parent.reserve(4 * (2 * nn)));
     CK(h->live.reserve(4 * ni)); CK(h->newidx.reserve(4 * ni)); CK(h->arrive.reserve(4 * ni));
     CK(h->nbox_lo.reserve(16 * ni)); CK(h->nbox_hi.reserve(16 * ni)); CK(h->nsum.reserve(16 * ni));
-    if (kind == TGQ_KIND_TRIANGLES) { CK(h->obbinfo.reserve(64 * ni)); CK(h->big.reserve(4 * ni)); CK(h->big_count.reserve(4)); }
+    if (kind == TGQ_KIND_TRIANGLES) { CK(h->obbinfo.reserve(16 * TGQ_OBB_F4 * ni)); CK(h->big.reserve(4 * ni)); CK(h->big_count.reserve(4)); }
     k_hierarchy<<<grid_for(n - 1), TGQ_BLOCK, 0, s>>>(h->keys_b.as<uint64_t>(), n, h->first.as<int>(), h->last.as<int>(), h->split.as<int>(),
                                                       h->parent.as<int>());
     k_live<<<grid_for(n - 1), TGQ_BLOCK, 0, s>>>(n, h->leaf_built, h->first.as<int>(), h->last.as<int>(), h->live.as<int>());

@@ -9,8 +9,9 @@
 //        q2 = (c1.lo.z, c1.hi.x, c1.hi.y, c1.hi.z)   q3 = (child0, child1, count0, count1) as int bits
 //        child >= 0: index of an inner node; child < 0: leaf holding elements [~child, ~child + count) of the
 //        Morton-ordered element array.
-//   Obb   (128 B) : triangle structures only, same index as Node: per child (centre, h0) (axis0, h1) (axis1, h2)
-//        (axis2, child link); read by closest-point queries INSTEAD of Node (rays, k-NN and ball queries read Node).
+//   Obb   (96 B)  : triangle structures only, same index as Node: per child (centre, h0) (axis0, h1|h2 as two round-up
+//        bfloat16) (axis1, child link); axis2 = axis0 x axis1 is recomputed.  Read by closest-point queries INSTEAD of
+//        Node (rays, k-NN and ball queries read Node): three 256-bit loads per node instead of four.
 //   Tri   (128 B) : q0 = (v0, orig_index)  q1 = (v1, axis)  q2 = (v2, plane d)  q3 = (unit normal, screening radius about the centroid)
 //        e0 e1 e2 = (unit direction, length) of the edges v0->v1, v1->v2, v2->v0   x = (1 / area2, area2, -, -)
 //        (ray queries read q0..q2 = 48 B; a closest-point step reads the whole 128-byte line, the same fetch shape as an
@@ -24,7 +25,8 @@ namespace tgq {
 
 struct NodeRec { f4 q0, q1, q2, q3; };
 struct TriRec  { f4 q0, q1, q2, q3, e0, e1, e2, x; };
-struct ObbNode { f4 q[8]; };     // oriented boxes of both children, see tgq_traverse.cuh
+#define TGQ_OBB_F4 3              // float4 per child of an ObbNode
+struct ObbNode { f4 q[2 * TGQ_OBB_F4]; };     // oriented boxes of both children (96 B), see tgq_traverse.cuh
 
 // ---- Morton codes: 21 bits per axis, 63-bit keys --------------------------------------------------------------------
 TGQ_HD uint64_t expand21(uint64_t v)

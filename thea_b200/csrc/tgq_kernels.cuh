@@ -164,7 +164,7 @@ __global__ void k_live(int n, int leaf, int const * __restrict__ first, int cons
 }
 
 // ---- oriented boxes of every radix-tree node that a surviving node references as a child --------------------------------
-// obbinfo[4x .. 4x+3] = child half of an ObbNode (without the link) for inner radix node x, extents taken over all vertices of
+// obbinfo[3x .. 3x+2] = child half of an ObbNode (without the link) for inner radix node x, extents taken over all vertices of
 // the node's triangles along the frame derived from the node's normal sum (obb_frame).
 __device__ __forceinline__ void obb_add_tri(ObbAcc & a, TriRec const * tris, int k)
 {
@@ -189,7 +189,7 @@ __global__ void k_obb_small(int n, int leaf, int const * __restrict__ first, int
   f4 ns = nsum[x];
   ObbAcc a; obb_acc_begin(a, mk3(ns.x, ns.y, ns.z));
   for (int k = f; k <= l; ++k) obb_add_tri(a, tris, k);
-  obb_acc_store(a, pad, 0, obbinfo + 4 * (size_t)x);
+  obb_acc_store(a, pad, 0, obbinfo + TGQ_OBB_F4 * (size_t)x);
 }
 
 // Larger nodes: one thread block per node, block-wide min / max reduction (exact, order independent).
@@ -218,7 +218,7 @@ k_obb_big(int const * __restrict__ big, int const * __restrict__ big_count, int 
         a.mn[j] = fminf(fminf(s_mn[0][j], s_mn[1][j]), fminf(s_mn[2][j], s_mn[3][j]));
         a.mx[j] = fmaxf(fmaxf(s_mx[0][j], s_mx[1][j]), fmaxf(s_mx[2][j], s_mx[3][j]));
       }
-      obb_acc_store(a, pad, 0, obbinfo + 4 * (size_t)x);
+      obb_acc_store(a, pad, 0, obbinfo + TGQ_OBB_F4 * (size_t)x);
     }
   }
 }
@@ -260,12 +260,12 @@ __global__ void k_emit(int n, int leaf, int const * __restrict__ first, int cons
         v3 v0 = mk3(q0.x, q0.y, q0.z), v1 = mk3(q1.x, q1.y, q1.z), v2 = mk3(q2.x, q2.y, q2.z);
         ObbAcc a; obb_acc_begin(a, cross3(sub3(v1, v0), sub3(v2, v0)));
         obb_acc_point(a, v0); obb_acc_point(a, v1); obb_acc_point(a, v2);
-        obb_acc_store(a, pad, child[c], r.q + 4 * c);
+        obb_acc_store(a, pad, child[c], r.q + TGQ_OBB_F4 * c);
       }
       else
       {
-        for (int j = 0; j < 4; ++j) r.q[4 * c + j] = obbinfo[4 * (size_t)inner + j];
-        r.q[4 * c + 3].w = __int_as_float(child[c]);
+        for (int j = 0; j < TGQ_OBB_F4; ++j) r.q[TGQ_OBB_F4 * c + j] = obbinfo[TGQ_OBB_F4 * (size_t)inner + j];
+        r.q[TGQ_OBB_F4 * c + 2].w = __int_as_float(child[c]);
       }
     }
     obbs[newidx[i]] = r;
@@ -286,7 +286,7 @@ __global__ void k_emit_single(f4 const * pbox_lo, f4 const * pbox_hi, SceneBox c
     ObbAcc a; obb_acc_begin(a, cross3(sub3(v1, v0), sub3(v2, v0)));
     obb_acc_point(a, v0); obb_acc_point(a, v1); obb_acc_point(a, v2);
     obb_acc_store(a, pad, leaf0, r.q);
-    obb_store_empty(~0, r.q + 4);
+    obb_store_empty(~0, r.q + TGQ_OBB_F4);
     obbs[0] = r;
   }
   f4 blo = pbox_lo[0], bhi = pbox_hi[0];

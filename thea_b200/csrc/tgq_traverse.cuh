@@ -128,8 +128,8 @@ TGQ_HD void trav_pop(Trav & t) { t.cur = TGQ_ST_POP; }
 // a wide disc around its foot point (hundreds of leaves on a 1M-triangle mesh).  Each child of a triangle-structure
 // node therefore carries a box oriented along the mean normal of its triangles (axis a0) and two tangent directions:
 //     |p - x|^2 >= sum_i max(|a_i . (p - c)| - h_i, 0)^2   for every x in the child,
-// which is thin across the surface and keeps the lateral offset.  ObbNode (128 B), per child four float4:
-//     (c.xyz, h0) (a0.xyz, h1) (a1.xyz, h2) (a2.xyz, child link)
+// which is thin across the surface and keeps the lateral offset.  ObbNode (96 B), per child three float4:
+//     (c.xyz, h0) (a0.xyz, h1|h2 as round-up bfloat16) (a1.xyz, child link)        a2 = a0 x a1 is recomputed
 // Half extents are padded outwards at build time (scene pad); `mq` absorbs the rounding of the query-side products (it
 // grows with the magnitude of the query coordinates), and the result is deflated.  Children are visited in the order
 // of their centre distance (a better predictor of where the foot point lies than the lower bound for far queries:
@@ -159,12 +159,28 @@ TGQ_HD void trav_pop(Trav & t) { t.cur = TGQ_ST_POP; }
 TGQ_HD float query_margin(v3 p, float scene_pad)
 { return TGQ_MARGIN_SCALE * (0.5f * scene_pad + 5.9604645e-7f * (fabsf(p.x) + fabsf(p.y) + fabsf(p.z))); }
 
-TGQ_HD void obb_bounds(f4 q0, f4 q1, f4 q2, f4 q3, v3 p, float mq, float & lb, float & key)
+// Two non-negative floats as round-UP bfloat16 in one word (the lateral half extents: 0.8 % slack at most, never too small).
+TGQ_HD float pack_bf16_up(float a, float b)
 {
+  unsigned ua = (unsigned)f2i(a), ub = (unsigned)f2i(b);
+  ua = (ua + 0xffffu) & 0xffff0000u; ub = (ub + 0xffffu) >> 16;
+  return i2f((int)(ua | ub));
+}
+TGQ_HD void unpack_bf16(float w, float & a, float & b)
+{
+  unsigned u = (unsigned)f2i(w);
+  a = i2f((int)(u & 0xffff0000u)); b = i2f((int)(u << 16));
+}
+
+TGQ_HD void obb_bounds(f4 q0, f4 q1, f4 q2, v3 p, float mq, float & lb, float & key)
+{
+  v3 a0 = mk3(q1.x, q1.y, q1.z), a1 = mk3(q2.x, q2.y, q2.z);
+  v3 a2 = cross3(a0, a1);                       // exactly the a2 the build measured the extents along (obb_frame)
+  float h1, h2; unpack_bf16(q1.w, h1, h2);
   v3 pc = sub3(p, mk3(q0.x, q0.y, q0.z));
-  float x = fmaxf(fabsf(fdot3(mk3(q1.x, q1.y, q1.z), pc)) - (q0.w + mq), 0.0f);
-  float y = fmaxf(fabsf(fdot3(mk3(q2.x, q2.y, q2.z), pc)) - (q1.w + mq), 0.0f);
-  float z = fmaxf(fabsf(fdot3(mk3(q3.x, q3.y, q3.z), pc)) - (q2.w + mq), 0.0f);
+  float x = fmaxf(fabsf(fdot3(a0, pc)) - (q0.w + mq), 0.0f);
+  float y = fmaxf(fabsf(fdot3(a1, pc)) - (h1 + mq), 0.0f);
+  float z = fmaxf(fabsf(fdot3(a2, pc)) - (h2 + mq), 0.0f);
   lb = fdot3(mk3(x, y, z), mk3(x, y, z)) * TGQ_LB_DEFLATE;
   key = fdot3(pc, pc);
 }
@@ -215,17 +231,15 @@ TGQ_HD void obb_acc_store(ObbAcc const & a, float pad, int child, f4 * out4)
   float hp = TGQ_MARGIN_SCALE * pad;
   float h0 = 0.5f * (a.mx[0] - a.mn[0]) * 1.000001f + hp, h1 = 0.5f * (a.mx[1] - a.mn[1]) * 1.000001f + hp, h2 = 0.5f * (a.mx[2] - a.mn[2]) * 1.000001f + hp;
   out4[0].x = c.x; out4[0].y = c.y; out4[0].z = c.z; out4[0].w = h0;
-  out4[1].x = a.f.a0.x; out4[1].y = a.f.a0.y; out4[1].z = a.f.a0.z; out4[1].w = h1;
-  out4[2].x = a.f.a1.x; out4[2].y = a.f.a1.y; out4[2].z = a.f.a1.z; out4[2].w = h2;
-  out4[3].x = a.f.a2.x; out4[3].y = a.f.a2.y; out4[3].z = a.f.a2.z; out4[3].w = i2f(child);
+  out4[1].x = a.f.a0.x; out4[1].y = a.f.a0.y; out4[1].z = a.f.a0.z; out4[1].w = pack_bf16_up(h1, h2);
+  out4[2].x = a.f.a1.x; out4[2].y = a.f.a1.y; out4[2].z = a.f.a1.z; out4[2].w = i2f(child);
 }
 // An oriented box that no query can reach (the missing second child of a one-element structure).
 TGQ_HD void obb_store_empty(int child, f4 * out4)
 {
   out4[0].x = 0.0f; out4[0].y = 0.0f; out4[0].z = 0.0f; out4[0].w = -1e30f;
-  out4[1].x = 1.0f; out4[1].y = 0.0f; out4[1].z = 0.0f; out4[1].w = -1e30f;
-  out4[2].x = 0.0f; out4[2].y = 1.0f; out4[2].z = 0.0f; out4[2].w = -1e30f;
-  out4[3].x = 0.0f; out4[3].y = 0.0f; out4[3].z = 1.0f; out4[3].w = i2f(child);
+  out4[1].x = 1.0f; out4[1].y = 0.0f; out4[1].z = 0.0f; out4[1].w = 0.0f;
+  out4[2].x = 0.0f; out4[2].y = 1.0f; out4[2].z = 0.0f; out4[2].w = i2f(child);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -298,7 +312,12 @@ TGQ_HD void closest_fetch(ClosestState<TRI> const & s, BvhView const & b, f4 * r
   f4 const * q;
   if (TRI) q = s.t.cur >= 0 ? (f4 const *)(b.obbs + s.t.cur) : (f4 const *)(b.tris + s.t.k);
   else q = s.t.cur >= 0 ? (f4 const *)(b.nodes + s.t.cur) : b.pts + s.t.k;
-  if (TRI) { for (int i = 0; i < ClosestFetch<TRI>::N; i += 2) ldq2(q + i, r[i], r[i + 1]); }       // records are 128-byte aligned
+  if (TRI)
+  {
+    // 32-byte aligned records: a node is 96 bytes (three 256-bit loads), a triangle 128 (four)
+    ldq2(q, r[0], r[1]); ldq2(q + 2, r[2], r[3]); ldq2(q + 4, r[4], r[5]);
+    if (s.t.cur < 0) ldq2(q + 6, r[6], r[7]);
+  }
   else { for (int i = 0; i < ClosestFetch<TRI>::N; ++i) r[i] = ldq(q + i); }                        // point leaves start anywhere
 }
 
@@ -323,9 +342,9 @@ TGQ_HD void closest_node_compute(ClosestState<TRI> & s, BvhView const & b, f4 co
   float lb0, lb1, key0, key1; int c0, c1;
   if (TRI)
   {
-    obb_bounds(r[0], r[1], r[2], r[3], s.p, s.mq, lb0, key0);
-    obb_bounds(r[4], r[5], r[6], r[7], s.p, s.mq, lb1, key1);
-    c0 = f2i(r[3].w); c1 = f2i(r[7].w);
+    obb_bounds(r[0], r[1], r[2], s.p, s.mq, lb0, key0);
+    obb_bounds(r[3], r[4], r[5], s.p, s.mq, lb1, key1);
+    c0 = f2i(r[2].w); c1 = f2i(r[5].w);
   }
   else
   {
