@@ -38,9 +38,12 @@ struct DevBuf
 };
 
 #define TGQ_MAX_ARGS 8
+#ifndef TGQ_SLOTS
+#define TGQ_SLOTS 3       // pipeline depth of host-pointer calls (measured on cfg5: 2 -> 462, 3 -> 475, 4 -> 474 M queries/s end to end)
+#endif
 
-// Scratch of one pipeline slot.  Host-pointer calls alternate two slots, each with its own stream, so that the copies of
-// one chunk overlap the kernels of the other.
+// Scratch of one pipeline slot.  Host-pointer calls rotate over TGQ_SLOTS slots, each with its own stream, so that the
+// copies of one chunk overlap the kernels of the others.
 struct Slot
 {
   cudaStream_t stream = nullptr;
@@ -68,7 +71,7 @@ struct tgq_handle
   bool cum_valid = false;
   float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}; float pad = 0;
 
-  Slot slot[2];
+  Slot slot[TGQ_SLOTS];
   std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
   tgq_stats st = {};
 };
@@ -349,7 +352,7 @@ int run_batched(tgq_handle * h, int64_t Q, Arg * args, int nargs, bool sortable,
     if (p && !is_device_ptr(p)) all_dev = false;
   }
   int64_t chunk = all_dev ? ((int64_t)1 << 26) : std::max<int64_t>(1024, h->opt_chunk);
-  int nslots = all_dev ? 1 : 2;
+  int nslots = all_dev ? 1 : TGQ_SLOTS;
   if (!all_dev) CK(cudaStreamSynchronize(h->stream));     // the structure must be complete before other streams read it
   std::vector<cudaEvent_t> evs;
   int ci = 0;
@@ -387,7 +390,7 @@ int run_batched(tgq_handle * h, int64_t Q, Arg * args, int nargs, bool sortable,
   }
   if (all_dev && h->opt_async) return TGQ_OK;
   if (all_dev) CK(cudaStreamSynchronize(h->stream));
-  else for (int s = 0; s < 2; ++s) CK(cudaStreamSynchronize(h->slot[s].stream));
+  else for (int s = 0; s < TGQ_SLOTS; ++s) CK(cudaStreamSynchronize(h->slot[s].stream));
   for (size_t i = 0; i + 2 < evs.size() + 0 && i < evs.size(); i += 3)
   {
     float a = 0, b = 0;
@@ -465,7 +468,7 @@ int tgq_create(int device, tgq_handle ** out)
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
   if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
   h->stream = h->own_stream;
-  for (int s = 0; s < 2; ++s)
+  for (int s = 0; s < TGQ_SLOTS; ++s)
   {
     if ((e = cudaStreamCreateWithFlags(&h->slot[s].stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = h->slot[s].counter.reserve(sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -488,7 +491,7 @@ int tgq_destroy(tgq_handle * h)
                      &h->newidx, &h->pbox_lo, &h->pbox_hi, &h->nbox_lo, &h->nbox_hi, &h->arrive, &h->keys_a, &h->keys_b, &h->vals_a,
                      &h->cubtmp, &h->src, &h->src2, &h->misc, &h->icp_cur, &h->icp_orig, &h->icp_to, &h->icp_idx, &h->area_by_elem, &h->cum, &h->obbs, &h->pnrm, &h->nsum, &h->obbinfo, &h->big, &h->big_count};
   for (DevBuf * b : bufs) b->release();
-  for (int s = 0; s < 2; ++s)
+  for (int s = 0; s < TGQ_SLOTS; ++s)
   {
     Slot & sl = h->slot[s];
     for (int a = 0; a < TGQ_MAX_ARGS; ++a) { sl.in[a].release(); sl.out[a].release(); }
