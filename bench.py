@@ -239,6 +239,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     grid, nq_total, nr_total, desc = WORKLOADS[args.workload]
@@ -268,34 +270,76 @@ def main():
         o, d = torch_random_rays(n, bounds, gen.SEED_RAYS, r_off + b, dev)
         dro[b:b + n] = o
         drd[b:b + n] = d
-    c_idx = torch.empty(nq, dtype=torch.int32, device=dev)
-    c_d2 = torch.empty(nq, dtype=torch.float32, device=dev)
-    c_cp = torch.empty((nq, 3), dtype=torch.float32, device=dev)
-    r_t = torch.empty(nr, dtype=torch.float32, device=dev)
-    r_idx = torch.empty(nr, dtype=torch.int32, device=dev)
-
     kern = {"closest_ms": 0.0, "closest_q": 0, "ray_ms": 0.0, "ray_q": 0, "sort_ms": 0.0, "launches": 0}
 
-    # N > 1: the one real exchange of the path -- every rank ends a step holding the results of the WHOLE batch
-    # (all-gather of the per-shard result arrays over NCCL / NVLink).  Equal shard sizes by construction.
-    gathered = None
+    # N > 1: the one real exchange of the path -- every rank ends a step holding the results of the WHOLE batch (SURVEY.md
+    # 8e).  Equal shard sizes by construction.  Preferred transport: the gathered arrays live in symmetric (peer-mapped)
+    # memory, every rank's kernels write their shard straight into the local copy, and the shard is then PUSHED into every
+    # peer's copy with peer-to-peer copies over NVLink on a side stream -- copy engines, no SMs, so the transfer really runs
+    # under the next kernel (NCCL's all-gather kernels cannot: the persistent traversal kernels leave them no SM until they
+    # finish).  Fallback when symmetric memory is unavailable: asynchronous NCCL all-gather.
+    gathered, symm, transport = None, None, "none"
+    shapes = {"c_idx": ((nq_total,), torch.int32), "c_d2": ((nq_total,), torch.float32), "c_cp": ((nq_total, 3), torch.float32),
+              "r_t": ((nr_total,), torch.float32), "r_idx": ((nr_total,), torch.int32)}
+    offs = {"c_idx": (q_off, nq), "c_d2": (q_off, nq), "c_cp": (q_off, nq), "r_t": (r_off, nr), "r_idx": (r_off, nr)}
     if world > 1:
         assert nq_total % world == 0 and nr_total % world == 0, "bench workloads shard evenly over 1/2/4/8 ranks"
-        gathered = {"c_idx": torch.empty(nq_total, dtype=torch.int32, device=dev), "c_d2": torch.empty(nq_total, dtype=torch.float32, device=dev),
-                    "c_cp": torch.empty((nq_total, 3), dtype=torch.float32, device=dev), "r_t": torch.empty(nr_total, dtype=torch.float32, device=dev),
-                    "r_idx": torch.empty(nr_total, dtype=torch.int32, device=dev)}
+        if os.environ.get("TGQ_BENCH_TRANSPORT", "p2p") == "p2p":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                gathered, symm = {}, {}
+                for name, (shape, dt) in shapes.items():
+                    t = symm_mem.empty(max(1, int(np.prod(shape))), dtype=dt, device=dev)
+                    hdl = symm_mem.rendezvous(t, dist.group.WORLD)
+                    gathered[name] = t[:int(np.prod(shape))].view(shape)
+                    symm[name] = [hdl.get_buffer(r, (max(1, int(np.prod(shape))),), dt)[:int(np.prod(shape))].view(shape) for r in range(world)]
+                transport = "p2p copy engines over symmetric memory"
+            except Exception as exc:      # noqa: BLE001 -- any failure here means: use NCCL
+                if rank == 0:
+                    print(f"bench.py: symmetric memory unavailable ({type(exc).__name__}: {exc}); using NCCL all-gather", file=sys.stderr)
+                gathered, symm = None, None
+        if gathered is None:
+            gathered = {name: torch.empty(shape, dtype=dt, device=dev) for name, (shape, dt) in shapes.items()}
+            transport = "NCCL all-gather"
+    if symm is not None:
+        c_idx, c_d2, c_cp = (gathered[k][q_off:q_off + nq] for k in ("c_idx", "c_d2", "c_cp"))
+        r_t, r_idx = (gathered[k][r_off:r_off + nr] for k in ("r_t", "r_idx"))
+        comm_stream = torch.cuda.Stream(device=dev)
+    else:
+        c_idx = torch.empty(nq, dtype=torch.int32, device=dev)
+        c_d2 = torch.empty(nq, dtype=torch.float32, device=dev)
+        c_cp = torch.empty((nq, 3), dtype=torch.float32, device=dev)
+        r_t = torch.empty(nr, dtype=torch.float32, device=dev)
+        r_idx = torch.empty(nr, dtype=torch.int32, device=dev)
 
     pending = {"c": [], "r": []}
 
     def wait_gathers(groups=("c", "r")):
-        # makes the compute stream wait for the gathers that still read the buffers the next kernel overwrites
+        # makes the compute stream wait for the transfers that still read the buffers the next kernel overwrites
         for g in groups:
             while pending[g]:
-                pending[g].pop().wait()
+                w = pending[g].pop()
+                if symm is not None:
+                    torch.cuda.current_stream().wait_event(w)
+                else:
+                    w.wait()
 
     def gather(names):
-        # asynchronous: NCCL moves the shard results over NVLink on its own stream while the next kernel runs
+        # asynchronous: the shard results move over NVLink while the next kernel runs
         if world == 1:
+            return
+        if symm is not None:
+            comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(comm_stream):
+                for name in names:
+                    o, n = offs[name]
+                    if n:
+                        for peer in range(1, world):
+                            r = (rank + peer) % world
+                            symm[name][r][o:o + n].copy_(gathered[name][o:o + n], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(comm_stream)
+            pending[names[0][0]].append(ev)
             return
         src = {"c_idx": c_idx, "c_d2": c_d2, "c_cp": c_cp, "r_t": r_t, "r_idx": r_idx}
         for name in names:
@@ -343,7 +387,7 @@ def main():
     e0.record()
     for _ in range(args.steps):
         step_device(True)
-    wait_gathers()                           # the last step's results are complete on every rank inside the timed region
+    wait_gathers()                           # the last step's results have left this rank ...
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -462,7 +506,7 @@ def main():
         "metric": "bvh_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": desc, "triangles": T, "closest_queries": nq_total, "ray_queries": nr_total, "sharding": f"queries/{world}, BVH replicated" + (", results all-gathered every step (NCCL, overlapped with the next kernel)" if world > 1 else ""),
+        "config": {"workload": desc, "triangles": T, "closest_queries": nq_total, "ray_queries": nr_total, "sharding": f"queries/{world}, BVH replicated" + (f", results gathered on every rank every step ({transport}, overlapped with the next kernel)" if world > 1 else ""),
                    "l2_policy": "inputs_exceed_l2" if (nq_total * 32 + nr_total * 32) / world > 126e6 else "structure+inputs may be L2 resident",
                    "scale": args.scale, "build_ms": build_ms},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": kern["launches"], "clocks": clocks,
