@@ -239,8 +239,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL logs (its version banner) go to stderr: stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     grid, nq_total, nr_total, desc = WORKLOADS[args.workload]
