@@ -239,7 +239,6 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL logs (its version banner) go to stderr: stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     grid, nq_total, nr_total, desc = WORKLOADS[args.workload]
