@@ -490,6 +490,24 @@ class GpuPointBvhT : public GpuBvhBase<VectorT>
                             bool exclude_self = false) const
     { detail::check(h, tgq_knn(h, q3, Q, k, dist_bound, exclude_self ? 1 : 0, idx, d2), "tgq_knn"); }
 
+    /** Q ball range queries, BvhN::rangeQueryIndices<IntersectionTester>(Ball3(c_i, r_i), ...) (BvhN.hpp:1208-1220): count[Q] and
+     *  the max_out (<= TGQ_MAX_K) lowest element indices in range per query, ascending, -1 padded. */
+    void rangeQueryIndicesBatch(float const * c3, float const * radius, intx Q, int32_t max_out, int32_t * idx, int32_t * count,
+                                bool exclude_self = false) const
+    { detail::check(h, tgq_ball_range(h, c3, radius, Q, max_out, exclude_self ? 1 : 0, idx, count), "tgq_ball_range"); }
+    /** The reference's scalar form for a ball: appends the indices of all elements in range to `result` (ascending here; the
+     *  reference reports traversal order).  More than TGQ_MAX_K elements in range is an error of this adaptor, not a truncation. */
+    template <typename IntersectionTesterT>
+    void rangeQueryIndices(VectorT const & center, Real radius, std::vector<intx> & result, bool discard_prior_results = true) const
+    {
+      if (discard_prior_results) result.clear();
+      float c[3]; detail::put3(c, center);
+      int32_t idx[TGQ_MAX_K]; int32_t count = 0;
+      detail::check(h, tgq_ball_range(h, c, &radius, 1, TGQ_MAX_K, 0, idx, &count), "tgq_ball_range");
+      if (count > TGQ_MAX_K) throw Error("TheaGpu: rangeQueryIndices found more than TGQ_MAX_K elements; use rangeQueryIndicesBatch for counts");
+      for (int32_t j = 0; j < count; ++j) result.push_back(idx[j]);
+    }
+
     /** PointSet3::updateGraph's neighbour search for every sample (PointSet3.hpp:324-391,586-681). */
     void sampleGraphBatch(int32_t max_degree, float init_radius, int32_t * idx, float * sep, int32_t * count = nullptr, int32_t rounds = 3,
                           float min_dot = -0.5f, int32_t min_degree = -1) const

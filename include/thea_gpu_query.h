@@ -128,6 +128,15 @@ int tgq_closest_filtered(tgq_handle * h, const float * q3, const float * qn3, co
 int tgq_knn_filtered(tgq_handle * h, const float * q3, const float * qn3, const int32_t * qlabel, int64_t Q, int32_t k, float min_dot,
                      double dist_bound, int32_t * idx, float * d2);
 
+/* Q ball range queries on a point structure (the primitive under the local surface features).  Replaces
+ *   BvhN::rangeQueryIndices<IntersectionTester>(Ball3(c_i, r_i), result) / processRange (BvhN.hpp:1208-1264,2118-2171;
+ *   BallN.hpp:77-100): every element e with sq(x_e - c_i) <= r_i * r_i in fp32, as the reference tests it.
+ * count[Q] = how many elements are in range; idx[Q x max_out] = the max_out LOWEST element indices in range, ascending, unused
+ * slots -1 (the reference reports them in traversal order: compare as sets; the set is complete iff count <= max_out).
+ * max_out = 0 only counts (idx may be null).  A negative radius matches nothing.  exclude_self != 0: query i ignores element i. */
+int tgq_ball_range(tgq_handle * h, const float * c3, const float * radius, int64_t Q, int32_t max_out, int32_t exclude_self,
+                   int32_t * idx, int32_t * count);
+
 /* Proximity graph over the P points of a point structure.  Replaces the loop of PointSet3::updateGraph over
  * findSampleNeighbors (PointSet3.hpp:380-381,586-681): for every sample, a ball range query of radius init_radius
  * (doubled for up to `rounds` rounds while fewer than min_degree neighbours were found), candidates filtered by

@@ -247,6 +247,30 @@ void orc_knn_filtered(void * h, float const * q3, float const * qn3, int32_t con
   });
 }
 
+// BvhN::rangeQueryIndices with Ball3(c, r) on a point structure (BvhN.hpp:1208-1220, BallN.hpp:83): brute force over all
+// elements; count and the max_out lowest indices ascending.
+void orc_ball_range(void * h, float const * c3, float const * radius, int64_t Q, int max_out, int exclude_self, int nthreads, int64_t * idx,
+                    int32_t * count)
+{
+  KdTree const & T = ((Handle *)h)->tree;
+  parallel_for(Q, nthreads, [&](int64_t b, int64_t e) {
+    for (int64_t i = b; i < e; ++i)
+    {
+      V3 c = ld3(c3, i); float r = radius[i]; float r2 = r * r; int n = 0;
+      for (int j = 0; j < max_out; ++j) idx[i * max_out + j] = -1;
+      if (r >= 0)
+        for (int64_t el = 0; el < T.size(); ++el)
+        {
+          if (exclude_self && el == i) continue;
+          if (!(sqnorm(T.pts[(size_t)el] - c) <= r2)) continue;
+          if (n < max_out) idx[i * max_out + n] = el;
+          ++n;
+        }
+      count[i] = n;
+    }
+  });
+}
+
 void orc_ray_first(void * h, float const * o3, float const * d3, float const * tmax, int64_t R, int mode, int nthreads,
                    int64_t * idx, float * t)
 {

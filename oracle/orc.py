@@ -54,6 +54,7 @@ def lib():
                                            C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_knn_filtered.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_double, C.c_int, C.c_int,
                                        C.c_void_p, C.c_void_p]
+        L.orc_ball_range.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_avg_separation.restype = C.c_float
         L.orc_avg_separation.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_ball_graph.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -177,6 +178,15 @@ class Oracle:
         d2 = np.empty((Q, k), np.float32)
         lib().orc_knn_filtered(self.h, _p(q), _p(qn), _p(ql), Q, int(k), float(min_dot), float(dist_bound), mode, threads or ncores(), _p(idx), _p(d2))
         return idx, d2
+
+    def ball_range(self, c, radius, max_out=32, exclude_self=False, threads=None):
+        c = _f32(c).reshape(-1, 3)
+        Q = c.shape[0]
+        rad = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float32), (Q,)), np.float32)
+        idx = np.empty((Q, max_out), np.int64)
+        cnt = np.empty(Q, np.int32)
+        lib().orc_ball_range(self.h, _p(c), _p(rad), Q, int(max_out), int(exclude_self), threads or ncores(), _p(idx), _p(cnt))
+        return idx, cnt
 
     def avg_separation(self, seeds):
         s = np.ascontiguousarray(seeds, np.int64)

@@ -259,6 +259,19 @@ void emu_knn_filtered(void * h, float const * q3, float const * qn3, int32_t con
   }
 }
 
+void emu_ball_range(void * h, float const * c3, float const * radius, int64_t Q, int max_out, int exclude_self, int32_t * idx, int32_t * count)
+{
+  Emu & E = *(Emu *)h; BvhView v = E.view();
+  std::vector<float> keys((size_t)max_out + 1); std::vector<int> ids((size_t)max_out + 1);
+  for (int64_t i = 0; i < Q; ++i)
+  {
+    SortedSet set; set.init(keys.data(), ids.data(), 1, max_out); int cnt = 0;
+    range_query(v, ld(c3, i), radius[i], exclude_self ? (int)i : -1, set, cnt);
+    for (int j = 0; j < max_out; ++j) idx[i * max_out + j] = j < set.n ? ids[(size_t)j] : -1;
+    count[i] = cnt;
+  }
+}
+
 void emu_ball_graph(void * h, int k, float init_radius, int rounds, float min_dot, int min_degree, int32_t * idx, float * sep, int32_t * count)
 {
   Emu & E = *(Emu *)h; BvhView v = E.view();

@@ -24,6 +24,7 @@ def lib():
         L.emu_knn.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_float, C.c_int, vp, vp]
         L.emu_ball_graph.argtypes = [vp, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, vp, vp, vp]
         L.emu_set_labels.argtypes = [vp, vp]
+        L.emu_ball_range.argtypes = [vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp, vp]
         L.emu_closest_filtered.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, vp, vp, vp]
         L.emu_knn_filtered.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, C.c_float, C.c_float, vp, vp]
         L.emu_ray.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, vp, vp]
@@ -72,6 +73,15 @@ class Emu:
         flag = int(exclude_self) if seeded else -int(exclude_self) - 1
         lib().emu_closest(self.h, _p(q), Q, float(bound_ub), flag, _p(idx), _p(d2), _p(cp))
         return idx, d2, cp
+
+    def ball_range(self, c, radius, max_out=32, exclude_self=False):
+        c = np.ascontiguousarray(c, np.float32)
+        Q = len(c)
+        rad = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float32), (Q,)), np.float32)
+        idx = np.empty((Q, max_out), np.int32)
+        cnt = np.empty(Q, np.int32)
+        lib().emu_ball_range(self.h, _p(c), _p(rad), Q, int(max_out), int(exclude_self), _p(idx), _p(cnt))
+        return idx, cnt
 
     def set_labels(self, labels):
         self._lab = None if labels is None else np.ascontiguousarray(labels, np.int32)

@@ -273,3 +273,20 @@ def test_filtered_nearest_neighbours_register_semantics():
     ui, _, _ = E.closest(q)
     fi, _, _ = E.closest_filtered(q, qn=qn, qlabel=ql)
     assert 0.2 < (ui != fi).mean() < 0.95
+
+
+def test_ball_range_query_matches_brute_force():
+    """SURVEY 8f rank 3 primitive: rangeQueryIndices with a Ball3 per query (count + lowest indices)."""
+    mesh = gen.torus_mesh(24)
+    p, n, _ = gen.area_samples(mesh, 3000)
+    E = emu_lib.Emu(points=p)
+    ora = orc.Oracle(points=p)
+    rng = np.random.default_rng(4)
+    c = (p[:800] + rng.normal(scale=0.02, size=(800, 3))).astype(np.float32)
+    rad = rng.uniform(0.0, 0.25, 800).astype(np.float32)
+    rad[:5] = [0.0, -1.0, 10.0, 1e-6, 0.05]
+    for max_out, excl in ((16, False), (64, True)):
+        gi, gc = E.ball_range(c, rad, max_out, excl)
+        oi, oc = ora.ball_range(c, rad, max_out, excl)
+        assert np.array_equal(gc, oc) and np.array_equal(gi, oi.astype(np.int32))
+    assert gc[1] == 0 and gc[2] == len(p) - 1          # negative radius: nothing; huge radius: everything but self

@@ -200,3 +200,24 @@ def test_device_resident_icp_equals_the_host_driven_loop(setup):
     tr_c, err_c, nb = e.icp_align(torch.from_numpy(src).cuda(), want_correspondences=False)
     assert nb == corr_a.shape[0] or nb > 0
     assert np.allclose(tr_c, e.icp_align(src)[0], rtol=0, atol=0)
+
+
+def test_ball_range_queries(built):
+    """rangeQueryIndices with a Ball3 per query (SURVEY 8f rank 3 primitive): counts and lowest indices, bit-exact membership."""
+    from thea_b200 import Engine
+    mesh = gen.torus_mesh(64)
+    p, n, _ = gen.area_samples(mesh, 20000)
+    e = Engine(0)
+    e.build_points(p)
+    ora = orc.Oracle(points=p)
+    rng = np.random.default_rng(4)
+    c = (p[:6000] + rng.normal(scale=0.01, size=(6000, 3))).astype(np.float32)
+    rad = rng.uniform(0.0, 0.08, 6000).astype(np.float32)
+    rad[:4] = [0.0, -1.0, 10.0, 1e-6]
+    for max_out, excl in ((16, False), (64, True), (0, False)):
+        gi, gc = e.ball_range(c, rad, max_out, excl)
+        oi, oc = ora.ball_range(c, rad, max(max_out, 1), excl)
+        assert np.array_equal(gc, oc)
+        if max_out:
+            assert np.array_equal(gi, oi.astype(np.int32))
+    assert gc[1] == 0 and gc[2] == len(p)

@@ -749,6 +749,27 @@ int tgq_ball_graph(tgq_handle * h, int32_t max_degree, float init_radius, int32_
   return TGQ_OK;
 }
 
+int tgq_ball_range(tgq_handle * h, const float * c3, const float * radius, int64_t Q, int32_t max_out, int32_t exclude_self, int32_t * idx,
+                   int32_t * count)
+{
+  CKRC(need_built(h, 1 << TGQ_KIND_POINTS));
+  if (Q < 0 || (Q > 0 && (!c3 || !radius)) || max_out < 0) return fail(h, TGQ_EINVAL, "tgq_ball_range: bad arguments");
+  if (max_out > TGQ_MAX_K) return fail(h, TGQ_ELIMIT, "tgq_ball_range: max_out exceeds TGQ_MAX_K");
+  Guard g(h);
+  int k = max_out;
+  Arg args[4] = {{c3, nullptr, 12}, {radius, nullptr, 4}, {nullptr, k > 0 ? idx : nullptr, 4 * (size_t)k}, {nullptr, count, 4}};
+  BvhView v = view_of(h);
+  size_t smem = trav_smem_bytes(RangeW::STAGE) + 2 * (size_t)k * TGQ_BLOCK * 4;
+  return run_batched(h, Q, args, 4, true, [&](ChunkCtx & c) -> int {
+    int grid = 0; int * cnt = c.slot->counter.as<int>();
+    CKRC(persistent_grid(h, k_ball_range, smem, c.n, cnt, c.stream, &grid));
+    k_ball_range<<<grid, TGQ_BLOCK, smem, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], c.perm, c.n, k, exclude_self, c.offset, cnt,
+                                                      (int *)c.dout[2], (int *)c.dout[3]);
+    h->st.last_launches += 1; h->st.total_launches += 1;
+    return TGQ_OK;
+  });
+}
+
 int tgq_avg_separation(tgq_handle * h, const int32_t * seeds, int32_t n, float * out)
 {
   CKRC(need_built(h, 1 << TGQ_KIND_POINTS));

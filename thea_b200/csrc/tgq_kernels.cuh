@@ -560,6 +560,50 @@ k_ball_graph(BvhView b, int n, int k, float init_radius, int rounds, float min_d
   warp_run(w, n, counter, stage);
 }
 
+// ---- ball range queries on a point structure (rangeQueryIndices with a Ball3) ---------------------------------------------
+struct RangeW
+{
+  static constexpr int STAGE = 1;       // (centre, query index)
+  RangeState s; BvhView b; float const * c3; float const * rad; uint32_t const * perm; int k; int exclude_self; int64_t self_offset;
+  int * idx; int * count; int64_t qi;
+  __device__ __forceinline__ int state() const { return s.t.cur; }
+  __device__ __forceinline__ void stage(int t, f4 * dst) const
+  {
+    int i = perm ? (int)perm[t] : t; v3 p = ld3(c3, i);
+    *dst = make_float4(p.x, p.y, p.z, __int_as_float(i));
+  }
+  __device__ __forceinline__ void begin(int, f4 const * src)
+  {
+    f4 r = *src; qi = __float_as_int(r.w);
+    range_begin(s, b, mk3(r.x, r.y, r.z), rad[qi], exclude_self ? (int)(self_offset + qi) : -1);
+  }
+  static constexpr int FETCH = TGQ_FETCH_BOX;
+  __device__ __forceinline__ void pop_step() { trav_pop_step(s.t, s.r2); }
+  __device__ __forceinline__ void fetch(f4 * r) const { range_fetch(s, b, r); }
+  __device__ __forceinline__ void node_compute(f4 const * r) { range_node_compute(s, b, r); }
+  __device__ __forceinline__ void leaf_compute(f4 const * r) { range_leaf_compute(s, b, r); }
+  __device__ __forceinline__ void finish()
+  {
+    for (int j = 0; j < k; ++j) if (idx) idx[qi * k + j] = j < s.set.n ? s.set.idx[j * s.set.stride] : -1;
+    if (count) count[qi] = s.count;
+    s.t.cur = TGQ_ST_IDLE;
+  }
+};
+
+__global__ void __launch_bounds__(TGQ_BLOCK)
+k_ball_range(BvhView b, float const * __restrict__ c3, float const * __restrict__ rad, uint32_t const * __restrict__ perm, int n, int k,
+             int exclude_self, int64_t self_offset, int * counter, int * idx, int * count)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  RangeW w;
+  w.b = b; w.c3 = c3; w.rad = rad; w.perm = perm; w.k = k; w.exclude_self = exclude_self; w.self_offset = self_offset; w.idx = idx; w.count = count;
+  w.qi = 0; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
+  unsigned char * extra; f4 * stage = trav_setup(w.s.t, st, smem, RangeW::STAGE, &extra);
+  float * sets = (float *)extra;
+  w.s.set.init(sets + threadIdx.x, (int *)(sets + (size_t)k * blockDim.x) + threadIdx.x, blockDim.x, k);
+  warp_run(w, n, counter, stage);
+}
+
 // ---- K8 ray first hit / any hit ------------------------------------------------------------------------------------------
 template <bool ANY>
 struct RayW

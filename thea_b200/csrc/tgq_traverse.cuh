@@ -603,6 +603,59 @@ TGQ_HD void ball_graph_query(BvhView const & b, v3 c, v3 nc, bool has_n, float m
   set.n = s.set.n;
 }
 
+// Ball range query on a point structure: BvhN::rangeQueryIndices / processRange<IntersectionTester>(Ball3(c, r)) (BvhN.hpp:1208-
+// 1220,2118-2171; BallN.hpp:77-100): every element with sq(x_e - c) <= r * r (the reference's fp32 test).  Counts all of them and
+// keeps the `cap` lowest element indices, ascending (SortedSet with a constant key orders by index alone).
+struct RangeState
+{
+  v3 c; float r2; int self; int count;
+  SortedSet set;
+  Trav t;
+};
+TGQ_HD void range_begin(RangeState & s, BvhView const & b, v3 c, float radius, int self)
+{
+  s.c = c; s.r2 = radius * radius; s.self = self; s.count = 0; s.set.n = 0;
+  trav_begin(s.t, (radius >= 0.0f) ? b.n_nodes : 0);
+}
+TGQ_HD void range_fetch(RangeState const & s, BvhView const & b, f4 * r) { box_fetch(s.t, b, r); }
+TGQ_HD void range_node_compute(RangeState & s, BvhView const & b, f4 const * r)
+{
+  TGQ_COUNT_NODE();
+  float lb0, lb1; int c0, c1; box_node_bounds(r, s.c, lb0, lb1, c0, c1);
+  trav_descend(s.t, lb0, lb1, 0.0f, 0.0f, c0, c1, s.r2);
+}
+TGQ_HD void range_leaf_compute(RangeState & s, BvhView const & b, f4 const * r)
+{
+  int cnt = s.t.kend - s.t.k; if (cnt > TGQ_FETCH_BOX) cnt = TGQ_FETCH_BOX;
+  for (int j = 0; j < TGQ_FETCH_BOX; ++j)
+  {
+    if (j >= cnt) break;
+    TGQ_COUNT_PRIM();
+    f4 e = r[j];
+    int idx = f2i(e.w);
+    if (idx == s.self) continue;
+    float d2 = sqn3(sub3(mk3(e.x, e.y, e.z), s.c));
+    if (!(d2 <= s.r2)) continue;
+    ++s.count;
+    if (s.set.accepts(0.0f, idx)) s.set.insert(0.0f, idx);
+  }
+  s.t.k += cnt;
+  if (s.t.k >= s.t.kend) trav_pop(s.t);
+}
+TGQ_HD void range_query(BvhView const & b, v3 c, float radius, int self, SortedSet & set, int & count)
+{
+  RangeState s; TravStack st; trav_bind(s.t, st); s.set = set;
+  range_begin(s, b, c, radius, self);
+  f4 r[TGQ_FETCH_BOX];
+  while (s.t.cur != TGQ_ST_DONE)
+  {
+    if (s.t.cur == TGQ_ST_POP) { trav_pop_step(s.t, s.r2); continue; }
+    range_fetch(s, b, r);
+    if (s.t.cur >= 0) range_node_compute(s, b, r); else range_leaf_compute(s, b, r);
+  }
+  set.n = s.set.n; count = s.count;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Ray first hit.  best_t starts as max_time (negative = unbounded), best_idx as -1; best_k is the Morton position of
 // the hit triangle (for its cached normal).  A hit is accepted iff t >= 0 and (unbounded or t < best_t) or it ties the

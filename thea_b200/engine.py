@@ -23,7 +23,7 @@ SYMBOLS = [
     "tgq_build_triangles", "tgq_build_triangles_indexed", "tgq_build_points", "tgq_refit_triangles",
     "tgq_info", "tgq_triangle_cache", "tgq_closest", "tgq_knn", "tgq_ball_graph", "tgq_avg_separation",
     "tgq_ray_first", "tgq_ray_any", "tgq_sdf", "tgq_icp_sums", "tgq_transform_points", "tgq_area_sample",
-    "tgq_get_stats", "tgq_set_point_labels", "tgq_closest_filtered", "tgq_knn_filtered", "tgq_icp_align",
+    "tgq_get_stats", "tgq_set_point_labels", "tgq_closest_filtered", "tgq_knn_filtered", "tgq_icp_align", "tgq_ball_range",
 ]
 
 
@@ -84,6 +84,7 @@ def load_library(path=None):
     L.tgq_area_sample.argtypes = [vp, i64, C.c_uint64, vp, vp, vp]
     L.tgq_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.tgq_set_point_labels.argtypes = [vp, vp]
+    L.tgq_ball_range.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
     L.tgq_icp_align.argtypes = [vp, vp, i64, i32, i32, f64, i32, vp, vp, vp, vp]
     L.tgq_closest_filtered.argtypes = [vp, vp, vp, vp, i64, f32, f64, vp, vp, vp]
     L.tgq_knn_filtered.argtypes = [vp, vp, vp, vp, i64, i32, f32, f64, vp, vp]
@@ -257,6 +258,16 @@ class Engine:
         d2 = np.empty((Q, k), np.float32)
         self._ck(self._L.tgq_knn_filtered(self._h, _ptr(q3), _ptr(qn3), _ptr(qlabel), Q, int(k), float(min_dot), float(dist_bound), _ptr(idx), _ptr(d2)))
         return idx, d2
+
+    def ball_range(self, c3, radius, max_out=32, exclude_self=False):
+        """rangeQueryIndices with a ball per query: (idx [Q x max_out] lowest indices ascending, count [Q])."""
+        c3 = _as_in(c3)
+        Q = int(c3.shape[0])
+        rad = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float32), (Q,)), np.float32)
+        idx = np.empty((Q, max_out), np.int32) if max_out > 0 else None
+        cnt = np.empty(Q, np.int32)
+        self._ck(self._L.tgq_ball_range(self._h, _ptr(c3), _ptr(rad), Q, int(max_out), int(exclude_self), _ptr(idx), _ptr(cnt)))
+        return idx, cnt
 
     def ball_graph(self, max_degree, init_radius, rounds=3, min_dot=-0.5, min_degree=None, out=None):
         _, n, _, _ = self.info()
