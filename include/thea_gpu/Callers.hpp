@@ -4,6 +4,7 @@
 //   shapeDiameter             <- the per-sample loop over ShapeDiameter::compute                (Tools/MeshLocalFeatures/MeshLocalFeatures.cpp:747-764,
 //                                                                                                Algorithms/SurfaceFeatures/Local/ShapeDiameter.hpp:168-258)
 //   sampleGraph               <- PointSet3::updateGraph without oversampling / reachability     (Algorithms/PointSet3.hpp:324-391)
+//   saveGraph / loadGraph     <- PointSet3::save / load, graph file                             (Algorithms/PointSet3.cpp:222-354)
 //
 // Each loop body of the reference issues one structure query per iteration; here one C-ABI call answers the whole loop
 // and the O(1) epilogue (3x3 polar decomposition, transform composition, convergence test) stays on the host (inside the
@@ -16,6 +17,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <fstream>
+#include <sstream>
+#include <string>
 #include <limits>
 #include <vector>
 
@@ -105,6 +109,75 @@ inline float sampleGraph(GpuPointBvhT<VectorT> const & bvh, int32_t max_degree, 
   float sep_scale = std::sqrt((float)max_degree);
   bvh.sampleGraphBatch(max_degree, sep_scale * avg, idx, sep, count);
   return avg;
+}
+
+/** PointSet3::save, graph part (PointSet3.cpp:331-354): first line max_degree, then one line per sample,
+ *  `degree nbr_0 .. nbr_{d-1} [sep_0 .. sep_{d-1}]`, floats with the default ostream precision as the reference writes them.
+ *  idx / sep are P x max_degree as sampleGraph returns them (unused slots -1). */
+inline bool saveGraph(std::string const & graph_path, intx P, int32_t max_degree, int32_t const * idx, float const * sep = nullptr,
+                      bool write_distances = false)
+{
+  std::ofstream gout(graph_path.c_str(), std::ios::binary);
+  if (!gout) return false;
+  gout << max_degree << '\n';
+  for (intx i = 0; i < P; ++i)
+  {
+    int32_t d = 0; while (d < max_degree && idx[i * max_degree + d] >= 0) ++d;
+    gout << d;
+    for (int32_t j = 0; j < d; ++j) gout << ' ' << idx[i * max_degree + j];
+    if (write_distances && sep) for (int32_t j = 0; j < d; ++j) gout << ' ' << sep[i * max_degree + j];
+    gout << '\n';
+  }
+  return (bool)gout;
+}
+
+/** PointSet3::load, graph part (PointSet3.cpp:222-321) for P samples: fills max_degree, idx and sep (P x max_degree, -1 padded),
+ *  neighbours ordered by (separation, index) as BoundedSortedArray::insert leaves them.  Without stored separations they are the
+ *  Euclidean distances of positions3 (PointSet3.cpp:304-311; positions3 may be null: separations stay -1).  Returns false with
+ *  a message in *error on malformed input.  The reference re-inserts all max_degree slots of its scratch array, including
+ *  stale ones from earlier lines when a sample has fewer neighbours (PointSet3.cpp:296-315); that is not reproduced. */
+inline bool loadGraph(std::string const & graph_path, intx P, float const * positions3, int32_t & max_degree, std::vector<int32_t> & idx,
+                      std::vector<float> & sep, std::string * error = nullptr)
+{
+  auto fail = [&](std::string const & m) { if (error) *error = "PointSet3: " + m + " '" + graph_path + "'"; return false; };
+  std::ifstream gin(graph_path.c_str());
+  if (!gin) return fail("Could not open graph file for reading");
+  std::string line; long long md = -1;
+  if (!std::getline(gin, line)) return fail("Could not read maximum degree from");
+  { std::istringstream in(line); if (!(in >> md) || md < 0) return fail("Could not read valid maximum degree from"); }
+  max_degree = (int32_t)md;
+  idx.assign((size_t)P * (size_t)md, -1); sep.assign((size_t)P * (size_t)md, -1.0f);
+  std::vector<std::pair<float, long long>> nb;
+  for (intx i = 0; i < P; ++i)
+  {
+    if (!std::getline(gin, line)) return fail("Could not read neighbors of vertex " + std::to_string(i) + " from");
+    std::istringstream in(line); long long d = -1;
+    if (!(in >> d) || d < 0) return fail("Could not read valid degree of vertex " + std::to_string(i) + " from");
+    nb.assign((size_t)d, std::make_pair(-1.0f, -1LL));
+    for (long long j = 0; j < d; ++j)
+      if (!(in >> nb[(size_t)j].second) || nb[(size_t)j].second < 0 || nb[(size_t)j].second >= P)
+        return fail("Could not read valid neighbor " + std::to_string(j) + " of vertex " + std::to_string(i) + " from");
+    float s;
+    if (d > 0 && (in >> s))
+    {
+      nb[0].first = s;
+      for (long long j = 1; j < d; ++j)
+      {
+        if (!(in >> s)) return fail("Could not read separation of neighbor " + std::to_string(j) + " of vertex " + std::to_string(i) + " from");
+        nb[(size_t)j].first = s;
+      }
+    }
+    else if (positions3)
+      for (long long j = 0; j < d; ++j)
+      {
+        float const * a = positions3 + 3 * i; float const * b = positions3 + 3 * nb[(size_t)j].second;
+        float dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+        nb[(size_t)j].first = std::sqrt(dx * dx + (dy * dy + dz * dz));
+      }
+    std::sort(nb.begin(), nb.end());
+    for (long long j = 0; j < d && j < md; ++j) { idx[(size_t)(i * md + j)] = (int32_t)nb[(size_t)j].second; sep[(size_t)(i * md + j)] = nb[(size_t)j].first; }
+  }
+  return true;
 }
 
 }  // namespace TheaGpu

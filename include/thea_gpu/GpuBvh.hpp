@@ -380,6 +380,12 @@ class GpuMeshBvhT : public GpuBvhBase<VectorT>
                             float * ray_t = nullptr, int32_t * ray_idx = nullptr) const
     { detail::check(h, tgq_sdf(h, p3, n3, S, scale, only_hit_interior_surfaces ? 1 : 0, sdf, ray_t, ray_idx), "tgq_sdf"); }
 
+    /** The loop of Visibility::compute over S points (SurfaceFeatures/Local/Visibility.hpp:104-125) with caller-supplied ray
+     *  directions (num_dirs x 3 shared, or S x num_dirs x 3 when per_sample_dirs). */
+    void visibilityBatch(float const * p3, intx S, float const * dirs3, int32_t num_dirs, bool per_sample_dirs, float scale, double * visibility,
+                         int32_t * num_escaped = nullptr) const
+    { detail::check(h, tgq_visibility(h, p3, S, dirs3, num_dirs, per_sample_dirs ? 1 : 0, scale, visibility, num_escaped), "tgq_visibility"); }
+
     /** MeshSampler::sampleEvenlyByArea, EXACT mode (MeshSampler.hpp:147-185), with the engine's counter-based generator. */
     void sampleEvenlyByArea(intx S, uint64_t seed, float * p3, float * n3 = nullptr, int32_t * tri = nullptr) const
     { detail::check(h, tgq_area_sample(h, S, seed, p3, n3, tri), "tgq_area_sample"); }
@@ -507,6 +513,11 @@ class GpuPointBvhT : public GpuBvhBase<VectorT>
       if (count > TGQ_MAX_K) throw Error("TheaGpu: rangeQueryIndices found more than TGQ_MAX_K elements; use rangeQueryIndicesBatch for counts");
       for (int32_t j = 0; j < count; ++j) result.push_back(idx[j]);
     }
+
+    /** Q processRange<IntersectionTester>(Ball3(c_i, r_i), functor) calls with the accumulating functors of AverageDistance /
+     *  Curvature / LocalPca in one pass: out16 is Q x 16 doubles (layout: tgq_ball_stats in thea_gpu_query.h).  qn3 may be null. */
+    void ballStatsBatch(float const * c3, float const * qn3, float const * radius, intx Q, double * out16) const
+    { detail::check(h, tgq_ball_stats(h, c3, qn3, radius, Q, out16), "tgq_ball_stats"); }
 
     /** PointSet3::updateGraph's neighbour search for every sample (PointSet3.hpp:324-391,586-681). */
     void sampleGraphBatch(int32_t max_degree, float init_radius, int32_t * idx, float * sep, int32_t * count = nullptr, int32_t rounds = 3,

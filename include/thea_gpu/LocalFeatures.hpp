@@ -1,0 +1,217 @@
+// LocalFeatures.hpp -- the local surface features of Thea that are ball range queries with an accumulating functor, or
+// any-hit ray fans, on top of GpuBvh.hpp.  Class and member names follow the reference:
+//
+//   SurfaceFeatures::Local::AverageDistance::compute(position, EUCLIDEAN, max_distance)   (Algorithms/SurfaceFeatures/Local/AverageDistance.cpp:63-81,133-143)
+//   SurfaceFeatures::Local::Curvature::computeProjectedCurvature(position[, normal], r)    (…/Local/Curvature.cpp:69-98)
+//   SurfaceFeatures::Local::LocalPca::compute(position, eigenvectors, r)                   (…/Local/LocalPca.cpp:32-62, Algorithms/PcaN.hpp:150-197)
+//   SurfaceFeatures::Local::Visibility::compute(position, num_rays)                        (…/Local/Visibility.hpp:104-125)
+//
+// The reference classes take a PointSet3 (samples + BvhN + scale); here they take the GpuPointBvh built over the same samples
+// plus the shape scale PointSet3::getScale() would return (the diameter of its bounding sphere, PointSet3.hpp:560-572), which the
+// caller supplies.  Scalar calls are batches of one; *Batch members answer a whole loop in one C-ABI call.  Not covered:
+// GEODESIC average distance (Dijkstra on the sample graph), LocalDistanceHistogram, SpinImage, RandomWalks.
+// File:line citations are relative to /root/reference/Code/Source/.
+#ifndef THEA_GPU_LOCALFEATURES_HPP
+#define THEA_GPU_LOCALFEATURES_HPP
+
+#include "GpuBvh.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace TheaGpu {
+namespace SurfaceFeatures {
+namespace Local {
+
+namespace detail_lf {
+
+/** Eigen decomposition of a symmetric 3x3 matrix (cyclic Jacobi, double): eigenvalues descending, unit eigenvectors as rows.
+ *  Stands in for Eigen::SelfAdjointEigenSolver (PcaN.hpp:187-195, third party). */
+inline void symmetricEigen3(double const A[9], double evals[3], double evecs[9])
+{
+  double a[3][3], v[3][3];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { a[i][j] = A[3 * i + j]; v[i][j] = i == j ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 64; ++sweep)
+  {
+    double off = std::fabs(a[0][1]) + std::fabs(a[0][2]) + std::fabs(a[1][2]);
+    double diag = std::fabs(a[0][0]) + std::fabs(a[1][1]) + std::fabs(a[2][2]);
+    if (off <= 1e-300 || off <= 1e-17 * diag) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q)
+      {
+        if (a[p][q] == 0.0) continue;
+        double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; ++k) { double x = a[k][p], y = a[k][q]; a[k][p] = c * x - s * y; a[k][q] = s * x + c * y; }
+        for (int k = 0; k < 3; ++k) { double x = a[p][k], y = a[q][k]; a[p][k] = c * x - s * y; a[q][k] = s * x + c * y; }
+        for (int k = 0; k < 3; ++k) { double x = v[k][p], y = v[k][q]; v[k][p] = c * x - s * y; v[k][q] = s * x + c * y; }
+      }
+  }
+  int order[3] = {0, 1, 2};
+  std::sort(order, order + 3, [&](int i, int j) { return a[i][i] > a[j][j]; });
+  for (int r = 0; r < 3; ++r)
+  {
+    int k = order[r]; evals[r] = a[k][k];
+    double n = std::sqrt(v[0][k] * v[0][k] + v[1][k] * v[1][k] + v[2][k] * v[2][k]);
+    for (int i = 0; i < 3; ++i) evecs[3 * r + i] = n > 0 ? v[i][k] / n : 0.0;
+  }
+}
+
+}  // namespace detail_lf
+
+/** AverageDistance (EUCLIDEAN): mean distance from the query to the samples within max_distance, over max_distance. */
+template <typename VectorT = Vec3>
+class AverageDistanceT
+{
+  public:
+    AverageDistanceT(GpuPointBvhT<VectorT> const * surf_, Real scale_) : surf(surf_), scale(scale_)
+    { if (!surf) throw Error("AverageDistance: Cannot construct with a null surface"); }
+
+    /** max_distance < 0 selects the shape scale, as the reference does (AverageDistance.cpp:66-68; there it also switches to a
+     *  loop over all samples, which is the same set whenever the scale covers the shape). */
+    double compute(VectorT const & position, Real max_distance = -1) const
+    {
+      float c[3]; detail::put3(c, position); double out = 0;
+      computeBatch(c, 1, max_distance, &out);
+      return out;
+    }
+    void computeBatch(float const * p3, intx Q, Real max_distance, double * out) const
+    {
+      if (max_distance < 0) max_distance = scale;
+      std::vector<float> rad((size_t)Q, max_distance); std::vector<double> st(16 * (size_t)Q);
+      surf->ballStatsBatch(p3, nullptr, rad.data(), Q, st.data());
+      for (intx i = 0; i < Q; ++i)
+      {
+        double n = st[16 * (size_t)i], sum = st[16 * (size_t)i + 1];
+        out[i] = (n <= 0 ? 0.0 : sum / n) / max_distance;
+      }
+    }
+
+  private:
+    GpuPointBvhT<VectorT> const * surf; Real scale;
+};
+
+/** Curvature: projected curvature -(sum of unit offsets to the visible-side samples in the ball) . n / count. */
+template <typename VectorT = Vec3>
+class CurvatureT
+{
+  public:
+    /** n3: the sample normals the structure was built with (P x 3, host), for the overload that looks the normal up. */
+    CurvatureT(GpuPointBvhT<VectorT> const * surf_, Real scale_, float const * sample_normals3 = nullptr)
+    : surf(surf_), scale(scale_), normals(sample_normals3)
+    { if (!surf) throw Error("Curvature: Cannot construct with a null surface"); }
+
+    /** Curvature.cpp:69-81: normal of the nearest sample; 0 when the query cannot be mapped to the surface. */
+    double computeProjectedCurvature(VectorT const & position, Real nbd_radius = -1) const
+    {
+      if (!normals) throw Error("Curvature: sample normals were not supplied");
+      intx nn = surf->template closestElement<MetricL2>(position);
+      if (nn < 0) return 0.0;
+      return computeProjectedCurvature(position, detail::get3<VectorT>(normals + 3 * nn), nbd_radius);
+    }
+    double computeProjectedCurvature(VectorT const & position, VectorT const & normal, Real nbd_radius = -1) const
+    {
+      float c[3], n[3]; detail::put3(c, position); detail::put3(n, normal); double out = 0;
+      computeProjectedCurvatureBatch(c, n, 1, nbd_radius, &out);
+      return out;
+    }
+    void computeProjectedCurvatureBatch(float const * p3, float const * n3, intx Q, Real nbd_radius, double * out) const
+    {
+      if (nbd_radius < 0) nbd_radius = 0.1f;             // Curvature.cpp:88-91
+      nbd_radius *= scale;
+      std::vector<float> rad((size_t)Q, nbd_radius); std::vector<double> st(16 * (size_t)Q);
+      surf->ballStatsBatch(p3, n3, rad.data(), Q, st.data());
+      for (intx i = 0; i < Q; ++i)
+      {
+        double const * s = &st[16 * (size_t)i];
+        double proj = s[3] * n3[3 * i] + s[4] * n3[3 * i + 1] + s[5] * n3[3 * i + 2];
+        out[i] = s[2] > 0 ? -proj / s[2] : 0.0;
+      }
+    }
+
+  private:
+    GpuPointBvhT<VectorT> const * surf; Real scale; float const * normals;
+};
+
+/** LocalPca: eigenvalues (descending) and eigenvectors of the covariance of the samples in the ball. */
+template <typename VectorT = Vec3>
+class LocalPcaT
+{
+  public:
+    LocalPcaT(GpuPointBvhT<VectorT> const * surf_, Real scale_) : surf(surf_), scale(scale_)
+    { if (!surf) throw Error("LocalPca: Cannot construct with a null surface"); }
+
+    VectorT compute(VectorT const & position, VectorT * eigenvectors = nullptr, Real nbd_radius = -1) const
+    {
+      float c[3]; detail::put3(c, position); float ev[3], evec[9];
+      computeBatch(c, 1, nbd_radius, ev, eigenvectors ? evec : nullptr);
+      if (eigenvectors) for (int k = 0; k < 3; ++k) eigenvectors[k] = detail::get3<VectorT>(evec + 3 * k);
+      return detail::get3<VectorT>(ev);
+    }
+    /** evals: Q x 3; evecs (may be null): Q x 3 x 3, row k = eigenvector of eigenvalue k.  n < 2 samples give zeros (PcaN.hpp:177-182). */
+    void computeBatch(float const * p3, intx Q, Real nbd_radius, float * evals, float * evecs = nullptr) const
+    {
+      if (nbd_radius < 0) nbd_radius = 0.1f;             // LocalPca.cpp:52-55
+      nbd_radius *= scale;
+      std::vector<float> rad((size_t)Q, nbd_radius); std::vector<double> st(16 * (size_t)Q);
+      surf->ballStatsBatch(p3, nullptr, rad.data(), Q, st.data());
+      for (intx i = 0; i < Q; ++i)
+      {
+        double const * s = &st[16 * (size_t)i];
+        double n = s[0], w[3] = {0, 0, 0}, v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (n >= 2)
+        {
+          double m[3] = {s[6] / n, s[7] / n, s[8] / n};
+          double S2[9] = {s[9], s[10], s[11], s[10], s[12], s[13], s[11], s[13], s[14]}, cov[9];
+          for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) cov[3 * r + c] = (S2[3 * r + c] - n * m[r] * m[c]) / (n - 1);
+          detail_lf::symmetricEigen3(cov, w, v);
+        }
+        for (int k = 0; k < 3; ++k) evals[3 * i + k] = (float)w[k];
+        if (evecs) for (int k = 0; k < 9; ++k) evecs[9 * i + k] = (float)v[k];
+      }
+    }
+
+  private:
+    GpuPointBvhT<VectorT> const * surf; Real scale;
+};
+
+/** Visibility: fraction of rays from the query point that do not hit the shape again.  The reference draws num_rays random
+ *  directions from Random::common() per call; here the caller fixes the directions at construction. */
+template <typename VectorT = Vec3>
+class VisibilityT
+{
+  public:
+    VisibilityT(GpuMeshBvhT<VectorT> const * bvh_, float const * dirs3, int32_t num_dirs) : bvh(bvh_), dirs(dirs3, dirs3 + 3 * (size_t)num_dirs)
+    {
+      if (!bvh) throw Error("Visibility: Precomputed BVH cannot be null");
+      VectorT lo, hi; bvh->getBounds(lo, hi);
+      float e0 = hi[0] - lo[0], e1 = hi[1] - lo[1], e2 = hi[2] - lo[2];
+      scale = std::sqrt(e0 * e0 + (e1 * e1 + e2 * e2));   // getBounds().getExtent().norm(), Visibility.hpp:73,88
+    }
+    Real getScale() const { return scale; }
+
+    double compute(VectorT const & position) const
+    {
+      float p[3]; detail::put3(p, position); double out = 0;
+      computeBatch(p, 1, &out);
+      return out;
+    }
+    void computeBatch(float const * p3, intx S, double * visibility) const
+    { bvh->visibilityBatch(p3, S, dirs.data(), (int32_t)(dirs.size() / 3), false, scale, visibility); }
+
+  private:
+    GpuMeshBvhT<VectorT> const * bvh; std::vector<float> dirs; Real scale;
+};
+
+typedef AverageDistanceT<Vec3> AverageDistance;
+typedef CurvatureT<Vec3> Curvature;
+typedef LocalPcaT<Vec3> LocalPca;
+typedef VisibilityT<Vec3> Visibility;
+
+}  // namespace Local
+}  // namespace SurfaceFeatures
+}  // namespace TheaGpu
+
+#endif

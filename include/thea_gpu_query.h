@@ -137,6 +137,21 @@ int tgq_knn_filtered(tgq_handle * h, const float * q3, const float * qn3, const 
 int tgq_ball_range(tgq_handle * h, const float * c3, const float * radius, int64_t Q, int32_t max_out, int32_t exclude_self,
                    int32_t * idx, int32_t * count);
 
+/* Q ball neighbourhood statistics on a point structure (the local surface features are processRange calls
+ * with an accumulating functor).  Replaces, for every query ball (c_i, r_i),
+ *   surf->getBvh().processRange<IntersectionTester>(Ball3(c_i, r_i), functor)                    (BvhN.hpp:1238-1264,2118-2171)
+ * with the functors of AverageDistance (EuclideanCallback, SurfaceFeatures/Local/AverageDistance.cpp:39-81), Curvature
+ * (ProjectedCurvatureFunctor, Curvature.cpp:37-98) and LocalPca (LocalPcaFunctor, LocalPca.hpp:58-75, LocalPca.cpp:32-62,
+ * PcaN.hpp:150-197), all in ONE pass over the elements e with sq(x_e - c_i) <= r_i * r_i.  out16[Q x 16] doubles:
+ *   [0] n  [1] sum |x_e - c_i| (fp32 norm per element)
+ *   [2] #{e : n_e . qn_i > -1e-5}  [3..5] sum stableNormalized(x_e - c_i) over those   (zero when qn3 is null)
+ *   [6..8] sum (x_e - c_i)  [9..14] sum (x_e - c_i)(x_e - c_i)^T as xx xy xz yy yz zz  [15] 0
+ * Per-element terms are the reference's fp32 expressions; sums are double.  The reference accumulates in its own traversal
+ * order (fp32 for the curvature offsets and the covariance), so it is itself tree dependent at fp32 rounding level; the caller
+ * epilogues (include/thea_gpu/LocalFeatures.hpp) turn the sums into the features.  A negative radius matches nothing.
+ * qn3 needs a structure built with normals (else TGQ_ESTATE). */
+int tgq_ball_stats(tgq_handle * h, const float * c3, const float * qn3, const float * radius, int64_t Q, double * out16);
+
 /* Proximity graph over the P points of a point structure.  Replaces the loop of PointSet3::updateGraph over
  * findSampleNeighbors (PointSet3.hpp:380-381,586-681): for every sample, a ball range query of radius init_radius
  * (doubled for up to `rounds` rounds while fewer than min_degree neighbours were found), candidates filtered by
@@ -167,6 +182,15 @@ int tgq_ray_any(tgq_handle * h, const float * o3, const float * d3, const float 
  * Outputs (may be null): sdf[S] (double), ray_t[S x 30], ray_idx[S x 30]. */
 int tgq_sdf(tgq_handle * h, const float * p3, const float * n3, int64_t S, float scale, int32_t only_hit_interior,
             double * sdf, float * ray_t, int32_t * ray_idx);
+
+/* External visibility of S points against a triangle structure.  Replaces the loop of
+ * Visibility::compute(position, num_rays) (Algorithms/SurfaceFeatures/Local/Visibility.hpp:104-125): for every direction u,
+ * the ray (p + 0.001f * scale * u, u) is tested with rayIntersects; visibility[i] = (double)num_escaped / num_dirs.
+ * The reference draws u from Random::common().sphere() per ray; here the caller supplies the directions: dirs3 is
+ * num_dirs x 3 shared by all samples (per_sample_dirs == 0) or S x num_dirs x 3.  scale = diagonal of the structure's bounds
+ * (Visibility.hpp:73,88).  Outputs may be null: visibility[S], num_escaped[S]. */
+int tgq_visibility(tgq_handle * h, const float * p3, int64_t S, const float * dirs3, int32_t num_dirs, int32_t per_sample_dirs, float scale,
+                   double * visibility, int32_t * num_escaped);
 
 /* ICP sums for n correspondences (from3[i] -> to3[i]) in fixed-order double precision (deterministic for any GPU
  * count): out[0..2] = mean p, out[3..5] = mean q, out[6..14] = sum (p - pm)(q - qm)^T row-major, and with tr12

@@ -271,6 +271,103 @@ void orc_ball_range(void * h, float const * c3, float const * radius, int64_t Q,
   });
 }
 
+// Local surface features that are processRange calls with an accumulating functor, restated with the
+// reference's arithmetic in the reference's traversal order (mode 0: kd-tree processRange) or in element order (mode 2).
+//   AverageDistance (EUCLIDEAN, explicit max_distance): AverageDistance.cpp:39-81 -- Real d = (x - c).norm(); double sum.
+//   Curvature::computeProjectedCurvature(p, n, r):     Curvature.cpp:37-98     -- fp32 sum of stableNormalized offsets over
+//       samples with n_e . n > -1e-5; -sum.dot(n) / num (fp32).
+//   LocalPca::compute(p, evecs, r):                     LocalPca.cpp:32-62, PcaN.hpp:150-197, CentroidN.hpp:80-97 -- fp32
+//       centroid (sum / (float)n), fp32 covariance of x - ctr, / (n - 1).  The eigen decomposition itself is Eigen's
+//       SelfAdjointEigenSolver (third party, not restated); tests compare covariances and solve both sides the same way.
+// radius[i] is the ABSOLUTE ball radius (the callers multiply nbd_radius by surf->getScale()).
+// out[Q x 16]: [0] n, [1] sum_distances / n (0 when n == 0), [2] num_offsets, [3] curvature, [4..6] centroid,
+//              [7..12] covariance xx xy xz yy yz zz (zeros when n < 2), [13..15] 0.
+void orc_ball_stats(void * h, float const * c3, float const * qn3, float const * radius, int64_t Q, int mode, int nthreads, double * out)
+{
+  KdTree const & T = ((Handle *)h)->tree;
+  int64_t P = T.size();
+  bool has_n = !T.nrm.empty() && qn3;
+  parallel_for(Q, nthreads, [&](int64_t b, int64_t e) {
+    std::vector<int64_t> nb;
+    for (int64_t i = b; i < e; ++i)
+    {
+      V3 c = ld3(c3, i); float r = radius[i]; float r2 = r * r;
+      double * o = out + 16 * i; for (int j = 0; j < 16; ++j) o[j] = 0;
+      nb.clear();
+      auto emit = [&](int64_t j) { nb.push_back(j); };
+      if (r >= 0)
+      {
+        if (mode == 2) { for (int64_t j = 0; j < P; ++j) if (sqnorm(T.pts[(size_t)j] - c) <= r2) emit(j); }
+        else if (!T.nodes.empty()) kd_ball_range(T, 0, c, r2, emit);
+      }
+      // AverageDistance
+      double sum_d = 0; int64_t n = 0;
+      for (int64_t j : nb) { float d = std::sqrt(sqnorm(T.pts[(size_t)j] - c)); sum_d += d; ++n; }
+      o[0] = (double)n; o[1] = n <= 0 ? 0.0 : sum_d / (double)n;
+      // Curvature
+      if (has_n)
+      {
+        V3 nq = ld3(qn3, i), so = mk(0, 0, 0); int64_t no = 0;
+        for (int64_t j : nb)
+          if (dot(T.nrm[(size_t)j], nq) > -1.0e-05f)
+          {
+            V3 a = T.pts[(size_t)j] - c;
+            float w = std::max(std::max(std::fabs(a.x), std::fabs(a.y)), std::fabs(a.z));
+            float z = sqnorm(a / w);
+            V3 off = z > 0 ? a / (std::sqrt(z) * w) : a;
+            so = so + off; ++no;
+          }
+        o[2] = (double)no;
+        o[3] = no > 0 ? (double)(-dot(so, nq) / (float)no) : 0.0;
+      }
+      // LocalPca
+      if (n > 0)
+      {
+        V3 sp = mk(0, 0, 0);
+        for (int64_t j : nb) sp = sp + T.pts[(size_t)j];
+        V3 ctr = sp / (float)(double)n;
+        o[4] = ctr.x; o[5] = ctr.y; o[6] = ctr.z;
+        if (n >= 2)
+        {
+          float cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+          for (int64_t j : nb)
+          {
+            V3 p = T.pts[(size_t)j] * 1.0f - ctr;
+            for (int rr = 0; rr < 3; ++rr) for (int cc = 0; cc < 3; ++cc) cov[3 * rr + cc] += p[rr] * p[cc];
+          }
+          float den = (float)(n - 1);
+          for (int k = 0; k < 9; ++k) cov[k] /= den;
+          o[7] = cov[0]; o[8] = cov[1]; o[9] = cov[2]; o[10] = cov[4]; o[11] = cov[5]; o[12] = cov[8];
+        }
+      }
+    }
+  });
+}
+
+// Visibility::compute (SurfaceFeatures/Local/Visibility.hpp:104-125) with caller-supplied directions: ray (p + 0.001f * scale * u, u),
+// rayIntersects (= full first hit >= 0, BvhN.hpp:1266-1269); vis = (double)num_escaped / num_rays.
+void orc_visibility(void * h, float const * p3, int64_t S, float const * dirs3, int D, int per_sample, float scale, int mode, int nthreads,
+                    double * vis, int32_t * nesc)
+{
+  KdTree const & T = ((Handle *)h)->tree;
+  parallel_for(S, nthreads, [&](int64_t b, int64_t e) {
+    for (int64_t i = b; i < e; ++i)
+    {
+      V3 p = ld3(p3, i); int64_t esc = 0;
+      for (int k = 0; k < D; ++k)
+      {
+        V3 u = ld3(dirs3, per_sample ? i * D + k : k);
+        V3 offset = u * (0.001f * scale);
+        V3 o = p + offset;
+        RayHit r = mode == 0 ? T.ray_first_ref(o, u, -1.0f) : mode == 1 ? T.ray_first_canon(o, u, -1.0f) : brute_ray_first(T, o, u, -1.0f);
+        if (r.idx < 0) ++esc;
+      }
+      if (vis) vis[i] = (double)esc / (double)D;
+      if (nesc) nesc[i] = (int32_t)esc;
+    }
+  });
+}
+
 void orc_ray_first(void * h, float const * o3, float const * d3, float const * tmax, int64_t R, int mode, int nthreads,
                    int64_t * idx, float * t)
 {

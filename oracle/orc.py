@@ -55,6 +55,8 @@ def lib():
         L.orc_knn_filtered.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_double, C.c_int, C.c_int,
                                        C.c_void_p, C.c_void_p]
         L.orc_ball_range.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_ball_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]
+        L.orc_visibility.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_avg_separation.restype = C.c_float
         L.orc_avg_separation.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_ball_graph.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -187,6 +189,29 @@ class Oracle:
         cnt = np.empty(Q, np.int32)
         lib().orc_ball_range(self.h, _p(c), _p(rad), Q, int(max_out), int(exclude_self), threads or ncores(), _p(idx), _p(cnt))
         return idx, cnt
+
+    def ball_stats(self, c, radius, qn=None, mode=MODE_REFERENCE, threads=None):
+        """Local-feature functors over ball neighbourhoods (see orc_ball_stats): dict of n, avg_dist, num_offsets, curvature,
+        centroid [Q,3], cov [Q,6] (xx xy xz yy yz zz)."""
+        c = _f32(c).reshape(-1, 3)
+        Q = c.shape[0]
+        rad = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float32), (Q,)), np.float32)
+        qn = None if qn is None else _f32(qn).reshape(-1, 3)
+        out = np.empty((Q, 16), np.float64)
+        lib().orc_ball_stats(self.h, _p(c), _p(qn), _p(rad), Q, mode, threads or ncores(), _p(out))
+        return {"n": out[:, 0].astype(np.int64), "avg_dist": out[:, 1], "num_offsets": out[:, 2].astype(np.int64), "curvature": out[:, 3],
+                "centroid": out[:, 4:7], "cov": out[:, 7:13]}
+
+    def visibility(self, p, dirs, scale, mode=MODE_CANON, threads=None):
+        p = _f32(p).reshape(-1, 3)
+        S = p.shape[0]
+        dirs = _f32(dirs)
+        per_sample = dirs.ndim == 3
+        D = dirs.shape[-2]
+        vis = np.empty(S, np.float64)
+        nesc = np.empty(S, np.int32)
+        lib().orc_visibility(self.h, _p(p), S, _p(dirs), int(D), int(per_sample), float(scale), mode, threads or ncores(), _p(vis), _p(nesc))
+        return vis, nesc
 
     def avg_separation(self, seeds):
         s = np.ascontiguousarray(seeds, np.int64)

@@ -2,6 +2,7 @@
 // would (member templates with MetricL2 / RayIntersectionTester tags, scalar and batch forms) and dumps the results for
 // tests/test_adaptor.py to compare with the oracle.  Usage: adaptor_driver <in.bin> <out.bin>
 #include "../../include/thea_gpu/Callers.hpp"
+#include "../../include/thea_gpu/LocalFeatures.hpp"
 
 #include <cstdio>
 #include <cstdlib>
@@ -129,6 +130,44 @@ int main(int argc, char ** argv)
       if (nn != fci[i]) { fprintf(stderr, "scalar filtered closestElement disagrees with the batch\n"); return 3; }
       for (size_t j = 0; j < set.size(); ++j)
         if (set[j].getTargetIndex() != fki[4 * i + (int64_t)j]) { fprintf(stderr, "scalar filtered kClosestPairs disagrees with the batch\n"); return 3; }
+    }
+
+    // ---- graph file round trip (PointSet3::save / load format) ----
+    {
+      std::string gp = std::string(argv[2]) + ".graph";
+      if (!saveGraph(gp, NS, 6, gi.data(), gs.data(), true)) { fprintf(stderr, "saveGraph failed\n"); return 3; }
+      int32_t md = 0; std::vector<int32_t> li; std::vector<float> ls; std::string emsg;
+      if (!loadGraph(gp, NS, sp.data(), md, li, ls, &emsg)) { fprintf(stderr, "loadGraph failed: %s\n", emsg.c_str()); return 3; }
+      if (md != 6 || li != gi) { fprintf(stderr, "graph file round trip changed the adjacency\n"); return 3; }
+      for (size_t j = 0; j < ls.size(); ++j)
+        if (gi[j] >= 0 && std::fabs(ls[j] - gs[j]) > 1e-5f * std::fabs(gs[j])) { fprintf(stderr, "graph file round trip changed a separation\n"); return 3; }
+      std::remove(gp.c_str());
+    }
+
+    // ---- local surface features (SurfaceFeatures::Local classes): batch, then the reference's scalar form for the first few ----
+    {
+      using namespace TheaGpu::SurfaceFeatures::Local;
+      AverageDistance avgd(&pts, diag); Curvature curv(&pts, diag, sn.data()); LocalPca pca(&pts, diag);
+      std::vector<double> fa(NS), fc(NS); std::vector<float> fe(3 * NS), fv(9 * NS);
+      avgd.computeBatch(sp.data(), NS, 0.1f * diag, fa.data());
+      curv.computeProjectedCurvatureBatch(sp.data(), sn.data(), NS, 0.05f, fc.data());
+      pca.computeBatch(sp.data(), NS, 0.05f, fe.data(), fv.data());
+      wr(fo, fa); wr(fo, fc); wr(fo, fe); wr(fo, fv);
+      for (int64_t i = 0; i < nk; ++i)
+      {
+        Vec3 p(sp[3 * i], sp[3 * i + 1], sp[3 * i + 2]), n(sn[3 * i], sn[3 * i + 1], sn[3 * i + 2]), ev[3];
+        if (avgd.compute(p, 0.1f * diag) != fa[i] || curv.computeProjectedCurvature(p, n, 0.05f) != fc[i])
+        { fprintf(stderr, "scalar local feature disagrees with the batch\n"); return 3; }
+        if (curv.computeProjectedCurvature(p, 0.05f) != fc[i]) { fprintf(stderr, "curvature with looked-up normal disagrees\n"); return 3; }
+        Vec3 e = pca.compute(p, ev, 0.05f);
+        for (int k = 0; k < 3; ++k) if (e[k] != fe[3 * i + k] || ev[k][0] != fv[9 * i + 3 * k]) { fprintf(stderr, "scalar LocalPca disagrees with the batch\n"); return 3; }
+      }
+      std::vector<float> dirs; for (int k = 0; k < 3 * 32 && k < (int)d3.size(); ++k) dirs.push_back(d3[k]);
+      Visibility visf(&bvh, dirs.data(), (int32_t)(dirs.size() / 3));
+      std::vector<double> vis(NS);
+      visf.computeBatch(sp.data(), NS, vis.data());
+      std::vector<float> vsc(1, visf.getScale()); wr(fo, vsc); wr(fo, vis);
+      if (NS > 0 && visf.compute(Vec3(sp[0], sp[1], sp[2])) != vis[0]) { fprintf(stderr, "scalar Visibility disagrees with the batch\n"); return 3; }
     }
 
     // ---- error behaviour: filters are refused loudly, wrong structure kind raises ----

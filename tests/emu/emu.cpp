@@ -272,6 +272,13 @@ void emu_ball_range(void * h, float const * c3, float const * radius, int64_t Q,
   }
 }
 
+void emu_ball_stats(void * h, float const * c3, float const * qn3, float const * radius, int64_t Q, double * out16)
+{
+  Emu & E = *(Emu *)h; BvhView v = E.view();
+  for (int64_t i = 0; i < Q; ++i)
+    stats_query(v, ld(c3, i), radius[i], qn3 ? ld(qn3, i) : mk3(0, 0, 0), qn3 != nullptr, out16 + 16 * i);
+}
+
 void emu_ball_graph(void * h, int k, float init_radius, int rounds, float min_dot, int min_degree, int32_t * idx, float * sep, int32_t * count)
 {
   Emu & E = *(Emu *)h; BvhView v = E.view();

@@ -25,6 +25,7 @@ def lib():
         L.emu_ball_graph.argtypes = [vp, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, vp, vp, vp]
         L.emu_set_labels.argtypes = [vp, vp]
         L.emu_ball_range.argtypes = [vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp, vp]
+        L.emu_ball_stats.argtypes = [vp, vp, vp, vp, C.c_int64, vp]
         L.emu_closest_filtered.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, vp, vp, vp]
         L.emu_knn_filtered.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, C.c_float, C.c_float, vp, vp]
         L.emu_ray.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, vp, vp]
@@ -82,6 +83,15 @@ class Emu:
         cnt = np.empty(Q, np.int32)
         lib().emu_ball_range(self.h, _p(c), _p(rad), Q, int(max_out), int(exclude_self), _p(idx), _p(cnt))
         return idx, cnt
+
+    def ball_stats(self, c, radius, qn=None):
+        c = np.ascontiguousarray(c, np.float32)
+        Q = len(c)
+        rad = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float32), (Q,)), np.float32)
+        qn = None if qn is None else np.ascontiguousarray(qn, np.float32)
+        out = np.empty((Q, 16), np.float64)
+        lib().emu_ball_stats(self.h, _p(c), _p(qn), _p(rad), Q, _p(out))
+        return out
 
     def set_labels(self, labels):
         self._lab = None if labels is None else np.ascontiguousarray(labels, np.int32)

@@ -134,4 +134,24 @@ def test_adaptor_driver_matches_oracle(built, tmp_path):
     oki, okd = po.knn_filtered(sp, 4, sn, labels, mode=orc.MODE_BRUTE)
     assert np.array_equal(take(np.int32, NS * 4).reshape(NS, 4), oki.astype(np.int32))
     assert np.array_equal(take(np.float32, NS * 4).reshape(NS, 4), okd)
+    # local surface features through the SurfaceFeatures::Local classes (tolerances: tests/test_local_features.py)
+    fa, fc = take(np.float64, NS), take(np.float64, NS)
+    fe, fv = take(np.float32, 3 * NS).reshape(NS, 3), take(np.float32, 9 * NS).reshape(NS, 3, 3)
+    dg = np.float32(diag)
+    ra, rc = np.float32(np.float32(0.1) * dg), np.float32(np.float32(0.05) * dg)
+    ref_a = po.ball_stats(sp, ra, sn)
+    assert np.allclose(fa, ref_a["avg_dist"] / np.float64(ra), rtol=1e-12)
+    ref_c = po.ball_stats(sp, rc, sn)
+    assert np.abs(fc - ref_c["curvature"]).max() <= 2e-5
+    c6 = ref_c["cov"]
+    cov = np.stack([c6[:, 0], c6[:, 1], c6[:, 2], c6[:, 1], c6[:, 3], c6[:, 4], c6[:, 2], c6[:, 4], c6[:, 5]], axis=1).reshape(NS, 3, 3)
+    w = np.linalg.eigvalsh(cov)[:, ::-1]
+    assert np.abs(fe - w).max() <= 2e-5 * float(rc) ** 2
+    rec = np.einsum("qk,qki,qkj->qij", fe.astype(np.float64), fv.astype(np.float64), fv.astype(np.float64))
+    assert np.abs(rec - cov).max() <= 4e-5 * float(rc) ** 2
+    vscale = float(take(np.float32, 1)[0])
+    assert vscale == diag
+    vis = take(np.float64, NS)
+    ovis, _ = ora.visibility(sp, d[:32], vscale, mode=orc.MODE_BRUTE)
+    assert np.array_equal(vis, ovis)
     assert pos[0] == len(buf)

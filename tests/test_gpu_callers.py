@@ -221,3 +221,73 @@ def test_ball_range_queries(built):
         if max_out:
             assert np.array_equal(gi, oi.astype(np.int32))
     assert gc[1] == 0 and gc[2] == len(p)
+
+
+def test_local_features_ball_stats(built):
+    """AverageDistance / Curvature / LocalPca as one ball-statistics pass, against the oracle's restatement of
+    the reference functors in the reference's traversal order (tolerances stated in tests/test_local_features.py)."""
+    import torch
+    from thea_b200 import Engine
+    from test_local_features import check_against_oracle
+    mesh = gen.torus_mesh(64)
+    p, n, _ = gen.area_samples(mesh, 30000)
+    e = Engine(0)
+    e.build_points(p, n)
+    ora = orc.Oracle(points=p, normals=n)
+    rng = np.random.default_rng(5)
+    Q = 5000
+    sel = rng.integers(0, len(p), Q)
+    c = (p[sel] + rng.normal(scale=0.005, size=(Q, 3))).astype(np.float32)
+    qn = n[sel].copy()
+    rad = rng.uniform(0.01, 0.15, Q).astype(np.float32)
+    rad[:4] = [0.0, -1.0, 10.0, 1e-6]
+    st = e.ball_stats(c, rad, qn)
+    assert st[1, 0] == 0 and st[2, 0] == len(p)
+    check_against_oracle(st, c, qn, rad, ora.ball_stats(c, rad, qn, mode=orc.MODE_REFERENCE))
+    _, cnt = e.ball_range(c, rad, 0)
+    assert np.array_equal(cnt, st[:, 0].astype(np.int32))
+    # device pointers give the same bits as host pointers (one lane per ball, fixed traversal order: deterministic)
+    dc, dn, dr = (torch.from_numpy(a).cuda() for a in (c, qn, rad))
+    dout = torch.empty((Q, 16), dtype=torch.float64, device="cuda")
+    e.ball_stats(dc, dr, dn, out=dout)
+    assert np.array_equal(dout.cpu().numpy(), st)
+    assert np.array_equal(e.ball_stats(c, rad, qn), st)
+    # epilogues
+    r = np.float32(0.1)
+    ad = callers.average_distance(e, c, r)
+    assert np.allclose(ad, ora.ball_stats(c, r)["avg_dist"] / np.float64(r), rtol=1e-12)
+    evals, evecs = callers.local_pca(e, c, r)
+    assert np.median(np.abs((evecs[:, 2, :] * qn).sum(axis=1))) > 0.95
+    cu = callers.projected_curvature(e, c, qn, r)
+    assert np.abs(cu - ora.ball_stats(c, r, qn)["curvature"]).max() <= 2e-5
+    # a structure without normals refuses query normals loudly
+    e2 = Engine(0)
+    e2.build_points(p)
+    with pytest.raises(Exception):
+        e2.ball_stats(c[:4], rad[:4], qn[:4])
+    assert (e2.ball_stats(c[:64], rad[:64])[:, 2:6] == 0).all()
+
+
+def test_visibility(setup):
+    """Visibility::compute with fixed directions: escaped-ray counts equal to the oracle's (hit / miss flags are bit-exact)."""
+    e, mesh, ora = setup
+    rng = np.random.default_rng(8)
+    D = 48
+    dirs = rng.normal(size=(D, 3))
+    dirs = (dirs / np.linalg.norm(dirs, axis=1, keepdims=True)).astype(np.float32)
+    p, n, _ = gen.area_samples(mesh, 3000)
+    pts = np.concatenate([(p + 0.02 * n).astype(np.float32), np.array([[1, 0, 0], [5, 5, 5]], np.float32)])
+    lo, hi = gen.mesh_bounds(mesh)
+    ext = (hi - lo).astype(np.float32)
+    scale = float(np.sqrt(np.float32(ext[0] * ext[0]) + (np.float32(ext[1] * ext[1]) + np.float32(ext[2] * ext[2]))))
+    vis, nesc = e.visibility(pts, dirs, scale)
+    ovis, onesc = ora.visibility(pts, dirs, scale, mode=orc.MODE_CANON)
+    assert np.array_equal(nesc, onesc) and np.array_equal(vis, ovis)
+    assert vis[-2] == 0.0 and vis[-1] > 0.5
+    assert np.array_equal(callers.visibility(e, pts, dirs), vis)
+    # per-sample directions
+    pd = rng.normal(size=(200, 7, 3))
+    pd = (pd / np.linalg.norm(pd, axis=2, keepdims=True)).astype(np.float32)
+    v2, n2 = e.visibility(pts[:200], pd, scale)
+    o2, on2 = ora.visibility(pts[:200], pd, scale, mode=orc.MODE_CANON)
+    assert np.array_equal(n2, on2) and np.array_equal(v2, o2)

@@ -3,6 +3,11 @@
     icp_align        <- Algorithms::Icp3<Real>::align               (Algorithms/Icp3.hpp:110-126,193-275)
     shape_diameter   <- loop over ShapeDiameter::compute (+ retry)   (Tools/MeshLocalFeatures/MeshLocalFeatures.cpp:747-764)
     sample_graph     <- PointSet3::updateGraph                       (Algorithms/PointSet3.hpp:324-391)
+    average_distance <- loop over AverageDistance::compute (EUCLIDEAN) (Algorithms/SurfaceFeatures/Local/AverageDistance.cpp:63-81)
+    projected_curvature <- loop over Curvature::computeProjectedCurvature (…/Local/Curvature.cpp:69-98)
+    local_pca        <- loop over LocalPca::compute                   (…/Local/LocalPca.cpp:49-62, Algorithms/PcaN.hpp:150-197)
+    visibility       <- loop over Visibility::compute                 (…/Local/Visibility.hpp:104-125)
+    save_graph / load_graph / save_samples / load_samples <- PointSet3::save / load (Algorithms/PointSet3.cpp:180-375)
 
 Every query batch and every reduction runs on the GPU through the C ABI; only the O(1) epilogues (3x3 polar
 decomposition, transform composition, convergence test) are host arithmetic.  Nothing here imports the oracle.
@@ -134,3 +139,162 @@ def sample_graph(eng, max_degree, seeds):
     radius = np.float32(np.sqrt(np.float32(max_degree))) * np.float32(avg)
     idx, sep, cnt = eng.ball_graph(max_degree, float(radius))
     return idx, sep, cnt, avg
+
+
+# ---- local surface features: processRange calls with an accumulating functor ------------------------
+
+def average_distance(eng, p3, max_distance, stats=None):
+    """AverageDistance::compute(p, EUCLIDEAN, max_distance) with max_distance >= 0 (absolute) for every p:
+    mean |x - p| over the samples in Ball3(p, max_distance), divided by max_distance (AverageDistance.cpp:63-81)."""
+    st = eng.ball_stats(p3, max_distance) if stats is None else stats
+    n = st[:, 0]
+    avg = np.where(n > 0, st[:, 1] / np.maximum(n, 1.0), 0.0)
+    return avg / np.float64(np.float32(max_distance))
+
+
+def projected_curvature(eng, p3, n3, nbd_radius, stats=None):
+    """Curvature::computeProjectedCurvature(p, n, r) for every (p, n); nbd_radius is the ABSOLUTE ball radius (the reference
+    multiplies its argument by surf->getScale(), Curvature.cpp:88-91).  -sum(offsets) . n / num_offsets, 0 when none."""
+    n3 = np.ascontiguousarray(n3, np.float32).reshape(-1, 3)
+    st = eng.ball_stats(p3, nbd_radius, qn3=n3) if stats is None else stats
+    k = st[:, 2]
+    proj = (st[:, 3:6] * n3.astype(np.float64)).sum(axis=1)
+    return np.where(k > 0, -proj / np.maximum(k, 1.0), 0.0)
+
+
+def pca_from_stats(st, centres):
+    """(eigenvalues [Q,3] descending, eigenvectors [Q,3,3] rows = unit vectors, centroid [Q,3], cov [Q,3,3]) from tgq_ball_stats
+    sums: covariance about the centroid, divided by n - 1 (PcaN.hpp:163-184); zeros when n < 2 (PcaN.hpp:177-182)."""
+    n = st[:, 0]
+    m = st[:, 6:9] / np.maximum(n, 1.0)[:, None]
+    S2 = np.empty((len(st), 3, 3))
+    S2[:, 0, 0], S2[:, 0, 1], S2[:, 0, 2] = st[:, 9], st[:, 10], st[:, 11]
+    S2[:, 1, 0], S2[:, 1, 1], S2[:, 1, 2] = st[:, 10], st[:, 12], st[:, 13]
+    S2[:, 2, 0], S2[:, 2, 1], S2[:, 2, 2] = st[:, 11], st[:, 13], st[:, 14]
+    cov = (S2 - n[:, None, None] * m[:, :, None] * m[:, None, :]) / np.maximum(n - 1.0, 1.0)[:, None, None]
+    ok = n >= 2
+    cov[~ok] = 0.0
+    w, v = np.linalg.eigh(cov)                      # ascending; SelfAdjointEigenSolver sorts the same way (PcaN.hpp:193)
+    evals = w[:, ::-1].copy()
+    evecs = np.transpose(v, (0, 2, 1))[:, ::-1, :].copy()
+    evals[~ok] = 0.0
+    evecs[~ok] = 0.0
+    centroid = np.asarray(centres, np.float64).reshape(-1, 3) + m
+    return evals, evecs, centroid, cov
+
+
+def local_pca(eng, p3, nbd_radius):
+    """LocalPca::compute(p, eigenvectors, r) for every p; nbd_radius absolute (LocalPca.cpp:52-55 multiplies by getScale())."""
+    st = eng.ball_stats(p3, nbd_radius)
+    evals, evecs, _, _ = pca_from_stats(st, p3)
+    return evals, evecs
+
+
+def visibility(eng, p3, dirs3, scale=None):
+    """Visibility::compute for every p with the given ray directions; scale defaults to the diagonal of the structure's bounds
+    (Visibility.hpp:73,88)."""
+    if scale is None:
+        _, _, lo, hi = eng.info()
+        ext = (np.asarray(hi, np.float32) - np.asarray(lo, np.float32)).astype(np.float32)
+        scale = float(np.sqrt(np.float32(ext[0] * ext[0]) + (np.float32(ext[1] * ext[1]) + np.float32(ext[2] * ext[2]))))
+    vis, _ = eng.visibility(p3, dirs3, scale)
+    return vis
+
+
+# ---- PointSet3 on-disk formats (SURVEY.md 8f rank 2, Appendix C): plain text, one line per sample ---------------------------
+
+def _fmt(x):
+    """operator<< of a float with the default ostream precision (6 significant digits, %g)."""
+    return "%g" % float(x)
+
+
+def save_graph(path, max_degree, idx, sep=None, count=None, write_distances=False):
+    """PointSet3::save, graph part (PointSet3.cpp:331-354): first line max_degree, then per sample
+    `degree nbr_0 ... nbr_{d-1} [sep_0 ... sep_{d-1}]`."""
+    idx = np.asarray(idx)
+    if count is None:
+        count = (idx >= 0).sum(axis=1)
+    with open(path, "wb") as f:
+        f.write(b"%d\n" % int(max_degree))
+        for i in range(idx.shape[0]):
+            d = int(count[i])
+            parts = [str(d)] + [str(int(j)) for j in idx[i, :d]]
+            if write_distances:
+                parts += [_fmt(x) for x in sep[i, :d]]
+            f.write((" ".join(parts) + "\n").encode())
+
+
+def load_graph(path, positions=None):
+    """PointSet3::load, graph part (PointSet3.cpp:222-321): returns (max_degree, idx [P x max_degree] int32 padded with -1,
+    sep [P x max_degree] float32 padded with -1, count [P]).  Without stored separations they are the Euclidean distances of
+    `positions` (PointSet3.cpp:304-311); neighbours are re-sorted by (separation, index) as BoundedSortedArray::insert does."""
+    with open(path, "r") as f:
+        lines = f.read().split("\n")
+    try:
+        max_degree = int(lines[0].split()[0])
+    except (IndexError, ValueError):
+        raise ValueError(f"PointSet3: Could not read valid maximum degree from '{path}'")
+    if max_degree < 0:
+        raise ValueError(f"PointSet3: Could not read valid maximum degree from '{path}'")
+    rows = [ln for ln in lines[1:] if ln.strip() != ""]
+    P = len(rows) if positions is None else len(positions)
+    if len(rows) < P:
+        raise ValueError(f"PointSet3: Could not read neighbors of vertex {len(rows)} from '{path}'")
+    idx = np.full((P, max_degree), -1, np.int32)
+    sep = np.full((P, max_degree), -1.0, np.float32)
+    count = np.zeros(P, np.int32)
+    pos = None if positions is None else np.asarray(positions, np.float32).reshape(-1, 3)
+    for i in range(P):
+        tok = rows[i].split()
+        d = int(tok[0])
+        if d < 0:
+            raise ValueError(f"PointSet3: Could not read valid degree of vertex {i} from '{path}'")
+        nb = np.array([int(t) for t in tok[1:1 + d]], np.int64)
+        if len(nb) != d or (nb < 0).any() or (nb >= P).any():
+            raise ValueError(f"PointSet3: Could not read valid neighbor of vertex {i} from '{path}'")
+        rest = tok[1 + d:]
+        if rest:
+            if len(rest) < d:
+                raise ValueError(f"PointSet3: Could not read separation of neighbor {len(rest)} of vertex {i} from '{path}'")
+            sp = np.array([float(t) for t in rest[:d]], np.float32)
+        elif pos is not None:
+            df = pos[nb] - pos[i]
+            sp = np.sqrt(df[:, 0] * df[:, 0] + (df[:, 1] * df[:, 1] + df[:, 2] * df[:, 2])).astype(np.float32)
+        else:
+            sp = np.full(d, -1.0, np.float32)
+        order = np.lexsort((nb, sp))[:max_degree]
+        k = len(order)
+        idx[i, :k], sep[i, :k], count[i] = nb[order], sp[order], k
+    return max_degree, idx, sep, count
+
+
+def save_samples(path, p3, n3=None):
+    """PointSet3::save, samples part (PointSet3.cpp:356-372): `x y z [nx ny nz]` per line."""
+    p3 = np.asarray(p3, np.float32).reshape(-1, 3)
+    with open(path, "wb") as f:
+        for i in range(len(p3)):
+            vals = list(p3[i]) + ([] if n3 is None else list(np.asarray(n3, np.float32).reshape(-1, 3)[i]))
+            f.write((" ".join(_fmt(v) for v in vals) + "\n").encode())
+
+
+def load_samples(path):
+    """PointSet3::load, samples part (PointSet3.cpp:186-216): (positions, normals or None); mixed lines are an error."""
+    P, N = [], []
+    has_n = None
+    with open(path, "r") as f:
+        for ln in f.read().split("\n"):
+            tok = ln.split()
+            if not tok:
+                continue
+            if len(tok) < 3:
+                raise ValueError(f"Could not read sample {len(P)} from '{path}'")
+            P.append([float(t) for t in tok[:3]])
+            hn = len(tok) >= 6
+            if has_n is None:
+                has_n = hn
+            elif has_n != hn:
+                raise ValueError(f"PointSet3: Some samples in '{path}' have normals and some don't")
+            if hn:
+                N.append([float(t) for t in tok[3:6]])
+    p = np.asarray(P, np.float32).reshape(-1, 3)
+    return p, (np.asarray(N, np.float32).reshape(-1, 3) if has_n else None)

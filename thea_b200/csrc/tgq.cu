@@ -770,6 +770,62 @@ int tgq_ball_range(tgq_handle * h, const float * c3, const float * radius, int64
   });
 }
 
+int tgq_ball_stats(tgq_handle * h, const float * c3, const float * qn3, const float * radius, int64_t Q, double * out16)
+{
+  CKRC(need_built(h, 1 << TGQ_KIND_POINTS));
+  if (Q < 0 || (Q > 0 && (!c3 || !radius || !out16))) return fail(h, TGQ_EINVAL, "tgq_ball_stats: bad arguments");
+  if (qn3 && !h->has_normals) return fail(h, TGQ_ESTATE, "tgq_ball_stats: query normals given but the structure was built without normals");
+  Guard g(h);
+  Arg args[4] = {{c3, nullptr, 12}, {qn3, nullptr, 12}, {radius, nullptr, 4}, {nullptr, out16, 128}};
+  BvhView v = view_of(h);
+  size_t smem = trav_smem_bytes(StatsW::STAGE);
+  return run_batched(h, Q, args, 4, true, [&](ChunkCtx & c) -> int {
+    int grid = 0; int * cnt = c.slot->counter.as<int>();
+    CKRC(persistent_grid(h, k_ball_stats, smem, c.n, cnt, c.stream, &grid));
+    k_ball_stats<<<grid, TGQ_BLOCK, smem, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], (float const *)c.din[2], c.perm, c.n, cnt,
+                                                      (double *)c.dout[3]);
+    h->st.last_launches += 1; h->st.total_launches += 1;
+    return TGQ_OK;
+  });
+}
+
+int tgq_visibility(tgq_handle * h, const float * p3, int64_t S, const float * dirs3, int32_t num_dirs, int32_t per_sample_dirs, float scale,
+                   double * visibility, int32_t * num_escaped)
+{
+  CKRC(need_built(h, 1 << TGQ_KIND_TRIANGLES));
+  if (S < 0 || num_dirs < 1 || num_dirs > 4096 || (S > 0 && (!p3 || !dirs3))) return fail(h, TGQ_EINVAL, "tgq_visibility: bad arguments");
+  if (S == 0) return TGQ_OK;
+  Guard g(h);
+  BvhView v = view_of(h);
+  int D = num_dirs;
+  void const * ddirs = nullptr;
+  if (!per_sample_dirs)
+  {
+    CKRC(to_device(h, dirs3, 12 * (size_t)D, h->misc, h->stream, &ddirs));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  size_t smem = trav_smem_bytes(VisW::STAGE);
+  Arg args[4] = {{p3, nullptr, 12}, {per_sample_dirs ? dirs3 : nullptr, nullptr, 12 * (size_t)D}, {nullptr, visibility, 8}, {nullptr, num_escaped, 4}};
+  int64_t saved_chunk = h->opt_chunk;
+  h->opt_chunk = std::max<int64_t>(1024, std::min<int64_t>(saved_chunk, ((int64_t)1 << 24) / D));   // rays per chunk stay below 2^24 + slack
+  int rc = run_batched(h, S, args, 4, false, [&](ChunkCtx & c) -> int {
+    if ((int64_t)c.n * D > (int64_t)1 << 30) return fail(h, TGQ_ELIMIT, "tgq_visibility: more than 2^30 rays in one device-resident call; split the batch");
+    Slot & sl = *c.slot; size_t nr = (size_t)D * (size_t)c.n;
+    CK(sl.keys[1].reserve(nr));
+    uint8_t * esc = sl.keys[1].as<uint8_t>();
+    int grid = 0; int * cnt = sl.counter.as<int>();
+    CKRC(persistent_grid(h, k_vis_rays, smem, (int64_t)nr, cnt, c.stream, &grid));
+    k_vis_rays<<<grid, TGQ_BLOCK, smem, c.stream>>>(v, (float const *)c.din[0], per_sample_dirs ? (float const *)c.din[1] : (float const *)ddirs, D,
+                                                    per_sample_dirs ? 1 : 0, (int)nr, scale, cnt, esc);
+    int blocks = (int)(((int64_t)c.n * 32 + TGQ_BLOCK - 1) / TGQ_BLOCK);
+    k_vis_count<<<blocks, TGQ_BLOCK, 0, c.stream>>>(esc, c.n, D, (double *)c.dout[2], (int *)c.dout[3]);
+    h->st.last_launches += 2; h->st.total_launches += 2;
+    return TGQ_OK;
+  });
+  h->opt_chunk = saved_chunk;
+  return rc;
+}
+
 int tgq_avg_separation(tgq_handle * h, const int32_t * seeds, int32_t n, float * out)
 {
   CKRC(need_built(h, 1 << TGQ_KIND_POINTS));

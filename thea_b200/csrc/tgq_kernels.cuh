@@ -604,6 +604,98 @@ k_ball_range(BvhView b, float const * __restrict__ c3, float const * __restrict_
   warp_run(w, n, counter, stage);
 }
 
+// ---- ball neighbourhood statistics on a point structure (processRange with the local-feature functors) ----------------------
+struct StatsW
+{
+  static constexpr int STAGE = 1;       // (centre, query index)
+  StatsState s; BvhView b; float const * c3; float const * qn3; float const * rad; uint32_t const * perm; double * out; int64_t qi;
+  __device__ __forceinline__ int state() const { return s.t.cur; }
+  __device__ __forceinline__ void stage(int t, f4 * dst) const
+  {
+    int i = perm ? (int)perm[t] : t; v3 p = ld3(c3, i);
+    *dst = make_float4(p.x, p.y, p.z, __int_as_float(i));
+  }
+  __device__ __forceinline__ void begin(int, f4 const * src)
+  {
+    f4 r = *src; qi = __float_as_int(r.w);
+    stats_begin(s, b, mk3(r.x, r.y, r.z), rad[qi], qn3 ? ld3(qn3, (int)qi) : mk3(0.0f, 0.0f, 0.0f), qn3 != nullptr);
+  }
+  static constexpr int FETCH = TGQ_FETCH_BOX;
+  __device__ __forceinline__ void pop_step() { trav_pop_step(s.t, s.r2); }
+  __device__ __forceinline__ void fetch(f4 * r) const { stats_fetch(s, b, r); }
+  __device__ __forceinline__ void node_compute(f4 const * r) { stats_node_compute(s, b, r); }
+  __device__ __forceinline__ void leaf_compute(f4 const * r) { stats_leaf_compute(s, b, r); }
+  __device__ __forceinline__ void finish()
+  {
+    double2 * o = (double2 *)(out + 16 * qi);
+    for (int j = 0; j < 7; ++j) o[j] = make_double2(s.acc[2 * j], s.acc[2 * j + 1]);
+    o[7] = make_double2(s.acc[14], 0.0);
+    s.t.cur = TGQ_ST_IDLE;
+  }
+};
+
+__global__ void __launch_bounds__(TGQ_BLOCK)
+k_ball_stats(BvhView b, float const * __restrict__ c3, float const * __restrict__ qn3, float const * __restrict__ rad,
+             uint32_t const * __restrict__ perm, int n, int * counter, double * out)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  StatsW w;
+  w.b = b; w.c3 = c3; w.qn3 = qn3; w.rad = rad; w.perm = perm; w.out = out; w.qi = 0; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
+  f4 * stage = trav_setup(w.s.t, st, smem, StatsW::STAGE, nullptr);
+  warp_run(w, n, counter, stage);
+}
+
+// Visibility rays (SurfaceFeatures/Local/Visibility.hpp:104-125): thread = (sample, direction).  Ray (p + 0.001 * scale * u, u),
+// unbounded, any hit; escaped[t] = 1 when nothing was hit.  Directions: D x 3 shared by every sample, or S x D x 3 per sample.
+struct VisW
+{
+  static constexpr int STAGE = 2;       // (origin, ray number) (direction, -)
+  RayState<true> s; BvhView b; float const * p3; float const * dirs; int D; int per_sample; float scale; uint8_t * escaped; int64_t r;
+  __device__ __forceinline__ int state() const { return s.t.cur; }
+  __device__ __forceinline__ void stage(int t, f4 * dst) const
+  {
+    int sm = t / D, k = t - sm * D;
+    v3 u = ld3(dirs, per_sample ? t : k), p = ld3(p3, sm);
+    v3 o = add3(p, mul3(u, 0.001f * scale));        // position + (0.001f * scale) * u
+    dst[0] = make_float4(o.x, o.y, o.z, __int_as_float(t));
+    dst[1] = make_float4(u.x, u.y, u.z, 0.0f);
+  }
+  __device__ __forceinline__ void begin(int, f4 const * src)
+  {
+    f4 o = src[0], d = src[1]; r = __float_as_int(o.w);
+    ray_begin(s, b, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), -1.0f);
+  }
+  static constexpr int FETCH = TGQ_FETCH_BOX;
+  __device__ __forceinline__ void pop_step() { trav_pop_step(s.t, ray_limit(s)); }
+  __device__ __forceinline__ void fetch(f4 * r_) const { ray_fetch(s, b, r_); }
+  __device__ __forceinline__ void node_compute(f4 const * r_) { ray_node_compute(s, b, r_); }
+  __device__ __forceinline__ void leaf_compute(f4 const * r_) { ray_leaf_compute(s, b, r_); }
+  __device__ __forceinline__ void finish() { escaped[r] = s.best_idx >= 0 ? 0 : 1; s.t.cur = TGQ_ST_IDLE; }
+};
+
+__global__ void __launch_bounds__(TGQ_BLOCK)
+k_vis_rays(BvhView b, float const * __restrict__ p3, float const * __restrict__ dirs, int D, int per_sample, int nrays, float scale,
+           int * counter, uint8_t * escaped)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  VisW w;
+  w.b = b; w.p3 = p3; w.dirs = dirs; w.D = D; w.per_sample = per_sample; w.scale = scale; w.escaped = escaped; w.r = 0;
+  w.s.t.cur = TGQ_ST_IDLE; TravStack st;
+  f4 * stage = trav_setup(w.s.t, st, smem, VisW::STAGE, nullptr);
+  warp_run(w, nrays, counter, stage);
+}
+
+// (double)num_escaped / num_rays per sample (Visibility.hpp:122); one warp per sample.
+__global__ void k_vis_count(uint8_t const * __restrict__ escaped, int S, int D, double * vis, int * n_escaped)
+{
+  int warp = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (warp >= S) return;
+  int c = 0;
+  for (int k = lane; k < D; k += 32) c += escaped[(size_t)warp * D + k];
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) { if (vis) vis[warp] = (double)c / (double)D; if (n_escaped) n_escaped[warp] = c; }
+}
+
 // ---- K8 ray first hit / any hit ------------------------------------------------------------------------------------------
 template <bool ANY>
 struct RayW

@@ -50,6 +50,14 @@ TGQ_HD float ffma(float a, float b, float c)
 TGQ_HD float fdot3(v3 a, v3 b) { return ffma(a.x, b.x, ffma(a.y, b.y, a.z * b.z)); }
 TGQ_HD v3 cross3(v3 l, v3 r) { return mk3(l.y * r.z - l.z * r.y, l.z * r.x - l.x * r.z, l.x * r.y - l.y * r.x); }
 TGQ_HD v3 normalized3(v3 a) { float z = sqn3(a); return z > 0.0f ? div3(a, sqrtf(z)) : a; }
+// Eigen 3.4 MatrixBase::stableNormalized (Dot.h): w = max |a_i|, z = sq(a / w); z > 0 ? a / (sqrt(z) * w) : a  (w == 0 gives
+// z = NaN and returns a unchanged).  Used by Curvature's ProjectedCurvatureFunctor (SurfaceFeatures/Local/Curvature.cpp:46).
+TGQ_HD v3 stable_normalized3(v3 a)
+{
+  float w = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fabsf(a.z));
+  float z = sqn3(div3(a, w));
+  return z > 0.0f ? div3(a, sqrtf(z) * w) : a;
+}
 TGQ_HD float comp3(v3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
 // MatrixUtil.hpp:108-115 maxAbsAxis: first maximum of |v_i|.
 TGQ_HD int max_abs_axis3(v3 v)

@@ -656,6 +656,81 @@ TGQ_HD void range_query(BvhView const & b, v3 c, float radius, int self, SortedS
   set.n = s.set.n; count = s.count;
 }
 
+// Ball neighbourhood statistics on a point structure: BvhN::processRange<IntersectionTester>(Ball3(c, r), functor) (BvhN.hpp:1238-
+// 1264,2118-2171) with the accumulating functors of the local surface features, all in one pass over the
+// elements with sq(x_e - c) <= r * r:
+//   acc[0]      n                                                  every functor's point count
+//   acc[1]      sum |x_e - c|  (fp32 norm per element)             AverageDistance EuclideanCallback (AverageDistance.cpp:39-61)
+//   acc[2]      #{e : n_e . qn > -1e-5}, acc[3..5] sum stableNormalized(x_e - c) over those
+//                                                                  Curvature ProjectedCurvatureFunctor (Curvature.cpp:37-66)
+//   acc[6..8]   sum (x_e - c), acc[9..14] sum (x_e - c)(x_e - c)^T (xx xy xz yy yz zz)
+//                                                                  LocalPca: moments of the neighbourhood (LocalPca.cpp:32-47, PcaN.hpp:163-184)
+// Per-element terms are the reference's fp32 expressions; the sums are taken in double, one lane per ball, in this tree's
+// traversal order (the reference sums in ITS traversal order, in fp32 for the curvature offsets and the PCA moments: its own
+// result is tree dependent at fp32 rounding level, which is the tolerance the tests state).
+struct StatsState
+{
+  v3 c, qn; float r2; int has_qn;
+  double acc[15];
+  Trav t;
+};
+TGQ_HD void stats_begin(StatsState & s, BvhView const & b, v3 c, float radius, v3 qn, bool has_qn)
+{
+  s.c = c; s.qn = qn; s.has_qn = (has_qn && b.nrm) ? 1 : 0; s.r2 = radius * radius;
+  for (int j = 0; j < 15; ++j) s.acc[j] = 0.0;
+  trav_begin(s.t, (radius >= 0.0f) ? b.n_nodes : 0);
+}
+TGQ_HD void stats_fetch(StatsState const & s, BvhView const & b, f4 * r) { box_fetch(s.t, b, r); }
+TGQ_HD void stats_node_compute(StatsState & s, BvhView const & b, f4 const * r)
+{
+  TGQ_COUNT_NODE();
+  float lb0, lb1; int c0, c1; box_node_bounds(r, s.c, lb0, lb1, c0, c1);
+  trav_descend(s.t, lb0, lb1, 0.0f, 0.0f, c0, c1, s.r2);
+}
+TGQ_HD void stats_leaf_compute(StatsState & s, BvhView const & b, f4 const * r)
+{
+  int cnt = s.t.kend - s.t.k; if (cnt > TGQ_FETCH_BOX) cnt = TGQ_FETCH_BOX;
+  for (int j = 0; j < TGQ_FETCH_BOX; ++j)
+  {
+    if (j >= cnt) break;
+    TGQ_COUNT_PRIM();
+    f4 e = r[j];
+    v3 diff = sub3(mk3(e.x, e.y, e.z), s.c);
+    float d2 = sqn3(diff);
+    if (!(d2 <= s.r2)) continue;
+    s.acc[0] += 1.0;
+    s.acc[1] += (double)sqrtf(d2);
+    if (s.has_qn)
+    {
+      f4 nj = ldq(b.nrm + s.t.k + j);
+      if (dot3(mk3(nj.x, nj.y, nj.z), s.qn) > -1.0e-05f)
+      {
+        v3 o = stable_normalized3(diff);
+        s.acc[2] += 1.0; s.acc[3] += (double)o.x; s.acc[4] += (double)o.y; s.acc[5] += (double)o.z;
+      }
+    }
+    double dx = diff.x, dy = diff.y, dz = diff.z;
+    s.acc[6] += dx; s.acc[7] += dy; s.acc[8] += dz;
+    s.acc[9] += dx * dx; s.acc[10] += dx * dy; s.acc[11] += dx * dz; s.acc[12] += dy * dy; s.acc[13] += dy * dz; s.acc[14] += dz * dz;
+  }
+  s.t.k += cnt;
+  if (s.t.k >= s.t.kend) trav_pop(s.t);
+}
+TGQ_HD void stats_query(BvhView const & b, v3 c, float radius, v3 qn, bool has_qn, double * out16)
+{
+  StatsState s; TravStack st; trav_bind(s.t, st);
+  stats_begin(s, b, c, radius, qn, has_qn);
+  f4 r[TGQ_FETCH_BOX];
+  while (s.t.cur != TGQ_ST_DONE)
+  {
+    if (s.t.cur == TGQ_ST_POP) { trav_pop_step(s.t, s.r2); continue; }
+    stats_fetch(s, b, r);
+    if (s.t.cur >= 0) stats_node_compute(s, b, r); else stats_leaf_compute(s, b, r);
+  }
+  for (int j = 0; j < 15; ++j) out16[j] = s.acc[j];
+  out16[15] = 0.0;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Ray first hit.  best_t starts as max_time (negative = unbounded), best_idx as -1; best_k is the Morton position of
 // the hit triangle (for its cached normal).  A hit is accepted iff t >= 0 and (unbounded or t < best_t) or it ties the

@@ -24,6 +24,7 @@ SYMBOLS = [
     "tgq_info", "tgq_triangle_cache", "tgq_closest", "tgq_knn", "tgq_ball_graph", "tgq_avg_separation",
     "tgq_ray_first", "tgq_ray_any", "tgq_sdf", "tgq_icp_sums", "tgq_transform_points", "tgq_area_sample",
     "tgq_get_stats", "tgq_set_point_labels", "tgq_closest_filtered", "tgq_knn_filtered", "tgq_icp_align", "tgq_ball_range",
+    "tgq_ball_stats", "tgq_visibility",
 ]
 
 
@@ -85,6 +86,8 @@ def load_library(path=None):
     L.tgq_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.tgq_set_point_labels.argtypes = [vp, vp]
     L.tgq_ball_range.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
+    L.tgq_ball_stats.argtypes = [vp, vp, vp, vp, i64, vp]
+    L.tgq_visibility.argtypes = [vp, vp, i64, vp, i32, i32, f32, vp, vp]
     L.tgq_icp_align.argtypes = [vp, vp, i64, i32, i32, f64, i32, vp, vp, vp, vp]
     L.tgq_closest_filtered.argtypes = [vp, vp, vp, vp, i64, f32, f64, vp, vp, vp]
     L.tgq_knn_filtered.argtypes = [vp, vp, vp, vp, i64, i32, f32, f64, vp, vp]
@@ -268,6 +271,33 @@ class Engine:
         cnt = np.empty(Q, np.int32)
         self._ck(self._L.tgq_ball_range(self._h, _ptr(c3), _ptr(rad), Q, int(max_out), int(exclude_self), _ptr(idx), _ptr(cnt)))
         return idx, cnt
+
+    def ball_stats(self, c3, radius, qn3=None, out=None):
+        """Per-ball neighbourhood sums (tgq_ball_stats): [Q x 16] doubles, layout in include/thea_gpu_query.h."""
+        c3 = _as_in(c3)
+        Q = int(c3.shape[0])
+        if _is_torch(radius):
+            rad = radius
+        else:
+            rad = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float32), (Q,)), np.float32)
+        qn3 = _as_in(qn3)
+        if out is None:
+            out = np.empty((Q, 16), np.float64)
+        self._ck(self._L.tgq_ball_stats(self._h, _ptr(c3), _ptr(qn3), _ptr(rad), Q, _ptr(out)))
+        return out
+
+    def visibility(self, p3, dirs3, scale):
+        """Visibility::compute for every sample with caller-supplied directions ([D x 3] shared or [S x D x 3]):
+        (visibility [S] float64, num_escaped [S] int32)."""
+        p3 = _as_in(p3)
+        dirs3 = _as_in(dirs3)
+        S = int(p3.shape[0])
+        per_sample = len(dirs3.shape) == 3
+        D = int(dirs3.shape[-2])
+        vis = np.empty(S, np.float64)
+        nesc = np.empty(S, np.int32)
+        self._ck(self._L.tgq_visibility(self._h, _ptr(p3), S, _ptr(dirs3), D, int(per_sample), float(scale), _ptr(vis), _ptr(nesc)))
+        return vis, nesc
 
     def ball_graph(self, max_degree, init_radius, rounds=3, min_dot=-0.5, min_degree=None, out=None):
         _, n, _, _ = self.info()
