@@ -111,6 +111,17 @@ inline float sampleGraph(GpuPointBvhT<VectorT> const & bvh, int32_t max_degree, 
   return avg;
 }
 
+/** PointSet3::updateGraph(surface): the same with the reachability test against the mesh the samples came from. */
+template <typename VectorT>
+inline float sampleGraph(GpuPointBvhT<VectorT> const & bvh, GpuMeshBvhT<VectorT> const & surface, int32_t max_degree, int32_t const * seeds,
+                         int32_t num_seeds, int32_t * idx, float * sep, int32_t * count = nullptr)
+{
+  float avg = bvh.averageSeparation(seeds, num_seeds);
+  float sep_scale = std::sqrt((float)max_degree);
+  bvh.sampleGraphBatch(surface, max_degree, sep_scale * avg, idx, sep, count);
+  return avg;
+}
+
 /** PointSet3::save, graph part (PointSet3.cpp:331-354): first line max_degree, then one line per sample,
  *  `degree nbr_0 .. nbr_{d-1} [sep_0 .. sep_{d-1}]`, floats with the default ostream precision as the reference writes them.
  *  idx / sep are P x max_degree as sampleGraph returns them (unused slots -1). */

@@ -526,6 +526,15 @@ class GpuPointBvhT : public GpuBvhBase<VectorT>
       if (min_degree < 0) { min_degree = (int32_t)(0.25 * max_degree); if (min_degree < 4) min_degree = 4; if (min_degree > max_degree) min_degree = max_degree; }
       detail::check(h, tgq_ball_graph(h, max_degree, init_radius, rounds, min_dot, min_degree, idx, sep, count), "tgq_ball_graph");
     }
+    /** PointSet3::updateGraph(surface) (PointSet3.hpp:324-391,639-648): the same search with the reachability ray test against a
+     *  triangle structure on the same device. */
+    void sampleGraphBatch(GpuMeshBvhT<VectorT> const & surface, int32_t max_degree, float init_radius, int32_t * idx, float * sep,
+                          int32_t * count = nullptr, int32_t rounds = 3, float min_dot = -0.5f, int32_t min_degree = -1) const
+    {
+      if (min_degree < 0) { min_degree = (int32_t)(0.25 * max_degree); if (min_degree < 4) min_degree = 4; if (min_degree > max_degree) min_degree = max_degree; }
+      detail::check(h, tgq_ball_graph_surface(h, surface.handle(), max_degree, init_radius, rounds, min_dot, min_degree, idx, sep, count),
+                    "tgq_ball_graph_surface");
+    }
     /** PointSet3.hpp:363-376 with caller-fixed seed samples. */
     float averageSeparation(int32_t const * seeds, int32_t n) const
     { float out = 0; detail::check(h, tgq_avg_separation(h, seeds, n, &out), "tgq_avg_separation"); return out; }

@@ -161,6 +161,13 @@ int tgq_ball_stats(tgq_handle * h, const float * c3, const float * qn3, const fl
 int tgq_ball_graph(tgq_handle * h, int32_t max_degree, float init_radius, int32_t rounds, float min_dot, int32_t min_degree,
                    int32_t * idx, float * sep, int32_t * count);
 
+/* The same with PointSet3's reachability test: updateGraph(surface) (PointSet3.hpp:324-391,639-648).  A
+ * candidate j of sample i is dropped when rayIntersects(Ray3(x_i + 5 * sep * normalized(n_i + n_j), x_j - x_i), max_time = 1)
+ * holds on the triangle structure `surface` (same device), i.e. when the lifted segment towards it is blocked by the surface.
+ * The point structure must have normals (the reference skips the test without them; here that is TGQ_ESTATE). */
+int tgq_ball_graph_surface(tgq_handle * h, tgq_handle * surface, int32_t max_degree, float init_radius, int32_t rounds, float min_dot,
+                           int32_t min_degree, int32_t * idx, float * sep, int32_t * count);
+
 /* RMS nearest-neighbour separation over n seed samples (PointSet3.hpp:363-376; the reference draws the seeds from
  * Random::common(), here the caller fixes them): sqrt(sum_f32 |x_nn(s) - x_s|^2 / n). */
 int tgq_avg_separation(tgq_handle * h, const int32_t * seeds, int32_t n, float * out);

@@ -442,6 +442,36 @@ void orc_ball_graph(void * h, int max_degree, float init_radius, int mode, int n
   });
 }
 
+// PointSet3::updateGraph(surface) (PointSet3.hpp:324-391,639-648): the neighbour search with the reachability test against a
+// triangle structure.  Ray3(x_i + 5 * sep * normalized(n_i + n_j), x_j - x_i), rayIntersects(ray, 1).  mode as orc_ball_graph;
+// the ray is answered by the reference-order traversal (mode 0) or by brute force (mode 2) of the surface oracle.
+void orc_ball_graph_surface(void * h, void * hs, int max_degree, float init_radius, int mode, int nthreads, int64_t * idx, float * sep,
+                            int32_t * count)
+{
+  KdTree const & T = ((Handle *)h)->tree;
+  KdTree const & S = ((Handle *)hs)->tree;
+  int64_t P = T.size();
+  bool has_n = !T.nrm.empty();
+  parallel_for(P, nthreads, [&](int64_t b, int64_t e) {
+    for (int64_t i = b; i < e; ++i)
+    {
+      auto range = [&](V3 c, float r2, std::function<void(int64_t)> emit) {
+        if (mode == 2) { for (int64_t j = 0; j < P; ++j) if (sqnorm(T.pts[(size_t)j] - c) <= r2) emit(j); }
+        else kd_ball_range(T, 0, c, r2, emit);
+      };
+      auto blocked = [&](int64_t j, float s, V3 diff) {
+        if (!has_n) return false;
+        V3 lift_dir = normalized(T.nrm[(size_t)i] + T.nrm[(size_t)j]);
+        V3 o = T.pts[(size_t)i] + (5.0f * s) * lift_dir;
+        RayHit r = mode == 2 ? brute_ray_first(S, o, diff, 1.0f) : S.ray_first_ref(o, diff, 1.0f);
+        return r.idx >= 0;
+      };
+      int c = ball_graph_one(T, i, max_degree, init_radius, range, idx + (int64_t)max_degree * i, sep + (int64_t)max_degree * i, blocked);
+      if (count) count[i] = c;
+    }
+  });
+}
+
 // ShapeDiameter::compute(p, n, only_hit_interior) for S samples: emits the 30 rays, their first hits and the SDF.
 void orc_sdf(void * h, float const * p3, float const * n3, int64_t S, float scale, int only_interior, int mode, int nthreads,
              float * ray_o3, float * ray_d3, int64_t * hit_idx, float * hit_t, double * sdf)

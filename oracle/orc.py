@@ -55,6 +55,7 @@ def lib():
         L.orc_knn_filtered.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_double, C.c_int, C.c_int,
                                        C.c_void_p, C.c_void_p]
         L.orc_ball_range.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_ball_graph_surface.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_ball_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]
         L.orc_visibility.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_avg_separation.restype = C.c_float
@@ -189,6 +190,14 @@ class Oracle:
         cnt = np.empty(Q, np.int32)
         lib().orc_ball_range(self.h, _p(c), _p(rad), Q, int(max_out), int(exclude_self), threads or ncores(), _p(idx), _p(cnt))
         return idx, cnt
+
+    def ball_graph_surface(self, surface, max_degree, init_radius, mode=MODE_REFERENCE, threads=None):
+        """PointSet3::updateGraph(surface): neighbour search with the reachability ray test against the triangle oracle `surface`."""
+        idx = np.empty((self.n, max_degree), np.int64)
+        sep = np.empty((self.n, max_degree), np.float32)
+        cnt = np.empty(self.n, np.int32)
+        lib().orc_ball_graph_surface(self.h, surface.h, max_degree, float(init_radius), mode, threads or ncores(), _p(idx), _p(sep), _p(cnt))
+        return idx, sep, cnt
 
     def ball_stats(self, c, radius, qn=None, mode=MODE_REFERENCE, threads=None):
         """Local-feature functors over ball neighbourhoods (see orc_ball_stats): dict of n, avg_dist, num_offsets, curvature,

@@ -629,9 +629,11 @@ inline int brute_knn(KdTree const & T, V3 q, int k, double dist_bound, int64_t s
 // Candidate j of sample i at radius r: j != i; sq(x_j - x_i) <= r*r (BallN.hpp:83); n_i . n_j >= min_dot when
 // normals exist; key (fastSqrt(d2), j) ascending, keep the max_degree smallest.  Up to 3 rounds, radius doubled
 // while fewer than clamp(int(0.25*max_degree), 4, max_degree) neighbours were found.
-template <typename RangeFn>
+// `blocked(j, sep, diff)`: the reachability test of NeighborFunctor::isValidNeighbor (PointSet3.hpp:639-648), evaluated after the
+// identity / angle tests and the separation, before insertion, for every candidate in range -- as the reference orders them.
+template <typename RangeFn, typename BlockedFn>
 inline int ball_graph_one(KdTree const & T, int64_t i, int max_degree, float init_radius, RangeFn range,
-                          int64_t * idx, float * sep)
+                          int64_t * idx, float * sep, BlockedFn blocked)
 {
   int min_degree = std::min(std::max((int)(0.25 * max_degree), 4), max_degree);
   float radius = init_radius;
@@ -647,6 +649,7 @@ inline int ball_graph_one(KdTree const & T, int64_t i, int max_degree, float ini
       if (has_n && dot(T.nrm[(size_t)i], T.nrm[(size_t)j]) < -0.5f) return;
       V3 diff = T.pts[(size_t)j] - c;
       float s = fast_sqrt(sqnorm(diff));
+      if (blocked(j, s, diff)) return;
       std::pair<float, int64_t> cand(s, j);
       if ((int)nb.size() < max_degree) nb.insert(std::upper_bound(nb.begin(), nb.end(), cand), cand);
       else if (max_degree > 0 && cand < nb.back()) { nb.pop_back(); nb.insert(std::upper_bound(nb.begin(), nb.end(), cand), cand); }
@@ -660,6 +663,10 @@ inline int ball_graph_one(KdTree const & T, int64_t i, int max_degree, float ini
 }
 
 // BvhN.hpp:2118-2171 processRange with a Ball3 range on a point kd-tree (reference traversal).
+template <typename RangeFn>
+inline int ball_graph_one(KdTree const & T, int64_t i, int max_degree, float init_radius, RangeFn range, int64_t * idx, float * sep)
+{ return ball_graph_one(T, i, max_degree, init_radius, range, idx, sep, [](int64_t, float, V3) { return false; }); }
+
 template <typename Emit>
 inline void kd_ball_range(KdTree const & T, int64_t ni, V3 c, float r2, Emit & emit)
 {

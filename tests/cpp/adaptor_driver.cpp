@@ -132,6 +132,14 @@ int main(int argc, char ** argv)
         if (set[j].getTargetIndex() != fki[4 * i + (int64_t)j]) { fprintf(stderr, "scalar filtered kClosestPairs disagrees with the batch\n"); return 3; }
     }
 
+    // ---- the graph again with the reachability test against the mesh (PointSet3::updateGraph(surface)) ----
+    {
+      std::vector<int32_t> si_(NS * 6), sc_(NS); std::vector<float> ss_(NS * 6);
+      float avg2 = sampleGraph(pts, bvh, 6, seeds.data(), (int32_t)seeds.size(), si_.data(), ss_.data(), sc_.data());
+      if (avg2 != avg) { fprintf(stderr, "average separation changed\n"); return 3; }
+      wr(fo, si_); wr(fo, ss_); wr(fo, sc_);
+    }
+
     // ---- graph file round trip (PointSet3::save / load format) ----
     {
       std::string gp = std::string(argv[2]) + ".graph";

@@ -272,6 +272,22 @@ void emu_ball_range(void * h, float const * c3, float const * radius, int64_t Q,
   }
 }
 
+void emu_ball_graph_surface(void * h, void * hs, int k, float init_radius, int rounds, float min_dot, int min_degree, int32_t * idx, float * sep,
+                            int32_t * count)
+{
+  Emu & E = *(Emu *)h; BvhView v = E.view(); BvhView sv = ((Emu *)hs)->view();
+  std::vector<float> keys((size_t)k); std::vector<int> ids((size_t)k);
+  for (int s = 0; s < E.n; ++s)
+  {
+    f4 e = E.pts[(size_t)s]; int64_t i = f2i(e.w);
+    v3 nc = mk3(0, 0, 0); if (E.has_n) nc = mk3(E.nrm[(size_t)s].x, E.nrm[(size_t)s].y, E.nrm[(size_t)s].z);
+    SortedSet set; set.init(keys.data(), ids.data(), 1, k);
+    ball_graph_surface_query(v, sv, mk3(e.x, e.y, e.z), nc, E.has_n, min_dot, (int)i, init_radius, rounds, min_degree, set);
+    for (int j = 0; j < k; ++j) { idx[i * k + j] = j < set.n ? ids[(size_t)j] : -1; sep[i * k + j] = j < set.n ? keys[(size_t)j] : -1.0f; }
+    if (count) count[i] = set.n;
+  }
+}
+
 void emu_ball_stats(void * h, float const * c3, float const * qn3, float const * radius, int64_t Q, double * out16)
 {
   Emu & E = *(Emu *)h; BvhView v = E.view();

@@ -25,6 +25,7 @@ def lib():
         L.emu_ball_graph.argtypes = [vp, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, vp, vp, vp]
         L.emu_set_labels.argtypes = [vp, vp]
         L.emu_ball_range.argtypes = [vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp, vp]
+        L.emu_ball_graph_surface.argtypes = [vp, vp, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, vp, vp, vp]
         L.emu_ball_stats.argtypes = [vp, vp, vp, vp, C.c_int64, vp]
         L.emu_closest_filtered.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, vp, vp, vp]
         L.emu_knn_filtered.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, C.c_float, C.c_float, vp, vp]
@@ -133,6 +134,15 @@ class Emu:
         sep = np.empty((self.n, k), np.float32)
         cnt = np.empty(self.n, np.int32)
         lib().emu_ball_graph(self.h, k, float(r0), rounds, float(min_dot), min_degree, _p(idx), _p(sep), _p(cnt))
+        return idx, sep, cnt
+
+    def ball_graph_surface(self, surface, k, r0, rounds=3, min_dot=-0.5, min_degree=None):
+        if min_degree is None:
+            min_degree = min(max(int(0.25 * k), 4), k)
+        idx = np.empty((self.n, k), np.int32)
+        sep = np.empty((self.n, k), np.float32)
+        cnt = np.empty(self.n, np.int32)
+        lib().emu_ball_graph_surface(self.h, surface.h, k, float(r0), rounds, float(min_dot), min_degree, _p(idx), _p(sep), _p(cnt))
         return idx, sep, cnt
 
     def ray(self, o, d, tmax=None, any_hit=False):

@@ -134,6 +134,10 @@ def test_adaptor_driver_matches_oracle(built, tmp_path):
     oki, okd = po.knn_filtered(sp, 4, sn, labels, mode=orc.MODE_BRUTE)
     assert np.array_equal(take(np.int32, NS * 4).reshape(NS, 4), oki.astype(np.int32))
     assert np.array_equal(take(np.float32, NS * 4).reshape(NS, 4), okd)
+    osi, oss, osc = po.ball_graph_surface(ora, 6, float(np.float32(np.sqrt(np.float32(6))) * np.float32(avg)))
+    assert np.array_equal(take(np.int32, NS * 6).reshape(NS, 6), osi.astype(np.int32))
+    assert np.array_equal(take(np.float32, NS * 6).reshape(NS, 6), oss)
+    assert np.array_equal(take(np.int32, NS), osc)
     # local surface features through the SurfaceFeatures::Local classes (tolerances: tests/test_local_features.py)
     fa, fc = take(np.float64, NS), take(np.float64, NS)
     fe, fv = take(np.float32, 3 * NS).reshape(NS, 3), take(np.float32, 9 * NS).reshape(NS, 3, 3)

@@ -291,3 +291,40 @@ def test_visibility(setup):
     v2, n2 = e.visibility(pts[:200], pd, scale)
     o2, on2 = ora.visibility(pts[:200], pd, scale, mode=orc.MODE_CANON)
     assert np.array_equal(n2, on2) and np.array_equal(v2, o2)
+
+
+def test_sample_graph_with_reachability(setup):
+    """PointSet3::updateGraph(surface) on the GPU (SURVEY 8f rank 2): bit-equal to the oracle's reference-order restatement."""
+    from thea_b200 import Engine
+    from test_local_features import thin_slab_case
+    mesh, p, nrm = thin_slab_case()
+    pe, se = Engine(0), Engine(0)
+    pe.build_points(p, nrm)
+    se.build_triangles(mesh)
+    ora, oS = orc.Oracle(points=p, normals=nrm), orc.Oracle(tris9=mesh)
+    gi, gs, gc = pe.ball_graph_surface(se, 8, 0.06)
+    oi, osep, oc = ora.ball_graph_surface(oS, 8, 0.06)
+    assert np.array_equal(gi, oi.astype(np.int32)) and np.array_equal(gs, osep) and np.array_equal(gc, oc)
+    si, _, _ = pe.ball_graph_surface(se, 8, 0.06, min_dot=-2.0)
+    side = (np.arange(len(p)) >= len(p) // 2)
+    assert ((side[si.clip(0)] != side[:, None]) & (si >= 0)).sum() == 0
+    pi, _, _ = pe.ball_graph(8, 0.06, min_dot=-2.0)
+    assert ((side[pi.clip(0)] != side[:, None]) & (pi >= 0)).sum() > 100
+    # the torus: samples of a closed smooth surface, graph through the caller with and without the surface
+    e, tmesh, tora = setup
+    sp, sn, _ = e.area_sample(6000, gen.SEED_SAMPLES)
+    te = Engine(0)
+    te.build_points(sp, sn)
+    seeds = (gen.splitmix64(0x5EED, 100) % np.uint64(len(sp))).astype(np.int64)
+    ti, ts, tc, avg = callers.sample_graph(te, 8, seeds, surface=e)
+    po = orc.Oracle(points=sp, normals=sn)
+    r0 = float(np.float32(np.sqrt(np.float32(8))) * np.float32(avg))
+    oi, osep, oc = po.ball_graph_surface(tora, 8, r0)
+    assert np.array_equal(ti, oi.astype(np.int32)) and np.array_equal(ts, osep) and np.array_equal(tc, oc)
+    # errors: no normals / wrong surface kind
+    nn = Engine(0)
+    nn.build_points(p)
+    with pytest.raises(Exception):
+        nn.ball_graph_surface(se, 8, 0.06)
+    with pytest.raises(Exception):
+        pe.ball_graph_surface(pe, 8, 0.06)

@@ -157,3 +157,47 @@ def test_graph_and_samples_files_round_trip(tmp_path, cloud):
         f.write("4\n1 7\n")
     with pytest.raises(ValueError):
         callers.load_graph(g, positions=p[:1])
+
+
+def thin_slab_case():
+    """Samples on both faces of a thin slab: Euclidean neighbours across the slab exist (0.03 apart) but the surface blocks them."""
+    g = 14
+    xs = np.linspace(0, 1, g + 1, dtype=np.float32)
+    tris = []
+    for z, flip in ((0.0, True), (0.03, False)):
+        for i in range(g):
+            for j in range(g):
+                a = [xs[i], xs[j], z]; b = [xs[i + 1], xs[j], z]; c = [xs[i + 1], xs[j + 1], z]; d = [xs[i], xs[j + 1], z]
+                tris += ([[a, c, b], [a, d, c]] if flip else [[a, b, c], [a, c, d]])
+    mesh = np.asarray(tris, np.float32).reshape(-1, 9)
+    rng = np.random.default_rng(3)
+    n_s = 700
+    xy = rng.uniform(0.02, 0.98, (2 * n_s, 2)).astype(np.float32)
+    p = np.concatenate([np.c_[xy[:n_s], np.zeros(n_s, np.float32)], np.c_[xy[n_s:], np.full(n_s, 0.03, np.float32)]]).astype(np.float32)
+    nrm = np.concatenate([np.tile([0, 0, -1], (n_s, 1)), np.tile([0, 0, 1], (n_s, 1))]).astype(np.float32)
+    return mesh, p, nrm
+
+
+def test_graph_with_reachability_test_against_the_surface():
+    """PointSet3::updateGraph(surface): SURVEY 8f rank 2.  With min_dot = -2 (angle test off) the plain graph links the two faces
+    of the slab; the reachability rays remove exactly those links."""
+    mesh, p, nrm = thin_slab_case()
+    E, ES = emu_lib.Emu(points=p, normals=nrm), emu_lib.Emu(tris9=mesh)
+    ora, oS = orc.Oracle(points=p, normals=nrm), orc.Oracle(tris9=mesh)
+    k, r0 = 8, 0.06
+    for mode in (orc.MODE_REFERENCE, orc.MODE_BRUTE):
+        oi, osep, oc = ora.ball_graph_surface(oS, k, r0, mode=mode)
+        gi, gs, gc = E.ball_graph_surface(ES, k, r0)
+        assert np.array_equal(gi, oi.astype(np.int32)) and np.array_equal(gs, osep) and np.array_equal(gc, oc)
+    # default min_dot = -0.5 already separates opposite normals; switch it off to see the rays do the work
+    pi, ps, pc = E.ball_graph(k, r0, min_dot=-2.0)
+    si, ss, sc = E.ball_graph_surface(ES, k, r0, min_dot=-2.0)
+    side = (np.arange(len(p)) >= len(p) // 2)
+    cross_plain = (side[pi.clip(0)] != side[:, None]) & (pi >= 0)
+    cross_surf = (side[si.clip(0)] != side[:, None]) & (si >= 0)
+    assert cross_plain.sum() > 100 and cross_surf.sum() == 0
+    # a surface that blocks nothing leaves the plain graph untouched
+    far = emu_lib.Emu(tris9=(mesh + np.float32(10.0)))
+    fi, fs, fc = E.ball_graph_surface(far, k, r0)
+    qi, qs, qc = E.ball_graph(k, r0)
+    assert np.array_equal(fi, qi) and np.array_equal(fs, qs) and np.array_equal(fc, qc)

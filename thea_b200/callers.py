@@ -133,11 +133,15 @@ def shape_diameter(eng, p3, n3, scale, retry=True):
     return sdf
 
 
-def sample_graph(eng, max_degree, seeds):
-    """PointSet3::updateGraph's neighbour search over the point structure held by `eng`; returns (idx, sep, count, avg_sep)."""
+def sample_graph(eng, max_degree, seeds, surface=None):
+    """PointSet3::updateGraph's neighbour search over the point structure held by `eng`; returns (idx, sep, count, avg_sep).
+    `surface`: a triangle Engine for the reachability test of updateGraph(surface) (PointSet3.hpp:639-648), or None."""
     avg = eng.avg_separation(seeds)
     radius = np.float32(np.sqrt(np.float32(max_degree))) * np.float32(avg)
-    idx, sep, cnt = eng.ball_graph(max_degree, float(radius))
+    if surface is not None:
+        idx, sep, cnt = eng.ball_graph_surface(surface, max_degree, float(radius))
+    else:
+        idx, sep, cnt = eng.ball_graph(max_degree, float(radius))
     return idx, sep, cnt, avg
 
 

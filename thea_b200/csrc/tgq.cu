@@ -476,7 +476,8 @@ int tgq_create(int device, tgq_handle ** out)
   if ((e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return bail("cudaDeviceGetAttribute", e);
   int const smem = 2 * TGQ_MAX_K * TGQ_BLOCK * 4;
   if ((e = cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute(k_knn)", e);
-  if ((e = cudaFuncSetAttribute(k_ball_graph, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute(k_ball_graph)", e);
+  if ((e = cudaFuncSetAttribute(k_ball_graph<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute(k_ball_graph)", e);
+  if ((e = cudaFuncSetAttribute(k_ball_graph<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute(k_ball_graph)", e);
   if (prev >= 0) cudaSetDevice(prev);
   *out = h;
   return TGQ_OK;
@@ -718,12 +719,21 @@ int tgq_knn_filtered(tgq_handle * h, const float * q3, const float * qn3, const 
   return knn_common(h, q3, qn3, qlabel, min_dot, Q, k, dist_bound, 0, idx, d2);
 }
 
-int tgq_ball_graph(tgq_handle * h, int32_t max_degree, float init_radius, int32_t rounds, float min_dot, int32_t min_degree, int32_t * idx,
-                   float * sep, int32_t * count)
+static int ball_graph_common(tgq_handle * h, tgq_handle * surface, int32_t max_degree, float init_radius, int32_t rounds, float min_dot,
+                             int32_t min_degree, int32_t * idx, float * sep, int32_t * count)
 {
   CKRC(need_built(h, 1 << TGQ_KIND_POINTS));
   if (max_degree < 1 || rounds < 1) return fail(h, TGQ_EINVAL, "tgq_ball_graph: bad arguments");
   if (max_degree > TGQ_MAX_K) return fail(h, TGQ_ELIMIT, "tgq_ball_graph: max_degree exceeds TGQ_MAX_K");
+  BvhView sv = view_of(h);
+  if (surface)
+  {
+    if (surface->kind != TGQ_KIND_TRIANGLES) return fail(h, TGQ_ESTATE, "tgq_ball_graph_surface: the surface handle holds no triangle structure");
+    if (surface->device != h->device) return fail(h, TGQ_EINVAL, "tgq_ball_graph_surface: both structures must live on the same device");
+    if (!h->has_normals) return fail(h, TGQ_ESTATE, "tgq_ball_graph_surface: the reachability test needs sample normals (PointSet3.hpp:639)");
+    CK(cudaStreamSynchronize(surface->stream));      // the surface structure must be complete before this handle's stream reads it
+    sv = view_of(surface);
+  }
   Guard g(h);
   h->st.last_query_ms = 0; h->st.last_sort_ms = 0; h->st.last_launches = 0; h->ev_used = 0;
   if (h->n == 0) return TGQ_OK;
@@ -735,9 +745,17 @@ int tgq_ball_graph(tgq_handle * h, int32_t max_degree, float init_radius, int32_
   cudaEvent_t e0 = get_event(h), e1 = get_event(h);
   CK(cudaEventRecord(e0, s));
   int grid = 0; int * cnt = h->slot[0].counter.as<int>();
-  size_t smem = trav_smem_bytes(BallW::STAGE) + 2 * k * TGQ_BLOCK * 4;
-  CKRC(persistent_grid(h, k_ball_graph, smem, h->n, cnt, s, &grid));
-  k_ball_graph<<<grid, TGQ_BLOCK, smem, s>>>(view_of(h), h->n, max_degree, init_radius, rounds, min_dot, min_degree, cnt, di, ds, dc);
+  size_t smem = trav_smem_bytes(BallW<false>::STAGE) + 2 * k * TGQ_BLOCK * 4;
+  if (surface)
+  {
+    CKRC(persistent_grid(h, k_ball_graph<true>, smem, h->n, cnt, s, &grid));
+    k_ball_graph<true><<<grid, TGQ_BLOCK, smem, s>>>(view_of(h), sv, h->n, max_degree, init_radius, rounds, min_dot, min_degree, cnt, di, ds, dc);
+  }
+  else
+  {
+    CKRC(persistent_grid(h, k_ball_graph<false>, smem, h->n, cnt, s, &grid));
+    k_ball_graph<false><<<grid, TGQ_BLOCK, smem, s>>>(view_of(h), sv, h->n, max_degree, init_radius, rounds, min_dot, min_degree, cnt, di, ds, dc);
+  }
   CK(cudaGetLastError());
   CK(cudaEventRecord(e1, s));
   h->st.last_launches += 1; h->st.total_launches += 1;
@@ -747,6 +765,18 @@ int tgq_ball_graph(tgq_handle * h, int32_t max_degree, float init_radius, int32_
   CK(cudaStreamSynchronize(s));
   float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1)); h->st.last_query_ms = ms;
   return TGQ_OK;
+}
+
+int tgq_ball_graph(tgq_handle * h, int32_t max_degree, float init_radius, int32_t rounds, float min_dot, int32_t min_degree, int32_t * idx,
+                   float * sep, int32_t * count)
+{ return ball_graph_common(h, nullptr, max_degree, init_radius, rounds, min_dot, min_degree, idx, sep, count); }
+
+int tgq_ball_graph_surface(tgq_handle * h, tgq_handle * surface, int32_t max_degree, float init_radius, int32_t rounds, float min_dot,
+                           int32_t min_degree, int32_t * idx, float * sep, int32_t * count)
+{
+  if (!h) return TGQ_EINVAL;
+  if (!surface) return fail(h, TGQ_EINVAL, "tgq_ball_graph_surface: null surface handle");
+  return ball_graph_common(h, surface, max_degree, init_radius, rounds, min_dot, min_degree, idx, sep, count);
 }
 
 int tgq_ball_range(tgq_handle * h, const float * c3, const float * radius, int64_t Q, int32_t max_out, int32_t exclude_self, int32_t * idx,

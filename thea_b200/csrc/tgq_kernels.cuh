@@ -512,10 +512,11 @@ k_knn(BvhView b, float const * __restrict__ q3, uint32_t const * __restrict__ pe
 }
 
 // ---- K7 ball graph over the structure's own points (query t is the point at Morton position t) ---------------------------
+template <bool SURF>
 struct BallW
 {
   static constexpr int STAGE = 2;       // (x, y, z, element index) (normal, -)
-  BallState s; BvhView b; int k; float init_radius; int rounds; float min_dot; int min_degree;
+  BallState s; BvhView b; BvhView surf; int k; float init_radius; int rounds; float min_dot; int min_degree;
   int * idx; float * sep; int * count; int64_t qi;
   __device__ __forceinline__ int state() const { return s.t.cur; }
   __device__ __forceinline__ void stage(int t, f4 * dst) const
@@ -532,7 +533,7 @@ struct BallW
   __device__ __forceinline__ void pop_step() { trav_pop_step(s.t, s.r2); }
   __device__ __forceinline__ void fetch(f4 * r) const { ball_fetch(s, b, r); }
   __device__ __forceinline__ void node_compute(f4 const * r) { ball_node_compute(s, b, r); }
-  __device__ __forceinline__ void leaf_compute(f4 const * r) { ball_leaf_compute(s, b, r); }
+  __device__ __forceinline__ void leaf_compute(f4 const * r) { if (SURF) ball_leaf_compute_surf(s, b, surf, r); else ball_leaf_compute(s, b, r); }
   __device__ __forceinline__ void finish()
   {
     if (!ball_round_done(s, b)) return;          // next round started
@@ -547,14 +548,16 @@ struct BallW
   }
 };
 
+template <bool SURF>
 __global__ void __launch_bounds__(TGQ_BLOCK)
-k_ball_graph(BvhView b, int n, int k, float init_radius, int rounds, float min_dot, int min_degree, int * counter, int * idx, float * sep, int * count)
+k_ball_graph(BvhView b, BvhView surf, int n, int k, float init_radius, int rounds, float min_dot, int min_degree, int * counter, int * idx, float * sep,
+             int * count)
 {
   extern __shared__ __align__(16) unsigned char smem[];
-  BallW w;
-  w.b = b; w.k = k; w.init_radius = init_radius; w.rounds = rounds; w.min_dot = min_dot; w.min_degree = min_degree;
+  BallW<SURF> w;
+  w.b = b; w.surf = surf; w.k = k; w.init_radius = init_radius; w.rounds = rounds; w.min_dot = min_dot; w.min_degree = min_degree;
   w.idx = idx; w.sep = sep; w.count = count; w.qi = 0; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
-  unsigned char * extra; f4 * stage = trav_setup(w.s.t, st, smem, BallW::STAGE, &extra);
+  unsigned char * extra; f4 * stage = trav_setup(w.s.t, st, smem, BallW<SURF>::STAGE, &extra);
   float * sets = (float *)extra;
   w.s.set.init(sets + threadIdx.x, (int *)(sets + (size_t)k * blockDim.x) + threadIdx.x, blockDim.x, k);
   warp_run(w, n, counter, stage);

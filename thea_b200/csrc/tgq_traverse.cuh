@@ -825,4 +825,67 @@ TGQ_HD void ray_query(BvhView const & b, v3 o, v3 d, float & best_t, int & best_
   best_t = s.best_t; best_idx = s.best_idx; best_k = s.best_k;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Proximity graph with the reachability test of PointSet3's NeighborFunctor (PointSet3.hpp:639-648): a candidate that passed the
+// identity, angle and range tests is dropped when the segment from the lifted sample position towards it is blocked by the
+// surface: Ray3(x_i + 5 * sep * normalized(n_i + n_j), x_j - x_i), rayIntersects(ray, max_time = 1) on the triangle structure
+// `surf`.  The ray is cast only for candidates the bounded set would accept: a blocked candidate never enters the set and the
+// set only improves, so the result is the max_degree smallest valid candidates either way, as in the reference (which tests
+// every candidate in range).  Needs normals (the reference skips the test without them).
+TGQ_HD bool graph_edge_blocked(BvhView const & surf, v3 c, v3 nc, v3 nj, v3 diff, float sep)
+{
+  v3 lift_dir = normalized3(add3(nc, nj));
+  v3 o = add3(c, mul3(lift_dir, 5.0f * sep));
+  float best_t = 1.0f; int best_idx = -1, best_k = -1;
+  ray_query<true>(surf, o, diff, best_t, best_idx, best_k);
+  return best_idx >= 0;
+}
+
+TGQ_HD void ball_leaf_compute_surf(BallState & s, BvhView const & b, BvhView const & surf, f4 const * r)
+{
+  int cnt = s.t.kend - s.t.k; if (cnt > TGQ_FETCH_BOX) cnt = TGQ_FETCH_BOX;
+  for (int j = 0; j < TGQ_FETCH_BOX; ++j)
+  {
+    if (j >= cnt) break;
+    TGQ_COUNT_PRIM();
+    f4 e = r[j];
+    int idx = f2i(e.w);
+    if (idx == s.self) continue;
+    v3 diff = sub3(mk3(e.x, e.y, e.z), s.c);
+    float d2 = sqn3(diff);
+    if (!(d2 <= s.r2)) continue;
+    v3 nj = mk3(0.0f, 0.0f, 0.0f);
+    if (s.has_n)
+    {
+      f4 q = ldq(b.nrm + s.t.k + j); nj = mk3(q.x, q.y, q.z);
+      if (dot3(s.nc, nj) < s.min_dot) continue;
+    }
+    float sep = fast_sqrt(d2);
+    if (!s.set.accepts(sep, idx)) continue;
+    if (s.has_n && graph_edge_blocked(surf, s.c, s.nc, nj, diff, sep)) continue;
+    s.set.insert(sep, idx);
+  }
+  s.t.k += cnt;
+  if (s.t.k >= s.t.kend) trav_pop(s.t);
+}
+
+TGQ_HD void ball_graph_surface_query(BvhView const & b, BvhView const & surf, v3 c, v3 nc, bool has_n, float min_dot, int self,
+                                     float init_radius, int rounds, int min_degree, SortedSet & set)
+{
+  BallState s; TravStack st; trav_bind(s.t, st); s.set = set;
+  ball_begin(s, b, c, nc, has_n, min_dot, self, init_radius, rounds, min_degree);
+  f4 r[TGQ_FETCH_BOX];
+  for (;;)
+  {
+    while (s.t.cur != TGQ_ST_DONE)
+    {
+      if (s.t.cur == TGQ_ST_POP) { trav_pop_step(s.t, s.r2); continue; }
+      ball_fetch(s, b, r);
+      if (s.t.cur >= 0) ball_node_compute(s, b, r); else ball_leaf_compute_surf(s, b, surf, r);
+    }
+    if (ball_round_done(s, b)) break;
+  }
+  set.n = s.set.n;
+}
+
 }  // namespace tgq

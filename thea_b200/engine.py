@@ -24,7 +24,7 @@ SYMBOLS = [
     "tgq_info", "tgq_triangle_cache", "tgq_closest", "tgq_knn", "tgq_ball_graph", "tgq_avg_separation",
     "tgq_ray_first", "tgq_ray_any", "tgq_sdf", "tgq_icp_sums", "tgq_transform_points", "tgq_area_sample",
     "tgq_get_stats", "tgq_set_point_labels", "tgq_closest_filtered", "tgq_knn_filtered", "tgq_icp_align", "tgq_ball_range",
-    "tgq_ball_stats", "tgq_visibility",
+    "tgq_ball_stats", "tgq_visibility", "tgq_ball_graph_surface",
 ]
 
 
@@ -86,6 +86,7 @@ def load_library(path=None):
     L.tgq_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.tgq_set_point_labels.argtypes = [vp, vp]
     L.tgq_ball_range.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
+    L.tgq_ball_graph_surface.argtypes = [vp, vp, i32, f32, i32, f32, i32, vp, vp, vp]
     L.tgq_ball_stats.argtypes = [vp, vp, vp, vp, i64, vp]
     L.tgq_visibility.argtypes = [vp, vp, i64, vp, i32, i32, f32, vp, vp]
     L.tgq_icp_align.argtypes = [vp, vp, i64, i32, i32, f64, i32, vp, vp, vp, vp]
@@ -311,6 +312,18 @@ class Engine:
             idx, sep, cnt = out
         self._ck(self._L.tgq_ball_graph(self._h, int(max_degree), float(init_radius), int(rounds), float(min_dot), int(min_degree),
                                         _ptr(idx), _ptr(sep), _ptr(cnt)))
+        return idx, sep, cnt
+
+    def ball_graph_surface(self, surface, max_degree, init_radius, rounds=3, min_dot=-0.5, min_degree=None):
+        """PointSet3::updateGraph(surface): the ball graph with the reachability ray test against the triangle Engine `surface`."""
+        _, n, _, _ = self.info()
+        if min_degree is None:
+            min_degree = min(max(int(0.25 * max_degree), 4), max_degree)   # PointSet3.hpp:665
+        idx = np.empty((n, max_degree), np.int32)
+        sep = np.empty((n, max_degree), np.float32)
+        cnt = np.empty(n, np.int32)
+        self._ck(self._L.tgq_ball_graph_surface(self._h, surface._h, int(max_degree), float(init_radius), int(rounds), float(min_dot),
+                                                int(min_degree), _ptr(idx), _ptr(sep), _ptr(cnt)))
         return idx, sep, cnt
 
     def avg_separation(self, seeds):
