@@ -519,6 +519,10 @@ class GpuPointBvhT : public GpuBvhBase<VectorT>
     void ballStatsBatch(float const * c3, float const * qn3, float const * radius, intx Q, double * out16) const
     { detail::check(h, tgq_ball_stats(h, c3, qn3, radius, Q, out16), "tgq_ball_stats"); }
 
+    /** Q LocalDistanceHistogram::compute(c_i, histogram, EUCLIDEAN, r_i) calls: hist is Q x num_bins raw counts. */
+    void ballHistogramBatch(float const * c3, float const * radius, intx Q, int32_t num_bins, uint32_t * hist) const
+    { detail::check(h, tgq_ball_histogram(h, c3, radius, Q, num_bins, hist), "tgq_ball_histogram"); }
+
     /** PointSet3::updateGraph's neighbour search for every sample (PointSet3.hpp:324-391,586-681). */
     void sampleGraphBatch(int32_t max_degree, float init_radius, int32_t * idx, float * sep, int32_t * count = nullptr, int32_t rounds = 3,
                           float min_dot = -0.5f, int32_t min_degree = -1) const

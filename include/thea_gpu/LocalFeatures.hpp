@@ -5,11 +5,13 @@
 //   SurfaceFeatures::Local::Curvature::computeProjectedCurvature(position[, normal], r)    (…/Local/Curvature.cpp:69-98)
 //   SurfaceFeatures::Local::LocalPca::compute(position, eigenvectors, r)                   (…/Local/LocalPca.cpp:32-62, Algorithms/PcaN.hpp:150-197)
 //   SurfaceFeatures::Local::Visibility::compute(position, num_rays)                        (…/Local/Visibility.hpp:104-125)
+//   SurfaceFeatures::Local::LocalDistanceHistogram::compute(position, histogram, EUCLIDEAN, max_distance)  (…/Local/LocalDistanceHistogram.cpp:36-88)
 //
 // The reference classes take a PointSet3 (samples + BvhN + scale); here they take the GpuPointBvh built over the same samples
 // plus the shape scale PointSet3::getScale() would return (the diameter of its bounding sphere, PointSet3.hpp:560-572), which the
 // caller supplies.  Scalar calls are batches of one; *Batch members answer a whole loop in one C-ABI call.  Not covered:
-// GEODESIC average distance (Dijkstra on the sample graph), LocalDistanceHistogram, SpinImage, RandomWalks.
+// GEODESIC distances (Dijkstra on the sample graph), random subsampling of the histogram, SpinImage (a loop over all samples, no
+// structure query), RandomWalks.
 // File:line citations are relative to /root/reference/Code/Source/.
 #ifndef THEA_GPU_LOCALFEATURES_HPP
 #define THEA_GPU_LOCALFEATURES_HPP
@@ -177,6 +179,30 @@ class LocalPcaT
     GpuPointBvhT<VectorT> const * surf; Real scale;
 };
 
+/** LocalDistanceHistogram (EUCLIDEAN, every sample accepted): histogram of the distances from the query to the samples within
+ *  max_distance, over [0, max_distance].  bins receives num_bins doubles per query, like Histogram::getBins(). */
+template <typename VectorT = Vec3>
+class LocalDistanceHistogramT
+{
+  public:
+    LocalDistanceHistogramT(GpuPointBvhT<VectorT> const * surf_, Real scale_) : surf(surf_), scale(scale_)
+    { if (!surf) throw Error("LocalDistanceHistogram: Cannot construct with a null surface"); }
+
+    void compute(VectorT const & position, intx num_bins, double * bins, Real max_distance = -1) const
+    { float c[3]; detail::put3(c, position); computeBatch(c, 1, num_bins, bins, max_distance); }
+    /** max_distance < 0 selects the shape scale (LocalDistanceHistogram.cpp:65-67). */
+    void computeBatch(float const * p3, intx Q, intx num_bins, double * bins, Real max_distance = -1) const
+    {
+      if (max_distance < 0) max_distance = scale;
+      std::vector<float> rad((size_t)Q, max_distance); std::vector<uint32_t> h((size_t)Q * (size_t)num_bins);
+      surf->ballHistogramBatch(p3, rad.data(), Q, (int32_t)num_bins, h.data());
+      for (size_t i = 0; i < h.size(); ++i) bins[i] = (double)h[i];
+    }
+
+  private:
+    GpuPointBvhT<VectorT> const * surf; Real scale;
+};
+
 /** Visibility: fraction of rays from the query point that do not hit the shape again.  The reference draws num_rays random
  *  directions from Random::common() per call; here the caller fixes the directions at construction. */
 template <typename VectorT = Vec3>
@@ -209,6 +235,7 @@ typedef AverageDistanceT<Vec3> AverageDistance;
 typedef CurvatureT<Vec3> Curvature;
 typedef LocalPcaT<Vec3> LocalPca;
 typedef VisibilityT<Vec3> Visibility;
+typedef LocalDistanceHistogramT<Vec3> LocalDistanceHistogram;
 
 }  // namespace Local
 }  // namespace SurfaceFeatures

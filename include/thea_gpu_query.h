@@ -54,7 +54,7 @@ enum
   TGQ_OPT_SORT_QUERIES = 1,   /* 0 = never, 1 = always, 2 = auto (default: batches >= 4096 are Morton-ordered first) */
   TGQ_OPT_LEAF_SIZE = 2,      /* max elements per leaf, 1..15 (default 4); takes effect at the next build */
   TGQ_OPT_ASYNC = 3,          /* 1: device-pointer calls return without synchronising the stream (default 0) */
-  TGQ_OPT_CHUNK = 4           /* queries per staged chunk for host-pointer calls (default 8388608) */
+  TGQ_OPT_CHUNK = 4           /* queries per staged chunk for host-pointer calls (default 16777216) */
 };
 
 #define TGQ_MAX_K 64
@@ -151,6 +151,15 @@ int tgq_ball_range(tgq_handle * h, const float * c3, const float * radius, int64
  * epilogues (include/thea_gpu/LocalFeatures.hpp) turn the sums into the features.  A negative radius matches nothing.
  * qn3 needs a structure built with normals (else TGQ_ESTATE). */
 int tgq_ball_stats(tgq_handle * h, const float * c3, const float * qn3, const float * radius, int64_t Q, double * out16);
+
+/* Q local distance histograms on a point structure.  Replaces the loop of
+ *   LocalDistanceHistogram::compute(c_i, histogram, EUCLIDEAN, max_distance = r_i, sample_reduction_ratio >= 1)
+ * (Algorithms/SurfaceFeatures/Local/LocalDistanceHistogram.cpp:36-88; Algorithms/Histogram.hpp:110-150): every element e in
+ * Ball3(c_i, r_i) falls in bin clamp((intx)floor((double)|x_e - c_i| / bin_size), 0, num_bins - 1), bin_size =
+ * max((double)r_i, 1e-30) / num_bins.  hist[Q x num_bins] are the raw counts (the reference's bins hold the same integers as
+ * doubles, sumValues() is their sum); num_bins <= 256.  Integer counts: bit exact, order independent.  The reference's random
+ * subsampling (sample_reduction_ratio < 1, Random::common()) is not reproduced. */
+int tgq_ball_histogram(tgq_handle * h, const float * c3, const float * radius, int64_t Q, int32_t num_bins, uint32_t * hist);
 
 /* Proximity graph over the P points of a point structure.  Replaces the loop of PointSet3::updateGraph over
  * findSampleNeighbors (PointSet3.hpp:380-381,586-681): for every sample, a ball range query of radius init_radius

@@ -344,6 +344,35 @@ void orc_ball_stats(void * h, float const * c3, float const * qn3, float const *
   });
 }
 
+// LocalDistanceHistogram::compute(c, histogram, EUCLIDEAN, max_distance, ratio >= 1) (LocalDistanceHistogram.cpp:36-88) with
+// Histogram::setRange / insert (Histogram.hpp:110-150), in the reference's traversal order (mode 0) or element order (mode 2).
+void orc_ball_hist(void * h, float const * c3, float const * radius, int64_t Q, int nbins, int mode, int nthreads, double * hist)
+{
+  KdTree const & T = ((Handle *)h)->tree;
+  int64_t P = T.size();
+  parallel_for(Q, nthreads, [&](int64_t b, int64_t e) {
+    for (int64_t i = b; i < e; ++i)
+    {
+      V3 c = ld3(c3, i); float r = radius[i]; float r2 = r * r;
+      double * bins = hist + (int64_t)nbins * i;
+      double min_value = 0, max_value = std::max((double)r, 1.0e-30);
+      double bin_size = (max_value - min_value) / nbins;
+      for (int j = 0; j < nbins; ++j) bins[j] = 0;
+      auto emit = [&](int64_t j) {
+        float d = std::sqrt(sqnorm(T.pts[(size_t)j] - c));
+        int64_t bin = (int64_t)std::floor(((double)d - min_value) / bin_size);
+        bin = bin < 0 ? 0 : (bin > nbins - 1 ? nbins - 1 : bin);
+        bins[bin] += 1.0;
+      };
+      if (r >= 0)
+      {
+        if (mode == 2) { for (int64_t j = 0; j < P; ++j) if (sqnorm(T.pts[(size_t)j] - c) <= r2) emit(j); }
+        else if (!T.nodes.empty()) kd_ball_range(T, 0, c, r2, emit);
+      }
+    }
+  });
+}
+
 // Visibility::compute (SurfaceFeatures/Local/Visibility.hpp:104-125) with caller-supplied directions: ray (p + 0.001f * scale * u, u),
 // rayIntersects (= full first hit >= 0, BvhN.hpp:1266-1269); vis = (double)num_escaped / num_rays.
 void orc_visibility(void * h, float const * p3, int64_t S, float const * dirs3, int D, int per_sample, float scale, int mode, int nthreads,

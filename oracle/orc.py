@@ -56,6 +56,7 @@ def lib():
                                        C.c_void_p, C.c_void_p]
         L.orc_ball_range.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_ball_graph_surface.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_ball_hist.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.orc_ball_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]
         L.orc_visibility.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_avg_separation.restype = C.c_float
@@ -198,6 +199,15 @@ class Oracle:
         cnt = np.empty(self.n, np.int32)
         lib().orc_ball_graph_surface(self.h, surface.h, max_degree, float(init_radius), mode, threads or ncores(), _p(idx), _p(sep), _p(cnt))
         return idx, sep, cnt
+
+    def ball_hist(self, c, radius, nbins, mode=MODE_REFERENCE, threads=None):
+        """LocalDistanceHistogram (EUCLIDEAN, explicit max_distance): [Q, nbins] float64 bin contents."""
+        c = _f32(c).reshape(-1, 3)
+        Q = c.shape[0]
+        rad = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float32), (Q,)), np.float32)
+        out = np.empty((Q, nbins), np.float64)
+        lib().orc_ball_hist(self.h, _p(c), _p(rad), Q, int(nbins), mode, threads or ncores(), _p(out))
+        return out
 
     def ball_stats(self, c, radius, qn=None, mode=MODE_REFERENCE, threads=None):
         """Local-feature functors over ball neighbourhoods (see orc_ball_stats): dict of n, avg_dist, num_offsets, curvature,

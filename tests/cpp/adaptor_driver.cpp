@@ -170,6 +170,10 @@ int main(int argc, char ** argv)
         Vec3 e = pca.compute(p, ev, 0.05f);
         for (int k = 0; k < 3; ++k) if (e[k] != fe[3 * i + k] || ev[k][0] != fv[9 * i + 3 * k]) { fprintf(stderr, "scalar LocalPca disagrees with the batch\n"); return 3; }
       }
+      LocalDistanceHistogram ldh(&pts, diag);
+      std::vector<double> hb(8 * NS);
+      ldh.computeBatch(sp.data(), NS, 8, hb.data(), 0.1f * diag);
+      wr(fo, hb);
       std::vector<float> dirs; for (int k = 0; k < 3 * 32 && k < (int)d3.size(); ++k) dirs.push_back(d3[k]);
       Visibility visf(&bvh, dirs.data(), (int32_t)(dirs.size() / 3));
       std::vector<double> vis(NS);

@@ -288,6 +288,12 @@ void emu_ball_graph_surface(void * h, void * hs, int k, float init_radius, int r
   }
 }
 
+void emu_ball_hist(void * h, float const * c3, float const * radius, int64_t Q, int nbins, uint32_t * hist)
+{
+  Emu & E = *(Emu *)h; BvhView v = E.view();
+  for (int64_t i = 0; i < Q; ++i) hist_query(v, ld(c3, i), radius[i], nbins, hist + (size_t)i * nbins);
+}
+
 void emu_ball_stats(void * h, float const * c3, float const * qn3, float const * radius, int64_t Q, double * out16)
 {
   Emu & E = *(Emu *)h; BvhView v = E.view();

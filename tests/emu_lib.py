@@ -26,6 +26,7 @@ def lib():
         L.emu_set_labels.argtypes = [vp, vp]
         L.emu_ball_range.argtypes = [vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp, vp]
         L.emu_ball_graph_surface.argtypes = [vp, vp, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, vp, vp, vp]
+        L.emu_ball_hist.argtypes = [vp, vp, vp, C.c_int64, C.c_int, vp]
         L.emu_ball_stats.argtypes = [vp, vp, vp, vp, C.c_int64, vp]
         L.emu_closest_filtered.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, vp, vp, vp]
         L.emu_knn_filtered.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, C.c_float, C.c_float, vp, vp]
@@ -84,6 +85,14 @@ class Emu:
         cnt = np.empty(Q, np.int32)
         lib().emu_ball_range(self.h, _p(c), _p(rad), Q, int(max_out), int(exclude_self), _p(idx), _p(cnt))
         return idx, cnt
+
+    def ball_hist(self, c, radius, nbins):
+        c = np.ascontiguousarray(c, np.float32)
+        Q = len(c)
+        rad = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float32), (Q,)), np.float32)
+        out = np.empty((Q, nbins), np.uint32)
+        lib().emu_ball_hist(self.h, _p(c), _p(rad), Q, int(nbins), _p(out))
+        return out
 
     def ball_stats(self, c, radius, qn=None):
         c = np.ascontiguousarray(c, np.float32)

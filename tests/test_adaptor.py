@@ -153,6 +153,7 @@ def test_adaptor_driver_matches_oracle(built, tmp_path):
     assert np.abs(fe - w).max() <= 2e-5 * float(rc) ** 2
     rec = np.einsum("qk,qki,qkj->qij", fe.astype(np.float64), fv.astype(np.float64), fv.astype(np.float64))
     assert np.abs(rec - cov).max() <= 4e-5 * float(rc) ** 2
+    assert np.array_equal(take(np.float64, 8 * NS).reshape(NS, 8), po.ball_hist(sp, ra, 8))
     vscale = float(take(np.float32, 1)[0])
     assert vscale == diag
     vis = take(np.float64, NS)

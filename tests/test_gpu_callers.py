@@ -260,6 +260,9 @@ def test_local_features_ball_stats(built):
     assert np.median(np.abs((evecs[:, 2, :] * qn).sum(axis=1))) > 0.95
     cu = callers.projected_curvature(e, c, qn, r)
     assert np.abs(cu - ora.ball_stats(c, r, qn)["curvature"]).max() <= 2e-5
+    # LocalDistanceHistogram: integer counts, bit exact
+    for nb in (5, 64):
+        assert np.array_equal(e.ball_histogram(c, rad, nb).astype(np.float64), ora.ball_hist(c, rad, nb))
     # a structure without normals refuses query normals loudly
     e2 = Engine(0)
     e2.build_points(p)

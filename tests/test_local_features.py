@@ -201,3 +201,17 @@ def test_graph_with_reachability_test_against_the_surface():
     fi, fs, fc = E.ball_graph_surface(far, k, r0)
     qi, qs, qc = E.ball_graph(k, r0)
     assert np.array_equal(fi, qi) and np.array_equal(fs, qs) and np.array_equal(fc, qc)
+
+
+def test_local_distance_histogram_is_bit_exact(cloud):
+    """LocalDistanceHistogram (EUCLIDEAN, explicit max_distance): integer bin counts equal the oracle's in both orders."""
+    p, nrm, c, qn, rad, E, ora = cloud
+    for nb in (1, 7, 32):
+        h = E.ball_hist(c, rad, nb)
+        for mode in (orc.MODE_REFERENCE, orc.MODE_BRUTE):
+            assert np.array_equal(h.astype(np.float64), ora.ball_hist(c, rad, nb, mode=mode))
+        assert np.array_equal(h.sum(axis=1), E.ball_stats(c, rad)[:, 0].astype(np.uint32))
+    # known answer: distances r * (j + 0.5) / 4 from the centre fall in bin j; the distance r itself goes to the last bin (clamp)
+    pts = np.array([[0.125, 0, 0], [0, 0.375, 0], [0, 0, 0.625], [0.875, 0, 0], [0, 1.0, 0], [0, 0, 1.5]], np.float32)
+    K = emu_lib.Emu(points=pts)
+    assert np.array_equal(K.ball_hist(np.zeros((1, 3), np.float32), 1.0, 4)[0], [1, 1, 1, 2])

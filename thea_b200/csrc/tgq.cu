@@ -58,7 +58,7 @@ struct tgq_handle
   std::string err;
   cudaStream_t own_stream = nullptr, stream = nullptr;
 
-  int opt_sort = 2, opt_leaf = 4, opt_async = 0; int64_t opt_chunk = 8388608;
+  int opt_sort = 2, opt_leaf = 4, opt_async = 0; int64_t opt_chunk = 16777216;
 
   int kind = TGQ_KIND_NONE; int n = 0; int n_nodes = 0; bool has_normals = false, has_labels = false; int leaf_built = 4;
   DevBuf nodes, elems, nrm, lab, scene;                                // NodeRec[], TriRec[] | f4[], f4[], SceneBox
@@ -814,6 +814,24 @@ int tgq_ball_stats(tgq_handle * h, const float * c3, const float * qn3, const fl
     CKRC(persistent_grid(h, k_ball_stats, smem, c.n, cnt, c.stream, &grid));
     k_ball_stats<<<grid, TGQ_BLOCK, smem, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], (float const *)c.din[2], c.perm, c.n, cnt,
                                                       (double *)c.dout[3]);
+    h->st.last_launches += 1; h->st.total_launches += 1;
+    return TGQ_OK;
+  });
+}
+
+int tgq_ball_histogram(tgq_handle * h, const float * c3, const float * radius, int64_t Q, int32_t num_bins, uint32_t * hist)
+{
+  CKRC(need_built(h, 1 << TGQ_KIND_POINTS));
+  if (Q < 0 || num_bins < 1 || (Q > 0 && (!c3 || !radius || !hist))) return fail(h, TGQ_EINVAL, "tgq_ball_histogram: bad arguments");
+  if (num_bins > 256) return fail(h, TGQ_ELIMIT, "tgq_ball_histogram: more than 256 bins");
+  Guard g(h);
+  Arg args[3] = {{c3, nullptr, 12}, {radius, nullptr, 4}, {nullptr, hist, 4 * (size_t)num_bins}};
+  BvhView v = view_of(h);
+  size_t smem = trav_smem_bytes(HistW::STAGE) + (size_t)num_bins * TGQ_BLOCK * 4;
+  return run_batched(h, Q, args, 3, true, [&](ChunkCtx & c) -> int {
+    int grid = 0; int * cnt = c.slot->counter.as<int>();
+    CKRC(persistent_grid(h, k_ball_hist, smem, c.n, cnt, c.stream, &grid));
+    k_ball_hist<<<grid, TGQ_BLOCK, smem, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], c.perm, c.n, num_bins, cnt, (unsigned *)c.dout[2]);
     h->st.last_launches += 1; h->st.total_launches += 1;
     return TGQ_OK;
   });

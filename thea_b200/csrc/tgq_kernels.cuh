@@ -648,6 +648,46 @@ k_ball_stats(BvhView b, float const * __restrict__ c3, float const * __restrict_
   warp_run(w, n, counter, stage);
 }
 
+// Local distance histograms: one lane per ball, its bins in shared memory (bank-conflict-free strided layout, like the k-NN sets).
+struct HistW
+{
+  static constexpr int STAGE = 1;       // (centre, query index)
+  HistState s; BvhView b; float const * c3; float const * rad; uint32_t const * perm; unsigned * out; int64_t qi;
+  __device__ __forceinline__ int state() const { return s.t.cur; }
+  __device__ __forceinline__ void stage(int t, f4 * dst) const
+  {
+    int i = perm ? (int)perm[t] : t; v3 p = ld3(c3, i);
+    *dst = make_float4(p.x, p.y, p.z, __int_as_float(i));
+  }
+  __device__ __forceinline__ void begin(int, f4 const * src)
+  {
+    f4 r = *src; qi = __float_as_int(r.w);
+    hist_begin(s, b, mk3(r.x, r.y, r.z), rad[qi]);
+  }
+  static constexpr int FETCH = TGQ_FETCH_BOX;
+  __device__ __forceinline__ void pop_step() { trav_pop_step(s.t, s.r2); }
+  __device__ __forceinline__ void fetch(f4 * r) const { hist_fetch(s, b, r); }
+  __device__ __forceinline__ void node_compute(f4 const * r) { hist_node_compute(s, b, r); }
+  __device__ __forceinline__ void leaf_compute(f4 const * r) { hist_leaf_compute(s, b, r); }
+  __device__ __forceinline__ void finish()
+  {
+    for (int j = 0; j < s.nbins; ++j) out[qi * s.nbins + j] = s.bins[j * s.stride];
+    s.t.cur = TGQ_ST_IDLE;
+  }
+};
+
+__global__ void __launch_bounds__(TGQ_BLOCK)
+k_ball_hist(BvhView b, float const * __restrict__ c3, float const * __restrict__ rad, uint32_t const * __restrict__ perm, int n, int nbins,
+            int * counter, unsigned * out)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  HistW w;
+  w.b = b; w.c3 = c3; w.rad = rad; w.perm = perm; w.out = out; w.qi = 0; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
+  unsigned char * extra; f4 * stage = trav_setup(w.s.t, st, smem, HistW::STAGE, &extra);
+  w.s.nbins = nbins; w.s.stride = blockDim.x; w.s.bins = (unsigned *)extra + threadIdx.x;
+  warp_run(w, n, counter, stage);
+}
+
 // Visibility rays (SurfaceFeatures/Local/Visibility.hpp:104-125): thread = (sample, direction).  Ray (p + 0.001 * scale * u, u),
 // unbounded, any hit; escaped[t] = 1 when nothing was hit.  Directions: D x 3 shared by every sample, or S x D x 3 per sample.
 struct VisW

@@ -826,6 +826,65 @@ TGQ_HD void ray_query(BvhView const & b, v3 o, v3 d, float & best_t, int & best_
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Local distance histogram (SurfaceFeatures/Local/LocalDistanceHistogram.cpp:36-88, EUCLIDEAN with an explicit max_distance and
+// every sample accepted): processRange<IntersectionTester>(Ball3(c, max_distance), callback) with
+//   Real d = (x_e - c).norm();  histogram.insert(d)
+// and Histogram::insert (Algorithms/Histogram.hpp:110-150): bin = clamp((intx)floor(((double)d - min) / bin_size), 0, B - 1) with
+// min = 0 and bin_size = max((double)max_distance, 1e-30) / B in double.  Counts are integers: order independent, bit exact.
+struct HistState
+{
+  v3 c; float r2; double bin_size; int nbins; int stride; unsigned * bins;
+  Trav t;
+};
+TGQ_HD double hist_bin_size(float max_distance, int nbins)
+{
+  double mx = (double)max_distance; if (mx < 1.0e-30) mx = 1.0e-30;
+  return (mx - 0.0) / (double)nbins;
+}
+TGQ_HD void hist_begin(HistState & s, BvhView const & b, v3 c, float radius)
+{
+  s.c = c; s.r2 = radius * radius; s.bin_size = hist_bin_size(radius, s.nbins);
+  for (int j = 0; j < s.nbins; ++j) s.bins[j * s.stride] = 0u;
+  trav_begin(s.t, (radius >= 0.0f) ? b.n_nodes : 0);
+}
+TGQ_HD void hist_fetch(HistState const & s, BvhView const & b, f4 * r) { box_fetch(s.t, b, r); }
+TGQ_HD void hist_node_compute(HistState & s, BvhView const & b, f4 const * r)
+{
+  TGQ_COUNT_NODE();
+  float lb0, lb1; int c0, c1; box_node_bounds(r, s.c, lb0, lb1, c0, c1);
+  trav_descend(s.t, lb0, lb1, 0.0f, 0.0f, c0, c1, s.r2);
+}
+TGQ_HD void hist_leaf_compute(HistState & s, BvhView const & b, f4 const * r)
+{
+  int cnt = s.t.kend - s.t.k; if (cnt > TGQ_FETCH_BOX) cnt = TGQ_FETCH_BOX;
+  for (int j = 0; j < TGQ_FETCH_BOX; ++j)
+  {
+    if (j >= cnt) break;
+    TGQ_COUNT_PRIM();
+    f4 e = r[j];
+    float d2 = sqn3(sub3(mk3(e.x, e.y, e.z), s.c));
+    if (!(d2 <= s.r2)) continue;
+    double q = floor(((double)sqrtf(d2) - 0.0) / s.bin_size);
+    int bin = q < 0.0 ? 0 : (q > (double)(s.nbins - 1) ? s.nbins - 1 : (int)q);
+    s.bins[bin * s.stride] += 1u;
+  }
+  s.t.k += cnt;
+  if (s.t.k >= s.t.kend) trav_pop(s.t);
+}
+TGQ_HD void hist_query(BvhView const & b, v3 c, float radius, int nbins, unsigned * bins)
+{
+  HistState s; TravStack st; trav_bind(s.t, st); s.nbins = nbins; s.stride = 1; s.bins = bins;
+  hist_begin(s, b, c, radius);
+  f4 r[TGQ_FETCH_BOX];
+  while (s.t.cur != TGQ_ST_DONE)
+  {
+    if (s.t.cur == TGQ_ST_POP) { trav_pop_step(s.t, s.r2); continue; }
+    hist_fetch(s, b, r);
+    if (s.t.cur >= 0) hist_node_compute(s, b, r); else hist_leaf_compute(s, b, r);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Proximity graph with the reachability test of PointSet3's NeighborFunctor (PointSet3.hpp:639-648): a candidate that passed the
 // identity, angle and range tests is dropped when the segment from the lifted sample position towards it is blocked by the
 // surface: Ray3(x_i + 5 * sep * normalized(n_i + n_j), x_j - x_i), rayIntersects(ray, max_time = 1) on the triangle structure

@@ -24,7 +24,7 @@ SYMBOLS = [
     "tgq_info", "tgq_triangle_cache", "tgq_closest", "tgq_knn", "tgq_ball_graph", "tgq_avg_separation",
     "tgq_ray_first", "tgq_ray_any", "tgq_sdf", "tgq_icp_sums", "tgq_transform_points", "tgq_area_sample",
     "tgq_get_stats", "tgq_set_point_labels", "tgq_closest_filtered", "tgq_knn_filtered", "tgq_icp_align", "tgq_ball_range",
-    "tgq_ball_stats", "tgq_visibility", "tgq_ball_graph_surface",
+    "tgq_ball_stats", "tgq_visibility", "tgq_ball_graph_surface", "tgq_ball_histogram",
 ]
 
 
@@ -87,6 +87,7 @@ def load_library(path=None):
     L.tgq_set_point_labels.argtypes = [vp, vp]
     L.tgq_ball_range.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
     L.tgq_ball_graph_surface.argtypes = [vp, vp, i32, f32, i32, f32, i32, vp, vp, vp]
+    L.tgq_ball_histogram.argtypes = [vp, vp, vp, i64, i32, vp]
     L.tgq_ball_stats.argtypes = [vp, vp, vp, vp, i64, vp]
     L.tgq_visibility.argtypes = [vp, vp, i64, vp, i32, i32, f32, vp, vp]
     L.tgq_icp_align.argtypes = [vp, vp, i64, i32, i32, f64, i32, vp, vp, vp, vp]
@@ -272,6 +273,15 @@ class Engine:
         cnt = np.empty(Q, np.int32)
         self._ck(self._L.tgq_ball_range(self._h, _ptr(c3), _ptr(rad), Q, int(max_out), int(exclude_self), _ptr(idx), _ptr(cnt)))
         return idx, cnt
+
+    def ball_histogram(self, c3, radius, num_bins):
+        """LocalDistanceHistogram (EUCLIDEAN) for every ball: [Q x num_bins] uint32 counts (tgq_ball_histogram)."""
+        c3 = _as_in(c3)
+        Q = int(c3.shape[0])
+        rad = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float32), (Q,)), np.float32)
+        hist = np.empty((Q, num_bins), np.uint32)
+        self._ck(self._L.tgq_ball_histogram(self._h, _ptr(c3), _ptr(rad), Q, int(num_bins), _ptr(hist)))
+        return hist
 
     def ball_stats(self, c3, radius, qn3=None, out=None):
         """Per-ball neighbourhood sums (tgq_ball_stats): [Q x 16] doubles, layout in include/thea_gpu_query.h."""
