@@ -54,7 +54,8 @@ enum
   TGQ_OPT_SORT_QUERIES = 1,   /* 0 = never, 1 = always, 2 = auto (default: batches >= 4096 are Morton-ordered first) */
   TGQ_OPT_LEAF_SIZE = 2,      /* max elements per leaf, 1..15 (default 4); takes effect at the next build */
   TGQ_OPT_ASYNC = 3,          /* 1: device-pointer calls return without synchronising the stream (default 0) */
-  TGQ_OPT_CHUNK = 4           /* queries per staged chunk for host-pointer calls (default 16777216) */
+  TGQ_OPT_CHUNK = 4,          /* queries per staged chunk for host-pointer calls (default 16777216) */
+  TGQ_OPT_POOL = 5            /* closest point on triangle structures: 1 = leaf tests pooled across the warp (default), 0 = per lane */
 };
 
 #define TGQ_MAX_K 64

@@ -58,7 +58,7 @@ struct tgq_handle
   std::string err;
   cudaStream_t own_stream = nullptr, stream = nullptr;
 
-  int opt_sort = 2, opt_leaf = 4, opt_async = 0; int64_t opt_chunk = 16777216;
+  int opt_sort = 2, opt_leaf = 4, opt_async = 0, opt_pool = 1; int64_t opt_chunk = 16777216;
 
   int kind = TGQ_KIND_NONE; int n = 0; int n_nodes = 0; bool has_normals = false, has_labels = false; int leaf_built = 4;
   DevBuf nodes, elems, nrm, lab, scene;                                // NodeRec[], TriRec[] | f4[], f4[], SceneBox
@@ -522,6 +522,7 @@ int tgq_set_option(tgq_handle * h, int option, int64_t value)
     case TGQ_OPT_SORT_QUERIES: if (value < 0 || value > 2) return fail(h, TGQ_EINVAL, "TGQ_OPT_SORT_QUERIES takes 0, 1 or 2"); h->opt_sort = (int)value; return TGQ_OK;
     case TGQ_OPT_LEAF_SIZE: if (value < 1 || value > TGQ_LEAF_MASK) return fail(h, TGQ_EINVAL, "TGQ_OPT_LEAF_SIZE takes 1..15"); h->opt_leaf = (int)value; return TGQ_OK;
     case TGQ_OPT_ASYNC: h->opt_async = value ? 1 : 0; return TGQ_OK;
+    case TGQ_OPT_POOL: h->opt_pool = value ? 1 : 0; return TGQ_OK;
     case TGQ_OPT_CHUNK: if (value < 1024) return fail(h, TGQ_EINVAL, "TGQ_OPT_CHUNK must be >= 1024"); h->opt_chunk = value; return TGQ_OK;
     default: return fail(h, TGQ_EINVAL, "unknown option");
   }
@@ -632,7 +633,14 @@ static int closest_common(tgq_handle * h, const float * q3, const float * qn3, c
   size_t smem = trav_smem_bytes(1);
   return run_batched(h, Q, args, 6, true, [&](ChunkCtx & c) -> int {
     int grid = 0; int * cnt = c.slot->counter.as<int>();
-    if (tri)
+    if (tri && h->opt_pool && h->leaf_built <= 4)
+    {
+      size_t psmem = smem + (TGQ_BLOCK / 32) * sizeof(PoolWarp);
+      CKRC(persistent_grid(h, k_closest_pool, psmem, c.n, cnt, c.stream, &grid));
+      k_closest_pool<<<grid, TGQ_BLOCK, psmem, c.stream>>>(v, h->pad, (float const *)c.din[0], c.perm, c.n, ub, exclude_self, c.offset, cnt,
+                                                          (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3]);
+    }
+    else if (tri)
     {
       CKRC(persistent_grid(h, k_closest<true>, smem, c.n, cnt, c.stream, &grid));
       k_closest<true><<<grid, TGQ_BLOCK, smem, c.stream>>>(v, h->pad, (float const *)c.din[0], c.perm, c.n, ub, exclude_self, c.offset, cnt,

@@ -8,7 +8,9 @@
 
 namespace tgq {
 
+#ifndef TGQ_BLOCK
 #define TGQ_BLOCK 128
+#endif
 
 // ---- ordered-int encoding so that float min/max can use integer atomics ---------------------------------------------
 __device__ __forceinline__ int float_to_ordered(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
@@ -329,11 +331,16 @@ __global__ void k_query_codes(float const * __restrict__ q3, int n, SceneBox con
 // also balances the load across SMs.
 //   W: FETCH, STAGE ; int state() ; void stage(t, dst) ; void begin(t, src) ; void fetch(r) ; void node_compute(r) ;
 //      void leaf_compute(r) ; void finish()  [finish leaves the lane in TGQ_ST_IDLE, or restarts it]
+#ifndef TGQ_CHUNK
 #define TGQ_CHUNK 64
+#endif
 #ifndef TGQ_POPS
 #define TGQ_POPS 2
 #endif
-#define TGQ_SSTACK 20    // stack entries per thread kept in shared memory (deeper ones spill to local memory)
+#ifndef TGQ_SSTACK
+#define TGQ_SSTACK 20
+#endif
+// stack entries per thread kept in shared memory (deeper ones spill to local memory)
 #define TGQ_WARPS (TGQ_BLOCK / 32)
 
 // Shared memory of one block of a traversal kernel: the short stacks, then one staging buffer of TGQ_CHUNK query records
@@ -454,6 +461,171 @@ k_closest(BvhView b, float scene_pad, float const * __restrict__ q3, uint32_t co
   w.idx = idx; w.d2 = d2; w.cp3 = cp3; w.qi = 0; w.seed = -1; w.qn3 = qn3; w.qlabel = qlabel; w.min_dot = min_dot; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
   f4 * stage = trav_setup(w.s.t, st, smem, ClosestW<TRI>::STAGE, nullptr);
   warp_run(w, n, counter, stage);
+}
+
+// ---- K5b closest element on triangle structures, leaf tests pooled across the warp ----------------------------------------
+// In k_closest<true> a lane that reaches a leaf runs the triangle screen and the reference's point-triangle arithmetic in its own
+// step, so every warp iteration pays for the node arithmetic AND the leaf arithmetic while only about a third of the lanes are at a
+// leaf (ncu: 11 of 32 lanes active per issued instruction in the leaf code).  Here a lane that reaches a leaf appends its triangles
+// to a per-warp queue in shared memory -- entries (owner lane, Morton position) -- and goes straight back to its stack; when 32
+// entries are waiting (or nobody can traverse) the whole warp runs ONE leaf iteration with every lane on a different entry: the
+// owner's query is read with shuffles, the result is merged into the owner's best with a 64-bit shared-memory atomicMin on
+// (squared distance bits, element index) -- exactly the canonical order: smaller distance, then lower index.  The owner's pruning
+// bound is therefore a few iterations stale, which only makes pruning more conservative; the answer is the minimum over the same
+// exact per-element values and does not depend on the order in which elements are tested.  A query seeded with its lane's previous
+// answer holds its traversal until that one test has come back (traversing with an infinite bound would open the whole tree).
+#ifndef TGQ_QCAP
+#define TGQ_QCAP 256          // >= 31 waiting + 32 seeds + 32 lanes x 4 leaf triangles per iteration (leaf size <= 4)
+#endif
+struct PoolWarp
+{
+  unsigned long long best[32];
+  f4 cp[32];                  // closest point + Morton position of the winning element
+  int done[32];
+  unsigned q[TGQ_QCAP];
+  int tail; int pad_[3];
+};
+
+__device__ __forceinline__ unsigned long long pool_key(float d2, int idx)
+{ return ((unsigned long long)(unsigned)__float_as_int(d2) << 32) | (unsigned long long)(unsigned)idx; }
+
+__global__ void __launch_bounds__(TGQ_BLOCK)
+k_closest_pool(BvhView b, float scene_pad, float const * __restrict__ q3, uint32_t const * __restrict__ perm, int n, float bound_ub, int exclude_self,
+               int64_t self_offset, int * counter, int * idx_out, float * d2_out, float * cp3)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned const FULL = 0xffffffffu;
+  int const lane = threadIdx.x & 31;
+  ClosestState<true> s; TravStack st; s.t.cur = TGQ_ST_IDLE;
+  unsigned char * extra; f4 * stage = trav_setup(s.t, st, smem, 1, &extra);
+  PoolWarp & pw = ((PoolWarp *)extra)[threadIdx.x >> 5];
+  pw.best[lane] = 0ull; pw.done[lane] = 0; if (lane == 0) pw.tail = 0;
+  __syncwarp();
+  int qi = 0, seed = -1, pending = 0, head = 0; bool hold = false;
+  int chunk_base = 0, chunk_next = 0, chunk_end = 0; bool exhausted = false;
+  for (;;)
+  {
+    // ---- finished queries write their results; idle lanes take the next queries of the warp's chunk -----------------------------
+    if (s.t.cur == TGQ_ST_DONE && pending == 0)
+    {
+      if (idx_out) idx_out[qi] = s.best_idx;
+      if (d2_out) d2_out[qi] = s.best_idx >= 0 ? s.best_d2 : -1.0f;
+      if (cp3) st3(cp3, qi, s.best_cp);
+      seed = perm ? s.best_k : -1;
+      s.t.cur = TGQ_ST_IDLE;
+    }
+    unsigned idle = __ballot_sync(FULL, s.t.cur == TGQ_ST_IDLE);
+    if (idle != 0u && !exhausted)
+    {
+      if (chunk_next >= chunk_end)
+      {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(counter, TGQ_CHUNK);
+        base = __shfl_sync(FULL, base, 0);
+        chunk_base = chunk_next = base; chunk_end = min(base + TGQ_CHUNK, n);
+        if (base >= n) exhausted = true;
+        else
+        {
+          __syncwarp();
+          for (int j = lane; j < chunk_end - chunk_base; j += 32)
+          {
+            int t = chunk_base + j; int i = perm ? (int)perm[t] : t; v3 p = ld3(q3, i);
+            stage[j] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+          }
+          __syncwarp();
+        }
+      }
+      if (!exhausted)
+      {
+        int t = chunk_next + __popc(idle & ((1u << lane) - 1u));
+        if (s.t.cur == TGQ_ST_IDLE && t < chunk_end)
+        {
+          f4 r = stage[t - chunk_base]; qi = __float_as_int(r.w);
+          closest_begin(s, b, scene_pad, mk3(r.x, r.y, r.z), exclude_self ? (int)(self_offset + qi) : -1, bound_ub, seed);
+          hold = s.t.cur == TGQ_ST_LEAF;          // seeded: the seed element is tested before the traversal starts
+        }
+        chunk_next = min(chunk_next + __popc(idle), chunk_end);
+      }
+    }
+    // ---- leaves reached (by the last node step, the last pops, or a seed) go to the warp's queue ---------------------------------
+    if (s.t.cur == TGQ_ST_LEAF)
+    {
+      int cnt = s.t.kend - s.t.k;
+      int pos = atomicAdd(&pw.tail, cnt);
+      for (int j = 0; j < cnt; ++j) pw.q[(pos + j) & (TGQ_QCAP - 1)] = ((unsigned)lane << 27) | (unsigned)(s.t.k + j);
+      pending += cnt;
+      trav_pop(s.t);
+    }
+    __syncwarp();
+    // ---- leaf iterations: 32 queued (owner, triangle) pairs at a time, every lane on its own pair ---------------------------------
+    for (;;)
+    {
+      int avail = pw.tail - head;
+      bool runnable = (s.t.cur >= 0 || s.t.cur == TGQ_ST_POP) && !hold;
+      if (!(avail >= 32 || (avail > 0 && !__any_sync(FULL, runnable)))) break;
+      int m = min(avail, 32);
+      pw.best[lane] = pool_key(s.best_d2, s.best_idx < 0 ? 0 : s.best_idx);      // (ub, 0) when nothing was found yet: only d2 < ub wins
+      unsigned long long published = pw.best[lane];
+      bool valid = lane < m;
+      unsigned e = valid ? pw.q[(head + lane) & (TGQ_QCAP - 1)] : ((unsigned)lane << 27);
+      int o = (int)(e >> 27), k = (int)(e & 0x7ffffffu);
+      __syncwarp();
+      v3 p = mk3(__shfl_sync(FULL, s.p.x, o), __shfl_sync(FULL, s.p.y, o), __shfl_sync(FULL, s.p.z, o));
+      float mq = __shfl_sync(FULL, s.mq, o), bd2 = __shfl_sync(FULL, s.best_d2, o);
+      int skip = __shfl_sync(FULL, s.skip, o);
+      unsigned long long mykey = ~0ull; v3 cp = mk3(0.0f, 0.0f, 0.0f);
+      if (valid)
+      {
+        f4 const * q = (f4 const *)(b.tris + k);
+        f4 r0, r1, r2, r3; ldq2(q, r0, r1); ldq2(q + 2, r2, r3);
+        v3 v0 = mk3(r0.x, r0.y, r0.z), v1 = mk3(r1.x, r1.y, r1.z), v2 = mk3(r2.x, r2.y, r2.z), nn = mk3(r3.x, r3.y, r3.z);
+        v3 cen = mul3(add3(add3(v0, v1), v2), 0.33333334f);
+        float sd = fmaxf(fabsf(fdot3(p, nn) - r2.w) - mq, 0.0f);
+        v3 pc = sub3(p, cen);
+        v3 perp = sub3(pc, mul3(nn, fdot3(nn, pc)));
+        float lat = fmaxf(sqrtf(fdot3(perp, perp)) - r3.w - mq, 0.0f);
+        int idx = f2i(r0.w);
+        if ((sd * sd + lat * lat) * TGQ_LB_DEFLATE <= bd2 && idx != skip)
+        {
+          f4 r4, r5, r6, r7; ldq2(q + 4, r4, r5); ldq2(q + 6, r6, r7);
+          float d2 = tri_point_sqdist_pre(v0, v1, v2, nn, r2.w, f2i(r1.w), r4, r5, r6, r7, p, cp);
+          if (d2 == d2) { mykey = pool_key(d2, idx); atomicMin(&pw.best[o], mykey); }
+        }
+        atomicAdd(&pw.done[o], 1);
+      }
+      __syncwarp();
+      if (mykey != ~0ull && pw.best[o] == mykey) pw.cp[o] = make_float4(cp.x, cp.y, cp.z, __int_as_float(k));
+      __syncwarp();
+      unsigned long long now = pw.best[lane];
+      if (now != published)
+      {
+        f4 c = pw.cp[lane];
+        s.best_d2 = __int_as_float((int)(unsigned)(now >> 32)); s.best_idx = (int)(unsigned)(now & 0xffffffffull);
+        s.best_cp = mk3(c.x, c.y, c.z); s.best_k = __float_as_int(c.w);
+      }
+      pending -= pw.done[lane]; pw.done[lane] = 0;
+      if (pending == 0) hold = false;
+      head += m;
+      __syncwarp();
+    }
+    // ---- node step for the lanes at a node, then the pop phase --------------------------------------------------------------------
+    bool at_node = s.t.cur >= 0 && !hold;
+    bool want_pop = s.t.cur == TGQ_ST_POP && !hold;
+    if (!__any_sync(FULL, at_node || want_pop))
+    {
+      bool busy = s.t.cur != TGQ_ST_IDLE;        // waiting for queued tests, or about to be finished at the top of the loop
+      if (exhausted && !__any_sync(FULL, busy)) break;
+      continue;
+    }
+    if (at_node)
+    {
+      f4 r[6]; f4 const * q = (f4 const *)(b.obbs + s.t.cur);
+      ldq2(q, r[0], r[1]); ldq2(q + 2, r[2], r[3]); ldq2(q + 4, r[4], r[5]);
+      closest_node_compute(s, b, r);
+    }
+#pragma unroll
+    for (int j = 0; j < TGQ_POPS; ++j) if (s.t.cur == TGQ_ST_POP && !hold) trav_pop_step(s.t, s.best_d2);
+  }
 }
 
 // ---- K6 k nearest neighbours: one bounded sorted set per thread in shared memory -------------------------------------

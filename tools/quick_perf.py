@@ -9,9 +9,11 @@ def run(n_grid, Q, leaf=4, sort=2, what=("closest", "ray")):
     b = gen.mesh_bounds(mesh)
     e = Engine(0)
     e.set_option(2, leaf); e.set_option(1, sort)
+    if os.environ.get("TGQ_POOL") is not None:
+        e.set_option(5, int(os.environ["TGQ_POOL"]))
     e.build_triangles(torch.from_numpy(mesh).cuda())
     st = e.stats()
-    out = {"tris": len(mesh), "Q": Q, "leaf": leaf, "sort": sort, "nodes": st["num_nodes"], "build_ms": round(st["last_build_ms"], 3)}
+    out = {"pool": os.environ.get("TGQ_POOL", "default"), "tris": len(mesh), "Q": Q, "leaf": leaf, "sort": sort, "nodes": st["num_nodes"], "build_ms": round(st["last_build_ms"], 3)}
     if "closest" in what:
         q = torch.from_numpy(gen.closest_queries(Q, b)).cuda()
         for _ in range(3):
@@ -31,7 +33,9 @@ def run(n_grid, Q, leaf=4, sort=2, what=("closest", "ray")):
     e.close()
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "short":
+    if len(sys.argv) > 1 and sys.argv[1] == "big":
+        run(2236, 50_000_000, what=("closest",))
+    elif len(sys.argv) > 1 and sys.argv[1] == "short":
         run(708, 4_000_000)
         run(2236, 8_000_000)
     elif len(sys.argv) > 1 and sys.argv[1] == "leaf":
