@@ -39,6 +39,11 @@ struct DevBuf
 
 #define TGQ_MAX_ARGS 8
 #ifndef TGQ_SLOTS
+// Ray kernels: resident blocks per SM (the rest of the shared-memory array becomes L1).  Measured on B200, 8 M rays on the 10 M-triangle
+// mesh: 7 blocks with the maximum carve-out 1.75 G rays/s, 6 blocks 2.27 G, 5 blocks 2.11 G (1 M triangles: 2.24 / 2.73 / 2.53 G).
+#ifndef TGQ_RAY_BLOCKS
+#define TGQ_RAY_BLOCKS 6
+#endif
 #define TGQ_SLOTS 3       // pipeline depth of host-pointer calls (measured on cfg5: 2 -> 462, 3 -> 475, 4 -> 474 M queries/s end to end)
 #endif
 
@@ -403,7 +408,7 @@ int run_batched(tgq_handle * h, int64_t Q, Arg * args, int nargs, bool sortable,
 // Grid of a persistent kernel: enough blocks to fill the device (resident blocks per SM x SMs), fewer for small batches.
 // Also zeroes the chunk counter the kernel's warps draw work from.
 template <typename K>
-int persistent_grid(tgq_handle * h, K kernel, size_t smem, int64_t n, int * counter, cudaStream_t s, int * grid_out)
+int persistent_grid(tgq_handle * h, K kernel, size_t smem, int64_t n, int * counter, cudaStream_t s, int * grid_out, int max_blocks = 0)
 {
   auto key = std::make_pair((void const *)kernel, smem);
   auto it = h->occupancy.find(key);
@@ -411,8 +416,13 @@ int persistent_grid(tgq_handle * h, K kernel, size_t smem, int64_t n, int * coun
   {
     int per_sm = 0;
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int carve = cudaSharedmemCarveoutMaxShared;
+    char const * dev_blocks = getenv("TGQ_DEV_BLOCKS");     // development aid: cap resident blocks per SM and give the rest of the array to L1
+    int cap = dev_blocks ? atoi(dev_blocks) : max_blocks;   // max_blocks: kernels that run faster with fewer resident blocks and a larger L1
+    if (cap > 0) carve = (int)std::min<size_t>(100, ((size_t)cap * (smem + 1024) * 100 + 233471) / 233472);
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TGQ_BLOCK, smem));
+    if (cap > 0) per_sm = std::min(per_sm, cap);
     it = h->occupancy.insert(std::make_pair(key, std::max(1, per_sm))).first;
   }
   int64_t want = (n + (int64_t)TGQ_CHUNK * (TGQ_BLOCK / 32) - 1) / ((int64_t)TGQ_CHUNK * (TGQ_BLOCK / 32));
@@ -870,7 +880,7 @@ int tgq_visibility(tgq_handle * h, const float * p3, int64_t S, const float * di
     CK(sl.keys[1].reserve(nr));
     uint8_t * esc = sl.keys[1].as<uint8_t>();
     int grid = 0; int * cnt = sl.counter.as<int>();
-    CKRC(persistent_grid(h, k_vis_rays, smem, (int64_t)nr, cnt, c.stream, &grid));
+    CKRC(persistent_grid(h, k_vis_rays, smem, (int64_t)nr, cnt, c.stream, &grid, TGQ_RAY_BLOCKS));
     k_vis_rays<<<grid, TGQ_BLOCK, smem, c.stream>>>(v, (float const *)c.din[0], per_sample_dirs ? (float const *)c.din[1] : (float const *)ddirs, D,
                                                     per_sample_dirs ? 1 : 0, (int)nr, scale, cnt, esc);
     int blocks = (int)(((int64_t)c.n * 32 + TGQ_BLOCK - 1) / TGQ_BLOCK);
@@ -920,13 +930,13 @@ static int ray_common(tgq_handle * h, const float * o3, const float * d3, const 
     int grid = 0; int * cnt = c.slot->counter.as<int>();
     if (any)
     {
-      CKRC(persistent_grid(h, k_ray<true>, smem, c.n, cnt, c.stream, &grid));
+      CKRC(persistent_grid(h, k_ray<true>, smem, c.n, cnt, c.stream, &grid, TGQ_RAY_BLOCKS));
       k_ray<true><<<grid, TGQ_BLOCK, smem, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], (float const *)c.din[2], c.perm, c.n, cnt,
                                                     (float *)c.dout[3], (int *)c.dout[4], (float *)c.dout[5], (uint8_t *)c.dout[6]);
     }
     else
     {
-      CKRC(persistent_grid(h, k_ray<false>, smem, c.n, cnt, c.stream, &grid));
+      CKRC(persistent_grid(h, k_ray<false>, smem, c.n, cnt, c.stream, &grid, TGQ_RAY_BLOCKS));
       k_ray<false><<<grid, TGQ_BLOCK, smem, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], (float const *)c.din[2], c.perm, c.n, cnt,
                                                      (float *)c.dout[3], (int *)c.dout[4], (float *)c.dout[5], (uint8_t *)c.dout[6]);
     }
@@ -957,7 +967,7 @@ int tgq_sdf(tgq_handle * h, const float * p3, const float * n3, int64_t S, float
     float * dt = c.dout[3] ? (float *)c.dout[3] : sl.keys[0].as<float>();
     uint8_t * dv = sl.keys[1].as<uint8_t>();
     int grid = 0; int * cnt = sl.counter.as<int>();
-    CKRC(persistent_grid(h, k_sdf_rays, smem, (int64_t)nr, cnt, c.stream, &grid));
+    CKRC(persistent_grid(h, k_sdf_rays, smem, (int64_t)nr, cnt, c.stream, &grid, TGQ_RAY_BLOCKS));
     k_sdf_rays<<<grid, TGQ_BLOCK, smem, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], (int)nr, scale, only_hit_interior, cnt, dt,
                                                  (int *)c.dout[4], dv);
     if (c.dout[2]) k_sdf_stats<<<grid_for(c.n), TGQ_BLOCK, 0, c.stream>>>(dt, dv, c.n, scale, (double *)c.dout[2]);
