@@ -447,7 +447,7 @@ def main():
 
     # ---- roofline of the dominant kernel ----
     peak, peak_kind = measured_peak()
-    dominant = "k_closest<true>" if kern["closest_ms"] >= kern["ray_ms"] else "k_ray<false>"
+    dominant = "k_closest_pool" if kern["closest_ms"] >= kern["ray_ms"] else "k_ray<false>"
     if dominant.startswith("k_closest"):
         bytes_per_q, k_ms, k_q, k_n = algorithmic_bytes(T, "closest"), kern["closest_ms"], kern["closest_q"], kern.get("closest_launches", 1)
     else:
