@@ -589,7 +589,7 @@ k_closest_pool(BvhView b, float scene_pad, float const * __restrict__ q3, uint32
         {
           f4 r4, r5, r6, r7; ldq2(q + 4, r4, r5); ldq2(q + 6, r6, r7);
           float d2 = tri_point_sqdist_pre(v0, v1, v2, nn, r2.w, f2i(r1.w), r4, r5, r6, r7, p, cp);
-          if (d2 == d2) { mykey = pool_key(d2, idx); atomicMin(&pw.best[o], mykey); }
+          if (d2 <= bd2) { mykey = pool_key(d2, idx); atomicMin(&pw.best[o], mykey); }     // only candidates that can win (NaN fails, as in the reference's d2 < best)
         }
         atomicAdd(&pw.done[o], 1);
       }
