@@ -21,7 +21,7 @@
 //   - pushFilter with arbitrary host callables and compatibility functors other than UniversalCompatibility (they cannot
 //     run on the device): pushFilter throws, except for the built-in NNFilter (same label, compatible normal) on point
 //     structures; the other device predicates are `exclude_self` and the ball-graph normal test.
-//   - metrics other than L2, BVH-to-BVH queries, setTransform.
+//   - metrics other than L2, BVH-to-BVH queries.
 #ifndef THEA_GPU_GPUBVH_HPP
 #define THEA_GPU_GPUBVH_HPP
 
@@ -218,6 +218,11 @@ class GpuBvhBase
       float l[3], u[3]; detail::check(h, tgq_info(h, nullptr, nullptr, l, u), "tgq_info");
       lo = detail::get3<VectorT>(l); hi = detail::get3<VectorT>(u);
     }
+
+    /** BvhN::setTransform / clearTransform (BvhN.hpp:903-925): queries see every element transformed by the affine map
+     *  (row-major 3 x 4 [L | t]); the reference evaluates its metrics on the transformed element (MetricL2_Transform.hpp). */
+    void setTransform(float const * tr12) { detail::check(h, tgq_set_transform(h, tr12), "tgq_set_transform"); }
+    void clearTransform() { detail::check(h, tgq_set_transform(h, nullptr), "tgq_set_transform"); }
 
     /** Result-neutral in the reference (it only seeds the pruning bound, BvhN.hpp:2365-2377): accepted and ignored. */
     void enableNearestNeighborAcceleration(intx = -1) {}

@@ -90,6 +90,16 @@ int tgq_build_points(tgq_handle * h, const float * p3, int64_t P, const float * 
  * (MeshBvh.hpp:123-134, BvhN.hpp:816-834,1694-1730). */
 int tgq_refit_triangles(tgq_handle * h, const float * v9, int64_t T);
 
+/* BvhN::setTransform / clearTransform (BvhN.hpp:903-925): queries then see every element transformed by the
+ * affine map tr12 (row-major 3x4 [L | t]) -- the reference evaluates its metrics on Transformer::transform(element, transform)
+ * (Algorithms/MetricL2_Transform.hpp), i.e. points L p + t (AffineTransformN.hpp:160 operation order) and triangles rebuilt from
+ * their transformed vertices (TriangleN::transform).  The structure is rebuilt over the transformed elements (same element indices;
+ * normals and labels of point structures are the elements' own and stay as they are); closest points, distances, hit times and
+ * tgq_info bounds are in the transformed space.  tr12 = null clears the transform: the structure is rebuilt from the untransformed
+ * elements the library kept, bit-identical to the original build.  A new build or refit forgets the transform.
+ * Used by Tools/Register/Register.cpp:644-650 (bounding-box alignment before the first correspondence search). */
+int tgq_set_transform(tgq_handle * h, const float * tr12);
+
 /* BvhN::numElements / getBounds (BvhN.hpp:952-995): kind, element count, unpadded bounds (lo[3], hi[3]; may be null). */
 int tgq_info(tgq_handle * h, int32_t * kind, int64_t * num_elements, float * lo3, float * hi3);
 /* Per-triangle cache in element order (any pointer may be null): unit normals T x 3 (what

@@ -331,3 +331,61 @@ def test_sample_graph_with_reachability(setup):
         nn.ball_graph_surface(se, 8, 0.06)
     with pytest.raises(Exception):
         pe.ball_graph_surface(pe, 8, 0.06)
+
+
+def test_set_transform(setup):
+    """BvhN::setTransform / clearTransform (SURVEY 8f rank 4): queries see the transformed elements, as the reference's
+    MetricL2 on Transformer::transform(element, transform) does; clearing restores the original answers bit for bit."""
+    from thea_b200 import Engine
+    e0, mesh, ora0 = setup
+    tr = np.array([[0.9, 0.1, 0.0, 0.3], [-0.1, 1.1, 0.05, -0.2], [0.02, 0.0, 0.8, 0.1]], np.float32)   # Register aligns boxes with scale + shift
+    b = gen.mesh_bounds(mesh)
+    q = gen.closest_queries(20000, b)
+    o, d = gen.random_rays(20000, b)
+    e = Engine(0)
+    e.build_triangles(mesh)
+    i0, d0, c0 = e.closest(q)
+    t0, r0, _ = e.ray_first(o, d)
+    moved = e.transform_points(mesh.reshape(-1, 3), tr).reshape(-1, 9)
+    ora = orc.Oracle(tris9=moved)
+    e.set_transform(tr)
+    i1, d1, c1 = e.closest(q)
+    oi, od, oc = ora.closest(q, mode=orc.MODE_CANON)
+    assert np.array_equal(i1, oi.astype(np.int32)) and np.array_equal(d1, od) and np.array_equal(c1, oc)
+    t1, r1, _ = e.ray_first(o, d)
+    ori, ort = ora.ray_first(o, d, mode=orc.MODE_CANON)
+    assert np.array_equal(r1, ori.astype(np.int32)) and np.array_equal(t1, ort)
+    _, _, lo, hi = e.info()
+    assert np.array_equal(lo, moved.reshape(-1, 3).min(axis=0)) and np.array_equal(hi, moved.reshape(-1, 3).max(axis=0))
+    e.set_transform(tr)                                  # setting it again starts from the untransformed elements, not from the moved ones
+    assert np.array_equal(e.closest(q)[1], od)
+    e.set_transform(None)
+    i2, d2, c2 = e.closest(q)
+    assert np.array_equal(i2, i0) and np.array_equal(d2, d0) and np.array_equal(c2, c0)
+    assert np.array_equal(e.ray_first(o, d)[0], t0)
+    # point structure with normals and labels: the filters keep working on the elements' own normals / labels
+    p, n, _ = gen.area_samples(mesh, 8000)
+    lab = (np.arange(len(p)) % 3).astype(np.int32)
+    pe = Engine(0)
+    pe.build_points(p, n)
+    pe.set_point_labels(lab)
+    pe.set_transform(tr)
+    pm = pe.transform_points(p, tr)
+    po = orc.Oracle(points=pm, normals=n)
+    po.set_labels(lab)
+    fi, fd, _ = pe.closest_filtered(q[:5000], n[:5000], lab[:5000])
+    ofi, ofd, _ = po.closest_filtered(q[:5000], n[:5000], lab[:5000], mode=orc.MODE_CANON)
+    assert np.array_equal(fi, ofi.astype(np.int32)) and np.array_equal(fd, ofd)
+    ki, kd = pe.knn(q[:3000], 5)
+    oki, okd = po.knn(q[:3000], 5, mode=orc.MODE_CANON)
+    assert np.array_equal(ki, oki.astype(np.int32)) and np.array_equal(kd, okd)
+    pe.set_transform(None)
+    po0 = orc.Oracle(points=p, normals=n)
+    po0.set_labels(lab)
+    fi, fd, _ = pe.closest_filtered(q[:5000], n[:5000], lab[:5000])
+    ofi, ofd, _ = po0.closest_filtered(q[:5000], n[:5000], lab[:5000], mode=orc.MODE_CANON)
+    assert np.array_equal(fi, ofi.astype(np.int32)) and np.array_equal(fd, ofd)
+    # a refit forgets the transform (new elements)
+    e.set_transform(tr)
+    e.refit_triangles(mesh)
+    assert np.array_equal(e.closest(q)[1], d0)

@@ -74,6 +74,7 @@ struct tgq_handle
   DevBuf obbs, pnrm, nsum, obbinfo, big, big_count;                   // oriented boxes (triangle structures)
   int sm_count = 148; std::map<std::pair<void const *, size_t>, int> occupancy;   // resident blocks per SM of the persistent kernels
   bool cum_valid = false;
+  bool orig_valid = false; DevBuf orig, orig_n, orig_lab, xf;           // untransformed source elements (tgq_set_transform)
   float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}; float pad = 0;
 
   Slot slot[TGQ_SLOTS];
@@ -238,7 +239,7 @@ int build_common(tgq_handle * h, int kind, float const * d_src, float const * d_
   CK(cudaEventRecord(e0, s));
 
   h->kind = kind; h->n = n; h->n_nodes = 0; h->has_normals = (kind == TGQ_KIND_POINTS && d_n3 != nullptr);
-  h->leaf_built = h->opt_leaf; h->cum_valid = false; h->has_labels = false;
+  h->leaf_built = h->opt_leaf; h->cum_valid = false; h->has_labels = false; h->orig_valid = false;
   h->st.num_elements = n;
   for (int a = 0; a < 3; ++a) { h->lo[a] = 0; h->hi[a] = 0; }
   if (n == 0) { h->st.num_nodes = 0; h->st.node_bytes = 0; h->st.element_bytes = 0; h->st.last_build_ms = 0; return TGQ_OK; }
@@ -500,7 +501,8 @@ int tgq_destroy(tgq_handle * h)
   cudaDeviceSynchronize();
   DevBuf * bufs[] = {&h->nodes, &h->elems, &h->nrm, &h->lab, &h->scene, &h->perm, &h->pos_of_elem, &h->first, &h->last, &h->split, &h->parent, &h->live,
                      &h->newidx, &h->pbox_lo, &h->pbox_hi, &h->nbox_lo, &h->nbox_hi, &h->arrive, &h->keys_a, &h->keys_b, &h->vals_a,
-                     &h->cubtmp, &h->src, &h->src2, &h->misc, &h->icp_cur, &h->icp_orig, &h->icp_to, &h->icp_idx, &h->area_by_elem, &h->cum, &h->obbs, &h->pnrm, &h->nsum, &h->obbinfo, &h->big, &h->big_count};
+                     &h->cubtmp, &h->src, &h->src2, &h->misc, &h->icp_cur, &h->icp_orig, &h->icp_to, &h->icp_idx, &h->area_by_elem, &h->cum, &h->obbs, &h->pnrm, &h->nsum, &h->obbinfo, &h->big, &h->big_count,
+                     &h->orig, &h->orig_n, &h->orig_lab, &h->xf};
   for (DevBuf * b : bufs) b->release();
   for (int s = 0; s < TGQ_SLOTS; ++s)
   {
@@ -575,6 +577,62 @@ int tgq_build_points(tgq_handle * h, const float * p3, int64_t P, const float * 
   return build_common(h, TGQ_KIND_POINTS, (float const *)d, (float const *)dn, P);
 }
 
+int tgq_set_transform(tgq_handle * h, const float * tr12)
+{
+  CKRC(need_built(h, (1 << TGQ_KIND_TRIANGLES) | (1 << TGQ_KIND_POINTS)));
+  if (h->n == 0) return TGQ_OK;
+  Guard g(h);
+  cudaStream_t s = h->stream;
+  int n = h->n, kind = h->kind; bool tri = kind == TGQ_KIND_TRIANGLES, has_n = h->has_normals, has_l = h->has_labels;
+  size_t np = (tri ? 3 : 1) * (size_t)n;
+  if (!h->orig_valid)
+  {
+    // first transform since the build: the records still hold the caller's elements bit for bit
+    CK(h->orig.reserve(12 * np));
+    if (tri) k_extract_tris<<<grid_for(n), TGQ_BLOCK, 0, s>>>(h->elems.as<TriRec>(), n, h->orig.as<float>());
+    else
+    {
+      if (has_n) CK(h->orig_n.reserve(12 * (size_t)n));
+      if (has_l) CK(h->orig_lab.reserve(4 * (size_t)n));
+      k_extract_points<<<grid_for(n), TGQ_BLOCK, 0, s>>>(h->elems.as<f4>(), has_n ? h->nrm.as<f4>() : nullptr, has_l ? h->lab.as<int>() : nullptr, n,
+                                                         h->orig.as<float>(), has_n ? h->orig_n.as<float>() : nullptr, has_l ? h->orig_lab.as<int>() : nullptr);
+    }
+    CK(cudaGetLastError());
+    h->st.total_launches += 1;
+  }
+  else if (has_l)
+  {
+    // labels may have been (re)set since the originals were taken: refresh them from the current Morton order
+    CK(h->orig_lab.reserve(4 * (size_t)n));
+    k_extract_points<<<grid_for(n), TGQ_BLOCK, 0, s>>>(h->elems.as<f4>(), nullptr, h->lab.as<int>(), n, nullptr, nullptr, h->orig_lab.as<int>());
+    CK(cudaGetLastError());
+    h->st.total_launches += 1;
+  }
+  float const * src = h->orig.as<float>();
+  if (tr12)
+  {
+    CK(h->xf.reserve(12 * np)); CK(h->misc.reserve(64));
+    CK(cudaMemcpyAsync(h->misc.p, tr12, 48, is_device_ptr(tr12) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    k_transform<<<grid_for((int64_t)np), TGQ_BLOCK, 0, s>>>(h->orig.as<float>(), (int64_t)np, h->misc.as<float>(), h->xf.as<float>());
+    CK(cudaGetLastError());
+    h->st.total_launches += 1;
+    src = h->xf.as<float>();
+  }
+  int rc = build_common(h, kind, src, (!tri && has_n) ? h->orig_n.as<float>() : nullptr, n);
+  if (rc != TGQ_OK) return rc;
+  h->orig_valid = true;
+  if (has_l)
+  {
+    CK(h->lab.reserve(4 * (size_t)n));
+    k_gather_labels<<<grid_for(n), TGQ_BLOCK, 0, s>>>(h->orig_lab.as<int>(), h->perm.as<uint32_t>(), n, h->lab.as<int>());
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    h->st.total_launches += 1;
+    h->has_labels = true;
+  }
+  return TGQ_OK;
+}
+
 int tgq_refit_triangles(tgq_handle * h, const float * v9, int64_t T)
 {
   CKRC(need_built(h, 1 << TGQ_KIND_TRIANGLES));
@@ -592,7 +650,7 @@ int tgq_refit_triangles(tgq_handle * h, const float * v9, int64_t T)
                                                      h->pbox_lo.as<f4>(), h->pbox_hi.as<f4>(), h->pos_of_elem.as<int>(), h->pnrm.as<f4>(),
                                                      h->area_by_elem.as<float>());
   CK(cudaGetLastError());
-  h->st.total_launches += 1; h->cum_valid = false;
+  h->st.total_launches += 1; h->cum_valid = false; h->orig_valid = false;
   CKRC(refit_and_emit(h, s));
   CK(cudaEventRecord(e1, s));
   CKRC(fetch_scene(h, s));

@@ -111,6 +111,26 @@ __global__ void k_gather_labels(int const * __restrict__ labels, uint32_t const 
   out[s] = labels[perm[s]];
 }
 
+// Source elements back out of the Morton-ordered records, in element order (tgq_set_transform keeps them as the untransformed
+// originals): triangles -> 9 floats, points -> 3 floats (+ normal, + label).
+__global__ void k_extract_tris(TriRec const * __restrict__ tris, int n, float * out9)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x; if (k >= n) return;
+  f4 const * q = (f4 const *)(tris + k);
+  f4 a = q[0], b = q[1], c = q[2];
+  float * o = out9 + 9 * (size_t)__float_as_int(a.w);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = b.x; o[4] = b.y; o[5] = b.z; o[6] = c.x; o[7] = c.y; o[8] = c.z;
+}
+__global__ void k_extract_points(f4 const * __restrict__ pts, f4 const * __restrict__ nrm, int const * __restrict__ lab, int n, float * out3, float * outn3,
+                                 int * outlab)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x; if (k >= n) return;
+  f4 a = pts[k]; size_t i = (size_t)__float_as_int(a.w);
+  if (out3) { out3[3 * i] = a.x; out3[3 * i + 1] = a.y; out3[3 * i + 2] = a.z; }
+  if (nrm) { f4 m = nrm[k]; outn3[3 * i] = m.x; outn3[3 * i + 1] = m.y; outn3[3 * i + 2] = m.z; }
+  if (lab) outlab[i] = lab[k];
+}
+
 // K3: binary radix tree over the sorted keys.  Inner node i: range [first,last], split; parents of inner nodes at
 // parent[i], of leaves (sorted position s) at parent[n - 1 + s].
 __global__ void k_hierarchy(uint64_t const * __restrict__ keys, int n, int * first, int * last, int * split, int * parent)

@@ -24,7 +24,7 @@ SYMBOLS = [
     "tgq_info", "tgq_triangle_cache", "tgq_closest", "tgq_knn", "tgq_ball_graph", "tgq_avg_separation",
     "tgq_ray_first", "tgq_ray_any", "tgq_sdf", "tgq_icp_sums", "tgq_transform_points", "tgq_area_sample",
     "tgq_get_stats", "tgq_set_point_labels", "tgq_closest_filtered", "tgq_knn_filtered", "tgq_icp_align", "tgq_ball_range",
-    "tgq_ball_stats", "tgq_visibility", "tgq_ball_graph_surface", "tgq_ball_histogram",
+    "tgq_ball_stats", "tgq_visibility", "tgq_ball_graph_surface", "tgq_ball_histogram", "tgq_set_transform",
 ]
 
 
@@ -88,6 +88,7 @@ def load_library(path=None):
     L.tgq_ball_range.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
     L.tgq_ball_graph_surface.argtypes = [vp, vp, i32, f32, i32, f32, i32, vp, vp, vp]
     L.tgq_ball_histogram.argtypes = [vp, vp, vp, i64, i32, vp]
+    L.tgq_set_transform.argtypes = [vp, vp]
     L.tgq_ball_stats.argtypes = [vp, vp, vp, vp, i64, vp]
     L.tgq_visibility.argtypes = [vp, vp, i64, vp, i32, i32, f32, vp, vp]
     L.tgq_icp_align.argtypes = [vp, vp, i64, i32, i32, f64, i32, vp, vp, vp, vp]
@@ -181,6 +182,11 @@ class Engine:
         n3 = _as_in(n3)
         self._ck(self._L.tgq_build_points(self._h, _ptr(p3), int(p3.shape[0]), _ptr(n3)))
         return int(p3.shape[0])
+
+    def set_transform(self, tr12=None):
+        """BvhN::setTransform (3x4 [L|t], row-major) / clearTransform (None): queries see the transformed elements."""
+        tr = None if tr12 is None else np.ascontiguousarray(tr12, np.float32).reshape(12)
+        self._ck(self._L.tgq_set_transform(self._h, _ptr(tr)))
 
     def refit_triangles(self, v9):
         v9 = _as_in(v9)
