@@ -73,6 +73,49 @@ def torus48():
     print("torus48: ray hits", int((out["r_idx"] >= 0).sum()), "of 2000; sdf valid", int((out["sdf"] >= 0).sum()), "of 200; icp batches", len(corr))
 
 
+def torus48_features():
+    """SURVEY 8f rows (local surface features, graph with the surface, transform) on the same torus: torus48_features.npz."""
+    mesh = gen.torus_mesh(48)
+    lo, hi = gen.mesh_bounds(mesh)
+    ext = (hi - lo).astype(np.float32)
+    scale = float(np.sqrt(np.float32(ext[0] * ext[0]) + (np.float32(ext[1] * ext[1]) + np.float32(ext[2] * ext[2]))))
+    ora = orc.Oracle(tris9=mesh)
+    p, n, _ = gen.area_samples(mesh, 1000)
+    po = orc.Oracle(points=p, normals=n)
+    out = {"scale": np.float32(scale)}
+    r = np.float32(np.float32(0.1) * np.float32(scale))
+    out["radius"] = r
+    st = po.ball_stats(p, r, n, mode=orc.MODE_BRUTE)
+    out["bs_n"], out["bs_avg_dist"], out["bs_num_offsets"], out["bs_curvature"] = st["n"], st["avg_dist"], st["num_offsets"], st["curvature"]
+    out["bs_centroid"], out["bs_cov"] = st["centroid"], st["cov"]
+    out["hist16"] = po.ball_hist(p, r, 16, mode=orc.MODE_BRUTE)
+    dirs = gen.u01(0xB2000F10, 3 * 24).reshape(24, 3).astype(np.float32) * np.float32(2) - np.float32(1)
+    dirs = (dirs / np.sqrt((dirs.astype(np.float64) ** 2).sum(axis=1, keepdims=True))).astype(np.float32)
+    out["vis_dirs"] = dirs
+    out["vis_pts"] = (p[:300] + np.float32(0.02) * n[:300]).astype(np.float32)
+    out["vis"], out["vis_escaped"] = ora.visibility(out["vis_pts"], dirs, scale, mode=orc.MODE_BRUTE)
+    seeds = (gen.splitmix64(0x5EED, 100) % np.uint64(1000)).astype(np.int64)
+    avg = po.avg_separation(seeds)
+    out["gs_r0"] = np.float32(np.float32(np.sqrt(np.float32(16))) * np.float32(avg))
+    out["gs_idx"], out["gs_sep"], out["gs_cnt"] = po.ball_graph_surface(ora, 16, float(out["gs_r0"]), mode=orc.MODE_BRUTE)
+    tr = np.array([[0.9, 0.1, 0.0, 0.3], [-0.1, 1.1, 0.05, -0.2], [0.02, 0.0, 0.8, 0.1]], np.float32)
+    out["tr"] = tr
+    v = mesh.reshape(-1, 3)
+    moved = np.empty_like(v)
+    for c in range(3):      # AffineTransformN.hpp:160 with Eigen's row . vector order t0 + (t1 + t2), then + translation
+        moved[:, c] = (tr[c, 0] * v[:, 0] + (tr[c, 1] * v[:, 1] + tr[c, 2] * v[:, 2])) + tr[c, 3]
+    out["tr_mesh_sample"] = moved.reshape(-1, 9)[::64]
+    q = gen.closest_queries(1000, (lo, hi))
+    out["tr_idx"], out["tr_d2"], out["tr_cp"] = orc.Oracle(tris9=moved.reshape(-1, 9)).closest(q, mode=orc.MODE_BRUTE)
+    np.savez_compressed(os.path.join(HERE, "torus48_features.npz"), **out)
+    print("torus48_features: mean ball population", float(out["bs_n"].mean()), "mean visibility", float(out["vis"].mean()),
+          "graph edges", int(out["gs_cnt"].sum()))
+
+
 if __name__ == "__main__":
-    testbvh()
-    torus48()
+    if len(sys.argv) > 1 and sys.argv[1] == "features":
+        torus48_features()
+    else:
+        testbvh()
+        torus48()
+        torus48_features()
