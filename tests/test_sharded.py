@@ -59,6 +59,9 @@ class _OracleEngine:
         i, t = self.o.ray_first(o, d, mode=self.orc.MODE_CANON, threads=2)
         return t, i.astype(np.int32), None
 
+    def visibility(self, p, dirs, scale):
+        return self.o.visibility(p, dirs, scale, mode=self.orc.MODE_CANON, threads=2)
+
     def icp_sums(self, p, q, tr=None):
         p, q = np.asarray(p, np.float64), np.asarray(q, np.float64)
         L = np.eye(3, 4) if tr is None else np.asarray(tr, np.float64).reshape(3, 4)
@@ -66,6 +69,23 @@ class _OracleEngine:
         r = L[:, :3] @ pm + L[:, 3] - qm
         e = r @ r + (((p - pm) @ L[:, :3].T - (q - qm)) ** 2).sum()
         return np.concatenate([pm, qm, ((p - pm).T @ (q - qm)).reshape(9), [e]])
+
+
+class _OraclePointEngine:
+    """Point oracle behind the Engine method shapes of the local-feature calls (tests only)."""
+
+    def __init__(self, pts, nrm):
+        from oracle import orc
+        self.orc = orc
+        self.o = orc.Oracle(points=pts, normals=nrm)
+
+    def ball_stats(self, c, radius, qn=None):
+        d = self.o.ball_stats(c, radius, qn, mode=self.orc.MODE_BRUTE, threads=2)
+        return np.concatenate([d["n"][:, None].astype(np.float64), d["avg_dist"][:, None], d["num_offsets"][:, None].astype(np.float64),
+                               d["curvature"][:, None], d["centroid"], d["cov"], np.zeros((len(d["n"]), 3))], axis=1)
+
+    def ball_histogram(self, c, radius, nb):
+        return self.o.ball_hist(c, radius, nb, mode=self.orc.MODE_BRUTE, threads=2)
 
 
 def _worker(rank, world, port, out_dir):
@@ -85,7 +105,15 @@ def _worker(rank, world, port, out_dir):
     t, ri = eng.ray_first(o, d)
     s0, c0 = shard_range(len(q), rank, world)
     sums = eng.icp_sums(q[s0:s0 + c0], cp[s0:s0 + c0])
-    np.savez(os.path.join(out_dir, f"r{rank}.npz"), idx=idx, d2=d2, cp=cp, t=t, ri=ri, sums=sums)
+    dirs = d[:9].copy()
+    vis, nesc = eng.visibility(q[:501], dirs, 3.0)
+    # a point structure behind the same front end: per-ball statistics and histograms with per-query radii
+    pts, nrm, _ = gen.area_samples(mesh, 1500)
+    peng = ShardedEngine(_OraclePointEngine(pts, nrm))
+    rad = (0.05 + 0.2 * gen.u01(77, 701)).astype(np.float32)
+    st = peng.ball_stats(pts[:701], rad, nrm[:701])
+    hist = peng.ball_histogram(pts[:701], np.float32(0.2), 8)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), idx=idx, d2=d2, cp=cp, t=t, ri=ri, sums=sums, vis=vis, nesc=nesc, st=st, hist=hist)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -106,8 +134,16 @@ def test_two_rank_gather_is_byte_identical_to_one_rank(built, tmp_path):
     idx, d2, cp = one.closest(q)
     t, ri, _ = one.ray_first(o, d)
     whole = one.icp_sums(q, cp)
+    vis, nesc = one.visibility(q[:501], d[:9].copy(), 3.0)
+    pts, nrm, _ = gen.area_samples(mesh, 1500)
+    pone = _OraclePointEngine(pts, nrm)
+    rad = (0.05 + 0.2 * gen.u01(77, 701)).astype(np.float32)
+    st = pone.ball_stats(pts[:701], rad, nrm[:701])
+    hist = pone.ball_histogram(pts[:701], np.float32(0.2), 8)
     for r in range(2):
         z = np.load(tmp_path / f"r{r}.npz")
+        assert z["vis"].tobytes() == vis.tobytes() and z["nesc"].tobytes() == nesc.tobytes()
+        assert z["st"].tobytes() == st.tobytes() and z["hist"].tobytes() == hist.tobytes()
         assert z["idx"].tobytes() == idx.tobytes() and z["d2"].tobytes() == d2.tobytes() and z["cp"].tobytes() == cp.tobytes()
         assert z["t"].tobytes() == t.tobytes() and z["ri"].tobytes() == ri.tobytes()
         assert np.allclose(z["sums"], whole, rtol=1e-9, atol=1e-12)

@@ -135,6 +135,31 @@ class ShardedEngine:
         idx, d2 = self.engine.knn(q, k, **kw)
         return gather_shards(idx, total, self.group), gather_shards(d2, total, self.group)
 
+    def _slice_per_query(self, a, total, local):
+        """Per-query arguments (radii) follow the query shard; scalars are shared by every query."""
+        if a is None or np.ndim(a) == 0:
+            return a
+        return self._slice(a, total, local)
+
+    def ball_stats(self, c3, radius, qn3=None, total=None, local=False):
+        """Per-ball neighbourhood sums (tgq_ball_stats) of the query shard, gathered: [total x 16] float64 on every rank."""
+        total = int(c3.shape[0]) if total is None else total
+        st = self.engine.ball_stats(self._slice(c3, total, local), self._slice_per_query(radius, total, local),
+                                    None if qn3 is None else self._slice(qn3, total, local))
+        return gather_shards(st, total, self.group)
+
+    def ball_histogram(self, c3, radius, num_bins, total=None, local=False):
+        total = int(c3.shape[0]) if total is None else total
+        h = self.engine.ball_histogram(self._slice(c3, total, local), self._slice_per_query(radius, total, local), num_bins)
+        return gather_shards(h, total, self.group)
+
+    def visibility(self, p3, dirs3, scale, total=None, local=False):
+        """Visibility of the sample shard ([D x 3] shared directions, or [S x D x 3] sharded with the samples)."""
+        total = int(p3.shape[0]) if total is None else total
+        d = dirs3 if np.ndim(dirs3) == 2 else self._slice(dirs3, total, local)
+        vis, nesc = self.engine.visibility(self._slice(p3, total, local), d, scale)
+        return gather_shards(vis, total, self.group), gather_shards(nesc, total, self.group)
+
     def icp_sums(self, from3, to3, tr12=None):
         """from3 / to3: this rank's shard of the correspondences; returns the pooled 16 sums on every rank."""
         import torch
