@@ -7,13 +7,22 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_NAME = "libtgq_emu.so"
+
+
+def use_variant(name):
+    """Switches every later Emu to another host build of the same headers (e.g. "libtgq_emu64.so", the 64-byte-node experiment);
+    returns the previous name.  Existing Emu objects must be dropped first."""
+    global _LIB, _NAME
+    prev, _NAME, _LIB = _NAME, name, None
+    return prev
 
 
 def lib():
     global _LIB
     if _LIB is None:
         subprocess.check_call(["make", "-C", os.path.join(_HERE, "emu"), "-s"])
-        L = C.CDLL(os.path.join(_HERE, "emu", "libtgq_emu.so"))
+        L = C.CDLL(os.path.join(_HERE, "emu", _NAME))
         vp = C.c_void_p
         L.emu_build.restype = vp
         L.emu_build.argtypes = [vp, C.c_int64, C.c_int, vp, C.c_int]

@@ -290,3 +290,44 @@ def test_ball_range_query_matches_brute_force():
         oi, oc = ora.ball_range(c, rad, max_out, excl)
         assert np.array_equal(gc, oc) and np.array_equal(gi, oi.astype(np.int32))
     assert gc[1] == 0 and gc[2] == len(p) - 1          # negative radius: nothing; huge radius: everything but self
+
+
+def test_experimental_64_byte_nodes_keep_parity_and_visit_counts():
+    """-DTGQ_NODE64: the oriented-box node with a quantised frame (octahedral normal + in-plane
+    (cos, sin), 16 bits each; bfloat16 extents) answers exactly like brute force, and opens about as many nodes as the 96-byte one."""
+    import ctypes as C
+
+    def run(variant):
+        prev = emu_lib.use_variant(variant)
+        try:
+            L = emu_lib.lib()
+            L.emu_closest_counts.argtypes = [C.c_void_p] * 2 + [C.c_int64] + [C.c_void_p] * 3
+            out = []
+            for grid, Q in ((24, 3000), (56, 12000)):
+                mesh = gen.torus_mesh(grid)
+                q = gen.closest_queries(Q, gen.mesh_bounds(mesh))
+                E = emu_lib.Emu(tris9=mesh)
+                res = E.closest(q)
+                nodes, prims = np.empty(Q, np.int32), np.empty(Q, np.int32)
+                L.emu_closest_counts(E.h, q.ctypes.data_as(C.c_void_p), Q, None, nodes.ctypes.data_as(C.c_void_p), prims.ctypes.data_as(C.c_void_p))
+                out.append((mesh, q, res, float(nodes.mean())))
+                del E
+            # degenerate inputs: a flat axis-aligned grid and a single triangle
+            flat = gen.torus_mesh(16).copy()
+            flat[:, 2::3] = 0.25
+            one = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32)
+            for mesh in (flat, one):
+                q = gen.closest_queries(1500, (np.array([-1, -1, -1], np.float32), np.array([1, 1, 1], np.float32)))
+                E = emu_lib.Emu(tris9=mesh)
+                out.append((mesh, q, E.closest(q), 0.0))
+                del E
+            return out
+        finally:
+            emu_lib.use_variant(prev)
+
+    base, exp = run("libtgq_emu.so"), run("libtgq_emu64.so")
+    for (mesh, q, (i0, d0, c0), n0), (_, _, (i1, d1, c1), n1) in zip(base, exp):
+        oi, od, oc = orc.Oracle(tris9=mesh).closest(q, mode=orc.MODE_BRUTE)
+        for i, d, c in ((i0, d0, c0), (i1, d1, c1)):
+            assert np.array_equal(i, oi.astype(np.int32)) and np.array_equal(d, od) and np.array_equal(c, oc)
+        assert n1 <= 1.03 * n0 + 1e-9

@@ -287,7 +287,7 @@ __global__ void k_emit(int n, int leaf, int const * __restrict__ first, int cons
       else
       {
         for (int j = 0; j < TGQ_OBB_F4; ++j) r.q[TGQ_OBB_F4 * c + j] = obbinfo[TGQ_OBB_F4 * (size_t)inner + j];
-        r.q[TGQ_OBB_F4 * c + 2].w = __int_as_float(child[c]);
+        r.q[TGQ_OBB_F4 * c + TGQ_OBB_LINK_F4].w = __int_as_float(child[c]);
       }
     }
     obbs[newidx[i]] = r;
@@ -639,8 +639,11 @@ k_closest_pool(BvhView b, float scene_pad, float const * __restrict__ q3, uint32
     }
     if (at_node)
     {
-      f4 r[6]; f4 const * q = (f4 const *)(b.obbs + s.t.cur);
-      ldq2(q, r[0], r[1]); ldq2(q + 2, r[2], r[3]); ldq2(q + 4, r[4], r[5]);
+      f4 r[2 * TGQ_OBB_F4]; f4 const * q = (f4 const *)(b.obbs + s.t.cur);
+      ldq2(q, r[0], r[1]); ldq2(q + 2, r[2], r[3]);
+#ifndef TGQ_NODE64
+      ldq2(q + 4, r[4], r[5]);
+#endif
       closest_node_compute(s, b, r);
     }
 #pragma unroll

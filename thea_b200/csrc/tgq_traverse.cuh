@@ -172,6 +172,62 @@ TGQ_HD void unpack_bf16(float w, float & a, float & b)
   a = i2f((int)(u & 0xffff0000u)); b = i2f((int)(u << 16));
 }
 
+#ifdef TGQ_NODE64
+// ---- 64-byte node: frame codec.  Both the build and the query decode with these very functions, so the extents are measured along
+// exactly the axes the query uses; the decoded frame is orthonormal to a few u (normalised normal, Duff et al. tangent basis,
+// normalised in-plane direction, a2 = a0 x a1), inside the relative slack of TGQ_LB_DEFLATE.
+TGQ_HD float snorm16_dec(unsigned v) { return (float)((int)(v & 0xffffu) - 32767) * (1.0f / 32767.0f); }
+TGQ_HD unsigned snorm16_enc(float x)
+{
+  float t = fminf(fmaxf(x, -1.0f), 1.0f) * 32767.0f;
+  int i = (int)floorf(t + 0.5f);
+  return (unsigned)(i + 32767);
+}
+TGQ_HD void oct_fold(float & ox, float & oy)
+{
+  float tx = (1.0f - fabsf(oy)) * (ox >= 0.0f ? 1.0f : -1.0f), ty = (1.0f - fabsf(ox)) * (oy >= 0.0f ? 1.0f : -1.0f);
+  ox = tx; oy = ty;
+}
+TGQ_HD unsigned obb_encode_normal(v3 a0)
+{
+  float s = fabsf(a0.x) + fabsf(a0.y) + fabsf(a0.z);
+  float ox = a0.x / s, oy = a0.y / s;
+  if (a0.z < 0.0f) oct_fold(ox, oy);
+  return snorm16_enc(ox) | (snorm16_enc(oy) << 16);
+}
+TGQ_HD v3 obb_decode_normal(unsigned w)
+{
+  float ox = snorm16_dec(w), oy = snorm16_dec(w >> 16);
+  float oz = 1.0f - fabsf(ox) - fabsf(oy);
+  if (oz < 0.0f) oct_fold(ox, oy);
+  return normalized3(mk3(ox, oy, oz));
+}
+TGQ_HD void obb_tangents(v3 n, v3 & t1, v3 & t2)
+{
+  float sg = n.z >= 0.0f ? 1.0f : -1.0f;
+  float a = -1.0f / (sg + n.z), b = n.x * n.y * a;
+  t1 = mk3(1.0f + sg * n.x * n.x * a, sg * b, -sg * n.x);
+  t2 = mk3(b, sg + n.y * n.y * a, -n.y);
+}
+TGQ_HD void obb_decode_frame(unsigned wn, unsigned wr, v3 & a0, v3 & a1, v3 & a2)
+{
+  a0 = obb_decode_normal(wn);
+  v3 t1, t2; obb_tangents(a0, t1, t2);
+  a1 = normalized3(add3(mul3(t1, snorm16_dec(wr)), mul3(t2, snorm16_dec(wr >> 16))));
+  a2 = cross3(a0, a1);
+}
+TGQ_HD void obb_bounds(f4 q0, f4 q1, v3 p, float mq, float & lb, float & key)
+{
+  v3 a0, a1, a2; obb_decode_frame((unsigned)f2i(q1.x), (unsigned)f2i(q1.y), a0, a1, a2);
+  float h0, h1, h2, unused; unpack_bf16(q1.z, h0, h1); unpack_bf16(q1.w, h2, unused);
+  v3 pc = sub3(p, mk3(q0.x, q0.y, q0.z));
+  float x = fmaxf(fabsf(fdot3(a0, pc)) - (h0 + mq), 0.0f);
+  float y = fmaxf(fabsf(fdot3(a1, pc)) - (h1 + mq), 0.0f);
+  float z = fmaxf(fabsf(fdot3(a2, pc)) - (h2 + mq), 0.0f);
+  lb = fdot3(mk3(x, y, z), mk3(x, y, z)) * TGQ_LB_DEFLATE;
+  key = fdot3(pc, pc);
+}
+#else
 TGQ_HD void obb_bounds(f4 q0, f4 q1, f4 q2, v3 p, float mq, float & lb, float & key)
 {
   v3 a0 = mk3(q1.x, q1.y, q1.z), a1 = mk3(q2.x, q2.y, q2.z);
@@ -184,6 +240,7 @@ TGQ_HD void obb_bounds(f4 q0, f4 q1, f4 q2, v3 p, float mq, float & lb, float & 
   lb = fdot3(mk3(x, y, z), mk3(x, y, z)) * TGQ_LB_DEFLATE;
   key = fdot3(pc, pc);
 }
+#endif
 
 TGQ_HD float slab_radius(float r2, float pad) { return sqrtf(r2) * 1.000001f + TGQ_MARGIN_SCALE * 0.5f * pad; }
 TGQ_HD v3 box_centre(v3 lo, v3 hi) { return mul3(add3(lo, hi), 0.5f); }
@@ -210,10 +267,21 @@ TGQ_HD ObbFrame obb_frame(v3 nsum)
   return f;
 }
 // Extent accumulator of one oriented box.
-struct ObbAcc { ObbFrame f; float mn[3], mx[3]; };
+struct ObbAcc { ObbFrame f; float mn[3], mx[3]; unsigned wn, wr; };
 TGQ_HD void obb_acc_begin(ObbAcc & a, v3 nsum)
 {
-  a.f = obb_frame(nsum);
+  a.f = obb_frame(nsum); a.wn = 0u; a.wr = 0u;
+#ifdef TGQ_NODE64
+  {
+    // quantise the frame first: the extents below are then measured along the decoded axes, the ones every query will use
+    a.wn = obb_encode_normal(a.f.a0);
+    v3 n = obb_decode_normal(a.wn), t1, t2; obb_tangents(n, t1, t2);
+    float c = dot3(a.f.a1, t1), s = dot3(a.f.a1, t2), len = sqrtf(c * c + s * s);
+    if (!(len > 0.0f)) { c = 1.0f; s = 0.0f; len = 1.0f; }
+    a.wr = snorm16_enc(c / len) | (snorm16_enc(s / len) << 16);
+    obb_decode_frame(a.wn, a.wr, a.f.a0, a.f.a1, a.f.a2);
+  }
+#endif
   for (int j = 0; j < 3; ++j) { a.mn[j] = FLT_MAX; a.mx[j] = -FLT_MAX; }
 }
 TGQ_HD void obb_acc_point(ObbAcc & a, v3 v)
@@ -230,13 +298,25 @@ TGQ_HD void obb_acc_store(ObbAcc const & a, float pad, int child, f4 * out4)
   v3 c = add3(add3(mul3(a.f.a0, c0), mul3(a.f.a1, c1)), mul3(a.f.a2, c2));
   float hp = TGQ_MARGIN_SCALE * pad;
   float h0 = 0.5f * (a.mx[0] - a.mn[0]) * 1.000001f + hp, h1 = 0.5f * (a.mx[1] - a.mn[1]) * 1.000001f + hp, h2 = 0.5f * (a.mx[2] - a.mn[2]) * 1.000001f + hp;
+#ifdef TGQ_NODE64
+  out4[0].x = c.x; out4[0].y = c.y; out4[0].z = c.z; out4[0].w = i2f(child);
+  out4[1].x = i2f((int)a.wn); out4[1].y = i2f((int)a.wr); out4[1].z = pack_bf16_up(h0, h1); out4[1].w = pack_bf16_up(h2, 0.0f);
+#else
   out4[0].x = c.x; out4[0].y = c.y; out4[0].z = c.z; out4[0].w = h0;
   out4[1].x = a.f.a0.x; out4[1].y = a.f.a0.y; out4[1].z = a.f.a0.z; out4[1].w = pack_bf16_up(h1, h2);
   out4[2].x = a.f.a1.x; out4[2].y = a.f.a1.y; out4[2].z = a.f.a1.z; out4[2].w = i2f(child);
+#endif
 }
 // An oriented box that no query can reach (the missing second child of a one-element structure).
 TGQ_HD void obb_store_empty(int child, f4 * out4)
 {
+#ifdef TGQ_NODE64
+  // a box at an unreachable distance (the packed extents cannot be negative); its link is an empty leaf anyway
+  out4[0].x = 1e30f; out4[0].y = 1e30f; out4[0].z = 1e30f; out4[0].w = i2f(child);
+  out4[1].x = i2f((int)(snorm16_enc(0.0f) | (snorm16_enc(0.0f) << 16))); out4[1].y = i2f((int)(snorm16_enc(1.0f) | (snorm16_enc(0.0f) << 16)));
+  out4[1].z = 0.0f; out4[1].w = 0.0f;
+  return;
+#endif
   out4[0].x = 0.0f; out4[0].y = 0.0f; out4[0].z = 0.0f; out4[0].w = -1e30f;
   out4[1].x = 1.0f; out4[1].y = 0.0f; out4[1].z = 0.0f; out4[1].w = 0.0f;
   out4[2].x = 0.0f; out4[2].y = 1.0f; out4[2].z = 0.0f; out4[2].w = i2f(child);
@@ -315,8 +395,13 @@ TGQ_HD void closest_fetch(ClosestState<TRI> const & s, BvhView const & b, f4 * r
   if (TRI)
   {
     // 32-byte aligned records: a node is 96 bytes (three 256-bit loads), a triangle 128 (four)
+#ifdef TGQ_NODE64
+    ldq2(q, r[0], r[1]); ldq2(q + 2, r[2], r[3]);
+    if (s.t.cur < 0) { ldq2(q + 4, r[4], r[5]); ldq2(q + 6, r[6], r[7]); }
+#else
     ldq2(q, r[0], r[1]); ldq2(q + 2, r[2], r[3]); ldq2(q + 4, r[4], r[5]);
     if (s.t.cur < 0) ldq2(q + 6, r[6], r[7]);
+#endif
   }
   else { for (int i = 0; i < ClosestFetch<TRI>::N; ++i) r[i] = ldq(q + i); }                        // point leaves start anywhere
 }
@@ -342,9 +427,15 @@ TGQ_HD void closest_node_compute(ClosestState<TRI> & s, BvhView const & b, f4 co
   float lb0, lb1, key0, key1; int c0, c1;
   if (TRI)
   {
+#ifdef TGQ_NODE64
+    obb_bounds(r[0], r[1], s.p, s.mq, lb0, key0);
+    obb_bounds(r[2], r[3], s.p, s.mq, lb1, key1);
+    c0 = f2i(r[0].w); c1 = f2i(r[2].w);
+#else
     obb_bounds(r[0], r[1], r[2], s.p, s.mq, lb0, key0);
     obb_bounds(r[3], r[4], r[5], s.p, s.mq, lb1, key1);
     c0 = f2i(r[2].w); c1 = f2i(r[5].w);
+#endif
   }
   else
   {
