@@ -27,7 +27,7 @@ struct NodeRec { f4 q0, q1, q2, q3; };
 struct TriRec  { f4 q0, q1, q2, q3, e0, e1, e2, x; };
 // EXPERIMENTAL (-DTGQ_NODE64, off by default): 64-byte ObbNode, two float4 per child -- centre + link, then the
 // frame as an octahedral-encoded normal and an in-plane (cos, sin), 16 bits each, and the three half extents as round-up bfloat16.
-// Checked on the CPU by tests/test_emu.py against brute force (host build libtgq_emu64.so); not yet measured on a GPU.
+// Checked against brute force on the CPU by the host build of these headers in the test suite; not yet measured on a GPU.
 #ifdef TGQ_NODE64
 #define TGQ_OBB_F4 2              // float4 per child of an ObbNode
 #define TGQ_OBB_LINK_F4 0         // which float4 of a child carries the link in .w
