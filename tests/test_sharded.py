@@ -25,6 +25,25 @@ def test_shard_ranges_tile_the_batch():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_space_shards_partition_the_batch_and_are_dense():
+    from thea_b200 import gen
+    from thea_b200.sharded import space_shard_indices
+    import torch
+    mesh = gen.torus_mesh(16)
+    b = gen.mesh_bounds(mesh)
+    lo, hi = gen.box_scaled(*b, 1.5)
+    q = gen.closest_queries(20000, b)
+    q[:3] = [[100, 100, 100], [-100, 0, 0], [0, 0, 1e9]]          # outside the box: border cells
+    for world in (1, 2, 3, 8):
+        parts = [space_shard_indices(q, lo, hi, r, world) for r in range(world)]
+        allidx = np.sort(np.concatenate(parts))
+        assert np.array_equal(allidx, np.arange(len(q)))
+        sizes = np.array([len(p) for p in parts])
+        assert sizes.max() <= 1.25 * sizes.mean() + 50                # round-robin cells balance a uniform batch
+        tparts = [space_shard_indices(torch.from_numpy(q), lo, hi, r, world).numpy() for r in range(world)]
+        assert all(np.array_equal(a, c) for a, c in zip(parts, tparts))
+
+
 def test_combine_icp_sums_matches_pooled_statistics():
     from thea_b200.sharded import combine_icp_sums
     rng = np.random.default_rng(0)
@@ -105,6 +124,12 @@ def _worker(rank, world, port, out_dir):
     t, ri = eng.ray_first(o, d)
     s0, c0 = shard_range(len(q), rank, world)
     sums = eng.icp_sums(q[s0:s0 + c0], cp[s0:s0 + c0])
+    # the same batch sharded by space: Morton cells of the x1.5 box dealt round-robin
+    lo, hi = gen.box_scaled(*b, 1.5)
+    sidx, sd2, scp = eng.closest(q, space_box=(lo, hi))
+    st_, sri = eng.ray_first(o, d, space_box=(lo, hi))
+    assert sidx.tobytes() == idx.tobytes() and sd2.tobytes() == d2.tobytes() and scp.tobytes() == cp.tobytes()
+    assert st_.tobytes() == t.tobytes() and sri.tobytes() == ri.tobytes()
     dirs = d[:9].copy()
     vis, nesc = eng.visibility(q[:501], dirs, 3.0)
     # a point structure behind the same front end: per-ball statistics and histograms with per-query radii
