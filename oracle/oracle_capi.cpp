@@ -618,9 +618,15 @@ float orc_tri_point(float const * v9, float const * p, float * cp)
 }
 float orc_ray_tri(float const * v9, float const * o, float const * d)
 { Tri t = make_tri(ld3(v9, 0), ld3(v9, 1), ld3(v9, 2)); return ray_tri_time(ld3(o, 0), ld3(d, 0), t.v0, t.e01, t.e02); }
+void orc_tri_point_batch(float const * v9, float const * p3, int64_t n, float * d2, float * cp3)
+{ for (int64_t i = 0; i < n; ++i) d2[i] = orc_tri_point(v9 + 9 * i, p3 + 3 * i, cp3 + 3 * i); }
+void orc_ray_tri_batch(float const * v9, float const * o3, float const * d3, int64_t n, float * t)
+{ for (int64_t i = 0; i < n; ++i) t[i] = orc_ray_tri(v9 + 9 * i, o3 + 3 * i, d3 + 3 * i); }
 float orc_fast_sqrt(float x) { return fast_sqrt(x); }
+float orc_box_point_sqdist(float const * lo, float const * hi, float const * p) { Box b; b.merge(ld3(lo, 0), ld3(hi, 0)); return b.sqdist_point(ld3(p, 0)); }
 float orc_box_ray_time(float const * lo, float const * hi, float const * o, float const * d, float max_time)
 { Box b; b.merge(ld3(lo, 0), ld3(hi, 0)); return b.ray_time(ld3(o, 0), ld3(d, 0), max_time); }
+int orc_tree_depth(int64_t n, int leaf) { return KdTree::tree_depth(n, leaf, 0.5f); }
 void orc_polar_rotation(double const * M, double * R) { polar_rotation(M, R); }
 
 // Thea::Random (Random.cpp:48-125): MT19937 whose regeneration skips state[227]; uniform01 (Random.hpp:126-130).

@@ -1,7 +1,8 @@
 """ctypes binding of the CPU oracle (oracle/liborc.so).
 
 TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
---impl reference legs.  The product package (thea_b200) never imports this module.  PARITY UNPINNED
+--impl reference legs.  The product package (thea_b200) never imports this module.  Pinned to the reference's
+own code by tests/test_ref_pin.py (oracle/ref.py, oracle/_ref); what remains assumed is Eigen's evaluation order
 (see oracle/thea_oracle.hpp).
 """
 from __future__ import annotations

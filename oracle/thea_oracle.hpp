@@ -3,12 +3,16 @@
 // TEST INFRASTRUCTURE ONLY.  This is the *checker* for the CUDA engine in thea_b200/csrc and the
 // timed CPU baseline of bench.py.  Nothing in the product path may include, link or call it.
 //
-// PARITY UNPINNED: the reference (sidch/Thea @ 30b86b95) has no golden vectors or asserting tests
-// on this path (Test/TestBvh.cpp:26-40 only prints) and cannot be compiled here (Eigen >= 3.4 is
-// an un-vendored hard dependency, MatVec.hpp:27-28).  The restatement follows the reference source
-// line by line (citations on every function, paths relative to Code/Source/) and Eigen 3.4's
-// fixed-size-3 evaluation order (sum of three terms = t0 + (t1 + t2); normalized() = v / sqrt(|v|^2)
-// by true division; maxCoeff(&i) returns the first maximum).  Build with
+// PARITY PINNED TO THE REFERENCE'S CODE, NOT TO EIGEN: the reference (sidch/Thea @ 30b86b95) has no golden vectors or
+// asserting tests on this path (Test/TestBvh.cpp:26-40 only prints) and its hard dependency Eigen >= 3.4 is absent
+// (MatVec.hpp:27-28).  oracle/_ref/libthea_ref.so is the reference's own, unmodified BvhN / Triangle3 / AxisAlignedBoxN /
+// MetricL2 / Icp3 / ShapeDiameter / PointSet3 sources compiled against the Eigen stand-in of oracle/eigen_shim/ (recipe:
+// oracle/Makefile, target `ref`), and tests/test_ref_pin.py demands bit equality between it and this restatement on 10^7
+// point-triangle pairs, 10^7 ray-triangle pairs, and every structure query.  What remains ASSUMED is only what the stand-in
+// assumes about Eigen (header of oracle/eigen_shim/Eigen/Core): Eigen 3.4's fixed-size-3 evaluation order (sum of three
+// terms = t0 + (t1 + t2); normalized() = v / sqrt(|v|^2) by true division; maxCoeff(&i) returns the first maximum), and
+// JacobiSVD for ICP (tolerance 1e-5 there).  The restatement follows the reference source line by line (citations on
+// every function, paths relative to Code/Source/).  Build with
 //   g++ -std=c++17 -O2 -ffp-contract=off      (the reference: -O2, no -march, no fast-math,
 //                                               Code/Build/Common/BuildSetup.cmake:95-111)
 // so that every fp32 operation is a single IEEE-754 round-to-nearest op (no FMA contraction).
@@ -416,16 +420,30 @@ struct KdTree
     }
   }
 
+  // What BvhN::closestPair does with a non-negative distance bound (BvhN.hpp:1081-1114), found by running the reference's own code
+  // (oracle/_ref): (1) the query is rejected outright when the (padded) root box is farther than the bound (:1093-1098); (2)
+  // accelerationBound() hands the caller's bound straight back (:2369-2370), so closestPair takes the `accel_bound >= 0` branch and
+  // WIDENS the bound by max(0.001 * |extent of the root box|, 100 eps) (:1101-1107) before ClosestPairFunctor squares it (:446-447).
+  // An element up to that fudge beyond dist_bound is therefore still returned.  kClosestPairs has no such widening (:478).
+  bool closest_bound(V3 q, double dist_bound, double & bound2) const
+  {
+    bound2 = -1;
+    if (!(dist_bound >= 0)) return true;
+    double lb = (double)nodes[0].bounds.sqdist_point_as_box(q);
+    if (lb >= 0 && lb > dist_bound * dist_bound) return false;      // MetricL2::computeMonotoneApprox of the caller's bound
+    float diag = norm(nodes[0].bounds.extent());
+    double fudge = std::max((double)(0.001 * diag), (double)(100 * std::numeric_limits<float>::epsilon()));
+    double eff = dist_bound + fudge;
+    bound2 = eff * eff;
+    return true;
+  }
+
   template <bool Canon> Closest closest(V3 q, double dist_bound, int64_t skip = -1) const
   {
     Closest r; r.idx = -1; r.d2 = -1; r.cp = mk(0, 0, 0);
     if (nodes.empty()) return r;
-    double bound2 = dist_bound >= 0 ? dist_bound * dist_bound : -1;   // MetricL2::computeMonotoneApprox
-    if (bound2 >= 0)
-    {
-      double lb = (double)nodes[0].bounds.sqdist_point_as_box(q);
-      if (lb >= 0 && lb > bound2) return r;
-    }
+    double bound2;
+    if (!closest_bound(q, dist_bound, bound2)) return r;
     ClosestState s; s.best = bound2; s.idx = -1; s.cp = mk(0, 0, 0); s.skip = skip;
     closest_rec<Canon>(0, q, s);
     if (s.idx >= 0) { r.idx = s.idx; r.d2 = (float)s.best; r.cp = s.cp; }
@@ -574,8 +592,9 @@ struct KdTree
 // ------------------------------------------------------------------------------------------------
 inline Closest brute_closest(KdTree const & T, V3 q, double dist_bound, int64_t skip = -1)
 {
-  double bound2 = dist_bound >= 0 ? dist_bound * dist_bound : -1;
   Closest r; r.idx = -1; r.d2 = -1; r.cp = mk(0, 0, 0);
+  double bound2 = -1;
+  if (T.size() == 0 || !T.closest_bound(q, dist_bound, bound2)) return r;
   float best = 0; bool have = false;
   int64_t n = T.size();
   for (int64_t e = 0; e < n; ++e)

@@ -23,7 +23,7 @@ namespace {
 struct Emu
 {
   bool tri = false, has_n = false;
-  int n = 0, leaf = 4; float pad = 0;
+  int n = 0, leaf = 4; float pad = 0; float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};     // exact element bounds (tgq_handle::lo / hi)
   std::vector<TriRec> tris; std::vector<f4> pts, nrm; std::vector<int> lab; std::vector<uint32_t> perm_keep;
   std::vector<NodeRec> nodes;
   std::vector<ObbNode> obbs;
@@ -50,6 +50,7 @@ void build(Emu & E, float const * src, float const * n3)
   float m = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))), fmaxf(fabsf(lo.z), fabsf(hi.z)));
   float pad = m * 1.9073486328125e-06f + FLT_MIN;
   E.pad = pad;
+  E.lo[0] = lo.x; E.lo[1] = lo.y; E.lo[2] = lo.z; E.hi[0] = hi.x; E.hi[1] = hi.y; E.hi[2] = hi.z;
   // keys + stable sort (k_morton_*, radix sort)
   std::vector<uint64_t> keys((size_t)n); std::vector<uint32_t> perm((size_t)n);
   for (int i = 0; i < n; ++i)
@@ -174,15 +175,16 @@ void * emu_build(float const * src, int64_t n, int is_tri, float const * n3, int
 void emu_destroy(void * h) { delete (Emu *)h; }
 int64_t emu_num_nodes(void * h) { return (int64_t)((Emu *)h)->nodes.size(); }
 
-void emu_closest(void * h, float const * q3, int64_t Q, float bound_ub, int exclude_self, int32_t * idx, float * d2, float * cp3)
+void emu_closest(void * h, float const * q3, int64_t Q, double dist_bound, int exclude_self, int32_t * idx, float * d2, float * cp3)
 {
   Emu & E = *(Emu *)h; BvhView v = E.view();
+  float bound_ub; BoundGate gate; closest_bound_gate(E.lo, E.hi, dist_bound, bound_ub, gate);      // as tgq.cu: closest_common does
   // every query is seeded with the Morton position of the previous query's answer, as a lane of the kernel does
   // (exclude_self < 0: unseeded)
   int seed = -1; bool seeded = exclude_self >= 0; if (!seeded) exclude_self = -exclude_self - 1;
   for (int64_t i = 0; i < Q; ++i)
   {
-    float best = bound_ub; int bi = -1; v3 cp = mk3(0, 0, 0);
+    float best = gated_ub(gate, ld(q3, i), bound_ub); int bi = -1; v3 cp = mk3(0, 0, 0);
     if (E.tri) closest_query<true>(v, E.pad, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp, seeded ? &seed : nullptr);
     else closest_query<false>(v, 0.0f, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp, seeded ? &seed : nullptr);
     idx[i] = bi; d2[i] = bi >= 0 ? best : -1.0f; cp3[3 * i] = cp.x; cp3[3 * i + 1] = cp.y; cp3[3 * i + 2] = cp.z;
@@ -232,13 +234,14 @@ static ElemFilterD make_filter(float const * qn3, int32_t const * qlabel, int64_
   return f;
 }
 
-void emu_closest_filtered(void * h, float const * q3, float const * qn3, int32_t const * qlabel, int64_t Q, float min_dot, float bound_ub,
+void emu_closest_filtered(void * h, float const * q3, float const * qn3, int32_t const * qlabel, int64_t Q, float min_dot, double dist_bound,
                           int32_t * idx, float * d2, float * cp3)
 {
   Emu & E = *(Emu *)h; BvhView v = E.view(); int seed = -1;
+  float bound_ub; BoundGate gate; closest_bound_gate(E.lo, E.hi, dist_bound, bound_ub, gate);
   for (int64_t i = 0; i < Q; ++i)
   {
-    float best = bound_ub; int bi = -1; v3 cp = mk3(0, 0, 0);
+    float best = gated_ub(gate, ld(q3, i), bound_ub); int bi = -1; v3 cp = mk3(0, 0, 0);
     ElemFilterD f = make_filter(qn3, qlabel, i, min_dot);
     closest_query<false>(v, 0.0f, ld(q3, i), -1, best, bi, cp, &seed, &f);
     idx[i] = bi; d2[i] = bi >= 0 ? best : -1.0f; cp3[3 * i] = cp.x; cp3[3 * i + 1] = cp.y; cp3[3 * i + 2] = cp.z;

@@ -29,7 +29,7 @@ def lib():
         L.emu_destroy.argtypes = [vp]
         L.emu_num_nodes.restype = C.c_int64
         L.emu_num_nodes.argtypes = [vp]
-        L.emu_closest.argtypes = [vp, vp, C.c_int64, C.c_float, C.c_int, vp, vp, vp]
+        L.emu_closest.argtypes = [vp, vp, C.c_int64, C.c_double, C.c_int, vp, vp, vp]
         L.emu_knn.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_float, C.c_int, vp, vp]
         L.emu_ball_graph.argtypes = [vp, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, vp, vp, vp]
         L.emu_set_labels.argtypes = [vp, vp]
@@ -37,7 +37,7 @@ def lib():
         L.emu_ball_graph_surface.argtypes = [vp, vp, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, vp, vp, vp]
         L.emu_ball_hist.argtypes = [vp, vp, vp, C.c_int64, C.c_int, vp]
         L.emu_ball_stats.argtypes = [vp, vp, vp, vp, C.c_int64, vp]
-        L.emu_closest_filtered.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, vp, vp, vp]
+        L.emu_closest_filtered.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_double, vp, vp, vp]
         L.emu_knn_filtered.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, C.c_float, C.c_float, vp, vp]
         L.emu_ray.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, vp, vp]
         L.emu_select.argtypes = [vp, C.c_int, C.c_int]
@@ -75,7 +75,7 @@ class Emu:
     def num_nodes(self):
         return lib().emu_num_nodes(self.h)
 
-    def closest(self, q, bound_ub=np.inf, exclude_self=False, seeded=True):
+    def closest(self, q, dist_bound=-1.0, exclude_self=False, seeded=True):
         """seeded: every query starts from the previous query's answer (what a kernel lane does on ordered batches)."""
         q = np.ascontiguousarray(q, np.float32)
         Q = len(q)
@@ -83,7 +83,7 @@ class Emu:
         d2 = np.empty(Q, np.float32)
         cp = np.empty((Q, 3), np.float32)
         flag = int(exclude_self) if seeded else -int(exclude_self) - 1
-        lib().emu_closest(self.h, _p(q), Q, float(bound_ub), flag, _p(idx), _p(d2), _p(cp))
+        lib().emu_closest(self.h, _p(q), Q, float(dist_bound), flag, _p(idx), _p(d2), _p(cp))
         return idx, d2, cp
 
     def ball_range(self, c, radius, max_out=32, exclude_self=False):
@@ -116,7 +116,7 @@ class Emu:
         self._lab = None if labels is None else np.ascontiguousarray(labels, np.int32)
         lib().emu_set_labels(self.h, _p(self._lab))
 
-    def closest_filtered(self, q, qn=None, qlabel=None, min_dot=0.0, bound_ub=np.inf):
+    def closest_filtered(self, q, qn=None, qlabel=None, min_dot=0.0, dist_bound=-1.0):
         q = np.ascontiguousarray(q, np.float32)
         qn = None if qn is None else np.ascontiguousarray(qn, np.float32)
         ql = None if qlabel is None else np.ascontiguousarray(qlabel, np.int32)
@@ -124,7 +124,7 @@ class Emu:
         idx = np.empty(Q, np.int32)
         d2 = np.empty(Q, np.float32)
         cp = np.empty((Q, 3), np.float32)
-        lib().emu_closest_filtered(self.h, _p(q), _p(qn), _p(ql), Q, float(min_dot), float(bound_ub), _p(idx), _p(d2), _p(cp))
+        lib().emu_closest_filtered(self.h, _p(q), _p(qn), _p(ql), Q, float(min_dot), float(dist_bound), _p(idx), _p(d2), _p(cp))
         return idx, d2, cp
 
     def knn_filtered(self, q, k, qn=None, qlabel=None, min_dot=0.0, bound_ub=np.inf):

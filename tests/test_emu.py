@@ -210,7 +210,7 @@ def test_seeding_a_query_with_any_element_never_changes_the_answer():
     for r in (a, b):
         assert np.array_equal(r[0], oi.astype(np.int32)) and np.array_equal(r[1], od) and np.array_equal(r[2], oc)
     # with a bound: the seed must not leak an element at or beyond the bound
-    a = E.closest(q, bound_ub=0.01, seeded=True)
+    a = E.closest(q, dist_bound=0.1, seeded=True)
     oi, od, _ = orc.Oracle(tris9=mesh).closest(q, dist_bound=0.1, mode=orc.MODE_BRUTE)
     assert np.array_equal(a[0], oi.astype(np.int32))
 

@@ -1,0 +1,262 @@
+"""Pins the CPU oracle (oracle/thea_oracle.hpp, a restatement) to the reference's OWN code.
+
+oracle/_ref/libthea_ref.so is sidch/Thea's unmodified BvhN / Triangle3 / AxisAlignedBoxN / MetricL2 / Icp3 / ShapeDiameter / PointSet3
+sources compiled against the Eigen stand-in of oracle/eigen_shim/ (oracle/Makefile target `ref`; the container has no Eigen).
+Every comparison below is BIT EXACT unless a tolerance is stated.  What the pin still assumes is written at the top of
+oracle/eigen_shim/Eigen/Core (Eigen's evaluation order of fixed-size reductions and a handful of member semantics).
+
+Skipped when the library is neither present nor buildable (no /root/reference): the GPU box gets the prebuilt file with the snapshot.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import orc, ref
+from thea_b200 import gen
+
+pytestmark = pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libthea_ref.so not present and /root/reference not available to build it")
+
+
+def _orc_tri_point_batch(v, p):
+    L = orc.lib()
+    L.orc_tri_point_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    d2, cp = np.empty(len(v), np.float32), np.empty((len(v), 3), np.float32)
+    L.orc_tri_point_batch(v.ctypes.data, p.ctypes.data, len(v), d2.ctypes.data, cp.ctypes.data)
+    return d2, cp
+
+
+def _orc_ray_tri_batch(v, o, d):
+    L = orc.lib()
+    L.orc_ray_tri_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    t = np.empty(len(v), np.float32)
+    L.orc_ray_tri_batch(v.ctypes.data, o.ctypes.data, d.ctypes.data, len(v), t.ctypes.data)
+    return t
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _same(a, b):
+    """Bit equality of float arrays, NaN payloads included (degenerate triangles produce NaNs in the reference)."""
+    return np.array_equal(_bits(a), _bits(b))
+
+
+def _triangle_cases(rng, n):
+    """Random triangles of mixed scale with a share of degenerate ones (Appendix B, Q7): collinear, two or three equal vertices,
+    needle and sliver shapes, axis-aligned planes (exercise every primary axis and the first-maximum rule)."""
+    v = rng.random((n, 9), dtype=np.float32)
+    scale = np.float32(10.0) ** rng.integers(-3, 3, size=(n, 1)).astype(np.float32)
+    v = (v * scale).astype(np.float32)
+    k = n // 10
+    v[0 * k:1 * k, 6:9] = v[0 * k:1 * k, 0:3] + np.float32(2.0) * (v[0 * k:1 * k, 3:6] - v[0 * k:1 * k, 0:3])      # collinear
+    v[1 * k:2 * k, 3:6] = v[1 * k:2 * k, 0:3]                                                                      # v1 == v0
+    v[2 * k:2 * k + k // 2, 3:6] = v[2 * k:2 * k + k // 2, 0:3]; v[2 * k:2 * k + k // 2, 6:9] = v[2 * k:2 * k + k // 2, 0:3]   # a point
+    v[3 * k:4 * k, 6:9] = v[3 * k:4 * k, 3:6] + np.float32(1e-6) * rng.standard_normal((k, 3)).astype(np.float32)   # needles
+    v[4 * k:5 * k, [2, 5, 8]] = np.float32(0.25)                                                                    # z = const plane
+    v[5 * k:5 * k + k // 2, [0, 3, 6]] = np.float32(-1.5)                                                           # x = const plane
+    return np.ascontiguousarray(v, np.float32)
+
+
+def test_point_triangle_1e7_pairs_bit_exact():
+    """MetricL2::closestPoints(Triangle3, point) (MetricL2.hpp:196-216 -> Triangle3.hpp:294-304,1310-1462) vs the oracle."""
+    rng = np.random.default_rng(20261018)
+    total = 0
+    for chunk in range(5):
+        n = 2_000_000
+        v = _triangle_cases(rng, n)
+        p = (rng.random((n, 3), dtype=np.float32) * 3 - 1).astype(np.float32)
+        # a share of points ON the triangles (vertices, edge midpoints, interior) and on their planes
+        k = n // 8
+        p[:k] = v[:k, 0:3]
+        p[k:2 * k] = (np.float32(0.5) * (v[k:2 * k, 0:3] + v[k:2 * k, 3:6])).astype(np.float32)
+        w = rng.random((k, 3), dtype=np.float32); w /= w.sum(axis=1, keepdims=True)
+        p[2 * k:3 * k] = (w[:, 0:1] * v[2 * k:3 * k, 0:3] + w[:, 1:2] * v[2 * k:3 * k, 3:6] + w[:, 2:3] * v[2 * k:3 * k, 6:9]).astype(np.float32)
+        rd2, rcp = ref.tri_point_batch(v, p)
+        od2, ocp = _orc_tri_point_batch(v, p)
+        assert _same(rd2, od2), f"chunk {chunk}: {np.count_nonzero(_bits(rd2) != _bits(od2))} squared distances differ"
+        assert _same(rcp, ocp), f"chunk {chunk}: closest points differ"
+        total += n
+    assert total == 10_000_000
+
+
+def test_ray_triangle_1e7_pairs_bit_exact():
+    """Triangle3::rayIntersectionTime (Triangle3.hpp:536-540,1464-1524) vs the oracle, incl. rays aimed at the triangles."""
+    rng = np.random.default_rng(7)
+    hits = 0
+    for chunk in range(5):
+        n = 2_000_000
+        v = _triangle_cases(rng, n)
+        o = (rng.random((n, 3), dtype=np.float32) * 3 - 1).astype(np.float32)
+        d = rng.standard_normal((n, 3)).astype(np.float32)
+        k = n // 2
+        w = rng.random((k, 3), dtype=np.float32); w /= w.sum(axis=1, keepdims=True)
+        tgt = (w[:, 0:1] * v[:k, 0:3] + w[:, 1:2] * v[:k, 3:6] + w[:, 2:3] * v[:k, 6:9]).astype(np.float32)
+        d[:k] = (tgt - o[:k]) * rng.random((k, 1), dtype=np.float32) * np.float32(2.0)       # aimed at the triangle, any length
+        d[k:k + 1000] = (v[k:k + 1000, 3:6] - v[k:k + 1000, 0:3])                           # parallel to the plane
+        rt = ref.ray_tri_batch(v, o, d)
+        ot = _orc_ray_tri_batch(v, o, d)
+        assert _same(rt, ot), f"chunk {chunk}: {np.count_nonzero(_bits(rt) != _bits(ot))} hit times differ"
+        hits += int((rt >= 0).sum())
+    assert hits > 1_000_000      # the aimed half hits unless the triangle is degenerate or below the absolute epsilon
+
+
+def test_fast_sqrt_random_boxes():
+    rng = np.random.default_rng(3)
+    xs = np.concatenate([rng.random(200_000, dtype=np.float32) * np.float32(10.0) ** rng.integers(-12, 12, 200_000).astype(np.float32),
+                         np.array([0.0, 1.0, 2.0, 4.0, 1e-30, 1e30, 0.25, 3.0], np.float32)])
+    for x in xs[:20000]:
+        assert _same(np.float32(ref.fast_sqrt(float(x))), np.float32(orc.fast_sqrt(float(x)))), x
+    for seed in (0xFFFF, 1, 0xB2000001):
+        assert np.array_equal(ref.random_uniform01(seed, 100_000), orc.thea_random_uniform01(seed, 100_000))
+    L = orc.lib()
+    L.orc_box_point_sqdist.restype = C.c_float
+    L.orc_box_point_sqdist.argtypes = [C.c_void_p] * 3
+    for _ in range(5000):
+        lo = rng.random(3, dtype=np.float32); hi = lo + rng.random(3, dtype=np.float32)
+        p = (rng.random(3, dtype=np.float32) * 3 - 1).astype(np.float32)
+        o = (rng.random(3, dtype=np.float32) * 3 - 1).astype(np.float32); d = rng.standard_normal(3).astype(np.float32)
+        if rng.random() < 0.2:
+            d[rng.integers(0, 3)] = 0.0
+        assert _same(np.float32(ref.box_point_sqdist(lo, hi, p)), np.float32(L.orc_box_point_sqdist(lo.ctypes.data, hi.ctypes.data, p.ctypes.data)))
+        for mt in (-1.0, 0.7):
+            assert _same(np.float32(ref.box_ray_time(lo, hi, o, d, mt)), np.float32(orc.box_ray_time(lo, hi, o, d, mt)))
+    for n in list(range(0, 200)) + [1000, 4608, 70688, 1002528, 9999392]:
+        assert ref.tree_depth(n, 5) == orc.lib().orc_tree_depth(C.c_int64(n), 5), n
+
+
+def _testbvh_inputs():
+    """Test/TestBvh.cpp:120-126,315-321: 10,000 points then (in a second run of the generator) 1,000 triangles in [0,1]^3."""
+    u = ref.random_uniform01(0xFFFF, 30000 + 30000 + 9000)
+    return u[:30000].reshape(-1, 3).copy(), u[60000:].reshape(-1, 9).copy()
+
+
+@pytest.fixture(scope="module")
+def torus():
+    mesh = gen.torus_mesh(48)
+    return mesh, gen.mesh_bounds(mesh), ref.Reference(tris9=mesh), orc.Oracle(tris9=mesh)
+
+
+def test_closest_element_structure(torus):
+    """BvhN::closestPair / closestElement on the kd-tree the reference builds vs the oracle's reference-order mode: same element
+    (first-found ties included), same squared distance, same closest point; canonical / brute-force modes: same distance always,
+    same element unless the reference's answer is an exact tie."""
+    mesh, bounds, R, O = torus
+    q = gen.closest_queries(60000, bounds)
+    for bound in (-1.0, 0.35):
+        ri, rd, rc = R.closest(q, dist_bound=bound)
+        oi, od, oc = O.closest(q, dist_bound=bound, mode=orc.MODE_REFERENCE)
+        assert np.array_equal(ri, oi)
+        found = ri >= 0
+        assert _same(rd[found], od[found]) and _same(rc[found], oc[found])
+        ci, cd, _ = O.closest(q, dist_bound=bound, mode=orc.MODE_BRUTE)
+        assert np.array_equal(ci >= 0, found) and _same(cd[found], rd[found])
+        differ = np.flatnonzero(ci != ri)
+        # every disagreement is an exact tie: the brute-force winner has the same distance and a LOWER index
+        assert np.all(ci[differ] < ri[differ])
+    ei, ed, ec = R.closest_element(q[:5000])
+    ri, rd, rc = R.closest(q[:5000])
+    assert np.array_equal(ei, ri) and np.array_equal(ed, np.sqrt(rd.astype(np.float64))) and _same(ec, rc)
+    assert R.num_nodes() == orc.lib().orc_num_nodes(O.h)
+
+
+def test_testbvh_recipe_structures():
+    pts, tris = _testbvh_inputs()
+    R, O = ref.Reference(tris9=tris), orc.Oracle(tris9=tris)
+    q = np.vstack([np.float32([[0.5, 0.5, 0.5]]), gen.closest_queries(20000, (np.zeros(3, np.float32), np.ones(3, np.float32)))])
+    for bound in (-1.0, 0.25):
+        ri, rd, rc = R.closest(q, dist_bound=bound)
+        oi, od, oc = O.closest(q, dist_bound=bound, mode=orc.MODE_REFERENCE)
+        assert np.array_equal(ri, oi) and _same(rd[ri >= 0], od[ri >= 0]) and _same(rc[ri >= 0], oc[ri >= 0])
+    RP, OP = ref.Reference(points=pts), orc.Oracle(points=pts)
+    for k in (1, 3, 16):
+        for bound in (-1.0, 0.25, 0.02):
+            ri, rd = RP.knn(q[:5000], k, dist_bound=bound)
+            oi, od = OP.knn(q[:5000], k, dist_bound=bound, mode=orc.MODE_REFERENCE)
+            assert np.array_equal(ri, oi) and _same(rd, od), (k, bound)
+    ri, rd, rc = RP.closest(q, dist_bound=-1.0)
+    oi, od, oc = OP.closest(q, dist_bound=-1.0, mode=orc.MODE_REFERENCE)
+    assert np.array_equal(ri, oi) and _same(rd, od) and _same(rc, oc)
+    # ball range: the same SET of indices (the oracle returns the lowest `max_out` in ascending order)
+    for c, r in ((q[0], 0.25), (q[1], 0.05), (q[2], 0.11)):
+        ridx, n = RP.ball_range(c, r)
+        oidx, ocnt = OP.ball_range(c[None], r, max_out=32)
+        assert n == int(ocnt[0]) and len(set(ridx.tolist())) == n
+        assert np.array_equal(np.sort(ridx)[:32], oidx[0][:min(32, n)])
+
+
+def test_ray_structure(torus):
+    mesh, bounds, R, O = torus
+    o, d = gen.random_rays(60000, bounds)
+    ri, rt, rn = R.ray_first(o, d, normals=True)
+    oi, ot = O.ray_first(o, d, mode=orc.MODE_REFERENCE)
+    assert np.array_equal(ri, oi) and _same(rt, ot)
+    assert (ri >= 0).sum() > 5000
+    n, _, _, _ = O.tri_cache()
+    hit = ri >= 0
+    assert _same(rn[hit], n[ri[hit]])
+    tmax = np.where(np.arange(len(o)) % 2 == 0, np.float32(0.8), np.float32(-1.0)).astype(np.float32)
+    ri, rt = R.ray_first(o, d, tmax=tmax)
+    oi, ot = O.ray_first(o, d, tmax=tmax, mode=orc.MODE_REFERENCE)
+    assert np.array_equal(ri, oi) and _same(rt, ot)
+    ci, ct = O.ray_first(o, d, tmax=tmax, mode=orc.MODE_BRUTE)
+    assert np.array_equal(ci >= 0, ri >= 0) and _same(ct, rt) and np.all(ci[ci != ri] < ri[ci != ri])
+    t2, h2 = R.ray_time(o[:4000], d[:4000], tmax=tmax[:4000])
+    assert _same(t2, rt[:4000]) and np.array_equal(h2.astype(bool), ri[:4000] >= 0)
+
+
+def test_triangle_cache(torus):
+    mesh, _, _, O = torus
+    n, d, ax, ar = O.tri_cache()
+    for i in range(0, len(mesh), 7):
+        rn, _, rax, rar, _ = ref.tri_cache(mesh[i])
+        assert _same(rn, n[i]) and rax == ax[i] and _same(np.float32(rar), ar[i])
+
+
+def test_shape_diameter(torus):
+    """ShapeDiameter::compute(position, normal, interior) (ShapeDiameter.hpp:168-258), double statistics, nth_element quirk."""
+    mesh, bounds, R, O = torus
+    p, n, _ = gen.area_samples(mesh, 1500)
+    scale = float(np.linalg.norm(bounds[1] - bounds[0]))
+    for interior in (True, False):
+        rs = R.sdf(p, n, scale, only_interior=interior)
+        os_ = O.sdf(p, n, scale, only_interior=interior, mode=orc.MODE_REFERENCE)[0]
+        assert np.array_equal(rs, os_), np.abs(rs - os_).max()
+    assert (rs >= 0).sum() > 1000
+
+
+def test_sample_graph(torus):
+    """PointSet3::findSampleNeighbors (PointSet3.hpp:586-681): neighbour indices and fastSqrt separations, with and without the
+    reachability ray test against the surface; the average-separation estimate for given seed samples (:363-376)."""
+    mesh, bounds, R, O = torus
+    p, n, _ = gen.area_samples(mesh, 3000)
+    OP = orc.Oracle(points=p, normals=n)
+    seeds = (gen.splitmix64(gen.SEED_SAMPLES, 100) % np.uint64(len(p))).astype(np.int64)
+    sep = ref.avg_separation(p, seeds)
+    assert _same(np.float32(sep), np.float32(OP.avg_separation(seeds)))
+    for k in (8, 16):
+        r0 = np.float32(np.sqrt(np.float32(k))) * np.float32(sep)
+        ri, rs, rc = ref.graph(p, n, k, float(r0))
+        oi, os_, oc = OP.ball_graph(k, float(r0), mode=orc.MODE_REFERENCE)
+        assert np.array_equal(rc, oc) and np.array_equal(ri, oi) and _same(rs, os_)
+    ri, rs, rc = ref.graph(p, n, 8, float(np.float32(np.sqrt(np.float32(8))) * np.float32(sep)), surface=R)
+    oi, os_, oc = OP.ball_graph_surface(O, 8, float(np.float32(np.sqrt(np.float32(8))) * np.float32(sep)), mode=orc.MODE_REFERENCE)
+    assert np.array_equal(rc, oc) and np.array_equal(ri, oi) and _same(rs, os_)
+    # without normals the angle and reachability tests are skipped
+    OP2 = orc.Oracle(points=p)
+    ri, rs, rc = ref.graph(p, None, 8, float(np.float32(np.sqrt(np.float32(8))) * np.float32(sep)))
+    oi, os_, oc = OP2.ball_graph(8, float(np.float32(np.sqrt(np.float32(8))) * np.float32(sep)), mode=orc.MODE_REFERENCE)
+    assert np.array_equal(rc, oc) and np.array_equal(ri, oi) and _same(rs, os_)
+
+
+def test_icp(torus):
+    """Icp3<Real>::align (Icp3.hpp:193-464).  Everything but the 3 x 3 SVD is the reference's code; the SVD comes from the Eigen
+    stand-in, so the comparison uses the tolerance north_star states for floats (1e-5) instead of bit equality."""
+    mesh, bounds, R, O = torus
+    p, _, _ = gen.area_samples(mesh, 4000)
+    src = gen.apply_pose(p, *gen.rigid_pose())
+    rtr, rerr = R.icp(src, min_iters=8, max_iters=8, frac_thresh=1e-4)
+    otr, oerr, _ = O.icp(src, min_iters=8, max_iters=8, frac_thresh=1e-4, mode=orc.MODE_REFERENCE)
+    assert np.allclose(rtr, otr, rtol=1e-5, atol=1e-5), np.abs(rtr - otr).max()
+    assert abs(rerr - oerr) <= 1e-5 * max(1.0, abs(rerr))

@@ -132,11 +132,7 @@ cudaEvent_t get_event(tgq_handle * h)
 float bound_to_ub(double dist_bound)
 {
   if (!(dist_bound >= 0)) return INFINITY;
-  double b2 = dist_bound * dist_bound;
-  if (b2 > (double)FLT_MAX) return INFINITY;
-  float f = (float)b2;
-  if ((double)f < b2) f = std::nextafterf(f, INFINITY);
-  return f;   // smallest float >= bound^2
+  return float_at_least(dist_bound * dist_bound);   // smallest float >= bound^2 (kClosestPairs: no widening, BvhN.hpp:478)
 }
 
 // Returns a device pointer holding `bytes` of p (copying when p is a host pointer).
@@ -695,7 +691,7 @@ static int closest_common(tgq_handle * h, const float * q3, const float * qn3, c
   CKRC(need_built(h, (1 << TGQ_KIND_TRIANGLES) | (1 << TGQ_KIND_POINTS)));
   if (Q < 0 || (Q > 0 && !q3)) return fail(h, TGQ_EINVAL, "tgq_closest: bad arguments");
   Guard g(h);
-  float ub = bound_to_ub(dist_bound);
+  float ub; BoundGate gate; closest_bound_gate(h->lo, h->hi, dist_bound, ub, gate);     // BvhN::closestPair's root rejection and bound widening
   Arg args[6] = {{q3, nullptr, 12}, {nullptr, idx, 4}, {nullptr, d2, 4}, {nullptr, cp3, 12}, {qn3, nullptr, 12}, {qlabel, nullptr, 4}};
   BvhView v = view_of(h); bool tri = h->kind == TGQ_KIND_TRIANGLES;
   size_t smem = trav_smem_bytes(1);
@@ -705,19 +701,19 @@ static int closest_common(tgq_handle * h, const float * q3, const float * qn3, c
     {
       size_t psmem = smem + (TGQ_BLOCK / 32) * sizeof(PoolWarp);
       CKRC(persistent_grid(h, k_closest_pool, psmem, c.n, cnt, c.stream, &grid));
-      k_closest_pool<<<grid, TGQ_BLOCK, psmem, c.stream>>>(v, h->pad, (float const *)c.din[0], c.perm, c.n, ub, exclude_self, c.offset, cnt,
+      k_closest_pool<<<grid, TGQ_BLOCK, psmem, c.stream>>>(v, h->pad, (float const *)c.din[0], c.perm, c.n, ub, gate, exclude_self, c.offset, cnt,
                                                           (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3]);
     }
     else if (tri)
     {
       CKRC(persistent_grid(h, k_closest<true>, smem, c.n, cnt, c.stream, &grid));
-      k_closest<true><<<grid, TGQ_BLOCK, smem, c.stream>>>(v, h->pad, (float const *)c.din[0], c.perm, c.n, ub, exclude_self, c.offset, cnt,
+      k_closest<true><<<grid, TGQ_BLOCK, smem, c.stream>>>(v, h->pad, (float const *)c.din[0], c.perm, c.n, ub, gate, exclude_self, c.offset, cnt,
                                                          (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3], nullptr, nullptr, 0.0f);
     }
     else
     {
       CKRC(persistent_grid(h, k_closest<false>, smem, c.n, cnt, c.stream, &grid));
-      k_closest<false><<<grid, TGQ_BLOCK, smem, c.stream>>>(v, 0.0f, (float const *)c.din[0], c.perm, c.n, ub, exclude_self, c.offset, cnt,
+      k_closest<false><<<grid, TGQ_BLOCK, smem, c.stream>>>(v, 0.0f, (float const *)c.din[0], c.perm, c.n, ub, gate, exclude_self, c.offset, cnt,
                                                           (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3], (float const *)c.din[4],
                                                           (int const *)c.din[5], min_dot);
     }

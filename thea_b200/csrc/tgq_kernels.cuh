@@ -434,7 +434,7 @@ template <bool TRI>
 struct ClosestW
 {
   static constexpr int STAGE = 1;       // (x, y, z, query index)
-  ClosestState<TRI> s; BvhView b; float scene_pad; float const * q3; uint32_t const * perm; float ub; int exclude_self; int64_t self_offset;
+  ClosestState<TRI> s; BvhView b; float scene_pad; float const * q3; uint32_t const * perm; float ub; BoundGate gate; int exclude_self; int64_t self_offset;
   int * idx; float * d2; float * cp3; int qi; int seed;
   float const * qn3; int const * qlabel; float min_dot;      // per-query element filter (point structures), null = none
   __device__ __forceinline__ int state() const { return s.t.cur; }
@@ -446,7 +446,8 @@ struct ClosestW
   __device__ __forceinline__ void begin(int, f4 const * src)
   {
     f4 r = *src; qi = __float_as_int(r.w);
-    closest_begin(s, b, scene_pad, mk3(r.x, r.y, r.z), exclude_self ? (int)(self_offset + qi) : -1, ub, seed);
+    v3 p = mk3(r.x, r.y, r.z);
+    closest_begin(s, b, scene_pad, p, exclude_self ? (int)(self_offset + qi) : -1, gated_ub(gate, p, ub), seed);
     if (!TRI && (qn3 || qlabel))
     {
       s.f.mode = (qn3 ? 1 : 0) | (qlabel ? 2 : 0); s.f.min_dot = min_dot;
@@ -471,13 +472,13 @@ struct ClosestW
 
 template <bool TRI>
 __global__ void __launch_bounds__(TGQ_BLOCK)
-k_closest(BvhView b, float scene_pad, float const * __restrict__ q3, uint32_t const * __restrict__ perm, int n, float bound_ub, int exclude_self,
-          int64_t self_offset, int * counter, int * idx, float * d2, float * cp3, float const * __restrict__ qn3, int const * __restrict__ qlabel,
-          float min_dot)
+k_closest(BvhView b, float scene_pad, float const * __restrict__ q3, uint32_t const * __restrict__ perm, int n, float bound_ub, BoundGate gate,
+          int exclude_self, int64_t self_offset, int * counter, int * idx, float * d2, float * cp3, float const * __restrict__ qn3,
+          int const * __restrict__ qlabel, float min_dot)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   ClosestW<TRI> w;
-  w.b = b; w.scene_pad = scene_pad; w.q3 = q3; w.perm = perm; w.ub = bound_ub; w.exclude_self = exclude_self; w.self_offset = self_offset;
+  w.b = b; w.scene_pad = scene_pad; w.q3 = q3; w.perm = perm; w.ub = bound_ub; w.gate = gate; w.exclude_self = exclude_self; w.self_offset = self_offset;
   w.idx = idx; w.d2 = d2; w.cp3 = cp3; w.qi = 0; w.seed = -1; w.qn3 = qn3; w.qlabel = qlabel; w.min_dot = min_dot; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
   f4 * stage = trav_setup(w.s.t, st, smem, ClosestW<TRI>::STAGE, nullptr);
   warp_run(w, n, counter, stage);
@@ -510,8 +511,8 @@ __device__ __forceinline__ unsigned long long pool_key(float d2, int idx)
 { return ((unsigned long long)(unsigned)__float_as_int(d2) << 32) | (unsigned long long)(unsigned)idx; }
 
 __global__ void __launch_bounds__(TGQ_BLOCK)
-k_closest_pool(BvhView b, float scene_pad, float const * __restrict__ q3, uint32_t const * __restrict__ perm, int n, float bound_ub, int exclude_self,
-               int64_t self_offset, int * counter, int * idx_out, float * d2_out, float * cp3)
+k_closest_pool(BvhView b, float scene_pad, float const * __restrict__ q3, uint32_t const * __restrict__ perm, int n, float bound_ub, BoundGate gate,
+               int exclude_self, int64_t self_offset, int * counter, int * idx_out, float * d2_out, float * cp3)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned const FULL = 0xffffffffu;
@@ -561,7 +562,8 @@ k_closest_pool(BvhView b, float scene_pad, float const * __restrict__ q3, uint32
         if (s.t.cur == TGQ_ST_IDLE && t < chunk_end)
         {
           f4 r = stage[t - chunk_base]; qi = __float_as_int(r.w);
-          closest_begin(s, b, scene_pad, mk3(r.x, r.y, r.z), exclude_self ? (int)(self_offset + qi) : -1, bound_ub, seed);
+          v3 p = mk3(r.x, r.y, r.z);
+          closest_begin(s, b, scene_pad, p, exclude_self ? (int)(self_offset + qi) : -1, gated_ub(gate, p, bound_ub), seed);
           hold = s.t.cur == TGQ_ST_LEAF;          // seeded: the seed element is tested before the traversal starts
         }
         chunk_next = min(chunk_next + __popc(idle), chunk_end);

@@ -379,6 +379,63 @@ TGQ_HD bool filtered_out(BvhView const & b, int k, ElemFilterD const & f)
   return false;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// What BvhN::closestPair does with a non-negative distance bound (BvhN.hpp:1081-1114; established by running the reference's own
+// code, oracle/_ref, against the first version of this engine, which took the bound at face value):
+//   (1) the query is rejected outright when the reference's root box -- the union of all element AABBs, scaleCentered(1.05)
+//       (BvhN.hpp:1437-1439) -- is farther than the bound: fp32 AxisAlignedBoxN::squaredDistance, compared in double with
+//       dist_bound^2 (:1093-1098);
+//   (2) otherwise accelerationBound() returns the caller's bound unchanged (:2369-2370), closestPair takes its `accel_bound >= 0`
+//       branch and WIDENS the bound by max(0.001 * |extent of the root box|, 100 eps) (:1101-1107); ClosestPairFunctor squares the
+//       widened bound (:446-447) and accepts d2 < that, strictly, in double.
+// So an element up to the fudge beyond dist_bound is still returned, unless (1) fires.  kClosestPairs has no widening (:478).
+// Both the root box and the fudge depend on the element set only, not on the tree, so the LBVH reproduces them exactly.
+// ---------------------------------------------------------------------------------------------------------------------
+struct BoundGate { v3 lo, hi; float reject; int on; };      // reference root box; a query with fp32 box distance > reject finds nothing
+TGQ_HD BoundGate no_gate() { BoundGate g; g.lo = g.hi = mk3(0.0f, 0.0f, 0.0f); g.reject = 0.0f; g.on = 0; return g; }
+// AxisAlignedBoxN::squaredDistance(point) in the reference's operation order (AxisAlignedBoxN.hpp:429-442)
+TGQ_HD float ref_box_point_sqdist(v3 lo, v3 hi, v3 p) { return sqn3(max3(sub3(max3(lo, p), min3(hi, p)), mk3(0.0f, 0.0f, 0.0f))); }
+// The exclusive squared bound of one query: `ub` unless the gate rejects the query (then nothing can be accepted).
+TGQ_HD float gated_ub(BoundGate const & g, v3 p, float ub) { return (g.on && ref_box_point_sqdist(g.lo, g.hi, p) > g.reject) ? -1.0f : ub; }
+
+// Host only.  Smallest float >= x (x >= 0): d2 < ub  <=>  (double)d2 < x for every float d2.
+inline float float_at_least(double x)
+{
+  if (x > (double)FLT_MAX) return INFINITY;
+  float f = (float)x;
+  if ((double)f < x) f = nextafterf(f, INFINITY);
+  return f;
+}
+// Host side of the above: from the structure's exact element bounds [lo, hi] and the caller's dist_bound, the exclusive squared
+// bound `ub` the kernels test d2 against and the gate.  dist_bound < 0 (or NaN): unbounded, gate off.
+inline void closest_bound_gate(float const lo[3], float const hi[3], double dist_bound, float & ub, BoundGate & g)
+{
+  g = no_gate(); ub = INFINITY;
+  if (!(dist_bound >= 0)) return;
+  // AxisAlignedBoxN::scaleCentered(1.05) (AxisAlignedBoxN.hpp:316-324): c = 0.5 * (hi + lo); lo' = s * (lo - c) + c
+  float rlo[3], rhi[3];
+  for (int a = 0; a < 3; ++a)
+  {
+    float c = 0.5f * (hi[a] + lo[a]);
+    float l = 1.05f * (lo[a] - c); l = l + c;
+    float u = 1.05f * (hi[a] - c); u = u + c;
+    rlo[a] = l; rhi[a] = u;
+  }
+  float ex = rhi[0] - rlo[0], ey = rhi[1] - rlo[1], ez = rhi[2] - rlo[2];
+  float xx = ex * ex, yy = ey * ey, zz = ez * ez;
+  float t = yy + zz; float sq = xx + t;
+  float diag = sqrtf(sq);
+  double fudge = 0.001 * (double)diag;
+  double floor_fudge = (double)(100 * FLT_EPSILON);
+  if (fudge < floor_fudge) fudge = floor_fudge;
+  double eff = dist_bound + fudge;
+  ub = float_at_least(eff * eff);
+  double b2 = dist_bound * dist_bound;
+  float rj = b2 > (double)FLT_MAX ? FLT_MAX : (float)b2;
+  if ((double)rj > b2) rj = nextafterf(rj, -INFINITY);        // largest float <= dist_bound^2: lb > b2 <=> lb > rj for a float lb
+  g.lo = mk3(rlo[0], rlo[1], rlo[2]); g.hi = mk3(rhi[0], rhi[1], rhi[2]); g.reject = rj; g.on = 1;
+}
+
 template <bool TRI>
 struct ClosestState
 {
