@@ -536,8 +536,10 @@ double orc_sdf_stats(float const * t30, uint8_t const * valid30, float scale)
 
 // Icp3<float>::align (Icp3.hpp:193-275) against a triangle structure; records the per-batch correspondences.
 // out_idx: (iters_done + 1) x n ; out_tr: 12 floats row-major [L | t]; returns the number of query batches run.
-int orc_icp(void * h, float const * from3, int64_t n, int min_iters, int max_iters, double frac_thresh, int mode, int nthreads,
-            int64_t * out_idx, float * out_tr, float * out_err)
+// out_from (optional): the source positions every batch queried, (iters_done + 1) x n x 3 -- lets a test feed the very same iterates
+// to another implementation and demand identical correspondences batch by batch.
+int orc_icp_ex(void * h, float const * from3, int64_t n, int min_iters, int max_iters, double frac_thresh, int mode, int nthreads,
+               int64_t * out_idx, float * out_tr, float * out_err, float * out_from)
 {
   KdTree const & T = ((Handle *)h)->tree;
   std::vector<V3> orig((size_t)n), from((size_t)n), to((size_t)n);
@@ -545,6 +547,7 @@ int orc_icp(void * h, float const * from3, int64_t n, int min_iters, int max_ite
   int batches = 0;
   auto correspond = [&]() {
     int64_t * oi = out_idx ? out_idx + (int64_t)batches * n : nullptr;
+    if (out_from) for (int64_t i = 0; i < n; ++i) st3(out_from + 3 * (int64_t)batches * n, i, from[(size_t)i]);
     parallel_for(n, nthreads, [&](int64_t b, int64_t e) {
       for (int64_t i = b; i < e; ++i)
       {
@@ -585,6 +588,27 @@ int orc_icp(void * h, float const * from3, int64_t n, int min_iters, int max_ite
   }
   emit(new_tr, new_err);
   return batches;
+}
+
+int orc_icp(void * h, float const * from3, int64_t n, int min_iters, int max_iters, double frac_thresh, int mode, int nthreads,
+            int64_t * out_idx, float * out_tr, float * out_err)
+{ return orc_icp_ex(h, from3, n, min_iters, max_iters, frac_thresh, mode, nthreads, out_idx, out_tr, out_err, nullptr); }
+
+// The two accumulation loops of Icp3 on their own, with given correspondences (pinned bit for bit to the reference's code by
+// tests/test_ref_pin.py): measureError (Icp3.hpp:418-464) and alignOneStep (:298-384).  tr12 = row-major [L | t].
+float orc_icp_error(float const * tr12, int64_t n, float const * from3, float const * to3)
+{
+  Affine a; for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) a.L[3 * r + c] = tr12[4 * r + c]; a.t[r] = tr12[4 * r + 3]; }
+  std::vector<V3> f((size_t)n), t((size_t)n);
+  for (int64_t i = 0; i < n; ++i) { f[(size_t)i] = ld3(from3, i); t[(size_t)i] = ld3(to3, i); }
+  return icp_error(a, n, f.data(), t.data());
+}
+void orc_icp_step(int64_t n, float const * from3, float const * to3, float * tr12)
+{
+  std::vector<V3> f((size_t)n), t((size_t)n);
+  for (int64_t i = 0; i < n; ++i) { f[(size_t)i] = ld3(from3, i); t[(size_t)i] = ld3(to3, i); }
+  Affine a = icp_step(n, f.data(), t.data());
+  for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) tr12[4 * r + c] = a.L[3 * r + c]; tr12[4 * r + 3] = a.t[r]; }
 }
 
 // MeshSampler::sampleEvenlyByArea EXACT mode (MeshSampler.hpp:147-185, Triangle3.hpp:179-195) driven by the

@@ -70,6 +70,12 @@ def lib():
         L.orc_icp.restype = C.c_int
         L.orc_icp.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                               C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_icp_ex.restype = C.c_int
+        L.orc_icp_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_icp_error.restype = C.c_float
+        L.orc_icp_error.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.orc_icp_step.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_area_sample.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_tri_point.restype = C.c_float
         L.orc_tri_point.argtypes = [C.c_void_p] * 3
@@ -267,6 +273,18 @@ class Oracle:
                           _p(idx), _p(tr), _p(err))
         return tr, float(err[0]), idx[:b]
 
+    def icp_iterates(self, src, min_iters=3, max_iters=10, frac_thresh=1e-4, mode=MODE_CANON, threads=None):
+        """icp() that also returns the source positions each batch queried: (tr, err, idx [B, n], positions [B, n, 3])."""
+        s = _f32(src).reshape(-1, 3)
+        n = s.shape[0]
+        idx = np.full((max_iters + 1, n), -1, np.int64)
+        pos = np.zeros((max_iters + 1, n, 3), np.float32)
+        tr = np.zeros((3, 4), np.float32)
+        err = np.zeros(1, np.float32)
+        b = lib().orc_icp_ex(self.h, _p(s), n, min_iters, max_iters, float(frac_thresh), mode, threads or ncores(),
+                             _p(idx), _p(tr), _p(err), _p(pos))
+        return tr, float(err[0]), idx[:b], pos[:b]
+
     def area_sample(self, count, seed):
         p = np.empty((count, 3), np.float32)
         n = np.empty((count, 3), np.float32)
@@ -293,6 +311,18 @@ def fast_sqrt(x):
 
 def box_ray_time(lo, hi, o, d, max_time=-1.0):
     return float(lib().orc_box_ray_time(_p(_f32(lo)), _p(_f32(hi)), _p(_f32(o)), _p(_f32(d)), float(max_time)))
+
+
+def icp_error(tr12, src, dst):
+    s, d, t = _f32(src).reshape(-1, 3), _f32(dst).reshape(-1, 3), _f32(tr12).reshape(12)
+    return float(lib().orc_icp_error(_p(t), s.shape[0], _p(s), _p(d)))
+
+
+def icp_step(src, dst):
+    s, d = _f32(src).reshape(-1, 3), _f32(dst).reshape(-1, 3)
+    tr = np.zeros((3, 4), np.float32)
+    lib().orc_icp_step(s.shape[0], _p(s), _p(d), _p(tr))
+    return tr
 
 
 def polar_rotation(M):

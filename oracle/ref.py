@@ -72,6 +72,9 @@ def lib():
         L.ref_tree_depth.restype = i32
         L.ref_tree_depth.argtypes = [i64, i32]
         L.ref_icp.argtypes = [vp, vp, i64, i32, i32, f64, vp, vp]
+        L.ref_icp_error.restype = f32
+        L.ref_icp_error.argtypes = [vp, i64, vp, vp]
+        L.ref_icp_step.argtypes = [i64, vp, vp, vp]
         L.ref_sdf.argtypes = [vp, vp, vp, i64, f32, i32, i32, vp]
         L.ref_graph.argtypes = [vp, vp, i64, i32, f32, vp, vp, vp, vp]
         L.ref_avg_separation.restype = f32
@@ -206,6 +209,18 @@ def avg_separation(points, seeds):
     p = _f32(points).reshape(-1, 3)
     s = np.ascontiguousarray(seeds, np.int64)
     return float(lib().ref_avg_separation(_p(p), p.shape[0], _p(s), len(s)))
+
+
+def icp_error(tr12, src, dst):
+    s, d, t = _f32(src).reshape(-1, 3), _f32(dst).reshape(-1, 3), _f32(tr12).reshape(12)
+    return float(lib().ref_icp_error(_p(t), s.shape[0], _p(s), _p(d)))
+
+
+def icp_step(src, dst):
+    s, d = _f32(src).reshape(-1, 3), _f32(dst).reshape(-1, 3)
+    tr = np.zeros((3, 4), np.float32)
+    lib().ref_icp_step(s.shape[0], _p(s), _p(d), _p(tr))
+    return tr
 
 
 def tri_point_batch(v9, p3):

@@ -48,10 +48,10 @@
 #define private public
 #define protected public
 #include "Algorithms/PointSet3.hpp"
+#include "Algorithms/Icp3.hpp"
 #undef private
 #undef protected
 #include "Algorithms/BvhN.hpp"
-#include "Algorithms/Icp3.hpp"
 #include "Algorithms/SurfaceFeatures/Local/ShapeDiameter.hpp"
 #include "Graphics/GeneralMesh.hpp"
 #include "Algorithms/IntersectionTester.hpp"
@@ -339,6 +339,26 @@ void ref_icp(void * hv, float const * from3, int64_t n, int min_iters, int max_i
   AffineTransform3 tr = icp.align((intx)n, from.data(), *h->tri, &err);
   for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) tr12[4 * r + c] = tr.getLinear()(r, c); tr12[4 * r + 3] = tr.getTranslation()[r]; }
   if (error) *error = err;
+}
+
+// Icp3<Real>::measureError(tr, n, from, nullptr, to) (Icp3.hpp:418-464) and alignOneStep(n, from, nullptr, nullptr, to, nullptr)
+// (:298-384) with given correspondences (private members, called as they are).
+float ref_icp_error(float const * tr12, int64_t n, float const * from3, float const * to3)
+{
+  Matrix3 L; Vector3 t;
+  for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) L(r, c) = tr12[4 * r + c]; t[r] = tr12[4 * r + 3]; }
+  std::vector<Vector3> f((size_t)n), q((size_t)n);
+  for (int64_t i = 0; i < n; ++i) { f[(size_t)i] = v3(from3 + 3 * i); q[(size_t)i] = v3(to3 + 3 * i); }
+  return Icp3<Real>::measureError(AffineTransform3(L, t), (intx)n, f.data(), (Icp3<Real>::DefaultWeightFunc<Vector3> *)nullptr, q.data());
+}
+void ref_icp_step(int64_t n, float const * from3, float const * to3, float * tr12)
+{
+  std::vector<Vector3> f((size_t)n), q((size_t)n);
+  for (int64_t i = 0; i < n; ++i) { f[(size_t)i] = v3(from3 + 3 * i); q[(size_t)i] = v3(to3 + 3 * i); }
+  Icp3<Real> icp(1e-4, 3, 10, false);
+  AffineTransform3 tr = icp.alignOneStep((intx)n, f.data(), (Icp3<Real>::DefaultWeightFunc<Vector3> *)nullptr, (Plane3 const *)nullptr, q.data(),
+                                         (Plane3 const *)nullptr);
+  for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) tr12[4 * r + c] = tr.getLinear()(r, c); tr12[4 * r + 3] = tr.getTranslation()[r]; }
 }
 
 // ShapeDiameter<Mesh, ExternalBvh>::compute(position, normal, only_hit_interior_surfaces) (ShapeDiameter.hpp:168-258) on the handle's

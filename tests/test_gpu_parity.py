@@ -202,3 +202,101 @@ def test_degenerate_triangles_match_the_reference_quirk(built):
     t, ri, _ = e.ray_first(o, d)
     ori, ort = ora.ray_first(o, d, mode=orc.MODE_BRUTE)
     assert np.array_equal(ri, ori.astype(np.int32)) and np.array_equal(t, ort)
+
+
+def test_shared_memory_limit_survives_smaller_launches(built):
+    """The dynamic shared-memory limit of a kernel is process-wide state: a large k, then a small k, then the large k again, on
+    one handle and across two handles (and a second handle created in between), must all launch."""
+    from thea_b200 import Engine
+    mesh = gen.torus_mesh(32)
+    p, n, _ = gen.area_samples(mesh, 3000)
+    ora = orc.Oracle(points=p, normals=n)
+    ref48 = ora.knn(p[:500], 48, mode=orc.MODE_BRUTE)
+    ref8 = ora.knn(p[:500], 8, mode=orc.MODE_BRUTE)
+    a = Engine(0)
+    a.build_points(p, n)
+    for k, want in ((48, ref48), (8, ref8), (48, ref48), (64, None), (8, ref8), (48, ref48)):
+        ki, kd = a.knn(p[:500], k)
+        if want is not None:
+            assert np.array_equal(ki, want[0].astype(np.int32)) and np.array_equal(kd, want[1])
+    b = Engine(0)                       # creating a second handle must not lower the first one's limits
+    b.build_points(p, n)
+    ki, kd = b.knn(p[:500], 8)
+    assert np.array_equal(ki, ref8[0].astype(np.int32))
+    ki, kd = a.knn(p[:500], 48)
+    assert np.array_equal(ki, ref48[0].astype(np.int32)) and np.array_equal(kd, ref48[1])
+    gi, _, _ = a.ball_graph(48, 0.2)
+    gi2, _, _ = b.ball_graph(4, 0.2)
+    gi3, _, _ = a.ball_graph(48, 0.2)
+    assert np.array_equal(gi, gi3)
+
+
+def test_device_pointer_arguments_and_dtype_checks(built):
+    torch = pytest.importorskip("torch")
+    from thea_b200 import Engine, TgqError
+    mesh = gen.torus_mesh(32)
+    p, n, _ = gen.area_samples(mesh, 3000)
+    e = Engine(0)
+    e.build_points(p, n)
+    seeds = (gen.splitmix64(7, 100) % np.uint64(len(p))).astype(np.int32)
+    want = e.avg_separation(seeds.astype(np.int64))
+    import ctypes as C
+    out = C.c_float()
+    ds = torch.from_numpy(seeds).cuda()
+    rc = e._L.tgq_avg_separation(e._h, C.c_void_p(ds.data_ptr()), 100, C.byref(out))      # seeds as a DEVICE pointer
+    assert rc == 0 and out.value == want
+    with pytest.raises(TypeError):
+        e.closest(torch.zeros((4, 3), dtype=torch.float64, device="cuda"))
+    # torch tensors produced on the current stream are consumed in order without an explicit set_stream
+    q = torch.from_numpy(gen.closest_queries(200000, gen.mesh_bounds(mesh))).cuda()
+    q2 = q * 1.0 + 0.0
+    i1, d1, _ = e.closest(q2)
+    i0, d0, _ = e.closest(q.cpu().numpy())
+    torch.cuda.synchronize()
+    assert np.array_equal(i1.cpu().numpy(), i0) and np.array_equal(d1.cpu().numpy(), d0)
+    t = Engine(0)
+    verts, tris = gen.torus_vertices(12), gen.torus_indices(12).copy()
+    tris[5, 1] = len(verts) + 3
+    with pytest.raises(TgqError):
+        t.build_triangles_indexed(verts, tris)
+    flat = gen.torus_mesh(12)
+    t.build_triangles(flat)
+    t.refit_triangles(flat.reshape(-1))          # flat arrays are accepted by refit as by build
+
+
+def test_engine_against_the_reference_library_directly(built):
+    """Where oracle/_ref/libthea_ref.so travelled with the snapshot: the engine against the REFERENCE'S OWN CODE (no restatement in
+    between): squared distances, closest points and hit times bit-equal on every query, indices equal wherever the reference's
+    first-found answer is the lowest-index one (all differences are exact ties, checked)."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libthea_ref.so not present")
+    from thea_b200 import Engine
+    mesh = gen.torus_mesh(gen.TORUS_70K)
+    b = gen.mesh_bounds(mesh)
+    R = ref.Reference(tris9=mesh)
+    e = Engine(0)
+    e.build_triangles(mesh)
+    q = gen.closest_queries(300_000, b)
+    for bound in (-1.0, 0.3):
+        gi, gd, gc = e.closest(q, dist_bound=bound)
+        ri, rd, rc = R.closest(q, dist_bound=bound)
+        assert np.array_equal(gi >= 0, ri >= 0)
+        f = ri >= 0
+        assert np.array_equal(gd[f], rd[f])
+        same = gi == ri
+        assert np.array_equal(gc[same & f], rc[same & f])
+        assert np.all(gi[~same] < ri[~same])                    # ties: the engine returns the lowest index, the reference the first found
+        assert (~same).mean() < 0.5
+    o, d = gen.random_rays(300_000, b)
+    gt, gri, _ = e.ray_first(o, d)
+    rri, rt = R.ray_first(o, d)
+    assert np.array_equal(gt, rt) and np.array_equal(gri >= 0, rri >= 0) and np.all(gri[gri != rri] < rri[gri != rri])
+    p, n, _ = gen.area_samples(mesh, 100_000)
+    pe = Engine(0)
+    pe.build_points(p, n)
+    RP = ref.Reference(points=p)
+    ki, kd = pe.knn(q[:50_000], 16, dist_bound=0.2)
+    rki, rkd = RP.knn(q[:50_000], 16, dist_bound=0.2)
+    assert np.array_equal(kd, rkd)
+    assert (ki != rki).any(axis=1).mean() < 0.01

@@ -260,3 +260,17 @@ def test_icp(torus):
     otr, oerr, _ = O.icp(src, min_iters=8, max_iters=8, frac_thresh=1e-4, mode=orc.MODE_REFERENCE)
     assert np.allclose(rtr, otr, rtol=1e-5, atol=1e-5), np.abs(rtr - otr).max()
     assert abs(rerr - oerr) <= 1e-5 * max(1.0, abs(rerr))
+
+
+def test_icp_accumulation_loops_bit_exact(torus):
+    """The two sequential fp32 loops of Icp3 with given correspondences: measureError (Icp3.hpp:418-464) bit for bit; alignOneStep
+    (:298-384) to 1e-6 (its rotation goes through the stand-in's SVD on the reference side)."""
+    mesh, bounds, R, O = torus
+    p, _, _ = gen.area_samples(mesh, 20000)
+    src = gen.apply_pose(p, *gen.rigid_pose())
+    _, _, dst = O.closest(src, mode=orc.MODE_CANON)
+    Rm, t = gen.rigid_pose()
+    for tr in (np.hstack([np.eye(3, dtype=np.float32), np.zeros((3, 1), np.float32)]), np.hstack([Rm.astype(np.float32), t.reshape(3, 1).astype(np.float32)])):
+        assert _same(np.float32(ref.icp_error(tr, src, dst)), np.float32(orc.icp_error(tr, src, dst)))
+    a, b = ref.icp_step(src, dst), orc.icp_step(src, dst)
+    assert np.allclose(a, b, rtol=1e-6, atol=1e-6), np.abs(a - b).max()

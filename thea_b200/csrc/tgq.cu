@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -20,6 +21,8 @@ using namespace tgq;
 namespace {
 
 std::string g_create_error;
+std::mutex g_smem_mutex;
+std::map<std::pair<int, void const *>, size_t> g_smem_limit;      // (device, kernel) -> dynamic shared memory limit set so far
 
 struct DevBuf
 {
@@ -63,7 +66,7 @@ struct tgq_handle
   std::string err;
   cudaStream_t own_stream = nullptr, stream = nullptr;
 
-  int opt_sort = 2, opt_leaf = 4, opt_async = 0, opt_pool = 1; int64_t opt_chunk = 16777216;
+  int opt_sort = 2, opt_leaf = 4, opt_async = 0, opt_pool = 1, opt_icp_ref = 0; int64_t opt_chunk = 16777216;
 
   int kind = TGQ_KIND_NONE; int n = 0; int n_nodes = 0; bool has_normals = false, has_labels = false; int leaf_built = 4;
   DevBuf nodes, elems, nrm, lab, scene;                                // NodeRec[], TriRec[] | f4[], f4[], SceneBox
@@ -408,11 +411,18 @@ template <typename K>
 int persistent_grid(tgq_handle * h, K kernel, size_t smem, int64_t n, int * counter, cudaStream_t s, int * grid_out, int max_blocks = 0)
 {
   auto key = std::make_pair((void const *)kernel, smem);
+  // cudaFuncAttributeMaxDynamicSharedMemorySize is state of the FUNCTION (per device), shared by every handle and every launch
+  // configuration of the process: it is only ever raised, so that a cached larger configuration (k-NN with a larger k, another
+  // handle) never launches above a limit that a later, smaller configuration lowered.
+  {
+    std::lock_guard<std::mutex> lock(g_smem_mutex);
+    size_t & cur = g_smem_limit[std::make_pair(h->device, (void const *)kernel)];
+    if (smem > cur) { CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cur = smem; }
+  }
   auto it = h->occupancy.find(key);
   if (it == h->occupancy.end())
   {
     int per_sm = 0;
-    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int carve = cudaSharedmemCarveoutMaxShared;
     char const * dev_blocks = getenv("TGQ_DEV_BLOCKS");     // development aid: cap resident blocks per SM and give the rest of the array to L1
     int cap = dev_blocks ? atoi(dev_blocks) : max_blocks;   // max_blocks: kernels that run faster with fewer resident blocks and a larger L1
@@ -481,10 +491,6 @@ int tgq_create(int device, tgq_handle ** out)
     if ((e = h->slot[s].counter.reserve(sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
   }
   if ((e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return bail("cudaDeviceGetAttribute", e);
-  int const smem = 2 * TGQ_MAX_K * TGQ_BLOCK * 4;
-  if ((e = cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute(k_knn)", e);
-  if ((e = cudaFuncSetAttribute(k_ball_graph<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute(k_ball_graph)", e);
-  if ((e = cudaFuncSetAttribute(k_ball_graph<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute(k_ball_graph)", e);
   if (prev >= 0) cudaSetDevice(prev);
   *out = h;
   return TGQ_OK;
@@ -531,6 +537,7 @@ int tgq_set_option(tgq_handle * h, int option, int64_t value)
     case TGQ_OPT_LEAF_SIZE: if (value < 1 || value > TGQ_LEAF_MASK) return fail(h, TGQ_EINVAL, "TGQ_OPT_LEAF_SIZE takes 1..15"); h->opt_leaf = (int)value; return TGQ_OK;
     case TGQ_OPT_ASYNC: h->opt_async = value ? 1 : 0; return TGQ_OK;
     case TGQ_OPT_POOL: h->opt_pool = value ? 1 : 0; return TGQ_OK;
+    case TGQ_OPT_ICP_REFERENCE_ORDER: h->opt_icp_ref = value ? 1 : 0; return TGQ_OK;
     case TGQ_OPT_CHUNK: if (value < 1024) return fail(h, TGQ_EINVAL, "TGQ_OPT_CHUNK must be >= 1024"); h->opt_chunk = value; return TGQ_OK;
     default: return fail(h, TGQ_EINVAL, "unknown option");
   }
@@ -556,9 +563,13 @@ int tgq_build_triangles_indexed(tgq_handle * h, const float * verts3, int64_t V,
   CKRC(to_device(h, verts3, sizeof(float) * 3 * (size_t)V, h->src2, h->stream, &dv));
   CKRC(to_device(h, tri3, sizeof(int32_t) * 3 * (size_t)T, h->misc, h->stream, &di));
   CK(h->src.reserve(sizeof(float) * 9 * (size_t)T));
-  k_expand_indexed<<<grid_for(3 * T), TGQ_BLOCK, 0, h->stream>>>((float const *)dv, (int const *)di, 3 * T, V, h->src.as<float>());
+  CK(h->big_count.reserve(4)); CK(cudaMemsetAsync(h->big_count.p, 0, 4, h->stream));
+  k_expand_indexed<<<grid_for(3 * T), TGQ_BLOCK, 0, h->stream>>>((float const *)dv, (int const *)di, 3 * T, V, h->src.as<float>(), h->big_count.as<int>());
   CK(cudaGetLastError());
   h->st.total_launches += 1;
+  int bad = 0;
+  CK(cudaMemcpyAsync(&bad, h->big_count.p, 4, cudaMemcpyDeviceToHost, h->stream)); CK(cudaStreamSynchronize(h->stream));
+  if (bad) return fail(h, TGQ_EINVAL, "tgq_build_triangles_indexed: vertex index out of range");
   return build_common(h, TGQ_KIND_TRIANGLES, h->src.as<float>(), nullptr, T);
 }
 
@@ -953,8 +964,9 @@ int tgq_avg_separation(tgq_handle * h, const int32_t * seeds, int32_t n, float *
   if (h->n < 2) return fail(h, TGQ_ESTATE, "tgq_avg_separation: needs at least two points");
   Guard g(h);
   cudaStream_t s = h->stream;
-  std::vector<int32_t> hs(seeds, seeds + n);
+  std::vector<int32_t> hs((size_t)n);
   if (is_device_ptr(seeds)) { CK(cudaMemcpyAsync(hs.data(), seeds, 4 * (size_t)n, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s)); }
+  else memcpy(hs.data(), seeds, 4 * (size_t)n);
   for (int i = 0; i < n; ++i) if (hs[(size_t)i] < 0 || hs[(size_t)i] >= h->n) return fail(h, TGQ_EINVAL, "tgq_avg_separation: seed index out of range");
   CK(h->misc.reserve(8 * (size_t)n));
   int * ds = h->misc.as<int>(); float * dd = (float *)(ds + n);
@@ -1043,6 +1055,20 @@ int tgq_icp_sums(tgq_handle * h, const float * from3, const float * to3, int64_t
   long long * acc = h->misc.as<long long>(); float * dtr = (float *)(acc + 16); int * dexp = (int *)(dtr + 12);
   CK(cudaMemsetAsync(acc, 0, 16 * 8, s));
   if (tr12) CK(cudaMemcpyAsync(dtr, tr12, 48, is_device_ptr(tr12) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  if (h->opt_icp_ref)
+  {
+    // the reference's own accumulation order (Icp3.hpp:306-367,418-463): one warp, one lane per chain
+    float * dout = (float *)acc; float hf[16];
+    k_icp_ref_order<<<1, 32, 0, s>>>((float const *)df, (float const *)dt, n, tr12 ? dtr : nullptr, dout);
+    CK(cudaGetLastError());
+    h->st.total_launches += 1;
+    CK(cudaMemcpyAsync(hf, dout, 64, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    double res[16]; for (int i = 0; i < 16; ++i) res[i] = (double)hf[i];
+    if (is_device_ptr(out16)) { CK(cudaMemcpyAsync(out16, res, 128, cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s)); }
+    else memcpy(out16, res, 128);
+    return TGQ_OK;
+  }
   // fixed-point units from the data range: 2^-34 of the largest coordinate magnitude (2^-34 of its square for products)
   CK(cudaMemsetAsync(dexp, 0, 4, s));
   k_max_abs<<<148 * 4, 256, 0, s>>>((float const *)df, (float const *)dt, 3 * n, dexp);

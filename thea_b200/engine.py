@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 KIND_NONE, KIND_TRIANGLES, KIND_POINTS = 0, 1, 2
-OPT_SORT_QUERIES, OPT_LEAF_SIZE, OPT_ASYNC, OPT_CHUNK = 1, 2, 3, 4
+OPT_SORT_QUERIES, OPT_LEAF_SIZE, OPT_ASYNC, OPT_CHUNK, OPT_POOL, OPT_ICP_REFERENCE_ORDER = 1, 2, 3, 4, 5, 6
 MAX_K = 64
 
 SYMBOLS = [
@@ -119,13 +119,20 @@ def _is_torch(a):
     return a is not None and not isinstance(a, np.ndarray) and hasattr(a, "data_ptr")
 
 
+_TORCH_DTYPE = {np.dtype(np.float32): "float32", np.dtype(np.int32): "int32", np.dtype(np.float64): "float64", np.dtype(np.uint8): "uint8"}
+
+
 def _as_in(a, dtype=np.float32):
-    """Contiguous input of the right dtype: numpy arrays are converted, torch tensors must already match."""
+    """Contiguous input of the right dtype: numpy arrays are converted, torch tensors must already match (a tensor of another
+    dtype would be reinterpreted, not converted, by the C ABI: refused here)."""
     if a is None:
         return None
     if _is_torch(a):
         if not a.is_contiguous():
             raise ValueError("torch inputs must be contiguous")
+        want = _TORCH_DTYPE.get(np.dtype(dtype))
+        if want is not None and str(a.dtype) != "torch." + want:
+            raise TypeError(f"torch input has dtype {a.dtype}, the engine needs torch.{want}")
         return a
     return np.ascontiguousarray(a, dtype=dtype)
 
@@ -141,6 +148,20 @@ class Engine:
             raise TgqError(rc, self._L.tgq_last_error(None).decode())
         self._h = h
         self.device = device
+        self._explicit_stream = False
+
+    def _in(self, a, dtype=np.float32):
+        """_as_in plus the two things a CUDA tensor needs: it must live on this engine's device, and the handle's work must be
+        ordered after whatever produced it.  Unless set_stream() was called explicitly, the handle is therefore moved onto torch's
+        CURRENT stream of the device whenever a CUDA tensor is passed (results written into CUDA tensors are ordered the same way)."""
+        a = _as_in(a, dtype)
+        if _is_torch(a) and getattr(a, "is_cuda", False):
+            if a.device.index != self.device:
+                raise ValueError(f"tensor lives on {a.device}, the engine on cuda:{self.device}")
+            if not self._explicit_stream:
+                import torch
+                self._ck(self._L.tgq_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return a
 
     def close(self):
         if getattr(self, "_h", None):
@@ -162,24 +183,27 @@ class Engine:
         self._ck(self._L.tgq_set_option(self._h, opt, int(value)))
 
     def set_stream(self, cuda_stream_ptr):
+        """Pins the handle to one CUDA stream (0 / None: back to following torch's current stream for CUDA tensors, the handle's
+        own stream otherwise)."""
+        self._explicit_stream = bool(cuda_stream_ptr)
         self._ck(self._L.tgq_set_stream(self._h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
 
     # ---- build ----
     def build_triangles(self, v9):
-        v9 = _as_in(v9)
+        v9 = self._in(v9)
         T = int((v9.size if isinstance(v9, np.ndarray) else v9.numel()) // 9)
         self._ck(self._L.tgq_build_triangles(self._h, _ptr(v9), T))
         return T
 
     def build_triangles_indexed(self, verts, tris):
-        verts = _as_in(verts)
-        tris = _as_in(tris, np.int32)
+        verts = self._in(verts)
+        tris = self._in(tris, np.int32)
         self._ck(self._L.tgq_build_triangles_indexed(self._h, _ptr(verts), int(verts.shape[0]), _ptr(tris), int(tris.shape[0])))
         return int(tris.shape[0])
 
     def build_points(self, p3, n3=None):
-        p3 = _as_in(p3)
-        n3 = _as_in(n3)
+        p3 = self._in(p3)
+        n3 = self._in(n3)
         self._ck(self._L.tgq_build_points(self._h, _ptr(p3), int(p3.shape[0]), _ptr(n3)))
         return int(p3.shape[0])
 
@@ -189,8 +213,9 @@ class Engine:
         self._ck(self._L.tgq_set_transform(self._h, _ptr(tr)))
 
     def refit_triangles(self, v9):
-        v9 = _as_in(v9)
-        self._ck(self._L.tgq_refit_triangles(self._h, _ptr(v9), int(v9.shape[0])))
+        v9 = self._in(v9)
+        T = int((v9.size if isinstance(v9, np.ndarray) else v9.numel()) // 9)
+        self._ck(self._L.tgq_refit_triangles(self._h, _ptr(v9), T))
 
     def info(self):
         kind = C.c_int32()
@@ -211,7 +236,7 @@ class Engine:
 
     # ---- queries (numpy in -> numpy out; torch in -> caller supplies torch outputs) ----
     def closest(self, q3, dist_bound=-1.0, exclude_self=False, out=None, want_cp=True):
-        q3 = _as_in(q3)
+        q3 = self._in(q3)
         Q = int(q3.shape[0])
         if out is None:
             if _is_torch(q3):
@@ -229,7 +254,7 @@ class Engine:
         return idx, d2, cp
 
     def knn(self, q3, k, dist_bound=-1.0, exclude_self=False, out=None):
-        q3 = _as_in(q3)
+        q3 = self._in(q3)
         Q = int(q3.shape[0])
         if out is None:
             if _is_torch(q3):
@@ -246,13 +271,13 @@ class Engine:
 
     # ---- filtered nearest neighbours (point structures; Register.cpp NNFilter semantics) ----
     def set_point_labels(self, labels):
-        lab = None if labels is None else _as_in(labels, np.int32)
+        lab = None if labels is None else self._in(labels, np.int32)
         self._ck(self._L.tgq_set_point_labels(self._h, _ptr(lab)))
 
     def closest_filtered(self, q3, qn3=None, qlabel=None, min_dot=0.0, dist_bound=-1.0):
-        q3 = _as_in(q3)
-        qn3 = _as_in(qn3)
-        qlabel = _as_in(qlabel, np.int32)
+        q3 = self._in(q3)
+        qn3 = self._in(qn3)
+        qlabel = self._in(qlabel, np.int32)
         Q = int(q3.shape[0])
         idx = np.empty(Q, np.int32)
         d2 = np.empty(Q, np.float32)
@@ -261,9 +286,9 @@ class Engine:
         return idx, d2, cp
 
     def knn_filtered(self, q3, k, qn3=None, qlabel=None, min_dot=0.0, dist_bound=-1.0):
-        q3 = _as_in(q3)
-        qn3 = _as_in(qn3)
-        qlabel = _as_in(qlabel, np.int32)
+        q3 = self._in(q3)
+        qn3 = self._in(qn3)
+        qlabel = self._in(qlabel, np.int32)
         Q = int(q3.shape[0])
         idx = np.empty((Q, k), np.int32)
         d2 = np.empty((Q, k), np.float32)
@@ -272,7 +297,7 @@ class Engine:
 
     def ball_range(self, c3, radius, max_out=32, exclude_self=False):
         """rangeQueryIndices with a ball per query: (idx [Q x max_out] lowest indices ascending, count [Q])."""
-        c3 = _as_in(c3)
+        c3 = self._in(c3)
         Q = int(c3.shape[0])
         rad = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float32), (Q,)), np.float32)
         idx = np.empty((Q, max_out), np.int32) if max_out > 0 else None
@@ -282,7 +307,7 @@ class Engine:
 
     def ball_histogram(self, c3, radius, num_bins):
         """LocalDistanceHistogram (EUCLIDEAN) for every ball: [Q x num_bins] uint32 counts (tgq_ball_histogram)."""
-        c3 = _as_in(c3)
+        c3 = self._in(c3)
         Q = int(c3.shape[0])
         rad = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float32), (Q,)), np.float32)
         hist = np.empty((Q, num_bins), np.uint32)
@@ -291,13 +316,13 @@ class Engine:
 
     def ball_stats(self, c3, radius, qn3=None, out=None):
         """Per-ball neighbourhood sums (tgq_ball_stats): [Q x 16] doubles, layout in include/thea_gpu_query.h."""
-        c3 = _as_in(c3)
+        c3 = self._in(c3)
         Q = int(c3.shape[0])
         if _is_torch(radius):
             rad = radius
         else:
             rad = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float32), (Q,)), np.float32)
-        qn3 = _as_in(qn3)
+        qn3 = self._in(qn3)
         if out is None:
             out = np.empty((Q, 16), np.float64)
         self._ck(self._L.tgq_ball_stats(self._h, _ptr(c3), _ptr(qn3), _ptr(rad), Q, _ptr(out)))
@@ -306,8 +331,8 @@ class Engine:
     def visibility(self, p3, dirs3, scale):
         """Visibility::compute for every sample with caller-supplied directions ([D x 3] shared or [S x D x 3]):
         (visibility [S] float64, num_escaped [S] int32)."""
-        p3 = _as_in(p3)
-        dirs3 = _as_in(dirs3)
+        p3 = self._in(p3)
+        dirs3 = self._in(dirs3)
         S = int(p3.shape[0])
         per_sample = len(dirs3.shape) == 3
         D = int(dirs3.shape[-2])
@@ -349,9 +374,9 @@ class Engine:
         return float(out.value)
 
     def ray_first(self, o3, d3, tmax=None, out=None, want_normal=False):
-        o3 = _as_in(o3)
-        d3 = _as_in(d3)
-        tmax = _as_in(tmax)
+        o3 = self._in(o3)
+        d3 = self._in(d3)
+        tmax = self._in(tmax)
         R = int(o3.shape[0])
         if out is None:
             if _is_torch(o3):
@@ -369,17 +394,17 @@ class Engine:
         return t, idx, nrm
 
     def ray_any(self, o3, d3, tmax=None):
-        o3 = _as_in(o3)
-        d3 = _as_in(d3)
-        tmax = _as_in(tmax)
+        o3 = self._in(o3)
+        d3 = self._in(d3)
+        tmax = self._in(tmax)
         R = int(o3.shape[0])
         hit = np.empty(R, np.uint8)
         self._ck(self._L.tgq_ray_any(self._h, _ptr(o3), _ptr(d3), _ptr(tmax), R, _ptr(hit)))
         return hit
 
     def sdf(self, p3, n3, scale, only_hit_interior=True, want_rays=True):
-        p3 = _as_in(p3)
-        n3 = _as_in(n3)
+        p3 = self._in(p3)
+        n3 = self._in(n3)
         S = int(p3.shape[0])
         sdf = np.empty(S, np.float64)
         rt = np.empty((S, 30), np.float32) if want_rays else None
@@ -388,8 +413,8 @@ class Engine:
         return sdf, rt, ri
 
     def icp_sums(self, from3, to3, tr12=None):
-        from3 = _as_in(from3)
-        to3 = _as_in(to3)
+        from3 = self._in(from3)
+        to3 = self._in(to3)
         tr = None if tr12 is None else np.ascontiguousarray(tr12, np.float32).reshape(12)
         out = np.empty(16, np.float64)
         self._ck(self._L.tgq_icp_sums(self._h, _ptr(from3), _ptr(to3), int(from3.shape[0]), _ptr(tr), _ptr(out)))
@@ -397,7 +422,7 @@ class Engine:
 
     def icp_align(self, from3, min_iterations=3, max_iterations=10, fractional_error_threshold=1e-4, want_error=True, want_correspondences=True):
         """Icp3<Real>::align on the device (tgq_icp_align): returns (transform 3x4, error, correspondences [batches x n])."""
-        from3 = _as_in(from3)
+        from3 = self._in(from3)
         n = int(from3.shape[0])
         tr = np.empty(12, np.float32)
         err = C.c_float()
@@ -408,7 +433,7 @@ class Engine:
         return tr.reshape(3, 4), float(err.value), (corr[:nb.value] if corr is not None else nb.value)
 
     def transform_points(self, in3, tr12, out=None):
-        in3 = _as_in(in3)
+        in3 = self._in(in3)
         tr = np.ascontiguousarray(tr12, np.float32).reshape(12)
         n = int(in3.shape[0])
         if out is None:

@@ -124,7 +124,8 @@ def combine_icp_sums(parts, tr12=None):
     """Combines per-shard tgq_icp_sums outputs [(n_s, out16_s), ...] (in rank order) into the sums of the whole set.
 
     out16 = (mean p, mean q, centred cross-covariance, error) as documented in include/thea_gpu_query.h; the pooled
-    statistics follow from the raw sums, accumulated in float64 in rank order (deterministic for a given world size).
+    statistics follow from the raw sums, accumulated in float64 in rank order (deterministic for a given world size; every
+    shard quantises its fixed-point sums with its own unit, so different world sizes agree to ~1e-9 relative, not bit for bit).
     """
     L = np.eye(3, 4) if tr12 is None else np.asarray(tr12, np.float64).reshape(3, 4)
     N = 0.0
@@ -176,12 +177,15 @@ class ShardedEngine:
     def closest(self, q3, total=None, local=False, space_box=None, **kw):
         """space_box = (lo, hi): shard the GLOBAL batch by space (space_shard_indices) instead of by position."""
         total = int(q3.shape[0]) if total is None else total
+        if kw.get("exclude_self"):
+            # "self" is the element with the query's GLOBAL position; a shard only knows local positions
+            raise ValueError("exclude_self needs global query positions: query the shard through Engine.closest on a slice of the build array")
         if space_box is not None:
             sel = space_shard_indices(q3, space_box[0], space_box[1], self.rank, self.world)
             idx, d2, cp = self.engine.closest(q3[sel], **kw)
-            return tuple(gather_scattered(x, sel, total, self.group) for x in (idx, d2, cp))
+            return tuple(None if x is None else gather_scattered(x, sel, total, self.group) for x in (idx, d2, cp))
         idx, d2, cp = self.engine.closest(self._slice(q3, total, local), **kw)
-        return tuple(gather_shards(x, total, self.group) for x in (idx, d2, cp))
+        return tuple(None if x is None else gather_shards(x, total, self.group) for x in (idx, d2, cp))
 
     def ray_first(self, o3, d3, total=None, local=False, space_box=None, **kw):
         total = int(o3.shape[0]) if total is None else total
