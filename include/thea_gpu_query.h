@@ -56,9 +56,11 @@ enum
   TGQ_OPT_ASYNC = 3,          /* 1: device-pointer calls return without synchronising the stream (default 0) */
   TGQ_OPT_CHUNK = 4,          /* queries per staged chunk for host-pointer calls (default 16777216) */
   TGQ_OPT_POOL = 5,           /* closest point on triangle structures: 1 = leaf tests pooled across the warp (default), 0 = per lane */
-  TGQ_OPT_ICP_REFERENCE_ORDER = 6   /* 1: tgq_icp_sums / tgq_icp_align accumulate in the reference's own order -- sequential fp32, the loops of
-                                       Icp3.hpp:306-367,418-463 -- so iterates and per-iteration correspondences equal the reference's bit for
-                                       bit (about 1 ms per 100,000 points and call); 0 (default): order-independent fixed-point sums */
+  TGQ_OPT_ICP_REFERENCE_ORDER = 6   /* 1 (default): tgq_icp_sums / tgq_icp_align accumulate in the reference's own order -- sequential fp32, the
+                                       loops of Icp3.hpp:306-367,418-463 -- so iterates, per-iteration correspondences and the final transform
+                                       equal the reference's bit for bit; 0: order-independent fixed-point (exact) sums, 20x faster per call, but
+                                       the reference's fp32 chains carry ~1e-4 of summation noise over 10^5 points that exact sums do not
+                                       reproduce (cfg3: final transform differs by 3e-4 after 50 iterations) */
 };
 
 #define TGQ_MAX_K 64
@@ -222,10 +224,10 @@ int tgq_sdf(tgq_handle * h, const float * p3, const float * n3, int64_t S, float
 int tgq_visibility(tgq_handle * h, const float * p3, int64_t S, const float * dirs3, int32_t num_dirs, int32_t per_sample_dirs, float scale,
                    double * visibility, int32_t * num_escaped);
 
-/* ICP sums for n correspondences (from3[i] -> to3[i]).  Default: order-independent fixed-point accumulation, identical for any
+/* ICP sums for n correspondences (from3[i] -> to3[i]).  Default (TGQ_OPT_ICP_REFERENCE_ORDER = 1): the reference's sequential
+ * fp32 loops, every output an fp32 value.  With the option at 0: order-independent fixed-point accumulation, identical for any
  * launch shape on one device (sharded front ends that combine per-shard sums quantise each shard with its own unit: equal to
- * 1e-9 relative, not bit for bit, across GPU counts).  With TGQ_OPT_ICP_REFERENCE_ORDER: the reference's sequential fp32 loops,
- * every output an fp32 value.  out[0..2] = mean p, out[3..5] = mean q, out[6..14] = sum (p - pm)(q - qm)^T row-major, and with tr12
+ * 1e-9 relative, not bit for bit, across GPU counts).  out[0..2] = mean p, out[3..5] = mean q, out[6..14] = sum (p - pm)(q - qm)^T row-major, and with tr12
  * (row-major 3x4 [L|t], may be null = identity) out[15] = |tr pm - qm|^2 + sum |L (p - pm) - (q - qm)|^2.
  * Replaces the accumulation loops of Icp3::alignOneStep / measureError (Algorithms/Icp3.hpp:298-367,410-464). */
 int tgq_icp_sums(tgq_handle * h, const float * from3, const float * to3, int64_t n, const float * tr12, double * out16);

@@ -46,6 +46,9 @@ def test_icp_cfg3_shape(setup):
     assert np.array_equal(corr[1], ocorr[1].astype(np.int32))          # (batch 1 queries the same, not yet moved, positions)
     assert np.allclose(tr, otr, rtol=1e-5, atol=1e-5)
     assert abs(err - oerr) <= 1e-4 * max(abs(oerr), 1e-12) + 1e-9
+    # the in-library loop (tgq_icp_align) accumulates in the reference's order by default: every batch and the transform are equal
+    tr3, err3, corr3 = e.icp_align(src, min_iterations=8, max_iterations=8)
+    assert np.array_equal(corr3, ocorr.astype(np.int32)) and np.array_equal(tr3, otr) and err3 == oerr
     # convergence-controlled run (Icp3 defaults) stops after the same number of batches
     tr2, err2, corr2 = callers.icp_align(e, src)
     otr2, oerr2, ocorr2 = ora.icp(src, mode=orc.MODE_BRUTE)
@@ -57,6 +60,22 @@ def test_icp_sums_are_launch_shape_independent(setup):
     e, mesh, _ = setup
     p, _, _ = gen.area_samples(mesh, 10001)
     q = p[::-1].copy()
+    e.set_option(6, 0)                 # TGQ_OPT_ICP_REFERENCE_ORDER off: the order-independent fixed-point sums
+    try:
+        _check_fixed_point_sums(e, p, q)
+    finally:
+        e.set_option(6, 1)
+    # default (reference order): the reference's sequential fp32 loops, bit for bit
+    tr = np.hstack([gen.rigid_pose()[0].astype(np.float32), gen.rigid_pose()[1].reshape(3, 1).astype(np.float32)])
+    s = e.icp_sums(p, q, tr)
+    assert np.float32(s[15]) == np.float32(orc.icp_error(tr, p, q))
+    pm = np.zeros(3, np.float32)
+    for x in p:
+        pm = pm + x
+    assert np.array_equal(s[0:3].astype(np.float32), pm / np.float32(len(p)))
+
+
+def _check_fixed_point_sums(e, p, q):
     a = e.icp_sums(p, q)
     # the same pairs in another order give bit-identical sums (fixed-point accumulation)
     perm = np.random.default_rng(3).permutation(len(p))

@@ -66,7 +66,7 @@ struct tgq_handle
   std::string err;
   cudaStream_t own_stream = nullptr, stream = nullptr;
 
-  int opt_sort = 2, opt_leaf = 4, opt_async = 0, opt_pool = 1, opt_icp_ref = 0; int64_t opt_chunk = 16777216;
+  int opt_sort = 2, opt_leaf = 4, opt_async = 0, opt_pool = 1, opt_icp_ref = 1; int64_t opt_chunk = 16777216;
 
   int kind = TGQ_KIND_NONE; int n = 0; int n_nodes = 0; bool has_normals = false, has_labels = false; int leaf_built = 4;
   DevBuf nodes, elems, nrm, lab, scene;                                // NodeRec[], TriRec[] | f4[], f4[], SceneBox
@@ -1059,7 +1059,7 @@ int tgq_icp_sums(tgq_handle * h, const float * from3, const float * to3, int64_t
   {
     // the reference's own accumulation order (Icp3.hpp:306-367,418-463): one warp, one lane per chain
     float * dout = (float *)acc; float hf[16];
-    k_icp_ref_order<<<1, 32, 0, s>>>((float const *)df, (float const *)dt, n, tr12 ? dtr : nullptr, dout);
+    k_icp_ref_order<<<1, TGQ_ICP_THREADS, 0, s>>>((float const *)df, (float const *)dt, n, tr12 ? dtr : nullptr, dout);
     CK(cudaGetLastError());
     h->st.total_launches += 1;
     CK(cudaMemcpyAsync(hf, dout, 64, cudaMemcpyDeviceToHost, s));

@@ -1076,67 +1076,88 @@ __global__ void k_icp_sums(float const * __restrict__ from3, float const * __res
   }
 }
 
-// ---- K9b ICP sums in the REFERENCE'S order (TGQ_OPT_ICP_REFERENCE_ORDER) -----------------------------------------------------
+// ---- K9b ICP sums in the REFERENCE'S order (TGQ_OPT_ICP_REFERENCE_ORDER, the default) ---------------------------------------
 // Icp3::alignOneStep / measureError (Algorithms/Icp3.hpp:306-367,418-463) are sequential fp32 loops over the correspondences:
 //   pass 1   p_mean += p; q_mean += q; sum_weights += 1   (7 chains)   then   p_mean /= sum_weights; q_mean /= sum_weights
 //   pass 2   cov(r, c) += (p - p_mean)[r] * (q - q_mean)[c]   (9 chains)
 //            err = |tr p_mean - q_mean|^2;  err += |L (p - p_mean) - (q - q_mean)|^2   (1 chain)
-// A chain is a dependent sequence of single fp32 additions, so its value is fixed by the order; the chains are independent of
-// each other.  One warp: lane j owns chain j and walks the points in index order (the per-point terms of a tile of 32 points are
-// computed by all lanes first, from a shared-memory tile loaded with coalesced reads).  Result: bit for bit what the reference's
-// loops give, at about 1 ms per 100,000 points -- the fixed-point kernel above is 40x faster and stays the default.
+// A chain is a dependent sequence of single fp32 additions, so its value is fixed by the order (and, over 10^5 terms, carries
+// ~1e-4 of summation noise that an exact sum does not reproduce: after 50 ICP iterations on cfg3 the exact-sum transform differs
+// from the reference's by 3e-4).  The chains are independent of each other: one thread block, whose threads stage tiles of
+// TGQ_ICP_TILE points in shared memory (coalesced) and compute the per-point error terms, while lane j of warp 0 owns chain j and
+// walks the tile in index order.  Bit for bit what the reference's loops give.
 // out16: [0..2] p_mean, [3..5] q_mean, [6..14] cov row-major, [15] err  (all fp32 values, stored as float).
-__global__ void __launch_bounds__(32)
+#define TGQ_ICP_TILE 1024
+#define TGQ_ICP_THREADS 256
+__global__ void __launch_bounds__(TGQ_ICP_THREADS)
 k_icp_ref_order(float const * __restrict__ from3, float const * __restrict__ to3, int64_t n, float const * __restrict__ tr12, float * out16)
 {
-  unsigned const FULL = 0xffffffffu;
-  int const lane = threadIdx.x;
-  __shared__ float sp[96], sq[96], sterm[32];
+  int const tid = threadIdx.x, lane = tid & 31;
+  bool const chain_warp = tid < 32;
+  __shared__ float sp[3 * TGQ_ICP_TILE], sq[3 * TGQ_ICP_TILE], sterm[TGQ_ICP_TILE], smean[8];
   float L[12];
   for (int j = 0; j < 12; ++j) L[j] = tr12 ? tr12[j] : ((j % 5 == 0) ? 1.0f : 0.0f);
   float acc = 0.0f;
-  for (int64_t base = 0; base < n; base += 32)
+  // lane j < 3 walks p[j], 3 <= j < 6 walks q[j - 3], lane 6 counts
+  float const * src1 = lane < 3 ? sp + lane : sq + (lane < 6 ? lane - 3 : 0);
+  for (int64_t base = 0; base < n; base += TGQ_ICP_TILE)
   {
-    int m = (int)min((int64_t)32, n - base);
-    for (int j = lane; j < 3 * m; j += 32) { sp[j] = from3[3 * base + j]; sq[j] = to3[3 * base + j]; }
-    __syncwarp();
-    if (lane < 7)
-      for (int k = 0; k < m; ++k) { float v = lane < 3 ? sp[3 * k + lane] : (lane < 6 ? sq[3 * k + lane - 3] : 1.0f); acc = acc + v; }
-    __syncwarp();
+    int m = (int)min((int64_t)TGQ_ICP_TILE, n - base);
+    for (int j = tid; j < 3 * m; j += TGQ_ICP_THREADS) { sp[j] = from3[3 * base + j]; sq[j] = to3[3 * base + j]; }
+    __syncthreads();
+    if (chain_warp && lane < 6)
+    {
+#pragma unroll 8
+      for (int k = 0; k < m; ++k) acc = acc + src1[3 * k];
+    }
+    else if (chain_warp && lane == 6)
+      for (int k = 0; k < m; ++k) acc = acc + 1.0f;
+    __syncthreads();
   }
-  float sw = __shfl_sync(FULL, acc, 6);
-  float mean = acc / sw;
-  v3 pm = mk3(__shfl_sync(FULL, mean, 0), __shfl_sync(FULL, mean, 1), __shfl_sync(FULL, mean, 2));
-  v3 qm = mk3(__shfl_sync(FULL, mean, 3), __shfl_sync(FULL, mean, 4), __shfl_sync(FULL, mean, 5));
+  if (chain_warp)
+  {
+    float sw = __shfl_sync(0xffffffffu, acc, 6);
+    float mean = acc / sw;
+    if (lane < 6) smean[lane] = mean;
+  }
+  __syncthreads();
+  v3 pm = mk3(smean[0], smean[1], smean[2]), qm = mk3(smean[3], smean[4], smean[5]);
   // err starts from |tr p_mean - q_mean|^2 (AffineTransformN.hpp:160: linear * v + translation, Eigen's row . vector order)
   v3 tpm = mk3(sum3(L[0] * pm.x, L[1] * pm.y, L[2] * pm.z) + L[3], sum3(L[4] * pm.x, L[5] * pm.y, L[6] * pm.z) + L[7],
                sum3(L[8] * pm.x, L[9] * pm.y, L[10] * pm.z) + L[11]);
   float chain = (lane == 9) ? sqn3(sub3(tpm, qm)) : 0.0f;
   int const r = lane / 3, c = lane - 3 * (lane / 3);
-  for (int64_t base = 0; base < n; base += 32)
+  float const pmr = comp3(pm, r < 3 ? r : 0), qmc = comp3(qm, c);
+  for (int64_t base = 0; base < n; base += TGQ_ICP_TILE)
   {
-    int m = (int)min((int64_t)32, n - base);
-    for (int j = lane; j < 3 * m; j += 32) { sp[j] = from3[3 * base + j]; sq[j] = to3[3 * base + j]; }
-    __syncwarp();
-    if (lane < m)
+    int m = (int)min((int64_t)TGQ_ICP_TILE, n - base);
+    for (int j = tid; j < 3 * m; j += TGQ_ICP_THREADS) { sp[j] = from3[3 * base + j]; sq[j] = to3[3 * base + j]; }
+    __syncthreads();
+    for (int k = tid; k < m; k += TGQ_ICP_THREADS)
     {
-      v3 dp = sub3(mk3(sp[3 * lane], sp[3 * lane + 1], sp[3 * lane + 2]), pm), dq = sub3(mk3(sq[3 * lane], sq[3 * lane + 1], sq[3 * lane + 2]), qm);
+      v3 dp = sub3(mk3(sp[3 * k], sp[3 * k + 1], sp[3 * k + 2]), pm), dq = sub3(mk3(sq[3 * k], sq[3 * k + 1], sq[3 * k + 2]), qm);
       v3 ld = mk3(sum3(L[0] * dp.x, L[1] * dp.y, L[2] * dp.z), sum3(L[4] * dp.x, L[5] * dp.y, L[6] * dp.z), sum3(L[8] * dp.x, L[9] * dp.y, L[10] * dp.z));
-      sterm[lane] = sqn3(sub3(ld, dq));
+      sterm[k] = sqn3(sub3(ld, dq));
     }
-    __syncwarp();
-    if (lane < 9)
+    __syncthreads();
+    if (chain_warp && lane < 9)
     {
-      float pmr = comp3(pm, r), qmc = comp3(qm, c);
+#pragma unroll 8
       for (int k = 0; k < m; ++k) { float dpr = sp[3 * k + r] - pmr, dqc = sq[3 * k + c] - qmc; chain = chain + dpr * dqc; }
     }
-    else if (lane == 9)
+    else if (chain_warp && lane == 9)
+    {
+#pragma unroll 8
       for (int k = 0; k < m; ++k) chain = chain + sterm[k];
-    __syncwarp();
+    }
+    __syncthreads();
   }
-  if (lane < 6) out16[lane] = mean;
-  if (lane < 9) out16[6 + lane] = chain;
-  if (lane == 9) out16[15] = chain;
+  if (chain_warp)
+  {
+    if (lane < 6) out16[lane] = smean[lane];
+    if (lane < 9) out16[6 + lane] = chain;
+    if (lane == 9) out16[15] = chain;
+  }
 }
 
 // out = L in + t, AffineTransformN.hpp:160 with Eigen's row . vector order.
