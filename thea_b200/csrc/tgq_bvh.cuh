@@ -36,6 +36,17 @@ struct TriRec  { f4 q0, q1, q2, q3, e0, e1, e2, x; };
 #define TGQ_OBB_LINK_F4 2
 #endif
 struct ObbNode { f4 q[2 * TGQ_OBB_F4]; };     // oriented boxes of both children (96 B; 64 B with TGQ_NODE64), see tgq_traverse.cuh
+// 4-wide node of the closest-point traversal on triangle structures (k_closest_wide): every second level of the binary tree
+// collapsed, so a node has 2..4 children.  One query is traversed by FOUR lanes, lane i testing child i: the record is laid out so
+// that the four lanes' 256-bit loads are one contiguous, aligned 128-byte line each (two L1 wavefronts per node visit and query,
+// against three wavefronts per BINARY node when every lane walks its own query):
+//   q[2 i], q[2 i + 1]          (a0, -a0 . c) (a1, -a1 . c)      first line:  children 0..3
+//   q[8 + 2 i], q[8 + 2 i + 1]  (a2, -a2 . c) (h0, h1, h2, link)  second line: children 0..3
+// a0..a2: the child's own orthonormal frame (a0 = mean normal), c its box centre, h its half extents; link as in NodeRec, or
+// TGQ_WIDE_EMPTY for an unused slot.  Everything is fp32 and nothing is recomputed per visit (the 96-byte binary record packs two
+// extents as bfloat16 and rebuilds a2 with a cross product): with coalesced loads bytes are cheap and instructions are not.
+struct WideNode { f4 q[16]; };
+#define TGQ_WIDE_EMPTY (-1)     // == ~0: a leaf of no elements
 
 // ---- Morton codes: 21 bits per axis, 63-bit keys --------------------------------------------------------------------
 TGQ_HD uint64_t expand21(uint64_t v)

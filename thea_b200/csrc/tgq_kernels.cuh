@@ -198,8 +198,8 @@ __device__ __forceinline__ void obb_add_tri(ObbAcc & a, TriRec const * tris, int
 #define TGQ_SLAB_SMALL 32
 // Nodes of up to TGQ_SLAB_SMALL elements: one thread scans the node's element range; larger nodes are appended to `big`.
 __global__ void k_obb_small(int n, int leaf, int const * __restrict__ first, int const * __restrict__ last, int const * __restrict__ parent,
-                            f4 const * __restrict__ nsum, TriRec const * __restrict__ tris, SceneBox const * sb, f4 * obbinfo, int * big,
-                            int * big_count)
+                            f4 const * __restrict__ nsum, TriRec const * __restrict__ tris, SceneBox const * sb, f4 * obbinfo, f4 * obbinfo_w,
+                            int * big, int * big_count)
 {
   int x = blockIdx.x * blockDim.x + threadIdx.x; if (x >= n - 1 || x == 0) return;
   int pa = parent[x];
@@ -212,12 +212,13 @@ __global__ void k_obb_small(int n, int leaf, int const * __restrict__ first, int
   ObbAcc a; obb_acc_begin(a, mk3(ns.x, ns.y, ns.z));
   for (int k = f; k <= l; ++k) obb_add_tri(a, tris, k);
   obb_acc_store(a, pad, 0, obbinfo + TGQ_OBB_F4 * (size_t)x);
+  obb_acc_store_wide(a, pad, 0, obbinfo_w + 4 * (size_t)x);
 }
 
 // Larger nodes: one thread block per node, block-wide min / max reduction (exact, order independent).
 __global__ void __launch_bounds__(128)
 k_obb_big(int const * __restrict__ big, int const * __restrict__ big_count, int const * __restrict__ first, int const * __restrict__ last,
-          f4 const * __restrict__ nsum, TriRec const * __restrict__ tris, SceneBox const * sb, f4 * obbinfo)
+          f4 const * __restrict__ nsum, TriRec const * __restrict__ tris, SceneBox const * sb, f4 * obbinfo, f4 * obbinfo_w)
 {
   __shared__ float s_mn[4][3], s_mx[4][3];
   for (int w = blockIdx.x; w < *big_count; w += gridDim.x)
@@ -241,6 +242,7 @@ k_obb_big(int const * __restrict__ big, int const * __restrict__ big_count, int 
         a.mx[j] = fmaxf(fmaxf(s_mx[0][j], s_mx[1][j]), fmaxf(s_mx[2][j], s_mx[3][j]));
       }
       obb_acc_store(a, pad, 0, obbinfo + TGQ_OBB_F4 * (size_t)x);
+      obb_acc_store_wide(a, pad, 0, obbinfo_w + 4 * (size_t)x);
     }
   }
 }
@@ -292,6 +294,81 @@ __global__ void k_emit(int n, int leaf, int const * __restrict__ first, int cons
     }
     obbs[newidx[i]] = r;
   }
+}
+
+// ---- 4-wide nodes (WideNode, tgq_bvh.cuh): every second level of the surviving binary tree ---------------------------------------
+// A surviving inner node is a wide node iff its depth below the root is even; its wide children are its binary grandchildren (or a
+// binary child that is a leaf).  Depth by walking up the parent chain (<= ~100 steps, all in L2).
+__global__ void k_wide_flags(int n, int const * __restrict__ live, int const * __restrict__ parent, int * wide)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n - 1) return;
+  int w = 0;
+  if (live[i])
+  {
+    int d = 0;
+    for (int y = parent[i]; y >= 0; y = parent[y]) ++d;
+    w = (d & 1) ? 0 : 1;
+  }
+  wide[i] = w;
+}
+
+__device__ __forceinline__ void wide_put_child(WideNode & r, int slot, f4 const * c4)
+{ r.q[2 * slot] = c4[0]; r.q[2 * slot + 1] = c4[1]; r.q[8 + 2 * slot] = c4[2]; r.q[8 + 2 * slot + 1] = c4[3]; }
+
+// Child record of the element range [cf, cl] hanging below a wide node: its oriented box from obbinfo_w (ranges of two or more
+// elements: inner radix node `inner`) or from the single triangle, and the link (a leaf code, or the wide index of `inner`).
+__device__ __forceinline__ void wide_child_record(int cf, int cl, int inner, int leaf, int const * __restrict__ widx, TriRec const * __restrict__ tris,
+                                                  f4 const * __restrict__ obbinfo_w, float pad, f4 * c4)
+{
+  int cnt = cl - cf + 1;
+  int link = (cnt <= leaf) ? ~((cf << TGQ_LEAF_BITS) | cnt) : widx[inner];
+  if (cnt == 1)
+  {
+    f4 const * t = (f4 const *)(tris + cf);
+    f4 q0 = __ldg(t), q1 = __ldg(t + 1), q2 = __ldg(t + 2);
+    v3 v0 = mk3(q0.x, q0.y, q0.z), v1 = mk3(q1.x, q1.y, q1.z), v2 = mk3(q2.x, q2.y, q2.z);
+    ObbAcc a; obb_acc_begin(a, cross3(sub3(v1, v0), sub3(v2, v0)));
+    obb_acc_point(a, v0); obb_acc_point(a, v1); obb_acc_point(a, v2);
+    obb_acc_store_wide(a, pad, link, c4);
+  }
+  else
+  {
+    for (int j = 0; j < 4; ++j) c4[j] = obbinfo_w[4 * (size_t)inner + j];
+    c4[3].w = __int_as_float(link);
+  }
+}
+
+__global__ void k_emit_wide(int n, int leaf, int const * __restrict__ first, int const * __restrict__ last, int const * __restrict__ split,
+                            int const * __restrict__ wide, int const * __restrict__ widx, SceneBox const * sb, TriRec const * __restrict__ tris,
+                            f4 const * __restrict__ obbinfo_w, WideNode * out)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n - 1 || !wide[i]) return;
+  float pad = scene_decode(sb).pad;
+  WideNode r; int slot = 0; f4 c4[4];
+  int f = first[i], l = last[i], sp = split[i];
+  for (int c = 0; c < 2; ++c)
+  {
+    int cf = c == 0 ? f : sp + 1, cl = c == 0 ? sp : l, inner = c == 0 ? sp : sp + 1;
+    if (cl - cf + 1 <= leaf) { wide_child_record(cf, cl, inner, leaf, widx, tris, obbinfo_w, pad, c4); wide_put_child(r, slot++, c4); continue; }
+    // the binary child is an inner node (odd depth): its two children become children of this wide node
+    int gsp = split[inner];
+    for (int g = 0; g < 2; ++g)
+    {
+      int gf = g == 0 ? cf : gsp + 1, gl = g == 0 ? gsp : cl, ginner = g == 0 ? gsp : gsp + 1;
+      wide_child_record(gf, gl, ginner, leaf, widx, tris, obbinfo_w, pad, c4); wide_put_child(r, slot++, c4);
+    }
+  }
+  for (; slot < 4; ++slot) { wide_store_empty(c4); wide_put_child(r, slot, c4); }
+  out[widx[i]] = r;
+}
+
+__global__ void k_emit_wide_single(SceneBox const * sb, TriRec const * tris, WideNode * out)
+{
+  float pad = scene_decode(sb).pad;
+  WideNode r; f4 c4[4];
+  wide_child_record(0, 0, 0, 1, nullptr, tris, nullptr, pad, c4); wide_put_child(r, 0, c4);
+  for (int slot = 1; slot < 4; ++slot) { wide_store_empty(c4); wide_put_child(r, slot, c4); }
+  out[0] = r;
 }
 
 // Structure with a single element: one node whose second child is an empty leaf behind an unreachable box.
@@ -651,6 +728,246 @@ k_closest_pool(BvhView b, float scene_pad, float const * __restrict__ q3, uint32
 #pragma unroll
     for (int j = 0; j < TGQ_POPS; ++j) if (s.t.cur == TGQ_ST_POP && !hold) trav_pop_step(s.t, s.best_d2);
   }
+}
+
+// ---- K5c closest element on triangle structures: FOUR lanes per query on 4-wide nodes, leaf tests pooled across the warp -------
+// ncu on k_closest_pool (profiles/r01_v_*): L1 LSU data-pipe wavefronts at 87 % of peak with every lane reading its own line
+// (528 global wavefronts per query, 70 % of them the three 256-bit loads of a binary node), 18.5 of 32 lanes per instruction.  Here a
+// warp carries EIGHT queries; the four lanes of a group hold the query state redundantly and each tests one child of the current
+// WideNode, whose record is laid out so that the group's loads are two full 128-byte lines (2 wavefronts per visit of a node with up
+// to four children).  The children that pass the bound are ranked by centre distance with three shuffles; the nearest is entered,
+// the others go to the query's stack in shared memory (one entry written by each lane, popped by all four as a broadcast read).
+// Leaves go to the per-warp queue of (owner group, triangle) pairs exactly as in k_closest_pool: 32 pairs at a time, every lane on
+// its own pair, the reference's point-triangle arithmetic, 64-bit atomicMin merge in (distance, index) order.  The answer is the
+// minimum over the same exact per-element values as before, so parity does not depend on any of this.
+#ifndef TGQ_WSTACK
+#define TGQ_WSTACK 32          // stack entries per query kept in shared memory (deeper ones spill to local memory)
+#endif
+#define TGQ_WOVF 96            // > 3 x (63 Morton + 32 tie-break bits) / 2 levels beyond the shared part cannot occur in ordered DFS
+struct WidePool
+{
+  unsigned long long best[8];
+  f4 cp[8];
+  int done[8];
+  unsigned q[TGQ_QCAP];
+  int tail; int pad_[3];
+};
+__host__ __device__ constexpr size_t wide_smem_bytes()
+{ return (size_t)TGQ_WARPS * 8 * TGQ_WSTACK * sizeof(StackEntry) + (size_t)TGQ_WARPS * TGQ_CHUNK * sizeof(f4) + (size_t)TGQ_WARPS * sizeof(WidePool); }
+
+__global__ void __launch_bounds__(TGQ_BLOCK)
+k_closest_wide(BvhView b, float scene_pad, float const * __restrict__ q3, uint32_t const * __restrict__ perm, int n, float bound_ub, BoundGate gate,
+               int exclude_self, int64_t self_offset, int * counter, int * idx_out, float * d2_out, float * cp3)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned const FULL = 0xffffffffu;
+  int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 3, gbase = lane & ~3, g = lane >> 2;
+  StackEntry * stk = (StackEntry *)smem + (size_t)(warp * 8 + g) * TGQ_WSTACK;
+  f4 * stage = (f4 *)(smem + (size_t)TGQ_WARPS * 8 * TGQ_WSTACK * sizeof(StackEntry)) + (size_t)warp * TGQ_CHUNK;
+  WidePool & pw = ((WidePool *)(smem + (size_t)TGQ_WARPS * 8 * TGQ_WSTACK * sizeof(StackEntry) + (size_t)TGQ_WARPS * TGQ_CHUNK * sizeof(f4)))[warp];
+  int ovf_node[TGQ_WOVF]; float ovf_key[TGQ_WOVF];
+  if (lane < 8) { pw.best[lane] = 0ull; pw.done[lane] = 0; }
+  if (lane == 0) pw.tail = 0;
+  __syncwarp();
+  // query state, identical in the four lanes of a group
+  v3 p = mk3(0.0f, 0.0f, 0.0f), best_cp = p; float mq = 0.0f, best_d2 = 0.0f; int best_idx = -1, best_k = -1, skip = -1;
+  int cur = TGQ_ST_IDLE, sp = 0, leaf_k = 0, leaf_end = 0;
+  int qi = 0, seed = -1, pending = 0, head = 0; bool hold = false;
+  int chunk_base = 0, chunk_next = 0, chunk_end = 0; bool exhausted = false;
+#define TGQ_WIDE_ENTER(code)                                                                                              \
+  { int code_ = (code);                                                                                                   \
+    if (code_ >= 0) cur = code_;                                                                                          \
+    else { int c_ = ~code_; leaf_k = c_ >> TGQ_LEAF_BITS; leaf_end = leaf_k + (c_ & TGQ_LEAF_MASK); cur = leaf_end > leaf_k ? TGQ_ST_LEAF : TGQ_ST_POP; } }
+  for (;;)
+  {
+    // ---- finished queries write their results; idle groups take the next queries of the warp's chunk ----------------------------
+    if (cur == TGQ_ST_DONE && pending == 0)
+    {
+      if (sub == 0) { if (idx_out) idx_out[qi] = best_idx; if (d2_out) d2_out[qi] = best_idx >= 0 ? best_d2 : -1.0f; }
+      if (cp3 && sub < 3) cp3[3 * (size_t)qi + sub] = comp3(best_cp, sub);
+      seed = perm ? best_k : -1;
+      cur = TGQ_ST_IDLE;
+    }
+    unsigned idle = __ballot_sync(FULL, cur == TGQ_ST_IDLE);
+    if (idle != 0u && !exhausted)
+    {
+      if (chunk_next >= chunk_end)
+      {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(counter, TGQ_CHUNK);
+        base = __shfl_sync(FULL, base, 0);
+        chunk_base = chunk_next = base; chunk_end = min(base + TGQ_CHUNK, n);
+        if (base >= n) exhausted = true;
+        else
+        {
+          __syncwarp();
+          for (int j = lane; j < chunk_end - chunk_base; j += 32)
+          {
+            int t = chunk_base + j; int i = perm ? (int)perm[t] : t; v3 pp = ld3(q3, i);
+            stage[j] = make_float4(pp.x, pp.y, pp.z, __int_as_float(i));
+          }
+          __syncwarp();
+        }
+      }
+      if (!exhausted)
+      {
+        int t = chunk_next + (__popc(idle & ((1u << gbase) - 1u)) >> 2);
+        if (cur == TGQ_ST_IDLE && t < chunk_end)
+        {
+          f4 r = stage[t - chunk_base]; qi = __float_as_int(r.w);
+          p = mk3(r.x, r.y, r.z); mq = query_margin(p, scene_pad); skip = exclude_self ? (int)(self_offset + qi) : -1;
+          best_d2 = gated_ub(gate, p, bound_ub); best_idx = -1; best_k = -1; best_cp = mk3(0.0f, 0.0f, 0.0f);
+          sp = 0; cur = b.n_wide > 0 ? 0 : TGQ_ST_DONE; hold = false;
+          if (seed >= 0 && seed < b.n_prims && cur == 0)
+          {
+            // the previous answer of this group is tested first; the root waits on the stack until that test is back
+            if (sub == 0) { StackEntry e; e.node = 0; e.key = 0.0f; stk[0] = e; }
+            sp = 1; leaf_k = seed; leaf_end = seed + 1; cur = TGQ_ST_LEAF; hold = true;
+          }
+        }
+        chunk_next = min(chunk_next + (__popc(idle) >> 2), chunk_end);
+      }
+    }
+    // ---- leaves reached go to the warp's queue ------------------------------------------------------------------------------------
+    {
+      bool at_leaf = cur == TGQ_ST_LEAF;
+      int cnt = leaf_end - leaf_k, pos = 0;
+      if (at_leaf && sub == 0) pos = atomicAdd(&pw.tail, cnt);
+      pos = __shfl_sync(FULL, pos, gbase);
+      if (at_leaf)
+      {
+        for (int j = sub; j < cnt; j += 4) pw.q[(pos + j) & (TGQ_QCAP - 1)] = ((unsigned)g << 27) | (unsigned)(leaf_k + j);
+        pending += cnt; cur = TGQ_ST_POP;
+      }
+    }
+    __syncwarp();
+    // ---- leaf iterations: 32 queued (owner, triangle) pairs at a time, every lane on its own pair -----------------------------------
+    for (;;)
+    {
+      int avail = *(volatile int *)&pw.tail - head;
+      bool runnable = (cur >= 0 || cur == TGQ_ST_POP) && !hold;
+      if (!(avail >= 32 || (avail > 0 && !__any_sync(FULL, runnable)))) break;
+      int m = min(avail, 32);
+      unsigned long long published = pool_key(best_d2, best_idx < 0 ? 0 : best_idx);      // (ub, 0) when nothing was found yet: only d2 < ub wins
+      if (sub == 0) pw.best[g] = published;
+      bool valid = lane < m;
+      unsigned e = valid ? pw.q[(head + lane) & (TGQ_QCAP - 1)] : ((unsigned)g << 27);
+      int og = (int)(e >> 27), ol = og << 2, k = (int)(e & 0x7ffffffu);
+      __syncwarp();
+      v3 po = mk3(__shfl_sync(FULL, p.x, ol), __shfl_sync(FULL, p.y, ol), __shfl_sync(FULL, p.z, ol));
+      float mqo = __shfl_sync(FULL, mq, ol), bd2 = __shfl_sync(FULL, best_d2, ol);
+      int skipo = __shfl_sync(FULL, skip, ol);
+      unsigned long long mykey = ~0ull; v3 cp = mk3(0.0f, 0.0f, 0.0f);
+      if (valid)
+      {
+        f4 const * q = (f4 const *)(b.tris + k);
+        f4 r0, r1, r2, r3; ldq2(q, r0, r1); ldq2(q + 2, r2, r3);
+        v3 v0 = mk3(r0.x, r0.y, r0.z), v1 = mk3(r1.x, r1.y, r1.z), v2 = mk3(r2.x, r2.y, r2.z), nn = mk3(r3.x, r3.y, r3.z);
+        v3 cen = mul3(add3(add3(v0, v1), v2), 0.33333334f);
+        float sd = fmaxf(fabsf(fdot3(po, nn) - r2.w) - mqo, 0.0f);
+        v3 pc = sub3(po, cen);
+        v3 perp = sub3(pc, mul3(nn, fdot3(nn, pc)));
+        float lat = fmaxf(sqrtf(fdot3(perp, perp)) - r3.w - mqo, 0.0f);
+        int idx = f2i(r0.w);
+        if ((sd * sd + lat * lat) * TGQ_LB_DEFLATE <= bd2 && idx != skipo)
+        {
+          f4 r4, r5, r6, r7; ldq2(q + 4, r4, r5); ldq2(q + 6, r6, r7);
+          float d2 = tri_point_sqdist_pre(v0, v1, v2, nn, r2.w, f2i(r1.w), r4, r5, r6, r7, po, cp);
+          if (d2 <= bd2) { mykey = pool_key(d2, idx); atomicMin(&pw.best[og], mykey); }     // only candidates that can win (NaN fails, as in the reference's d2 < best)
+        }
+        atomicAdd(&pw.done[og], 1);
+      }
+      __syncwarp();
+      if (mykey != ~0ull && pw.best[og] == mykey) pw.cp[og] = make_float4(cp.x, cp.y, cp.z, __int_as_float(k));
+      __syncwarp();
+      unsigned long long now = pw.best[g];
+      int dn = pw.done[g];
+      if (now != published)
+      {
+        f4 c = pw.cp[g];
+        best_d2 = __int_as_float((int)(unsigned)(now >> 32)); best_idx = (int)(unsigned)(now & 0xffffffffull);
+        best_cp = mk3(c.x, c.y, c.z); best_k = __float_as_int(c.w);
+      }
+      pending -= dn;
+      if (pending == 0) hold = false;
+      head += m;
+      __syncwarp();
+      if (sub == 0) pw.done[g] = 0;
+      __syncwarp();
+    }
+    // ---- node step for the groups at a node: lane i tests child i ---------------------------------------------------------------------
+    bool at_node = cur >= 0 && !hold;
+    bool want_pop = cur == TGQ_ST_POP && !hold;
+    if (!__any_sync(FULL, at_node || want_pop))
+    {
+      bool busy = cur != TGQ_ST_IDLE;        // waiting for queued tests, or about to be finished at the top of the loop
+      if (exhausted && !__any_sync(FULL, busy)) break;
+      continue;
+    }
+    float lb = 0.0f, key = 0.0f; int link = TGQ_WIDE_EMPTY; bool pass = false;
+    if (at_node)
+    {
+      f4 const * nd = (f4 const *)(b.wide + cur);
+      f4 A0, A1, B0, B1; ldq2(nd + 2 * sub, A0, A1); ldq2(nd + 8 + 2 * sub, B0, B1);
+      wide_child_bounds(A0, A1, B0, B1, p, mq, lb, key, link);
+      pass = link != TGQ_WIDE_EMPTY && lb <= best_d2;
+    }
+    unsigned gm = (__ballot_sync(FULL, pass) >> gbase) & 15u;
+    float k1 = __shfl_xor_sync(FULL, key, 1), k2 = __shfl_xor_sync(FULL, key, 2), k3 = __shfl_xor_sync(FULL, key, 3);
+    int rank = 0;
+    {
+      int j1 = sub ^ 1, j2 = sub ^ 2, j3 = sub ^ 3;
+      rank += ((gm >> j1) & 1u) && (k1 < key || (k1 == key && j1 < sub));
+      rank += ((gm >> j2) & 1u) && (k2 < key || (k2 == key && j2 < sub));
+      rank += ((gm >> j3) & 1u) && (k3 < key || (k3 == key && j3 < sub));
+    }
+    unsigned r0m = (__ballot_sync(FULL, pass && rank == 0) >> gbase) & 15u;
+    int nearest = __shfl_sync(FULL, link, gbase + (r0m ? __ffs((int)r0m) - 1 : 0));
+    if (at_node)
+    {
+      int npass = __popc(gm);
+      if (npass == 0) cur = TGQ_ST_POP;
+      else
+      {
+        if (sp + npass - 1 <= TGQ_WSTACK)
+        {
+          if (pass && rank > 0) { StackEntry e; e.node = link; e.key = lb; stk[sp + npass - 1 - rank] = e; }
+          sp += npass - 1;
+        }
+        else
+        {
+          // rare: the shared part of the stack is full -- every lane keeps the overflow in its own local memory
+          for (int r = npass - 1; r >= 1; --r)
+          {
+            unsigned rm = (__ballot_sync(0xfu << gbase, pass && rank == r) >> gbase) & 15u;
+            int src = gbase + __ffs((int)rm) - 1;
+            int ln = __shfl_sync(0xfu << gbase, link, src); float lk = __shfl_sync(0xfu << gbase, lb, src);
+            if (sp < TGQ_WSTACK) { if (sub == 0) { StackEntry e; e.node = ln; e.key = lk; stk[sp] = e; } }
+            else if (sp - TGQ_WSTACK < TGQ_WOVF) { ovf_node[sp - TGQ_WSTACK] = ln; ovf_key[sp - TGQ_WSTACK] = lk; }
+            ++sp;
+          }
+        }
+        TGQ_WIDE_ENTER(nearest)
+      }
+    }
+    __syncwarp();
+    // ---- pop phase ------------------------------------------------------------------------------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < TGQ_POPS; ++j)
+      if (cur == TGQ_ST_POP && !hold)
+      {
+        if (sp <= 0) cur = TGQ_ST_DONE;
+        else
+        {
+          --sp;
+          int code; float kk;
+          if (sp < TGQ_WSTACK) { StackEntry e = stk[sp]; code = e.node; kk = e.key; }
+          else { code = ovf_node[sp - TGQ_WSTACK]; kk = ovf_key[sp - TGQ_WSTACK]; }
+          if (kk <= best_d2) TGQ_WIDE_ENTER(code)
+        }
+      }
+  }
+#undef TGQ_WIDE_ENTER
 }
 
 // ---- K6 k nearest neighbours: one bounded sorted set per thread in shared memory -------------------------------------

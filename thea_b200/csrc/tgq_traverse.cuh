@@ -41,6 +41,8 @@ struct BvhView
 {
   NodeRec const * nodes;   // n_nodes inner nodes with the AABBs of both children, root = 0
   ObbNode const * obbs;    // same nodes with oriented boxes of both children (triangle structures), or null
+  WideNode const * wide;   // 4-wide oriented-box nodes (triangle structures), root = 0, or null
+  int n_wide;
   TriRec const * tris;     // Morton-ordered triangle records (triangle structures)
   f4 const * pts;          // Morton-ordered points (point structures)
   f4 const * nrm;          // Morton-ordered normals or null
@@ -327,6 +329,39 @@ TGQ_HD void obb_acc_store(ObbAcc const & a, float pad, int child, f4 * out4)
   out4[2].x = a.f.a1.x; out4[2].y = a.f.a1.y; out4[2].z = a.f.a1.z; out4[2].w = i2f(child);
 #endif
 }
+// Child record of a WideNode (four float4: A0, A1, B0, B1 as laid out in tgq_bvh.cuh).  The box is kept in its own frame
+// coordinates: s_i = a_i . v was measured over the child's vertices, so the slab along a_i is [mn_i, mx_i] and the query side needs
+// u_i = a_i . p - 0.5 (mn_i + mx_i) only -- no world-space centre is reconstructed.  Error budget as for obb_bounds: the build-side
+// projections are off by <= 3 sqrt3 u M (inside pad = 32 u M, added to h), the query-side fused chains by <= 4u (|p|_1 + sqrt3 M)
+// (inside mq), the frame is orthonormal to 4u per pair (inside TGQ_LB_DEFLATE).
+TGQ_HD void obb_acc_store_wide(ObbAcc const & a, float pad, int child, f4 * out4)
+{
+  float c0 = 0.5f * (a.mn[0] + a.mx[0]), c1 = 0.5f * (a.mn[1] + a.mx[1]), c2 = 0.5f * (a.mn[2] + a.mx[2]);
+  float hp = TGQ_MARGIN_SCALE * pad;
+  float h0 = 0.5f * (a.mx[0] - a.mn[0]) * 1.000001f + hp, h1 = 0.5f * (a.mx[1] - a.mn[1]) * 1.000001f + hp, h2 = 0.5f * (a.mx[2] - a.mn[2]) * 1.000001f + hp;
+  out4[0].x = a.f.a0.x; out4[0].y = a.f.a0.y; out4[0].z = a.f.a0.z; out4[0].w = -c0;
+  out4[1].x = a.f.a1.x; out4[1].y = a.f.a1.y; out4[1].z = a.f.a1.z; out4[1].w = -c1;
+  out4[2].x = a.f.a2.x; out4[2].y = a.f.a2.y; out4[2].z = a.f.a2.z; out4[2].w = -c2;
+  out4[3].x = h0; out4[3].y = h1; out4[3].z = h2; out4[3].w = i2f(child);
+}
+TGQ_HD void wide_store_empty(f4 * out4)
+{
+  out4[0] = mkf4(1.0f, 0.0f, 0.0f, 0.0f); out4[1] = mkf4(0.0f, 1.0f, 0.0f, 0.0f); out4[2] = mkf4(0.0f, 0.0f, 1.0f, 0.0f);
+  out4[3] = mkf4(-1e30f, -1e30f, -1e30f, i2f(TGQ_WIDE_EMPTY));
+}
+// Lower bound (deflated) of the squared distance from p to anything in the child, the ordering key (squared distance to the
+// box centre) and the link.
+TGQ_HD void wide_child_bounds(f4 A0, f4 A1, f4 B0, f4 B1, v3 p, float mq, float & lb, float & key, int & link)
+{
+  float u0 = ffma(A0.x, p.x, ffma(A0.y, p.y, ffma(A0.z, p.z, A0.w)));
+  float u1 = ffma(A1.x, p.x, ffma(A1.y, p.y, ffma(A1.z, p.z, A1.w)));
+  float u2 = ffma(B0.x, p.x, ffma(B0.y, p.y, ffma(B0.z, p.z, B0.w)));
+  float x = fmaxf(fabsf(u0) - (B1.x + mq), 0.0f), y = fmaxf(fabsf(u1) - (B1.y + mq), 0.0f), z = fmaxf(fabsf(u2) - (B1.z + mq), 0.0f);
+  lb = ffma(x, x, ffma(y, y, z * z)) * TGQ_LB_DEFLATE;
+  key = ffma(u0, u0, ffma(u1, u1, u2 * u2));
+  link = f2i(B1.w);
+}
+
 // An oriented box that no query can reach (the missing second child of a one-element structure).
 TGQ_HD void obb_store_empty(int child, f4 * out4)
 {
@@ -582,6 +617,52 @@ TGQ_HD void closest_query(BvhView const & b, float scene_pad, v3 p, int skip, fl
     closest_fetch(s, b, r);
     if (s.t.cur >= 0) closest_node_compute(s, b, r); else closest_leaf_compute(s, b, r);
   }
+  best_d2 = s.best_d2; best_idx = s.best_idx; best_cp = s.best_cp;
+  if (seed_k) *seed_k = s.best_k;
+}
+
+// The closest-element query over the 4-wide nodes, one query at a time: the sequential statement of what k_closest_wide does with
+// four lanes per query (same child bounds, same ordering -- passing children by increasing centre distance, child slot as the tie
+// break --, same pruning rule, same leaf arithmetic).  Drives the host emulation of the test suite.
+template <int DUMMY = 0>
+TGQ_HD void closest_query_wide(BvhView const & b, float scene_pad, v3 p, int skip, float & best_d2, int & best_idx, v3 & best_cp, int * seed_k = nullptr)
+{
+  ClosestState<true> s; TravStack st; trav_bind(s.t, st);
+  closest_begin(s, b, scene_pad, p, skip, best_d2, -1);
+  s.t.cur = TGQ_ST_DONE;
+  f4 r[TGQ_FETCH_TRI];
+  int sn[4 * TGQ_STACK]; float sk[4 * TGQ_STACK]; int sp = 0;
+  // leaf helper: all elements of a leaf link
+  #define TGQ_WIDE_LEAF(code) { int c_ = ~(code); s.t.k = c_ >> TGQ_LEAF_BITS; s.t.kend = s.t.k + (c_ & TGQ_LEAF_MASK); \
+                                while (s.t.k < s.t.kend) { s.t.cur = TGQ_ST_LEAF; closest_fetch(s, b, r); closest_leaf_compute(s, b, r); } }
+  if (b.n_wide > 0)
+  {
+    if (seed_k && *seed_k >= 0 && *seed_k < b.n_prims) { TGQ_WIDE_LEAF(~((*seed_k << TGQ_LEAF_BITS) | 1)) }
+    sn[sp] = 0; sk[sp] = 0.0f; ++sp;
+    while (sp > 0)
+    {
+      --sp;
+      int code = sn[sp]; float klb = sk[sp];
+      if (!(klb <= s.best_d2)) continue;
+      if (code < 0) { TGQ_WIDE_LEAF(code) continue; }
+      TGQ_COUNT_NODE();
+      f4 const * nd = (f4 const *)(b.wide + code);
+      float lb[4], key[4]; int link[4]; bool pass[4];
+      for (int i = 0; i < 4; ++i)
+      {
+        wide_child_bounds(ldq(nd + 2 * i), ldq(nd + 2 * i + 1), ldq(nd + 8 + 2 * i), ldq(nd + 8 + 2 * i + 1), p, s.mq, lb[i], key[i], link[i]);
+        pass[i] = link[i] != TGQ_WIDE_EMPTY && lb[i] <= s.best_d2;
+      }
+      // push far to near: the nearest passing child is popped next
+      int order[4], m = 0;
+      for (int i = 0; i < 4; ++i) if (pass[i]) order[m++] = i;
+      for (int x = 1; x < m; ++x)
+        for (int y = x; y > 0 && (key[order[y]] < key[order[y - 1]] || (key[order[y]] == key[order[y - 1]] && order[y] < order[y - 1])); --y)
+        { int t_ = order[y]; order[y] = order[y - 1]; order[y - 1] = t_; }
+      for (int x = m - 1; x >= 0; --x) { sn[sp] = link[order[x]]; sk[sp] = lb[order[x]]; ++sp; }
+    }
+  }
+  #undef TGQ_WIDE_LEAF
   best_d2 = s.best_d2; best_idx = s.best_idx; best_cp = s.best_cp;
   if (seed_k) *seed_k = s.best_k;
 }
