@@ -27,10 +27,13 @@ struct Emu
   std::vector<TriRec> tris; std::vector<f4> pts, nrm; std::vector<int> lab; std::vector<uint32_t> perm_keep;
   std::vector<NodeRec> nodes;
   std::vector<ObbNode> obbs;
+  std::vector<WideNode> wide;   // 4-wide nodes (k_emit_wide)
+  int use_wide = 0;             // the product default is the binary traversal; emu_set_wide(1) selects the 4-wide one
   BvhView view() const
   {
     BvhView v; v.nodes = nodes.data(); v.obbs = tri ? obbs.data() : nullptr; v.tris = tri ? tris.data() : nullptr; v.pts = tri ? nullptr : pts.data(); v.lab = lab.empty() ? nullptr : lab.data();
-    v.nrm = has_n ? nrm.data() : nullptr; v.n_nodes = (int)nodes.size(); v.n_prims = n; return v;
+    v.nrm = has_n ? nrm.data() : nullptr; v.n_nodes = (int)nodes.size(); v.n_prims = n;
+    v.wide = tri ? wide.data() : nullptr; v.n_wide = tri ? (int)wide.size() : 0; return v;
   }
 };
 
@@ -98,6 +101,11 @@ void build(Emu & E, float const * src, float const * n3)
       obb_acc_point(a, v0); obb_acc_point(a, v1); obb_acc_point(a, v2);
       obb_acc_store(a, pad, ~((0 << TGQ_LEAF_BITS) | 1), r.q); obb_store_empty(~0, r.q + TGQ_OBB_F4);
       E.obbs.assign(1, r);
+      WideNode w; f4 c4[4];
+      obb_acc_store_wide(a, pad, ~((0 << TGQ_LEAF_BITS) | 1), c4);
+      w.q[0] = c4[0]; w.q[1] = c4[1]; w.q[8] = c4[2]; w.q[9] = c4[3];
+      for (int slot = 1; slot < 4; ++slot) { wide_store_empty(c4); w.q[2 * slot] = c4[0]; w.q[2 * slot + 1] = c4[1]; w.q[8 + 2 * slot] = c4[2]; w.q[8 + 2 * slot + 1] = c4[3]; }
+      E.wide.assign(1, w);
     }
     E.nodes.push_back(make_node(mk3(plo[0].x - pad, plo[0].y - pad, plo[0].z - pad), mk3(phi[0].x + pad, phi[0].y + pad, phi[0].z + pad),
                                 mk3(FLT_MAX, FLT_MAX, FLT_MAX), mk3(-FLT_MAX, -FLT_MAX, -FLT_MAX), ~((0 << TGQ_LEAF_BITS) | 1), ~0, 0, 0));
@@ -160,6 +168,52 @@ void build(Emu & E, float const * src, float const * n3)
       E.obbs[(size_t)newidx[(size_t)i]] = r;
     }
   }
+  if (E.tri)
+  {
+    // 4-wide nodes (k_wide_flags / k_emit_wide): surviving nodes at even depth; children = binary grandchildren or leaf children.
+    // Emitted depth first from the root (the device numbers them by a scan: the numbering is irrelevant to the answers).
+    auto child_record = [&](int cf, int cl, int link, f4 * c4) {
+      v3 sum = mk3(0, 0, 0);
+      for (int k = cf; k <= cl; ++k)
+      {
+        TriRec const & t = E.tris[(size_t)k];
+        v3 v0 = mk3(t.q0.x, t.q0.y, t.q0.z);
+        sum = add3(sum, cross3(sub3(mk3(t.q1.x, t.q1.y, t.q1.z), v0), sub3(mk3(t.q2.x, t.q2.y, t.q2.z), v0)));
+      }
+      ObbAcc a; obb_acc_begin(a, sum);
+      for (int k = cf; k <= cl; ++k)
+      {
+        TriRec const & t = E.tris[(size_t)k];
+        obb_acc_point(a, mk3(t.q0.x, t.q0.y, t.q0.z)); obb_acc_point(a, mk3(t.q1.x, t.q1.y, t.q1.z)); obb_acc_point(a, mk3(t.q2.x, t.q2.y, t.q2.z));
+      }
+      obb_acc_store_wide(a, pad, link, c4);
+    };
+    auto put = [](WideNode & r, int slot, f4 const * c4) { r.q[2 * slot] = c4[0]; r.q[2 * slot + 1] = c4[1]; r.q[8 + 2 * slot] = c4[2]; r.q[8 + 2 * slot + 1] = c4[3]; };
+    E.wide.clear(); E.wide.push_back(WideNode());
+    std::vector<std::pair<int, int>> todo;     // (radix node, wide index)
+    todo.push_back(std::make_pair(0, 0));
+    while (!todo.empty())
+    {
+      int i = todo.back().first, wi = todo.back().second; todo.pop_back();
+      WideNode r; int slot = 0; f4 c4[4];
+      int f = first[(size_t)i], l = last[(size_t)i], sp = split[(size_t)i];
+      auto add_child = [&](int cf, int cl, int inner) {
+        int k = cl - cf + 1, link;
+        if (k <= E.leaf) link = ~((cf << TGQ_LEAF_BITS) | k);
+        else { link = (int)E.wide.size(); E.wide.push_back(WideNode()); todo.push_back(std::make_pair(inner, link)); }
+        child_record(cf, cl, link, c4); put(r, slot++, c4);
+      };
+      for (int c = 0; c < 2; ++c)
+      {
+        int cf = c == 0 ? f : sp + 1, cl = c == 0 ? sp : l, inner = c == 0 ? sp : sp + 1;
+        if (cl - cf + 1 <= E.leaf) { add_child(cf, cl, inner); continue; }
+        int gsp = split[(size_t)inner];
+        add_child(cf, gsp, gsp); add_child(gsp + 1, cl, gsp + 1);
+      }
+      for (; slot < 4; ++slot) { wide_store_empty(c4); put(r, slot, c4); }
+      E.wide[(size_t)wi] = r;
+    }
+  }
 }
 
 }  // namespace
@@ -173,6 +227,8 @@ void * emu_build(float const * src, int64_t n, int is_tri, float const * n3, int
   return E;
 }
 void emu_destroy(void * h) { delete (Emu *)h; }
+void emu_set_wide(void * h, int on) { ((Emu *)h)->use_wide = on; }        // closest point on triangles: 4-wide nodes (default) or binary nodes
+int64_t emu_num_wide(void * h) { return (int64_t)((Emu *)h)->wide.size(); }
 int64_t emu_num_nodes(void * h) { return (int64_t)((Emu *)h)->nodes.size(); }
 
 void emu_closest(void * h, float const * q3, int64_t Q, double dist_bound, int exclude_self, int32_t * idx, float * d2, float * cp3)
@@ -185,7 +241,8 @@ void emu_closest(void * h, float const * q3, int64_t Q, double dist_bound, int e
   for (int64_t i = 0; i < Q; ++i)
   {
     float best = gated_ub(gate, ld(q3, i), bound_ub); int bi = -1; v3 cp = mk3(0, 0, 0);
-    if (E.tri) closest_query<true>(v, E.pad, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp, seeded ? &seed : nullptr);
+    if (E.tri && E.use_wide) closest_query_wide(v, E.pad, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp, seeded ? &seed : nullptr);
+    else if (E.tri) closest_query<true>(v, E.pad, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp, seeded ? &seed : nullptr);
     else closest_query<false>(v, 0.0f, ld(q3, i), exclude_self ? (int)i : -1, best, bi, cp, seeded ? &seed : nullptr);
     idx[i] = bi; d2[i] = bi >= 0 ? best : -1.0f; cp3[3 * i] = cp.x; cp3[3 * i + 1] = cp.y; cp3[3 * i + 2] = cp.z;
   }
@@ -199,7 +256,8 @@ void emu_closest_counts(void * h, float const * q3, int64_t Q, float const * ub,
   {
     long long n0 = g_cnt_node, p0 = g_cnt_prim;
     float best = ub ? ub[i] : INFINITY; int bi = -1; v3 cp = mk3(0, 0, 0);
-    if (E.tri) closest_query<true>(v, E.pad, ld(q3, i), -1, best, bi, cp);
+    if (E.tri && E.use_wide) closest_query_wide(v, E.pad, ld(q3, i), -1, best, bi, cp);
+    else if (E.tri) closest_query<true>(v, E.pad, ld(q3, i), -1, best, bi, cp);
     else closest_query<false>(v, 0.0f, ld(q3, i), -1, best, bi, cp);
     nodes[i] = (int32_t)(g_cnt_node - n0); prims[i] = (int32_t)(g_cnt_prim - p0);
   }

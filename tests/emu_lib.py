@@ -29,6 +29,9 @@ def lib():
         L.emu_destroy.argtypes = [vp]
         L.emu_num_nodes.restype = C.c_int64
         L.emu_num_nodes.argtypes = [vp]
+        L.emu_num_wide.restype = C.c_int64
+        L.emu_num_wide.argtypes = [vp]
+        L.emu_set_wide.argtypes = [vp, C.c_int]
         L.emu_closest.argtypes = [vp, vp, C.c_int64, C.c_double, C.c_int, vp, vp, vp]
         L.emu_knn.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_float, C.c_int, vp, vp]
         L.emu_ball_graph.argtypes = [vp, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, vp, vp, vp]
@@ -71,6 +74,13 @@ class Emu:
             lib().emu_destroy(self.h)
         except Exception:
             pass
+
+    def set_wide(self, on):
+        """Closest point on triangle structures through the 4-wide nodes (default) or the binary oriented-box nodes."""
+        lib().emu_set_wide(self.h, int(bool(on)))
+
+    def num_wide(self):
+        return lib().emu_num_wide(self.h)
 
     def num_nodes(self):
         return lib().emu_num_nodes(self.h)

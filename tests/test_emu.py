@@ -331,3 +331,27 @@ def test_experimental_64_byte_nodes_keep_parity_and_visit_counts():
         for i, d, c in ((i0, d0, c0), (i1, d1, c1)):
             assert np.array_equal(i, oi.astype(np.int32)) and np.array_equal(d, od) and np.array_equal(c, oc)
         assert n1 <= 1.03 * n0 + 1e-9
+
+
+def test_four_wide_traversal_equals_binary_traversal_and_brute_force():
+    """TGQ_OPT_WIDE: the closest-point traversal over 4-wide nodes (four lanes per query on the device; here its sequential
+    statement, closest_query_wide) answers exactly like the binary traversal and like brute force, bounded and unbounded, seeded
+    and unseeded, on a smooth mesh, on random triangle soup and on tiny structures (1..9 triangles: partially filled nodes)."""
+    from emu_lib import Emu
+    rng = np.random.default_rng(5)
+    cases = [gen.torus_mesh(40), rng.random((3000, 9), dtype=np.float32)] + [rng.random((k, 9), dtype=np.float32) for k in (1, 2, 3, 4, 5, 6, 9)]
+    for mesh in cases:
+        lo, hi = gen.mesh_bounds(mesh)
+        q = gen.closest_queries(3000, (lo, hi), seed=len(mesh))
+        ora = orc.Oracle(tris9=mesh)
+        E = Emu(tris9=mesh)
+        assert E.num_wide() >= 1
+        for bound in (-1.0, 0.3):
+            oi, od, oc = ora.closest(q, dist_bound=bound, mode=orc.MODE_BRUTE)
+            for seeded in (True, False):
+                E.set_wide(0)
+                bi, bd, bc = E.closest(q, dist_bound=bound, seeded=seeded)
+                E.set_wide(1)
+                wi, wd, wc = E.closest(q, dist_bound=bound, seeded=seeded)
+                assert np.array_equal(wi, bi) and np.array_equal(wd, bd) and np.array_equal(wc, bc)
+                assert np.array_equal(wi, oi.astype(np.int32)) and np.array_equal(wd, od)

@@ -300,3 +300,33 @@ def test_engine_against_the_reference_library_directly(built):
     rki, rkd = RP.knn(q[:50_000], 16, dist_bound=0.2)
     assert np.array_equal(kd, rkd)
     assert (ki != rki).any(axis=1).mean() < 0.01
+
+
+def test_four_lane_wide_node_kernel_matches_the_default(built):
+    """TGQ_OPT_WIDE = 1 (k_closest_wide: four lanes per query on 4-wide nodes; slower than the default, kept as an option with its
+    ncu evidence in profiles/r02_b_*): identical bits to the default kernel and to the oracle."""
+    from thea_b200 import Engine, engine as eng_mod
+    mesh = gen.torus_mesh(gen.TORUS_70K)
+    b = gen.mesh_bounds(mesh)
+    q = gen.closest_queries(400_000, b)
+    d = Engine(0)
+    d.build_triangles(mesh)
+    w = Engine(0)
+    w.set_option(eng_mod.OPT_WIDE, 1)
+    w.build_triangles(mesh)
+    ora = orc.Oracle(tris9=mesh)
+    for bound in (-1.0, 0.25):
+        di, dd, dc = d.closest(q, dist_bound=bound)
+        wi, wd, wc = w.closest(q, dist_bound=bound)
+        assert np.array_equal(di, wi) and np.array_equal(dd, wd) and np.array_equal(dc, wc)
+    oi, od, oc = ora.closest(q[:100_000], mode=orc.MODE_CANON)
+    wi, wd, wc = w.closest(q[:100_000])
+    assert np.array_equal(wi, oi.astype(np.int32)) and np.array_equal(wd, od) and np.array_equal(wc, oc)
+    for k in (1, 2, 3, 5):
+        small = mesh[:k]
+        s = Engine(0)
+        s.set_option(eng_mod.OPT_WIDE, 1)
+        s.build_triangles(small)
+        si, sd, _ = s.closest(q[:2000])
+        bi, bd, _ = orc.Oracle(tris9=small).closest(q[:2000], mode=orc.MODE_BRUTE)
+        assert np.array_equal(si, bi.astype(np.int32)) and np.array_equal(sd, bd)

@@ -66,7 +66,7 @@ struct tgq_handle
   std::string err;
   cudaStream_t own_stream = nullptr, stream = nullptr;
 
-  int opt_sort = 2, opt_leaf = 4, opt_async = 0, opt_pool = 1, opt_icp_ref = 1; int64_t opt_chunk = 16777216;
+  int opt_sort = 2, opt_leaf = 4, opt_async = 0, opt_pool = 1, opt_icp_ref = 1, opt_wide = 0; bool wide_built = false; int64_t opt_chunk = 16777216;
 
   int kind = TGQ_KIND_NONE; int n = 0; int n_nodes = 0; bool has_normals = false, has_labels = false; int leaf_built = 4;
   DevBuf nodes, elems, nrm, lab, scene;                                // NodeRec[], TriRec[] | f4[], f4[], SceneBox
@@ -75,6 +75,7 @@ struct tgq_handle
   DevBuf icp_cur, icp_orig, icp_to, icp_idx;                          // device-resident ICP loop
   DevBuf area_by_elem, cum;                                           // float[n] in element order; double[n] cumulative
   DevBuf obbs, pnrm, nsum, obbinfo, big, big_count;                   // oriented boxes (triangle structures)
+  DevBuf wide, wflag, widx, obbinfo_w; int n_wide = 0;                 // 4-wide nodes of the closest-point traversal
   int sm_count = 148; std::map<std::pair<void const *, size_t>, int> occupancy;   // resident blocks per SM of the persistent kernels
   bool cum_valid = false;
   bool orig_valid = false; DevBuf orig, orig_n, orig_lab, xf;           // untransformed source elements (tgq_set_transform)
@@ -122,6 +123,8 @@ BvhView view_of(tgq_handle * h)
   v.nrm = (h->kind == TGQ_KIND_POINTS && h->has_normals) ? h->nrm.as<f4>() : nullptr;
   v.lab = (h->kind == TGQ_KIND_POINTS && h->has_labels) ? h->lab.as<int>() : nullptr;
   v.n_nodes = h->n_nodes; v.n_prims = h->n;
+  bool wide = h->kind == TGQ_KIND_TRIANGLES && h->wide_built;
+  v.wide = wide ? h->wide.as<WideNode>() : nullptr; v.n_wide = wide ? h->n_wide : 0;
   return v;
 }
 
@@ -171,11 +174,15 @@ int refit_and_emit(tgq_handle * h, cudaStream_t s)
       CK(cudaMemsetAsync(h->big_count.p, 0, 4, s));
       k_obb_small<<<grid_for(n - 1), TGQ_BLOCK, 0, s>>>(n, h->leaf_built, h->first.as<int>(), h->last.as<int>(), h->parent.as<int>(),
                                                         h->nsum.as<f4>(), h->elems.as<TriRec>(), h->scene.as<SceneBox>(), h->obbinfo.as<f4>(),
-                                                        h->big.as<int>(), h->big_count.as<int>());
+                                                        h->wide_built ? h->obbinfo_w.as<f4>() : nullptr, h->big.as<int>(), h->big_count.as<int>());
       int big_grid = std::max(1, std::min(n / TGQ_SLAB_SMALL + 1, 148 * 64));
       k_obb_big<<<big_grid, 128, 0, s>>>(h->big.as<int>(), h->big_count.as<int>(), h->first.as<int>(), h->last.as<int>(), h->nsum.as<f4>(),
-                                         h->elems.as<TriRec>(), h->scene.as<SceneBox>(), h->obbinfo.as<f4>());
-      h->st.total_launches += 2;
+                                         h->elems.as<TriRec>(), h->scene.as<SceneBox>(), h->obbinfo.as<f4>(), h->wide_built ? h->obbinfo_w.as<f4>() : nullptr);
+      if (h->wide_built)
+      k_emit_wide<<<grid_for(n - 1), TGQ_BLOCK, 0, s>>>(n, h->leaf_built, h->first.as<int>(), h->last.as<int>(), h->split.as<int>(), h->wflag.as<int>(),
+                                                        h->widx.as<int>(), h->scene.as<SceneBox>(), h->elems.as<TriRec>(), h->obbinfo_w.as<f4>(),
+                                                        h->wide.as<WideNode>());
+      h->st.total_launches += 3;
     }
     k_emit<<<grid_for(n - 1), TGQ_BLOCK, 0, s>>>(n, h->leaf_built, h->first.as<int>(), h->last.as<int>(), h->split.as<int>(),
                                                  h->live.as<int>(), h->newidx.as<int>(), h->pbox_lo.as<f4>(), h->pbox_hi.as<f4>(),
@@ -189,7 +196,8 @@ int refit_and_emit(tgq_handle * h, cudaStream_t s)
     bool tri = h->kind == TGQ_KIND_TRIANGLES;
     k_emit_single<<<1, 1, 0, s>>>(h->pbox_lo.as<f4>(), h->pbox_hi.as<f4>(), h->scene.as<SceneBox>(), h->nodes.as<NodeRec>(),
                                   tri ? h->elems.as<TriRec>() : nullptr, tri ? h->obbs.as<ObbNode>() : nullptr);
-    h->st.total_launches += 1;
+    if (tri && h->wide_built) k_emit_wide_single<<<1, 1, 0, s>>>(h->scene.as<SceneBox>(), h->elems.as<TriRec>(), h->wide.as<WideNode>());
+    h->st.total_launches += tri ? 2 : 1;
   }
   CK(cudaGetLastError());
   return TGQ_OK;
@@ -237,7 +245,7 @@ int build_common(tgq_handle * h, int kind, float const * d_src, float const * d_
   h->ev_used = 0; e0 = get_event(h); e1 = get_event(h);
   CK(cudaEventRecord(e0, s));
 
-  h->kind = kind; h->n = n; h->n_nodes = 0; h->has_normals = (kind == TGQ_KIND_POINTS && d_n3 != nullptr);
+  h->kind = kind; h->n = n; h->n_nodes = 0; h->n_wide = 0; h->wide_built = false; h->has_normals = (kind == TGQ_KIND_POINTS && d_n3 != nullptr);
   h->leaf_built = h->opt_leaf; h->cum_valid = false; h->has_labels = false; h->orig_valid = false;
   h->st.num_elements = n;
   for (int a = 0; a < 3; ++a) { h->lo[a] = 0; h->hi[a] = 0; }
@@ -282,7 +290,11 @@ int build_common(tgq_handle * h, int kind, float const * d_src, float const * d_
     CK(h->first.reserve(4 * ni)); CK(h->last.reserve(4 * ni)); CK(h->split.reserve(4 * ni)); CK(h->parent.reserve(4 * (2 * nn)));
     CK(h->live.reserve(4 * ni)); CK(h->newidx.reserve(4 * ni)); CK(h->arrive.reserve(4 * ni));
     CK(h->nbox_lo.reserve(16 * ni)); CK(h->nbox_hi.reserve(16 * ni)); CK(h->nsum.reserve(16 * ni));
-    if (kind == TGQ_KIND_TRIANGLES) { CK(h->obbinfo.reserve(16 * TGQ_OBB_F4 * ni)); CK(h->big.reserve(4 * ni)); CK(h->big_count.reserve(4)); }
+    if (kind == TGQ_KIND_TRIANGLES)
+    {
+      CK(h->obbinfo.reserve(16 * TGQ_OBB_F4 * ni)); CK(h->big.reserve(4 * ni)); CK(h->big_count.reserve(4));
+      if (h->opt_wide) { CK(h->obbinfo_w.reserve(64 * ni)); CK(h->wflag.reserve(4 * ni)); CK(h->widx.reserve(4 * ni)); }
+    }
     k_hierarchy<<<grid_for(n - 1), TGQ_BLOCK, 0, s>>>(h->keys_b.as<uint64_t>(), n, h->first.as<int>(), h->last.as<int>(), h->split.as<int>(),
                                                       h->parent.as<int>());
     k_live<<<grid_for(n - 1), TGQ_BLOCK, 0, s>>>(n, h->leaf_built, h->first.as<int>(), h->last.as<int>(), h->live.as<int>());
@@ -297,18 +309,36 @@ int build_common(tgq_handle * h, int kind, float const * d_src, float const * d_
     CK(cudaStreamSynchronize(s));
     h->n_nodes = tail[0] + tail[1];
     h->st.total_launches += 4;
+    h->wide_built = false;
+    if (kind == TGQ_KIND_TRIANGLES && h->opt_wide)
+    {
+      h->wide_built = true;
+      // which surviving nodes are 4-wide nodes (even depth), and their compacted indices
+      k_wide_flags<<<grid_for(n - 1), TGQ_BLOCK, 0, s>>>(n, h->live.as<int>(), h->parent.as<int>(), h->wflag.as<int>());
+      CK(cudaGetLastError());
+      CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, h->wflag.as<int>(), h->widx.as<int>(), n - 1, s));
+      CK(h->cubtmp.reserve(scan_bytes));
+      CK(cub::DeviceScan::ExclusiveSum(h->cubtmp.p, scan_bytes, h->wflag.as<int>(), h->widx.as<int>(), n - 1, s));
+      CK(cudaMemcpyAsync(&tail[0], h->widx.as<int>() + (n - 2), 4, cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(&tail[1], h->wflag.as<int>() + (n - 2), 4, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      h->n_wide = tail[0] + tail[1];
+      h->st.total_launches += 3;
+    }
   }
-  else h->n_nodes = 1;
+  else { h->n_nodes = 1; h->n_wide = 1; h->wide_built = kind == TGQ_KIND_TRIANGLES && h->opt_wide; }
 
   CK(h->nodes.reserve(sizeof(NodeRec) * (size_t)h->n_nodes));
-  if (kind == TGQ_KIND_TRIANGLES) CK(h->obbs.reserve(sizeof(ObbNode) * (size_t)h->n_nodes));
+  if (kind == TGQ_KIND_TRIANGLES) { CK(h->obbs.reserve(sizeof(ObbNode) * (size_t)h->n_nodes)); if (h->wide_built) CK(h->wide.reserve(sizeof(WideNode) * (size_t)std::max(1, h->n_wide))); }
   CKRC(refit_and_emit(h, s));
   CK(cudaEventRecord(e1, s));
   CKRC(fetch_scene(h, s));
   float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
   h->st.last_build_ms = ms;
   h->st.num_nodes = h->n_nodes;
-  h->st.node_bytes = (int64_t)(sizeof(NodeRec) + (kind == TGQ_KIND_TRIANGLES ? sizeof(ObbNode) : 0)) * h->n_nodes; h->st.element_bytes = (int64_t)(rec * nn);
+  h->st.node_bytes = (int64_t)(sizeof(NodeRec) + (kind == TGQ_KIND_TRIANGLES ? sizeof(ObbNode) : 0)) * h->n_nodes
+                   + (h->wide_built ? (int64_t)sizeof(WideNode) * h->n_wide : 0);
+  h->st.element_bytes = (int64_t)(rec * nn);
   return TGQ_OK;
 }
 
@@ -503,7 +533,7 @@ int tgq_destroy(tgq_handle * h)
   cudaDeviceSynchronize();
   DevBuf * bufs[] = {&h->nodes, &h->elems, &h->nrm, &h->lab, &h->scene, &h->perm, &h->pos_of_elem, &h->first, &h->last, &h->split, &h->parent, &h->live,
                      &h->newidx, &h->pbox_lo, &h->pbox_hi, &h->nbox_lo, &h->nbox_hi, &h->arrive, &h->keys_a, &h->keys_b, &h->vals_a,
-                     &h->cubtmp, &h->src, &h->src2, &h->misc, &h->icp_cur, &h->icp_orig, &h->icp_to, &h->icp_idx, &h->area_by_elem, &h->cum, &h->obbs, &h->pnrm, &h->nsum, &h->obbinfo, &h->big, &h->big_count,
+                     &h->cubtmp, &h->src, &h->src2, &h->misc, &h->icp_cur, &h->icp_orig, &h->icp_to, &h->icp_idx, &h->area_by_elem, &h->cum, &h->obbs, &h->pnrm, &h->nsum, &h->obbinfo, &h->big, &h->big_count, &h->wide, &h->wflag, &h->widx, &h->obbinfo_w,
                      &h->orig, &h->orig_n, &h->orig_lab, &h->xf};
   for (DevBuf * b : bufs) b->release();
   for (int s = 0; s < TGQ_SLOTS; ++s)
@@ -538,6 +568,7 @@ int tgq_set_option(tgq_handle * h, int option, int64_t value)
     case TGQ_OPT_ASYNC: h->opt_async = value ? 1 : 0; return TGQ_OK;
     case TGQ_OPT_POOL: h->opt_pool = value ? 1 : 0; return TGQ_OK;
     case TGQ_OPT_ICP_REFERENCE_ORDER: h->opt_icp_ref = value ? 1 : 0; return TGQ_OK;
+    case TGQ_OPT_WIDE: h->opt_wide = value ? 1 : 0; return TGQ_OK;
     case TGQ_OPT_CHUNK: if (value < 1024) return fail(h, TGQ_EINVAL, "TGQ_OPT_CHUNK must be >= 1024"); h->opt_chunk = value; return TGQ_OK;
     default: return fail(h, TGQ_EINVAL, "unknown option");
   }
@@ -708,7 +739,14 @@ static int closest_common(tgq_handle * h, const float * q3, const float * qn3, c
   size_t smem = trav_smem_bytes(1);
   return run_batched(h, Q, args, 6, true, [&](ChunkCtx & c) -> int {
     int grid = 0; int * cnt = c.slot->counter.as<int>();
-    if (tri && h->opt_pool && h->leaf_built <= 4)
+    if (tri && h->opt_wide && h->wide_built && h->leaf_built <= 4)
+    {
+      size_t wsmem = wide_smem_bytes();
+      CKRC(persistent_grid(h, k_closest_wide, wsmem, c.n, cnt, c.stream, &grid));
+      k_closest_wide<<<grid, TGQ_BLOCK, wsmem, c.stream>>>(v, h->pad, (float const *)c.din[0], c.perm, c.n, ub, gate, exclude_self, c.offset, cnt,
+                                                          (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3]);
+    }
+    else if (tri && h->opt_pool && h->leaf_built <= 4)
     {
       size_t psmem = smem + (TGQ_BLOCK / 32) * sizeof(PoolWarp);
       CKRC(persistent_grid(h, k_closest_pool, psmem, c.n, cnt, c.stream, &grid));

@@ -212,7 +212,7 @@ __global__ void k_obb_small(int n, int leaf, int const * __restrict__ first, int
   ObbAcc a; obb_acc_begin(a, mk3(ns.x, ns.y, ns.z));
   for (int k = f; k <= l; ++k) obb_add_tri(a, tris, k);
   obb_acc_store(a, pad, 0, obbinfo + TGQ_OBB_F4 * (size_t)x);
-  obb_acc_store_wide(a, pad, 0, obbinfo_w + 4 * (size_t)x);
+  if (obbinfo_w) obb_acc_store_wide(a, pad, 0, obbinfo_w + 4 * (size_t)x);
 }
 
 // Larger nodes: one thread block per node, block-wide min / max reduction (exact, order independent).
@@ -242,7 +242,7 @@ k_obb_big(int const * __restrict__ big, int const * __restrict__ big_count, int 
         a.mx[j] = fmaxf(fmaxf(s_mx[0][j], s_mx[1][j]), fmaxf(s_mx[2][j], s_mx[3][j]));
       }
       obb_acc_store(a, pad, 0, obbinfo + TGQ_OBB_F4 * (size_t)x);
-      obb_acc_store_wide(a, pad, 0, obbinfo_w + 4 * (size_t)x);
+      if (obbinfo_w) obb_acc_store_wide(a, pad, 0, obbinfo_w + 4 * (size_t)x);
     }
   }
 }
@@ -744,6 +744,9 @@ k_closest_pool(BvhView b, float scene_pad, float const * __restrict__ q3, uint32
 #define TGQ_WSTACK 32          // stack entries per query kept in shared memory (deeper ones spill to local memory)
 #endif
 #define TGQ_WOVF 96            // > 3 x (63 Morton + 32 tie-break bits) / 2 levels beyond the shared part cannot occur in ordered DFS
+#ifndef TGQ_WIDE_THRESH
+#define TGQ_WIDE_THRESH 32     // queued (owner, triangle) pairs that trigger a leaf iteration
+#endif
 struct WidePool
 {
   unsigned long long best[8];
@@ -846,7 +849,7 @@ k_closest_wide(BvhView b, float scene_pad, float const * __restrict__ q3, uint32
     {
       int avail = *(volatile int *)&pw.tail - head;
       bool runnable = (cur >= 0 || cur == TGQ_ST_POP) && !hold;
-      if (!(avail >= 32 || (avail > 0 && !__any_sync(FULL, runnable)))) break;
+      if (!(avail >= TGQ_WIDE_THRESH || (avail > 0 && !__any_sync(FULL, runnable)))) break;
       int m = min(avail, 32);
       unsigned long long published = pool_key(best_d2, best_idx < 0 ? 0 : best_idx);      // (ub, 0) when nothing was found yet: only d2 < ub wins
       if (sub == 0) pw.best[g] = published;

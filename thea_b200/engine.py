@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 KIND_NONE, KIND_TRIANGLES, KIND_POINTS = 0, 1, 2
-OPT_SORT_QUERIES, OPT_LEAF_SIZE, OPT_ASYNC, OPT_CHUNK, OPT_POOL, OPT_ICP_REFERENCE_ORDER = 1, 2, 3, 4, 5, 6
+OPT_SORT_QUERIES, OPT_LEAF_SIZE, OPT_ASYNC, OPT_CHUNK, OPT_POOL, OPT_ICP_REFERENCE_ORDER, OPT_WIDE = 1, 2, 3, 4, 5, 6, 7
 MAX_K = 64
 
 SYMBOLS = [

@@ -6,9 +6,11 @@ from thea_b200 import Engine, gen
 
 def main(kind, grid, Q, reps=3):
     mesh = gen.torus_mesh(grid); b = gen.mesh_bounds(mesh)
-    e = Engine(0)
+    e = Engine(0, lib=os.environ.get("TGQ_LIB") or None)
     if os.environ.get("TGQ_POOL") is not None:
         e.set_option(5, int(os.environ["TGQ_POOL"]))
+    if os.environ.get("TGQ_WIDE") is not None:
+        e.set_option(7, int(os.environ["TGQ_WIDE"]))
     e.build_triangles(torch.from_numpy(mesh).cuda())
     if kind == "closest":
         q = torch.from_numpy(gen.closest_queries(Q, b)).cuda()

@@ -7,13 +7,15 @@ from thea_b200 import Engine, gen
 def run(n_grid, Q, leaf=4, sort=2, what=("closest", "ray")):
     mesh = gen.torus_mesh(n_grid)
     b = gen.mesh_bounds(mesh)
-    e = Engine(0)
+    e = Engine(0, lib=os.environ.get("TGQ_LIB") or None)
     e.set_option(2, leaf); e.set_option(1, sort)
     if os.environ.get("TGQ_POOL") is not None:
         e.set_option(5, int(os.environ["TGQ_POOL"]))
+    if os.environ.get("TGQ_WIDE") is not None:
+        e.set_option(7, int(os.environ["TGQ_WIDE"]))
     e.build_triangles(torch.from_numpy(mesh).cuda())
     st = e.stats()
-    out = {"pool": os.environ.get("TGQ_POOL", "default"), "tris": len(mesh), "Q": Q, "leaf": leaf, "sort": sort, "nodes": st["num_nodes"], "build_ms": round(st["last_build_ms"], 3)}
+    out = {"wide": os.environ.get("TGQ_WIDE", "default"), "pool": os.environ.get("TGQ_POOL", "default"), "tris": len(mesh), "Q": Q, "leaf": leaf, "sort": sort, "nodes": st["num_nodes"], "build_ms": round(st["last_build_ms"], 3)}
     if "closest" in what:
         q = torch.from_numpy(gen.closest_queries(Q, b)).cuda()
         for _ in range(3):
