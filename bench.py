@@ -152,30 +152,54 @@ def blocks(n: int):
     return [(b, min(BLOCK, n - b)) for b in range(0, n, BLOCK)]
 
 
+class _CpuArm:
+    """The CPU side timed by the reference arm and the cpu_baseline leg: closest(q) / ray_first(o, d) on all host cores."""
+
+    def __init__(self, obj, closest, ray_first):
+        self.obj, self.closest, self.ray_first = obj, closest, ray_first
+
+
+def cpu_reference(mesh):
+    """(arm, kind, cores, description): the reference's OWN BvhN code (oracle/_ref/libthea_ref.so: sidch/Thea's unmodified sources
+    compiled against the Eigen stand-in of oracle/eigen_shim) when that library exists, else the oracle port in reference order."""
+    from oracle import orc
+    cores = orc.ncores()
+    try:
+        from oracle import ref
+        if ref.available():
+            R = ref.Reference(tris9=mesh)
+            return (_CpuArm(R, lambda q: R.closest(q, threads=cores), lambda o, d: R.ray_first(o, d, threads=cores)), "reference", cores,
+                    "CPU = the reference's own BvhN::closestPair / rayStructureIntersection (Thea sources compiled unmodified against an Eigen "
+                    "stand-in), its single-threaded query loop spread over the host threads")
+    except Exception as exc:      # noqa: BLE001
+        print(f"bench.py: reference library unavailable ({type(exc).__name__}: {exc}); timing the oracle port", file=sys.stderr)
+    O = orc.Oracle(tris9=mesh)
+    return (_CpuArm(O, lambda q: O.closest(q, mode=orc.MODE_REFERENCE, threads=cores), lambda o, d: O.ray_first(o, d, mode=orc.MODE_REFERENCE, threads=cores)),
+            "port", cores, "CPU = oracle port of the reference kd-tree (leaf 5, x1.05 boxes) in DFS order")
+
+
 def run_reference(args, world, rank):
     """--impl reference: the CPU restatement of the reference's BvhN (kd-tree, DFS order) on all host cores."""
     if rank != 0:
         return
-    from oracle import orc
     grid, nq, nr, desc = WORKLOADS[args.workload]
     mesh = gen.torus_mesh(max(8, int(grid * args.scale)))
     T = len(mesh)
     bounds = gen.mesh_bounds(mesh)
-    cores = orc.ncores()
     t0 = time.time()
-    ora = orc.Oracle(tris9=mesh)
+    ora, kind, cores, what = cpu_reference(mesh)
     build_s = time.time() - t0
     # bounded sample per step, sized from a pilot so that steps+warmup stay within a few minutes
     sq = 2000 if nq else 0
     sr = 20000 if nr else 0
     t0 = time.time()
     if sq:
-        ora.closest(gen.closest_queries(sq, bounds), mode=orc.MODE_REFERENCE, threads=cores)
+        ora.closest(gen.closest_queries(sq, bounds))
     tq = time.time() - t0
     t0 = time.time()
     if sr:
         o, d = gen.random_rays(sr, bounds)
-        ora.ray_first(o, d, mode=orc.MODE_REFERENCE, threads=cores)
+        ora.ray_first(o, d)
     tr = time.time() - t0
     budget = 60.0 / max(1, args.steps + args.warmup)          # seconds per step
     mix_q = nq / max(1, nq + nr)
@@ -190,20 +214,20 @@ def run_reference(args, world, rank):
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         if n_q:
-            ora.closest(q, mode=orc.MODE_REFERENCE, threads=cores)
+            ora.closest(q)
         if n_r:
-            ora.ray_first(o, d, mode=orc.MODE_REFERENCE, threads=cores)
+            ora.ray_first(o, d)
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             times.append(dt)
     total = sum(times)
     value = (n_q + n_r) * len(times) / total
-    sample = f"{n_q} closest + {n_r} rays per step (prefix of the same streams), kd-tree build {build_s:.1f}s excluded"
+    sample = f"{n_q} closest + {n_r} rays per step (prefix of the same streams), kd-tree build {build_s:.1f}s excluded; {what}"
     line = {"impl": "reference", "metric": "bvh_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "triangles": T, "scale": args.scale},
-            "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -256,118 +280,91 @@ def main():
     build_ms = eng.stats()["last_build_ms"]
     del d_mesh
 
-    # this rank's contiguous shard of both query streams, generated on the device from the counter-based streams
+    # ---- device-resident leg -------------------------------------------------------------------------------------------------------
+    # Every rank holds the WHOLE batch (generated on the device from the counter-based streams) and, inside the timed step, takes the
+    # queries whose Morton cell it owns (tgq_*_records: cells dealt round-robin, so its share keeps the density of the full batch -- a
+    # contiguous index range of a random batch is `world` times sparser after the Morton sort, which cost 24 % per rank at N = 8 in
+    # round 1).  The one real exchange of the path -- every rank ends a step holding the results of the WHOLE batch --
+    # is fused into the traversal kernels: finish() stores each result as one aligned record (32 B closest, 8 B ray) straight into
+    # EVERY rank's copy of the gathered arrays, which live in symmetric (peer-mapped) memory, over NVLink.  No NCCL kernel, no copy
+    # engine, nothing to overlap by hand.  Fallback when symmetric memory is unavailable: contiguous shards + NCCL all-gather.
     q_off, nq = shard(nq_total, rank, world)
     r_off, nr = shard(nr_total, rank, world)
-    dq = torch.empty((nq, 3), dtype=torch.float32, device=dev)
-    for b, n in blocks(nq):
-        dq[b:b + n] = torch_closest_queries(n, bounds, gen.SEED_CLOSEST, q_off + b, dev)
-    dro = torch.empty((nr, 3), dtype=torch.float32, device=dev)
-    drd = torch.empty((nr, 3), dtype=torch.float32, device=dev)
-    for b, n in blocks(nr):
-        o, d = torch_random_rays(n, bounds, gen.SEED_RAYS, r_off + b, dev)
+    dq = torch.empty((nq_total, 3), dtype=torch.float32, device=dev)
+    for b, n in blocks(nq_total):
+        dq[b:b + n] = torch_closest_queries(n, bounds, gen.SEED_CLOSEST, b, dev)
+    dro = torch.empty((nr_total, 3), dtype=torch.float32, device=dev)
+    drd = torch.empty((nr_total, 3), dtype=torch.float32, device=dev)
+    for b, n in blocks(nr_total):
+        o, d = torch_random_rays(n, bounds, gen.SEED_RAYS, b, dev)
         dro[b:b + n] = o
         drd[b:b + n] = d
     kern = {"closest_ms": 0.0, "closest_q": 0, "ray_ms": 0.0, "ray_q": 0, "sort_ms": 0.0, "launches": 0}
 
-    # N > 1: the one real exchange of the path -- every rank ends a step holding the results of the WHOLE batch (SURVEY.md
-    # 8e).  Equal shard sizes by construction.  Preferred transport: the gathered arrays live in symmetric (peer-mapped)
-    # memory, every rank's kernels write their shard straight into the local copy, and the shard is then PUSHED into every
-    # peer's copy with peer-to-peer copies over NVLink on a side stream -- copy engines, no SMs, so the transfer really runs
-    # under the next kernel (NCCL's all-gather kernels cannot: the persistent traversal kernels leave them no SM until they
-    # finish).  Fallback when symmetric memory is unavailable: asynchronous NCCL all-gather.
-    gathered, symm, transport = None, None, "none"
-    shapes = {"c_idx": ((nq_total,), torch.int32), "c_d2": ((nq_total,), torch.float32), "c_cp": ((nq_total, 3), torch.float32),
-              "r_t": ((nr_total,), torch.float32), "r_idx": ((nr_total,), torch.int32)}
-    offs = {"c_idx": (q_off, nq), "c_d2": (q_off, nq), "c_cp": (q_off, nq), "r_t": (r_off, nr), "r_idx": (r_off, nr)}
-    if world > 1:
-        assert nq_total % world == 0 and nr_total % world == 0, "bench workloads shard evenly over 1/2/4/8 ranks"
-        if os.environ.get("TGQ_BENCH_TRANSPORT", "p2p") == "p2p":
-            try:
-                import torch.distributed._symmetric_memory as symm_mem
-                gathered, symm = {}, {}
-                for name, (shape, dt) in shapes.items():
-                    t = symm_mem.empty(max(1, int(np.prod(shape))), dtype=dt, device=dev)
-                    hdl = symm_mem.rendezvous(t, dist.group.WORLD)
-                    gathered[name] = t[:int(np.prod(shape))].view(shape)
-                    symm[name] = [hdl.get_buffer(r, (max(1, int(np.prod(shape))),), dt)[:int(np.prod(shape))].view(shape) for r in range(world)]
-                transport = "p2p copy engines over symmetric memory"
-            except Exception as exc:      # noqa: BLE001 -- any failure here means: use NCCL
-                if rank == 0:
-                    print(f"bench.py: symmetric memory unavailable ({type(exc).__name__}: {exc}); using NCCL all-gather", file=sys.stderr)
-                gathered, symm = None, None
-        if gathered is None:
-            gathered = {name: torch.empty(shape, dtype=dt, device=dev) for name, (shape, dt) in shapes.items()}
-            transport = "NCCL all-gather"
-    if symm is not None:
-        c_idx, c_d2, c_cp = (gathered[k][q_off:q_off + nq] for k in ("c_idx", "c_d2", "c_cp"))
-        r_t, r_idx = (gathered[k][r_off:r_off + nr] for k in ("r_t", "r_idx"))
-        comm_stream = torch.cuda.Stream(device=dev)
-    else:
-        c_idx = torch.empty(nq, dtype=torch.int32, device=dev)
-        c_d2 = torch.empty(nq, dtype=torch.float32, device=dev)
-        c_cp = torch.empty((nq, 3), dtype=torch.float32, device=dev)
-        r_t = torch.empty(nr, dtype=torch.float32, device=dev)
-        r_idx = torch.empty(nr, dtype=torch.int32, device=dev)
+    crec = rrec = None
+    c_dest, r_dest = [], []
+    transport = "none"
+    if world > 1 and os.environ.get("TGQ_BENCH_TRANSPORT", "p2p") == "p2p":
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            bufs = []
+            for numel in (max(8, nq_total * 8), max(2, nr_total * 2)):
+                t = symm_mem.empty(numel, dtype=torch.float32, device=dev)
+                hdl = symm_mem.rendezvous(t, dist.group.WORLD)
+                bufs.append((t, [hdl.get_buffer(r, (numel,), torch.float32) for r in range(world)]))
+            crec, c_peers = bufs[0][0][:nq_total * 8].view(nq_total, 8), bufs[0][1]
+            rrec, r_peers = bufs[1][0][:nr_total * 2].view(nr_total, 2), bufs[1][1]
+            # own copy first, then the peers starting after this rank (spreads the NVLink traffic of a step over the links)
+            order = [(rank + k) % world for k in range(world)]
+            c_dest = [c_peers[r] for r in order]
+            r_dest = [r_peers[r] for r in order]
+            transport = "kernel stores into every rank's symmetric-memory copy (NVLink P2P)"
+        except Exception as exc:      # noqa: BLE001 -- any failure here means: use NCCL
+            if rank == 0:
+                print(f"bench.py: symmetric memory unavailable ({type(exc).__name__}: {exc}); using contiguous shards + NCCL all-gather", file=sys.stderr)
+            crec = None
+    space_sharded = world == 1 or crec is not None
+    if crec is None:
+        crec = torch.empty((nq_total, 8), dtype=torch.float32, device=dev)
+        rrec = torch.empty((nr_total, 2), dtype=torch.float32, device=dev)
+        c_dest, r_dest = [crec], [rrec]
+        if world > 1:
+            transport = "NCCL all-gather of contiguous shards"
+    crec.zero_()
+    rrec.zero_()
 
-    pending = {"c": [], "r": []}
-
-    def wait_gathers(groups=("c", "r")):
-        # makes the compute stream wait for the transfers that still read the buffers the next kernel overwrites
-        for g in groups:
-            while pending[g]:
-                w = pending[g].pop()
-                if symm is not None:
-                    torch.cuda.current_stream().wait_event(w)
-                else:
-                    w.wait()
-
-    def gather(names):
-        # asynchronous: the shard results move over NVLink while the next kernel runs
-        if world == 1:
-            return
-        if symm is not None:
-            comm_stream.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(comm_stream):
-                for name in names:
-                    o, n = offs[name]
-                    if n:
-                        for peer in range(1, world):
-                            r = (rank + peer) % world
-                            symm[name][r][o:o + n].copy_(gathered[name][o:o + n], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(comm_stream)
-            pending[names[0][0]].append(ev)
-            return
-        src = {"c_idx": c_idx, "c_d2": c_d2, "c_cp": c_cp, "r_t": r_t, "r_idx": r_idx}
-        for name in names:
-            if src[name].numel():
-                pending[name[0]].append(dist.all_gather_into_tensor(gathered[name], src[name], async_op=True))
+    pending = []
 
     def step_device(record: bool):
-        # one C-ABI call per query kind over the whole shard (the library splits batches above 2^26 queries)
-        if nq:
-            wait_gathers(("c",))             # the previous step's gathers read the result buffers this kernel overwrites
-            eng.closest(dq, out=(c_idx, c_d2, c_cp))
+        # one C-ABI call per query kind over the whole batch; the library selects this rank's share and writes the records
+        if nq_total:
+            if space_sharded:
+                eng.closest_records(dq, c_dest, rank, world)
+            else:
+                eng.closest_records(dq[q_off:q_off + nq], [crec[q_off:q_off + nq]])
+                pending.append(dist.all_gather_into_tensor(crec.view(-1), crec[q_off:q_off + nq].reshape(-1), async_op=True))
             if record:
                 s = eng.stats()
                 kern["closest_ms"] += s["last_query_ms"] - s["last_sort_ms"]
                 kern["sort_ms"] += s["last_sort_ms"]
-                kern["closest_q"] += nq
+                kern["closest_q"] += nq_total / world
                 kern["closest_launches"] = kern.get("closest_launches", 0) + 1
                 kern["launches"] += s["last_launches"]
-            gather(("c_idx", "c_d2", "c_cp"))
-        if nr:
-            wait_gathers(("r",))
-            eng.ray_first(dro, drd, out=(r_t, r_idx, None))
+        if nr_total:
+            if space_sharded:
+                eng.ray_first_records(dro, drd, r_dest, rank, world)
+            else:
+                eng.ray_first_records(dro[r_off:r_off + nr], drd[r_off:r_off + nr], [rrec[r_off:r_off + nr]])
+                pending.append(dist.all_gather_into_tensor(rrec.view(-1), rrec[r_off:r_off + nr].reshape(-1), async_op=True))
             if record:
                 s = eng.stats()
                 kern["ray_ms"] += s["last_query_ms"] - s["last_sort_ms"]
                 kern["sort_ms"] += s["last_sort_ms"]
-                kern["ray_q"] += nr
+                kern["ray_q"] += nr_total / world
                 kern["ray_launches"] = kern.get("ray_launches", 0) + 1
                 kern["launches"] += s["last_launches"]
-            gather(("r_t", "r_idx"))
+        while pending:
+            pending.pop().wait()
 
     def barrier():
         if world > 1:
@@ -376,7 +373,6 @@ def main():
 
     for _ in range(args.warmup):
         step_device(False)
-    wait_gathers()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -385,9 +381,8 @@ def main():
     e0.record()
     for _ in range(args.steps):
         step_device(True)
-    wait_gathers()                           # the last step's results have left this rank ...
-    e1.record()
-    barrier()
+    e1.record()                              # this rank's kernels, including their stores into the peers' copies, are complete
+    barrier()                                # ... and so are everybody else's into this rank's copy
     clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -396,17 +391,20 @@ def main():
     total_queries = nq_total + nr_total
     value = total_queries * args.steps / (dev_ms / 1e3)
 
-    # checksum of the results (device resident) so that the timed work cannot be optimised away and runs can be compared
+    # checksum of the gathered results on THIS rank's copy (every rank holds all of them), so that the timed work cannot be optimised
+    # away and runs at different N can be compared; all ranks must agree
+    checksum = int((crec.view(torch.int32)[:, 0].long().sum() + rrec.view(torch.int32)[:, 1].long().sum()).item())
     if world > 1:
-        checksum = int((gathered["c_idx"].long().sum() + gathered["r_idx"].long().sum()).item())
-    else:
-        checksum = int((c_idx.long().sum() + r_idx.long().sum()).item())
+        cs = torch.tensor([checksum, -checksum], dtype=torch.int64, device=dev)
+        dist.all_reduce(cs, op=dist.ReduceOp.MAX)
+        assert int(cs[0].item()) == checksum and int(cs[1].item()) == -checksum, "ranks hold different gathered results"
 
     # ---- e2e: same calls, pinned host buffers, copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        hq = dq.cpu().pin_memory().numpy()
-        hro, hrd = dro.cpu().pin_memory().numpy(), drd.cpu().pin_memory().numpy()
+        # host-buffer leg: every rank answers a contiguous shard of the batch from / to pinned host memory
+        hq = dq[q_off:q_off + nq].cpu().pin_memory().numpy()
+        hro, hrd = dro[r_off:r_off + nr].cpu().pin_memory().numpy(), drd[r_off:r_off + nr].cpu().pin_memory().numpy()
         h_idx = torch.empty(nq, dtype=torch.int32).pin_memory().numpy()
         h_d2 = torch.empty(nq, dtype=torch.float32).pin_memory().numpy()
         h_cp = torch.empty((nq, 3), dtype=torch.float32).pin_memory().numpy()
@@ -416,11 +414,14 @@ def main():
         if args.chunk:
             eng.set_option(4, args.chunk)
 
+        eng.set_option(3, 1)          # TGQ_OPT_ASYNC: the two calls of a step overlap (downloads of one under the uploads of the next)
+
         def step_host():
             if nq:
                 eng.closest(hq, out=(h_idx, h_d2, h_cp))
             if nr:
                 eng.ray_first(hro, hrd, out=(h_t, h_ri, None))
+            eng.synchronize()         # results are in the host buffers
 
         step_host()
         barrier()
@@ -464,39 +465,41 @@ def main():
         limiter = (json.load(open(tp)).get(f"{args.workload}:{dominant}") or {}).get("limiter")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "limiter": limiter,
                 "kernel": dominant, "peak_source": peak_kind, "algorithmic_bytes_per_query": bytes_per_q,
-                "queries_per_launch": k_q // max(1, k_n), "avg_launch_ms": k_ms / max(1, k_n)}
+                "queries_per_launch": int(k_q // max(1, k_n)), "avg_launch_ms": k_ms / max(1, k_n)}
 
-    # ---- CPU baseline on rank 0: oracle in reference traversal order, all host cores, bounded sample ----
+    # ---- CPU baseline on rank 0: the reference's own code (or the oracle port) on all host cores, bounded sample ----
     cpu = None
     if not args.no_cpu:
         from oracle import orc
-        cores = orc.ncores()
-        ora = orc.Oracle(tris9=mesh)
-        sq, sr = (2000 if nq_total else 0), (200000 if nr_total else 0)
+        arm, kind, cores, what = cpu_reference(mesh)
+        sq, sr = (1000 if nq_total else 0), (100000 if nr_total else 0)
         t0 = time.perf_counter()
         if sq:
-            qs = gen.closest_queries(sq, bounds)
-            oi, od, _ = ora.closest(qs, mode=orc.MODE_REFERENCE, threads=cores)
+            arm.closest(gen.closest_queries(sq, bounds))
         tq = time.perf_counter() - t0
         # scale the closest sample to ~10 s of CPU work
         if sq and tq < 8.0:
             sq = int(min(2_000_000, sq * 10.0 / max(tq, 1e-3)))
             qs = gen.closest_queries(sq, bounds)
             t0 = time.perf_counter()
-            oi, od, _ = ora.closest(qs, mode=orc.MODE_REFERENCE, threads=cores)
+            oi, od, _ = arm.closest(qs)
             tq = time.perf_counter() - t0
+        else:
+            qs = gen.closest_queries(sq, bounds) if sq else None
+            od = arm.closest(qs)[1] if sq else None
         t0 = time.perf_counter()
         if sr:
             o, d = gen.random_rays(sr, bounds)
-            ora.ray_first(o, d, mode=orc.MODE_REFERENCE, threads=cores)
+            arm.ray_first(o, d)
         tr = time.perf_counter() - t0
         # per-query costs combined in the workload's mix
         per_q = (tq / sq if sq else 0.0) * nq_total + (tr / sr if sr else 0.0) * nr_total
-        cpu = {"value": total_queries / per_q if per_q > 0 else None, "unit": "queries/s", "cores": cores, "kind": "port",
+        cpu = {"value": total_queries / per_q if per_q > 0 else None, "unit": "queries/s", "cores": cores, "kind": kind,
                "sample": f"{sq} closest-point ({tq:.2f}s) + {sr} rays ({tr:.2f}s) of the same streams, combined in the workload's "
-                         f"{nq_total}:{nr_total} mix; oracle = reference kd-tree (leaf 5, x1.05 boxes) in DFS order"}
-        # the same prefix through the GPU path must agree with the canonical oracle distances (sanity, not timing)
+                         f"{nq_total}:{nr_total} mix; {what}"}
+        # the same prefix through the GPU path must agree with the CPU side's distances (sanity, not timing)
         if sq:
+            eng.set_option(3, 0)
             gi, gd, _ = eng.closest(qs[:2000])
             assert np.array_equal(gd, od[:2000]), "GPU closest-point distances differ from the CPU reference on the bench sample"
 
@@ -504,7 +507,7 @@ def main():
         "metric": "bvh_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": desc, "triangles": T, "closest_queries": nq_total, "ray_queries": nr_total, "sharding": f"queries/{world}, BVH replicated" + (f", results gathered on every rank every step ({transport}, overlapped with the next kernel)" if world > 1 else ""),
+        "config": {"workload": desc, "triangles": T, "closest_queries": nq_total, "ray_queries": nr_total, "sharding": f"BVH replicated; batch replicated, each rank answers the queries of its Morton cells (1/{world})" + (f"; results gathered on every rank every step: {transport}" if world > 1 else ""),
                    "l2_policy": "inputs_exceed_l2" if (nq_total * 32 + nr_total * 32) / world > 126e6 else "structure+inputs may be L2 resident",
                    "scale": args.scale, "build_ms": build_ms},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": kern["launches"], "clocks": clocks,

@@ -53,7 +53,9 @@ enum
 {
   TGQ_OPT_SORT_QUERIES = 1,   /* 0 = never, 1 = always, 2 = auto (default: batches >= 4096 are Morton-ordered first) */
   TGQ_OPT_LEAF_SIZE = 2,      /* max elements per leaf, 1..15 (default 4); takes effect at the next build */
-  TGQ_OPT_ASYNC = 3,          /* 1: device-pointer calls return without synchronising the stream (default 0) */
+  TGQ_OPT_ASYNC = 3,          /* 1: batched query calls return without waiting: device-pointer calls are ordered on the handle's stream,
+                                 host-pointer calls on the internal pipeline streams -- call tgq_synchronize before reading host outputs
+                                 (lets consecutive calls overlap: the downloads of one with the uploads of the next).  Default 0 */
   TGQ_OPT_CHUNK = 4,          /* queries per staged chunk for host-pointer calls (default 16777216) */
   TGQ_OPT_POOL = 5,           /* closest point on triangle structures: 1 = leaf tests pooled across the warp (default), 0 = per lane */
   TGQ_OPT_WIDE = 7,           /* closest point on triangle structures: 1 = four lanes per query on 4-wide nodes (set BEFORE the build; measured
@@ -78,6 +80,10 @@ const char * tgq_last_error(tgq_handle * h);
 /* Issue all work on this cudaStream_t (passed as void*); null = the handle's own stream. */
 int tgq_set_stream(tgq_handle * h, void * cuda_stream);
 int tgq_set_option(tgq_handle * h, int option, int64_t value);
+
+/* Waits for everything the handle has in flight (the stream of device-pointer calls and the pipeline streams of host-pointer
+ * calls).  Needed only with TGQ_OPT_ASYNC. */
+int tgq_synchronize(tgq_handle * h);
 
 /* ---- build ------------------------------------------------------------------------------------------------------ */
 
@@ -204,6 +210,19 @@ int tgq_avg_separation(tgq_handle * h, const int32_t * seeds, int32_t n, float *
  * tmax may be null (unbounded) else tmax[R], negative = unbounded; hits need 0 <= t and t < tmax (strict, BvhN.hpp:2257).
  * Outputs (each may be null): t[R] (-1 = miss), idx[R] (-1 = miss), normal3[R x 3] = unit normal of the hit triangle
  * (RayStructureIntersectionN::getNormal, Algorithms/RayQueryStructureN.hpp:28-53). */
+/* The same queries with RECORD outputs and optional sharding of a replicated batch by space -- the multi-GPU form (SURVEY.md 8e:
+ * BVH replicated, queries sharded, every rank ends holding all results).  All pointers are device pointers.  Every rank calls with
+ * the SAME whole batch; rank `shard_rank` of `shard_world` answers the queries whose Morton cell it owns (cells dealt round-robin,
+ * so each rank's share keeps the density of the full batch) and the kernel stores each result as one aligned record
+ *     closest: 32 bytes { int32 idx; float d2 (-1 = none); float cp[3]; int32 pad[3] }      ray: 8 bytes { float t (-1 = miss); int32 idx }
+ * at position [query index] of EVERY destination array dest[0 .. n_dest) (n_dest <= 8): the rank's own copy and, peer-mapped, the
+ * copies of the other ranks (e.g. torch symmetric memory), written straight over NVLink while the traversal runs.  shard_world = 1,
+ * n_dest = 1 is the plain single-GPU call with record output.  Records of queries other ranks own are left untouched. */
+int tgq_closest_records(tgq_handle * h, const float * q3, int64_t Q, double dist_bound, int32_t shard_rank, int32_t shard_world,
+                        void * const * dest, int32_t n_dest);
+int tgq_ray_first_records(tgq_handle * h, const float * o3, const float * d3, const float * tmax, int64_t R, int32_t shard_rank,
+                          int32_t shard_world, void * const * dest, int32_t n_dest);
+
 int tgq_ray_first(tgq_handle * h, const float * o3, const float * d3, const float * tmax, int64_t R,
                   float * t, int32_t * idx, float * normal3);
 /* BvhN::rayIntersects (BvhN.hpp:1266-1269) with early exit: hit[R] = 1/0. */

@@ -41,6 +41,7 @@ struct DevBuf
 };
 
 #define TGQ_MAX_ARGS 8
+#define TGQ_SHARD_CELL_BITS 18       // 2^18 Morton cells over the scene box grown x2, dealt round-robin to the ranks
 #ifndef TGQ_SLOTS
 // Ray kernels: resident blocks per SM (the rest of the shared-memory array becomes L1).  Measured on B200, 8 M rays on the 10 M-triangle
 // mesh: 7 blocks with the maximum carve-out 1.75 G rays/s, 6 blocks 2.27 G, 5 blocks 2.11 G (1 M triangles: 2.24 / 2.73 / 2.53 G).
@@ -76,6 +77,8 @@ struct tgq_handle
   DevBuf area_by_elem, cum;                                           // float[n] in element order; double[n] cumulative
   DevBuf obbs, pnrm, nsum, obbinfo, big, big_count;                   // oriented boxes (triangle structures)
   DevBuf wide, wflag, widx, obbinfo_w; int n_wide = 0;                 // 4-wide nodes of the closest-point traversal
+  int shard_rank = 0, shard_world = 1;                                 // set by the *_records entry points for the duration of one call
+  PeerOut peers = {};
   int sm_count = 148; std::map<std::pair<void const *, size_t>, int> occupancy;   // resident blocks per SM of the persistent kernels
   bool cum_valid = false;
   bool orig_valid = false; DevBuf orig, orig_n, orig_lab, xf;           // untransformed source elements (tgq_set_transform)
@@ -358,8 +361,36 @@ int sort_chunk(tgq_handle * h, ChunkCtx & c)
 {
   bool want = h->opt_sort == 1 || (h->opt_sort == 2 && c.n >= 4096);
   c.perm = nullptr;
-  if (!want || h->n == 0) return TGQ_OK;
   Slot & sl = *c.slot; size_t nn = (size_t)c.n;
+  if (h->shard_world > 1)
+  {
+    // this rank's share of the replicated batch (Morton cells dealt round-robin), then the Morton order of the share alone
+    for (int i = 0; i < 2; ++i) { CK(sl.keys[i].reserve(4 * nn)); CK(sl.vals[i].reserve(4 * nn)); }
+    int * cnt = sl.counter.as<int>() + 1;
+    CK(cudaMemsetAsync(cnt, 0, 4, c.stream));
+    int grid = (int)std::min<int64_t>((c.n + 255) / 256, (int64_t)h->sm_count * 16);
+    k_query_codes_shard<<<grid, 256, 0, c.stream>>>((float const *)c.din[0], c.n, h->scene.as<SceneBox>(), h->shard_rank, h->shard_world, 30 - TGQ_SHARD_CELL_BITS,
+                                                    sl.keys[0].as<uint32_t>(), sl.vals[0].as<uint32_t>(), cnt);
+    CK(cudaGetLastError());
+    int own = 0;
+    CK(cudaMemcpyAsync(&own, cnt, 4, cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    c.n = own;
+    h->st.last_launches += 1; h->st.total_launches += 1;
+    if (own > 0)
+    {
+      size_t tmp = 0;
+      CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, sl.keys[0].as<uint32_t>(), sl.keys[1].as<uint32_t>(), sl.vals[0].as<uint32_t>(),
+                                         sl.vals[1].as<uint32_t>(), own, 0, 30, c.stream));
+      CK(sl.cubtmp.reserve(tmp));
+      CK(cub::DeviceRadixSort::SortPairs(sl.cubtmp.p, tmp, sl.keys[0].as<uint32_t>(), sl.keys[1].as<uint32_t>(), sl.vals[0].as<uint32_t>(),
+                                         sl.vals[1].as<uint32_t>(), own, 0, 30, c.stream));
+      h->st.last_launches += 3; h->st.total_launches += 3;
+    }
+    c.perm = sl.vals[1].as<uint32_t>();
+    return TGQ_OK;
+  }
+  if (!want || h->n == 0) return TGQ_OK;
   for (int i = 0; i < 2; ++i) { CK(sl.keys[i].reserve(4 * nn)); CK(sl.vals[i].reserve(4 * nn)); }
   k_query_codes<<<grid_for(c.n), TGQ_BLOCK, 0, c.stream>>>((float const *)c.din[0], c.n, h->scene.as<SceneBox>(), sl.keys[0].as<uint32_t>(),
                                                            sl.vals[0].as<uint32_t>());
@@ -386,7 +417,9 @@ int run_batched(tgq_handle * h, int64_t Q, Arg * args, int nargs, bool sortable,
     void const * p = args[a].in ? args[a].in : args[a].out;
     if (p && !is_device_ptr(p)) all_dev = false;
   }
-  int64_t chunk = all_dev ? ((int64_t)1 << 26) : std::max<int64_t>(1024, h->opt_chunk);
+  // host-pointer calls: at least four chunks, so that the upload of one chunk, the kernels of another and the download of a third
+  // overlap even when the batch is smaller than TGQ_OPT_CHUNK (a 6 M-query shard used to be ONE chunk: copy, sort, kernel, copy in series)
+  int64_t chunk = all_dev ? ((int64_t)1 << 26) : std::max<int64_t>(1024, std::min<int64_t>(h->opt_chunk, ((Q + 3) / 4 + 1023) / 1024 * 1024));
   int nslots = all_dev ? 1 : TGQ_SLOTS;
   if (!all_dev) CK(cudaStreamSynchronize(h->stream));     // the structure must be complete before other streams read it
   std::vector<cudaEvent_t> evs;
@@ -415,7 +448,7 @@ int run_batched(tgq_handle * h, int64_t Q, Arg * args, int nargs, bool sortable,
     CK(cudaEventRecord(e0, c.stream));
     if (sortable) CKRC(sort_chunk(h, c));
     CK(cudaEventRecord(e1, c.stream));
-    CKRC(launch(c));
+    if (c.n > 0) CKRC(launch(c));
     CK(cudaGetLastError());
     CK(cudaEventRecord(e2, c.stream));
     evs.push_back(e0); evs.push_back(e1); evs.push_back(e2);
@@ -423,7 +456,7 @@ int run_batched(tgq_handle * h, int64_t Q, Arg * args, int nargs, bool sortable,
       if (args[a].out && !is_device_ptr(args[a].out))
         CK(cudaMemcpyAsync((char *)args[a].out + args[a].stride * (size_t)off, c.dout[a], args[a].stride * (size_t)c.n, cudaMemcpyDeviceToHost, c.stream));
   }
-  if (all_dev && h->opt_async) return TGQ_OK;
+  if (h->opt_async) return TGQ_OK;          // the caller orders later work on the stream / calls tgq_synchronize before reading host outputs
   if (all_dev) CK(cudaStreamSynchronize(h->stream));
   else for (int s = 0; s < TGQ_SLOTS; ++s) CK(cudaStreamSynchronize(h->slot[s].stream));
   for (size_t i = 0; i + 2 < evs.size() + 0 && i < evs.size(); i += 3)
@@ -518,7 +551,7 @@ int tgq_create(int device, tgq_handle ** out)
   for (int s = 0; s < TGQ_SLOTS; ++s)
   {
     if ((e = cudaStreamCreateWithFlags(&h->slot[s].stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-    if ((e = h->slot[s].counter.reserve(sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = h->slot[s].counter.reserve(4 * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
   }
   if ((e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return bail("cudaDeviceGetAttribute", e);
   if (prev >= 0) cudaSetDevice(prev);
@@ -555,6 +588,15 @@ int tgq_set_stream(tgq_handle * h, void * cuda_stream)
 {
   if (!h) return TGQ_EINVAL;
   h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return TGQ_OK;
+}
+
+int tgq_synchronize(tgq_handle * h)
+{
+  if (!h) return TGQ_EINVAL;
+  Guard g(h);
+  CK(cudaStreamSynchronize(h->stream));
+  for (int s = 0; s < TGQ_SLOTS; ++s) CK(cudaStreamSynchronize(h->slot[s].stream));
   return TGQ_OK;
 }
 
@@ -745,13 +787,14 @@ static int closest_common(tgq_handle * h, const float * q3, const float * qn3, c
       CKRC(persistent_grid(h, k_closest_wide, wsmem, c.n, cnt, c.stream, &grid));
       k_closest_wide<<<grid, TGQ_BLOCK, wsmem, c.stream>>>(v, h->pad, (float const *)c.din[0], c.perm, c.n, ub, gate, exclude_self, c.offset, cnt,
                                                           (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3]);
+      if (h->peers.n) return fail(h, TGQ_EINVAL, "record outputs are not available with TGQ_OPT_WIDE");
     }
     else if (tri && h->opt_pool && h->leaf_built <= 4)
     {
       size_t psmem = smem + (TGQ_BLOCK / 32) * sizeof(PoolWarp);
       CKRC(persistent_grid(h, k_closest_pool, psmem, c.n, cnt, c.stream, &grid));
       k_closest_pool<<<grid, TGQ_BLOCK, psmem, c.stream>>>(v, h->pad, (float const *)c.din[0], c.perm, c.n, ub, gate, exclude_self, c.offset, cnt,
-                                                          (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3]);
+                                                          (int *)c.dout[1], (float *)c.dout[2], (float *)c.dout[3], h->peers);
     }
     else if (tri)
     {
@@ -1036,17 +1079,52 @@ static int ray_common(tgq_handle * h, const float * o3, const float * d3, const 
     {
       CKRC(persistent_grid(h, k_ray<true>, smem, c.n, cnt, c.stream, &grid, TGQ_RAY_BLOCKS));
       k_ray<true><<<grid, TGQ_BLOCK, smem, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], (float const *)c.din[2], c.perm, c.n, cnt,
-                                                    (float *)c.dout[3], (int *)c.dout[4], (float *)c.dout[5], (uint8_t *)c.dout[6]);
+                                                    (float *)c.dout[3], (int *)c.dout[4], (float *)c.dout[5], (uint8_t *)c.dout[6], h->peers);
     }
     else
     {
       CKRC(persistent_grid(h, k_ray<false>, smem, c.n, cnt, c.stream, &grid, TGQ_RAY_BLOCKS));
       k_ray<false><<<grid, TGQ_BLOCK, smem, c.stream>>>(v, (float const *)c.din[0], (float const *)c.din[1], (float const *)c.din[2], c.perm, c.n, cnt,
-                                                     (float *)c.dout[3], (int *)c.dout[4], (float *)c.dout[5], (uint8_t *)c.dout[6]);
+                                                     (float *)c.dout[3], (int *)c.dout[4], (float *)c.dout[5], (uint8_t *)c.dout[6], h->peers);
     }
     h->st.last_launches += 1; h->st.total_launches += 1;
     return TGQ_OK;
   });
+}
+
+// Common argument checks and handle state of the *_records entry points.
+static int records_begin(tgq_handle * h, void const * in0, int32_t shard_rank, int32_t shard_world, void * const * dest, int32_t n_dest)
+{
+  if (!h) return TGQ_EINVAL;
+  if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return fail(h, TGQ_EINVAL, "record query: bad shard rank / world");
+  if (n_dest < 1 || n_dest > 8 || !dest) return fail(h, TGQ_EINVAL, "record query: 1..8 destination arrays");
+  if (in0 && !is_device_ptr(in0)) return fail(h, TGQ_EINVAL, "record query: inputs must be device pointers");
+  for (int j = 0; j < n_dest; ++j) if (!dest[j] || !is_device_ptr(dest[j])) return fail(h, TGQ_EINVAL, "record query: destinations must be device (or peer-mapped) pointers");
+  h->peers.n = n_dest; for (int j = 0; j < 8; ++j) h->peers.base[j] = j < n_dest ? dest[j] : nullptr;
+  h->shard_rank = shard_rank; h->shard_world = shard_world;
+  return TGQ_OK;
+}
+static void records_end(tgq_handle * h) { h->peers.n = 0; h->shard_rank = 0; h->shard_world = 1; }
+
+int tgq_closest_records(tgq_handle * h, const float * q3, int64_t Q, double dist_bound, int32_t shard_rank, int32_t shard_world, void * const * dest,
+                        int32_t n_dest)
+{
+  CKRC(records_begin(h, q3, shard_rank, shard_world, dest, n_dest));
+  int rc = (h->kind == TGQ_KIND_TRIANGLES && h->opt_pool && !h->opt_wide && h->leaf_built <= 4)
+             ? closest_common(h, q3, nullptr, nullptr, 0.0f, Q, dist_bound, 0, nullptr, nullptr, nullptr)
+             : fail(h, TGQ_ESTATE, "tgq_closest_records needs a triangle structure with the default (pooled) closest-point kernel");
+  records_end(h);
+  return rc;
+}
+
+int tgq_ray_first_records(tgq_handle * h, const float * o3, const float * d3, const float * tmax, int64_t R, int32_t shard_rank, int32_t shard_world,
+                          void * const * dest, int32_t n_dest)
+{
+  CKRC(records_begin(h, o3, shard_rank, shard_world, dest, n_dest));
+  int rc = (is_device_ptr(d3) && (!tmax || is_device_ptr(tmax))) ? ray_common(h, o3, d3, tmax, R, nullptr, nullptr, nullptr, nullptr, false)
+                                                                : fail(h, TGQ_EINVAL, "record query: inputs must be device pointers");
+  records_end(h);
+  return rc;
 }
 
 int tgq_ray_first(tgq_handle * h, const float * o3, const float * d3, const float * tmax, int64_t R, float * t, int32_t * idx, float * normal3)

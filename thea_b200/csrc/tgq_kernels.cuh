@@ -417,6 +417,47 @@ __global__ void k_query_codes(float const * __restrict__ q3, int n, SceneBox con
   keys[i] = morton30(ld3(q3, i), lo, inv); vals[i] = (uint32_t)i;
 }
 
+// ---- sharding a replicated batch by space (multi-GPU) --------------------------------------------------------------------------
+// Every rank holds the whole batch and takes the queries whose Morton cell (the top `cell_bits` bits of the 30-bit code) it owns:
+// cells are dealt round-robin, cell % world == rank, so a rank's share is spread over the whole scene in fine cells (cost balances
+// statistically) while the queries inside a cell stay as dense as in the full batch -- a contiguous index range of a random batch
+// would be `world` times sparser, and neighbouring queries of the Morton-ordered launch would share fewer nodes.  One pass over the
+// batch: own (code, index) pairs are appended in arbitrary order (warp-aggregated atomic), then only they are sorted.
+__global__ void k_query_codes_shard(float const * __restrict__ q3, int n, SceneBox const * sb, int rank, int world, int shift, uint32_t * keys,
+                                    uint32_t * vals, int * count)
+{
+  SceneF s = scene_decode(sb);
+  v3 c = mul3(add3(s.lo, s.hi), 0.5f), e = sub3(s.hi, s.lo);
+  v3 lo = sub3(c, e);
+  v3 inv = mk3(e.x > 0 ? 0.5f / e.x : 0.0f, e.y > 0 ? 0.5f / e.y : 0.0f, e.z > 0 ? 0.5f / e.z : 0.0f);
+  int const lane = threadIdx.x & 31;
+  for (int64_t base = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) - lane; base < n; base += (int64_t)gridDim.x * blockDim.x)
+  {
+    int64_t i = base + lane;
+    uint32_t code = 0; bool own = false;
+    if (i < n) { code = morton30(ld3(q3, i), lo, inv); own = (int)((code >> shift) % (uint32_t)world) == rank; }
+    unsigned m = __ballot_sync(0xffffffffu, own);
+    if (m == 0u) continue;
+    int pos = 0;
+    if (lane == __ffs((int)m) - 1) pos = atomicAdd(count, __popc(m));
+    pos = __shfl_sync(0xffffffffu, pos, __ffs((int)m) - 1) + __popc(m & ((1u << lane) - 1u));
+    if (own) { keys[pos] = code; vals[pos] = (uint32_t)i; }
+  }
+}
+
+// Result records of the *_records entry points: one aligned vector store per result and destination, so that a rank can write its
+// results straight into every peer's copy of the gathered array over NVLink (fire-and-forget stores under the traversal).
+//   closest: 32 bytes  (element index, squared distance or -1, closest point xyz, 3 words of padding)
+//   ray:      8 bytes  (hit time or -1, element index or -1)
+struct PeerOut { void * base[8]; int n; };        // n == 0: the ordinary per-field outputs are used
+__device__ __forceinline__ void st_rec32(void * base, int64_t i, float4 a, float4 b)
+{
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"((char *)base + 32 * i), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y),
+               "f"(b.z), "f"(b.w) : "memory");
+}
+__device__ __forceinline__ void st_rec8(void * base, int64_t i, float a, float b)
+{ asm volatile("st.global.v2.f32 [%0], {%1,%2};" :: "l"((char *)base + 8 * i), "f"(a), "f"(b) : "memory"); }
+
 // ---- persistent warp scheduler -------------------------------------------------------------------------------------------
 // Query costs are heavy tailed and lanes follow different paths, so a thread-per-query kernel leaves most lanes of a warp
 // idle (ncu: 1.2 - 10 active threads per instruction on the bench workload).  Instead every warp drives 32 resumable
@@ -589,7 +630,7 @@ __device__ __forceinline__ unsigned long long pool_key(float d2, int idx)
 
 __global__ void __launch_bounds__(TGQ_BLOCK)
 k_closest_pool(BvhView b, float scene_pad, float const * __restrict__ q3, uint32_t const * __restrict__ perm, int n, float bound_ub, BoundGate gate,
-               int exclude_self, int64_t self_offset, int * counter, int * idx_out, float * d2_out, float * cp3)
+               int exclude_self, int64_t self_offset, int * counter, int * idx_out, float * d2_out, float * cp3, PeerOut peers)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned const FULL = 0xffffffffu;
@@ -606,6 +647,11 @@ k_closest_pool(BvhView b, float scene_pad, float const * __restrict__ q3, uint32
     // ---- finished queries write their results; idle lanes take the next queries of the warp's chunk -----------------------------
     if (s.t.cur == TGQ_ST_DONE && pending == 0)
     {
+      if (peers.n)
+      {
+        float4 ra = make_float4(__int_as_float(s.best_idx), s.best_idx >= 0 ? s.best_d2 : -1.0f, s.best_cp.x, s.best_cp.y), rb = make_float4(s.best_cp.z, 0.0f, 0.0f, 0.0f);
+        for (int j = 0; j < peers.n; ++j) st_rec32(peers.base[j], qi, ra, rb);
+      }
       if (idx_out) idx_out[qi] = s.best_idx;
       if (d2_out) d2_out[qi] = s.best_idx >= 0 ? s.best_d2 : -1.0f;
       if (cp3) st3(cp3, qi, s.best_cp);
@@ -1262,7 +1308,7 @@ struct RayW
 {
   static constexpr int STAGE = 2;       // (origin, query index) (direction, max time)
   RayState<ANY> s; BvhView b; float const * o3; float const * d3; float const * tmax; uint32_t const * perm;
-  float * t_out; int * idx; float * normal3; uint8_t * hit; int qi;
+  float * t_out; int * idx; float * normal3; uint8_t * hit; int qi; PeerOut peers;
   __device__ __forceinline__ int state() const { return s.t.cur; }
   __device__ __forceinline__ void stage(int t, f4 * dst) const
   {
@@ -1282,6 +1328,7 @@ struct RayW
   __device__ __forceinline__ void leaf_compute(f4 const * r) { ray_leaf_compute(s, b, r); }
   __device__ __forceinline__ void finish()
   {
+    for (int j = 0; j < peers.n; ++j) st_rec8(peers.base[j], qi, s.best_idx >= 0 ? s.best_t : -1.0f, __int_as_float(s.best_idx));
     if (t_out) t_out[qi] = s.best_idx >= 0 ? s.best_t : -1.0f;
     if (idx) idx[qi] = s.best_idx;
     if (hit) hit[qi] = s.best_idx >= 0 ? 1 : 0;
@@ -1298,11 +1345,11 @@ struct RayW
 template <bool ANY>
 __global__ void __launch_bounds__(TGQ_BLOCK)
 k_ray(BvhView b, float const * __restrict__ o3, float const * __restrict__ d3, float const * __restrict__ tmax,
-      uint32_t const * __restrict__ perm, int n, int * counter, float * t_out, int * idx, float * normal3, uint8_t * hit)
+      uint32_t const * __restrict__ perm, int n, int * counter, float * t_out, int * idx, float * normal3, uint8_t * hit, PeerOut peers)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   RayW<ANY> w;
-  w.b = b; w.o3 = o3; w.d3 = d3; w.tmax = tmax; w.perm = perm; w.t_out = t_out; w.idx = idx; w.normal3 = normal3; w.hit = hit; w.qi = 0;
+  w.b = b; w.o3 = o3; w.d3 = d3; w.tmax = tmax; w.perm = perm; w.t_out = t_out; w.idx = idx; w.normal3 = normal3; w.hit = hit; w.qi = 0; w.peers = peers;
   w.s.t.cur = TGQ_ST_IDLE; TravStack st;
   f4 * stage = trav_setup(w.s.t, st, smem, RayW<ANY>::STAGE, nullptr);
   warp_run(w, n, counter, stage);

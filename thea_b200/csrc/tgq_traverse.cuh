@@ -416,7 +416,7 @@ TGQ_HD bool filtered_out(BvhView const & b, int k, ElemFilterD const & f)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // What BvhN::closestPair does with a non-negative distance bound (BvhN.hpp:1081-1114; established by running the reference's own
-// code, oracle/_ref, against the first version of this engine, which took the bound at face value):
+// code against the first version of this engine, which took the bound at face value):
 //   (1) the query is rejected outright when the reference's root box -- the union of all element AABBs, scaleCentered(1.05)
 //       (BvhN.hpp:1437-1439) -- is farther than the bound: fp32 AxisAlignedBoxN::squaredDistance, compared in double with
 //       dist_bound^2 (:1093-1098);

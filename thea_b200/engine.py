@@ -25,6 +25,7 @@ SYMBOLS = [
     "tgq_ray_first", "tgq_ray_any", "tgq_sdf", "tgq_icp_sums", "tgq_transform_points", "tgq_area_sample",
     "tgq_get_stats", "tgq_set_point_labels", "tgq_closest_filtered", "tgq_knn_filtered", "tgq_icp_align", "tgq_ball_range",
     "tgq_ball_stats", "tgq_visibility", "tgq_ball_graph_surface", "tgq_ball_histogram", "tgq_set_transform",
+    "tgq_closest_records", "tgq_ray_first_records", "tgq_synchronize",
 ]
 
 
@@ -94,6 +95,8 @@ def load_library(path=None):
     L.tgq_icp_align.argtypes = [vp, vp, i64, i32, i32, f64, i32, vp, vp, vp, vp]
     L.tgq_closest_filtered.argtypes = [vp, vp, vp, vp, i64, f32, f64, vp, vp, vp]
     L.tgq_knn_filtered.argtypes = [vp, vp, vp, vp, i64, i32, f32, f64, vp, vp]
+    L.tgq_closest_records.argtypes = [vp, vp, i64, f64, i32, i32, vp, i32]
+    L.tgq_ray_first_records.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, i32]
     for name in SYMBOLS:
         if name not in ("tgq_last_error",):
             getattr(L, name).restype = C.c_int
@@ -181,6 +184,9 @@ class Engine:
     # ---- configuration ----
     def set_option(self, opt, value):
         self._ck(self._L.tgq_set_option(self._h, opt, int(value)))
+
+    def synchronize(self):
+        self._ck(self._L.tgq_synchronize(self._h))
 
     def set_stream(self, cuda_stream_ptr):
         """Pins the handle to one CUDA stream (0 / None: back to following torch's current stream for CUDA tensors, the handle's
@@ -392,6 +398,27 @@ class Engine:
             t, idx, nrm = out
         self._ck(self._L.tgq_ray_first(self._h, _ptr(o3), _ptr(d3), _ptr(tmax), R, _ptr(t), _ptr(idx), _ptr(nrm)))
         return t, idx, nrm
+
+    # ---- record outputs / sharding of a replicated batch by space (multi-GPU form; device tensors only) ----
+    @staticmethod
+    def _dest_array(dest):
+        ptrs = [int(d.data_ptr()) if hasattr(d, "data_ptr") else int(d) for d in dest]
+        return (C.c_void_p * len(ptrs))(*ptrs), len(ptrs)
+
+    def closest_records(self, q3, dest, rank=0, world=1, dist_bound=-1.0):
+        """tgq_closest_records: q3 = the WHOLE batch (CUDA tensor); dest = the record arrays ([Q, 8] int32 / float32 views of 32-byte
+        records) of every rank that must receive this rank's results, own copy included (tensors or raw device pointers)."""
+        q3 = self._in(q3)
+        arr, n = self._dest_array(dest)
+        self._ck(self._L.tgq_closest_records(self._h, _ptr(q3), int(q3.shape[0]), float(dist_bound), int(rank), int(world), arr, n))
+
+    def ray_first_records(self, o3, d3, dest, rank=0, world=1, tmax=None):
+        """tgq_ray_first_records: 8-byte records (t, idx) at the ray's position in every destination array."""
+        o3 = self._in(o3)
+        d3 = self._in(d3)
+        tmax = self._in(tmax)
+        arr, n = self._dest_array(dest)
+        self._ck(self._L.tgq_ray_first_records(self._h, _ptr(o3), _ptr(d3), _ptr(tmax), int(o3.shape[0]), int(rank), int(world), arr, n))
 
     def ray_any(self, o3, d3, tmax=None):
         o3 = self._in(o3)
