@@ -273,8 +273,13 @@ def main():
     T = len(mesh)
     bounds = gen.mesh_bounds(mesh)
 
+    # everything below -- torch ops and the engine's kernels -- is ordered on ONE non-default stream
+    main_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(main_stream)
     eng = Engine(local_rank)
-    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    eng.set_stream(main_stream.cuda_stream)
+    if os.environ.get("TGQ_BENCH_CELL_BITS"):
+        eng.set_option(8, int(os.environ["TGQ_BENCH_CELL_BITS"]))
     d_mesh = torch.from_numpy(mesh).to(dev)
     eng.build_triangles(d_mesh)
     build_ms = eng.stats()["last_build_ms"]
@@ -283,11 +288,15 @@ def main():
     # ---- device-resident leg -------------------------------------------------------------------------------------------------------
     # Every rank holds the WHOLE batch (generated on the device from the counter-based streams) and, inside the timed step, takes the
     # queries whose Morton cell it owns (tgq_*_records: cells dealt round-robin, so its share keeps the density of the full batch -- a
-    # contiguous index range of a random batch is `world` times sparser after the Morton sort, which cost 24 % per rank at N = 8 in
-    # round 1).  The one real exchange of the path -- every rank ends a step holding the results of the WHOLE batch --
-    # is fused into the traversal kernels: finish() stores each result as one aligned record (32 B closest, 8 B ray) straight into
-    # EVERY rank's copy of the gathered arrays, which live in symmetric (peer-mapped) memory, over NVLink.  No NCCL kernel, no copy
-    # engine, nothing to overlap by hand.  Fallback when symmetric memory is unavailable: contiguous shards + NCCL all-gather.
+    # contiguous index range of a random batch is `world` times sparser after the Morton sort, which cost 22 % per rank at N = 8 in
+    # round 1).  The one real exchange of the path -- every rank ends a step holding the results of the WHOLE batch, in query order
+    #  -- goes like this: the traversal kernels write the rank's share as a dense array of records (32 B closest, 16 B
+    # ray, each carrying its query index); the array is pushed into every peer's receive slot with ONE contiguous peer-to-peer copy
+    # per peer (copy engines over NVLink, on a side stream, under the next kernel), a device-side barrier on the side stream tells
+    # everybody that all pushes have landed, and one scatter kernel per query kind puts the records of all ranks at [query index] of
+    # the local result arrays.  (Storing each result straight into every peer's copy from the traversal kernel was measured first:
+    # small scattered peer stores cost the ray kernel 56 % and the closest kernel 14 % at N = 8.)
+    # Fallback when symmetric memory is unavailable: contiguous shards + NCCL all-gather.
     q_off, nq = shard(nq_total, rank, world)
     r_off, nr = shard(nr_total, rank, world)
     dq = torch.empty((nq_total, 3), dtype=torch.float32, device=dev)
@@ -299,70 +308,106 @@ def main():
         o, d = torch_random_rays(n, bounds, gen.SEED_RAYS, b, dev)
         dro[b:b + n] = o
         drd[b:b + n] = d
-    kern = {"closest_ms": 0.0, "closest_q": 0, "ray_ms": 0.0, "ray_q": 0, "sort_ms": 0.0, "launches": 0}
+    kern = {"closest_ms": 0.0, "closest_q": 0, "ray_ms": 0.0, "ray_q": 0, "sort_ms": 0.0, "launches": 0, "scatter_ms": 0.0}
 
-    crec = rrec = None
-    c_dest, r_dest = [], []
-    transport = "none"
+    crec = torch.zeros((max(1, nq_total), 8), dtype=torch.float32, device=dev)     # gathered results, query order: 32-byte records
+    rrec = torch.zeros((max(1, nr_total), 2), dtype=torch.float32, device=dev)     # 8-byte records
+    transport, sym = "none", None
+    cap_c = int(nq_total / world * 1.25) + 4096
+    cap_r = int(nr_total / world * 1.25) + 4096
     if world > 1 and os.environ.get("TGQ_BENCH_TRANSPORT", "p2p") == "p2p":
         try:
             import torch.distributed._symmetric_memory as symm_mem
-            bufs = []
-            for numel in (max(8, nq_total * 8), max(2, nr_total * 2)):
+            sym = {}
+            for name, words in (("c", cap_c * 8), ("r", cap_r * 4)):
+                numel = 2 * world * words + 2 * world * 2               # [parity][source rank][cap records] + int64 counts [parity][source rank]
                 t = symm_mem.empty(numel, dtype=torch.float32, device=dev)
                 hdl = symm_mem.rendezvous(t, dist.group.WORLD)
-                bufs.append((t, [hdl.get_buffer(r, (numel,), torch.float32) for r in range(world)]))
-            crec, c_peers = bufs[0][0][:nq_total * 8].view(nq_total, 8), bufs[0][1]
-            rrec, r_peers = bufs[1][0][:nr_total * 2].view(nr_total, 2), bufs[1][1]
-            # own copy first, then the peers starting after this rank (spreads the NVLink traffic of a step over the links)
-            order = [(rank + k) % world for k in range(world)]
-            c_dest = [c_peers[r] for r in order]
-            r_dest = [r_peers[r] for r in order]
-            transport = "kernel stores into every rank's symmetric-memory copy (NVLink P2P)"
+                views = []
+                for r in range(world):
+                    buf = hdl.get_buffer(r, (numel,), torch.float32)
+                    data = buf[:2 * world * words].view(2, world, words)
+                    cnt = buf[2 * world * words:].view(torch.int64).view(2, world)
+                    views.append((data, cnt))
+                sym[name] = {"hdl": hdl, "views": views, "words": words, "mine": torch.zeros(2, dtype=torch.int64, device=dev)}
+                t.zero_()
+            comm_stream = torch.cuda.Stream(device=dev)
+            transport = "dense per-rank record arrays pushed by copy engines into symmetric memory (NVLink P2P) + local scatter"
         except Exception as exc:      # noqa: BLE001 -- any failure here means: use NCCL
             if rank == 0:
                 print(f"bench.py: symmetric memory unavailable ({type(exc).__name__}: {exc}); using contiguous shards + NCCL all-gather", file=sys.stderr)
-            crec = None
-    space_sharded = world == 1 or crec is not None
-    if crec is None:
-        crec = torch.empty((nq_total, 8), dtype=torch.float32, device=dev)
-        rrec = torch.empty((nr_total, 2), dtype=torch.float32, device=dev)
-        c_dest, r_dest = [crec], [rrec]
-        if world > 1:
-            transport = "NCCL all-gather of contiguous shards"
-    crec.zero_()
-    rrec.zero_()
-
+            sym = None
+    space_sharded = world == 1 or sym is not None
+    if world > 1 and sym is None:
+        transport = "NCCL all-gather of contiguous shards"
+    eng.set_option(3, 1)              # TGQ_OPT_ASYNC: calls are ordered on the stream; the step is timed with CUDA events
+    timers = {"c": [], "r": [], "s": []}
     pending = []
+    step_no = [0]
+
+    def timed(kind, fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        timers[kind].append((a, b))
+        return out
+
+    def push(name, n_own, par):
+        # this rank's dense share -> slot [par][rank] of every peer, counts alongside; then everybody waits for everybody's pushes
+        S = sym[name]
+        data, cnt = S["views"][rank]
+        S["mine"][par] = n_own
+        cur = torch.cuda.current_stream()
+        comm_stream.wait_stream(cur)
+        with torch.cuda.stream(comm_stream):
+            words = n_own * (8 if name == "c" else 4)
+            cnt[par, rank].copy_(S["mine"][par], non_blocking=True)
+            for k in range(1, world):
+                pdata, pcnt = S["views"][(rank + k) % world]
+                pdata[par, rank, :words].copy_(data[par, rank, :words], non_blocking=True)
+                pcnt[par, rank].copy_(S["mine"][par], non_blocking=True)
+            S["hdl"].barrier(channel=par)
+            ev = torch.cuda.Event()
+            ev.record(comm_stream)
+        return ev
 
     def step_device(record: bool):
-        # one C-ABI call per query kind over the whole batch; the library selects this rank's share and writes the records
+        par = step_no[0] & 1
+        step_no[0] += 1
+        if world > 1 and space_sharded:
+            evc = evr = None
+            if nq_total:
+                n_c = timed("c", lambda: eng.closest_records(dq, [sym["c"]["views"][rank][0][par, rank]], rank, world, compact=True))
+                assert n_c <= cap_c, "closest share exceeds the receive slot"
+                evc = push("c", n_c, par)
+            if nr_total:
+                n_r = timed("r", lambda: eng.ray_first_records(dro, drd, [sym["r"]["views"][rank][0][par, rank]], rank, world, compact=True))
+                assert n_r <= cap_r, "ray share exceeds the receive slot"
+                evr = push("r", n_r, par)
+            cur = torch.cuda.current_stream()
+            if evc is not None:
+                cur.wait_event(evc)
+                data, cnt = sym["c"]["views"][rank]
+                timed("s", lambda: eng.scatter_records(data[par], world, cap_c, cnt[par], 0, crec))
+            if evr is not None:
+                cur.wait_event(evr)
+                data, cnt = sym["r"]["views"][rank]
+                timed("s", lambda: eng.scatter_records(data[par], world, cap_r, cnt[par], 1, rrec))
+            return
+        # one GPU (or the NCCL fallback): records straight to [query index]
         if nq_total:
             if space_sharded:
-                eng.closest_records(dq, c_dest, rank, world)
+                timed("c", lambda: eng.closest_records(dq, [crec], 0, 1))
             else:
-                eng.closest_records(dq[q_off:q_off + nq], [crec[q_off:q_off + nq]])
+                timed("c", lambda: eng.closest_records(dq[q_off:q_off + nq], [crec[q_off:q_off + nq]]))
                 pending.append(dist.all_gather_into_tensor(crec.view(-1), crec[q_off:q_off + nq].reshape(-1), async_op=True))
-            if record:
-                s = eng.stats()
-                kern["closest_ms"] += s["last_query_ms"] - s["last_sort_ms"]
-                kern["sort_ms"] += s["last_sort_ms"]
-                kern["closest_q"] += nq_total / world
-                kern["closest_launches"] = kern.get("closest_launches", 0) + 1
-                kern["launches"] += s["last_launches"]
         if nr_total:
             if space_sharded:
-                eng.ray_first_records(dro, drd, r_dest, rank, world)
+                timed("r", lambda: eng.ray_first_records(dro, drd, [rrec], 0, 1))
             else:
-                eng.ray_first_records(dro[r_off:r_off + nr], drd[r_off:r_off + nr], [rrec[r_off:r_off + nr]])
+                timed("r", lambda: eng.ray_first_records(dro[r_off:r_off + nr], drd[r_off:r_off + nr], [rrec[r_off:r_off + nr]]))
                 pending.append(dist.all_gather_into_tensor(rrec.view(-1), rrec[r_off:r_off + nr].reshape(-1), async_op=True))
-            if record:
-                s = eng.stats()
-                kern["ray_ms"] += s["last_query_ms"] - s["last_sort_ms"]
-                kern["sort_ms"] += s["last_sort_ms"]
-                kern["ray_q"] += nr_total / world
-                kern["ray_launches"] = kern.get("ray_launches", 0) + 1
-                kern["launches"] += s["last_launches"]
         while pending:
             pending.pop().wait()
 
@@ -373,6 +418,10 @@ def main():
 
     for _ in range(args.warmup):
         step_device(False)
+    barrier()
+    for k in timers:
+        timers[k].clear()
+    launches0 = eng.stats()["total_launches"]
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -381,8 +430,8 @@ def main():
     e0.record()
     for _ in range(args.steps):
         step_device(True)
-    e1.record()                              # this rank's kernels, including their stores into the peers' copies, are complete
-    barrier()                                # ... and so are everybody else's into this rank's copy
+    e1.record()                              # this rank holds the results of the whole batch of the last step
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -390,6 +439,14 @@ def main():
     dev_ms = float(ms.item())
     total_queries = nq_total + nr_total
     value = total_queries * args.steps / (dev_ms / 1e3)
+    # per-call device times (select + sort + traversal kernel of the rank's share; scatter kernels)
+    kern["closest_ms"] = sum(a.elapsed_time(b) for a, b in timers["c"])
+    kern["ray_ms"] = sum(a.elapsed_time(b) for a, b in timers["r"])
+    kern["scatter_ms"] = sum(a.elapsed_time(b) for a, b in timers["s"])
+    kern["closest_q"], kern["ray_q"] = nq_total / world * len(timers["c"]), nr_total / world * len(timers["r"])
+    kern["closest_launches"], kern["ray_launches"] = max(1, len(timers["c"])), max(1, len(timers["r"]))
+    kern["launches"] = int(eng.stats()["total_launches"] - launches0)
+    eng.set_option(3, 0)
 
     # checksum of the gathered results on THIS rank's copy (every rank holds all of them), so that the timed work cannot be optimised
     # away and runs at different N can be compared; all ranks must agree
@@ -513,7 +570,8 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": kern["launches"], "clocks": clocks,
         "breakdown": {"closest_Mqps_kernel": kern["closest_q"] / kern["closest_ms"] / 1e3 if kern["closest_ms"] else None,
                       "ray_Mqps_kernel": kern["ray_q"] / kern["ray_ms"] / 1e3 if kern["ray_ms"] else None,
-                      "sort_ms_per_step": kern["sort_ms"] / args.steps, "checksum": checksum},
+                      "per_call": "device time of one C-ABI call on this rank's share: query selection + Morton sort + traversal kernel",
+                      "scatter_ms_per_step": kern["scatter_ms"] / args.steps, "checksum": checksum},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -60,6 +60,7 @@ enum
   TGQ_OPT_POOL = 5,           /* closest point on triangle structures: 1 = leaf tests pooled across the warp (default), 0 = per lane */
   TGQ_OPT_WIDE = 7,           /* closest point on triangle structures: 1 = four lanes per query on 4-wide nodes (set BEFORE the build; measured
                                  1.5x slower than the default: profiles/r02_b_closest_wide_vs_pool_ncu.txt), 0 = binary nodes (default) */
+  TGQ_OPT_SHARD_CELL_BITS = 8,   /* *_records with shard_world > 1: the batch is dealt to the ranks in 2^bits Morton cells (default 15) */
   TGQ_OPT_ICP_REFERENCE_ORDER = 6   /* 1 (default): tgq_icp_sums / tgq_icp_align accumulate in the reference's own order -- sequential fp32, the
                                        loops of Icp3.hpp:306-367,418-463 -- so iterates, per-iteration correspondences and the final transform
                                        equal the reference's bit for bit; 0: order-independent fixed-point (exact) sums, 20x faster per call, but
@@ -217,11 +218,20 @@ int tgq_avg_separation(tgq_handle * h, const int32_t * seeds, int32_t n, float *
  *     closest: 32 bytes { int32 idx; float d2 (-1 = none); float cp[3]; int32 pad[3] }      ray: 8 bytes { float t (-1 = miss); int32 idx }
  * at position [query index] of EVERY destination array dest[0 .. n_dest) (n_dest <= 8): the rank's own copy and, peer-mapped, the
  * copies of the other ranks (e.g. torch symmetric memory), written straight over NVLink while the traversal runs.  shard_world = 1,
- * n_dest = 1 is the plain single-GPU call with record output.  Records of queries other ranks own are left untouched. */
+ * n_dest = 1 is the plain single-GPU call with record output.  Records of queries other ranks own are left untouched.
+ * Measured on 8 x B200: small scattered peer stores are expensive on both ends (7 peers: rays -56 %, closest -14 % per rank), so
+ * the bench uses the COMPACT form instead: compact != 0 (n_dest = 1) writes the rank's share as a dense array in the order the
+ * share was processed -- closest: the same 32-byte record with the query index in pad[0]; ray: 16 bytes { t, idx, query index, 0 }
+ * -- which moves to the other ranks as one contiguous block per peer (copy engines) and is put in place there by
+ * tgq_scatter_records.  *share (may be null) receives the number of queries this rank answered. */
 int tgq_closest_records(tgq_handle * h, const float * q3, int64_t Q, double dist_bound, int32_t shard_rank, int32_t shard_world,
-                        void * const * dest, int32_t n_dest);
+                        void * const * dest, int32_t n_dest, int32_t compact, int64_t * share);
 int tgq_ray_first_records(tgq_handle * h, const float * o3, const float * d3, const float * tmax, int64_t R, int32_t shard_rank,
-                          int32_t shard_world, void * const * dest, int32_t n_dest);
+                          int32_t shard_world, void * const * dest, int32_t n_dest, int32_t compact, int64_t * share);
+/* Compact records -> dest[query index] in the non-compact record layout.  compact: `slots` dense arrays of up to `cap` records each
+ * (slot j starts at record j * cap; kind 0: closest, 32 bytes; kind 1: ray, 16 bytes), counts[slots] (int64, DEVICE memory: they
+ * travel with the data) of them valid.  Runs on the handle's stream; returns without waiting when TGQ_OPT_ASYNC is set. */
+int tgq_scatter_records(tgq_handle * h, const void * compact, int32_t slots, int64_t cap, const int64_t * counts, int32_t kind, void * dest);
 
 int tgq_ray_first(tgq_handle * h, const float * o3, const float * d3, const float * tmax, int64_t R,
                   float * t, int32_t * idx, float * normal3);

@@ -41,7 +41,7 @@ struct DevBuf
 };
 
 #define TGQ_MAX_ARGS 8
-#define TGQ_SHARD_CELL_BITS 18       // 2^18 Morton cells over the scene box grown x2, dealt round-robin to the ranks
+#define TGQ_SHARD_CELL_BITS 15       // default of TGQ_OPT_SHARD_CELL_BITS: 2^15 Morton cells over the scene box grown x2, dealt round-robin to the ranks
 #ifndef TGQ_SLOTS
 // Ray kernels: resident blocks per SM (the rest of the shared-memory array becomes L1).  Measured on B200, 8 M rays on the 10 M-triangle
 // mesh: 7 blocks with the maximum carve-out 1.75 G rays/s, 6 blocks 2.27 G, 5 blocks 2.11 G (1 M triangles: 2.24 / 2.73 / 2.53 G).
@@ -77,8 +77,9 @@ struct tgq_handle
   DevBuf area_by_elem, cum;                                           // float[n] in element order; double[n] cumulative
   DevBuf obbs, pnrm, nsum, obbinfo, big, big_count;                   // oriented boxes (triangle structures)
   DevBuf wide, wflag, widx, obbinfo_w; int n_wide = 0;                 // 4-wide nodes of the closest-point traversal
+  int opt_cell_bits = TGQ_SHARD_CELL_BITS;
   int shard_rank = 0, shard_world = 1;                                 // set by the *_records entry points for the duration of one call
-  PeerOut peers = {};
+  PeerOut peers = {}; int64_t last_share = 0;                          // queries this rank answered in the last *_records call
   int sm_count = 148; std::map<std::pair<void const *, size_t>, int> occupancy;   // resident blocks per SM of the persistent kernels
   bool cum_valid = false;
   bool orig_valid = false; DevBuf orig, orig_n, orig_lab, xf;           // untransformed source elements (tgq_set_transform)
@@ -369,13 +370,13 @@ int sort_chunk(tgq_handle * h, ChunkCtx & c)
     int * cnt = sl.counter.as<int>() + 1;
     CK(cudaMemsetAsync(cnt, 0, 4, c.stream));
     int grid = (int)std::min<int64_t>((c.n + 255) / 256, (int64_t)h->sm_count * 16);
-    k_query_codes_shard<<<grid, 256, 0, c.stream>>>((float const *)c.din[0], c.n, h->scene.as<SceneBox>(), h->shard_rank, h->shard_world, 30 - TGQ_SHARD_CELL_BITS,
+    k_query_codes_shard<<<grid, 256, 0, c.stream>>>((float const *)c.din[0], c.n, h->scene.as<SceneBox>(), h->shard_rank, h->shard_world, 30 - h->opt_cell_bits,
                                                     sl.keys[0].as<uint32_t>(), sl.vals[0].as<uint32_t>(), cnt);
     CK(cudaGetLastError());
     int own = 0;
     CK(cudaMemcpyAsync(&own, cnt, 4, cudaMemcpyDeviceToHost, c.stream));
     CK(cudaStreamSynchronize(c.stream));
-    c.n = own;
+    c.n = own; h->last_share += own;
     h->st.last_launches += 1; h->st.total_launches += 1;
     if (own > 0)
     {
@@ -611,6 +612,7 @@ int tgq_set_option(tgq_handle * h, int option, int64_t value)
     case TGQ_OPT_POOL: h->opt_pool = value ? 1 : 0; return TGQ_OK;
     case TGQ_OPT_ICP_REFERENCE_ORDER: h->opt_icp_ref = value ? 1 : 0; return TGQ_OK;
     case TGQ_OPT_WIDE: h->opt_wide = value ? 1 : 0; return TGQ_OK;
+    case TGQ_OPT_SHARD_CELL_BITS: if (value < 3 || value > 30) return fail(h, TGQ_EINVAL, "TGQ_OPT_SHARD_CELL_BITS takes 3..30"); h->opt_cell_bits = (int)value; return TGQ_OK;
     case TGQ_OPT_CHUNK: if (value < 1024) return fail(h, TGQ_EINVAL, "TGQ_OPT_CHUNK must be >= 1024"); h->opt_chunk = value; return TGQ_OK;
     default: return fail(h, TGQ_EINVAL, "unknown option");
   }
@@ -1093,38 +1095,58 @@ static int ray_common(tgq_handle * h, const float * o3, const float * d3, const 
 }
 
 // Common argument checks and handle state of the *_records entry points.
-static int records_begin(tgq_handle * h, void const * in0, int32_t shard_rank, int32_t shard_world, void * const * dest, int32_t n_dest)
+static int records_begin(tgq_handle * h, void const * in0, int32_t shard_rank, int32_t shard_world, void * const * dest, int32_t n_dest, int32_t compact)
 {
   if (!h) return TGQ_EINVAL;
+  if (compact && n_dest != 1) return fail(h, TGQ_EINVAL, "record query: the compact form takes one destination");
   if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return fail(h, TGQ_EINVAL, "record query: bad shard rank / world");
   if (n_dest < 1 || n_dest > 8 || !dest) return fail(h, TGQ_EINVAL, "record query: 1..8 destination arrays");
   if (in0 && !is_device_ptr(in0)) return fail(h, TGQ_EINVAL, "record query: inputs must be device pointers");
   for (int j = 0; j < n_dest; ++j) if (!dest[j] || !is_device_ptr(dest[j])) return fail(h, TGQ_EINVAL, "record query: destinations must be device (or peer-mapped) pointers");
-  h->peers.n = n_dest; for (int j = 0; j < 8; ++j) h->peers.base[j] = j < n_dest ? dest[j] : nullptr;
-  h->shard_rank = shard_rank; h->shard_world = shard_world;
+  h->peers.n = n_dest; h->peers.compact = compact ? 1 : 0; for (int j = 0; j < 8; ++j) h->peers.base[j] = j < n_dest ? dest[j] : nullptr;
+  h->shard_rank = shard_rank; h->shard_world = shard_world; h->last_share = 0;
   return TGQ_OK;
 }
-static void records_end(tgq_handle * h) { h->peers.n = 0; h->shard_rank = 0; h->shard_world = 1; }
+static void records_end(tgq_handle * h, int64_t Q, int64_t * share)
+{
+  if (share) *share = h->shard_world > 1 ? h->last_share : Q;
+  h->peers.n = 0; h->peers.compact = 0; h->shard_rank = 0; h->shard_world = 1;
+}
 
 int tgq_closest_records(tgq_handle * h, const float * q3, int64_t Q, double dist_bound, int32_t shard_rank, int32_t shard_world, void * const * dest,
-                        int32_t n_dest)
+                        int32_t n_dest, int32_t compact, int64_t * share)
 {
-  CKRC(records_begin(h, q3, shard_rank, shard_world, dest, n_dest));
+  CKRC(records_begin(h, q3, shard_rank, shard_world, dest, n_dest, compact));
   int rc = (h->kind == TGQ_KIND_TRIANGLES && h->opt_pool && !h->opt_wide && h->leaf_built <= 4)
              ? closest_common(h, q3, nullptr, nullptr, 0.0f, Q, dist_bound, 0, nullptr, nullptr, nullptr)
              : fail(h, TGQ_ESTATE, "tgq_closest_records needs a triangle structure with the default (pooled) closest-point kernel");
-  records_end(h);
+  records_end(h, Q, share);
   return rc;
 }
 
 int tgq_ray_first_records(tgq_handle * h, const float * o3, const float * d3, const float * tmax, int64_t R, int32_t shard_rank, int32_t shard_world,
-                          void * const * dest, int32_t n_dest)
+                          void * const * dest, int32_t n_dest, int32_t compact, int64_t * share)
 {
-  CKRC(records_begin(h, o3, shard_rank, shard_world, dest, n_dest));
+  CKRC(records_begin(h, o3, shard_rank, shard_world, dest, n_dest, compact));
   int rc = (is_device_ptr(d3) && (!tmax || is_device_ptr(tmax))) ? ray_common(h, o3, d3, tmax, R, nullptr, nullptr, nullptr, nullptr, false)
                                                                 : fail(h, TGQ_EINVAL, "record query: inputs must be device pointers");
-  records_end(h);
+  records_end(h, R, share);
   return rc;
+}
+
+int tgq_scatter_records(tgq_handle * h, const void * compact, int32_t slots, int64_t cap, const int64_t * counts, int32_t kind, void * dest)
+{
+  if (!h) return TGQ_EINVAL;
+  if (slots < 1 || cap < 0 || kind < 0 || kind > 1 || !compact || !dest || !counts) return fail(h, TGQ_EINVAL, "tgq_scatter_records: bad arguments");
+  if (!is_device_ptr(compact) || !is_device_ptr(dest) || !is_device_ptr(counts)) return fail(h, TGQ_EINVAL, "tgq_scatter_records: device pointers only");
+  if (cap == 0) return TGQ_OK;
+  Guard g(h);
+  int grid = (int)std::min<int64_t>((cap + 255) / 256, (int64_t)h->sm_count * 32);
+  k_scatter_records<<<grid, 256, 0, h->stream>>>(compact, slots, cap, (long long const *)counts, kind, dest);
+  CK(cudaGetLastError());
+  h->st.total_launches += 1;
+  if (!h->opt_async) CK(cudaStreamSynchronize(h->stream));
+  return TGQ_OK;
 }
 
 int tgq_ray_first(tgq_handle * h, const float * o3, const float * d3, const float * tmax, int64_t R, float * t, int32_t * idx, float * normal3)

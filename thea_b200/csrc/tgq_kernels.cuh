@@ -423,25 +423,33 @@ __global__ void k_query_codes(float const * __restrict__ q3, int n, SceneBox con
 // statistically) while the queries inside a cell stay as dense as in the full batch -- a contiguous index range of a random batch
 // would be `world` times sparser, and neighbouring queries of the Morton-ordered launch would share fewer nodes.  One pass over the
 // batch: own (code, index) pairs are appended in arbitrary order (warp-aggregated atomic), then only they are sorted.
-__global__ void k_query_codes_shard(float const * __restrict__ q3, int n, SceneBox const * sb, int rank, int world, int shift, uint32_t * keys,
-                                    uint32_t * vals, int * count)
+__global__ void __launch_bounds__(256)
+k_query_codes_shard(float const * __restrict__ q3, int n, SceneBox const * sb, int rank, int world, int shift, uint32_t * keys, uint32_t * vals, int * count)
 {
   SceneF s = scene_decode(sb);
   v3 c = mul3(add3(s.lo, s.hi), 0.5f), e = sub3(s.hi, s.lo);
   v3 lo = sub3(c, e);
   v3 inv = mk3(e.x > 0 ? 0.5f / e.x : 0.0f, e.y > 0 ? 0.5f / e.y : 0.0f, e.z > 0 ? 0.5f / e.z : 0.0f);
-  int const lane = threadIdx.x & 31;
-  for (int64_t base = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) - lane; base < n; base += (int64_t)gridDim.x * blockDim.x)
+  int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ int s_warp[8], s_base;
+  // one global atomic per block and tile of 256 queries (per-warp atomics on a single address serialise: 1.5 M of them cost 4 ms)
+  for (int64_t tile = blockIdx.x * (int64_t)256; tile < n; tile += (int64_t)gridDim.x * 256)
   {
-    int64_t i = base + lane;
+    int64_t i = tile + threadIdx.x;
     uint32_t code = 0; bool own = false;
     if (i < n) { code = morton30(ld3(q3, i), lo, inv); own = (int)((code >> shift) % (uint32_t)world) == rank; }
     unsigned m = __ballot_sync(0xffffffffu, own);
-    if (m == 0u) continue;
-    int pos = 0;
-    if (lane == __ffs((int)m) - 1) pos = atomicAdd(count, __popc(m));
-    pos = __shfl_sync(0xffffffffu, pos, __ffs((int)m) - 1) + __popc(m & ((1u << lane) - 1u));
-    if (own) { keys[pos] = code; vals[pos] = (uint32_t)i; }
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      int tot = 0;
+      for (int w = 0; w < 8; ++w) { int t = s_warp[w]; s_warp[w] = tot; tot += t; }
+      s_base = tot ? atomicAdd(count, tot) : 0;
+    }
+    __syncthreads();
+    if (own) { int pos = s_base + s_warp[warp] + __popc(m & ((1u << lane) - 1u)); keys[pos] = code; vals[pos] = (uint32_t)i; }
+    __syncthreads();
   }
 }
 
@@ -449,7 +457,10 @@ __global__ void k_query_codes_shard(float const * __restrict__ q3, int n, SceneB
 // results straight into every peer's copy of the gathered array over NVLink (fire-and-forget stores under the traversal).
 //   closest: 32 bytes  (element index, squared distance or -1, closest point xyz, 3 words of padding)
 //   ray:      8 bytes  (hit time or -1, element index or -1)
-struct PeerOut { void * base[8]; int n; };        // n == 0: the ordinary per-field outputs are used
+//   compact form (one destination): the record goes to position [rank of the query in this rank's Morton-ordered share] instead, and
+//   carries the query index -- closest: word 5 of the 32 bytes; ray: 16 bytes { t, idx, query index, 0 } -- so that the share can be
+//   moved to the other ranks as ONE contiguous block (copy engines) and scattered to [query index] there (k_scatter_records).
+struct PeerOut { void * base[8]; int n; int compact; };        // n == 0: the ordinary per-field outputs are used
 __device__ __forceinline__ void st_rec32(void * base, int64_t i, float4 a, float4 b)
 {
   asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"((char *)base + 32 * i), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y),
@@ -457,6 +468,31 @@ __device__ __forceinline__ void st_rec32(void * base, int64_t i, float4 a, float
 }
 __device__ __forceinline__ void st_rec8(void * base, int64_t i, float a, float b)
 { asm volatile("st.global.v2.f32 [%0], {%1,%2};" :: "l"((char *)base + 8 * i), "f"(a), "f"(b) : "memory"); }
+
+// Compact records of the ranks' shares -> [query index] of the gathered array.  `slots` dense arrays of up to `cap` records each
+// (slot j at src + j * cap records), counts[j] of them valid (device memory: the counts arrive with the data).  kind 0: 32-byte
+// closest records (query index in word 5), kind 1: 16-byte ray records { t, idx, query index, - } -> 8-byte records.
+__global__ void k_scatter_records(void const * __restrict__ src, int slots, int64_t cap, long long const * __restrict__ counts, int kind, void * dst)
+{
+  for (int j = 0; j < slots; ++j)
+  {
+    int64_t n = counts[j]; if (n > cap) n = cap;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    {
+      if (kind == 0)
+      {
+        float4 const * p = (float4 const *)src + 2 * (j * cap + i);
+        float4 a = __ldg(p), b = __ldg(p + 1);
+        st_rec32(dst, __float_as_int(b.y), a, b);
+      }
+      else
+      {
+        float4 a = __ldg((float4 const *)src + (j * cap + i));
+        st_rec8(dst, __float_as_int(a.z), a.x, a.y);
+      }
+    }
+  }
+}
 
 // ---- persistent warp scheduler -------------------------------------------------------------------------------------------
 // Query costs are heavy tailed and lanes follow different paths, so a thread-per-query kernel leaves most lanes of a warp
@@ -640,7 +676,7 @@ k_closest_pool(BvhView b, float scene_pad, float const * __restrict__ q3, uint32
   PoolWarp & pw = ((PoolWarp *)extra)[threadIdx.x >> 5];
   pw.best[lane] = 0ull; pw.done[lane] = 0; if (lane == 0) pw.tail = 0;
   __syncwarp();
-  int qi = 0, seed = -1, pending = 0, head = 0; bool hold = false;
+  int qi = 0, slot = 0, seed = -1, pending = 0, head = 0; bool hold = false;
   int chunk_base = 0, chunk_next = 0, chunk_end = 0; bool exhausted = false;
   for (;;)
   {
@@ -649,8 +685,10 @@ k_closest_pool(BvhView b, float scene_pad, float const * __restrict__ q3, uint32
     {
       if (peers.n)
       {
-        float4 ra = make_float4(__int_as_float(s.best_idx), s.best_idx >= 0 ? s.best_d2 : -1.0f, s.best_cp.x, s.best_cp.y), rb = make_float4(s.best_cp.z, 0.0f, 0.0f, 0.0f);
-        for (int j = 0; j < peers.n; ++j) st_rec32(peers.base[j], qi, ra, rb);
+        float4 ra = make_float4(__int_as_float(s.best_idx), s.best_idx >= 0 ? s.best_d2 : -1.0f, s.best_cp.x, s.best_cp.y);
+        float4 rb = make_float4(s.best_cp.z, __int_as_float(qi), 0.0f, 0.0f);
+        if (peers.compact) st_rec32(peers.base[0], slot, ra, rb);
+        else for (int j = 0; j < peers.n; ++j) st_rec32(peers.base[j], qi, ra, rb);
       }
       if (idx_out) idx_out[qi] = s.best_idx;
       if (d2_out) d2_out[qi] = s.best_idx >= 0 ? s.best_d2 : -1.0f;
@@ -684,7 +722,7 @@ k_closest_pool(BvhView b, float scene_pad, float const * __restrict__ q3, uint32
         int t = chunk_next + __popc(idle & ((1u << lane) - 1u));
         if (s.t.cur == TGQ_ST_IDLE && t < chunk_end)
         {
-          f4 r = stage[t - chunk_base]; qi = __float_as_int(r.w);
+          f4 r = stage[t - chunk_base]; qi = __float_as_int(r.w); slot = t;
           v3 p = mk3(r.x, r.y, r.z);
           closest_begin(s, b, scene_pad, p, exclude_self ? (int)(self_offset + qi) : -1, gated_ub(gate, p, bound_ub), seed);
           hold = s.t.cur == TGQ_ST_LEAF;          // seeded: the seed element is tested before the traversal starts
@@ -1308,7 +1346,7 @@ struct RayW
 {
   static constexpr int STAGE = 2;       // (origin, query index) (direction, max time)
   RayState<ANY> s; BvhView b; float const * o3; float const * d3; float const * tmax; uint32_t const * perm;
-  float * t_out; int * idx; float * normal3; uint8_t * hit; int qi; PeerOut peers;
+  float * t_out; int * idx; float * normal3; uint8_t * hit; int qi; int slot; PeerOut peers;
   __device__ __forceinline__ int state() const { return s.t.cur; }
   __device__ __forceinline__ void stage(int t, f4 * dst) const
   {
@@ -1316,9 +1354,9 @@ struct RayW
     dst[0] = make_float4(o.x, o.y, o.z, __int_as_float(i));
     dst[1] = make_float4(d.x, d.y, d.z, tmax ? tmax[i] : -1.0f);
   }
-  __device__ __forceinline__ void begin(int, f4 const * src)
+  __device__ __forceinline__ void begin(int t, f4 const * src)
   {
-    f4 o = src[0], d = src[1]; qi = __float_as_int(o.w);
+    f4 o = src[0], d = src[1]; qi = __float_as_int(o.w); slot = t;
     ray_begin(s, b, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), d.w);
   }
   static constexpr int FETCH = TGQ_FETCH_BOX;
@@ -1328,7 +1366,9 @@ struct RayW
   __device__ __forceinline__ void leaf_compute(f4 const * r) { ray_leaf_compute(s, b, r); }
   __device__ __forceinline__ void finish()
   {
-    for (int j = 0; j < peers.n; ++j) st_rec8(peers.base[j], qi, s.best_idx >= 0 ? s.best_t : -1.0f, __int_as_float(s.best_idx));
+    if (peers.n && peers.compact)
+      ((float4 *)peers.base[0])[slot] = make_float4(s.best_idx >= 0 ? s.best_t : -1.0f, __int_as_float(s.best_idx), __int_as_float(qi), 0.0f);
+    else for (int j = 0; j < peers.n; ++j) st_rec8(peers.base[j], qi, s.best_idx >= 0 ? s.best_t : -1.0f, __int_as_float(s.best_idx));
     if (t_out) t_out[qi] = s.best_idx >= 0 ? s.best_t : -1.0f;
     if (idx) idx[qi] = s.best_idx;
     if (hit) hit[qi] = s.best_idx >= 0 ? 1 : 0;
@@ -1349,7 +1389,7 @@ k_ray(BvhView b, float const * __restrict__ o3, float const * __restrict__ d3, f
 {
   extern __shared__ __align__(16) unsigned char smem[];
   RayW<ANY> w;
-  w.b = b; w.o3 = o3; w.d3 = d3; w.tmax = tmax; w.perm = perm; w.t_out = t_out; w.idx = idx; w.normal3 = normal3; w.hit = hit; w.qi = 0; w.peers = peers;
+  w.b = b; w.o3 = o3; w.d3 = d3; w.tmax = tmax; w.perm = perm; w.t_out = t_out; w.idx = idx; w.normal3 = normal3; w.hit = hit; w.qi = 0; w.slot = 0; w.peers = peers;
   w.s.t.cur = TGQ_ST_IDLE; TravStack st;
   f4 * stage = trav_setup(w.s.t, st, smem, RayW<ANY>::STAGE, nullptr);
   warp_run(w, n, counter, stage);

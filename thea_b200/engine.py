@@ -25,7 +25,7 @@ SYMBOLS = [
     "tgq_ray_first", "tgq_ray_any", "tgq_sdf", "tgq_icp_sums", "tgq_transform_points", "tgq_area_sample",
     "tgq_get_stats", "tgq_set_point_labels", "tgq_closest_filtered", "tgq_knn_filtered", "tgq_icp_align", "tgq_ball_range",
     "tgq_ball_stats", "tgq_visibility", "tgq_ball_graph_surface", "tgq_ball_histogram", "tgq_set_transform",
-    "tgq_closest_records", "tgq_ray_first_records", "tgq_synchronize",
+    "tgq_closest_records", "tgq_ray_first_records", "tgq_synchronize", "tgq_scatter_records",
 ]
 
 
@@ -95,8 +95,9 @@ def load_library(path=None):
     L.tgq_icp_align.argtypes = [vp, vp, i64, i32, i32, f64, i32, vp, vp, vp, vp]
     L.tgq_closest_filtered.argtypes = [vp, vp, vp, vp, i64, f32, f64, vp, vp, vp]
     L.tgq_knn_filtered.argtypes = [vp, vp, vp, vp, i64, i32, f32, f64, vp, vp]
-    L.tgq_closest_records.argtypes = [vp, vp, i64, f64, i32, i32, vp, i32]
-    L.tgq_ray_first_records.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, i32]
+    L.tgq_closest_records.argtypes = [vp, vp, i64, f64, i32, i32, vp, i32, i32, vp]
+    L.tgq_ray_first_records.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, i32, i32, vp]
+    L.tgq_scatter_records.argtypes = [vp, vp, i32, i64, vp, i32, vp]
     for name in SYMBOLS:
         if name not in ("tgq_last_error",):
             getattr(L, name).restype = C.c_int
@@ -163,7 +164,9 @@ class Engine:
                 raise ValueError(f"tensor lives on {a.device}, the engine on cuda:{self.device}")
             if not self._explicit_stream:
                 import torch
-                self._ck(self._L.tgq_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+                # torch's default stream has handle 0, which tgq_set_stream reads as "the handle's own stream": name it by
+                # cudaStreamLegacy (0x1) instead
+                self._ck(self._L.tgq_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream or 1)))
         return a
 
     def close(self):
@@ -405,20 +408,31 @@ class Engine:
         ptrs = [int(d.data_ptr()) if hasattr(d, "data_ptr") else int(d) for d in dest]
         return (C.c_void_p * len(ptrs))(*ptrs), len(ptrs)
 
-    def closest_records(self, q3, dest, rank=0, world=1, dist_bound=-1.0):
+    def closest_records(self, q3, dest, rank=0, world=1, dist_bound=-1.0, compact=False):
         """tgq_closest_records: q3 = the WHOLE batch (CUDA tensor); dest = the record arrays ([Q, 8] int32 / float32 views of 32-byte
-        records) of every rank that must receive this rank's results, own copy included (tensors or raw device pointers)."""
+        records) of every rank that must receive this rank's results, own copy included (tensors or raw device pointers); compact:
+        one dense destination in processing order.  Returns the number of queries this rank answered."""
         q3 = self._in(q3)
         arr, n = self._dest_array(dest)
-        self._ck(self._L.tgq_closest_records(self._h, _ptr(q3), int(q3.shape[0]), float(dist_bound), int(rank), int(world), arr, n))
+        share = C.c_int64()
+        self._ck(self._L.tgq_closest_records(self._h, _ptr(q3), int(q3.shape[0]), float(dist_bound), int(rank), int(world), arr, n, int(compact), C.byref(share)))
+        return int(share.value)
 
-    def ray_first_records(self, o3, d3, dest, rank=0, world=1, tmax=None):
-        """tgq_ray_first_records: 8-byte records (t, idx) at the ray's position in every destination array."""
+    def ray_first_records(self, o3, d3, dest, rank=0, world=1, tmax=None, compact=False):
+        """tgq_ray_first_records: 8-byte records (t, idx) at the ray's position in every destination array (compact: 16-byte records
+        (t, idx, ray index, 0) in processing order in one destination).  Returns the number of rays this rank answered."""
         o3 = self._in(o3)
         d3 = self._in(d3)
         tmax = self._in(tmax)
         arr, n = self._dest_array(dest)
-        self._ck(self._L.tgq_ray_first_records(self._h, _ptr(o3), _ptr(d3), _ptr(tmax), int(o3.shape[0]), int(rank), int(world), arr, n))
+        share = C.c_int64()
+        self._ck(self._L.tgq_ray_first_records(self._h, _ptr(o3), _ptr(d3), _ptr(tmax), int(o3.shape[0]), int(rank), int(world), arr, n, int(compact), C.byref(share)))
+        return int(share.value)
+
+    def scatter_records(self, compact, slots, cap, counts, kind, dest):
+        """tgq_scatter_records: `slots` dense arrays of up to `cap` compact records, counts (int64 CUDA tensor) valid -> dest[query index]."""
+        self._ck(self._L.tgq_scatter_records(self._h, C.c_void_p(int(compact.data_ptr())), int(slots), int(cap), C.c_void_p(int(counts.data_ptr())), int(kind),
+                                             C.c_void_p(int(dest.data_ptr()))))
 
     def ray_any(self, o3, d3, tmax=None):
         o3 = self._in(o3)
