@@ -290,12 +290,16 @@ def main():
     # queries whose Morton cell it owns (tgq_*_records: cells dealt round-robin, so its share keeps the density of the full batch -- a
     # contiguous index range of a random batch is `world` times sparser after the Morton sort, which cost 22 % per rank at N = 8 in
     # round 1).  The one real exchange of the path -- every rank ends a step holding the results of the WHOLE batch, in query order
-    #  -- goes like this: the traversal kernels write the rank's share as a dense array of records (32 B closest, 16 B
-    # ray, each carrying its query index); the array is pushed into every peer's receive slot with ONE contiguous peer-to-peer copy
-    # per peer (copy engines over NVLink, on a side stream, under the next kernel), a device-side barrier on the side stream tells
-    # everybody that all pushes have landed, and one scatter kernel per query kind puts the records of all ranks at [query index] of
-    # the local result arrays.  (Storing each result straight into every peer's copy from the traversal kernel was measured first:
-    # small scattered peer stores cost the ray kernel 56 % and the closest kernel 14 % at N = 8.)
+    #  -- is built from contiguous copy-engine transfers only, so that nothing but 1/N of the work is ever exposed:
+    #   1. the traversal kernels write the rank's share as a dense array of records (32 B closest, 16 B ray, each carrying its query
+    #      index); a bucket kernel splits it by the rank that OWNS each record's position in the result array (query index // (Q/N));
+    #   2. all-to-all by peer-to-peer copies over NVLink on a side stream (one contiguous copy per peer, the counts alongside), then
+    #      a device-side barrier on that stream: everybody's buckets have landed;
+    #   3. a scatter kernel puts the records a rank received at [query index] -- all inside ITS contiguous 1/N of the result arrays;
+    #   4. that finished 1/N is pushed into every peer's copy of the result arrays (contiguous, copy engines, under the next kernels).
+    # Measured and dropped: storing each result from the traversal kernel straight into every peer's copy (small scattered peer
+    # stores cost the ray kernel 56 % and the closest kernel 14 % at N = 8), and pushing whole shares to every rank and scattering
+    # all 100 M records everywhere (3.6 ms per step whatever N is).
     # Fallback when symmetric memory is unavailable: contiguous shards + NCCL all-gather.
     q_off, nq = shard(nq_total, rank, world)
     r_off, nr = shard(nr_total, rank, world)
@@ -310,36 +314,49 @@ def main():
         drd[b:b + n] = d
     kern = {"closest_ms": 0.0, "closest_q": 0, "ray_ms": 0.0, "ray_q": 0, "sort_ms": 0.0, "launches": 0, "scatter_ms": 0.0}
 
-    crec = torch.zeros((max(1, nq_total), 8), dtype=torch.float32, device=dev)     # gathered results, query order: 32-byte records
-    rrec = torch.zeros((max(1, nr_total), 2), dtype=torch.float32, device=dev)     # 8-byte records
     transport, sym = "none", None
-    cap_c = int(nq_total / world * 1.25) + 4096
-    cap_r = int(nr_total / world * 1.25) + 4096
+    totals = {"c": nq_total, "r": nr_total}
+    cwords, fwords, kinds = {"c": 8, "r": 4}, {"c": 8, "r": 2}, {"c": 0, "r": 1}
     if world > 1 and os.environ.get("TGQ_BENCH_TRANSPORT", "p2p") == "p2p":
         try:
             import torch.distributed._symmetric_memory as symm_mem
+            assert nq_total % world == 0 and nr_total % world == 0, "bench workloads shard evenly over 1/2/4/8 ranks"
             sym = {}
-            for name, words in (("c", cap_c * 8), ("r", cap_r * 4)):
-                numel = 2 * world * words + 2 * world * 2               # [parity][source rank][cap records] + int64 counts [parity][source rank]
+            for name in ("c", "r"):
+                tot = totals[name]
+                cap_pair = int(tot / world / world * 1.1) + 4096                 # records one rank sends to one rank
+                words = cap_pair * cwords[name]
+                n_recv = 2 * world * words                                        # [parity][source rank][cap_pair records]
+                n_cnt = 2 * world * 2                                             # int64 counts [parity][source rank]
+                n_fin = max(1, tot) * fwords[name]                                # the gathered result array, query order
+                numel = n_recv + n_cnt + n_fin
                 t = symm_mem.empty(numel, dtype=torch.float32, device=dev)
                 hdl = symm_mem.rendezvous(t, dist.group.WORLD)
+                t.zero_()
                 views = []
                 for r in range(world):
                     buf = hdl.get_buffer(r, (numel,), torch.float32)
-                    data = buf[:2 * world * words].view(2, world, words)
-                    cnt = buf[2 * world * words:].view(torch.int64).view(2, world)
-                    views.append((data, cnt))
-                sym[name] = {"hdl": hdl, "views": views, "words": words, "mine": torch.zeros(2, dtype=torch.int64, device=dev)}
-                t.zero_()
+                    views.append({"recv": buf[:n_recv].view(2, world, words), "cnt": buf[n_recv:n_recv + n_cnt].view(torch.int64).view(2, world),
+                                  "final": buf[n_recv + n_cnt:].view(max(1, tot), fwords[name])})
+                cap_share = int(tot / world * 1.25) + 4096
+                sym[name] = {"hdl": hdl, "views": views, "cap_pair": cap_pair, "cap_share": cap_share, "shard_len": tot // world,
+                             "share": torch.empty(cap_share * cwords[name], dtype=torch.float32, device=dev),
+                             "buckets": torch.empty((world, words), dtype=torch.float32, device=dev),
+                             "bcnt": torch.zeros(world, dtype=torch.int64, device=dev)}
+            crec, rrec = sym["c"]["views"][rank]["final"], sym["r"]["views"][rank]["final"]
             comm_stream = torch.cuda.Stream(device=dev)
-            transport = "dense per-rank record arrays pushed by copy engines into symmetric memory (NVLink P2P) + local scatter"
+            transport = ("dense per-rank record arrays, bucketed by owner of the result position; all-to-all and all-gather by copy-engine "
+                         "P2P copies into symmetric memory (NVLink), device-side barrier, local scatter of 1/N of the records")
         except Exception as exc:      # noqa: BLE001 -- any failure here means: use NCCL
             if rank == 0:
                 print(f"bench.py: symmetric memory unavailable ({type(exc).__name__}: {exc}); using contiguous shards + NCCL all-gather", file=sys.stderr)
             sym = None
     space_sharded = world == 1 or sym is not None
-    if world > 1 and sym is None:
-        transport = "NCCL all-gather of contiguous shards"
+    if sym is None:
+        crec = torch.zeros((max(1, nq_total), 8), dtype=torch.float32, device=dev)     # gathered results, query order: 32-byte records
+        rrec = torch.zeros((max(1, nr_total), 2), dtype=torch.float32, device=dev)     # 8-byte records
+        if world > 1:
+            transport = "NCCL all-gather of contiguous shards"
     eng.set_option(3, 1)              # TGQ_OPT_ASYNC: calls are ordered on the stream; the step is timed with CUDA events
     timers = {"c": [], "r": [], "s": []}
     pending = []
@@ -353,24 +370,36 @@ def main():
         timers[kind].append((a, b))
         return out
 
-    def push(name, n_own, par):
-        # this rank's dense share -> slot [par][rank] of every peer, counts alongside; then everybody waits for everybody's pushes
+    def exchange_a(name, n_own, par):
+        """Steps 1b-2 for one query kind: bucket the share, all-to-all on the side stream; returns the event 'all buckets landed'."""
         S = sym[name]
-        data, cnt = S["views"][rank]
-        S["mine"][par] = n_own
         cur = torch.cuda.current_stream()
+        timed("s", lambda: eng.bucket_records(S["share"], n_own, kinds[name], S["shard_len"], world, S["buckets"], S["cap_pair"], S["bcnt"]))
         comm_stream.wait_stream(cur)
         with torch.cuda.stream(comm_stream):
-            words = n_own * (8 if name == "c" else 4)
-            cnt[par, rank].copy_(S["mine"][par], non_blocking=True)
-            for k in range(1, world):
-                pdata, pcnt = S["views"][(rank + k) % world]
-                pdata[par, rank, :words].copy_(data[par, rank, :words], non_blocking=True)
-                pcnt[par, rank].copy_(S["mine"][par], non_blocking=True)
+            for k in range(world):
+                p = (rank + k) % world
+                dst = S["views"][p]
+                dst["recv"][par, rank].copy_(S["buckets"][p], non_blocking=True)
+                dst["cnt"][par, rank].copy_(S["bcnt"][p], non_blocking=True)
             S["hdl"].barrier(channel=par)
             ev = torch.cuda.Event()
             ev.record(comm_stream)
         return ev
+
+    def exchange_b(name, ev, par):
+        """Steps 3-4: scatter what this rank received into its 1/N of the result array, push that 1/N to every peer."""
+        S = sym[name]
+        mine = S["views"][rank]
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        timed("s", lambda: eng.scatter_records(mine["recv"][par], world, S["cap_pair"], mine["cnt"][par], kinds[name], mine["final"]))
+        comm_stream.wait_stream(cur)
+        with torch.cuda.stream(comm_stream):
+            lo = rank * S["shard_len"]
+            for k in range(1, world):
+                p = (rank + k) % world
+                S["views"][p]["final"][lo:lo + S["shard_len"]].copy_(mine["final"][lo:lo + S["shard_len"]], non_blocking=True)
 
     def step_device(record: bool):
         par = step_no[0] & 1
@@ -378,22 +407,17 @@ def main():
         if world > 1 and space_sharded:
             evc = evr = None
             if nq_total:
-                n_c = timed("c", lambda: eng.closest_records(dq, [sym["c"]["views"][rank][0][par, rank]], rank, world, compact=True))
-                assert n_c <= cap_c, "closest share exceeds the receive slot"
-                evc = push("c", n_c, par)
+                n_c = timed("c", lambda: eng.closest_records(dq, [sym["c"]["share"]], rank, world, compact=True))
+                assert n_c <= sym["c"]["cap_share"], "closest share exceeds its buffer"
+                evc = exchange_a("c", n_c, par)                   # the all-to-all of the closest records runs under the ray kernel
             if nr_total:
-                n_r = timed("r", lambda: eng.ray_first_records(dro, drd, [sym["r"]["views"][rank][0][par, rank]], rank, world, compact=True))
-                assert n_r <= cap_r, "ray share exceeds the receive slot"
-                evr = push("r", n_r, par)
-            cur = torch.cuda.current_stream()
+                n_r = timed("r", lambda: eng.ray_first_records(dro, drd, [sym["r"]["share"]], rank, world, compact=True))
+                assert n_r <= sym["r"]["cap_share"], "ray share exceeds its buffer"
+                evr = exchange_a("r", n_r, par)
             if evc is not None:
-                cur.wait_event(evc)
-                data, cnt = sym["c"]["views"][rank]
-                timed("s", lambda: eng.scatter_records(data[par], world, cap_c, cnt[par], 0, crec))
+                exchange_b("c", evc, par)
             if evr is not None:
-                cur.wait_event(evr)
-                data, cnt = sym["r"]["views"][rank]
-                timed("s", lambda: eng.scatter_records(data[par], world, cap_r, cnt[par], 1, rrec))
+                exchange_b("r", evr, par)
             return
         # one GPU (or the NCCL fallback): records straight to [query index]
         if nq_total:
@@ -430,8 +454,10 @@ def main():
     e0.record()
     for _ in range(args.steps):
         step_device(True)
-    e1.record()                              # this rank holds the results of the whole batch of the last step
-    barrier()
+    if world > 1 and sym is not None:
+        torch.cuda.current_stream().wait_stream(comm_stream)      # this rank's last pushes into the peers' result arrays are done
+    e1.record()
+    barrier()                                # ... and so are everybody else's into this rank's: every rank holds the whole batch's results
     clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:

@@ -228,6 +228,11 @@ int tgq_closest_records(tgq_handle * h, const float * q3, int64_t Q, double dist
                         void * const * dest, int32_t n_dest, int32_t compact, int64_t * share);
 int tgq_ray_first_records(tgq_handle * h, const float * o3, const float * d3, const float * tmax, int64_t R, int32_t shard_rank,
                           int32_t shard_world, void * const * dest, int32_t n_dest, int32_t compact, int64_t * share);
+/* Splits n compact records by the rank that owns each record's position in the result array (query index / shard_len, the last
+ * rank takes the remainder): bucket d = records [d * cap, d * cap + counts[d]) of `buckets`; counts[world] is int64 DEVICE memory
+ * and is (re)written by the call.  Runs on the handle's stream (asynchronously with TGQ_OPT_ASYNC). */
+int tgq_bucket_records(tgq_handle * h, const void * compact, int64_t n, int32_t kind, int64_t shard_len, int32_t world, void * buckets,
+                       int64_t cap, int64_t * counts);
 /* Compact records -> dest[query index] in the non-compact record layout.  compact: `slots` dense arrays of up to `cap` records each
  * (slot j starts at record j * cap; kind 0: closest, 32 bytes; kind 1: ray, 16 bytes), counts[slots] (int64, DEVICE memory: they
  * travel with the data) of them valid.  Runs on the handle's stream; returns without waiting when TGQ_OPT_ASYNC is set. */

@@ -1134,6 +1134,26 @@ int tgq_ray_first_records(tgq_handle * h, const float * o3, const float * d3, co
   return rc;
 }
 
+int tgq_bucket_records(tgq_handle * h, const void * compact, int64_t n, int32_t kind, int64_t shard_len, int32_t world, void * buckets, int64_t cap,
+                       int64_t * counts)
+{
+  if (!h) return TGQ_EINVAL;
+  if (n < 0 || kind < 0 || kind > 1 || shard_len < 1 || world < 1 || world > 8 || cap < 1 || !buckets || !counts || (n > 0 && !compact))
+    return fail(h, TGQ_EINVAL, "tgq_bucket_records: bad arguments");
+  if ((n > 0 && !is_device_ptr(compact)) || !is_device_ptr(buckets) || !is_device_ptr(counts)) return fail(h, TGQ_EINVAL, "tgq_bucket_records: device pointers only");
+  Guard g(h);
+  CK(cudaMemsetAsync(counts, 0, 8 * (size_t)world, h->stream));
+  if (n > 0)
+  {
+    int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 16);
+    k_bucket_records<<<grid, 256, 0, h->stream>>>(compact, n, kind, shard_len, world, buckets, cap, (unsigned long long *)counts);
+    CK(cudaGetLastError());
+    h->st.total_launches += 1;
+  }
+  if (!h->opt_async) CK(cudaStreamSynchronize(h->stream));
+  return TGQ_OK;
+}
+
 int tgq_scatter_records(tgq_handle * h, const void * compact, int32_t slots, int64_t cap, const int64_t * counts, int32_t kind, void * dest)
 {
   if (!h) return TGQ_EINVAL;

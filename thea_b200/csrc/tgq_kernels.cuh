@@ -469,6 +469,41 @@ __device__ __forceinline__ void st_rec32(void * base, int64_t i, float4 a, float
 __device__ __forceinline__ void st_rec8(void * base, int64_t i, float a, float b)
 { asm volatile("st.global.v2.f32 [%0], {%1,%2};" :: "l"((char *)base + 8 * i), "f"(a), "f"(b) : "memory"); }
 
+// A rank's dense share of records, split by the rank that owns each record's POSITION in the result array (query index /
+// shard_len): bucket d of `out` (cap records each) receives the records for rank d, counts[d] how many (zeroed by the caller).
+// One shared-memory histogram and `world` global atomics per tile of 256 records.
+__global__ void __launch_bounds__(256)
+k_bucket_records(void const * __restrict__ src, int64_t n, int kind, int64_t shard_len, int world, void * out, int64_t cap, unsigned long long * counts)
+{
+  __shared__ int s_cnt[8]; __shared__ unsigned long long s_base[8];
+  for (int64_t tile = blockIdx.x * (int64_t)256; tile < n; tile += (int64_t)gridDim.x * 256)
+  {
+    if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    int64_t i = tile + threadIdx.x;
+    float4 a = make_float4(0, 0, 0, 0), b = a; int d = 0, local = 0;
+    if (i < n)
+    {
+      if (kind == 0) { a = __ldg((float4 const *)src + 2 * i); b = __ldg((float4 const *)src + 2 * i + 1); d = (int)min((int64_t)__float_as_int(b.y) / shard_len, (int64_t)world - 1); }
+      else { a = __ldg((float4 const *)src + i); d = (int)min((int64_t)__float_as_int(a.z) / shard_len, (int64_t)world - 1); }
+      local = atomicAdd(&s_cnt[d], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < world) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]) : 0ull;
+    __syncthreads();
+    if (i < n)
+    {
+      int64_t slot = (int64_t)s_base[d] + local;
+      if (slot < cap)
+      {
+        if (kind == 0) { float4 * o = (float4 *)out + 2 * (d * cap + slot); o[0] = a; o[1] = b; }
+        else ((float4 *)out)[d * cap + slot] = a;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // Compact records of the ranks' shares -> [query index] of the gathered array.  `slots` dense arrays of up to `cap` records each
 // (slot j at src + j * cap records), counts[j] of them valid (device memory: the counts arrive with the data).  kind 0: 32-byte
 // closest records (query index in word 5), kind 1: 16-byte ray records { t, idx, query index, - } -> 8-byte records.

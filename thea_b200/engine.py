@@ -25,7 +25,7 @@ SYMBOLS = [
     "tgq_ray_first", "tgq_ray_any", "tgq_sdf", "tgq_icp_sums", "tgq_transform_points", "tgq_area_sample",
     "tgq_get_stats", "tgq_set_point_labels", "tgq_closest_filtered", "tgq_knn_filtered", "tgq_icp_align", "tgq_ball_range",
     "tgq_ball_stats", "tgq_visibility", "tgq_ball_graph_surface", "tgq_ball_histogram", "tgq_set_transform",
-    "tgq_closest_records", "tgq_ray_first_records", "tgq_synchronize", "tgq_scatter_records",
+    "tgq_closest_records", "tgq_ray_first_records", "tgq_synchronize", "tgq_scatter_records", "tgq_bucket_records",
 ]
 
 
@@ -98,6 +98,7 @@ def load_library(path=None):
     L.tgq_closest_records.argtypes = [vp, vp, i64, f64, i32, i32, vp, i32, i32, vp]
     L.tgq_ray_first_records.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, i32, i32, vp]
     L.tgq_scatter_records.argtypes = [vp, vp, i32, i64, vp, i32, vp]
+    L.tgq_bucket_records.argtypes = [vp, vp, i64, i32, i64, i32, vp, i64, vp]
     for name in SYMBOLS:
         if name not in ("tgq_last_error",):
             getattr(L, name).restype = C.c_int
@@ -428,6 +429,11 @@ class Engine:
         share = C.c_int64()
         self._ck(self._L.tgq_ray_first_records(self._h, _ptr(o3), _ptr(d3), _ptr(tmax), int(o3.shape[0]), int(rank), int(world), arr, n, int(compact), C.byref(share)))
         return int(share.value)
+
+    def bucket_records(self, compact, n, kind, shard_len, world, buckets, cap, counts):
+        """tgq_bucket_records: n compact records split by the rank owning their position (query index // shard_len)."""
+        self._ck(self._L.tgq_bucket_records(self._h, C.c_void_p(int(compact.data_ptr())), int(n), int(kind), int(shard_len), int(world),
+                                            C.c_void_p(int(buckets.data_ptr())), int(cap), C.c_void_p(int(counts.data_ptr()))))
 
     def scatter_records(self, compact, slots, cap, counts, kind, dest):
         """tgq_scatter_records: `slots` dense arrays of up to `cap` compact records, counts (int64 CUDA tensor) valid -> dest[query index]."""
