@@ -41,7 +41,7 @@ struct DevBuf
 };
 
 #define TGQ_MAX_ARGS 8
-#define TGQ_SHARD_CELL_BITS 15       // default of TGQ_OPT_SHARD_CELL_BITS: 2^15 Morton cells over the scene box grown x2, dealt round-robin to the ranks
+#define TGQ_SHARD_CELL_BITS 12       // default of TGQ_OPT_SHARD_CELL_BITS (measured on cfg5, 8 ranks: 9..12 bits 17.6 ms per closest share, 18 bits 18.5, 21 bits 19.3): 2^12 Morton cells over the scene box grown x2, dealt round-robin to the ranks
 #ifndef TGQ_SLOTS
 // Ray kernels: resident blocks per SM (the rest of the shared-memory array becomes L1).  Measured on B200, 8 M rays on the 10 M-triangle
 // mesh: 7 blocks with the maximum carve-out 1.75 G rays/s, 6 blocks 2.27 G, 5 blocks 2.11 G (1 M triangles: 2.24 / 2.73 / 2.53 G).
@@ -369,7 +369,7 @@ int sort_chunk(tgq_handle * h, ChunkCtx & c)
     for (int i = 0; i < 2; ++i) { CK(sl.keys[i].reserve(4 * nn)); CK(sl.vals[i].reserve(4 * nn)); }
     int * cnt = sl.counter.as<int>() + 1;
     CK(cudaMemsetAsync(cnt, 0, 4, c.stream));
-    int grid = (int)std::min<int64_t>((c.n + 255) / 256, (int64_t)h->sm_count * 16);
+    int grid = (int)std::min<int64_t>((c.n + 1023) / 1024, (int64_t)h->sm_count * 8);
     k_query_codes_shard<<<grid, 256, 0, c.stream>>>((float const *)c.din[0], c.n, h->scene.as<SceneBox>(), h->shard_rank, h->shard_world, 30 - h->opt_cell_bits,
                                                     sl.keys[0].as<uint32_t>(), sl.vals[0].as<uint32_t>(), cnt);
     CK(cudaGetLastError());

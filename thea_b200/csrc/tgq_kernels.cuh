@@ -432,14 +432,20 @@ k_query_codes_shard(float const * __restrict__ q3, int n, SceneBox const * sb, i
   v3 inv = mk3(e.x > 0 ? 0.5f / e.x : 0.0f, e.y > 0 ? 0.5f / e.y : 0.0f, e.z > 0 ? 0.5f / e.z : 0.0f);
   int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __shared__ int s_warp[8], s_base;
-  // one global atomic per block and tile of 256 queries (per-warp atomics on a single address serialise: 1.5 M of them cost 4 ms)
-  for (int64_t tile = blockIdx.x * (int64_t)256; tile < n; tile += (int64_t)gridDim.x * 256)
+  // one global atomic per block and tile of 1024 queries (per-warp atomics on a single address serialise: 1.5 M of them cost 4 ms)
+  for (int64_t tile = blockIdx.x * (int64_t)1024; tile < n; tile += (int64_t)gridDim.x * 1024)
   {
-    int64_t i = tile + threadIdx.x;
-    uint32_t code = 0; bool own = false;
-    if (i < n) { code = morton30(ld3(q3, i), lo, inv); own = (int)((code >> shift) % (uint32_t)world) == rank; }
-    unsigned m = __ballot_sync(0xffffffffu, own);
-    if (lane == 0) s_warp[warp] = __popc(m);
+    uint32_t code[4]; unsigned m[4]; int mine = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+      int64_t i = tile + k * 256 + threadIdx.x;
+      bool own = false; code[k] = 0;
+      if (i < n) { code[k] = morton30(ld3(q3, i), lo, inv); own = (int)((code[k] >> shift) % (uint32_t)world) == rank; }
+      m[k] = __ballot_sync(0xffffffffu, own);
+      mine += __popc(m[k]);
+    }
+    if (lane == 0) s_warp[warp] = mine;          // `mine` is warp uniform: the warp's count over its four rows
     __syncthreads();
     if (threadIdx.x == 0)
     {
@@ -448,7 +454,13 @@ k_query_codes_shard(float const * __restrict__ q3, int n, SceneBox const * sb, i
       s_base = tot ? atomicAdd(count, tot) : 0;
     }
     __syncthreads();
-    if (own) { int pos = s_base + s_warp[warp] + __popc(m & ((1u << lane) - 1u)); keys[pos] = code; vals[pos] = (uint32_t)i; }
+    int pos = s_base + s_warp[warp];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+      if ((m[k] >> lane) & 1u) { int p = pos + __popc(m[k] & ((1u << lane) - 1u)); keys[p] = code[k]; vals[p] = (uint32_t)(tile + k * 256 + threadIdx.x); }
+      pos += __popc(m[k]);
+    }
     __syncthreads();
   }
 }
