@@ -730,12 +730,21 @@ k_closest_pool(BvhView b, float scene_pad, float const * __restrict__ q3, uint32
     // ---- finished queries write their results; idle lanes take the next queries of the warp's chunk -----------------------------
     if (s.t.cur == TGQ_ST_DONE && pending == 0)
     {
+#ifndef TGQ_NO_PEERS
       if (peers.n)
+#else
+      if (false)
+#endif
       {
         float4 ra = make_float4(__int_as_float(s.best_idx), s.best_idx >= 0 ? s.best_d2 : -1.0f, s.best_cp.x, s.best_cp.y);
         float4 rb = make_float4(s.best_cp.z, __int_as_float(qi), 0.0f, 0.0f);
         if (peers.compact) st_rec32(peers.base[0], slot, ra, rb);
-        else for (int j = 0; j < peers.n; ++j) st_rec32(peers.base[j], qi, ra, rb);
+        else
+        {
+          // constant indices only: a run-time index would move the parameter array to local memory (measured: -5 % on the whole kernel)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (j < peers.n) st_rec32(peers.base[j], qi, ra, rb);
+        }
       }
       if (idx_out) idx_out[qi] = s.best_idx;
       if (d2_out) d2_out[qi] = s.best_idx >= 0 ? s.best_d2 : -1.0f;
@@ -1415,7 +1424,11 @@ struct RayW
   {
     if (peers.n && peers.compact)
       ((float4 *)peers.base[0])[slot] = make_float4(s.best_idx >= 0 ? s.best_t : -1.0f, __int_as_float(s.best_idx), __int_as_float(qi), 0.0f);
-    else for (int j = 0; j < peers.n; ++j) st_rec8(peers.base[j], qi, s.best_idx >= 0 ? s.best_t : -1.0f, __int_as_float(s.best_idx));
+    else
+    {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (j < peers.n) st_rec8(peers.base[j], qi, s.best_idx >= 0 ? s.best_t : -1.0f, __int_as_float(s.best_idx));
+    }
     if (t_out) t_out[qi] = s.best_idx >= 0 ? s.best_t : -1.0f;
     if (idx) idx[qi] = s.best_idx;
     if (hit) hit[qi] = s.best_idx >= 0 ? 1 : 0;
