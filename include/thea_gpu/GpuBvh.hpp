@@ -21,7 +21,7 @@
 //   - pushFilter with arbitrary host callables and compatibility functors other than UniversalCompatibility (they cannot
 //     run on the device): pushFilter throws, except for the built-in NNFilter (same label, compatible normal) on point
 //     structures; the other device predicates are `exclude_self` and the ball-graph normal test.
-//   - metrics other than L2, BVH-to-BVH queries.
+//   - metrics other than L2; range queries on triangle structures (they need the reference's triangle-box / triangle-ball tests).
 #ifndef THEA_GPU_GPUBVH_HPP
 #define THEA_GPU_GPUBVH_HPP
 
@@ -32,6 +32,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 namespace TheaGpu {
@@ -112,8 +113,53 @@ class RayStructureIntersectionT
     intx getElementIndex() const { return element_index; }
     void setElementIndex(intx i) { element_index = i; }
 
+    /** Converts to any type with the reference's constructor (time, normal *, element index) -- i.e. to Thea's own
+     *  RayStructureIntersectionN (RayQueryStructureN.hpp:37-39), so that reference code such as
+     *  `RayStructureIntersection3 isec = external ? external->rayStructureIntersection<...>(ray) : own->rayStructureIntersection<...>(ray);`
+     *  (ShapeDiameter.hpp:215-217) compiles with this structure as the external one. */
+    template <typename U, typename std::enable_if<std::is_constructible<U, Real, VectorT const *, intx>::value
+                                               && !std::is_same<U, RayStructureIntersectionT>::value, int>::type = 0>
+    operator U() const { return U(time, has_normal ? &normal : nullptr, element_index); }
+
   private:
     Real time; bool has_normal; VectorT normal; intx element_index;
+};
+
+/** Ball3 / AxisAlignedBox3 as range-query arguments (BallN.hpp:28-66, AxisAlignedBoxN.hpp:40-120): any type with
+ *  getCenter() / getRadius(), respectively getLow() / getHigh(), works -- Thea's own classes included. */
+template <typename VectorT>
+struct Ball3T
+{
+  VectorT center; Real radius;
+  Ball3T(VectorT const & c, Real r) : center(c), radius(r) {}
+  VectorT const & getCenter() const { return center; }
+  Real getRadius() const { return radius; }
+};
+template <typename VectorT>
+struct AxisAlignedBox3T
+{
+  VectorT lo, hi;
+  AxisAlignedBox3T() {}
+  AxisAlignedBox3T(VectorT const & l, VectorT const & h_) : lo(l), hi(h_) {}
+  VectorT const & getLow() const { return lo; }
+  VectorT const & getHigh() const { return hi; }
+  VectorT getExtent() const { VectorT e; for (int a = 0; a < 3; ++a) e[a] = hi[a] - lo[a]; return e; }                 // AxisAlignedBoxN.hpp:288
+  VectorT getCenter() const { VectorT c; for (int a = 0; a < 3; ++a) c[a] = 0.5f * (hi[a] + lo[a]); return c; }        // :274
+};
+
+/** What getElements()[i] of a triangle structure offers the reference's callers (MeshBvh elements are Triangle3 objects;
+ *  ShapeDiameter.hpp:152-153 reads getNormal(), Triangle3.hpp:143-155,206-219): the vertices as given and the cached unit normal as
+ *  the DEVICE computed it with the reference's arithmetic (bit-equal to Triangle3's own cache). */
+template <typename VectorT>
+class TriangleElementT
+{
+  public:
+    TriangleElementT() {}
+    TriangleElementT(VectorT const & a, VectorT const & b, VectorT const & c, VectorT const & n) : normal(n) { v[0] = a; v[1] = b; v[2] = c; }
+    VectorT const & getVertex(int i) const { return v[i]; }
+    VectorT const & getNormal() const { return normal; }
+  private:
+    VectorT v[3], normal;
 };
 
 /** RayN<3> (RayN.hpp:27-139): origin + direction, direction NOT normalised by the structure. */
@@ -212,8 +258,25 @@ class GpuBvhBase
     intx numElements() const { int64_t n = 0; detail::check(h, tgq_info(h, nullptr, &n, nullptr, nullptr), "tgq_info"); return (intx)n; }
     bool isEmpty() const { return numElements() <= 0; }
     bool empty() const { return isEmpty(); }
-    /** Unpadded bounds of all elements (BvhN::getBounds, BvhN.hpp:981-995). */
-    void getBounds(VectorT & lo, VectorT & hi) const
+    /** BvhN::getBounds (BvhN.hpp:990-995,1740-1756): the reference returns its ROOT NODE's box, i.e. the union of the element
+     *  boxes scaled by 1.05 about its centre (createTree pads every node box, BvhN.hpp:1437-1439; AxisAlignedBoxN::scaleCentered,
+     *  AxisAlignedBoxN.hpp:316-324) -- reproduced here in the same fp32 operations, because callers derive scales from it
+     *  (ShapeDiameter.hpp:116, Visibility.hpp:73). */
+    AxisAlignedBox3T<VectorT> getBounds() const
+    {
+      float l[3], u[3]; detail::check(h, tgq_info(h, nullptr, nullptr, l, u), "tgq_info");
+      for (int a = 0; a < 3; ++a)
+      {
+        float c = 0.5f * (u[a] + l[a]);
+        float lo = 1.05f * (l[a] - c); lo = lo + c;
+        float hi = 1.05f * (u[a] - c); hi = hi + c;
+        l[a] = lo; u[a] = hi;
+      }
+      return AxisAlignedBox3T<VectorT>(detail::get3<VectorT>(l), detail::get3<VectorT>(u));
+    }
+    void getBounds(VectorT & lo, VectorT & hi) const { AxisAlignedBox3T<VectorT> b = getBounds(); lo = b.getLow(); hi = b.getHigh(); }
+    /** The exact (unpadded) bounds of the elements. */
+    void getElementBounds(VectorT & lo, VectorT & hi) const
     {
       float l[3], u[3]; detail::check(h, tgq_info(h, nullptr, nullptr, l, u), "tgq_info");
       lo = detail::get3<VectorT>(l); hi = detail::get3<VectorT>(u);
@@ -282,16 +345,46 @@ class GpuMeshBvhT : public GpuBvhBase<VectorT>
     {
       if (max_elems_per_leaf > 0) this->setOption(TGQ_OPT_LEAF_SIZE, max_elems_per_leaf > 15 ? 15 : max_elems_per_leaf);
       detail::check(h, tgq_build_triangles(h, soup.data(), (int64_t)(soup.size() / 9)), "tgq_build_triangles");
-      std::vector<float>().swap(soup); built = true;
+      kept.swap(soup); std::vector<float>().swap(soup); elements.clear(); built = true;      // the host copy backs getElements()
     }
-    /** Build straight from caller-owned (host or device) memory. */
-    void init(float const * v9, intx T) { detail::check(h, tgq_build_triangles(h, v9, T), "tgq_build_triangles"); built = true; }
+    /** Build straight from caller-owned (host or device) memory (no host copy is kept: getElements() is then unavailable). */
+    void init(float const * v9, intx T)
+    { detail::check(h, tgq_build_triangles(h, v9, T), "tgq_build_triangles"); kept.clear(); elements.clear(); built = true; }
 
-    void clear() { soup.clear(); detail::check(h, tgq_build_triangles(h, nullptr, 0), "tgq_build_triangles"); built = false; }
+    /** MeshBvh::add(mesh) (MeshBvh.hpp:55-67) for any mesh-like object that can enumerate its triangles: `visit` is called with a
+     *  callable taking three vertex positions, once per triangle, in the order MeshTriangles would push them
+     *  (MeshTriangles.hpp:173-339,411-418) -- with Thea: `bvh.add([&](auto emit) { MeshTriangles<Mesh> t; t.add(mesh); for (auto const &
+     *  x : t.getTriangles()) emit(x.getVertex(0), x.getVertex(1), x.getVertex(2)); });` */
+    template <typename VisitorT> void add(VisitorT visit)
+    { visit([this](VectorT const & a, VectorT const & b, VectorT const & c) { this->addTriangle(a, b, c); }); }
+
+    void clear() { soup.clear(); kept.clear(); elements.clear(); detail::check(h, tgq_build_triangles(h, nullptr, 0), "tgq_build_triangles"); built = false; }
+
+    /** BvhN::getElements() (BvhN.hpp:952-965): the elements in index order.  Backed by the host copy of the triangles given to
+     *  add* / init() and the device-computed triangle cache; fetched once per build. */
+    std::vector< TriangleElementT<VectorT> > const & getElements() const
+    {
+      size_t T = kept.size() / 9;
+      if (elements.size() != T)
+      {
+        if ((intx)T != this->numElements()) throw Error("TheaGpu: getElements() needs the structure to be built from host triangles (add* + init())");
+        std::vector<float> n3; getElementNormals(n3);
+        elements.resize(T);
+        for (size_t i = 0; i < T; ++i)
+          elements[i] = TriangleElementT<VectorT>(detail::get3<VectorT>(&kept[9 * i]), detail::get3<VectorT>(&kept[9 * i + 3]),
+                                                  detail::get3<VectorT>(&kept[9 * i + 6]), detail::get3<VectorT>(&n3[3 * i]));
+      }
+      return elements;
+    }
 
     /** MeshBvh::updateElements + BvhN::updateNodeBounds (MeshBvh.hpp:123-134, BvhN.hpp:816-834): same triangles, moved
      *  vertices. */
-    void updateElements(float const * v9, intx T) { detail::check(h, tgq_refit_triangles(h, v9, T), "tgq_refit_triangles"); }
+    void updateElements(float const * v9, intx T)
+    {
+      detail::check(h, tgq_refit_triangles(h, v9, T), "tgq_refit_triangles");
+      if (!kept.empty()) kept.assign(v9, v9 + 9 * T);        // (host pointers only, like the build that filled it)
+      elements.clear();
+    }
 
     /** getElements()[i].getNormal() for all i (used by ShapeDiameter.hpp:152-153). */
     void getElementNormals(std::vector<float> & n3) const
@@ -346,24 +439,24 @@ class GpuMeshBvhT : public GpuBvhBase<VectorT>
     // ---- RayQueryStructureN ---------------------------------------------------------------------------------------------
 
     /** BvhN::rayIntersects (BvhN.hpp:1266-1269). */
-    template <typename RayIntersectionTesterT>
-    bool rayIntersects(Ray3 const & ray, Real max_time = -1) const
+    template <typename RayIntersectionTesterT, typename RayLikeT = Ray3>
+    bool rayIntersects(RayLikeT const & ray, Real max_time = -1) const
     {
       float o[3], d[3]; uint8_t hit = 0; detail::put3(o, ray.getOrigin()); detail::put3(d, ray.getDirection());
       detail::check(h, tgq_ray_any(h, o, d, &max_time, 1, &hit), "tgq_ray_any");
       return hit != 0;
     }
     /** BvhN::rayIntersectionTime (BvhN.hpp:1271-1289). */
-    template <typename RayIntersectionTesterT>
-    Real rayIntersectionTime(Ray3 const & ray, Real max_time = -1) const
+    template <typename RayIntersectionTesterT, typename RayLikeT = Ray3>
+    Real rayIntersectionTime(RayLikeT const & ray, Real max_time = -1) const
     {
       float o[3], d[3], t = -1; detail::put3(o, ray.getOrigin()); detail::put3(d, ray.getDirection());
       detail::check(h, tgq_ray_first(h, o, d, &max_time, 1, &t, nullptr, nullptr), "tgq_ray_first");
       return t;
     }
     /** BvhN::rayStructureIntersection (BvhN.hpp:1291-1316). */
-    template <typename RayIntersectionTesterT>
-    RayStructureIntersection3 rayStructureIntersection(Ray3 const & ray, Real max_time = -1) const
+    template <typename RayIntersectionTesterT, typename RayLikeT = Ray3>
+    RayStructureIntersection3 rayStructureIntersection(RayLikeT const & ray, Real max_time = -1) const
     {
       float o[3], d[3], t = -1, n[3]; int32_t idx = -1; detail::put3(o, ray.getOrigin()); detail::put3(d, ray.getDirection());
       detail::check(h, tgq_ray_first(h, o, d, &max_time, 1, &t, &idx, n), "tgq_ray_first");
@@ -396,7 +489,8 @@ class GpuMeshBvhT : public GpuBvhBase<VectorT>
     { detail::check(h, tgq_area_sample(h, S, seed, p3, n3, tri), "tgq_area_sample"); }
 
   private:
-    std::vector<float> soup;
+    std::vector<float> soup, kept;
+    mutable std::vector< TriangleElementT<VectorT> > elements;
     bool built;
 };
 
@@ -427,8 +521,64 @@ class GpuPointBvhT : public GpuBvhBase<VectorT>
     void popFilter() { filter = nullptr; }
 
     /** BvhN::init over P points with optional unit normals (P x 3 each; host or device pointers). */
-    void init(float const * p3, intx P, float const * n3 = nullptr) { detail::check(h, tgq_build_points(h, p3, P, n3), "tgq_build_points"); }
-    void clear() { detail::check(h, tgq_build_points(h, nullptr, 0, nullptr), "tgq_build_points"); }
+    void init(float const * p3, intx P, float const * n3 = nullptr) { detail::check(h, tgq_build_points(h, p3, P, n3), "tgq_build_points"); elems.clear(); }
+    /** BvhN::init(begin, end) (BvhN.hpp:704-794) over a host range of points: the copy the reference makes (:722-724) backs getElements(). */
+    template <typename IteratorT> void init(IteratorT begin, IteratorT end)
+    {
+      elems.assign(begin, end);
+      std::vector<float> p3(3 * elems.size());
+      for (size_t i = 0; i < elems.size(); ++i) detail::put3(&p3[3 * i], elems[i]);
+      detail::check(h, tgq_build_points(h, p3.data(), (int64_t)elems.size(), nullptr), "tgq_build_points");
+    }
+    void clear() { elems.clear(); detail::check(h, tgq_build_points(h, nullptr, 0, nullptr), "tgq_build_points"); }
+    /** BvhN::getElements() (BvhN.hpp:952-965); available when the structure was built from a host range (init(begin, end)). */
+    std::vector<VectorT> const & getElements() const
+    {
+      if ((intx)elems.size() != this->numElements()) throw Error("TheaGpu: getElements() needs the structure to be built with init(begin, end)");
+      return elems;
+    }
+
+    // ---- RangeQueryStructure (Algorithms/RangeQueryStructure.hpp:27-95; BvhN.hpp:1208-1264) -------------------------------------
+    // RangeT: a ball (getCenter / getRadius) or an axis-aligned box (getLow / getHigh) -- Thea's Ball3 / AxisAlignedBox3 or the
+    // bundled Ball3T / AxisAlignedBox3T.  The elements in range are found on the device in one call and reported in ASCENDING
+    // element index (the reference reports them in its tree's traversal order).
+
+    /** BvhN::rangeQueryIndices (BvhN.hpp:1215-1220). */
+    template <typename IntersectionTesterT, typename RangeT, typename IndexArrayT>
+    void rangeQueryIndices(RangeT const & range, IndexArrayT & result, bool discard_prior_results = true) const
+    {
+      if (discard_prior_results) result.clear();
+      std::vector<int32_t> idx; rangeIndices(range, idx);
+      for (size_t j = 0; j < idx.size(); ++j) result.push_back((intx)idx[j]);
+    }
+    /** BvhN::rangeQuery (BvhN.hpp:1208-1213): the elements themselves. */
+    template <typename IntersectionTesterT, typename RangeT, typename ElementArrayT>
+    void rangeQuery(RangeT const & range, ElementArrayT & result, bool discard_prior_results = true) const
+    {
+      if (discard_prior_results) result.clear();
+      std::vector<int32_t> idx; rangeIndices(range, idx);
+      std::vector<VectorT> const & e = getElements();
+      for (size_t j = 0; j < idx.size(); ++j) result.push_back(e[(size_t)idx[j]]);
+    }
+    /** BvhN::processRange (BvhN.hpp:1238-1264): functor(index, element) for every element in range until it returns true; returns
+     *  that element's index, else a negative value.  The functor runs on the host over the device's result. */
+    template <typename IntersectionTesterT, typename RangeT, typename FunctorT>
+    intx processRange(RangeT const & range, FunctorT functor) const
+    {
+      std::vector<int32_t> idx; rangeIndices(range, idx);
+      std::vector<VectorT> const & e = getElements();
+      for (size_t j = 0; j < idx.size(); ++j)
+        if (functor((intx)idx[j], e[(size_t)idx[j]])) return (intx)idx[j];
+      return -1;
+    }
+    /** Q ranges in one call, CSR output: kind 0 = balls (a3 centres, b radii), 1 = boxes (a3 low, b high corners). */
+    void rangeQueryBatch(int kind, float const * a3, float const * b, intx Q, std::vector<int64_t> & offsets, std::vector<int32_t> & idx) const
+    {
+      offsets.assign((size_t)Q + 1, 0); int64_t total = 0;
+      detail::check(h, tgq_range_query(h, kind, a3, b, Q, offsets.data(), nullptr, 0, &total), "tgq_range_query");
+      idx.resize((size_t)total);
+      if (total > 0) detail::check(h, tgq_range_query(h, kind, a3, b, Q, offsets.data(), idx.data(), total, &total), "tgq_range_query");
+    }
 
     template <typename MetricT, typename CompatibilityFunctorT = UniversalCompatibility>
     intx closestElement(VectorT const & query, double dist_bound = -1, CompatibilityFunctorT = CompatibilityFunctorT(),
@@ -509,7 +659,7 @@ class GpuPointBvhT : public GpuBvhBase<VectorT>
     /** The reference's scalar form for a ball: appends the indices of all elements in range to `result` (ascending here; the
      *  reference reports traversal order).  More than TGQ_MAX_K elements in range is an error of this adaptor, not a truncation. */
     template <typename IntersectionTesterT>
-    void rangeQueryIndices(VectorT const & center, Real radius, std::vector<intx> & result, bool discard_prior_results = true) const
+    void rangeQueryIndicesBall(VectorT const & center, Real radius, std::vector<intx> & result, bool discard_prior_results = true) const
     {
       if (discard_prior_results) result.clear();
       float c[3]; detail::put3(c, center);
@@ -549,7 +699,19 @@ class GpuPointBvhT : public GpuBvhBase<VectorT>
     { float out = 0; detail::check(h, tgq_avg_separation(h, seeds, n, &out), "tgq_avg_separation"); return out; }
 
   private:
+    template <typename RangeT> auto rangeIndices(RangeT const & range, std::vector<int32_t> & idx) const -> decltype(range.getRadius(), void())
+    {
+      float c[3], r = (float)range.getRadius(); detail::put3(c, range.getCenter());
+      std::vector<int64_t> off; rangeQueryBatch(0, c, &r, 1, off, idx);
+    }
+    template <typename RangeT> auto rangeIndices(RangeT const & range, std::vector<int32_t> & idx) const -> decltype(range.getLow(), void())
+    {
+      float lo[3], hi[3]; detail::put3(lo, range.getLow()); detail::put3(hi, range.getHigh());
+      std::vector<int64_t> off; rangeQueryBatch(1, lo, hi, 1, off, idx);
+    }
+
     NNFilter const * filter;
+    std::vector<VectorT> elems;
 };
 
 typedef GpuMeshBvhT<Vec3> GpuMeshBvh;

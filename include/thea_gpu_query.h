@@ -162,6 +162,17 @@ int tgq_knn_filtered(tgq_handle * h, const float * q3, const float * qn3, const 
 int tgq_ball_range(tgq_handle * h, const float * c3, const float * radius, int64_t Q, int32_t max_out, int32_t exclude_self,
                    int32_t * idx, int32_t * count);
 
+/* Q unbounded range queries on a point structure.  Replaces BvhN::rangeQueryIndices / rangeQuery / processRange
+ * <IntersectionTester>(range, ...) (BvhN.hpp:1208-1264,2118-2171) for the two range types the reference's callers and tests use:
+ * kind 0: Ball3(a3[i], b[i])  -- every element with sq(x - c) <= r * r in fp32 (BallN.hpp:83);   b = Q radii
+ * kind 1: AxisAlignedBox3(a3[i], b[3 i ..])  -- every element with lo <= x <= hi (AxisAlignedBoxN.hpp:401-412);   b = Q x 3 high corners
+ * Output in CSR form: offsets[Q + 1] (int64) and idx[total] (int32), the elements of range i at idx[offsets[i] .. offsets[i + 1]) in
+ * ASCENDING element index (the reference reports its tree's traversal order; the set is the same).  *total always receives the
+ * number of (range, element) pairs; when it exceeds `capacity` (the size of idx, 0 allowed to ask for the counts only) the call
+ * fills offsets only and, for capacity > 0, returns TGQ_ELIMIT. */
+int tgq_range_query(tgq_handle * h, int32_t kind, const float * a3, const float * b, int64_t Q, int64_t * offsets, int32_t * idx,
+                    int64_t capacity, int64_t * total);
+
 /* Q ball neighbourhood statistics on a point structure (the local surface features are processRange calls
  * with an accumulating functor).  Replaces, for every query ball (c_i, r_i),
  *   surf->getBvh().processRange<IntersectionTester>(Ball3(c_i, r_i), functor)                    (BvhN.hpp:1238-1264,2118-2171)

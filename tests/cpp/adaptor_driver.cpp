@@ -112,6 +112,44 @@ int main(int argc, char ** argv)
     float avg = sampleGraph(pts, 6, seeds.data(), (int32_t)seeds.size(), gi.data(), gs.data(), gc.data());
     std::vector<float> av(1, avg); wr(fo, av); wr(fo, gi); wr(fo, gs); wr(fo, gc);
 
+    // ---- range queries the way Test/TestBvh.cpp:174-197 writes them (ball and box ranges, functor / elements / indices), on a
+    //      structure built from a host range so that getElements() is available; checked here against the definition ----
+    {
+      std::vector<Vec3> pv; for (int64_t i = 0; i < NS; ++i) pv.push_back(Vec3(sp[3 * i], sp[3 * i + 1], sp[3 * i + 2]));
+      GpuPointBvh rb; rb.init(pv.begin(), pv.end());
+      if ((int64_t)rb.getElements().size() != NS) { fprintf(stderr, "getElements size\n"); return 3; }
+      Vec3 c(sp[0], sp[1], sp[2]);
+      Ball3T<Vec3> ball(c, 0.25f);
+      AxisAlignedBox3T<Vec3> box(Vec3(c[0] - 0.3f, c[1] - 0.2f, c[2] - 0.1f), Vec3(c[0] + 0.1f, c[1] + 0.2f, c[2] + 0.3f));
+      std::vector<intx> want_ball, want_box;
+      for (int64_t i = 0; i < NS; ++i)
+      {
+        float dx = pv[i][0] - c[0], dy = pv[i][1] - c[1], dz = pv[i][2] - c[2];
+        if (dx * dx + (dy * dy + dz * dz) <= 0.25f * 0.25f) want_ball.push_back(i);
+        bool in = true; for (int a = 0; a < 3; ++a) in = in && !(pv[i][a] < box.getLow()[a]) && !(pv[i][a] > box.getHigh()[a]);
+        if (in) want_box.push_back(i);
+      }
+      std::vector<intx> got; rb.rangeQueryIndices<IntersectionTester>(ball, got);
+      if (got != want_ball || got.empty()) { fprintf(stderr, "rangeQueryIndices(ball) %zu vs %zu\n", got.size(), want_ball.size()); return 3; }
+      rb.rangeQueryIndices<IntersectionTester>(box, got);
+      if (got != want_box || got.empty()) { fprintf(stderr, "rangeQueryIndices(box) %zu vs %zu\n", got.size(), want_box.size()); return 3; }
+      std::vector<Vec3> elems; rb.rangeQuery<IntersectionTester>(box, elems);
+      if (elems.size() != want_box.size() || elems[0][0] != pv[want_box[0]][0]) { fprintf(stderr, "rangeQuery(box)\n"); return 3; }
+      size_t visited = 0; intx stop = want_box[want_box.size() / 2];
+      intx r = rb.processRange<IntersectionTester>(box, [&](intx index, Vec3 const &) { ++visited; return index == stop; });
+      if (r != stop || visited != want_box.size() / 2 + 1) { fprintf(stderr, "processRange early termination\n"); return 3; }
+      r = rb.processRange<IntersectionTester>(ball, [&](intx, Vec3 const &) { return false; });
+      if (r >= 0) { fprintf(stderr, "processRange full pass\n"); return 3; }
+    }
+    // getElements() of the triangle structure: vertices as given, normals as the device cached them
+    {
+      std::vector<float> n3; bvh.getElementNormals(n3);
+      auto const & el = bvh.getElements();
+      if ((int64_t)el.size() != T || el[T - 1].getVertex(2)[1] != v9[9 * (T - 1) + 7] || el[3].getNormal()[2] != n3[11]) { fprintf(stderr, "getElements (mesh)\n"); return 3; }
+      auto bb = bvh.getBounds();
+      if (!(bb.getExtent()[0] > 0) || !(bb.getLow()[0] < lo[0])) { fprintf(stderr, "getBounds is not the padded root box\n"); return 3; }
+    }
+
     // ---- filtered nearest neighbours the way Tools/Register/Register.cpp:210-236,262-287 writes them ----
     std::vector<int32_t> labels(NS); for (int64_t i = 0; i < NS; ++i) labels[i] = (int32_t)(i % 3);
     pts.setLabels(labels.data());

@@ -320,6 +320,17 @@ void emu_knn_filtered(void * h, float const * q3, float const * qn3, int32_t con
   }
 }
 
+// Unbounded range query (tgq_range_query): returns the number of elements in the range, writes up to cap indices (traversal order).
+int64_t emu_range_all(void * h, int box, float const * a3, float const * b3, float radius, int32_t * idx, int64_t cap)
+{
+  Emu & E = *(Emu *)h; BvhView v = E.view();
+  std::vector<int> out((size_t)E.n + 4);
+  int n = box ? range_all_query<true, true>(v, ld(a3, 0), ld(b3, 0), out.data())
+              : (radius >= 0.0f ? range_all_query<false, true>(v, ld(a3, 0), mk3(radius * radius, radius, 0.0f), out.data()) : 0);
+  for (int j = 0; j < n && j < cap; ++j) idx[j] = out[(size_t)j];
+  return n;
+}
+
 void emu_ball_range(void * h, float const * c3, float const * radius, int64_t Q, int max_out, int exclude_self, int32_t * idx, int32_t * count)
 {
   Emu & E = *(Emu *)h; BvhView v = E.view();

@@ -96,6 +96,18 @@ class Emu:
         lib().emu_closest(self.h, _p(q), Q, float(dist_bound), flag, _p(idx), _p(d2), _p(cp))
         return idx, d2, cp
 
+    def range_all(self, a, b, box=False):
+        """All elements in Ball3(a, b) or AxisAlignedBox3(a, b): ascending element indices."""
+        L = lib()
+        L.emu_range_all.restype = C.c_int64
+        L.emu_range_all.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int64]
+        a = np.ascontiguousarray(a, np.float32)
+        bb = np.ascontiguousarray(b, np.float32).reshape(3) if box else np.zeros(3, np.float32)
+        cap = 1 << 22
+        idx = np.empty(cap, np.int32)
+        n = L.emu_range_all(self.h, int(box), _p(a), _p(bb), 0.0 if box else float(b), _p(idx), cap)
+        return np.sort(idx[:n])
+
     def ball_range(self, c, radius, max_out=32, exclude_self=False):
         c = np.ascontiguousarray(c, np.float32)
         Q = len(c)

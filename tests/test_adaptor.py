@@ -213,3 +213,29 @@ def test_adaptor_driver_matches_oracle(built, tmp_path):
     ovis, _ = ora.visibility(sp, d[:32], vscale, mode=orc.MODE_BRUTE)
     assert np.array_equal(vis, ovis)
     assert pos[0] == len(buf)
+
+
+@pytest.mark.gpu
+def test_reference_caller_templates_run_on_the_adaptor(built, tmp_path):
+    """tests/cpp/thea_callers_driver: Thea's OWN ShapeDiameter<Mesh, ExternalBvhT>, Icp3<Real>::align(n, from, structure) and the
+    range / nearest-neighbour call shapes of Test/TestBvh.cpp, compiled unmodified with TheaGpu::GpuMeshBvhT<Thea::Vector3> /
+    GpuPointBvhT<Thea::Vector3> as the structure, against the same templates on Thea's BvhN.  The binary is built where
+    /root/reference exists and travels to the GPU box."""
+    exe = os.path.join(ROOT, "tests", "cpp", "thea_callers_driver")
+    if not os.path.exists(exe):
+        pytest.skip("thea_callers_driver was not built (needs /root/reference at build time)")
+    mesh = gen.torus_mesh(40)
+    S, NI, P = 400, 1500, 6000
+    sp, sn, _ = gen.area_samples(mesh, S)
+    p, _, _ = gen.area_samples(mesh, NI, seed=5)
+    src = gen.apply_pose(p, *gen.rigid_pose())
+    pts, _, _ = gen.area_samples(mesh, P, seed=6)
+    inp = tmp_path / "in.bin"
+    with open(inp, "wb") as f:
+        f.write(struct.pack("<4q", len(mesh), S, NI, P))
+        for a in (mesh, sp, sn, src, pts):
+            f.write(np.ascontiguousarray(a, np.float32).tobytes())
+    r = subprocess.run([exe, str(inp)], capture_output=True, text=True)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert '"fails": 0' in r.stdout

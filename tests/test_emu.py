@@ -355,3 +355,33 @@ def test_four_wide_traversal_equals_binary_traversal_and_brute_force():
                 wi, wd, wc = E.closest(q, dist_bound=bound, seeded=seeded)
                 assert np.array_equal(wi, bi) and np.array_equal(wd, bd) and np.array_equal(wc, bc)
                 assert np.array_equal(wi, oi.astype(np.int32)) and np.array_equal(wd, od)
+
+
+def _in_ball_f32(p, c, r):
+    d = (p - c).astype(np.float32)
+    xx, yy, zz = d[:, 0] * d[:, 0], d[:, 1] * d[:, 1], d[:, 2] * d[:, 2]
+    return (xx + (yy + zz)) <= np.float32(r) * np.float32(r)          # BallN::contains in Eigen's order
+
+
+def test_unbounded_range_queries_ball_and_box():
+    """tgq_range_query's traversal: every element with sq(x - c) <= r * r (BallN.hpp:83) / lo <= x <= hi (AxisAlignedBoxN.hpp:401-412),
+    against the fp32 definition evaluated over all elements; points on the boundary are in."""
+    from emu_lib import Emu
+    mesh = gen.torus_mesh(40)
+    p, _, _ = gen.area_samples(mesh, 20000)
+    E = Emu(points=p)
+    rng = np.random.default_rng(11)
+    for _ in range(40):
+        c = p[rng.integers(0, len(p))] + rng.normal(0, 0.02, 3).astype(np.float32)
+        r = np.float32(rng.choice([0.0, 0.01, 0.05, 0.2, 0.7, 5.0]))
+        assert np.array_equal(E.range_all(c, r), np.flatnonzero(_in_ball_f32(p, c.astype(np.float32), r)))
+        lo = (c - rng.random(3).astype(np.float32) * np.float32(0.3)).astype(np.float32)
+        hi = (c + rng.random(3).astype(np.float32) * np.float32(0.3)).astype(np.float32)
+        want = np.flatnonzero(np.all((p >= lo) & (p <= hi), axis=1))
+        assert np.array_equal(E.range_all(lo, hi, box=True), want)
+    # boundary points: a ball through a sample, a box with a sample on its face
+    c = p[5]
+    r = np.float32(np.sqrt(np.float32(((p[9] - c) ** 2).sum())))
+    got = E.range_all(c, r)
+    assert np.array_equal(got, np.flatnonzero(_in_ball_f32(p, c, r)))
+    assert 9 in E.range_all(np.minimum(p[5], p[9]), np.maximum(p[5], p[9]), box=True).tolist()

@@ -6,6 +6,7 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_segmented_radix_sort.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -964,6 +965,63 @@ int tgq_ball_range(tgq_handle * h, const float * c3, const float * radius, int64
     h->st.last_launches += 1; h->st.total_launches += 1;
     return TGQ_OK;
   });
+}
+
+int tgq_range_query(tgq_handle * h, int32_t kind, const float * a3, const float * b, int64_t Q, int64_t * offsets, int32_t * idx, int64_t capacity,
+                    int64_t * total)
+{
+  CKRC(need_built(h, 1 << TGQ_KIND_POINTS));
+  if (kind < 0 || kind > 1 || Q < 0 || capacity < 0 || !offsets || !total || (Q > 0 && (!a3 || !b)) || (capacity > 0 && !idx))
+    return fail(h, TGQ_EINVAL, "tgq_range_query: bad arguments");
+  if (Q >= ((int64_t)1 << 31)) return fail(h, TGQ_ELIMIT, "tgq_range_query: more than 2^31 - 1 ranges in one call");
+  Guard g(h);
+  cudaStream_t s = h->stream;
+  *total = 0;
+  if (Q == 0)
+  {
+    int64_t z = 0;
+    if (!is_device_ptr(offsets)) offsets[0] = 0;
+    else { CK(cudaMemcpyAsync(offsets, &z, 8, cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s)); }
+    return TGQ_OK;
+  }
+  size_t nq = (size_t)Q; bool box = kind == 1;
+  void const * da = nullptr; void const * db = nullptr;
+  CKRC(to_device(h, a3, 12 * nq, h->slot[0].in[0], s, &da));
+  CKRC(to_device(h, b, (box ? 12 : 4) * nq, h->slot[0].in[1], s, &db));
+  // pass 1: counts; exclusive scan -> offsets; pass 2: indices; segmented sort -> ascending element index per range
+  CK(h->slot[0].out[0].reserve(4 * nq)); CK(h->slot[0].out[1].reserve(8 * (nq + 1)));
+  int * dcount = h->slot[0].out[0].as<int>(); long long * doff = h->slot[0].out[1].as<long long>();
+  BvhView v = view_of(h);
+  size_t smem = trav_smem_bytes(2);
+  int grid = 0; int * cnt = h->slot[0].counter.as<int>();
+  if (box) { CKRC(persistent_grid(h, k_range_all<true, false>, smem, Q, cnt, s, &grid)); k_range_all<true, false><<<grid, TGQ_BLOCK, smem, s>>>(v, (float const *)da, (float const *)db, nullptr, (int)Q, cnt, nullptr, nullptr, dcount); }
+  else     { CKRC(persistent_grid(h, k_range_all<false, false>, smem, Q, cnt, s, &grid)); k_range_all<false, false><<<grid, TGQ_BLOCK, smem, s>>>(v, (float const *)da, (float const *)db, nullptr, (int)Q, cnt, nullptr, nullptr, dcount); }
+  CK(cudaGetLastError());
+  CK(cudaMemsetAsync(doff, 0, 8 * (nq + 1), s));
+  size_t tmp = 0;
+  CK(cub::DeviceScan::InclusiveSum(nullptr, tmp, dcount, doff + 1, (int)Q, s));
+  CK(h->cubtmp.reserve(tmp));
+  CK(cub::DeviceScan::InclusiveSum(h->cubtmp.p, tmp, dcount, doff + 1, (int)Q, s));
+  long long tot = 0;
+  CK(cudaMemcpyAsync(&tot, doff + nq, 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  *total = (int64_t)tot;
+  h->st.total_launches += 3;
+  CKRC(from_device(h, offsets, doff, 8 * (nq + 1), s));
+  if (tot > capacity || tot == 0) { CK(cudaStreamSynchronize(s)); return tot > capacity && capacity > 0 ? fail(h, TGQ_ELIMIT, "tgq_range_query: index buffer too small (see *total)") : TGQ_OK; }
+  CK(h->slot[0].out[2].reserve(4 * (size_t)tot)); CK(h->slot[0].out[3].reserve(4 * (size_t)tot));
+  int * raw = h->slot[0].out[2].as<int>(); int * sorted = is_device_ptr(idx) ? idx : h->slot[0].out[3].as<int>();
+  if (box) { CKRC(persistent_grid(h, k_range_all<true, true>, smem, Q, cnt, s, &grid)); k_range_all<true, true><<<grid, TGQ_BLOCK, smem, s>>>(v, (float const *)da, (float const *)db, nullptr, (int)Q, cnt, doff, raw, nullptr); }
+  else     { CKRC(persistent_grid(h, k_range_all<false, true>, smem, Q, cnt, s, &grid)); k_range_all<false, true><<<grid, TGQ_BLOCK, smem, s>>>(v, (float const *)da, (float const *)db, nullptr, (int)Q, cnt, doff, raw, nullptr); }
+  CK(cudaGetLastError());
+  tmp = 0;
+  CK(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tmp, raw, sorted, (int)tot, (int)Q, doff, doff + 1, 0, 32, s));
+  CK(h->cubtmp.reserve(tmp));
+  CK(cub::DeviceSegmentedRadixSort::SortKeys(h->cubtmp.p, tmp, raw, sorted, (int)tot, (int)Q, doff, doff + 1, 0, 32, s));
+  h->st.total_launches += 2;
+  if (sorted != idx) CKRC(from_device(h, idx, sorted, 4 * (size_t)tot, s));
+  CK(cudaStreamSynchronize(s));
+  return TGQ_OK;
 }
 
 int tgq_ball_stats(tgq_handle * h, const float * c3, const float * qn3, const float * radius, int64_t Q, double * out16)

@@ -1264,6 +1264,46 @@ k_ball_range(BvhView b, float const * __restrict__ c3, float const * __restrict_
   warp_run(w, n, counter, stage);
 }
 
+// ---- unbounded range queries on a point structure (ball or axis-aligned box ranges) ------------------------------------------
+template <bool BOX, bool FILL>
+struct RangeAllW
+{
+  static constexpr int STAGE = 2;       // (a, query index) (b, -)
+  RangeAllState<BOX> s; BvhView b; float const * a3; float const * bq; uint32_t const * perm; long long const * offsets; int * idx; int * count; int64_t qi;
+  __device__ __forceinline__ int state() const { return s.t.cur; }
+  __device__ __forceinline__ void stage(int t, f4 * dst) const
+  {
+    int i = perm ? (int)perm[t] : t; v3 a = ld3(a3, i);
+    dst[0] = make_float4(a.x, a.y, a.z, __int_as_float(i));
+    if (BOX) { v3 h = ld3(bq, i); dst[1] = make_float4(h.x, h.y, h.z, 0.0f); }
+    else { float r = bq[i]; dst[1] = make_float4(r * r, r, 0.0f, 0.0f); }       // BallN::contains: r * r in fp32
+  }
+  __device__ __forceinline__ void begin(int, f4 const * src)
+  {
+    f4 a = src[0], h = src[1]; qi = __float_as_int(a.w);
+    bool valid = BOX ? true : h.y >= 0.0f;
+    range_all_begin(s, b, mk3(a.x, a.y, a.z), mk3(h.x, h.y, h.z), FILL ? idx + offsets[qi] : nullptr, valid);
+  }
+  static constexpr int FETCH = TGQ_FETCH_BOX;
+  __device__ __forceinline__ void pop_step() { trav_pop_step(s.t, 0.5f); }
+  __device__ __forceinline__ void fetch(f4 * r) const { box_fetch(s.t, b, r); }
+  __device__ __forceinline__ void node_compute(f4 const * r) { range_all_node_compute(s, b, r); }
+  __device__ __forceinline__ void leaf_compute(f4 const * r) { range_all_leaf_compute<BOX, FILL>(s, b, r); }
+  __device__ __forceinline__ void finish() { if (!FILL) count[qi] = s.count; s.t.cur = TGQ_ST_IDLE; }
+};
+
+template <bool BOX, bool FILL>
+__global__ void __launch_bounds__(TGQ_BLOCK)
+k_range_all(BvhView b, float const * __restrict__ a3, float const * __restrict__ bq, uint32_t const * __restrict__ perm, int n, int * counter,
+            long long const * __restrict__ offsets, int * idx, int * count)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  RangeAllW<BOX, FILL> w;
+  w.b = b; w.a3 = a3; w.bq = bq; w.perm = perm; w.offsets = offsets; w.idx = idx; w.count = count; w.qi = 0; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
+  f4 * stage = trav_setup(w.s.t, st, smem, RangeAllW<BOX, FILL>::STAGE, nullptr);
+  warp_run(w, n, counter, stage);
+}
+
 // ---- ball neighbourhood statistics on a point structure (processRange with the local-feature functors) ----------------------
 struct StatsW
 {

@@ -905,6 +905,78 @@ TGQ_HD void range_query(BvhView const & b, v3 c, float radius, int self, SortedS
   set.n = s.set.n; count = s.count;
 }
 
+// Unbounded range queries on a point structure: BvhN::processRange / rangeQuery / rangeQueryIndices<IntersectionTester>(range, ...)
+// (BvhN.hpp:1208-1264,2118-2171) with a Ball3 or an AxisAlignedBox3 as the range.  The element tests are the reference's
+// (IntersectionTester.hpp:105-125 -> BallN::contains, BallN.hpp:83: sq(x - c) <= r * r;  AxisAlignedBoxN::contains,
+// AxisAlignedBoxN.hpp:401-412: lo <= x <= hi in every coordinate); the reference's shortcut for nodes wholly inside the range
+// (BvhN.hpp:2129-2143) takes every element of such a node without testing it, which is the same set because a node's padded box
+// contains its elements.  The result is the SET of elements in range; the reference reports it in its tree's traversal order,
+// here it is canonical: ascending element index.  FILL == false counts, FILL == true writes the indices at out[n++].
+template <bool BOX>
+struct RangeAllState
+{
+  v3 a, b;          // ball: centre, (r * r, -, -);  box: lo, hi
+  int count; int * out;
+  Trav t;
+};
+template <bool BOX>
+TGQ_HD void range_all_begin(RangeAllState<BOX> & s, BvhView const & bv, v3 a, v3 b, int * out, bool valid)
+{ s.a = a; s.b = b; s.count = 0; s.out = out; trav_begin(s.t, valid ? bv.n_nodes : 0); }
+template <bool BOX>
+TGQ_HD void range_all_node_compute(RangeAllState<BOX> & s, BvhView const &, f4 const * r)
+{
+  TGQ_COUNT_NODE();
+  NodeRec nd; nd.q0 = r[0]; nd.q1 = r[1]; nd.q2 = r[2]; nd.q3 = r[3];
+  v3 lo0, hi0, lo1, hi1; node_boxes(nd, lo0, hi0, lo1, hi1);
+  int c0 = f2i(nd.q3.x), c1 = f2i(nd.q3.y);
+  float k0, k1;            // 0: the child's (padded) box meets the range, 1: it cannot
+  if (BOX)
+  {
+    k0 = (lo0.x > s.b.x || hi0.x < s.a.x || lo0.y > s.b.y || hi0.y < s.a.y || lo0.z > s.b.z || hi0.z < s.a.z) ? 1.0f : 0.0f;
+    k1 = (lo1.x > s.b.x || hi1.x < s.a.x || lo1.y > s.b.y || hi1.y < s.a.y || lo1.z > s.b.z || hi1.z < s.a.z) ? 1.0f : 0.0f;
+  }
+  else
+  {
+    k0 = box_point_sqdist(lo0, hi0, s.a) * TGQ_LB_DEFLATE <= s.b.x ? 0.0f : 1.0f;
+    k1 = box_point_sqdist(lo1, hi1, s.a) * TGQ_LB_DEFLATE <= s.b.x ? 0.0f : 1.0f;
+  }
+  trav_descend(s.t, k0, k1, 0.0f, 0.0f, c0, c1, 0.5f);
+}
+template <bool BOX, bool FILL>
+TGQ_HD void range_all_leaf_compute(RangeAllState<BOX> & s, BvhView const &, f4 const * r)
+{
+  int cnt = s.t.kend - s.t.k; if (cnt > TGQ_FETCH_BOX) cnt = TGQ_FETCH_BOX;
+  for (int j = 0; j < TGQ_FETCH_BOX; ++j)
+  {
+    if (j >= cnt) break;
+    TGQ_COUNT_PRIM();
+    f4 e = r[j];
+    bool in;
+    if (BOX) in = !(e.x < s.a.x || e.x > s.b.x || e.y < s.a.y || e.y > s.b.y || e.z < s.a.z || e.z > s.b.z);
+    else in = sqn3(sub3(mk3(e.x, e.y, e.z), s.a)) <= s.b.x;
+    if (!in) continue;
+    if (FILL) s.out[s.count] = f2i(e.w);
+    ++s.count;
+  }
+  s.t.k += cnt;
+  if (s.t.k >= s.t.kend) trav_pop(s.t);
+}
+// Whole query in one go (host emulation).
+template <bool BOX, bool FILL>
+TGQ_HD int range_all_query(BvhView const & bv, v3 a, v3 b, int * out)
+{
+  RangeAllState<BOX> s; TravStack st; trav_bind(s.t, st);
+  range_all_begin(s, bv, a, b, out, true);
+  f4 r[TGQ_FETCH_BOX];
+  while (s.t.cur != TGQ_ST_DONE)
+  {
+    if (s.t.cur == TGQ_ST_POP) { trav_pop_step(s.t, 0.5f); continue; }
+    box_fetch(s.t, bv, r);
+    if (s.t.cur >= 0) range_all_node_compute(s, bv, r); else range_all_leaf_compute<BOX, FILL>(s, bv, r);
+  }
+  return s.count;
+}
+
 // Ball neighbourhood statistics on a point structure: BvhN::processRange<IntersectionTester>(Ball3(c, r), functor) (BvhN.hpp:1238-
 // 1264,2118-2171) with the accumulating functors of the local surface features, all in one pass over the
 // elements with sq(x_e - c) <= r * r:

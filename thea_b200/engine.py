@@ -25,7 +25,7 @@ SYMBOLS = [
     "tgq_ray_first", "tgq_ray_any", "tgq_sdf", "tgq_icp_sums", "tgq_transform_points", "tgq_area_sample",
     "tgq_get_stats", "tgq_set_point_labels", "tgq_closest_filtered", "tgq_knn_filtered", "tgq_icp_align", "tgq_ball_range",
     "tgq_ball_stats", "tgq_visibility", "tgq_ball_graph_surface", "tgq_ball_histogram", "tgq_set_transform",
-    "tgq_closest_records", "tgq_ray_first_records", "tgq_synchronize", "tgq_scatter_records", "tgq_bucket_records",
+    "tgq_closest_records", "tgq_ray_first_records", "tgq_synchronize", "tgq_scatter_records", "tgq_bucket_records", "tgq_range_query",
 ]
 
 
@@ -99,6 +99,7 @@ def load_library(path=None):
     L.tgq_ray_first_records.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, i32, i32, vp]
     L.tgq_scatter_records.argtypes = [vp, vp, i32, i64, vp, i32, vp]
     L.tgq_bucket_records.argtypes = [vp, vp, i64, i32, i64, i32, vp, i64, vp]
+    L.tgq_range_query.argtypes = [vp, i32, vp, vp, i64, vp, vp, i64, vp]
     for name in SYMBOLS:
         if name not in ("tgq_last_error",):
             getattr(L, name).restype = C.c_int
@@ -323,6 +324,20 @@ class Engine:
         hist = np.empty((Q, num_bins), np.uint32)
         self._ck(self._L.tgq_ball_histogram(self._h, _ptr(c3), _ptr(rad), Q, int(num_bins), _ptr(hist)))
         return hist
+
+    def range_query(self, a3, b, box=False):
+        """tgq_range_query: all elements of a point structure in Q balls (a3 = centres, b = radii) or boxes (a3 = low, b = high corners).
+        Returns (offsets [Q + 1] int64, idx [total] int32): CSR, ascending element index per range."""
+        a3 = np.ascontiguousarray(a3, np.float32).reshape(-1, 3)
+        Q = a3.shape[0]
+        b = np.ascontiguousarray(b, np.float32).reshape(-1, 3) if box else np.ascontiguousarray(np.broadcast_to(np.asarray(b, np.float32), (Q,)), np.float32)
+        off = np.zeros(Q + 1, np.int64)
+        total = C.c_int64()
+        self._ck(self._L.tgq_range_query(self._h, 1 if box else 0, _ptr(a3), _ptr(b), Q, _ptr(off), None, 0, C.byref(total)))
+        idx = np.empty(max(1, total.value), np.int32)
+        if total.value:
+            self._ck(self._L.tgq_range_query(self._h, 1 if box else 0, _ptr(a3), _ptr(b), Q, _ptr(off), _ptr(idx), total.value, C.byref(total)))
+        return off, idx[:total.value]
 
     def ball_stats(self, c3, radius, qn3=None, out=None):
         """Per-ball neighbourhood sums (tgq_ball_stats): [Q x 16] doubles, layout in include/thea_gpu_query.h."""
