@@ -147,7 +147,8 @@ int main(int argc, char ** argv)
       auto const & el = bvh.getElements();
       if ((int64_t)el.size() != T || el[T - 1].getVertex(2)[1] != v9[9 * (T - 1) + 7] || el[3].getNormal()[2] != n3[11]) { fprintf(stderr, "getElements (mesh)\n"); return 3; }
       auto bb = bvh.getBounds();
-      if (!(bb.getExtent()[0] > 0) || !(bb.getLow()[0] < lo[0])) { fprintf(stderr, "getBounds is not the padded root box\n"); return 3; }
+      Vec3 el_lo, el_hi; bvh.getElementBounds(el_lo, el_hi);
+      if (!(bb.getExtent()[0] > 0) || !(bb.getLow()[0] < el_lo[0]) || !(bb.getHigh()[2] > el_hi[2])) { fprintf(stderr, "getBounds is not the padded root box\n"); return 3; }
     }
 
     // ---- filtered nearest neighbours the way Tools/Register/Register.cpp:210-236,262-287 writes them ----
