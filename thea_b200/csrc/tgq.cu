@@ -78,7 +78,7 @@ struct tgq_handle
   DevBuf area_by_elem, cum;                                           // float[n] in element order; double[n] cumulative
   DevBuf obbs, pnrm, nsum, obbinfo, big, big_count;                   // oriented boxes (triangle structures)
   DevBuf wide, wflag, widx, obbinfo_w; int n_wide = 0;                 // 4-wide nodes of the closest-point traversal
-  int opt_cell_bits = TGQ_SHARD_CELL_BITS;
+  int opt_cell_bits = TGQ_SHARD_CELL_BITS, opt_ray_order = 0; bool sorting_rays = false;
   int shard_rank = 0, shard_world = 1;                                 // set by the *_records entry points for the duration of one call
   PeerOut peers = {}; int64_t last_share = 0;                          // queries this rank answered in the last *_records call
   int sm_count = 148; std::map<std::pair<void const *, size_t>, int> occupancy;   // resident blocks per SM of the persistent kernels
@@ -395,7 +395,7 @@ int sort_chunk(tgq_handle * h, ChunkCtx & c)
   if (!want || h->n == 0) return TGQ_OK;
   for (int i = 0; i < 2; ++i) { CK(sl.keys[i].reserve(4 * nn)); CK(sl.vals[i].reserve(4 * nn)); }
   k_query_codes<<<grid_for(c.n), TGQ_BLOCK, 0, c.stream>>>((float const *)c.din[0], c.n, h->scene.as<SceneBox>(), sl.keys[0].as<uint32_t>(),
-                                                           sl.vals[0].as<uint32_t>());
+                                                           sl.vals[0].as<uint32_t>(), h->sorting_rays ? (float const *)c.din[1] : nullptr, h->opt_ray_order);
   CK(cudaGetLastError());
   size_t tmp = 0;
   CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, sl.keys[0].as<uint32_t>(), sl.keys[1].as<uint32_t>(), sl.vals[0].as<uint32_t>(),
@@ -613,6 +613,7 @@ int tgq_set_option(tgq_handle * h, int option, int64_t value)
     case TGQ_OPT_POOL: h->opt_pool = value ? 1 : 0; return TGQ_OK;
     case TGQ_OPT_ICP_REFERENCE_ORDER: h->opt_icp_ref = value ? 1 : 0; return TGQ_OK;
     case TGQ_OPT_WIDE: h->opt_wide = value ? 1 : 0; return TGQ_OK;
+    case TGQ_OPT_RAY_ORDER: if (value != 0 && (value < 3 || value > 30)) return fail(h, TGQ_EINVAL, "TGQ_OPT_RAY_ORDER takes 0 or 3..30"); h->opt_ray_order = (int)value; return TGQ_OK;
     case TGQ_OPT_SHARD_CELL_BITS: if (value < 3 || value > 30) return fail(h, TGQ_EINVAL, "TGQ_OPT_SHARD_CELL_BITS takes 3..30"); h->opt_cell_bits = (int)value; return TGQ_OK;
     case TGQ_OPT_CHUNK: if (value < 1024) return fail(h, TGQ_EINVAL, "TGQ_OPT_CHUNK must be >= 1024"); h->opt_chunk = value; return TGQ_OK;
     default: return fail(h, TGQ_EINVAL, "unknown option");
@@ -1133,6 +1134,8 @@ static int ray_common(tgq_handle * h, const float * o3, const float * d3, const 
   BvhView v = view_of(h);
   size_t smem = trav_smem_bytes(2);
   Arg args[7] = {{o3, nullptr, 12}, {d3, nullptr, 12}, {tmax, nullptr, 4}, {nullptr, t, 4}, {nullptr, idx, 4}, {nullptr, normal3, 12}, {nullptr, hit, 1}};
+  h->sorting_rays = h->opt_ray_order >= 3;
+  struct Reset { tgq_handle * h; ~Reset() { h->sorting_rays = false; } } reset = {h};
   return run_batched(h, R, args, 7, true, [&](ChunkCtx & c) -> int {
     int grid = 0; int * cnt = c.slot->counter.as<int>();
     if (any)

@@ -406,7 +406,10 @@ __global__ void k_scatter_cache(TriRec const * __restrict__ tris, float const * 
 }
 
 // ---- query ordering ---------------------------------------------------------------------------------------------------
-__global__ void k_query_codes(float const * __restrict__ q3, int n, SceneBox const * sb, uint32_t * keys, uint32_t * vals)
+// dir3 != null (ray batches, TGQ_OPT_RAY_ORDER): the `obits` lowest bits of the origin's code are replaced by the direction's sign
+// octant (3 bits) above the remaining origin bits -- rays of one cell are grouped by the octant they head into.
+__global__ void k_query_codes(float const * __restrict__ q3, int n, SceneBox const * sb, uint32_t * keys, uint32_t * vals, float const * __restrict__ dir3 = nullptr,
+                              int obits = 0)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
   SceneF s = scene_decode(sb);
@@ -414,7 +417,15 @@ __global__ void k_query_codes(float const * __restrict__ q3, int n, SceneBox con
   v3 c = mul3(add3(s.lo, s.hi), 0.5f), e = sub3(s.hi, s.lo);
   v3 lo = sub3(c, e);
   v3 inv = mk3(e.x > 0 ? 0.5f / e.x : 0.0f, e.y > 0 ? 0.5f / e.y : 0.0f, e.z > 0 ? 0.5f / e.z : 0.0f);
-  keys[i] = morton30(ld3(q3, i), lo, inv); vals[i] = (uint32_t)i;
+  uint32_t code = morton30(ld3(q3, i), lo, inv);
+  if (dir3 && obits >= 3)
+  {
+    v3 d = ld3(dir3, i);
+    uint32_t oct = (d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u);
+    uint32_t low = code & ((1u << obits) - 1u);
+    code = (code & ~((1u << obits) - 1u)) | (oct << (obits - 3)) | (low >> 3);
+  }
+  keys[i] = code; vals[i] = (uint32_t)i;
 }
 
 // ---- sharding a replicated batch by space (multi-GPU) --------------------------------------------------------------------------

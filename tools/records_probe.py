@@ -10,6 +10,7 @@ def main(N=50_000_000):
     s = torch.cuda.Stream(device=dev); torch.cuda.set_stream(s)
     mesh = gen.torus_mesh(gen.TORUS_10M); bounds = gen.mesh_bounds(mesh)
     e = Engine(0); e.set_stream(s.cuda_stream)
+    if os.environ.get("TGQ_RAY_ORDER"): e.set_option(9, int(os.environ["TGQ_RAY_ORDER"]))
     e.build_triangles(torch.from_numpy(mesh).to(dev))
     q = torch.empty((N, 3), dtype=torch.float32, device=dev); ro = torch.empty_like(q); rd = torch.empty_like(q)
     for b, n in bench.blocks(N):
@@ -19,8 +20,10 @@ def main(N=50_000_000):
     idx = torch.empty(N, dtype=torch.int32, device=dev); d2 = torch.empty(N, dtype=torch.float32, device=dev); cp = torch.empty((N, 3), dtype=torch.float32, device=dev)
     t = torch.empty(N, dtype=torch.float32, device=dev); ri = torch.empty(N, dtype=torch.int32, device=dev)
     out = {}
-    for name, fn in (("closest_fields", lambda: e.closest(q, out=(idx, d2, cp))), ("closest_records", lambda: e.closest_records(q, [crec])),
-                     ("ray_fields", lambda: e.ray_first(ro, rd, out=(t, ri, None))), ("ray_records", lambda: e.ray_first_records(ro, rd, [rrec]))):
+    tests = (("closest_fields", lambda: e.closest(q, out=(idx, d2, cp))), ("closest_records", lambda: e.closest_records(q, [crec])),
+                     ("ray_fields", lambda: e.ray_first(ro, rd, out=(t, ri, None))), ("ray_records", lambda: e.ray_first_records(ro, rd, [rrec])))
+    if os.environ.get("TGQ_RAY_ORDER"): tests = tests[2:3]
+    for name, fn in tests:
         ms = []
         for it in range(5):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
