@@ -292,6 +292,19 @@ class GpuBvhBase
     void disableNearestNeighborAcceleration(bool = true) {}
     bool hasNearestNeighborAcceleration() const { return false; }
 
+    /** BvhN::closestPair<MetricL2>(query_structure, dist_bound, compatibility, get_closest_points) (BvhN.hpp:1081-1114,1900-2009;
+     *  Test/TestBvh.cpp:251-258): the closest pair of elements between this structure and a POINT structure on the same device. */
+    template <typename MetricT, typename QueryVectorT, typename CompatibilityFunctorT = UniversalCompatibility>
+    NeighborPair closestPair(GpuBvhBase<QueryVectorT> const & query, double dist_bound = -1, CompatibilityFunctorT = CompatibilityFunctorT(),
+                             bool get_closest_points = false) const
+    {
+      int64_t ti = -1, qi = -1; float d2 = -1, qp[3] = {0, 0, 0}, tp[3] = {0, 0, 0};
+      detail::check(h, tgq_closest_pair(h, query.handle(), dist_bound, &ti, &qi, &d2, get_closest_points ? qp : nullptr, get_closest_points ? tp : nullptr),
+                    "tgq_closest_pair");
+      if (ti < 0) return NeighborPair();
+      return NeighborPair((intx)qi, (intx)ti, (double)d2, detail::get3<VectorT>(qp), detail::get3<VectorT>(tp));
+    }
+
     /** Host-side filters cannot run on the device and there is no CPU fallback. */
     template <typename FilterT> void pushFilter(FilterT *) { throw Error("TheaGpu: element filters are not supported by the GPU structure"); }
     void popFilter() {}
@@ -316,6 +329,7 @@ class GpuMeshBvhT : public GpuBvhBase<VectorT>
     typedef typename Base::Ray3 Ray3;
 
     explicit GpuMeshBvhT(int device = 0) : Base(device), built(false) {}
+    using Base::closestPair;         // the structure-to-structure form
 
     /** MeshBvh::addTriangles analogue: appends one triangle to the pending soup (MeshTriangles.hpp:361-370). */
     void addTriangle(VectorT const & v0, VectorT const & v1, VectorT const & v2)
@@ -510,6 +524,7 @@ class GpuPointBvhT : public GpuBvhBase<VectorT>
     typedef NNFilterT<VectorT> NNFilter;
 
     explicit GpuPointBvhT(int device = 0) : Base(device), filter(nullptr) {}
+    using Base::closestPair;         // the structure-to-structure form
 
     /** Per-element labels (P int32, element order; null clears): the `label` member of Register's samples. */
     void setLabels(int32_t const * labels) { detail::check(h, tgq_set_point_labels(h, labels), "tgq_set_point_labels"); }

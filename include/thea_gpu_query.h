@@ -164,6 +164,16 @@ int tgq_knn_filtered(tgq_handle * h, const float * q3, const float * qn3, const 
 int tgq_ball_range(tgq_handle * h, const float * c3, const float * radius, int64_t Q, int32_t max_out, int32_t exclude_self,
                    int32_t * idx, int32_t * count);
 
+/* Closest pair of elements between two structures.  Replaces BvhN::closestPair<MetricL2>(query_bvh, dist_bound, compatibility,
+ * get_closest_points) (BvhN.hpp:1081-1114 with a structure as the query; processNeighborsBvh :1900-2009; Test/TestBvh.cpp:251-258):
+ * the minimum over all (target element, query element) pairs of the reference's per-pair squared distance, accepted when
+ * (double)d2 < dist_bound^2 (dist_bound < 0: unbounded; a structure query gets no bound widening, BvhN.hpp:2384-2416), ties to the
+ * lowest target index, then the lowest query index.  `h` is the target (points or triangles), `query` a POINT structure on the
+ * same device (triangle-triangle distances, Triangle3.hpp:314-534, are not implemented: TGQ_EINVAL).  Outputs are host memory:
+ * *target_index / *query_index (-1: no pair), *d2, the closest points on the query and the target element (each may be null). */
+int tgq_closest_pair(tgq_handle * h, tgq_handle * query, double dist_bound, int64_t * target_index, int64_t * query_index, float * d2,
+                     float * query_point3, float * target_point3);
+
 /* Q unbounded range queries on a point structure.  Replaces BvhN::rangeQueryIndices / rangeQuery / processRange
  * <IntersectionTester>(range, ...) (BvhN.hpp:1208-1264,2118-2171) for the two range types the reference's callers and tests use:
  * kind 0: Ball3(a3[i], b[i])  -- every element with sq(x - c) <= r * r in fp32 (BallN.hpp:83);   b = Q radii

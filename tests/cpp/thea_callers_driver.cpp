@@ -162,9 +162,33 @@ int main(int argc, char ** argv)
     EXPECT(nn_equal == nq, "closestElement with dist_bound: %d of %d equal", nn_equal, nq);
     EXPECT(knn_equal >= nq - 2, "kClosestPairs: %d of %d equal", knn_equal, nq);
 
+    // ---- structure-to-structure closestPair (TestBvh.cpp:251-258): point structure vs point structure, triangles vs points -------
+    int pair_ok = 0;
+    {
+      std::vector<Vector3> other; for (int64_t i = 0; i < P; i += 3) other.push_back(points[(size_t)i] + Vector3(0.013f, 0.007f, -0.011f));
+      RefPointBvh oref(other.begin(), other.end());
+      GpuPointBvh ogpu; ogpu.init(other.begin(), other.end());
+      for (double bound : { -1.0, 0.5 * (double)diag, 1e-4 })
+      {
+        RefPointBvh::NeighborPair a = pref.closestPair<MetricL2>(oref, bound, UniversalCompatibility(), true);
+        GpuPointBvh::NeighborPair b = pgpu.closestPair<MetricL2>(ogpu, bound, UniversalCompatibility(), true);
+        bool same = a.isValid() == b.isValid() && (!a.isValid() || (a.getMonotoneApproxDistance() == b.getMonotoneApproxDistance()));
+        // indices may differ only through exact ties (the reference keeps the first pair it finds)
+        if (same && a.isValid() && (a.getTargetIndex() != b.getTargetIndex() || a.getQueryIndex() != b.getQueryIndex()))
+          same = (points[(size_t)b.getTargetIndex()] - other[(size_t)b.getQueryIndex()]).squaredNorm() == (Real)a.getMonotoneApproxDistance();
+        pair_ok += same;
+        EXPECT(same, "closestPair(points, points, bound %g): %g vs %g", bound, a.getMonotoneApproxDistance(), b.getMonotoneApproxDistance());
+        RefMeshBvh::NeighborPair c = ref.closestPair<MetricL2>(oref, bound, UniversalCompatibility(), true);
+        GpuMeshBvh::NeighborPair d = gpu.closestPair<MetricL2>(ogpu, bound, UniversalCompatibility(), true);
+        bool same2 = c.isValid() == d.isValid() && (!c.isValid() || c.getMonotoneApproxDistance() == d.getMonotoneApproxDistance());
+        pair_ok += same2;
+        EXPECT(same2, "closestPair(triangles, points, bound %g): %g vs %g", bound, c.getMonotoneApproxDistance(), d.getMonotoneApproxDistance());
+      }
+    }
+
     printf("{\"triangles\": %ld, \"sdf_equal\": %d, \"sdf_samples\": %ld, \"sdf_position_equal\": %d, \"sdf_position_samples\": %ld, \"icp_max_transform_diff\": %g, "
-           "\"range_sets_equal\": %d, \"nn_equal\": %d, \"knn_equal\": %d, \"queries\": %d, \"fails\": %d}\n",
-           (long)T, sdf_equal, (long)S, sdf_pos_equal, (long)(S / 4), tdiff, range_ok, nn_equal, knn_equal, nq, fails);
+           "\"range_sets_equal\": %d, \"nn_equal\": %d, \"knn_equal\": %d, \"queries\": %d, \"closest_pairs_equal\": %d, \"fails\": %d}\n",
+           (long)T, sdf_equal, (long)S, sdf_pos_equal, (long)(S / 4), tdiff, range_ok, nn_equal, knn_equal, nq, pair_ok, fails);
   }
   catch (std::exception const & e) { fprintf(stderr, "exception: %s\n", e.what()); return 4; }
   return fails ? 3 : 0;

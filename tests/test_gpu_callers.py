@@ -408,3 +408,44 @@ def test_set_transform(setup):
     e.set_transform(tr)
     e.refit_triangles(mesh)
     assert np.array_equal(e.closest(q)[1], d0)
+
+
+def test_structure_to_structure_closest_pair(built):
+    """tgq_closest_pair (BvhN::closestPair with a structure as the query, BvhN.hpp:1081-1114,1900-2009): the canonical minimum over
+    all (target element, query element) pairs, against the fp32 definition; against the reference's own code where its library
+    travelled."""
+    from thea_b200 import Engine
+    mesh = gen.torus_mesh(40)
+    a, _, _ = gen.area_samples(mesh, 4000, seed=1)
+    b = (gen.area_samples(mesh, 3000, seed=2)[0] + np.float32([0.011, -0.006, 0.009])).astype(np.float32)
+    ea, eb, et = Engine(0), Engine(0), Engine(0)
+    ea.build_points(a)
+    eb.build_points(b)
+    et.build_triangles(mesh)
+    d = (a[:, None, :] - b[None, :, :]).astype(np.float32)
+    xx, yy, zz = d[..., 0] * d[..., 0], d[..., 1] * d[..., 1], d[..., 2] * d[..., 2]
+    m = xx + (yy + zz)                                   # MetricL2 point-point in Eigen's order
+    for bound in (-1.0, 0.05, float(np.sqrt(np.float64(m.min()))) * 0.999):
+        ti, qi, d2, qp, tp = ea.closest_pair(eb, dist_bound=bound)
+        ok = m < np.float32(bound) ** 2 if bound >= 0 else np.ones_like(m, bool)
+        ok = (m.astype(np.float64) < bound * bound) if bound >= 0 else ok
+        if not ok.any():
+            assert ti == -1 and qi == -1
+            continue
+        best = np.where(ok, m, np.float32(np.inf)).min()
+        cand = np.argwhere(ok & (m == best))
+        want = cand[np.lexsort((cand[:, 1], cand[:, 0]))][0]          # lowest target index, then lowest query index
+        assert (ti, qi) == (int(want[0]), int(want[1])) and np.float32(d2) == best
+        assert np.array_equal(qp, b[qi]) and np.array_equal(tp, a[ti])
+    # triangles as the target: per query point the canonical closest triangle, then the minimum
+    oi, od, oc = orc.Oracle(tris9=mesh).closest(b, mode=orc.MODE_BRUTE)
+    ti, qi, d2, qp, tp = et.closest_pair(eb)
+    best = od.min()
+    cand = np.flatnonzero(od == best)
+    k = cand[np.lexsort((cand, oi[cand]))][0]
+    assert (ti, qi) == (int(oi[k]), int(k)) and np.float32(d2) == best and np.array_equal(tp, oc[k])
+    from oracle import ref
+    if ref.available():
+        found, rti, rqi, rd2, ra, rb = ref.Reference(points=a).closest_pair(ref.Reference(points=b))
+        ti, qi, d2, _, _ = ea.closest_pair(eb)
+        assert found and np.float32(rd2) == np.float32(d2)

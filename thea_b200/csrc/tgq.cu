@@ -774,12 +774,13 @@ int tgq_triangle_cache(tgq_handle * h, float * n3, float * d, int32_t * axis, fl
 }
 
 static int closest_common(tgq_handle * h, const float * q3, const float * qn3, const int32_t * qlabel, float min_dot, int64_t Q, double dist_bound,
-                          int32_t exclude_self, int32_t * idx, float * d2, float * cp3)
+                          int32_t exclude_self, int32_t * idx, float * d2, float * cp3, bool plain_bound = false)
 {
   CKRC(need_built(h, (1 << TGQ_KIND_TRIANGLES) | (1 << TGQ_KIND_POINTS)));
   if (Q < 0 || (Q > 0 && !q3)) return fail(h, TGQ_EINVAL, "tgq_closest: bad arguments");
   Guard g(h);
   float ub; BoundGate gate; closest_bound_gate(h->lo, h->hi, dist_bound, ub, gate);     // BvhN::closestPair's root rejection and bound widening
+  if (plain_bound) { ub = bound_to_ub(dist_bound); gate = no_gate(); }                  // structure-to-structure queries: the bound as given
   Arg args[6] = {{q3, nullptr, 12}, {nullptr, idx, 4}, {nullptr, d2, 4}, {nullptr, cp3, 12}, {qn3, nullptr, 12}, {qlabel, nullptr, 4}};
   BvhView v = view_of(h); bool tri = h->kind == TGQ_KIND_TRIANGLES;
   size_t smem = trav_smem_bytes(1);
@@ -836,6 +837,51 @@ int tgq_closest_filtered(tgq_handle * h, const float * q3, const float * qn3, co
   if (!h) return TGQ_EINVAL;
   CKRC(check_filter(h, qn3, qlabel));
   return closest_common(h, q3, qn3, qlabel, min_dot, Q, dist_bound, 0, idx, d2, cp3);
+}
+
+int tgq_closest_pair(tgq_handle * h, tgq_handle * query, double dist_bound, int64_t * target_index, int64_t * query_index, float * d2, float * query_point3,
+                     float * target_point3)
+{
+  CKRC(need_built(h, (1 << TGQ_KIND_TRIANGLES) | (1 << TGQ_KIND_POINTS)));
+  if (!query || !target_index || !query_index) return fail(h, TGQ_EINVAL, "tgq_closest_pair: bad arguments");
+  if (query->kind != TGQ_KIND_POINTS) return fail(h, TGQ_EINVAL, "tgq_closest_pair: the query structure must be a point structure (triangle-triangle distances are not implemented)");
+  if (query->device != h->device) return fail(h, TGQ_EINVAL, "tgq_closest_pair: both structures must live on the same device");
+  *target_index = -1; *query_index = -1; if (d2) *d2 = -1.0f;
+  if (query->n == 0 || h->n == 0) return TGQ_OK;
+  Guard g(h);
+  cudaStream_t s = h->stream;
+  CK(cudaStreamSynchronize(query->stream));
+  size_t P = (size_t)query->n;
+  // the query structure's elements in element order, answered one by one by this structure, then the canonical minimum
+  CK(h->src2.reserve(12 * P)); CK(h->slot[0].out[4].reserve(4 * P)); CK(h->slot[0].out[5].reserve(4 * P)); CK(h->slot[0].out[6].reserve(12 * P));
+  k_extract_points<<<grid_for((int64_t)P), TGQ_BLOCK, 0, s>>>(query->elems.as<f4>(), nullptr, nullptr, (int)P, h->src2.as<float>(), nullptr, nullptr);
+  CK(cudaGetLastError());
+  int * di = h->slot[0].out[4].as<int>(); float * dd = h->slot[0].out[5].as<float>(); float * dc = h->slot[0].out[6].as<float>();
+  int saved_async = h->opt_async; h->opt_async = 0;
+  int rc = closest_common(h, h->src2.as<float>(), nullptr, nullptr, 0.0f, (int64_t)P, dist_bound, 0, di, dd, dc, true);
+  h->opt_async = saved_async;
+  if (rc != TGQ_OK) return rc;
+  CK(h->misc.reserve(64));
+  unsigned long long * best = h->misc.as<unsigned long long>();
+  CK(cudaMemsetAsync(best, 0xff, 16, s));
+  int grid = (int)std::min<int64_t>((int64_t)(P + 255) / 256, (int64_t)h->sm_count * 8);
+  k_pair_min_key<<<grid, 256, 0, s>>>(di, dd, (int64_t)P, best);
+  k_pair_min_query<<<grid, 256, 0, s>>>(di, dd, (int64_t)P, best);
+  CK(cudaGetLastError());
+  h->st.total_launches += 3;
+  unsigned long long hb[2];
+  CK(cudaMemcpyAsync(hb, best, 16, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (hb[0] == ~0ull || hb[1] == ~0ull) return TGQ_OK;
+  *target_index = (int64_t)(unsigned)(hb[0] & 0xffffffffull); *query_index = (int64_t)hb[1];
+  float hd = 0, hq[3], ht[3];
+  CK(cudaMemcpyAsync(&hd, dd + hb[1], 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(hq, h->src2.as<float>() + 3 * hb[1], 12, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(ht, dc + 3 * hb[1], 12, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (d2) *d2 = hd;
+  for (int a = 0; a < 3; ++a) { if (query_point3) query_point3[a] = hq[a]; if (target_point3) target_point3[a] = ht[a]; }
+  return TGQ_OK;
 }
 
 int tgq_set_point_labels(tgq_handle * h, const int32_t * labels)

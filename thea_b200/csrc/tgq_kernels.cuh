@@ -1756,6 +1756,26 @@ __global__ void k_sdf_stats(float const * __restrict__ ray_t, uint8_t const * __
   sdf[s] = sdf_statistics(values, weights, nv, scale);
 }
 
+// Structure-to-structure closestPair (BvhN.hpp:1081-1114 with a structure as the query, :1900-2009): the winner among the per-element
+// answers of the query structure's elements, in the canonical order (squared distance, target index, query index).
+// best[0] = (d2 bits << 32 | target index) minimum, best[1] = lowest query index attaining it.
+__global__ void k_pair_min_key(int const * __restrict__ idx, float const * __restrict__ d2, int64_t n, unsigned long long * best)
+{
+  unsigned long long m = ~0ull;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (idx[i] >= 0) { unsigned long long k = ((unsigned long long)(unsigned)__float_as_int(d2[i]) << 32) | (unsigned)idx[i]; m = k < m ? k : m; }
+  for (int o = 16; o > 0; o >>= 1) { unsigned long long x = __shfl_xor_sync(0xffffffffu, m, o); m = x < m ? x : m; }
+  if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(&best[0], m);
+}
+__global__ void k_pair_min_query(int const * __restrict__ idx, float const * __restrict__ d2, int64_t n, unsigned long long * best)
+{
+  unsigned long long want = best[0], m = ~0ull;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (idx[i] >= 0 && ((((unsigned long long)(unsigned)__float_as_int(d2[i]) << 32) | (unsigned)idx[i]) == want)) m = (unsigned long long)i < m ? (unsigned long long)i : m;
+  for (int o = 16; o > 0; o >>= 1) { unsigned long long x = __shfl_xor_sync(0xffffffffu, m, o); m = x < m ? x : m; }
+  if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(&best[1], m);
+}
+
 // max |x| over two float arrays, as int bits (non-negative floats order like ints).
 __global__ void k_max_abs(float const * __restrict__ a, float const * __restrict__ b, int64_t n, int * out_bits)
 {

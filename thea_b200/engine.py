@@ -25,7 +25,7 @@ SYMBOLS = [
     "tgq_ray_first", "tgq_ray_any", "tgq_sdf", "tgq_icp_sums", "tgq_transform_points", "tgq_area_sample",
     "tgq_get_stats", "tgq_set_point_labels", "tgq_closest_filtered", "tgq_knn_filtered", "tgq_icp_align", "tgq_ball_range",
     "tgq_ball_stats", "tgq_visibility", "tgq_ball_graph_surface", "tgq_ball_histogram", "tgq_set_transform",
-    "tgq_closest_records", "tgq_ray_first_records", "tgq_synchronize", "tgq_scatter_records", "tgq_bucket_records", "tgq_range_query",
+    "tgq_closest_records", "tgq_ray_first_records", "tgq_synchronize", "tgq_scatter_records", "tgq_bucket_records", "tgq_range_query", "tgq_closest_pair",
 ]
 
 
@@ -100,6 +100,7 @@ def load_library(path=None):
     L.tgq_scatter_records.argtypes = [vp, vp, i32, i64, vp, i32, vp]
     L.tgq_bucket_records.argtypes = [vp, vp, i64, i32, i64, i32, vp, i64, vp]
     L.tgq_range_query.argtypes = [vp, i32, vp, vp, i64, vp, vp, i64, vp]
+    L.tgq_closest_pair.argtypes = [vp, vp, f64, vp, vp, vp, vp, vp]
     for name in SYMBOLS:
         if name not in ("tgq_last_error",):
             getattr(L, name).restype = C.c_int
@@ -324,6 +325,14 @@ class Engine:
         hist = np.empty((Q, num_bins), np.uint32)
         self._ck(self._L.tgq_ball_histogram(self._h, _ptr(c3), _ptr(rad), Q, int(num_bins), _ptr(hist)))
         return hist
+
+    def closest_pair(self, query, dist_bound=-1.0):
+        """tgq_closest_pair: BvhN::closestPair between this structure (the target) and the point structure `query`.
+        Returns (target index, query index, d2, point on the query element, point on the target element); indices -1 when none."""
+        ti, qi, d2 = C.c_int64(), C.c_int64(), C.c_float()
+        qp, tp = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        self._ck(self._L.tgq_closest_pair(self._h, query._h, float(dist_bound), C.byref(ti), C.byref(qi), C.byref(d2), _ptr(qp), _ptr(tp)))
+        return int(ti.value), int(qi.value), float(d2.value), qp, tp
 
     def range_query(self, a3, b, box=False):
         """tgq_range_query: all elements of a point structure in Q balls (a3 = centres, b = radii) or boxes (a3 = low, b = high corners).
