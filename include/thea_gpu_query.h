@@ -63,6 +63,8 @@ enum
   TGQ_OPT_SHARD_CELL_BITS = 8,   /* *_records with shard_world > 1: the batch is dealt to the ranks in 2^bits Morton cells (default 12) */
   TGQ_OPT_RAY_ORDER = 9,      /* ray batches: 0 (default) = launch order by the Morton code of the origin; b in 3..30 = the b lowest code bits give way to
                                  the direction's sign octant (rays of one cell of 2^(30-b) ... grouped by heading) */
+  TGQ_OPT_SET_BUFFER = 10,    /* k-NN and the sample graph: 1 (default) = candidate buffers compacted by the whole warp (k_knn_buf / k_ball_graph_buf),
+                                 0 = one sorted set per lane (k_knn / k_ball_graph); same results */
   TGQ_OPT_ICP_REFERENCE_ORDER = 6   /* 1 (default): tgq_icp_sums / tgq_icp_align accumulate in the reference's own order -- sequential fp32, the
                                        loops of Icp3.hpp:306-367,418-463 -- so iterates, per-iteration correspondences and the final transform
                                        equal the reference's bit for bit; 0: order-independent fixed-point (exact) sums, 20x faster per call, but

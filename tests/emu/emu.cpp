@@ -1,3 +1,4 @@
+#include <cstdlib>
 // emu.cpp -- TEST-ONLY host build of the engine's __host__ __device__ headers (thea_b200/csrc/tgq_*.cuh).
 //
 // There is no GPU in the development container, so the traversal / hierarchy / selection code is written as
@@ -5,9 +6,11 @@
 // suite (-m "not gpu") check the pruning logic, tie rules and the libstdc++ nth_element restatement against the oracle
 // before any GPU time is spent.  It is NOT a fallback: nothing under thea_b200/ links or loads it, and libtgq.so has
 // no code path that reaches it.
-static thread_local long long g_cnt_node = 0, g_cnt_prim = 0;
+static thread_local long long g_cnt_node = 0, g_cnt_prim = 0, g_cnt_append = 0, g_cnt_compact = 0;
 #define TGQ_COUNT_NODE() (++g_cnt_node)
 #define TGQ_COUNT_PRIM() (++g_cnt_prim)
+#define TGQ_COUNT_APPEND() (++g_cnt_append)
+#define TGQ_COUNT_COMPACT() (++g_cnt_compact)
 #include "../../thea_b200/csrc/tgq_traverse.cuh"
 #include "../../thea_b200/csrc/tgq_select.cuh"
 
@@ -263,9 +266,27 @@ void emu_closest_counts(void * h, float const * q3, int64_t Q, float const * ub,
   }
 }
 
+// k-NN / sample graph: 1 (default, as the engine) = the candidate-buffer traversals (CandBuf; serial compaction stands in for the
+// warp's), 0 = the sorted-set traversals.
+static int g_buffered = 1;
+void emu_set_buffered(int on) { g_buffered = on; }
+static void buf_out(CandBuf const & buf, int k, int32_t * idx, float * key)
+{ for (int j = 0; j < k; ++j) { idx[j] = j < buf.n ? cand_idx(buf.at(j)) : -1; key[j] = j < buf.n ? cand_key(buf.at(j)) : -1.0f; } }
+
 void emu_knn(void * h, float const * q3, int64_t Q, int k, float bound_ub, int exclude_self, int32_t * idx, float * d2)
 {
   Emu & E = *(Emu *)h; BvhView v = E.view();
+  if (g_buffered)
+  {
+    std::vector<unsigned long long> row((size_t)cand_cap(k));
+    for (int64_t i = 0; i < Q; ++i)
+    {
+      CandBuf buf; buf.init(row.data(), (int)(i % 32), k);
+      knn_query_buf(v, ld(q3, i), exclude_self ? (int)i : -1, bound_ub, buf);
+      buf_out(buf, k, idx + i * k, d2 + i * k);
+    }
+    return;
+  }
   std::vector<float> keys((size_t)k); std::vector<int> ids((size_t)k);
   for (int64_t i = 0; i < Q; ++i)
   {
@@ -310,6 +331,18 @@ void emu_knn_filtered(void * h, float const * q3, float const * qn3, int32_t con
                       int32_t * idx, float * d2)
 {
   Emu & E = *(Emu *)h; BvhView v = E.view();
+  if (g_buffered)
+  {
+    std::vector<unsigned long long> row((size_t)cand_cap(k));
+    for (int64_t i = 0; i < Q; ++i)
+    {
+      CandBuf buf; buf.init(row.data(), (int)(i % 32), k);
+      ElemFilterD f = make_filter(qn3, qlabel, i, min_dot);
+      knn_query_buf(v, ld(q3, i), -1, bound_ub, buf, &f);
+      buf_out(buf, k, idx + i * k, d2 + i * k);
+    }
+    return;
+  }
   std::vector<float> keys((size_t)k); std::vector<int> ids((size_t)k);
   for (int64_t i = 0; i < Q; ++i)
   {
@@ -376,6 +409,20 @@ void emu_ball_stats(void * h, float const * c3, float const * qn3, float const *
 void emu_ball_graph(void * h, int k, float init_radius, int rounds, float min_dot, int min_degree, int32_t * idx, float * sep, int32_t * count)
 {
   Emu & E = *(Emu *)h; BvhView v = E.view();
+  if (g_buffered)
+  {
+    std::vector<unsigned long long> row((size_t)cand_cap(k));
+    for (int s = 0; s < E.n; ++s)
+    {
+      f4 e = E.pts[(size_t)s]; int64_t i = f2i(e.w);
+      v3 nc = mk3(0, 0, 0); if (E.has_n) nc = mk3(E.nrm[(size_t)s].x, E.nrm[(size_t)s].y, E.nrm[(size_t)s].z);
+      CandBuf buf; buf.init(row.data(), s % 32, k);
+      ball_graph_query_buf(v, mk3(e.x, e.y, e.z), nc, E.has_n, min_dot, (int)i, init_radius, rounds, min_degree, buf);
+      buf_out(buf, k, idx + i * k, sep + i * k);
+      if (count) count[i] = buf.n;
+    }
+    return;
+  }
   std::vector<float> keys((size_t)k); std::vector<int> ids((size_t)k);
   for (int s = 0; s < E.n; ++s)
   {
@@ -401,6 +448,8 @@ void emu_ray(void * h, float const * o3, float const * d3, float const * tmax, i
 
 void emu_counters(long long * nodes, long long * prims, int reset)
 { *nodes = g_cnt_node; *prims = g_cnt_prim; if (reset) { g_cnt_node = 0; g_cnt_prim = 0; } }
+void emu_set_counters(long long * appends, long long * compactions, int reset)
+{ *appends = g_cnt_append; *compactions = g_cnt_compact; if (reset) { g_cnt_append = 0; g_cnt_compact = 0; } }
 
 // libstdc++'s own std::nth_element next to the restatement, for permutation-exact comparison.
 void emu_select(double * a, int n, int nth) { sdf_select(a, n, nth); }

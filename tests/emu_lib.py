@@ -32,6 +32,7 @@ def lib():
         L.emu_num_wide.restype = C.c_int64
         L.emu_num_wide.argtypes = [vp]
         L.emu_set_wide.argtypes = [vp, C.c_int]
+        L.emu_set_buffered.argtypes = [C.c_int]
         L.emu_closest.argtypes = [vp, vp, C.c_int64, C.c_double, C.c_int, vp, vp, vp]
         L.emu_knn.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_float, C.c_int, vp, vp]
         L.emu_ball_graph.argtypes = [vp, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, vp, vp, vp]
@@ -54,6 +55,11 @@ def lib():
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def set_buffered(on):
+    """k-NN / sample graph emulation: candidate buffers (True, what the engine runs by default) or sorted sets (TGQ_OPT_SET_BUFFER = 0)."""
+    lib().emu_set_buffered(int(bool(on)))
 
 
 class Emu:

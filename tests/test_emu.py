@@ -85,12 +85,19 @@ def test_axis_aligned_flat_mesh_degenerate_boxes():
     assert np.array_equal(ridx, ri.astype(np.int32)) and np.array_equal(t, rt)
 
 
-def test_point_queries_knn_and_graph():
+@pytest.fixture(params=[True, False], ids=["candidate-buffer", "sorted-set"])
+def set_kind(request):
+    emu_lib.set_buffered(request.param)
+    yield request.param
+    emu_lib.set_buffered(True)
+
+
+def test_point_queries_knn_and_graph(set_kind):
     mesh = gen.torus_mesh(40)
     p, n, _ = gen.area_samples(mesh, 4000)
     e = emu_lib.Emu(points=p, normals=n)
     ora = orc.Oracle(points=p, normals=n)
-    for k in (1, 5, 16):
+    for k in (1, 5, 16, 24, 40, 64):
         ki, kd = e.knn(p, k, exclude_self=True)
         oi, od = ora.knn(p, k, exclude_self=True, mode=orc.MODE_BRUTE)
         assert np.array_equal(ki, oi.astype(np.int32)) and np.array_equal(kd, od)
@@ -102,7 +109,29 @@ def test_point_queries_knn_and_graph():
         assert np.array_equal(gi, oi.astype(np.int32)) and np.array_equal(gs, os_) and np.array_equal(gc, oc)
 
 
-def test_duplicates_and_tiny_structures():
+def test_knn_on_coherent_queries_with_duplicates(set_kind):
+    """Spatially ordered queries, a block of duplicated points (exact ties at every rank), with and without self exclusion, with a
+    distance bound, on a query set that is not the point set."""
+    mesh = gen.torus_mesh(40)
+    p, n, _ = gen.area_samples(mesh, 6000)
+    key = np.floor(p * 8).astype(np.int64)
+    order = np.lexsort((p[:, 0], key[:, 2], key[:, 1], key[:, 0]))          # coarse cells, then x: neighbours follow each other
+    p = np.ascontiguousarray(p[order])
+    p[100:160] = p[100]                                                     # a block of duplicates
+    e = emu_lib.Emu(points=p)
+    ora = orc.Oracle(points=p)
+    for k in (1, 4, 16, 30):
+        for ex in (True, False):
+            ki, kd = e.knn(p, k, exclude_self=ex)
+            oi, od = ora.knn(p, k, exclude_self=ex, mode=orc.MODE_BRUTE)
+            assert np.array_equal(ki, oi.astype(np.int32)) and np.array_equal(kd, od)
+    q = (p[::2] + np.float32(0.003)).astype(np.float32)
+    ki, kd = e.knn(q, 12, bound_ub=np.float32(0.05) ** 2)
+    oi, od = ora.knn(q, 12, dist_bound=0.05, mode=orc.MODE_BRUTE)
+    assert np.array_equal(ki, oi.astype(np.int32)) and np.array_equal(kd, od)
+
+
+def test_duplicates_and_tiny_structures(set_kind):
     rng = np.random.default_rng(2)
     pts = np.repeat(rng.random((30, 3)).astype(np.float32), 6, axis=0)
     e = emu_lib.Emu(points=pts)
@@ -243,7 +272,7 @@ def test_degenerate_triangles_behave_like_the_reference():
     assert np.array_equal(ri, ori.astype(np.int32)) and np.array_equal(t, ort)
 
 
-def test_filtered_nearest_neighbours_register_semantics():
+def test_filtered_nearest_neighbours_register_semantics(set_kind):
     """NNFilter of Tools/Register/Register.cpp:92-101 (same label, n . n_e >= 0) pushed around
     closestElement / kClosestPairs; all three oracle modes and the engine's traversal agree."""
     mesh = gen.torus_mesh(24)

@@ -86,14 +86,16 @@ def test_ray_max_time_is_strict(eng_mesh):
     assert np.array_equal(idx2, oi.astype(np.int32)) and np.array_equal(t2, ot)
 
 
-def test_points_knn_closest_graph(built):
-    from thea_b200 import Engine
+@pytest.mark.parametrize("set_buffer", [1, 0], ids=["candidate-buffer", "sorted-set"])
+def test_points_knn_closest_graph(built, set_buffer):
+    from thea_b200 import Engine, engine as _eng
     mesh = gen.torus_mesh(48)
     p, n, _ = gen.area_samples(mesh, 6000)
     e = Engine(0)
+    e.set_option(_eng.OPT_SET_BUFFER, set_buffer)       # 1 (default): k_knn_buf / k_ball_graph_buf; 0: k_knn / k_ball_graph
     e.build_points(p, n)
     ora = orc.Oracle(points=p, normals=n)
-    for k in (1, 3, 16, 33):
+    for k in (1, 3, 16, 24, 33, 64):
         ki, kd = e.knn(p, k, exclude_self=True)
         oi, od = ora.knn(p, k, exclude_self=True, mode=orc.MODE_BRUTE)
         assert np.array_equal(ki, oi.astype(np.int32)) and np.array_equal(kd, od)

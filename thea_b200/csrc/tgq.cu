@@ -68,7 +68,7 @@ struct tgq_handle
   std::string err;
   cudaStream_t own_stream = nullptr, stream = nullptr;
 
-  int opt_sort = 2, opt_leaf = 4, opt_async = 0, opt_pool = 1, opt_icp_ref = 1, opt_wide = 0; bool wide_built = false; int64_t opt_chunk = 16777216;
+  int opt_sort = 2, opt_leaf = 4, opt_async = 0, opt_pool = 1, opt_icp_ref = 1, opt_wide = 0, opt_setbuf = 1; bool wide_built = false; int64_t opt_chunk = 16777216;
 
   int kind = TGQ_KIND_NONE; int n = 0; int n_nodes = 0; bool has_normals = false, has_labels = false; int leaf_built = 4;
   DevBuf nodes, elems, nrm, lab, scene;                                // NodeRec[], TriRec[] | f4[], f4[], SceneBox
@@ -613,6 +613,7 @@ int tgq_set_option(tgq_handle * h, int option, int64_t value)
     case TGQ_OPT_POOL: h->opt_pool = value ? 1 : 0; return TGQ_OK;
     case TGQ_OPT_ICP_REFERENCE_ORDER: h->opt_icp_ref = value ? 1 : 0; return TGQ_OK;
     case TGQ_OPT_WIDE: h->opt_wide = value ? 1 : 0; return TGQ_OK;
+    case TGQ_OPT_SET_BUFFER: h->opt_setbuf = value ? 1 : 0; return TGQ_OK;
     case TGQ_OPT_RAY_ORDER: if (value != 0 && (value < 3 || value > 30)) return fail(h, TGQ_EINVAL, "TGQ_OPT_RAY_ORDER takes 0 or 3..30"); h->opt_ray_order = (int)value; return TGQ_OK;
     case TGQ_OPT_SHARD_CELL_BITS: if (value < 3 || value > 30) return fail(h, TGQ_EINVAL, "TGQ_OPT_SHARD_CELL_BITS takes 3..30"); h->opt_cell_bits = (int)value; return TGQ_OK;
     case TGQ_OPT_CHUNK: if (value < 1024) return fail(h, TGQ_EINVAL, "TGQ_OPT_CHUNK must be >= 1024"); h->opt_chunk = value; return TGQ_OK;
@@ -912,11 +913,24 @@ static int knn_common(tgq_handle * h, const float * q3, const float * qn3, const
   Arg args[5] = {{q3, nullptr, 12}, {nullptr, idx, 4 * (size_t)k}, {nullptr, d2, 4 * (size_t)k}, {qn3, nullptr, 12}, {qlabel, nullptr, 4}};
   BvhView v = view_of(h);
   size_t smem = trav_smem_bytes(KnnW::STAGE) + 2 * (size_t)k * TGQ_BLOCK * 4;
+  int const cap = cand_cap(k), epl = (cap + 31) / 32;
+  size_t bsmem = trav_smem_bytes(1) + (size_t)cap * TGQ_BLOCK * 8;
+  bool const buffered = h->opt_setbuf != 0;
   return run_batched(h, Q, args, 5, true, [&](ChunkCtx & c) -> int {
     int grid = 0; int * cnt = c.slot->counter.as<int>();
+#define TGQ_KNN_BUF(E) { CKRC(persistent_grid(h, k_knn_buf<E>, bsmem, c.n, cnt, c.stream, &grid)); \
+      k_knn_buf<E><<<grid, TGQ_BLOCK, bsmem, c.stream>>>(v, (float const *)c.din[0], c.perm, c.n, k, ub, exclude_self, c.offset, cnt, (int *)c.dout[1], \
+                                                         (float *)c.dout[2], (float const *)c.din[3], (int const *)c.din[4], min_dot); }
+    if (buffered && epl == 1) TGQ_KNN_BUF(1)
+    else if (buffered && epl == 2) TGQ_KNN_BUF(2)
+    else if (buffered) TGQ_KNN_BUF(3)
+#undef TGQ_KNN_BUF
+    else
+    {
     CKRC(persistent_grid(h, k_knn, smem, c.n, cnt, c.stream, &grid));
     k_knn<<<grid, TGQ_BLOCK, smem, c.stream>>>(v, (float const *)c.din[0], c.perm, c.n, k, ub, exclude_self, c.offset, cnt, (int *)c.dout[1],
                                                (float *)c.dout[2], (float const *)c.din[3], (int const *)c.din[4], min_dot);
+    }
     h->st.last_launches += 1; h->st.total_launches += 1;
     return TGQ_OK;
   });
@@ -964,6 +978,15 @@ static int ball_graph_common(tgq_handle * h, tgq_handle * surface, int32_t max_d
   {
     CKRC(persistent_grid(h, k_ball_graph<true>, smem, h->n, cnt, s, &grid));
     k_ball_graph<true><<<grid, TGQ_BLOCK, smem, s>>>(view_of(h), sv, h->n, max_degree, init_radius, rounds, min_dot, min_degree, cnt, di, ds, dc);
+  }
+  else if (h->opt_setbuf)
+  {
+    int const cap = cand_cap(max_degree), epl = (cap + 31) / 32;
+    size_t bsmem = trav_smem_bytes(2) + (size_t)cap * TGQ_BLOCK * 8;
+#define TGQ_BALL_BUF(E) { CKRC(persistent_grid(h, k_ball_graph_buf<E>, bsmem, h->n, cnt, s, &grid)); \
+      k_ball_graph_buf<E><<<grid, TGQ_BLOCK, bsmem, s>>>(view_of(h), h->n, max_degree, init_radius, rounds, min_dot, min_degree, cnt, di, ds, dc); }
+    if (epl == 1) TGQ_BALL_BUF(1) else if (epl == 2) TGQ_BALL_BUF(2) else TGQ_BALL_BUF(3)
+#undef TGQ_BALL_BUF
   }
   else
   {

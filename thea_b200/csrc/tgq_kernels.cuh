@@ -1231,6 +1231,263 @@ k_ball_graph(BvhView b, BvhView surf, int n, int k, float init_radius, int round
   warp_run(w, n, counter, stage);
 }
 
+// ---- K6b / K7b k-NN and the sample graph on candidate buffers, compacted by the whole warp ------------------------------------------
+// (CandBuf, tgq_traverse.cuh.)  The scheduler is warp_run with two warp-cooperative hooks: after every step the lanes whose buffer is
+// nearly full are served one after the other, and a finished query is compacted the same way and written out by the warp (k
+// consecutive outputs: coalesced).  Compacting one lane's row (n <= cap entries, keep the k smallest in ascending order):
+//   cap <= 32 (k <= 16, EPL = 1): every lane takes one entry and the warp runs a 32-wide bitonic network on the packed 64-bit
+//     (key, index) values -- 15 compare-exchange stages of two shuffles each, about 130 instructions at full lane utilisation,
+//     against an insertion loop per candidate at 5 of 32 lanes in the sorted-set kernels;
+//   larger buffers (EPL = 2, 3): rank sort -- every lane holds EPL entries in registers and counts, over broadcast reads of the
+//     row, how many entries are smaller (the first version used this for every size: ncu's source view showed the rank loop at
+//     34 % of all warp instructions for k = 16, profiles/r02_t_knn_buf_source_lines.txt).
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long x, int m)
+{
+  unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)x, m), hi = __shfl_xor_sync(0xffffffffu, (unsigned)(x >> 32), m);
+  return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ unsigned long long bitonic_sort32(unsigned long long x)
+{
+  int const lane = threadIdx.x & 31;
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1)
+  {
+    bool const up = (lane & size) == 0 || size == 32;
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1)
+    {
+      unsigned long long y = shfl_xor_u64(x, stride);
+      bool const low = (lane & stride) == 0;
+      bool const take_min = low == up;
+      x = take_min ? (y < x ? y : x) : (y > x ? y : x);
+    }
+  }
+  return x;
+}
+
+template <int EPL>
+__device__ __forceinline__ void coop_compact(unsigned long long * rows, int cap, int k, int o, int & my_n, float & my_thr)
+{
+  unsigned const FULL = 0xffffffffu;
+  int const lane = threadIdx.x & 31;
+  int n_o = __shfl_sync(FULL, my_n, o);
+  unsigned long long * row = rows + (size_t)o * cap;
+  #define TGQ_PHYS(i) (((i) & ~15) | (((i) + o) & 15))
+  if (EPL == 1)
+  {
+    unsigned long long x = lane < n_o ? row[TGQ_PHYS(lane)] : ~0ull;
+    x = bitonic_sort32(x);
+    int keep = min(n_o, k);
+    if (lane < keep) row[TGQ_PHYS(lane)] = x;
+    float kth = cand_key(__shfl_sync(FULL, x, max(k - 1, 0)));
+    __syncwarp();
+    if (lane == o) { my_n = keep; if (n_o >= k && k > 0) my_thr = kth; }
+  }
+  else
+  {
+    unsigned long long mine[EPL]; int rank[EPL];
+#pragma unroll
+    for (int t = 0; t < EPL; ++t) { int i = lane + 32 * t; mine[t] = i < n_o ? row[TGQ_PHYS(i)] : ~0ull; rank[t] = 0; }
+    for (int i = 0; i < n_o; ++i)
+    {
+      unsigned long long x = row[TGQ_PHYS(i)];
+#pragma unroll
+      for (int t = 0; t < EPL; ++t) rank[t] += x < mine[t] ? 1 : 0;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < EPL; ++t) if (lane + 32 * t < n_o && rank[t] < k) row[TGQ_PHYS(rank[t])] = mine[t];
+    __syncwarp();
+    if (lane == o)
+    {
+      my_n = min(n_o, k);
+      if (n_o >= k && k > 0) my_thr = cand_key(row[TGQ_PHYS(k - 1)]);
+    }
+  }
+  #undef TGQ_PHYS
+}
+
+// Writes the (compacted) buffer of lane o: k outputs per query, entry j or (-1, -1.0f).
+__device__ __forceinline__ void coop_write(unsigned long long const * rows, int cap, int k, int o, int n_o, int64_t qi, int * idx, float * key)
+{
+  int const lane = threadIdx.x & 31;
+  unsigned long long const * row = rows + (size_t)o * cap;
+  for (int j = lane; j < k; j += 32)
+  {
+    bool v = j < n_o;
+    unsigned long long e = v ? row[((j) & ~15) | (((j) + o) & 15)] : 0ull;
+    if (idx) idx[qi * k + j] = v ? cand_idx(e) : -1;
+    if (key) key[qi * k + j] = v ? cand_key(e) : -1.0f;
+  }
+}
+
+template <typename W>
+__device__ __forceinline__ void warp_run_coop(W & w, int n, int * counter, f4 * stage)
+{
+  unsigned const FULL = 0xffffffffu;
+  int lane = threadIdx.x & 31;
+  int chunk_base = 0, chunk_next = 0, chunk_end = 0; bool exhausted = false;
+  for (;;)
+  {
+    unsigned fin = __ballot_sync(FULL, w.state() == TGQ_ST_DONE);
+    while (fin) { int o = __ffs(fin) - 1; fin &= fin - 1; w.coop_finish(o); }
+    unsigned idle = __ballot_sync(FULL, w.state() == TGQ_ST_IDLE);
+    if (idle != 0u && !exhausted)
+    {
+      if (chunk_next >= chunk_end)
+      {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(counter, TGQ_CHUNK);
+        base = __shfl_sync(FULL, base, 0);
+        chunk_base = chunk_next = base; chunk_end = min(base + TGQ_CHUNK, n);
+        if (base >= n) exhausted = true;
+        else
+        {
+          __syncwarp();
+          for (int j = lane; j < chunk_end - chunk_base; j += 32) w.stage(chunk_base + j, stage + (size_t)j * W::STAGE);
+          __syncwarp();
+        }
+      }
+      if (!exhausted)
+      {
+        int t = chunk_next + __popc(idle & ((1u << lane) - 1u));
+        if (w.state() == TGQ_ST_IDLE && t < chunk_end) w.begin(t, stage + (size_t)(t - chunk_base) * W::STAGE);
+        chunk_next = min(chunk_next + __popc(idle), chunk_end);
+      }
+    }
+    int st = w.state();
+    bool at_node = st >= 0, at_leaf = st == TGQ_ST_LEAF;
+    if (!__any_sync(FULL, at_node || at_leaf || st == TGQ_ST_POP))
+    {
+      if (exhausted && __all_sync(FULL, w.state() != TGQ_ST_DONE)) break;
+      continue;
+    }
+    f4 r[W::FETCH];
+    if (at_node || at_leaf) w.fetch(r);
+    if (at_node) w.node_compute(r);
+    else if (at_leaf) w.leaf_compute(r);
+    unsigned cm = __ballot_sync(FULL, w.wants_compact());
+    while (cm) { int o = __ffs(cm) - 1; cm &= cm - 1; w.coop_compact_lane(o); }
+#pragma unroll
+    for (int j = 0; j < TGQ_POPS; ++j) if (w.state() == TGQ_ST_POP) w.pop_step();
+  }
+}
+
+template <int EPL>
+struct KnnBufW
+{
+  static constexpr int STAGE = 1;
+  KnnBufState s; BvhView b; float const * q3; uint32_t const * perm; int k; float ub; int exclude_self; int64_t self_offset;
+  int * idx; float * d2; int64_t qi; unsigned long long * rows;
+  float const * qn3; int const * qlabel; float min_dot;
+  __device__ __forceinline__ int state() const { return s.t.cur; }
+  __device__ __forceinline__ void stage(int t, f4 * dst) const
+  {
+    int i = perm ? (int)perm[t] : t; v3 p = ld3(q3, i);
+    *dst = make_float4(p.x, p.y, p.z, __int_as_float(i));
+  }
+  __device__ __forceinline__ void begin(int, f4 const * src)
+  {
+    f4 r = *src; qi = __float_as_int(r.w);
+    knnb_begin(s, b, mk3(r.x, r.y, r.z), exclude_self ? (int)(self_offset + qi) : -1, ub);
+    if (qn3 || qlabel)
+    {
+      s.f.mode = (qn3 ? 1 : 0) | (qlabel ? 2 : 0); s.f.min_dot = min_dot;
+      if (qn3) s.f.n = ld3(qn3, qi);
+      if (qlabel) s.f.label = qlabel[qi];
+    }
+  }
+  static constexpr int FETCH = TGQ_FETCH_BOX;
+  __device__ __forceinline__ void pop_step() { trav_pop_step(s.t, s.worst); }
+  __device__ __forceinline__ void fetch(f4 * r) const { box_fetch(s.t, b, r); }
+  __device__ __forceinline__ void node_compute(f4 const * r) { knnb_node_compute(s, b, r); }
+  __device__ __forceinline__ void leaf_compute(f4 const * r) { knnb_leaf_compute(s, b, r); }
+  __device__ __forceinline__ bool wants_compact() const { return s.buf.wants_compact(); }
+  __device__ __forceinline__ void coop_compact_lane(int o) { coop_compact<EPL>(rows, s.buf.cap, k, o, s.buf.n, s.worst); }
+  __device__ __forceinline__ void coop_finish(int o)
+  {
+    float unused = 0.0f;
+    coop_compact<EPL>(rows, s.buf.cap, k, o, s.buf.n, unused);
+    int n_o = __shfl_sync(0xffffffffu, s.buf.n, o);
+    int64_t q_o = __shfl_sync(0xffffffffu, qi, o);
+    coop_write(rows, s.buf.cap, k, o, n_o, q_o, idx, d2);
+    __syncwarp();
+    if ((threadIdx.x & 31) == o) s.t.cur = TGQ_ST_IDLE;
+  }
+};
+
+template <int EPL>
+__global__ void __launch_bounds__(TGQ_BLOCK)
+k_knn_buf(BvhView b, float const * __restrict__ q3, uint32_t const * __restrict__ perm, int n, int k, float bound_ub, int exclude_self,
+          int64_t self_offset, int * counter, int * idx, float * d2, float const * __restrict__ qn3, int const * __restrict__ qlabel, float min_dot)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  KnnBufW<EPL> w;
+  w.b = b; w.q3 = q3; w.perm = perm; w.k = k; w.ub = bound_ub; w.exclude_self = exclude_self; w.self_offset = self_offset;
+  w.idx = idx; w.d2 = d2; w.qi = 0; w.qn3 = qn3; w.qlabel = qlabel; w.min_dot = min_dot; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
+  unsigned char * extra; f4 * stage = trav_setup(w.s.t, st, smem, KnnBufW<EPL>::STAGE, &extra);
+  int cap = cand_cap(k);
+  w.rows = (unsigned long long *)extra + (size_t)(threadIdx.x >> 5) * 32 * cap;
+  w.s.buf.init(w.rows + (size_t)(threadIdx.x & 31) * cap, threadIdx.x & 31, k);
+  warp_run_coop(w, n, counter, stage);
+}
+
+template <int EPL>
+struct BallBufW
+{
+  static constexpr int STAGE = 2;
+  BallBufState s; BvhView b; int k; float init_radius; int rounds; float min_dot; int min_degree;
+  int * idx; float * sep; int * count; int64_t qi; unsigned long long * rows;
+  __device__ __forceinline__ int state() const { return s.t.cur; }
+  __device__ __forceinline__ void stage(int t, f4 * dst) const
+  {
+    dst[0] = b.pts[t];
+    dst[1] = b.nrm ? b.nrm[t] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  }
+  __device__ __forceinline__ void begin(int, f4 const * src)
+  {
+    f4 e = src[0], q = src[1]; qi = __float_as_int(e.w);
+    ballb_begin(s, b, mk3(e.x, e.y, e.z), mk3(q.x, q.y, q.z), b.nrm != nullptr, min_dot, (int)qi, init_radius, rounds, min_degree);
+  }
+  static constexpr int FETCH = TGQ_FETCH_BOX;
+  __device__ __forceinline__ void pop_step() { trav_pop_step(s.t, s.r2); }
+  __device__ __forceinline__ void fetch(f4 * r) const { box_fetch(s.t, b, r); }
+  __device__ __forceinline__ void node_compute(f4 const * r) { ballb_node_compute(s, b, r); }
+  __device__ __forceinline__ void leaf_compute(f4 const * r) { ballb_leaf_compute(s, b, r); }
+  __device__ __forceinline__ bool wants_compact() const { return s.buf.wants_compact(); }
+  __device__ __forceinline__ void coop_compact_lane(int o) { coop_compact<EPL>(rows, s.buf.cap, k, o, s.buf.n, s.worst_key); }
+  __device__ __forceinline__ void coop_finish(int o)
+  {
+    unsigned const FULL = 0xffffffffu;
+    float unused = 0.0f;
+    coop_compact<EPL>(rows, s.buf.cap, k, o, s.buf.n, unused);
+    int complete = 0;
+    if ((threadIdx.x & 31) == o) complete = ballb_round_done(s, b) ? 1 : 0;          // otherwise the next round has started
+    complete = __shfl_sync(FULL, complete, o);
+    if (!complete) return;
+    int n_o = __shfl_sync(FULL, s.buf.n, o);
+    int64_t q_o = __shfl_sync(FULL, qi, o);
+    coop_write(rows, s.buf.cap, k, o, n_o, q_o, idx, sep);
+    __syncwarp();
+    if ((threadIdx.x & 31) == o) { if (count) count[qi] = s.buf.n; s.t.cur = TGQ_ST_IDLE; }
+  }
+};
+
+template <int EPL>
+__global__ void __launch_bounds__(TGQ_BLOCK)
+k_ball_graph_buf(BvhView b, int n, int k, float init_radius, int rounds, float min_dot, int min_degree, int * counter, int * idx, float * sep, int * count)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  BallBufW<EPL> w;
+  w.b = b; w.k = k; w.init_radius = init_radius; w.rounds = rounds; w.min_dot = min_dot; w.min_degree = min_degree;
+  w.idx = idx; w.sep = sep; w.count = count; w.qi = 0; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
+  unsigned char * extra; f4 * stage = trav_setup(w.s.t, st, smem, BallBufW<EPL>::STAGE, &extra);
+  int cap = cand_cap(k);
+  w.rows = (unsigned long long *)extra + (size_t)(threadIdx.x >> 5) * 32 * cap;
+  w.s.buf.init(w.rows + (size_t)(threadIdx.x & 31) * cap, threadIdx.x & 31, k);
+  warp_run_coop(w, n, counter, stage);
+}
+
 // ---- ball range queries on a point structure (rangeQueryIndices with a Ball3) ---------------------------------------------
 struct RangeW
 {

@@ -36,6 +36,10 @@ namespace tgq {
 #define TGQ_COUNT_NODE()
 #define TGQ_COUNT_PRIM()
 #endif
+#ifndef TGQ_COUNT_APPEND
+#define TGQ_COUNT_APPEND()
+#define TGQ_COUNT_COMPACT()
+#endif
 
 struct BvhView
 {
@@ -696,6 +700,48 @@ struct SortedSet
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Candidate buffer: the k-NN / graph "heap" of the warp-cooperative kernels (k_knn_buf, k_ball_graph_buf).  ncu on the sorted-set
+// kernels (profiles/r02_p_knn_ball_graph_ncu.csv): 5.2 of 32 lanes active per instruction -- every accepted candidate runs a
+// data-dependent insertion loop inside divergent leaf code.  Here a lane only APPENDS accepted candidates, packed as
+// (key bits << 32 | element index) -- one store, no loop; the packed value orders exactly like the canonical (key, index) order because
+// keys are non-negative floats.  When fewer than TGQ_FETCH_BOX free slots remain, the buffer is COMPACTED: the k smallest entries
+// are kept, sorted ascending, and the k-th becomes the lane's acceptance / pruning threshold.  On the device the compaction of one
+// lane's buffer is done by the whole warp (rank sort with broadcast reads, tgq_kernels.cuh); `compact_serial` is the same operation
+// in one thread (host emulation, k_self_nn-style single-thread callers).  The result -- the k smallest (key, index) pairs of all
+// candidates ever offered with key <= threshold at the time -- does not depend on when compactions happen: an entry is only ever
+// dropped when k smaller ones are present.
+// Row layout: entry i of the lane with swizzle `lane` lives at row[(i & ~15) | ((i + lane) & 15)], so that lanes appending at equal
+// fill levels hit different banks and a whole-warp read of one row is conflict free.
+// ---------------------------------------------------------------------------------------------------------------------
+TGQ_HD unsigned long long cand_pack(float key, int idx) { return ((unsigned long long)(unsigned)f2i(key) << 32) | (unsigned long long)(unsigned)idx; }
+TGQ_HD float cand_key(unsigned long long e) { return i2f((int)(unsigned)(e >> 32)); }
+TGQ_HD int cand_idx(unsigned long long e) { return (int)(unsigned)(e & 0xffffffffull); }
+TGQ_HD int cand_cap(int k) { int room = k < 8 ? 8 : (k > 24 ? 24 : k); return (k + room + 15) & ~15; }      // k = 16: 32 slots
+struct CandBuf
+{
+  unsigned long long * row; int lane, cap, k, n;
+  TGQ_HD void init(unsigned long long * row_, int lane_, int k_) { row = row_; lane = lane_; k = k_; cap = cand_cap(k_); n = 0; }
+  TGQ_HD int phys(int i) const { return (i & ~15) | ((i + lane) & 15); }
+  TGQ_HD void append(float key, int idx) { TGQ_COUNT_APPEND(); row[phys(n)] = cand_pack(key, idx); ++n; }
+  TGQ_HD bool wants_compact() const { return n > cap - TGQ_FETCH_BOX; }
+  TGQ_HD unsigned long long at(int i) const { return row[phys(i)]; }
+  // keeps the min(n, k) smallest entries, ascending; returns true (and the k-th key) when the buffer then holds k entries
+  TGQ_HD bool compact_serial(float & kth)
+  {
+    TGQ_COUNT_COMPACT();
+    for (int i = 1; i < n; ++i)
+    {
+      unsigned long long x = row[phys(i)]; int j = i;
+      while (j > 0 && row[phys(j - 1)] > x) { row[phys(j)] = row[phys(j - 1)]; --j; }
+      row[phys(j)] = x;
+    }
+    if (n > k) n = k;
+    if (n == k && k > 0) { kth = cand_key(row[phys(k - 1)]); return true; }
+    return false;
+  }
+};
+
 // Fetch of the AABB tree over points: a 64-byte node or the next (up to) four 16-byte points of the pending leaf.
 TGQ_HD void box_fetch(Trav const & t, BvhView const & b, f4 * r)
 {
@@ -768,6 +814,60 @@ TGQ_HD void knn_query(BvhView const & b, v3 p, int skip, float bound_ub, SortedS
     if (s.t.cur >= 0) knn_node_compute(s, b, r); else knn_leaf_compute(s, b, r);
   }
   set.n = s.set.n;
+}
+
+// The same query on a candidate buffer (k_knn_buf): candidates with d2 <= worst are appended, `worst` tightens at compactions.
+struct KnnBufState
+{
+  v3 p; int skip; float bound_ub; float worst; ElemFilterD f; CandBuf buf; Trav t;
+};
+TGQ_HD void knnb_begin(KnnBufState & s, BvhView const & b, v3 p, int skip, float bound_ub)
+{
+  s.p = p; s.skip = skip; s.bound_ub = bound_ub; s.worst = bound_ub; s.buf.n = 0; s.f = no_filter();
+  trav_begin(s.t, s.buf.k > 0 ? b.n_nodes : 0);
+}
+TGQ_HD void knnb_node_compute(KnnBufState & s, BvhView const & b, f4 const * r)
+{
+  TGQ_COUNT_NODE();
+  float lb0, lb1; int c0, c1; box_node_bounds(r, s.p, lb0, lb1, c0, c1);
+  trav_descend(s.t, lb0, lb1, lb0, lb1, c0, c1, s.worst);
+}
+TGQ_HD void knnb_leaf_compute(KnnBufState & s, BvhView const & b, f4 const * r)
+{
+  int cnt = s.t.kend - s.t.k; if (cnt > TGQ_FETCH_BOX) cnt = TGQ_FETCH_BOX;
+  // straight-line over the four fetched slots (no early exit): the lanes of a warp that are at a leaf stay converged
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int j = 0; j < TGQ_FETCH_BOX; ++j)
+  {
+    f4 e = r[j];
+    int idx = f2i(e.w);
+    float d2 = sqn3(sub3(mk3(e.x, e.y, e.z), s.p));
+    bool ok = j < cnt && idx != s.skip && d2 < s.bound_ub && d2 <= s.worst;
+    if (j < cnt) { TGQ_COUNT_PRIM(); }
+    if (ok && s.f.mode != 0) ok = !filtered_out(b, s.t.k + j, s.f);
+    if (ok) s.buf.append(d2, idx);
+  }
+  s.t.k += cnt;
+  if (s.t.k >= s.t.kend) trav_pop(s.t);
+}
+// One-thread driver (host emulation): out_n entries ascending in buf.
+TGQ_HD void knn_query_buf(BvhView const & b, v3 p, int skip, float bound_ub, CandBuf & buf, ElemFilterD const * filter = nullptr)
+{
+  KnnBufState s; TravStack st; trav_bind(s.t, st); s.buf = buf;
+  knnb_begin(s, b, p, skip, bound_ub);
+  if (filter) s.f = *filter;
+  f4 r[TGQ_FETCH_BOX];
+  while (s.t.cur != TGQ_ST_DONE)
+  {
+    if (s.t.cur == TGQ_ST_POP) { trav_pop_step(s.t, s.worst); continue; }
+    box_fetch(s.t, b, r);
+    if (s.t.cur >= 0) knnb_node_compute(s, b, r);
+    else { knnb_leaf_compute(s, b, r); if (s.buf.wants_compact()) { float kth; if (s.buf.compact_serial(kth)) s.worst = kth; } }
+  }
+  float kth; s.buf.compact_serial(kth);
+  buf.n = s.buf.n;
 }
 
 // PointSet3::findSampleNeighbors for sample `self` (position c, normal nc): in each round every point j != self with
@@ -850,6 +950,82 @@ TGQ_HD void ball_graph_query(BvhView const & b, v3 c, v3 nc, bool has_n, float m
     if (ball_round_done(s, b)) break;
   }
   set.n = s.set.n;
+}
+
+// The sample graph on a candidate buffer (k_ball_graph_buf): every admissible point of the ball is appended with key fastSqrt(d2);
+// once a compaction has left max_degree entries, candidates with a larger key than the last of them are not offered any more (they
+// could never be among the max_degree smallest).  Rounds as above.
+struct BallBufState
+{
+  v3 c, nc; bool has_n; float min_dot; int self; float radius, r2; int round, rounds, min_degree; float worst_key;
+  CandBuf buf; Trav t;
+};
+TGQ_HD void ballb_begin(BallBufState & s, BvhView const & b, v3 c, v3 nc, bool has_n, float min_dot, int self, float init_radius, int rounds,
+                        int min_degree)
+{
+  s.c = c; s.nc = nc; s.has_n = has_n; s.min_dot = min_dot; s.self = self; s.radius = init_radius; s.r2 = init_radius * init_radius;
+  s.round = 0; s.rounds = rounds; s.min_degree = min_degree; s.buf.n = 0; s.worst_key = INFINITY;
+  trav_begin(s.t, b.n_nodes);
+}
+TGQ_HD void ballb_node_compute(BallBufState & s, BvhView const & b, f4 const * r)
+{
+  TGQ_COUNT_NODE();
+  float lb0, lb1; int c0, c1; box_node_bounds(r, s.c, lb0, lb1, c0, c1);
+  trav_descend(s.t, lb0, lb1, 0.0f, 0.0f, c0, c1, s.r2);
+}
+TGQ_HD void ballb_leaf_compute(BallBufState & s, BvhView const & b, f4 const * r)
+{
+  int cnt = s.t.kend - s.t.k; if (cnt > TGQ_FETCH_BOX) cnt = TGQ_FETCH_BOX;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int j = 0; j < TGQ_FETCH_BOX; ++j)
+  {
+    f4 e = r[j];
+    int idx = f2i(e.w);
+    v3 diff = sub3(mk3(e.x, e.y, e.z), s.c);
+    float d2 = sqn3(diff);
+    bool ok = j < cnt && idx != s.self && d2 <= s.r2;
+    if (j < cnt) { TGQ_COUNT_PRIM(); }
+    if (ok && s.has_n)
+    {
+      f4 nj = ldq(b.nrm + s.t.k + j);
+      ok = !(dot3(s.nc, mk3(nj.x, nj.y, nj.z)) < s.min_dot);
+    }
+    float sep = fast_sqrt(d2);
+    if (ok && sep <= s.worst_key) s.buf.append(sep, idx);
+  }
+  s.t.k += cnt;
+  if (s.t.k >= s.t.kend) trav_pop(s.t);
+}
+// Called (after a compaction of the finished round's buffer) when a round's traversal is done: true = the query is complete.
+TGQ_HD bool ballb_round_done(BallBufState & s, BvhView const & b)
+{
+  ++s.round;
+  if (s.buf.n >= s.min_degree || s.round >= s.rounds) return true;
+  s.radius *= 2.0f; s.r2 = s.radius * s.radius; s.buf.n = 0; s.worst_key = INFINITY;
+  trav_begin(s.t, b.n_nodes);
+  return s.t.cur == TGQ_ST_DONE;
+}
+TGQ_HD void ball_graph_query_buf(BvhView const & b, v3 c, v3 nc, bool has_n, float min_dot, int self, float init_radius, int rounds, int min_degree,
+                                 CandBuf & buf)
+{
+  BallBufState s; TravStack st; trav_bind(s.t, st); s.buf = buf;
+  ballb_begin(s, b, c, nc, has_n, min_dot, self, init_radius, rounds, min_degree);
+  f4 r[TGQ_FETCH_BOX];
+  for (;;)
+  {
+    while (s.t.cur != TGQ_ST_DONE)
+    {
+      if (s.t.cur == TGQ_ST_POP) { trav_pop_step(s.t, s.r2); continue; }
+      box_fetch(s.t, b, r);
+      if (s.t.cur >= 0) ballb_node_compute(s, b, r);
+      else { ballb_leaf_compute(s, b, r); if (s.buf.wants_compact()) { float kth; if (s.buf.compact_serial(kth)) s.worst_key = kth; } }
+    }
+    float kth; s.buf.compact_serial(kth);
+    if (ballb_round_done(s, b)) break;
+  }
+  buf.n = s.buf.n;
 }
 
 // Ball range query on a point structure: BvhN::rangeQueryIndices / processRange<IntersectionTester>(Ball3(c, r)) (BvhN.hpp:1208-

@@ -16,6 +16,7 @@ _LIB = None
 
 KIND_NONE, KIND_TRIANGLES, KIND_POINTS = 0, 1, 2
 OPT_SORT_QUERIES, OPT_LEAF_SIZE, OPT_ASYNC, OPT_CHUNK, OPT_POOL, OPT_ICP_REFERENCE_ORDER, OPT_WIDE = 1, 2, 3, 4, 5, 6, 7
+OPT_SET_BUFFER = 10
 MAX_K = 64
 
 SYMBOLS = [
