@@ -914,7 +914,7 @@ static int knn_common(tgq_handle * h, const float * q3, const float * qn3, const
   BvhView v = view_of(h);
   size_t smem = trav_smem_bytes(KnnW::STAGE) + 2 * (size_t)k * TGQ_BLOCK * 4;
   int const cap = cand_cap(k), epl = (cap + 31) / 32;
-  size_t bsmem = trav_smem_bytes(1) + (size_t)cap * TGQ_BLOCK * 8;
+  size_t bsmem = trav_smem_bytes(1, TGQ_BUF_SSTACK) + (size_t)cap * TGQ_BLOCK * 8;
   bool const buffered = h->opt_setbuf != 0;
   return run_batched(h, Q, args, 5, true, [&](ChunkCtx & c) -> int {
     int grid = 0; int * cnt = c.slot->counter.as<int>();
@@ -982,7 +982,7 @@ static int ball_graph_common(tgq_handle * h, tgq_handle * surface, int32_t max_d
   else if (h->opt_setbuf)
   {
     int const cap = cand_cap(max_degree), epl = (cap + 31) / 32;
-    size_t bsmem = trav_smem_bytes(2) + (size_t)cap * TGQ_BLOCK * 8;
+    size_t bsmem = trav_smem_bytes(2, TGQ_BUF_SSTACK) + (size_t)cap * TGQ_BLOCK * 8;
 #define TGQ_BALL_BUF(E) { CKRC(persistent_grid(h, k_ball_graph_buf<E>, bsmem, h->n, cnt, s, &grid)); \
       k_ball_graph_buf<E><<<grid, TGQ_BLOCK, bsmem, s>>>(view_of(h), h->n, max_degree, init_radius, rounds, min_dot, min_degree, cnt, di, ds, dc); }
     if (epl == 1) TGQ_BALL_BUF(1) else if (epl == 2) TGQ_BALL_BUF(2) else TGQ_BALL_BUF(3)

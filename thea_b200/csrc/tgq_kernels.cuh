@@ -577,7 +577,7 @@ __global__ void k_scatter_records(void const * __restrict__ src, int slots, int6
 
 // Shared memory of one block of a traversal kernel: the short stacks, then one staging buffer of TGQ_CHUNK query records
 // per warp (STAGE float4 per record), then whatever the kernel itself needs (k-NN sets).
-__host__ __device__ constexpr size_t trav_smem_bytes(int stage_f4) { return (size_t)TGQ_SSTACK * TGQ_BLOCK * sizeof(StackEntry) + (size_t)TGQ_WARPS * TGQ_CHUNK * stage_f4 * sizeof(f4); }
+__host__ __device__ constexpr size_t trav_smem_bytes(int stage_f4, int sstack = TGQ_SSTACK) { return (size_t)sstack * TGQ_BLOCK * sizeof(StackEntry) + (size_t)TGQ_WARPS * TGQ_CHUNK * stage_f4 * sizeof(f4); }
 
 template <typename W>
 __device__ __forceinline__ void warp_run(W & w, int n, int * counter, f4 * stage)
@@ -632,11 +632,11 @@ __device__ __forceinline__ void warp_run(W & w, int n, int * counter, f4 * stage
 }
 
 // Binds the calling thread's short stack and returns its warp's staging buffer; `extra` = first byte after both.
-__device__ __forceinline__ f4 * trav_setup(Trav & t, TravStack & st, unsigned char * smem, int stage_f4, unsigned char ** extra)
+__device__ __forceinline__ f4 * trav_setup(Trav & t, TravStack & st, unsigned char * smem, int stage_f4, unsigned char ** extra, int sstack = TGQ_SSTACK)
 {
   trav_bind(t, st);
-  trav_bind_fast(t, (StackEntry *)smem + threadIdx.x, TGQ_BLOCK, TGQ_SSTACK);
-  f4 * stage_all = (f4 *)(smem + (size_t)TGQ_SSTACK * TGQ_BLOCK * sizeof(StackEntry));
+  trav_bind_fast(t, (StackEntry *)smem + threadIdx.x, TGQ_BLOCK, sstack);
+  f4 * stage_all = (f4 *)(smem + (size_t)sstack * TGQ_BLOCK * sizeof(StackEntry));
   if (extra) *extra = (unsigned char *)(stage_all + (size_t)TGQ_WARPS * TGQ_CHUNK * stage_f4);
   return stage_all + (size_t)(threadIdx.x >> 5) * TGQ_CHUNK * stage_f4;
 }
@@ -1241,6 +1241,11 @@ k_ball_graph(BvhView b, BvhView surf, int n, int k, float init_radius, int round
 //   larger buffers (EPL = 2, 3): rank sort -- every lane holds EPL entries in registers and counts, over broadcast reads of the
 //     row, how many entries are smaller (the first version used this for every size: ncu's source view showed the rank loop at
 //     34 % of all warp instructions for k = 16, profiles/r02_t_knn_buf_source_lines.txt).
+// The buffer kernels are short of resident warps (shared memory: 256 bytes of buffer per lane for k = 16), so they keep only the first
+// TGQ_BUF_SSTACK stack entries per lane in shared memory (deeper ones in local memory; ordered DFS over points rarely gets there).
+#ifndef TGQ_BUF_SSTACK
+#define TGQ_BUF_SSTACK 8
+#endif
 __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long x, int m)
 {
   unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)x, m), hi = __shfl_xor_sync(0xffffffffu, (unsigned)(x >> 32), m);
@@ -1425,7 +1430,7 @@ k_knn_buf(BvhView b, float const * __restrict__ q3, uint32_t const * __restrict_
   KnnBufW<EPL> w;
   w.b = b; w.q3 = q3; w.perm = perm; w.k = k; w.ub = bound_ub; w.exclude_self = exclude_self; w.self_offset = self_offset;
   w.idx = idx; w.d2 = d2; w.qi = 0; w.qn3 = qn3; w.qlabel = qlabel; w.min_dot = min_dot; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
-  unsigned char * extra; f4 * stage = trav_setup(w.s.t, st, smem, KnnBufW<EPL>::STAGE, &extra);
+  unsigned char * extra; f4 * stage = trav_setup(w.s.t, st, smem, KnnBufW<EPL>::STAGE, &extra, TGQ_BUF_SSTACK);
   int cap = cand_cap(k);
   w.rows = (unsigned long long *)extra + (size_t)(threadIdx.x >> 5) * 32 * cap;
   w.s.buf.init(w.rows + (size_t)(threadIdx.x & 31) * cap, threadIdx.x & 31, k);
@@ -1481,7 +1486,7 @@ k_ball_graph_buf(BvhView b, int n, int k, float init_radius, int rounds, float m
   BallBufW<EPL> w;
   w.b = b; w.k = k; w.init_radius = init_radius; w.rounds = rounds; w.min_dot = min_dot; w.min_degree = min_degree;
   w.idx = idx; w.sep = sep; w.count = count; w.qi = 0; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
-  unsigned char * extra; f4 * stage = trav_setup(w.s.t, st, smem, BallBufW<EPL>::STAGE, &extra);
+  unsigned char * extra; f4 * stage = trav_setup(w.s.t, st, smem, BallBufW<EPL>::STAGE, &extra, TGQ_BUF_SSTACK);
   int cap = cand_cap(k);
   w.rows = (unsigned long long *)extra + (size_t)(threadIdx.x >> 5) * 32 * cap;
   w.s.buf.init(w.rows + (size_t)(threadIdx.x & 31) * cap, threadIdx.x & 31, k);

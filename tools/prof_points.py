@@ -9,7 +9,7 @@ def main(grid=708, P=1_000_000):
     mesh = gen.torus_mesh(grid)
     e = Engine(0); e.build_triangles(torch.from_numpy(mesh).cuda())
     p, n, _ = e.area_sample(P, gen.SEED_SAMPLES)
-    pe = Engine(0); pe.set_option(_eng.OPT_SET_BUFFER, int(os.environ.get("TGQ_SET_BUFFER", "1"))); pe.build_points(p, n)
+    pe = Engine(0, lib=(os.environ.get("TGQ_LIB") or None)); pe.set_option(_eng.OPT_SET_BUFFER, int(os.environ.get("TGQ_SET_BUFFER", "1"))); pe.build_points(p, n)
     dp = torch.from_numpy(p).cuda()
     for _ in range(2):
         pe.knn(dp, 16, exclude_self=True)
