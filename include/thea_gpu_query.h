@@ -211,6 +211,48 @@ int tgq_ball_stats(tgq_handle * h, const float * c3, const float * qn3, const fl
  * subsampling (sample_reduction_ratio < 1, Random::common()) is not reproduced. */
 int tgq_ball_histogram(tgq_handle * h, const float * c3, const float * radius, int64_t Q, int32_t num_bins, uint32_t * hist);
 
+/* SpinImage::compute(position, normal, num_radial_bins, num_height_bins, spin_image) for Q queries on a point structure
+ * (Algorithms/SurfaceFeatures/Local/SpinImage.cpp:47-75): every query bins ALL samples of the structure by (radius about the axis
+ * through the query along stableNormalized(normal), height along it), radial limits [0, max_extent], height limits
+ * [-max_extent, max_extent], with the reference's fp32 expressions; the reference uses max_extent = 0.75f * surf->getScale().
+ * image: [Q x num_radial_bins x num_height_bins] counts, radial bin major (the reference's spin_image(radial_bin, height_bin)).
+ * Exact integers.  num_radial_bins * num_height_bins <= 1024. */
+int tgq_spin_image(tgq_handle * h, const float * q3, const float * qn3, int64_t Q, int32_t num_radial_bins, int32_t num_height_bins,
+                   float max_extent, uint32_t * image);
+
+/* ---- shortest paths on the sample graph (what the reference does with ShortestPaths::dijkstraWithCallback, Algorithms/ShortestPaths.hpp:
+ * 166-353, on PointSet3's proximity graph).  The graph is given as the (P x max_degree) rows tgq_ball_graph produces: idx (-1 padded)
+ * and sep (the float separations), directed, host or device.  Path lengths are the reference's: left-to-right double sums of the
+ * float edge lengths, minimised over paths -- bit-identical to Dijkstra's values.  The handle only supplies device, stream and
+ * scratch; it needs no structure. */
+
+/* PointSet3::extractOriginalAdjacencies (Algorithms/PointSet3.cpp:96-178): the oversampling contraction of updateGraph.  Samples
+ * 0 .. n_orig-1 are the original ones, n_orig .. P-1 the dense oversampling.  For every original sample s: the max_degree original
+ * samples v != s with the smallest graph distance over ALL samples (equal distances: lower index; the reference: heap pop order),
+ * as rows ordered like the reference's neighbour set, by (float(distance), index); out_idx / out_sep [n_orig x max_degree], -1 / -1.0f
+ * padded; out_count (may be null) [n_orig]. */
+int tgq_graph_contract(tgq_handle * h, const int32_t * idx, const float * sep, int64_t P, int32_t max_degree, int64_t n_orig, int32_t * out_idx,
+                       float * out_sep, int32_t * out_count);
+
+/* The geodesic neighbourhood of Q seed samples: AverageDistance::compute(p, GEODESIC, d) and LocalDistanceHistogram::compute(p, hist,
+ * GEODESIC, d, ratio >= 1) (Algorithms/SurfaceFeatures/Local/AverageDistance.cpp:84-118, LocalDistanceHistogram.cpp:90-137) after their
+ * nearest-sample lookup (seeds[i] = closestElement(p_i), e.g. from tgq_closest on the point structure).  Every vertex with graph
+ * distance <= max_distance from its seed (max_distance < 0: the whole component) contributes: sum [Q] (double; summed in device
+ * order, the reference sums in ascending distance: equal to about 1e-15 relative), count [Q], and -- when hist is given -- one count
+ * in bin clamp(floor(d / (max(hist_range, 1e-30) / num_bins))) of hist [Q x num_bins] (Histogram.hpp:110-150; the reference uses
+ * hist_range = max_distance, or the scale when max_distance < 0).  The average distance is sum / count / hist_range.  Any output may
+ * be null. */
+int tgq_graph_geodesic(tgq_handle * h, const int32_t * idx, const float * sep, int64_t P, int32_t max_degree, const int32_t * seeds, int64_t Q,
+                       float max_distance, float hist_range, int32_t num_bins, double * sum, int32_t * count, uint32_t * hist);
+
+/* FurthestPointSampling::subsample (Algorithms/FurthestPointSampling.cpp:48-125; MeshSampler::sampleEvenlyBySeparation, MeshSampler.hpp:
+ * 270-329, calls it on a 3x area oversampling): sample 0 first, then repeatedly the sample the reference's multi-source search
+ * reports last -- the highest-index sample not reachable from the selected set if there is one, else the sample of maximal graph
+ * distance to the set (equal distances: higher index; the reference: heap pop order).  Stops early, like the reference, when nothing
+ * but selected samples is left.  selected [n_desired] (host or device), *n_selected (host) = number written. */
+int tgq_graph_fps(tgq_handle * h, const int32_t * idx, const float * sep, int64_t P, int32_t max_degree, int64_t n_desired, int32_t * selected,
+                  int64_t * n_selected);
+
 /* Proximity graph over the P points of a point structure.  Replaces the loop of PointSet3::updateGraph over
  * findSampleNeighbors (PointSet3.hpp:380-381,586-681): for every sample, a ball range query of radius init_radius
  * (doubled for up to `rounds` rounds while fewer than min_degree neighbours were found), candidates filtered by

@@ -6,6 +6,7 @@
 #include <chrono>
 #include <functional>
 #include <thread>
+#include <queue>
 
 using namespace oracle;
 
@@ -136,6 +137,38 @@ Affine icp_step(int64_t n, V3 const * from, V3 const * to)
   return a;
 }
 
+}  // namespace
+
+// Dijkstra on a sample graph with the reference's arithmetic (see the graph section below).
+namespace {
+struct GraphDijkstra
+{
+  int64_t const * idx; float const * sep; int64_t P; int K;
+  std::vector<double> dist; std::vector<char> black; std::vector<int64_t> touched;
+  GraphDijkstra(int64_t const * i, float const * s, int64_t P_, int K_) : idx(i), sep(s), P(P_), K(K_), dist((size_t)P_, INFINITY), black((size_t)P_, 0) {}
+  template <typename Visit> void run(std::vector<std::pair<int64_t, double>> const & sources, double limit, Visit visit)
+  {
+    typedef std::pair<double, int64_t> E;
+    std::priority_queue<E, std::vector<E>, std::greater<E>> pq;
+    for (auto const & sd : sources) { dist[(size_t)sd.first] = sd.second; touched.push_back(sd.first); pq.push(E(sd.second, sd.first)); }
+    while (!pq.empty())
+    {
+      E top = pq.top(); pq.pop();
+      int64_t u = top.second;
+      if (black[(size_t)u] || top.first != dist[(size_t)u]) continue;
+      for (int e = 0; e < K; ++e)
+      {
+        int64_t v = idx[u * K + e]; if (v < 0 || black[(size_t)v]) continue;
+        double t = (double)sep[u * K + e] + dist[(size_t)u];
+        if (t < dist[(size_t)v]) { if (dist[(size_t)v] == INFINITY) touched.push_back(v); dist[(size_t)v] = t; pq.push(E(t, v)); }
+      }
+      black[(size_t)u] = 1;
+      if (limit >= 0 && dist[(size_t)u] > limit) break;
+      if (visit(u, dist[(size_t)u])) break;
+    }
+  }
+  void reset() { for (int64_t v : touched) { dist[(size_t)v] = INFINITY; black[(size_t)v] = 0; } touched.clear(); }
+};
 }  // namespace
 
 extern "C" {
@@ -339,6 +372,35 @@ void orc_ball_stats(void * h, float const * c3, float const * qn3, float const *
           for (int k = 0; k < 9; ++k) cov[k] /= den;
           o[7] = cov[0]; o[8] = cov[1]; o[9] = cov[2]; o[10] = cov[4]; o[11] = cov[5]; o[12] = cov[8];
         }
+      }
+    }
+  });
+}
+
+// SpinImage::compute(position, normal, num_radial_bins, num_height_bins, spin_image) (SurfaceFeatures/Local/SpinImage.cpp:47-75):
+// axis = normal.stableNormalized(); every sample of the set is binned by (radius about the axis, height along it) with
+// max_radius = max_height = max_extent (the reference passes 0.75f * surf->getScale()).  image: [Q x nr x nh], radial bin major.
+void orc_spin_image(void * h, float const * q3, float const * qn3, int64_t Q, int nr, int nh, float max_extent, int nthreads, double * image)
+{
+  KdTree const & T = ((Handle *)h)->tree;
+  int64_t P = T.size();
+  parallel_for(Q, nthreads, [&](int64_t b, int64_t e) {
+    for (int64_t i = b; i < e; ++i)
+    {
+      V3 position = ld3(q3, i); V3 axis = stable_normalized(ld3(qn3, i));
+      double * img = image + (int64_t)nr * nh * i;
+      for (int j = 0; j < nr * nh; ++j) img[j] = 0;
+      float max_radius = max_extent, max_height = max_extent;
+      for (int64_t j = 0; j < P; ++j)
+      {
+        V3 offset = T.pts[(size_t)j] - position;
+        float height = dot(offset, axis);
+        float radius = std::sqrt(sqnorm(offset - axis * height));
+        int radial_bin = (int)std::floor(nr * (radius / max_radius));
+        radial_bin = radial_bin < 0 ? 0 : (radial_bin > nr - 1 ? nr - 1 : radial_bin);
+        int height_bin = (int)std::floor(nh * (0.5f * (height / max_height + 1)));
+        height_bin = height_bin < 0 ? 0 : (height_bin > nh - 1 ? nh - 1 : height_bin);
+        img[radial_bin * nh + height_bin] += 1;
       }
     }
   });
@@ -674,6 +736,93 @@ void orc_thea_random_uniform01(uint32_t seed, int64_t n, float * out)
     r ^= r >> 11; r ^= (r << 7) & 0x9D2C5680u; r ^= (r << 15) & 0xEFC60000u; r ^= r >> 18;
     out[k] = (float)r * (1.0f / (float)0xFFFFFFFFu);
   }
+}
+
+
+// ---- shortest paths on the sample graph: ShortestPaths::dijkstraWithCallback (Algorithms/ShortestPaths.hpp:166-353) restated with a
+// binary heap.  The reference's Fibonacci heap pops equal distances in an order of its own; here equal distances pop in index order
+// (the canonical order the engine reproduces).  Distances are the reference's: test_dist = nbr_dist + data->dist in double (:304),
+// adopted when strictly smaller (:305).  visit(vertex, distance) returns true to stop (the callback's return value, :346).
+
+// PointSet3::extractOriginalAdjacencies (PointSet3.cpp:96-178).
+void orc_graph_contract(int64_t const * idx, float const * sep, int64_t P, int K, int64_t n_orig, int nthreads, int64_t * out_idx, float * out_sep,
+                        int32_t * out_count)
+{
+  parallel_for(n_orig, nthreads, [&](int64_t b, int64_t e) {
+    GraphDijkstra D(idx, sep, P, K);
+    for (int64_t s = b; s < e; ++s)
+    {
+      std::vector<std::pair<float, int64_t>> nb;         // the neighbour set: ordered by (Real separation, sample address) (SamplePoint3.hpp:52-55)
+      D.run({{s, 0.0}}, -1.0, [&](int64_t v, double d) {
+        if (v != s && v < n_orig) nb.push_back(std::make_pair((float)d, v));
+        return (int)nb.size() >= K;
+      });
+      D.reset();
+      std::sort(nb.begin(), nb.end());
+      if (out_count) out_count[s] = (int32_t)nb.size();
+      for (int j = 0; j < K; ++j)
+      {
+        bool ok = j < (int)nb.size();
+        out_idx[s * K + j] = ok ? nb[(size_t)j].second : -1; out_sep[s * K + j] = ok ? nb[(size_t)j].first : -1.0f;
+      }
+    }
+  });
+}
+
+// AverageDistance / LocalDistanceHistogram, DistanceType::GEODESIC, from given seed samples (AverageDistance.cpp:84-118,
+// LocalDistanceHistogram.cpp:90-137; Histogram.hpp:110-150).  sum in the callback's order: ascending distance.
+void orc_graph_geodesic(int64_t const * idx, float const * sep, int64_t P, int K, int64_t const * seeds, int64_t Q, float max_distance, float hist_range,
+                        int nbins, int nthreads, double * sum, int64_t * count, double * hist)
+{
+  parallel_for(Q, nthreads, [&](int64_t b, int64_t e) {
+    GraphDijkstra D(idx, sep, P, K);
+    for (int64_t i = b; i < e; ++i)
+    {
+      double s = 0; int64_t n = 0;
+      double hi = std::max((double)hist_range, 1.0e-30), bin_size = nbins > 0 ? (hi - 0.0) / nbins : 1.0;
+      if (hist) for (int j = 0; j < nbins; ++j) hist[i * nbins + j] = 0;
+      if (seeds[i] >= 0 && seeds[i] < P)
+      {
+        D.run({{seeds[i], 0.0}}, max_distance < 0 ? -1.0 : (double)max_distance, [&](int64_t, double d) {
+          s += d; ++n;
+          if (hist)
+          {
+            int64_t bin = (int64_t)std::floor((d - 0.0) / bin_size);
+            bin = bin < 0 ? 0 : (bin > nbins - 1 ? nbins - 1 : bin);
+            hist[i * nbins + bin] += 1.0;
+          }
+          return false;
+        });
+        D.reset();
+      }
+      if (sum) sum[i] = s;
+      if (count) count[i] = n;
+    }
+  });
+}
+
+// FurthestPointSampling::subsample (FurthestPointSampling.cpp:48-125): sample 0, then repeatedly the vertex the multi-source search
+// from the selected set reports last -- unreachable vertices are reported after the search in vertex order (ShortestPaths.hpp:350-362).
+int64_t orc_graph_fps(int64_t const * idx, float const * sep, int64_t P, int K, int64_t n_desired, int64_t * selected)
+{
+  std::vector<std::pair<int64_t, double>> region; std::vector<char> in_region((size_t)P, 0);
+  for (int64_t i = 0; i < n_desired; ++i)
+  {
+    int64_t furthest = -1;
+    if (region.empty()) furthest = 0;
+    else
+    {
+      GraphDijkstra D(idx, sep, P, K);
+      // equal distances: the higher index is reported last (canonical; the reference: its heap's order)
+      double best = -1; int64_t bi = -1;
+      D.run(region, -1.0, [&](int64_t v, double d) { if (d > best || (d == best && v > bi)) { best = d; bi = v; } return false; });
+      furthest = bi;
+      for (int64_t v = 0; v < P; ++v) if (!D.black[(size_t)v]) furthest = v;
+      if (furthest < 0 || in_region[(size_t)furthest]) return i;
+    }
+    selected[i] = furthest; region.push_back(std::make_pair(furthest, 0.0)); in_region[(size_t)furthest] = 1;
+  }
+  return n_desired;
 }
 
 }  // extern "C"

@@ -58,6 +58,11 @@ def lib():
         L.orc_ball_range.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_ball_graph_surface.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_ball_hist.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orc_graph_contract.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_graph_geodesic.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_graph_fps.restype = C.c_int64
+        L.orc_graph_fps.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p]
+        L.orc_spin_image.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]
         L.orc_ball_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]
         L.orc_visibility.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_avg_separation.restype = C.c_float
@@ -207,6 +212,14 @@ class Oracle:
         lib().orc_ball_graph_surface(self.h, surface.h, max_degree, float(init_radius), mode, threads or ncores(), _p(idx), _p(sep), _p(cnt))
         return idx, sep, cnt
 
+    def spin_image(self, q, qn, nr, nh, max_extent, threads=None):
+        """SpinImage::compute(position, normal, nr, nh) for every query: [Q x nr x nh] float64 counts (SpinImage.cpp:47-75)."""
+        q = np.ascontiguousarray(q, np.float32); qn = np.ascontiguousarray(qn, np.float32)
+        Q = len(q)
+        out = np.empty((Q, int(nr), int(nh)), np.float64)
+        lib().orc_spin_image(self.h, _p(q), _p(qn), Q, int(nr), int(nh), float(max_extent), threads or ncores(), _p(out))
+        return out
+
     def ball_hist(self, c, radius, nbins, mode=MODE_REFERENCE, threads=None):
         """LocalDistanceHistogram (EUCLIDEAN, explicit max_distance): [Q, nbins] float64 bin contents."""
         c = _f32(c).reshape(-1, 3)
@@ -336,3 +349,36 @@ def thea_random_uniform01(seed, n):
     out = np.empty(n, np.float32)
     lib().orc_thea_random_uniform01(seed, n, _p(out))
     return out
+
+
+# ---- shortest paths on a given sample graph (idx / sep: P x K rows, -1 padded): ShortestPaths.hpp:166-353 restated ----
+def _graph(idx, sep):
+    idx = np.ascontiguousarray(idx, np.int64)
+    sep = np.ascontiguousarray(sep, np.float32)
+    return idx, sep, idx.shape[0], idx.shape[1]
+
+
+def graph_contract(idx, sep, n_orig, threads=None):
+    """PointSet3::extractOriginalAdjacencies: (idx, sep, count) rows of the first n_orig samples."""
+    idx, sep, P, K = _graph(idx, sep)
+    oi, os_, oc = np.empty((n_orig, K), np.int64), np.empty((n_orig, K), np.float32), np.empty(n_orig, np.int32)
+    lib().orc_graph_contract(_p(idx), _p(sep), P, K, int(n_orig), threads or ncores(), _p(oi), _p(os_), _p(oc))
+    return oi, os_, oc
+
+
+def graph_geodesic(idx, sep, seeds, max_distance, hist_range, nbins, threads=None):
+    """Geodesic neighbourhood of every seed: (sum [Q] float64, count [Q] int64, hist [Q x nbins] float64)."""
+    idx, sep, P, K = _graph(idx, sep)
+    seeds = np.ascontiguousarray(seeds, np.int64)
+    Q = len(seeds)
+    s, c, h = np.empty(Q, np.float64), np.empty(Q, np.int64), np.empty((Q, max(nbins, 1)), np.float64)
+    lib().orc_graph_geodesic(_p(idx), _p(sep), P, K, _p(seeds), Q, float(max_distance), float(hist_range), int(nbins), threads or ncores(), _p(s), _p(c), _p(h) if nbins > 0 else None)
+    return s, c, h
+
+
+def graph_fps(idx, sep, n_desired):
+    """FurthestPointSampling::subsample's selection on a given graph."""
+    idx, sep, P, K = _graph(idx, sep)
+    sel = np.full(int(n_desired), -1, np.int64)
+    n = lib().orc_graph_fps(_p(idx), _p(sep), P, K, int(n_desired), _p(sel))
+    return sel[:n]

@@ -79,6 +79,11 @@ def lib():
         L.ref_graph.argtypes = [vp, vp, i64, i32, f32, vp, vp, vp, vp]
         L.ref_avg_separation.restype = f32
         L.ref_avg_separation.argtypes = [vp, i64, vp, i32]
+        L.ref_graph_contract.argtypes = [vp, i64, i64, i32, vp, vp, vp, vp, vp]
+        L.ref_geodesic_features.argtypes = [vp, i64, i32, vp, vp, f32, vp, i64, f32, i32, vp, vp]
+        L.ref_fps.restype = i64
+        L.ref_fps.argtypes = [vp, i64, i32, vp, vp, i64, vp]
+        L.ref_spin_image.argtypes = [vp, vp, i64, f32, vp, vp, i64, i32, i32, vp]
         _LIB = L
     return _LIB
 
@@ -263,3 +268,46 @@ def random_uniform01(seed, n):
 
 def tree_depth(n, leaf):
     return int(lib().ref_tree_depth(n, leaf))
+
+
+# ---- sample-graph consumers and SpinImage: the reference's own PointSet3 / ShortestPaths / SurfaceFeatures::Local code on a GIVEN graph ----
+def _graph_args(idx, sep):
+    idx = np.ascontiguousarray(idx, np.int64)
+    sep = np.ascontiguousarray(sep, np.float32)
+    return idx, sep, idx.shape[0], idx.shape[1]
+
+
+def graph_contract(points, n_orig, idx, sep):
+    """PointSet3::extractOriginalAdjacencies on a graph over n_orig original + the remaining dense samples: (idx, sep, count) of the originals."""
+    p = _f32(points).reshape(-1, 3)
+    idx, sep, P, K = _graph_args(idx, sep)
+    oi, os_, oc = np.empty((n_orig, K), np.int64), np.empty((n_orig, K), np.float32), np.empty(n_orig, np.int32)
+    lib().ref_graph_contract(_p(p), int(n_orig), int(P - n_orig), K, _p(idx), _p(sep), _p(oi), _p(os_), _p(oc))
+    return oi, os_, oc
+
+
+def geodesic_features(points, idx, sep, scale, q, max_distance, nbins):
+    """AverageDistance / LocalDistanceHistogram ::compute(q, GEODESIC, max_distance): (avg [Q] float64, hist [Q x nbins] float64)."""
+    p = _f32(points).reshape(-1, 3)
+    q = _f32(q).reshape(-1, 3)
+    idx, sep, P, K = _graph_args(idx, sep)
+    avg, hist = np.empty(len(q), np.float64), np.empty((len(q), nbins), np.float64)
+    lib().ref_geodesic_features(_p(p), P, K, _p(idx), _p(sep), float(scale), _p(q), len(q), float(max_distance), int(nbins), _p(avg), _p(hist))
+    return avg, hist
+
+
+def fps(points, idx, sep, n_desired):
+    """FurthestPointSampling::subsample's selection loop around the reference's ShortestPaths, on a given graph."""
+    p = _f32(points).reshape(-1, 3)
+    idx, sep, P, K = _graph_args(idx, sep)
+    sel = np.full(int(n_desired), -1, np.int64)
+    n = lib().ref_fps(_p(p), P, K, _p(idx), _p(sep), int(n_desired), _p(sel))
+    return sel[:n]
+
+
+def spin_image(points, normals, scale, q, qn, nr, nh):
+    """SpinImage::compute(position, normal, nr, nh): [Q x nr x nh] float64."""
+    p, n, q, qn = _f32(points).reshape(-1, 3), _f32(normals).reshape(-1, 3), _f32(q).reshape(-1, 3), _f32(qn).reshape(-1, 3)
+    out = np.empty((len(q), int(nr), int(nh)), np.float64)
+    lib().ref_spin_image(_p(p), _p(n), len(p), float(scale), _p(q), _p(qn), len(q), int(nr), int(nh), _p(out))
+    return out

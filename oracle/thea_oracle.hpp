@@ -56,6 +56,13 @@ inline V3 cross(V3 l, V3 r)
 { return mk(l.y * r.z - l.z * r.y, l.z * r.x - l.x * r.z, l.x * r.y - l.y * r.x); }
 // Eigen MatrixBase::normalized(): z = squaredNorm; z > 0 ? n / sqrt(z) : n.
 inline V3 normalized(V3 a) { float z = sqnorm(a); return z > 0.0f ? a / std::sqrt(z) : a; }
+// Eigen 3.4 MatrixBase::stableNormalized() (Dot.h): w = cwiseAbs().maxCoeff(); z = (v / w).squaredNorm(); z > 0 ? v / (sqrt(z) * w) : v.
+inline V3 stable_normalized(V3 a)
+{
+  float w = std::max(std::max(std::fabs(a.x), std::fabs(a.y)), std::fabs(a.z));
+  float z = sqnorm(a / w);
+  return z > 0.0f ? a / (std::sqrt(z) * w) : a;
+}
 // MatrixUtil.hpp:108-115 maxAbsAxis / :84-91 maxAxis -- first maximum wins.
 inline int max_axis(V3 v) { int m = 0; if (v[1] > v[m]) m = 1; if (v[2] > v[m]) m = 2; return m; }
 inline int max_abs_axis(V3 v) { return max_axis(mk(std::fabs(v.x), std::fabs(v.y), std::fabs(v.z))); }

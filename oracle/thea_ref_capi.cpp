@@ -53,6 +53,11 @@
 #undef protected
 #include "Algorithms/BvhN.hpp"
 #include "Algorithms/SurfaceFeatures/Local/ShapeDiameter.hpp"
+#include "Algorithms/SurfaceFeatures/Local/SpinImage.hpp"
+#include "Algorithms/SurfaceFeatures/Local/AverageDistance.hpp"
+#include "Algorithms/SurfaceFeatures/Local/LocalDistanceHistogram.hpp"
+#include "Algorithms/Histogram.hpp"
+#include "Algorithms/ShortestPaths.hpp"
 #include "Graphics/GeneralMesh.hpp"
 #include "Algorithms/IntersectionTester.hpp"
 #include "Algorithms/MetricL2.hpp"
@@ -426,6 +431,128 @@ float ref_avg_separation(float const * p3, int64_t P, int64_t const * seeds, int
     bvh.popFilter();
   }
   return std::sqrt(avg / n);
+}
+
+// ---- sample-graph consumers.  The reference derives the graph radius from the time-seeded Random::common()
+// (PointSet3.hpp:363-376), so a graph cannot be replayed; instead a GIVEN graph (idx / sep: P x max_degree, -1 padded) is injected into
+// a PointSet3 -- neighbour sets filled through SamplePoint3::addNeighbor, valid_graph set -- and the reference's own code runs on it.
+namespace {
+void fill_samples(PointSet3 & ps, float const * p3, float const * n3, int64_t n_orig, int64_t n_dense)
+{
+  std::vector<Vector3> pos((size_t)(n_orig + n_dense)), nrm((size_t)(n_orig + n_dense));
+  for (int64_t i = 0; i < n_orig + n_dense; ++i) { pos[(size_t)i] = v3(p3 + 3 * i); if (n3) nrm[(size_t)i] = v3(n3 + 3 * i); }
+  ps.addSamples((intx)n_orig, pos.data(), n3 ? nrm.data() : nullptr);
+  if (n_dense > 0) ps.addOversampling((intx)n_dense, pos.data() + n_orig, n3 ? nrm.data() + n_orig : nullptr);
+}
+PointSet3::Sample * sample_at(PointSet3 & ps, int64_t i)
+{
+  int64_t n = (int64_t)ps.samples.size();
+  return i < n ? &ps.samples[(size_t)i] : &ps.dense_samples[(size_t)(i - n)];
+}
+void inject_graph(PointSet3 & ps, int64_t P, int max_degree, int64_t const * idx, float const * sep)
+{
+  for (int64_t i = 0; i < P; ++i)
+  {
+    PointSet3::Sample * s = sample_at(ps, i); s->setIndex((intx)i); s->clearNeighbors();
+    for (int j = 0; j < max_degree; ++j)
+      if (idx[i * max_degree + j] >= 0) s->addNeighbor(PointSet3::Sample::Neighbor(sample_at(ps, idx[i * max_degree + j]), sep[i * max_degree + j]));
+  }
+  ps.valid_graph = true;
+}
+}  // namespace
+
+// PointSet3::extractOriginalAdjacencies (PointSet3.cpp:158-178) on a given graph over n_orig original + n_dense dense samples.
+void ref_graph_contract(float const * p3, int64_t n_orig, int64_t n_dense, int max_degree, int64_t const * idx, float const * sep,
+                        int64_t * out_idx, float * out_sep, int32_t * out_count)
+{
+  PointSet3::Options opts = PointSet3::Options::defaults(); opts.setMaxDegree(max_degree);
+  PointSet3 ps(opts);
+  fill_samples(ps, p3, nullptr, n_orig, n_dense);
+  int64_t P = n_orig + n_dense;
+  inject_graph(ps, P, max_degree, idx, sep);
+  std::vector<PointSet3::Sample *> ptrs((size_t)P);
+  for (int64_t i = 0; i < P; ++i) ptrs[(size_t)i] = sample_at(ps, i);
+  ps.extractOriginalAdjacencies((intx)P, ptrs.data());
+  for (int64_t i = 0; i < n_orig; ++i)
+  {
+    PointSet3::Sample const & s = ps.samples[(size_t)i];
+    if (out_count) out_count[i] = (int32_t)s.numNeighbors();
+    for (int j = 0; j < max_degree; ++j)
+    {
+      bool v = j < s.numNeighbors();
+      out_idx[i * max_degree + j] = v ? (int64_t)s.getNeighbor(j).getSample()->getIndex() : -1;
+      out_sep[i * max_degree + j] = v ? (float)s.getNeighbor(j).getSeparation() : -1.0f;
+    }
+  }
+}
+
+// AverageDistance::compute(position, GEODESIC, max_distance) and LocalDistanceHistogram::compute(position, histogram, GEODESIC,
+// max_distance, ratio >= 1) (SurfaceFeatures/Local/AverageDistance.cpp:84-118, LocalDistanceHistogram.cpp:90-137) on a given graph.
+void ref_geodesic_features(float const * p3, int64_t P, int max_degree, int64_t const * idx, float const * sep, float scale, float const * q3, int64_t Q,
+                           float max_distance, int nbins, double * avg, double * hist)
+{
+  PointSet3::Options opts = PointSet3::Options::defaults(); opts.setMaxDegree(max_degree);
+  PointSet3 ps(opts);
+  fill_samples(ps, p3, nullptr, P, 0);
+  inject_graph(ps, P, max_degree, idx, sep);
+  ps.setScale(scale);
+  SurfaceFeatures::Local::AverageDistance ad(&ps);
+  SurfaceFeatures::Local::LocalDistanceHistogram ldh(&ps);
+  for (int64_t i = 0; i < Q; ++i)
+  {
+    if (avg) avg[i] = ad.compute(v3(q3 + 3 * i), DistanceType::GEODESIC, max_distance);
+    if (hist)
+    {
+      Histogram h(nbins, hist + (int64_t)nbins * i);
+      ldh.compute(v3(q3 + 3 * i), h, DistanceType::GEODESIC, max_distance, 2.0f);
+    }
+  }
+}
+
+// FurthestPointSampling::subsample (FurthestPointSampling.cpp:48-125) on a given graph: the selection loop of :72-100 -- first sample 0,
+// then repeatedly the LAST vertex the reference's own ShortestPaths::dijkstraWithCallback reports from the selected set
+// (include_unreachable = true) -- around the reference's Dijkstra.
+int64_t ref_fps(float const * p3, int64_t P, int max_degree, int64_t const * idx, float const * sep, int64_t n_desired, int64_t * selected)
+{
+  PointSet3::Options opts = PointSet3::Options::defaults(); opts.setMaxDegree(max_degree);
+  PointSet3 surf(opts);
+  fill_samples(surf, p3, nullptr, P, 0);
+  inject_graph(surf, P, max_degree, idx, sep);
+  typedef PointSet3::SampleGraph::VertexHandle VH;
+  struct Callback { VH furthest = nullptr; bool operator()(VH vertex, double, bool, VH) { furthest = vertex; return false; } };
+  ShortestPaths<PointSet3::SampleGraph> shortest_paths;
+  UnorderedMap<VH, double> src_region;
+  for (int64_t i = 0; i < n_desired; ++i)
+  {
+    VH furthest_sample = nullptr;
+    if (src_region.empty()) furthest_sample = const_cast<VH>(&surf.getSample(0));
+    else
+    {
+      Callback callback;
+      shortest_paths.dijkstraWithCallback(const_cast<PointSet3::SampleGraph &>(surf.getGraph()), nullptr, std::ref(callback), -1, &src_region, true);
+      if (!callback.furthest || src_region.find(callback.furthest) != src_region.end()) return i;
+      furthest_sample = callback.furthest;
+    }
+    selected[i] = (int64_t)furthest_sample->getIndex();
+    src_region[furthest_sample] = 0;
+  }
+  return n_desired;
+}
+
+// SpinImage::compute(position, normal, num_radial_bins, num_height_bins, spin_image) (SurfaceFeatures/Local/SpinImage.cpp:47-75);
+// PointSet3::setScale fixes the scale the reference would derive from the samples' bounding sphere.  image: [Q x nr x nh].
+void ref_spin_image(float const * p3, float const * n3, int64_t P, float scale, float const * q3, float const * qn3, int64_t Q, int nr, int nh, double * image)
+{
+  PointSet3 ps;
+  fill_samples(ps, p3, n3, P, 0);
+  ps.setScale(scale);
+  SurfaceFeatures::Local::SpinImage si(&ps);
+  MatrixX<double> m;
+  for (int64_t i = 0; i < Q; ++i)
+  {
+    si.compute(v3(q3 + 3 * i), v3(qn3 + 3 * i), nr, nh, m);
+    for (int r = 0; r < nr; ++r) for (int c = 0; c < nh; ++c) image[((int64_t)i * nr + r) * nh + c] = m(r, c);
+  }
 }
 
 int ref_tree_depth(int64_t n, int leaf) { return (int)Math::treeDepth((intx)n, leaf); }

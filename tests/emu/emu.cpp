@@ -399,6 +399,24 @@ void emu_ball_hist(void * h, float const * c3, float const * radius, int64_t Q, 
   for (int64_t i = 0; i < Q; ++i) hist_query(v, ld(c3, i), radius[i], nbins, hist + (size_t)i * nbins);
 }
 
+// SpinImage (tgq_spin_image): the engine's per-pair arithmetic (spin_bins, tgq_math.cuh) over all samples of the structure.
+void emu_spin_image(void * h, float const * q3, float const * qn3, int64_t Q, int nr, int nh, float max_extent, uint32_t * image)
+{
+  Emu & E = *(Emu *)h;
+  for (int64_t i = 0; i < Q; ++i)
+  {
+    v3 pos = ld(q3, i), axis = stable_normalized3(ld(qn3, i));
+    uint32_t * img = image + (size_t)i * nr * nh;
+    for (int j = 0; j < nr * nh; ++j) img[j] = 0;
+    for (int s = 0; s < E.n; ++s)
+    {
+      f4 e = E.pts[(size_t)s]; int rb, hb;
+      spin_bins(mk3(e.x, e.y, e.z), pos, axis, nr, nh, max_extent, max_extent, rb, hb);
+      img[rb * nh + hb] += 1;
+    }
+  }
+}
+
 void emu_ball_stats(void * h, float const * c3, float const * qn3, float const * radius, int64_t Q, double * out16)
 {
   Emu & E = *(Emu *)h; BvhView v = E.view();

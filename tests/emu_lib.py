@@ -40,6 +40,7 @@ def lib():
         L.emu_ball_range.argtypes = [vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp, vp]
         L.emu_ball_graph_surface.argtypes = [vp, vp, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, vp, vp, vp]
         L.emu_ball_hist.argtypes = [vp, vp, vp, C.c_int64, C.c_int, vp]
+        L.emu_spin_image.argtypes = [vp, vp, vp, C.c_int64, C.c_int, C.c_int, C.c_float, vp]
         L.emu_ball_stats.argtypes = [vp, vp, vp, vp, C.c_int64, vp]
         L.emu_closest_filtered.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_double, vp, vp, vp]
         L.emu_knn_filtered.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, C.c_float, C.c_float, vp, vp]
@@ -122,6 +123,12 @@ class Emu:
         cnt = np.empty(Q, np.int32)
         lib().emu_ball_range(self.h, _p(c), _p(rad), Q, int(max_out), int(exclude_self), _p(idx), _p(cnt))
         return idx, cnt
+
+    def spin_image(self, q, qn, nr, nh, max_extent):
+        q = np.ascontiguousarray(q, np.float32); qn = np.ascontiguousarray(qn, np.float32)
+        out = np.empty((len(q), nr, nh), np.uint32)
+        lib().emu_spin_image(self.h, _p(q), _p(qn), len(q), int(nr), int(nh), float(max_extent), _p(out))
+        return out
 
     def ball_hist(self, c, radius, nbins):
         c = np.ascontiguousarray(c, np.float32)

@@ -449,3 +449,61 @@ def test_structure_to_structure_closest_pair(built):
         found, rti, rqi, rd2, ra, rb = ref.Reference(points=a).closest_pair(ref.Reference(points=b))
         ti, qi, d2, _, _ = ea.closest_pair(eb)
         assert found and np.float32(rd2) == np.float32(d2)
+
+
+def test_spin_images(built):
+    """tgq_spin_image vs the oracle (SpinImage.cpp:47-75): exact counts, host and device buffers, bin counts that change the block shape."""
+    import torch
+    from thea_b200 import Engine
+    mesh = gen.torus_mesh(64)
+    p, n, _ = gen.area_samples(mesh, 20_000)
+    e = Engine(0)
+    e.build_points(p, n)
+    ora = orc.Oracle(points=p, normals=n)
+    rng = np.random.default_rng(3)
+    q = (p[:700] + rng.normal(scale=0.02, size=(700, 3))).astype(np.float32)
+    qn = n[:700].copy(); qn[::5] *= np.float32(4.0); qn[3] = 0
+    ext = np.float32(0.75) * np.float32(2.9)
+    for nr, nh in ((8, 8), (15, 15), (32, 32), (1, 3)):
+        img = e.spin_image(q, qn, nr, nh, ext)
+        assert np.array_equal(img.astype(np.float64), ora.spin_image(q, qn, nr, nh, ext))
+    dimg = torch.zeros((700, 8, 8), dtype=torch.int32, device="cuda")
+    dq, dqn = torch.from_numpy(q).cuda(), torch.from_numpy(qn).cuda()
+    e._ck(e._L.tgq_spin_image(e._h, dq.data_ptr(), dqn.data_ptr(), 700, 8, 8, float(ext), dimg.data_ptr()))
+    torch.cuda.synchronize()
+    assert np.array_equal(dimg.cpu().numpy().astype(np.float64), ora.spin_image(q, qn, 8, 8, ext))
+
+
+def test_sample_graph_shortest_paths(built):
+    """tgq_graph_contract / tgq_graph_geodesic / tgq_graph_fps vs the oracle's Dijkstra (ShortestPaths.hpp:166-353 restated; pinned to the
+    reference's own code in tests/test_ref_pin.py).  Contraction rows, geodesic counts and histograms and the selections are exact; the
+    geodesic distance sums are compared to 1e-12 relative (the engine adds the same doubles in another order)."""
+    from thea_b200 import Engine
+    mesh = gen.torus_mesh(64)
+    p, n, _ = gen.area_samples(mesh, 12_000)
+    e = Engine(0)
+    e.build_points(p, n)
+    ora = orc.Oracle(points=p, normals=n)
+    seeds = (gen.splitmix64(7, 100) % np.uint64(len(p))).astype(np.int64)
+    avg = np.float32(e.avg_separation(seeds))
+    for K in (8, 16, 5):
+        gi, gs, gc = e.ball_graph(K, np.float32(np.sqrt(np.float32(K))) * avg)
+        # contraction: the first 3000 samples are the originals, the rest the dense oversampling
+        ci, cs, cc = e.graph_contract(gi, gs, 3000)
+        oi, os_, oc = orc.graph_contract(gi, gs, 3000)
+        assert np.array_equal(ci, oi.astype(np.int32)) and np.array_equal(cs, os_) and np.array_equal(cc, oc)
+        sd = np.arange(0, 12_000, 23)
+        for md, rng_ in ((np.float32(0.25), np.float32(0.25)), (np.float32(-1.0), np.float32(2.9))):
+            s_, c_, h_ = e.graph_geodesic(gi, gs, sd, md, rng_, 16)
+            rs, rc, rh = orc.graph_geodesic(gi, gs, sd, md, rng_, 16)
+            assert np.array_equal(c_, rc.astype(np.int32)) and np.array_equal(h_.astype(np.float64), rh)
+            assert np.allclose(s_, rs, rtol=1e-12, atol=0)
+        assert np.array_equal(e.graph_fps(gi, gs, 300), orc.graph_fps(gi, gs, 300).astype(np.int32))
+    # a graph with unreachable parts: two far clusters with short neighbour lists
+    q = np.concatenate([p[:500], p[500:1000] + np.float32(10.0)])
+    e2 = Engine(0); e2.build_points(q)
+    gi, gs, gc = e2.ball_graph(4, np.float32(2.0) * avg, rounds=1)
+    assert np.array_equal(e2.graph_fps(gi, gs, 40), orc.graph_fps(gi, gs, 40).astype(np.int32))
+    ci, cs, cc = e2.graph_contract(gi, gs, 600)
+    oi, os_, oc = orc.graph_contract(gi, gs, 600)
+    assert np.array_equal(ci, oi.astype(np.int32)) and np.array_equal(cs, os_) and np.array_equal(cc, oc)

@@ -215,3 +215,16 @@ def test_local_distance_histogram_is_bit_exact(cloud):
     pts = np.array([[0.125, 0, 0], [0, 0.375, 0], [0, 0, 0.625], [0.875, 0, 0], [0, 1.0, 0], [0, 0, 1.5]], np.float32)
     K = emu_lib.Emu(points=pts)
     assert np.array_equal(K.ball_hist(np.zeros((1, 3), np.float32), 1.0, 4)[0], [1, 1, 1, 2])
+
+
+def test_spin_image_is_bit_exact(cloud):
+    """SpinImage::compute (SpinImage.cpp:47-75): integer counts over all samples; unnormalised and degenerate query normals
+    (stableNormalized returns a zero vector unchanged), queries far outside the limits (everything clamps into the border bins)."""
+    p, n, c, qn, rad, E, ora = cloud
+    qn = qn.copy(); qn[::5] *= np.float32(7.5); qn[3] = 0
+    c = c.copy(); c[7] += np.float32(50.0)
+    ext = np.float32(0.75) * np.float32(2.4)
+    for nr, nh in ((8, 8), (5, 12), (1, 1)):
+        img = E.spin_image(c, qn, nr, nh, ext)
+        assert np.array_equal(img.astype(np.float64), ora.spin_image(c, qn, nr, nh, ext))
+        assert (img.reshape(len(c), -1).sum(axis=1) == len(p)).all()

@@ -274,3 +274,41 @@ def test_icp_accumulation_loops_bit_exact(torus):
         assert _same(np.float32(ref.icp_error(tr, src, dst)), np.float32(orc.icp_error(tr, src, dst)))
     a, b = ref.icp_step(src, dst), orc.icp_step(src, dst)
     assert np.allclose(a, b, rtol=1e-6, atol=1e-6), np.abs(a - b).max()
+
+
+def test_spin_image():
+    """oracle spin image == the reference's SurfaceFeatures::Local::SpinImage on a PointSet3 with the scale set explicitly."""
+    mesh = gen.torus_mesh(40)
+    p, n, _ = gen.area_samples(mesh, 3000)
+    ora = orc.Oracle(points=p, normals=n)
+    rng = np.random.default_rng(1)
+    q = (p[:300] + rng.normal(scale=0.02, size=(300, 3))).astype(np.float32)
+    qn = n[:300].copy(); qn[::7] *= np.float32(3.0)
+    scale = np.float32(2.9)
+    for nr, nh in ((9, 7), (15, 15)):
+        assert np.array_equal(ora.spin_image(q, qn, nr, nh, np.float32(0.75) * scale), ref.spin_image(p, n, scale, q, qn, nr, nh))
+
+
+def test_sample_graph_shortest_paths():
+    """The oracle's restatement of the ShortestPaths consumers == the reference's own code (PointSet3::extractOriginalAdjacencies,
+    AverageDistance / LocalDistanceHistogram GEODESIC, FurthestPointSampling's selection around ShortestPaths) on an injected graph.
+    Bit-equal: indices, float separations, histogram counts, selections; the average distance to 1e-15 (same sums, one division)."""
+    mesh = gen.torus_mesh(40)
+    p, n, _ = gen.area_samples(mesh, 3000)
+    ora = orc.Oracle(points=p, normals=n)
+    seeds = (gen.splitmix64(7, 100) % np.uint64(len(p))).astype(np.int64)
+    avg = np.float32(ora.avg_separation(seeds))
+    for K in (8, 5):
+        gi, gs, gc = ora.ball_graph(K, np.float32(np.sqrt(np.float32(K))) * avg)
+        a = orc.graph_contract(gi, gs, 700)
+        b = ref.graph_contract(p, 700, gi, gs)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+        sd = np.arange(0, 3000, 37)
+        scale = np.float32(2.9)
+        for md in (np.float32(0.3), np.float32(-1.0)):
+            rng_ = md if md > 0 else scale
+            s_, c_, h_ = orc.graph_geodesic(gi, gs, sd, md, rng_, 12)
+            ravg, rh = ref.geodesic_features(p, gi, gs, scale, p[sd], md, 12)
+            mine = np.where(c_ > 0, s_ / np.maximum(c_, 1), 0.0) / np.float64(rng_)
+            assert np.allclose(mine, ravg, rtol=1e-15, atol=0) and np.array_equal(h_, rh)
+        assert np.array_equal(orc.graph_fps(gi, gs, 80), ref.fps(p, gi, gs, 80))

@@ -3,6 +3,7 @@
 // tgq_kernels.cuh, and tgq_create fails when there is no CUDA device.
 #include "../../include/thea_gpu_query.h"
 #include "tgq_kernels.cuh"
+#include "tgq_graph.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -83,6 +84,7 @@ struct tgq_handle
   PeerOut peers = {}; int64_t last_share = 0;                          // queries this rank answered in the last *_records call
   int sm_count = 148; std::map<std::pair<void const *, size_t>, int> occupancy;   // resident blocks per SM of the persistent kernels
   bool cum_valid = false;
+  DevBuf g_idx, g_sep, g_dist, g_stamp, g_touched, g_queue, g_seeds, g_out0, g_out1, g_out2;   // sample-graph searches (tgq_graph_*)
   bool orig_valid = false; DevBuf orig, orig_n, orig_lab, xf;           // untransformed source elements (tgq_set_transform)
   float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}; float pad = 0;
 
@@ -569,7 +571,8 @@ int tgq_destroy(tgq_handle * h)
   DevBuf * bufs[] = {&h->nodes, &h->elems, &h->nrm, &h->lab, &h->scene, &h->perm, &h->pos_of_elem, &h->first, &h->last, &h->split, &h->parent, &h->live,
                      &h->newidx, &h->pbox_lo, &h->pbox_hi, &h->nbox_lo, &h->nbox_hi, &h->arrive, &h->keys_a, &h->keys_b, &h->vals_a,
                      &h->cubtmp, &h->src, &h->src2, &h->misc, &h->icp_cur, &h->icp_orig, &h->icp_to, &h->icp_idx, &h->area_by_elem, &h->cum, &h->obbs, &h->pnrm, &h->nsum, &h->obbinfo, &h->big, &h->big_count, &h->wide, &h->wflag, &h->widx, &h->obbinfo_w,
-                     &h->orig, &h->orig_n, &h->orig_lab, &h->xf};
+                     &h->orig, &h->orig_n, &h->orig_lab, &h->xf, &h->g_idx, &h->g_sep, &h->g_dist, &h->g_stamp, &h->g_touched, &h->g_queue, &h->g_seeds,
+                     &h->g_out0, &h->g_out1, &h->g_out2};
   for (DevBuf * b : bufs) b->release();
   for (int s = 0; s < TGQ_SLOTS; ++s)
   {
@@ -885,6 +888,117 @@ int tgq_closest_pair(tgq_handle * h, tgq_handle * query, double dist_bound, int6
   return TGQ_OK;
 }
 
+// ---- sample-graph searches (tgq_graph.cuh) --------------------------------------------------------------------------------------
+// Uploads the graph if it lives on the host, sizes the per-warp scratch rows (at most `budget` bytes) and initialises them.
+static int graph_setup(tgq_handle * h, const int32_t * idx, const float * sep, int64_t P, int32_t K, int64_t sources, GraphView * g, GraphScratch * sc,
+                       int * blocks)
+{
+  if (P < 1 || P > 0x7fffffff || K < 1 || K > TGQ_MAX_K || !idx || !sep) return fail(h, TGQ_EINVAL, "graph query: bad graph arguments");
+  cudaStream_t s = h->stream;
+  void const * di = nullptr; void const * ds = nullptr;
+  CKRC(to_device(h, idx, 4 * (size_t)P * K, h->g_idx, s, &di));
+  CKRC(to_device(h, sep, 4 * (size_t)P * K, h->g_sep, s, &ds));
+  g->idx = (int const *)di; g->sep = (float const *)ds; g->P = (int)P; g->K = K;
+  if (!sc) return TGQ_OK;
+  size_t const row = 24 * (size_t)P;                                     // 8 (distance) + 4 (stamp) + 4 (touched) + 8 (two queues) bytes per node
+  size_t const budget = (size_t)16 << 30;
+  int64_t workers = std::min<int64_t>((int64_t)h->sm_count * 2 * TGQ_GRAPH_WARPS, std::max<int64_t>(TGQ_GRAPH_WARPS, (int64_t)(budget / row)));
+  workers = std::min<int64_t>(workers, (sources + TGQ_GRAPH_WARPS - 1) / TGQ_GRAPH_WARPS * TGQ_GRAPH_WARPS);
+  workers = std::max<int64_t>(TGQ_GRAPH_WARPS, workers / TGQ_GRAPH_WARPS * TGQ_GRAPH_WARPS);
+  *blocks = (int)(workers / TGQ_GRAPH_WARPS);
+  size_t const n = (size_t)workers * (size_t)P;
+  CK(h->g_dist.reserve(8 * n)); CK(h->g_stamp.reserve(4 * n)); CK(h->g_touched.reserve(4 * n)); CK(h->g_queue.reserve(8 * n));
+  sc->dist = h->g_dist.as<unsigned long long>(); sc->stamp = h->g_stamp.as<int>(); sc->touched = h->g_touched.as<int>(); sc->queue = h->g_queue.as<int>();
+  k_graph_init<<<h->sm_count * 8, 256, 0, s>>>(sc->dist, sc->stamp, n);
+  CK(cudaGetLastError());
+  h->st.total_launches += 1;
+  return TGQ_OK;
+}
+
+int tgq_graph_contract(tgq_handle * h, const int32_t * idx, const float * sep, int64_t P, int32_t max_degree, int64_t n_orig, int32_t * out_idx,
+                       float * out_sep, int32_t * out_count)
+{
+  if (!h) return TGQ_EINVAL;
+  if (n_orig < 0 || n_orig > P || (n_orig > 0 && (!out_idx || !out_sep))) return fail(h, TGQ_EINVAL, "tgq_graph_contract: bad arguments");
+  if (n_orig == 0) return TGQ_OK;
+  Guard g(h);
+  cudaStream_t s = h->stream;
+  GraphView gv; GraphScratch sc; int blocks = 0;
+  CKRC(graph_setup(h, idx, sep, P, max_degree, n_orig, &gv, &sc, &blocks));
+  size_t const nk = (size_t)n_orig * max_degree;
+  CK(h->g_out0.reserve(4 * nk)); CK(h->g_out1.reserve(4 * nk)); CK(h->g_out2.reserve(4 * (size_t)n_orig)); CK(h->g_seeds.reserve(4));
+  int * di = is_device_ptr(out_idx) ? out_idx : h->g_out0.as<int>();
+  float * ds = is_device_ptr(out_sep) ? out_sep : h->g_out1.as<float>();
+  int * dc = out_count ? (is_device_ptr(out_count) ? out_count : h->g_out2.as<int>()) : nullptr;
+  CK(cudaMemsetAsync(h->g_seeds.p, 0, 4, s));
+  k_graph_contract<<<blocks, 32 * TGQ_GRAPH_WARPS, 0, s>>>(gv, sc, (int)n_orig, h->g_seeds.as<int>(), di, ds, dc);
+  CK(cudaGetLastError());
+  h->st.total_launches += 1;
+  if (!is_device_ptr(out_idx)) CKRC(from_device(h, out_idx, di, 4 * nk, s));
+  if (!is_device_ptr(out_sep)) CKRC(from_device(h, out_sep, ds, 4 * nk, s));
+  if (out_count && !is_device_ptr(out_count)) CKRC(from_device(h, out_count, dc, 4 * (size_t)n_orig, s));
+  CK(cudaStreamSynchronize(s));
+  return TGQ_OK;
+}
+
+int tgq_graph_geodesic(tgq_handle * h, const int32_t * idx, const float * sep, int64_t P, int32_t max_degree, const int32_t * seeds, int64_t Q,
+                       float max_distance, float hist_range, int32_t num_bins, double * sum, int32_t * count, uint32_t * hist)
+{
+  if (!h) return TGQ_EINVAL;
+  if (Q < 0 || Q > 0x7fffffff || (Q > 0 && !seeds) || num_bins < 0 || (hist && num_bins < 1)) return fail(h, TGQ_EINVAL, "tgq_graph_geodesic: bad arguments");
+  if (Q == 0) return TGQ_OK;
+  Guard g(h);
+  cudaStream_t s = h->stream;
+  GraphView gv; GraphScratch sc; int blocks = 0;
+  CKRC(graph_setup(h, idx, sep, P, max_degree, Q, &gv, &sc, &blocks));
+  void const * dseeds = nullptr;
+  CK(h->g_seeds.reserve(4 * (size_t)Q + 16));
+  int * cnt = h->g_seeds.as<int>();                                       // [0]: work counter, [4..]: seeds when they come from the host
+  if (is_device_ptr(seeds)) dseeds = seeds;
+  else { CK(cudaMemcpyAsync(cnt + 4, seeds, 4 * (size_t)Q, cudaMemcpyHostToDevice, s)); dseeds = cnt + 4; }
+  CK(cudaMemsetAsync(cnt, 0, 4, s));
+  size_t const nb = (size_t)Q * (size_t)(hist ? num_bins : 0);
+  CK(h->g_out0.reserve(8 * (size_t)Q)); CK(h->g_out1.reserve(4 * (size_t)Q)); if (hist) CK(h->g_out2.reserve(4 * nb));
+  double * dsum = sum ? (is_device_ptr(sum) ? sum : h->g_out0.as<double>()) : nullptr;
+  int * dcount = count ? (is_device_ptr(count) ? count : h->g_out1.as<int>()) : nullptr;
+  unsigned * dhist = hist ? (is_device_ptr(hist) ? hist : h->g_out2.as<unsigned>()) : nullptr;
+  if (dhist) CK(cudaMemsetAsync(dhist, 0, 4 * nb, s));
+  k_graph_geodesic<<<blocks, 32 * TGQ_GRAPH_WARPS, 0, s>>>(gv, sc, (int const *)dseeds, (int)Q, max_distance, hist_range, num_bins, cnt, dsum, dcount, dhist);
+  CK(cudaGetLastError());
+  h->st.total_launches += 1;
+  if (sum && !is_device_ptr(sum)) CKRC(from_device(h, sum, dsum, 8 * (size_t)Q, s));
+  if (count && !is_device_ptr(count)) CKRC(from_device(h, count, dcount, 4 * (size_t)Q, s));
+  if (hist && !is_device_ptr(hist)) CKRC(from_device(h, hist, dhist, 4 * nb, s));
+  CK(cudaStreamSynchronize(s));
+  return TGQ_OK;
+}
+
+int tgq_graph_fps(tgq_handle * h, const int32_t * idx, const float * sep, int64_t P, int32_t max_degree, int64_t n_desired, int32_t * selected,
+                  int64_t * n_selected)
+{
+  if (!h) return TGQ_EINVAL;
+  if (n_desired < 0 || n_desired > P || (n_desired > 0 && !selected) || !n_selected) return fail(h, TGQ_EINVAL, "tgq_graph_fps: bad arguments");
+  *n_selected = 0;
+  if (n_desired == 0) return TGQ_OK;
+  Guard g(h);
+  cudaStream_t s = h->stream;
+  GraphView gv; int blocks = 0;
+  CKRC(graph_setup(h, idx, sep, P, max_degree, 1, &gv, nullptr, &blocks));
+  CK(h->g_dist.reserve(8 * (size_t)P)); CK(h->g_stamp.reserve(4 * (size_t)P)); CK(h->g_queue.reserve(8 * (size_t)P));
+  CK(h->g_out0.reserve(4 * (size_t)n_desired)); CK(h->g_seeds.reserve(4));
+  int * dsel = is_device_ptr(selected) ? selected : h->g_out0.as<int>();
+  k_graph_fps<<<1, TGQ_FPS_THREADS, 0, s>>>(gv, h->g_dist.as<unsigned long long>(), h->g_stamp.as<int>(), h->g_queue.as<int>(), h->g_queue.as<int>() + P,
+                                           (int)n_desired, dsel, h->g_seeds.as<int>());
+  CK(cudaGetLastError());
+  h->st.total_launches += 1;
+  int n = 0;
+  CK(cudaMemcpyAsync(&n, h->g_seeds.p, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (!is_device_ptr(selected) && n > 0) { CKRC(from_device(h, selected, dsel, 4 * (size_t)n, s)); CK(cudaStreamSynchronize(s)); }
+  *n_selected = n;
+  return TGQ_OK;
+}
+
 int tgq_set_point_labels(tgq_handle * h, const int32_t * labels)
 {
   CKRC(need_built(h, 1 << TGQ_KIND_POINTS));
@@ -1129,6 +1243,47 @@ int tgq_ball_histogram(tgq_handle * h, const float * c3, const float * radius, i
     h->st.last_launches += 1; h->st.total_launches += 1;
     return TGQ_OK;
   });
+}
+
+int tgq_spin_image(tgq_handle * h, const float * q3, const float * qn3, int64_t Q, int32_t num_radial_bins, int32_t num_height_bins,
+                   float max_extent, uint32_t * image)
+{
+  CKRC(need_built(h, 1 << TGQ_KIND_POINTS));
+  int64_t const bins = (int64_t)num_radial_bins * num_height_bins;
+  if (Q < 0 || num_radial_bins < 1 || num_height_bins < 1 || !(max_extent > 0.0f) || (Q > 0 && (!q3 || !qn3 || !image)))
+    return fail(h, TGQ_EINVAL, "tgq_spin_image: bad arguments");
+  if (bins > 1024) return fail(h, TGQ_ELIMIT, "tgq_spin_image: more than 1024 bins");
+  if (Q == 0) return TGQ_OK;
+  Guard g(h);
+  Arg args[3] = {{q3, nullptr, 12}, {qn3, nullptr, 12}, {nullptr, image, 4 * (size_t)bins}};
+  f4 const * pts = h->elems.as<f4>(); int const P = h->n;
+  // threads per block: as many private histograms as fit next to the tile in ~100 KB (two blocks per SM), a multiple of 32
+  int T = (int)std::min<int64_t>(128, ((100 * 1024 - TGQ_SPIN_TILE * 16) / (4 * bins)) / 32 * 32);
+  if (T < 32) T = 32;
+  size_t smem = (size_t)TGQ_SPIN_TILE * 16 + (size_t)bins * T * 4;
+  {
+    std::lock_guard<std::mutex> lock(g_smem_mutex);
+    size_t & cur = g_smem_limit[std::make_pair(h->device, (void const *)k_spin_image)];
+    if (smem > cur) { CK(cudaFuncSetAttribute(k_spin_image, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cur = smem; }
+  }
+  int64_t saved_chunk = h->opt_chunk;
+  h->opt_chunk = std::max<int64_t>(1024, std::min<int64_t>(saved_chunk, ((int64_t)1 << 26) / bins));   // staged image bytes per chunk stay bounded
+  int rc = run_batched(h, Q, args, 3, false, [&](ChunkCtx & c) -> int {
+    int gx = (int)((c.n + T - 1) / T);
+    // enough sample slices for about four blocks per SM, each at least one tile long
+    int want = std::max(1, (4 * h->sm_count + gx - 1) / gx);
+    int slices = (int)std::max<int64_t>(1, std::min<int64_t>(want, ((int64_t)P + TGQ_SPIN_TILE - 1) / TGQ_SPIN_TILE));
+    int slice_len = (int)(((int64_t)P + slices - 1) / slices);
+    slice_len = (slice_len + TGQ_SPIN_TILE - 1) / TGQ_SPIN_TILE * TGQ_SPIN_TILE;
+    slices = std::max(1, (int)(((int64_t)P + slice_len - 1) / slice_len));
+    CK(cudaMemsetAsync(c.dout[2], 0, 4 * (size_t)bins * (size_t)c.n, c.stream));
+    k_spin_image<<<dim3(gx, slices), T, smem, c.stream>>>(pts, P, (float const *)c.din[0], (float const *)c.din[1], c.n, num_radial_bins, num_height_bins,
+                                                          max_extent, max_extent, slice_len, (unsigned *)c.dout[2]);
+    h->st.last_launches += 1; h->st.total_launches += 1;
+    return TGQ_OK;
+  });
+  h->opt_chunk = saved_chunk;
+  return rc;
 }
 
 int tgq_visibility(tgq_handle * h, const float * p3, int64_t S, const float * dirs3, int32_t num_dirs, int32_t per_sample_dirs, float scale,

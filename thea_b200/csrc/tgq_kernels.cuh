@@ -1658,6 +1658,49 @@ k_ball_hist(BvhView b, float const * __restrict__ c3, float const * __restrict__
   warp_run(w, n, counter, stage);
 }
 
+// ---- SpinImage (SurfaceFeatures/Local/SpinImage.cpp:47-75): every query bins ALL samples of the point structure ------------------
+// No traversal: a streaming pass.  Thread = one query (position, axis) with a private histogram in shared memory (bin b of thread t at
+// hist[b * T + t]: conflict free); the block walks its slice of the samples through a shared-memory tile (coalesced loads, every
+// thread then reads the same sample: a broadcast).  grid = (query groups, sample slices); slices add their partial counts to the
+// output with integer atomics, so the result does not depend on the launch shape.  Bound by the fp32 pipes (one square root and two
+// IEEE divisions per pair), not by memory: P x 16 bytes are read once per block.
+#define TGQ_SPIN_TILE 512
+__global__ void k_spin_image(f4 const * __restrict__ pts, int P, float const * __restrict__ q3, float const * __restrict__ qn3, int Q, int nr, int nh,
+                             float max_radius, float max_height, int slice_len, unsigned * out)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  int const T = blockDim.x, tid = threadIdx.x, bins = nr * nh;
+  f4 * tile = (f4 *)smem; unsigned * hist = (unsigned *)(tile + TGQ_SPIN_TILE);
+  int q = blockIdx.x * T + tid; bool live = q < Q;
+  v3 pos = mk3(0.0f, 0.0f, 0.0f), axis = mk3(0.0f, 0.0f, 1.0f);
+  if (live) { pos = ld3(q3, q); axis = stable_normalized3(ld3(qn3, q)); }
+  for (int b = 0; b < bins; ++b) hist[b * T + tid] = 0u;
+  int s0 = blockIdx.y * slice_len, s1 = min(P, s0 + slice_len);
+  for (int base = s0; base < s1; base += TGQ_SPIN_TILE)
+  {
+    int m = min(TGQ_SPIN_TILE, s1 - base);
+    __syncthreads();
+    for (int j = tid; j < m; j += T) tile[j] = pts[base + j];
+    __syncthreads();
+    if (live)
+    {
+#pragma unroll 4
+      for (int j = 0; j < m; ++j)
+      {
+        f4 e = tile[j]; int rb, hb;
+        spin_bins(mk3(e.x, e.y, e.z), pos, axis, nr, nh, max_radius, max_height, rb, hb);
+        hist[(rb * nh + hb) * T + tid] += 1u;
+      }
+    }
+  }
+  if (live)
+    for (int b = 0; b < bins; ++b)
+    {
+      unsigned c = hist[b * T + tid];
+      if (c) atomicAdd(out + (size_t)q * bins + b, c);
+    }
+}
+
 // Visibility rays (SurfaceFeatures/Local/Visibility.hpp:104-125): thread = (sample, direction).  Ray (p + 0.001 * scale * u, u),
 // unbounded, any hit; escaped[t] = 1 when nothing was hit.  Directions: D x 3 shared by every sample, or S x D x 3 per sample.
 struct VisW

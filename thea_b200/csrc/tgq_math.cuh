@@ -58,6 +58,17 @@ TGQ_HD v3 stable_normalized3(v3 a)
   float z = sqn3(div3(a, w));
   return z > 0.0f ? div3(a, sqrtf(z) * w) : a;
 }
+// SpinImage::compute, one sample (SurfaceFeatures/Local/SpinImage.cpp:64-74): cylindrical coordinates of the sample about the axis
+// through `position`, binned with the reference's fp32 expressions (Real = float).  max_radius = max_height = 0.75f * scale.
+TGQ_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+TGQ_HD void spin_bins(v3 sample, v3 position, v3 axis, int nr, int nh, float max_radius, float max_height, int & radial_bin, int & height_bin)
+{
+  v3 offset = sub3(sample, position);
+  float height = dot3(offset, axis);
+  float radius = sqrtf(sqn3(sub3(offset, mul3(axis, height))));
+  radial_bin = clampi((int)floorf((float)nr * (radius / max_radius)), 0, nr - 1);
+  height_bin = clampi((int)floorf((float)nh * (0.5f * (height / max_height + 1.0f))), 0, nh - 1);
+}
 TGQ_HD float comp3(v3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
 // MatrixUtil.hpp:108-115 maxAbsAxis: first maximum of |v_i|.
 TGQ_HD int max_abs_axis3(v3 v)

@@ -25,7 +25,7 @@ SYMBOLS = [
     "tgq_info", "tgq_triangle_cache", "tgq_closest", "tgq_knn", "tgq_ball_graph", "tgq_avg_separation",
     "tgq_ray_first", "tgq_ray_any", "tgq_sdf", "tgq_icp_sums", "tgq_transform_points", "tgq_area_sample",
     "tgq_get_stats", "tgq_set_point_labels", "tgq_closest_filtered", "tgq_knn_filtered", "tgq_icp_align", "tgq_ball_range",
-    "tgq_ball_stats", "tgq_visibility", "tgq_ball_graph_surface", "tgq_ball_histogram", "tgq_set_transform",
+    "tgq_ball_stats", "tgq_visibility", "tgq_ball_graph_surface", "tgq_ball_histogram", "tgq_spin_image", "tgq_graph_contract", "tgq_graph_geodesic", "tgq_graph_fps", "tgq_set_transform",
     "tgq_closest_records", "tgq_ray_first_records", "tgq_synchronize", "tgq_scatter_records", "tgq_bucket_records", "tgq_range_query", "tgq_closest_pair",
 ]
 
@@ -90,6 +90,10 @@ def load_library(path=None):
     L.tgq_ball_range.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
     L.tgq_ball_graph_surface.argtypes = [vp, vp, i32, f32, i32, f32, i32, vp, vp, vp]
     L.tgq_ball_histogram.argtypes = [vp, vp, vp, i64, i32, vp]
+    L.tgq_spin_image.argtypes = [vp, vp, vp, i64, i32, i32, C.c_float, vp]
+    L.tgq_graph_contract.argtypes = [vp, vp, vp, i64, i32, i64, vp, vp, vp]
+    L.tgq_graph_geodesic.argtypes = [vp, vp, vp, i64, i32, vp, i64, C.c_float, C.c_float, i32, vp, vp, vp]
+    L.tgq_graph_fps.argtypes = [vp, vp, vp, i64, i32, i64, vp, vp]
     L.tgq_set_transform.argtypes = [vp, vp]
     L.tgq_ball_stats.argtypes = [vp, vp, vp, vp, i64, vp]
     L.tgq_visibility.argtypes = [vp, vp, i64, vp, i32, i32, f32, vp, vp]
@@ -317,6 +321,45 @@ class Engine:
         cnt = np.empty(Q, np.int32)
         self._ck(self._L.tgq_ball_range(self._h, _ptr(c3), _ptr(rad), Q, int(max_out), int(exclude_self), _ptr(idx), _ptr(cnt)))
         return idx, cnt
+
+    def spin_image(self, q3, qn3, num_radial_bins, num_height_bins, max_extent):
+        """SpinImage::compute(position, normal, ...) for every query: [Q x radial x height] uint32 counts over ALL samples of the
+        point structure (tgq_spin_image); max_extent = 0.75f * scale in the reference."""
+        q3 = self._in(q3)
+        qn3 = self._in(qn3)
+        Q = int(q3.shape[0])
+        img = np.zeros((Q, int(num_radial_bins), int(num_height_bins)), np.uint32)
+        self._ck(self._L.tgq_spin_image(self._h, _ptr(q3), _ptr(qn3), Q, int(num_radial_bins), int(num_height_bins), float(max_extent), _ptr(img)))
+        return img
+
+    # ---- shortest paths on a sample graph (rows as ball_graph returns them) ----
+    def graph_contract(self, idx, sep, n_orig):
+        """PointSet3::extractOriginalAdjacencies: the graph over originals [0, n_orig) + dense samples contracted to the originals
+        (tgq_graph_contract): (idx [n_orig x K], sep, count)."""
+        idx = self._in(idx, np.int32); sep = self._in(sep)
+        P, K = int(idx.shape[0]), int(idx.shape[1])
+        oi, os_, oc = np.empty((n_orig, K), np.int32), np.empty((n_orig, K), np.float32), np.empty(n_orig, np.int32)
+        self._ck(self._L.tgq_graph_contract(self._h, _ptr(idx), _ptr(sep), P, K, int(n_orig), _ptr(oi), _ptr(os_), _ptr(oc)))
+        return oi, os_, oc
+
+    def graph_geodesic(self, idx, sep, seeds, max_distance, hist_range, num_bins=0):
+        """Geodesic neighbourhood of every seed sample (tgq_graph_geodesic): (sum [Q] float64, count [Q] int32, hist [Q x num_bins] or None)."""
+        idx = self._in(idx, np.int32); sep = self._in(sep); seeds = self._in(seeds, np.int32)
+        P, K, Q = int(idx.shape[0]), int(idx.shape[1]), int(seeds.shape[0])
+        s, c = np.empty(Q, np.float64), np.empty(Q, np.int32)
+        h = np.empty((Q, num_bins), np.uint32) if num_bins > 0 else None
+        self._ck(self._L.tgq_graph_geodesic(self._h, _ptr(idx), _ptr(sep), P, K, _ptr(seeds), Q, float(max_distance), float(hist_range), int(num_bins),
+                                            _ptr(s), _ptr(c), _ptr(h)))
+        return s, c, h
+
+    def graph_fps(self, idx, sep, n_desired):
+        """FurthestPointSampling::subsample on a given graph (tgq_graph_fps): selected sample indices (possibly fewer than asked)."""
+        idx = self._in(idx, np.int32); sep = self._in(sep)
+        P, K = int(idx.shape[0]), int(idx.shape[1])
+        sel = np.full(int(n_desired), -1, np.int32)
+        n = C.c_int64(0)
+        self._ck(self._L.tgq_graph_fps(self._h, _ptr(idx), _ptr(sep), P, K, int(n_desired), _ptr(sel), C.byref(n)))
+        return sel[:n.value]
 
     def ball_histogram(self, c3, radius, num_bins):
         """LocalDistanceHistogram (EUCLIDEAN) for every ball: [Q x num_bins] uint32 counts (tgq_ball_histogram)."""
