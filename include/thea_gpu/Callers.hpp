@@ -122,6 +122,61 @@ inline float sampleGraph(GpuPointBvhT<VectorT> const & bvh, GpuMeshBvhT<VectorT>
   return avg;
 }
 
+/** PointSet3::updateGraph with a dense oversampling (PointSet3.hpp:329-386, PointSet3.cpp:96-178): `all` is a structure over the n_orig
+ *  original samples followed by the dense ones (the reference's aggregated BVH); the proximity graph over all of them is built on the
+ *  device and contracted to the originals by shortest paths (extractOriginalAdjacencies).  idx / sep / count: n_orig x max_degree
+ *  rows of the contracted graph.  seeds: sample indices for the average-separation estimate (see sampleGraph).  Returns it. */
+template <typename VectorT>
+float sampleGraphOversampled(GpuPointBvhT<VectorT> const & all, intx n_orig, int32_t max_degree, int32_t const * seeds, int32_t num_seeds,
+                             int32_t * idx, float * sep, int32_t * count = nullptr)
+{
+  intx P = all.numElements();
+  std::vector<int32_t> gi((size_t)P * (size_t)max_degree); std::vector<float> gs((size_t)P * (size_t)max_degree);
+  float avg = sampleGraph(all, max_degree, seeds, num_seeds, gi.data(), gs.data(), nullptr);
+  all.graphContractBatch(gi.data(), gs.data(), P, max_degree, n_orig, idx, sep, count);
+  return avg;
+}
+
+/** FurthestPointSampling::subsample(num_orig_points, orig_points, num_desired_points, selected_indices, GEODESIC)
+ *  (Algorithms/FurthestPointSampling.cpp:48-125): proximity graph over the points (PointSet3's defaults: max_degree 8), then sample 0
+ *  and repeatedly the sample furthest from the selected set along the graph.  seeds fix the average-separation estimate the reference
+ *  draws from Random::common().  Returns the number of points selected (fewer than desired when the reference would give up). */
+inline intx furthestPointSubsample(intx num_orig_points, float const * orig_points3, intx num_desired_points, int32_t * selected_indices,
+                                   int32_t const * seeds, int32_t num_seeds, int32_t max_degree = 8, int device = 0)
+{
+  if (num_desired_points < 0) throw Error("FurthestPointSampling: Can't sample a negative number of points");
+  if (num_orig_points < num_desired_points) throw Error("FurthestPointSampling: Can't subsample more points than there are");
+  if (num_desired_points == 0) return 0;
+  GpuPointBvh surf(device); surf.init(orig_points3, num_orig_points);
+  std::vector<int32_t> gi((size_t)num_orig_points * (size_t)max_degree); std::vector<float> gs(gi.size());
+  sampleGraph(surf, max_degree, seeds, num_seeds, gi.data(), gs.data(), nullptr);
+  return surf.graphFurthestPointsBatch(gi.data(), gs.data(), num_orig_points, max_degree, num_desired_points, selected_indices);
+}
+
+/** MeshSampler::sampleEvenlyBySeparation (Algorithms/MeshSampler.hpp:270-329): area oversampling (default factor 3, EXACT count) on
+ *  the device, furthest point subsampling of it, gather.  p3 / n3 / tri receive desired_num_samples entries (n3, tri may be null).
+ *  seed: the counter-based stream of the area sampler; graph_seeds as in furthestPointSubsample. */
+template <typename VectorT>
+intx sampleEvenlyBySeparation(GpuMeshBvhT<VectorT> const & bvh, intx desired_num_samples, uint64_t seed, int32_t const * graph_seeds, int32_t num_graph_seeds,
+                              float * p3, float * n3 = nullptr, int32_t * tri = nullptr, float oversampling_factor = -1)
+{
+  if (desired_num_samples <= 0) return 0;
+  if (oversampling_factor < 0) oversampling_factor = 3;
+  intx num_oversampling = (intx)std::ceil(oversampling_factor * desired_num_samples);
+  std::vector<float> op(3 * (size_t)num_oversampling), on(3 * (size_t)num_oversampling); std::vector<int32_t> ot((size_t)num_oversampling);
+  bvh.sampleEvenlyByArea(num_oversampling, seed, op.data(), on.data(), ot.data());
+  std::vector<int32_t> selected((size_t)desired_num_samples);
+  if (furthestPointSubsample(num_oversampling, op.data(), desired_num_samples, selected.data(), graph_seeds, num_graph_seeds, 8, bvh.device()) < desired_num_samples)
+    return 0;
+  for (intx i = 0; i < desired_num_samples; ++i)
+  {
+    size_t k = (size_t)selected[(size_t)i];
+    for (int a = 0; a < 3; ++a) { p3[3 * i + a] = op[3 * k + a]; if (n3) n3[3 * i + a] = on[3 * k + a]; }
+    if (tri) tri[i] = ot[k];
+  }
+  return desired_num_samples;
+}
+
 /** PointSet3::save, graph part (PointSet3.cpp:331-354): first line max_degree, then one line per sample,
  *  `degree nbr_0 .. nbr_{d-1} [sep_0 .. sep_{d-1}]`, floats with the default ostream precision as the reference writes them.
  *  idx / sep are P x max_degree as sampleGraph returns them (unused slots -1). */

@@ -242,7 +242,7 @@ class GpuBvhBase
     typedef RayStructureIntersectionT<VectorT> RayStructureIntersection3;
     typedef RayT<VectorT> Ray3;
 
-    explicit GpuBvhBase(int device = 0) : h(nullptr)
+    explicit GpuBvhBase(int device = 0) : h(nullptr), dev(device)
     {
       int rc = tgq_create(device, &h);
       if (rc != TGQ_OK) throw Error(std::string("TheaGpu: no engine (") + std::to_string(rc) + "): " + tgq_last_error(nullptr));
@@ -252,6 +252,7 @@ class GpuBvhBase
     GpuBvhBase & operator=(GpuBvhBase const &) = delete;
 
     tgq_handle * handle() const { return h; }
+    int device() const { return dev; }
     void setStream(void * cuda_stream) { detail::check(h, tgq_set_stream(h, cuda_stream), "tgq_set_stream"); }
     void setOption(int option, int64_t value) { detail::check(h, tgq_set_option(h, option, value), "tgq_set_option"); }
 
@@ -310,7 +311,7 @@ class GpuBvhBase
     void popFilter() {}
 
   protected:
-    tgq_handle * h;
+    tgq_handle * h; int dev;
 };
 
 /**
@@ -692,6 +693,23 @@ class GpuPointBvhT : public GpuBvhBase<VectorT>
     /** Q LocalDistanceHistogram::compute(c_i, histogram, EUCLIDEAN, r_i) calls: hist is Q x num_bins raw counts. */
     void ballHistogramBatch(float const * c3, float const * radius, intx Q, int32_t num_bins, uint32_t * hist) const
     { detail::check(h, tgq_ball_histogram(h, c3, radius, Q, num_bins, hist), "tgq_ball_histogram"); }
+
+    /** Q SpinImage::compute(position_i, normal_i, num_radial_bins, num_height_bins, image) calls (SurfaceFeatures/Local/SpinImage.cpp:
+     *  47-75): image is Q x num_radial_bins x num_height_bins raw counts over all samples; max_extent = 0.75f * scale there. */
+    void spinImageBatch(float const * q3, float const * qn3, intx Q, int32_t num_radial_bins, int32_t num_height_bins, float max_extent,
+                        uint32_t * image) const
+    { detail::check(h, tgq_spin_image(h, q3, qn3, Q, num_radial_bins, num_height_bins, max_extent, image), "tgq_spin_image"); }
+
+    /** Shortest paths on a sample graph given as sampleGraphBatch rows (the reference: ShortestPaths::dijkstraWithCallback on
+     *  PointSet3's graph).  The structure only lends its device and stream. */
+    void graphContractBatch(int32_t const * idx, float const * sep, intx P, int32_t max_degree, intx n_orig, int32_t * out_idx, float * out_sep,
+                            int32_t * out_count = nullptr) const
+    { detail::check(h, tgq_graph_contract(h, idx, sep, P, max_degree, n_orig, out_idx, out_sep, out_count), "tgq_graph_contract"); }
+    void graphGeodesicBatch(int32_t const * idx, float const * sep, intx P, int32_t max_degree, int32_t const * seeds, intx Q, float max_distance,
+                            float hist_range, int32_t num_bins, double * sum, int32_t * count, uint32_t * hist) const
+    { detail::check(h, tgq_graph_geodesic(h, idx, sep, P, max_degree, seeds, Q, max_distance, hist_range, num_bins, sum, count, hist), "tgq_graph_geodesic"); }
+    intx graphFurthestPointsBatch(int32_t const * idx, float const * sep, intx P, int32_t max_degree, intx n_desired, int32_t * selected) const
+    { int64_t n = 0; detail::check(h, tgq_graph_fps(h, idx, sep, P, max_degree, n_desired, selected, &n), "tgq_graph_fps"); return (intx)n; }
 
     /** PointSet3::updateGraph's neighbour search for every sample (PointSet3.hpp:324-391,586-681). */
     void sampleGraphBatch(int32_t max_degree, float init_radius, int32_t * idx, float * sep, int32_t * count = nullptr, int32_t rounds = 3,

@@ -9,9 +9,12 @@
 //
 // The reference classes take a PointSet3 (samples + BvhN + scale); here they take the GpuPointBvh built over the same samples
 // plus the shape scale PointSet3::getScale() would return (the diameter of its bounding sphere, PointSet3.hpp:560-572), which the
-// caller supplies.  Scalar calls are batches of one; *Batch members answer a whole loop in one C-ABI call.  Not covered:
-// GEODESIC distances (Dijkstra on the sample graph), random subsampling of the histogram, SpinImage (a loop over all samples, no
-// structure query), RandomWalks.
+// caller supplies.  Scalar calls are batches of one; *Batch members answer a whole loop in one C-ABI call.
+//   DistanceType::GEODESIC of AverageDistance / LocalDistanceHistogram (AverageDistance.cpp:84-118, LocalDistanceHistogram.cpp:90-137):
+//     computeGeodesicBatch(graph rows, ...) -- nearest-sample lookup on the structure, then the bounded shortest-path search of
+//     tgq_graph_geodesic on the sample graph the caller built with sampleGraph / sampleGraphBatch;
+//   SurfaceFeatures::Local::SpinImage::compute(position[, normal], radial bins, height bins, image)   (…/Local/SpinImage.cpp:30-75).
+// Not covered: random subsampling of the histograms (Random::common()), RandomWalks.
 // File:line citations are relative to /root/reference/Code/Source/.
 #ifndef THEA_GPU_LOCALFEATURES_HPP
 #define THEA_GPU_LOCALFEATURES_HPP
@@ -89,6 +92,18 @@ class AverageDistanceT
         double n = st[16 * (size_t)i], sum = st[16 * (size_t)i + 1];
         out[i] = (n <= 0 ? 0.0 : sum / n) / max_distance;
       }
+    }
+
+    /** DistanceType::GEODESIC (AverageDistance.cpp:84-118): seed = closestElement(position), then the mean graph distance over the
+     *  samples within max_distance of it, over max_distance (< 0: the whole component, over the scale).  idx / sep: the sample graph,
+     *  P x max_degree rows of sampleGraphBatch over this structure's samples. */
+    void computeGeodesicBatch(int32_t const * idx, float const * sep, int32_t max_degree, float const * p3, intx Q, Real max_distance, double * out) const
+    {
+      std::vector<int32_t> seed((size_t)Q), cnt((size_t)Q); std::vector<float> d2((size_t)Q); std::vector<double> sum((size_t)Q);
+      surf->closestElementBatch(p3, Q, seed.data(), d2.data(), nullptr);
+      Real range = max_distance < 0 ? scale : max_distance;
+      surf->graphGeodesicBatch(idx, sep, surf->numElements(), max_degree, seed.data(), Q, max_distance, range, 0, sum.data(), cnt.data(), nullptr);
+      for (intx i = 0; i < Q; ++i) out[i] = (cnt[(size_t)i] <= 0 ? 0.0 : sum[(size_t)i] / cnt[(size_t)i]) / range;
     }
 
   private:
@@ -198,9 +213,61 @@ class LocalDistanceHistogramT
       surf->ballHistogramBatch(p3, rad.data(), Q, (int32_t)num_bins, h.data());
       for (size_t i = 0; i < h.size(); ++i) bins[i] = (double)h[i];
     }
+    /** DistanceType::GEODESIC (LocalDistanceHistogram.cpp:90-137): graph distances from the nearest sample, range [0, max_distance]
+     *  (< 0: the whole component, range [0, scale]); every sample accepted. */
+    void computeGeodesicBatch(int32_t const * idx, float const * sep, int32_t max_degree, float const * p3, intx Q, intx num_bins, double * bins,
+                              Real max_distance = -1) const
+    {
+      std::vector<int32_t> seed((size_t)Q); std::vector<float> d2((size_t)Q); std::vector<uint32_t> h((size_t)Q * (size_t)num_bins);
+      surf->closestElementBatch(p3, Q, seed.data(), d2.data(), nullptr);
+      Real range = max_distance < 0 ? scale : max_distance;
+      surf->graphGeodesicBatch(idx, sep, surf->numElements(), max_degree, seed.data(), Q, max_distance, range, (int32_t)num_bins, nullptr, nullptr, h.data());
+      for (size_t i = 0; i < h.size(); ++i) bins[i] = (double)h[i];
+    }
 
   private:
     GpuPointBvhT<VectorT> const * surf; Real scale;
+};
+
+/** SpinImage (SpinImage.cpp:30-75): every sample of the surface binned by (radius about the axis through the query, height along it),
+ *  limits 0.75f * scale.  image receives num_radial_bins x num_height_bins doubles per query, radial bin major -- the reference's
+ *  spin_image(radial_bin, height_bin). */
+template <typename VectorT = Vec3>
+class SpinImageT
+{
+  public:
+    /** sample_normals3 (P x 3, host, may be null): the samples' normals, needed only by the overloads that infer the query normal. */
+    SpinImageT(GpuPointBvhT<VectorT> const * surf_, Real scale_, float const * sample_normals3 = nullptr) : surf(surf_), scale(scale_), sn(sample_normals3)
+    { if (!surf) throw Error("SpinImage: Cannot construct with a null surface"); }
+
+    void compute(VectorT const & position, VectorT const & normal, int num_radial_bins, int num_height_bins, double * image) const
+    { float p[3], n[3]; detail::put3(p, position); detail::put3(n, normal); computeBatch(p, n, 1, num_radial_bins, num_height_bins, image); }
+    /** The reference's first overload: the normal of the sample nearest to the query (SpinImage.cpp:30-45); the surface needs normals. */
+    void compute(VectorT const & position, int num_radial_bins, int num_height_bins, double * image) const
+    { float p[3]; detail::put3(p, position); computeBatch(p, nullptr, 1, num_radial_bins, num_height_bins, image); }
+    /** qn3 == nullptr: normals of the nearest samples (a query that maps to no sample gets a zero image, as in the reference). */
+    void computeBatch(float const * p3, float const * qn3, intx Q, int num_radial_bins, int num_height_bins, double * image) const
+    {
+      if (num_radial_bins <= 0) throw Error("SpinImage: Number of radial bins must be positive");
+      if (num_height_bins <= 0) throw Error("SpinImage: Number of height bins must be positive");
+      size_t bins = (size_t)num_radial_bins * (size_t)num_height_bins;
+      std::vector<float> nn; std::vector<int32_t> seed;
+      if (!qn3)
+      {
+        if (!sn) throw Error("SpinImage: Cannot infer query normal from surface lacking normals");
+        seed.resize((size_t)Q); std::vector<float> d2((size_t)Q); nn.assign(3 * (size_t)Q, 0.0f);
+        surf->closestElementBatch(p3, Q, seed.data(), d2.data(), nullptr);
+        for (intx i = 0; i < Q; ++i) if (seed[(size_t)i] >= 0) for (int a = 0; a < 3; ++a) nn[3 * (size_t)i + a] = sn[3 * (size_t)seed[(size_t)i] + a];
+        qn3 = nn.data();
+      }
+      std::vector<uint32_t> img((size_t)Q * bins);
+      surf->spinImageBatch(p3, qn3, Q, num_radial_bins, num_height_bins, 0.75f * scale, img.data());
+      for (size_t i = 0; i < img.size(); ++i) image[i] = (double)img[i];
+      if (!seed.empty()) for (intx i = 0; i < Q; ++i) if (seed[(size_t)i] < 0) for (size_t b = 0; b < bins; ++b) image[(size_t)i * bins + b] = 0.0;
+    }
+
+  private:
+    GpuPointBvhT<VectorT> const * surf; Real scale; float const * sn;
 };
 
 /** Visibility: fraction of rays from the query point that do not hit the shape again.  The reference draws num_rays random
@@ -236,6 +303,7 @@ typedef CurvatureT<Vec3> Curvature;
 typedef LocalPcaT<Vec3> LocalPca;
 typedef VisibilityT<Vec3> Visibility;
 typedef LocalDistanceHistogramT<Vec3> LocalDistanceHistogram;
+typedef SpinImageT<Vec3> SpinImage;
 
 }  // namespace Local
 }  // namespace SurfaceFeatures

@@ -219,6 +219,35 @@ int main(int argc, char ** argv)
       visf.computeBatch(sp.data(), NS, vis.data());
       std::vector<float> vsc(1, visf.getScale()); wr(fo, vsc); wr(fo, vis);
       if (NS > 0 && visf.compute(Vec3(sp[0], sp[1], sp[2])) != vis[0]) { fprintf(stderr, "scalar Visibility disagrees with the batch\n"); return 3; }
+
+      // SpinImage: batch with given normals, then the reference's first overload (normal of the nearest sample: the sample itself)
+      SpinImage spin(&pts, diag, sn.data());
+      std::vector<double> im(20 * NS);
+      spin.computeBatch(sp.data(), sn.data(), NS, 5, 4, im.data());
+      wr(fo, im);
+      for (int64_t i = 0; i < nk; ++i)
+      {
+        double one[20]; spin.compute(Vec3(sp[3 * i], sp[3 * i + 1], sp[3 * i + 2]), 5, 4, one);
+        for (int k = 0; k < 20; ++k) if (one[k] != im[20 * i + k]) { fprintf(stderr, "scalar SpinImage disagrees with the batch\n"); return 3; }
+      }
+      // DistanceType::GEODESIC on the sample graph built above (max_degree 6)
+      std::vector<double> ga(NS), gh(8 * NS);
+      avgd.computeGeodesicBatch(gi.data(), gs.data(), 6, sp.data(), NS, 0.1f * diag, ga.data());
+      ldh.computeGeodesicBatch(gi.data(), gs.data(), 6, sp.data(), NS, 8, gh.data(), 0.1f * diag);
+      wr(fo, ga); wr(fo, gh);
+    }
+
+    // ---- PointSet3::updateGraph with a dense oversampling (the first third of the samples play the originals) and
+    //      FurthestPointSampling::subsample ----
+    {
+      int64_t NO = NS / 3;
+      std::vector<int32_t> ci(NO * 6), cc(NO); std::vector<float> cs(NO * 6);
+      float avg3 = sampleGraphOversampled(pts, NO, 6, seeds.data(), (int32_t)seeds.size(), ci.data(), cs.data(), cc.data());
+      if (avg3 != avg) { fprintf(stderr, "average separation changed (oversampled graph)\n"); return 3; }
+      wr(fo, ci); wr(fo, cs); wr(fo, cc);
+      std::vector<int32_t> sel(NS / 10, -1);
+      std::vector<int64_t> nsel(1, (int64_t)furthestPointSubsample(NS, sp.data(), NS / 10, sel.data(), seeds.data(), (int32_t)seeds.size()));
+      wr(fo, nsel); wr(fo, sel);
     }
 
     // ---- error behaviour: filters are refused loudly, wrong structure kind raises ----

@@ -212,6 +212,22 @@ def test_adaptor_driver_matches_oracle(built, tmp_path):
     vis = take(np.float64, NS)
     ovis, _ = ora.visibility(sp, d[:32], vscale, mode=orc.MODE_BRUTE)
     assert np.array_equal(vis, ovis)
+    # SpinImage, the GEODESIC features, the oversampled graph and furthest point sampling
+    assert np.array_equal(take(np.float64, 20 * NS).reshape(NS, 5, 4), po.spin_image(sp, sn, 5, 4, np.float32(0.75) * dg))
+    ga, gh = take(np.float64, NS), take(np.float64, 8 * NS).reshape(NS, 8)
+    gseed = po.closest(sp, mode=orc.MODE_BRUTE)[0]
+    rs, rcnt, rh = orc.graph_geodesic(ogi, ogs, gseed, ra, ra, 8)
+    assert np.array_equal(gh, rh)
+    assert np.allclose(ga, np.where(rcnt > 0, rs / np.maximum(rcnt, 1), 0.0) / np.float64(ra), rtol=1e-12, atol=0)
+    NO = NS // 3
+    oci, ocs, occ = orc.graph_contract(ogi, ogs, NO)
+    assert np.array_equal(take(np.int32, NO * 6).reshape(NO, 6), oci.astype(np.int32))
+    assert np.array_equal(take(np.float32, NO * 6).reshape(NO, 6), ocs)
+    assert np.array_equal(take(np.int32, NO), occ)
+    g8i, g8s, _ = orc.Oracle(points=sp).ball_graph(8, float(np.float32(np.sqrt(np.float32(8))) * np.float32(avg)), mode=orc.MODE_BRUTE)
+    ofps = orc.graph_fps(g8i, g8s, NS // 10)
+    assert int(take(np.int64, 1)[0]) == len(ofps)
+    assert np.array_equal(take(np.int32, NS // 10)[:len(ofps)], ofps.astype(np.int32))
     assert pos[0] == len(buf)
 
 

@@ -1257,10 +1257,7 @@ int tgq_spin_image(tgq_handle * h, const float * q3, const float * qn3, int64_t 
   Guard g(h);
   Arg args[3] = {{q3, nullptr, 12}, {qn3, nullptr, 12}, {nullptr, image, 4 * (size_t)bins}};
   f4 const * pts = h->elems.as<f4>(); int const P = h->n;
-  // threads per block: as many private histograms as fit next to the tile in ~100 KB (two blocks per SM), a multiple of 32
-  int T = (int)std::min<int64_t>(128, ((100 * 1024 - TGQ_SPIN_TILE * 16) / (4 * bins)) / 32 * 32);
-  if (T < 32) T = 32;
-  size_t smem = (size_t)TGQ_SPIN_TILE * 16 + (size_t)bins * T * 4;
+  size_t smem = (size_t)TGQ_SPIN_TILE * 16 + (size_t)bins * TGQ_SPIN_WARPS * 4;
   {
     std::lock_guard<std::mutex> lock(g_smem_mutex);
     size_t & cur = g_smem_limit[std::make_pair(h->device, (void const *)k_spin_image)];
@@ -1269,15 +1266,15 @@ int tgq_spin_image(tgq_handle * h, const float * q3, const float * qn3, int64_t 
   int64_t saved_chunk = h->opt_chunk;
   h->opt_chunk = std::max<int64_t>(1024, std::min<int64_t>(saved_chunk, ((int64_t)1 << 26) / bins));   // staged image bytes per chunk stay bounded
   int rc = run_batched(h, Q, args, 3, false, [&](ChunkCtx & c) -> int {
-    int gx = (int)((c.n + T - 1) / T);
-    // enough sample slices for about four blocks per SM, each at least one tile long
-    int want = std::max(1, (4 * h->sm_count + gx - 1) / gx);
+    int gx = (int)((c.n + TGQ_SPIN_WARPS - 1) / TGQ_SPIN_WARPS);
+    // enough sample slices for about eight blocks per SM, each at least one tile long
+    int want = std::max(1, (8 * h->sm_count + gx - 1) / gx);
     int slices = (int)std::max<int64_t>(1, std::min<int64_t>(want, ((int64_t)P + TGQ_SPIN_TILE - 1) / TGQ_SPIN_TILE));
     int slice_len = (int)(((int64_t)P + slices - 1) / slices);
     slice_len = (slice_len + TGQ_SPIN_TILE - 1) / TGQ_SPIN_TILE * TGQ_SPIN_TILE;
     slices = std::max(1, (int)(((int64_t)P + slice_len - 1) / slice_len));
     CK(cudaMemsetAsync(c.dout[2], 0, 4 * (size_t)bins * (size_t)c.n, c.stream));
-    k_spin_image<<<dim3(gx, slices), T, smem, c.stream>>>(pts, P, (float const *)c.din[0], (float const *)c.din[1], c.n, num_radial_bins, num_height_bins,
+    k_spin_image<<<dim3(gx, slices), 32 * TGQ_SPIN_WARPS, smem, c.stream>>>(pts, P, (float const *)c.din[0], (float const *)c.din[1], c.n, num_radial_bins, num_height_bins,
                                                           max_extent, max_extent, slice_len, (unsigned *)c.dout[2]);
     h->st.last_launches += 1; h->st.total_launches += 1;
     return TGQ_OK;

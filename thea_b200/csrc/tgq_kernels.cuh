@@ -1659,44 +1659,54 @@ k_ball_hist(BvhView b, float const * __restrict__ c3, float const * __restrict__
 }
 
 // ---- SpinImage (SurfaceFeatures/Local/SpinImage.cpp:47-75): every query bins ALL samples of the point structure ------------------
-// No traversal: a streaming pass.  Thread = one query (position, axis) with a private histogram in shared memory (bin b of thread t at
-// hist[b * T + t]: conflict free); the block walks its slice of the samples through a shared-memory tile (coalesced loads, every
-// thread then reads the same sample: a broadcast).  grid = (query groups, sample slices); slices add their partial counts to the
-// output with integer atomics, so the result does not depend on the launch shape.  Bound by the fp32 pipes (one square root and two
-// IEEE divisions per pair), not by memory: P x 16 bytes are read once per block.
-#define TGQ_SPIN_TILE 512
-__global__ void k_spin_image(f4 const * __restrict__ pts, int P, float const * __restrict__ q3, float const * __restrict__ qn3, int Q, int nr, int nh,
-                             float max_radius, float max_height, int slice_len, unsigned * out)
+// No traversal: a streaming pass, bound by the fp32 pipes (one square root and two IEEE divisions per pair), not by memory.  One WARP
+// per query: its lanes take 32 samples at a time from a shared-memory tile the block's warps (= queries) share, and the warp keeps ONE
+// histogram (bins x 4 bytes) in shared memory -- lanes that hit the same bin are found with a match and their leader adds the count,
+// so no atomics are needed.  The first version gave every THREAD a query and a private histogram (900 bytes per thread at 15 x 15 bins):
+// six resident warps per SM, latency bound at 94 G pairs/s; a histogram per warp lets the SM fill up.  grid = (query groups, sample
+// slices); slices add their partial counts to the output with integer atomics, so the result does not depend on the launch shape.
+#define TGQ_SPIN_TILE 1024
+#define TGQ_SPIN_WARPS 8
+__global__ void __launch_bounds__(32 * TGQ_SPIN_WARPS)
+k_spin_image(f4 const * __restrict__ pts, int P, float const * __restrict__ q3, float const * __restrict__ qn3, int Q, int nr, int nh,
+             float max_radius, float max_height, int slice_len, unsigned * out)
 {
   extern __shared__ __align__(16) unsigned char smem[];
-  int const T = blockDim.x, tid = threadIdx.x, bins = nr * nh;
-  f4 * tile = (f4 *)smem; unsigned * hist = (unsigned *)(tile + TGQ_SPIN_TILE);
-  int q = blockIdx.x * T + tid; bool live = q < Q;
+  unsigned const FULL = 0xffffffffu;
+  int const tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, bins = nr * nh;
+  f4 * tile = (f4 *)smem; unsigned * hist = (unsigned *)(tile + TGQ_SPIN_TILE) + (size_t)wid * bins;
+  int q = blockIdx.x * TGQ_SPIN_WARPS + wid; bool live = q < Q;
   v3 pos = mk3(0.0f, 0.0f, 0.0f), axis = mk3(0.0f, 0.0f, 1.0f);
   if (live) { pos = ld3(q3, q); axis = stable_normalized3(ld3(qn3, q)); }
-  for (int b = 0; b < bins; ++b) hist[b * T + tid] = 0u;
+  for (int b = lane; b < bins; b += 32) hist[b] = 0u;
   int s0 = blockIdx.y * slice_len, s1 = min(P, s0 + slice_len);
   for (int base = s0; base < s1; base += TGQ_SPIN_TILE)
   {
     int m = min(TGQ_SPIN_TILE, s1 - base);
     __syncthreads();
-    for (int j = tid; j < m; j += T) tile[j] = pts[base + j];
+    for (int j = tid; j < m; j += 32 * TGQ_SPIN_WARPS) tile[j] = pts[base + j];
     __syncthreads();
     if (live)
-    {
-#pragma unroll 4
-      for (int j = 0; j < m; ++j)
+      for (int j0 = 0; j0 < m; j0 += 32)
       {
-        f4 e = tile[j]; int rb, hb;
-        spin_bins(mk3(e.x, e.y, e.z), pos, axis, nr, nh, max_radius, max_height, rb, hb);
-        hist[(rb * nh + hb) * T + tid] += 1u;
+        int j = j0 + lane; bool have = j < m;
+        int bin = -1 - lane;                                     // lanes without a sample match nobody
+        if (have)
+        {
+          f4 e = tile[j]; int rb, hb;
+          spin_bins(mk3(e.x, e.y, e.z), pos, axis, nr, nh, max_radius, max_height, rb, hb);
+          bin = rb * nh + hb;
+        }
+        unsigned same = __match_any_sync(FULL, bin);
+        if (have && lane == __ffs(same) - 1) hist[bin] += (unsigned)__popc(same);
+        __syncwarp();
       }
-    }
   }
+  __syncwarp();
   if (live)
-    for (int b = 0; b < bins; ++b)
+    for (int b = lane; b < bins; b += 32)
     {
-      unsigned c = hist[b * T + tid];
+      unsigned c = hist[b];
       if (c) atomicAdd(out + (size_t)q * bins + b, c);
     }
 }
