@@ -507,3 +507,37 @@ def test_sample_graph_shortest_paths(built):
     ci, cs, cc = e2.graph_contract(gi, gs, 600)
     oi, os_, oc = orc.graph_contract(gi, gs, 600)
     assert np.array_equal(ci, oi.astype(np.int32)) and np.array_equal(cs, os_) and np.array_equal(cc, oc)
+
+
+def test_python_callers_for_the_graph_and_spin_features(built):
+    """thea_b200.callers twins of the new adaptor members: oversampled graph, geodesic features, spin images with inferred normals,
+    furthest point subsampling, sampleEvenlyBySeparation -- against the oracle on the same inputs."""
+    from thea_b200 import Engine, callers
+    mesh = gen.torus_mesh(48)
+    p, n, _ = gen.area_samples(mesh, 6000)
+    e = Engine(0)
+    e.build_points(p, n)
+    ora = orc.Oracle(points=p, normals=n)
+    seeds = (gen.splitmix64(7, 100) % np.uint64(len(p))).astype(np.int64)
+    K = 6
+    ci, cs, cc, avg = callers.sample_graph_oversampled(e, 1500, K, seeds)
+    gi, gs, _ = ora.ball_graph(K, np.float32(np.sqrt(np.float32(K))) * np.float32(avg), mode=orc.MODE_BRUTE)
+    oi, os_, oc = orc.graph_contract(gi, gs, 1500)
+    assert np.array_equal(ci, oi.astype(np.int32)) and np.array_equal(cs, os_) and np.array_equal(cc, oc)
+    rng = np.random.default_rng(5)
+    q = (p[:400] + rng.normal(scale=0.01, size=(400, 3))).astype(np.float32)
+    seed_idx = ora.closest(q, mode=orc.MODE_BRUTE)[0]
+    scale, md = np.float32(2.9), np.float32(0.3)
+    rs, rc, rh = orc.graph_geodesic(gi, gs, seed_idx, md, md, 10)
+    ga = callers.geodesic_average_distance(e, gi.astype(np.int32), gs, q, md, scale)
+    assert np.allclose(ga, np.where(rc > 0, rs / np.maximum(rc, 1), 0.0) / np.float64(md), rtol=1e-12, atol=0)
+    assert np.array_equal(callers.geodesic_distance_histogram(e, gi.astype(np.int32), gs, q, 10, md, scale), rh)
+    img = callers.spin_images(e, q, None, 6, 6, scale, sample_normals=n)
+    assert np.array_equal(img, ora.spin_image(q, n[seed_idx], 6, 6, np.float32(0.75) * scale))
+    sel = callers.furthest_point_subsample(p, 200, seeds)
+    g8i, g8s, _ = orc.Oracle(points=p).ball_graph(8, np.float32(np.sqrt(np.float32(8))) * np.float32(avg), mode=orc.MODE_BRUTE)
+    assert np.array_equal(sel, orc.graph_fps(g8i, g8s, 200).astype(np.int32))
+    te = Engine(0)
+    te.build_triangles(mesh)
+    out = callers.sample_evenly_by_separation(te, 300, 99, np.arange(100, dtype=np.int64))
+    assert out is not None and out[0].shape == (300, 3) and len(np.unique(out[0], axis=0)) == 300

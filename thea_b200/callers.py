@@ -8,6 +8,12 @@
     local_pca        <- loop over LocalPca::compute                   (…/Local/LocalPca.cpp:49-62, Algorithms/PcaN.hpp:150-197)
     visibility       <- loop over Visibility::compute                 (…/Local/Visibility.hpp:104-125)
     save_graph / load_graph / save_samples / load_samples <- PointSet3::save / load (Algorithms/PointSet3.cpp:180-375)
+    sample_graph_oversampled <- PointSet3::updateGraph with a dense oversampling (PointSet3.hpp:329-386, PointSet3.cpp:96-178)
+    geodesic_average_distance / geodesic_distance_histogram <- AverageDistance / LocalDistanceHistogram, GEODESIC
+                                                                (…/Local/AverageDistance.cpp:84-118, LocalDistanceHistogram.cpp:90-137)
+    spin_images      <- loop over SpinImage::compute                  (…/Local/SpinImage.cpp:30-75)
+    furthest_point_subsample <- FurthestPointSampling::subsample     (Algorithms/FurthestPointSampling.cpp:48-125)
+    sample_evenly_by_separation <- MeshSampler::sampleEvenlyBySeparation (Algorithms/MeshSampler.hpp:270-329)
 
 Every query batch and every reduction runs on the GPU through the C ABI; only the O(1) epilogues (3x3 polar
 decomposition, transform composition, convergence test) are host arithmetic.  Nothing here imports the oracle.
@@ -143,6 +149,67 @@ def sample_graph(eng, max_degree, seeds, surface=None):
     else:
         idx, sep, cnt = eng.ball_graph(max_degree, float(radius))
     return idx, sep, cnt, avg
+
+
+def sample_graph_oversampled(eng_all, n_orig, max_degree, seeds):
+    """PointSet3::updateGraph with a dense oversampling: `eng_all` holds the n_orig original samples followed by the dense ones; the
+    proximity graph over all of them is contracted to the originals by shortest paths (extractOriginalAdjacencies).
+    Returns (idx [n_orig x max_degree], sep, count, avg_sep)."""
+    idx, sep, _, avg = sample_graph(eng_all, max_degree, seeds)
+    ci, cs, cc = eng_all.graph_contract(idx, sep, int(n_orig))
+    return ci, cs, cc, avg
+
+
+def _geodesic(eng, graph_idx, graph_sep, p3, max_distance, scale, num_bins):
+    seed = eng.closest(p3, want_cp=False)[0]
+    rng = np.float32(scale) if max_distance < 0 else np.float32(max_distance)
+    return eng.graph_geodesic(graph_idx, graph_sep, np.ascontiguousarray(seed, np.int32), np.float32(max_distance), rng, num_bins), rng
+
+
+def geodesic_average_distance(eng, graph_idx, graph_sep, p3, max_distance, scale):
+    """AverageDistance::compute(p, GEODESIC, max_distance): seed = nearest sample, mean graph distance over the samples within
+    max_distance of it (< 0: the whole component), divided by max_distance (or the scale)."""
+    (s, c, _), rng = _geodesic(eng, graph_idx, graph_sep, p3, max_distance, scale, 0)
+    return np.where(c > 0, s / np.maximum(c, 1), 0.0) / np.float64(rng)
+
+
+def geodesic_distance_histogram(eng, graph_idx, graph_sep, p3, num_bins, max_distance, scale):
+    """LocalDistanceHistogram::compute(p, histogram, GEODESIC, max_distance) with every sample accepted: [Q x num_bins] counts."""
+    (_, _, h), _ = _geodesic(eng, graph_idx, graph_sep, p3, max_distance, scale, num_bins)
+    return h.astype(np.float64)
+
+
+def spin_images(eng, p3, n3, num_radial_bins, num_height_bins, scale, sample_normals=None):
+    """SpinImage::compute(position[, normal], ...) for every query: [Q x radial x height] float64.  n3 None: the normal of the sample
+    nearest to each query (sample_normals, P x 3, must then be given)."""
+    if n3 is None:
+        if sample_normals is None:
+            raise ValueError("SpinImage: Cannot infer query normal from surface lacking normals")
+        seed = eng.closest(p3)[0]
+        n3 = np.where((seed >= 0)[:, None], np.asarray(sample_normals, np.float32)[np.maximum(seed, 0)], np.float32(0))
+    img = eng.spin_image(p3, n3, num_radial_bins, num_height_bins, np.float32(0.75) * np.float32(scale))
+    return img.astype(np.float64)
+
+
+def furthest_point_subsample(points3, num_desired, seeds, max_degree=8, device=0):
+    """FurthestPointSampling::subsample(..., GEODESIC): graph over the points (PointSet3 default max_degree 8), then sample 0 and
+    repeatedly the sample furthest from the selected set along the graph.  Returns the selected indices."""
+    from .engine import Engine
+    e = Engine(device)
+    e.build_points(points3)
+    idx, sep, _, _ = sample_graph(e, max_degree, seeds)
+    return e.graph_fps(idx, sep, int(num_desired))
+
+
+def sample_evenly_by_separation(eng_mesh, desired, seed, graph_seeds, oversampling_factor=3.0, device=0):
+    """MeshSampler::sampleEvenlyBySeparation: area oversampling on the device, furthest point subsampling, gather.
+    Returns (positions, face normals, triangle indices) or None when the subsampling comes up short (the reference returns 0)."""
+    n_over = int(np.ceil(np.float32(oversampling_factor) * desired))
+    p, n, t = eng_mesh.area_sample(n_over, seed)
+    sel = furthest_point_subsample(p, desired, graph_seeds, device=device)
+    if len(sel) < desired:
+        return None
+    return p[sel], n[sel], t[sel]
 
 
 # ---- local surface features: processRange calls with an accumulating functor (SURVEY.md 8f rank 3) ------------------------
