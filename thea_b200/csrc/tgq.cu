@@ -50,7 +50,9 @@ struct DevBuf
 #ifndef TGQ_RAY_BLOCKS
 #define TGQ_RAY_BLOCKS 6
 #endif
-#define TGQ_SLOTS 3       // pipeline depth of host-pointer calls (measured on cfg5: 2 -> 462, 3 -> 475, 4 -> 474 M queries/s end to end)
+#define TGQ_SLOTS 4       // pipeline depth of host-pointer calls (within ONE call, measured on cfg5: 2 -> 462, 3 -> 475, 4 -> 474 M queries/s end to end;
+                          // four slots, handed out round-robin ACROSS calls, let an asynchronous ray call upload all of its four chunks under the
+                          // kernels of the closest-point call before it instead of queueing behind that call's last chunks)
 #endif
 
 // Scratch of one pipeline slot.  Host-pointer calls rotate over TGQ_SLOTS slots, each with its own stream, so that the
@@ -69,7 +71,7 @@ struct tgq_handle
   std::string err;
   cudaStream_t own_stream = nullptr, stream = nullptr;
 
-  int opt_sort = 2, opt_leaf = 4, opt_async = 0, opt_pool = 1, opt_icp_ref = 1, opt_wide = 0, opt_setbuf = 1; bool wide_built = false; int64_t opt_chunk = 16777216;
+  int opt_sort = 2, opt_leaf = 4, opt_async = 0, opt_pool = 1, opt_icp_ref = 1, opt_wide = 0, opt_setbuf = 1; unsigned slot_rr = 0; bool wide_built = false; int64_t opt_chunk = 16777216;
 
   int kind = TGQ_KIND_NONE; int n = 0; int n_nodes = 0; bool has_normals = false, has_labels = false; int leaf_built = 4;
   DevBuf nodes, elems, nrm, lab, scene;                                // NodeRec[], TriRec[] | f4[], f4[], SceneBox
@@ -430,7 +432,7 @@ int run_batched(tgq_handle * h, int64_t Q, Arg * args, int nargs, bool sortable,
   int ci = 0;
   for (int64_t off = 0; off < Q; off += chunk, ++ci)
   {
-    ChunkCtx c; c.slot = &h->slot[ci % nslots]; c.stream = all_dev ? h->stream : c.slot->stream; c.offset = off;
+    ChunkCtx c; c.slot = &h->slot[all_dev ? 0 : (h->slot_rr++ % nslots)]; c.stream = all_dev ? h->stream : c.slot->stream; c.offset = off;
     c.n = (int)std::min<int64_t>(chunk, Q - off); c.perm = nullptr;
     for (int a = 0; a < nargs; ++a)
     {
