@@ -282,6 +282,8 @@ def main():
         eng.set_option(8, int(os.environ["TGQ_BENCH_CELL_BITS"]))
     d_mesh = torch.from_numpy(mesh).to(dev)
     eng.build_triangles(d_mesh)
+    build_first_ms = eng.stats()["last_build_ms"]        # includes the first-call allocation of every build and structure buffer
+    eng.build_triangles(d_mesh)                          # the same structure again: the steady-state build time
     build_ms = eng.stats()["last_build_ms"]
     del d_mesh
 
@@ -592,7 +594,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": desc, "triangles": T, "closest_queries": nq_total, "ray_queries": nr_total, "sharding": f"BVH replicated; batch replicated, each rank answers the queries of its Morton cells (1/{world})" + (f"; results gathered on every rank every step: {transport}" if world > 1 else ""),
                    "l2_policy": "inputs_exceed_l2" if (nq_total * 32 + nr_total * 32) / world > 126e6 else "structure+inputs may be L2 resident",
-                   "scale": args.scale, "build_ms": build_ms},
+                   "scale": args.scale, "build_ms": build_ms, "build_first_ms": build_first_ms},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": kern["launches"], "clocks": clocks,
         "breakdown": {"closest_Mqps_kernel": kern["closest_q"] / kern["closest_ms"] / 1e3 if kern["closest_ms"] else None,
                       "ray_Mqps_kernel": kern["ray_q"] / kern["ray_ms"] / 1e3 if kern["ray_ms"] else None,

@@ -35,7 +35,9 @@ def run(n_grid, Q, leaf=4, sort=2, what=("closest", "ray")):
     e.close()
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "big":
+    if len(sys.argv) > 1 and sys.argv[1] == "rays":
+        run(2236, 50_000_000, what=("ray",))
+    elif len(sys.argv) > 1 and sys.argv[1] == "big":
         run(2236, 50_000_000, what=("closest",))
     elif len(sys.argv) > 1 and sys.argv[1] == "short":
         run(708, 4_000_000)
