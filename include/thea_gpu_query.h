@@ -52,7 +52,8 @@ enum
 enum
 {
   TGQ_OPT_SORT_QUERIES = 1,   /* 0 = never, 1 = always, 2 = auto (default: batches >= 4096 are Morton-ordered first) */
-  TGQ_OPT_LEAF_SIZE = 2,      /* max elements per leaf, 1..15 (default 4); takes effect at the next build */
+  TGQ_OPT_LEAF_SIZE = 2,      /* max elements per leaf: 0 (default) = by kind, 4 for triangle and 15 for point structures; or 1..15; takes effect at
+                                 the next build */
   TGQ_OPT_ASYNC = 3,          /* 1: batched query calls return without waiting: device-pointer calls are ordered on the handle's stream,
                                  host-pointer calls on the internal pipeline streams -- call tgq_synchronize before reading host outputs
                                  (lets consecutive calls overlap: the downloads of one with the uploads of the next).  Default 0 */

@@ -64,8 +64,10 @@ def set_buffered(on):
 
 
 class Emu:
-    def __init__(self, tris9=None, points=None, normals=None, leaf=4):
+    def __init__(self, tris9=None, points=None, normals=None, leaf=None):
         L = lib()
+        if leaf is None:
+            leaf = 4 if tris9 is not None else 15          # the engine's defaults by structure kind (TGQ_OPT_LEAF_SIZE = 0)
         if tris9 is not None:
             self.src = np.ascontiguousarray(tris9, np.float32).reshape(-1, 9)
             self.n = len(self.src)

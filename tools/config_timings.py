@@ -35,7 +35,7 @@ def main():
     build_1m = e.stats()["last_build_ms"]
     # cfg2: k = 16 neighbour graph over 1M area samples of the 1M-triangle torus (k-NN and the PointSet3 ball graph)
     t0 = time.perf_counter(); p, n, _ = e.area_sample(1_000_000, gen.SEED_SAMPLES); t_sample = time.perf_counter() - t0
-    pe = Engine(0); pe.build_points(p, n)
+    pe = Engine(0); pe.set_option(2, int(os.environ.get("TGQ_LEAF", "0"))); pe.build_points(p, n)
     dp = torch.from_numpy(p).cuda()
     dt_knn, (ki, kd) = timed(lambda: pe.knn(dp, 16, exclude_self=True))
     seeds = (gen.splitmix64(0x5EED, 100) % np.uint64(len(p))).astype(np.int64)

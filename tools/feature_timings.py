@@ -23,7 +23,7 @@ def main():
     mesh = gen.torus_mesh(gen.TORUS_1M); b = gen.mesh_bounds(mesh)
     e = Engine(0); e.build_triangles(torch.from_numpy(mesh).cuda())
     p, n, _ = e.area_sample(1_000_000, gen.SEED_SAMPLES)
-    pe = Engine(0); pe.build_points(p, n)
+    pe = Engine(0); pe.set_option(2, int(os.environ.get("TGQ_LEAF", "0"))); pe.build_points(p, n)
     lo, hi = b; scale = float(np.linalg.norm((hi - lo).astype(np.float32)))
     dp, dn = torch.from_numpy(p).cuda(), torch.from_numpy(n).cuda()
     po = orc.Oracle(points=p, normals=n)

@@ -9,7 +9,7 @@ def main(grid=708, P=1_000_000):
     mesh = gen.torus_mesh(grid)
     e = Engine(0); e.build_triangles(torch.from_numpy(mesh).cuda())
     p, n, _ = e.area_sample(P, gen.SEED_SAMPLES)
-    pe = Engine(0, lib=(os.environ.get("TGQ_LIB") or None)); pe.set_option(_eng.OPT_SET_BUFFER, int(os.environ.get("TGQ_SET_BUFFER", "1"))); pe.build_points(p, n)
+    pe = Engine(0, lib=(os.environ.get("TGQ_LIB") or None)); pe.set_option(_eng.OPT_SET_BUFFER, int(os.environ.get("TGQ_SET_BUFFER", "1"))); pe.set_option(_eng.OPT_LEAF_SIZE, int(os.environ.get("TGQ_LEAF", "0"))); pe.build_points(p, n)
     dp = torch.from_numpy(p).cuda()
     for _ in range(2):
         pe.knn(dp, 16, exclude_self=True)
@@ -26,7 +26,7 @@ def main(grid=708, P=1_000_000):
     for _ in range(2):
         pe.knn_filtered(dp, 24, qn3=dn, qlabel=dl)
     s3 = pe.stats()
-    print(json.dumps({"set_buffer": int(os.environ.get("TGQ_SET_BUFFER", "1")), "filtered_knn24_ms": s3["last_query_ms"], "filtered_knn24_Mqps": P / s3["last_query_ms"] / 1e3, "P": P, "knn_ms": s1["last_query_ms"], "knn_Mqps": P / s1["last_query_ms"] / 1e3, "graph_ms": s2["last_query_ms"],
+    print(json.dumps({"leaf": int(os.environ.get("TGQ_LEAF", "0")), "set_buffer": int(os.environ.get("TGQ_SET_BUFFER", "1")), "filtered_knn24_ms": s3["last_query_ms"], "filtered_knn24_Mqps": P / s3["last_query_ms"] / 1e3, "P": P, "knn_ms": s1["last_query_ms"], "knn_Mqps": P / s1["last_query_ms"] / 1e3, "graph_ms": s2["last_query_ms"],
                       "graph_Mqps": P / s2["last_query_ms"] / 1e3, "mean_degree": float(dc.float().mean().item())}))
 
 if __name__ == "__main__":
