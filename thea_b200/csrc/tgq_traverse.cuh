@@ -103,8 +103,11 @@ TGQ_HD void trav_bind_fast(Trav & t, StackEntry * fast, int stride, int cap) { t
 
 TGQ_HD void trav_enter(Trav & t, int code)
 {
-  if (code >= 0) t.cur = code;
-  else { int c = ~code; t.k = c >> TGQ_LEAF_BITS; t.kend = t.k + (c & TGQ_LEAF_MASK); t.cur = (t.kend > t.k) ? TGQ_ST_LEAF : TGQ_ST_POP; }
+  // branch free: inlined at every descend / pop site inside divergent code, where a branch per site cost more than the selects
+  bool leaf = code < 0; int c = ~code;
+  int k = c >> TGQ_LEAF_BITS, kend = k + (c & TGQ_LEAF_MASK);
+  t.k = leaf ? k : t.k; t.kend = leaf ? kend : t.kend;
+  t.cur = leaf ? ((c & TGQ_LEAF_MASK) > 0 ? TGQ_ST_LEAF : TGQ_ST_POP) : code;
 }
 TGQ_HD void trav_begin(Trav & t, int n_nodes) { t.sp = 0; t.k = t.kend = 0; t.cur = n_nodes > 0 ? 0 : TGQ_ST_DONE; }
 TGQ_HD void trav_push(Trav & t, int code, float key)
