@@ -403,9 +403,56 @@ def main():
                 p = (rank + k) % world
                 S["views"][p]["final"][lo:lo + S["shard_len"]].copy_(mine["final"][lo:lo + S["shard_len"]], non_blocking=True)
 
+    pipelined = os.environ.get("TGQ_BENCH_PIPELINE", "1") == "1"
+
+    def exchange_pipelined(name, n_own, par):
+        """The whole exchange of one query kind with only the bucketing on the main stream: all-to-all, device-side barrier, local
+        scatter and the pushes of the scattered slice run on the side stream, so the next traversal kernel starts at once -- the closest
+        records are exchanged under the ray kernel of the same step, the ray records under the closest kernel of the NEXT step (a
+        software pipeline one step deep: the timed region still ends only after every transfer has completed).  Buffer reuse: the
+        main stream waits, before it buckets the next step's records of this kind, for the event 'this step's buckets have left';
+        the receive buffers alternate by step parity and are released by the next step's barrier on the same (in-order) side stream."""
+        S = sym[name]
+        mine = S["views"][rank]
+        cur = torch.cuda.current_stream()
+        if S.get("ev_left") is not None:
+            cur.wait_event(S["ev_left"])
+        timed("s", lambda: eng.bucket_records(S["share"], n_own, kinds[name], S["shard_len"], world, S["buckets"], S["cap_pair"], S["bcnt"]))
+        comm_stream.wait_stream(cur)
+        with torch.cuda.stream(comm_stream):
+            for k in range(world):
+                p = (rank + k) % world
+                dst = S["views"][p]
+                dst["recv"][par, rank].copy_(S["buckets"][p], non_blocking=True)
+                dst["cnt"][par, rank].copy_(S["bcnt"][p], non_blocking=True)
+            S["ev_left"] = torch.cuda.Event()
+            S["ev_left"].record(comm_stream)
+            S["hdl"].barrier(channel=par)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(comm_stream)
+            eng.set_stream(comm_stream.cuda_stream)
+            eng.scatter_records(mine["recv"][par], world, S["cap_pair"], mine["cnt"][par], kinds[name], mine["final"])
+            eng.set_stream(main_stream.cuda_stream)
+            b.record(comm_stream)
+            timers["s"].append((a, b))
+            lo = rank * S["shard_len"]
+            for k in range(1, world):
+                p = (rank + k) % world
+                S["views"][p]["final"][lo:lo + S["shard_len"]].copy_(mine["final"][lo:lo + S["shard_len"]], non_blocking=True)
+
     def step_device(record: bool):
         par = step_no[0] & 1
         step_no[0] += 1
+        if world > 1 and space_sharded and pipelined:
+            if nq_total:
+                n_c = timed("c", lambda: eng.closest_records(dq, [sym["c"]["share"]], rank, world, compact=True))
+                assert n_c <= sym["c"]["cap_share"], "closest share exceeds its buffer"
+                exchange_pipelined("c", n_c, par)
+            if nr_total:
+                n_r = timed("r", lambda: eng.ray_first_records(dro, drd, [sym["r"]["share"]], rank, world, compact=True))
+                assert n_r <= sym["r"]["cap_share"], "ray share exceeds its buffer"
+                exchange_pipelined("r", n_r, par)
+            return
         if world > 1 and space_sharded:
             evc = evr = None
             if nq_total:
