@@ -427,7 +427,13 @@ int run_batched(tgq_handle * h, int64_t Q, Arg * args, int nargs, bool sortable,
   }
   // host-pointer calls: at least four chunks, so that the upload of one chunk, the kernels of another and the download of a third
   // overlap even when the batch is smaller than TGQ_OPT_CHUNK (a 6 M-query shard used to be ONE chunk: copy, sort, kernel, copy in series)
-  int64_t chunk = all_dev ? ((int64_t)1 << 26) : std::max<int64_t>(1024, std::min<int64_t>(h->opt_chunk, ((Q + 3) / 4 + 1023) / 1024 * 1024));
+  // ... but not below about 6 M queries per chunk: a smaller Morton-ordered batch is sparser and the traversal kernels lose more on it
+  // than the exposed copies cost -- and consecutive asynchronous calls overlap each other's copies anyway.  Measured on one rank's
+  // 6.25 M + 6.25 M share of the cfg5 batches through pinned host buffers (tools/e2e_shard_probe.py): four chunks per call 29.7 ms per
+  // step, two 25.9 ms, one 25.0 ms.  TGQ_DEV_MIN_CHUNK overrides the floor for experiments.
+  static int64_t const min_chunk = getenv("TGQ_DEV_MIN_CHUNK") ? atoll(getenv("TGQ_DEV_MIN_CHUNK")) : 6000000;
+  int64_t nchunks = std::max<int64_t>(1, std::min<int64_t>(4, (Q + min_chunk / 2) / std::max<int64_t>(1, min_chunk)));
+  int64_t chunk = all_dev ? ((int64_t)1 << 26) : std::max<int64_t>(1024, std::min<int64_t>(h->opt_chunk, ((Q + nchunks - 1) / nchunks + 1023) / 1024 * 1024));
   int nslots = all_dev ? 1 : TGQ_SLOTS;
   if (!all_dev) CK(cudaStreamSynchronize(h->stream));     // the structure must be complete before other streams read it
   std::vector<cudaEvent_t> evs;
