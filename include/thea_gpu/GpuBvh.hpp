@@ -306,6 +306,26 @@ class GpuBvhBase
       return NeighborPair((intx)qi, (intx)ti, (double)d2, detail::get3<VectorT>(qp), detail::get3<VectorT>(tp));
     }
 
+    /** BvhN::kClosestPairs<MetricL2>(query_structure, k_closest_pairs, dist_bound, ...) (BvhN.hpp:1137-1146 with a structure as the query):
+     *  the k closest pairs between this POINT structure and the point structure `query`, offered to the caller's bounded set in ascending
+     *  order through its own isInsertable / insert (the set is not cleared, as in the reference).  Returns its size. */
+    template <typename MetricT, typename QueryVectorT, typename BoundedNeighborPairSetT, typename CompatibilityFunctorT = UniversalCompatibility>
+    intx kClosestPairs(GpuBvhBase<QueryVectorT> const & query, BoundedNeighborPairSetT & k_closest_pairs, double dist_bound = -1,
+                       CompatibilityFunctorT = CompatibilityFunctorT(), bool = false) const
+    {
+      int32_t k = (int32_t)k_closest_pairs.getCapacity(), found = 0;
+      if (k <= 0) return (intx)k_closest_pairs.size();
+      if (k > TGQ_MAX_K) throw Error("TheaGpu: kClosestPairs capacity exceeds TGQ_MAX_K");
+      std::vector<int64_t> ti((size_t)k), qi((size_t)k); std::vector<float> d2((size_t)k);
+      detail::check(h, tgq_k_closest_pairs(h, query.handle(), k, dist_bound, ti.data(), qi.data(), d2.data(), &found), "tgq_k_closest_pairs");
+      for (int32_t j = 0; j < found; ++j)
+      {
+        NeighborPair pair((intx)qi[(size_t)j], (intx)ti[(size_t)j], (double)d2[(size_t)j]);
+        if (k_closest_pairs.isInsertable(pair)) k_closest_pairs.insert(pair);
+      }
+      return (intx)k_closest_pairs.size();
+    }
+
     /** Host-side filters cannot run on the device and there is no CPU fallback. */
     template <typename FilterT> void pushFilter(FilterT *) { throw Error("TheaGpu: element filters are not supported by the GPU structure"); }
     void popFilter() {}
@@ -526,6 +546,7 @@ class GpuPointBvhT : public GpuBvhBase<VectorT>
 
     explicit GpuPointBvhT(int device = 0) : Base(device), filter(nullptr) {}
     using Base::closestPair;         // the structure-to-structure form
+    using Base::kClosestPairs;       // likewise
 
     /** Per-element labels (P int32, element order; null clears): the `label` member of Register's samples. */
     void setLabels(int32_t const * labels) { detail::check(h, tgq_set_point_labels(h, labels), "tgq_set_point_labels"); }

@@ -177,6 +177,14 @@ int tgq_ball_range(tgq_handle * h, const float * c3, const float * radius, int64
 int tgq_closest_pair(tgq_handle * h, tgq_handle * query, double dist_bound, int64_t * target_index, int64_t * query_index, float * d2,
                      float * query_point3, float * target_point3);
 
+/* BvhN::kClosestPairs with another structure as the query (Algorithms/BvhN.hpp:1137-1146 with QueryT = BvhN; the pair traversal of
+ * :1900-2009): the k closest (target element, query element) pairs between this POINT structure and the point structure `query`, in
+ * the canonical order (squared distance, target index, query index); dist_bound < 0: unbounded, else only pairs strictly closer.
+ * target_index / query_index / d2 (may be null): k entries on the host, -1 / -1.0f padded; *n_found = pairs found (<= k).
+ * Every query element's k nearest targets are found in one batch, then one device sort picks the k smallest. */
+int tgq_k_closest_pairs(tgq_handle * h, tgq_handle * query, int32_t k, double dist_bound, int64_t * target_index, int64_t * query_index, float * d2,
+                        int32_t * n_found);
+
 /* Q unbounded range queries on a point structure.  Replaces BvhN::rangeQueryIndices / rangeQuery / processRange
  * <IntersectionTester>(range, ...) (BvhN.hpp:1208-1264,2118-2171) for the two range types the reference's callers and tests use:
  * kind 0: Ball3(a3[i], b[i])  -- every element with sq(x - c) <= r * r in fp32 (BallN.hpp:83);   b = Q radii

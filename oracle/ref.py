@@ -79,6 +79,8 @@ def lib():
         L.ref_graph.argtypes = [vp, vp, i64, i32, f32, vp, vp, vp, vp]
         L.ref_avg_separation.restype = f32
         L.ref_avg_separation.argtypes = [vp, i64, vp, i32]
+        L.ref_k_closest_pairs_bvh.restype = i32
+        L.ref_k_closest_pairs_bvh.argtypes = [vp, vp, i32, f64, vp, vp, vp]
         L.ref_graph_contract.argtypes = [vp, i64, i64, i32, vp, vp, vp, vp, vp]
         L.ref_geodesic_features.argtypes = [vp, i64, i32, vp, vp, f32, vp, i64, f32, i32, vp, vp]
         L.ref_fps.restype = i64
@@ -173,6 +175,12 @@ class Reference:
         idx = np.empty(cap, np.int64)
         n = lib().ref_box_range(self.h, _p(_f32(lo).reshape(3)), _p(_f32(hi).reshape(3)), cap, _p(idx))
         return idx[:min(n, cap)].copy(), int(n)
+
+    def k_closest_pairs(self, other, k, dist_bound=-1.0):
+        """kClosestPairs<MetricL2>(other structure, set of k): (target indices, query indices, squared distances), ascending."""
+        ti, qi, d2 = np.empty(k, np.int64), np.empty(k, np.int64), np.empty(k, np.float32)
+        n = lib().ref_k_closest_pairs_bvh(self.h, other.h, int(k), float(dist_bound), _p(ti), _p(qi), _p(d2))
+        return ti[:n], qi[:n], d2[:n]
 
     def closest_pair(self, other, dist_bound=-1.0):
         """BVH-to-BVH closestPair: (found, target index in self, query index in other, d2, query point, target point)."""

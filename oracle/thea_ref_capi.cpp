@@ -248,6 +248,19 @@ int64_t ref_box_range(void * hv, float const * lo3, float const * hi3, int64_t c
   return (int64_t)out.size();
 }
 
+// BVH-to-BVH kClosestPairs between two point structures (BvhN.hpp:1137-1146 with a structure as the query, :1900-2009): returns the
+// number of pairs found; rows ascending as the reference's bounded set orders them.
+int ref_k_closest_pairs_bvh(void * hv, void * qv, int k, double dist_bound, int64_t * target_idx, int64_t * query_idx, float * d2)
+{
+  RefHandle * h = (RefHandle *)hv; RefHandle * q = (RefHandle *)qv;
+  if (!h->pts || !q->pts) return -1;
+  BoundedSortedArray<PointBvh::NeighborPair> set((size_t)k);
+  h->pts->kClosestPairs<MetricL2>(*q->pts, set, dist_bound, UniversalCompatibility(), false);
+  for (size_t j = 0; j < set.size(); ++j)
+  { target_idx[j] = (int64_t)set[j].getTargetIndex(); query_idx[j] = (int64_t)set[j].getQueryIndex(); d2[j] = (float)set[j].getMonotoneApproxDistance(); }
+  return (int)set.size();
+}
+
 // BVH-to-BVH closestPair (BvhN.hpp:1081-1114 with a structure as the query, :1900-2009).  Returns 1 when a pair was found.
 int ref_closest_pair_bvh(void * hv, void * qv, double dist_bound, int64_t * target_idx, int64_t * query_idx, float * d2, float * cp_query3,
                          float * cp_target3)

@@ -17,6 +17,7 @@
 #include "AxisAlignedBox3.hpp"
 #include "Ball3.hpp"
 #include "BoundedSortedArrayN.hpp"
+#include "BoundedSortedArray.hpp"
 #include "Graphics/GeneralMesh.hpp"
 #include "Triangle3.hpp"
 
@@ -183,6 +184,21 @@ int main(int argc, char ** argv)
         bool same2 = c.isValid() == d.isValid() && (!c.isValid() || c.getMonotoneApproxDistance() == d.getMonotoneApproxDistance());
         pair_ok += same2;
         EXPECT(same2, "closestPair(triangles, points, bound %g): %g vs %g", bound, c.getMonotoneApproxDistance(), d.getMonotoneApproxDistance());
+      }
+      // kClosestPairs with a structure as the query (BvhN.hpp:1137-1146): the reference's own template on both sides
+      for (int k : { 1, 7, 20 })
+      {
+        Thea::BoundedSortedArray<RefPointBvh::NeighborPair> ra((size_t)k);
+        Thea::BoundedSortedArray<GpuPointBvh::NeighborPair> ga((size_t)k);
+        pref.kClosestPairs<MetricL2>(oref, ra, -1, UniversalCompatibility(), false);
+        pgpu.kClosestPairs<MetricL2>(ogpu, ga, -1, UniversalCompatibility(), false);
+        bool same3 = ra.size() == ga.size();
+        for (size_t j = 0; same3 && j < ra.size(); ++j)
+          same3 = ra[j].getMonotoneApproxDistance() == ga[j].getMonotoneApproxDistance()
+                  && ((ra[j].getTargetIndex() == ga[j].getTargetIndex() && ra[j].getQueryIndex() == ga[j].getQueryIndex())
+                      || (points[(size_t)ga[j].getTargetIndex()] - other[(size_t)ga[j].getQueryIndex()]).squaredNorm() == (Real)ra[j].getMonotoneApproxDistance());
+        pair_ok += same3;
+        EXPECT(same3, "kClosestPairs(points, points, k = %d): %zu vs %zu pairs", k, ra.size(), ga.size());
       }
     }
 

@@ -541,3 +541,22 @@ def test_python_callers_for_the_graph_and_spin_features(built):
     te.build_triangles(mesh)
     out = callers.sample_evenly_by_separation(te, 300, 99, np.arange(100, dtype=np.int64))
     assert out is not None and out[0].shape == (300, 3) and len(np.unique(out[0], axis=0)) == 300
+
+
+def test_k_closest_pairs_between_point_structures(built):
+    """tgq_k_closest_pairs vs the k smallest (d2, target, query) over the oracle's brute-force k-NN rows (pinned to the reference's own
+    BvhN::kClosestPairs(BvhN) in tests/test_ref_pin.py)."""
+    from thea_b200 import Engine
+    mesh = gen.torus_mesh(30)
+    a, _, _ = gen.area_samples(mesh, 3000)
+    b, _, _ = gen.area_samples(mesh, 2000, seed=9)
+    b = (b + np.float32(0.01)).astype(np.float32)
+    ea, eb = Engine(0), Engine(0)
+    ea.build_points(a); eb.build_points(b)
+    ora = orc.Oracle(points=a)
+    for k, bound in ((12, -1.0), (1, -1.0), (64, -1.0), (16, 0.0052)):
+        ti, qi, d2 = ea.k_closest_pairs(eb, k, bound)
+        ki, kd = ora.knn(b, k, dist_bound=bound, mode=orc.MODE_BRUTE)
+        rows = sorted((float(kd[q, j]), int(ki[q, j]), q) for q in range(len(b)) for j in range(k) if ki[q, j] >= 0)[:k]
+        assert [(int(t), int(q)) for t, q in zip(ti, qi)] == [(t, q) for _, t, q in rows]
+        assert np.array_equal(d2, np.array([r[0] for r in rows], np.float32))

@@ -312,3 +312,21 @@ def test_sample_graph_shortest_paths():
             mine = np.where(c_ > 0, s_ / np.maximum(c_, 1), 0.0) / np.float64(rng_)
             assert np.allclose(mine, ravg, rtol=1e-15, atol=0) and np.array_equal(h_, rh)
         assert np.array_equal(orc.graph_fps(gi, gs, 80), ref.fps(p, gi, gs, 80))
+
+
+def test_k_closest_pairs_between_point_structures():
+    """BvhN::kClosestPairs with a structure as the query (BvhN.hpp:1137-1146,1900-2009) == the k smallest (d2, target, query) over the
+    oracle's brute-force k-NN rows of the query points: what tgq_k_closest_pairs computes on the device."""
+    mesh = gen.torus_mesh(30)
+    a, _, _ = gen.area_samples(mesh, 3000)
+    b, _, _ = gen.area_samples(mesh, 2000, seed=9)
+    b = (b + np.float32(0.01)).astype(np.float32)
+    R, Q = ref.Reference(points=a), ref.Reference(points=b)
+    ora = orc.Oracle(points=a)
+    for k, bound in ((12, -1.0), (5, -1.0), (16, 0.0052)):
+        ti, qi, d2 = R.k_closest_pairs(Q, k, bound)
+        ki, kd = ora.knn(b, k, dist_bound=bound, mode=orc.MODE_BRUTE)
+        rows = sorted((float(kd[q, j]), int(ki[q, j]), q) for q in range(len(b)) for j in range(k) if ki[q, j] >= 0)[:k]
+        assert [(int(t), int(q)) for t, q in zip(ti, qi)] == [(t, q) for _, t, q in rows]
+        assert np.array_equal(d2, np.array([r[0] for r in rows], np.float32))
+    assert 0 < len(R.k_closest_pairs(Q, 16, 0.0052)[0]) < 16          # the bound bites

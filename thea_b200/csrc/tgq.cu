@@ -1071,6 +1071,59 @@ int tgq_knn_filtered(tgq_handle * h, const float * q3, const float * qn3, const 
   return knn_common(h, q3, qn3, qlabel, min_dot, Q, k, dist_bound, 0, idx, d2);
 }
 
+int tgq_k_closest_pairs(tgq_handle * h, tgq_handle * query, int32_t k, double dist_bound, int64_t * target_index, int64_t * query_index, float * d2,
+                        int32_t * n_found)
+{
+  CKRC(need_built(h, 1 << TGQ_KIND_POINTS));
+  if (!query || k < 1 || !target_index || !query_index || !n_found) return fail(h, TGQ_EINVAL, "tgq_k_closest_pairs: bad arguments");
+  if (k > TGQ_MAX_K) return fail(h, TGQ_ELIMIT, "tgq_k_closest_pairs: k exceeds TGQ_MAX_K");
+  if (query->kind != TGQ_KIND_POINTS) return fail(h, TGQ_EINVAL, "tgq_k_closest_pairs: the query structure must be a point structure");
+  if (query->device != h->device) return fail(h, TGQ_EINVAL, "tgq_k_closest_pairs: both structures must live on the same device");
+  *n_found = 0;
+  for (int j = 0; j < k; ++j) { target_index[j] = -1; query_index[j] = -1; if (d2) d2[j] = -1.0f; }
+  if (query->n == 0 || h->n == 0) return TGQ_OK;
+  size_t const P = (size_t)query->n, n = P * (size_t)k;
+  if (n >= ((size_t)1 << 32)) return fail(h, TGQ_ELIMIT, "tgq_k_closest_pairs: query elements x k exceeds 2^32");
+  Guard g(h);
+  cudaStream_t s = h->stream;
+  CK(cudaStreamSynchronize(query->stream));
+  CK(h->src2.reserve(12 * P)); CK(h->slot[0].out[4].reserve(4 * n)); CK(h->slot[0].out[5].reserve(4 * n));
+  k_extract_points<<<grid_for((int64_t)P), TGQ_BLOCK, 0, s>>>(query->elems.as<f4>(), nullptr, nullptr, (int)P, h->src2.as<float>(), nullptr, nullptr);
+  CK(cudaGetLastError());
+  int * di = h->slot[0].out[4].as<int>(); float * dd = h->slot[0].out[5].as<float>();
+  int saved_async = h->opt_async; h->opt_async = 0;
+  int rc = knn_common(h, h->src2.as<float>(), nullptr, nullptr, 0.0f, (int64_t)P, k, dist_bound, 0, di, dd);
+  h->opt_async = saved_async;
+  if (rc != TGQ_OK) return rc;
+  Slot & sl = h->slot[0];
+  CK(sl.keys[0].reserve(8 * n)); CK(sl.keys[1].reserve(8 * n)); CK(sl.vals[0].reserve(4 * n)); CK(sl.vals[1].reserve(4 * n));
+  int grid = (int)std::min<int64_t>((int64_t)(n + 255) / 256, (int64_t)h->sm_count * 8);
+  k_pair_keys<<<grid, 256, 0, s>>>(di, dd, (int64_t)n, sl.keys[0].as<unsigned long long>(), sl.vals[0].as<unsigned>());
+  CK(cudaGetLastError());
+  size_t tmp = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, sl.keys[0].as<unsigned long long>(), sl.keys[1].as<unsigned long long>(), sl.vals[0].as<unsigned>(),
+                                     sl.vals[1].as<unsigned>(), (int64_t)n, 0, 64, s));
+  CK(sl.cubtmp.reserve(tmp));
+  CK(cub::DeviceRadixSort::SortPairs(sl.cubtmp.p, tmp, sl.keys[0].as<unsigned long long>(), sl.keys[1].as<unsigned long long>(), sl.vals[0].as<unsigned>(),
+                                     sl.vals[1].as<unsigned>(), (int64_t)n, 0, 64, s));
+  int const kk = (int)std::min<size_t>((size_t)k, n);
+  CK(h->misc.reserve(20 * (size_t)k));
+  long long * dt = h->misc.as<long long>(); long long * dq = dt + k; float * df = (float *)(dq + k);
+  k_pair_rows<<<1, 64, 0, s>>>(sl.keys[1].as<unsigned long long>(), sl.vals[1].as<unsigned>(), k, kk, dt, dq, df);
+  CK(cudaGetLastError());
+  h->st.total_launches += 4;
+  std::vector<long long> ht((size_t)kk), hq((size_t)kk); std::vector<float> hf((size_t)kk);
+  CK(cudaMemcpyAsync(ht.data(), dt, 8 * (size_t)kk, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(hq.data(), dq, 8 * (size_t)kk, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(hf.data(), df, 4 * (size_t)kk, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  int found = 0;
+  for (int j = 0; j < kk; ++j)
+    if (ht[(size_t)j] >= 0) { target_index[found] = ht[(size_t)j]; query_index[found] = hq[(size_t)j]; if (d2) d2[found] = hf[(size_t)j]; ++found; }
+  *n_found = found;
+  return TGQ_OK;
+}
+
 static int ball_graph_common(tgq_handle * h, tgq_handle * surface, int32_t max_degree, float init_radius, int32_t rounds, float min_dot,
                              int32_t min_degree, int32_t * idx, float * sep, int32_t * count)
 {

@@ -2095,6 +2095,26 @@ __global__ void k_pair_min_query(int const * __restrict__ idx, float const * __r
   if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(&best[1], m);
 }
 
+// Structure-to-structure kClosestPairs: the k-NN rows of the query structure's points (P x k, ascending per row, -1 padded) become sort
+// keys (d2 bits << 32 | target index) with the flat position as the value; a stable radix sort then leaves the k smallest pairs in the
+// canonical order (squared distance, target index, query index) at the front.  k_pair_rows decodes them.
+__global__ void k_pair_keys(int const * __restrict__ idx, float const * __restrict__ d2, int64_t n, unsigned long long * keys, unsigned * vals)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+  {
+    keys[i] = idx[i] >= 0 ? (((unsigned long long)(unsigned)__float_as_int(d2[i]) << 32) | (unsigned)idx[i]) : ~0ull;
+    vals[i] = (unsigned)i;
+  }
+}
+__global__ void k_pair_rows(unsigned long long const * __restrict__ keys, unsigned const * __restrict__ vals, int k, int kk, long long * target, long long * query, float * d2)
+{
+  int j = blockIdx.x * blockDim.x + threadIdx.x; if (j >= kk) return;
+  bool ok = keys[j] != ~0ull;
+  target[j] = ok ? (long long)(unsigned)(keys[j] & 0xffffffffull) : -1;
+  query[j] = ok ? (long long)(vals[j] / (unsigned)k) : -1;
+  d2[j] = ok ? __int_as_float((int)(unsigned)(keys[j] >> 32)) : -1.0f;
+}
+
 // max |x| over two float arrays, as int bits (non-negative floats order like ints).
 __global__ void k_max_abs(float const * __restrict__ a, float const * __restrict__ b, int64_t n, int * out_bits)
 {

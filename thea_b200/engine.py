@@ -26,7 +26,7 @@ SYMBOLS = [
     "tgq_ray_first", "tgq_ray_any", "tgq_sdf", "tgq_icp_sums", "tgq_transform_points", "tgq_area_sample",
     "tgq_get_stats", "tgq_set_point_labels", "tgq_closest_filtered", "tgq_knn_filtered", "tgq_icp_align", "tgq_ball_range",
     "tgq_ball_stats", "tgq_visibility", "tgq_ball_graph_surface", "tgq_ball_histogram", "tgq_spin_image", "tgq_graph_contract", "tgq_graph_geodesic", "tgq_graph_fps", "tgq_set_transform",
-    "tgq_closest_records", "tgq_ray_first_records", "tgq_synchronize", "tgq_scatter_records", "tgq_bucket_records", "tgq_range_query", "tgq_closest_pair",
+    "tgq_closest_records", "tgq_ray_first_records", "tgq_synchronize", "tgq_scatter_records", "tgq_bucket_records", "tgq_range_query", "tgq_closest_pair", "tgq_k_closest_pairs",
 ]
 
 
@@ -106,6 +106,7 @@ def load_library(path=None):
     L.tgq_bucket_records.argtypes = [vp, vp, i64, i32, i64, i32, vp, i64, vp]
     L.tgq_range_query.argtypes = [vp, i32, vp, vp, i64, vp, vp, i64, vp]
     L.tgq_closest_pair.argtypes = [vp, vp, f64, vp, vp, vp, vp, vp]
+    L.tgq_k_closest_pairs.argtypes = [vp, vp, i32, f64, vp, vp, vp, vp]
     for name in SYMBOLS:
         if name not in ("tgq_last_error",):
             getattr(L, name).restype = C.c_int
@@ -369,6 +370,14 @@ class Engine:
         hist = np.empty((Q, num_bins), np.uint32)
         self._ck(self._L.tgq_ball_histogram(self._h, _ptr(c3), _ptr(rad), Q, int(num_bins), _ptr(hist)))
         return hist
+
+    def k_closest_pairs(self, query, k, dist_bound=-1.0):
+        """tgq_k_closest_pairs: BvhN::kClosestPairs between this point structure (the target) and the point structure `query`:
+        (target indices, query indices, squared distances) of the k closest pairs, ascending."""
+        t, q, d = np.empty(k, np.int64), np.empty(k, np.int64), np.empty(k, np.float32)
+        n = C.c_int32(0)
+        self._ck(self._L.tgq_k_closest_pairs(self._h, query._h, int(k), float(dist_bound), _ptr(t), _ptr(q), _ptr(d), C.byref(n)))
+        return t[:n.value], q[:n.value], d[:n.value]
 
     def closest_pair(self, query, dist_bound=-1.0):
         """tgq_closest_pair: BvhN::closestPair between this structure (the target) and the point structure `query`.
