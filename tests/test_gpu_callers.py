@@ -499,6 +499,16 @@ def test_sample_graph_shortest_paths(built):
             assert np.array_equal(c_, rc.astype(np.int32)) and np.array_equal(h_.astype(np.float64), rh)
             assert np.allclose(s_, rs, rtol=1e-12, atol=0)
         assert np.array_equal(e.graph_fps(gi, gs, 300), orc.graph_fps(gi, gs, 300).astype(np.int32))
+    # tiny graphs (fewer samples than 2 * max_degree: the contraction's pick area is larger than a queue row)
+    tiny = p[:9].copy()
+    e3 = Engine(0); e3.build_points(tiny)
+    gi, gs, gc = e3.ball_graph(16, np.float32(10.0))
+    for got, want in zip(e3.graph_contract(gi, gs, 5), orc.graph_contract(gi, gs, 5)):
+        assert np.array_equal(got, want.astype(got.dtype))
+    assert np.array_equal(e3.graph_fps(gi, gs, 9), orc.graph_fps(gi, gs, 9).astype(np.int32))
+    s_, c_, _ = e3.graph_geodesic(gi, gs, np.arange(9), np.float32(-1.0), np.float32(1.0), 0)
+    rs, rc, _ = orc.graph_geodesic(gi, gs, np.arange(9), np.float32(-1.0), np.float32(1.0), 0)
+    assert np.array_equal(c_, rc.astype(np.int32)) and np.allclose(s_, rs, rtol=1e-12, atol=0)
     # a graph with unreachable parts: two far clusters with short neighbour lists
     q = np.concatenate([p[:500], p[500:1000] + np.float32(10.0)])
     e2 = Engine(0); e2.build_points(q)

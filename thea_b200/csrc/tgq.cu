@@ -917,7 +917,8 @@ static int graph_setup(tgq_handle * h, const int32_t * idx, const float * sep, i
   workers = std::max<int64_t>(TGQ_GRAPH_WARPS, workers / TGQ_GRAPH_WARPS * TGQ_GRAPH_WARPS);
   *blocks = (int)(workers / TGQ_GRAPH_WARPS);
   size_t const n = (size_t)workers * (size_t)P;
-  CK(h->g_dist.reserve(8 * n)); CK(h->g_stamp.reserve(4 * n)); CK(h->g_touched.reserve(4 * n)); CK(h->g_queue.reserve(8 * n));
+  sc->qlen = (int)std::max<int64_t>(P, 2 * TGQ_MAX_K);
+  CK(h->g_dist.reserve(8 * n)); CK(h->g_stamp.reserve(4 * n)); CK(h->g_touched.reserve(4 * n)); CK(h->g_queue.reserve(8 * (size_t)workers * (size_t)sc->qlen));
   sc->dist = h->g_dist.as<unsigned long long>(); sc->stamp = h->g_stamp.as<int>(); sc->touched = h->g_touched.as<int>(); sc->queue = h->g_queue.as<int>();
   k_graph_init<<<h->sm_count * 8, 256, 0, s>>>(sc->dist, sc->stamp, n);
   CK(cudaGetLastError());

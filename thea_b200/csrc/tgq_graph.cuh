@@ -31,7 +31,8 @@ struct GraphScratch
   unsigned long long * dist;   // [workers x P] bit patterns of doubles, TGQ_GRAPH_INF when untouched
   int * stamp;                 // [workers x P] round in which the node was last queued, -1 when untouched
   int * touched;               // [workers x P]
-  int * queue;                 // [workers x 2 x P]
+  int * queue;                 // [workers x 2 x qlen], qlen = max(P, 2 * TGQ_MAX_K): the second half also holds the picks of the contraction
+  int qlen;
 };
 
 // Distances are updated with atomics (performed in L2): every read goes to L2 as well, never to a possibly stale L1 line.
@@ -138,7 +139,7 @@ k_graph_geodesic(GraphView g, GraphScratch sc, int const * __restrict__ seeds, i
   int const lane = threadIdx.x & 31;
   size_t const worker = (size_t)blockIdx.x * TGQ_GRAPH_WARPS + (threadIdx.x >> 5);
   unsigned long long * dist = sc.dist + worker * g.P; int * stamp = sc.stamp + worker * g.P; int * touched = sc.touched + worker * g.P;
-  int * q0 = sc.queue + worker * 2 * (size_t)g.P; int * q1 = q0 + g.P;
+  int * q0 = sc.queue + worker * 2 * (size_t)sc.qlen; int * q1 = q0 + sc.qlen;
   double const limit = max_distance < 0.0f ? -1.0 : (double)max_distance;
   double const hi = fmax((double)hist_range, 1.0e-30), bin_size = hi / (double)(num_bins > 0 ? num_bins : 1);
   for (;;)
@@ -190,7 +191,7 @@ k_graph_contract(GraphView g, GraphScratch sc, int n_orig, int * counter, int * 
   int const lane = threadIdx.x & 31, K = g.K;
   size_t const worker = (size_t)blockIdx.x * TGQ_GRAPH_WARPS + (threadIdx.x >> 5);
   unsigned long long * dist = sc.dist + worker * g.P; int * stamp = sc.stamp + worker * g.P; int * touched = sc.touched + worker * g.P;
-  int * q0 = sc.queue + worker * 2 * (size_t)g.P; int * q1 = q0 + g.P;
+  int * q0 = sc.queue + worker * 2 * (size_t)sc.qlen; int * q1 = q0 + sc.qlen;
   for (;;)
   {
     int s = 0;
