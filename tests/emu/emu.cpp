@@ -102,7 +102,13 @@ void build(Emu & E, float const * src, float const * n3)
       v3 v0 = mk3(t.q0.x, t.q0.y, t.q0.z), v1 = mk3(t.q1.x, t.q1.y, t.q1.z), v2 = mk3(t.q2.x, t.q2.y, t.q2.z);
       ObbAcc a; obb_acc_begin(a, cross3(sub3(v1, v0), sub3(v2, v0)));
       obb_acc_point(a, v0); obb_acc_point(a, v1); obb_acc_point(a, v2);
+#ifdef TGQ_NODE64
+      f4 half0[2], half1[2];
+      obb_acc_store(a, pad, ~((0 << TGQ_LEAF_BITS) | 1), half0); obb_store_empty(~0, half1);
+      obb_pack_node64(a, half0, half1, r.q);
+#else
       obb_acc_store(a, pad, ~((0 << TGQ_LEAF_BITS) | 1), r.q); obb_store_empty(~0, r.q + TGQ_OBB_F4);
+#endif
       E.obbs.assign(1, r);
       WideNode w; f4 c4[4];
       obb_acc_store_wide(a, pad, ~((0 << TGQ_LEAF_BITS) | 1), c4);
@@ -150,11 +156,21 @@ void build(Emu & E, float const * src, float const * n3)
     {
       // oriented boxes through the same helpers as k_obb_small / k_obb_big / k_emit (normal sum taken in plain order here)
       ObbNode r;
+#ifdef TGQ_NODE64
+      f4 half[2][2];
+#endif
       for (int c = 0; c < 2; ++c)
       {
         int cf = c == 0 ? f : sp + 1, cl = c == 0 ? sp : l;
         v3 sum = mk3(0, 0, 0);
-        for (int k = cf; k <= cl; ++k)
+        // both children in the frame of the NODE's normal sum: always with 64-byte nodes, else only for visit-count studies
+        // (EMU_SHARED_FRAME=1)
+#ifdef TGQ_NODE64
+        static bool const shared_frame = true;
+#else
+        static bool const shared_frame = getenv("EMU_SHARED_FRAME") != nullptr;
+#endif
+        for (int k = shared_frame ? f : cf; k <= (shared_frame ? l : cl); ++k)
         {
           TriRec const & t = E.tris[(size_t)k];
           v3 v0 = mk3(t.q0.x, t.q0.y, t.q0.z);
@@ -166,7 +182,12 @@ void build(Emu & E, float const * src, float const * n3)
           TriRec const & t = E.tris[(size_t)k];
           obb_acc_point(a, mk3(t.q0.x, t.q0.y, t.q0.z)); obb_acc_point(a, mk3(t.q1.x, t.q1.y, t.q1.z)); obb_acc_point(a, mk3(t.q2.x, t.q2.y, t.q2.z));
         }
+#ifdef TGQ_NODE64
+        obb_acc_store(a, pad, child[c], half[c]);
+        if (c == 1) obb_pack_node64(a, half[0], half[1], r.q);          // a: carries the node's frame words (same normal sum for both children)
+#else
         obb_acc_store(a, pad, child[c], r.q + TGQ_OBB_F4 * c);
+#endif
       }
       E.obbs[(size_t)newidx[(size_t)i]] = r;
     }
@@ -262,6 +283,24 @@ void emu_closest_counts(void * h, float const * q3, int64_t Q, float const * ub,
     if (E.tri && E.use_wide) closest_query_wide(v, E.pad, ld(q3, i), -1, best, bi, cp);
     else if (E.tri) closest_query<true>(v, E.pad, ld(q3, i), -1, best, bi, cp);
     else closest_query<false>(v, 0.0f, ld(q3, i), -1, best, bi, cp);
+    nodes[i] = (int32_t)(g_cnt_node - n0); prims[i] = (int32_t)(g_cnt_prim - p0);
+  }
+}
+
+// Visit counts when query i is seeded with the answer of query i - stride of the same (Morton-ordered) array: stride 1 = the
+// neighbouring query, stride 32 = what a lane of a 32-lane warp sees when queries are dealt to idle lanes one at a time
+// (tools/seed_stride_stats.py).
+void emu_closest_counts_stride(void * h, float const * q3, int64_t Q, int stride, int32_t * nodes, int32_t * prims)
+{
+  Emu & E = *(Emu *)h; BvhView v = E.view();
+  std::vector<int> ans((size_t)Q, -1);
+  for (int64_t i = 0; i < Q; ++i)
+  {
+    long long n0 = g_cnt_node, p0 = g_cnt_prim;
+    float best = INFINITY; int bi = -1; v3 cp = mk3(0, 0, 0);
+    int seed = (stride > 0 && i >= stride) ? ans[(size_t)(i - stride)] : -1;
+    closest_query<true>(v, E.pad, ld(q3, i), -1, best, bi, cp, &seed);
+    ans[(size_t)i] = seed;
     nodes[i] = (int32_t)(g_cnt_node - n0); prims[i] = (int32_t)(g_cnt_prim - p0);
   }
 }

@@ -11,7 +11,7 @@ _NAME = "libtgq_emu.so"
 
 
 def use_variant(name):
-    """Switches every later Emu to another host build of the same headers (e.g. "libtgq_emu64.so", the 64-byte-node experiment);
+    """Switches every later Emu to another host build of the same headers (e.g. "libtgq_emu96.so", the 96-byte oriented-box node);
     returns the previous name.  Existing Emu objects must be dropped first."""
     global _LIB, _NAME
     prev, _NAME, _LIB = _NAME, name, None

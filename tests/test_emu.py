@@ -321,9 +321,10 @@ def test_ball_range_query_matches_brute_force():
     assert gc[1] == 0 and gc[2] == len(p) - 1          # negative radius: nothing; huge radius: everything but self
 
 
-def test_experimental_64_byte_nodes_keep_parity_and_visit_counts():
-    """-DTGQ_NODE64: the oriented-box node with a quantised frame (octahedral normal + in-plane
-    (cos, sin), 16 bits each; bfloat16 extents) answers exactly like brute force, and opens about as many nodes as the 96-byte one."""
+def test_64_byte_nodes_keep_parity_and_visit_counts():
+    """The 64-byte oriented-box node (one fp16 frame for both children, re-orthonormalised by the decode; bfloat16 extents; the default)
+    answers exactly like brute force, and opens about as many nodes as the 96-byte node with a full-precision frame per child
+    (-DTGQ_NODE96, libtgq_emu96.so)."""
     import ctypes as C
 
     def run(variant):
@@ -354,7 +355,7 @@ def test_experimental_64_byte_nodes_keep_parity_and_visit_counts():
         finally:
             emu_lib.use_variant(prev)
 
-    base, exp = run("libtgq_emu.so"), run("libtgq_emu64.so")
+    base, exp = run("libtgq_emu96.so"), run("libtgq_emu.so")
     for (mesh, q, (i0, d0, c0), n0), (_, _, (i1, d1, c1), n1) in zip(base, exp):
         oi, od, oc = orc.Oracle(tris9=mesh).closest(q, mode=orc.MODE_BRUTE)
         for i, d, c in ((i0, d0, c0), (i1, d1, c1)):

@@ -185,7 +185,7 @@ int refit_and_emit(tgq_handle * h, cudaStream_t s)
                                                         h->nsum.as<f4>(), h->elems.as<TriRec>(), h->scene.as<SceneBox>(), h->obbinfo.as<f4>(),
                                                         h->wide_built ? h->obbinfo_w.as<f4>() : nullptr, h->big.as<int>(), h->big_count.as<int>());
       int big_grid = std::max(1, std::min(n / TGQ_SLAB_SMALL + 1, 148 * 64));
-      k_obb_big<<<big_grid, 128, 0, s>>>(h->big.as<int>(), h->big_count.as<int>(), h->first.as<int>(), h->last.as<int>(), h->nsum.as<f4>(),
+      k_obb_big<<<big_grid, 128, 0, s>>>(h->big.as<int>(), h->big_count.as<int>(), h->first.as<int>(), h->last.as<int>(), h->parent.as<int>(), h->nsum.as<f4>(),
                                          h->elems.as<TriRec>(), h->scene.as<SceneBox>(), h->obbinfo.as<f4>(), h->wide_built ? h->obbinfo_w.as<f4>() : nullptr);
       if (h->wide_built)
       k_emit_wide<<<grid_for(n - 1), TGQ_BLOCK, 0, s>>>(n, h->leaf_built, h->first.as<int>(), h->last.as<int>(), h->split.as<int>(), h->wflag.as<int>(),
@@ -197,7 +197,7 @@ int refit_and_emit(tgq_handle * h, cudaStream_t s)
                                                  h->live.as<int>(), h->newidx.as<int>(), h->pbox_lo.as<f4>(), h->pbox_hi.as<f4>(),
                                                  h->nbox_lo.as<f4>(), h->nbox_hi.as<f4>(), h->scene.as<SceneBox>(), h->nodes.as<NodeRec>(),
                                                  tri ? h->elems.as<TriRec>() : nullptr, tri ? h->obbinfo.as<f4>() : nullptr,
-                                                 tri ? h->obbs.as<ObbNode>() : nullptr);
+                                                 tri ? h->obbs.as<ObbNode>() : nullptr, tri ? h->nsum.as<f4>() : nullptr);
     h->st.total_launches += 2;
   }
   else if (n == 1)

@@ -25,17 +25,22 @@ namespace tgq {
 
 struct NodeRec { f4 q0, q1, q2, q3; };
 struct TriRec  { f4 q0, q1, q2, q3, e0, e1, e2, x; };
-// EXPERIMENTAL (-DTGQ_NODE64, off by default): 64-byte ObbNode, two float4 per child -- centre + link, then the
-// frame as an octahedral-encoded normal and an in-plane (cos, sin), 16 bits each, and the three half extents as round-up bfloat16.
-// Checked against brute force on the CPU by the host build of these headers in the test suite; not yet measured on a GPU.
+// ObbNode, the oriented-box node of the closest-point traversal on triangle structures: 64 bytes since round 2 -- ONE frame for both
+// children (fp16 axes, re-orthonormalised by the decode), two centres + links, six half extents as round-up bfloat16; layout and
+// error budget in tgq_traverse.cuh.  -DTGQ_NODE96 builds the earlier 96-byte record (a full-precision frame per child, three 256-bit
+// loads per visit instead of two): measured on B200, 64 against 96 bytes: cfg5 closest point 407 against 395 M queries/s on the 50 M
+// batch, 357 against 324 M/s on 8 M batches, 509 against 500 M/s on the 1 M-triangle mesh.
+#if !defined(TGQ_NODE96) && !defined(TGQ_NODE64)
+#define TGQ_NODE64
+#endif
 #ifdef TGQ_NODE64
-#define TGQ_OBB_F4 2              // float4 per child of an ObbNode
+#define TGQ_OBB_F4 2              // float4 per child half (unpacked build-time form); the packed node is 4 float4
 #define TGQ_OBB_LINK_F4 0         // which float4 of a child carries the link in .w
 #else
 #define TGQ_OBB_F4 3
 #define TGQ_OBB_LINK_F4 2
 #endif
-struct ObbNode { f4 q[2 * TGQ_OBB_F4]; };     // oriented boxes of both children (96 B; 64 B with TGQ_NODE64), see tgq_traverse.cuh
+struct ObbNode { f4 q[2 * TGQ_OBB_F4]; };     // oriented boxes of both children (64 B; 96 B with TGQ_NODE96), see tgq_traverse.cuh
 // 4-wide node of the closest-point traversal on triangle structures (k_closest_wide): every second level of the binary tree
 // collapsed, so a node has 2..4 children.  One query is traversed by FOUR lanes, lane i testing child i: the record is laid out so
 // that the four lanes' 256-bit loads are one contiguous, aligned 128-byte line each (two L1 wavefronts per node visit and query,

@@ -208,7 +208,11 @@ __global__ void k_obb_small(int n, int leaf, int const * __restrict__ first, int
   int f = first[x], l = last[x];
   if (l - f + 1 > TGQ_SLAB_SMALL) { big[atomicAdd(big_count, 1)] = x; return; }
   float pad = scene_decode(sb).pad;
+#ifdef TGQ_NODE64
+  f4 ns = nsum[pa];                             // 64-byte nodes: both children are measured in the frame of the node they belong to
+#else
   f4 ns = nsum[x];
+#endif
   ObbAcc a; obb_acc_begin(a, mk3(ns.x, ns.y, ns.z));
   for (int k = f; k <= l; ++k) obb_add_tri(a, tris, k);
   obb_acc_store(a, pad, 0, obbinfo + TGQ_OBB_F4 * (size_t)x);
@@ -218,14 +222,18 @@ __global__ void k_obb_small(int n, int leaf, int const * __restrict__ first, int
 // Larger nodes: one thread block per node, block-wide min / max reduction (exact, order independent).
 __global__ void __launch_bounds__(128)
 k_obb_big(int const * __restrict__ big, int const * __restrict__ big_count, int const * __restrict__ first, int const * __restrict__ last,
-          f4 const * __restrict__ nsum, TriRec const * __restrict__ tris, SceneBox const * sb, f4 * obbinfo, f4 * obbinfo_w)
+          int const * __restrict__ parent, f4 const * __restrict__ nsum, TriRec const * __restrict__ tris, SceneBox const * sb, f4 * obbinfo, f4 * obbinfo_w)
 {
   __shared__ float s_mn[4][3], s_mx[4][3];
   for (int w = blockIdx.x; w < *big_count; w += gridDim.x)
   {
     int x = big[w];
     float pad = scene_decode(sb).pad;
+#ifdef TGQ_NODE64
+    f4 ns = nsum[parent[x]];
+#else
     f4 ns = nsum[x];
+#endif
     ObbAcc a; obb_acc_begin(a, mk3(ns.x, ns.y, ns.z));
     for (int k = first[x] + threadIdx.x; k <= last[x]; k += blockDim.x) obb_add_tri(a, tris, k);
     for (int j = 0; j < 3; ++j)
@@ -252,7 +260,8 @@ k_obb_big(int const * __restrict__ big, int const * __restrict__ big_count, int 
 __global__ void k_emit(int n, int leaf, int const * __restrict__ first, int const * __restrict__ last, int const * __restrict__ split,
                        int const * __restrict__ live, int const * __restrict__ newidx, f4 const * __restrict__ pbox_lo,
                        f4 const * __restrict__ pbox_hi, f4 const * __restrict__ nbox_lo, f4 const * __restrict__ nbox_hi,
-                       SceneBox const * sb, NodeRec * nodes, TriRec const * __restrict__ tris, f4 const * __restrict__ obbinfo, ObbNode * obbs)
+                       SceneBox const * sb, NodeRec * nodes, TriRec const * __restrict__ tris, f4 const * __restrict__ obbinfo, ObbNode * obbs,
+                       f4 const * __restrict__ nsum)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n - 1 || !live[i]) return;
   float pad = scene_decode(sb).pad;
@@ -269,6 +278,35 @@ __global__ void k_emit(int n, int leaf, int const * __restrict__ first, int cons
     lo[c] = mk3(blo.x - pad, blo.y - pad, blo.z - pad); hi[c] = mk3(bhi.x + pad, bhi.y + pad, bhi.z + pad);
   }
   nodes[newidx[i]] = make_node(lo[0], hi[0], lo[1], hi[1], child[0], child[1], 0, 0);
+#ifdef TGQ_NODE64
+  if (obbs)
+  {
+    // one frame per node: the children's centres and extents (measured in this frame by k_obb_small / k_obb_big, or here for a single
+    // triangle) are packed behind it
+    f4 ns = nsum[i]; v3 nsv = mk3(ns.x, ns.y, ns.z);
+    f4 half[2][2];
+    for (int c = 0; c < 2; ++c)
+    {
+      int cf = c == 0 ? f : sp + 1, cl = c == 0 ? sp : l;
+      int inner = c == 0 ? sp : sp + 1;
+      if (cl == cf)
+      {
+        f4 const * t = (f4 const *)(tris + cf);
+        f4 q0 = __ldg(t), q1 = __ldg(t + 1), q2 = __ldg(t + 2);
+        ObbAcc a; obb_acc_begin(a, nsv);
+        obb_acc_point(a, mk3(q0.x, q0.y, q0.z)); obb_acc_point(a, mk3(q1.x, q1.y, q1.z)); obb_acc_point(a, mk3(q2.x, q2.y, q2.z));
+        obb_acc_store(a, pad, child[c], half[c]);
+      }
+      else
+      {
+        half[c][0] = obbinfo[TGQ_OBB_F4 * (size_t)inner]; half[c][1] = obbinfo[TGQ_OBB_F4 * (size_t)inner + 1];
+        half[c][0].w = __int_as_float(child[c]);
+      }
+    }
+    ObbNode r; obb_pack_node64(obb_node_frame64(nsv), half[0], half[1], r.q);
+    obbs[newidx[i]] = r;
+  }
+#else
   if (obbs)
   {
     ObbNode r;
@@ -294,6 +332,7 @@ __global__ void k_emit(int n, int leaf, int const * __restrict__ first, int cons
     }
     obbs[newidx[i]] = r;
   }
+#endif
 }
 
 // ---- 4-wide nodes (WideNode, tgq_bvh.cuh): every second level of the surviving binary tree ---------------------------------------
@@ -384,8 +423,14 @@ __global__ void k_emit_single(f4 const * pbox_lo, f4 const * pbox_hi, SceneBox c
     v3 v0 = mk3(q0.x, q0.y, q0.z), v1 = mk3(q1.x, q1.y, q1.z), v2 = mk3(q2.x, q2.y, q2.z);
     ObbAcc a; obb_acc_begin(a, cross3(sub3(v1, v0), sub3(v2, v0)));
     obb_acc_point(a, v0); obb_acc_point(a, v1); obb_acc_point(a, v2);
+#ifdef TGQ_NODE64
+    f4 half0[2], half1[2];
+    obb_acc_store(a, pad, leaf0, half0); obb_store_empty(~0, half1);
+    obb_pack_node64(a, half0, half1, r.q);
+#else
     obb_acc_store(a, pad, leaf0, r.q);
     obb_store_empty(~0, r.q + TGQ_OBB_F4);
+#endif
     obbs[0] = r;
   }
   f4 blo = pbox_lo[0], bhi = pbox_hi[0];

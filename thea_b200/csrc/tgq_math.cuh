@@ -5,6 +5,9 @@
 // -fmad=false and IEEE division / square root (nvcc defaults -prec-div=true -prec-sqrt=true).  Three-term sums use
 // Eigen's fixed-size-3 reduction order t0 + (t1 + t2).  Citations are relative to /root/reference/Code/Source/.
 #pragma once
+#ifdef __CUDACC__
+#include <cuda_fp16.h>
+#endif
 #include <stdint.h>
 #include <math.h>
 #include <float.h>

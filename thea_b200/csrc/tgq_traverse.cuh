@@ -182,79 +182,95 @@ TGQ_HD void unpack_bf16(float w, float & a, float & b)
 }
 
 #ifdef TGQ_NODE64
-// ---- 64-byte node: frame codec.  Both the build and the query decode with these very functions, so the extents are measured along
-// exactly the axes the query uses; the decoded frame is orthonormal to a few u (normalised normal, Duff et al. tangent basis,
-// normalised in-plane direction, a2 = a0 x a1), inside the relative slack of TGQ_LB_DEFLATE.
-// Reciprocal square root / reciprocal of the decode: MUFU approximations on the device (the first version normalised with IEEE
-// division and square root -- 12 divisions and 4 square roots per node visit -- and ran 33 % slower than the 96-byte node on B200).
-// Exact rounding is not needed, only that build and query run the same function on the same device.
-TGQ_HD float dec_rsqrt(float x)
+// ---- 64-byte node with ONE frame for both children --------------------------------------------------------------------------------
+// The two children of a node are neighbouring patches of the surface, so their mean normals differ by about the patch's own angular
+// size: measuring both boxes in the frame of the NODE's mean normal makes them thicker by about their own sag again.  Host counters on
+// the bench workload (tools/seed_stride_stats.py with EMU_SHARED_FRAME=1): 132 / 96 / 167 node visits per query against 135 / 95 / 161
+// with a frame per child -- no difference.  With one frame the record fits 64 bytes without any expensive decode:
+//     q0 = (c0.xyz, link0)   q1 = (c1.xyz, link1)
+//     q2 = (a0.x|a0.y, a0.z|a1.x, a1.y|a1.z as fp16 pairs, h0|h1 of child 0 as round-up bfloat16)
+//     q3 = (h2 of child 0|h0 of child 1, h1|h2 of child 1, 0, 0)
+// i.e. two 256-bit loads per node visit instead of three (the closest-point kernels are bound by L1 wavefronts, one per lane and
+// load), the third axis by ONE cross product per node instead of one per child, six half-to-float conversions.  The earlier 64-byte
+// experiments kept a frame per child (octahedral normal + in-plane angle, or a quaternion) and lost on their decode.
+// The fp16 axes are not orthonormal (components off by up to 2^-11), and a RELATIVE slack eps of the lower bound lets every box within
+// d sqrt(eps) of a far query's foot point through -- a first version that simply deflated the bound by 0.4 % opened 4-6x the nodes on
+// the bench workload.  So the decoded axes are re-orthonormalised (Gram-Schmidt with the reciprocal-square-root approximation: two
+// MUFU operations and ~20 multiply-adds per NODE, not per child), by the same function in the build -- which measures the extents
+// along the result -- and in the query.  After it |a_i|^2 = 1 +- 4 u_r and a_i . a_j = +- 4 u_r with u_r ~ 2^-22 the error of the
+// approximation: lambda_max of the Gram matrix <= 1 + 1.5e-6, covered together with the 36 u of the other relative terms by
+// TGQ_OBB_DEFLATE = 1 - 96 u.  (Host emulation: 1 / sqrtf; build and query agree on each side, which is all that is needed.)
+#define TGQ_OBB_DEFLATE 0.99999428f
+TGQ_HD float obb_rsqrt(float x)
 {
 #ifdef __CUDA_ARCH__
-  return rsqrtf(x);
+  float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 #else
   return 1.0f / sqrtf(x);
 #endif
 }
-TGQ_HD float dec_rcp(float x)
+// IEEE binary16 <-> binary32 in integer arithmetic (round to nearest even; inputs here are axis components in [-1, 1]): the same bits
+// on the host and on the device, so that build (device), emulation (host) and query (hardware conversion, exact) agree.
+TGQ_HD unsigned f32_to_f16_bits(float x)
+{
+  unsigned u = (unsigned)f2i(x), sign = (u >> 16) & 0x8000u; u &= 0x7fffffffu;
+  if (u >= 0x47800000u) return sign | 0x7bffu;                       // >= 65536 (never for unit axes): largest finite half
+  if (u < 0x38800000u)                                               // below the smallest normal half (2^-14): subnormal or zero
+  {
+    if (u < 0x33000000u) return sign;                                // < 2^-25: zero
+    unsigned e = u >> 23, m = (u & 0x7fffffu) | 0x800000u, sh = 126u - e;      // value = m * 2^(e - 150); half subnormal unit 2^-24
+    unsigned h = m >> sh, rem = m & ((1u << sh) - 1u), half = 1u << (sh - 1u);
+    if (rem > half || (rem == half && (h & 1u))) ++h;
+    return sign | h;
+  }
+  unsigned h = ((u - 0x38000000u) >> 13), rem = u & 0x1fffu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;
+  return sign | h;
+}
+TGQ_HD float f16_bits_to_f32(unsigned h)
 {
 #ifdef __CUDA_ARCH__
-  return __fdividef(1.0f, x);
+  return __half2float(__ushort_as_half((unsigned short)h));
 #else
-  return 1.0f / x;
+  unsigned sign = (h & 0x8000u) << 16, e = (h >> 10) & 0x1fu, m = h & 0x3ffu;
+  if (e == 0)
+  {
+    if (m == 0) return i2f((int)sign);
+    float v = (float)m * 5.9604644775390625e-08f;                    // m * 2^-24, exact
+    return sign ? -v : v;
+  }
+  return i2f((int)(sign | ((e + 112u) << 23) | (m << 13)));         // no infinities / NaNs are ever encoded
 #endif
 }
-TGQ_HD v3 dec_normalized(v3 a) { float z = sqn3(a); return z > 0.0f ? mul3(a, dec_rsqrt(z)) : a; }
-TGQ_HD float snorm16_dec(unsigned v) { return (float)((int)(v & 0xffffu) - 32767) * (1.0f / 32767.0f); }
-TGQ_HD unsigned snorm16_enc(float x)
+TGQ_HD unsigned pack_f16x2(float a, float b) { return f32_to_f16_bits(a) | (f32_to_f16_bits(b) << 16); }
+TGQ_HD void unpack_f16x2(unsigned w, float & a, float & b) { a = f16_bits_to_f32(w & 0xffffu); b = f16_bits_to_f32(w >> 16); }
+// The frame of a 64-byte node from its three axis words.
+TGQ_HD void obb_decode_frame64(unsigned w0, unsigned w1, unsigned w2, v3 & a0, v3 & a1, v3 & a2)
 {
-  float t = fminf(fmaxf(x, -1.0f), 1.0f) * 32767.0f;
-  int i = (int)floorf(t + 0.5f);
-  return (unsigned)(i + 32767);
+  float t0, t1;
+  unpack_f16x2(w0, a0.x, a0.y); unpack_f16x2(w1, t0, t1); a0.z = t0; a1.x = t1; unpack_f16x2(w2, a1.y, a1.z);
+  a0 = mul3(a0, obb_rsqrt(fdot3(a0, a0)));
+  float d = fdot3(a0, a1);
+  a1 = mk3(ffma(-d, a0.x, a1.x), ffma(-d, a0.y, a1.y), ffma(-d, a0.z, a1.z));
+  a1 = mul3(a1, obb_rsqrt(fdot3(a1, a1)));
+  a2 = mk3(ffma(a0.y, a1.z, -(a0.z * a1.y)), ffma(a0.z, a1.x, -(a0.x * a1.z)), ffma(a0.x, a1.y, -(a0.y * a1.x)));
 }
-TGQ_HD void oct_fold(float & ox, float & oy)
+// Both children of one 64-byte node: lower bounds (deflated), ordering keys, links.
+TGQ_HD void obb_node_bounds64(f4 const * r, v3 p, float mq, float & lb0, float & key0, int & c0, float & lb1, float & key1, int & c1)
 {
-  float tx = (1.0f - fabsf(oy)) * (ox >= 0.0f ? 1.0f : -1.0f), ty = (1.0f - fabsf(ox)) * (oy >= 0.0f ? 1.0f : -1.0f);
-  ox = tx; oy = ty;
-}
-TGQ_HD unsigned obb_encode_normal(v3 a0)
-{
-  float s = fabsf(a0.x) + fabsf(a0.y) + fabsf(a0.z);
-  float ox = a0.x / s, oy = a0.y / s;
-  if (a0.z < 0.0f) oct_fold(ox, oy);
-  return snorm16_enc(ox) | (snorm16_enc(oy) << 16);
-}
-TGQ_HD v3 obb_decode_normal(unsigned w)
-{
-  float ox = snorm16_dec(w), oy = snorm16_dec(w >> 16);
-  float oz = 1.0f - fabsf(ox) - fabsf(oy);
-  if (oz < 0.0f) oct_fold(ox, oy);
-  return dec_normalized(mk3(ox, oy, oz));
-}
-TGQ_HD void obb_tangents(v3 n, v3 & t1, v3 & t2)
-{
-  float sg = n.z >= 0.0f ? 1.0f : -1.0f;
-  float a = -dec_rcp(sg + n.z), b = n.x * n.y * a;
-  t1 = mk3(1.0f + sg * n.x * n.x * a, sg * b, -sg * n.x);
-  t2 = mk3(b, sg + n.y * n.y * a, -n.y);
-}
-TGQ_HD void obb_decode_frame(unsigned wn, unsigned wr, v3 & a0, v3 & a1, v3 & a2)
-{
-  a0 = obb_decode_normal(wn);
-  v3 t1, t2; obb_tangents(a0, t1, t2);
-  a1 = dec_normalized(add3(mul3(t1, snorm16_dec(wr)), mul3(t2, snorm16_dec(wr >> 16))));
-  a2 = cross3(a0, a1);
-}
-TGQ_HD void obb_bounds(f4 q0, f4 q1, v3 p, float mq, float & lb, float & key)
-{
-  v3 a0, a1, a2; obb_decode_frame((unsigned)f2i(q1.x), (unsigned)f2i(q1.y), a0, a1, a2);
-  float h0, h1, h2, unused; unpack_bf16(q1.z, h0, h1); unpack_bf16(q1.w, h2, unused);
-  v3 pc = sub3(p, mk3(q0.x, q0.y, q0.z));
-  float x = fmaxf(fabsf(fdot3(a0, pc)) - (h0 + mq), 0.0f);
-  float y = fmaxf(fabsf(fdot3(a1, pc)) - (h1 + mq), 0.0f);
-  float z = fmaxf(fabsf(fdot3(a2, pc)) - (h2 + mq), 0.0f);
-  lb = fdot3(mk3(x, y, z), mk3(x, y, z)) * TGQ_LB_DEFLATE;
-  key = fdot3(pc, pc);
+  v3 a0, a1, a2; obb_decode_frame64((unsigned)f2i(r[2].x), (unsigned)f2i(r[2].y), (unsigned)f2i(r[2].z), a0, a1, a2);
+  float h00, h01, h02, h10, h11, h12;
+  unpack_bf16(r[2].w, h00, h01); unpack_bf16(r[3].x, h02, h10); unpack_bf16(r[3].y, h11, h12);
+  {
+    v3 pc = sub3(p, mk3(r[0].x, r[0].y, r[0].z));
+    float x = fmaxf(fabsf(fdot3(a0, pc)) - (h00 + mq), 0.0f), y = fmaxf(fabsf(fdot3(a1, pc)) - (h01 + mq), 0.0f), z = fmaxf(fabsf(fdot3(a2, pc)) - (h02 + mq), 0.0f);
+    lb0 = fdot3(mk3(x, y, z), mk3(x, y, z)) * TGQ_OBB_DEFLATE; key0 = fdot3(pc, pc); c0 = f2i(r[0].w);
+  }
+  {
+    v3 pc = sub3(p, mk3(r[1].x, r[1].y, r[1].z));
+    float x = fmaxf(fabsf(fdot3(a0, pc)) - (h10 + mq), 0.0f), y = fmaxf(fabsf(fdot3(a1, pc)) - (h11 + mq), 0.0f), z = fmaxf(fabsf(fdot3(a2, pc)) - (h12 + mq), 0.0f);
+    lb1 = fdot3(mk3(x, y, z), mk3(x, y, z)) * TGQ_OBB_DEFLATE; key1 = fdot3(pc, pc); c1 = f2i(r[1].w);
+  }
 }
 #else
 TGQ_HD void obb_bounds(f4 q0, f4 q1, f4 q2, v3 p, float mq, float & lb, float & key)
@@ -296,19 +312,16 @@ TGQ_HD ObbFrame obb_frame(v3 nsum)
   return f;
 }
 // Extent accumulator of one oriented box.
-struct ObbAcc { ObbFrame f; float mn[3], mx[3]; unsigned wn, wr; };
+struct ObbAcc { ObbFrame f; float mn[3], mx[3]; unsigned wn, wr, wx; };      // wn, wr, wx: the frame words of a 64-byte node
 TGQ_HD void obb_acc_begin(ObbAcc & a, v3 nsum)
 {
-  a.f = obb_frame(nsum); a.wn = 0u; a.wr = 0u;
+  a.f = obb_frame(nsum); a.wn = 0u; a.wr = 0u; a.wx = 0u;
 #ifdef TGQ_NODE64
   {
-    // quantise the frame first: the extents below are then measured along the decoded axes, the ones every query will use
-    a.wn = obb_encode_normal(a.f.a0);
-    v3 n = obb_decode_normal(a.wn), t1, t2; obb_tangents(n, t1, t2);
-    float c = dot3(a.f.a1, t1), s = dot3(a.f.a1, t2), len = sqrtf(c * c + s * s);
-    if (!(len > 0.0f)) { c = 1.0f; s = 0.0f; len = 1.0f; }
-    a.wr = snorm16_enc(c / len) | (snorm16_enc(s / len) << 16);
-    obb_decode_frame(a.wn, a.wr, a.f.a0, a.f.a1, a.f.a2);
+    // the frame as the node record will carry it (fp16 axes, a2 by the cross product of the decoded ones): the extents below are then
+    // measured along exactly the axes every query uses.  The caller passes the normal sum of the NODE the box is a child of.
+    a.wn = pack_f16x2(a.f.a0.x, a.f.a0.y); a.wr = pack_f16x2(a.f.a0.z, a.f.a1.x); a.wx = pack_f16x2(a.f.a1.y, a.f.a1.z);
+    obb_decode_frame64(a.wn, a.wr, a.wx, a.f.a0, a.f.a1, a.f.a2);
   }
 #endif
   for (int j = 0; j < 3; ++j) { a.mn[j] = FLT_MAX; a.mx[j] = -FLT_MAX; }
@@ -328,8 +341,12 @@ TGQ_HD void obb_acc_store(ObbAcc const & a, float pad, int child, f4 * out4)
   float hp = TGQ_MARGIN_SCALE * pad;
   float h0 = 0.5f * (a.mx[0] - a.mn[0]) * 1.000001f + hp, h1 = 0.5f * (a.mx[1] - a.mn[1]) * 1.000001f + hp, h2 = 0.5f * (a.mx[2] - a.mn[2]) * 1.000001f + hp;
 #ifdef TGQ_NODE64
+  // child half of a 64-byte node, unpacked: (centre, link) (h0, h1, h2, -).  The decoded frame is not exactly orthonormal, so the
+  // centre's own projections are taken again and each half extent covers the measured range about THEM.
+  float s0 = dot3(a.f.a0, c), s1 = dot3(a.f.a1, c), s2 = dot3(a.f.a2, c);
+  h0 = fmaxf(a.mx[0] - s0, s0 - a.mn[0]) * 1.000001f + hp; h1 = fmaxf(a.mx[1] - s1, s1 - a.mn[1]) * 1.000001f + hp; h2 = fmaxf(a.mx[2] - s2, s2 - a.mn[2]) * 1.000001f + hp;
   out4[0].x = c.x; out4[0].y = c.y; out4[0].z = c.z; out4[0].w = i2f(child);
-  out4[1].x = i2f((int)a.wn); out4[1].y = i2f((int)a.wr); out4[1].z = pack_bf16_up(h0, h1); out4[1].w = pack_bf16_up(h2, 0.0f);
+  out4[1].x = h0; out4[1].y = h1; out4[1].z = h2; out4[1].w = 0.0f;
 #else
   out4[0].x = c.x; out4[0].y = c.y; out4[0].z = c.z; out4[0].w = h0;
   out4[1].x = a.f.a0.x; out4[1].y = a.f.a0.y; out4[1].z = a.f.a0.z; out4[1].w = pack_bf16_up(h1, h2);
@@ -375,14 +392,26 @@ TGQ_HD void obb_store_empty(int child, f4 * out4)
 #ifdef TGQ_NODE64
   // a box at an unreachable distance (the packed extents cannot be negative); its link is an empty leaf anyway
   out4[0].x = 1e30f; out4[0].y = 1e30f; out4[0].z = 1e30f; out4[0].w = i2f(child);
-  out4[1].x = i2f((int)(snorm16_enc(0.0f) | (snorm16_enc(0.0f) << 16))); out4[1].y = i2f((int)(snorm16_enc(1.0f) | (snorm16_enc(0.0f) << 16)));
-  out4[1].z = 0.0f; out4[1].w = 0.0f;
+  out4[1].x = 0.0f; out4[1].y = 0.0f; out4[1].z = 0.0f; out4[1].w = 0.0f;
   return;
 #endif
   out4[0].x = 0.0f; out4[0].y = 0.0f; out4[0].z = 0.0f; out4[0].w = -1e30f;
   out4[1].x = 1.0f; out4[1].y = 0.0f; out4[1].z = 0.0f; out4[1].w = 0.0f;
   out4[2].x = 0.0f; out4[2].y = 1.0f; out4[2].z = 0.0f; out4[2].w = i2f(child);
 }
+
+#ifdef TGQ_NODE64
+// The 64-byte record from the node's (quantised) frame and the two unpacked child halves written by obb_acc_store / obb_store_empty.
+TGQ_HD void obb_pack_node64(ObbAcc const & fr, f4 const * half0, f4 const * half1, f4 * out4)
+{
+  out4[0] = half0[0]; out4[1] = half1[0];
+  out4[2].x = i2f((int)fr.wn); out4[2].y = i2f((int)fr.wr); out4[2].z = i2f((int)fr.wx);
+  out4[2].w = pack_bf16_up(half0[1].x, half0[1].y);
+  out4[3].x = pack_bf16_up(half0[1].z, half1[1].x); out4[3].y = pack_bf16_up(half1[1].y, half1[1].z); out4[3].z = 0.0f; out4[3].w = 0.0f;
+}
+// The frame a node record carries for the normal sum `nsum` of the node's triangles (what obb_acc_begin measures along).
+TGQ_HD ObbAcc obb_node_frame64(v3 nsum) { ObbAcc a; obb_acc_begin(a, nsum); return a; }
+#endif
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Step protocol.  Every traversal advances in steps of ONE record fetch followed by arithmetic on the fetched registers:
@@ -547,9 +576,7 @@ TGQ_HD void closest_node_compute(ClosestState<TRI> & s, BvhView const & b, f4 co
   if (TRI)
   {
 #ifdef TGQ_NODE64
-    obb_bounds(r[0], r[1], s.p, s.mq, lb0, key0);
-    obb_bounds(r[2], r[3], s.p, s.mq, lb1, key1);
-    c0 = f2i(r[0].w); c1 = f2i(r[2].w);
+    obb_node_bounds64(r, s.p, s.mq, lb0, key0, c0, lb1, key1, c1);
 #else
     obb_bounds(r[0], r[1], r[2], s.p, s.mq, lb0, key0);
     obb_bounds(r[3], r[4], r[5], s.p, s.mq, lb1, key1);

@@ -29,6 +29,7 @@ def main(grid=2236, total=50_000_000, window=20000, nwin=3):
     code = morton30(q.astype(np.float64), np.asarray(b[0], np.float64), np.asarray(b[1], np.float64))
     order = np.argsort(code, kind="stable")
     print("queries sorted %.0fs" % (time.time() - t0), flush=True)
+    if os.environ.get("EMU_VARIANT"): emu_lib.use_variant(os.environ["EMU_VARIANT"])
     E = emu_lib.Emu(tris9=mesh, leaf=4); E.set_wide(False)
     print("emu built %.0fs" % (time.time() - t0), flush=True)
     L = emu_lib.lib()
@@ -36,7 +37,7 @@ def main(grid=2236, total=50_000_000, window=20000, nwin=3):
     for w in range(nwin):
         start = (w + 1) * total // (nwin + 1)
         qs = np.ascontiguousarray(q[order[start:start + window]])
-        for stride in (0, 64, 32, 8, 2, 1):
+        for stride in ((32,) if os.environ.get("EMU_ONLY32") else (0, 64, 32, 8, 2, 1)):
             nodes = np.empty(window, np.int32); prims = np.empty(window, np.int32)
             L.emu_closest_counts_stride(E.h, qs.ctypes.data_as(C.c_void_p), window, stride, nodes.ctypes.data_as(C.c_void_p), prims.ctypes.data_as(C.c_void_p))
             s = slice(64, None)
