@@ -427,11 +427,12 @@ int run_batched(tgq_handle * h, int64_t Q, Arg * args, int nargs, bool sortable,
   }
   // host-pointer calls: at least four chunks, so that the upload of one chunk, the kernels of another and the download of a third
   // overlap even when the batch is smaller than TGQ_OPT_CHUNK (a 6 M-query shard used to be ONE chunk: copy, sort, kernel, copy in series)
-  // ... but not below about 6 M queries per chunk: a smaller Morton-ordered batch is sparser and the traversal kernels lose more on it
-  // than the exposed copies cost -- and consecutive asynchronous calls overlap each other's copies anyway.  Measured on one rank's
-  // 6.25 M + 6.25 M share of the cfg5 batches through pinned host buffers (tools/e2e_shard_probe.py): four chunks per call 29.7 ms per
-  // step, two 25.9 ms, one 25.0 ms.  TGQ_DEV_MIN_CHUNK overrides the floor for experiments.
-  static int64_t const min_chunk = getenv("TGQ_DEV_MIN_CHUNK") ? atoll(getenv("TGQ_DEV_MIN_CHUNK")) : 6000000;
+  // ... but not below about 1.5 M queries per chunk (a smaller Morton-ordered batch is sparser and the traversal kernels lose more on
+  // it than the exposed copies cost).  The floor is deliberately low: on ONE GPU a rank's 6.25 M + 6.25 M share of the cfg5 batches runs
+  // faster through host buffers with one chunk per call (25.0 ms per step against 29.7 ms with four, tools/e2e_shard_probe.py), but with
+  // eight ranks on one host the unchunked calls all upload, compute and download at the same moments and the step takes 36.1 ms
+  // against 32.7 ms with four chunks per call (bench.py --gpus 8).  TGQ_DEV_MIN_CHUNK overrides the floor for experiments.
+  static int64_t const min_chunk = getenv("TGQ_DEV_MIN_CHUNK") ? atoll(getenv("TGQ_DEV_MIN_CHUNK")) : 1500000;
   int64_t nchunks = std::max<int64_t>(1, std::min<int64_t>(4, (Q + min_chunk / 2) / std::max<int64_t>(1, min_chunk)));
   int64_t chunk = all_dev ? ((int64_t)1 << 26) : std::max<int64_t>(1024, std::min<int64_t>(h->opt_chunk, ((Q + nchunks - 1) / nchunks + 1023) / 1024 * 1024));
   int nslots = all_dev ? 1 : TGQ_SLOTS;
