@@ -438,6 +438,21 @@ void emu_ball_hist(void * h, float const * c3, float const * radius, int64_t Q, 
   for (int64_t i = 0; i < Q; ++i) hist_query(v, ld(c3, i), radius[i], nbins, hist + (size_t)i * nbins);
 }
 
+#ifdef TGQ_NODE64
+// The decoded frame of a 64-byte node for a given normal sum (what both the build and the query use): three axes, row major.
+void emu_node_frame64(float const * nsum3, int64_t n, float * axes9)
+{
+  for (int64_t i = 0; i < n; ++i)
+  {
+    ObbAcc a = obb_node_frame64(ld(nsum3, i));
+    v3 d0, d1, d2; obb_decode_frame64(a.wn, a.wr, a.wx, d0, d1, d2);          // decoding the packed words again must give the same frame
+    float * o = axes9 + 9 * i;
+    o[0] = d0.x; o[1] = d0.y; o[2] = d0.z; o[3] = d1.x; o[4] = d1.y; o[5] = d1.z; o[6] = d2.x; o[7] = d2.y; o[8] = d2.z;
+    if (d0.x != a.f.a0.x || d1.y != a.f.a1.y || d2.z != a.f.a2.z) o[0] = NAN;
+  }
+}
+#endif
+
 // SpinImage (tgq_spin_image): the engine's per-pair arithmetic (spin_bins, tgq_math.cuh) over all samples of the structure.
 void emu_spin_image(void * h, float const * q3, float const * qn3, int64_t Q, int nr, int nh, float max_extent, uint32_t * image)
 {

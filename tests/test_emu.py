@@ -415,3 +415,29 @@ def test_unbounded_range_queries_ball_and_box():
     got = E.range_all(c, r)
     assert np.array_equal(got, np.flatnonzero(_in_ball_f32(p, c, r)))
     assert 9 in E.range_all(np.minimum(p[5], p[9]), np.maximum(p[5], p[9]), box=True).tolist()
+
+
+def test_64_byte_node_frame_is_orthonormal_to_the_budget():
+    """The error budget of the 64-byte node (tgq_traverse.cuh) rests on the decoded frame -- six fp16 values, Gram-Schmidt, one cross
+    product -- being orthonormal to about 1.5e-6 (largest eigenvalue of its Gram matrix <= 1 + 1.5e-6), which the deflation 1 - 96 u of
+    the oriented-box bound covers; and on build and query decoding the same words to the same frame.  Random and adversarial normal
+    sums: axis aligned, nearly aligned, tiny components (fp16 subnormals), large magnitudes."""
+    import ctypes as C
+    L = emu_lib.lib()
+    L.emu_node_frame64.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    rng = np.random.default_rng(4)
+    n = rng.standard_normal((200_000, 3)).astype(np.float32)
+    n[:1000] *= np.float32(1e-3); n[1000:2000] *= np.float32(1e4)
+    n[2000:2300] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 300)] * rng.choice([-1, 1], 300)[:, None]
+    n[2300:3300, 1:] *= np.float32(1e-5)                     # nearly axis aligned: components in the fp16 subnormal range
+    n[3300:3400] = 0                                         # cancelling normals: the frame falls back to +z
+    axes = np.empty((len(n), 3, 3), np.float32)
+    L.emu_node_frame64(n.ctypes.data_as(C.c_void_p), len(n), axes.ctypes.data_as(C.c_void_p))
+    assert np.isfinite(axes).all()
+    a = axes.astype(np.float64)
+    gram = np.einsum("nik,njk->nij", a, a)
+    lam = np.linalg.eigvalsh(gram)
+    assert lam.max() <= 1.0 + 1.5e-6 and lam.min() >= 1.0 - 1.5e-6
+    # and the frame follows the normal: the first axis is within the fp16 quantisation of the normalised normal sum
+    nn = n[:2000] / np.linalg.norm(n[:2000].astype(np.float64), axis=1, keepdims=True)
+    assert (np.einsum("ni,ni->n", a[:2000, 0], nn) > 1.0 - 1e-6).all()
