@@ -33,6 +33,7 @@
 #include <stdexcept>
 #include <string>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 namespace TheaGpu {
@@ -145,6 +146,18 @@ struct AxisAlignedBox3T
   VectorT const & getHigh() const { return hi; }
   VectorT getExtent() const { VectorT e; for (int a = 0; a < 3; ++a) e[a] = hi[a] - lo[a]; return e; }                 // AxisAlignedBoxN.hpp:288
   VectorT getCenter() const { VectorT c; for (int a = 0; a < 3; ++a) c[a] = 0.5f * (hi[a] + lo[a]); return c; }        // :274
+};
+
+/** LineSegment3 as a query object (LineSegmentN.hpp:38-92): stored as (point, direction = end1 - end0), like the reference's class.  Any
+ *  type with getEndpoint(0) and getDirection() works as a segment query -- Thea's own LineSegment3 included. */
+template <typename VectorT>
+struct LineSegment3T
+{
+  VectorT point, direction;
+  LineSegment3T() {}
+  LineSegment3T(VectorT const & end0, VectorT const & end1) : point(end0) { for (int a = 0; a < 3; ++a) direction[a] = end1[a] - end0[a]; }
+  VectorT getEndpoint(int i) const { if (i == 0) return point; VectorT e; for (int a = 0; a < 3; ++a) e[a] = point[a] + direction[a]; return e; }
+  VectorT const & getDirection() const { return direction; }
 };
 
 /** What getElements()[i] of a triangle structure offers the reference's callers (MeshBvh elements are Triangle3 objects;
@@ -326,6 +339,45 @@ class GpuBvhBase
       return (intx)k_closest_pairs.size();
     }
 
+    /** BvhN::closestPair<MetricL2>(LineSegment3, dist_bound, compatibility, get_closest_points) (BvhN.hpp:1081-1114 with a bounded,
+     *  non-structure query; per-element metric LineSegmentN.hpp:106-145 on point structures, Triangle3.hpp:495-509,559-577 on triangle
+     *  structures): query index 0, query point on the segment, target point on the element. */
+    template <typename MetricT, typename SegmentT, typename CompatibilityFunctorT = UniversalCompatibility,
+              typename = decltype(std::declval<SegmentT const &>().getDirection()), typename = decltype(std::declval<SegmentT const &>().getEndpoint(0))>
+    NeighborPair closestPair(SegmentT const & seg, double dist_bound = -1, CompatibilityFunctorT = CompatibilityFunctorT(),
+                             bool get_closest_points = false) const
+    {
+      float a[3], d[3], d2 = -1, ep[3] = {0, 0, 0}, sp[3] = {0, 0, 0}; int32_t idx = -1;
+      detail::put3(a, seg.getEndpoint(0)); detail::put3(d, seg.getDirection());
+      detail::check(h, tgq_closest_segment(h, a, d, 1, 1, dist_bound, nullptr, 0, &idx, &d2, get_closest_points ? ep : nullptr, get_closest_points ? sp : nullptr),
+                    "tgq_closest_segment");
+      if (idx < 0) return NeighborPair();
+      return NeighborPair(0, idx, (double)d2, detail::get3<VectorT>(sp), detail::get3<VectorT>(ep));
+    }
+    /** BvhN::closestElement<MetricL2>(LineSegment3, dist_bound, compatibility, &dist, &closest_point) (BvhN.hpp:1049-1063;
+     *  Tools/MeshFix/MeshFix.cpp:762): *closest_point is the point on the ELEMENT (NeighborPair::getTargetPoint). */
+    template <typename MetricT, typename SegmentT, typename CompatibilityFunctorT = UniversalCompatibility,
+              typename = decltype(std::declval<SegmentT const &>().getDirection()), typename = decltype(std::declval<SegmentT const &>().getEndpoint(0))>
+    intx closestElement(SegmentT const & seg, double dist_bound = -1, CompatibilityFunctorT c = CompatibilityFunctorT(), double * dist = nullptr,
+                        VectorT * closest_point = nullptr) const
+    {
+      NeighborPair pair = closestPair<MetricT>(seg, dist_bound, c, closest_point != nullptr);
+      if (!pair.isValid()) return -1;
+      if (dist) *dist = MetricT::invertMonotoneApprox(pair.getMonotoneApproxDistance());
+      if (closest_point) *closest_point = pair.getTargetPoint();
+      return pair.getTargetIndex();
+    }
+    /** Q segment queries in one launch: the loop of Tools/MeshFix/MeshFix.cpp:756-763 (one closestElement per boundary edge, each under
+     *  a VertexFilter) as a batch.  a3 / b3: Q x 3 endpoints (b_is_direction: b3 holds the stored directions instead); exclude: Q x
+     *  n_exclude element indices each query's filter rejects (-1 = unused, n_exclude <= 4) or null; outputs may be null; host or device
+     *  pointers. */
+    void closestElementSegmentBatch(float const * a3, float const * b3, intx Q, int32_t * idx, float * d2, float * element_point3, float * segment_point3,
+                                    double dist_bound = -1, int32_t const * exclude = nullptr, int32_t n_exclude = 0, bool b_is_direction = false) const
+    {
+      detail::check(h, tgq_closest_segment(h, a3, b3, b_is_direction ? 1 : 0, Q, dist_bound, exclude, n_exclude, idx, d2, element_point3, segment_point3),
+                    "tgq_closest_segment");
+    }
+
     /** Host-side filters cannot run on the device and there is no CPU fallback. */
     template <typename FilterT> void pushFilter(FilterT *) { throw Error("TheaGpu: element filters are not supported by the GPU structure"); }
     void popFilter() {}
@@ -350,7 +402,8 @@ class GpuMeshBvhT : public GpuBvhBase<VectorT>
     typedef typename Base::Ray3 Ray3;
 
     explicit GpuMeshBvhT(int device = 0) : Base(device), built(false) {}
-    using Base::closestPair;         // the structure-to-structure form
+    using Base::closestPair;         // the structure-to-structure and line-segment forms
+    using Base::closestElement;      // the line-segment form
 
     /** MeshBvh::addTriangles analogue: appends one triangle to the pending soup (MeshTriangles.hpp:361-370). */
     void addTriangle(VectorT const & v0, VectorT const & v1, VectorT const & v2)
@@ -545,7 +598,8 @@ class GpuPointBvhT : public GpuBvhBase<VectorT>
     typedef NNFilterT<VectorT> NNFilter;
 
     explicit GpuPointBvhT(int device = 0) : Base(device), filter(nullptr) {}
-    using Base::closestPair;         // the structure-to-structure form
+    using Base::closestPair;         // the structure-to-structure and line-segment forms
+    using Base::closestElement;      // the line-segment form
     using Base::kClosestPairs;       // likewise
 
     /** Per-element labels (P int32, element order; null clears): the `label` member of Register's samples. */

@@ -167,6 +167,23 @@ int tgq_knn_filtered(tgq_handle * h, const float * q3, const float * qn3, const 
 int tgq_ball_range(tgq_handle * h, const float * c3, const float * radius, int64_t Q, int32_t max_out, int32_t exclude_self,
                    int32_t * idx, int32_t * count);
 
+/* Q closest-element queries whose query object is a LINE SEGMENT.  Replaces Q calls of
+ *   BvhN::closestElement<MetricL2>(LineSegment3(a_i, b_i), dist_bound, ...) / closestPair<MetricL2>(segment, dist_bound, compat, true)
+ * (BvhN.hpp:1049-1114; the per-element metric is MetricL2Impl<LineSegmentN, point> -> LineSegmentN::closestPoint, LineSegmentN.hpp:106-145,
+ * on point structures and MetricL2Impl<LineSegmentN, TriangleN> -> TriangleN<3>::squaredDistance(LineSegmentN), Triangle3.hpp:495-509,559-577
+ * with Internal::closestPtSegmentSegment, LineSegmentN.hpp:262-357, on triangle structures).  This is the query loop of the T-junction
+ * repair in Tools/MeshFix/MeshFix.cpp:756-763, which pushes a VertexFilter (the edge's own endpoints and the other vertices of its faces,
+ * MeshFix.cpp:678-697) around every call: `exclude` (Q x n_exclude element indices, -1 = unused slot, n_exclude <= 4, null / 0 = none)
+ * is that filter as data.  dist_bound as in tgq_closest (the segment's bounding box takes the place of the point in the root rejection).
+ * b_is_direction = 0: b3 holds the second endpoints, the direction is taken as b_i - a_i like the LineSegment3(a, b) constructor does
+ * (LineSegmentN.hpp:56-58); != 0: b3 holds the stored direction vectors themselves (LineSegmentN::getDirection of an existing object --
+ * the segment's far end is point + direction in the reference's arithmetic, which need not be the endpoint it was built from).
+ * Outputs (each may be null): idx[Q] (-1: none), d2[Q] = fp32 squared distance (-1 when none), element_point3 / segment_point3
+ * [Q x 3] = the closest pair of points on the element and on the segment (NeighborPair::getTargetPoint / getQueryPoint).  Ties go to the
+ * lowest element index. */
+int tgq_closest_segment(tgq_handle * h, const float * a3, const float * b3, int32_t b_is_direction, int64_t Q, double dist_bound,
+                        const int32_t * exclude, int32_t n_exclude, int32_t * idx, float * d2, float * element_point3, float * segment_point3);
+
 /* Closest pair of elements between two structures.  Replaces BvhN::closestPair<MetricL2>(query_bvh, dist_bound, compatibility,
  * get_closest_points) (BvhN.hpp:1081-1114 with a structure as the query; processNeighborsBvh :1900-2009; Test/TestBvh.cpp:251-258):
  * the minimum over all (target element, query element) pairs of the reference's per-pair squared distance, accepted when

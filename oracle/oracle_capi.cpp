@@ -1,6 +1,6 @@
 // oracle_capi.cpp -- C ABI over thea_oracle.hpp for ctypes (tests/, bench.py cpu_baseline / --impl reference).
 //
-// TEST INFRASTRUCTURE ONLY (see the header of thea_oracle.hpp).  PARITY UNPINNED.
+// TEST INFRASTRUCTURE ONLY (see the header of thea_oracle.hpp: parity is pinned to the reference's own compiled code, oracle/_ref).
 #include "thea_oracle.hpp"
 
 #include <chrono>
@@ -218,6 +218,20 @@ void orc_closest(void * h, float const * q3, int64_t Q, double dist_bound, int m
       Closest r = mode == 0 ? T.closest<false>(q, dist_bound, skip)
                 : mode == 1 ? T.closest<true>(q, dist_bound, skip) : brute_closest(T, q, dist_bound, skip);
       idx[i] = r.idx; if (d2) d2[i] = r.d2; if (cp3) st3(cp3, i, r.cp);
+    }
+  });
+}
+
+// Closest element to a line-segment query object (KdTree::closest_segment): excl = Q x n_excl element indices (-1 unused) or null.
+void orc_closest_segment(void * h, float const * a3, float const * b3, int64_t Q, double dist_bound, int64_t const * excl, int n_excl, int mode,
+                         int nthreads, int64_t * idx, float * d2, float * ep3, float * sp3)
+{
+  KdTree const & T = ((Handle *)h)->tree;
+  parallel_for(Q, nthreads, [&](int64_t b, int64_t e) {
+    for (int64_t i = b; i < e; ++i)
+    {
+      KdTree::SegClosest r = T.closest_segment(mode, ld3(a3, i), ld3(b3, i), dist_bound, excl ? excl + i * n_excl : nullptr, excl ? n_excl : 0);
+      idx[i] = r.idx; if (d2) d2[i] = r.d2; if (ep3) st3(ep3, i, r.on_elem); if (sp3) st3(sp3, i, r.on_seg);
     }
   });
 }
@@ -708,6 +722,22 @@ void orc_tri_point_batch(float const * v9, float const * p3, int64_t n, float * 
 { for (int64_t i = 0; i < n; ++i) d2[i] = orc_tri_point(v9 + 9 * i, p3 + 3 * i, cp3 + 3 * i); }
 void orc_ray_tri_batch(float const * v9, float const * o3, float const * d3, int64_t n, float * t)
 { for (int64_t i = 0; i < n; ++i) t[i] = orc_ray_tri(v9 + 9 * i, o3 + 3 * i, d3 + 3 * i); }
+// Line-segment query objects: point and triangle elements against LineSegment3(a, b) (known-answer and pin tests)
+void orc_seg_point_batch(float const * a3, float const * b3, float const * p3, int64_t n, float * d2, float * sp3)
+{
+  for (int64_t i = 0; i < n; ++i)
+  { V3 sp; d2[i] = seg_point_sqdist(make_seg(ld3(a3, i), ld3(b3, i)), ld3(p3, i), sp); if (sp3) st3(sp3, i, sp); }
+}
+void orc_tri_seg_batch(float const * v9, float const * a3, float const * b3, int64_t n, float * d2, float * tp3, float * sp3)
+{
+  for (int64_t i = 0; i < n; ++i)
+  {
+    Tri t = make_tri(ld3(v9, 3 * i), ld3(v9, 3 * i + 1), ld3(v9, 3 * i + 2)); V3 tp = mk(0, 0, 0), sp = mk(0, 0, 0);
+    d2[i] = tri_seg_sqdist(t, make_seg(ld3(a3, i), ld3(b3, i)), tp, sp);
+    if (tp3) st3(tp3, i, tp);
+    if (sp3) st3(sp3, i, sp);
+  }
+}
 float orc_fast_sqrt(float x) { return fast_sqrt(x); }
 float orc_box_point_sqdist(float const * lo, float const * hi, float const * p) { Box b; b.merge(ld3(lo, 0), ld3(hi, 0)); return b.sqdist_point(ld3(p, 0)); }
 float orc_box_ray_time(float const * lo, float const * hi, float const * o, float const * d, float max_time)

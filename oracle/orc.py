@@ -50,6 +50,10 @@ def lib():
                                     C.c_void_p, C.c_void_p]
         L.orc_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
                               C.c_void_p, C.c_void_p]
+        L.orc_closest_segment.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_seg_point_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.orc_tri_seg_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_set_labels.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_closest_filtered.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_double, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p]
@@ -150,6 +154,20 @@ class Oracle:
         lib().orc_closest(self.h, _p(q), Q, float(dist_bound), mode, int(exclude_self), threads or ncores(),
                           _p(idx), _p(d2), _p(cp))
         return idx, d2, cp
+
+    def closest_segment(self, a, b, dist_bound=-1.0, exclude=None, mode=MODE_CANON, threads=None):
+        """Closest element to LineSegment3(a_i, b_i): idx, d2, point on the element, point on the segment."""
+        a = _f32(a).reshape(-1, 3)
+        b = _f32(b).reshape(-1, 3)
+        Q = a.shape[0]
+        ex = None if exclude is None else np.ascontiguousarray(exclude, np.int64).reshape(Q, -1)
+        idx = np.empty(Q, np.int64)
+        d2 = np.empty(Q, np.float32)
+        ep = np.empty((Q, 3), np.float32)
+        sp = np.empty((Q, 3), np.float32)
+        lib().orc_closest_segment(self.h, _p(a), _p(b), Q, float(dist_bound), _p(ex), 0 if ex is None else ex.shape[1], mode,
+                                  threads or ncores(), _p(idx), _p(d2), _p(ep), _p(sp))
+        return idx, d2, ep, sp
 
     def ray_first(self, o, d, tmax=None, mode=MODE_CANON, threads=None):
         o = _f32(o).reshape(-1, 3)
@@ -316,6 +334,28 @@ def tri_point(v9, p):
 
 def ray_tri(v9, o, d):
     return float(lib().orc_ray_tri(_p(_f32(v9).reshape(9)), _p(_f32(o).reshape(3)), _p(_f32(d).reshape(3))))
+
+
+def seg_point(a, b, p):
+    """LineSegment3(a_i, b_i) against point p_i: squared distance and the closest point on the segment."""
+    a, b, p = (_f32(x).reshape(-1, 3) for x in (a, b, p))
+    n = a.shape[0]
+    d2 = np.empty(n, np.float32)
+    sp = np.empty((n, 3), np.float32)
+    lib().orc_seg_point_batch(_p(a), _p(b), _p(p), n, _p(d2), _p(sp))
+    return d2, sp
+
+
+def tri_seg(v9, a, b):
+    """Triangle i against LineSegment3(a_i, b_i): squared distance, closest point on the triangle, on the segment."""
+    v9 = _f32(v9).reshape(-1, 9)
+    a, b = (_f32(x).reshape(-1, 3) for x in (a, b))
+    n = a.shape[0]
+    d2 = np.empty(n, np.float32)
+    tp = np.empty((n, 3), np.float32)
+    sp = np.empty((n, 3), np.float32)
+    lib().orc_tri_seg_batch(_p(v9), _p(a), _p(b), n, _p(d2), _p(tp), _p(sp))
+    return d2, tp, sp
 
 
 def fast_sqrt(x):

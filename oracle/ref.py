@@ -55,6 +55,9 @@ def lib():
         L.ref_closest_pair_bvh.argtypes = [vp, vp, f64, vp, vp, vp, vp, vp]
         L.ref_closest_segment.restype = i64
         L.ref_closest_segment.argtypes = [vp, vp, vp, f64, vp, vp, vp]
+        L.ref_closest_segment_batch.argtypes = [vp, vp, vp, i64, f64, vp, i32, vp, vp, vp, vp]
+        L.ref_seg_point_batch.argtypes = [vp, vp, vp, i64, vp, vp]
+        L.ref_tri_seg_batch.argtypes = [vp, vp, vp, i64, vp, vp, vp]
         L.ref_tri_cache.argtypes = [vp] * 6
         L.ref_tri_point.restype = f32
         L.ref_tri_point.argtypes = [vp, vp, vp]
@@ -194,6 +197,19 @@ class Reference:
         i = lib().ref_closest_segment(self.h, _p(_f32(a).reshape(3)), _p(_f32(b).reshape(3)), float(dist_bound), _p(d2), _p(ca), _p(cb))
         return int(i), float(d2[0]), ca, cb
 
+    def closest_segments(self, a, b, dist_bound=-1.0, exclude=None):
+        """BvhN::closestPair<MetricL2>(LineSegment3(a_i, b_i), dist_bound, ..., true) per query, under a pushed index filter:
+        idx, d2, point on the element, point on the segment."""
+        a = _f32(a).reshape(-1, 3)
+        b = _f32(b).reshape(-1, 3)
+        Q = a.shape[0]
+        ex = None if exclude is None else np.ascontiguousarray(exclude, np.int64).reshape(Q, -1)
+        idx, d2 = np.empty(Q, np.int64), np.empty(Q, np.float32)
+        ep, sp = np.empty((Q, 3), np.float32), np.empty((Q, 3), np.float32)
+        lib().ref_closest_segment_batch(self.h, _p(a), _p(b), Q, float(dist_bound), _p(ex), 0 if ex is None else ex.shape[1],
+                                        _p(idx), _p(d2), _p(ep), _p(sp))
+        return idx, d2, ep, sp
+
     def icp(self, src, min_iters=3, max_iters=10, frac_thresh=1e-4):
         s = _f32(src).reshape(-1, 3)
         tr, err = np.zeros((3, 4), np.float32), np.zeros(1, np.float32)
@@ -248,6 +264,23 @@ def ray_tri_batch(v9, o3, d3):
     t = np.empty(len(v), np.float32)
     lib().ref_ray_tri_batch(_p(v), _p(o), _p(d), len(v), _p(t))
     return t
+
+
+def seg_point_batch(a3, b3, p3):
+    a, b, p = (_f32(x).reshape(-1, 3) for x in (a3, b3, p3))
+    n = a.shape[0]
+    d2, sp = np.empty(n, np.float32), np.empty((n, 3), np.float32)
+    lib().ref_seg_point_batch(_p(a), _p(b), _p(p), n, _p(d2), _p(sp))
+    return d2, sp
+
+
+def tri_seg_batch(v9, a3, b3):
+    v = _f32(v9).reshape(-1, 9)
+    a, b = (_f32(x).reshape(-1, 3) for x in (a3, b3))
+    n = a.shape[0]
+    d2, tp, sp = np.empty(n, np.float32), np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+    lib().ref_tri_seg_batch(_p(v), _p(a), _p(b), n, _p(d2), _p(tp), _p(sp))
+    return d2, tp, sp
 
 
 def tri_cache(v9):

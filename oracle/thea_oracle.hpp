@@ -210,6 +210,88 @@ inline bool fuzzy_ne0(float a)
   return !((a == 0.0f) || std::fabs(a - 0.0f) <= tol);
 }
 
+inline bool fuzzy_eq0(float a) { return !fuzzy_ne0(a) && !std::isinf(a); }      // eps(a, b) keeps the plain epsilon for infinite operands (Math.hpp:137-138)
+
+// ------------------------------------------------------------------------------------------------
+// Line-segment query objects.  LineSegmentN stores (point, direction = end1 - end0),
+// LineSegmentN.hpp:56-58; its far end is point + direction.
+// ------------------------------------------------------------------------------------------------
+struct Seg { V3 point, direction; };
+inline Seg make_seg(V3 end0, V3 end1) { Seg s; s.point = end0; s.direction = end1 - end0; return s; }
+inline float clamp01(float x) { return x < 0 ? 0.0f : (x > 1 ? 1.0f : x); }       // Math::clamp, Math.hpp:247-252
+
+// LineSegmentN::closestPoint, LineSegmentN.hpp:106-145 (from G3D::LineSegment).
+inline V3 seg_closest_point(Seg const & g, V3 p)
+{
+  float d2 = sqnorm(g.direction);
+  if (fuzzy_eq0(d2)) return g.point;
+  V3 v = p - g.point;
+  float t = dot(g.direction, v);
+  if (t >= 0 && t <= d2) return g.point + (t / d2) * g.direction;
+  float d0_squared = sqnorm(v);
+  float d1_squared = sqnorm(v - g.direction);
+  if (d0_squared < d1_squared) return g.point;
+  return g.point + g.direction;
+}
+// MetricL2Impl<LineSegmentN, point>::closestPoints, MetricL2.hpp:210-215: cpb = p; cpa = a.closestPoint(cpb); |cpa - cpb|^2.
+inline float seg_point_sqdist(Seg const & g, V3 p, V3 & on_seg) { on_seg = seg_closest_point(g, p); return sqnorm(on_seg - p); }
+
+// Internal::closestPtSegmentSegment, LineSegmentN.hpp:262-357.
+inline float seg_seg_sqdist(V3 p1, V3 q1, bool is_line1, V3 p2, V3 q2, bool is_line2, float & s, float & t, V3 & c1, V3 & c2)
+{
+  V3 d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
+  float a = sqnorm(d1), e = sqnorm(d2), f = dot(d2, r);
+  if (fuzzy_eq0(a))
+  {
+    if (fuzzy_eq0(e)) { s = t = 0; c1 = p1; c2 = p2; return dot(c1 - c2, c1 - c2); }
+    s = 0; t = f / e;
+    if (!is_line2) t = clamp01(t);
+  }
+  else
+  {
+    float c = dot(d1, r);
+    if (fuzzy_eq0(e))
+    {
+      t = 0; s = -c / a;
+      if (!is_line1) s = clamp01(s);
+    }
+    else
+    {
+      float b = dot(d1, d2);
+      float denom = a * e - b * b;
+      if (denom != 0) { s = (b * f - c * e) / denom; if (!is_line1) s = clamp01(s); }
+      else s = 0;
+      t = (b * s + f) / e;
+      if (!is_line2)
+      {
+        if (t < 0) { t = 0; s = -c / a; if (!is_line1) s = clamp01(s); }
+        else if (t > 1) { t = 1; s = (b - c) / a; if (!is_line1) s = clamp01(s); }
+      }
+    }
+  }
+  c1 = p1 + s * d1; c2 = p2 + t * d2;
+  return sqnorm(c1 - c2);
+}
+
+// TriangleN<3>::squaredDistance(LineSegmentN, this_pt, seg_pt), Triangle3.hpp:495-509: the segment as a ray over t in [0, 1]
+// (rayIntersectionTime on the cached edges, :536-540), else squaredDistanceToPerimeter (:559-577): each edge as
+// LineSegmentN(v_i, v_j) against the query via LineSegmentN::squaredDistance(LineSegmentN) (LineSegmentN.hpp:153-164).
+inline float tri_seg_sqdist(Tri const & tri, Seg const & g, V3 & on_tri, V3 & on_seg)
+{
+  float t = ray_tri_time(g.point, g.direction, tri.v0, tri.e01, tri.e02);
+  if (t >= 0 && t <= 1) { V3 c = g.point + t * g.direction; on_tri = c; on_seg = c; return 0; }
+  V3 const vv[3] = {tri.v0, tri.v1, tri.v2};
+  float d2 = -1;
+  for (int i = 0; i < 3; ++i)
+  {
+    Seg edge = make_seg(vv[i], vv[(i + 1) % 3]);
+    V3 c1, c2; float s, u;
+    float edge_d2 = seg_seg_sqdist(edge.point, edge.point + edge.direction, false, g.point, g.point + g.direction, false, s, u, c1, c2);
+    if (d2 < 0 || edge_d2 < d2) { d2 = edge_d2; on_tri = c1; on_seg = c2; }
+  }
+  return d2;
+}
+
 // ------------------------------------------------------------------------------------------------
 // AABB: AxisAlignedBoxN.hpp:237-271 (merge), 274 (getCenter), 316-324 (scaleCentered),
 // 429-456 (squaredDistance), 576-658 (Woo ray test).
@@ -234,6 +316,14 @@ struct Box
   {
     if (null) return 0;
     V3 vmx = vmin(p, hi), vmn = vmax(p, lo);
+    V3 g = vmax(vmn - vmx, mk(0, 0, 0));
+    return sqnorm(g);
+  }
+  // squaredDistance(box) :429-442: vmax = hi.cwiseMin(other.hi), vmin = lo.cwiseMax(other.lo), |max(vmin - vmax, 0)|^2
+  float sqdist_box(Box const & o) const
+  {
+    if (null || o.null) return 0;
+    V3 vmx = vmin(hi, o.hi), vmn = vmax(lo, o.lo);
     V3 g = vmax(vmn - vmx, mk(0, 0, 0));
     return sqnorm(g);
   }
@@ -454,6 +544,77 @@ struct KdTree
     ClosestState s; s.best = bound2; s.idx = -1; s.cp = mk(0, 0, 0); s.skip = skip;
     closest_rec<Canon>(0, q, s);
     if (s.idx >= 0) { r.idx = s.idx; r.d2 = (float)s.best; r.cp = s.cp; }
+    return r;
+  }
+
+  // ---- closest element to a LineSegment3 query object: the same closestPair / processNeighbors / processNeighborsLeaf code
+  // (BvhN.hpp:1081-1114,1866-1893,2036-2089) with QueryT = LineSegmentN, a BOUNDED query: every node bound is the box-box distance
+  // between the segment's bounding box (LineSegmentN::getBounds, LineSegmentN.hpp:219-224) and the node box (:1794-1803).
+  // `excl`: element indices a pushed filter rejects (MeshFix's VertexFilter, Tools/MeshFix/MeshFix.cpp:678-697).
+  struct SegClosest { int64_t idx; float d2; V3 on_elem, on_seg; };
+  struct SegQuery { Seg g; Box qb; int64_t const * excl; int n_excl; double best; int64_t idx; V3 on_elem, on_seg; };
+  static bool seg_excluded(SegQuery const & s, int64_t e) { for (int j = 0; j < s.n_excl; ++j) if (s.excl[j] == e) return true; return false; }
+  float elem_seg_sqdist(int64_t e, Seg const & g, V3 & on_elem, V3 & on_seg) const
+  {
+    if (is_points) { on_elem = pts[(size_t)e]; return seg_point_sqdist(g, pts[(size_t)e], on_seg); }
+    return tri_seg_sqdist(tris[(size_t)e], g, on_elem, on_seg);
+  }
+  template <bool Canon> void seg_rec(int64_t ni, SegQuery & s) const
+  {
+    KdNode const & nd = nodes[(size_t)ni];
+    if (is_leaf(nd))
+    {
+      for (int64_t k = nd.begin; k < nd.begin + nd.count; ++k)
+      {
+        int64_t e = order[(size_t)k];
+        if (seg_excluded(s, e)) continue;
+        V3 oe, os; double mad = (double)elem_seg_sqdist(e, s.g, oe, os);
+        bool take = Canon ? (s.best < 0 ? (mad == mad) : (mad < s.best || (mad == s.best && s.idx >= 0 && e < s.idx)))
+                          : (s.best < 0 || mad < s.best);
+        if (take) { s.best = mad; s.idx = e; s.on_elem = oe; s.on_seg = os; }
+      }
+      return;
+    }
+    double lb[2]; int64_t ch[2] = {nd.child[0], nd.child[1]};
+    for (int c = 0; c < 2; ++c) lb[c] = (double)s.qb.sqdist_box(nodes[(size_t)ch[c]].bounds);
+    if (dist_less(lb[1], lb[0])) { std::swap(lb[0], lb[1]); std::swap(ch[0], ch[1]); }
+    for (int c = 0; c < 2; ++c)
+    {
+      bool go = Canon ? (s.best < 0 || lb[c] <= s.best) : (lb[c] < 0 || s.best < 0 || lb[c] < s.best);
+      if (go) seg_rec<Canon>(ch[c], s);
+    }
+  }
+  // The bound handling of closestPair (see closest_bound) with the query's bounding box in place of the point.
+  bool seg_bound(Box const & qb, double dist_bound, double & bound2) const
+  {
+    bound2 = -1;
+    if (!(dist_bound >= 0)) return true;
+    double lb = (double)qb.sqdist_box(nodes[0].bounds);
+    if (lb >= 0 && lb > dist_bound * dist_bound) return false;
+    float diag = norm(nodes[0].bounds.extent());
+    double fudge = std::max((double)(0.001 * diag), (double)(100 * std::numeric_limits<float>::epsilon()));
+    double eff = dist_bound + fudge;
+    bound2 = eff * eff;
+    return true;
+  }
+  // mode 0: reference order (first found wins ties), 1: canonical (lowest index), 2: brute force over all elements (canonical)
+  SegClosest closest_segment(int mode, V3 end0, V3 end1, double dist_bound, int64_t const * excl, int n_excl) const
+  {
+    SegClosest r; r.idx = -1; r.d2 = -1; r.on_elem = r.on_seg = mk(0, 0, 0);
+    if (nodes.empty()) return r;
+    SegQuery s; s.g = make_seg(end0, end1); s.excl = excl; s.n_excl = n_excl; s.idx = -1; s.on_elem = s.on_seg = mk(0, 0, 0);
+    s.qb.merge(s.g.point, s.g.point); V3 far = s.g.point + s.g.direction; s.qb.merge(far, far);
+    if (!seg_bound(s.qb, dist_bound, s.best)) return r;
+    if (mode == 0) seg_rec<false>(0, s);
+    else if (mode == 1) seg_rec<true>(0, s);
+    else
+      for (int64_t e = 0; e < size(); ++e)
+      {
+        if (seg_excluded(s, e)) continue;
+        V3 oe, os; double mad = (double)elem_seg_sqdist(e, s.g, oe, os);
+        if (s.best < 0 ? (mad == mad) : (mad < s.best || (mad == s.best && s.idx >= 0 && e < s.idx))) { s.best = mad; s.idx = e; s.on_elem = oe; s.on_seg = os; }
+      }
+    if (s.idx >= 0) { r.idx = s.idx; r.d2 = (float)s.best; r.on_elem = s.on_elem; r.on_seg = s.on_seg; }
     return r;
   }
 

@@ -296,6 +296,71 @@ int64_t ref_closest_segment(void * hv, float const * a3, float const * b3, doubl
   return ok ? (int64_t)ti : -1;
 }
 
+// The same query as a batch, under a pushed filter that rejects up to n_excl elements per query by INDEX -- what MeshFix's VertexFilter
+// (Tools/MeshFix/MeshFix.cpp:678-697) does by vertex identity.  BvhN hands a filter the element itself (elementPassesFilters,
+// BvhN.hpp:1674-1683, called with elems[index], :2044-2047), so the index is recovered from the element's address in getElements().
+// pushFilter mutates the structure (:1005-1032): one thread, as the reference's callers do.
+extern "C++" {
+namespace {
+template <typename ElemT>
+struct IndexFilter : public Filter<ElemT>
+{
+  ElemT const * base; int64_t const * excl; int n;
+  bool allows(ElemT const & e) const
+  {
+    int64_t i = (int64_t)(&e - base);
+    for (int j = 0; j < n; ++j) if (excl[j] == i) return false;
+    return true;
+  }
+};
+template <typename BvhT, typename ElemT>
+void closest_segment_impl(BvhT & bvh, float const * a3, float const * b3, int64_t Q, double dist_bound, int64_t const * excl, int n_excl,
+                          int64_t * idx, float * d2, float * ep3, float * sp3)
+{
+  for (int64_t i = 0; i < Q; ++i)
+  {
+    LineSegment3 seg(v3(a3 + 3 * i), v3(b3 + 3 * i));
+    IndexFilter<ElemT> f; f.base = bvh.numElements() > 0 ? &bvh.getElements()[0] : nullptr; f.excl = excl ? excl + i * n_excl : nullptr; f.n = excl ? n_excl : 0;
+    if (f.n > 0) bvh.pushFilter(&f);
+    auto pair = bvh.template closestPair<MetricL2>(seg, dist_bound, UniversalCompatibility(), true);
+    if (f.n > 0) bvh.popFilter();
+    bool ok = pair.isValid();
+    idx[i] = ok ? (int64_t)pair.getTargetIndex() : -1;
+    if (d2) d2[i] = ok ? (float)pair.getMonotoneApproxDistance() : -1.0f;
+    Vector3 q = ok ? pair.getQueryPoint() : Vector3::Zero(), t = ok ? pair.getTargetPoint() : Vector3::Zero();
+    for (int c = 0; c < 3; ++c) { if (ep3) ep3[3 * i + c] = t[c]; if (sp3) sp3[3 * i + c] = q[c]; }
+  }
+}
+}  // namespace
+}  // extern "C++"
+void ref_closest_segment_batch(void * hv, float const * a3, float const * b3, int64_t Q, double dist_bound, int64_t const * excl, int n_excl,
+                               int64_t * idx, float * d2, float * ep3, float * sp3)
+{
+  RefHandle * h = (RefHandle *)hv;
+  if (h->tri) closest_segment_impl<TriBvh, Triangle3>(*h->tri, a3, b3, Q, dist_bound, excl, n_excl, idx, d2, ep3, sp3);
+  else closest_segment_impl<PointBvh, Vector3>(*h->pts, a3, b3, Q, dist_bound, excl, n_excl, idx, d2, ep3, sp3);
+}
+// Per-pair metrics: MetricL2::closestPoints<3, Real>(element, LineSegment3) exactly as processNeighborsLeaf calls it (BvhN.hpp:2063)
+void ref_seg_point_batch(float const * a3, float const * b3, float const * p3, int64_t n, float * d2, float * sp3)
+{
+  for (int64_t i = 0; i < n; ++i)
+  {
+    LineSegment3 seg(v3(a3 + 3 * i), v3(b3 + 3 * i)); Vector3 p = v3(p3 + 3 * i), tp, qp;
+    d2[i] = MetricL2::closestPoints<3, Real>(p, seg, tp, qp);
+    for (int c = 0; c < 3; ++c) sp3[3 * i + c] = qp[c];
+  }
+}
+void ref_tri_seg_batch(float const * v9, float const * a3, float const * b3, int64_t n, float * d2, float * tp3, float * sp3)
+{
+  for (int64_t i = 0; i < n; ++i)
+  {
+    Triangle3 tri(v3(v9 + 9 * i), v3(v9 + 9 * i + 3), v3(v9 + 9 * i + 6));
+    LineSegment3 seg(v3(a3 + 3 * i), v3(b3 + 3 * i)); Vector3 tp = Vector3::Zero(), qp = Vector3::Zero();
+    d2[i] = MetricL2::closestPoints<3, Real>(tri, seg, tp, qp);
+    for (int c = 0; c < 3; ++c) { tp3[3 * i + c] = tp[c]; sp3[3 * i + c] = qp[c]; }
+  }
+}
+
 // ---- free functions ----------------------------------------------------------------------------------------------------------
 // Triangle cache (Triangle3.hpp:143-155): unit normal, plane offset, primary axis, area, centroid
 void ref_tri_cache(float const * v9, float * n3, float * d, int32_t * axis, float * area, float * centroid3)

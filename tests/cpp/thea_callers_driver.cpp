@@ -19,6 +19,7 @@
 #include "BoundedSortedArrayN.hpp"
 #include "BoundedSortedArray.hpp"
 #include "Graphics/GeneralMesh.hpp"
+#include "LineSegment3.hpp"
 #include "Triangle3.hpp"
 
 #include "../../include/thea_gpu/GpuBvh.hpp"
@@ -202,9 +203,39 @@ int main(int argc, char ** argv)
       }
     }
 
+    // ---- line-segment query objects: Thea's own LineSegment3 handed to both structures (the call of Tools/MeshFix/MeshFix.cpp:762) ----
+    int seg_ok = 0, nseg = 200;
+    for (int i = 0; i < nseg; ++i)
+    {
+      Vector3 a = points[(size_t)((i * 104729) % P)] + Vector3(0.004f, 0.001f, -0.003f) * (Real)(i % 7);
+      Vector3 b = points[(size_t)((i * 7919 + 13) % P)] * (i % 3 == 0 ? 1.0f : 0.02f) + a * (i % 3 == 0 ? 0.0f : 0.98f);
+      LineSegment3 seg(a, b);
+      double bound = (i % 4 == 3) ? 0.01 * (double)diag : -1.0;
+      RefPointBvh::NeighborPair pa = pref.closestPair<MetricL2>(seg, bound, UniversalCompatibility(), true);
+      GpuPointBvh::NeighborPair pb = pgpu.closestPair<MetricL2>(seg, bound, UniversalCompatibility(), true);
+      bool same = pa.isValid() == pb.isValid()
+               && (!pa.isValid() || (pa.getMonotoneApproxDistance() == pb.getMonotoneApproxDistance()
+                                     && (pa.getTargetIndex() != pb.getTargetIndex()          // exact ties: the reference keeps the first it finds
+                                         || (pa.getQueryPoint() == pb.getQueryPoint() && pa.getTargetPoint() == pb.getTargetPoint()))));
+      RefMeshBvh::NeighborPair ta = ref.closestPair<MetricL2>(seg, bound, UniversalCompatibility(), true);
+      GpuMeshBvh::NeighborPair tb = gpu.closestPair<MetricL2>(seg, bound, UniversalCompatibility(), true);
+      bool same2 = ta.isValid() == tb.isValid()
+                && (!ta.isValid() || (ta.getMonotoneApproxDistance() == tb.getMonotoneApproxDistance()
+                                      && (ta.getTargetIndex() != tb.getTargetIndex()
+                                          || (ta.getQueryPoint() == tb.getQueryPoint() && ta.getTargetPoint() == tb.getTargetPoint()))));
+      double da = -1, db = -1;
+      intx ia = pref.closestElement<MetricL2>(seg, bound, UniversalCompatibility(), &da);
+      intx ib = pgpu.closestElement<MetricL2>(seg, bound, UniversalCompatibility(), &db);
+      bool same3 = da == db && (ia == ib || ia < 0 == ib < 0);
+      seg_ok += (same && same2 && same3);
+      EXPECT(same && same2 && same3, "segment query %d: points %g vs %g, triangles %g vs %g, closestElement %ld vs %ld", i, pa.getMonotoneApproxDistance(),
+             pb.getMonotoneApproxDistance(), ta.getMonotoneApproxDistance(), tb.getMonotoneApproxDistance(), (long)ia, (long)ib);
+    }
+
     printf("{\"triangles\": %ld, \"sdf_equal\": %d, \"sdf_samples\": %ld, \"sdf_position_equal\": %d, \"sdf_position_samples\": %ld, \"icp_max_transform_diff\": %g, "
-           "\"range_sets_equal\": %d, \"nn_equal\": %d, \"knn_equal\": %d, \"queries\": %d, \"closest_pairs_equal\": %d, \"fails\": %d}\n",
-           (long)T, sdf_equal, (long)S, sdf_pos_equal, (long)(S / 4), tdiff, range_ok, nn_equal, knn_equal, nq, pair_ok, fails);
+           "\"range_sets_equal\": %d, \"nn_equal\": %d, \"knn_equal\": %d, \"queries\": %d, \"closest_pairs_equal\": %d, \"segment_queries_equal\": %d, \"segment_queries\": %d, "
+           "\"fails\": %d}\n",
+           (long)T, sdf_equal, (long)S, sdf_pos_equal, (long)(S / 4), tdiff, range_ok, nn_equal, knn_equal, nq, pair_ok, seg_ok, nseg, fails);
   }
   catch (std::exception const & e) { fprintf(stderr, "exception: %s\n", e.what()); return 4; }
   return fails ? 3 : 0;

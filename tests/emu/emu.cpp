@@ -272,6 +272,23 @@ void emu_closest(void * h, float const * q3, int64_t Q, double dist_bound, int e
   }
 }
 
+// Closest element to a line-segment query object, as tgq.cu: tgq_closest_segment drives it (gate on the segment's bounding box).
+void emu_closest_segment(void * h, float const * a3, float const * b3, int64_t Q, double dist_bound, int32_t const * excl, int n_excl,
+                         int32_t * idx, float * d2, float * ep3, float * sp3)
+{
+  Emu & E = *(Emu *)h; BvhView v = E.view();
+  float bound_ub; BoundGate gate; closest_bound_gate(E.lo, E.hi, dist_bound, bound_ub, gate);
+  for (int64_t i = 0; i < Q; ++i)
+  {
+    v3 a = ld(a3, i), b = sub3(ld(b3, i), a), far = add3(a, b);        // b: the direction, as LineSegment3(end0, end1) stores it
+    float best = gated_ub_box(gate, min3(a, far), max3(a, far), bound_ub); int bi = -1; v3 ep = mk3(0, 0, 0), sp = mk3(0, 0, 0);
+    if (E.tri) seg_query<true>(v, E.pad, a, b, excl ? excl + i * n_excl : nullptr, excl ? n_excl : 0, best, bi, ep, sp);
+    else seg_query<false>(v, E.pad, a, b, excl ? excl + i * n_excl : nullptr, excl ? n_excl : 0, best, bi, ep, sp);
+    idx[i] = bi; d2[i] = bi >= 0 ? best : -1.0f;
+    ep3[3 * i] = ep.x; ep3[3 * i + 1] = ep.y; ep3[3 * i + 2] = ep.z; sp3[3 * i] = sp.x; sp3[3 * i + 1] = sp.y; sp3[3 * i + 2] = sp.z;
+  }
+}
+
 // Per-query visit counts (development aid for studying pruning quality).
 void emu_closest_counts(void * h, float const * q3, int64_t Q, float const * ub, int32_t * nodes, int32_t * prims)
 {

@@ -105,6 +105,19 @@ class Emu:
         lib().emu_closest(self.h, _p(q), Q, float(dist_bound), flag, _p(idx), _p(d2), _p(cp))
         return idx, d2, cp
 
+    def closest_segment(self, a, b, dist_bound=-1.0, exclude=None):
+        """Closest element to LineSegment3(a_i, b_i): idx, d2, point on the element, point on the segment."""
+        L = lib()
+        L.emu_closest_segment.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_int] + [C.c_void_p] * 4
+        a = np.ascontiguousarray(a, np.float32).reshape(-1, 3)
+        b = np.ascontiguousarray(b, np.float32).reshape(-1, 3)
+        Q = len(a)
+        ex = None if exclude is None else np.ascontiguousarray(exclude, np.int32).reshape(Q, -1)
+        idx, d2 = np.empty(Q, np.int32), np.empty(Q, np.float32)
+        ep, sp = np.empty((Q, 3), np.float32), np.empty((Q, 3), np.float32)
+        L.emu_closest_segment(self.h, _p(a), _p(b), Q, float(dist_bound), _p(ex), 0 if ex is None else ex.shape[1], _p(idx), _p(d2), _p(ep), _p(sp))
+        return idx, d2, ep, sp
+
     def range_all(self, a, b, box=False):
         """All elements in Ball3(a, b) or AxisAlignedBox3(a, b): ascending element indices."""
         L = lib()

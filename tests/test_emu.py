@@ -441,3 +441,37 @@ def test_64_byte_node_frame_is_orthonormal_to_the_budget():
     # and the frame follows the normal: the first axis is within the fp16 quantisation of the normalised normal sum
     nn = n[:2000] / np.linalg.norm(n[:2000].astype(np.float64), axis=1, keepdims=True)
     assert (np.einsum("ni,ni->n", a[:2000, 0], nn) > 1.0 - 1e-6).all()
+
+
+@pytest.mark.parametrize("kind", ["triangles", "points"])
+def test_line_segment_queries_equal_brute_force(kind):
+    """the segment traversal of tgq_traverse.cuh (SegState: box-box and centre-sphere bounds with the margins of its
+    error budget, on the LBVH) returns the canonical answer -- the oracle's exhaustive minimum of the reference's per-element value -- with
+    distance bounds, per-query exclusions, zero-length segments and exact ties."""
+    rng = np.random.default_rng(31)
+    Q = 4000
+    if kind == "triangles":
+        elems = gen.torus_mesh(28)
+        lo, hi = gen.mesh_bounds(elems)
+        lo, hi = float(np.min(lo)) * 1.3, float(np.max(hi)) * 1.3
+        e, ora, n, bound = emu_lib.Emu(tris9=elems), orc.Oracle(tris9=elems), len(elems), 0.12
+    else:
+        elems = rng.uniform(-1, 1, (30000, 3)).astype(np.float32)
+        elems[7000:7300] = elems[100:400]
+        lo, hi = -1.2, 1.2
+        e, ora, n, bound = emu_lib.Emu(points=elems), orc.Oracle(points=elems), len(elems), 0.04
+    a = rng.uniform(lo, hi, (Q, 3)).astype(np.float32)
+    d = rng.standard_normal((Q, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    b = (a + d * rng.choice([0.0, 1e-3, 0.05, 0.4, 3.0], (Q, 1))).astype(np.float32)
+    excl = rng.integers(0, n, (Q, 4))
+    excl[::3, 1:] = -1
+    excl[::2, 0] = ora.closest_segment(a, b, mode=orc.MODE_BRUTE)[0][::2]
+    for db in (-1.0, bound):
+        for ex in (None, excl):
+            got = e.closest_segment(a, b, db, ex)
+            want = ora.closest_segment(a, b, db, ex, mode=orc.MODE_BRUTE)
+            assert np.array_equal(got[0], want[0].astype(np.int32))
+            assert np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32))
+            found = want[0] >= 0
+            assert np.array_equal(got[2][found], want[2][found]) and np.array_equal(got[3][found], want[3][found])
+    assert 0 < (want[0] >= 0).sum() < Q

@@ -259,3 +259,26 @@ def test_icp_translation_only_converges_for_a_few_steps():
     src = (p + np.array([0.01, -0.005, 0.008], np.float32)).astype(np.float32)
     errs = [ora.icp(src, min_iters=k, max_iters=k, mode=orc.MODE_CANON)[1] for k in (1, 2)]
     assert errs[1] < errs[0]
+
+
+def test_line_segment_known_answers():
+    """Hand-derivable answers of the segment metrics (LineSegmentN.hpp:106-145,262-357; Triangle3.hpp:495-509,559-577)."""
+    f = np.float32
+    # point against the segment (0,0,0)-(2,0,0): interior projection, beyond either end, zero-length segment
+    a = np.array([[0, 0, 0]] * 3 + [[1, 1, 1]], f); b = np.array([[2, 0, 0]] * 3 + [[1, 1, 1]], f)
+    p = np.array([[1, 3, 0], [-1, 0, 0], [5, 4, 0], [1, 1, 3]], f)
+    d2, sp = orc.seg_point(a, b, p)
+    assert d2.tolist() == [9.0, 1.0, 25.0, 4.0]
+    assert sp.tolist() == [[1, 0, 0], [0, 0, 0], [2, 0, 0], [1, 1, 1]]
+    # triangle (0,0,0) (4,0,0) (0,4,0): a piercing segment (distance 0 at the hit point), a parallel segment one unit above an edge
+    # region, a segment whose nearest feature is a vertex, and one that stops short of the plane above the interior
+    tri = np.array([[0, 0, 0, 4, 0, 0, 0, 4, 0]] * 4, f)
+    a = np.array([[1, 1, 1], [1, -2, 1], [6, -1, 0], [1, 1, 3]], f)
+    b = np.array([[1, 1, -1], [3, -2, 1], [8, -3, 0], [1, 1, 2]], f)
+    d2, tp, sp = orc.tri_seg(tri, a, b)
+    assert d2[0] == 0.0 and tp[0].tolist() == [1, 1, 0] and sp[0].tolist() == [1, 1, 0]
+    assert d2[1] == 5.0 and tp[1][1] == 0.0 and sp[1][1] == -2.0 and sp[1][2] == 1.0
+    assert d2[2] == 5.0 and tp[2].tolist() == [4, 0, 0] and sp[2].tolist() == [6, -1, 0]
+    # the reference measures the perimeter only when the ray test misses: a segment ending above the interior gets its distance to
+    # the nearest EDGE, not to the face (Triangle3.hpp:495-509 -- reproduced, not fixed)
+    assert d2[3] == 5.0 and sp[3].tolist() == [1, 1, 2]

@@ -330,3 +330,77 @@ def test_k_closest_pairs_between_point_structures():
         assert [(int(t), int(q)) for t, q in zip(ti, qi)] == [(t, q) for _, t, q in rows]
         assert np.array_equal(d2, np.array([r[0] for r in rows], np.float32))
     assert 0 < len(R.k_closest_pairs(Q, 16, 0.0052)[0]) < 16          # the bound bites
+
+
+def _segment_cases(rng, n, lo=-1.0, hi=1.0):
+    """Segments of mixed length (some of zero length, some built from far apart endpoints) in the box [lo, hi]^3."""
+    a = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    d = rng.standard_normal((n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    b = (a + d * rng.choice([1e-4, 1e-2, 0.3, 2.0], (n, 1))).astype(np.float32)
+    b[::97] = a[::97]
+    return a, b
+
+
+def test_line_segment_query_arithmetic_matches_reference():
+    """SURVEY 8f rank 4, per-pair: MetricL2::closestPoints(point, LineSegment3) -> LineSegmentN::closestPoint (LineSegmentN.hpp:106-145)
+    and MetricL2::closestPoints(Triangle3, LineSegment3) -> TriangleN<3>::squaredDistance(LineSegmentN) (Triangle3.hpp:495-509,559-577,
+    LineSegmentN.hpp:262-357), called exactly as BvhN::processNeighborsLeaf calls them (BvhN.hpp:2063), 10^6 pairs each: squared distance
+    and both closest points bit for bit, degenerate segments and triangles included."""
+    rng = np.random.default_rng(21)
+    n = 1_000_000
+    a, b = _segment_cases(rng, n)
+    p = rng.uniform(-1.5, 1.5, (n, 3)).astype(np.float32)
+    p[::53] = a[::53]
+    d_o, s_o = orc.seg_point(a, b, p)
+    d_r, s_r = ref.seg_point_batch(a, b, p)
+    assert _same(d_o, d_r) and _same(s_o, s_r)
+    v = _triangle_cases(rng, n)
+    a, b = _segment_cases(rng, n, 0.0, 1.0)
+    a = (a * np.float32(10.0) ** rng.integers(-3, 3, size=(n, 1))).astype(np.float32)
+    # a share of segments that pierce their triangle (the ray-test branch) and of segments lying in the triangle's plane
+    k = n // 4
+    c = (v[:k, 0:3] + v[:k, 3:6] + v[:k, 6:9]) / np.float32(3.0)
+    nrm = np.cross(v[:k, 3:6] - v[:k, 0:3], v[:k, 6:9] - v[:k, 0:3])
+    a[:k] = (c + nrm * np.float32(0.7)).astype(np.float32)
+    b[:k] = (c - nrm * rng.uniform(0.2, 1.5, (k, 1)) + rng.standard_normal((k, 3)) * 1e-3 * np.abs(c)).astype(np.float32)
+    a[k:k + k // 2] = v[k:k + k // 2, 0:3] * np.float32(1.5) - v[k:k + k // 2, 3:6] * np.float32(0.5)       # in the plane, through v0
+    d_o, t_o, s_o = orc.tri_seg(v, a, b)
+    d_r, t_r, s_r = ref.tri_seg_batch(v, a, b)
+    assert _same(d_o, d_r) and _same(t_o, t_r) and _same(s_o, s_r)
+    assert (d_r == 0).sum() > n // 10 and (d_r > 0).sum() > n // 3       # both branches are exercised
+
+
+@pytest.mark.parametrize("kind", ["triangles", "points"])
+def test_line_segment_queries_match_reference_bvh(kind):
+    """BvhN::closestPair<MetricL2>(LineSegment3, dist_bound, compat, true) on Thea's own BvhN (a bounded query object: box-box node
+    bounds, BvhN.hpp:1794-1803; root rejection and bound widening :1081-1114), with and without a pushed element filter that rejects
+    elements by identity (Tools/MeshFix/MeshFix.cpp:678-697,756-763), against the oracle's reference-order traversal: index, squared
+    distance and both closest points bit for bit; the canonical answer equals brute force."""
+    rng = np.random.default_rng(22)
+    Q = 3000
+    if kind == "triangles":
+        elems = gen.torus_mesh(24)
+        lo, hi = gen.mesh_bounds(elems)
+        a, b = _segment_cases(rng, Q, float(np.min(lo)) * 1.3, float(np.max(hi)) * 1.3)
+        R, ora, n, bound = ref.Reference(tris9=elems), orc.Oracle(tris9=elems), len(elems), 0.15
+    else:
+        elems = rng.uniform(-1, 1, (20000, 3)).astype(np.float32)
+        elems[5000:5200] = elems[4000:4200]                     # duplicates: exact ties
+        a, b = _segment_cases(rng, Q, -1.2, 1.2)
+        R, ora, n, bound = ref.Reference(points=elems), orc.Oracle(points=elems), len(elems), 0.05
+    excl = rng.integers(0, n, (Q, 3))
+    excl[::4] = -1
+    # every third query excludes what it would otherwise have found (the filter must change the answer)
+    first = R.closest_segments(a, b)[0]
+    excl[::3, 0] = first[::3]
+    for db in (-1.0, bound):
+        for ex in (None, excl):
+            r = R.closest_segments(a, b, db, ex)
+            o = ora.closest_segment(a, b, db, ex, mode=orc.MODE_REFERENCE)
+            assert np.array_equal(r[0], o[0]) and _same(r[1], o[1]) and _same(r[2], o[2]) and _same(r[3], o[3])
+            c = ora.closest_segment(a, b, db, ex, mode=orc.MODE_CANON)
+            bf = ora.closest_segment(a, b, db, ex, mode=orc.MODE_BRUTE)
+            assert np.array_equal(c[0], bf[0]) and _same(c[1], bf[1]) and _same(c[1], o[1])
+            if ex is not None:
+                assert not (r[0][::3] == first[::3]).any() or (first[::3] < 0).any()
+    assert 0 < (R.closest_segments(a, b, bound)[0] >= 0).sum() < Q          # the bound bites

@@ -854,6 +854,40 @@ int tgq_closest_filtered(tgq_handle * h, const float * q3, const float * qn3, co
   return closest_common(h, q3, qn3, qlabel, min_dot, Q, dist_bound, 0, idx, d2, cp3);
 }
 
+int tgq_closest_segment(tgq_handle * h, const float * a3, const float * b3, int32_t b_is_direction, int64_t Q, double dist_bound, const int32_t * exclude, int32_t n_exclude,
+                        int32_t * idx, float * d2, float * element_point3, float * segment_point3)
+{
+  CKRC(need_built(h, (1 << TGQ_KIND_TRIANGLES) | (1 << TGQ_KIND_POINTS)));
+  if (Q < 0 || (Q > 0 && (!a3 || !b3))) return fail(h, TGQ_EINVAL, "tgq_closest_segment: bad arguments");
+  if (n_exclude < 0 || n_exclude > TGQ_SEG_EXCL || (n_exclude > 0 && !exclude)) return fail(h, TGQ_ELIMIT, "tgq_closest_segment: at most 4 excluded elements per query");
+  Guard g(h);
+  float ub; BoundGate gate; closest_bound_gate(h->lo, h->hi, dist_bound, ub, gate);     // BvhN::closestPair's root rejection and bound widening
+  if (n_exclude == 0) exclude = nullptr;
+  Arg args[7] = {{a3, nullptr, 12}, {b3, nullptr, 12}, {exclude, nullptr, 4 * (size_t)std::max(1, n_exclude)}, {nullptr, idx, 4}, {nullptr, d2, 4},
+                 {nullptr, element_point3, 12}, {nullptr, segment_point3, 12}};
+  BvhView v = view_of(h); bool tri = h->kind == TGQ_KIND_TRIANGLES;
+  size_t smem = trav_smem_bytes(2);
+  return run_batched(h, Q, args, 7, true, [&](ChunkCtx & c) -> int {
+    int grid = 0; int * cnt = c.slot->counter.as<int>();
+    if (tri)
+    {
+      CKRC(persistent_grid(h, k_closest_seg<true>, smem, c.n, cnt, c.stream, &grid));
+      k_closest_seg<true><<<grid, TGQ_BLOCK, smem, c.stream>>>(v, h->pad, (float const *)c.din[0], (float const *)c.din[1], c.perm, c.n, b_is_direction, ub, gate,
+                                                             (int const *)c.din[2], n_exclude, cnt, (int *)c.dout[3], (float *)c.dout[4],
+                                                             (float *)c.dout[5], (float *)c.dout[6]);
+    }
+    else
+    {
+      CKRC(persistent_grid(h, k_closest_seg<false>, smem, c.n, cnt, c.stream, &grid));
+      k_closest_seg<false><<<grid, TGQ_BLOCK, smem, c.stream>>>(v, h->pad, (float const *)c.din[0], (float const *)c.din[1], c.perm, c.n, b_is_direction, ub, gate,
+                                                              (int const *)c.din[2], n_exclude, cnt, (int *)c.dout[3], (float *)c.dout[4],
+                                                              (float *)c.dout[5], (float *)c.dout[6]);
+    }
+    h->st.last_launches += 1; h->st.total_launches += 1;
+    return TGQ_OK;
+  });
+}
+
 int tgq_closest_pair(tgq_handle * h, tgq_handle * query, double dist_bound, int64_t * target_index, int64_t * query_index, float * d2, float * query_point3,
                      float * target_point3)
 {

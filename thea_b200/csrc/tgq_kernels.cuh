@@ -1870,6 +1870,62 @@ k_ray(BvhView b, float const * __restrict__ o3, float const * __restrict__ d3, f
   warp_run(w, n, counter, stage);
 }
 
+// ---- closest element to a line-segment query object (SegState in tgq_traverse.cuh) ------------------------
+template <bool TRI>
+struct SegW
+{
+  static constexpr int STAGE = 2;       // (endpoint 0, query index) (endpoint 1 or direction, -)
+  SegState<TRI> s; BvhView b; float scene_pad; float const * a3; float const * b3; uint32_t const * perm; float ub; BoundGate gate;
+  int const * excl; int n_excl; int dir_form;
+  int * idx; float * d2; float * ep3; float * sp3; int qi;
+  __device__ __forceinline__ int state() const { return s.t.cur; }
+  __device__ __forceinline__ void stage(int t, f4 * dst) const
+  {
+    int i = perm ? (int)perm[t] : t; v3 a = ld3(a3, i), e = ld3(b3, i);
+    dst[0] = make_float4(a.x, a.y, a.z, __int_as_float(i));
+    dst[1] = make_float4(e.x, e.y, e.z, 0.0f);
+  }
+  __device__ __forceinline__ void begin(int, f4 const * src)
+  {
+    f4 a = src[0], e = src[1]; qi = __float_as_int(a.w);
+    v3 p0 = mk3(a.x, a.y, a.z), p1 = mk3(e.x, e.y, e.z);
+    seg_begin(s, b, scene_pad, p0, dir_form ? p1 : sub3(p1, p0), ub);
+    s.best_d2 = gated_ub_box(gate, s.blo, s.bhi, ub);
+    if (excl)
+    {
+#pragma unroll
+      for (int j = 0; j < TGQ_SEG_EXCL; ++j) if (j < n_excl) s.excl[j] = excl[(int64_t)qi * n_excl + j];
+    }
+  }
+  static constexpr int FETCH = TGQ_FETCH_BOX;
+  __device__ __forceinline__ void pop_step() { trav_pop_step(s.t, s.best_d2); }
+  __device__ __forceinline__ void fetch(f4 * r) const { seg_fetch(s, b, r); }
+  __device__ __forceinline__ void node_compute(f4 const * r) { seg_node_compute(s, b, r); }
+  __device__ __forceinline__ void leaf_compute(f4 const * r) { seg_leaf_compute(s, b, r); }
+  __device__ __forceinline__ void finish()
+  {
+    if (idx) idx[qi] = s.best_idx;
+    if (d2) d2[qi] = s.best_idx >= 0 ? s.best_d2 : -1.0f;
+    if (ep3) st3(ep3, qi, s.best_ep);
+    if (sp3) st3(sp3, qi, s.best_sp);
+    s.t.cur = TGQ_ST_IDLE;
+  }
+};
+
+template <bool TRI>
+__global__ void __launch_bounds__(TGQ_BLOCK)
+k_closest_seg(BvhView b, float scene_pad, float const * __restrict__ a3, float const * __restrict__ b3, uint32_t const * __restrict__ perm, int n,
+              int dir_form, float bound_ub, BoundGate gate, int const * __restrict__ excl, int n_excl, int * counter, int * idx, float * d2, float * ep3,
+              float * sp3)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  SegW<TRI> w;
+  w.b = b; w.scene_pad = scene_pad; w.a3 = a3; w.b3 = b3; w.perm = perm; w.ub = bound_ub; w.gate = gate; w.excl = excl; w.n_excl = n_excl; w.dir_form = dir_form;
+  w.idx = idx; w.d2 = d2; w.ep3 = ep3; w.sp3 = sp3; w.qi = 0; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
+  f4 * stage = trav_setup(w.s.t, st, smem, SegW<TRI>::STAGE, nullptr);
+  warp_run(w, n, counter, stage);
+}
+
 // SDF cone rays (ShapeDiameter.hpp:168-220): thread = (sample, ray).  valid = hit && (!interior || n_hit . dir >= 0).
 __constant__ float c_cone_dirs[30][3] = {
   { 0.407497f,  0.134086f,  0.903309f}, { 0.128722f, -0.822715f,  0.553688f}, { 0.359298f,  0.686129f,  0.632560f},

@@ -256,6 +256,88 @@ TGQ_HD float ray_tri_time(v3 o, v3 D, v3 v0, v3 e01, v3 e02)
   return q / DdN;
 }
 
+// ---- Line-segment query objects -----------------------------------------------------------------
+// Math::fuzzyEq(a, 0) with the default tolerance eps(a, 0) (Math.hpp:131-148): FLT_EPSILON, scaled by |a| above 1; an infinite
+// operand keeps the unscaled epsilon (so inf is never "equal"), NaN compares false everywhere.
+TGQ_HD bool fuzzy_eq0(float a)
+{
+  if (a == 0.0f) return true;
+  float mag = fabsf(a);
+  float tol = (!isinf(a) && mag > 1.0f) ? mag * FLT_EPSILON : FLT_EPSILON;
+  return mag <= tol;
+}
+// Math::clamp(x, 0, 1) (Math.hpp:247-252): NaN passes through.
+TGQ_HD float clamp01(float x) { return x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x); }
+
+// LineSegmentN::closestPoint (LineSegmentN.hpp:106-145).  The segment is (point, direction) with direction = endpoint 1 - endpoint 0 as
+// its constructor stores it (:56-58); the far end is point + direction, which need not equal the endpoint that was passed in.
+TGQ_HD v3 seg_closest_point(v3 point, v3 dir, v3 p)
+{
+  float d2 = sqn3(dir);
+  if (fuzzy_eq0(d2)) return point;
+  v3 v = sub3(p, point);
+  float t = dot3(dir, v);
+  if (t >= 0.0f && t <= d2) return add3(point, mul3(dir, t / d2));
+  float d0 = sqn3(v), d1 = sqn3(sub3(v, dir));
+  return d0 < d1 ? point : add3(point, dir);
+}
+// MetricL2Impl<LineSegmentN, point>::closestPoints (Algorithms/MetricL2.hpp:210-215): squared distance of a point element from the segment.
+TGQ_HD float seg_point_sqdist(v3 point, v3 dir, v3 p, v3 & seg_pt)
+{ seg_pt = seg_closest_point(point, dir, p); return sqn3(sub3(seg_pt, p)); }
+
+// Internal::closestPtSegmentSegment (LineSegmentN.hpp:262-357; Ericson's routine with the reference's fuzzy degeneracy tests).
+TGQ_HD float seg_seg_sqdist(v3 p1, v3 q1, bool line1, v3 p2, v3 q2, bool line2, float & s, float & t, v3 & c1, v3 & c2)
+{
+  v3 d1 = sub3(q1, p1), d2 = sub3(q2, p2), r = sub3(p1, p2);
+  float a = sqn3(d1), e = sqn3(d2), f = dot3(d2, r);
+  if (fuzzy_eq0(a))
+  {
+    if (fuzzy_eq0(e)) { s = t = 0.0f; c1 = p1; c2 = p2; v3 w = sub3(c1, c2); return dot3(w, w); }
+    s = 0.0f; t = f / e;
+    if (!line2) t = clamp01(t);
+  }
+  else
+  {
+    float c = dot3(d1, r);
+    if (fuzzy_eq0(e)) { t = 0.0f; s = -c / a; if (!line1) s = clamp01(s); }
+    else
+    {
+      float b = dot3(d1, d2);
+      float denom = a * e - b * b;
+      if (denom != 0.0f) { s = (b * f - c * e) / denom; if (!line1) s = clamp01(s); }
+      else s = 0.0f;
+      t = (b * s + f) / e;
+      if (!line2)
+      {
+        if (t < 0.0f) { t = 0.0f; s = -c / a; if (!line1) s = clamp01(s); }
+        else if (t > 1.0f) { t = 1.0f; s = (b - c) / a; if (!line1) s = clamp01(s); }
+      }
+    }
+  }
+  c1 = add3(p1, mul3(d1, s)); c2 = add3(p2, mul3(d2, t));
+  return sqn3(sub3(c1, c2));
+}
+
+// TriangleN<3>::squaredDistance(LineSegmentN, &this_pt, &seg_pt) (Triangle3.hpp:495-509) with squaredDistanceToPerimeter (:559-577):
+// zero when the segment, cast as a ray over t in [0, 1], hits the triangle; else the nearest of the three edges, each an edge
+// LineSegment (v_i, v_j - v_i) against the query through LineSegmentN::squaredDistance(LineSegmentN) (LineSegmentN.hpp:153-164), whose
+// far ends are point + direction on both sides.
+TGQ_HD float tri_seg_sqdist(v3 v0, v3 v1, v3 v2, v3 sp, v3 sdir, v3 & tri_pt, v3 & seg_pt)
+{
+  float t = ray_tri_time(sp, sdir, v0, sub3(v1, v0), sub3(v2, v0));
+  if (t >= 0.0f && t <= 1.0f) { v3 c = add3(sp, mul3(sdir, t)); tri_pt = c; seg_pt = c; return 0.0f; }
+  float d2 = -1.0f;
+  v3 sq = add3(sp, sdir);
+  for (int i = 0; i < 3; ++i)
+  {
+    v3 a = i == 0 ? v0 : (i == 1 ? v1 : v2), b = i == 0 ? v1 : (i == 1 ? v2 : v0);
+    v3 c1, c2; float s_, t_;
+    float ed2 = seg_seg_sqdist(a, add3(a, sub3(b, a)), false, sp, sq, false, s_, t_, c1, c2);
+    if (d2 < 0.0f || ed2 < d2) { d2 = ed2; tri_pt = c1; seg_pt = c2; }
+  }
+  return d2;
+}
+
 // ---- Math::fastSqrt (Math.hpp:194-223) -------------------------------------------------------------------------
 TGQ_HD float fast_sqrt(float x)
 {

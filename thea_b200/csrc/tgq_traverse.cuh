@@ -1485,4 +1485,146 @@ TGQ_HD void ball_graph_surface_query(BvhView const & b, BvhView const & surf, v3
   set.n = s.set.n;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Closest element to a LINE SEGMENT query object: BvhN::closestElement / closestPair<MetricL2>(LineSegment3, ...)
+// (BvhN.hpp:1049-1114,1866-1893,2036-2089), as Tools/MeshFix/MeshFix.cpp:756-763 runs it once per boundary edge against a vertex
+// structure under a VertexFilter, and as MetricL2Impl<LineSegmentN, TriangleN> (Algorithms/MetricL2.hpp:286-295) defines it on meshes.
+// Per-element arithmetic: seg_point_sqdist / tri_seg_sqdist (tgq_math.cuh, reference order); the answer is canonical -- the smallest
+// (d2, element index) over all admissible elements.  The reference prunes on the box-box distance between the segment's bounding box
+// and the node box (monotonePruningDistance for a bounded query, BvhN.hpp:1794-1803); any conservative bound returns the same answer,
+// so the larger of that and a centre-sphere bound (distance of the box centre from the segment minus the half diagonal: tight for long
+// oblique segments, whose own box is mostly empty) is used on the AABB nodes of either structure kind.
+// Error budget (u = 2^-24, M = largest |coordinate| of the scene, A, B the segment's ends): the reference's closest points are
+// point + s * direction with s clamped to [0, 1] on BOTH objects -- whatever the conditioning of s and t -- so they lie within
+// 3u(|A| + |B|) of the segment and 5u M of the element, and the returned fl(|c1 - c2|^2) is at least (D - eps)^2 (1 - 4u) with D the true
+// distance and eps their sum; a "hit" of the ray test (d2 = 0) on a segment that truly misses the triangle by more than that needs the
+// segment to graze the triangle's plane, the same residual the ray traversal accepts.  Box bounds are evaluated with fused
+// products (4u per term).  Absolute terms -> mq = 2 pad + 64u(|A|_1 + |B|_1) (pad = 32u M), relative terms -> TGQ_LB_DEFLATE.
+#define TGQ_SEG_EXCL 4            // excluded element indices per query (MeshFix's VertexFilter: the edge's ends and its faces' vertices)
+template <bool TRI>
+struct SegState
+{
+  v3 a, dir, blo, bhi; float mq;
+  int excl[TGQ_SEG_EXCL];
+  float best_d2; int best_idx; v3 best_ep, best_sp;       // closest point on the element / on the segment
+  Trav t;
+};
+
+TGQ_HD float seg_query_margin(v3 a, v3 b, float scene_pad)
+{ return TGQ_MARGIN_SCALE * (2.0f * scene_pad + 3.8146973e-6f * (fabsf(a.x) + fabsf(a.y) + fabsf(a.z) + fabsf(b.x) + fabsf(b.y) + fabsf(b.z))); }
+
+template <bool TRI>
+TGQ_HD float seg_box_lb(SegState<TRI> const & s, v3 lo, v3 hi)
+{
+  v3 g = max3(sub3(max3(lo, s.blo), min3(hi, s.bhi)), mk3(0.0f, 0.0f, 0.0f));
+  float d_box = sqrtf(fdot3(g, g));
+  v3 c = box_centre(lo, hi), h = sub3(hi, c), w = sub3(c, s.a);
+  float dd = fdot3(s.dir, s.dir);
+  float tt = dd > 0.0f ? fminf(fmaxf(fdot3(w, s.dir) / dd, 0.0f), 1.0f) : 0.0f;
+  v3 x = sub3(w, mul3(s.dir, tt));
+  float d_sph = sqrtf(fdot3(x, x)) * 0.999999f - sqrtf(fdot3(h, h)) * 1.000001f;
+  float d = fmaxf(fmaxf(d_box, d_sph) - s.mq, 0.0f);
+  return d * d * TGQ_LB_DEFLATE;
+}
+
+// (point, direction): the segment as LineSegmentN stores it; a caller holding the two endpoints passes direction = end1 - end0, the
+// subtraction LineSegment3(end0, end1) performs (LineSegmentN.hpp:56-58).
+template <bool TRI>
+TGQ_HD void seg_begin(SegState<TRI> & s, BvhView const & b, float scene_pad, v3 a, v3 dir, float bound_ub)
+{
+  s.a = a; s.dir = dir;
+  v3 far = add3(a, s.dir);
+  s.blo = min3(a, far); s.bhi = max3(a, far);
+  s.mq = seg_query_margin(a, far, scene_pad);
+  for (int j = 0; j < TGQ_SEG_EXCL; ++j) s.excl[j] = -1;
+  s.best_d2 = bound_ub; s.best_idx = -1; s.best_ep = s.best_sp = mk3(0.0f, 0.0f, 0.0f);
+  trav_begin(s.t, b.n_nodes);
+}
+
+template <bool TRI>
+TGQ_HD void seg_fetch(SegState<TRI> const & s, BvhView const & b, f4 * r)
+{
+  if (TRI)
+  {
+    f4 const * q = s.t.cur >= 0 ? (f4 const *)(b.nodes + s.t.cur) : (f4 const *)(b.tris + s.t.k);
+    ldq2(q, r[0], r[1]); ldq2(q + 2, r[2], r[3]);
+  }
+  else box_fetch(s.t, b, r);
+}
+
+template <bool TRI>
+TGQ_HD void seg_node_compute(SegState<TRI> & s, BvhView const & b, f4 const * r)
+{
+  TGQ_COUNT_NODE();
+  NodeRec nd; nd.q0 = r[0]; nd.q1 = r[1]; nd.q2 = r[2]; nd.q3 = r[3];
+  v3 lo0, hi0, lo1, hi1; node_boxes(nd, lo0, hi0, lo1, hi1);
+  float lb0 = seg_box_lb(s, lo0, hi0), lb1 = seg_box_lb(s, lo1, hi1);
+  trav_descend(s.t, lb0, lb1, lb0, lb1, f2i(nd.q3.x), f2i(nd.q3.y), s.best_d2);
+}
+
+template <bool TRI>
+TGQ_HD bool seg_excluded(SegState<TRI> const & s, int idx)
+{
+  bool out = false;
+  for (int j = 0; j < TGQ_SEG_EXCL; ++j) out = out || idx == s.excl[j];
+  return out;
+}
+
+// One pending triangle (triangle structures) or up to four pending points of the leaf (point structures).
+template <bool TRI>
+TGQ_HD void seg_leaf_compute(SegState<TRI> & s, BvhView const & b, f4 const * r)
+{
+  if (TRI)
+  {
+    ++s.t.k;
+    TGQ_COUNT_PRIM();
+    int idx = f2i(r[0].w);
+    if (!seg_excluded(s, idx))
+    {
+      v3 ep, sp;
+      float d2 = tri_seg_sqdist(mk3(r[0].x, r[0].y, r[0].z), mk3(r[1].x, r[1].y, r[1].z), mk3(r[2].x, r[2].y, r[2].z), s.a, s.dir, ep, sp);
+      if (d2 < s.best_d2 || (d2 == s.best_d2 && idx < s.best_idx)) { s.best_d2 = d2; s.best_idx = idx; s.best_ep = ep; s.best_sp = sp; }
+    }
+  }
+  else
+  {
+    int cnt = s.t.kend - s.t.k; if (cnt > TGQ_FETCH_BOX) cnt = TGQ_FETCH_BOX;
+    for (int j = 0; j < TGQ_FETCH_BOX; ++j)
+    {
+      if (j >= cnt) break;
+      TGQ_COUNT_PRIM();
+      f4 e = r[j];
+      int idx = f2i(e.w); v3 p = mk3(e.x, e.y, e.z);
+      if (seg_excluded(s, idx)) continue;
+      v3 sp; float d2 = seg_point_sqdist(s.a, s.dir, p, sp);
+      if (d2 < s.best_d2 || (d2 == s.best_d2 && idx < s.best_idx)) { s.best_d2 = d2; s.best_idx = idx; s.best_ep = p; s.best_sp = sp; }
+    }
+    s.t.k += cnt;
+  }
+  if (s.t.k >= s.t.kend) trav_pop(s.t);
+}
+
+// Whole query in one go (host emulation).
+template <bool TRI>
+TGQ_HD void seg_query(BvhView const & b, float scene_pad, v3 a, v3 dir, int const * excl, int n_excl, float & best_d2, int & best_idx, v3 & elem_pt, v3 & seg_pt)
+{
+  SegState<TRI> s; TravStack st; trav_bind(s.t, st);
+  seg_begin(s, b, scene_pad, a, dir, best_d2);
+  for (int j = 0; j < n_excl && j < TGQ_SEG_EXCL; ++j) s.excl[j] = excl[j];
+  f4 r[TGQ_FETCH_BOX];
+  while (s.t.cur != TGQ_ST_DONE)
+  {
+    if (s.t.cur == TGQ_ST_POP) { trav_pop_step(s.t, s.best_d2); continue; }
+    seg_fetch(s, b, r);
+    if (s.t.cur >= 0) seg_node_compute(s, b, r); else seg_leaf_compute(s, b, r);
+  }
+  best_d2 = s.best_d2; best_idx = s.best_idx; elem_pt = s.best_ep; seg_pt = s.best_sp;
+}
+
+// BvhN::closestPair's treatment of a non-negative distance bound (see BoundGate above) for a BOUNDED query object: the root rejection
+// uses the box-box distance between the query's bounding box and the reference's root box (AxisAlignedBoxN::squaredDistance(box),
+// AxisAlignedBoxN.hpp:429-442: vmin - vmax clamped at zero, squared norm in Eigen's order).
+TGQ_HD float ref_box_box_sqdist(v3 lo, v3 hi, v3 olo, v3 ohi) { return sqn3(max3(sub3(max3(lo, olo), min3(hi, ohi)), mk3(0.0f, 0.0f, 0.0f))); }
+TGQ_HD float gated_ub_box(BoundGate const & g, v3 blo, v3 bhi, float ub) { return (g.on && ref_box_box_sqdist(blo, bhi, g.lo, g.hi) > g.reject) ? -1.0f : ub; }
+
 }  // namespace tgq

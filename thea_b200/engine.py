@@ -27,6 +27,7 @@ SYMBOLS = [
     "tgq_get_stats", "tgq_set_point_labels", "tgq_closest_filtered", "tgq_knn_filtered", "tgq_icp_align", "tgq_ball_range",
     "tgq_ball_stats", "tgq_visibility", "tgq_ball_graph_surface", "tgq_ball_histogram", "tgq_spin_image", "tgq_graph_contract", "tgq_graph_geodesic", "tgq_graph_fps", "tgq_set_transform",
     "tgq_closest_records", "tgq_ray_first_records", "tgq_synchronize", "tgq_scatter_records", "tgq_bucket_records", "tgq_range_query", "tgq_closest_pair", "tgq_k_closest_pairs",
+    "tgq_closest_segment",
 ]
 
 
@@ -100,6 +101,7 @@ def load_library(path=None):
     L.tgq_icp_align.argtypes = [vp, vp, i64, i32, i32, f64, i32, vp, vp, vp, vp]
     L.tgq_closest_filtered.argtypes = [vp, vp, vp, vp, i64, f32, f64, vp, vp, vp]
     L.tgq_knn_filtered.argtypes = [vp, vp, vp, vp, i64, i32, f32, f64, vp, vp]
+    L.tgq_closest_segment.argtypes = [vp, vp, vp, i32, i64, f64, vp, i32, vp, vp, vp, vp]
     L.tgq_closest_records.argtypes = [vp, vp, i64, f64, i32, i32, vp, i32, i32, vp]
     L.tgq_ray_first_records.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, i32, i32, vp]
     L.tgq_scatter_records.argtypes = [vp, vp, i32, i64, vp, i32, vp]
@@ -302,6 +304,24 @@ class Engine:
         cp = np.empty((Q, 3), np.float32)
         self._ck(self._L.tgq_closest_filtered(self._h, _ptr(q3), _ptr(qn3), _ptr(qlabel), Q, float(min_dot), float(dist_bound), _ptr(idx), _ptr(d2), _ptr(cp)))
         return idx, d2, cp
+
+    def closest_segment(self, a3, b3, dist_bound=-1.0, exclude=None, b_is_direction=False):
+        """closestElement / closestPair<MetricL2>(LineSegment3(a_i, b_i), dist_bound) per query (Tools/MeshFix/MeshFix.cpp:756-763):
+        (idx, d2, closest point on the element, closest point on the segment).  exclude: Q x (<= 4) element indices each query
+        ignores, -1 = unused (MeshFix's VertexFilter as data).  b_is_direction: b3 holds the stored direction vectors, not the second endpoints."""
+        a3 = self._in(a3)
+        b3 = self._in(b3)
+        Q = int(a3.shape[0])
+        ex = None
+        if exclude is not None:
+            ex = np.ascontiguousarray(exclude, np.int32).reshape(Q, -1)
+        idx = np.empty(Q, np.int32)
+        d2 = np.empty(Q, np.float32)
+        ep = np.empty((Q, 3), np.float32)
+        sp = np.empty((Q, 3), np.float32)
+        self._ck(self._L.tgq_closest_segment(self._h, _ptr(a3), _ptr(b3), int(b_is_direction), Q, float(dist_bound), _ptr(ex), 0 if ex is None else int(ex.shape[1]),
+                                             _ptr(idx), _ptr(d2), _ptr(ep), _ptr(sp)))
+        return idx, d2, ep, sp
 
     def knn_filtered(self, q3, k, qn3=None, qlabel=None, min_dot=0.0, dist_bound=-1.0):
         q3 = self._in(q3)
