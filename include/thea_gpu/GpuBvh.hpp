@@ -224,6 +224,13 @@ inline void check(tgq_handle * h, int rc, char const * what)
     throw Error(std::string("TheaGpu: ") + what + " failed (" + std::to_string(rc) + "): " + tgq_last_error(h));
 }
 
+/** Query-object kinds by their members: a line segment has getEndpoint(i) and getDirection() (LineSegmentN.hpp:72-78), a triangle has
+ *  getVertex(i) and getNormal() (Triangle3.hpp:130-141). */
+template <typename T, typename = void> struct is_segment : std::false_type {};
+template <typename T> struct is_segment<T, decltype((void)std::declval<T const &>().getDirection(), (void)std::declval<T const &>().getEndpoint(0))> : std::true_type {};
+template <typename T, typename = void> struct is_triangle : std::false_type {};
+template <typename T> struct is_triangle<T, decltype((void)std::declval<T const &>().getVertex(0), (void)std::declval<T const &>().getNormal())> : std::true_type {};
+
 template <typename VectorT> inline void put3(float * dst, VectorT const & v) { dst[0] = (float)v[0]; dst[1] = (float)v[1]; dst[2] = (float)v[2]; }
 template <typename VectorT> inline VectorT get3(float const * src) { VectorT v; v[0] = src[0]; v[1] = src[1]; v[2] = src[2]; return v; }
 
@@ -307,7 +314,8 @@ class GpuBvhBase
     bool hasNearestNeighborAcceleration() const { return false; }
 
     /** BvhN::closestPair<MetricL2>(query_structure, dist_bound, compatibility, get_closest_points) (BvhN.hpp:1081-1114,1900-2009;
-     *  Test/TestBvh.cpp:251-258): the closest pair of elements between this structure and a POINT structure on the same device. */
+     *  Test/TestBvh.cpp:251-258,380-385): the closest pair of elements between this structure and another one (points or triangles) on the
+     *  same device; pairs are evaluated as MetricL2::closestPoints(target element, query element), see tgq_closest_pair. */
     template <typename MetricT, typename QueryVectorT, typename CompatibilityFunctorT = UniversalCompatibility>
     NeighborPair closestPair(GpuBvhBase<QueryVectorT> const & query, double dist_bound = -1, CompatibilityFunctorT = CompatibilityFunctorT(),
                              bool get_closest_points = false) const
@@ -343,7 +351,7 @@ class GpuBvhBase
      *  non-structure query; per-element metric LineSegmentN.hpp:106-145 on point structures, Triangle3.hpp:495-509,559-577 on triangle
      *  structures): query index 0, query point on the segment, target point on the element. */
     template <typename MetricT, typename SegmentT, typename CompatibilityFunctorT = UniversalCompatibility,
-              typename = decltype(std::declval<SegmentT const &>().getDirection()), typename = decltype(std::declval<SegmentT const &>().getEndpoint(0))>
+              typename std::enable_if<detail::is_segment<SegmentT>::value, int>::type = 0>
     NeighborPair closestPair(SegmentT const & seg, double dist_bound = -1, CompatibilityFunctorT = CompatibilityFunctorT(),
                              bool get_closest_points = false) const
     {
@@ -357,7 +365,7 @@ class GpuBvhBase
     /** BvhN::closestElement<MetricL2>(LineSegment3, dist_bound, compatibility, &dist, &closest_point) (BvhN.hpp:1049-1063;
      *  Tools/MeshFix/MeshFix.cpp:762): *closest_point is the point on the ELEMENT (NeighborPair::getTargetPoint). */
     template <typename MetricT, typename SegmentT, typename CompatibilityFunctorT = UniversalCompatibility,
-              typename = decltype(std::declval<SegmentT const &>().getDirection()), typename = decltype(std::declval<SegmentT const &>().getEndpoint(0))>
+              typename std::enable_if<detail::is_segment<SegmentT>::value, int>::type = 0>
     intx closestElement(SegmentT const & seg, double dist_bound = -1, CompatibilityFunctorT c = CompatibilityFunctorT(), double * dist = nullptr,
                         VectorT * closest_point = nullptr) const
     {
@@ -367,6 +375,36 @@ class GpuBvhBase
       if (closest_point) *closest_point = pair.getTargetPoint();
       return pair.getTargetIndex();
     }
+    /** BvhN::closestPair<MetricL2>(Triangle3, dist_bound, compatibility, get_closest_points) (BvhN.hpp:1081-1114 with a triangle as the
+     *  bounded query object; per-element metric Triangle3.hpp:314-392 on triangle structures, :294-304 on point structures): query index
+     *  0, query point on the query triangle, target point on the element.  Any type with getVertex(i) and getNormal() is a triangle. */
+    template <typename MetricT, typename TriangleT, typename CompatibilityFunctorT = UniversalCompatibility,
+              typename std::enable_if<detail::is_triangle<TriangleT>::value, long>::type = 0>
+    NeighborPair closestPair(TriangleT const & tri, double dist_bound = -1, CompatibilityFunctorT = CompatibilityFunctorT(),
+                             bool get_closest_points = false) const
+    {
+      float q[9], d2 = -1, ep[3] = {0, 0, 0}, qp[3] = {0, 0, 0}; int32_t idx = -1;
+      detail::put3(q, tri.getVertex(0)); detail::put3(q + 3, tri.getVertex(1)); detail::put3(q + 6, tri.getVertex(2));
+      detail::check(h, tgq_closest_triangle(h, q, 1, dist_bound, &idx, &d2, get_closest_points ? ep : nullptr, get_closest_points ? qp : nullptr),
+                    "tgq_closest_triangle");
+      if (idx < 0) return NeighborPair();
+      return NeighborPair(0, idx, (double)d2, detail::get3<VectorT>(qp), detail::get3<VectorT>(ep));
+    }
+    template <typename MetricT, typename TriangleT, typename CompatibilityFunctorT = UniversalCompatibility,
+              typename std::enable_if<detail::is_triangle<TriangleT>::value, long>::type = 0>
+    intx closestElement(TriangleT const & tri, double dist_bound = -1, CompatibilityFunctorT c = CompatibilityFunctorT(), double * dist = nullptr,
+                        VectorT * closest_point = nullptr) const
+    {
+      NeighborPair pair = closestPair<MetricT>(tri, dist_bound, c, closest_point != nullptr);
+      if (!pair.isValid()) return -1;
+      if (dist) *dist = MetricT::invertMonotoneApprox(pair.getMonotoneApproxDistance());
+      if (closest_point) *closest_point = pair.getTargetPoint();
+      return pair.getTargetIndex();
+    }
+    /** Q triangle queries in one launch (q9: Q x 9 floats; outputs may be null; host or device pointers). */
+    void closestElementTriangleBatch(float const * q9, intx Q, int32_t * idx, float * d2, float * element_point3, float * query_point3, double dist_bound = -1) const
+    { detail::check(h, tgq_closest_triangle(h, q9, Q, dist_bound, idx, d2, element_point3, query_point3), "tgq_closest_triangle"); }
+
     /** Q segment queries in one launch: the loop of Tools/MeshFix/MeshFix.cpp:756-763 (one closestElement per boundary edge, each under
      *  a VertexFilter) as a batch.  a3 / b3: Q x 3 endpoints (b_is_direction: b3 holds the stored directions instead); exclude: Q x
      *  n_exclude element indices each query's filter rejects (-1 = unused, n_exclude <= 4) or null; outputs may be null; host or device

@@ -184,12 +184,28 @@ int tgq_ball_range(tgq_handle * h, const float * c3, const float * radius, int64
 int tgq_closest_segment(tgq_handle * h, const float * a3, const float * b3, int32_t b_is_direction, int64_t Q, double dist_bound,
                         const int32_t * exclude, int32_t n_exclude, int32_t * idx, float * d2, float * element_point3, float * segment_point3);
 
+/* Q closest-element queries whose query object is a TRIANGLE.  Replaces Q calls of
+ *   BvhN::closestPair<MetricL2>(Triangle3(q_i), dist_bound, compatibility, true)            (BvhN.hpp:1081-1114,1866-1893,2036-2089)
+ * q9: Q x 9 floats (v0 v1 v2).  Per-element value: element.squaredDistance(query) on triangle structures -- Moeller's triangle-triangle
+ * intersection test with the intersection segment, else nine edge pairs and six vertex-plane projections (Triangle3.hpp:314-392,597-1300)
+ * --, query.closestPoint(element) on point structures (Algorithms/MetricL2.hpp:219-233, Triangle3.hpp:294-304).  dist_bound as in
+ * tgq_closest (the query's bounding box in the root rejection).  Outputs (each may be null): idx[Q], d2[Q] (-1 when none),
+ * element_point3 / query_point3 [Q x 3] = NeighborPair::getTargetPoint / getQueryPoint.  Ties go to the lowest element index.
+ * Zero-area triangles (elements or queries) make the reference's intersection test a 2-D overlap test in a coordinate plane; results
+ * on such inputs are outside the parity guarantee. */
+int tgq_closest_triangle(tgq_handle * h, const float * q9, int64_t Q, double dist_bound, int32_t * idx, float * d2, float * element_point3,
+                         float * query_point3);
+
 /* Closest pair of elements between two structures.  Replaces BvhN::closestPair<MetricL2>(query_bvh, dist_bound, compatibility,
  * get_closest_points) (BvhN.hpp:1081-1114 with a structure as the query; processNeighborsBvh :1900-2009; Test/TestBvh.cpp:251-258):
  * the minimum over all (target element, query element) pairs of the reference's per-pair squared distance, accepted when
  * (double)d2 < dist_bound^2 (dist_bound < 0: unbounded; a structure query gets no bound widening, BvhN.hpp:2384-2416), ties to the
- * lowest target index, then the lowest query index.  `h` is the target (points or triangles), `query` a POINT structure on the
- * same device (triangle-triangle distances, Triangle3.hpp:314-534, are not implemented: TGQ_EINVAL).  Outputs are host memory:
+ * lowest target index, then the lowest query index.  `h` is the target, `query` the other structure on the same device; either may hold
+ * points or triangles (Test/TestBvh.cpp:251-258 points, :380-385 meshes).  Every pair is evaluated as the reference's leaf code does
+ * without role swapping, MetricL2::closestPoints(target element, query element) (BvhN.hpp:2063): for two triangles that is
+ * target.squaredDistance(query) (Triangle3.hpp:314-392), whose rounding is not symmetric in its arguments -- the reference's dual-tree
+ * traversal swaps the roles of some pairs depending on the shapes of its two trees (:1960-1985), so between two MESHES its result can
+ * differ from this one in the last bit; with a point structure on either side the value is symmetric and equal.  Outputs are host memory:
  * *target_index / *query_index (-1: no pair), *d2, the closest points on the query and the target element (each may be null). */
 int tgq_closest_pair(tgq_handle * h, tgq_handle * query, double dist_bound, int64_t * target_index, int64_t * query_index, float * d2,
                      float * query_point3, float * target_point3);

@@ -236,6 +236,20 @@ void orc_closest_segment(void * h, float const * a3, float const * b3, int64_t Q
   });
 }
 
+// Closest element to a triangle query object (KdTree::closest_triangle); plain_bound = the structure-to-structure bound semantics.
+void orc_closest_triangle(void * h, float const * q9, int64_t Q, double dist_bound, int plain_bound, int mode, int nthreads, int64_t * idx, float * d2,
+                          float * ep3, float * qp3)
+{
+  KdTree const & T = ((Handle *)h)->tree;
+  parallel_for(Q, nthreads, [&](int64_t b, int64_t e) {
+    for (int64_t i = b; i < e; ++i)
+    {
+      KdTree::SegClosest r = T.closest_triangle(mode, ld3(q9, 3 * i), ld3(q9, 3 * i + 1), ld3(q9, 3 * i + 2), dist_bound, plain_bound != 0);
+      idx[i] = r.idx; if (d2) d2[i] = r.d2; if (ep3) st3(ep3, i, r.on_elem); if (qp3) st3(qp3, i, r.on_seg);
+    }
+  });
+}
+
 // Labels of a point structure (element order) and the per-query filter of filtered queries: query i admits element e iff
 // (qlabel == null or label[e] == qlabel[i]) and (qn3 == null or qn[i] . n[e] >= min_dot)   (Register.cpp:92-101 NNFilter).
 void orc_set_labels(void * h, int32_t const * labels)
@@ -736,6 +750,17 @@ void orc_tri_seg_batch(float const * v9, float const * a3, float const * b3, int
     d2[i] = tri_seg_sqdist(t, make_seg(ld3(a3, i), ld3(b3, i)), tp, sp);
     if (tp3) st3(tp3, i, tp);
     if (sp3) st3(sp3, i, sp);
+  }
+}
+void orc_tri_tri_batch(float const * va9, float const * vb9, int64_t n, float * d2, float * pa3, float * pb3)
+{
+  for (int64_t i = 0; i < n; ++i)
+  {
+    Tri a = make_tri(ld3(va9, 3 * i), ld3(va9, 3 * i + 1), ld3(va9, 3 * i + 2)), b = make_tri(ld3(vb9, 3 * i), ld3(vb9, 3 * i + 1), ld3(vb9, 3 * i + 2));
+    V3 pa = mk(0, 0, 0), pb = mk(0, 0, 0);
+    d2[i] = tri_tri_sqdist(a, b, pa, pb);
+    if (pa3) st3(pa3, i, pa);
+    if (pb3) st3(pb3, i, pb);
   }
 }
 float orc_fast_sqrt(float x) { return fast_sqrt(x); }

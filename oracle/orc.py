@@ -52,6 +52,8 @@ def lib():
                               C.c_void_p, C.c_void_p]
         L.orc_closest_segment.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_closest_triangle.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4
+        L.orc_tri_tri_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_seg_point_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.orc_tri_seg_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_set_labels.argtypes = [C.c_void_p, C.c_void_p]
@@ -168,6 +170,17 @@ class Oracle:
         lib().orc_closest_segment(self.h, _p(a), _p(b), Q, float(dist_bound), _p(ex), 0 if ex is None else ex.shape[1], mode,
                                   threads or ncores(), _p(idx), _p(d2), _p(ep), _p(sp))
         return idx, d2, ep, sp
+
+    def closest_triangle(self, q9, dist_bound=-1.0, mode=MODE_CANON, plain_bound=False, threads=None):
+        """Closest element to Triangle3(q_i): idx, d2, point on the element, point on the query triangle."""
+        q = _f32(q9).reshape(-1, 9)
+        Q = q.shape[0]
+        idx = np.empty(Q, np.int64)
+        d2 = np.empty(Q, np.float32)
+        ep = np.empty((Q, 3), np.float32)
+        qp = np.empty((Q, 3), np.float32)
+        lib().orc_closest_triangle(self.h, _p(q), Q, float(dist_bound), int(plain_bound), mode, threads or ncores(), _p(idx), _p(d2), _p(ep), _p(qp))
+        return idx, d2, ep, qp
 
     def ray_first(self, o, d, tmax=None, mode=MODE_CANON, threads=None):
         o = _f32(o).reshape(-1, 3)
@@ -356,6 +369,17 @@ def tri_seg(v9, a, b):
     sp = np.empty((n, 3), np.float32)
     lib().orc_tri_seg_batch(_p(v9), _p(a), _p(b), n, _p(d2), _p(tp), _p(sp))
     return d2, tp, sp
+
+
+def tri_tri(va9, vb9):
+    """Triangle a_i .squaredDistance(b_i): squared distance, closest point on a, on b."""
+    a, b = (_f32(x).reshape(-1, 9) for x in (va9, vb9))
+    n = a.shape[0]
+    d2 = np.empty(n, np.float32)
+    pa = np.empty((n, 3), np.float32)
+    pb = np.empty((n, 3), np.float32)
+    lib().orc_tri_tri_batch(_p(a), _p(b), n, _p(d2), _p(pa), _p(pb))
+    return d2, pa, pb
 
 
 def fast_sqrt(x):

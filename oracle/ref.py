@@ -58,6 +58,8 @@ def lib():
         L.ref_closest_segment_batch.argtypes = [vp, vp, vp, i64, f64, vp, i32, vp, vp, vp, vp]
         L.ref_seg_point_batch.argtypes = [vp, vp, vp, i64, vp, vp]
         L.ref_tri_seg_batch.argtypes = [vp, vp, vp, i64, vp, vp, vp]
+        L.ref_tri_tri_batch.argtypes = [vp, vp, i64, vp, vp, vp]
+        L.ref_closest_triangle_batch.argtypes = [vp, vp, i64, f64, vp, vp, vp, vp]
         L.ref_tri_cache.argtypes = [vp] * 6
         L.ref_tri_point.restype = f32
         L.ref_tri_point.argtypes = [vp, vp, vp]
@@ -210,6 +212,15 @@ class Reference:
                                         _p(idx), _p(d2), _p(ep), _p(sp))
         return idx, d2, ep, sp
 
+    def closest_triangles(self, q9, dist_bound=-1.0):
+        """BvhN::closestPair<MetricL2>(Triangle3(q_i), dist_bound, ..., true) per query: idx, d2, point on the element, point on the query."""
+        q = _f32(q9).reshape(-1, 9)
+        Q = q.shape[0]
+        idx, d2 = np.empty(Q, np.int64), np.empty(Q, np.float32)
+        ep, qp = np.empty((Q, 3), np.float32), np.empty((Q, 3), np.float32)
+        lib().ref_closest_triangle_batch(self.h, _p(q), Q, float(dist_bound), _p(idx), _p(d2), _p(ep), _p(qp))
+        return idx, d2, ep, qp
+
     def icp(self, src, min_iters=3, max_iters=10, frac_thresh=1e-4):
         s = _f32(src).reshape(-1, 3)
         tr, err = np.zeros((3, 4), np.float32), np.zeros(1, np.float32)
@@ -281,6 +292,15 @@ def tri_seg_batch(v9, a3, b3):
     d2, tp, sp = np.empty(n, np.float32), np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
     lib().ref_tri_seg_batch(_p(v), _p(a), _p(b), n, _p(d2), _p(tp), _p(sp))
     return d2, tp, sp
+
+
+def tri_tri_batch(va9, vb9):
+    """Triangle3 a_i.squaredDistance(b_i, &pa, &pb): squared distance, point on a, point on b."""
+    a, b = (_f32(x).reshape(-1, 9) for x in (va9, vb9))
+    n = a.shape[0]
+    d2, pa, pb = np.empty(n, np.float32), np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+    lib().ref_tri_tri_batch(_p(a), _p(b), n, _p(d2), _p(pa), _p(pb))
+    return d2, pa, pb
 
 
 def tri_cache(v9):

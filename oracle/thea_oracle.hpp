@@ -293,6 +293,194 @@ inline float tri_seg_sqdist(Tri const & tri, Seg const & g, V3 & on_tri, V3 & on
 }
 
 // ------------------------------------------------------------------------------------------------
+// Triangle query objects: TriangleN<3>::squaredDistance(TriangleN<3>), Triangle3.hpp:314-392, on top of
+// Moeller's tri_tri_intersect_with_isectline as the reference carries it (Triangle3.hpp:597-1300).  The macros there are plain C on
+// float[3]: THEA_TRI3_DOT sums left to right, (x + y) + z -- not Eigen's order.
+// ------------------------------------------------------------------------------------------------
+namespace moeller {
+typedef float const * P3;
+inline float DOT(P3 a, P3 b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+inline void SUB(float * d, P3 a, P3 b) { d[0] = a[0] - b[0]; d[1] = a[1] - b[1]; d[2] = a[2] - b[2]; }
+inline void CROSS(float * d, P3 a, P3 b) { d[0] = a[1] * b[2] - a[2] * b[1]; d[1] = a[2] * b[0] - a[0] * b[2]; d[2] = a[0] * b[1] - a[1] * b[0]; }
+
+// THEA_TRI3_EDGE_EDGE_TEST (:649-669), THEA_TRI3_EDGE_AGAINST_TRI_EDGES (:671-683)
+inline bool edge_against_tri_edges(P3 V0, P3 V1, P3 U0, P3 U1, P3 U2, int i0, int i1)
+{
+  float Ax = V1[i0] - V0[i0], Ay = V1[i1] - V0[i1];
+  P3 ua[3] = {U0, U1, U2}, ub[3] = {U1, U2, U0};
+  for (int k = 0; k < 3; ++k)
+  {
+    float Bx = ua[k][i0] - ub[k][i0], By = ua[k][i1] - ub[k][i1];
+    float Cx = V0[i0] - ua[k][i0], Cy = V0[i1] - ua[k][i1];
+    float f = Ay * Bx - Ax * By;
+    float d = By * Cx - Bx * Cy;
+    if ((f > 0 && d >= 0 && d <= f) || (f < 0 && d <= 0 && d >= f))
+    {
+      float e = Ax * Cy - Ay * Cx;
+      if (f > 0) { if (e >= 0 && e <= f) return true; }
+      else       { if (e <= 0 && e >= f) return true; }
+    }
+  }
+  return false;
+}
+// THEA_TRI3_POINT_IN_TRI (:685-709)
+inline bool point_in_tri(P3 V0, P3 U0, P3 U1, P3 U2, int i0, int i1)
+{
+  float a, b, c, d0, d1, d2;
+  a = U1[i1] - U0[i1]; b = -(U1[i0] - U0[i0]); c = -a * U0[i0] - b * U0[i1]; d0 = a * V0[i0] + b * V0[i1] + c;
+  a = U2[i1] - U1[i1]; b = -(U2[i0] - U1[i0]); c = -a * U1[i0] - b * U1[i1]; d1 = a * V0[i0] + b * V0[i1] + c;
+  a = U0[i1] - U2[i1]; b = -(U0[i0] - U2[i0]); c = -a * U2[i0] - b * U2[i1]; d2 = a * V0[i0] + b * V0[i1] + c;
+  if (d0 * d1 > 0) { if (d0 * d2 > 0) return true; }
+  return false;
+}
+// coplanar_tri_tri (:711-760)
+inline int coplanar_tri_tri(P3 N, P3 V0, P3 V1, P3 V2, P3 U0, P3 U1, P3 U2)
+{
+  float A[3] = {std::fabs(N[0]), std::fabs(N[1]), std::fabs(N[2])};
+  int i0, i1;
+  if (A[0] > A[1]) { if (A[0] > A[2]) { i0 = 1; i1 = 2; } else { i0 = 0; i1 = 1; } }
+  else             { if (A[2] > A[1]) { i0 = 0; i1 = 1; } else { i0 = 0; i1 = 2; } }
+  if (edge_against_tri_edges(V0, V1, U0, U1, U2, i0, i1)) return 1;
+  if (edge_against_tri_edges(V1, V2, U0, U1, U2, i0, i1)) return 1;
+  if (edge_against_tri_edges(V2, V0, U0, U1, U2, i0, i1)) return 1;
+  if (point_in_tri(V0, U0, U1, U2, i0, i1)) return 1;
+  if (point_in_tri(U0, V0, V1, V2, i0, i1)) return 1;
+  return 0;
+}
+// isect2 (:1024-1039)
+inline void isect2(P3 VTX0, P3 VTX1, P3 VTX2, float VV0, float VV1, float VV2, float D0, float D1, float D2, float * isect0, float * isect1,
+                   float * isectpoint0, float * isectpoint1)
+{
+  float tmp = D0 / (D0 - D1), diff[3];
+  *isect0 = VV0 + (VV1 - VV0) * tmp;
+  SUB(diff, VTX1, VTX0);
+  for (int k = 0; k < 3; ++k) diff[k] = tmp * diff[k];
+  for (int k = 0; k < 3; ++k) isectpoint0[k] = diff[k] + VTX0[k];
+  tmp = D0 / (D0 - D2);
+  *isect1 = VV0 + (VV2 - VV0) * tmp;
+  SUB(diff, VTX2, VTX0);
+  for (int k = 0; k < 3; ++k) diff[k] = tmp * diff[k];
+  for (int k = 0; k < 3; ++k) isectpoint1[k] = VTX0[k] + diff[k];
+}
+// compute_intervals_isectline (:1041-1077)
+inline int compute_intervals_isectline(P3 VERT0, P3 VERT1, P3 VERT2, float VV0, float VV1, float VV2, float D0, float D1, float D2, float D0D1, float D0D2,
+                                       float * isect0, float * isect1, float * isectpoint0, float * isectpoint1)
+{
+  if (D0D1 > 0)                 isect2(VERT2, VERT0, VERT1, VV2, VV0, VV1, D2, D0, D1, isect0, isect1, isectpoint0, isectpoint1);
+  else if (D0D2 > 0)            isect2(VERT1, VERT0, VERT2, VV1, VV0, VV2, D1, D0, D2, isect0, isect1, isectpoint0, isectpoint1);
+  else if (D1 * D2 > 0 || D0 != 0) isect2(VERT0, VERT1, VERT2, VV0, VV1, VV2, D0, D1, D2, isect0, isect1, isectpoint0, isectpoint1);
+  else if (D1 != 0)             isect2(VERT1, VERT0, VERT2, VV1, VV0, VV2, D1, D0, D2, isect0, isect1, isectpoint0, isectpoint1);
+  else if (D2 != 0)             isect2(VERT2, VERT0, VERT1, VV2, VV0, VV1, D2, D0, D1, isect0, isect1, isectpoint0, isectpoint1);
+  else return 1;                // coplanar
+  return 0;
+}
+// tri_tri_intersect_with_isectline (:1115-1300)
+inline int tri_tri_intersect_with_isectline(P3 V0, P3 V1, P3 V2, P3 U0, P3 U1, P3 U2, int * coplanar, float * isectpt1, float * isectpt2)
+{
+  float const EPSILON = std::numeric_limits<float>::epsilon();
+  float E1[3], E2[3], N1[3], N2[3], D[3];
+  float isect1[2] = {0, 0}, isect2_[2] = {0, 0};
+  float isectpointA1[3] = {0, 0, 0}, isectpointA2[3] = {0, 0, 0}, isectpointB1[3] = {0, 0, 0}, isectpointB2[3] = {0, 0, 0};
+  SUB(E1, V1, V0); SUB(E2, V2, V0); CROSS(N1, E1, E2);
+  float d1 = -DOT(N1, V0);
+  float du0 = DOT(N1, U0) + d1, du1 = DOT(N1, U1) + d1, du2 = DOT(N1, U2) + d1;
+  if (std::fabs(du0) < EPSILON) du0 = 0;
+  if (std::fabs(du1) < EPSILON) du1 = 0;
+  if (std::fabs(du2) < EPSILON) du2 = 0;
+  float du0du1 = du0 * du1, du0du2 = du0 * du2;
+  if (du0du1 > 0 && du0du2 > 0) return 0;
+  SUB(E1, U1, U0); SUB(E2, U2, U0); CROSS(N2, E1, E2);
+  float d2 = -DOT(N2, U0);
+  float dv0 = DOT(N2, V0) + d2, dv1 = DOT(N2, V1) + d2, dv2 = DOT(N2, V2) + d2;
+  if (std::fabs(dv0) < EPSILON) dv0 = 0;
+  if (std::fabs(dv1) < EPSILON) dv1 = 0;
+  if (std::fabs(dv2) < EPSILON) dv2 = 0;
+  float dv0dv1 = dv0 * dv1, dv0dv2 = dv0 * dv2;
+  if (dv0dv1 > 0 && dv0dv2 > 0) return 0;
+  CROSS(D, N1, N2);
+  float max = std::fabs(D[0]); int index = 0;
+  float b = std::fabs(D[1]), c = std::fabs(D[2]);
+  if (b > max) { max = b; index = 1; }
+  if (c > max) { max = c; index = 2; }
+  float vp0 = V0[index], vp1 = V1[index], vp2 = V2[index], up0 = U0[index], up1 = U1[index], up2 = U2[index];
+  *coplanar = compute_intervals_isectline(V0, V1, V2, vp0, vp1, vp2, dv0, dv1, dv2, dv0dv1, dv0dv2, &isect1[0], &isect1[1], isectpointA1, isectpointA2);
+  if (*coplanar) return coplanar_tri_tri(N1, V0, V1, V2, U0, U1, U2);
+  compute_intervals_isectline(U0, U1, U2, up0, up1, up2, du0, du1, du2, du0du1, du0du2, &isect2_[0], &isect2_[1], isectpointB1, isectpointB2);
+  int smallest1, smallest2;
+  if (isect1[0] > isect1[1]) { std::swap(isect1[0], isect1[1]); smallest1 = 1; } else smallest1 = 0;       // THEA_TRI3_SORT2
+  if (isect2_[0] > isect2_[1]) { std::swap(isect2_[0], isect2_[1]); smallest2 = 1; } else smallest2 = 0;
+  if (isect1[1] < isect2_[0] || isect2_[1] < isect1[0]) return 0;
+  float const * p1; float const * p2;
+  if (isect2_[0] < isect1[0])
+  {
+    p1 = smallest1 == 0 ? isectpointA1 : isectpointA2;
+    if (isect2_[1] < isect1[1]) p2 = smallest2 == 0 ? isectpointB2 : isectpointB1;
+    else                        p2 = smallest1 == 0 ? isectpointA2 : isectpointA1;
+  }
+  else
+  {
+    p1 = smallest2 == 0 ? isectpointB1 : isectpointB2;
+    if (isect2_[1] > isect1[1]) p2 = smallest1 == 0 ? isectpointA2 : isectpointA1;
+    else                        p2 = smallest2 == 0 ? isectpointB2 : isectpointB1;
+  }
+  for (int k = 0; k < 3; ++k) { isectpt1[k] = p1[k]; isectpt2[k] = p2[k]; }
+  return 1;
+}
+}  // namespace moeller
+
+// TriangleN<3>::squaredDistance(other, this_pt, other_pt), Triangle3.hpp:314-392 (Ericson): `a` is the triangle the member is called on.
+inline float tri_tri_sqdist(Tri const & a, Tri const & b, V3 & on_a, V3 & on_b)
+{
+  V3 c1 = mk(0, 0, 0), c2 = mk(0, 0, 0);
+  float min_sqdist = std::numeric_limits<float>::max();
+  int i_coplanar = 0; V3 isectpt1 = mk(0, 0, 0), isectpt2 = mk(0, 0, 0);
+  int isec = moeller::tri_tri_intersect_with_isectline(&a.v0.x, &a.v1.x, &a.v2.x, &b.v0.x, &b.v1.x, &b.v2.x, &i_coplanar, &isectpt1.x, &isectpt2.x);
+  if (isec)
+  {
+    if (i_coplanar) c1 = c2 = 0.5f * (a.centroid + b.centroid);
+    else
+    {
+      Seg seg = make_seg(isectpt1, isectpt2);                                               // LineSegmentN(isectpt1, isectpt2)
+      c1 = c2 = 0.5f * ((seg.point + 0.0f * seg.direction) + (seg.point + 1.0f * seg.direction));      // getPoint(0) + getPoint(1)
+    }
+    min_sqdist = 0;
+  }
+  else
+  {
+    V3 const av[3] = {a.v0, a.v1, a.v2}, bv[3] = {b.v0, b.v1, b.v2};
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+      {
+        V3 p, q; float s, t;
+        float d2 = seg_seg_sqdist(av[i], av[(i + 1) % 3], false, bv[j], bv[(j + 1) % 3], false, s, t, p, q);
+        if (d2 < min_sqdist) { min_sqdist = d2; c1 = p; c2 = q; }
+      }
+    for (int i = 0; i < 3; ++i)      // vertex of b projecting inside a: getPlane().closestPoint(q) = q - signedDistance(q) * normal
+    {
+      V3 q = bv[i];
+      V3 p = q - (dot(q, a.n) - a.d) * a.n;
+      if (point_inside_tri(a.v0, a.v1, a.v2, a.axis, p))
+      {
+        float d2 = sqnorm(p - q);
+        if (d2 < min_sqdist) { min_sqdist = d2; c1 = p; c2 = q; }
+      }
+    }
+    for (int i = 0; i < 3; ++i)      // vertex of a projecting inside b
+    {
+      V3 p = av[i];
+      V3 q = p - (dot(p, b.n) - b.d) * b.n;
+      if (point_inside_tri(b.v0, b.v1, b.v2, b.axis, q))
+      {
+        float d2 = sqnorm(p - q);
+        if (d2 < min_sqdist) { min_sqdist = d2; c1 = p; c2 = q; }
+      }
+    }
+  }
+  on_a = c1; on_b = c2;
+  return min_sqdist;
+}
+
+// ------------------------------------------------------------------------------------------------
 // AABB: AxisAlignedBoxN.hpp:237-271 (merge), 274 (getCenter), 316-324 (scaleCentered),
 // 429-456 (squaredDistance), 576-658 (Woo ray test).
 // ------------------------------------------------------------------------------------------------
@@ -615,6 +803,61 @@ struct KdTree
         if (s.best < 0 ? (mad == mad) : (mad < s.best || (mad == s.best && s.idx >= 0 && e < s.idx))) { s.best = mad; s.idx = e; s.on_elem = oe; s.on_seg = os; }
       }
     if (s.idx >= 0) { r.idx = s.idx; r.d2 = (float)s.best; r.on_elem = s.on_elem; r.on_seg = s.on_seg; }
+    return r;
+  }
+
+  // ---- closest element to a Triangle3 query object: closestPair / processNeighbors / processNeighborsLeaf (BvhN.hpp:1081-1114,1866-1893,
+  // 2036-2089) with QueryT = Triangle3 (bounded: box-box node bounds against the query's bounding box, :1794-1803).  Per element:
+  // MetricL2::closestPoints(elem, query) = elem.squaredDistance(query) for triangles (tri_tri_sqdist), query.closestPoint(elem) for points.
+  float elem_tri_sqdist(int64_t e, Tri const & q, V3 & on_elem, V3 & on_query) const
+  {
+    if (is_points) { on_elem = pts[(size_t)e]; return tri_point_sqdist(q, pts[(size_t)e], on_query); }
+    return tri_tri_sqdist(tris[(size_t)e], q, on_elem, on_query);
+  }
+  struct TriQuery { Tri q; Box qb; double best; int64_t idx; V3 on_elem, on_query; };
+  template <bool Canon> void triq_rec(int64_t ni, TriQuery & s) const
+  {
+    KdNode const & nd = nodes[(size_t)ni];
+    if (is_leaf(nd))
+    {
+      for (int64_t k = nd.begin; k < nd.begin + nd.count; ++k)
+      {
+        int64_t e = order[(size_t)k];
+        V3 oe, oq; double mad = (double)elem_tri_sqdist(e, s.q, oe, oq);
+        bool take = Canon ? (s.best < 0 ? (mad == mad) : (mad < s.best || (mad == s.best && s.idx >= 0 && e < s.idx)))
+                          : (s.best < 0 || mad < s.best);
+        if (take) { s.best = mad; s.idx = e; s.on_elem = oe; s.on_query = oq; }
+      }
+      return;
+    }
+    double lb[2]; int64_t ch[2] = {nd.child[0], nd.child[1]};
+    for (int c = 0; c < 2; ++c) lb[c] = (double)s.qb.sqdist_box(nodes[(size_t)ch[c]].bounds);
+    if (dist_less(lb[1], lb[0])) { std::swap(lb[0], lb[1]); std::swap(ch[0], ch[1]); }
+    for (int c = 0; c < 2; ++c)
+    {
+      bool go = Canon ? (s.best < 0 || lb[c] <= s.best) : (lb[c] < 0 || s.best < 0 || lb[c] < s.best);
+      if (go) triq_rec<Canon>(ch[c], s);
+    }
+  }
+  // mode 0: reference order, 1: canonical through the kd-tree (box bounds only: valid where no false intersection lies beyond a pruned
+  // box, see the engine's floor), 2: brute force (the definition).  plain_bound: the structure-to-structure form (no root rejection, no
+  // widening of the bound).
+  SegClosest closest_triangle(int mode, V3 v0, V3 v1, V3 v2, double dist_bound, bool plain_bound = false) const
+  {
+    SegClosest r; r.idx = -1; r.d2 = -1; r.on_elem = r.on_seg = mk(0, 0, 0);
+    if (nodes.empty()) return r;
+    TriQuery s; s.q = make_tri(v0, v1, v2); s.qb.merge(s.q.lo, s.q.hi); s.idx = -1; s.on_elem = s.on_query = mk(0, 0, 0);
+    if (plain_bound) s.best = dist_bound >= 0 ? dist_bound * dist_bound : -1;
+    else if (!seg_bound(s.qb, dist_bound, s.best)) return r;
+    if (mode == 0) triq_rec<false>(0, s);
+    else if (mode == 1) triq_rec<true>(0, s);
+    else
+      for (int64_t e = 0; e < size(); ++e)
+      {
+        V3 oe, oq; double mad = (double)elem_tri_sqdist(e, s.q, oe, oq);
+        if (s.best < 0 ? (mad == mad) : (mad < s.best || (mad == s.best && s.idx >= 0 && e < s.idx))) { s.best = mad; s.idx = e; s.on_elem = oe; s.on_query = oq; }
+      }
+    if (s.idx >= 0) { r.idx = s.idx; r.d2 = (float)s.best; r.on_elem = s.on_elem; r.on_seg = s.on_query; }
     return r;
   }
 

@@ -361,6 +361,34 @@ void ref_tri_seg_batch(float const * v9, float const * a3, float const * b3, int
   }
 }
 
+// MetricL2::closestPoints<3, Real>(Triangle3 a, Triangle3 b) -> a.squaredDistance(b, &cpa, &cpb) (Triangle3.hpp:314-392), per pair
+void ref_tri_tri_batch(float const * va9, float const * vb9, int64_t n, float * d2, float * pa3, float * pb3)
+{
+  for (int64_t i = 0; i < n; ++i)
+  {
+    Triangle3 a(v3(va9 + 9 * i), v3(va9 + 9 * i + 3), v3(va9 + 9 * i + 6)), b(v3(vb9 + 9 * i), v3(vb9 + 9 * i + 3), v3(vb9 + 9 * i + 6));
+    Vector3 pa = Vector3::Zero(), pb = Vector3::Zero();
+    d2[i] = MetricL2::closestPoints<3, Real>(a, b, pa, pb);
+    for (int c = 0; c < 3; ++c) { pa3[3 * i + c] = pa[c]; pb3[3 * i + c] = pb[c]; }
+  }
+}
+// BvhN::closestPair<MetricL2>(Triangle3 query object, dist_bound, compat, true), one query triangle at a time
+void ref_closest_triangle_batch(void * hv, float const * q9, int64_t Q, double dist_bound, int64_t * idx, float * d2, float * ep3, float * qp3)
+{
+  RefHandle * h = (RefHandle *)hv;
+  for (int64_t i = 0; i < Q; ++i)
+  {
+    Triangle3 q(v3(q9 + 9 * i), v3(q9 + 9 * i + 3), v3(q9 + 9 * i + 6));
+    bool ok; intx ti = -1; double m = -1; Vector3 a = Vector3::Zero(), b = Vector3::Zero();
+    if (h->tri) { auto pair = h->tri->closestPair<MetricL2>(q, dist_bound, UniversalCompatibility(), true); ok = pair.isValid();
+                  if (ok) { ti = pair.getTargetIndex(); m = pair.getMonotoneApproxDistance(); a = pair.getQueryPoint(); b = pair.getTargetPoint(); } }
+    else        { auto pair = h->pts->closestPair<MetricL2>(q, dist_bound, UniversalCompatibility(), true); ok = pair.isValid();
+                  if (ok) { ti = pair.getTargetIndex(); m = pair.getMonotoneApproxDistance(); a = pair.getQueryPoint(); b = pair.getTargetPoint(); } }
+    idx[i] = ok ? (int64_t)ti : -1; if (d2) d2[i] = ok ? (float)m : -1.0f;
+    for (int c = 0; c < 3; ++c) { if (ep3) ep3[3 * i + c] = b[c]; if (qp3) qp3[3 * i + c] = a[c]; }
+  }
+}
+
 // ---- free functions ----------------------------------------------------------------------------------------------------------
 // Triangle cache (Triangle3.hpp:143-155): unit normal, plane offset, primary axis, area, centroid
 void ref_tri_cache(float const * v9, float * n3, float * d, int32_t * axis, float * area, float * centroid3)

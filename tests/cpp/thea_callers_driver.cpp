@@ -232,10 +232,63 @@ int main(int argc, char ** argv)
              pb.getMonotoneApproxDistance(), ta.getMonotoneApproxDistance(), tb.getMonotoneApproxDistance(), (long)ia, (long)ib);
     }
 
+    // ---- triangle query objects and mesh-to-mesh closestPair (Test/TestBvh.cpp:380-385): Thea's own Triangle3 on both sides ----------------
+    int triq_ok = 0, ntriq = 120, mesh_pair_ok = 0, mesh_pair_bit_equal = 0;
+    for (int i = 0; i < ntriq; ++i)
+    {
+      Vector3 c = points[(size_t)((i * 15485863) % P)] * (1.0f + 0.05f * (Real)(i % 5)) + Vector3(0.002f, -0.001f, 0.003f);
+      Real sz = (i % 3 == 0 ? 0.15f : 0.01f) * diag;
+      Triangle3 q(c, c + Vector3(sz, 0.1f * sz, 0), c + Vector3(0.2f * sz, sz, 0.3f * sz));
+      double bound = (i % 4 == 3) ? 0.02 * (double)diag : -1.0;
+      RefMeshBvh::NeighborPair ta = ref.closestPair<MetricL2>(q, bound, UniversalCompatibility(), true);
+      GpuMeshBvh::NeighborPair tb = gpu.closestPair<MetricL2>(q, bound, UniversalCompatibility(), true);
+      bool same = ta.isValid() == tb.isValid()
+               && (!ta.isValid() || (ta.getMonotoneApproxDistance() == tb.getMonotoneApproxDistance()
+                                     && (ta.getTargetIndex() != tb.getTargetIndex()
+                                         || (ta.getQueryPoint() == tb.getQueryPoint() && ta.getTargetPoint() == tb.getTargetPoint()))));
+      RefPointBvh::NeighborPair pa = pref.closestPair<MetricL2>(q, bound, UniversalCompatibility(), true);
+      GpuPointBvh::NeighborPair pb = pgpu.closestPair<MetricL2>(q, bound, UniversalCompatibility(), true);
+      bool same2 = pa.isValid() == pb.isValid()
+                && (!pa.isValid() || (pa.getMonotoneApproxDistance() == pb.getMonotoneApproxDistance()
+                                      && (pa.getTargetIndex() != pb.getTargetIndex()
+                                          || (pa.getQueryPoint() == pb.getQueryPoint() && pa.getTargetPoint() == pb.getTargetPoint()))));
+      triq_ok += (same && same2);
+      EXPECT(same && same2, "triangle query %d: triangles %g vs %g, points %g vs %g", i, ta.getMonotoneApproxDistance(), tb.getMonotoneApproxDistance(),
+             pa.getMonotoneApproxDistance(), pb.getMonotoneApproxDistance());
+    }
+    {
+      // a second mesh: every 5th triangle, shrunk about its centroid and pushed off the surface along its normal
+      for (Real off : { 0.03f, 0.004f })
+      {
+        std::vector<Triangle3> other;
+        for (int64_t t = 0; t < T; t += 5)
+        {
+          Vector3 cen = tris[(size_t)t].getCentroid(), n = tris[(size_t)t].getNormal();
+          Vector3 shift = (off * diag) * n + Vector3(0.0007f, 0.0003f, -0.0005f) * diag;
+          other.push_back(Triangle3(cen + 0.8f * (tris[(size_t)t].getVertex(0) - cen) + shift, cen + 0.8f * (tris[(size_t)t].getVertex(1) - cen) + shift,
+                                    cen + 0.8f * (tris[(size_t)t].getVertex(2) - cen) + shift));
+        }
+        RefMeshBvh oref(other.begin(), other.end());
+        GpuMeshBvh ogpu;
+        ogpu.add([&](auto emit) { for (auto const & x : other) emit(x.getVertex(0), x.getVertex(1), x.getVertex(2)); });
+        ogpu.init();
+        RefMeshBvh::NeighborPair a = ref.closestPair<MetricL2>(oref, -1, UniversalCompatibility(), true);
+        GpuMeshBvh::NeighborPair b = gpu.closestPair<MetricL2>(ogpu, -1, UniversalCompatibility(), true);
+        double da = a.getMonotoneApproxDistance(), db = b.getMonotoneApproxDistance();
+        // the reference swaps the roles of some pairs depending on its trees, and triangle-triangle rounding is not symmetric: 1e-5
+        bool close = a.isValid() && b.isValid() && std::fabs(da - db) <= 1e-5 * std::max(da, db);
+        mesh_pair_ok += close; mesh_pair_bit_equal += (da == db);
+        EXPECT(close, "closestPair(mesh, mesh, offset %g): %g vs %g", (double)off, da, db);
+        // the GPU pair re-evaluated by the reference's own Triangle3::squaredDistance in the non-swapped orientation: bit equal
+        Real chk = tris[(size_t)b.getTargetIndex()].squaredDistance(other[(size_t)b.getQueryIndex()]);
+        EXPECT((double)chk == db, "closestPair(mesh, mesh): pair value %g re-evaluated as %g", db, (double)chk);
+      }
+    }
+
     printf("{\"triangles\": %ld, \"sdf_equal\": %d, \"sdf_samples\": %ld, \"sdf_position_equal\": %d, \"sdf_position_samples\": %ld, \"icp_max_transform_diff\": %g, "
            "\"range_sets_equal\": %d, \"nn_equal\": %d, \"knn_equal\": %d, \"queries\": %d, \"closest_pairs_equal\": %d, \"segment_queries_equal\": %d, \"segment_queries\": %d, "
-           "\"fails\": %d}\n",
-           (long)T, sdf_equal, (long)S, sdf_pos_equal, (long)(S / 4), tdiff, range_ok, nn_equal, knn_equal, nq, pair_ok, seg_ok, nseg, fails);
+           "\"triangle_queries_equal\": %d, \"triangle_queries\": %d, \"mesh_pairs_within_1e-5\": %d, \"mesh_pairs_bit_equal\": %d, \"fails\": %d}\n",
+           (long)T, sdf_equal, (long)S, sdf_pos_equal, (long)(S / 4), tdiff, range_ok, nn_equal, knn_equal, nq, pair_ok, seg_ok, nseg, triq_ok, ntriq, mesh_pair_ok, mesh_pair_bit_equal, fails);
   }
   catch (std::exception const & e) { fprintf(stderr, "exception: %s\n", e.what()); return 4; }
   return fails ? 3 : 0;

@@ -289,6 +289,46 @@ void emu_closest_segment(void * h, float const * a3, float const * b3, int64_t Q
   }
 }
 
+// Closest element to a triangle query object, as tgq.cu: tgq_closest_triangle drives it.
+void emu_closest_triangle(void * h, float const * q9, int64_t Q, double dist_bound, int32_t * idx, float * d2, float * ep3, float * qp3)
+{
+  Emu & E = *(Emu *)h; BvhView v = E.view();
+  float bound_ub; BoundGate gate; closest_bound_gate(E.lo, E.hi, dist_bound, bound_ub, gate);
+  // FLT_EPSILON over the smallest positive |N| of the elements (k_min_normal in the engine)
+  float elem_tau = 0.0f;
+  if (E.tri)
+  {
+    float mn = INFINITY;
+    for (int i = 0; i < E.n; ++i)
+    {
+      TriRec const & t = E.tris[(size_t)i];
+      v3 a = mk3(t.q0.x, t.q0.y, t.q0.z), N = cross3(sub3(mk3(t.q1.x, t.q1.y, t.q1.z), a), sub3(mk3(t.q2.x, t.q2.y, t.q2.z), a));
+      float nn = sqrtf(fdot3(N, N)); if (nn > 0.0f && nn < mn) mn = nn;
+    }
+    elem_tau = mn < INFINITY ? FLT_EPSILON / mn : 0.0f;
+  }
+  for (int64_t i = 0; i < Q; ++i)
+  {
+    v3 v0 = ld(q9, 3 * i), v1 = ld(q9, 3 * i + 1), v2 = ld(q9, 3 * i + 2);
+    float best = gated_ub_box(gate, min3(v0, min3(v1, v2)), max3(v0, max3(v1, v2)), bound_ub); int bi = -1; v3 ep = mk3(0, 0, 0), qp = mk3(0, 0, 0);
+    if (E.tri) triq_query<true>(v, E.pad, elem_tau, v0, v1, v2, best, bi, ep, qp);
+    else triq_query<false>(v, E.pad, 0.0f, v0, v1, v2, best, bi, ep, qp);
+    idx[i] = bi; d2[i] = bi >= 0 ? best : -1.0f;
+    ep3[3 * i] = ep.x; ep3[3 * i + 1] = ep.y; ep3[3 * i + 2] = ep.z; qp3[3 * i] = qp.x; qp3[3 * i + 1] = qp.y; qp3[3 * i + 2] = qp.z;
+  }
+}
+
+// Per-pair triangle-triangle distance of the device headers (tgq_math.cuh: tri_tri_sqdist), for the pin against the reference.
+void emu_tri_tri_batch(float const * va9, float const * vb9, int64_t n, float * d2, float * pa3, float * pb3)
+{
+  for (int64_t i = 0; i < n; ++i)
+  {
+    TriQ a = make_triq(ld(va9, 3 * i), ld(va9, 3 * i + 1), ld(va9, 3 * i + 2)), b = make_triq(ld(vb9, 3 * i), ld(vb9, 3 * i + 1), ld(vb9, 3 * i + 2));
+    v3 pa, pb; d2[i] = tri_tri_sqdist(a, b, pa, pb);
+    pa3[3 * i] = pa.x; pa3[3 * i + 1] = pa.y; pa3[3 * i + 2] = pa.z; pb3[3 * i] = pb.x; pb3[3 * i + 1] = pb.y; pb3[3 * i + 2] = pb.z;
+  }
+}
+
 // Per-query visit counts (development aid for studying pruning quality).
 void emu_closest_counts(void * h, float const * q3, int64_t Q, float const * ub, int32_t * nodes, int32_t * prims)
 {

@@ -118,6 +118,17 @@ class Emu:
         L.emu_closest_segment(self.h, _p(a), _p(b), Q, float(dist_bound), _p(ex), 0 if ex is None else ex.shape[1], _p(idx), _p(d2), _p(ep), _p(sp))
         return idx, d2, ep, sp
 
+    def closest_triangle(self, q9, dist_bound=-1.0):
+        """Closest element to Triangle3(q_i): idx, d2, point on the element, point on the query triangle."""
+        L = lib()
+        L.emu_closest_triangle.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double] + [C.c_void_p] * 4
+        q = np.ascontiguousarray(q9, np.float32).reshape(-1, 9)
+        Q = len(q)
+        idx, d2 = np.empty(Q, np.int32), np.empty(Q, np.float32)
+        ep, qp = np.empty((Q, 3), np.float32), np.empty((Q, 3), np.float32)
+        L.emu_closest_triangle(self.h, _p(q), Q, float(dist_bound), _p(idx), _p(d2), _p(ep), _p(qp))
+        return idx, d2, ep, qp
+
     def range_all(self, a, b, box=False):
         """All elements in Ball3(a, b) or AxisAlignedBox3(a, b): ascending element indices."""
         L = lib()

@@ -475,3 +475,29 @@ def test_line_segment_queries_equal_brute_force(kind):
             found = want[0] >= 0
             assert np.array_equal(got[2][found], want[2][found]) and np.array_equal(got[3][found], want[3][found])
     assert 0 < (want[0] >= 0).sum() < Q
+
+
+@pytest.mark.parametrize("kind", ["triangles", "points"])
+def test_triangle_queries_equal_brute_force(kind):
+    """the triangle-query traversal of tgq_traverse.cuh (TriQState: box-box and bounding-sphere bounds, the floor that
+    keeps every node within Moeller's coplanarity tolerance) returns the oracle's exhaustive minimum of the reference's per-element value."""
+    rng = np.random.default_rng(32)
+    Q = 3000
+    if kind == "triangles":
+        elems = gen.torus_mesh(28)
+        e, ora, lo, hi, sizes, bound = emu_lib.Emu(tris9=elems), orc.Oracle(tris9=elems), -1.6, 1.6, [0.005, 0.05, 0.3], 0.15
+    else:
+        elems = rng.uniform(-1, 1, (30000, 3)).astype(np.float32)
+        e, ora, lo, hi, sizes, bound = emu_lib.Emu(points=elems), orc.Oracle(points=elems), -1.2, 1.2, [0.01, 0.1, 0.5], 0.04
+    c = rng.uniform(lo, hi, (Q, 1, 3))
+    q = (c + rng.normal(0, 1, (Q, 3, 3)) * rng.choice(sizes, (Q, 1, 1))).reshape(Q, 9).astype(np.float32)
+    if kind == "triangles":
+        q[:200] = (elems[:200] + np.float32(1e-3)).astype(np.float32)          # near copies of elements: intersections and near misses
+    for db in (-1.0, bound):
+        got = e.closest_triangle(q, db)
+        want = ora.closest_triangle(q, db, mode=orc.MODE_BRUTE)
+        assert np.array_equal(got[0], want[0].astype(np.int32))
+        assert np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32))
+        f = want[0] >= 0
+        assert np.array_equal(got[2][f], want[2][f]) and np.array_equal(got[3][f], want[3][f])
+    assert 0 < (want[0] >= 0).sum() < Q

@@ -120,3 +120,83 @@ def test_meshfix_t_junction_queries(built):
     if ref.available():
         r = ref.Reference(points=pts).closest_segments(a, b, 2 * tol, excl)
         assert np.array_equal(r[0], want[0]) and np.array_equal(r[1].view(np.uint32), want[1].view(np.uint32))
+
+
+@pytest.mark.parametrize("kind", ["triangles", "points"])
+def test_triangle_queries_match_oracle(built, kind):
+    """tgq_closest_triangle (BvhN::closestPair<MetricL2>(Triangle3, ...)) against the oracle's exhaustive minimum of the reference's
+    per-element value -- element.squaredDistance(query) with Moeller's intersection test on triangle structures (Triangle3.hpp:314-392),
+    query.closestPoint(element) on point structures -- bit for bit, with and without a distance bound, host and device buffers."""
+    from thea_b200 import Engine
+    rng = np.random.default_rng(42)
+    e = Engine(0)
+    if kind == "triangles":
+        elems = gen.torus_mesh(96)
+        e.build_triangles(elems)
+        ora, Q, lo, hi, sizes, bound = orc.Oracle(tris9=elems), 2500, -1.6, 1.6, [0.005, 0.05, 0.3], 0.1
+    else:
+        elems = rng.uniform(-1, 1, (50000, 3)).astype(np.float32)
+        e.build_points(elems)
+        ora, Q, lo, hi, sizes, bound = orc.Oracle(points=elems), 3000, -1.1, 1.1, [0.01, 0.1, 0.5], 0.02
+    c = rng.uniform(lo, hi, (Q, 1, 3))
+    q = (c + rng.normal(0, 1, (Q, 3, 3)) * rng.choice(sizes, (Q, 1, 1))).reshape(Q, 9).astype(np.float32)
+    if kind == "triangles":
+        q[:300] = (elems[:300] + np.float32(1e-3)).astype(np.float32)        # near copies of elements: intersections and near misses
+    free = ora.closest_triangle(q, mode=orc.MODE_BRUTE)
+    _check(e.closest_triangle(q), free, f"{kind} triangle queries")
+    want = ora.closest_triangle(q, bound, mode=orc.MODE_BRUTE)
+    assert 0 < (want[0] >= 0).sum() < Q
+    _check(e.closest_triangle(q, bound), want, f"{kind} bounded triangle queries")
+    _check(e.closest_triangle(q[:50]), tuple(x[:50] for x in free), f"{kind} small batch")
+    import torch
+    _check(e.closest_triangle(torch.from_numpy(q).cuda()), free, f"{kind} device inputs")
+    wide = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "thea_b200", "libtgq_wide.so")
+    if os.path.exists(wide):
+        w = Engine(0, lib=wide)
+        if kind == "triangles":
+            w.build_triangles(elems)
+        else:
+            w.build_points(elems)
+        _check(w.closest_triangle(q), free, f"{kind} wide margins")
+
+
+def test_mesh_to_mesh_closest_pair(built):
+    """tgq_closest_pair with a TRIANGLE structure as the query (BvhN::closestPair(BvhN) between two meshes, BvhN.hpp:1900-2009,
+    Test/TestBvh.cpp:380-385): the minimum over query triangles of the canonical closest target triangle, every pair evaluated as
+    target.squaredDistance(query); against the reference's own dual-tree traversal where its library travelled (1e-5: the reference swaps
+    the roles of some pairs, and the triangle-triangle arithmetic is not symmetric in the last bit)."""
+    from thea_b200 import Engine
+    mesh = gen.torus_mesh(64)
+    ora = orc.Oracle(tris9=mesh)
+    n = ora.tri_cache()[0]
+    lo, hi = gen.mesh_bounds(mesh)
+    diag = float(np.linalg.norm(np.asarray(hi) - np.asarray(lo)))
+    sel = np.arange(0, len(mesh), 5)
+    v = mesh[sel].reshape(-1, 3, 3)
+    cen = v.mean(1, keepdims=True)
+    et = Engine(0)
+    et.build_triangles(mesh)
+    from oracle import ref
+    for off in (0.03, 0.004, -0.002):
+        other = (cen + 0.8 * (v - cen) + (off * diag) * n[sel][:, None, :] + np.float32([0.0007, 0.0003, -0.0005]) * diag).astype(np.float32).reshape(-1, 9)
+        eq = Engine(0)
+        eq.build_triangles(other)
+        bi, bd, bep, bqp = ora.closest_triangle(other, plain_bound=True, mode=orc.MODE_BRUTE)
+        k = np.lexsort((np.arange(len(bd)), bi, bd))[0]
+        ti, qi, d2, qp, tp = et.closest_pair(eq)
+        assert (ti, qi) == (int(bi[k]), int(k)) and np.float32(d2) == bd[k], (off, ti, qi, d2, int(bi[k]), int(k), float(bd[k]))
+        assert np.array_equal(qp, bqp[k]) and np.array_equal(tp, bep[k])
+        # bounded: nothing closer than half the minimum
+        ti2, qi2, _, _, _ = et.closest_pair(eq, dist_bound=0.5 * float(np.sqrt(np.float64(bd[k]))))
+        assert (ti2, qi2) == ((-1, -1) if bd[k] > 0 else (ti, qi))
+        if ref.available():
+            found, rti, rqi, rd2, _, _ = ref.Reference(tris9=mesh).closest_pair(ref.Reference(tris9=other))
+            assert found and abs(rd2 - d2) <= 1e-5 * max(rd2, d2)
+    # a point structure against the mesh as the query: the value is symmetric, indices swap roles
+    pts = (gen.area_samples(mesh, 3000, seed=3)[0] + np.float32([0.02, 0.0, -0.01])).astype(np.float32)
+    ep = Engine(0)
+    ep.build_points(pts)
+    ti, qi, d2, qp, tp = ep.closest_pair(et)                      # target = points, query = mesh
+    pi, pd, pep, pqp = orc.Oracle(points=pts).closest_triangle(mesh, plain_bound=True, mode=orc.MODE_BRUTE)
+    k = np.lexsort((np.arange(len(pd)), pi, pd))[0]
+    assert (ti, qi) == (int(pi[k]), int(k)) and np.float32(d2) == pd[k]

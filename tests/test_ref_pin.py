@@ -404,3 +404,93 @@ def test_line_segment_queries_match_reference_bvh(kind):
             if ex is not None:
                 assert not (r[0][::3] == first[::3]).any() or (first[::3] < 0).any()
     assert 0 < (R.closest_segments(a, b, bound)[0] >= 0).sum() < Q          # the bound bites
+
+
+def _triangle_pairs(rng, n):
+    """Pairs of triangles of mixed size and separation: overlapping, far apart, coplanar, sharing a vertex or an edge (mesh neighbours),
+    identical, degenerate."""
+    a = rng.uniform(-1, 1, (n, 9))
+    size = rng.choice([0.05, 0.3, 1.0], (n, 1))
+    a[:, 3:6] = a[:, 0:3] + rng.normal(0, 1, (n, 3)) * size
+    a[:, 6:9] = a[:, 0:3] + rng.normal(0, 1, (n, 3)) * size
+    b = rng.uniform(-1, 1, (n, 9))
+    b[:, 0:3] = a[:, 0:3] + rng.normal(0, 1, (n, 3)) * rng.choice([0.0, 0.02, 0.2, 1.0], (n, 1))
+    b[:, 3:6] = b[:, 0:3] + rng.normal(0, 1, (n, 3)) * size
+    b[:, 6:9] = b[:, 0:3] + rng.normal(0, 1, (n, 3)) * size
+    a, b = a.astype(np.float32), b.astype(np.float32)
+    k = n // 10
+    a[:k, [2, 5, 8]] = 0.25; b[:k, [2, 5, 8]] = 0.25                                  # coplanar
+    b[k:2 * k, 0:3] = a[k:2 * k, 0:3]                                                 # shared vertex
+    b[2 * k:3 * k, 0:3] = a[2 * k:3 * k, 3:6]; b[2 * k:3 * k, 3:6] = a[2 * k:3 * k, 0:3]    # shared edge
+    b[3 * k:3 * k + k // 4] = a[3 * k:3 * k + k // 4]                                 # identical
+    a[4 * k:4 * k + k // 4, 6:9] = a[4 * k:4 * k + k // 4, 3:6]                       # degenerate
+    b[5 * k:5 * k + k // 4, 3:6] = b[5 * k:5 * k + k // 4, 0:3]
+    return np.ascontiguousarray(a), np.ascontiguousarray(b)
+
+
+def test_triangle_triangle_distance_matches_reference():
+    """SURVEY 8f rank 4, per pair: MetricL2::closestPoints(Triangle3 a, Triangle3 b) = a.squaredDistance(b, &pa, &pb) (Triangle3.hpp:314-392
+    with Moeller's tri_tri_intersect_with_isectline, :597-1300) on 10^6 pairs: the oracle's restatement AND the engine's own headers (host
+    build, tgq_math.cuh: tri_tri_sqdist) both return the reference's squared distance and closest points bit for bit."""
+    import ctypes as C
+    import emu_lib
+    rng = np.random.default_rng(23)
+    n = 1_000_000
+    a, b = _triangle_pairs(rng, n)
+    r = ref.tri_tri_batch(a, b)
+    o = orc.tri_tri(a, b)
+    assert _same(r[0], o[0]) and _same(r[1], o[1]) and _same(r[2], o[2])
+    L = emu_lib.lib()
+    L.emu_tri_tri_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    d2, pa, pb = np.empty(n, np.float32), np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+    L.emu_tri_tri_batch(a.ctypes.data, b.ctypes.data, n, d2.ctypes.data, pa.ctypes.data, pb.ctypes.data)
+    assert _same(r[0], d2) and _same(r[1], pa) and _same(r[2], pb)
+    assert (r[0] == 0).sum() > n // 5 and (r[0] > 0).sum() > n // 5
+
+
+def _query_triangles(rng, Q, lo, hi, sizes):
+    c = rng.uniform(lo, hi, (Q, 1, 3))
+    return (c + rng.normal(0, 1, (Q, 3, 3)) * rng.choice(sizes, (Q, 1, 1))).reshape(Q, 9).astype(np.float32)
+
+
+@pytest.mark.parametrize("kind", ["triangles", "points"])
+def test_triangle_queries_match_reference_bvh(kind):
+    """BvhN::closestPair<MetricL2>(Triangle3, dist_bound, compat, true) on Thea's own BvhN against the oracle's reference-order traversal:
+    index, squared distance and both closest points bit for bit; canonical == brute force."""
+    rng = np.random.default_rng(24)
+    Q = 2000
+    if kind == "triangles":
+        elems = gen.torus_mesh(24)
+        R, ora, q, bound = ref.Reference(tris9=elems), orc.Oracle(tris9=elems), _query_triangles(rng, Q, -1.6, 1.6, [0.01, 0.05, 0.3]), 0.2
+    else:
+        elems = rng.uniform(-1, 1, (20000, 3)).astype(np.float32)
+        R, ora, q, bound = ref.Reference(points=elems), orc.Oracle(points=elems), _query_triangles(rng, Q, -1.2, 1.2, [0.01, 0.1, 0.5]), 0.05
+    for db in (-1.0, bound):
+        r = R.closest_triangles(q, db)
+        o = ora.closest_triangle(q, db, mode=orc.MODE_REFERENCE)
+        assert np.array_equal(r[0], o[0]) and _same(r[1], o[1]) and _same(r[2], o[2]) and _same(r[3], o[3])
+        c = ora.closest_triangle(q, db, mode=orc.MODE_CANON)
+        bf = ora.closest_triangle(q, db, mode=orc.MODE_BRUTE)
+        assert np.array_equal(c[0], bf[0]) and _same(c[1], bf[1]) and _same(c[1], o[1])
+    assert 0 < (r[0] >= 0).sum() < Q
+
+
+def test_mesh_to_mesh_closest_pair_matches_reference():
+    """BvhN::closestPair(BvhN) between two MESHES (BvhN.hpp:1900-2009, Test/TestBvh.cpp:380-385) against the definition the engine
+    computes: the minimum over query triangles of the canonical closest target triangle, every pair as target.squaredDistance(query)."""
+    mesh = gen.torus_mesh(40)
+    ora = orc.Oracle(tris9=mesh)
+    n = ora.tri_cache()[0]
+    lo, hi = gen.mesh_bounds(mesh)
+    diag = float(np.linalg.norm(np.asarray(hi) - np.asarray(lo)))
+    sel = np.arange(0, len(mesh), 5)
+    v = mesh[sel].reshape(-1, 3, 3)
+    cen = v.mean(1, keepdims=True)
+    for off in (0.03, 0.004, -0.002):
+        other = (cen + 0.8 * (v - cen) + (off * diag) * n[sel][:, None, :] + np.float32([0.0007, 0.0003, -0.0005]) * diag).astype(np.float32).reshape(-1, 9)
+        found, ti, qi, d2, _, _ = ref.Reference(tris9=mesh).closest_pair(ref.Reference(tris9=other))
+        bi, bd, _, _ = ora.closest_triangle(other, plain_bound=True, mode=orc.MODE_BRUTE)
+        k = np.lexsort((np.arange(len(bd)), bi, bd))[0]
+        assert found and abs(d2 - float(bd[k])) <= 1e-5 * max(d2, float(bd[k]))       # role swapping in the reference: last-bit differences allowed
+        if d2 > 0:
+            assert (ti, qi) == (int(bi[k]), int(k))

@@ -81,7 +81,7 @@ struct tgq_handle
   DevBuf area_by_elem, cum;                                           // float[n] in element order; double[n] cumulative
   DevBuf obbs, pnrm, nsum, obbinfo, big, big_count;                   // oriented boxes (triangle structures)
   DevBuf wide, wflag, widx, obbinfo_w; int n_wide = 0;                 // 4-wide nodes of the closest-point traversal
-  int opt_cell_bits = TGQ_SHARD_CELL_BITS, opt_ray_order = 0; bool sorting_rays = false;
+  int opt_cell_bits = TGQ_SHARD_CELL_BITS, opt_ray_order = 0; bool sorting_rays = false; int sort_stride3 = 1;
   int shard_rank = 0, shard_world = 1;                                 // set by the *_records entry points for the duration of one call
   PeerOut peers = {}; int64_t last_share = 0;                          // queries this rank answered in the last *_records call
   int sm_count = 148; std::map<std::pair<void const *, size_t>, int> occupancy;   // resident blocks per SM of the persistent kernels
@@ -401,7 +401,7 @@ int sort_chunk(tgq_handle * h, ChunkCtx & c)
   if (!want || h->n == 0) return TGQ_OK;
   for (int i = 0; i < 2; ++i) { CK(sl.keys[i].reserve(4 * nn)); CK(sl.vals[i].reserve(4 * nn)); }
   k_query_codes<<<grid_for(c.n), TGQ_BLOCK, 0, c.stream>>>((float const *)c.din[0], c.n, h->scene.as<SceneBox>(), sl.keys[0].as<uint32_t>(),
-                                                           sl.vals[0].as<uint32_t>(), h->sorting_rays ? (float const *)c.din[1] : nullptr, h->opt_ray_order);
+                                                           sl.vals[0].as<uint32_t>(), h->sorting_rays ? (float const *)c.din[1] : nullptr, h->opt_ray_order, h->sort_stride3);
   CK(cudaGetLastError());
   size_t tmp = 0;
   CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, sl.keys[0].as<uint32_t>(), sl.keys[1].as<uint32_t>(), sl.vals[0].as<uint32_t>(),
@@ -888,26 +888,86 @@ int tgq_closest_segment(tgq_handle * h, const float * a3, const float * b3, int3
   });
 }
 
+// Q triangle query objects against the structure (plain_bound: the bound as given, without closestPair's root rejection and widening --
+// the structure-to-structure form).
+static int closest_triangle_common(tgq_handle * h, const float * q9, int64_t Q, double dist_bound, int32_t * idx, float * d2, float * element_point3,
+                                   float * query_point3, bool plain_bound)
+{
+  CKRC(need_built(h, (1 << TGQ_KIND_TRIANGLES) | (1 << TGQ_KIND_POINTS)));
+  if (Q < 0 || (Q > 0 && !q9)) return fail(h, TGQ_EINVAL, "tgq_closest_triangle: bad arguments");
+  Guard g(h);
+  float ub; BoundGate gate; closest_bound_gate(h->lo, h->hi, dist_bound, ub, gate);
+  if (plain_bound) { ub = bound_to_ub(dist_bound); gate = no_gate(); }
+  BvhView v = view_of(h); bool tri = h->kind == TGQ_KIND_TRIANGLES;
+  float elem_tau = 0.0f;
+  if (tri && h->n > 0)
+  {
+    // FLT_EPSILON over the smallest positive |N| of the elements: how far apart Moeller's test can still report an intersection
+    CK(h->misc.reserve(64));
+    int * bits = h->misc.as<int>();
+    int inf_bits = 0x7f800000;
+    CK(cudaMemcpyAsync(bits, &inf_bits, 4, cudaMemcpyHostToDevice, h->stream));
+    k_min_normal<<<std::min(grid_for(h->n, 256), h->sm_count * 8), 256, 0, h->stream>>>(v.tris, h->n, bits);
+    CK(cudaGetLastError());
+    int got = 0;
+    CK(cudaMemcpyAsync(&got, bits, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float mn; memcpy(&mn, &got, 4);
+    elem_tau = (mn > 0.0f && mn < INFINITY) ? FLT_EPSILON / mn : 0.0f;
+    h->st.total_launches += 1;
+  }
+  Arg args[5] = {{q9, nullptr, 36}, {nullptr, idx, 4}, {nullptr, d2, 4}, {nullptr, element_point3, 12}, {nullptr, query_point3, 12}};
+  size_t smem = trav_smem_bytes(3);
+  h->sort_stride3 = 3;                      // the launch order follows the Morton code of each query triangle's first vertex
+  struct Restore { tgq_handle * h; ~Restore() { h->sort_stride3 = 1; } } restore{h};
+  return run_batched(h, Q, args, 5, true, [&](ChunkCtx & c) -> int {
+    int grid = 0; int * cnt = c.slot->counter.as<int>();
+    if (tri)
+    {
+      CKRC(persistent_grid(h, k_closest_tri<true>, smem, c.n, cnt, c.stream, &grid));
+      k_closest_tri<true><<<grid, TGQ_BLOCK, smem, c.stream>>>(v, h->pad, elem_tau, (float const *)c.din[0], c.perm, c.n, ub, gate, cnt, (int *)c.dout[1],
+                                                             (float *)c.dout[2], (float *)c.dout[3], (float *)c.dout[4]);
+    }
+    else
+    {
+      CKRC(persistent_grid(h, k_closest_tri<false>, smem, c.n, cnt, c.stream, &grid));
+      k_closest_tri<false><<<grid, TGQ_BLOCK, smem, c.stream>>>(v, h->pad, elem_tau, (float const *)c.din[0], c.perm, c.n, ub, gate, cnt, (int *)c.dout[1],
+                                                              (float *)c.dout[2], (float *)c.dout[3], (float *)c.dout[4]);
+    }
+    h->st.last_launches += 1; h->st.total_launches += 1;
+    return TGQ_OK;
+  });
+}
+
+int tgq_closest_triangle(tgq_handle * h, const float * q9, int64_t Q, double dist_bound, int32_t * idx, float * d2, float * element_point3,
+                         float * query_point3)
+{ return closest_triangle_common(h, q9, Q, dist_bound, idx, d2, element_point3, query_point3, false); }
+
 int tgq_closest_pair(tgq_handle * h, tgq_handle * query, double dist_bound, int64_t * target_index, int64_t * query_index, float * d2, float * query_point3,
                      float * target_point3)
 {
   CKRC(need_built(h, (1 << TGQ_KIND_TRIANGLES) | (1 << TGQ_KIND_POINTS)));
   if (!query || !target_index || !query_index) return fail(h, TGQ_EINVAL, "tgq_closest_pair: bad arguments");
-  if (query->kind != TGQ_KIND_POINTS) return fail(h, TGQ_EINVAL, "tgq_closest_pair: the query structure must be a point structure (triangle-triangle distances are not implemented)");
+  if (query->kind != TGQ_KIND_POINTS && query->kind != TGQ_KIND_TRIANGLES) return fail(h, TGQ_ESTATE, "tgq_closest_pair: no structure built on the query handle");
   if (query->device != h->device) return fail(h, TGQ_EINVAL, "tgq_closest_pair: both structures must live on the same device");
   *target_index = -1; *query_index = -1; if (d2) *d2 = -1.0f;
   if (query->n == 0 || h->n == 0) return TGQ_OK;
   Guard g(h);
   cudaStream_t s = h->stream;
   CK(cudaStreamSynchronize(query->stream));
-  size_t P = (size_t)query->n;
+  bool const qtri = query->kind == TGQ_KIND_TRIANGLES;
+  size_t P = (size_t)query->n, qw = qtri ? 9 : 3;
   // the query structure's elements in element order, answered one by one by this structure, then the canonical minimum
-  CK(h->src2.reserve(12 * P)); CK(h->slot[0].out[4].reserve(4 * P)); CK(h->slot[0].out[5].reserve(4 * P)); CK(h->slot[0].out[6].reserve(12 * P));
-  k_extract_points<<<grid_for((int64_t)P), TGQ_BLOCK, 0, s>>>(query->elems.as<f4>(), nullptr, nullptr, (int)P, h->src2.as<float>(), nullptr, nullptr);
+  CK(h->src2.reserve(4 * qw * P)); CK(h->slot[0].out[4].reserve(4 * P)); CK(h->slot[0].out[5].reserve(4 * P)); CK(h->slot[0].out[6].reserve(12 * P));
+  CK(h->slot[0].out[7].reserve(12 * P));
+  if (qtri) k_extract_tris<<<grid_for((int64_t)P), TGQ_BLOCK, 0, s>>>(query->elems.as<TriRec>(), (int)P, h->src2.as<float>());
+  else k_extract_points<<<grid_for((int64_t)P), TGQ_BLOCK, 0, s>>>(query->elems.as<f4>(), nullptr, nullptr, (int)P, h->src2.as<float>(), nullptr, nullptr);
   CK(cudaGetLastError());
   int * di = h->slot[0].out[4].as<int>(); float * dd = h->slot[0].out[5].as<float>(); float * dc = h->slot[0].out[6].as<float>();
+  float * dq = h->slot[0].out[7].as<float>();
   int saved_async = h->opt_async; h->opt_async = 0;
-  int rc = closest_common(h, h->src2.as<float>(), nullptr, nullptr, 0.0f, (int64_t)P, dist_bound, 0, di, dd, dc, true);
+  int rc = qtri ? closest_triangle_common(h, h->src2.as<float>(), (int64_t)P, dist_bound, di, dd, dc, dq, true)
+                : closest_common(h, h->src2.as<float>(), nullptr, nullptr, 0.0f, (int64_t)P, dist_bound, 0, di, dd, dc, true);
   h->opt_async = saved_async;
   if (rc != TGQ_OK) return rc;
   CK(h->misc.reserve(64));
@@ -925,7 +985,7 @@ int tgq_closest_pair(tgq_handle * h, tgq_handle * query, double dist_bound, int6
   *target_index = (int64_t)(unsigned)(hb[0] & 0xffffffffull); *query_index = (int64_t)hb[1];
   float hd = 0, hq[3], ht[3];
   CK(cudaMemcpyAsync(&hd, dd + hb[1], 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(hq, h->src2.as<float>() + 3 * hb[1], 12, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(hq, (qtri ? dq : h->src2.as<float>()) + 3 * hb[1], 12, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(ht, dc + 3 * hb[1], 12, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   if (d2) *d2 = hd;

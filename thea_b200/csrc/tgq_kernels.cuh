@@ -454,7 +454,7 @@ __global__ void k_scatter_cache(TriRec const * __restrict__ tris, float const * 
 // dir3 != null (ray batches, TGQ_OPT_RAY_ORDER): the `obits` lowest bits of the origin's code are replaced by the direction's sign
 // octant (3 bits) above the remaining origin bits -- rays of one cell are grouped by the octant they head into.
 __global__ void k_query_codes(float const * __restrict__ q3, int n, SceneBox const * sb, uint32_t * keys, uint32_t * vals, float const * __restrict__ dir3 = nullptr,
-                              int obits = 0)
+                              int obits = 0, int stride3 = 1)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
   SceneF s = scene_decode(sb);
@@ -462,7 +462,7 @@ __global__ void k_query_codes(float const * __restrict__ q3, int n, SceneBox con
   v3 c = mul3(add3(s.lo, s.hi), 0.5f), e = sub3(s.hi, s.lo);
   v3 lo = sub3(c, e);
   v3 inv = mk3(e.x > 0 ? 0.5f / e.x : 0.0f, e.y > 0 ? 0.5f / e.y : 0.0f, e.z > 0 ? 0.5f / e.z : 0.0f);
-  uint32_t code = morton30(ld3(q3, i), lo, inv);
+  uint32_t code = morton30(ld3(q3, (int64_t)i * stride3), lo, inv);      // stride3 = 3: triangle query objects, ordered by their first vertex
   if (dir3 && obits >= 3)
   {
     v3 d = ld3(dir3, i);
@@ -1923,6 +1923,73 @@ k_closest_seg(BvhView b, float scene_pad, float const * __restrict__ a3, float c
   w.b = b; w.scene_pad = scene_pad; w.a3 = a3; w.b3 = b3; w.perm = perm; w.ub = bound_ub; w.gate = gate; w.excl = excl; w.n_excl = n_excl; w.dir_form = dir_form;
   w.idx = idx; w.d2 = d2; w.ep3 = ep3; w.sp3 = sp3; w.qi = 0; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
   f4 * stage = trav_setup(w.s.t, st, smem, SegW<TRI>::STAGE, nullptr);
+  warp_run(w, n, counter, stage);
+}
+
+// ---- closest element to a triangle query object (TriQState in tgq_traverse.cuh) -----------------------------
+// Smallest positive |N| = |(v1 - v0) x (v2 - v0)| over the structure's triangles, as int bits (positive floats order like ints): the
+// coplanarity tolerance of Moeller's test is FLT_EPSILON / |N| (triq_begin).
+__global__ void k_min_normal(TriRec const * __restrict__ tris, int n, int * out_bits)
+{
+  float m = INFINITY;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+  {
+    f4 const * q = (f4 const *)(tris + k);
+    f4 a = q[0], b = q[1], c = q[2];
+    v3 v0 = mk3(a.x, a.y, a.z);
+    v3 N = cross3(sub3(mk3(b.x, b.y, b.z), v0), sub3(mk3(c.x, c.y, c.z), v0));
+    float nn = sqrtf(fdot3(N, N));
+    if (nn > 0.0f) m = fminf(m, nn);
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMin(out_bits, __float_as_int(m));
+}
+
+template <bool TRI>
+struct TriQW
+{
+  static constexpr int STAGE = 3;       // (v0, query index) (v1, -) (v2, -)
+  TriQState<TRI> s; BvhView b; float scene_pad, elem_tau; float const * q9; uint32_t const * perm; float ub; BoundGate gate;
+  int * idx; float * d2; float * ep3; float * qp3; int qi;
+  __device__ __forceinline__ int state() const { return s.t.cur; }
+  __device__ __forceinline__ void stage(int t, f4 * dst) const
+  {
+    int i = perm ? (int)perm[t] : t; v3 v0 = ld3(q9, 3 * (int64_t)i), v1 = ld3(q9, 3 * (int64_t)i + 1), v2 = ld3(q9, 3 * (int64_t)i + 2);
+    dst[0] = make_float4(v0.x, v0.y, v0.z, __int_as_float(i));
+    dst[1] = make_float4(v1.x, v1.y, v1.z, 0.0f);
+    dst[2] = make_float4(v2.x, v2.y, v2.z, 0.0f);
+  }
+  __device__ __forceinline__ void begin(int, f4 const * src)
+  {
+    f4 a = src[0], e = src[1], c = src[2]; qi = __float_as_int(a.w);
+    triq_begin(s, b, scene_pad, elem_tau, mk3(a.x, a.y, a.z), mk3(e.x, e.y, e.z), mk3(c.x, c.y, c.z), ub);
+    s.best_d2 = gated_ub_box(gate, s.blo, s.bhi, ub);
+  }
+  static constexpr int FETCH = TGQ_FETCH_BOX;
+  __device__ __forceinline__ void pop_step() { trav_pop_step(s.t, triq_limit(s)); }
+  __device__ __forceinline__ void fetch(f4 * r) const { triq_fetch(s, b, r); }
+  __device__ __forceinline__ void node_compute(f4 const * r) { triq_node_compute(s, b, r); }
+  __device__ __forceinline__ void leaf_compute(f4 const * r) { triq_leaf_compute(s, b, r); }
+  __device__ __forceinline__ void finish()
+  {
+    if (idx) idx[qi] = s.best_idx;
+    if (d2) d2[qi] = s.best_idx >= 0 ? s.best_d2 : -1.0f;
+    if (ep3) st3(ep3, qi, s.best_ep);
+    if (qp3) st3(qp3, qi, s.best_qp);
+    s.t.cur = TGQ_ST_IDLE;
+  }
+};
+
+template <bool TRI>
+__global__ void __launch_bounds__(TGQ_BLOCK)
+k_closest_tri(BvhView b, float scene_pad, float elem_tau, float const * __restrict__ q9, uint32_t const * __restrict__ perm, int n, float bound_ub,
+              BoundGate gate, int * counter, int * idx, float * d2, float * ep3, float * qp3)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  TriQW<TRI> w;
+  w.b = b; w.scene_pad = scene_pad; w.elem_tau = elem_tau; w.q9 = q9; w.perm = perm; w.ub = bound_ub; w.gate = gate;
+  w.idx = idx; w.d2 = d2; w.ep3 = ep3; w.qp3 = qp3; w.qi = 0; w.s.t.cur = TGQ_ST_IDLE; TravStack st;
+  f4 * stage = trav_setup(w.s.t, st, smem, TriQW<TRI>::STAGE, nullptr);
   warp_run(w, n, counter, stage);
 }
 

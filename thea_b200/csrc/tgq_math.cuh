@@ -338,6 +338,194 @@ TGQ_HD float tri_seg_sqdist(v3 v0, v3 v1, v3 v2, v3 sp, v3 sdir, v3 & tri_pt, v3
   return d2;
 }
 
+// ---- Triangle query objects: TriangleN<3>::squaredDistance(TriangleN<3>) -------------------------------------
+// Moeller's triangle-triangle test as the reference carries it (Triangle3.hpp:597-1300).  Its macros are plain C: dot products are
+// summed left to right, (x + y) + z, NOT in Eigen's order.
+TGQ_HD float cdot3(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+TGQ_HD float tt_abs(float x) { return fabsf(x); }
+// THEA_TRI3_EDGE_EDGE_TEST (Triangle3.hpp:649-669) in the projection plane (i0, i1); A = V1 - V0 of the edge being tested
+TGQ_HD bool tt_edge_edge(float Ax, float Ay, v3 V0, v3 U0, v3 U1, int i0, int i1)
+{
+  float Bx = comp3(U0, i0) - comp3(U1, i0), By = comp3(U0, i1) - comp3(U1, i1);
+  float Cx = comp3(V0, i0) - comp3(U0, i0), Cy = comp3(V0, i1) - comp3(U0, i1);
+  float f = Ay * Bx - Ax * By, d = By * Cx - Bx * Cy;
+  if ((f > 0.0f && d >= 0.0f && d <= f) || (f < 0.0f && d <= 0.0f && d >= f))
+  {
+    float e = Ax * Cy - Ay * Cx;
+    if (f > 0.0f) { if (e >= 0.0f && e <= f) return true; }
+    else { if (e <= 0.0f && e >= f) return true; }
+  }
+  return false;
+}
+// THEA_TRI3_EDGE_AGAINST_TRI_EDGES (:671-683)
+TGQ_HD bool tt_edge_tri(v3 V0, v3 V1, v3 U0, v3 U1, v3 U2, int i0, int i1)
+{
+  float Ax = comp3(V1, i0) - comp3(V0, i0), Ay = comp3(V1, i1) - comp3(V0, i1);
+  return tt_edge_edge(Ax, Ay, V0, U0, U1, i0, i1) || tt_edge_edge(Ax, Ay, V0, U1, U2, i0, i1) || tt_edge_edge(Ax, Ay, V0, U2, U0, i0, i1);
+}
+// THEA_TRI3_POINT_IN_TRI (:685-709)
+TGQ_HD bool tt_point_in_tri(v3 V0, v3 U0, v3 U1, v3 U2, int i0, int i1)
+{
+  float a = comp3(U1, i1) - comp3(U0, i1), b = -(comp3(U1, i0) - comp3(U0, i0));
+  float c = -a * comp3(U0, i0) - b * comp3(U0, i1);
+  float d0 = a * comp3(V0, i0) + b * comp3(V0, i1) + c;
+  a = comp3(U2, i1) - comp3(U1, i1); b = -(comp3(U2, i0) - comp3(U1, i0));
+  c = -a * comp3(U1, i0) - b * comp3(U1, i1);
+  float d1 = a * comp3(V0, i0) + b * comp3(V0, i1) + c;
+  a = comp3(U0, i1) - comp3(U2, i1); b = -(comp3(U0, i0) - comp3(U2, i0));
+  c = -a * comp3(U2, i0) - b * comp3(U2, i1);
+  float d2 = a * comp3(V0, i0) + b * comp3(V0, i1) + c;
+  return d0 * d1 > 0.0f && d0 * d2 > 0.0f;
+}
+// coplanar_tri_tri (:711-760)
+TGQ_HD bool tt_coplanar(v3 N, v3 V0, v3 V1, v3 V2, v3 U0, v3 U1, v3 U2)
+{
+  float A0 = fabsf(N.x), A1 = fabsf(N.y), A2 = fabsf(N.z);
+  int i0, i1;
+  if (A0 > A1) { if (A0 > A2) { i0 = 1; i1 = 2; } else { i0 = 0; i1 = 1; } }
+  else { if (A2 > A1) { i0 = 0; i1 = 1; } else { i0 = 0; i1 = 2; } }
+  if (tt_edge_tri(V0, V1, U0, U1, U2, i0, i1)) return true;
+  if (tt_edge_tri(V1, V2, U0, U1, U2, i0, i1)) return true;
+  if (tt_edge_tri(V2, V0, U0, U1, U2, i0, i1)) return true;
+  if (tt_point_in_tri(V0, U0, U1, U2, i0, i1)) return true;
+  if (tt_point_in_tri(U0, V0, V1, V2, i0, i1)) return true;
+  return false;
+}
+// isect2 (:1024-1039)
+TGQ_HD void tt_isect2(v3 X0, v3 X1, v3 X2, float VV0, float VV1, float VV2, float D0, float D1, float D2, float & isect0, float & isect1, v3 & p0, v3 & p1)
+{
+  float tmp = D0 / (D0 - D1);
+  isect0 = VV0 + (VV1 - VV0) * tmp;
+  v3 diff = sub3(X1, X0); diff = mk3(tmp * diff.x, tmp * diff.y, tmp * diff.z);
+  p0 = add3(diff, X0);
+  tmp = D0 / (D0 - D2);
+  isect1 = VV0 + (VV2 - VV0) * tmp;
+  diff = sub3(X2, X0); diff = mk3(tmp * diff.x, tmp * diff.y, tmp * diff.z);
+  p1 = add3(X0, diff);
+}
+// compute_intervals_isectline (:1041-1077): true when the triangles are coplanar
+TGQ_HD bool tt_intervals(v3 X0, v3 X1, v3 X2, float VV0, float VV1, float VV2, float D0, float D1, float D2, float D0D1, float D0D2,
+                         float & isect0, float & isect1, v3 & p0, v3 & p1)
+{
+  if (D0D1 > 0.0f) tt_isect2(X2, X0, X1, VV2, VV0, VV1, D2, D0, D1, isect0, isect1, p0, p1);
+  else if (D0D2 > 0.0f) tt_isect2(X1, X0, X2, VV1, VV0, VV2, D1, D0, D2, isect0, isect1, p0, p1);
+  else if (D1 * D2 > 0.0f || D0 != 0.0f) tt_isect2(X0, X1, X2, VV0, VV1, VV2, D0, D1, D2, isect0, isect1, p0, p1);
+  else if (D1 != 0.0f) tt_isect2(X1, X0, X2, VV1, VV0, VV2, D1, D0, D2, isect0, isect1, p0, p1);
+  else if (D2 != 0.0f) tt_isect2(X2, X0, X1, VV2, VV0, VV1, D2, D0, D1, isect0, isect1, p0, p1);
+  else return true;
+  return false;
+}
+// tri_tri_intersect_with_isectline (:1115-1300): 0 = disjoint, 1 = intersecting; coplanar and the two ends of the intersection segment
+TGQ_HD int tt_intersect_line(v3 V0, v3 V1, v3 V2, v3 U0, v3 U1, v3 U2, bool & coplanar, v3 & pt1, v3 & pt2)
+{
+  coplanar = false;
+  v3 E1 = sub3(V1, V0), E2 = sub3(V2, V0);
+  v3 N1 = cross3(E1, E2);
+  float d1 = -cdot3(N1, V0);
+  float du0 = cdot3(N1, U0) + d1, du1 = cdot3(N1, U1) + d1, du2 = cdot3(N1, U2) + d1;
+  if (fabsf(du0) < FLT_EPSILON) du0 = 0.0f;
+  if (fabsf(du1) < FLT_EPSILON) du1 = 0.0f;
+  if (fabsf(du2) < FLT_EPSILON) du2 = 0.0f;
+  float du0du1 = du0 * du1, du0du2 = du0 * du2;
+  if (du0du1 > 0.0f && du0du2 > 0.0f) return 0;
+  E1 = sub3(U1, U0); E2 = sub3(U2, U0);
+  v3 N2 = cross3(E1, E2);
+  float d2 = -cdot3(N2, U0);
+  float dv0 = cdot3(N2, V0) + d2, dv1 = cdot3(N2, V1) + d2, dv2 = cdot3(N2, V2) + d2;
+  if (fabsf(dv0) < FLT_EPSILON) dv0 = 0.0f;
+  if (fabsf(dv1) < FLT_EPSILON) dv1 = 0.0f;
+  if (fabsf(dv2) < FLT_EPSILON) dv2 = 0.0f;
+  float dv0dv1 = dv0 * dv1, dv0dv2 = dv0 * dv2;
+  if (dv0dv1 > 0.0f && dv0dv2 > 0.0f) return 0;
+  v3 D = cross3(N1, N2);
+  float mx = fabsf(D.x); int index = 0;
+  float b = fabsf(D.y), c = fabsf(D.z);
+  if (b > mx) { mx = b; index = 1; }
+  if (c > mx) { mx = c; index = 2; }
+  float vp0 = comp3(V0, index), vp1 = comp3(V1, index), vp2 = comp3(V2, index);
+  float up0 = comp3(U0, index), up1 = comp3(U1, index), up2 = comp3(U2, index);
+  float i1a = 0.0f, i1b = 0.0f, i2a = 0.0f, i2b = 0.0f;
+  v3 z = mk3(0.0f, 0.0f, 0.0f), A1 = z, A2 = z, B1 = z, B2 = z;
+  coplanar = tt_intervals(V0, V1, V2, vp0, vp1, vp2, dv0, dv1, dv2, dv0dv1, dv0dv2, i1a, i1b, A1, A2);
+  if (coplanar) return tt_coplanar(N1, V0, V1, V2, U0, U1, U2) ? 1 : 0;
+  tt_intervals(U0, U1, U2, up0, up1, up2, du0, du1, du2, du0du1, du0du2, i2a, i2b, B1, B2);
+  int smallest1, smallest2;
+  if (i1a > i1b) { float t_ = i1a; i1a = i1b; i1b = t_; smallest1 = 1; } else smallest1 = 0;
+  if (i2a > i2b) { float t_ = i2a; i2a = i2b; i2b = t_; smallest2 = 1; } else smallest2 = 0;
+  if (i1b < i2a || i2b < i1a) return 0;
+  if (i2a < i1a)
+  {
+    pt1 = smallest1 == 0 ? A1 : A2;
+    if (i2b < i1b) pt2 = smallest2 == 0 ? B2 : B1;
+    else pt2 = smallest1 == 0 ? A2 : A1;
+  }
+  else
+  {
+    pt1 = smallest2 == 0 ? B1 : B2;
+    if (i2b > i1b) pt2 = smallest1 == 0 ? A2 : A1;
+    else pt2 = smallest2 == 0 ? B2 : B1;
+  }
+  return 1;
+}
+
+// One triangle with the cached members the distance routines read (Triangle3.hpp:143-155): unit normal, plane offset, primary axis.
+struct TriQ { v3 v0, v1, v2, n; float d; int axis; };
+TGQ_HD TriQ make_triq(v3 v0, v3 v1, v3 v2) { TriPlane p = tri_plane(v0, v1, v2); TriQ t; t.v0 = v0; t.v1 = v1; t.v2 = v2; t.n = p.n; t.d = p.d; t.axis = p.axis; return t; }
+TGQ_HD v3 triq_vertex(TriQ const & t, int i) { return i == 0 ? t.v0 : (i == 1 ? t.v1 : t.v2); }
+// TriangleN<3>::squaredDistance(other, &this_pt, &other_pt) (Triangle3.hpp:314-392; Ericson): `a` is the triangle the member is called
+// on -- the structure's element in BvhN::processNeighborsLeaf (MetricL2::closestPoints(elem, query), BvhN.hpp:2063) --, `b` the other.
+TGQ_HD float tri_tri_sqdist(TriQ const & a, TriQ const & b, v3 & a_pt, v3 & b_pt)
+{
+  v3 c1 = mk3(0.0f, 0.0f, 0.0f), c2 = c1;
+  float min_sqdist = FLT_MAX;
+  bool coplanar; v3 s1, s2;
+  if (tt_intersect_line(a.v0, a.v1, a.v2, b.v0, b.v1, b.v2, coplanar, s1, s2))
+  {
+    if (coplanar) c1 = c2 = mul3(add3(tri_centroid(a.v0, a.v1, a.v2), tri_centroid(b.v0, b.v1, b.v2)), 0.5f);
+    else
+    {
+      v3 dir = sub3(s2, s1);                                                     // LineSegmentN(isectpt1, isectpt2)
+      c1 = c2 = mul3(add3(add3(s1, mul3(dir, 0.0f)), add3(s1, mul3(dir, 1.0f))), 0.5f);     // 0.5 * (seg.getPoint(0) + seg.getPoint(1))
+    }
+    min_sqdist = 0.0f;
+  }
+  else
+  {
+    for (int i = 0; i < 3; ++i)
+    {
+      v3 ai = triq_vertex(a, i), ai2 = triq_vertex(a, (i + 1) % 3);
+      for (int j = 0; j < 3; ++j)
+      {
+        v3 p, q; float s, t;
+        float d2 = seg_seg_sqdist(ai, ai2, false, triq_vertex(b, j), triq_vertex(b, (j + 1) % 3), false, s, t, p, q);
+        if (d2 < min_sqdist) { min_sqdist = d2; c1 = p; c2 = q; }
+      }
+    }
+    for (int i = 0; i < 3; ++i)          // a vertex of `b` that projects inside `a`
+    {
+      v3 q = triq_vertex(b, i);
+      v3 p = sub3(q, mul3(a.n, dot3(q, a.n) - a.d));
+      if (point_inside_tri(a.v0, a.v1, a.v2, a.axis, p))
+      {
+        float d2 = sqn3(sub3(p, q));
+        if (d2 < min_sqdist) { min_sqdist = d2; c1 = p; c2 = q; }
+      }
+    }
+    for (int i = 0; i < 3; ++i)          // a vertex of `a` that projects inside `b`
+    {
+      v3 p = triq_vertex(a, i);
+      v3 q = sub3(p, mul3(b.n, dot3(p, b.n) - b.d));
+      if (point_inside_tri(b.v0, b.v1, b.v2, b.axis, q))
+      {
+        float d2 = sqn3(sub3(p, q));
+        if (d2 < min_sqdist) { min_sqdist = d2; c1 = p; c2 = q; }
+      }
+    }
+  }
+  a_pt = c1; b_pt = c2;
+  return min_sqdist;
+}
+
 // ---- Math::fastSqrt (Math.hpp:194-223) -------------------------------------------------------------------------
 TGQ_HD float fast_sqrt(float x)
 {

@@ -1621,6 +1621,128 @@ TGQ_HD void seg_query(BvhView const & b, float scene_pad, v3 a, v3 dir, int cons
   best_d2 = s.best_d2; best_idx = s.best_idx; elem_pt = s.best_ep; seg_pt = s.best_sp;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Closest element to a TRIANGLE query object: BvhN::closestPair<MetricL2>(Triangle3, ...) and, one query triangle per
+// element of the query structure, the leaf work of BvhN::closestPair(BvhN) between two meshes (BvhN.hpp:1900-2009, Test/TestBvh.cpp:380-385).
+// Per-element value: element.squaredDistance(query) on triangle structures (tri_tri_sqdist: Moeller's intersection test, then nine
+// edge pairs and six vertex-plane projections, Triangle3.hpp:314-392), query.closestPoint(element) on point structures
+// (MetricL2Impl<point, TriangleN>, Algorithms/MetricL2.hpp:219-233 -> Triangle3.hpp:294-304).  Canonical answer: smallest (d2, index).
+// Bounds: box-box distance to the query's bounding box, or centre distance minus both bounding radii, less the margin mq.
+// `floor2`: Moeller's test snaps a vertex within FLT_EPSILON / |N| of the other triangle's plane (N the UNNORMALISED normal, |N| = twice
+// the area) onto that plane (THEA_TRI3_USE_EPSILON_TEST, Triangle3.hpp:602-603,1141-1147), so a pair up to eps / |N_element| + eps / |N_query|
+// apart can be reported as intersecting (d2 = 0).  No node within that distance is ever pruned: floor = eps / (smallest positive
+// |N| of the structure's elements) + eps / |N_query| + mq.  Zero-area triangles make the reference's test degenerate to a 2-D overlap test in
+// a coordinate plane (:711-760 with N = 0); they are outside this guarantee (documented in DESIGN.md).
+template <bool TRI>
+struct TriQState
+{
+  TriQ q; v3 blo, bhi, cen; float rad, mq, floor2;
+  float best_d2; int best_idx; v3 best_ep, best_qp;       // closest point on the element / on the query triangle
+  Trav t;
+};
+template <bool TRI> TGQ_HD float triq_limit(TriQState<TRI> const & s) { return fmaxf(s.best_d2, s.floor2); }
+
+template <bool TRI>
+TGQ_HD void triq_begin(TriQState<TRI> & s, BvhView const & b, float scene_pad, float elem_tau, v3 v0, v3 v1, v3 v2, float bound_ub)
+{
+  s.q = make_triq(v0, v1, v2);
+  s.blo = min3(v0, min3(v1, v2)); s.bhi = max3(v0, max3(v1, v2));
+  s.cen = mul3(add3(add3(v0, v1), v2), 0.33333334f);
+  s.rad = sqrtf(fmaxf(fdot3(sub3(v0, s.cen), sub3(v0, s.cen)), fmaxf(fdot3(sub3(v1, s.cen), sub3(v1, s.cen)), fdot3(sub3(v2, s.cen), sub3(v2, s.cen))))) * 1.000001f;
+  s.mq = TGQ_MARGIN_SCALE * (2.0f * scene_pad + 3.8146973e-6f * (fabsf(v0.x) + fabsf(v0.y) + fabsf(v0.z) + fabsf(v1.x) + fabsf(v1.y) + fabsf(v1.z)
+                                                               + fabsf(v2.x) + fabsf(v2.y) + fabsf(v2.z)));
+  s.floor2 = 0.0f;
+  if (TRI)
+  {
+    v3 N = cross3(sub3(v1, v0), sub3(v2, v0));
+    float nn = sqrtf(fdot3(N, N));
+    float tau = (nn > 0.0f ? FLT_EPSILON / nn : 0.0f) + elem_tau;
+    float f = (tau + s.mq) * 1.000001f;
+    s.floor2 = f * f;
+  }
+  s.best_d2 = bound_ub; s.best_idx = -1; s.best_ep = s.best_qp = mk3(0.0f, 0.0f, 0.0f);
+  trav_begin(s.t, b.n_nodes);
+}
+
+template <bool TRI>
+TGQ_HD float triq_box_lb(TriQState<TRI> const & s, v3 lo, v3 hi)
+{
+  v3 g = max3(sub3(max3(lo, s.blo), min3(hi, s.bhi)), mk3(0.0f, 0.0f, 0.0f));
+  float d_box = sqrtf(fdot3(g, g));
+  v3 c = box_centre(lo, hi), h = sub3(hi, c), w = sub3(c, s.cen);
+  float d_sph = sqrtf(fdot3(w, w)) * 0.999999f - sqrtf(fdot3(h, h)) * 1.000001f - s.rad;
+  float d = fmaxf(fmaxf(d_box, d_sph) - s.mq, 0.0f);
+  return d * d * TGQ_LB_DEFLATE;
+}
+
+template <bool TRI>
+TGQ_HD void triq_fetch(TriQState<TRI> const & s, BvhView const & b, f4 * r)
+{
+  if (TRI)
+  {
+    f4 const * q = s.t.cur >= 0 ? (f4 const *)(b.nodes + s.t.cur) : (f4 const *)(b.tris + s.t.k);
+    ldq2(q, r[0], r[1]); ldq2(q + 2, r[2], r[3]);
+  }
+  else box_fetch(s.t, b, r);
+}
+
+template <bool TRI>
+TGQ_HD void triq_node_compute(TriQState<TRI> & s, BvhView const & b, f4 const * r)
+{
+  TGQ_COUNT_NODE();
+  NodeRec nd; nd.q0 = r[0]; nd.q1 = r[1]; nd.q2 = r[2]; nd.q3 = r[3];
+  v3 lo0, hi0, lo1, hi1; node_boxes(nd, lo0, hi0, lo1, hi1);
+  float lb0 = triq_box_lb(s, lo0, hi0), lb1 = triq_box_lb(s, lo1, hi1);
+  trav_descend(s.t, lb0, lb1, lb0, lb1, f2i(nd.q3.x), f2i(nd.q3.y), triq_limit(s));
+}
+
+template <bool TRI>
+TGQ_HD void triq_leaf_compute(TriQState<TRI> & s, BvhView const & b, f4 const * r)
+{
+  if (TRI)
+  {
+    ++s.t.k;
+    TGQ_COUNT_PRIM();
+    int idx = f2i(r[0].w);
+    TriQ a; a.v0 = mk3(r[0].x, r[0].y, r[0].z); a.v1 = mk3(r[1].x, r[1].y, r[1].z); a.v2 = mk3(r[2].x, r[2].y, r[2].z);
+    a.n = mk3(r[3].x, r[3].y, r[3].z); a.d = r[2].w; a.axis = f2i(r[1].w);
+    v3 ep, qp;
+    float d2 = tri_tri_sqdist(a, s.q, ep, qp);
+    if (d2 < s.best_d2 || (d2 == s.best_d2 && idx < s.best_idx)) { s.best_d2 = d2; s.best_idx = idx; s.best_ep = ep; s.best_qp = qp; }
+  }
+  else
+  {
+    int cnt = s.t.kend - s.t.k; if (cnt > TGQ_FETCH_BOX) cnt = TGQ_FETCH_BOX;
+    for (int j = 0; j < TGQ_FETCH_BOX; ++j)
+    {
+      if (j >= cnt) break;
+      TGQ_COUNT_PRIM();
+      f4 e = r[j];
+      int idx = f2i(e.w); v3 p = mk3(e.x, e.y, e.z);
+      v3 qp; float d2 = tri_point_sqdist(s.q.v0, s.q.v1, s.q.v2, s.q.n, s.q.d, s.q.axis, p, qp);
+      if (d2 < s.best_d2 || (d2 == s.best_d2 && idx < s.best_idx)) { s.best_d2 = d2; s.best_idx = idx; s.best_ep = p; s.best_qp = qp; }
+    }
+    s.t.k += cnt;
+  }
+  if (s.t.k >= s.t.kend) trav_pop(s.t);
+}
+
+// Whole query in one go (host emulation).
+template <bool TRI>
+TGQ_HD void triq_query(BvhView const & b, float scene_pad, float elem_tau, v3 v0, v3 v1, v3 v2, float & best_d2, int & best_idx, v3 & elem_pt, v3 & query_pt)
+{
+  TriQState<TRI> s; TravStack st; trav_bind(s.t, st);
+  triq_begin(s, b, scene_pad, elem_tau, v0, v1, v2, best_d2);
+  f4 r[TGQ_FETCH_BOX];
+  while (s.t.cur != TGQ_ST_DONE)
+  {
+    if (s.t.cur == TGQ_ST_POP) { trav_pop_step(s.t, triq_limit(s)); continue; }
+    triq_fetch(s, b, r);
+    if (s.t.cur >= 0) triq_node_compute(s, b, r); else triq_leaf_compute(s, b, r);
+  }
+  best_d2 = s.best_d2; best_idx = s.best_idx; elem_pt = s.best_ep; query_pt = s.best_qp;
+}
+
 // BvhN::closestPair's treatment of a non-negative distance bound (see BoundGate above) for a BOUNDED query object: the root rejection
 // uses the box-box distance between the query's bounding box and the reference's root box (AxisAlignedBoxN::squaredDistance(box),
 // AxisAlignedBoxN.hpp:429-442: vmin - vmax clamped at zero, squared norm in Eigen's order).

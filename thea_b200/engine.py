@@ -27,7 +27,7 @@ SYMBOLS = [
     "tgq_get_stats", "tgq_set_point_labels", "tgq_closest_filtered", "tgq_knn_filtered", "tgq_icp_align", "tgq_ball_range",
     "tgq_ball_stats", "tgq_visibility", "tgq_ball_graph_surface", "tgq_ball_histogram", "tgq_spin_image", "tgq_graph_contract", "tgq_graph_geodesic", "tgq_graph_fps", "tgq_set_transform",
     "tgq_closest_records", "tgq_ray_first_records", "tgq_synchronize", "tgq_scatter_records", "tgq_bucket_records", "tgq_range_query", "tgq_closest_pair", "tgq_k_closest_pairs",
-    "tgq_closest_segment",
+    "tgq_closest_segment", "tgq_closest_triangle",
 ]
 
 
@@ -102,6 +102,7 @@ def load_library(path=None):
     L.tgq_closest_filtered.argtypes = [vp, vp, vp, vp, i64, f32, f64, vp, vp, vp]
     L.tgq_knn_filtered.argtypes = [vp, vp, vp, vp, i64, i32, f32, f64, vp, vp]
     L.tgq_closest_segment.argtypes = [vp, vp, vp, i32, i64, f64, vp, i32, vp, vp, vp, vp]
+    L.tgq_closest_triangle.argtypes = [vp, vp, i64, f64, vp, vp, vp, vp]
     L.tgq_closest_records.argtypes = [vp, vp, i64, f64, i32, i32, vp, i32, i32, vp]
     L.tgq_ray_first_records.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, i32, i32, vp]
     L.tgq_scatter_records.argtypes = [vp, vp, i32, i64, vp, i32, vp]
@@ -323,6 +324,18 @@ class Engine:
                                              _ptr(idx), _ptr(d2), _ptr(ep), _ptr(sp)))
         return idx, d2, ep, sp
 
+    def closest_triangle(self, q9, dist_bound=-1.0):
+        """closestPair<MetricL2>(Triangle3(q_i), dist_bound, ..., true) per query triangle (Q x 9 floats):
+        (idx, d2, closest point on the element, closest point on the query triangle)."""
+        q9 = self._in(q9)
+        Q = int(q9.size // 9) if isinstance(q9, np.ndarray) else int(q9.numel() // 9)
+        idx = np.empty(Q, np.int32)
+        d2 = np.empty(Q, np.float32)
+        ep = np.empty((Q, 3), np.float32)
+        qp = np.empty((Q, 3), np.float32)
+        self._ck(self._L.tgq_closest_triangle(self._h, _ptr(q9), Q, float(dist_bound), _ptr(idx), _ptr(d2), _ptr(ep), _ptr(qp)))
+        return idx, d2, ep, qp
+
     def knn_filtered(self, q3, k, qn3=None, qlabel=None, min_dot=0.0, dist_bound=-1.0):
         q3 = self._in(q3)
         qn3 = self._in(qn3)
@@ -400,7 +413,7 @@ class Engine:
         return t[:n.value], q[:n.value], d[:n.value]
 
     def closest_pair(self, query, dist_bound=-1.0):
-        """tgq_closest_pair: BvhN::closestPair between this structure (the target) and the point structure `query`.
+        """tgq_closest_pair: BvhN::closestPair between this structure (the target) and the structure `query` (points or triangles).
         Returns (target index, query index, d2, point on the query element, point on the target element); indices -1 when none."""
         ti, qi, d2 = C.c_int64(), C.c_int64(), C.c_float()
         qp, tp = np.zeros(3, np.float32), np.zeros(3, np.float32)
