@@ -5,6 +5,7 @@
 //                                                                                                Algorithms/SurfaceFeatures/Local/ShapeDiameter.hpp:168-258)
 //   sampleGraph               <- PointSet3::updateGraph without oversampling / reachability     (Algorithms/PointSet3.hpp:324-391)
 //   saveGraph / loadGraph     <- PointSet3::save / load, graph file                             (Algorithms/PointSet3.cpp:222-354)
+//   tJunctionCandidates       <- the query loop of MeshFix's T-junction repair                  (Tools/MeshFix/MeshFix.cpp:699-790)
 //
 // Each loop body of the reference issues one structure query per iteration; here one C-ABI call answers the whole loop
 // and the O(1) epilogue (3x3 polar decomposition, transform composition, convergence test) stays on the host (inside the
@@ -244,6 +245,46 @@ inline bool loadGraph(std::string const & graph_path, intx P, float const * posi
     for (long long j = 0; j < d && j < md; ++j) { idx[(size_t)(i * md + j)] = (int32_t)nb[(size_t)j].second; sep[(size_t)(i * md + j)] = nb[(size_t)j].first; }
   }
   return true;
+}
+
+/** The query half of MeshFix's T-junction repair (Tools/MeshFix/MeshFix.cpp:716-790) for E boundary edges at once.  `boundary_vertices`
+ *  is the structure over the boundary vertices (tJuncts builds a BvhN<Mesh::Vertex *, 3> over them, :729-730).  Per edge e with endpoints
+ *  p0_e, p1_e: the segment shrunk by `tol` at both ends (segFromEdge, :699-713: s = tol / len in double, t = 1 - s, ends
+ *  (1 - (Real)s) p0 + (Real)s p1 and (1 - (Real)t) p0 + (Real)t p1; edges shorter than 2 tol are skipped), one closestElement query
+ *  with dist_bound = 2 tol that ignores the `n_exclude` vertices listed for the edge (VertexFilter, :678-697: the edge's endpoints and the
+ *  other vertices of its faces, as positions in the structure, -1 = unused), and the acceptance test of :766-771 on the closest point
+ *  cp of the segment to the vertex found: |cp - p0|^2 > tol^2, |cp - p1|^2 > tol^2, |cp - vertex|^2 < tol^2.  split_vertex[e] = the vertex
+ *  to split edge e at, or -1; the splitting itself (mesh.splitEdge, :773) and the re-queries of later iterations stay with the caller. */
+template <typename PointBvhT>
+void tJunctionCandidates(PointBvhT const & boundary_vertices, float const * p0, float const * p1, intx E, double tol, int32_t const * exclude, int32_t n_exclude,
+                         int32_t * split_vertex)
+{
+  std::vector<float> a((size_t)(3 * E)), b((size_t)(3 * E)), d2((size_t)E), vp((size_t)(3 * E)), sp((size_t)(3 * E));
+  std::vector<int32_t> idx((size_t)E);
+  std::vector<char> skip((size_t)E, 0);
+  for (intx e = 0; e < E; ++e)
+  {
+    float const * u = p0 + 3 * e; float const * v = p1 + 3 * e;
+    float dx = v[0] - u[0], dy = v[1] - u[1], dz = v[2] - u[2];
+    float len = std::sqrt(dx * dx + (dy * dy + dz * dz));                 // LineSegmentN::length = direction.norm()
+    if (len < 2 * tol) { skip[(size_t)e] = 1; for (int c = 0; c < 3; ++c) a[(size_t)(3 * e + c)] = b[(size_t)(3 * e + c)] = u[c]; continue; }
+    double s = tol / len, t = 1 - s;
+    for (int c = 0; c < 3; ++c)
+    {
+      a[(size_t)(3 * e + c)] = (1 - (float)s) * u[c] + (float)s * v[c];
+      b[(size_t)(3 * e + c)] = (1 - (float)t) * u[c] + (float)t * v[c];
+    }
+  }
+  boundary_vertices.closestElementSegmentBatch(a.data(), b.data(), E, idx.data(), d2.data(), vp.data(), sp.data(), 2 * tol, exclude, n_exclude);
+  double sqtol = tol * tol;
+  for (intx e = 0; e < E; ++e)
+  {
+    split_vertex[e] = -1;
+    if (skip[(size_t)e] || idx[(size_t)e] < 0) continue;
+    float const * cp = &sp[(size_t)(3 * e)]; float const * vx = &vp[(size_t)(3 * e)];
+    auto sq = [](float const * x, float const * y) { float ex = x[0] - y[0], ey = x[1] - y[1], ez = x[2] - y[2]; return ex * ex + (ey * ey + ez * ez); };
+    if (sq(cp, p0 + 3 * e) > sqtol && sq(cp, p1 + 3 * e) > sqtol && sq(cp, vx) < sqtol) split_vertex[e] = idx[(size_t)e];
+  }
 }
 
 }  // namespace TheaGpu

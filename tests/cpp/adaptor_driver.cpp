@@ -13,8 +13,12 @@ using namespace TheaGpu;
 template <typename T> static std::vector<T> rd(FILE * f, size_t n) { std::vector<T> v(n); if (n && fread(v.data(), sizeof(T), n, f) != n) { fprintf(stderr, "short read\n"); exit(2); } return v; }
 template <typename T> static void wr(FILE * f, std::vector<T> const & v) { if (!v.empty()) fwrite(v.data(), sizeof(T), v.size(), f); }
 
+// compile check of the T-junction caller (exercised on the GPU through its Python twin, tests/test_gpu_segments.py)
+static auto const t_junction_caller = &TheaGpu::tJunctionCandidates<TheaGpu::GpuPointBvh>;
+
 int main(int argc, char ** argv)
 {
+  (void)t_junction_caller;
   if (argc < 3) { fprintf(stderr, "usage: %s in.bin out.bin\n", argv[0]); return 2; }
   try
   {

@@ -120,6 +120,13 @@ def test_meshfix_t_junction_queries(built):
     if ref.available():
         r = ref.Reference(points=pts).closest_segments(a, b, 2 * tol, excl)
         assert np.array_equal(r[0], want[0]) and np.array_equal(r[1].view(np.uint32), want[1].view(np.uint32))
+    # the same loop through the caller (thea_b200/callers.py: segFromEdge + the batch + the acceptance test of MeshFix.cpp:766-771)
+    from thea_b200 import callers
+    split, ca, cb = callers.t_junction_candidates(e, p0, p1, tol, excl)
+    assert np.allclose(ca, a, rtol=0, atol=1e-6) and np.allclose(cb, b, rtol=0, atol=1e-6)      # s = tol / len in double there, in float above
+    assert np.array_equal(np.flatnonzero(split >= 0), tj) and np.array_equal(split[tj], len(bverts) + np.arange(len(tj)))
+    cw = orc.Oracle(points=pts).closest_segment(ca, cb, 2 * tol, excl, mode=orc.MODE_CANON)
+    assert np.array_equal(split[tj], cw[0][tj].astype(np.int32))
 
 
 @pytest.mark.parametrize("kind", ["triangles", "points"])

@@ -214,6 +214,33 @@ def sample_evenly_by_separation(eng_mesh, desired, seed, graph_seeds, oversampli
 
 # ---- local surface features: processRange calls with an accumulating functor ------------------------
 
+def t_junction_candidates(eng_boundary_vertices, p0, p1, tol, exclude=None):
+    """The query half of MeshFix's T-junction repair (Tools/MeshFix/MeshFix.cpp:716-790) for E boundary edges at once: per edge the
+    segment shrunk by tol at both ends (segFromEdge, :699-713; edges shorter than 2 tol are skipped), one closestElement query with
+    dist_bound = 2 tol against the structure over the boundary vertices that ignores exclude[e] (VertexFilter, :678-697, as positions in
+    the structure, -1 = unused), and the acceptance test of :766-771.  Returns (split_vertex [E] or -1, segment ends a, b)."""
+    f = np.float32
+    p0 = np.ascontiguousarray(p0, f).reshape(-1, 3)
+    p1 = np.ascontiguousarray(p1, f).reshape(-1, 3)
+    d = p1 - p0
+    ln = np.sqrt(d[:, 0] * d[:, 0] + (d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2])).astype(f)        # LineSegmentN::length
+    ok = ~(ln.astype(np.float64) < 2 * tol)
+    s = np.where(ok, tol / np.where(ok, ln, 1).astype(np.float64), 0.0)
+    t = 1 - s
+    sf, tf = s.astype(f)[:, None], t.astype(f)[:, None]
+    a = ((f(1) - sf) * p0 + sf * p1).astype(f)
+    b = ((f(1) - tf) * p0 + tf * p1).astype(f)
+    idx, d2, vp, sp = eng_boundary_vertices.closest_segment(a, b, 2 * tol, exclude)
+
+    def sq(x, y):
+        e = (x - y).astype(f)
+        return (e[:, 0] * e[:, 0] + (e[:, 1] * e[:, 1] + e[:, 2] * e[:, 2])).astype(np.float64)
+
+    sqtol = tol * tol
+    take = ok & (idx >= 0) & (sq(sp, p0) > sqtol) & (sq(sp, p1) > sqtol) & (sq(sp, vp) < sqtol)
+    return np.where(take, idx, -1).astype(np.int32), a, b
+
+
 def average_distance(eng, p3, max_distance, stats=None):
     """AverageDistance::compute(p, EUCLIDEAN, max_distance) with max_distance >= 0 (absolute) for every p:
     mean |x - p| over the samples in Ball3(p, max_distance), divided by max_distance (AverageDistance.cpp:63-81)."""
