@@ -81,6 +81,14 @@ class _OracleEngine:
     def visibility(self, p, dirs, scale):
         return self.o.visibility(p, dirs, scale, mode=self.orc.MODE_CANON, threads=2)
 
+    def closest_segment(self, a, b, dist_bound=-1.0, exclude=None):
+        i, d, e, s = self.o.closest_segment(a, b, dist_bound, exclude, mode=self.orc.MODE_CANON, threads=2)
+        return i.astype(np.int32), d, e, s
+
+    def closest_triangle(self, q9, dist_bound=-1.0):
+        i, d, e, q = self.o.closest_triangle(q9, dist_bound, mode=self.orc.MODE_BRUTE, threads=2)
+        return i.astype(np.int32), d, e, q
+
     def icp_sums(self, p, q, tr=None):
         p, q = np.asarray(p, np.float64), np.asarray(q, np.float64)
         L = np.eye(3, 4) if tr is None else np.asarray(tr, np.float64).reshape(3, 4)
@@ -138,7 +146,18 @@ def _worker(rank, world, port, out_dir):
     rad = (0.05 + 0.2 * gen.u01(77, 701)).astype(np.float32)
     st = peng.ball_stats(pts[:701], rad, nrm[:701])
     hist = peng.ball_histogram(pts[:701], np.float32(0.2), 8)
-    np.savez(os.path.join(out_dir, f"r{rank}.npz"), idx=idx, d2=d2, cp=cp, t=t, ri=ri, sums=sums, vis=vis, nesc=nesc, st=st, hist=hist)
+    # query objects: segments with per-query exclusions, sharded by position and by space; triangles; a mesh pair
+    sa, sb = q[:1201], (q[:1201] + 0.1 * d[:1201]).astype(np.float32)
+    ex = (np.arange(1201 * 2).reshape(1201, 2) % len(mesh)).astype(np.int64)
+    seg = eng.closest_segment(sa, sb, 0.3, ex)
+    seg_sp = eng.closest_segment(sa, sb, 0.3, ex, space_box=(lo, hi))
+    assert all(x.tobytes() == y.tobytes() for x, y in zip(seg, seg_sp))
+    q9 = (mesh[::7] + np.float32(0.013)).astype(np.float32)
+    tq = eng.closest_triangle(q9)
+    pair = eng.closest_pair_of_triangles(q9)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), idx=idx, d2=d2, cp=cp, t=t, ri=ri, sums=sums, vis=vis, nesc=nesc, st=st, hist=hist,
+             seg_i=seg[0], seg_d=seg[1], seg_e=seg[2], seg_s=seg[3], tq_i=tq[0], tq_d=tq[1], tq_e=tq[2], tq_q=tq[3],
+             pair=np.array([pair[0], pair[1], np.float32(pair[2]).view(np.uint32)], np.int64))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -165,8 +184,17 @@ def test_two_rank_gather_is_byte_identical_to_one_rank(built, tmp_path):
     rad = (0.05 + 0.2 * gen.u01(77, 701)).astype(np.float32)
     st = pone.ball_stats(pts[:701], rad, nrm[:701])
     hist = pone.ball_histogram(pts[:701], np.float32(0.2), 8)
+    sa, sb = q[:1201], (q[:1201] + 0.1 * d[:1201]).astype(np.float32)
+    ex = (np.arange(1201 * 2).reshape(1201, 2) % len(mesh)).astype(np.int64)
+    seg = one.closest_segment(sa, sb, 0.3, ex)
+    q9 = (mesh[::7] + np.float32(0.013)).astype(np.float32)
+    tq = one.closest_triangle(q9)
+    k = np.lexsort((np.arange(len(tq[1])), tq[0], tq[1]))[0]
     for r in range(2):
         z = np.load(tmp_path / f"r{r}.npz")
+        assert all(z[n].tobytes() == x.tobytes() for n, x in zip(("seg_i", "seg_d", "seg_e", "seg_s"), seg))
+        assert all(z[n].tobytes() == x.tobytes() for n, x in zip(("tq_i", "tq_d", "tq_e", "tq_q"), tq))
+        assert z["pair"].tolist() == [int(tq[0][k]), int(k), int(np.float32(tq[1][k]).view(np.uint32))]
         assert z["vis"].tobytes() == vis.tobytes() and z["nesc"].tobytes() == nesc.tobytes()
         assert z["st"].tobytes() == st.tobytes() and z["hist"].tobytes() == hist.tobytes()
         assert z["idx"].tobytes() == idx.tobytes() and z["d2"].tobytes() == d2.tobytes() and z["cp"].tobytes() == cp.tobytes()

@@ -196,6 +196,37 @@ class ShardedEngine:
         t, idx, _ = self.engine.ray_first(self._slice(o3, total, local), self._slice(d3, total, local), **kw)
         return gather_shards(t, total, self.group), gather_shards(idx, total, self.group)
 
+    def closest_segment(self, a3, b3, dist_bound=-1.0, exclude=None, total=None, local=False, space_box=None, **kw):
+        """Line-segment query objects (tgq_closest_segment) of the query shard, gathered: (idx, d2, element point, segment point) for
+        the whole batch on every rank.  exclude follows the queries; space_box shards by the first endpoint."""
+        total = int(a3.shape[0]) if total is None else total
+        if space_box is not None:
+            sel = space_shard_indices(a3, space_box[0], space_box[1], self.rank, self.world)
+            out = self.engine.closest_segment(a3[sel], b3[sel], dist_bound, None if exclude is None else exclude[sel], **kw)
+            return tuple(gather_scattered(x, sel, total, self.group) for x in out)
+        out = self.engine.closest_segment(self._slice(a3, total, local), self._slice(b3, total, local), dist_bound,
+                                          None if exclude is None else self._slice(exclude, total, local), **kw)
+        return tuple(gather_shards(x, total, self.group) for x in out)
+
+    def closest_triangle(self, q9, dist_bound=-1.0, total=None, local=False):
+        """Triangle query objects (tgq_closest_triangle) of the query shard, gathered: (idx, d2, element point, query point)."""
+        total = int(q9.shape[0]) if total is None else total
+        out = self.engine.closest_triangle(self._slice(q9, total, local), dist_bound)
+        return tuple(gather_shards(x, total, self.group) for x in out)
+
+    def closest_pair_of_triangles(self, q9, dist_bound=-1.0):
+        """BvhN::closestPair between this (replicated) structure and the mesh given by its triangles q9 [T x 9]: every rank answers its
+        share of the query triangles, the canonical minimum -- smallest (d2, target index, query index) -- is taken over the gathered
+        rows, identically on every rank.  Returns (target index, query index, d2, query point, target point), -1 indices when none.
+        dist_bound here is a per-query-object bound (with the reference's widening); pass -1 and filter for the plain form."""
+        idx, d2, ep, qp = self.closest_triangle(q9, dist_bound)
+        idx, d2 = np.asarray(idx), np.asarray(d2)
+        ok = np.flatnonzero(idx >= 0)
+        if ok.size == 0:
+            return -1, -1, -1.0, np.zeros(3, np.float32), np.zeros(3, np.float32)
+        k = ok[np.lexsort((ok, idx[ok], d2[ok]))][0]
+        return int(idx[k]), int(k), float(d2[k]), np.asarray(qp)[k], np.asarray(ep)[k]
+
     def knn(self, q3, k, total=None, local=False, **kw):
         total = int(q3.shape[0]) if total is None else total
         b, _ = shard_range(total, self.rank, self.world)
