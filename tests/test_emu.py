@@ -501,3 +501,32 @@ def test_triangle_queries_equal_brute_force(kind):
         f = want[0] >= 0
         assert np.array_equal(got[2][f], want[2][f]) and np.array_equal(got[3][f], want[3][f])
     assert 0 < (want[0] >= 0).sum() < Q
+
+
+@pytest.mark.parametrize("scale,offset", [(1e-3, 0.0), (1.0, 1000.0), (100.0, -5000.0)])
+def test_query_object_margins_hold_for_scaled_and_offset_scenes(scale, offset):
+    """The absolute margins of the segment / triangle traversals grow with the magnitude of the coordinates, and the triangle traversal's
+    floor follows Moeller's ABSOLUTE coplanarity epsilon (FLT_EPSILON / |N|: at scale 1e-3 most query triangles "intersect" the mesh in
+    the reference's arithmetic): tiny scenes, scenes far from the origin and long segments still return the exhaustive minimum."""
+    rng = np.random.default_rng(33)
+    mesh = (gen.torus_mesh(20) * np.float32(scale) + np.float32(offset)).astype(np.float32)
+    v = mesh.reshape(-1, 3)
+    lo, hi = v.min(0), v.max(0)
+    ext = float((hi - lo).max())
+    Q = 1000
+    a = rng.uniform(lo - 0.3 * ext, hi + 0.3 * ext, (Q, 3)).astype(np.float32)
+    d = rng.standard_normal((Q, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    b = (a + d * rng.choice([0.0, 1e-3, 0.05, 0.5, 3.0], (Q, 1)) * ext).astype(np.float32)
+    a[::50] += np.float32(5 * ext)                     # far outside the scene
+    c = rng.uniform(lo - 0.2 * ext, hi + 0.2 * ext, (Q, 1, 3))
+    q9 = (c + rng.normal(0, 1, (Q, 3, 3)) * rng.choice([0.003, 0.03, 0.3], (Q, 1, 1)) * ext).reshape(Q, 9).astype(np.float32)
+    pts = v[::3].copy()
+    zero = 0
+    for e, ora in ((emu_lib.Emu(tris9=mesh), orc.Oracle(tris9=mesh)), (emu_lib.Emu(points=pts), orc.Oracle(points=pts))):
+        for got, want in ((e.closest_segment(a, b), ora.closest_segment(a, b, mode=orc.MODE_BRUTE)),
+                          (e.closest_triangle(q9), ora.closest_triangle(q9, mode=orc.MODE_BRUTE))):
+            assert np.array_equal(got[0], want[0].astype(np.int32))
+            assert np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32))
+            zero += int((want[1] == 0).sum())
+    if scale < 0.01:
+        assert zero > Q // 2          # the reference's scale-dependent tolerance at work
