@@ -14,7 +14,9 @@
 //     computeGeodesicBatch(graph rows, ...) -- nearest-sample lookup on the structure, then the bounded shortest-path search of
 //     tgq_graph_geodesic on the sample graph the caller built with sampleGraph / sampleGraphBatch;
 //   SurfaceFeatures::Local::SpinImage::compute(position[, normal], radial bins, height bins, image)   (…/Local/SpinImage.cpp:30-75).
-// Not covered: random subsampling of the histograms (Random::common()), RandomWalks.
+//   SurfaceFeatures::Local::RandomWalks::compute(position, num_steps, features, num_walks)            (…/Local/RandomWalks.cpp:30-117): seed
+//     lookup batched on the structure, the walks on the host over the caller's TheaRandom (the reference's shared Random::common()).
+// Not covered: random subsampling of the histograms (Random::common()).
 // File:line citations are relative to /root/reference/Code/Source/.
 #ifndef THEA_GPU_LOCALFEATURES_HPP
 #define THEA_GPU_LOCALFEATURES_HPP
@@ -298,12 +300,104 @@ class VisibilityT
     GpuMeshBvhT<VectorT> const * bvh; std::vector<float> dirs; Real scale;
 };
 
+/** Thea::Random (Random.cpp:48-158): MT19937 whose regeneration never touches state[227] (the loop bounds of Random::generate, :92-118,
+ *  as they are), bits() with its tempering (:68-90), integer(lo, hi) (:147-157).  The reference's features draw from the shared
+ *  Random::common(), seeded from the clock; a caller that wants reproducible features passes one of these. */
+class TheaRandom
+{
+  public:
+    explicit TheaRandom(uint32_t seed)
+    {
+      st[0] = seed;
+      for (index = 1; index < N; ++index) st[index] = 1812433253UL * (st[index - 1] ^ (st[index - 1] >> 30)) + (uint32_t)index;
+    }
+    uint32_t bits()
+    {
+      if ((uint32_t)index >= (uint32_t)N)
+      {
+        uint32_t const LOWER = (1u << 31) - 1, UPPER = 0xFFFFFFFFu << 31; uint32_t const mag[2] = {0u, 0x9908B0DFu};
+        for (int i = 0; i < N - M; ++i) { uint32_t x = (st[i] & UPPER) | (st[i + 1] & LOWER); st[i] = st[i + M] ^ (x >> 1) ^ mag[x & 1]; }
+        for (int i = N - M + 1; i < N - 1; ++i) { uint32_t x = (st[i] & UPPER) | (st[i + 1] & LOWER); st[i] = st[i + (M - N)] ^ (x >> 1) ^ mag[x & 1]; }
+        uint32_t y = (st[N - 1] & UPPER) | (st[0] & LOWER); st[N - 1] = st[M - 1] ^ (y >> 1) ^ mag[y & 1];
+        index = 0;
+      }
+      uint32_t r = st[index++];
+      r ^= r >> 11; r ^= (r << 7) & 0x9D2C5680u; r ^= (r << 15) & 0xEFC60000u; r ^= r >> 18;
+      return r;
+    }
+    int32_t integer(int32_t low, int32_t high)
+    {
+      int32_t r = (int32_t)std::floor(low + (high - low + 1) * (double)bits() / 0xFFFFFFFFUL);
+      return r > high ? high : r;
+    }
+
+  private:
+    enum { N = 624, M = 397 };
+    uint32_t st[N]; int index;
+};
+
+/** RandomWalks (RandomWalks.cpp:30-117): the average offset from the query position after each step of an n-step random walk on the
+ *  sample graph.  The surface is the structure over the samples plus their host positions and the neighbour rows sampleGraph returned
+ *  (graph_idx: P x max_degree, -1 padded); the generator is the caller's (see TheaRandom).  computeBatch looks up the seed samples of
+ *  all positions in ONE closestElement batch; the walks are the feature's own sequential arithmetic over one random stream -- position
+ *  major, walk major, step major, exactly the reference's draw order -- and stay on the host.
+ *  SurfaceT: anything with closestElementBatch(q3, Q, idx, d2, cp3) -- GpuPointBvhT by default (a host stand-in lets the CPU suite run the
+ *  walk arithmetic, tests/cpp/random_walks_host_check.cpp). */
+template <typename VectorT = Vec3, typename SurfaceT = GpuPointBvhT<VectorT> >
+class RandomWalksT
+{
+  public:
+    RandomWalksT(SurfaceT const * surf_, float const * sample_positions3, int32_t const * graph_idx_, intx max_degree_, TheaRandom * rng_)
+    : surf(surf_), pos(sample_positions3), gi(graph_idx_), md(max_degree_), rng(rng_)
+    { if (!surf || !pos || !gi || !rng) throw Error("RandomWalks: Cannot construct with a null surface"); }
+
+    void compute(VectorT const & position, intx num_steps, double * features, intx num_walks = -1) const
+    { float p[3]; detail::put3(p, position); computeBatch(p, 1, num_steps, features, num_walks); }
+
+    /** features: Q x num_steps x 3 doubles. */
+    void computeBatch(float const * p3, intx Q, intx num_steps, double * features, intx num_walks = -1) const
+    {
+      if (num_walks < 0) num_walks = 1000;                                           // DEFAULT_NUM_WALKS, RandomWalks.cpp:73
+      std::vector<int32_t> seed((size_t)Q);
+      surf->closestElementBatch(p3, Q, seed.data(), nullptr, nullptr);
+      std::vector<intx> counts((size_t)num_steps);
+      for (intx q = 0; q < Q; ++q)
+      {
+        double * f = features + 3 * num_steps * q;
+        for (intx i = 0; i < 3 * num_steps; ++i) f[i] = 0.0;
+        if (seed[(size_t)q] < 0) throw Error("RandomWalks: Seed sample for random walks not found");
+        std::fill(counts.begin(), counts.end(), (intx)0);
+        for (intx w = 0; w < num_walks; ++w)
+        {
+          intx cur = seed[(size_t)q], steps = num_steps;
+          for (intx i = 0; i < num_steps; ++i)
+          {
+            int32_t deg = 0; while (deg < md && gi[cur * md + deg] >= 0) ++deg;
+            if (deg == 0) { steps = i; break; }
+            cur = gi[cur * md + rng->integer(0, deg - 1)];
+            f[3 * i] += pos[3 * cur]; f[3 * i + 1] += pos[3 * cur + 1]; f[3 * i + 2] += pos[3 * cur + 2];
+          }
+          for (intx j = 0; j < steps; ++j) counts[(size_t)j]++;
+        }
+        for (intx i = 0; i < num_steps; ++i)
+        {
+          intx c = counts[(size_t)i];
+          f[3 * i] = f[3 * i] / c - p3[3 * q]; f[3 * i + 1] = f[3 * i + 1] / c - p3[3 * q + 1]; f[3 * i + 2] = f[3 * i + 2] / c - p3[3 * q + 2];
+        }
+      }
+    }
+
+  private:
+    SurfaceT const * surf; float const * pos; int32_t const * gi; intx md; TheaRandom * rng;
+};
+
 typedef AverageDistanceT<Vec3> AverageDistance;
 typedef CurvatureT<Vec3> Curvature;
 typedef LocalPcaT<Vec3> LocalPca;
 typedef VisibilityT<Vec3> Visibility;
 typedef LocalDistanceHistogramT<Vec3> LocalDistanceHistogram;
 typedef SpinImageT<Vec3> SpinImage;
+typedef RandomWalksT<Vec3> RandomWalks;
 
 }  // namespace Local
 }  // namespace SurfaceFeatures

@@ -794,6 +794,80 @@ void orc_thea_random_uniform01(uint32_t seed, int64_t n, float * out)
 }
 
 
+// Thea::Random as an object (Random.cpp:48-158): bits() and integer(lo, hi).
+namespace {
+struct TheaRandom
+{
+  enum { N = 624, M = 397 };
+  uint32_t st[N]; int index;
+  explicit TheaRandom(uint32_t seed)
+  {
+    st[0] = seed;
+    for (index = 1; index < N; ++index) st[index] = 1812433253UL * (st[index - 1] ^ (st[index - 1] >> 30)) + (uint32_t)index;
+  }
+  uint32_t bits()
+  {
+    if ((uint32_t)index >= (uint32_t)N)
+    {
+      uint32_t const LOWER = (1u << 31) - 1, UPPER = 0xFFFFFFFFu << 31; uint32_t const mag[2] = {0u, 0x9908B0DFu};
+      for (int i = 0; i < N - M; ++i) { uint32_t x = (st[i] & UPPER) | (st[i + 1] & LOWER); st[i] = st[i + M] ^ (x >> 1) ^ mag[x & 1]; }
+      for (int i = N - M + 1; i < N - 1; ++i) { uint32_t x = (st[i] & UPPER) | (st[i + 1] & LOWER); st[i] = st[i + (M - N)] ^ (x >> 1) ^ mag[x & 1]; }
+      uint32_t y = (st[N - 1] & UPPER) | (st[0] & LOWER); st[N - 1] = st[M - 1] ^ (y >> 1) ^ mag[y & 1];
+      index = 0;
+    }
+    uint32_t r = st[index++];
+    r ^= r >> 11; r ^= (r << 7) & 0x9D2C5680u; r ^= (r << 15) & 0xEFC60000u; r ^= r >> 18;
+    return r;
+  }
+  // Random::integer(low, high), Random.cpp:147-157
+  int32_t integer(int32_t low, int32_t high)
+  {
+    int32_t r = (int32_t)std::floor(low + (high - low + 1) * (double)bits() / 0xFFFFFFFFUL);
+    return r > high ? high : r;
+  }
+};
+}  // namespace
+
+// RandomWalks::compute (SurfaceFeatures/Local/RandomWalks.cpp:30-117) for Q positions in turn, all drawing from ONE generator in the
+// state of Random(seed) (the reference's shared Random::common()): seed sample = the structure's closest element to the position,
+// num_walks walks of up to num_steps steps over the neighbour rows idx [P x K] (-1 padded; a sample without neighbours ends the walk),
+// per step the running sum of the positions reached (float coordinates added into doubles, in walk order), divided by the number of walks
+// that got that far, less the query position.
+void orc_random_walks(void * h, int64_t const * idx, int64_t P, int K, float const * q3, int64_t Q, int64_t num_steps, int64_t num_walks, uint32_t seed,
+                      double * features)
+{
+  KdTree const & T = ((Handle *)h)->tree;
+  TheaRandom rnd(seed);
+  std::vector<int64_t> counts((size_t)num_steps);
+  for (int64_t qi = 0; qi < Q; ++qi)
+  {
+    double * f = features + 3 * num_steps * qi;
+    for (int64_t i = 0; i < 3 * num_steps; ++i) f[i] = 0.0;
+    V3 pos = ld3(q3, qi);
+    int64_t seed_index = T.closest<false>(pos, -1).idx;
+    std::fill(counts.begin(), counts.end(), 0);
+    for (int64_t w = 0; w < num_walks; ++w)
+    {
+      int64_t cur = seed_index, steps = num_steps;
+      for (int64_t i = 0; i < num_steps; ++i)
+      {
+        int64_t deg = 0; while (deg < K && idx[cur * K + deg] >= 0) ++deg;
+        if (deg == 0) { steps = i; break; }
+        int32_t next = rnd.integer(0, (int32_t)deg - 1);
+        cur = idx[cur * K + next];
+        V3 p = T.pts[(size_t)cur];
+        f[3 * i] += p.x; f[3 * i + 1] += p.y; f[3 * i + 2] += p.z;
+      }
+      for (int64_t j = 0; j < steps; ++j) counts[(size_t)j]++;
+    }
+    for (int64_t i = 0; i < num_steps; ++i)
+    {
+      int64_t c = counts[(size_t)i];
+      f[3 * i] = f[3 * i] / c - pos.x; f[3 * i + 1] = f[3 * i + 1] / c - pos.y; f[3 * i + 2] = f[3 * i + 2] / c - pos.z;
+    }
+  }
+}
+
 // ---- shortest paths on the sample graph: ShortestPaths::dijkstraWithCallback (Algorithms/ShortestPaths.hpp:166-353) restated with a
 // binary heap.  The reference's Fibonacci heap pops equal distances in an order of its own; here equal distances pop in index order
 // (the canonical order the engine reproduces).  Distances are the reference's: test_dist = nbr_dist + data->dist in double (:304),

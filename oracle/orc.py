@@ -54,6 +54,7 @@ def lib():
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_closest_triangle.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4
         L.orc_tri_tri_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_random_walks.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_uint32, C.c_void_p]
         L.orc_seg_point_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.orc_tri_seg_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_set_labels.argtypes = [C.c_void_p, C.c_void_p]
@@ -181,6 +182,14 @@ class Oracle:
         qp = np.empty((Q, 3), np.float32)
         lib().orc_closest_triangle(self.h, _p(q), Q, float(dist_bound), int(plain_bound), mode, threads or ncores(), _p(idx), _p(d2), _p(ep), _p(qp))
         return idx, d2, ep, qp
+
+    def random_walks(self, graph_idx, q, num_steps, num_walks, seed):
+        """RandomWalks::compute for every position of q in turn on the neighbour rows graph_idx [P x K], one shared Random(seed)."""
+        gi = np.ascontiguousarray(graph_idx, np.int64)
+        q = _f32(q).reshape(-1, 3)
+        out = np.empty((q.shape[0], int(num_steps), 3), np.float64)
+        lib().orc_random_walks(self.h, _p(gi), gi.shape[0], gi.shape[1], _p(q), q.shape[0], int(num_steps), int(num_walks), int(seed), _p(out))
+        return out
 
     def ray_first(self, o, d, tmax=None, mode=MODE_CANON, threads=None):
         o = _f32(o).reshape(-1, 3)

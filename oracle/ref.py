@@ -60,6 +60,7 @@ def lib():
         L.ref_tri_seg_batch.argtypes = [vp, vp, vp, i64, vp, vp, vp]
         L.ref_tri_tri_batch.argtypes = [vp, vp, i64, vp, vp, vp]
         L.ref_closest_triangle_batch.argtypes = [vp, vp, i64, f64, vp, vp, vp, vp]
+        L.ref_random_walks.argtypes = [vp, i64, i32, vp, vp, vp, i64, i64, i64, C.c_uint32, vp]
         L.ref_tri_cache.argtypes = [vp] * 6
         L.ref_tri_point.restype = f32
         L.ref_tri_point.argtypes = [vp, vp, vp]
@@ -364,6 +365,16 @@ def fps(points, idx, sep, n_desired):
     sel = np.full(int(n_desired), -1, np.int64)
     n = lib().ref_fps(_p(p), P, K, _p(idx), _p(sep), int(n_desired), _p(sel))
     return sel[:n]
+
+
+def random_walks(points, idx, sep, q, num_steps, num_walks, seed):
+    """The reference's RandomWalks::compute per position on an injected graph, Random::common() put into the state of Random(seed)."""
+    p = _f32(points).reshape(-1, 3)
+    gi, gs, _, _ = _graph_args(idx, sep)
+    q = _f32(q).reshape(-1, 3)
+    out = np.empty((q.shape[0], int(num_steps), 3), np.float64)
+    lib().ref_random_walks(_p(p), p.shape[0], gi.shape[1], _p(gi), _p(gs), _p(q), q.shape[0], int(num_steps), int(num_walks), int(seed), _p(out))
+    return out
 
 
 def spin_image(points, normals, scale, q, qn, nr, nh):

@@ -56,6 +56,7 @@
 #include "Algorithms/SurfaceFeatures/Local/SpinImage.hpp"
 #include "Algorithms/SurfaceFeatures/Local/AverageDistance.hpp"
 #include "Algorithms/SurfaceFeatures/Local/LocalDistanceHistogram.hpp"
+#include "Algorithms/SurfaceFeatures/Local/RandomWalks.hpp"
 #include "Algorithms/Histogram.hpp"
 #include "Algorithms/ShortestPaths.hpp"
 #include "Graphics/GeneralMesh.hpp"
@@ -659,6 +660,24 @@ void ref_spin_image(float const * p3, float const * n3, int64_t P, float scale, 
     si.compute(v3(q3 + 3 * i), v3(qn3 + 3 * i), nr, nh, m);
     for (int r = 0; r < nr; ++r) for (int c = 0; c < nh; ++c) image[((int64_t)i * nr + r) * nh + c] = m(r, c);
   }
+}
+
+// RandomWalks::compute (SurfaceFeatures/Local/RandomWalks.cpp:70-117) on a given graph.  The reference draws from Random::common(), which it
+// seeds from the clock; here the shared generator is put into the state of Random(seed) first (its members are reachable in this
+// translation unit only), so that the reference's own code runs on a known stream.
+void ref_random_walks(float const * p3, int64_t P, int max_degree, int64_t const * idx, float const * sep, float const * q3, int64_t Q, int64_t num_steps,
+                      int64_t num_walks, uint32_t seed, double * features)
+{
+  PointSet3::Options opts = PointSet3::Options::defaults(); opts.setMaxDegree(max_degree);
+  PointSet3 ps(opts);
+  fill_samples(ps, p3, nullptr, P, 0);
+  inject_graph(ps, P, max_degree, idx, sep);
+  Random fresh(seed);
+  Random & shared = Random::common();
+  for (int i = 0; i < 624; ++i) shared.state[i] = fresh.state[i];
+  shared.index = fresh.index;
+  SurfaceFeatures::Local::RandomWalks rw(&ps);
+  for (int64_t i = 0; i < Q; ++i) rw.compute(v3(q3 + 3 * i), (intx)num_steps, features + 3 * num_steps * i, (intx)num_walks);
 }
 
 int ref_tree_depth(int64_t n, int leaf) { return (int)Math::treeDepth((intx)n, leaf); }

@@ -15,10 +15,11 @@ template <typename T> static void wr(FILE * f, std::vector<T> const & v) { if (!
 
 // compile check of the T-junction caller (exercised on the GPU through its Python twin, tests/test_gpu_segments.py)
 static auto const t_junction_caller = &TheaGpu::tJunctionCandidates<TheaGpu::GpuPointBvh>;
+static auto const random_walks_caller = &TheaGpu::SurfaceFeatures::Local::RandomWalks::computeBatch;
 
 int main(int argc, char ** argv)
 {
-  (void)t_junction_caller;
+  (void)t_junction_caller; (void)random_walks_caller;
   if (argc < 3) { fprintf(stderr, "usage: %s in.bin out.bin\n", argv[0]); return 2; }
   try
   {

@@ -570,3 +570,21 @@ def test_k_closest_pairs_between_point_structures(built):
         rows = sorted((float(kd[q, j]), int(ki[q, j]), q) for q in range(len(b)) for j in range(k) if ki[q, j] >= 0)[:k]
         assert [(int(t), int(q)) for t, q in zip(ti, qi)] == [(t, q) for _, t, q in rows]
         assert np.array_equal(d2, np.array([r[0] for r in rows], np.float32))
+
+
+def test_random_walks_on_the_sample_graph(built):
+    """SurfaceFeatures::Local::RandomWalks (RandomWalks.cpp:30-117) through callers.random_walks: seed lookup (tgq_closest) and the sample
+    graph (tgq_ball_graph) on the device, the walks on the host over a TheaRandom; against the oracle, which is pinned to the reference's
+    own RandomWalks on an injected generator state (tests/test_ref_pin.py).  Every double bit for bit."""
+    from thea_b200 import Engine
+    mesh = gen.torus_mesh(30)
+    p, n, _ = gen.area_samples(mesh, 3000)
+    pe = Engine(0)
+    pe.build_points(p, n)
+    seeds = (gen.splitmix64(0x5EED, 100) % np.uint64(len(p))).astype(np.int64)
+    idx, sep, cnt, _ = callers.sample_graph(pe, 8, seeds)
+    q = (p[::100] + np.float32(0.01)).astype(np.float32)
+    got = callers.random_walks(pe, idx, p, q, 6, 200, callers.TheaRandom(5))
+    want = orc.Oracle(points=p).random_walks(idx.astype(np.int64), q, 6, 200, 5)
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(got[~np.isnan(got)].view(np.uint64), want[~np.isnan(want)].view(np.uint64))
+    assert np.isfinite(want).all() and np.abs(want).max() < 1.0

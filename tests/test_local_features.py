@@ -228,3 +228,72 @@ def test_spin_image_is_bit_exact(cloud):
         img = E.spin_image(c, qn, nr, nh, ext)
         assert np.array_equal(img.astype(np.float64), ora.spin_image(c, qn, nr, nh, ext))
         assert (img.reshape(len(c), -1).sum(axis=1) == len(p)).all()
+
+
+def _walk_case():
+    mesh = gen.torus_mesh(30)
+    p, n, _ = gen.area_samples(mesh, 3000)
+    ora = orc.Oracle(points=p, normals=n)
+    seeds = (gen.splitmix64(0x5EED, 100) % np.uint64(len(p))).astype(np.int64)
+    K = 8
+    gi, gs, _ = ora.ball_graph(K, float(np.float32(np.sqrt(np.float32(K))) * np.float32(ora.avg_separation(seeds))))
+    iso = gi.copy()
+    iso[17] = -1                                   # an isolated sample: walks that reach it stop and shift the stream
+    q = (p[::100] + np.float32(0.01)).astype(np.float32)
+    q[3] = p[17]
+    return p, gi, gs, iso, q
+
+
+class _SeedLookup:
+    """closest() of an Engine, answered by the oracle (CPU suite)."""
+
+    def __init__(self, pts):
+        self.o = orc.Oracle(points=pts)
+
+    def closest(self, q):
+        return self.o.closest(q, mode=orc.MODE_CANON)
+
+
+def _same_or_both_nan(a, b):
+    return np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)].view(np.uint64), b[~np.isnan(b)].view(np.uint64))
+
+
+def test_thea_random_restatement_in_the_callers():
+    """callers.TheaRandom (the vectorised MT19937 with the reference's loop bounds) against the oracle's scalar restatement, which
+    tests/test_oracle.py pins to the reference's Random; integer(lo, hi) against its definition."""
+    ur = orc.thea_random_uniform01(4321, 5000)
+    b = callers.TheaRandom(4321).bits(5000)
+    assert np.array_equal(b.astype(np.float32) * (np.float32(1.0) / np.float32(0xFFFFFFFF)), ur)
+    r = callers.TheaRandom(4321)
+    assert [r.bits() for _ in range(700)] == b[:700].tolist()          # scalar draws cross a regeneration boundary like bulk draws
+    v = callers.TheaRandom.to_integer(np.array([0, 1, 0x7FFFFFFF, 0xFFFFFFFE, 0xFFFFFFFF], np.uint32), 0, 7)
+    assert v.tolist() == [0, 0, 3, 7, 7]                                # bits = 0xFFFFFFFF would give 8: clamped (Random.cpp:152-156)
+
+
+def test_random_walks_caller_matches_the_oracle(tmp_path):
+    """SurfaceFeatures::Local::RandomWalks (RandomWalks.cpp:30-117): the Python caller (both of its paths) and the C++ caller of
+    LocalFeatures.hpp (run on the host with given seed samples) against the oracle, which tests/test_ref_pin.py pins to the reference's
+    own RandomWalks on an injected Random state.  Bit equality of every double."""
+    import os
+    import struct
+    import subprocess
+    p, gi, gs, iso, q = _walk_case()
+    eng = _SeedLookup(p)
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "random_walks_host_check")
+    for graph in (gi, iso):
+        for steps, walks, seed in ((5, 50, 1234), (6, 300, 7)):
+            want = orc.Oracle(points=p).random_walks(graph, q, steps, walks, seed)
+            got = callers.random_walks(eng, graph, p, q, steps, walks, callers.TheaRandom(seed))
+            assert _same_or_both_nan(got, want)
+            if os.path.exists(exe):
+                inp, out = tmp_path / "in.bin", tmp_path / "out.bin"
+                with open(inp, "wb") as f:
+                    f.write(struct.pack("<6q", len(p), graph.shape[1], len(q), steps, walks, seed))
+                    f.write(np.ascontiguousarray(p, np.float32).tobytes())
+                    f.write(np.ascontiguousarray(graph, np.int32).tobytes())
+                    f.write(np.ascontiguousarray(q, np.float32).tobytes())
+                    f.write(eng.closest(q)[0].astype(np.int32).tobytes())
+                assert subprocess.run([exe, str(inp), str(out)]).returncode == 0
+                cpp = np.fromfile(out, np.float64).reshape(want.shape)
+                assert _same_or_both_nan(cpp, want)
+    assert np.isnan(want).any()                     # the isolated sample was reached

@@ -494,3 +494,24 @@ def test_mesh_to_mesh_closest_pair_matches_reference():
         assert found and abs(d2 - float(bd[k])) <= 1e-5 * max(d2, float(bd[k]))       # role swapping in the reference: last-bit differences allowed
         if d2 > 0:
             assert (ti, qi) == (int(bi[k]), int(k))
+
+
+def test_random_walks_match_reference():
+    """SurfaceFeatures::Local::RandomWalks::compute (RandomWalks.cpp:30-117), the reference's own code on an injected sample graph with its
+    shared generator Random::common() put into the state of Random(seed), against the oracle: every feature double bit for bit, including
+    walks that stop at a sample without neighbours (0 / 0 = NaN where no walk got that far)."""
+    mesh = gen.torus_mesh(30)
+    p, n, _ = gen.area_samples(mesh, 3000)
+    ora = orc.Oracle(points=p, normals=n)
+    seeds = (gen.splitmix64(0x5EED, 100) % np.uint64(len(p))).astype(np.int64)
+    K = 8
+    gi, gs, _ = ora.ball_graph(K, float(np.float32(np.sqrt(np.float32(K))) * np.float32(ora.avg_separation(seeds))))
+    gi[17] = -1
+    gs[17] = -1
+    q = (p[::100] + np.float32(0.01)).astype(np.float32)
+    q[3] = p[17]
+    for steps, walks, seed in ((5, 50, 1234), (8, 1000, 99)):
+        a = orc.Oracle(points=p).random_walks(gi, q, steps, walks, seed)
+        b = ref.random_walks(p, gi, gs, q, steps, walks, seed)
+        assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)].view(np.uint64), b[~np.isnan(b)].view(np.uint64))
+        assert np.isnan(b).any() and np.isfinite(b).sum() > b.size // 2

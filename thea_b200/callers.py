@@ -241,6 +241,104 @@ def t_junction_candidates(eng_boundary_vertices, p0, p1, tol, exclude=None):
     return np.where(take, idx, -1).astype(np.int32), a, b
 
 
+class TheaRandom:
+    """Thea::Random (Random.cpp:48-158): MT19937 whose regeneration never touches state[227] (the loop bounds of Random::generate,
+    :92-118, reproduced as they are), tempering of bits() (:68-90), integer(lo, hi) = floor(lo + (hi - lo + 1) * bits / 0xFFFFFFFF)
+    clamped to hi (:147-157).  The reference's callers share one generator, Random::common(), seeded from the clock; a caller that
+    wants reproducible features hands one of these around instead."""
+    N, M = 624, 397
+
+    def __init__(self, seed):
+        st = np.empty(self.N, np.uint64)
+        st[0] = np.uint64(seed & 0xFFFFFFFF)
+        for i in range(1, self.N):
+            st[i] = (np.uint64(1812433253) * (st[i - 1] ^ (st[i - 1] >> np.uint64(30))) + np.uint64(i)) & np.uint64(0xFFFFFFFF)
+        self.st = st.astype(np.uint32)
+        self.index = self.N
+
+    def _generate(self):
+        st, N, M = self.st, self.N, self.M
+        U, L, A = np.uint32(0x80000000), np.uint32(0x7FFFFFFF), np.uint32(0x9908B0DF)
+
+        def step(dst, src):
+            x = (st[dst] & U) | (st[dst.start + 1:dst.stop + 1] & L)
+            st[dst] = st[src] ^ (x >> np.uint32(1)) ^ np.where(x & np.uint32(1), A, np.uint32(0))
+        step(slice(0, N - M), slice(M, N))                                   # i = 0 .. 226: reads old state[i + 1] and old state[i + 397]
+        step(slice(N - M + 1, 2 * (N - M) + 1), slice(1, N - M + 1))          # i = 228 .. 454: reads state[1 .. 227] (227 is never regenerated)
+        step(slice(2 * (N - M) + 1, N - 1), slice(N - M + 1, M - 1))          # i = 455 .. 622: reads state[228 .. 395], new
+        y = (st[N - 1] & U) | (st[0] & L)
+        st[N - 1] = st[M - 1] ^ (y >> np.uint32(1)) ^ (A if (y & np.uint32(1)) else np.uint32(0))
+        self.index = 0
+
+    def bits(self, n=None):
+        """n untempered-then-tempered draws as uint32 (a scalar int when n is None)."""
+        count = 1 if n is None else int(n)
+        out = np.empty(count, np.uint32)
+        k = 0
+        while k < count:
+            if self.index >= self.N:
+                self._generate()
+            m = min(count - k, self.N - self.index)
+            out[k:k + m] = self.st[self.index:self.index + m]
+            self.index += m
+            k += m
+        r = out
+        r = r ^ (r >> np.uint32(11))
+        r = r ^ ((r << np.uint32(7)) & np.uint32(0x9D2C5680))
+        r = r ^ ((r << np.uint32(15)) & np.uint32(0xEFC60000))
+        r = r ^ (r >> np.uint32(18))
+        return int(r[0]) if n is None else r
+
+    @staticmethod
+    def to_integer(bits, lo, hi):
+        """Random::integer(lo, hi) from raw draws (arrays broadcast)."""
+        r = np.floor(lo + (hi - lo + 1) * bits.astype(np.float64) / np.float64(0xFFFFFFFF)).astype(np.int64)
+        return np.minimum(r, hi)
+
+
+def random_walks(eng_samples, graph_idx, samples3, p3, num_steps, num_walks, rng):
+    """SurfaceFeatures::Local::RandomWalks::compute (Algorithms/SurfaceFeatures/Local/RandomWalks.cpp:30-117) for Q positions in turn:
+    the seed sample is the structure's closest element to the position (ONE batched closestElement call for all positions), then
+    num_walks walks of num_steps steps over the neighbour rows graph_idx [P x K] (-1 padded; what sample_graph returned), all drawing
+    from the shared generator `rng` (TheaRandom) in the reference's order -- position-major, walk-major, step-major --; per step the sum of
+    the sample positions reached (float coordinates added into doubles in walk order), divided by the number of walks that got that far,
+    less the position.  The walks themselves are the caller's own sequential arithmetic over one random stream, as in the reference; they
+    stay on the host.  Returns [Q x num_steps x 3] float64."""
+    f = np.float32
+    p3 = np.ascontiguousarray(p3, f).reshape(-1, 3)
+    pts = np.ascontiguousarray(samples3, f).reshape(-1, 3)
+    gi = np.asarray(graph_idx).astype(np.int64)
+    Q, S, W, K = len(p3), int(num_steps), int(num_walks), gi.shape[1]
+    seed_idx = np.asarray(eng_samples.closest(p3)[0]).astype(np.int64)
+    deg = (gi >= 0).sum(1)
+    assert np.array_equal(deg, np.where((gi >= 0).all(1), K, np.argmin(gi >= 0, axis=1))), "neighbour rows must be -1 padded at the end"
+    out = np.empty((Q, S, 3), np.float64)
+    if (deg > 0).all():
+        # no walk can stop early: walk w of position q takes draws ((q W + w) S + s), so the walks of one position advance together
+        for q in range(Q):
+            draws = rng.bits(W * S).reshape(W, S)
+            cur = np.full(W, seed_idx[q], np.int64)
+            for s_ in range(S):
+                nxt = TheaRandom.to_integer(draws[:, s_], 0, deg[cur] - 1)
+                cur = gi[cur, nxt]
+                out[q, s_] = np.cumsum(pts[cur].astype(np.float64), axis=0)[-1] / W - p3[q].astype(np.float64)      # cumsum: left to right
+        return out
+    for q in range(Q):                    # isolated samples exist: a walk that reaches one stops and leaves its remaining draws to the next walk
+        acc = np.zeros((S, 3), np.float64)
+        counts = np.zeros(S, np.int64)
+        for _ in range(W):
+            cur = seed_idx[q]
+            for s_ in range(S):
+                if deg[cur] == 0:
+                    break
+                cur = gi[cur, int(TheaRandom.to_integer(np.array([rng.bits()], np.uint32), 0, int(deg[cur]) - 1)[0])]
+                acc[s_] += pts[cur].astype(np.float64)
+                counts[s_] += 1
+        with np.errstate(invalid="ignore", divide="ignore"):
+            out[q] = acc / counts[:, None] - p3[q].astype(np.float64)
+    return out
+
+
 def average_distance(eng, p3, max_distance, stats=None):
     """AverageDistance::compute(p, EUCLIDEAN, max_distance) with max_distance >= 0 (absolute) for every p:
     mean |x - p| over the samples in Ball3(p, max_distance), divided by max_distance (AverageDistance.cpp:63-81)."""

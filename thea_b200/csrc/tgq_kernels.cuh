@@ -1,6 +1,7 @@
 // tgq_kernels.cuh -- __global__ kernels of the engine (sm_100a).  Build: K1 bounds+Morton, K3 hierarchy, K4 refit,
 // node emission; queries: K5 closest, K6 k-NN, K7 ball graph, K8 ray first/any hit (+ SDF cone rays), K9 ICP sums,
-// K11 area sampling.  Numbering follows SURVEY.md 2.2.
+// K11 area sampling; SURVEY.md 8f additions: ball range / statistics / histograms, visibility fans, spin images, the sample-graph searches
+// (tgq_graph.cuh), and the query objects of rank 4 (k_closest_seg, k_closest_tri).  Numbering follows SURVEY.md 2.2.
 #pragma once
 #include "tgq_traverse.cuh"
 #include "tgq_select.cuh"

@@ -7,6 +7,7 @@
 //   Knn*       <- BvhN::kClosestPairs                       (BvhN.hpp:1137-1146, functor :474-500)
 //   Ball*      <- processRange<Ball3> + NeighborFunctor     (BvhN.hpp:2118-2171, PointSet3.hpp:586-681)
 //   Ray*       <- BvhN::rayStructureIntersection / rayIntersectionTime / rayIntersects (BvhN.hpp:1266-1316,2188-2291)
+//   Seg*, TriQ* <- BvhN::closestPair with a LineSegment3 / Triangle3 query object                (BvhN.hpp:1081-1114; end of this file)
 //
 // Every traversal is a small state machine: `cur` >= 0 means "an inner node is pending", TGQ_ST_LEAF "elements
 // [k, kend) of a leaf are pending", TGQ_ST_DONE "finished".  One fetch + *_node_compute / *_leaf_compute advances the query
