@@ -530,3 +530,22 @@ def test_query_object_margins_hold_for_scaled_and_offset_scenes(scale, offset):
             zero += int((want[1] == 0).sum())
     if scale < 0.01:
         assert zero > Q // 2          # the reference's scale-dependent tolerance at work
+
+
+def test_query_objects_on_tiny_structures_and_with_everything_excluded():
+    """One- to five-element structures (the single-node special case, empty child slots with inverted boxes) and exclusion lists that
+    remove every element: the segment / triangle traversals still return the exhaustive answer, or "not found"."""
+    rng = np.random.default_rng(34)
+    a = rng.uniform(-1, 1, (50, 3)).astype(np.float32)
+    b = rng.uniform(-1, 1, (50, 3)).astype(np.float32)
+    q9 = rng.uniform(-1, 1, (50, 9)).astype(np.float32)
+    for n in (1, 2, 3, 5):
+        tris = rng.uniform(-1, 1, (n, 9)).astype(np.float32)
+        pts = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+        for e, ora in ((emu_lib.Emu(tris9=tris), orc.Oracle(tris9=tris)), (emu_lib.Emu(points=pts), orc.Oracle(points=pts))):
+            for got, want in ((e.closest_segment(a, b), ora.closest_segment(a, b, mode=orc.MODE_BRUTE)),
+                              (e.closest_triangle(q9), ora.closest_triangle(q9, mode=orc.MODE_BRUTE))):
+                assert np.array_equal(got[0], want[0].astype(np.int32)) and np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32))
+    e = emu_lib.Emu(tris9=rng.uniform(-1, 1, (2, 9)).astype(np.float32))
+    idx, d2, _, _ = e.closest_segment(a, b, -1.0, np.tile(np.array([[0, 1]]), (50, 1)))
+    assert (idx == -1).all() and (d2 == -1).all()
