@@ -405,6 +405,16 @@ class GpuBvhBase
     void closestElementTriangleBatch(float const * q9, intx Q, int32_t * idx, float * d2, float * element_point3, float * query_point3, double dist_bound = -1) const
     { detail::check(h, tgq_closest_triangle(h, q9, Q, dist_bound, idx, d2, element_point3, query_point3), "tgq_closest_triangle"); }
 
+    /** BvhN::distance<MetricL2>(query object, dist_bound, compatibility) (BvhN.hpp:1036-1047) for a segment or a triangle: -1 when nothing
+     *  lies within the bound. */
+    template <typename MetricT, typename QueryT, typename CompatibilityFunctorT = UniversalCompatibility,
+              typename std::enable_if<detail::is_segment<QueryT>::value || detail::is_triangle<QueryT>::value, short>::type = 0>
+    double distance(QueryT const & query, double dist_bound = -1, CompatibilityFunctorT c = CompatibilityFunctorT()) const
+    {
+      double result = -1;
+      return closestElement<MetricT>(query, dist_bound, c, &result) >= 0 ? result : -1;
+    }
+
     /** Q segment queries in one launch: the loop of Tools/MeshFix/MeshFix.cpp:756-763 (one closestElement per boundary edge, each under
      *  a VertexFilter) as a batch.  a3 / b3: Q x 3 endpoints (b_is_direction: b3 holds the stored directions instead); exclude: Q x
      *  n_exclude element indices each query's filter rejects (-1 = unused, n_exclude <= 4) or null; outputs may be null; host or device
@@ -441,7 +451,8 @@ class GpuMeshBvhT : public GpuBvhBase<VectorT>
 
     explicit GpuMeshBvhT(int device = 0) : Base(device), built(false) {}
     using Base::closestPair;         // the structure-to-structure and line-segment forms
-    using Base::closestElement;      // the line-segment form
+    using Base::closestElement;      // the line-segment and triangle forms
+    using Base::distance;
 
     /** MeshBvh::addTriangles analogue: appends one triangle to the pending soup (MeshTriangles.hpp:361-370). */
     void addTriangle(VectorT const & v0, VectorT const & v1, VectorT const & v2)
@@ -637,7 +648,8 @@ class GpuPointBvhT : public GpuBvhBase<VectorT>
 
     explicit GpuPointBvhT(int device = 0) : Base(device), filter(nullptr) {}
     using Base::closestPair;         // the structure-to-structure and line-segment forms
-    using Base::closestElement;      // the line-segment form
+    using Base::closestElement;      // the line-segment and triangle forms
+    using Base::distance;
     using Base::kClosestPairs;       // likewise
 
     /** Per-element labels (P int32, element order; null clears): the `label` member of Register's samples. */

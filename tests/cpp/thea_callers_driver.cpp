@@ -226,7 +226,7 @@ int main(int argc, char ** argv)
       double da = -1, db = -1;
       intx ia = pref.closestElement<MetricL2>(seg, bound, UniversalCompatibility(), &da);
       intx ib = pgpu.closestElement<MetricL2>(seg, bound, UniversalCompatibility(), &db);
-      bool same3 = da == db && (ia == ib || ia < 0 == ib < 0);
+      bool same3 = da == db && (ia == ib || ia < 0 == ib < 0) && pref.distance<MetricL2>(seg, bound) == pgpu.distance<MetricL2>(seg, bound);
       seg_ok += (same && same2 && same3);
       EXPECT(same && same2 && same3, "segment query %d: points %g vs %g, triangles %g vs %g, closestElement %ld vs %ld", i, pa.getMonotoneApproxDistance(),
              pb.getMonotoneApproxDistance(), ta.getMonotoneApproxDistance(), tb.getMonotoneApproxDistance(), (long)ia, (long)ib);
