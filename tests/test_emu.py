@@ -549,3 +549,83 @@ def test_query_objects_on_tiny_structures_and_with_everything_excluded():
     e = emu_lib.Emu(tris9=rng.uniform(-1, 1, (2, 9)).astype(np.float32))
     idx, d2, _, _ = e.closest_segment(a, b, -1.0, np.tile(np.array([[0, 1]]), (50, 1)))
     assert (idx == -1).all() and (d2 == -1).all()
+
+
+def _exact_tri_tri_distance(a, b):
+    """Distance between two triangles (3 x 3 float64 each) by the textbook decomposition: zero if an edge of one pierces the other, else the
+    minimum over nine edge pairs and six vertex-face pairs."""
+    def seg_seg(p1, q1, p2, q2):
+        d1, d2, r = q1 - p1, q2 - p2, p1 - p2
+        a_, e, f = d1 @ d1, d2 @ d2, d2 @ r
+        c, b_ = d1 @ r, d1 @ d2
+        den = a_ * e - b_ * b_
+        s = np.clip((b_ * f - c * e) / den, 0, 1) if den > 0 else 0.0
+        t = (b_ * s + f) / e if e > 0 else 0.0
+        if t < 0:
+            t, s = 0.0, (np.clip(-c / a_, 0, 1) if a_ > 0 else 0.0)
+        elif t > 1:
+            t, s = 1.0, (np.clip((b_ - c) / a_, 0, 1) if a_ > 0 else 0.0)
+        return np.linalg.norm(p1 + s * d1 - p2 - t * d2)
+
+    def point_tri(p, t):
+        n = np.cross(t[1] - t[0], t[2] - t[0])
+        nn = n @ n
+        if nn > 0:
+            proj = p - ((p - t[0]) @ n) / nn * n
+            w = [np.cross(t[(i + 1) % 3] - t[i], proj - t[i]) @ n for i in range(3)]
+            if min(w) >= 0:
+                return np.linalg.norm(p - proj)
+        return min(seg_seg(p, p, t[i], t[(i + 1) % 3]) for i in range(3))
+
+    def pierces(p, q, t):
+        n = np.cross(t[1] - t[0], t[2] - t[0])
+        dp, dq = (p - t[0]) @ n, (q - t[0]) @ n
+        if dp * dq > 0 or dp == dq:
+            return False
+        x = p + dp / (dp - dq) * (q - p)
+        return min(np.cross(t[(i + 1) % 3] - t[i], x - t[i]) @ n for i in range(3)) >= 0
+
+    for i in range(3):
+        if pierces(a[i], a[(i + 1) % 3], b) or pierces(b[i], b[(i + 1) % 3], a):
+            return 0.0
+    d = min(seg_seg(a[i], a[(i + 1) % 3], b[j], b[(j + 1) % 3]) for i in range(3) for j in range(3))
+    return min([d] + [point_tri(a[i], b) for i in range(3)] + [point_tri(b[i], a) for i in range(3)])
+
+
+def test_triangle_queries_differ_from_the_reference_only_where_it_reports_spurious_intersections():
+    """The documented exception of the triangle-query parity.  Moeller's test as the reference carries it snaps every signed
+    plane distance below FLT_EPSILON -- in units of the UNNORMALISED normal -- to zero; when all three vertices of the query lie that close to
+    an element's infinite plane, the query's interval on the intersection line is never computed and stays [0, 0] (Triangle3.hpp:1041-1077,
+    1209-1216), so the pair is called intersecting whenever the element's own interval contains the coordinate 0 -- at ANY lateral distance.
+    No spatial bound can anticipate that.  On a small-scale scene that provokes it, every query on which the engine's traversal and the
+    exhaustive minimum disagree is such a case: the reference's winner is a pair at a true distance far beyond the traversal's floor that it
+    calls intersecting, and the engine's answer is the minimum over a set that contains all the remaining pairs."""
+    rng = np.random.default_rng(233)
+    mesh = (gen.torus_mesh(6) * np.float32(0.01)).astype(np.float32)                 # 72 triangles of |N| ~ 4e-5: tolerance ~ 3e-3, a tenth of the scene
+    v = mesh.reshape(-1, 3)
+    lo, hi = v.min(0), v.max(0)
+    ext = float((hi - lo).max())
+    Q = 2000
+    c = rng.uniform(lo - 0.3 * ext, hi + 0.3 * ext, (Q, 1, 3))
+    q9 = (c + rng.normal(0, 1, (Q, 3, 3)) * rng.choice([0.02, 0.2, 0.4], (Q, 1, 1)) * ext).reshape(Q, 9).astype(np.float32)
+    got = emu_lib.Emu(tris9=mesh).closest_triangle(q9)
+    want = orc.Oracle(tris9=mesh).closest_triangle(q9, mode=orc.MODE_BRUTE)
+    differ = np.flatnonzero((got[0] != want[0].astype(np.int32)) | (got[1].view(np.uint32) != want[1].view(np.uint32)))
+    assert 0 < differ.size < Q // 20                                                 # it happens, and it is rare
+    tau_e = np.float64(np.finfo(np.float32).eps) / np.linalg.norm(np.cross(v[1::3] - v[0::3], v[2::3] - v[0::3]).astype(np.float64), axis=1).min()
+    for qi in differ:
+        assert want[1][qi] == 0.0                                                   # the reference's answer is an "intersection" ...
+        qt = q9[qi].reshape(3, 3).astype(np.float64)
+        tau_q = np.float64(np.finfo(np.float32).eps) / np.linalg.norm(np.cross(qt[1] - qt[0], qt[2] - qt[0]))
+        d2_all = orc.tri_tri(mesh, np.tile(q9[qi], (len(mesh), 1)))[0]
+        true = np.array([_exact_tri_tri_distance(mesh[e].reshape(3, 3).astype(np.float64), qt) for e in range(len(mesh))])
+        floor = tau_e + tau_q                                                       # the floor of the traversal (TriQState::floor2), to ~1e-3
+        spurious = (d2_all == 0) & (true > 0.98 * floor)                           # (the 2 % band around it may fall either way)
+        assert true[want[0][qi]] > 1.02 * floor or spurious[want[0][qi]]           # ... of a pair that is apart by more than the floor,
+        # and the engine returns the minimum over a set of pairs that contains every pair that is NOT such a case (it may also have visited
+        # some that are): a real pair value, no worse than the best legitimate pair, no better than the reference's exhaustive minimum
+        rest = np.where(spurious, np.float32(np.inf), d2_all)
+        k = int(np.lexsort((np.arange(len(rest)), rest))[0])
+        gi = int(got[0][qi])
+        assert got[1][qi] == d2_all[gi]
+        assert (got[1][qi], gi) <= (rest[k], k) and (got[1][qi], gi) > (want[1][qi], int(want[0][qi]))
