@@ -191,10 +191,11 @@ int tgq_closest_segment(tgq_handle * h, const float * a3, const float * b3, int3
  * --, query.closestPoint(element) on point structures (Algorithms/MetricL2.hpp:219-233, Triangle3.hpp:294-304).  dist_bound as in
  * tgq_closest (the query's bounding box in the root rejection).  Outputs (each may be null): idx[Q], d2[Q] (-1 when none),
  * element_point3 / query_point3 [Q x 3] = NeighborPair::getTargetPoint / getQueryPoint.  Ties go to the lowest element index.
- * Parity exception: the reference's triangle-triangle test calls a pair intersecting, at any lateral distance, when
- * all three query vertices lie within FLT_EPSILON / |N_element| of the element's infinite plane and the element's interval on the
- * intersection line contains the coordinate 0 (a defect of Triangle3.hpp:1041-1077,1209-1216); where the reference's exhaustive minimum is
- * such a pair, farther apart than that tolerance, this call returns the minimum over the other pairs.  Zero-area triangles (elements or
+ * Parity exception: the reference's triangle-triangle test snaps plane distances below FLT_EPSILON (in units of the
+ * unnormalised normal) to zero but keeps the unsnapped coordinates, and when all three query vertices are snapped it compares against an
+ * interval it never computed (Triangle3.hpp:1024-1077,1209-1216): it can call a pair intersecting that is farther apart than the
+ * tolerance FLT_EPSILON / |N| allows.  Where the reference's exhaustive minimum is such a pair, this call returns the minimum over the
+ * other pairs (rare unless triangles are small in absolute units).  Zero-area triangles (elements or
  * queries) make the reference's test a 2-D overlap test in a coordinate plane and are outside the guarantee as well. */
 int tgq_closest_triangle(tgq_handle * h, const float * q9, int64_t Q, double dist_bound, int32_t * idx, float * d2, float * element_point3,
                          float * query_point3);

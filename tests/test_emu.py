@@ -594,10 +594,10 @@ def _exact_tri_tri_distance(a, b):
 
 def test_triangle_queries_differ_from_the_reference_only_where_it_reports_spurious_intersections():
     """The documented exception of the triangle-query parity.  Moeller's test as the reference carries it snaps every signed
-    plane distance below FLT_EPSILON -- in units of the UNNORMALISED normal -- to zero; when all three vertices of the query lie that close to
-    an element's infinite plane, the query's interval on the intersection line is never computed and stays [0, 0] (Triangle3.hpp:1041-1077,
-    1209-1216), so the pair is called intersecting whenever the element's own interval contains the coordinate 0 -- at ANY lateral distance.
-    No spatial bound can anticipate that.  On a small-scale scene that provokes it, every query on which the engine's traversal and the
+    plane distance below FLT_EPSILON -- in units of the UNNORMALISED normal -- to zero but keeps the unsnapped coordinates (isect2,
+    Triangle3.hpp:1024-1039), and when all three vertices of the query are snapped its interval on the intersection line is never computed
+    and stays [0, 0] (:1041-1077,1209-1216): the reference can call pairs intersecting that are farther apart than the tolerance allows, in
+    the last case at ANY lateral distance.  No spatial bound can anticipate that.  On a small-scale scene that provokes it, every query on which the engine's traversal and the
     exhaustive minimum disagree is such a case: the reference's winner is a pair at a true distance far beyond the traversal's floor that it
     calls intersecting, and the engine's answer is the minimum over a set that contains all the remaining pairs."""
     rng = np.random.default_rng(233)

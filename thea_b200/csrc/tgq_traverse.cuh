@@ -1632,10 +1632,11 @@ TGQ_HD void seg_query(BvhView const & b, float scene_pad, v3 a, v3 dir, int cons
 // `floor2`: Moeller's test snaps a vertex within FLT_EPSILON / |N| of the other triangle's plane (N the UNNORMALISED normal, |N| = twice
 // the area) onto that plane (THEA_TRI3_USE_EPSILON_TEST, Triangle3.hpp:602-603,1141-1147), so a pair up to eps / |N_element| + eps / |N_query|
 // apart can be reported as intersecting (d2 = 0).  No node within that distance is ever pruned: floor = eps / (smallest positive
-// |N| of the structure's elements) + eps / |N_query| + mq.  That covers pairs of which SOME vertices are snapped.  When all three query
-// vertices are snapped (the query lies that close to the element's infinite plane) the reference never computes the query's interval on the
-// intersection line and compares the element's interval with [0, 0] (:1041-1077,1209-1216): an "intersection" at any lateral distance, decided
-// by where the origin lies -- no spatial bound covers it; DESIGN.md 4.3 states this exception and tests/test_emu.py characterises it.
+// |N| of the structure's elements) + eps / |N_query| + mq.  That is what a CONSISTENT perturbation of the vertices could reach; the reference
+// mixes snapped distances with unsnapped coordinates (isect2, :1024-1039), and when all three query vertices are snapped it never computes the
+// query's interval and compares the element's with [0, 0] (:1041-1077,1209-1216), so it can call pairs intersecting that are farther apart --
+// in the last case at any lateral distance, decided by where the origin lies.  No spatial bound covers that; DESIGN.md 4.3 states this
+// exception and tests/test_emu.py characterises it.
 // Zero-area triangles make the reference's test degenerate to a 2-D overlap test in a coordinate plane (:711-760 with N = 0) and are outside
 // the guarantee as well.
 template <bool TRI>
